@@ -1,0 +1,162 @@
+/* zb200.h — C ABI of the B200 engine behind the zlib drop-in.
+ *
+ * Plain pointers and sizes only; no CUDA or torch types in any signature
+ * (`stream` is a cudaStream_t passed as void*, NULL = the context's own
+ * stream).  Every entry point names the reference interface it stands in for
+ * (file:line under /root/reference, zlib 1.3.1.1-motley as shipped by
+ * discere-os/zlib.wasm).  The zlib.h-compatible surface (deflateInit2_,
+ * deflate, inflate, compress2, uncompress, crc32, adler32 ... and the
+ * src/wasm_module.c `zlib_*` exports) lives in the same shared object and is
+ * declared in include/zb200_zlib.h; it is a thin host layer over these calls.
+ *
+ * Conventions
+ *   - return value: ZB200_OK (0) or a negative ZB200_ERR_* code; never a CPU
+ *     fallback — without a usable CUDA device every call fails with
+ *     ZB200_ERR_NO_DEVICE.
+ *   - "_dev" entry points take DEVICE pointers and are asynchronous on
+ *     `stream` unless they return a value through a host pointer, in which
+ *     case they synchronise that stream before returning.
+ *   - "_host" entry points take HOST pointers, stage through the context's
+ *     pinned buffers with cudaMemcpyAsync, and are synchronous.
+ *   - unit of parallel work: a CHUNK (deflate: one Z_FULL_FLUSH-bounded block
+ *     run, deflate.c:1211-1226) or a MEMBER (inflate: one self-contained raw /
+ *     zlib / gzip stream, zlib.h:888-893).
+ */
+#ifndef ZB200_H
+#define ZB200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)   /* the library itself is built with -fvisibility=hidden */
+#endif
+
+#define ZB200_OK               0
+#define ZB200_ERR_NO_DEVICE   (-101)  /* no CUDA device / driver: there is no CPU path */
+#define ZB200_ERR_CUDA        (-102)  /* a CUDA runtime call failed: see zb200_last_error() */
+#define ZB200_ERR_PARAM       (-103)
+#define ZB200_ERR_NOMEM       (-104)
+#define ZB200_ERR_OUTPUT      (-105)  /* output capacity too small */
+
+typedef struct zb200_ctx zb200_ctx;
+
+/* ---- context ------------------------------------------------------------ */
+int         zb200_device_count(void);
+int         zb200_create(int device, zb200_ctx **out);   /* one context per GPU; owns stream, pinned staging, scratch */
+void        zb200_destroy(zb200_ctx *ctx);
+int         zb200_ctx_device(const zb200_ctx *ctx);
+int         zb200_sync(zb200_ctx *ctx, void *stream);
+const char *zb200_last_error(void);                      /* thread-local text of the last failure */
+const char *zb200_version(void);
+/* pinned host memory: *_host entry points DMA straight out of / into buffers
+ * obtained here (or registered with cudaHostRegister) instead of staging. */
+void       *zb200_host_alloc(size_t bytes);
+void        zb200_host_free(void *p);
+/* number of kernels this library has launched so far in this process (bench.py's gpu_launches) */
+uint64_t    zb200_launch_count(void);
+
+/* ---- checksums: crc32.c:694 crc32_z, adler32.c:61 adler32_z --------------
+ * which: bit 0 = CRC-32, bit 1 = Adler-32 (3 = one fused pass over the data). */
+#define ZB200_CRC32   1
+#define ZB200_ADLER32 2
+
+/* d_out2[0] = crc32(init_crc, data), d_out2[1] = adler32(init_adler, data); device memory, async. */
+int zb200_checksum_dev(zb200_ctx *ctx, const void *d_data, size_t len, int which,
+                       uint32_t init_crc, uint32_t init_adler, uint32_t *d_out2, void *stream);
+/* same, result returned to the host (synchronises). */
+int zb200_checksum_dev_sync(zb200_ctx *ctx, const void *d_data, size_t len, int which,
+                            uint32_t init_crc, uint32_t init_adler, uint32_t *crc, uint32_t *adler, void *stream);
+/* per-segment checksums (one per gzip member / chunk): segment i = d_base[off[i] .. off[i]+len[i]). */
+int zb200_checksum_segments_dev(zb200_ctx *ctx, const void *d_base, const uint64_t *d_off,
+                                const uint64_t *d_len, size_t nseg, int which,
+                                uint32_t *d_crc, uint32_t *d_adler, void *stream);
+/* host buffer, H2D through pinned staging inside the call. */
+int zb200_checksum_host(zb200_ctx *ctx, const void *data, size_t len, int which,
+                        uint32_t init_crc, uint32_t init_adler, uint32_t *crc, uint32_t *adler);
+
+/* crc32.c:1021-1049 / adler32.c:133: pure host arithmetic (no device needed). */
+uint32_t zb200_crc32_combine(uint32_t crc1, uint32_t crc2, uint64_t len2);
+uint32_t zb200_crc32_combine_gen(uint64_t len2);
+uint32_t zb200_crc32_combine_op(uint32_t crc1, uint32_t crc2, uint32_t op);
+uint32_t zb200_adler32_combine(uint32_t adler1, uint32_t adler2, int64_t len2);
+
+/* ---- deflate: deflate.c:954 deflate() over Z_FULL_FLUSH-bounded chunks ---- */
+#define ZB200_FRAME_RAW          0   /* chunks joined by 00 00 FF FF markers, last chunk BFINAL (windowBits -15) */
+#define ZB200_FRAME_ZLIB         1   /* + 2-byte header, Adler-32 trailer (deflate.c:1004-1037,1254) */
+#define ZB200_FRAME_GZIP         2   /* + 10-byte header, CRC-32/ISIZE trailer (deflate.c:1042-1054,1241) */
+#define ZB200_FRAME_GZIP_MEMBERS 3   /* every chunk its own gzip member (config C3 layout) */
+
+/* Worst-case output bytes for n input bytes cut into chunk_size chunks (compress.c:72, deflate.c:842). */
+size_t zb200_deflate_bound(size_t n, size_t chunk_size, int frame);
+/* Bytes of device scratch the engine will hold for a call of this shape. */
+size_t zb200_deflate_scratch_bytes(size_t n, size_t chunk_size);
+
+/* Compress d_in[0..n).  level 1..9 (deflate.c:112-124), strategy 0..4 (zlib.h:196-200),
+ * finish: 1 = last chunk carries BFINAL + trailer (Z_FINISH), 0 = every chunk ends
+ * with the sync marker (Z_FULL_FLUSH) and no trailer is written.
+ * d_out must be 4-byte aligned.  d_chunk_end (optional, nchunks entries) receives the
+ * exclusive end offset of every chunk inside d_out.  d_total receives the stream
+ * length (device uint64).  Asynchronous. */
+int zb200_deflate_dev(zb200_ctx *ctx, const void *d_in, size_t n, size_t chunk_size,
+                      int level, int strategy, int frame, int finish,
+                      void *d_out, size_t out_cap, uint64_t *d_chunk_end, uint64_t *d_total,
+                      void *stream);
+/* Host buffers: H2D, compress, D2H inside.  *out_len in: capacity, out: bytes written. */
+int zb200_deflate_host(zb200_ctx *ctx, const void *in, size_t n, size_t chunk_size,
+                       int level, int strategy, int frame, int finish,
+                       void *out, size_t *out_len, uint32_t *in_adler, uint32_t *in_crc);
+
+/* ---- inflate: inflate.c:590 inflate(), one warp per member ---------------- */
+#define ZB200_WRAP_RAW   0
+#define ZB200_WRAP_ZLIB  1
+#define ZB200_WRAP_GZIP  2
+#define ZB200_WRAP_AUTO  3   /* zlib or gzip by magic (inflateInit2 windowBits+32) */
+
+/* Per-member status: 0 = stream end reached and checks passed; otherwise the
+ * class of the reference's strm->msg (inflate.c:645-1212, inffast.c:158-283). */
+enum {
+    ZB200_INF_OK = 0,
+    ZB200_INF_HEADER_CHECK, ZB200_INF_METHOD, ZB200_INF_WINDOW, ZB200_INF_GZ_FLAGS, ZB200_INF_GZ_HCRC,
+    ZB200_INF_BLOCK_TYPE, ZB200_INF_STORED_LEN, ZB200_INF_TOO_MANY_SYMS, ZB200_INF_CODE_LENGTHS,
+    ZB200_INF_BIT_REPEAT, ZB200_INF_NO_EOB, ZB200_INF_LITLEN_SET, ZB200_INF_DIST_SET,
+    ZB200_INF_LITLEN_CODE, ZB200_INF_DIST_CODE, ZB200_INF_DIST_FAR, ZB200_INF_DATA_CHECK,
+    ZB200_INF_LENGTH_CHECK, ZB200_INF_TRUNCATED, ZB200_INF_OUTPUT_FULL, ZB200_INF_NEED_DICT,
+    ZB200_INF_COUNT
+};
+const char *zb200_inflate_msg(int status);   /* the reference's message literal for a status */
+
+typedef struct {
+    uint64_t in_off, in_len;     /* compressed bytes of this member inside d_in  */
+    uint64_t out_off, out_cap;   /* where its output goes inside d_out           */
+} zb200_member;
+
+typedef struct {
+    int32_t  status;             /* ZB200_INF_*                                   */
+    uint32_t check;              /* CRC-32 (gzip/raw) or Adler-32 (zlib) of the output */
+    uint64_t out_len;            /* bytes produced                                */
+    uint64_t in_used;            /* bytes consumed incl. header/trailer           */
+    uint64_t resume_bit;         /* bit offset of the last block boundary reached (for streaming resume) */
+    uint64_t resume_out;         /* output bytes complete at that boundary        */
+} zb200_member_result;
+
+/* Decode n_members independent members.  verify!=0 also checks the trailer
+ * (CRC-32 + ISIZE for gzip, Adler-32 for zlib) against the produced bytes.
+ * Asynchronous; d_members / d_results are device arrays. */
+int zb200_inflate_dev(zb200_ctx *ctx, const void *d_in, void *d_out,
+                      const zb200_member *d_members, size_t n_members, int wrap, int verify,
+                      zb200_member_result *d_results, void *stream);
+/* Host buffers, member table on the host; H2D/D2H inside; synchronous. */
+int zb200_inflate_host(zb200_ctx *ctx, const void *in, void *out,
+                       const zb200_member *members, size_t n_members, int wrap, int verify,
+                       zb200_member_result *results);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* ZB200_H */

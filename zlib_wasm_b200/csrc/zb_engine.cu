@@ -1,0 +1,312 @@
+// zb_engine.cu — context management, pinned staging, and the checksum part of
+// the C ABI (include/zb200.h).  The deflate / inflate entry points live next to
+// their kernels (zb_deflate.cu, zb_inflate.cu).
+#include "zb_internal.h"
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+#include <new>
+
+namespace zb {
+
+static thread_local char t_err[512];
+std::atomic<uint64_t> g_launches{0};
+
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(t_err, sizeof t_err, fmt, ap);
+    va_end(ap);
+}
+
+int ensure_scratch(zb200_ctx *ctx, size_t bytes) {
+    if (bytes <= ctx->scratch_bytes) return ZB200_OK;
+    if (ctx->d_scratch) {
+        ZB_CUDA(cudaDeviceSynchronize());   // nobody may still be using the old block
+        ZB_CUDA(cudaFree(ctx->d_scratch));
+        ctx->d_scratch = nullptr; ctx->scratch_bytes = 0;
+    }
+    size_t want = bytes + (bytes >> 3) + (1u << 20);
+    cudaError_t e = cudaMalloc(&ctx->d_scratch, want);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        want = bytes;
+        e = cudaMalloc(&ctx->d_scratch, want);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            set_error("device scratch of %zu bytes: %s", bytes, cudaGetErrorString(e));
+            return ZB200_ERR_NOMEM;
+        }
+    }
+    ctx->scratch_bytes = want;
+    return ZB200_OK;
+}
+
+static int grow(uint8_t **p, size_t *have, size_t need) {
+    if (need <= *have) return ZB200_OK;
+    if (*p) { ZB_CUDA(cudaDeviceSynchronize()); ZB_CUDA(cudaFree(*p)); *p = nullptr; *have = 0; }
+    size_t want = need + (need >> 3) + 4096;
+    cudaError_t e = cudaMalloc((void **)p, want);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        set_error("device buffer of %zu bytes: %s", want, cudaGetErrorString(e));
+        return ZB200_ERR_NOMEM;
+    }
+    *have = want;
+    return ZB200_OK;
+}
+
+int ensure_io(zb200_ctx *ctx, size_t in_bytes, size_t out_bytes) {
+    int r = grow(&ctx->d_io_in, &ctx->io_in_bytes, in_bytes);
+    if (r) return r;
+    return grow(&ctx->d_io_out, &ctx->io_out_bytes, out_bytes);
+}
+
+// Pageable host memory -> device through the two pinned stages: memcpy into
+// stage k on the CPU overlaps the DMA of stage k^1.
+int h2d_staged(zb200_ctx *ctx, void *d_dst, const void *h_src, size_t n, cudaStream_t s) {
+    const uint8_t *src = (const uint8_t *)h_src;
+    uint8_t *dst = (uint8_t *)d_dst;
+    int k = 0;
+    for (size_t off = 0; off < n;) {
+        size_t m = n - off < ctx->stage_bytes ? n - off : ctx->stage_bytes;
+        ZB_CUDA(cudaEventSynchronize(ctx->stage_ev[k]));
+        memcpy(ctx->h_stage[k], src + off, m);
+        ZB_CUDA(cudaMemcpyAsync(dst + off, ctx->h_stage[k], m, cudaMemcpyHostToDevice, s));
+        ZB_CUDA(cudaEventRecord(ctx->stage_ev[k], s));
+        off += m; k ^= 1;
+    }
+    return ZB200_OK;
+}
+
+int d2h_staged(zb200_ctx *ctx, void *h_dst, const void *d_src, size_t n, cudaStream_t s) {
+    uint8_t *dst = (uint8_t *)h_dst;
+    const uint8_t *src = (const uint8_t *)d_src;
+    size_t pend_off[2] = {0, 0}, pend_n[2] = {0, 0};
+    int k = 0;
+    for (size_t off = 0; off < n;) {
+        size_t m = n - off < ctx->stage_bytes ? n - off : ctx->stage_bytes;
+        if (pend_n[k]) {
+            ZB_CUDA(cudaEventSynchronize(ctx->stage_ev[k]));
+            memcpy(dst + pend_off[k], ctx->h_stage[k], pend_n[k]);
+            pend_n[k] = 0;
+        } else {
+            ZB_CUDA(cudaEventSynchronize(ctx->stage_ev[k]));
+        }
+        ZB_CUDA(cudaMemcpyAsync(ctx->h_stage[k], src + off, m, cudaMemcpyDeviceToHost, s));
+        ZB_CUDA(cudaEventRecord(ctx->stage_ev[k], s));
+        pend_off[k] = off; pend_n[k] = m;
+        off += m; k ^= 1;
+    }
+    for (int i = 0; i < 2; ++i, k ^= 1)
+        if (pend_n[k]) {
+            ZB_CUDA(cudaEventSynchronize(ctx->stage_ev[k]));
+            memcpy(dst + pend_off[k], ctx->h_stage[k], pend_n[k]);
+            pend_n[k] = 0;
+        }
+    return ZB200_OK;
+}
+
+}  // namespace zb
+
+using namespace zb;
+
+extern "C" {
+
+const char *zb200_version(void) { return "zlib-b200 0.1 (sm_100a) / zlib 1.3.1.1-motley API"; }
+const char *zb200_last_error(void) { return t_err; }
+uint64_t zb200_launch_count(void) { return g_launches.load(); }
+
+int zb200_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int zb200_create(int device, zb200_ctx **out) {
+    if (!out) return ZB200_ERR_PARAM;
+    *out = nullptr;
+    int n = zb200_device_count();
+    if (n <= 0) { set_error("no CUDA device available; this library has no CPU path"); return ZB200_ERR_NO_DEVICE; }
+    if (device < 0 || device >= n) { set_error("device %d out of range (have %d)", device, n); return ZB200_ERR_PARAM; }
+    ZB_CUDA(cudaSetDevice(device));
+    zb200_ctx *ctx = new (std::nothrow) zb200_ctx();
+    if (!ctx) return ZB200_ERR_NOMEM;
+    ctx->device = device;
+    int r = ZB200_OK;
+    auto fail = [&](int code) { zb200_destroy(ctx); return code; };
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return fail(ZB200_ERR_CUDA);
+    ctx->sm_count = prop.multiProcessorCount;
+    if (prop.major < 10) {
+        set_error("device %d is sm_%d%d; this library carries sm_100a code only", device, prop.major, prop.minor);
+        return fail(ZB200_ERR_NO_DEVICE);
+    }
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) return fail(ZB200_ERR_CUDA);
+    if (cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess) return fail(ZB200_ERR_CUDA);
+    ctx->stage_bytes = 32u << 20;
+    for (int k = 0; k < zb200_ctx::kStages; ++k) {
+        if (cudaMallocHost((void **)&ctx->h_stage[k], ctx->stage_bytes) != cudaSuccess) return fail(ZB200_ERR_NOMEM);
+        if (cudaEventCreateWithFlags(&ctx->stage_ev[k], cudaEventDisableTiming) != cudaSuccess) return fail(ZB200_ERR_CUDA);
+    }
+    if (cudaMalloc((void **)&ctx->d_small, 64 * sizeof(uint64_t)) != cudaSuccess) return fail(ZB200_ERR_NOMEM);
+    if (cudaMallocHost((void **)&ctx->h_small, 64 * sizeof(uint64_t)) != cudaSuccess) return fail(ZB200_ERR_NOMEM);
+    if ((r = checksum_init(ctx)) != ZB200_OK) return fail(r);
+    if ((r = deflate_init(ctx)) != ZB200_OK) return fail(r);
+    if ((r = inflate_init(ctx)) != ZB200_OK) return fail(r);
+    if ((r = ensure_scratch(ctx, 1u << 20)) != ZB200_OK) return fail(r);
+    *out = ctx;
+    return ZB200_OK;
+}
+
+void zb200_destroy(zb200_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    for (int k = 0; k < zb200_ctx::kStages; ++k) {
+        if (ctx->h_stage[k]) cudaFreeHost(ctx->h_stage[k]);
+        if (ctx->stage_ev[k]) cudaEventDestroy(ctx->stage_ev[k]);
+    }
+    if (ctx->d_small) cudaFree(ctx->d_small);
+    if (ctx->h_small) cudaFreeHost(ctx->h_small);
+    if (ctx->d_crc_tables) cudaFree(ctx->d_crc_tables);
+    if (ctx->d_deflate_tables) cudaFree(ctx->d_deflate_tables);
+    if (ctx->d_scratch) cudaFree(ctx->d_scratch);
+    if (ctx->d_io_in) cudaFree(ctx->d_io_in);
+    if (ctx->d_io_out) cudaFree(ctx->d_io_out);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    cudaGetLastError();
+    delete ctx;
+}
+
+int zb200_ctx_device(const zb200_ctx *ctx) { return ctx ? ctx->device : -1; }
+
+int zb200_sync(zb200_ctx *ctx, void *stream) {
+    if (!ctx) return ZB200_ERR_PARAM;
+    ZB_CUDA(cudaSetDevice(ctx->device));
+    ZB_CUDA(cudaStreamSynchronize(pick_stream(ctx, stream)));
+    return ZB200_OK;
+}
+
+// ---- checksums --------------------------------------------------------------
+int zb200_checksum_dev(zb200_ctx *ctx, const void *d_data, size_t len, int which,
+                       uint32_t init_crc, uint32_t init_adler, uint32_t *d_out2, void *stream) {
+    if (!ctx || !d_out2 || (!d_data && len)) return ZB200_ERR_PARAM;
+    ZB_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t s = pick_stream(ctx, stream);
+    // accumulators: one CkAccum at the front of the small area (slots 8..11)
+    CkAccum *acc = (CkAccum *)(ctx->d_small + 8);
+    return checksum_launch(ctx, (const uint8_t *)d_data, nullptr, nullptr, len, 1, which, init_crc, init_adler,
+                           d_out2, d_out2 + 1, acc, s);
+}
+
+int zb200_checksum_dev_sync(zb200_ctx *ctx, const void *d_data, size_t len, int which,
+                            uint32_t init_crc, uint32_t init_adler, uint32_t *crc, uint32_t *adler, void *stream) {
+    if (!ctx) return ZB200_ERR_PARAM;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    uint32_t *d_out2 = (uint32_t *)ctx->d_small;
+    int r = zb200_checksum_dev(ctx, d_data, len, which, init_crc, init_adler, d_out2, stream);
+    if (r) return r;
+    cudaStream_t s = pick_stream(ctx, stream);
+    ZB_CUDA(cudaMemcpyAsync(ctx->h_small, d_out2, 8, cudaMemcpyDeviceToHost, s));
+    ZB_CUDA(cudaStreamSynchronize(s));
+    const uint32_t *h = (const uint32_t *)ctx->h_small;
+    if (crc && (which & ZB200_CRC32)) *crc = h[0];
+    if (adler && (which & ZB200_ADLER32)) *adler = h[1];
+    return ZB200_OK;
+}
+
+int zb200_checksum_segments_dev(zb200_ctx *ctx, const void *d_base, const uint64_t *d_off,
+                                const uint64_t *d_len, size_t nseg, int which,
+                                uint32_t *d_crc, uint32_t *d_adler, void *stream) {
+    if (!ctx || !d_off || !d_len) return ZB200_ERR_PARAM;
+    if (nseg == 0) return ZB200_OK;
+    ZB_CUDA(cudaSetDevice(ctx->device));
+    std::lock_guard<std::mutex> g(ctx->mu);
+    int r = ensure_scratch(ctx, nseg * sizeof(CkAccum));
+    if (r) return r;
+    return checksum_launch(ctx, (const uint8_t *)d_base, d_off, d_len, 0, nseg, which, 0, 1,
+                           d_crc, d_adler, (CkAccum *)ctx->d_scratch, pick_stream(ctx, stream));
+}
+
+int zb200_checksum_host(zb200_ctx *ctx, const void *data, size_t len, int which,
+                        uint32_t init_crc, uint32_t init_adler, uint32_t *crc, uint32_t *adler) {
+    if (!ctx || (!data && len)) return ZB200_ERR_PARAM;
+    ZB_CUDA(cudaSetDevice(ctx->device));
+    std::lock_guard<std::mutex> g(ctx->mu);
+    // Stream the buffer through the device in pieces, chaining the running
+    // values on the device (crc32/adler32 are running checksums, zlib.h:1711-1768):
+    // host memory of any size needs O(piece) device memory and one final 8-byte
+    // read-back.  Pinned callers (zb200_host_alloc / cudaHostRegister) are DMA-ed
+    // directly; pageable memory goes through the two pinned stages.
+    const size_t piece = ctx->stage_bytes;
+    int r = ensure_io(ctx, piece, 0);
+    if (r) return r;
+    cudaStream_t s = ctx->stream;
+    cudaPointerAttributes attr;
+    bool pinned = false;
+    if (len && cudaPointerGetAttributes(&attr, data) == cudaSuccess) pinned = attr.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    uint32_t *d_run = (uint32_t *)ctx->d_small;            // running (crc, adler) on the device
+    uint32_t *h_run = (uint32_t *)ctx->h_small;
+    h_run[0] = init_crc; h_run[1] = init_adler;
+    ZB_CUDA(cudaMemcpyAsync(d_run, h_run, 8, cudaMemcpyHostToDevice, s));
+    const uint8_t *src = (const uint8_t *)data;
+    CkAccum *acc = (CkAccum *)(ctx->d_small + 8);
+    int k = 0;
+    for (size_t off = 0; off < len; ) {
+        size_t m = len - off < piece ? len - off : piece;
+        if (pinned) {
+            ZB_CUDA(cudaMemcpyAsync(ctx->d_io_in, src + off, m, cudaMemcpyHostToDevice, s));
+        } else {
+            ZB_CUDA(cudaEventSynchronize(ctx->stage_ev[k]));
+            memcpy(ctx->h_stage[k], src + off, m);
+            ZB_CUDA(cudaMemcpyAsync(ctx->d_io_in, ctx->h_stage[k], m, cudaMemcpyHostToDevice, s));
+            ZB_CUDA(cudaEventRecord(ctx->stage_ev[k], s));
+        }
+        r = checksum_launch(ctx, ctx->d_io_in, nullptr, nullptr, m, 1, which, 0, 1, d_run, d_run + 1, acc, s, d_run);
+        if (r) return r;
+        off += m; k ^= 1;
+    }
+    ZB_CUDA(cudaMemcpyAsync(h_run, d_run, 8, cudaMemcpyDeviceToHost, s));
+    ZB_CUDA(cudaStreamSynchronize(s));
+    if (crc && (which & ZB200_CRC32)) *crc = h_run[0];
+    if (adler && (which & ZB200_ADLER32)) *adler = h_run[1];
+    return ZB200_OK;
+}
+
+void *zb200_host_alloc(size_t bytes) {
+    void *p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+void zb200_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+// ---- combine (pure host arithmetic) -------------------------------------------
+static const uint32_t *host_x2n() {
+    static X2nTable t;
+    static std::once_flag once;
+    std::call_once(once, [] { gf2_fill_x2n(t); });
+    return t.v;
+}
+
+uint32_t zb200_crc32_combine_gen(uint64_t len2) { return gf2_xpow(host_x2n(), len2, 3); }        // crc32.c:1034
+uint32_t zb200_crc32_combine_op(uint32_t crc1, uint32_t crc2, uint32_t op) { return gf2_mul(op, crc1) ^ crc2; }  // :1047
+uint32_t zb200_crc32_combine(uint32_t crc1, uint32_t crc2, uint64_t len2) {                      // :1021
+    return gf2_mul(gf2_xpow(host_x2n(), len2, 3), crc1) ^ crc2;
+}
+
+uint32_t zb200_adler32_combine(uint32_t adler1, uint32_t adler2, int64_t len2) {                 // adler32.c:133-155
+    if (len2 < 0) return 0xffffffffu;
+    const uint64_t P = kAdlerBase;
+    const uint64_t rem = (uint64_t)len2 % P;
+    const uint64_t a1 = adler1 & 0xffff, b1 = (adler1 >> 16) & 0xffff;
+    const uint64_t a2 = adler2 & 0xffff, b2 = (adler2 >> 16) & 0xffff;
+    // s1 = a1 + a2 - 1 ; s2 = b1 + b2 + len2*(a1 - 1)   (mod P)
+    const uint64_t s1 = (a1 + a2 + P - 1) % P;
+    const uint64_t s2 = (b1 + b2 + rem * a1 + P - rem) % P;
+    return (uint32_t)(s1 | (s2 << 16));
+}
+
+}  // extern "C"

@@ -1,0 +1,101 @@
+// zb_internal.h — engine-private declarations shared by the CUDA translation
+// units and the host API layers.  Nothing here is part of the C ABI.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+#include <mutex>
+#include <atomic>
+
+#include "../../include/zb200.h"
+#include "zb_gf2.h"
+
+namespace zb {
+
+// ---- error plumbing --------------------------------------------------------
+void set_error(const char *fmt, ...);
+extern std::atomic<uint64_t> g_launches;
+
+#define ZB_CUDA(expr)                                                              \
+    do {                                                                           \
+        cudaError_t _e = (expr);                                                   \
+        if (_e != cudaSuccess) {                                                   \
+            ::zb::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr,          \
+                            cudaGetErrorString(_e));                               \
+            return ZB200_ERR_CUDA;                                                 \
+        }                                                                          \
+    } while (0)
+
+#define ZB_LAUNCHED() (::zb::g_launches.fetch_add(1, std::memory_order_relaxed))
+#define ZB_CHECK_LAUNCH() ZB_CUDA(cudaGetLastError())
+
+// ---- device-resident constant tables --------------------------------------
+// CRC "Horner" tables: row j, entry b = (b << 8j) * x^(8*stride) mod p, for the
+// two strides the kernels use (see zb_checksum.cu), plus x^(2^k) and x^32.
+struct CrcTables {
+    uint32_t big[4][256];   // stride 16 KiB  (1024 threads x 16 B)
+    uint32_t seg[4][256];   // stride  4 KiB  ( 256 threads x 16 B)
+    uint32_t x2n[32];
+    uint32_t x32;
+    uint32_t pad[31];
+};
+
+struct CkAccum {            // per-segment accumulators, zeroed before each launch
+    unsigned long long a;   // sum of per-part Adler s1 contributions (each < 65521)
+    unsigned long long b;   // sum of per-part Adler s2 contributions
+    uint32_t crc;           // xor of weighted pure-CRC partials
+    uint32_t pad;
+};
+
+}  // namespace zb
+
+// ---- the context -----------------------------------------------------------
+struct zb200_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;          // the context's own stream
+    cudaStream_t copy_stream = nullptr;     // H2D/D2H staging stream
+    std::mutex mu;                          // serialises use of the scratch/staging below
+
+    zb::CrcTables *d_crc_tables = nullptr;
+    void *d_deflate_tables = nullptr;       // zb::DeflateTables (zb_deflate.cu)
+
+    // grow-only device scratch (checksum accumulators, deflate/inflate workspaces)
+    void *d_scratch = nullptr;
+    size_t scratch_bytes = 0;
+    // small device result area + its pinned mirror
+    uint64_t *d_small = nullptr;            // 64 x u64
+    uint64_t *h_small = nullptr;
+    // pinned staging ring for *_host entry points
+    static constexpr int kStages = 2;
+    uint8_t *h_stage[kStages] = {nullptr, nullptr};
+    cudaEvent_t stage_ev[kStages] = {nullptr, nullptr};
+    size_t stage_bytes = 0;
+    // device I/O buffers for *_host entry points (grow-only)
+    uint8_t *d_io_in = nullptr;  size_t io_in_bytes = 0;
+    uint8_t *d_io_out = nullptr; size_t io_out_bytes = 0;
+};
+
+namespace zb {
+
+int ensure_scratch(zb200_ctx *ctx, size_t bytes);
+int ensure_io(zb200_ctx *ctx, size_t in_bytes, size_t out_bytes);
+int h2d_staged(zb200_ctx *ctx, void *d_dst, const void *h_src, size_t n, cudaStream_t s);
+int d2h_staged(zb200_ctx *ctx, void *h_dst, const void *d_src, size_t n, cudaStream_t s);
+inline cudaStream_t pick_stream(zb200_ctx *ctx, void *stream) {
+    return stream ? (cudaStream_t)stream : ctx->stream;
+}
+
+// zb_checksum.cu
+int checksum_init(zb200_ctx *ctx);
+int checksum_launch(zb200_ctx *ctx, const uint8_t *d_base, const uint64_t *d_off, const uint64_t *d_len,
+                    uint64_t single_len, size_t nseg, int which, uint32_t init_crc, uint32_t init_adler,
+                    uint32_t *d_crc, uint32_t *d_adler, CkAccum *d_acc, cudaStream_t s,
+                    const uint32_t *d_init2 = nullptr);
+
+// zb_deflate.cu
+int deflate_init(zb200_ctx *ctx);
+// zb_inflate.cu
+int inflate_init(zb200_ctx *ctx);
+
+}  // namespace zb
