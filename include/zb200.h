@@ -131,19 +131,24 @@ const char *zb200_inflate_msg(int status);   /* the reference's message literal 
 typedef struct {
     uint64_t in_off, in_len;     /* compressed bytes of this member inside d_in  */
     uint64_t out_off, out_cap;   /* where its output goes inside d_out           */
+    uint64_t resume_bit;         /* 0 = fresh member (parse the wrapper header); else continue at this */
+    uint64_t resume_out;         /*     block boundary with resume_out bytes of output already in place */
 } zb200_member;
 
 typedef struct {
     int32_t  status;             /* ZB200_INF_*                                   */
-    uint32_t check;              /* CRC-32 (gzip/raw) or Adler-32 (zlib) of the output */
-    uint64_t out_len;            /* bytes produced                                */
-    uint64_t in_used;            /* bytes consumed incl. header/trailer           */
-    uint64_t resume_bit;         /* bit offset of the last block boundary reached (for streaming resume) */
-    uint64_t resume_out;         /* output bytes complete at that boundary        */
+    uint32_t wrap_kind;          /* resolved wrapper: 0 raw, 1 zlib, 2 gzip       */
+    uint32_t check;              /* CRC-32 (gzip/raw) or Adler-32 (zlib) computed over the output */
+    uint32_t isize;              /* gzip ISIZE field as stored in the trailer     */
+    uint64_t out_len;            /* valid bytes produced                          */
+    uint64_t in_used;            /* bytes consumed incl. header/trailer (status 0) */
+    uint64_t resume_bit;         /* last deflate-block boundary reached: bit offset in the member ... */
+    uint64_t resume_out;         /* ... and the output bytes complete there (streaming resume point) */
 } zb200_member_result;
 
 /* Decode n_members independent members.  verify!=0 also checks the trailer
  * (CRC-32 + ISIZE for gzip, Adler-32 for zlib) against the produced bytes.
+ * For a member that resumes (resume_bit != 0) `wrap` must be the resolved kind.
  * Asynchronous; d_members / d_results are device arrays. */
 int zb200_inflate_dev(zb200_ctx *ctx, const void *d_in, void *d_out,
                       const zb200_member *d_members, size_t n_members, int wrap, int verify,

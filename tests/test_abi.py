@@ -1,0 +1,57 @@
+"""CPU-side checks of the drop-in boundary: the library loads and exports every
+symbol include/zb200.h declares; without a GPU every compute entry point fails
+loudly (no CPU fallback); the pure-host combine functions match the golden
+vectors."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+import refz
+import zlib_wasm_b200 as zb
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared(header):
+    src = open(os.path.join(ROOT, "include", header)).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(zb200_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_symbols_exported():
+    L = C.CDLL(zb.LIB_PATH, mode=C.RTLD_LOCAL)
+    names = _declared("zb200.h")
+    assert len(names) >= 20
+    missing = [n for n in names if not hasattr(L, n)]
+    assert not missing, missing
+    assert sorted(zb.ABI) == names, "python ABI table and header drifted apart"
+
+
+def test_combine_matches_golden(golden):
+    L = zb.lib()
+    for c in golden["checksums"]["combine"]:
+        assert L.zb200_crc32_combine(0x12345678, 0x9abcdef0, c["len2"]) == c["crc"]
+        assert L.zb200_crc32_combine_gen(c["len2"]) == c["gen"]
+        assert L.zb200_crc32_combine_op(0x12345678, 0x9abcdef0, c["gen"]) == c["crc"]
+        assert L.zb200_adler32_combine(0x00c8012d, 0x11e60398, c["len2"]) == c["adler"]
+    assert L.zb200_adler32_combine(1, 1, -1) == 0xffffffff
+
+
+def test_no_cpu_fallback():
+    L = zb.lib()
+    if L.zb200_device_count() > 0:
+        pytest.skip("a GPU is present")
+    h = C.c_void_p()
+    assert L.zb200_create(0, C.byref(h)) == zb.ERR_NO_DEVICE
+    assert b"no CPU path" in L.zb200_last_error()
+    with pytest.raises(zb.ZB200Error):
+        zb.Context(0)
+
+
+def test_inflate_messages_are_the_reference_literals():
+    L = zb.lib()
+    o = refz.oracle()
+    for i in range(22):
+        assert L.zb200_inflate_msg(i) == o.c_inflate_msg(i)

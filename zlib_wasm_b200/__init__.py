@@ -28,12 +28,13 @@ WRAP_RAW, WRAP_ZLIB, WRAP_GZIP, WRAP_AUTO = 0, 1, 2, 3
 
 
 class Member(C.Structure):
-    _fields_ = [("in_off", C.c_uint64), ("in_len", C.c_uint64), ("out_off", C.c_uint64), ("out_cap", C.c_uint64)]
+    _fields_ = [("in_off", C.c_uint64), ("in_len", C.c_uint64), ("out_off", C.c_uint64), ("out_cap", C.c_uint64),
+                ("resume_bit", C.c_uint64), ("resume_out", C.c_uint64)]
 
 
 class MemberResult(C.Structure):
-    _fields_ = [("status", C.c_int32), ("check", C.c_uint32), ("out_len", C.c_uint64), ("in_used", C.c_uint64),
-                ("resume_bit", C.c_uint64), ("resume_out", C.c_uint64)]
+    _fields_ = [("status", C.c_int32), ("wrap_kind", C.c_uint32), ("check", C.c_uint32), ("isize", C.c_uint32),
+                ("out_len", C.c_uint64), ("in_used", C.c_uint64), ("resume_bit", C.c_uint64), ("resume_out", C.c_uint64)]
 
 
 class ZB200Error(RuntimeError):
@@ -147,7 +148,7 @@ class Context:
     def inflate_host(self, blob, members, wrap=WRAP_GZIP, verify=1, out_size=None):
         """members: list of (in_off, in_len, out_off, out_cap).  Returns (output bytes, [MemberResult])."""
         n = len(members)
-        arr = (Member * max(n, 1))(*[Member(*m) for m in members])
+        arr = (Member * max(n, 1))(*[Member(*(tuple(m) + (0, 0))[:6]) for m in members])
         res = (MemberResult * max(n, 1))()
         if out_size is None:
             out_size = max([m[2] + m[3] for m in members] + [1])

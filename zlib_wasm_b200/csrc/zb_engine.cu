@@ -107,6 +107,25 @@ int d2h_staged(zb200_ctx *ctx, void *h_dst, const void *d_src, size_t n, cudaStr
     return ZB200_OK;
 }
 
+static bool is_pinned(const void *p) {
+    cudaPointerAttributes attr;
+    bool pinned = cudaPointerGetAttributes(&attr, p) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    return pinned;
+}
+
+int h2d_auto(zb200_ctx *ctx, void *d_dst, const void *h_src, size_t n, cudaStream_t s) {
+    if (n == 0) return ZB200_OK;
+    if (is_pinned(h_src)) { ZB_CUDA(cudaMemcpyAsync(d_dst, h_src, n, cudaMemcpyHostToDevice, s)); return ZB200_OK; }
+    return h2d_staged(ctx, d_dst, h_src, n, s);
+}
+
+int d2h_auto(zb200_ctx *ctx, void *h_dst, const void *d_src, size_t n, cudaStream_t s) {
+    if (n == 0) return ZB200_OK;
+    if (is_pinned(h_dst)) { ZB_CUDA(cudaMemcpyAsync(h_dst, d_src, n, cudaMemcpyDeviceToHost, s)); return ZB200_OK; }
+    return d2h_staged(ctx, h_dst, d_src, n, s);
+}
+
 }  // namespace zb
 
 using namespace zb;
@@ -171,6 +190,7 @@ void zb200_destroy(zb200_ctx *ctx) {
     if (ctx->h_small) cudaFreeHost(ctx->h_small);
     if (ctx->d_crc_tables) cudaFree(ctx->d_crc_tables);
     if (ctx->d_deflate_tables) cudaFree(ctx->d_deflate_tables);
+    if (ctx->d_inflate_tables) cudaFree(ctx->d_inflate_tables);
     if (ctx->d_scratch) cudaFree(ctx->d_scratch);
     if (ctx->d_io_in) cudaFree(ctx->d_io_in);
     if (ctx->d_io_out) cudaFree(ctx->d_io_out);

@@ -1,2 +1,286 @@
+// zb_inflate.cu — one warp per member inflate (north_star: "inffast.c/inflate.c
+// as one-warp-per-member inflate_fast") plus trailer verification.
+//
+// Kernel shape: CTAs of kInfWarps warps; every warp pulls member indices from a
+// global counter (members are 64 KiB..1 MiB, so static striping would leave
+// the tail unbalanced).  Per warp: 6.7 KiB of shared memory holds the decode
+// tables of the open block (zb_inflate.cuh InflateScratch).  Lane 0 runs the
+// state machine; match / stored copies are executed by all 32 lanes.
+//
+// Algorithmic bytes per member: C_i read + U_i written; the LZ
+// back-references re-read recently written output from L1/L2.
 #include "zb_internal.h"
-namespace zb { int inflate_init(zb200_ctx *) { return ZB200_OK; } }
+#include "zb_inflate.cuh"
+#include <string.h>
+
+namespace zb {
+
+constexpr int kInfWarps = 4;
+
+struct InflateDeviceTables {
+    uint32_t fixed_lit[512];
+    uint32_t fixed_dist[64];
+    FormatTables fmt;
+};
+
+struct InflateShared {
+    InflateScratch scr[kInfWarps];
+    uint32_t fixed_lit[512];
+    uint32_t fixed_dist[64];
+    FormatTables fmt;
+};
+
+__global__ void __launch_bounds__(kInfWarps * 32)
+inflate_kernel(const uint8_t *__restrict__ in, uint8_t *out, const zb200_member *__restrict__ members,
+               uint32_t n_members, int wrap, zb200_member_result *__restrict__ results,
+               const InflateDeviceTables *__restrict__ tabs, unsigned int *__restrict__ counter,
+               uint64_t *__restrict__ seg_off, uint64_t *__restrict__ seg_len) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    InflateShared &sh = *reinterpret_cast<InflateShared *>(smem_raw);
+    {
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(tabs);
+        uint32_t *dst = sh.fixed_lit;
+        constexpr int words = (int)(sizeof(InflateDeviceTables) / 4);
+        for (int i = threadIdx.x; i < words; i += blockDim.x) dst[i] = src[i];
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned full = 0xffffffffu;
+
+    for (;;) {
+        unsigned int m = 0;
+        if (lane == 0) m = atomicAdd(counter, 1u);
+        m = __shfl_sync(full, m, 0);
+        if (m >= n_members) break;
+        const zb200_member mb = members[m];
+        const uint8_t *src = in + mb.in_off;
+        uint8_t *dst = out + mb.out_off;
+
+        InflateState st;
+        int hs = ZB200_INF_OK;
+        if (lane == 0) {
+            st.init(src, mb.in_len, dst, mb.out_cap, &sh.scr[warp], sh.fixed_lit, sh.fixed_dist, &sh.fmt);
+            if (mb.resume_bit) st.resume(mb.resume_bit, mb.resume_out, wrap);
+            else hs = st.parse_header(wrap);
+            if (hs) st.status = hs;
+        }
+        hs = __shfl_sync(full, hs, 0);
+        while (hs == ZB200_INF_OK) {
+            InflateEvent ev;
+            ev.kind = EV_DONE; ev.len = 0; ev.dist = 0; ev.src = 0; ev.dst = 0;
+            if (lane == 0) ev = st.run();
+            const uint32_t kind = __shfl_sync(full, ev.kind, 0);
+            if (kind == EV_DONE) break;
+            const uint32_t len = __shfl_sync(full, ev.len, 0);
+            const uint32_t dist = __shfl_sync(full, ev.dist, 0);
+            const uint64_t to = __shfl_sync(full, ev.dst, 0);
+            __syncwarp(full);                                  // lane 0's literal stores -> visible to the copy
+            if (kind == EV_MATCH) {
+                uint8_t *d = dst + to;
+                const uint8_t *s = d - dist;
+                if (dist >= len) {
+                    for (uint32_t i = lane; i < len; i += 32) d[i] = s[i];
+                } else {                                       // overlapping: byte-serial semantics (inffast.c:249-260)
+                    for (uint32_t i = lane; i < len; i += 32) d[i] = s[i % dist];
+                }
+            } else {                                           // stored block: input -> output
+                const uint64_t from = __shfl_sync(full, ev.src, 0);
+                const uint8_t *s = src + from;
+                uint8_t *d = dst + to;
+                for (uint32_t i = lane; i < len; i += 32) d[i] = s[i];
+            }
+            __syncwarp(full);
+        }
+        if (lane == 0) {
+            zb200_member_result r;
+            r.status = st.status;
+            r.wrap_kind = (uint32_t)st.wrap_kind;
+            r.check = st.stored_check;                         // replaced by the computed value in inflate_verify_kernel
+            r.isize = st.stored_isize;
+            r.out_len = st.pos;
+            r.in_used = st.in_used;
+            r.resume_bit = st.ck_bit;
+            r.resume_out = st.ck_out;
+            results[m] = r;
+            seg_off[m] = mb.out_off;
+            seg_len[m] = st.status == ZB200_INF_OK ? st.pos : 0;
+        }
+    }
+}
+
+// Trailer check: inflate.c:1183-1219 ("incorrect data check" / "incorrect length check").
+__global__ void inflate_verify_kernel(zb200_member_result *__restrict__ results, uint32_t n, int verify,
+                                      const uint32_t *__restrict__ crc, const uint32_t *__restrict__ adler) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    zb200_member_result r = results[i];
+    if (r.status != ZB200_INF_OK) return;
+    const uint32_t stored = r.check;
+    if (r.wrap_kind == 1) {
+        r.check = adler[i];
+        if (verify && stored != r.check) r.status = ZB200_INF_DATA_CHECK;
+    } else {
+        r.check = crc[i];
+        if (verify && r.wrap_kind == 2) {
+            if (stored != r.check) r.status = ZB200_INF_DATA_CHECK;
+            else if (r.isize != (uint32_t)r.out_len) r.status = ZB200_INF_LENGTH_CHECK;
+        }
+    }
+    results[i] = r;
+}
+
+int inflate_init(zb200_ctx *ctx) {
+    static InflateDeviceTables h;          // host image, identical for every context
+    static std::once_flag once;
+    std::call_once(once, [] {
+        memset(&h, 0, sizeof h);
+        format_fill(h.fmt);
+        uint8_t lens[288]; uint16_t work[320];
+        int i = 0;                         // inflate.c:252-290 fixedtables: 8/9/7/8-bit literal/length code, 5-bit distances
+        for (; i < 144; ++i) lens[i] = 8;
+        for (; i < 256; ++i) lens[i] = 9;
+        for (; i < 280; ++i) lens[i] = 7;
+        for (; i < 288; ++i) lens[i] = 8;
+        build_decode_table(TBL_LITLEN, lens, 288, h.fixed_lit, 512, kLitRoot, work, h.fmt);
+        for (i = 0; i < 32; ++i) lens[i] = 5;
+        build_decode_table(TBL_DIST, lens, 32, h.fixed_dist, 64, kDistRoot, work, h.fmt);
+    });
+    void *d = nullptr;
+    ZB_CUDA(cudaMalloc(&d, sizeof h));
+    ZB_CUDA(cudaMemcpy(d, &h, sizeof h, cudaMemcpyHostToDevice));
+    ctx->d_inflate_tables = d;
+    ZB_CUDA(cudaFuncSetAttribute(inflate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(InflateShared)));
+    return ZB200_OK;
+}
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// scratch layout for one call
+struct InflateWork {
+    unsigned int *counter; uint64_t *seg_off, *seg_len; uint32_t *crc, *adler; CkAccum *acc;
+    static size_t bytes(size_t n) {
+        return 256 + align_up(n * 8, 256) * 2 + align_up(n * 4, 256) * 2 + align_up(n * sizeof(CkAccum), 256);
+    }
+    void carve(void *base, size_t n) {
+        uint8_t *p = (uint8_t *)base;
+        counter = (unsigned int *)p; p += 256;
+        seg_off = (uint64_t *)p; p += align_up(n * 8, 256);
+        seg_len = (uint64_t *)p; p += align_up(n * 8, 256);
+        crc = (uint32_t *)p; p += align_up(n * 4, 256);
+        adler = (uint32_t *)p; p += align_up(n * 4, 256);
+        acc = (CkAccum *)p;
+    }
+};
+
+size_t inflate_work_bytes(size_t n_members) { return InflateWork::bytes(n_members); }
+
+int inflate_launch(zb200_ctx *ctx, const uint8_t *d_in, uint8_t *d_out, const zb200_member *d_members,
+                   size_t n, int wrap, int verify, zb200_member_result *d_results, void *d_work, cudaStream_t s) {
+    InflateWork w;
+    w.carve(d_work, n);
+    ZB_CUDA(cudaMemsetAsync(w.counter, 0, 256, s));
+    const int per_sm = 6;                                      // 6 CTAs x 4 warps x 6.9 KiB tables fit one SM
+    size_t ctas = (n + kInfWarps - 1) / kInfWarps;
+    const size_t cap = (size_t)ctx->sm_count * per_sm;
+    if (ctas > cap) ctas = cap;
+    inflate_kernel<<<(unsigned)ctas, kInfWarps * 32, sizeof(InflateShared), s>>>(
+        d_in, d_out, d_members, (uint32_t)n, wrap, d_results,
+        (const InflateDeviceTables *)ctx->d_inflate_tables, w.counter, w.seg_off, w.seg_len);
+    ZB_LAUNCHED();
+    ZB_CHECK_LAUNCH();
+    const int which = wrap == ZB200_WRAP_ZLIB ? ZB200_ADLER32 : wrap == ZB200_WRAP_AUTO ? (ZB200_CRC32 | ZB200_ADLER32) : ZB200_CRC32;
+    int r = checksum_launch(ctx, d_out, w.seg_off, w.seg_len, 0, n, which, 0, 1, w.crc, w.adler, w.acc, s);
+    if (r) return r;
+    inflate_verify_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(d_results, (uint32_t)n, verify, w.crc, w.adler);
+    ZB_LAUNCHED();
+    ZB_CHECK_LAUNCH();
+    return ZB200_OK;
+}
+
+}  // namespace zb
+
+using namespace zb;
+
+extern "C" {
+
+const char *zb200_inflate_msg(int status) {
+    static const char *const msgs[ZB200_INF_COUNT] = {
+        "", "incorrect header check", "unknown compression method", "invalid window size",
+        "unknown header flags set", "header crc mismatch", "invalid block type",
+        "invalid stored block lengths", "too many length or distance symbols",
+        "invalid code lengths set", "invalid bit length repeat",
+        "invalid code -- missing end-of-block", "invalid literal/lengths set",
+        "invalid distances set", "invalid literal/length code", "invalid distance code",
+        "invalid distance too far back", "incorrect data check", "incorrect length check",
+        "truncated input", "output buffer full", "need dictionary"};
+    return (status >= 0 && status < ZB200_INF_COUNT) ? msgs[status] : "unknown status";
+}
+
+int zb200_inflate_dev(zb200_ctx *ctx, const void *d_in, void *d_out, const zb200_member *d_members,
+                      size_t n_members, int wrap, int verify, zb200_member_result *d_results, void *stream) {
+    if (!ctx || !d_members || !d_results || wrap < 0 || wrap > 3 || n_members > 0xfffffff0ull) return ZB200_ERR_PARAM;
+    if (n_members == 0) return ZB200_OK;
+    ZB_CUDA(cudaSetDevice(ctx->device));
+    std::lock_guard<std::mutex> g(ctx->mu);
+    int r = ensure_scratch(ctx, InflateWork::bytes(n_members));
+    if (r) return r;
+    return inflate_launch(ctx, (const uint8_t *)d_in, (uint8_t *)d_out, d_members, n_members, wrap, verify,
+                          d_results, ctx->d_scratch, pick_stream(ctx, stream));
+}
+
+int zb200_inflate_host(zb200_ctx *ctx, const void *in, void *out, const zb200_member *members,
+                       size_t n_members, int wrap, int verify, zb200_member_result *results) {
+    if (!ctx || !members || !results || wrap < 0 || wrap > 3) return ZB200_ERR_PARAM;
+    if (n_members == 0) return ZB200_OK;
+    ZB_CUDA(cudaSetDevice(ctx->device));
+    std::lock_guard<std::mutex> g(ctx->mu);
+    size_t in_bytes = 0, out_bytes = 0;
+    for (size_t i = 0; i < n_members; ++i) {
+        if (members[i].in_off + members[i].in_len > in_bytes) in_bytes = members[i].in_off + members[i].in_len;
+        if (members[i].out_off + members[i].out_cap > out_bytes) out_bytes = members[i].out_off + members[i].out_cap;
+    }
+    const size_t tbl = align_up(n_members * sizeof(zb200_member), 256);
+    const size_t rsl = align_up(n_members * sizeof(zb200_member_result), 256);
+    int r = ensure_io(ctx, in_bytes + 16, out_bytes + 16);
+    if (r) return r;
+    r = ensure_scratch(ctx, tbl + rsl + InflateWork::bytes(n_members));
+    if (r) return r;
+    cudaStream_t s = ctx->stream;
+    uint8_t *base = (uint8_t *)ctx->d_scratch;
+    zb200_member *d_members = (zb200_member *)base;
+    zb200_member_result *d_results = (zb200_member_result *)(base + tbl);
+    void *d_work = base + tbl + rsl;
+    if ((r = h2d_auto(ctx, ctx->d_io_in, in, in_bytes, s))) return r;
+    // members that resume need the output produced so far (back-references reach into it)
+    for (size_t i = 0; i < n_members; ++i)
+        if (members[i].resume_bit && members[i].resume_out)
+            if ((r = h2d_auto(ctx, ctx->d_io_out + members[i].out_off, (const uint8_t *)out + members[i].out_off,
+                              members[i].resume_out, s))) return r;
+    if ((r = h2d_auto(ctx, d_members, members, n_members * sizeof(zb200_member), s))) return r;
+    r = inflate_launch(ctx, ctx->d_io_in, ctx->d_io_out, d_members, n_members, wrap, verify, d_results, d_work, s);
+    if (r) return r;
+    if ((r = d2h_auto(ctx, results, d_results, n_members * sizeof(zb200_member_result), s))) return r;
+    ZB_CUDA(cudaStreamSynchronize(s));
+    // bring back only what was produced: per member for small batches, one
+    // covering range for large ones (members are normally laid out back to back)
+    if (n_members <= 64) {
+        for (size_t i = 0; i < n_members; ++i) {
+            const size_t from = members[i].resume_bit ? members[i].resume_out : 0;
+            if (results[i].out_len > from)
+                if ((r = d2h_auto(ctx, (uint8_t *)out + members[i].out_off + from, ctx->d_io_out + members[i].out_off + from,
+                                  results[i].out_len - from, s))) return r;
+        }
+    } else {
+        size_t lo = (size_t)-1, hi = 0;
+        for (size_t i = 0; i < n_members; ++i) {
+            if (!results[i].out_len) continue;
+            if (members[i].out_off < lo) lo = members[i].out_off;
+            if (members[i].out_off + results[i].out_len > hi) hi = members[i].out_off + results[i].out_len;
+        }
+        if (hi > lo && (r = d2h_auto(ctx, (uint8_t *)out + lo, ctx->d_io_out + lo, hi - lo, s))) return r;
+    }
+    ZB_CUDA(cudaStreamSynchronize(s));
+    return ZB200_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,405 @@
+// zb_inflate.cuh — the per-member inflate state machine.
+//
+// B200 replacement for inflate.c:590-1264 (inflate), inftrees.c:32-299
+// (inflate_table) and inffast.c:50-304 (inflate_fast) for members decoded into
+// one contiguous output buffer: all distances resolve inside the output, so the
+// 32 KiB side window of inflate.c:368-412 (updatewindow) is not needed
+// (inflate.c:362-366).
+//
+// Division of labour inside the warp that owns a member (zb_inflate.cu):
+//   lane 0   runs this state machine: wrapper header, block headers, dynamic
+//            table construction, Huffman decode.  Literals are stored as they
+//            are decoded.  It stops at the next EVENT.
+//   all 32   lanes execute the event: an LZ77 match copy or a stored-block
+//            copy, striped over lanes, then lane 0 resumes.
+// Everything here is __host__ __device__: tests/emul replays the identical code
+// on the CPU (events executed by a plain loop) before any GPU time is spent.
+#pragma once
+#include "zb_format.h"
+#include "../../include/zb200.h"
+
+namespace zb {
+
+// ---- decode tables -----------------------------------------------------------
+// entry: [31:16] value   [15:12] extra-bit count / sub-table index bits
+//        [11:8]  op      [7:0]   code bits consumed at this level
+enum : uint32_t { OP_LIT = 0, OP_BASE = 1, OP_EOB = 2, OP_SUB = 3, OP_BAD = 4 };
+ZB_HD uint32_t mk_entry(uint32_t val, uint32_t extra, uint32_t op, uint32_t bits) {
+    return (val << 16) | (extra << 12) | (op << 8) | bits;
+}
+#define ZB_E_BITS(e)  ((e) & 0xffu)
+#define ZB_E_OP(e)    (((e) >> 8) & 0xfu)
+#define ZB_E_EXTRA(e) (((e) >> 12) & 0xfu)
+#define ZB_E_VAL(e)   ((e) >> 16)
+
+constexpr int kLitRoot = 9, kDistRoot = 6, kClRoot = 7;        // inflate.c:927,1002,1011
+constexpr int kLitEntries = 852, kDistEntries = 592;           // inftrees.h:49-51 ENOUGH_LENS / ENOUGH_DISTS
+constexpr int kClEntries = 128;
+enum { TBL_CODELEN = 0, TBL_LITLEN = 1, TBL_DIST = 2 };
+
+// Per-warp working memory (shared memory on the device).
+struct InflateScratch {
+    uint32_t lit[kLitEntries];
+    uint32_t dist[kDistEntries];       // the first kClEntries double as the code-length table while a header is read
+    uint16_t work[320];                // symbols sorted by code length
+    uint8_t  lens[320];                // code lengths of the block being set up
+};
+
+// Build a two-level decode table from code lengths (the job of inftrees.c:32-299).
+// Returns 0 = complete code, 1 = incomplete, 2 = no codes at all, -1 = over-subscribed
+// or out of table space.  The caller applies the reference's acceptance rules.
+ZB_HD int build_decode_table(int type, const uint8_t *lens, int n, uint32_t *table, int cap, int root,
+                             uint16_t *work, const FormatTables &fmt) {
+    uint16_t count[16], offs[16];
+    for (int i = 0; i < 16; ++i) count[i] = 0;
+    for (int i = 0; i < n; ++i) count[lens[i]]++;
+    int max = 15;
+    while (max >= 1 && count[max] == 0) --max;
+    const int root_size = 1 << root;
+    if (max == 0) {                                   // inftrees.c:111-119: decode-time error markers
+        for (int i = 0; i < root_size; ++i) table[i] = mk_entry(0, 0, OP_BAD, 1);
+        return 2;
+    }
+    int left = 1;
+    for (int len = 1; len <= 15; ++len) {             // inftrees.c:125-131
+        left <<= 1;
+        left -= count[len];
+        if (left < 0) return -1;
+    }
+    offs[1] = 0;
+    for (int len = 1; len < 15; ++len) offs[len + 1] = (uint16_t)(offs[len] + count[len]);
+    for (int i = 0; i < n; ++i) if (lens[i]) work[offs[lens[i]]++] = (uint16_t)i;
+    if (left > 0)                                     // incomplete: unassigned patterns must fail at decode time
+        for (int i = 0; i < root_size; ++i) table[i] = mk_entry(0, 0, OP_BAD, 1);
+
+    auto entry_for = [&](int sym, int bits) -> uint32_t {
+        if (type == TBL_CODELEN) return mk_entry((uint32_t)sym, 0, OP_LIT, (uint32_t)bits);
+        if (type == TBL_LITLEN) {
+            if (sym < 256) return mk_entry((uint32_t)sym, 0, OP_LIT, (uint32_t)bits);
+            if (sym == 256) return mk_entry(0, 0, OP_EOB, (uint32_t)bits);
+            if (sym > 285) return mk_entry(0, 0, OP_BAD, (uint32_t)bits);      // inftrees.c:57-60: 286,287 invalid
+            return mk_entry(fmt.len_base[sym - 257], fmt.len_extra[sym - 257], OP_BASE, (uint32_t)bits);
+        }
+        if (sym > 29) return mk_entry(0, 0, OP_BAD, (uint32_t)bits);           // inftrees.c:65-68: 30,31 invalid
+        return mk_entry(fmt.dist_base[sym], fmt.dist_extra[sym], OP_BASE, (uint32_t)bits);
+    };
+
+    int used = root_size;                              // next free entry (sub-tables follow the root table)
+    uint32_t code = 0;                                 // canonical code, MSB-first, of the current symbol
+    int idx = 0;                                       // position in work[]
+    uint32_t cur_prefix = 0xffffffffu;                 // root index owning the open sub-table
+    int sub_base = 0, sub_bits = 0;
+    for (int len = 1; len <= max; ++len) {
+        for (int k = count[len]; k > 0; --k, ++idx, ++code) {
+            const int sym = work[idx];
+            // bit-reverse the len-bit code: DEFLATE packs Huffman codes MSB first into an LSB-first stream
+            uint32_t rc = 0;
+            for (int b = 0; b < len; ++b) rc |= ((code >> b) & 1u) << (len - 1 - b);
+            if (len <= root) {
+                const uint32_t e = entry_for(sym, len);
+                for (uint32_t i = rc; i < (uint32_t)root_size; i += 1u << len) table[i] = e;
+            } else {
+                const uint32_t prefix = rc & (uint32_t)(root_size - 1);
+                if (prefix != cur_prefix) {
+                    // size the sub-table: grow until the remaining codes under this prefix fit
+                    // (inftrees.c:243-252), counting the codes not yet placed
+                    int curr = len - root;
+                    int room = 1 << curr;
+                    int remaining = k;                 // codes of this length still to place, incl. this one
+                    int l2 = len;
+                    while (curr + root < max) {
+                        room -= remaining;
+                        if (room <= 0) break;
+                        ++curr; room <<= 1; ++l2;
+                        remaining = count[l2];
+                    }
+                    if (used + (1 << curr) > cap) return -1;
+                    sub_base = used; sub_bits = curr; used += 1 << curr;
+                    cur_prefix = prefix;
+                    for (int i = 0; i < (1 << curr); ++i) table[sub_base + i] = mk_entry(0, 0, OP_BAD, 1);
+                    table[prefix] = mk_entry((uint32_t)sub_base, (uint32_t)curr, OP_SUB, (uint32_t)root);
+                }
+                const uint32_t e = entry_for(sym, len - root);
+                for (uint32_t i = rc >> root; i < (1u << sub_bits); i += 1u << (len - root)) table[sub_base + i] = e;
+            }
+        }
+        code <<= 1;
+    }
+    return left > 0 ? 1 : 0;
+}
+
+// ---- events handed from lane 0 to the whole warp ---------------------------------
+enum : uint32_t { EV_MATCH = 1, EV_STORED = 2, EV_DONE = 3 };
+struct InflateEvent {
+    uint32_t kind;
+    uint32_t len;        // match length / stored byte count
+    uint32_t dist;       // match distance
+    uint64_t src;        // stored: byte offset inside the member's input
+    uint64_t dst;        // output position the copy starts at
+};
+
+// ---- the state machine -------------------------------------------------------------
+struct InflateState {
+    // input
+    const uint8_t *in; uint64_t in_len; uint64_t next;     // next = bytes of input already loaded into hold
+    uint64_t hold; int bits;                               // LSB-first accumulator; bits < 0 => ran past the end
+    // output
+    uint8_t *out; uint64_t out_cap; uint64_t pos;
+    // block state
+    int last; int in_block;                                // in_block: 1 = Huffman block open
+    const uint32_t *lt, *dt;                               // tables of the open block
+    int wrap_kind;                                         // 0 raw, 1 zlib, 2 gzip (resolved)
+    int status;
+    uint64_t ck_bit, ck_out;                               // last block boundary (resume point)
+    uint32_t stored_check, stored_isize;                   // trailer values
+    uint64_t in_used;
+    InflateScratch *scr;
+    const uint32_t *fixed_lit, *fixed_dist;
+    const FormatTables *fmt;
+
+    ZB_HD void refill() {
+        while (bits <= 32) {
+            if (next >= in_len) break;
+            const uint8_t *p = in + next;
+            if ((((uintptr_t)p) & 3) == 0 && next + 4 <= in_len) {
+                hold |= (uint64_t)(*reinterpret_cast<const uint32_t *>(p)) << bits;
+                next += 4; bits += 32;
+            } else {
+                hold |= (uint64_t)(*p) << bits;
+                next += 1; bits += 8;
+            }
+        }
+    }
+    ZB_HD uint32_t peek(int k) const { return (uint32_t)hold & ((1u << k) - 1u); }
+    ZB_HD void drop(int k) { hold >>= k; bits -= k; }
+    ZB_HD uint32_t take(int k) { uint32_t v = peek(k); drop(k); return v; }
+    ZB_HD uint32_t take32() { uint32_t v = (uint32_t)hold; drop(32); return v; }
+    ZB_HD uint64_t bitpos() const { return next * 8 - (uint64_t)(int64_t)bits; }
+    // bytes really available as bits (negative bits means we consumed zero padding)
+    ZB_HD bool overrun() const { return bits < 0; }
+
+    ZB_HD void init(const uint8_t *src, uint64_t n, uint8_t *dst, uint64_t cap, InflateScratch *s,
+                    const uint32_t *flit, const uint32_t *fdist, const FormatTables *f) {
+        in = src; in_len = n; next = 0; hold = 0; bits = 0;
+        out = dst; out_cap = cap; pos = 0; last = 0; in_block = 0; lt = dt = nullptr;
+        wrap_kind = 0; status = ZB200_INF_OK; ck_bit = 0; ck_out = 0; stored_check = 0; stored_isize = 0;
+        in_used = 0; scr = s; fixed_lit = flit; fixed_dist = fdist; fmt = f;
+    }
+
+    // Continue a member at a block boundary reported by an earlier, truncated run
+    // (the streaming inflate() of the host API feeds input piecewise).
+    ZB_HD void resume(uint64_t bit_off, uint64_t out_pos, int kind) {
+        next = bit_off >> 3; hold = 0; bits = 0;
+        refill();
+        drop((int)(bit_off & 7));
+        pos = out_pos; wrap_kind = kind; ck_bit = bit_off; ck_out = out_pos;
+    }
+
+    // Wrapper header: inflate.c:622-669 (zlib), :671-808 (gzip).  Returns status.
+    ZB_HD int parse_header(int wrap) {
+        if (wrap == ZB200_WRAP_RAW) { wrap_kind = 0; return ZB200_INF_OK; }
+        if (in_len < 2) return ZB200_INF_TRUNCATED;
+        const uint32_t h0 = in[0], h1 = in[1];
+        if ((wrap & ZB200_WRAP_GZIP) && h0 == 0x1f && h1 == 0x8b) {
+            wrap_kind = 2;
+            if (in_len < 10) return ZB200_INF_TRUNCATED;
+            if (in[2] != 8) return ZB200_INF_METHOD;
+            const uint32_t flg = in[3];
+            if (flg & 0xe0) return ZB200_INF_GZ_FLAGS;
+            uint64_t p = 10;
+            if (flg & 4) {
+                if (p + 2 > in_len) return ZB200_INF_TRUNCATED;
+                p += 2 + (uint64_t)(in[p] | (in[p + 1] << 8));
+            }
+            for (int f = 8; f <= 16; f <<= 1)
+                if (flg & f) {
+                    for (;;) { if (p >= in_len) return ZB200_INF_TRUNCATED; if (in[p++] == 0) break; }
+                }
+            if (flg & 2) {
+                if (p + 2 > in_len) return ZB200_INF_TRUNCATED;
+                uint32_t c = 0xffffffffu;
+                for (uint64_t i = 0; i < p; ++i) c = crc_byte_bitwise(c, in[i]);
+                if (((~c) & 0xffff) != (uint32_t)(in[p] | (in[p + 1] << 8))) return ZB200_INF_GZ_HCRC;
+                p += 2;
+            }
+            if (p > in_len) return ZB200_INF_TRUNCATED;
+            next = p;
+            return ZB200_INF_OK;
+        }
+        if (!(wrap & ZB200_WRAP_ZLIB)) return ZB200_INF_HEADER_CHECK;
+        if (((h0 << 8) + h1) % 31) return ZB200_INF_HEADER_CHECK;
+        if ((h0 & 0xf) != 8) return ZB200_INF_METHOD;
+        if ((h0 >> 4) + 8 > 15) return ZB200_INF_WINDOW;
+        if (h1 & 0x20) return ZB200_INF_NEED_DICT;
+        wrap_kind = 1; next = 2;
+        return ZB200_INF_OK;
+    }
+
+    // Dynamic block header: inflate.c:898-1022.
+    ZB_HD int read_dynamic() {
+        refill();
+        const int nlen = (int)take(5) + 257, ndist = (int)take(5) + 1, ncode = (int)take(4) + 4;
+        if (overrun()) return ZB200_INF_TRUNCATED;
+        if (nlen > 286 || ndist > 30) return ZB200_INF_TOO_MANY_SYMS;
+        uint8_t *lens = scr->lens;
+        for (int i = 0; i < 19; ++i) lens[i] = 0;
+        for (int i = 0; i < ncode; ++i) {
+            refill();
+            lens[fmt->cl_order[i]] = (uint8_t)take(3);
+        }
+        if (overrun()) return ZB200_INF_TRUNCATED;
+        uint32_t *cl = scr->dist;                      // reuse: the distance table is built afterwards
+        int r = build_decode_table(TBL_CODELEN, lens, 19, cl, kClEntries, kClRoot, scr->work, *fmt);
+        if (r < 0 || r == 1) return ZB200_INF_CODE_LENGTHS;       // inftrees.c:131: incomplete CODES set is an error
+        const int total = nlen + ndist;
+        int have = 0;
+        // lens[] is about to be overwritten with the real code lengths
+        while (have < total) {
+            refill();
+            uint32_t e = cl[peek(kClRoot)];
+            uint32_t sym, b;
+            if (ZB_E_OP(e) == OP_BAD) { sym = 0; b = 1; }          // empty code-length code: inflate.c:940-947 reads val 0, 1 bit
+            else { sym = ZB_E_VAL(e); b = ZB_E_BITS(e); }
+            if (sym < 16) { drop((int)b); if (overrun()) return ZB200_INF_TRUNCATED; lens[have++] = (uint8_t)sym; continue; }
+            int rep; uint8_t val = 0;
+            if (sym == 16) {
+                if (bits < (int)b + 2) return ZB200_INF_TRUNCATED;
+                drop((int)b);
+                if (have == 0) return ZB200_INF_BIT_REPEAT;
+                val = lens[have - 1];
+                rep = 3 + (int)take(2);
+            } else if (sym == 17) {
+                if (bits < (int)b + 3) return ZB200_INF_TRUNCATED;
+                drop((int)b); rep = 3 + (int)take(3);
+            } else {
+                if (bits < (int)b + 7) return ZB200_INF_TRUNCATED;
+                drop((int)b); rep = 11 + (int)take(7);
+            }
+            if (have + rep > total) return ZB200_INF_BIT_REPEAT;
+            while (rep--) lens[have++] = val;
+        }
+        if (lens[256] == 0) return ZB200_INF_NO_EOB;
+        r = build_decode_table(TBL_LITLEN, lens, nlen, scr->lit, kLitEntries, kLitRoot, scr->work, *fmt);
+        if (r < 0) return ZB200_INF_LITLEN_SET;
+        if (r == 1) {                                  // inftrees.c:131-132: incomplete only if a single 1-bit code
+            int nz = 0, ones = 0;
+            for (int i = 0; i < nlen; ++i) { nz += lens[i] != 0; ones += lens[i] == 1; }
+            if (!(nz == 1 && ones == 1)) return ZB200_INF_LITLEN_SET;
+        }
+        r = build_decode_table(TBL_DIST, lens + nlen, ndist, scr->dist, kDistEntries, kDistRoot, scr->work, *fmt);
+        if (r < 0) return ZB200_INF_DIST_SET;
+        if (r == 1) {
+            int nz = 0, ones = 0;
+            for (int i = 0; i < ndist; ++i) { nz += lens[nlen + i] != 0; ones += lens[nlen + i] == 1; }
+            if (!(nz == 1 && ones == 1)) return ZB200_INF_DIST_SET;
+        }
+        lt = scr->lit; dt = scr->dist;
+        return ZB200_INF_OK;
+    }
+
+    ZB_HD InflateEvent done(int st) {
+        status = st;
+        InflateEvent ev; ev.kind = EV_DONE; ev.len = 0; ev.dist = 0; ev.src = 0; ev.dst = pos;
+        return ev;
+    }
+
+    // Trailer: inflate.c:1183-1219.  Values are recorded; the comparison with the
+    // computed checksum happens in the verify kernel (zb_inflate.cu).
+    ZB_HD InflateEvent finish() {
+        drop(bits & 7);
+        uint64_t p = next - (uint64_t)(bits >> 3);     // first unread byte
+        if (wrap_kind == 2) {
+            if (p + 8 > in_len) { in_used = p; return done(ZB200_INF_TRUNCATED); }
+            stored_check = (uint32_t)in[p] | ((uint32_t)in[p + 1] << 8) | ((uint32_t)in[p + 2] << 16) | ((uint32_t)in[p + 3] << 24);
+            stored_isize = (uint32_t)in[p + 4] | ((uint32_t)in[p + 5] << 8) | ((uint32_t)in[p + 6] << 16) | ((uint32_t)in[p + 7] << 24);
+            p += 8;
+        } else if (wrap_kind == 1) {
+            if (p + 4 > in_len) { in_used = p; return done(ZB200_INF_TRUNCATED); }
+            stored_check = ((uint32_t)in[p] << 24) | ((uint32_t)in[p + 1] << 16) | ((uint32_t)in[p + 2] << 8) | (uint32_t)in[p + 3];
+            p += 4;
+        }
+        in_used = p;
+        ck_bit = p * 8; ck_out = pos;
+        return done(ZB200_INF_OK);
+    }
+
+    // Run until something needs the whole warp (or the member ends).
+    ZB_HD InflateEvent run() {
+        for (;;) {
+            if (!in_block) {
+                if (last) return finish();
+                ck_bit = bitpos(); ck_out = pos;       // a block boundary: safe resume point
+                refill();
+                last = (int)take(1);
+                const uint32_t type = take(2);         // inflate.c:827-862
+                if (overrun()) return done(ZB200_INF_TRUNCATED);
+                if (type == 0) {                       // stored: inflate.c:863-897
+                    drop(bits & 7);
+                    refill();
+                    if (bits < 32) return done(ZB200_INF_TRUNCATED);
+                    const uint32_t v = take32();
+                    const uint32_t len = v & 0xffff;
+                    if (len != ((v >> 16) ^ 0xffff)) return done(ZB200_INF_STORED_LEN);
+                    const uint64_t src = next - (uint64_t)(bits >> 3);
+                    if (len > in_len - src) return done(ZB200_INF_TRUNCATED);
+                    if (len > out_cap - pos) return done(ZB200_INF_OUTPUT_FULL);
+                    InflateEvent ev; ev.kind = EV_STORED; ev.len = len; ev.dist = 0; ev.src = src; ev.dst = pos;
+                    next = src + len; hold = 0; bits = 0; pos += len;
+                    if (len == 0) continue;
+                    return ev;
+                } else if (type == 1) {
+                    lt = fixed_lit; dt = fixed_dist;
+                } else if (type == 2) {
+                    const int st = read_dynamic();
+                    if (st) return done(st);
+                } else {
+                    return done(ZB200_INF_BLOCK_TYPE);
+                }
+                in_block = 1;
+            }
+            // ---- symbol loop: inffast.c:100-287 ----
+            for (;;) {
+                refill();
+                uint32_t e = lt[peek(kLitRoot)];
+                if (ZB_E_OP(e) == OP_SUB) {
+                    const uint32_t sub = ZB_E_VAL(e) + (((uint32_t)(hold >> kLitRoot)) & ((1u << ZB_E_EXTRA(e)) - 1u));
+                    drop(kLitRoot);
+                    e = lt[sub];
+                }
+                drop((int)ZB_E_BITS(e));
+                const uint32_t op = ZB_E_OP(e);
+                if (op == OP_LIT) {
+                    if (overrun()) return done(ZB200_INF_TRUNCATED);
+                    if (pos >= out_cap) return done(ZB200_INF_OUTPUT_FULL);
+                    out[pos++] = (uint8_t)ZB_E_VAL(e);
+                    continue;
+                }
+                if (op == OP_EOB) {
+                    if (overrun()) return done(ZB200_INF_TRUNCATED);
+                    in_block = 0;
+                    break;
+                }
+                if (op != OP_BASE) return done(overrun() ? ZB200_INF_TRUNCATED : ZB200_INF_LITLEN_CODE);
+                const uint32_t len = ZB_E_VAL(e) + take((int)ZB_E_EXTRA(e));
+                refill();
+                uint32_t d = dt[peek(kDistRoot)];
+                if (ZB_E_OP(d) == OP_SUB) {
+                    const uint32_t sub = ZB_E_VAL(d) + (((uint32_t)(hold >> kDistRoot)) & ((1u << ZB_E_EXTRA(d)) - 1u));
+                    drop(kDistRoot);
+                    d = dt[sub];
+                }
+                drop((int)ZB_E_BITS(d));
+                if (ZB_E_OP(d) != OP_BASE) return done(overrun() ? ZB200_INF_TRUNCATED : ZB200_INF_DIST_CODE);
+                const uint32_t dist = ZB_E_VAL(d) + take((int)ZB_E_EXTRA(d));
+                if (overrun()) return done(ZB200_INF_TRUNCATED);
+                if (dist > pos) return done(ZB200_INF_DIST_FAR);          // inffast.c:152-161
+                if (len > out_cap - pos) return done(ZB200_INF_OUTPUT_FULL);
+                InflateEvent ev; ev.kind = EV_MATCH; ev.len = len; ev.dist = dist; ev.src = 0; ev.dst = pos;
+                pos += len;
+                return ev;
+            }
+        }
+    }
+};
+
+}  // namespace zb

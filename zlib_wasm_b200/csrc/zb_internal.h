@@ -58,7 +58,8 @@ struct zb200_ctx {
     std::mutex mu;                          // serialises use of the scratch/staging below
 
     zb::CrcTables *d_crc_tables = nullptr;
-    void *d_deflate_tables = nullptr;       // zb::DeflateTables (zb_deflate.cu)
+    void *d_deflate_tables = nullptr;       // zb::DeflateDeviceTables (zb_deflate.cu)
+    void *d_inflate_tables = nullptr;       // zb::InflateDeviceTables (zb_inflate.cu)
 
     // grow-only device scratch (checksum accumulators, deflate/inflate workspaces)
     void *d_scratch = nullptr;
@@ -82,6 +83,9 @@ int ensure_scratch(zb200_ctx *ctx, size_t bytes);
 int ensure_io(zb200_ctx *ctx, size_t in_bytes, size_t out_bytes);
 int h2d_staged(zb200_ctx *ctx, void *d_dst, const void *h_src, size_t n, cudaStream_t s);
 int d2h_staged(zb200_ctx *ctx, void *h_dst, const void *d_src, size_t n, cudaStream_t s);
+// pinned host memory is DMA-ed directly (async); pageable memory goes through the stages
+int h2d_auto(zb200_ctx *ctx, void *d_dst, const void *h_src, size_t n, cudaStream_t s);
+int d2h_auto(zb200_ctx *ctx, void *h_dst, const void *d_src, size_t n, cudaStream_t s);
 inline cudaStream_t pick_stream(zb200_ctx *ctx, void *stream) {
     return stream ? (cudaStream_t)stream : ctx->stream;
 }
@@ -97,5 +101,8 @@ int checksum_launch(zb200_ctx *ctx, const uint8_t *d_base, const uint64_t *d_off
 int deflate_init(zb200_ctx *ctx);
 // zb_inflate.cu
 int inflate_init(zb200_ctx *ctx);
+size_t inflate_work_bytes(size_t n_members);
+int inflate_launch(zb200_ctx *ctx, const uint8_t *d_in, uint8_t *d_out, const zb200_member *d_members,
+                   size_t n, int wrap, int verify, zb200_member_result *d_results, void *d_work, cudaStream_t s);
 
 }  // namespace zb
