@@ -189,8 +189,12 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     L = zb.lib()
     ctx = zb.Context(local)
-    stream = torch.cuda.current_stream()
+    # a real (non-default) stream: the C ABI treats a NULL stream as "the context's
+    # own stream", and CUDA events only see the stream they are recorded on
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
     sp = C.c_void_p(stream.cuda_stream)
+    assert sp.value, "expected a non-default stream handle"
 
     def barrier():
         if world > 1:

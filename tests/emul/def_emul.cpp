@@ -1,0 +1,87 @@
+// Host replay of the deflate pipeline phases (TEST ONLY): the same
+// zb_deflate.cuh cores the kernels run, driven by plain loops.  Never linked
+// into libzb200.so.
+#include <stdint.h>
+#include <stddef.h>
+#include <string.h>
+#include <stdlib.h>
+#include <vector>
+#include "../../zlib_wasm_b200/csrc/zb_deflate.cuh"
+
+using namespace zb;
+
+static FormatTables g_fmt;
+static StaticTrees g_st;
+static int g_ready;
+
+struct BitSink {
+    uint8_t *out; size_t cap; uint64_t bit;
+    void put(uint64_t v, uint32_t nb) {
+        for (uint32_t i = 0; i < nb; ++i, ++bit)
+            if ((v >> i) & 1) { if ((bit >> 3) < cap) out[bit >> 3] |= (uint8_t)(1u << (bit & 7)); }
+    }
+};
+
+// One chunk -> raw deflate bytes (blocks + marker when !final).  Returns size or -1.
+extern "C" long emul_deflate_chunk(const uint8_t *data, uint32_t n, int level, int strategy, int final_chunk,
+                                   uint8_t *out, size_t cap, uint32_t *stats /* nsyms, nblocks */) {
+    if (!g_ready) { format_fill(g_fmt); static_trees_fill(g_st); g_ready = 1; }
+    const DeflateParams prm = deflate_params(level, strategy);
+    std::vector<uint16_t> prev(n + 1, 0);
+    std::vector<uint32_t> mf(n + 1, 0), mq(n + 1, 0);
+    if (prm.mode == MODE_FAST || prm.mode == MODE_SLOW) {
+        std::vector<int32_t> head(1u << kHashBits, -1);
+        for (uint32_t p = 0; p + kMinMatch <= n; ++p) {
+            const uint32_t h = hash3(data + p);
+            const int32_t q = head[h];
+            prev[p] = (q > 0 && p - (uint32_t)q <= 65535u) ? (uint16_t)(p - (uint32_t)q) : 0;
+            head[h] = (int32_t)p;
+        }
+        for (uint32_t p = 0; p < n; ++p) { MatchPair r = match_at(data, n, prev.data(), p, prm); mf[p] = r.full; mq[p] = r.quarter; }
+    } else if (prm.mode == MODE_RLE) {
+        for (uint32_t p = 0; p < n; ++p) mf[p] = rle_at(data, n, p);
+    }
+    std::vector<uint32_t> syms(n + 2);
+    std::vector<BlockInfo> blocks(max_blocks_for(n));
+    ParseSink sink; sink.syms = syms.data(); sink.blocks = blocks.data();
+    parse_chunk(data, n, mf.data(), mq.data(), prm, final_chunk != 0, sink);
+    if (sink.nblocks > blocks.size()) return -2;
+    if (stats) { stats[0] = sink.nsyms; stats[1] = sink.nblocks; }
+    memset(out, 0, cap);
+    BitSink bs{out, cap, 0};
+    static TreeWork w;
+    static BlockCode code;
+    for (uint32_t b = 0; b < sink.nblocks; ++b) {
+        const BlockInfo &bi = blocks[b];
+        for (int i = 0; i < 286; ++i) w.lt[i].fc = 0;
+        for (int i = 0; i < 30; ++i) w.dt[i].fc = 0;
+        w.lt[256].fc = 1;
+        for (uint32_t i = 0; i < bi.sym_count; ++i) {
+            const uint32_t s = syms[bi.sym_start + i], dist = s >> 16, lc = s & 0xffff;
+            if (!dist) w.lt[lc].fc++;
+            else { w.lt[257 + g_fmt.len_code[lc]].fc++; w.dt[dist_to_code(g_fmt, dist)].fc++; }
+        }
+        block_build(w, bi, strategy, g_st, g_fmt, code);
+        const uint64_t start = bs.bit;
+        const uint32_t last = bi.flags & BLK_LAST;
+        bs.put(last | (code.type << 1), 3);
+        if (code.type == 0) {
+            bs.bit = (bs.bit + 7) & ~7ull;
+            bs.put(bi.byte_len & 0xffff, 16); bs.put(~bi.byte_len & 0xffff, 16);
+            for (uint32_t i = 0; i < bi.byte_len; ++i) bs.put(data[bi.byte_start + i], 8);
+        } else {
+            for (uint32_t i = 0; i < code.hdr_bits; ++i) bs.put((code.hdr[i >> 5] >> (i & 31)) & 1, 1);
+            for (uint32_t i = 0; i < bi.sym_count; ++i) {
+                uint32_t nb; const uint64_t v = symbol_bits(syms[bi.sym_start + i], code.lcode, code.llen, code.dcode, code.dlen, g_fmt, nb);
+                bs.put(v, nb);
+            }
+            bs.put(code.lcode[256], code.llen[256]);
+            if (bs.bit - start != code.body_bits) return -3;      // trees.c:1075 bits_sent == compressed_len
+        }
+        if (last) bs.bit = (bs.bit + 7) & ~7ull;
+        if (bs.bit != block_end_bit(bi, code, start)) return -4;
+    }
+    if (!final_chunk) { bs.put(0, 3); bs.bit = (bs.bit + 7) & ~7ull; bs.put(0xffff0000u, 32); }
+    const size_t bytes = (size_t)((bs.bit + 7) >> 3);
+    return bytes > cap ? -1 : (long)bytes;
+}

@@ -1,10 +1,530 @@
+// zb_deflate.cu — the deflate pipeline kernels and their orchestration.
+// Algorithm and reference citations: zb_deflate.cuh.  Data layout in HBM for a
+// sub-batch of B chunks of S bytes (scratch, per input byte): prev_dist u16 (2 B),
+// match tables 2 x u32 (8 B), symbols u32 (4 B); per block 32 B of BlockInfo and
+// 1.6 KiB of BlockCode.  Algorithmic bytes per chunk: U read + C written.
 #include "zb_internal.h"
-namespace zb { int deflate_init(zb200_ctx *) { return ZB200_OK; } }
-extern "C" {
-size_t zb200_deflate_bound(size_t n, size_t, int) { return n + (n >> 12) + (n >> 14) + (n >> 25) + 13; }
-size_t zb200_deflate_scratch_bytes(size_t, size_t) { return 0; }
-int zb200_deflate_dev(zb200_ctx *, const void *, size_t, size_t, int, int, int, int, void *, size_t, uint64_t *, uint64_t *, void *) {
-    zb::set_error("deflate: not built yet"); return ZB200_ERR_PARAM; }
-int zb200_deflate_host(zb200_ctx *, const void *, size_t, size_t, int, int, int, int, void *, size_t *, uint32_t *, uint32_t *) {
-    zb::set_error("deflate: not built yet"); return ZB200_ERR_PARAM; }
+#include "zb_deflate.cuh"
+#include <string.h>
+
+namespace zb {
+
+struct DeflateDeviceTables {
+    FormatTables fmt;
+    StaticTrees st;
+};
+
+struct DeflateWork {
+    uint16_t *prev; uint32_t *mfull, *mquarter, *syms;
+    BlockInfo *blocks; BlockCode *codes;
+    uint32_t *nblocks; uint64_t *chunk_bytes, *chunk_off;
+    uint32_t *chunk_crc; uint64_t *seg_off, *seg_len; CkAccum *acc;
+};
+
+static size_t al(size_t v) { return (v + 255) & ~(size_t)255; }
+
+static size_t work_bytes(size_t nb, size_t S, uint32_t MB) {
+    const size_t np = nb * S;
+    return al(np * 2) + 3 * al(np * 4 + 16) + al(nb * MB * sizeof(BlockInfo)) + al(nb * MB * sizeof(BlockCode)) +
+           al(nb * 4) * 2 + al(nb * 8) * 4 + al(nb * sizeof(CkAccum)) + 4096;
 }
+
+static void carve(DeflateWork &w, void *base, size_t nb, size_t S, uint32_t MB) {
+    uint8_t *p = (uint8_t *)base;
+    const size_t np = nb * S;
+    w.prev = (uint16_t *)p; p += al(np * 2);
+    w.mfull = (uint32_t *)p; p += al(np * 4 + 16);
+    w.mquarter = (uint32_t *)p; p += al(np * 4 + 16);
+    w.syms = (uint32_t *)p; p += al(np * 4 + 16);
+    w.blocks = (BlockInfo *)p; p += al(nb * MB * sizeof(BlockInfo));
+    w.codes = (BlockCode *)p; p += al(nb * MB * sizeof(BlockCode));
+    w.nblocks = (uint32_t *)p; p += al(nb * 4);
+    w.chunk_crc = (uint32_t *)p; p += al(nb * 4);
+    w.chunk_bytes = (uint64_t *)p; p += al(nb * 8);
+    w.chunk_off = (uint64_t *)p; p += al(nb * 8);
+    w.seg_off = (uint64_t *)p; p += al(nb * 8);
+    w.seg_len = (uint64_t *)p; p += al(nb * 8);
+    w.acc = (CkAccum *)p;
+}
+
+struct Batch {                 // one sub-batch of chunks, passed by value to the kernels
+    const uint8_t *in;         // start of the sub-batch's input
+    uint64_t bytes;            // input bytes in the sub-batch
+    uint32_t S;                // chunk size
+    uint32_t nb;               // chunks in the sub-batch
+    uint32_t MB;               // block slots per chunk
+    int last_is_final;         // the last chunk of this sub-batch ends the stream (Z_FINISH)
+    int all_final;             // every chunk is its own stream (gzip members)
+};
+
+__device__ __forceinline__ uint32_t chunk_len(const Batch &b, uint32_t c) {
+    const uint64_t off = (uint64_t)c * b.S;
+    const uint64_t rem = b.bytes - off;
+    return (uint32_t)(rem < b.S ? rem : b.S);
+}
+__device__ __forceinline__ bool chunk_final(const Batch &b, uint32_t c) {
+    return b.all_final || (b.last_is_final && c + 1 == b.nb);
+}
+
+// ---- phase 1: hash chains, one warp per chunk --------------------------------------
+// 32 consecutive positions per step: same-hash positions inside the step are
+// linked with match.any, the rest through a 32K-entry u16 head table in shared
+// memory holding window-relative positions; every 32 KiB the table slides like
+// deflate.c:187-209 so that entries stay 16-bit.
+__global__ void __launch_bounds__(32) dfl_chain_kernel(Batch b, uint16_t *__restrict__ prev_all) {
+    extern __shared__ __align__(16) uint16_t head[];
+    const uint32_t c = blockIdx.x, lane = threadIdx.x;
+    const uint8_t *data = b.in + (uint64_t)c * b.S;
+    const uint32_t n = chunk_len(b, c);
+    uint16_t *prev = prev_all + (uint64_t)c * b.S;
+    uint4 *h4 = reinterpret_cast<uint4 *>(head);
+    for (int i = lane; i < 4096; i += 32) h4[i] = make_uint4(0, 0, 0, 0);
+    __syncwarp();
+    uint32_t base = 0;
+    for (uint32_t p0 = 0; p0 < n; p0 += 32) {
+        if (p0 - base == 65536u) {                                 // slide: subtract 32768, saturating at 0 (= NIL)
+            for (int i = lane; i < 4096; i += 32) {
+                uint4 v = h4[i];
+                v.x = __vsubus2(v.x, 0x80008000u); v.y = __vsubus2(v.y, 0x80008000u);
+                v.z = __vsubus2(v.z, 0x80008000u); v.w = __vsubus2(v.w, 0x80008000u);
+                h4[i] = v;
+            }
+            base += 32768u;
+            __syncwarp();
+        }
+        const uint32_t p = p0 + lane;
+        const bool valid = p + kMinMatch <= n;
+        uint32_t h = 0;
+        if (valid) h = hash3(data + p);
+        const uint32_t key = valid ? h : (0x10000u | lane);
+        const uint32_t mask = __match_any_sync(0xffffffffu, key);
+        const uint32_t lower = mask & ((1u << lane) - 1u);
+        uint32_t dist = 0;
+        if (valid) {
+            if (lower) {
+                const uint32_t q = p0 + (31u - (uint32_t)__clz(lower));
+                dist = q ? p - q : 0;                              // position 0 is never a match target (deflate.c:1366)
+            } else {
+                const uint32_t e = head[h];
+                dist = e ? (p - base) - e : 0;
+            }
+        }
+        if (p < n) prev[p] = (uint16_t)dist;
+        __syncwarp();
+        if (valid && (mask >> lane) == 1u) head[h] = (uint16_t)(p - base);   // highest lane of its group
+        __syncwarp();
+    }
+}
+
+// ---- phase 2: longest match per position --------------------------------------------
+__global__ void __launch_bounds__(256)
+dfl_match_kernel(Batch b, DeflateParams prm, const uint16_t *__restrict__ prev_all,
+                 uint32_t *__restrict__ mfull, uint32_t *__restrict__ mquarter) {
+    const uint32_t c = blockIdx.y;
+    const uint32_t n = chunk_len(b, c);
+    const uint32_t p = blockIdx.x * 256 + threadIdx.x;
+    if (p >= n) return;
+    const uint64_t off = (uint64_t)c * b.S;
+    const uint8_t *data = b.in + off;
+    if (prm.mode == MODE_RLE) { mfull[off + p] = rle_at(data, n, p); return; }
+    const MatchPair r = match_at(data, n, prev_all + off, p, prm);
+    mfull[off + p] = r.full;
+    if (prm.need_quarter) mquarter[off + p] = r.quarter;
+}
+
+// ---- phase 3: parse, one chunk per warp (lane 0 walks the tables) ---------------------
+__global__ void __launch_bounds__(32)
+dfl_parse_kernel(Batch b, DeflateParams prm, const uint32_t *__restrict__ mfull,
+                 const uint32_t *__restrict__ mquarter, uint32_t *__restrict__ syms,
+                 BlockInfo *__restrict__ blocks, uint32_t *__restrict__ nblocks) {
+    const uint32_t c = blockIdx.x;
+    if (threadIdx.x != 0) return;
+    const uint64_t off = (uint64_t)c * b.S;
+    ParseSink s;
+    s.syms = syms + off; s.blocks = blocks + (uint64_t)c * b.MB;
+    parse_chunk(b.in + off, chunk_len(b, c), mfull + off, prm.need_quarter ? mquarter + off : mfull + off, prm,
+                chunk_final(b, c), s);
+    nblocks[c] = s.nblocks;
+}
+
+// ---- phase 4: per-block histogram + Huffman construction -------------------------------
+__global__ void __launch_bounds__(128)
+dfl_tree_kernel(Batch b, int strategy, const uint32_t *__restrict__ syms, const BlockInfo *__restrict__ blocks,
+                const uint32_t *__restrict__ nblocks, const DeflateDeviceTables *__restrict__ tabs,
+                BlockCode *__restrict__ codes) {
+    const uint32_t c = blockIdx.y, bi = blockIdx.x;
+    if (bi >= nblocks[c]) return;
+    __shared__ TreeWork w;
+    __shared__ uint32_t hist[288 + 32];
+    for (int i = threadIdx.x; i < 320; i += 128) hist[i] = 0;
+    __syncthreads();
+    const BlockInfo blk = blocks[(uint64_t)c * b.MB + bi];
+    const uint32_t *s = syms + (uint64_t)c * b.S + blk.sym_start;
+    for (uint32_t i = threadIdx.x; i < blk.sym_count; i += 128) {
+        const uint32_t v = s[i], dist = v >> 16, lc = v & 0xffff;
+        if (!dist) atomicAdd(&hist[lc], 1u);
+        else {
+            atomicAdd(&hist[257 + tabs->fmt.len_code[lc]], 1u);
+            atomicAdd(&hist[288 + dist_to_code(tabs->fmt, dist)], 1u);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 286; i += 128) w.lt[i].fc = (uint16_t)hist[i];
+    for (int i = threadIdx.x; i < 30; i += 128) w.dt[i].fc = (uint16_t)hist[288 + i];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        w.lt[256].fc = 1;                                          // END_BLOCK (trees.c:480 init_block)
+        block_build(w, blk, strategy, tabs->st, tabs->fmt, codes[(uint64_t)c * b.MB + bi]);
+    }
+}
+
+// ---- layout: bit offsets of blocks inside their chunk, chunk sizes ---------------------
+__global__ void dfl_layout_kernel(Batch b, BlockInfo *__restrict__ blocks, const BlockCode *__restrict__ codes,
+                                  const uint32_t *__restrict__ nblocks, uint64_t *__restrict__ chunk_bytes,
+                                  uint32_t member_overhead) {
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= b.nb) return;
+    uint64_t bit = 0;
+    const uint32_t nbk = nblocks[c];
+    for (uint32_t i = 0; i < nbk; ++i) {
+        BlockInfo &bi = blocks[(uint64_t)c * b.MB + i];
+        bi.bit_start_lo = (uint32_t)bit; bi.bit_start_hi = (uint32_t)(bit >> 32);
+        bit = block_end_bit(bi, codes[(uint64_t)c * b.MB + i], bit);
+    }
+    if (!chunk_final(b, c)) bit = ((bit + 3 + 7) & ~7ull) + 32;   // 000 + pad + 00 00 FF FF
+    chunk_bytes[c] = ((bit + 7) >> 3) + member_overhead;
+}
+
+// Exclusive scan of the chunk sizes of a sub-batch onto the running stream length.
+__global__ void __launch_bounds__(1024)
+dfl_scan_kernel(uint32_t nb, const uint64_t *__restrict__ chunk_bytes, uint64_t *__restrict__ chunk_off,
+                uint64_t *running, uint64_t *chunk_end_out) {
+    __shared__ uint64_t wsum[32];
+    __shared__ uint64_t carry;
+    if (threadIdx.x == 0) carry = *running;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (uint32_t base = 0; base < nb; base += 1024) {
+        const uint32_t i = base + threadIdx.x;
+        const uint64_t v = i < nb ? chunk_bytes[i] : 0;
+        uint64_t x = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint64_t y = __shfl_up_sync(0xffffffffu, x, d); if (lane >= d) x += y; }
+        if (lane == 31) wsum[warp] = x;
+        __syncthreads();
+        if (warp == 0) {
+            uint64_t s = wsum[lane];
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const uint64_t y = __shfl_up_sync(0xffffffffu, s, d); if (lane >= d) s += y; }
+            wsum[lane] = s;
+        }
+        __syncthreads();
+        const uint64_t before = carry + (warp ? wsum[warp - 1] : 0) + (x - v);
+        if (i < nb) { chunk_off[i] = before; if (chunk_end_out) chunk_end_out[i] = before + v; }
+        __syncthreads();
+        if (threadIdx.x == 0) carry += wsum[31];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *running = carry;
+}
+
+// ---- phase 5: bit packing ------------------------------------------------------------
+__device__ __forceinline__ void or_bits(uint32_t *out32, uint64_t bit, uint64_t v, uint32_t nb) {
+    if (nb == 0) return;
+    const uint64_t w = bit >> 5;
+    const uint32_t sh = (uint32_t)bit & 31u;
+    const uint64_t lo = v << sh;
+    const uint32_t a = (uint32_t)lo, bb = (uint32_t)(lo >> 32);
+    if (a) atomicOr(out32 + w, a);
+    if (bb) atomicOr(out32 + w + 1, bb);
+    if (sh && nb + sh > 64) { const uint32_t cc = (uint32_t)(v >> (64 - sh)); if (cc) atomicOr(out32 + w + 2, cc); }
+}
+
+__global__ void __launch_bounds__(256)
+dfl_pack_kernel(Batch b, const uint32_t *__restrict__ syms, const BlockInfo *__restrict__ blocks,
+                const BlockCode *__restrict__ codes, const uint32_t *__restrict__ nblocks,
+                const uint64_t *__restrict__ chunk_off, const uint64_t *__restrict__ chunk_bytes,
+                const DeflateDeviceTables *__restrict__ tabs, uint32_t *__restrict__ out32,
+                uint32_t member_header) {
+    const uint32_t c = blockIdx.y, bi = blockIdx.x;
+    const uint32_t nbk = nblocks[c];
+    if (bi > nbk) return;
+    const uint64_t chunk_bit0 = (chunk_off[c] + member_header) * 8;
+    if (bi == nbk) {                                               // sync marker after the last block
+        if (chunk_final(b, c) || threadIdx.x != 0) return;
+        // the marker's only set bits are the FF FF of its last two bytes
+        const uint64_t end_bit = (chunk_off[c] + chunk_bytes[c]) * 8;
+        or_bits(out32, end_bit - 16, 0xffffu, 16);
+        return;
+    }
+    __shared__ uint16_t s_lcode[288]; __shared__ uint8_t s_llen[288];
+    __shared__ uint16_t s_dcode[32];  __shared__ uint8_t s_dlen[32];
+    __shared__ uint32_t s_warp[8];
+    const BlockInfo blk = blocks[(uint64_t)c * b.MB + bi];
+    const BlockCode &code = codes[(uint64_t)c * b.MB + bi];
+    const uint32_t type = code.type;
+    const uint64_t start = chunk_bit0 + (((uint64_t)blk.bit_start_hi << 32) | blk.bit_start_lo);
+    if (threadIdx.x == 0) or_bits(out32, start, (blk.flags & BLK_LAST) | (type << 1), 3);
+    if (type == 0) {                                               // stored: trees.c:860-875
+        const uint64_t body = (start + 3 + 7) & ~7ull;
+        if (threadIdx.x == 0)
+            or_bits(out32, body, (uint64_t)(blk.byte_len & 0xffff) | ((uint64_t)(~blk.byte_len & 0xffff) << 16), 32);
+        const uint8_t *src = b.in + (uint64_t)c * b.S + blk.byte_start;
+        for (uint32_t i = threadIdx.x; i < blk.byte_len; i += 256) or_bits(out32, body + 32 + 8ull * i, src[i], 8);
+        return;
+    }
+    for (int i = threadIdx.x; i < 288; i += 256) { s_lcode[i] = code.lcode[i]; s_llen[i] = code.llen[i]; }
+    if (threadIdx.x < 32) { s_dcode[threadIdx.x] = code.dcode[threadIdx.x]; s_dlen[threadIdx.x] = code.dlen[threadIdx.x]; }
+    const uint32_t hdr_bits = code.hdr_bits;
+    for (uint32_t wd = threadIdx.x; wd * 32 < hdr_bits; wd += 256) {
+        const uint32_t left = hdr_bits - wd * 32;
+        or_bits(out32, start + 3 + 32ull * wd, code.hdr[wd], left < 32 ? left : 32);
+    }
+    __syncthreads();
+    uint64_t cursor = start + 3 + hdr_bits;
+    const uint32_t *s = syms + (uint64_t)c * b.S + blk.sym_start;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (uint32_t base = 0; base < blk.sym_count; base += 256) {
+        const uint32_t i = base + threadIdx.x;
+        uint32_t nb = 0;
+        uint64_t v = 0;
+        if (i < blk.sym_count) v = symbol_bits(s[i], s_lcode, s_llen, s_dcode, s_dlen, tabs->fmt, nb);
+        uint32_t x = nb;                                           // inclusive scan of bit lengths
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, d); if (lane >= d) x += y; }
+        if (lane == 31) s_warp[warp] = x;
+        __syncthreads();
+        uint32_t before = 0, total = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { const uint32_t t = s_warp[k]; if (k < warp) before += t; total += t; }
+        or_bits(out32, cursor + before + (x - nb), v, nb);
+        cursor += total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) or_bits(out32, cursor, s_lcode[256], s_llen[256]);   // END_BLOCK
+}
+
+// ---- framing ---------------------------------------------------------------------------
+// Stream header at offset 0 and trailer after the last chunk (deflate.c:1004-1054,1239-1256).
+__global__ void dfl_frame_kernel(uint8_t *out, int frame, int level, int strategy, int finish, int write_header,
+                                 uint64_t *running, const uint32_t *sums /* crc, adler */, uint64_t n,
+                                 uint64_t *total_out) {
+    if (threadIdx.x || blockIdx.x) return;
+    if (write_header) {
+        if (frame == ZB200_FRAME_ZLIB) {
+            const uint32_t lf = (strategy >= STRAT_HUFFMAN || level < 2) ? 0 : level < 6 ? 1 : level == 6 ? 2 : 3;
+            uint32_t hdr = (0x78u << 8) | (lf << 6);
+            hdr += 31 - hdr % 31;
+            out[0] = (uint8_t)(hdr >> 8); out[1] = (uint8_t)hdr;
+        } else if (frame == ZB200_FRAME_GZIP) {
+            const uint8_t g[10] = {0x1f, 0x8b, 8, 0, 0, 0, 0, 0,
+                                   (uint8_t)(level == 9 ? 2 : (strategy >= STRAT_HUFFMAN || level < 2) ? 4 : 0), 3};
+            for (int i = 0; i < 10; ++i) out[i] = g[i];
+        }
+    }
+    uint64_t pos = *running;
+    if (finish) {
+        if (frame == ZB200_FRAME_ZLIB) {
+            const uint32_t a = sums[1];
+            out[pos++] = (uint8_t)(a >> 24); out[pos++] = (uint8_t)(a >> 16); out[pos++] = (uint8_t)(a >> 8); out[pos++] = (uint8_t)a;
+        } else if (frame == ZB200_FRAME_GZIP) {
+            const uint32_t cr = sums[0], l = (uint32_t)n;
+            for (int i = 0; i < 4; ++i) out[pos++] = (uint8_t)(cr >> (8 * i));
+            for (int i = 0; i < 4; ++i) out[pos++] = (uint8_t)(l >> (8 * i));
+        }
+    }
+    *running = pos;
+    if (total_out) *total_out = pos;
+}
+
+// One gzip member per chunk: header before, CRC-32 + ISIZE after each chunk's deflate data.
+__global__ void dfl_member_frame_kernel(Batch b, uint8_t *out, int level, int strategy,
+                                        const uint64_t *__restrict__ chunk_off, const uint64_t *__restrict__ chunk_bytes,
+                                        const uint32_t *__restrict__ crc) {
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= b.nb) return;
+    uint8_t *h = out + chunk_off[c];
+    const uint8_t g[10] = {0x1f, 0x8b, 8, 0, 0, 0, 0, 0,
+                           (uint8_t)(level == 9 ? 2 : (strategy >= STRAT_HUFFMAN || level < 2) ? 4 : 0), 3};
+    for (int i = 0; i < 10; ++i) h[i] = g[i];
+    uint8_t *t = out + chunk_off[c] + chunk_bytes[c] - 8;
+    const uint32_t cr = crc[c], l = chunk_len(b, c);
+    for (int i = 0; i < 4; ++i) t[i] = (uint8_t)(cr >> (8 * i));
+    for (int i = 0; i < 4; ++i) t[4 + i] = (uint8_t)(l >> (8 * i));
+}
+
+__global__ void dfl_segments_kernel(Batch b, uint64_t first_off, uint64_t *seg_off, uint64_t *seg_len) {
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= b.nb) return;
+    seg_off[c] = first_off + (uint64_t)c * b.S;
+    seg_len[c] = chunk_len(b, c);
+}
+
+// ---------------------------------------------------------------------------
+int deflate_init(zb200_ctx *ctx) {
+    static DeflateDeviceTables h;
+    static std::once_flag once;
+    std::call_once(once, [] { memset(&h, 0, sizeof h); format_fill(h.fmt); static_trees_fill(h.st); });
+    void *d = nullptr;
+    ZB_CUDA(cudaMalloc(&d, sizeof h));
+    ZB_CUDA(cudaMemcpy(d, &h, sizeof h, cudaMemcpyHostToDevice));
+    ctx->d_deflate_tables = d;
+    ZB_CUDA(cudaFuncSetAttribute(dfl_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+    return ZB200_OK;
+}
+
+static size_t chunk_bound(size_t len) {
+    // fixed-Huffman worst case (deflate.c:852-855) + per-block and marker slack
+    return len + (len >> 3) + (len >> 8) + (len >> 9) + 4 + 8 * (len / kSymLimit + 2) + 16;
+}
+
+static size_t frame_overhead(int frame) { return frame == ZB200_FRAME_ZLIB ? 6 : frame == ZB200_FRAME_GZIP ? 18 : 0; }
+
+constexpr size_t kBatchBytes = 256u << 20;    // input bytes per sub-batch (bounds scratch at ~14x this)
+
+static size_t batch_chunks(size_t n, size_t S) {
+    size_t nch = (n + S - 1) / S;
+    if (nch == 0) nch = 1;
+    size_t nb = kBatchBytes / S;
+    if (nb == 0) nb = 1;
+    if (nb > 32768) nb = 32768;                 // gridDim.y limit of the per-chunk kernels
+    return nb < nch ? nb : nch;
+}
+
+int deflate_launch(zb200_ctx *ctx, const uint8_t *d_in, size_t n, size_t S, int level, int strategy, int frame,
+                   int finish, uint8_t *d_out, size_t out_cap, uint64_t *d_chunk_end, uint64_t *d_total,
+                   uint32_t *d_sums_out, cudaStream_t s) {
+    if (level < 1 || level > 9 || strategy < 0 || strategy > 4 || frame < 0 || frame > 3 || S < 1 ||
+        S > 0x40000000ull || ((uintptr_t)d_out & 3)) {
+        set_error("deflate: bad parameter (level 1..9, strategy 0..4, frame 0..3, chunk 1..2^30, 4-byte aligned output)");
+        return ZB200_ERR_PARAM;
+    }
+    const bool members = frame == ZB200_FRAME_GZIP_MEMBERS;
+    size_t nch = (n + S - 1) / S;
+    if (nch == 0 && (finish || members)) nch = 1;
+    if (out_cap < zb200_deflate_bound(n, S, frame)) { set_error("deflate: output capacity below zb200_deflate_bound()"); return ZB200_ERR_OUTPUT; }
+    const DeflateParams prm = deflate_params(level, strategy);
+    const uint32_t MB = max_blocks_for((uint32_t)S);
+    const size_t nb_max = batch_chunks(n, S);
+    int r = ensure_scratch(ctx, work_bytes(nb_max, S, MB));
+    if (r) return r;
+    DeflateWork w;
+    carve(w, ctx->d_scratch, nb_max, S, MB);
+    const DeflateDeviceTables *tabs = (const DeflateDeviceTables *)ctx->d_deflate_tables;
+    uint64_t *running = ctx->d_small + 16;                         // stream length so far (device)
+    uint32_t *sums = (uint32_t *)(ctx->d_small + 20);              // crc, adler of the whole input
+    CkAccum *acc1 = (CkAccum *)(ctx->d_small + 24);
+    const size_t zero_bytes = zb200_deflate_bound(n, S, frame);
+    ZB_CUDA(cudaMemsetAsync(d_out, 0, (zero_bytes + 3) & ~(size_t)3, s));
+    const uint64_t hdr = frame == ZB200_FRAME_ZLIB ? 2 : frame == ZB200_FRAME_GZIP ? 10 : 0;
+    ZB_CUDA(cudaMemcpyAsync(running, &ctx->h_small[32 + (hdr == 2 ? 1 : hdr == 10 ? 2 : 0)], 8, cudaMemcpyHostToDevice, s));
+    if (frame == ZB200_FRAME_ZLIB || frame == ZB200_FRAME_GZIP || d_sums_out) {
+        r = checksum_launch(ctx, d_in, nullptr, nullptr, n, 1, ZB200_CRC32 | ZB200_ADLER32, 0, 1, sums, sums + 1, acc1, s);
+        if (r) return r;
+        if (d_sums_out) ZB_CUDA(cudaMemcpyAsync(d_sums_out, sums, 8, cudaMemcpyDeviceToDevice, s));
+    }
+    for (size_t c0 = 0; c0 < nch; c0 += nb_max) {
+        Batch b;
+        b.nb = (uint32_t)(nch - c0 < nb_max ? nch - c0 : nb_max);
+        b.in = d_in + c0 * S;
+        const size_t off = c0 * S;
+        const size_t span = (size_t)b.nb * S;
+        b.bytes = n - off < span ? n - off : span;
+        b.S = (uint32_t)S; b.MB = MB;
+        b.last_is_final = (finish && c0 + b.nb == nch) ? 1 : 0;
+        b.all_final = members ? 1 : 0;
+        if (prm.mode == MODE_FAST || prm.mode == MODE_SLOW) {
+            dfl_chain_kernel<<<b.nb, 32, 65536, s>>>(b, w.prev);
+            ZB_LAUNCHED(); ZB_CHECK_LAUNCH();
+        }
+        if (prm.mode != MODE_HUFF) {
+            dim3 g((unsigned)((S + 255) / 256), b.nb);
+            dfl_match_kernel<<<g, 256, 0, s>>>(b, prm, w.prev, w.mfull, w.mquarter);
+            ZB_LAUNCHED(); ZB_CHECK_LAUNCH();
+        }
+        dfl_parse_kernel<<<b.nb, 32, 0, s>>>(b, prm, w.mfull, w.mquarter, w.syms, w.blocks, w.nblocks);
+        ZB_LAUNCHED(); ZB_CHECK_LAUNCH();
+        dfl_tree_kernel<<<dim3(MB, b.nb), 128, 0, s>>>(b, strategy, w.syms, w.blocks, w.nblocks, tabs, w.codes);
+        ZB_LAUNCHED(); ZB_CHECK_LAUNCH();
+        dfl_layout_kernel<<<(b.nb + 127) / 128, 128, 0, s>>>(b, w.blocks, w.codes, w.nblocks, w.chunk_bytes, members ? 18 : 0);
+        ZB_LAUNCHED(); ZB_CHECK_LAUNCH();
+        dfl_scan_kernel<<<1, 1024, 0, s>>>(b.nb, w.chunk_bytes, w.chunk_off, running, d_chunk_end ? d_chunk_end + c0 : nullptr);
+        ZB_LAUNCHED(); ZB_CHECK_LAUNCH();
+        dfl_pack_kernel<<<dim3(MB + 1, b.nb), 256, 0, s>>>(b, w.syms, w.blocks, w.codes, w.nblocks, w.chunk_off, w.chunk_bytes,
+                                                          tabs, (uint32_t *)d_out, members ? 10 : 0);
+        ZB_LAUNCHED(); ZB_CHECK_LAUNCH();
+        if (members) {
+            dfl_segments_kernel<<<(b.nb + 127) / 128, 128, 0, s>>>(b, off, w.seg_off, w.seg_len);
+            ZB_LAUNCHED(); ZB_CHECK_LAUNCH();
+            r = checksum_launch(ctx, d_in, w.seg_off, w.seg_len, 0, b.nb, ZB200_CRC32, 0, 1, w.chunk_crc, nullptr, w.acc, s);
+            if (r) return r;
+            dfl_member_frame_kernel<<<(b.nb + 63) / 64, 64, 0, s>>>(b, d_out, level, strategy, w.chunk_off, w.chunk_bytes, w.chunk_crc);
+            ZB_LAUNCHED(); ZB_CHECK_LAUNCH();
+        }
+    }
+    dfl_frame_kernel<<<1, 32, 0, s>>>(d_out, frame, level, strategy, finish, 1, running, sums, n, d_total);
+    ZB_LAUNCHED(); ZB_CHECK_LAUNCH();
+    return ZB200_OK;
+}
+
+}  // namespace zb
+
+using namespace zb;
+
+extern "C" {
+
+size_t zb200_deflate_bound(size_t n, size_t chunk_size, int frame) {
+    if (chunk_size == 0) chunk_size = 1;
+    size_t nch = (n + chunk_size - 1) / chunk_size;
+    if (nch == 0) nch = 1;
+    const size_t full = n / chunk_size, rem = n % chunk_size;
+    size_t per_member = frame == ZB200_FRAME_GZIP_MEMBERS ? 18 : 0;
+    size_t total = full * (chunk_bound(chunk_size) + per_member);
+    if (rem || full == 0) total += chunk_bound(rem) + per_member;
+    return (total + frame_overhead(frame) + 64 + 15) & ~(size_t)15;
+}
+
+size_t zb200_deflate_scratch_bytes(size_t n, size_t chunk_size) {
+    if (chunk_size == 0 || chunk_size > 0x40000000ull) return 0;
+    return work_bytes(batch_chunks(n, chunk_size), chunk_size, max_blocks_for((uint32_t)chunk_size));
+}
+
+int zb200_deflate_dev(zb200_ctx *ctx, const void *d_in, size_t n, size_t chunk_size, int level, int strategy,
+                      int frame, int finish, void *d_out, size_t out_cap, uint64_t *d_chunk_end,
+                      uint64_t *d_total, void *stream) {
+    if (!ctx || (!d_in && n) || !d_out) return ZB200_ERR_PARAM;
+    ZB_CUDA(cudaSetDevice(ctx->device));
+    std::lock_guard<std::mutex> g(ctx->mu);
+    return deflate_launch(ctx, (const uint8_t *)d_in, n, chunk_size, level, strategy, frame, finish,
+                          (uint8_t *)d_out, out_cap, d_chunk_end, d_total, nullptr, pick_stream(ctx, stream));
+}
+
+int zb200_deflate_host(zb200_ctx *ctx, const void *in, size_t n, size_t chunk_size, int level, int strategy,
+                       int frame, int finish, void *out, size_t *out_len, uint32_t *in_adler, uint32_t *in_crc) {
+    if (!ctx || (!in && n) || !out || !out_len) return ZB200_ERR_PARAM;
+    ZB_CUDA(cudaSetDevice(ctx->device));
+    std::lock_guard<std::mutex> g(ctx->mu);
+    const size_t bound = zb200_deflate_bound(n, chunk_size ? chunk_size : 1, frame);
+    int r = ensure_io(ctx, n + 16, bound + 16);
+    if (r) return r;
+    cudaStream_t s = ctx->stream;
+    if ((r = h2d_auto(ctx, ctx->d_io_in, in, n, s))) return r;
+    uint64_t *d_total = ctx->d_small + 17;
+    uint32_t *d_sums = (uint32_t *)(ctx->d_small + 18);
+    r = deflate_launch(ctx, ctx->d_io_in, n, chunk_size, level, strategy, frame, finish, ctx->d_io_out, bound,
+                       nullptr, d_total, d_sums, s);
+    if (r) return r;
+    ZB_CUDA(cudaMemcpyAsync(ctx->h_small, ctx->d_small + 17, 16, cudaMemcpyDeviceToHost, s));
+    ZB_CUDA(cudaStreamSynchronize(s));
+    const uint64_t total = ctx->h_small[0];
+    const uint32_t *hs = (const uint32_t *)(ctx->h_small + 1);
+    if (in_crc) *in_crc = hs[0];
+    if (in_adler) *in_adler = hs[1];
+    if (total > *out_len) { *out_len = (size_t)total; set_error("deflate: %llu bytes do not fit the output buffer", (unsigned long long)total); return ZB200_ERR_OUTPUT; }
+    if ((r = d2h_auto(ctx, out, ctx->d_io_out, (size_t)total, s))) return r;
+    ZB_CUDA(cudaStreamSynchronize(s));
+    *out_len = (size_t)total;
+    return ZB200_OK;
+}
+
+}  // extern "C"

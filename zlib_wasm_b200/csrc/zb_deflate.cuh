@@ -1,0 +1,482 @@
+// zb_deflate.cuh — per-thread cores of the deflate pipeline.
+//
+// B200 re-design of deflate.c (fill_window / longest_match / deflate_fast /
+// deflate_slow) and trees.c (build_tree / gen_bitlen / gen_codes / scan_tree /
+// send_tree / send_all_trees / compress_block / _tr_flush_block) for inputs cut
+// into independent chunks (one Z_FULL_FLUSH-bounded block run each,
+// deflate.c:1211-1226).  The reference's single sequential loop is split into
+// data-parallel phases (kernels in zb_deflate.cu):
+//
+//   1 chains   prev_dist[p] = distance to the most recent earlier position with
+//              the same 15-bit hash of 3 bytes (deflate.c:141,160-163).  Because
+//              deflate_slow inserts EVERY position (deflate.c:1947,1994-2000),
+//              the chains do not depend on the parse and can be built up front.
+//   2 matches  one thread per position walks its chain exactly like
+//              longest_match (deflate.c:1356-1497: max_chain candidates, stop at
+//              nice_match, first-longest wins, MAX_DIST limit) and records the
+//              result for the full chain budget and for the quartered budget
+//              (deflate.c:1390-1392 good_match).
+//   3 parse    one sequential pass per chunk picks matches with the reference's
+//              lazy (deflate.c:1923-2043) or greedy (deflate.c:1824-1915) rule
+//              from the precomputed tables, emits symbols and cuts blocks every
+//              16383 symbols (deflate.c:455,512).
+//   4 trees    per block: histogram, the reference's exact heap Huffman
+//              construction + length limiting + header RLE, block type choice
+//              (trees.c:997-1089).
+//   5 pack     per block: symbol -> code bits, prefix sum of bit lengths,
+//              bit-packing into the output stream (trees.c:900-951).
+//
+// For levels 4..9 the result is byte-identical to the reference on the same
+// chunking (tests pin this).  Levels 1..3 use the same machinery with a greedy
+// parse over full-insertion chains: the reference's deflate_fast skips hash
+// insertions inside matches (deflate.c:1873-1897), which makes its chains depend
+// on the parse; ours see strictly more candidates, so the ratio is equal or
+// better, but the bytes differ.
+#pragma once
+#include "zb_format.h"
+
+namespace zb {
+
+constexpr int kMinMatch = 3, kMaxMatch = 258;
+constexpr int kWSize = 32768;
+constexpr int kMinLookahead = kMaxMatch + kMinMatch + 1;      // deflate.h:293
+constexpr int kMaxDist = kWSize - kMinLookahead;              // deflate.h:298  (32506)
+constexpr int kTooFar = 4096;                                 // deflate.c:88-90
+constexpr uint32_t kSymLimit = 16383;                         // deflate.c:455,512 (lit_bufsize - 1, memLevel 8)
+constexpr int kHashBits = 15, kHashShift = 5;                 // deflate.c:444-447 (memLevel 8)
+constexpr uint32_t kHashMask = (1u << kHashBits) - 1;
+
+enum { MODE_FAST = 0, MODE_SLOW = 1, MODE_HUFF = 2, MODE_RLE = 3 };
+enum { STRAT_DEFAULT = 0, STRAT_FILTERED = 1, STRAT_HUFFMAN = 2, STRAT_RLE = 3, STRAT_FIXED = 4 };
+
+struct DeflateParams {
+    int level, strategy, mode;
+    int good, lazy, nice, chain;      // deflate.c:112-124 configuration_table
+    int need_quarter;                 // the quartered-chain result can be asked for by the parse
+};
+
+ZB_HD DeflateParams deflate_params(int level, int strategy) {
+    //                      good lazy nice chain
+    const int cfg[10][4] = {{0, 0, 0, 0}, {4, 4, 8, 4}, {4, 5, 16, 8}, {4, 6, 32, 32}, {4, 4, 16, 16},
+                            {8, 16, 32, 32}, {8, 16, 128, 128}, {8, 32, 128, 256}, {32, 128, 258, 1024},
+                            {32, 258, 258, 4096}};
+    DeflateParams p;
+    p.level = level; p.strategy = strategy;
+    p.good = cfg[level][0]; p.lazy = cfg[level][1]; p.nice = cfg[level][2]; p.chain = cfg[level][3];
+    p.mode = strategy == STRAT_HUFFMAN ? MODE_HUFF : strategy == STRAT_RLE ? MODE_RLE : level >= 4 ? MODE_SLOW : MODE_FAST;
+    // a search happens only while prev_length < lazy; it is quartered when prev_length >= good
+    p.need_quarter = (p.mode == MODE_SLOW && p.good < p.lazy) ? 1 : 0;
+    return p;
+}
+
+ZB_HD uint32_t hash3(const uint8_t *s) {
+    return (((uint32_t)s[0] << (2 * kHashShift)) ^ ((uint32_t)s[1] << kHashShift) ^ s[2]) & kHashMask;
+}
+
+// ---- phase 2: longest match at one position -------------------------------------
+// Result encoding: 0 = no match of length >= 3, else (len << 16) | dist.
+struct MatchPair { uint32_t full, quarter; };
+
+ZB_HD MatchPair match_at(const uint8_t *data, uint32_t n, const uint16_t *prev_dist, uint32_t p,
+                         const DeflateParams &prm) {
+    MatchPair r{0, 0};
+    if (p + kMinMatch > n) return r;                  // lookahead < MIN_MATCH: no insertion, no search
+    uint32_t d = prev_dist[p];
+    if (d == 0 || d > (uint32_t)kMaxDist) return r;   // deflate.c:1857/1958: head must be within MAX_DIST
+    const uint32_t look = n - p;
+    const uint32_t maxlen = look < (uint32_t)kMaxMatch ? look : (uint32_t)kMaxMatch;
+    const uint32_t nice = (uint32_t)prm.nice > look ? look : (uint32_t)prm.nice;      // deflate.c:1396
+    const uint32_t chain_q = (uint32_t)prm.chain >> 2;
+    const uint8_t *scan = data + p;
+    uint32_t best = kMinMatch - 1, best_dist = 0, examined = 0;
+    uint32_t q = p - d;
+    bool have_q = false;
+    for (;;) {
+        const uint8_t *m = data + q;
+        // quick rejects (deflate.c:1449-1452); best < maxlen holds here (see nice clamp)
+        if (m[best] == scan[best] && m[0] == scan[0] && m[1] == scan[1]) {
+            uint32_t len = 2;                         // m[2]==scan[2] follows from the equal hash when bytes 0,1 agree
+            while (len < maxlen && m[len] == scan[len]) ++len;
+            if (len > best) {
+                best = len; best_dist = p - q;
+                if (len >= nice) break;
+            }
+        }
+        ++examined;
+        if (examined == chain_q && !have_q) { r.quarter = best >= (uint32_t)kMinMatch ? (best << 16) | best_dist : 0; have_q = true; }
+        if (examined == (uint32_t)prm.chain) break;  // deflate.c:1482 --chain_length
+        const uint32_t d2 = prev_dist[q];
+        if (d2 == 0) break;
+        q -= d2;
+        if (p - q >= (uint32_t)kMaxDist) break;       // deflate.c:1481: cur_match > limit
+    }
+    r.full = best >= (uint32_t)kMinMatch ? (best << 16) | best_dist : 0;
+    if (!have_q) r.quarter = r.full;
+    return r;
+}
+
+// Z_RLE (deflate.c:2051-2115): run of the previous byte, distance 1 only.
+ZB_HD uint32_t rle_at(const uint8_t *data, uint32_t n, uint32_t p) {
+    if (p == 0 || p + kMinMatch > n) return 0;
+    const uint32_t look = n - p;
+    const uint32_t maxlen = look < (uint32_t)kMaxMatch ? look : (uint32_t)kMaxMatch;
+    const uint8_t prev = data[p - 1];
+    uint32_t len = 0;
+    while (len < maxlen && data[p + len] == prev) ++len;
+    return len >= (uint32_t)kMinMatch ? (len << 16) | 1u : 0;
+}
+
+// ---- phase 3: parse ------------------------------------------------------------
+struct BlockInfo {
+    uint32_t sym_start, sym_count;    // symbols of this block inside the chunk's symbol array
+    uint32_t byte_start, byte_len;    // input bytes the block covers (stored_len)
+    uint32_t flags;                   // bit 0: last block of the stream; bit 1: stored form allowed
+    uint32_t bit_start_lo, bit_start_hi;  // filled by the layout step: bit offset inside the output stream
+    uint32_t pad;
+};
+constexpr uint32_t BLK_LAST = 1, BLK_STORED_OK = 2;
+
+ZB_HD uint32_t max_blocks_for(uint32_t chunk_bytes) { return chunk_bytes / kSymLimit + 2; }
+
+struct ParseSink {                    // where the parse writes
+    uint32_t *syms;                   // (dist << 16) | (len-3)   or   literal byte (dist == 0)
+    BlockInfo *blocks;
+    uint32_t nsyms, nblocks;
+    uint32_t blk_sym0, blk_byte0;     // start of the open block
+};
+
+ZB_HD void parse_close_block(ParseSink &s, uint32_t cover_end, uint32_t window_base, bool last) {
+    BlockInfo b;
+    b.sym_start = s.blk_sym0; b.sym_count = s.nsyms - s.blk_sym0;
+    b.byte_start = s.blk_byte0; b.byte_len = cover_end - s.blk_byte0;
+    // deflate.c:1597-1600: the stored form needs the block start still inside the window
+    b.flags = (last ? BLK_LAST : 0) | (s.blk_byte0 >= window_base ? BLK_STORED_OK : 0);
+    b.bit_start_lo = b.bit_start_hi = 0; b.pad = 0;
+    s.blocks[s.nblocks++] = b;
+    s.blk_sym0 = s.nsyms; s.blk_byte0 = cover_end;
+}
+
+// Sequential parse of one chunk.  `final_chunk`: flush == Z_FINISH (last block
+// gets BFINAL, an empty final block is emitted if nothing is pending,
+// deflate.c:1908-1913); otherwise flush == Z_FULL_FLUSH.
+ZB_HD void parse_chunk(const uint8_t *data, uint32_t n, const uint32_t *mfull, const uint32_t *mquarter,
+                       const DeflateParams &prm, bool final_chunk, ParseSink &s) {
+    s.nsyms = 0; s.nblocks = 0; s.blk_sym0 = 0; s.blk_byte0 = 0;
+    uint32_t base = 0;                // window origin: advances 32 KiB per slide (deflate.c:277-287)
+    // fill_window is entered when lookahead drops under this many bytes
+    const uint32_t trigger = prm.mode == MODE_HUFF ? 1 : prm.mode == MODE_RLE ? (uint32_t)kMaxMatch + 1 : (uint32_t)kMinLookahead;
+    auto slide_check = [&](uint32_t p) {
+        uint64_t fill_end = (uint64_t)base + 2 * kWSize;
+        if (fill_end > n) fill_end = n;
+        if (fill_end - p < trigger && p - base >= (uint32_t)(kWSize + kMaxDist)) base += kWSize;
+    };
+    auto emit = [&](uint32_t sym, uint32_t cover_end) {
+        s.syms[s.nsyms++] = sym;
+        if (s.nsyms - s.blk_sym0 == kSymLimit) parse_close_block(s, cover_end, base, false);
+    };
+    uint32_t p = 0;
+    if (prm.mode != MODE_SLOW) {                       // greedy: deflate_fast / deflate_rle / deflate_huff
+        while (p < n) {
+            slide_check(p);
+            const uint32_t m = prm.mode == MODE_HUFF ? 0 : mfull[p];
+            if (m) { const uint32_t len = m >> 16; emit(((m & 0xffff) << 16) | (len - kMinMatch), p + len); p += len; }
+            else { emit(data[p], p + 1); ++p; }
+        }
+    } else {                                           // lazy: deflate_slow
+        uint32_t match_length = kMinMatch - 1, cur_dist = 0;
+        bool match_available = false;
+        while (p < n) {
+            slide_check(p);
+            const uint32_t prev_length = match_length, prev_dist_v = cur_dist;
+            match_length = kMinMatch - 1;
+            if (prev_length < (uint32_t)prm.lazy) {
+                const uint32_t m = (prev_length >= (uint32_t)prm.good) ? mquarter[p] : mfull[p];
+                const uint32_t len = m >> 16;
+                if (m && len > prev_length) {
+                    match_length = len; cur_dist = m & 0xffff;
+                    if (match_length <= 5 && (prm.strategy == STRAT_FILTERED ||
+                                              (match_length == (uint32_t)kMinMatch && cur_dist > (uint32_t)kTooFar)))
+                        match_length = kMinMatch - 1;  // deflate.c:1964-1975
+                }
+            }
+            if (prev_length >= (uint32_t)kMinMatch && match_length <= prev_length) {
+                const uint32_t start = p - 1;
+                p = start + prev_length;
+                match_available = false; match_length = kMinMatch - 1;
+                emit((prev_dist_v << 16) | (prev_length - kMinMatch), p);
+            } else if (match_available) {
+                emit(data[p - 1], p);
+                ++p;
+            } else {
+                match_available = true; ++p;
+            }
+        }
+        // deflate.c:2026-2030: the pending literal is tallied but its flush flag is
+        // ignored (the block is closed by the flush below, never cut here)
+        if (match_available) s.syms[s.nsyms++] = data[n - 1];
+    }
+    slide_check(n);                                    // the loop-top fill_window call that finds lookahead == 0
+    if (final_chunk) parse_close_block(s, n, base, true);
+    else if (s.nsyms != s.blk_sym0) parse_close_block(s, n, base, false);
+}
+
+// ---- phase 4: per-block Huffman construction ---------------------------------------
+struct BlockCode {
+    uint16_t lcode[288]; uint8_t llen[288];   // bit-reversed codes / lengths, literal-length alphabet
+    uint16_t dcode[32];  uint8_t dlen[32];    // distance alphabet
+    uint32_t type;                            // 0 stored, 1 fixed, 2 dynamic
+    uint32_t hdr_bits;                        // bits of the dynamic header that follow the 3 block-header bits
+    uint32_t body_bits;                       // 3 + (static_len | opt_len): bits of a fixed/dynamic block
+    uint32_t pad;
+    uint32_t hdr[160];                        // dynamic header, LSB-first bit string
+};
+
+struct StaticTrees {                          // trees.h static_ltree / static_dtree, generated at start-up
+    uint16_t lcode[288]; uint8_t llen[288];
+    uint16_t dcode[32];  uint8_t dlen[32];
+};
+
+struct TreeNode { uint16_t fc; uint16_t dl; };   // Freq|Code, Dad|Len   (deflate.h:75-90)
+
+struct TreeWork {                             // one per CTA (shared memory)
+    TreeNode lt[2 * 286 + 1], dt[2 * 30 + 1], bt[2 * 19 + 1];
+    int16_t heap[2 * 286 + 1];
+    uint8_t depth[2 * 286 + 1];
+    uint16_t bl_count[16];
+    int heap_len, heap_max;
+    uint32_t opt_len, static_len;
+};
+
+ZB_HD uint32_t bit_reverse(uint32_t code, int len) {   // trees.c:154
+    uint32_t r = 0;
+    for (int i = 0; i < len; ++i) { r = (r << 1) | (code & 1); code >>= 1; }
+    return r;
+}
+
+ZB_HD void tree_gen_codes(TreeNode *t, int max_code, const uint16_t *blc) {   // trees.c:203-232
+    uint16_t next[16];
+    uint32_t code = 0;
+    for (int b = 1; b <= 15; ++b) { code = (code + blc[b - 1]) << 1; next[b] = (uint16_t)code; }
+    for (int n = 0; n <= max_code; ++n) {
+        const int len = t[n].dl;
+        if (len) t[n].fc = (uint16_t)bit_reverse(next[len]++, len);
+    }
+}
+
+inline void static_trees_fill(StaticTrees &st) {       // trees.c:374-390
+    TreeNode t[288];
+    uint16_t blc[16] = {0};
+    int n = 0;
+    for (; n <= 143; ++n) { t[n].dl = 8; blc[8]++; }
+    for (; n <= 255; ++n) { t[n].dl = 9; blc[9]++; }
+    for (; n <= 279; ++n) { t[n].dl = 7; blc[7]++; }
+    for (; n <= 287; ++n) { t[n].dl = 8; blc[8]++; }
+    tree_gen_codes(t, 287, blc);
+    for (n = 0; n < 288; ++n) { st.lcode[n] = t[n].fc; st.llen[n] = (uint8_t)t[n].dl; }
+    for (n = 0; n < 32; ++n) { st.dcode[n] = (uint16_t)bit_reverse((uint32_t)n, 5); st.dlen[n] = 5; }
+}
+
+#define ZB_SMALLER(t, n, m) ((t)[n].fc < (t)[m].fc || ((t)[n].fc == (t)[m].fc && w.depth[n] <= w.depth[m]))   // trees.c:499-501
+
+ZB_HD void tree_sift(TreeWork &w, TreeNode *t, int k) {  // trees.c:509 pqdownheap
+    const int v = w.heap[k];
+    for (int j = k << 1; j <= w.heap_len; j <<= 1) {
+        if (j < w.heap_len && ZB_SMALLER(t, w.heap[j + 1], w.heap[j])) ++j;
+        if (ZB_SMALLER(t, v, w.heap[j])) break;
+        w.heap[k] = w.heap[j]; k = j;
+    }
+    w.heap[k] = (int16_t)v;
+}
+
+// trees.c:540-613 gen_bitlen.  st_len: static code lengths (nullptr for the bit-length tree).
+ZB_HD void tree_gen_bitlen(TreeWork &w, TreeNode *t, int max_code, const uint8_t *st_len,
+                           const uint8_t *extra, int base, int max_length) {
+    constexpr int HEAP_SIZE = 2 * 286 + 1;
+    int h, overflow = 0;
+    for (int b = 0; b <= 15; ++b) w.bl_count[b] = 0;
+    t[w.heap[w.heap_max]].dl = 0;
+    for (h = w.heap_max + 1; h < HEAP_SIZE; ++h) {
+        const int n = w.heap[h];
+        int bits = t[t[n].dl].dl + 1;
+        if (bits > max_length) { bits = max_length; ++overflow; }
+        t[n].dl = (uint16_t)bits;
+        if (n > max_code) continue;
+        w.bl_count[bits]++;
+        const int xb = (n >= base) ? extra[n - base] : 0;
+        const uint32_t f = t[n].fc;
+        w.opt_len += f * (uint32_t)(bits + xb);
+        if (st_len) w.static_len += f * (uint32_t)(st_len[n] + xb);
+    }
+    if (!overflow) return;
+    do {
+        int bits = max_length - 1;
+        while (w.bl_count[bits] == 0) --bits;
+        w.bl_count[bits]--; w.bl_count[bits + 1] += 2; w.bl_count[max_length]--;
+        overflow -= 2;
+    } while (overflow > 0);
+    for (int bits = max_length; bits != 0; --bits) {
+        int n = w.bl_count[bits];
+        while (n != 0) {
+            const int m = w.heap[--h];
+            if (m > max_code) continue;
+            if (t[m].dl != (uint32_t)bits) {
+                w.opt_len += ((uint32_t)bits - t[m].dl) * t[m].fc;
+                t[m].dl = (uint16_t)bits;
+            }
+            --n;
+        }
+    }
+}
+
+// trees.c:627-706 build_tree; returns max_code.
+ZB_HD int tree_build(TreeWork &w, TreeNode *t, int elems, const uint8_t *st_len,
+                     const uint8_t *extra, int base, int max_length) {
+    constexpr int HEAP_SIZE = 2 * 286 + 1;
+    int max_code = -1, node;
+    w.heap_len = 0; w.heap_max = HEAP_SIZE;
+    for (int n = 0; n < elems; ++n) {
+        if (t[n].fc) { w.heap[++w.heap_len] = (int16_t)(max_code = n); w.depth[n] = 0; }
+        else t[n].dl = 0;
+    }
+    while (w.heap_len < 2) {                           // trees.c:655-661: force two codes
+        node = w.heap[++w.heap_len] = (int16_t)(max_code < 2 ? ++max_code : 0);
+        t[node].fc = 1; w.depth[node] = 0;
+        w.opt_len--; if (st_len) w.static_len -= st_len[node];
+    }
+    for (int n = w.heap_len / 2; n >= 1; --n) tree_sift(w, t, n);
+    node = elems;
+    do {
+        const int n = w.heap[1];
+        w.heap[1] = w.heap[w.heap_len--];
+        tree_sift(w, t, 1);
+        const int m = w.heap[1];
+        w.heap[--w.heap_max] = (int16_t)n;
+        w.heap[--w.heap_max] = (int16_t)m;
+        t[node].fc = (uint16_t)(t[n].fc + t[m].fc);
+        w.depth[node] = (uint8_t)((w.depth[n] >= w.depth[m] ? w.depth[n] : w.depth[m]) + 1);
+        t[n].dl = t[m].dl = (uint16_t)node;
+        w.heap[1] = (int16_t)node++;
+        tree_sift(w, t, 1);
+    } while (w.heap_len >= 2);
+    w.heap[--w.heap_max] = w.heap[1];
+    tree_gen_bitlen(w, t, max_code, st_len, extra, base, max_length);
+    tree_gen_codes(t, max_code, w.bl_count);
+    return max_code;
+}
+
+struct HdrWriter {                                    // LSB-first appender for the dynamic header
+    uint32_t *words; uint32_t nbits;
+    ZB_HD void put(uint32_t v, int len) {
+        const uint32_t w = nbits >> 5, sh = nbits & 31;
+        words[w] |= v << sh;
+        if (sh + (uint32_t)len > 32) words[w + 1] |= v >> (32 - sh);
+        nbits += (uint32_t)len;
+    }
+};
+
+// trees.c:712-745 scan_tree (out == nullptr) / :753-795 send_tree share the run-length walk.
+ZB_HD void tree_walk(TreeWork &w, TreeNode *t, int max_code, HdrWriter *out) {
+    int prevlen = -1, nextlen = t[0].dl, count = 0, max_count = 7, min_count = 4;
+    if (nextlen == 0) { max_count = 138; min_count = 3; }
+    if (!out) t[max_code + 1].dl = 0xffff;            // guard
+    TreeNode *bt = w.bt;
+    for (int n = 0; n <= max_code; ++n) {
+        const int curlen = nextlen;
+        nextlen = t[n + 1].dl;
+        if (++count < max_count && curlen == nextlen) continue;
+        if (count < min_count) {
+            if (out) { do out->put(bt[curlen].fc, bt[curlen].dl); while (--count); }
+            else bt[curlen].fc += (uint16_t)count;
+        } else if (curlen != 0) {
+            if (curlen != prevlen) {
+                if (out) { out->put(bt[curlen].fc, bt[curlen].dl); --count; }
+                else bt[curlen].fc++;
+            }
+            if (out) { out->put(bt[16].fc, bt[16].dl); out->put((uint32_t)count - 3, 2); }
+            else bt[16].fc++;
+        } else if (count <= 10) {
+            if (out) { out->put(bt[17].fc, bt[17].dl); out->put((uint32_t)count - 3, 3); }
+            else bt[17].fc++;
+        } else {
+            if (out) { out->put(bt[18].fc, bt[18].dl); out->put((uint32_t)count - 11, 7); }
+            else bt[18].fc++;
+        }
+        count = 0; prevlen = curlen;
+        if (nextlen == 0) { max_count = 138; min_count = 3; }
+        else if (curlen == nextlen) { max_count = 6; min_count = 3; }
+        else { max_count = 7; min_count = 4; }
+    }
+}
+
+// trees.c:997-1089 _tr_flush_block for one block whose symbol frequencies are
+// already in w.lt[0..285].fc / w.dt[0..29].fc (END_BLOCK counted).  Decides
+// stored / fixed / dynamic and fills `out`.
+ZB_HD void block_build(TreeWork &w, const BlockInfo &blk, int strategy, const StaticTrees &st,
+                       const FormatTables &fmt, BlockCode &out) {
+    const uint8_t bl_extra[19] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 2, 3, 7};
+    w.opt_len = 0; w.static_len = 0;
+    for (int n = 0; n < 19; ++n) w.bt[n].fc = 0;
+    const int l_max = tree_build(w, w.lt, 286, st.llen, fmt.len_extra, 257, 15);
+    const int d_max = tree_build(w, w.dt, 30, st.dlen, fmt.dist_extra, 0, 15);
+    tree_walk(w, w.lt, l_max, nullptr);                // trees.c:800-829 build_bl_tree
+    tree_walk(w, w.dt, d_max, nullptr);
+    tree_build(w, w.bt, 19, nullptr, bl_extra, 0, 7);
+    int mb;
+    for (mb = 18; mb >= 3; --mb) if (w.bt[fmt.cl_order[mb]].dl) break;
+    w.opt_len += 3 * ((uint32_t)mb + 1) + 5 + 5 + 4;
+    uint32_t opt_lenb = (w.opt_len + 3 + 7) >> 3;
+    const uint32_t static_lenb = (w.static_len + 3 + 7) >> 3;
+    if (static_lenb <= opt_lenb || strategy == STRAT_FIXED) opt_lenb = static_lenb;
+    out.hdr_bits = 0; out.pad = 0;
+    if (blk.byte_len + 4 <= opt_lenb && (blk.flags & BLK_STORED_OK)) {
+        out.type = 0; out.body_bits = 0;
+    } else if (static_lenb == opt_lenb) {
+        out.type = 1; out.body_bits = 3 + w.static_len;
+        for (int n = 0; n < 288; ++n) { out.lcode[n] = st.lcode[n]; out.llen[n] = st.llen[n]; }
+        for (int n = 0; n < 32; ++n) { out.dcode[n] = st.dcode[n]; out.dlen[n] = st.dlen[n]; }
+    } else {
+        out.type = 2; out.body_bits = 3 + w.opt_len;
+        for (int n = 0; n < 288; ++n) { out.lcode[n] = n < 286 ? w.lt[n].fc : 0; out.llen[n] = n <= l_max ? (uint8_t)w.lt[n].dl : 0; }
+        for (int n = 0; n < 32; ++n) { out.dcode[n] = n < 30 ? w.dt[n].fc : 0; out.dlen[n] = n <= d_max ? (uint8_t)w.dt[n].dl : 0; }
+        for (int i = 0; i < 160; ++i) out.hdr[i] = 0;
+        HdrWriter hw{out.hdr, 0};
+        hw.put((uint32_t)l_max + 1 - 257, 5);         // trees.c:833-855 send_all_trees
+        hw.put((uint32_t)d_max + 1 - 1, 5);
+        hw.put((uint32_t)mb + 1 - 4, 4);
+        for (int r = 0; r <= mb; ++r) hw.put(w.bt[fmt.cl_order[r]].dl, 3);
+        tree_walk(w, w.lt, l_max, &hw);
+        tree_walk(w, w.dt, d_max, &hw);
+        out.hdr_bits = hw.nbits;
+    }
+}
+
+// ---- phase 5: symbol -> bits (trees.c:900-951 compress_block) ----------------------
+ZB_HD uint64_t symbol_bits(uint32_t sym, const uint16_t *lcode, const uint8_t *llen, const uint16_t *dcode,
+                           const uint8_t *dlen, const FormatTables &fmt, uint32_t &nbits) {
+    const uint32_t dist = sym >> 16, lc = sym & 0xffff;
+    if (dist == 0) { nbits = llen[lc]; return lcode[lc]; }
+    uint32_t c = fmt.len_code[lc];
+    uint64_t v = lcode[257 + c];
+    uint32_t nb = llen[257 + c];
+    const uint32_t lx = fmt.len_extra[c];
+    if (lx) { v |= (uint64_t)(lc + kMinMatch - fmt.len_base[c]) << nb; nb += lx; }
+    c = dist_to_code(fmt, dist);
+    v |= (uint64_t)dcode[c] << nb; nb += dlen[c];
+    const uint32_t dx = fmt.dist_extra[c];
+    if (dx) { v |= (uint64_t)(dist - fmt.dist_base[c]) << nb; nb += dx; }
+    nbits = nb;
+    return v;
+}
+
+// Bit layout of a chunk: given each block's type and size, where does it start?
+// Returns the chunk's size in bytes.  `marker`: append the 00 00 FF FF sync
+// marker (non-final chunks, deflate.c:1214-1215 / trees.c:860-875).
+ZB_HD uint64_t block_end_bit(const BlockInfo &b, const BlockCode &c, uint64_t start) {
+    uint64_t end;
+    if (c.type == 0) end = ((start + 3 + 7) & ~7ull) + 32 + 8ull * b.byte_len;
+    else end = start + c.body_bits;
+    if (b.flags & BLK_LAST) end = (end + 7) & ~7ull;  // bi_windup
+    return end;
+}
+
+}  // namespace zb

@@ -170,6 +170,7 @@ int zb200_create(int device, zb200_ctx **out) {
     }
     if (cudaMalloc((void **)&ctx->d_small, 64 * sizeof(uint64_t)) != cudaSuccess) return fail(ZB200_ERR_NOMEM);
     if (cudaMallocHost((void **)&ctx->h_small, 64 * sizeof(uint64_t)) != cudaSuccess) return fail(ZB200_ERR_NOMEM);
+    ctx->h_small[32] = 0; ctx->h_small[33] = 2; ctx->h_small[34] = 10;   // constants DMA-ed by deflate_launch
     if ((r = checksum_init(ctx)) != ZB200_OK) return fail(r);
     if ((r = deflate_init(ctx)) != ZB200_OK) return fail(r);
     if ((r = inflate_init(ctx)) != ZB200_OK) return fail(r);

@@ -99,6 +99,9 @@ int checksum_launch(zb200_ctx *ctx, const uint8_t *d_base, const uint64_t *d_off
 
 // zb_deflate.cu
 int deflate_init(zb200_ctx *ctx);
+int deflate_launch(zb200_ctx *ctx, const uint8_t *d_in, size_t n, size_t S, int level, int strategy, int frame,
+                   int finish, uint8_t *d_out, size_t out_cap, uint64_t *d_chunk_end, uint64_t *d_total,
+                   uint32_t *d_sums_out, cudaStream_t s);
 // zb_inflate.cu
 int inflate_init(zb200_ctx *ctx);
 size_t inflate_work_bytes(size_t n_members);
