@@ -55,3 +55,30 @@ def test_inflate_messages_are_the_reference_literals():
     o = refz.oracle()
     for i in range(22):
         assert L.zb200_inflate_msg(i) == o.c_inflate_msg(i)
+
+
+def test_zlib_surface_exported():
+    """Every function include/zb200_zlib.h declares is exported by the library
+    (the reference's zlib.h names and the src/wasm_module.c exports)."""
+    src = open(os.path.join(ROOT, "include", "zb200_zlib.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    body = src[src.index("/* ---- basic") if "/* ---- basic" in src else 0:]
+    body = src.split("#endif /* ZLIB_H */")[-1] if "#endif /* ZLIB_H */" in open(os.path.join(ROOT, "include", "zb200_zlib.h")).read() else src
+    # after comment stripping the marker is gone: take everything after the last #define block instead
+    body = src[src.rindex("#define inflateInit2"):]
+    names = sorted(set(re.findall(r"\b([A-Za-z_][A-Za-z0-9_]*)\s*\(", body)) - {"inflateInit2", "inflateInit2_"} | {"inflateInit2_"})
+    names = [n for n in names if n not in ("defined", "sizeof", "push", "pop", "visibility")]
+    L = C.CDLL(zb.LIB_PATH, mode=C.RTLD_LOCAL)
+    missing = [n for n in names if not hasattr(L, n)]
+    assert len(names) >= 45 and not missing, missing
+
+
+def test_z_stream_layout_matches_reference():
+    assert C.sizeof(refz.ZStream) == 112          # zlib.h:90-110 on LP64
+    z = refz.ZlibBinding(zb.LIB_PATH, "")
+    s = refz.ZStream()
+    assert z.deflateInit2_(C.byref(s), 6, 8, 15, 8, 0, z.version, 111) == refz.Z_VERSION_ERROR
+    assert z.inflateInit2_(C.byref(s), 15, b"0.9", C.sizeof(refz.ZStream)) == refz.Z_VERSION_ERROR
+    if zb.lib().zb200_device_count() == 0:        # no GPU: init must fail loudly, never fall back
+        assert z.deflateInit2_(C.byref(s), 6, 8, 15, 8, 0, z.version, C.sizeof(refz.ZStream)) == refz.Z_STREAM_ERROR
+        assert b"no CPU path" in s.msg

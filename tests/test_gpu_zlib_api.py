@@ -1,0 +1,176 @@
+"""GPU parity of the drop-in boundary: the zlib.h API and the src/wasm_module.c
+exports served by libzb200.so, driven exactly like the reference's callers
+(one-shot compress2/uncompress, zpipe-style sliced deflate()/inflate(), the
+WASM shim's buffer and streaming functions), compared with the reference."""
+import ctypes as C
+import os
+import subprocess
+
+import pytest
+
+import refz
+import zlib_wasm_b200 as zb
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def z():
+    return refz.ZlibBinding(zb.LIB_PATH, "")
+
+
+def ref_or_oracle_stream(d, level, strategy, wrap, chunk):
+    return (refz.ref() if refz.have_ref() else refz.oracle()).deflate_stream(d, level, strategy, wrap, chunk)
+
+
+def test_version_and_init_errors(z):
+    assert z.zlibVersion() == b"1.3.1.1-motley"
+    s = refz.ZStream()
+    assert z.deflateInit2_(C.byref(s), 6, 8, 15, 8, 0, b"2.0", C.sizeof(refz.ZStream)) == refz.Z_VERSION_ERROR
+    assert z.deflateInit2_(C.byref(s), 6, 8, 15, 8, 0, z.version, C.sizeof(refz.ZStream) - 8) == refz.Z_VERSION_ERROR
+    for bad in ((10, 8, 15, 8, 0), (6, 7, 15, 8, 0), (6, 8, 7, 8, 0), (6, 8, 15, 0, 0), (6, 8, 15, 10, 0), (6, 8, 15, 8, 5), (6, 8, -16, 8, 0)):
+        assert z.deflateInit2_(C.byref(s), *bad, z.version, C.sizeof(refz.ZStream)) == refz.Z_STREAM_ERROR, bad
+    assert z.inflateInit2_(C.byref(s), 48, z.version, C.sizeof(refz.ZStream)) == refz.Z_STREAM_ERROR
+    assert z.zError(-3) == b"data error" and z.zError(1) == b"stream end"
+
+
+def test_checksums_like_zlib_h(z):
+    o = refz.oracle()
+    d = refz.gen(1 << 20, refz.GEN_TEXT)
+    assert z.crc32(0, None, 0) == 0 and z.adler32(0, None, 0) == 1
+    assert z.crc32(0, d, len(d)) == o.crc32(d) and z.adler32(1, d, len(d)) == o.adler32(d)
+    c = a = None
+    c, a = 0, 1
+    for k in range(0, len(d), 100001):      # running use, zlib.h:1711-1768
+        piece = d[k:k + 100001]
+        c, a = z.crc32(c, piece, len(piece)), z.adler32(a, piece, len(piece))
+    assert (c, a) == (o.crc32(d), o.adler32(d))
+    assert z.crc32_combine(o.crc32(d[:5]), o.crc32(d[5:]), len(d) - 5) == o.crc32(d)
+    assert z.adler32_combine(o.adler32(d[:5]), o.adler32(d[5:]), len(d) - 5) == o.adler32(d)
+
+
+def test_compress2_uncompress_config_c1(z):
+    """BASELINE config C1: level 6 round trip + checksums on a 1 MiB text buffer."""
+    d = refz.gen(1 << 20, refz.GEN_TEXT)
+    bound = z.compressBound(len(d))
+    dst = C.create_string_buffer(bound)
+    dl = C.c_ulong(bound)
+    assert z.compress2(dst, C.byref(dl), d, len(d), 6) == refz.Z_OK
+    s = dst.raw[:dl.value]
+    assert s == ref_or_oracle_stream(d, 6, 0, refz.WRAP_ZLIB, 262144)      # byte-identical on the same chunking
+    if refz.have_ref():                                                     # the reference's own uncompress takes it
+        r = refz.ref()
+        back = C.create_string_buffer(len(d))
+        bl = C.c_ulong(len(d))
+        assert r.uncompress(back, C.byref(bl), s, len(s)) == refz.Z_OK and back.raw == d
+    back = C.create_string_buffer(len(d))
+    bl = C.c_ulong(len(d))
+    assert z.uncompress(back, C.byref(bl), s, len(s)) == refz.Z_OK and bl.value == len(d) and back.raw == d
+    # error mapping of uncompr.c:76-79
+    bl = C.c_ulong(len(d) - 1)
+    assert z.uncompress(back, C.byref(bl), s, len(s)) == refz.Z_BUF_ERROR
+    bl = C.c_ulong(len(d))
+    assert z.uncompress(back, C.byref(bl), s, len(s) - 9) == refz.Z_DATA_ERROR
+    bad = bytearray(s); bad[len(s) // 2] ^= 0x10
+    bl = C.c_ulong(len(d))
+    assert z.uncompress(back, C.byref(bl), bytes(bad), len(s)) == refz.Z_DATA_ERROR
+    tiny = C.c_ulong(8)
+    assert z.compress2(dst, C.byref(tiny), d, len(d), 6) == refz.Z_BUF_ERROR
+
+
+@pytest.mark.parametrize("wrap", [refz.WRAP_RAW, refz.WRAP_ZLIB, refz.WRAP_GZIP])
+def test_streaming_zpipe_style(z, wrap):
+    """16 KiB in / 16 KiB out slicing (examples/zpipe.c:57-82,96-150)."""
+    d = refz.gen(1500000, refz.GEN_MIXED, seed=12)
+    for level in (1, 6):
+        s = z.deflate_stream(d, level, 0, wrap, chunk=0, in_slice=16384, out_slice=16384)
+        if level >= 4:
+            assert s == ref_or_oracle_stream(d, level, 0, wrap, 262144)
+        ret, msg, out, tin = z.inflate_all(s, wrap, cap=len(d) + 64, in_slice=16384, out_slice=16384)
+        assert ret == refz.Z_STREAM_END and out == d and tin == len(s), (ret, msg)
+        if refz.have_ref():
+            ret, msg, out, tin = refz.ref().inflate_all(s, wrap, cap=len(d) + 64)
+            assert ret == refz.Z_STREAM_END and out == d
+    # explicit full flushes at odd places stay decodable and resumable
+    s = z.deflate_stream(d, 6, 0, wrap, chunk=333333, in_slice=50000, out_slice=7777)
+    ret, msg, out, tin = z.inflate_all(s, wrap, cap=len(d) + 64, in_slice=1000, out_slice=100000)
+    assert ret == refz.Z_STREAM_END and out == d
+
+
+def test_inflate_errors_and_trailing_bytes(z):
+    d = refz.gen(300000, refz.GEN_MARKOV, seed=3)
+    s = ref_or_oracle_stream(d, 6, 0, refz.WRAP_GZIP, 0)
+    ret, msg, out, tin = z.inflate_all(s + b"TRAILING", refz.WRAP_GZIP, cap=len(d) + 64, in_slice=4096)
+    assert ret == refz.Z_STREAM_END and out == d and tin == len(s)          # next_in stops right after the member
+    bad = bytearray(s); bad[-5] ^= 1
+    ret, msg, out, tin = z.inflate_all(bytes(bad), refz.WRAP_GZIP, cap=len(d) + 64)
+    assert ret == refz.Z_DATA_ERROR and msg == "incorrect data check"
+    ret, msg, out, tin = z.inflate_all(s[:len(s) // 2], refz.WRAP_GZIP, cap=len(d) + 64)
+    assert ret == refz.Z_BUF_ERROR and out == d[:len(out)]
+    ret, msg, out, tin = z.inflate_all(b"\x78\x9c" + b"\x07" * 10, refz.WRAP_ZLIB, cap=64)
+    assert ret == refz.Z_DATA_ERROR and msg == "invalid block type"
+
+
+def test_wasm_module_exports():
+    L = C.CDLL(zb.LIB_PATH, mode=C.RTLD_LOCAL)
+    o = refz.oracle()
+    d = refz.gen(200000, refz.GEN_TEXT, seed=8)
+    L.zlib_compress_bound.restype = C.c_ulong
+    L.zlib_compress_bound.argtypes = [C.c_ulong]
+    L.zlib_crc32.restype = L.zlib_adler32.restype = C.c_ulong
+    L.zlib_crc32.argtypes = L.zlib_adler32.argtypes = [C.c_ulong, C.c_char_p, C.c_uint]
+    L.zlib_get_version.restype = C.c_char_p
+    L.zlib_compress_buffer.argtypes = [C.c_char_p, C.c_ulong, C.c_void_p, C.POINTER(C.c_ulong), C.c_int]
+    L.zlib_decompress_buffer.argtypes = [C.c_void_p, C.c_ulong, C.c_void_p, C.POINTER(C.c_ulong)]
+    assert L.zlib_get_version() == b"1.3.1.1-motley" and L.zlib_has_simd() == 0 and L.zlib_simd_capabilities() == 1
+    assert L.zlib_crc32(0, d, len(d)) == o.crc32(d) and L.zlib_adler32(1, d, len(d)) == o.adler32(d)
+    cap = L.zlib_compress_bound(len(d))
+    dst = C.create_string_buffer(cap)
+    dl = C.c_ulong(cap)
+    assert L.zlib_compress_buffer(d, len(d), dst, C.byref(dl), 99) == 0     # bad level -> default (wasm_module.c:41-43)
+    assert dst.raw[:dl.value] == ref_or_oracle_stream(d, 6, 0, refz.WRAP_ZLIB, 262144)
+    assert L.zlib_compress_buffer(None, len(d), dst, C.byref(dl), 6) == refz.Z_STREAM_ERROR
+    assert L.zlib_compress_buffer(d, 0, dst, C.byref(dl), 6) == refz.Z_STREAM_ERROR
+    back = C.create_string_buffer(len(d))
+    bl = C.c_ulong(len(d))
+    assert L.zlib_decompress_buffer(dst, dl.value, back, C.byref(bl)) == 0 and back.raw == d
+    # streaming context (wasm_module.c:153-288)
+    L.zlib_deflate_init.restype = L.zlib_inflate_init.restype = C.c_void_p
+    L.zlib_deflate_process.argtypes = [C.c_void_p, C.c_char_p, C.c_uint, C.c_void_p, C.c_uint, C.c_int]
+    L.zlib_inflate_process.argtypes = [C.c_void_p, C.c_void_p, C.c_uint, C.c_void_p, C.c_uint]
+    L.zlib_deflate_end.argtypes = L.zlib_inflate_end.argtypes = [C.c_void_p]
+    L.zlib_stream_total_out.restype = C.c_ulong
+    L.zlib_stream_total_out.argtypes = [C.c_void_p]
+    h = L.zlib_deflate_init(6, 15, 8, 0)
+    assert h
+    out = C.create_string_buffer(cap)
+    assert L.zlib_deflate_process(h, d, len(d), out, cap, refz.Z_FINISH) == refz.Z_STREAM_END
+    n = L.zlib_stream_total_out(h)
+    L.zlib_deflate_end(h)
+    assert out.raw[:n] == dst.raw[:dl.value]
+    h = L.zlib_inflate_init(15)
+    back = C.create_string_buffer(len(d))
+    assert L.zlib_inflate_process(h, out, n, back, len(d)) == refz.Z_STREAM_END and back.raw == d
+    L.zlib_inflate_end(h)
+    # raw-deflate "simd" one-shot (src/zlib_simd_optimized.c:354-383)
+    L.zlib_compress_simd.argtypes = [C.c_char_p, C.c_size_t, C.c_void_p, C.POINTER(C.c_size_t), C.c_int]
+    ol = C.c_size_t(cap)
+    assert L.zlib_compress_simd(d, len(d), out, C.byref(ol), 6) == 0
+    assert out.raw[:ol.value] == ref_or_oracle_stream(d, 6, 0, refz.WRAP_RAW, 262144)
+
+
+def test_reference_zpipe_linked_against_product(tmp_path):
+    """The reference's examples/zpipe.c, compiled against the reference's zlib.h
+    and linked to libzb200.so (prebuilt where /root/reference exists)."""
+    exe = os.path.join(refz.ROOT, "tests", "_bin", "zpipe_b200")
+    if not os.path.exists(exe):
+        pytest.skip("zpipe_b200 was not prebuilt (needs /root/reference at build time)")
+    d = refz.gen(1 << 20, refz.GEN_TEXT)
+    comp = subprocess.run([exe], input=d, capture_output=True, timeout=120)
+    assert comp.returncode == 0, comp.stderr
+    assert comp.stdout == ref_or_oracle_stream(d, 6, 0, refz.WRAP_ZLIB, 262144)   # zpipe uses Z_DEFAULT_COMPRESSION
+    back = subprocess.run([exe, "-d"], input=comp.stdout, capture_output=True, timeout=120)
+    assert back.returncode == 0 and back.stdout == d
+    if refz.have_ref():
+        zp = os.path.join(refz.ROOT, "oracle", "_ref", "zpipe")
+        assert subprocess.run([zp, "-d"], input=comp.stdout, capture_output=True, timeout=120).stdout == d

@@ -107,10 +107,27 @@ def build_oracle():
     return out
 
 
+def build_dropin_demo():
+    """The reference's own examples/zpipe.c (compiled against the reference's
+    zlib.h, untouched) linked to libzb200.so: the drop-in boundary exercised by
+    a reference caller.  Only possible where /root/reference exists; the binary
+    is git-ignored and travels with the gpurun snapshot."""
+    src = "/root/reference/examples/zpipe.c"
+    out = os.path.join(ROOT, "tests", "_bin", "zpipe_b200")
+    if not os.path.exists(src):
+        return None
+    if _newer(out, [src, LIB]):
+        os.makedirs(os.path.dirname(out), exist_ok=True)
+        _run(["gcc", "-O2", "-w", "-I/root/reference", "-o", out, src, "-L" + PKG, "-lzb200",
+              "-Wl,-rpath,$ORIGIN/../../zlib_wasm_b200"])
+    return out
+
+
 def build_all(verbose=False):
     build_tools()
     build_oracle()
     lib = build_product(verbose)
+    build_dropin_demo()
     if ROOT not in sys.path:
         sys.path.insert(0, ROOT)
     import zlib_wasm_b200  # noqa: F401  (import check)

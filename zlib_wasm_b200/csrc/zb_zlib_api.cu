@@ -1,0 +1,496 @@
+// zb_zlib_api.cu — the zlib.h-compatible host layer (include/zb200_zlib.h) over
+// the engine.  Mirrors the reference's interface for the hot path: same names,
+// argument meaning and return codes (zlib.h, deflate.c:371-430,954-1263,
+// inflate.c:141-250,590-1264, compress.c, uncompr.c), so the reference's own
+// callers (examples/zpipe.c, src/wasm_module.c) link against it unchanged.
+// Host code only: buffering, framing, return-code mapping.  All compression,
+// decompression and checksumming is done by the kernels.
+#include "zb_internal.h"
+#include "../../include/zb200_zlib.h"
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+#include <new>
+
+using namespace zb;
+
+namespace {
+
+std::mutex g_mu;
+zb200_ctx *g_ctx = nullptr;
+int g_ctx_err = 0;
+
+// The process-wide engine context behind the zlib API (device: $ZB200_DEVICE, default 0).
+zb200_ctx *api_ctx() {
+    std::lock_guard<std::mutex> g(g_mu);
+    if (!g_ctx && !g_ctx_err) {
+        const char *e = getenv("ZB200_DEVICE");
+        g_ctx_err = zb200_create(e ? atoi(e) : 0, &g_ctx);
+    }
+    return g_ctx;
+}
+
+size_t api_chunk() {
+    static size_t c = [] {
+        const char *e = getenv("ZB200_CHUNK");
+        long v = e ? atol(e) : 0;
+        return (size_t)(v >= 1024 ? v : 262144);
+    }();
+    return c;
+}
+
+[[noreturn]] void die_no_device(const char *fn) {
+    fprintf(stderr, "zlib-b200: %s: no usable CUDA device (%s); this library has no CPU path\n", fn, zb200_last_error());
+    abort();
+}
+
+const char *const kErrMsg[10] = {"need dictionary", "stream end", "", "file error", "stream error",
+                                 "data error", "insufficient memory", "buffer error", "incompatible version", ""};
+
+constexpr uint32_t kDeflateMagic = 0x5a42444cu, kInflateMagic = 0x5a42494eu;
+
+struct DeflateStream {
+    uint32_t magic;
+    int level, strategy, wrap;           // wrap: 0 raw, 1 zlib, 2 gzip
+    std::vector<uint8_t> in;             // input accepted but not yet compressed
+    std::vector<uint8_t> pending;        // compressed bytes not yet handed to the caller
+    size_t pending_pos;
+    bool header_done, finished, trailer_done;
+    uint32_t crc, adler;                 // running checksums of all compressed input
+    uint64_t total_in_hashed;
+    int last_flush;
+};
+
+struct InflateStream {
+    uint32_t magic;
+    int wrap;                            // ZB200_WRAP_*
+    int kind;                            // resolved wrapper kind once the header is parsed
+    std::vector<uint8_t> in;             // all compressed input seen so far
+    uint8_t *d_in, *d_out;               // device mirrors (grow-only)
+    size_t d_in_cap, d_out_cap, d_in_have;
+    std::vector<uint8_t> out;            // decoded bytes not yet delivered
+    size_t out_pos;                      // next byte of `out` to deliver
+    uint64_t out_base;                   // stream offset of out[0]
+    uint64_t decoded;                    // valid decoded bytes on the device
+    uint64_t resume_bit, resume_out;
+    bool started, done;
+    int error;                           // sticky ZB200_INF_* data error
+    uint64_t in_used;
+    uint32_t check;
+};
+
+int dev_grow(uint8_t **p, size_t *cap, size_t need, size_t keep, cudaStream_t s) {
+    if (need <= *cap) return ZB200_OK;
+    size_t want = need + (need >> 1) + 65536;
+    uint8_t *n = nullptr;
+    if (cudaMalloc((void **)&n, want) != cudaSuccess) { cudaGetLastError(); return ZB200_ERR_NOMEM; }
+    if (*p && keep) ZB_CUDA(cudaMemcpyAsync(n, *p, keep, cudaMemcpyDeviceToDevice, s));
+    ZB_CUDA(cudaStreamSynchronize(s));
+    if (*p) cudaFree(*p);
+    *p = n; *cap = want;
+    return ZB200_OK;
+}
+
+int map_engine_error(int r) { return r == ZB200_ERR_NOMEM ? Z_MEM_ERROR : r == ZB200_ERR_OUTPUT ? Z_BUF_ERROR : Z_STREAM_ERROR; }
+
+// Compress everything buffered in `st.in` (as `finish` ? the end of the stream : a
+// run of Z_FULL_FLUSH-terminated chunks) and append the bytes to st.pending.
+int compress_buffered(DeflateStream &st, bool finish) {
+    zb200_ctx *ctx = api_ctx();
+    if (!ctx) return Z_STREAM_ERROR;
+    const size_t n = st.in.size();
+    if (n == 0 && !finish) return Z_OK;
+    const size_t chunk = api_chunk();
+    size_t cap = zb200_deflate_bound(n, chunk, ZB200_FRAME_RAW);
+    const size_t at = st.pending.size();
+    st.pending.resize(at + cap);
+    uint32_t adler = 1, crc = 0;
+    int r = zb200_deflate_host(ctx, n ? st.in.data() : (const uint8_t *)"", n, chunk, st.level ? st.level : 1,
+                               st.level ? st.strategy : Z_HUFFMAN_ONLY, ZB200_FRAME_RAW, finish ? 1 : 0,
+                               st.pending.data() + at, &cap, &adler, &crc);
+    if (r != ZB200_OK) { st.pending.resize(at); return map_engine_error(r); }
+    st.pending.resize(at + cap);
+    st.crc = zb200_crc32_combine(st.crc, crc, n);
+    st.adler = zb200_adler32_combine(st.adler, adler, (int64_t)n);
+    st.total_in_hashed += n;
+    st.in.clear();
+    return Z_OK;
+}
+
+void put_header(DeflateStream &st) {
+    if (st.wrap == 1) {                                        // deflate.c:1004-1037
+        const unsigned lf = (st.strategy >= Z_HUFFMAN_ONLY || st.level < 2) ? 0 : st.level < 6 ? 1 : st.level == 6 ? 2 : 3;
+        unsigned hdr = (0x78u << 8) | (lf << 6);
+        hdr += 31 - hdr % 31;
+        st.pending.push_back((uint8_t)(hdr >> 8)); st.pending.push_back((uint8_t)hdr);
+    } else if (st.wrap == 2) {                                 // deflate.c:1042-1054
+        const uint8_t g[10] = {0x1f, 0x8b, 8, 0, 0, 0, 0, 0,
+                               (uint8_t)(st.level == 9 ? 2 : (st.strategy >= Z_HUFFMAN_ONLY || st.level < 2) ? 4 : 0), 3};
+        st.pending.insert(st.pending.end(), g, g + 10);
+    }
+    st.header_done = true;
+}
+
+void put_trailer(DeflateStream &st) {
+    if (st.wrap == 1) {                                        // deflate.c:1254-1255
+        for (int i = 3; i >= 0; --i) st.pending.push_back((uint8_t)(st.adler >> (8 * i)));
+    } else if (st.wrap == 2) {                                 // deflate.c:1241-1250
+        for (int i = 0; i < 4; ++i) st.pending.push_back((uint8_t)(st.crc >> (8 * i)));
+        for (int i = 0; i < 4; ++i) st.pending.push_back((uint8_t)(st.total_in_hashed >> (8 * i)));
+    }
+    st.trailer_done = true;
+}
+
+DeflateStream *dstate(z_streamp strm) {
+    if (!strm || !strm->state) return nullptr;
+    DeflateStream *s = reinterpret_cast<DeflateStream *>(strm->state);
+    return s->magic == kDeflateMagic ? s : nullptr;
+}
+InflateStream *istate(z_streamp strm) {
+    if (!strm || !strm->state) return nullptr;
+    InflateStream *s = reinterpret_cast<InflateStream *>(strm->state);
+    return s->magic == kInflateMagic ? s : nullptr;
+}
+
+void inflate_reset_state(InflateStream &s) {
+    s.kind = 0; s.in.clear(); s.d_in_have = 0; s.out.clear(); s.out_pos = 0; s.out_base = 0; s.decoded = 0;
+    s.resume_bit = s.resume_out = 0; s.started = s.done = false; s.error = 0; s.in_used = 0; s.check = 0;
+}
+
+// One decode attempt over everything received so far, resuming at the last
+// block boundary.  Updates the stream state; returns a ZB200_INF_* status.
+int inflate_attempt(InflateStream &s) {
+    zb200_ctx *ctx = api_ctx();
+    if (!ctx) return -1;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return -1;
+    cudaStream_t st = ctx->stream;
+    const size_t n = s.in.size();
+    if (dev_grow(&s.d_in, &s.d_in_cap, n + 16, s.d_in_have, st)) return -1;
+    if (n > s.d_in_have) {
+        if (cudaMemcpyAsync(s.d_in + s.d_in_have, s.in.data() + s.d_in_have, n - s.d_in_have, cudaMemcpyHostToDevice, st) != cudaSuccess) return -1;
+        s.d_in_have = n;
+    }
+    if (s.d_out_cap == 0 && dev_grow(&s.d_out, &s.d_out_cap, n * 4 + (1u << 20), 0, st)) return -1;
+    if (ensure_scratch(ctx, 1024 + inflate_work_bytes(1)) != ZB200_OK) return -1;
+    for (;;) {
+        zb200_member m;
+        m.in_off = 0; m.in_len = n; m.out_off = 0; m.out_cap = s.d_out_cap;
+        m.resume_bit = s.resume_bit; m.resume_out = s.resume_out;
+        uint8_t *base = (uint8_t *)ctx->d_scratch;
+        zb200_member *d_m = (zb200_member *)base;
+        zb200_member_result *d_r = (zb200_member_result *)(base + 256);
+        zb200_member_result *h_r = (zb200_member_result *)ctx->h_small;
+        memcpy(ctx->h_small + 40, &m, sizeof m);                 // pinned bounce for the descriptor
+        if (cudaMemcpyAsync(d_m, ctx->h_small + 40, sizeof m, cudaMemcpyHostToDevice, st) != cudaSuccess) return -1;
+        const int wrap = s.resume_bit ? s.kind : s.wrap;
+        if (inflate_launch(ctx, s.d_in, s.d_out, d_m, 1, wrap, 1, d_r, base + 1024, st) != ZB200_OK) return -1;
+        if (cudaMemcpyAsync(h_r, d_r, sizeof *h_r, cudaMemcpyDeviceToHost, st) != cudaSuccess) return -1;
+        if (cudaStreamSynchronize(st) != cudaSuccess) return -1;
+        const zb200_member_result r = *h_r;
+        if (r.status == ZB200_INF_OUTPUT_FULL) {                 // grow the device output and go again from the checkpoint
+            s.kind = (int)r.wrap_kind; s.resume_bit = r.resume_bit; s.resume_out = r.resume_out;
+            if (r.resume_bit == 0) { s.resume_bit = 0; s.resume_out = 0; }
+            if (dev_grow(&s.d_out, &s.d_out_cap, s.d_out_cap * 2 + (1u << 20), (size_t)r.out_len, st)) return -1;
+            continue;
+        }
+        // fetch the newly valid bytes
+        if (r.out_len > s.decoded) {
+            const size_t add = (size_t)(r.out_len - s.decoded);
+            const size_t at = s.out.size();
+            s.out.resize(at + add);
+            if (cudaMemcpyAsync(s.out.data() + at, s.d_out + s.decoded, add, cudaMemcpyDeviceToHost, st) != cudaSuccess) return -1;
+            if (cudaStreamSynchronize(st) != cudaSuccess) return -1;
+            s.decoded = r.out_len;
+        }
+        s.kind = (int)r.wrap_kind;
+        if (r.status == ZB200_INF_TRUNCATED) {
+            if (r.resume_bit) { s.resume_bit = r.resume_bit; s.resume_out = r.resume_out; }
+        } else if (r.status == ZB200_INF_OK) {
+            s.done = true; s.in_used = r.in_used; s.check = r.check;
+        }
+        return r.status;
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *zlibVersion(void) { return ZLIB_VERSION; }
+const char *zError(int err) { return (err >= -6 && err <= 2) ? kErrMsg[2 - err] : ""; }   // zutil.c:131
+
+// ---------------------------------------------------------------------------
+int deflateInit2_(z_streamp strm, int level, int method, int windowBits, int memLevel, int strategy,
+                  const char *version, int stream_size) {
+    if (version == Z_NULL || version[0] != ZLIB_VERSION[0] || stream_size != (int)sizeof(z_stream))
+        return Z_VERSION_ERROR;                                 // deflate.c:386-389
+    if (strm == Z_NULL) return Z_STREAM_ERROR;
+    strm->msg = Z_NULL;
+    if (level == Z_DEFAULT_COMPRESSION) level = 6;
+    int wrap = 1;
+    if (windowBits < 0) { wrap = 0; if (windowBits < -15) return Z_STREAM_ERROR; windowBits = -windowBits; }
+    else if (windowBits > 15) { wrap = 2; windowBits -= 16; }
+    if (memLevel < 1 || memLevel > 9 || method != Z_DEFLATED || windowBits < 8 || windowBits > 15 || level < 0 ||
+        level > 9 || strategy < 0 || strategy > Z_FIXED || (windowBits == 8 && wrap != 1))
+        return Z_STREAM_ERROR;                                  // deflate.c:426-430
+    if (!api_ctx()) { strm->msg = "zlib-b200: no usable CUDA device (no CPU path)"; return Z_STREAM_ERROR; }
+    DeflateStream *s = new (std::nothrow) DeflateStream();
+    if (!s) return Z_MEM_ERROR;
+    s->magic = kDeflateMagic; s->level = level; s->strategy = strategy; s->wrap = wrap;
+    strm->state = reinterpret_cast<struct internal_state *>(s);
+    return deflateReset(strm);
+}
+
+int deflateInit_(z_streamp strm, int level, const char *version, int stream_size) {
+    return deflateInit2_(strm, level, Z_DEFLATED, 15, 8, Z_DEFAULT_STRATEGY, version, stream_size);
+}
+
+int deflateReset(z_streamp strm) {
+    DeflateStream *s = dstate(strm);
+    if (!s) return Z_STREAM_ERROR;
+    s->in.clear(); s->pending.clear(); s->pending_pos = 0;
+    s->header_done = s->finished = s->trailer_done = false;
+    s->crc = 0; s->adler = 1; s->total_in_hashed = 0; s->last_flush = -2;
+    strm->total_in = strm->total_out = 0; strm->msg = Z_NULL; strm->data_type = Z_UNKNOWN;
+    strm->adler = s->wrap == 2 ? 0 : 1;                         // deflate.c:656-660
+    return Z_OK;
+}
+
+int deflateParams(z_streamp strm, int level, int strategy) {
+    DeflateStream *s = dstate(strm);
+    if (!s) return Z_STREAM_ERROR;
+    if (level == Z_DEFAULT_COMPRESSION) level = 6;
+    if (level < 0 || level > 9 || strategy < 0 || strategy > Z_FIXED) return Z_STREAM_ERROR;
+    if ((level != s->level || strategy != s->strategy) && !s->in.empty()) {
+        if (!s->header_done) put_header(*s);                    // deflate.c:779-790: flush what was taken with the old setting
+        const int r = compress_buffered(*s, false);
+        if (r != Z_OK) return r;
+    }
+    s->level = level; s->strategy = strategy;
+    return Z_OK;
+}
+
+uLong deflateBound(z_streamp strm, uLong n) {
+    (void)strm;                                                 // compress.c:72 / deflate.c:842 + one marker per chunk
+    return n + (n >> 12) + (n >> 14) + (n >> 25) + 13 + 18 + 5 * (n / api_chunk() + 1);
+}
+
+int deflate(z_streamp strm, int flush) {
+    DeflateStream *s = dstate(strm);
+    if (!s || flush > Z_BLOCK || flush < 0) return Z_STREAM_ERROR;
+    if (strm->next_out == Z_NULL || (strm->avail_in != 0 && strm->next_in == Z_NULL) || (s->finished && flush != Z_FINISH)) {
+        strm->msg = kErrMsg[2 - Z_STREAM_ERROR];
+        return Z_STREAM_ERROR;                                  // deflate.c:962-966
+    }
+    if (strm->avail_out == 0) { strm->msg = kErrMsg[2 - Z_BUF_ERROR]; return Z_BUF_ERROR; }
+    const uInt in0 = strm->avail_in, out0 = strm->avail_out;
+    if (strm->avail_in) {
+        if (s->finished) { strm->msg = kErrMsg[2 - Z_BUF_ERROR]; return Z_BUF_ERROR; }   // deflate.c:1184-1187
+        s->in.insert(s->in.end(), strm->next_in, strm->next_in + strm->avail_in);
+        strm->next_in += strm->avail_in; strm->total_in += strm->avail_in; strm->avail_in = 0;
+    }
+    if (!s->finished) {
+        const bool want_flush = flush != Z_NO_FLUSH;
+        // bound host buffering: hand whole chunks to the GPU once enough has piled up
+        const bool spill = !want_flush && s->in.size() >= (size_t)64 * api_chunk();
+        if (want_flush || spill) {
+            if (!s->header_done) put_header(*s);
+            int r;
+            if (spill) {
+                const size_t keep = s->in.size() % api_chunk();
+                std::vector<uint8_t> tail(s->in.end() - (long)keep, s->in.end());
+                s->in.resize(s->in.size() - keep);
+                r = compress_buffered(*s, false);
+                s->in = tail;
+            } else {
+                r = compress_buffered(*s, flush == Z_FINISH);
+            }
+            if (r != Z_OK) { strm->msg = kErrMsg[2 - r]; return r; }
+            if (flush == Z_FINISH) { s->finished = true; put_trailer(*s); }
+            strm->adler = s->wrap == 2 ? s->crc : s->adler;
+        }
+    }
+    s->last_flush = flush;
+    const size_t avail = s->pending.size() - s->pending_pos;
+    const size_t k = avail < strm->avail_out ? avail : strm->avail_out;
+    if (k) {
+        memcpy(strm->next_out, s->pending.data() + s->pending_pos, k);
+        strm->next_out += k; strm->avail_out -= (uInt)k; strm->total_out += k; s->pending_pos += k;
+        if (s->pending_pos == s->pending.size()) { s->pending.clear(); s->pending_pos = 0; }
+    }
+    if (s->finished && s->pending.empty()) return Z_STREAM_END;
+    if (in0 == 0 && out0 == strm->avail_out && flush != Z_FINISH) { strm->msg = kErrMsg[2 - Z_BUF_ERROR]; return Z_BUF_ERROR; }
+    return Z_OK;
+}
+
+int deflateEnd(z_streamp strm) {
+    DeflateStream *s = dstate(strm);
+    if (!s) return Z_STREAM_ERROR;
+    const bool busy = !s->finished && (s->header_done || !s->in.empty());
+    s->magic = 0;
+    delete s;
+    strm->state = Z_NULL;
+    return busy ? Z_DATA_ERROR : Z_OK;                          // deflate.c:1284
+}
+
+// ---------------------------------------------------------------------------
+int inflateInit2_(z_streamp strm, int windowBits, const char *version, int stream_size) {
+    if (version == Z_NULL || version[0] != ZLIB_VERSION[0] || stream_size != (int)sizeof(z_stream))
+        return Z_VERSION_ERROR;                                 // inflate.c:183-185
+    if (strm == Z_NULL) return Z_STREAM_ERROR;
+    strm->msg = Z_NULL;
+    if (!api_ctx()) { strm->msg = "zlib-b200: no usable CUDA device (no CPU path)"; return Z_STREAM_ERROR; }
+    InflateStream *s = new (std::nothrow) InflateStream();
+    if (!s) return Z_MEM_ERROR;
+    s->magic = kInflateMagic; s->d_in = s->d_out = nullptr; s->d_in_cap = s->d_out_cap = 0;
+    strm->state = reinterpret_cast<struct internal_state *>(s);
+    const int r = inflateReset2(strm, windowBits);
+    if (r != Z_OK) { delete s; strm->state = Z_NULL; }
+    return r;
+}
+
+int inflateInit_(z_streamp strm, const char *version, int stream_size) { return inflateInit2_(strm, 15, version, stream_size); }
+
+int inflateReset2(z_streamp strm, int windowBits) {
+    InflateStream *s = istate(strm);
+    if (!s) return Z_STREAM_ERROR;
+    int wrap;                                                   // inflate.c:152-172
+    if (windowBits < 0) { if (windowBits < -15) return Z_STREAM_ERROR; wrap = ZB200_WRAP_RAW; windowBits = -windowBits; }
+    else if (windowBits >= 48) return Z_STREAM_ERROR;
+    else if (windowBits >= 32) { wrap = ZB200_WRAP_AUTO; windowBits -= 32; }
+    else if (windowBits >= 16) { wrap = ZB200_WRAP_GZIP; windowBits -= 16; }
+    else wrap = ZB200_WRAP_ZLIB;
+    if (windowBits && (windowBits < 8 || windowBits > 15)) return Z_STREAM_ERROR;
+    s->wrap = wrap;
+    return inflateReset(strm);
+}
+
+int inflateReset(z_streamp strm) {
+    InflateStream *s = istate(strm);
+    if (!s) return Z_STREAM_ERROR;
+    inflate_reset_state(*s);
+    strm->total_in = strm->total_out = 0; strm->msg = Z_NULL; strm->data_type = 0;
+    strm->adler = s->wrap == ZB200_WRAP_RAW ? 0 : 1;
+    return Z_OK;
+}
+
+int inflate(z_streamp strm, int flush) {
+    InflateStream *s = istate(strm);
+    if (!s || strm->next_out == Z_NULL || (strm->next_in == Z_NULL && strm->avail_in != 0)) return Z_STREAM_ERROR;   // inflate.c:611-613
+    const uInt in0 = strm->avail_in, out0 = strm->avail_out;
+    const uLong total_in0 = strm->total_in;
+    int status = s->error ? s->error : (s->done ? ZB200_INF_OK : ZB200_INF_TRUNCATED);
+    if (!s->done && !s->error && strm->avail_in) {
+        s->in.insert(s->in.end(), strm->next_in, strm->next_in + strm->avail_in);
+        status = inflate_attempt(*s);
+        if (status < 0) { strm->msg = "zlib-b200: device error"; return Z_STREAM_ERROR; }
+        uLong used = in0;
+        if (status == ZB200_INF_OK) used = (uLong)(s->in_used - total_in0);   // give back bytes after the stream end
+        else if (status != ZB200_INF_TRUNCATED) s->error = status;
+        strm->next_in += used; strm->avail_in -= (uInt)used; strm->total_in += used;
+        if (status == ZB200_INF_OK) strm->adler = s->check;
+    }
+    // deliver decoded bytes
+    const size_t avail = s->out.size() - s->out_pos;
+    const size_t k = avail < strm->avail_out ? avail : strm->avail_out;
+    if (k) {
+        memcpy(strm->next_out, s->out.data() + s->out_pos, k);
+        strm->next_out += k; strm->avail_out -= (uInt)k; strm->total_out += k; s->out_pos += k;
+        if (s->out_pos == s->out.size()) { s->out.clear(); s->out_pos = 0; }
+    }
+    const bool drained = s->out.empty();
+    if (s->error && drained) {
+        if (s->error == ZB200_INF_NEED_DICT) return Z_NEED_DICT;
+        strm->msg = zb200_inflate_msg(s->error);
+        return Z_DATA_ERROR;
+    }
+    if (s->done && drained) return Z_STREAM_END;
+    if ((in0 == strm->avail_in && out0 == strm->avail_out) || (flush == Z_FINISH && !(s->done && drained)))
+        return Z_BUF_ERROR;                                     // inflate.c:1259-1261
+    return Z_OK;
+}
+
+int inflateEnd(z_streamp strm) {
+    InflateStream *s = istate(strm);
+    if (!s) return Z_STREAM_ERROR;
+    if (s->d_in) cudaFree(s->d_in);
+    if (s->d_out) cudaFree(s->d_out);
+    s->magic = 0;
+    delete s;
+    strm->state = Z_NULL;
+    return Z_OK;
+}
+
+// ---------------------------------------------------------------------------
+uLong compressBound(uLong n) { return deflateBound(Z_NULL, n) - 18 + 6; }
+
+int compress2(Bytef *dest, uLongf *destLen, const Bytef *source, uLong sourceLen, int level) {
+    zb200_ctx *ctx = api_ctx();                                 // compress.c:22-59 in one GPU call
+    if (!ctx) return Z_STREAM_ERROR;
+    if (level == Z_DEFAULT_COMPRESSION) level = 6;
+    if (level < 0 || level > 9 || !dest || !destLen || (!source && sourceLen)) return Z_STREAM_ERROR;
+    size_t cap = *destLen;
+    const int r = zb200_deflate_host(ctx, source ? source : (const Bytef *)"", sourceLen, api_chunk(), level ? level : 1,
+                                     level ? 0 : Z_HUFFMAN_ONLY, ZB200_FRAME_ZLIB, 1, dest, &cap, nullptr, nullptr);
+    if (r == ZB200_ERR_OUTPUT) return Z_BUF_ERROR;
+    if (r != ZB200_OK) return map_engine_error(r);
+    *destLen = cap;
+    return Z_OK;
+}
+
+int compress(Bytef *dest, uLongf *destLen, const Bytef *source, uLong sourceLen) {
+    return compress2(dest, destLen, source, sourceLen, Z_DEFAULT_COMPRESSION);
+}
+
+int uncompress2(Bytef *dest, uLongf *destLen, const Bytef *source, uLong *sourceLen) {
+    zb200_ctx *ctx = api_ctx();                                 // uncompr.c:27-80
+    if (!ctx) return Z_STREAM_ERROR;
+    if (!destLen || !sourceLen || (!source && *sourceLen)) return Z_STREAM_ERROR;
+    Bytef one[1];
+    const bool probe = (*destLen == 0);                         // uncompr.c:37-42: detect "would need output"
+    zb200_member m;
+    m.in_off = 0; m.in_len = *sourceLen; m.out_off = 0; m.out_cap = probe ? 1 : *destLen; m.resume_bit = m.resume_out = 0;
+    zb200_member_result res;
+    const int r = zb200_inflate_host(ctx, source, probe ? one : dest, &m, 1, ZB200_WRAP_ZLIB, 1, &res);
+    if (r != ZB200_OK) return map_engine_error(r);
+    *sourceLen = res.status == ZB200_INF_OK ? (uLong)res.in_used : *sourceLen;
+    *destLen = probe ? 0 : (uLong)res.out_len;
+    switch (res.status) {
+    case ZB200_INF_OK: return probe && res.out_len ? Z_BUF_ERROR : Z_OK;
+    case ZB200_INF_OUTPUT_FULL: return Z_BUF_ERROR;
+    case ZB200_INF_TRUNCATED: return Z_DATA_ERROR;              // uncompr.c:76-79
+    default: return Z_DATA_ERROR;
+    }
+}
+
+int uncompress(Bytef *dest, uLongf *destLen, const Bytef *source, uLong sourceLen) {
+    return uncompress2(dest, destLen, source, &sourceLen);
+}
+
+// ---------------------------------------------------------------------------
+uLong crc32_z(uLong crc, const Bytef *buf, z_size_t len) {
+    if (buf == Z_NULL) return 0;                                // crc32.c:697
+    zb200_ctx *ctx = api_ctx();
+    if (!ctx) die_no_device("crc32");
+    uint32_t c = (uint32_t)crc;
+    if (zb200_checksum_host(ctx, buf, len, ZB200_CRC32, (uint32_t)crc, 1, &c, nullptr) != ZB200_OK) die_no_device("crc32");
+    return c;
+}
+uLong crc32(uLong crc, const Bytef *buf, uInt len) { return crc32_z(crc, buf, len); }
+uLong adler32_z(uLong adler, const Bytef *buf, z_size_t len) {
+    if (buf == Z_NULL) return 1;                                // adler32.c:81
+    zb200_ctx *ctx = api_ctx();
+    if (!ctx) die_no_device("adler32");
+    uint32_t a = (uint32_t)adler;
+    if (zb200_checksum_host(ctx, buf, len, ZB200_ADLER32, 0, (uint32_t)adler, nullptr, &a) != ZB200_OK) die_no_device("adler32");
+    return a;
+}
+uLong adler32(uLong adler, const Bytef *buf, uInt len) { return adler32_z(adler, buf, len); }
+uLong crc32_combine(uLong c1, uLong c2, z_off_t len2) { return zb200_crc32_combine((uint32_t)c1, (uint32_t)c2, (uint64_t)len2); }
+uLong crc32_combine_gen(z_off_t len2) { return zb200_crc32_combine_gen((uint64_t)len2); }
+uLong crc32_combine_op(uLong c1, uLong c2, uLong op) { return zb200_crc32_combine_op((uint32_t)c1, (uint32_t)c2, (uint32_t)op); }
+uLong adler32_combine(uLong a1, uLong a2, z_off_t len2) { return zb200_adler32_combine((uint32_t)a1, (uint32_t)a2, (int64_t)len2); }
+
+}  // extern "C"
