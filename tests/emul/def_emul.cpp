@@ -43,8 +43,15 @@ extern "C" long emul_deflate_chunk(const uint8_t *data, uint32_t n, int level, i
     }
     std::vector<uint32_t> syms(n + 2);
     std::vector<BlockInfo> blocks(max_blocks_for(n));
-    ParseSink sink; sink.syms = syms.data(); sink.blocks = blocks.data();
-    parse_chunk(data, n, mf.data(), mq.data(), prm, final_chunk != 0, sink);
+    struct { uint32_t nsyms, nblocks; } sink;
+    // walk the chunk in tiles of odd size, as the kernel does, to exercise the resumable parse
+    {
+        ParseState ps; parse_init(ps, blocks.data());
+        ParseArrays acc{data, mf.data(), mq.data(), syms.data(), 0};
+        while (ps.p < n) { uint32_t lim = ps.p + 1000 < n ? ps.p + 1000 : n; parse_steps(ps, lim, n, prm, acc); }
+        parse_finish(ps, n, prm, final_chunk != 0, acc);
+        sink.nsyms = ps.nsyms; sink.nblocks = ps.nblocks;
+    }
     if (sink.nblocks > blocks.size()) return -2;
     if (stats) { stats[0] = sink.nsyms; stats[1] = sink.nblocks; }
     memset(out, 0, cap);

@@ -1,0 +1,116 @@
+"""Host replays of the product's __host__ __device__ cores (tests/emul/*.cpp compile
+the same csrc/*.cuh headers the kernels use, with g++).  These validate the GF(2)
+weighting, the inflate state machine and the deflate phases on the CPU before GPU
+time is spent.  The replays are test binaries; nothing here ships."""
+import ctypes as C
+import os
+import random
+import subprocess
+import zlib
+
+import pytest
+
+import refz
+
+EMUL = os.path.join(refz.ROOT, "tests", "emul")
+
+
+def _build(name):
+    src, out = os.path.join(EMUL, name + ".cpp"), os.path.join(EMUL, "lib" + name + ".so")
+    hdrs = [os.path.join(refz.ROOT, "zlib_wasm_b200", "csrc", f) for f in os.listdir(os.path.join(refz.ROOT, "zlib_wasm_b200", "csrc")) if f.endswith(("h", "cuh"))]
+    if not os.path.exists(out) or any(os.path.getmtime(f) > os.path.getmtime(out) for f in [src] + hdrs):
+        subprocess.check_call(["g++", "-O2", "-fPIC", "-shared", "-std=c++17", "-Wno-unknown-pragmas", "-o", out, src])
+    return C.CDLL(out)
+
+
+def test_checksum_thread_decomposition():
+    L = _build("ck_emul")
+    L.emul_checksum.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_int, C.c_uint32, C.c_uint32,
+                                C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+    rng = random.Random(1)
+    big = refz.gen(1500000, refz.GEN_BYTES)
+    buf = C.create_string_buffer(big, len(big) + 64)
+    base = C.addressof(buf)
+    for trial in range(120):
+        n = rng.choice([0, 1, 15, 16, 17, 31, 33, 100, 4095, 4096, 5000, 65536, 70001, rng.randrange(0, len(big))])
+        off = rng.randrange(0, 17) if trial % 2 else 0
+        n = min(n, len(big) - off)
+        T, parts = rng.choice([32, 256, 1024]), rng.choice([1, 2, 3, 7, 148])
+        ic, ia = rng.choice([0, 0xdeadbeef]), rng.choice([1, 0x12340005])
+        c, a = C.c_uint32(), C.c_uint32()
+        L.emul_checksum(base + off, n, T, parts, 3, ic, ia, C.byref(c), C.byref(a))
+        d = big[off:off + n]
+        assert (c.value, a.value) == (zlib.crc32(d, ic), zlib.adler32(d, ia)), (n, off, T, parts)
+
+
+def _inflate_emul():
+    L = _build("inf_emul")
+    u64 = C.c_uint64
+    L.emul_inflate.argtypes = [C.c_void_p, u64, C.c_void_p, u64, C.c_int, u64, u64] + [C.POINTER(u64)] * 2 + \
+        [C.POINTER(C.c_uint32)] * 2 + [C.POINTER(u64)] * 2 + [C.POINTER(C.c_int)]
+
+    def run(data, wrap, cap, off=0, resume=(0, 0), dst=None):
+        buf = C.create_string_buffer(len(data) + 8 + off)
+        C.memmove(C.addressof(buf) + off, data, len(data))
+        dst = dst if dst is not None else C.create_string_buffer(max(cap, 1))
+        iu, ol, cb, co = u64(), u64(), u64(), u64()
+        ck, isz, kind = C.c_uint32(), C.c_uint32(), C.c_int()
+        st = L.emul_inflate(C.addressof(buf) + off, len(data), dst, cap, wrap, resume[0], resume[1], C.byref(iu), C.byref(ol),
+                            C.byref(ck), C.byref(isz), C.byref(cb), C.byref(co), C.byref(kind))
+        return st, dst.raw[:ol.value], iu.value, ck.value, isz.value, cb.value, co.value, kind.value, dst
+    return run
+
+
+def test_inflate_state_machine(golden):
+    run = _inflate_emul()
+    o = refz.oracle()
+    msgs = [o.c_inflate_msg(i).decode() for i in range(22)]
+    for v in golden["puff_vectors"]:
+        st, out, iu = run(bytes.fromhex(v["hex"]), 0, 4096)[:3]
+        if v["ret"] == 1:
+            assert st == 0 and out.hex() == v["out_hex"] and iu == v["total_in"]
+        elif v["ret"] == -5:
+            assert msgs[st] == "truncated input"
+        else:
+            assert msgs[st] == v["msg"]
+    rng = random.Random(3)
+    for kind in (refz.GEN_TEXT, refz.GEN_MIXED, refz.GEN_RANDOM):
+        d = refz.gen(300000, kind, seed=42 + kind)
+        for lvl, strat, wrap, chunk in ((1, 0, 0, 0), (6, 0, 1, 100000), (9, 0, 2, 0), (6, 4, 0, 65536), (6, 2, 1, 0), (1, 3, 2, 0)):
+            s = o.deflate_stream(d, lvl, strat, wrap, chunk)
+            st, out, iu, ck, isz = run(s, wrap, len(d) + 3, off=rng.randrange(0, 8))[:5]
+            assert st == 0 and out == d and iu == len(s)
+            if wrap == 2:
+                assert ck == zlib.crc32(d) and isz == len(d)
+    # resume at a block boundary after truncated input
+    d = refz.gen(500000, refz.GEN_MARKOV, seed=9)
+    s = o.deflate_stream(d, 6, 0, refz.WRAP_GZIP, 0)
+    st, out, iu, ck, isz, cb, co, kind, dst = run(s[:len(s) // 2], 3, len(d) + 8)
+    assert msgs[st] == "truncated input" and cb > 0 and out == d[:len(out)] and kind == 2
+    st, out, iu = run(s, kind, len(d) + 8, resume=(cb, co), dst=dst)[:3]
+    assert st == 0 and out == d and iu == len(s)
+
+
+def test_deflate_phases_byte_exact():
+    L = _build("def_emul")
+    L.emul_deflate_chunk.restype = C.c_long
+    L.emul_deflate_chunk.argtypes = [C.c_char_p, C.c_uint32, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_uint32)]
+    o = refz.oracle()
+    for kind in range(5):
+        for n in (0, 1, 3, 300, 70000, 262144):
+            d = refz.gen(n, kind, seed=7 + kind)
+            for level, strat in ((1, 0), (3, 0), (4, 0), (6, 0), (6, 1), (6, 2), (6, 3), (6, 4), (9, 0)):
+                for final in (0, 1):
+                    cap = n + n // 8 + 1024
+                    out, st = C.create_string_buffer(cap), (C.c_uint32 * 2)()
+                    r = L.emul_deflate_chunk(d, n, level, strat, final, out, cap, st)
+                    assert r >= 0, (r, kind, n, level, strat)
+                    e = out.raw[:r]
+                    rb = C.create_string_buffer(cap)
+                    rn = o.c_deflate_chunk(d, n, level, strat, final, rb, cap)
+                    if level >= 4 or strat in (2, 3):
+                        assert e == rb.raw[:rn], (kind, n, level, strat, final)
+                    else:
+                        s = e if final else e + b"\x03\x00"
+                        err, msg, back, used = o.inflate_all(s, 0, cap=n + 16)
+                        assert err == 0 and back == d and len(e) <= 1.03 * rn + 8

@@ -71,6 +71,7 @@ __device__ __forceinline__ bool chunk_final(const Batch &b, uint32_t c) {
 // linked with match.any, the rest through a 32K-entry u16 head table in shared
 // memory holding window-relative positions; every 32 KiB the table slides like
 // deflate.c:187-209 so that entries stay 16-bit.
+constexpr int kChainSmem = 65536 + 67 * 16;   // head table + one staged input tile
 __global__ void __launch_bounds__(32) dfl_chain_kernel(Batch b, uint16_t *__restrict__ prev_all) {
     extern __shared__ __align__(16) uint16_t head[];
     const uint32_t c = blockIdx.x, lane = threadIdx.x;
@@ -79,9 +80,37 @@ __global__ void __launch_bounds__(32) dfl_chain_kernel(Batch b, uint16_t *__rest
     uint16_t *prev = prev_all + (uint64_t)c * b.S;
     uint4 *h4 = reinterpret_cast<uint4 *>(head);
     for (int i = lane; i < 4096; i += 32) h4[i] = make_uint4(0, 0, 0, 0);
+    // Input is staged through shared memory in tiles of kChainTile positions so the
+    // per-step byte reads never wait on DRAM: 16-byte aligned loads (by address)
+    // covering [tile, tile + kChainTile + 2), the next tile prefetched into
+    // registers while the current one is processed.
+    constexpr uint32_t kChainTile = 1024, kTileVecs = (kChainTile + 2 + 15) / 16 + 1;   // 66 uint4
+    uint8_t *tile = reinterpret_cast<uint8_t *>(head) + 65536;     // kTileVecs * 16 bytes after the head table
+    uint4 *tile4 = reinterpret_cast<uint4 *>(tile);
+    const uintptr_t addr0 = reinterpret_cast<uintptr_t>(data);
+    const uintptr_t end_addr = addr0 + n;
+    uint4 pre[3];
+    auto prefetch = [&](uint32_t t0) {                             // t0: chunk position of the tile start
+        const uintptr_t a = (addr0 + t0) & ~(uintptr_t)15;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const uint32_t v = lane + 32 * k;
+            const uintptr_t src = a + 16ull * v;
+            pre[k] = make_uint4(0, 0, 0, 0);
+            if (v < kTileVecs && src < end_addr) pre[k] = *reinterpret_cast<const uint4 *>(src);
+        }
+    };
+    prefetch(0);
     __syncwarp();
     uint32_t base = 0;
     for (uint32_t p0 = 0; p0 < n; p0 += 32) {
+        if ((p0 & (kChainTile - 1)) == 0) {                        // publish the prefetched tile, fetch the next
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < 3; ++k) if (lane + 32 * k < kTileVecs) tile4[lane + 32 * k] = pre[k];
+            if (p0 + kChainTile < n) prefetch(p0 + kChainTile);
+            __syncwarp();
+        }
         if (p0 - base == 65536u) {                                 // slide: subtract 32768, saturating at 0 (= NIL)
             for (int i = lane; i < 4096; i += 32) {
                 uint4 v = h4[i];
@@ -95,7 +124,11 @@ __global__ void __launch_bounds__(32) dfl_chain_kernel(Batch b, uint16_t *__rest
         const uint32_t p = p0 + lane;
         const bool valid = p + kMinMatch <= n;
         uint32_t h = 0;
-        if (valid) h = hash3(data + p);
+        if (valid) {
+            const uint32_t tile_pos = p0 & ~(kChainTile - 1);
+            const uint8_t *tp = tile + (((addr0 + tile_pos) & 15) + (p - tile_pos));
+            h = hash3(tp);
+        }
         const uint32_t key = valid ? h : (0x10000u | lane);
         const uint32_t mask = __match_any_sync(0xffffffffu, key);
         const uint32_t lower = mask & ((1u << lane) - 1u);
@@ -133,18 +166,67 @@ dfl_match_kernel(Batch b, DeflateParams prm, const uint16_t *__restrict__ prev_a
 }
 
 // ---- phase 3: parse, one chunk per warp (lane 0 walks the tables) ---------------------
+// The walk is a dependent chain (the next position depends on the entry just
+// read), so operands are staged: the warp loads a tile of kParseTile positions
+// (match entries + input bytes) into shared memory with coalesced loads, lane 0
+// walks the tile out of shared memory, emitted symbols are staged and flushed
+// with coalesced stores.
+constexpr uint32_t kParseTile = 1024;
+
+struct ParseTileAcc {
+    const uint32_t *tmf, *tmq; const uint8_t *tbytes; uint32_t *stage;
+    uint32_t tile0;            // chunk position of tile entry 0
+    uint32_t count;            // symbols staged in this tile
+    __device__ __forceinline__ uint32_t mf(uint32_t p) const { return tmf[p - tile0]; }
+    __device__ __forceinline__ uint32_t mq(uint32_t p) const { return tmq[p - tile0]; }
+    __device__ __forceinline__ uint32_t byte(uint32_t p) const { return tbytes[p + 1 - tile0]; }   // tbytes[0] = byte tile0-1
+    __device__ __forceinline__ void put(uint32_t sym) { stage[count++] = sym; }
+};
+
 __global__ void __launch_bounds__(32)
 dfl_parse_kernel(Batch b, DeflateParams prm, const uint32_t *__restrict__ mfull,
                  const uint32_t *__restrict__ mquarter, uint32_t *__restrict__ syms,
                  BlockInfo *__restrict__ blocks, uint32_t *__restrict__ nblocks) {
-    const uint32_t c = blockIdx.x;
-    if (threadIdx.x != 0) return;
+    __shared__ uint32_t tmf[kParseTile], tmq[kParseTile], stage[kParseTile + 2];
+    __shared__ uint8_t tbytes[kParseTile + 4];
+    const uint32_t c = blockIdx.x, lane = threadIdx.x;
     const uint64_t off = (uint64_t)c * b.S;
-    ParseSink s;
-    s.syms = syms + off; s.blocks = blocks + (uint64_t)c * b.MB;
-    parse_chunk(b.in + off, chunk_len(b, c), mfull + off, prm.need_quarter ? mquarter + off : mfull + off, prm,
-                chunk_final(b, c), s);
-    nblocks[c] = s.nblocks;
+    const uint8_t *data = b.in + off;
+    const uint32_t n = chunk_len(b, c);
+    const uint32_t *mf = mfull + off, *mq = (prm.need_quarter ? mquarter : mfull) + off;
+    uint32_t *out = syms + off;
+    ParseState st;
+    parse_init(st, blocks + (uint64_t)c * b.MB);
+    ParseTileAcc acc{tmf, tmq, tbytes, stage, 0, 0};
+    uint32_t flushed = 0;                              // symbols already written to global memory
+    for (;;) {
+        const uint32_t t0 = __shfl_sync(0xffffffffu, st.p, 0);
+        if (t0 >= n) break;
+        const uint32_t t1 = t0 + kParseTile < n ? t0 + kParseTile : n;
+        const uint32_t cnt = t1 - t0;
+        if (prm.mode != MODE_HUFF)
+            for (uint32_t i = lane; i < cnt; i += 32) { tmf[i] = mf[t0 + i]; if (prm.need_quarter) tmq[i] = mq[t0 + i]; }
+        for (uint32_t i = lane; i < cnt + 1; i += 32) tbytes[i] = (t0 + i) ? data[t0 + i - 1] : 0;
+        __syncwarp();
+        if (lane == 0) { acc.tile0 = t0; acc.count = 0; parse_steps(st, t1, n, prm, acc); }
+        const uint32_t made = __shfl_sync(0xffffffffu, acc.count, 0);
+        __syncwarp();
+        for (uint32_t i = lane; i < made; i += 32) out[flushed + i] = stage[i];
+        flushed += made;
+        __syncwarp();
+    }
+    if (lane == 0) {
+        // the trailing literal (if any) needs byte n-1: serve it straight from global memory
+        struct TailAcc {
+            const uint8_t *data; uint32_t *out; uint32_t at;
+            __device__ uint32_t mf(uint32_t) const { return 0; }
+            __device__ uint32_t mq(uint32_t) const { return 0; }
+            __device__ uint32_t byte(uint32_t p) const { return data[p]; }
+            __device__ void put(uint32_t sym) { out[at++] = sym; }
+        } tail{data, out, flushed};
+        parse_finish(st, n, prm, chunk_final(b, c), tail);
+        nblocks[c] = st.nblocks;
+    }
 }
 
 // ---- phase 4: per-block histogram + Huffman construction -------------------------------
@@ -369,7 +451,7 @@ int deflate_init(zb200_ctx *ctx) {
     ZB_CUDA(cudaMalloc(&d, sizeof h));
     ZB_CUDA(cudaMemcpy(d, &h, sizeof h, cudaMemcpyHostToDevice));
     ctx->d_deflate_tables = d;
-    ZB_CUDA(cudaFuncSetAttribute(dfl_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+    ZB_CUDA(cudaFuncSetAttribute(dfl_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kChainSmem));
     return ZB200_OK;
 }
 
@@ -434,7 +516,7 @@ int deflate_launch(zb200_ctx *ctx, const uint8_t *d_in, size_t n, size_t S, int 
         b.last_is_final = (finish && c0 + b.nb == nch) ? 1 : 0;
         b.all_final = members ? 1 : 0;
         if (prm.mode == MODE_FAST || prm.mode == MODE_SLOW) {
-            dfl_chain_kernel<<<b.nb, 32, 65536, s>>>(b, w.prev);
+            dfl_chain_kernel<<<b.nb, 32, kChainSmem, s>>>(b, w.prev);
             ZB_LAUNCHED(); ZB_CHECK_LAUNCH();
         }
         if (prm.mode != MODE_HUFF) {

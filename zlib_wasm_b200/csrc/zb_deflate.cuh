@@ -138,59 +138,71 @@ constexpr uint32_t BLK_LAST = 1, BLK_STORED_OK = 2;
 
 ZB_HD uint32_t max_blocks_for(uint32_t chunk_bytes) { return chunk_bytes / kSymLimit + 2; }
 
-struct ParseSink {                    // where the parse writes
-    uint32_t *syms;                   // (dist << 16) | (len-3)   or   literal byte (dist == 0)
-    BlockInfo *blocks;
-    uint32_t nsyms, nblocks;
+// The parse is a resumable state machine so that the kernel can run it tile by
+// tile over operands staged in shared memory.  `Acc` supplies the operands:
+//   mf(p), mq(p)  match table entries at position p
+//   byte(p)       input byte at position p
+//   put(sym)      append one symbol ((dist << 16) | (len-3), or a literal byte)
+struct ParseState {
+    uint32_t p;                       // next position to examine (strstart)
+    uint32_t match_length, cur_dist;  // deflate_slow carry: match found at p-1
+    uint32_t match_available;
+    uint32_t base;                    // window origin: advances 32 KiB per slide (deflate.c:277-287)
+    uint32_t nsyms, nblocks;          // totals so far for the chunk
     uint32_t blk_sym0, blk_byte0;     // start of the open block
+    BlockInfo *blocks;
 };
 
-ZB_HD void parse_close_block(ParseSink &s, uint32_t cover_end, uint32_t window_base, bool last) {
+ZB_HD void parse_init(ParseState &s, BlockInfo *blocks) {
+    s.p = 0; s.match_length = kMinMatch - 1; s.cur_dist = 0; s.match_available = 0; s.base = 0;
+    s.nsyms = 0; s.nblocks = 0; s.blk_sym0 = 0; s.blk_byte0 = 0; s.blocks = blocks;
+}
+
+ZB_HD void parse_close_block(ParseState &s, uint32_t cover_end, bool last) {
     BlockInfo b;
     b.sym_start = s.blk_sym0; b.sym_count = s.nsyms - s.blk_sym0;
     b.byte_start = s.blk_byte0; b.byte_len = cover_end - s.blk_byte0;
     // deflate.c:1597-1600: the stored form needs the block start still inside the window
-    b.flags = (last ? BLK_LAST : 0) | (s.blk_byte0 >= window_base ? BLK_STORED_OK : 0);
+    b.flags = (last ? BLK_LAST : 0) | (s.blk_byte0 >= s.base ? BLK_STORED_OK : 0);
     b.bit_start_lo = b.bit_start_hi = 0; b.pad = 0;
     s.blocks[s.nblocks++] = b;
     s.blk_sym0 = s.nsyms; s.blk_byte0 = cover_end;
 }
 
-// Sequential parse of one chunk.  `final_chunk`: flush == Z_FINISH (last block
-// gets BFINAL, an empty final block is emitted if nothing is pending,
-// deflate.c:1908-1913); otherwise flush == Z_FULL_FLUSH.
-ZB_HD void parse_chunk(const uint8_t *data, uint32_t n, const uint32_t *mfull, const uint32_t *mquarter,
-                       const DeflateParams &prm, bool final_chunk, ParseSink &s) {
-    s.nsyms = 0; s.nblocks = 0; s.blk_sym0 = 0; s.blk_byte0 = 0;
-    uint32_t base = 0;                // window origin: advances 32 KiB per slide (deflate.c:277-287)
-    // fill_window is entered when lookahead drops under this many bytes
+// fill_window is entered when lookahead drops under `trigger` bytes; it slides the
+// window when strstart has reached wsize + MAX_DIST (deflate.c:277).
+ZB_HD void parse_slide_check(ParseState &s, uint32_t p, uint32_t n, const DeflateParams &prm) {
     const uint32_t trigger = prm.mode == MODE_HUFF ? 1 : prm.mode == MODE_RLE ? (uint32_t)kMaxMatch + 1 : (uint32_t)kMinLookahead;
-    auto slide_check = [&](uint32_t p) {
-        uint64_t fill_end = (uint64_t)base + 2 * kWSize;
-        if (fill_end > n) fill_end = n;
-        if (fill_end - p < trigger && p - base >= (uint32_t)(kWSize + kMaxDist)) base += kWSize;
-    };
+    uint64_t fill_end = (uint64_t)s.base + 2 * kWSize;
+    if (fill_end > n) fill_end = n;
+    if (fill_end - p < trigger && p - s.base >= (uint32_t)(kWSize + kMaxDist)) s.base += kWSize;
+}
+
+// Examine positions while p < limit (limit <= n).  A match may carry p past limit.
+template <class Acc>
+ZB_HD void parse_steps(ParseState &s, uint32_t limit, uint32_t n, const DeflateParams &prm, Acc &acc) {
     auto emit = [&](uint32_t sym, uint32_t cover_end) {
-        s.syms[s.nsyms++] = sym;
-        if (s.nsyms - s.blk_sym0 == kSymLimit) parse_close_block(s, cover_end, base, false);
+        acc.put(sym);
+        ++s.nsyms;
+        if (s.nsyms - s.blk_sym0 == kSymLimit) parse_close_block(s, cover_end, false);
     };
-    uint32_t p = 0;
+    uint32_t p = s.p;
     if (prm.mode != MODE_SLOW) {                       // greedy: deflate_fast / deflate_rle / deflate_huff
-        while (p < n) {
-            slide_check(p);
-            const uint32_t m = prm.mode == MODE_HUFF ? 0 : mfull[p];
+        while (p < limit) {
+            parse_slide_check(s, p, n, prm);
+            const uint32_t m = prm.mode == MODE_HUFF ? 0 : acc.mf(p);
             if (m) { const uint32_t len = m >> 16; emit(((m & 0xffff) << 16) | (len - kMinMatch), p + len); p += len; }
-            else { emit(data[p], p + 1); ++p; }
+            else { emit(acc.byte(p), p + 1); ++p; }
         }
     } else {                                           // lazy: deflate_slow
-        uint32_t match_length = kMinMatch - 1, cur_dist = 0;
-        bool match_available = false;
-        while (p < n) {
-            slide_check(p);
+        uint32_t match_length = s.match_length, cur_dist = s.cur_dist;
+        bool match_available = s.match_available != 0;
+        while (p < limit) {
+            parse_slide_check(s, p, n, prm);
             const uint32_t prev_length = match_length, prev_dist_v = cur_dist;
             match_length = kMinMatch - 1;
             if (prev_length < (uint32_t)prm.lazy) {
-                const uint32_t m = (prev_length >= (uint32_t)prm.good) ? mquarter[p] : mfull[p];
+                const uint32_t m = (prev_length >= (uint32_t)prm.good) ? acc.mq(p) : acc.mf(p);
                 const uint32_t len = m >> 16;
                 if (m && len > prev_length) {
                     match_length = len; cur_dist = m & 0xffff;
@@ -205,19 +217,48 @@ ZB_HD void parse_chunk(const uint8_t *data, uint32_t n, const uint32_t *mfull, c
                 match_available = false; match_length = kMinMatch - 1;
                 emit((prev_dist_v << 16) | (prev_length - kMinMatch), p);
             } else if (match_available) {
-                emit(data[p - 1], p);
+                emit(acc.byte(p - 1), p);
                 ++p;
             } else {
                 match_available = true; ++p;
             }
         }
-        // deflate.c:2026-2030: the pending literal is tallied but its flush flag is
-        // ignored (the block is closed by the flush below, never cut here)
-        if (match_available) s.syms[s.nsyms++] = data[n - 1];
+        s.match_length = match_length; s.cur_dist = cur_dist; s.match_available = match_available ? 1 : 0;
     }
-    slide_check(n);                                    // the loop-top fill_window call that finds lookahead == 0
-    if (final_chunk) parse_close_block(s, n, base, true);
-    else if (s.nsyms != s.blk_sym0) parse_close_block(s, n, base, false);
+    s.p = p;
+}
+
+// End of the chunk (p == n).  `final_chunk`: flush == Z_FINISH (last block gets
+// BFINAL, an empty final block is emitted if nothing is pending,
+// deflate.c:1908-1913); otherwise flush == Z_FULL_FLUSH.
+template <class Acc>
+ZB_HD void parse_finish(ParseState &s, uint32_t n, const DeflateParams &prm, bool final_chunk, Acc &acc) {
+    // deflate.c:2026-2030: the pending literal is tallied but its flush flag is
+    // ignored (the block is closed by the flush below, never cut here)
+    if (prm.mode == MODE_SLOW && s.match_available) { acc.put(acc.byte(n - 1)); ++s.nsyms; s.match_available = 0; }
+    parse_slide_check(s, n, n, prm);                   // the loop-top fill_window call that finds lookahead == 0
+    if (final_chunk) parse_close_block(s, n, true);
+    else if (s.nsyms != s.blk_sym0) parse_close_block(s, n, false);
+}
+
+// Whole-chunk convenience over plain arrays (host replay, small inputs).
+struct ParseArrays {
+    const uint8_t *data; const uint32_t *mfull, *mquarter; uint32_t *syms; uint32_t count;
+    ZB_HD uint32_t mf(uint32_t p) const { return mfull[p]; }
+    ZB_HD uint32_t mq(uint32_t p) const { return mquarter[p]; }
+    ZB_HD uint32_t byte(uint32_t p) const { return data[p]; }
+    ZB_HD void put(uint32_t sym) { syms[count++] = sym; }
+};
+
+ZB_HD void parse_chunk(const uint8_t *data, uint32_t n, const uint32_t *mfull, const uint32_t *mquarter,
+                       const DeflateParams &prm, bool final_chunk, uint32_t *syms, BlockInfo *blocks,
+                       uint32_t &nsyms, uint32_t &nblocks) {
+    ParseState s;
+    parse_init(s, blocks);
+    ParseArrays acc{data, mfull, mquarter, syms, 0};
+    parse_steps(s, n, n, prm, acc);
+    parse_finish(s, n, prm, final_chunk, acc);
+    nsyms = s.nsyms; nblocks = s.nblocks;
 }
 
 // ---- phase 4: per-block Huffman construction ---------------------------------------
