@@ -46,7 +46,7 @@ extern "C" long emul_deflate_chunk(const uint8_t *data, uint32_t n, int level, i
     struct { uint32_t nsyms, nblocks; } sink;
     // walk the chunk in tiles of odd size, as the kernel does, to exercise the resumable parse
     {
-        ParseState ps; parse_init(ps, blocks.data());
+        ParseState ps; parse_init(ps, blocks.data(), n, prm);
         ParseArrays acc{data, mf.data(), mq.data(), syms.data(), 0};
         while (ps.p < n) { uint32_t lim = ps.p + 1000 < n ? ps.p + 1000 : n; parse_steps(ps, lim, n, prm, acc); }
         parse_finish(ps, n, prm, final_chunk != 0, acc);

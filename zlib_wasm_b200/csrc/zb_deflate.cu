@@ -103,7 +103,11 @@ __global__ void __launch_bounds__(32) dfl_chain_kernel(Batch b, uint16_t *__rest
     prefetch(0);
     __syncwarp();
     uint32_t base = 0;
-    for (uint32_t p0 = 0; p0 < n; p0 += 32) {
+    // 4 groups of 32 positions per trip: the hashes and match.any masks of the four
+    // groups do not depend on the head table, so they are issued together (their
+    // latencies overlap); only the short head read / write part runs in order.
+    constexpr int G = 4;
+    for (uint32_t p0 = 0; p0 < n; p0 += 32 * G) {
         if ((p0 & (kChainTile - 1)) == 0) {                        // publish the prefetched tile, fetch the next
             __syncwarp();
 #pragma unroll
@@ -121,31 +125,36 @@ __global__ void __launch_bounds__(32) dfl_chain_kernel(Batch b, uint16_t *__rest
             base += 32768u;
             __syncwarp();
         }
-        const uint32_t p = p0 + lane;
-        const bool valid = p + kMinMatch <= n;
-        uint32_t h = 0;
-        if (valid) {
-            const uint32_t tile_pos = p0 & ~(kChainTile - 1);
-            const uint8_t *tp = tile + (((addr0 + tile_pos) & 15) + (p - tile_pos));
-            h = hash3(tp);
+        const uint32_t tile_pos = p0 & ~(kChainTile - 1);
+        const uint8_t *tbase = tile + ((addr0 + tile_pos) & 15) - tile_pos;
+        uint32_t hs[G], masks[G];
+#pragma unroll
+        for (int j = 0; j < G; ++j) {
+            const uint32_t p = p0 + 32 * j + lane;
+            const bool valid = p + kMinMatch <= n;
+            hs[j] = valid ? hash3(tbase + p) : (0x10000u | lane);
+            masks[j] = __match_any_sync(0xffffffffu, hs[j]);
         }
-        const uint32_t key = valid ? h : (0x10000u | lane);
-        const uint32_t mask = __match_any_sync(0xffffffffu, key);
-        const uint32_t lower = mask & ((1u << lane) - 1u);
-        uint32_t dist = 0;
-        if (valid) {
-            if (lower) {
-                const uint32_t q = p0 + (31u - (uint32_t)__clz(lower));
-                dist = q ? p - q : 0;                              // position 0 is never a match target (deflate.c:1366)
-            } else {
-                const uint32_t e = head[h];
-                dist = e ? (p - base) - e : 0;
+#pragma unroll
+        for (int j = 0; j < G; ++j) {
+            const uint32_t g0 = p0 + 32 * j, p = g0 + lane;
+            const bool valid = p + kMinMatch <= n;
+            const uint32_t lower = masks[j] & ((1u << lane) - 1u);
+            uint32_t dist = 0;
+            if (valid) {
+                if (lower) {
+                    const uint32_t q = g0 + (31u - (uint32_t)__clz(lower));
+                    dist = q ? p - q : 0;                          // position 0 is never a match target (deflate.c:1366)
+                } else {
+                    const uint32_t e = head[hs[j]];
+                    dist = e ? (p - base) - e : 0;
+                }
             }
+            if (p < n) prev[p] = (uint16_t)dist;
+            __syncwarp();
+            if (valid && (masks[j] >> lane) == 1u) head[hs[j]] = (uint16_t)(p - base);   // highest lane of its group
+            __syncwarp();
         }
-        if (p < n) prev[p] = (uint16_t)dist;
-        __syncwarp();
-        if (valid && (mask >> lane) == 1u) head[h] = (uint16_t)(p - base);   // highest lane of its group
-        __syncwarp();
     }
 }
 
@@ -196,7 +205,7 @@ dfl_parse_kernel(Batch b, DeflateParams prm, const uint32_t *__restrict__ mfull,
     const uint32_t *mf = mfull + off, *mq = (prm.need_quarter ? mquarter : mfull) + off;
     uint32_t *out = syms + off;
     ParseState st;
-    parse_init(st, blocks + (uint64_t)c * b.MB);
+    parse_init(st, blocks + (uint64_t)c * b.MB, n, prm);
     ParseTileAcc acc{tmf, tmq, tbytes, stage, 0, 0};
     uint32_t flushed = 0;                              // symbols already written to global memory
     for (;;) {
@@ -462,7 +471,7 @@ static size_t chunk_bound(size_t len) {
 
 static size_t frame_overhead(int frame) { return frame == ZB200_FRAME_ZLIB ? 6 : frame == ZB200_FRAME_GZIP ? 18 : 0; }
 
-constexpr size_t kBatchBytes = 256u << 20;    // input bytes per sub-batch (bounds scratch at ~14x this)
+constexpr size_t kBatchBytes = 512u << 20;    // input bytes per sub-batch (bounds scratch at ~14x this)
 
 static size_t batch_chunks(size_t n, size_t S) {
     size_t nch = (n + S - 1) / S;

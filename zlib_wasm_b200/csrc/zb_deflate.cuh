@@ -148,12 +148,14 @@ struct ParseState {
     uint32_t match_length, cur_dist;  // deflate_slow carry: match found at p-1
     uint32_t match_available;
     uint32_t base;                    // window origin: advances 32 KiB per slide (deflate.c:277-287)
+    uint32_t slide_at;                // first loop-top position at which the next slide happens
     uint32_t nsyms, nblocks;          // totals so far for the chunk
     uint32_t blk_sym0, blk_byte0;     // start of the open block
     BlockInfo *blocks;
 };
 
-ZB_HD void parse_init(ParseState &s, BlockInfo *blocks) {
+ZB_HD void parse_init(ParseState &s, BlockInfo *blocks, uint32_t n, const DeflateParams &prm) {
+    s.slide_at = parse_next_slide(0, n, prm);
     s.p = 0; s.match_length = kMinMatch - 1; s.cur_dist = 0; s.match_available = 0; s.base = 0;
     s.nsyms = 0; s.nblocks = 0; s.blk_sym0 = 0; s.blk_byte0 = 0; s.blocks = blocks;
 }
@@ -169,13 +171,22 @@ ZB_HD void parse_close_block(ParseState &s, uint32_t cover_end, bool last) {
     s.blk_sym0 = s.nsyms; s.blk_byte0 = cover_end;
 }
 
-// fill_window is entered when lookahead drops under `trigger` bytes; it slides the
-// window when strstart has reached wsize + MAX_DIST (deflate.c:277).
-ZB_HD void parse_slide_check(ParseState &s, uint32_t p, uint32_t n, const DeflateParams &prm) {
+// fill_window is entered at a loop top when lookahead drops under `trigger` bytes,
+// and slides the window when strstart has reached wsize + MAX_DIST (deflate.c:277).
+// With the whole chunk available the window is always full (or holds the tail), so
+// the first loop top that slides is the first with p >= slide_at:
+ZB_HD uint32_t parse_next_slide(uint32_t base, uint32_t n, const DeflateParams &prm) {
     const uint32_t trigger = prm.mode == MODE_HUFF ? 1 : prm.mode == MODE_RLE ? (uint32_t)kMaxMatch + 1 : (uint32_t)kMinLookahead;
-    uint64_t fill_end = (uint64_t)s.base + 2 * kWSize;
+    uint64_t fill_end = (uint64_t)base + 2 * kWSize;
     if (fill_end > n) fill_end = n;
-    if (fill_end - p < trigger && p - s.base >= (uint32_t)(kWSize + kMaxDist)) s.base += kWSize;
+    // lookahead = fill_end - p < trigger  <=>  p > fill_end - trigger ;  and  p - base >= wsize + MAX_DIST
+    const uint64_t a = fill_end >= trigger ? fill_end - trigger + 1 : 0;
+    const uint64_t b = (uint64_t)base + kWSize + kMaxDist;
+    const uint64_t at = a > b ? a : b;
+    return at > 0xffffffffull ? 0xffffffffu : (uint32_t)at;
+}
+ZB_HD void parse_slide_check(ParseState &s, uint32_t p, uint32_t n, const DeflateParams &prm) {
+    if (p >= s.slide_at) { s.base += kWSize; s.slide_at = parse_next_slide(s.base, n, prm); }
 }
 
 // Examine positions while p < limit (limit <= n).  A match may carry p past limit.
@@ -254,7 +265,7 @@ ZB_HD void parse_chunk(const uint8_t *data, uint32_t n, const uint32_t *mfull, c
                        const DeflateParams &prm, bool final_chunk, uint32_t *syms, BlockInfo *blocks,
                        uint32_t &nsyms, uint32_t &nblocks) {
     ParseState s;
-    parse_init(s, blocks);
+    parse_init(s, blocks, n, prm);
     ParseArrays acc{data, mfull, mquarter, syms, 0};
     parse_steps(s, n, n, prm, acc);
     parse_finish(s, n, prm, final_chunk, acc);
