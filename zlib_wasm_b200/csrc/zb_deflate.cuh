@@ -154,6 +154,8 @@ struct ParseState {
     BlockInfo *blocks;
 };
 
+ZB_HD uint32_t parse_next_slide(uint32_t base, uint32_t n, const DeflateParams &prm);
+
 ZB_HD void parse_init(ParseState &s, BlockInfo *blocks, uint32_t n, const DeflateParams &prm) {
     s.slide_at = parse_next_slide(0, n, prm);
     s.p = 0; s.match_length = kMinMatch - 1; s.cur_dist = 0; s.match_available = 0; s.base = 0;

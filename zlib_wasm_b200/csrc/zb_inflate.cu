@@ -25,6 +25,7 @@ struct InflateDeviceTables {
 
 struct InflateShared {
     InflateScratch scr[kInfWarps];
+    QueuedMatch q[kInfWarps][kQueue];
     uint32_t fixed_lit[512];
     uint32_t fixed_dist[64];
     FormatTables fmt;
@@ -65,31 +66,58 @@ inflate_kernel(const uint8_t *__restrict__ in, uint8_t *out, const zb200_member 
             if (hs) st.status = hs;
         }
         hs = __shfl_sync(full, hs, 0);
+        QueuedMatch *q = sh.q[warp];
         while (hs == ZB200_INF_OK) {
             InflateEvent ev;
             ev.kind = EV_DONE; ev.len = 0; ev.dist = 0; ev.src = 0; ev.dst = 0;
-            if (lane == 0) ev = st.run();
+            if (lane == 0) ev = st.run_batch(q);
             const uint32_t kind = __shfl_sync(full, ev.kind, 0);
             if (kind == EV_DONE) break;
             const uint32_t len = __shfl_sync(full, ev.len, 0);
-            const uint32_t dist = __shfl_sync(full, ev.dist, 0);
-            const uint64_t to = __shfl_sync(full, ev.dst, 0);
-            __syncwarp(full);                                  // lane 0's literal stores -> visible to the copy
-            if (kind == EV_MATCH) {
-                uint8_t *d = dst + to;
-                const uint8_t *s = d - dist;
-                if (dist >= len) {
-                    for (uint32_t i = lane; i < len; i += 32) d[i] = s[i];
-                } else {                                       // overlapping: byte-serial semantics (inffast.c:249-260)
-                    for (uint32_t i = lane; i < len; i += 32) d[i] = s[i % dist];
+            __syncwarp(full);                                  // lane 0's literal stores and queue writes -> visible
+            if (kind == EV_BATCH) {
+                const bool mine = lane < len;
+                QueuedMatch e;
+                e.dst = 0; e.len = 0; e.dist_dep = 0;
+                if (mine) e = q[lane];
+                const bool dep = mine && (e.dist_dep >> 31);
+                uint32_t depmask = __ballot_sync(full, dep);
+                if (mine && !dep) {                            // independent: one lane per match, all in flight together
+                    uint8_t *d = dst + e.dst;
+                    const uint8_t *s = d - e.dist_dep;         // dist >= len: source and destination do not overlap
+                    uint32_t i = 0;
+                    for (; i + 8 <= e.len; i += 8) {
+                        uint8_t t[8];
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) t[k] = s[i + k];
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) d[i + k] = t[k];
+                    }
+                    for (; i < e.len; ++i) d[i] = s[i];
+                }
+                __syncwarp(full);
+                while (depmask) {                              // dependent: in order, striped over the warp
+                    const int j = __ffs(depmask) - 1;
+                    depmask &= depmask - 1;
+                    const QueuedMatch m = q[j];
+                    const uint32_t dist = m.dist_dep & 0x7fffffffu;
+                    uint8_t *d = dst + m.dst;
+                    const uint8_t *s = d - dist;
+                    if (dist >= m.len) {
+                        for (uint32_t i = lane; i < m.len; i += 32) d[i] = s[i];
+                    } else {                                   // overlapping: byte-serial semantics (inffast.c:249-260)
+                        for (uint32_t i = lane; i < m.len; i += 32) d[i] = s[i % dist];
+                    }
+                    __syncwarp(full);
                 }
             } else {                                           // stored block: input -> output
+                const uint64_t to = __shfl_sync(full, ev.dst, 0);
                 const uint64_t from = __shfl_sync(full, ev.src, 0);
                 const uint8_t *s = src + from;
                 uint8_t *d = dst + to;
                 for (uint32_t i = lane; i < len; i += 32) d[i] = s[i];
+                __syncwarp(full);
             }
-            __syncwarp(full);
         }
         if (lane == 0) {
             zb200_member_result r;

@@ -45,6 +45,18 @@ struct InflateScratch {
     uint8_t  lens[320];                // code lengths of the block being set up
 };
 
+// Decode-ahead queue: lane 0 keeps decoding past a match, parking up to kQueue
+// matches here; the warp then executes the whole batch.  A match whose source
+// cannot overlap the destination of an earlier parked match ("independent") is
+// copied by its own lane, all such lanes in parallel, so their L2 round trips
+// overlap; the others run afterwards, in order, striped over the warp.
+constexpr uint32_t kQueue = 32;
+struct QueuedMatch {
+    uint64_t dst;                      // output position
+    uint32_t len;
+    uint32_t dist_dep;                 // distance | (dependent ? 0x80000000 : 0)
+};
+
 // Build a two-level decode table from code lengths (the job of inftrees.c:32-299).
 // Returns 0 = complete code, 1 = incomplete, 2 = no codes at all, -1 = over-subscribed
 // or out of table space.  The caller applies the reference's acceptance rules.
@@ -129,7 +141,7 @@ ZB_HD int build_decode_table(int type, const uint8_t *lens, int n, uint32_t *tab
 }
 
 // ---- events handed from lane 0 to the whole warp ---------------------------------
-enum : uint32_t { EV_MATCH = 1, EV_STORED = 2, EV_DONE = 3 };
+enum : uint32_t { EV_MATCH = 1, EV_STORED = 2, EV_DONE = 3, EV_BATCH = 4 };
 struct InflateEvent {
     uint32_t kind;
     uint32_t len;        // match length / stored byte count
@@ -156,6 +168,7 @@ struct InflateState {
     InflateScratch *scr;
     const uint32_t *fixed_lit, *fixed_dist;
     const FormatTables *fmt;
+    InflateEvent parked; int has_parked;                   // event held back until the queue has been executed
 
     ZB_HD void refill() {
         while (bits <= 32) {
@@ -183,7 +196,7 @@ struct InflateState {
         in = src; in_len = n; next = 0; hold = 0; bits = 0;
         out = dst; out_cap = cap; pos = 0; last = 0; in_block = 0; lt = dt = nullptr;
         wrap_kind = 0; status = ZB200_INF_OK; ck_bit = 0; ck_out = 0; stored_check = 0; stored_isize = 0;
-        in_used = 0; scr = s; fixed_lit = flit; fixed_dist = fdist; fmt = f;
+        in_used = 0; scr = s; fixed_lit = flit; fixed_dist = fdist; fmt = f; has_parked = 0;
     }
 
     // Continue a member at a block boundary reported by an earlier, truncated run
@@ -324,7 +337,7 @@ struct InflateState {
     }
 
     // Run until something needs the whole warp (or the member ends).
-    ZB_HD InflateEvent run() {
+    ZB_HD InflateEvent step() {
         for (;;) {
             if (!in_block) {
                 if (last) return finish();
@@ -399,6 +412,32 @@ struct InflateState {
                 return ev;
             }
         }
+    }
+
+    // Decode until the queue is full or something other than a match happens.
+    // Returns EV_BATCH with ev.len parked matches in q[], or a STORED / DONE event
+    // (only once the queue has been handed over).
+    ZB_HD InflateEvent run_batch(QueuedMatch *q) {
+        InflateEvent ev;
+        if (has_parked) { has_parked = 0; return parked; }
+        uint32_t count = 0;
+        uint64_t first_dst = 0;
+        for (;;) {
+            ev = step();
+            if (ev.kind == EV_MATCH) {
+                // dependent: overlaps itself, or may read what an earlier parked match will write
+                const bool dep = ev.dist < ev.len || (count && ev.dst - ev.dist + ev.len > first_dst);
+                if (!count) first_dst = ev.dst;
+                q[count].dst = ev.dst; q[count].len = ev.len; q[count].dist_dep = ev.dist | (dep ? 0x80000000u : 0u);
+                if (++count == kQueue) break;
+                continue;
+            }
+            if (!count) return ev;
+            parked = ev; has_parked = 1;
+            break;
+        }
+        ev.kind = EV_BATCH; ev.len = count; ev.dist = 0; ev.src = 0; ev.dst = 0;
+        return ev;
     }
 };
 
