@@ -127,33 +127,40 @@ __global__ void __launch_bounds__(32) dfl_chain_kernel(Batch b, uint16_t *__rest
         }
         const uint32_t tile_pos = p0 & ~(kChainTile - 1);
         const uint8_t *tbase = tile + ((addr0 + tile_pos) & 15) - tile_pos;
-        uint32_t hs[G], masks[G];
+        uint32_t hs[G];
 #pragma unroll
         for (int j = 0; j < G; ++j) {
             const uint32_t p = p0 + 32 * j + lane;
-            const bool valid = p + kMinMatch <= n;
-            hs[j] = valid ? hash3(tbase + p) : (0x10000u | lane);
-            masks[j] = __match_any_sync(0xffffffffu, hs[j]);
+            hs[j] = (p + kMinMatch <= n) ? hash3(tbase + p) : (0x10000u | lane);
         }
 #pragma unroll
         for (int j = 0; j < G; ++j) {
             const uint32_t g0 = p0 + 32 * j, p = g0 + lane;
             const bool valid = p + kMinMatch <= n;
-            const uint32_t lower = masks[j] & ((1u << lane) - 1u);
-            uint32_t dist = 0;
-            if (valid) {
-                if (lower) {
+            const uint32_t rel = p - base;                         // window-relative position, 1..65535 here (0 = NIL)
+            // Optimistic step: read the old head, let every lane write its own position and
+            // read back.  If every lane reads back its own value the 32 hashes were distinct
+            // and the old heads are the links.  match.any (whose cost grows with the number
+            // of distinct values) is only needed when two lanes of the group collide.
+            uint32_t old = 0;
+            if (valid) old = head[hs[j]];
+            __syncwarp();
+            if (valid) head[hs[j]] = (uint16_t)rel;
+            __syncwarp();
+            const bool clash = valid && head[hs[j]] != (uint16_t)rel;
+            uint32_t dist = (valid && old) ? rel - old : 0;
+            if (__any_sync(0xffffffffu, clash)) {
+                const uint32_t mask = __match_any_sync(0xffffffffu, hs[j]);
+                const uint32_t lower = mask & ((1u << lane) - 1u);
+                if (valid && lower) {
                     const uint32_t q = g0 + (31u - (uint32_t)__clz(lower));
                     dist = q ? p - q : 0;                          // position 0 is never a match target (deflate.c:1366)
-                } else {
-                    const uint32_t e = head[hs[j]];
-                    dist = e ? (p - base) - e : 0;
                 }
+                __syncwarp();
+                if (valid && (mask >> lane) == 1u) head[hs[j]] = (uint16_t)rel;   // the group's highest lane wins
+                __syncwarp();
             }
             if (p < n) prev[p] = (uint16_t)dist;
-            __syncwarp();
-            if (valid && (masks[j] >> lane) == 1u) head[hs[j]] = (uint16_t)(p - base);   // highest lane of its group
-            __syncwarp();
         }
     }
 }
@@ -176,52 +183,104 @@ dfl_match_kernel(Batch b, DeflateParams prm, const uint16_t *__restrict__ prev_a
 
 // ---- phase 3: parse, one chunk per warp (lane 0 walks the tables) ---------------------
 // The walk is a dependent chain (the next position depends on the entry just
-// read), so operands are staged: the warp loads a tile of kParseTile positions
-// (match entries + input bytes) into shared memory with coalesced loads, lane 0
-// walks the tile out of shared memory, emitted symbols are staged and flushed
-// with coalesced stores.
-constexpr uint32_t kParseTile = 1024;
+// read), so its operands are staged in shared memory: positions are cut into
+// fixed tiles of kParseTile; while lane 0 walks tile k, tile k+1 (match entries
+// and input bytes) is already in flight as 16-byte cp.async copies into the other
+// buffer.  Emitted symbols are staged too and flushed with coalesced stores.
+constexpr uint32_t kParseTile = 512;
+constexpr uint32_t kPtVecsM = kParseTile / 4 + 1;      // uint4 of match entries per tile (+1: alignment slack)
+constexpr uint32_t kPtVecsB = kParseTile / 16 + 2;     // uint4 of input bytes per tile (+1 before, +1 slack)
+
+struct ParseBuf {
+    uint4 mf[kPtVecsM], mq[kPtVecsM], by[kPtVecsB];
+};
 
 struct ParseTileAcc {
-    const uint32_t *tmf, *tmq; const uint8_t *tbytes; uint32_t *stage;
-    uint32_t tile0;            // chunk position of tile entry 0
-    uint32_t count;            // symbols staged in this tile
-    __device__ __forceinline__ uint32_t mf(uint32_t p) const { return tmf[p - tile0]; }
-    __device__ __forceinline__ uint32_t mq(uint32_t p) const { return tmq[p - tile0]; }
-    __device__ __forceinline__ uint32_t byte(uint32_t p) const { return tbytes[p + 1 - tile0]; }   // tbytes[0] = byte tile0-1
+    const uint32_t *tmf, *tmq; const uint8_t *tby; uint32_t *stage;
+    uint32_t mbias, bbias;     // index of chunk position 0 inside tmf/tmq, resp. tby (may be "negative": wraps)
+    uint32_t count;            // symbols staged for this tile
+    __device__ __forceinline__ uint32_t mf(uint32_t p) const { return tmf[p + mbias]; }
+    __device__ __forceinline__ uint32_t mq(uint32_t p) const { return tmq[p + mbias]; }
+    __device__ __forceinline__ uint32_t byte(uint32_t p) const { return tby[p + bbias]; }
     __device__ __forceinline__ void put(uint32_t sym) { stage[count++] = sym; }
 };
+
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
 
 __global__ void __launch_bounds__(32)
 dfl_parse_kernel(Batch b, DeflateParams prm, const uint32_t *__restrict__ mfull,
                  const uint32_t *__restrict__ mquarter, uint32_t *__restrict__ syms,
                  BlockInfo *__restrict__ blocks, uint32_t *__restrict__ nblocks) {
-    __shared__ uint32_t tmf[kParseTile], tmq[kParseTile], stage[kParseTile + 2];
-    __shared__ uint8_t tbytes[kParseTile + 4];
+    __shared__ __align__(16) ParseBuf buf[2];
+    __shared__ uint32_t stage[kParseTile + kMaxMatch + 8];
     const uint32_t c = blockIdx.x, lane = threadIdx.x;
     const uint64_t off = (uint64_t)c * b.S;
     const uint8_t *data = b.in + off;
     const uint32_t n = chunk_len(b, c);
-    const uint32_t *mf = mfull + off, *mq = (prm.need_quarter ? mquarter : mfull) + off;
+    const bool use_m = prm.mode != MODE_HUFF, use_q = prm.need_quarter != 0;
     uint32_t *out = syms + off;
+    // absolute (array) indices / addresses, so that every cp.async is 16-byte aligned
+    const uint64_t m_abs0 = off;                                   // entry index of chunk position 0 in mfull/mquarter
+    const uintptr_t b_abs0 = reinterpret_cast<uintptr_t>(data);    // address of chunk position 0
+    const uintptr_t in_lo = reinterpret_cast<uintptr_t>(b.in), in_hi = in_lo + b.bytes;
+    const uint64_t m_hi = (uint64_t)b.nb * b.S + 4;                // entries allocated (see work_bytes: +16 bytes slack)
+
+    auto issue = [&](uint32_t tile, ParseBuf &pb) {                // start the copies for positions [tile*T, tile*T + T)
+        const uint64_t m_first = (m_abs0 + (uint64_t)tile * kParseTile) & ~3ull;
+        if (use_m)
+            for (uint32_t v = lane; v < kPtVecsM; v += 32) {
+                const uint64_t e = m_first + 4ull * v;
+                if (e + 4 <= m_hi) {
+                    cp_async16(&pb.mf[v], mfull + e);
+                    if (use_q) cp_async16(&pb.mq[v], mquarter + e);
+                }
+            }
+        const uintptr_t a_first = ((b_abs0 + (uintptr_t)tile * kParseTile) & ~(uintptr_t)15) - 16;
+        for (uint32_t v = lane; v < kPtVecsB; v += 32) {
+            const uintptr_t a = a_first + 16ull * v;
+            if (a + 16 > in_lo && a < in_hi) cp_async16(&pb.by[v], reinterpret_cast<const void *>(a));
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
     ParseState st;
     parse_init(st, blocks + (uint64_t)c * b.MB, n, prm);
-    ParseTileAcc acc{tmf, tmq, tbytes, stage, 0, 0};
+    ParseTileAcc acc;
+    acc.stage = stage; acc.count = 0;
     uint32_t flushed = 0;                              // symbols already written to global memory
-    for (;;) {
-        const uint32_t t0 = __shfl_sync(0xffffffffu, st.p, 0);
-        if (t0 >= n) break;
-        const uint32_t t1 = t0 + kParseTile < n ? t0 + kParseTile : n;
-        const uint32_t cnt = t1 - t0;
-        if (prm.mode != MODE_HUFF)
-            for (uint32_t i = lane; i < cnt; i += 32) { tmf[i] = mf[t0 + i]; if (prm.need_quarter) tmq[i] = mq[t0 + i]; }
-        for (uint32_t i = lane; i < cnt + 1; i += 32) tbytes[i] = (t0 + i) ? data[t0 + i - 1] : 0;
+    const uint32_t ntiles = (n + kParseTile - 1) / kParseTile;
+    if (ntiles) issue(0, buf[0]);
+    for (uint32_t t = 0; t < ntiles; ++t) {
+        ParseBuf &pb = buf[t & 1];
+        if (t + 1 < ntiles) {
+            issue(t + 1, buf[(t + 1) & 1]);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");   // tile t has landed, tile t+1 may still be in flight
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
         __syncwarp();
-        if (lane == 0) { acc.tile0 = t0; acc.count = 0; parse_steps(st, t1, n, prm, acc); }
+        const uint32_t t1 = (t + 1) * kParseTile < n ? (t + 1) * kParseTile : n;
+        if (lane == 0 && st.p < t1) {
+            const uint64_t m_first = (m_abs0 + (uint64_t)t * kParseTile) & ~3ull;
+            const uintptr_t a_first = ((b_abs0 + (uintptr_t)t * kParseTile) & ~(uintptr_t)15) - 16;
+            acc.tmf = reinterpret_cast<const uint32_t *>(pb.mf);
+            acc.tmq = use_q ? reinterpret_cast<const uint32_t *>(pb.mq) : acc.tmf;
+            acc.tby = reinterpret_cast<const uint8_t *>(pb.by);
+            acc.mbias = (uint32_t)(m_abs0 - m_first);              // entry of position p sits at p + m_abs0 - m_first ...
+            acc.mbias -= t * kParseTile;                           // ... minus nothing: m_first already includes the tile start
+            acc.mbias = (uint32_t)(m_abs0 - m_first);
+            acc.bbias = (uint32_t)(b_abs0 - a_first);
+            acc.count = 0;
+            parse_steps(st, t1, n, prm, acc);
+        }
         const uint32_t made = __shfl_sync(0xffffffffu, acc.count, 0);
         __syncwarp();
         for (uint32_t i = lane; i < made; i += 32) out[flushed + i] = stage[i];
         flushed += made;
+        acc.count = 0;
         __syncwarp();
     }
     if (lane == 0) {
@@ -237,6 +296,7 @@ dfl_parse_kernel(Batch b, DeflateParams prm, const uint32_t *__restrict__ mfull,
         nblocks[c] = st.nblocks;
     }
 }
+
 
 // ---- phase 4: per-block histogram + Huffman construction -------------------------------
 __global__ void __launch_bounds__(128)
