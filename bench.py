@@ -168,7 +168,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--bytes", type=int, default=4 * GIB, help="bytes per GPU (config C2: 4 GiB)")
     ap.add_argument("--no-extras", action="store_true", help="skip the inflate / deflate side measurements")
-    ap.add_argument("--extras-mib", type=int, default=256, help="uncompressed MiB used by each side measurement")
+    ap.add_argument("--extras-mib", type=int, default=512, help="uncompressed MiB used by each side measurement")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
