@@ -16,7 +16,7 @@ extern "C" int emul_checksum(const uint8_t *data, uint64_t len, uint32_t T, uint
     static uint32_t tab[4][256];
     ck_fill_horner(tab, x2n.v, T);
     const uint32_t x32 = x2n.v[5];
-    auto tf = [&](int j, uint32_t b) -> uint32_t { return tab[j][b]; };
+    auto tf = [&](int j, uint32_t v) -> uint32_t { return tab[j][(v >> (8 * j)) & 0xff]; };
     uint32_t acc_crc = 0;
     uint64_t acc_a = 0, acc_b = 0;
     for (uint32_t p = 0; p < parts; ++p) {

@@ -56,21 +56,33 @@ __global__ void __launch_bounds__(kBigThreads, 1)
 ck_big_kernel(const uint8_t *__restrict__ data, uint64_t len, const CrcTables *__restrict__ tabs,
               CkAccum *__restrict__ acc) {
     extern __shared__ __align__(16) uint32_t smem[];
-    uint32_t *rep = smem;                        // [4][256][32] lane-private copies
+    // Lane-private (bank-conflict-free) copies of the four 256-entry tables.  Byte
+    // offset of (table j, byte b, lane l):  (j>>1)*65536 + b*256 + (j&1)*128 + l*4,
+    // i.e. tables are interleaved in pairs so that one PRMT builds `b*256 + l*4`
+    // (byte b of the state into bits 8..15, the lane offset into bits 0..7) and the
+    // rest of the address is an immediate of the LDS.
+    uint32_t *rep = smem;
     uint32_t *x2n = smem + 4 * 256 * 32;         // [32]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (DO_CRC) {
-        // entry e (= j*256 + byte) replicated across the 32 banks: rep[e*32 + lane]
         const uint32_t *src = &tabs->big[0][0];
-        for (int e = warp; e < 1024; e += kBigThreads / 32) rep[e * 32 + lane] = src[e];
+        for (int e = warp; e < 1024; e += kBigThreads / 32) {
+            const int j = e >> 8, bb = e & 255;
+            rep[(j >> 1) * 16384 + bb * 64 + (j & 1) * 32 + lane] = src[e];
+        }
     }
     if (threadIdx.x < 32) x2n[threadIdx.x] = tabs->x2n[threadIdx.x];
     __syncthreads();
     const uint32_t x32 = tabs->x32;
 
     const CkPart part = ck_make_part(data, len, blockIdx.x, gridDim.x);
-    const uint32_t *mine = rep + lane;
-    auto tab = [mine](int j, uint32_t byte) -> uint32_t { return mine[(j * 256 + byte) * 32]; };
+    const uint32_t lane4 = (uint32_t)lane * 4u;
+    const char *repb = reinterpret_cast<const char *>(rep);
+    auto tab = [repb, lane4](int j, uint32_t v) -> uint32_t {
+        // selector: result byte0 <- lane4.byte0, byte1 <- v.byte j, bytes 2,3 <- lane4.byte1 (= 0)
+        const uint32_t off = __byte_perm(v, lane4, 0x5504u | ((uint32_t)j << 4));
+        return *reinterpret_cast<const uint32_t *>(repb + off + (j >> 1) * 65536 + (j & 1) * 128);
+    };
     CkPartial v = ck_thread_body<DO_CRC, DO_ADLER>(part, threadIdx.x, kBigThreads, tab, x2n, x32);
     if (threadIdx.x == 0) {
         CkPartial e = ck_edge_bytes<DO_CRC, DO_ADLER>(part, x2n);
@@ -91,7 +103,7 @@ ck_seg_kernel(const uint8_t *__restrict__ base, const uint64_t *__restrict__ seg
     if (threadIdx.x < 32) x2n[threadIdx.x] = tabs->x2n[threadIdx.x];
     __syncthreads();
     const uint32_t x32 = tabs->x32;
-    auto tab = [&](int j, uint32_t byte) -> uint32_t { return tab_s[j * 256 + byte]; };
+    auto tab = [&](int j, uint32_t v) -> uint32_t { return tab_s[j * 256 + ((v >> (8 * j)) & 0xff)]; };
 
     const uint64_t items = (uint64_t)nseg * parts;
     for (uint64_t it = blockIdx.x; it < items; it += gridDim.x) {

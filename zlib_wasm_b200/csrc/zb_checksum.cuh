@@ -90,7 +90,7 @@ ZB_HD CkPart ck_make_part(const uint8_t *seg, uint64_t seg_len, uint32_t part, u
 }
 
 // Contribution of thread t (of T) to the checksums of the segment, over the
-// body blocks of part `p`.  TabFn(j, byte) returns the Horner table entry.
+// body blocks of part `p`.  TabFn(j, v) returns the Horner table entry for byte j of v.
 template <bool DO_CRC, bool DO_ADLER, class TabFn>
 ZB_HD CkPartial ck_thread_body(const CkPart &p, uint32_t t, uint32_t T, TabFn tab,
                                const uint32_t *x2n, uint32_t x32) {
@@ -106,10 +106,10 @@ ZB_HD CkPartial ck_thread_body(const CkPart &p, uint32_t t, uint32_t T, TabFn ta
 
     auto step = [&](const U4 &w) {
         if (DO_CRC) {
-            v0 = tab(0, v0 & 0xff) ^ tab(1, (v0 >> 8) & 0xff) ^ tab(2, (v0 >> 16) & 0xff) ^ tab(3, v0 >> 24) ^ w.x;
-            v1 = tab(0, v1 & 0xff) ^ tab(1, (v1 >> 8) & 0xff) ^ tab(2, (v1 >> 16) & 0xff) ^ tab(3, v1 >> 24) ^ w.y;
-            v2 = tab(0, v2 & 0xff) ^ tab(1, (v2 >> 8) & 0xff) ^ tab(2, (v2 >> 16) & 0xff) ^ tab(3, v2 >> 24) ^ w.z;
-            v3 = tab(0, v3 & 0xff) ^ tab(1, (v3 >> 8) & 0xff) ^ tab(2, (v3 >> 16) & 0xff) ^ tab(3, v3 >> 24) ^ w.w;
+            v0 = tab(0, v0) ^ tab(1, v0) ^ tab(2, v0) ^ tab(3, v0) ^ w.x;
+            v1 = tab(0, v1) ^ tab(1, v1) ^ tab(2, v1) ^ tab(3, v1) ^ w.y;
+            v2 = tab(0, v2) ^ tab(1, v2) ^ tab(2, v2) ^ tab(3, v2) ^ w.z;
+            v3 = tab(0, v3) ^ tab(1, v3) ^ tab(2, v3) ^ tab(3, v3) ^ w.w;
         }
         if (DO_ADLER) {
             uint32_t s = dot4(w.x, 0x01010101u, 0);
