@@ -53,6 +53,28 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def profiled_traffic():
+    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full
+    capture (profiles/*ck_big_ncu_full.txt), or None."""
+    import glob
+    import re
+    best = None
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "*ck_big_ncu_full.txt"))):
+        rd = wr = None
+        for line in open(path):
+            m = re.search(r"dram__bytes_(read|write)\.sum\s+([0-9.]+)\s+(\w+)", line)
+            if m:
+                v = float(m.group(2)) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(m.group(3), 1)
+                if m.group(1) == "read":
+                    rd = v
+                else:
+                    wr = v
+            if rd is not None and wr is not None:
+                best = int(rd + wr)
+                break
+    return best
+
+
 class ClockSampler(threading.Thread):
     """nvidia-smi clocks / throttle reasons during the timed region."""
 
@@ -316,7 +338,7 @@ def main():
                        "l2": "input (4 GiB) is far larger than the 126 MB L2; no flush needed",
                        "checks": {"crc32": "%08x" % job_crc, "adler32": "%08x" % job_adler}},
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                         "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
+                         "frac": round(achieved / peak, 4), "traffic": profiled_traffic(), "peak_source": peak_src,
                          "kernel": "ck_big_kernel<crc,adler>", "algorithmic_bytes_per_launch": n},
             "cpu_baseline": cpu,
             "e2e": {"value": round(world * n / e2e_s / 1e9, 3), "unit": UNIT, "h2d_bytes_per_step": n, "d2h_bytes_per_step": 8,

@@ -31,6 +31,153 @@ struct InflateShared {
     FormatTables fmt;
 };
 
+
+// ---- warp-parallel Huffman block decode -----------------------------------------
+// Huffman decoding is serial per stream (the start of symbol k+1 is known only
+// once symbol k is decoded).  Inside a warp the serial chain is shortened by
+// speculation: lane i decodes the symbol that WOULD start at bit offset i of the
+// current 32-bit window (one table lookup per lane, in parallel), giving its
+// bit length u_i; the true symbol starts are then the chain 0 -> u_0 -> u_0 +
+// u_{u_0} -> ..., which pointer doubling over the 32 lanes resolves in five
+// shuffle steps.  Every round consumes >= 32 bits (3-5 symbols on text).  Output
+// offsets come from a warp scan; literals are stored by their own lanes;
+// matches whose source lies before this round's output are copied by their own
+// lanes concurrently, the few that depend on this round's output follow in order.
+struct HuffResult { int status; uint64_t bitpos; uint64_t pos; };   // status 0: end-of-block reached
+
+__device__ __forceinline__ HuffResult
+huff_decode_warp(const uint8_t *src, uint64_t in_len, uint8_t *dst, uint64_t out_cap, uint64_t bitpos, uint64_t pos,
+                 const uint32_t *__restrict__ lt, const uint32_t *__restrict__ dt) {
+    const unsigned full = 0xffffffffu;
+    const uint32_t lane = threadIdx.x & 31;
+    const uintptr_t a0 = reinterpret_cast<uintptr_t>(src) & ~(uintptr_t)3;
+    const uint32_t bias = (uint32_t)(reinterpret_cast<uintptr_t>(src) & 3) * 8;
+    const uint32_t *words = reinterpret_cast<const uint32_t *>(a0);
+    const uint64_t total_bits = bias + in_len * 8;                  // valid bits are [bias, total_bits)
+    const uint64_t nwords = (total_bits + 31) >> 5;
+    uint64_t B = bias + bitpos;
+    uint64_t wbase = ~0ull;
+    uint32_t win = 0;
+    enum { K_LIT = 0, K_MATCH = 1, K_EOB = 2, K_BADLIT = 3, K_BADDIST = 4, K_TRUNC = 5 };
+    HuffResult res;
+    for (;;) {
+        const uint64_t wi = B >> 5;
+        if (wbase == ~0ull || wi < wbase || wi + 3 >= wbase + 32) {  // (re)load the 32-word register window
+            wbase = wi;
+            const uint64_t w = wbase + lane;
+            win = w < nwords ? words[w] : 0u;
+        }
+        const int k = (int)(wi - wbase);
+        const uint32_t sh = (uint32_t)B & 31u;
+        const uint32_t W0 = __shfl_sync(full, win, k), W1 = __shfl_sync(full, win, k + 1);
+        const uint32_t W2 = __shfl_sync(full, win, k + 2), W3 = __shfl_sync(full, win, k + 3);
+        const uint32_t o = sh + lane;
+        const uint32_t x0 = o < 32 ? W0 : W1, x1 = o < 32 ? W1 : W2, x2 = o < 32 ? W2 : W3;
+        const uint32_t lo = __funnelshift_r(x0, x1, o & 31), hi = __funnelshift_r(x1, x2, o & 31);
+        const uint64_t v = ((uint64_t)hi << 32) | lo;               // the stream as seen from bit B + lane
+
+        // speculative decode of the symbol starting here
+        uint32_t e = lt[lo & ((1u << kLitRoot) - 1)];
+        uint32_t u = 0;
+        if (ZB_E_OP(e) == OP_SUB) { e = lt[ZB_E_VAL(e) + ((lo >> kLitRoot) & ((1u << ZB_E_EXTRA(e)) - 1u))]; u = kLitRoot; }
+        u += ZB_E_BITS(e);
+        const uint32_t op = ZB_E_OP(e);
+        uint32_t kind = op == OP_LIT ? K_LIT : op == OP_EOB ? K_EOB : op == OP_BASE ? K_MATCH : K_BADLIT;
+        uint32_t val = ZB_E_VAL(e), len = 0, dist = 0;
+        if (op == OP_BASE) {
+            const uint32_t x = ZB_E_EXTRA(e);
+            len = val + ((uint32_t)(v >> u) & ((1u << x) - 1u));
+            u += x;
+            const uint32_t db = (uint32_t)(v >> u);
+            uint32_t d = dt[db & ((1u << kDistRoot) - 1)], du = 0;
+            if (ZB_E_OP(d) == OP_SUB) { d = dt[ZB_E_VAL(d) + ((db >> kDistRoot) & ((1u << ZB_E_EXTRA(d)) - 1u))]; du = kDistRoot; }
+            du += ZB_E_BITS(d);
+            if (ZB_E_OP(d) != OP_BASE) kind = K_BADDIST;
+            else { const uint32_t dx = ZB_E_EXTRA(d); dist = ZB_E_VAL(d) + ((db >> du) & ((1u << dx) - 1u)); du += dx; }
+            u += du;
+        }
+        const uint64_t left = total_bits - B;                         // real bits from the window start
+        if ((uint64_t)lane + u > left) kind = K_TRUNC;
+        const bool stop = kind >= K_EOB;
+
+        // chain of true symbol starts from lane 0: pointer doubling with visit masks
+        uint32_t j = stop ? 32u : (lane + u < 32u ? lane + u : 32u);
+        uint32_t reach = 1u << lane;
+#pragma unroll
+        for (int r = 0; r < 5; ++r) {
+            const uint32_t jj = j < 32u ? j : 0u;
+            const uint32_t rj = __shfl_sync(full, reach, jj), j2 = __shfl_sync(full, j, jj);
+            if (j < 32u) { reach |= rj; j = j2; }
+        }
+        uint32_t vmask = __shfl_sync(full, reach, 0);
+        bool valid = (vmask >> lane) & 1u;
+
+        // output offsets: exclusive scan of produced lengths over the valid lanes
+        uint32_t olen = valid ? (kind == K_LIT ? 1u : kind == K_MATCH ? len : 0u) : 0u;
+        uint32_t inc = olen;
+#pragma unroll
+        for (int dlt = 1; dlt < 32; dlt <<= 1) { const uint32_t y = __shfl_up_sync(full, inc, dlt); if (lane >= (uint32_t)dlt) inc += y; }
+        uint64_t mydst = pos + (inc - olen);
+
+        // the first valid lane that cannot be committed ends the round
+        int err = 0;
+        if (valid) {
+            if (kind == K_BADLIT) err = ZB200_INF_LITLEN_CODE;
+            else if (kind == K_BADDIST) err = ZB200_INF_DIST_CODE;
+            else if (kind == K_TRUNC) err = ZB200_INF_TRUNCATED;
+            else if (kind == K_MATCH && dist > mydst) err = ZB200_INF_DIST_FAR;
+            else if (olen && olen > out_cap - mydst) err = ZB200_INF_OUTPUT_FULL;
+        }
+        const uint32_t emask = __ballot_sync(full, err != 0);
+        if (emask) {
+            const int first = __ffs(emask) - 1;
+            valid = valid && (int)lane < first;
+            if ((int)lane >= first) olen = 0;
+            vmask &= (1u << first) - 1u;
+            res.status = __shfl_sync(full, err, first);
+            res.pos = __shfl_sync(full, mydst, first);
+            res.bitpos = B + (uint32_t)first - bias;
+        }
+        const uint64_t round_pos = pos;
+        if (valid && kind == K_LIT) dst[mydst] = (uint8_t)val;
+        const bool is_m = valid && kind == K_MATCH;
+        const bool dep = is_m && (dist < len || mydst - dist + len > round_pos);
+        if (is_m && !dep) {
+            uint8_t *d = dst + mydst;
+            const uint8_t *s = d - dist;
+            uint32_t i = 0;
+            for (; i + 8 <= len; i += 8) {
+                uint8_t t[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) t[q] = s[i + q];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) d[i + q] = t[q];
+            }
+            for (; i < len; ++i) d[i] = s[i];
+        }
+        __syncwarp(full);
+        uint32_t depmask = __ballot_sync(full, dep);
+        while (depmask) {
+            const int jn = __ffs(depmask) - 1;
+            depmask &= depmask - 1;
+            const uint32_t mlen = __shfl_sync(full, len, jn), mdist = __shfl_sync(full, dist, jn);
+            const uint64_t to = __shfl_sync(full, mydst, jn);
+            uint8_t *d = dst + to;
+            const uint8_t *s = d - mdist;
+            if (mdist >= mlen) { for (uint32_t i = lane; i < mlen; i += 32) d[i] = s[i]; }
+            else { for (uint32_t i = lane; i < mlen; i += 32) d[i] = s[i % mdist]; }
+            __syncwarp(full);
+        }
+        if (emask) return res;
+        const int last = 31 - __clz(vmask);
+        const uint32_t consumed = __shfl_sync(full, lane + u, last);
+        const bool ended = __shfl_sync(full, (uint32_t)stop, last) != 0;   // only an EOB can be a committed stop
+        pos += __shfl_sync(full, inc, 31);
+        B += consumed;
+        if (ended) { res.status = 0; res.bitpos = B - bias; res.pos = pos; return res; }
+    }
+}
+
 __global__ void __launch_bounds__(kInfWarps * 32)
 inflate_kernel(const uint8_t *__restrict__ in, uint8_t *out, const zb200_member *__restrict__ members,
                uint32_t n_members, int wrap, zb200_member_result *__restrict__ results,
@@ -61,6 +208,7 @@ inflate_kernel(const uint8_t *__restrict__ in, uint8_t *out, const zb200_member 
         int hs = ZB200_INF_OK;
         if (lane == 0) {
             st.init(src, mb.in_len, dst, mb.out_cap, &sh.scr[warp], sh.fixed_lit, sh.fixed_dist, &sh.fmt);
+            st.huff_external = 1;
             if (mb.resume_bit) st.resume(mb.resume_bit, mb.resume_out, wrap);
             else hs = st.parse_header(wrap);
             if (hs) st.status = hs;
@@ -75,7 +223,17 @@ inflate_kernel(const uint8_t *__restrict__ in, uint8_t *out, const zb200_member 
             if (kind == EV_DONE) break;
             const uint32_t len = __shfl_sync(full, ev.len, 0);
             __syncwarp(full);                                  // lane 0's literal stores and queue writes -> visible
-            if (kind == EV_BATCH) {
+            if (kind == EV_HUFF) {                             // a Huffman block: all 32 lanes decode it
+                const uint64_t bp = __shfl_sync(full, ev.src, 0), op = __shfl_sync(full, ev.dst, 0);
+                const uint32_t *lt = len ? sh.fixed_lit : sh.scr[warp].lit;
+                const uint32_t *dt = len ? sh.fixed_dist : sh.scr[warp].dist;
+                const HuffResult hr = huff_decode_warp(src, mb.in_len, dst, mb.out_cap, bp, op, lt, dt);
+                if (lane == 0) {
+                    st.seek(hr.bitpos, hr.pos);
+                    if (hr.status) { st.status = hr.status; }
+                }
+                if (hr.status) break;
+            } else if (kind == EV_BATCH) {
                 const bool mine = lane < len;
                 QueuedMatch e;
                 e.dst = 0; e.len = 0; e.dist_dep = 0;

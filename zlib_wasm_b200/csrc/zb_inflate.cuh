@@ -141,7 +141,7 @@ ZB_HD int build_decode_table(int type, const uint8_t *lens, int n, uint32_t *tab
 }
 
 // ---- events handed from lane 0 to the whole warp ---------------------------------
-enum : uint32_t { EV_MATCH = 1, EV_STORED = 2, EV_DONE = 3, EV_BATCH = 4 };
+enum : uint32_t { EV_MATCH = 1, EV_STORED = 2, EV_DONE = 3, EV_BATCH = 4, EV_HUFF = 5 };
 struct InflateEvent {
     uint32_t kind;
     uint32_t len;        // match length / stored byte count
@@ -169,6 +169,7 @@ struct InflateState {
     const uint32_t *fixed_lit, *fixed_dist;
     const FormatTables *fmt;
     InflateEvent parked; int has_parked;                   // event held back until the queue has been executed
+    int huff_external;                                     // 1: hand Huffman blocks to the caller (EV_HUFF) instead of decoding them here
 
     ZB_HD void refill() {
         while (bits <= 32) {
@@ -196,7 +197,7 @@ struct InflateState {
         in = src; in_len = n; next = 0; hold = 0; bits = 0;
         out = dst; out_cap = cap; pos = 0; last = 0; in_block = 0; lt = dt = nullptr;
         wrap_kind = 0; status = ZB200_INF_OK; ck_bit = 0; ck_out = 0; stored_check = 0; stored_isize = 0;
-        in_used = 0; scr = s; fixed_lit = flit; fixed_dist = fdist; fmt = f; has_parked = 0;
+        in_used = 0; scr = s; fixed_lit = flit; fixed_dist = fdist; fmt = f; has_parked = 0; huff_external = 0;
     }
 
     // Continue a member at a block boundary reported by an earlier, truncated run
@@ -206,6 +207,14 @@ struct InflateState {
         refill();
         drop((int)(bit_off & 7));
         pos = out_pos; wrap_kind = kind; ck_bit = bit_off; ck_out = out_pos;
+    }
+
+    // Re-seed the bit reader at an absolute bit offset (after an externally decoded block).
+    ZB_HD void seek(uint64_t bit_off, uint64_t out_pos) {
+        next = bit_off >> 3; hold = 0; bits = 0;
+        refill();
+        drop((int)(bit_off & 7));
+        pos = out_pos; in_block = 0;
     }
 
     // Wrapper header: inflate.c:622-669 (zlib), :671-808 (gzip).  Returns status.
@@ -369,6 +378,11 @@ struct InflateState {
                     return done(ZB200_INF_BLOCK_TYPE);
                 }
                 in_block = 1;
+                if (huff_external) {                   // the warp-parallel decoder takes the symbols of this block
+                    InflateEvent ev; ev.kind = EV_HUFF; ev.len = (lt == fixed_lit) ? 1u : 0u; ev.dist = 0;
+                    ev.src = bitpos(); ev.dst = pos;
+                    return ev;
+                }
             }
             // ---- symbol loop: inffast.c:100-287 ----
             for (;;) {
