@@ -32,6 +32,49 @@ struct InflateShared {
 };
 
 
+
+// Execute `count` parked matches: independent ones one per lane (their L2 round
+// trips overlap), then the dependent ones in order, striped over the warp.
+__device__ __forceinline__ void exec_queue(uint8_t *dst, const QueuedMatch *q, uint32_t count) {
+    const unsigned full = 0xffffffffu;
+    const uint32_t lane = threadIdx.x & 31;
+    for (uint32_t base = 0; base < count; base += 32) {
+        const bool mine = base + lane < count;
+        QueuedMatch e;
+        e.dst = 0; e.len = 0; e.dist_dep = 0;
+        if (mine) e = q[base + lane];
+        if (mine && !(e.dist_dep >> 31)) {
+            uint8_t *d = dst + e.dst;
+            const uint8_t *s = d - e.dist_dep;                 // dist >= len: source and destination do not overlap
+            uint32_t i = 0;
+            for (; i + 8 <= e.len; i += 8) {
+                uint8_t t[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) t[k] = s[i + k];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) d[i + k] = t[k];
+            }
+            for (; i < e.len; ++i) d[i] = s[i];
+        }
+    }
+    __syncwarp(full);
+    for (uint32_t base = 0; base < count; base += 32) {
+        const bool mine = base + lane < count;
+        uint32_t depmask = __ballot_sync(full, mine && (q[base + lane].dist_dep >> 31));
+        while (depmask) {
+            const int j = __ffs(depmask) - 1;
+            depmask &= depmask - 1;
+            const QueuedMatch m = q[base + j];
+            const uint32_t dist = m.dist_dep & 0x7fffffffu;
+            uint8_t *d = dst + m.dst;
+            const uint8_t *s = d - dist;
+            if (dist >= m.len) { for (uint32_t i = lane; i < m.len; i += 32) d[i] = s[i]; }
+            else { for (uint32_t i = lane; i < m.len; i += 32) d[i] = s[i % dist]; }   // byte-serial semantics (inffast.c:249-260)
+            __syncwarp(full);
+        }
+    }
+}
+
 // ---- warp-parallel Huffman block decode -----------------------------------------
 // Huffman decoding is serial per stream (the start of symbol k+1 is known only
 // once symbol k is decoded).  Inside a warp the serial chain is shortened by
@@ -47,7 +90,7 @@ struct HuffResult { int status; uint64_t bitpos; uint64_t pos; };   // status 0:
 
 __device__ __forceinline__ HuffResult
 huff_decode_warp(const uint8_t *src, uint64_t in_len, uint8_t *dst, uint64_t out_cap, uint64_t bitpos, uint64_t pos,
-                 const uint32_t *__restrict__ lt, const uint32_t *__restrict__ dt) {
+                 const uint32_t *__restrict__ lt, const uint32_t *__restrict__ dt, QueuedMatch *q) {
     const unsigned full = 0xffffffffu;
     const uint32_t lane = threadIdx.x & 31;
     const uintptr_t a0 = reinterpret_cast<uintptr_t>(src) & ~(uintptr_t)3;
@@ -60,6 +103,8 @@ huff_decode_warp(const uint8_t *src, uint64_t in_len, uint8_t *dst, uint64_t out
     uint32_t win = 0;
     enum { K_LIT = 0, K_MATCH = 1, K_EOB = 2, K_BADLIT = 3, K_BADDIST = 4, K_TRUNC = 5 };
     HuffResult res;
+    uint32_t qcount = 0;                                            // matches parked in q[]
+    uint64_t qfirst = 0;                                            // destination of the first parked match
     for (;;) {
         const uint64_t wi = B >> 5;
         if (wbase == ~0ull || wi < wbase || wi + 3 >= wbase + 32) {  // (re)load the 32-word register window
@@ -138,35 +183,25 @@ huff_decode_warp(const uint8_t *src, uint64_t in_len, uint8_t *dst, uint64_t out
             res.pos = __shfl_sync(full, mydst, first);
             res.bitpos = B + (uint32_t)first - bias;
         }
-        const uint64_t round_pos = pos;
         if (valid && kind == K_LIT) dst[mydst] = (uint8_t)val;
+        // park the matches of this round; they are executed in batches so that their
+        // memory round trips overlap instead of stalling every round
         const bool is_m = valid && kind == K_MATCH;
-        const bool dep = is_m && (dist < len || mydst - dist + len > round_pos);
-        if (is_m && !dep) {
-            uint8_t *d = dst + mydst;
-            const uint8_t *s = d - dist;
-            uint32_t i = 0;
-            for (; i + 8 <= len; i += 8) {
-                uint8_t t[8];
-#pragma unroll
-                for (int q = 0; q < 8; ++q) t[q] = s[i + q];
-#pragma unroll
-                for (int q = 0; q < 8; ++q) d[i + q] = t[q];
+        const uint32_t mmask = __ballot_sync(full, is_m);
+        if (mmask) {
+            if (qcount == 0) qfirst = __shfl_sync(full, mydst, __ffs(mmask) - 1);
+            if (is_m) {
+                const bool dep = dist < len || mydst - dist + len > qfirst;
+                QueuedMatch m;
+                m.dst = mydst; m.len = len; m.dist_dep = dist | (dep ? 0x80000000u : 0u);
+                q[qcount + __popc(mmask & ((1u << lane) - 1u))] = m;
             }
-            for (; i < len; ++i) d[i] = s[i];
+            qcount += __popc(mmask);
         }
-        __syncwarp(full);
-        uint32_t depmask = __ballot_sync(full, dep);
-        while (depmask) {
-            const int jn = __ffs(depmask) - 1;
-            depmask &= depmask - 1;
-            const uint32_t mlen = __shfl_sync(full, len, jn), mdist = __shfl_sync(full, dist, jn);
-            const uint64_t to = __shfl_sync(full, mydst, jn);
-            uint8_t *d = dst + to;
-            const uint8_t *s = d - mdist;
-            if (mdist >= mlen) { for (uint32_t i = lane; i < mlen; i += 32) d[i] = s[i]; }
-            else { for (uint32_t i = lane; i < mlen; i += 32) d[i] = s[i % mdist]; }
+        if (qcount > kQueue - 32 || emask) {
             __syncwarp(full);
+            exec_queue(dst, q, qcount);
+            qcount = 0;
         }
         if (emask) return res;
         const int last = 31 - __clz(vmask);
@@ -174,7 +209,12 @@ huff_decode_warp(const uint8_t *src, uint64_t in_len, uint8_t *dst, uint64_t out
         const bool ended = __shfl_sync(full, (uint32_t)stop, last) != 0;   // only an EOB can be a committed stop
         pos += __shfl_sync(full, inc, 31);
         B += consumed;
-        if (ended) { res.status = 0; res.bitpos = B - bias; res.pos = pos; return res; }
+        if (ended) {
+            __syncwarp(full);
+            exec_queue(dst, q, qcount);
+            res.status = 0; res.bitpos = B - bias; res.pos = pos;
+            return res;
+        }
     }
 }
 
@@ -227,47 +267,14 @@ inflate_kernel(const uint8_t *__restrict__ in, uint8_t *out, const zb200_member 
                 const uint64_t bp = __shfl_sync(full, ev.src, 0), op = __shfl_sync(full, ev.dst, 0);
                 const uint32_t *lt = len ? sh.fixed_lit : sh.scr[warp].lit;
                 const uint32_t *dt = len ? sh.fixed_dist : sh.scr[warp].dist;
-                const HuffResult hr = huff_decode_warp(src, mb.in_len, dst, mb.out_cap, bp, op, lt, dt);
+                const HuffResult hr = huff_decode_warp(src, mb.in_len, dst, mb.out_cap, bp, op, lt, dt, q);
                 if (lane == 0) {
                     st.seek(hr.bitpos, hr.pos);
                     if (hr.status) { st.status = hr.status; }
                 }
                 if (hr.status) break;
             } else if (kind == EV_BATCH) {
-                const bool mine = lane < len;
-                QueuedMatch e;
-                e.dst = 0; e.len = 0; e.dist_dep = 0;
-                if (mine) e = q[lane];
-                const bool dep = mine && (e.dist_dep >> 31);
-                uint32_t depmask = __ballot_sync(full, dep);
-                if (mine && !dep) {                            // independent: one lane per match, all in flight together
-                    uint8_t *d = dst + e.dst;
-                    const uint8_t *s = d - e.dist_dep;         // dist >= len: source and destination do not overlap
-                    uint32_t i = 0;
-                    for (; i + 8 <= e.len; i += 8) {
-                        uint8_t t[8];
-#pragma unroll
-                        for (int k = 0; k < 8; ++k) t[k] = s[i + k];
-#pragma unroll
-                        for (int k = 0; k < 8; ++k) d[i + k] = t[k];
-                    }
-                    for (; i < e.len; ++i) d[i] = s[i];
-                }
-                __syncwarp(full);
-                while (depmask) {                              // dependent: in order, striped over the warp
-                    const int j = __ffs(depmask) - 1;
-                    depmask &= depmask - 1;
-                    const QueuedMatch m = q[j];
-                    const uint32_t dist = m.dist_dep & 0x7fffffffu;
-                    uint8_t *d = dst + m.dst;
-                    const uint8_t *s = d - dist;
-                    if (dist >= m.len) {
-                        for (uint32_t i = lane; i < m.len; i += 32) d[i] = s[i];
-                    } else {                                   // overlapping: byte-serial semantics (inffast.c:249-260)
-                        for (uint32_t i = lane; i < m.len; i += 32) d[i] = s[i % dist];
-                    }
-                    __syncwarp(full);
-                }
+                exec_queue(dst, q, len);
             } else {                                           // stored block: input -> output
                 const uint64_t to = __shfl_sync(full, ev.dst, 0);
                 const uint64_t from = __shfl_sync(full, ev.src, 0);

@@ -50,7 +50,7 @@ struct InflateScratch {
 // cannot overlap the destination of an earlier parked match ("independent") is
 // copied by its own lane, all such lanes in parallel, so their L2 round trips
 // overlap; the others run afterwards, in order, striped over the warp.
-constexpr uint32_t kQueue = 32;
+constexpr uint32_t kQueue = 64;
 struct QueuedMatch {
     uint64_t dst;                      // output position
     uint32_t len;
