@@ -16,6 +16,10 @@
 namespace zb {
 
 constexpr int kInfWarps = 4;
+// Two symbol decoders exist: the lean serial loop on lane 0 (InflateState::fast_symbols)
+// and the speculative warp-parallel one (huff_decode_warp).  Measured on B200 the
+// serial loop issues ~4x fewer warp instructions per symbol, so it is the default.
+constexpr bool kWarpParallelHuffman = false;
 
 struct InflateDeviceTables {
     uint32_t fixed_lit[512];
@@ -248,7 +252,7 @@ inflate_kernel(const uint8_t *__restrict__ in, uint8_t *out, const zb200_member 
         int hs = ZB200_INF_OK;
         if (lane == 0) {
             st.init(src, mb.in_len, dst, mb.out_cap, &sh.scr[warp], sh.fixed_lit, sh.fixed_dist, &sh.fmt);
-            st.huff_external = 1;
+            st.huff_external = kWarpParallelHuffman ? 1 : 0;
             if (mb.resume_bit) st.resume(mb.resume_bit, mb.resume_out, wrap);
             else hs = st.parse_header(wrap);
             if (hs) st.status = hs;
@@ -263,7 +267,7 @@ inflate_kernel(const uint8_t *__restrict__ in, uint8_t *out, const zb200_member 
             if (kind == EV_DONE) break;
             const uint32_t len = __shfl_sync(full, ev.len, 0);
             __syncwarp(full);                                  // lane 0's literal stores and queue writes -> visible
-            if (kind == EV_HUFF) {                             // a Huffman block: all 32 lanes decode it
+            if (kWarpParallelHuffman && kind == EV_HUFF) {     // a Huffman block: all 32 lanes decode it
                 const uint64_t bp = __shfl_sync(full, ev.src, 0), op = __shfl_sync(full, ev.dst, 0);
                 const uint32_t *lt = len ? sh.fixed_lit : sh.scr[warp].lit;
                 const uint32_t *dt = len ? sh.fixed_dist : sh.scr[warp].dist;

@@ -428,6 +428,78 @@ struct InflateState {
         }
     }
 
+    // The lean inner loop (the role of inflate_fast, inffast.c:50-304): while at least
+    // 16 input bytes and 264 output bytes remain, symbols are decoded with no
+    // per-symbol bounds or overrun checks, refills are single aligned 32-bit loads,
+    // literals are stored directly and matches are parked in q[].  Anything unusual
+    // (invalid code, distance too far, leaving the safe zone) rewinds to the start of
+    // the offending symbol and returns to the careful path (step()), which reports it.
+    // Returns 0: continue on the careful path, 1: queue full, 2: end of block consumed.
+    ZB_HD int fast_symbols(QueuedMatch *q, uint32_t &count, uint64_t &first_dst) {
+        if (in_len < 16 || out_cap < 264) return 0;
+        uint64_t h = hold; int b = bits; uint64_t nx = next;
+        // byte-align the loader to 4 so every refill is one aligned word
+        while (((reinterpret_cast<uintptr_t>(in) + nx) & 3) != 0) {
+            if (b > 56 || nx >= in_len) return 0;
+            h |= (uint64_t)in[nx++] << b; b += 8;
+        }
+        const uint64_t in_end = in_len - 16;
+        const uint64_t room = out_cap - 264;
+        if (pos > room) { hold = h; bits = b; next = nx; return 0; }
+        uint64_t span = room - pos;
+        if (span > 0x40000000ull) span = 0x40000000ull;
+        uint8_t *o = out + pos;                         // 32-bit offsets from here on
+        uint32_t rel = 0;
+        const uint32_t lim = (uint32_t)span;
+        const uint32_t *L = lt, *D = dt;
+        int reason = 0;
+        while (nx <= in_end && rel <= lim) {
+            if (b < 32) { h |= (uint64_t)(*reinterpret_cast<const uint32_t *>(in + nx)) << b; nx += 4; b += 32; }
+            uint32_t e = L[(uint32_t)h & ((1u << kLitRoot) - 1)];
+            if (ZB_E_OP(e) == OP_LIT) {                 // the common case: a literal straight from the root table
+                const int k = (int)ZB_E_BITS(e);
+                h >>= k; b -= k;
+                o[rel++] = (uint8_t)ZB_E_VAL(e);
+                continue;
+            }
+            const uint64_t h0 = h, nx0 = nx; const int b0 = b;       // rewind point
+            if (ZB_E_OP(e) == OP_SUB) {
+                const uint32_t sub = ZB_E_VAL(e) + (((uint32_t)(h >> kLitRoot)) & ((1u << ZB_E_EXTRA(e)) - 1u));
+                h >>= kLitRoot; b -= kLitRoot;
+                e = L[sub];
+            }
+            { const int k = (int)ZB_E_BITS(e); h >>= k; b -= k; }
+            const uint32_t op = ZB_E_OP(e);
+            if (op == OP_LIT) { o[rel++] = (uint8_t)ZB_E_VAL(e); continue; }
+            if (op == OP_EOB) { in_block = 0; reason = 2; break; }
+            if (op != OP_BASE) { h = h0; b = b0; nx = nx0; break; }
+            const uint32_t x = ZB_E_EXTRA(e);
+            const uint32_t len = ZB_E_VAL(e) + ((uint32_t)h & ((1u << x) - 1u));
+            h >>= x; b -= (int)x;
+            if (b < 32) { h |= (uint64_t)(*reinterpret_cast<const uint32_t *>(in + nx)) << b; nx += 4; b += 32; }
+            uint32_t d = D[(uint32_t)h & ((1u << kDistRoot) - 1)];
+            if (ZB_E_OP(d) == OP_SUB) {
+                const uint32_t sub = ZB_E_VAL(d) + (((uint32_t)(h >> kDistRoot)) & ((1u << ZB_E_EXTRA(d)) - 1u));
+                h >>= kDistRoot; b -= kDistRoot;
+                d = D[sub];
+            }
+            { const int k = (int)ZB_E_BITS(d); h >>= k; b -= k; }
+            if (ZB_E_OP(d) != OP_BASE) { h = h0; b = b0; nx = nx0; break; }
+            const uint32_t dx = ZB_E_EXTRA(d);
+            const uint32_t dist = ZB_E_VAL(d) + ((uint32_t)h & ((1u << dx) - 1u));
+            h >>= dx; b -= (int)dx;
+            const uint64_t at = pos + rel;
+            if (dist > at) { h = h0; b = b0; nx = nx0; break; }
+            const bool dep = dist < len || (count && at - dist + len > first_dst);
+            if (!count) first_dst = at;
+            q[count].dst = at; q[count].len = len; q[count].dist_dep = dist | (dep ? 0x80000000u : 0u);
+            rel += len;
+            if (++count == kQueue) { reason = 1; break; }
+        }
+        hold = h; bits = b; next = nx; pos += rel;
+        return reason;
+    }
+
     // Decode until the queue is full or something other than a match happens.
     // Returns EV_BATCH with ev.len parked matches in q[], or a STORED / DONE event
     // (only once the queue has been handed over).
@@ -437,6 +509,11 @@ struct InflateState {
         uint32_t count = 0;
         uint64_t first_dst = 0;
         for (;;) {
+            if (in_block) {
+                const int r = fast_symbols(q, count, first_dst);
+                if (r == 1) break;
+                if (r == 2) continue;                  // block done: step() reads the next header
+            }
             ev = step();
             if (ev.kind == EV_MATCH) {
                 // dependent: overlaps itself, or may read what an earlier parked match will write
