@@ -198,6 +198,15 @@ def main():
         run_reference_arm(args)
         return
 
+    # torchrun pins OMP_NUM_THREADS=1; the synthetic-data generator (OpenMP, not part of the
+    # timed region) may use this rank's share of the host cores
+    os.environ["OMP_NUM_THREADS"] = str(max(1, host_threads() // max(1, env_int("WORLD_SIZE", 1))))
+    # Libraries (NCCL's version banner, torch warnings) may write to stdout; the contract is
+    # ONE JSON line there.  Route fd 1 to stderr for the run and keep the real stdout aside.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
     import torch
     import torch.distributed as dist
     import zlib_wasm_b200 as zb
@@ -357,7 +366,8 @@ def main():
             if line is not None:
                 line["extra"] = {"error": repr(e)}
     if line is not None:
-        print(json.dumps(line), flush=True)
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
     L.zb200_host_free(h_in)
     if world > 1:
         dist.destroy_process_group()

@@ -133,3 +133,14 @@ def test_large_batch_ratio_and_roundtrip(ctx):
             refsz += len(ref_stream(d[c * chunk:(c + 1) * chunk], level, 0, refz.WRAP_RAW, 0))
         est = refsz / len(sample) * (n // chunk)
         assert ours <= TOL * est, (level, ours, est)
+
+
+def test_level0_stored_blocks(ctx):
+    """Level 0 (deflate.c:1635 deflate_stored): stored blocks only — valid stream,
+    reference decodes it, size = input + 5 bytes per block + framing."""
+    for kind, n in ((refz.GEN_TEXT, 100000), (refz.GEN_RANDOM, 300000), (refz.GEN_TEXT, 0)):
+        d = refz.gen(n, kind, seed=5)
+        s = ctx.deflate_host(d, 0, 0, zb.FRAME_ZLIB, 262144)
+        assert decode_ok(s, refz.WRAP_ZLIB, d)
+        assert s[:2] == b"\x78\x01"                       # level_flags 0 (deflate.c:1009)
+        assert n + 6 <= len(s) <= n + 6 + 5 * (n // 16383 + 2) + 5 * (n // 262144 + 1)

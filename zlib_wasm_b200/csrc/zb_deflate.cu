@@ -545,9 +545,9 @@ static size_t batch_chunks(size_t n, size_t S) {
 int deflate_launch(zb200_ctx *ctx, const uint8_t *d_in, size_t n, size_t S, int level, int strategy, int frame,
                    int finish, uint8_t *d_out, size_t out_cap, uint64_t *d_chunk_end, uint64_t *d_total,
                    uint32_t *d_sums_out, cudaStream_t s) {
-    if (level < 1 || level > 9 || strategy < 0 || strategy > 4 || frame < 0 || frame > 3 || S < 1 ||
+    if (level < 0 || level > 9 || strategy < 0 || strategy > 4 || frame < 0 || frame > 3 || S < 1 ||
         S > 0x40000000ull || ((uintptr_t)d_out & 3)) {
-        set_error("deflate: bad parameter (level 1..9, strategy 0..4, frame 0..3, chunk 1..2^30, 4-byte aligned output)");
+        set_error("deflate: bad parameter (level 0..9, strategy 0..4, frame 0..3, chunk 1..2^30, 4-byte aligned output)");
         return ZB200_ERR_PARAM;
     }
     const bool members = frame == ZB200_FRAME_GZIP_MEMBERS;
@@ -595,7 +595,7 @@ int deflate_launch(zb200_ctx *ctx, const uint8_t *d_in, size_t n, size_t S, int 
         }
         dfl_parse_kernel<<<b.nb, 32, 0, s>>>(b, prm, w.mfull, w.mquarter, w.syms, w.blocks, w.nblocks);
         ZB_LAUNCHED(); ZB_CHECK_LAUNCH();
-        dfl_tree_kernel<<<dim3(MB, b.nb), 128, 0, s>>>(b, strategy, w.syms, w.blocks, w.nblocks, tabs, w.codes);
+        dfl_tree_kernel<<<dim3(MB, b.nb), 128, 0, s>>>(b, strategy | (level == 0 ? 0x100 : 0), w.syms, w.blocks, w.nblocks, tabs, w.codes);
         ZB_LAUNCHED(); ZB_CHECK_LAUNCH();
         dfl_layout_kernel<<<(b.nb + 127) / 128, 128, 0, s>>>(b, w.blocks, w.codes, w.nblocks, w.chunk_bytes, members ? 18 : 0);
         ZB_LAUNCHED(); ZB_CHECK_LAUNCH();

@@ -63,7 +63,7 @@ ZB_HD DeflateParams deflate_params(int level, int strategy) {
     DeflateParams p;
     p.level = level; p.strategy = strategy;
     p.good = cfg[level][0]; p.lazy = cfg[level][1]; p.nice = cfg[level][2]; p.chain = cfg[level][3];
-    p.mode = strategy == STRAT_HUFFMAN ? MODE_HUFF : strategy == STRAT_RLE ? MODE_RLE : level >= 4 ? MODE_SLOW : MODE_FAST;
+    p.mode = (strategy == STRAT_HUFFMAN || level == 0) ? MODE_HUFF : strategy == STRAT_RLE ? MODE_RLE : level >= 4 ? MODE_SLOW : MODE_FAST;
     // a search happens only while prev_length < lazy; it is quartered when prev_length >= good
     p.need_quarter = (p.mode == MODE_SLOW && p.good < p.lazy) ? 1 : 0;
     return p;
@@ -480,9 +480,11 @@ ZB_HD void block_build(TreeWork &w, const BlockInfo &blk, int strategy, const St
     w.opt_len += 3 * ((uint32_t)mb + 1) + 5 + 5 + 4;
     uint32_t opt_lenb = (w.opt_len + 3 + 7) >> 3;
     const uint32_t static_lenb = (w.static_len + 3 + 7) >> 3;
+    const bool force_stored = (strategy & 0x100) != 0;   // level 0: trees.c:1041-1043 forces stored blocks
+    strategy &= 0xff;
     if (static_lenb <= opt_lenb || strategy == STRAT_FIXED) opt_lenb = static_lenb;
     out.hdr_bits = 0; out.pad = 0;
-    if (blk.byte_len + 4 <= opt_lenb && (blk.flags & BLK_STORED_OK)) {
+    if (force_stored || (blk.byte_len + 4 <= opt_lenb && (blk.flags & BLK_STORED_OK))) {
         out.type = 0; out.body_bits = 0;
     } else if (static_lenb == opt_lenb) {
         out.type = 1; out.body_bits = 3 + w.static_len;

@@ -106,8 +106,8 @@ int compress_buffered(DeflateStream &st, bool finish) {
     const size_t at = st.pending.size();
     st.pending.resize(at + cap);
     uint32_t adler = 1, crc = 0;
-    int r = zb200_deflate_host(ctx, n ? st.in.data() : (const uint8_t *)"", n, chunk, st.level ? st.level : 1,
-                               st.level ? st.strategy : Z_HUFFMAN_ONLY, ZB200_FRAME_RAW, finish ? 1 : 0,
+    int r = zb200_deflate_host(ctx, n ? st.in.data() : (const uint8_t *)"", n, chunk, st.level,
+                               st.strategy, ZB200_FRAME_RAW, finish ? 1 : 0,
                                st.pending.data() + at, &cap, &adler, &crc);
     if (r != ZB200_OK) { st.pending.resize(at); return map_engine_error(r); }
     st.pending.resize(at + cap);
@@ -432,8 +432,8 @@ int compress2(Bytef *dest, uLongf *destLen, const Bytef *source, uLong sourceLen
     if (level == Z_DEFAULT_COMPRESSION) level = 6;
     if (level < 0 || level > 9 || !dest || !destLen || (!source && sourceLen)) return Z_STREAM_ERROR;
     size_t cap = *destLen;
-    const int r = zb200_deflate_host(ctx, source ? source : (const Bytef *)"", sourceLen, api_chunk(), level ? level : 1,
-                                     level ? 0 : Z_HUFFMAN_ONLY, ZB200_FRAME_ZLIB, 1, dest, &cap, nullptr, nullptr);
+    const int r = zb200_deflate_host(ctx, source ? source : (const Bytef *)"", sourceLen, api_chunk(), level,
+                                     0, ZB200_FRAME_ZLIB, 1, dest, &cap, nullptr, nullptr);
     if (r == ZB200_ERR_OUTPUT) return Z_BUF_ERROR;
     if (r != ZB200_OK) return map_engine_error(r);
     *destLen = cap;
