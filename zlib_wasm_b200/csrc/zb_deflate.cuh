@@ -77,6 +77,25 @@ ZB_HD uint32_t hash3(const uint8_t *s) {
 // Result encoding: 0 = no match of length >= 3, else (len << 16) | dist.
 struct MatchPair { uint32_t full, quarter; };
 
+// Four bytes at an arbitrary address, little-endian, without unaligned accesses:
+// the two aligned words around it, funnel-shifted.
+ZB_HD uint32_t load4(const uint8_t *p) {
+#if defined(__CUDA_ARCH__)
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3);
+    return __funnelshift_r(w[0], w[1], (uint32_t)(a & 3) * 8);
+#else
+    return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
+#endif
+}
+ZB_HD uint32_t ctz32(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+    return (uint32_t)__ffs((int)x) - 1u;
+#else
+    return (uint32_t)__builtin_ctz(x);
+#endif
+}
+
 // The walk over one position's hash chain as a resumable object: begin() loads
 // the head, step() examines ONE candidate.  The kernel keeps one walk per lane and
 // hands a lane a new position as soon as its walk ends, so lanes with short chains
@@ -106,7 +125,13 @@ struct MatchWalk {
         // quick rejects (deflate.c:1449-1452); best < maxlen holds here (see nice clamp)
         if (m[best] == scan[best] && m[0] == scan[0] && m[1] == scan[1]) {
             uint32_t len = 2;                             // m[2]==scan[2] follows from the equal hash when bytes 0,1 agree
+            while (len + 4 <= maxlen) {                   // four bytes per step
+                const uint32_t x = load4(m + len) ^ load4(scan + len);
+                if (x) { len += ctz32(x) >> 3; goto measured; }
+                len += 4;
+            }
             while (len < maxlen && m[len] == scan[len]) ++len;
+        measured:
             if (len > best) {
                 best = len; best_dist = p - q;
                 if (len >= nice) return true;
