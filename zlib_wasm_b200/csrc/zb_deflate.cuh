@@ -105,11 +105,12 @@ struct MatchWalk {
     uint32_t best, best_dist, examined;
     uint32_t maxlen, nice;
     uint32_t quarter; bool have_q;
+    uint32_t off;                     // 0xffffffff: candidate not yet screened; else bytes [0, off) are known equal
 
     // Returns false if the position has no candidate at all (result() is then 0/0).
     ZB_HD bool begin(const uint8_t *data, uint32_t n, const uint16_t *prev_dist, uint32_t pos, const DeflateParams &prm) {
         (void)data;
-        p = pos; best = kMinMatch - 1; best_dist = 0; examined = 0; quarter = 0; have_q = false;
+        p = pos; best = kMinMatch - 1; best_dist = 0; examined = 0; quarter = 0; have_q = false; off = 0xffffffffu;
         if (p + kMinMatch > n) return false;              // lookahead < MIN_MATCH: no insertion, no search
         const uint32_t d = prev_dist[p];
         if (d == 0 || d > (uint32_t)kMaxDist) return false;   // deflate.c:1857/1958: head must be within MAX_DIST
@@ -119,23 +120,31 @@ struct MatchWalk {
         q = p - d;
         return true;
     }
-    // Examine the current candidate and move to the next; returns true when the walk is over.
+    // One unit of work = one 4-byte comparison, so that the lanes of a warp stay in
+    // step whatever their candidates look like.  Returns true when the walk is over.
+    //   screening (the quick rejects of deflate.c:1449-1452): a candidate can only beat
+    //   `best` if bytes [best-3, best] agree (best < maxlen holds, see the nice clamp);
+    //   measuring: common prefix from byte 0, four bytes per unit.
     ZB_HD bool step(const uint8_t *data, const uint16_t *prev_dist, const DeflateParams &prm) {
         const uint8_t *scan = data + p, *m = data + q;
-        // quick rejects (deflate.c:1449-1452); best < maxlen holds here (see nice clamp)
-        if (m[best] == scan[best] && m[0] == scan[0] && m[1] == scan[1]) {
-            uint32_t len = 2;                             // m[2]==scan[2] follows from the equal hash when bytes 0,1 agree
-            while (len + 4 <= maxlen) {                   // four bytes per step
-                const uint32_t x = load4(m + len) ^ load4(scan + len);
-                if (x) { len += ctz32(x) >> 3; goto measured; }
-                len += 4;
-            }
-            while (len < maxlen && m[len] == scan[len]) ++len;
-        measured:
-            if (len > best) {
-                best = len; best_dist = p - q;
-                if (len >= nice) return true;
-            }
+        uint32_t len;
+        if (off == 0xffffffffu) {
+            const uint32_t o = best >= 3 ? best - 3 : 0;
+            uint32_t x = load4(m + o) ^ load4(scan + o);
+            if (best < 3) x &= 0x00ffffffu;               // best == 2: only bytes 0..2 have to agree
+            if (x == 0) { off = 0; return false; }        // promising: measure it
+            len = 0;                                       // cannot beat best
+        } else {
+            uint32_t x = load4(m + off) ^ load4(scan + off);
+            const uint32_t room = maxlen - off;            // > 0
+            if (room < 4) x &= (1u << (8 * room)) - 1u;
+            if (x == 0 && room > 4) { off += 4; return false; }
+            len = x ? off + (ctz32(x) >> 3) : maxlen;
+        }
+        off = 0xffffffffu;
+        if (len > best) {
+            best = len; best_dist = p - q;
+            if (len >= nice) return true;
         }
         ++examined;
         if (examined == ((uint32_t)prm.chain >> 2) && !have_q) { quarter = best >= (uint32_t)kMinMatch ? (best << 16) | best_dist : 0; have_q = true; }
