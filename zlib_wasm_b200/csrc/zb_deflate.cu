@@ -66,11 +66,6 @@ __device__ __forceinline__ bool chunk_final(const Batch &b, uint32_t c) {
     return b.all_final || (b.last_is_final && c + 1 == b.nb);
 }
 
-__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
-    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
-}
-
 // ---- phase 1: hash chains, one warp per chunk --------------------------------------
 // 32 consecutive positions per step: same-hash positions inside the step are
 // linked with match.any, the rest through a 32K-entry u16 head table in shared
@@ -171,88 +166,19 @@ __global__ void __launch_bounds__(32) dfl_chain_kernel(Batch b, uint16_t *__rest
 }
 
 // ---- phase 2: longest match per position --------------------------------------------
-// One CTA owns a tile of kMatchTile consecutive positions of one chunk.  Every
-// candidate lies within MAX_DIST (32506) bytes before its position, so the whole
-// working set of the tile -- the input bytes [tile - 32 KiB, tile + T + 258) and
-// the chain links of the same range -- is first copied into shared memory with
-// 16-byte cp.async, and the walks then run entirely out of shared memory (random
-// byte / halfword reads that would otherwise be 32 separate L1 sectors per warp
-// load).  Chain lengths differ wildly between neighbouring positions (measured: 8
-// of 32 lanes active with one position per thread), so positions are not bound to
-// lanes: a warp owns a slice of the tile and each lane takes the next unprocessed
-// position as soon as its current walk ends.
-constexpr uint32_t kMatchTile = 4096, kMatchWarps = 16;
-constexpr uint32_t kMatchBack = 32512;                                  // >= MAX_DIST, multiple of 16
-constexpr uint32_t kMatchDataBytes = kMatchBack + kMatchTile + 272 + 16; // + match overhang + alignment slack
-constexpr uint32_t kMatchPrevEntries = kMatchBack + kMatchTile + 8;
-constexpr uint32_t kMatchSmem = kMatchDataBytes + kMatchPrevEntries * 2;
-
-__global__ void __launch_bounds__(kMatchWarps * 32, 2)
+__global__ void __launch_bounds__(256)
 dfl_match_kernel(Batch b, DeflateParams prm, const uint16_t *__restrict__ prev_all,
                  uint32_t *__restrict__ mfull, uint32_t *__restrict__ mquarter) {
-    extern __shared__ __align__(16) uint8_t msm[];
-    uint8_t *sdata = msm;
-    uint16_t *sprev = reinterpret_cast<uint16_t *>(msm + kMatchDataBytes);
     const uint32_t c = blockIdx.y;
     const uint32_t n = chunk_len(b, c);
-    const uint32_t t0 = blockIdx.x * kMatchTile;
-    if (t0 >= n) return;
-    const uint32_t t1 = t0 + kMatchTile < n ? t0 + kMatchTile : n;
-    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t p = blockIdx.x * 256 + threadIdx.x;
+    if (p >= n) return;
     const uint64_t off = (uint64_t)c * b.S;
     const uint8_t *data = b.in + off;
-    if (prm.mode == MODE_RLE) {
-        for (uint32_t p = t0 + threadIdx.x; p < t1; p += blockDim.x) mfull[off + p] = rle_at(data, n, p);
-        return;
-    }
-    // ---- stage the working set ----
-    const uint32_t w0 = t0 > kMatchBack ? t0 - kMatchBack : 0;          // first chunk position needed
-    const uint32_t wend = t1 + 272 < n ? t1 + 272 : n;                   // one past the last byte needed
-    const uintptr_t in_lo = reinterpret_cast<uintptr_t>(b.in), in_hi = in_lo + b.bytes;
-    const uintptr_t d_first = (reinterpret_cast<uintptr_t>(data) + w0) & ~(uintptr_t)15;
-    const uintptr_t d_last = reinterpret_cast<uintptr_t>(data) + wend;
-    for (uintptr_t a = d_first + 16ull * threadIdx.x; a < d_last; a += 16ull * blockDim.x)
-        if (a + 16 > in_lo && a < in_hi) cp_async16(sdata + (a - d_first), reinterpret_cast<const void *>(a));
-    const uint64_t p_first = (off + w0) & ~7ull;                         // absolute link index, 16-byte aligned
-    const uint64_t p_last = off + t1;
-    const uint64_t p_hi = (uint64_t)b.nb * b.S;                          // links allocated for the sub-batch
-    for (uint64_t e = p_first + 8ull * threadIdx.x; e < p_last; e += 8ull * blockDim.x)
-        if (e + 8 <= ((p_hi + 7) & ~7ull)) cp_async16(sprev + (e - p_first), prev_all + e);
-    asm volatile("cp.async.commit_group;" ::: "memory");
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    __syncthreads();
-    // pointers biased so that chunk positions index them directly
-    const uint8_t *ds = sdata + (reinterpret_cast<uintptr_t>(data) - d_first);          // ds[q] for w0 <= q < wend
-    const uint16_t *ps = sprev + (off - p_first);                                        // ps[q] for w0 <= q < t1
-    // ---- walks ----
-    const uint32_t per_warp = (t1 - t0 + kMatchWarps - 1) / kMatchWarps;
-    uint32_t next = t0 + warp * per_warp;
-    const uint32_t stop = next + per_warp < t1 ? next + per_warp : t1;
-    const unsigned full = 0xffffffffu;
-    MatchWalk w;
-    bool busy = false;
-    if (next < stop)
-        for (;;) {
-            const uint32_t idle = __ballot_sync(full, !busy);
-            if (idle) {
-                if (next < stop) {
-                    const uint32_t mine = next + __popc(idle & ((1u << lane) - 1u));
-                    if (!busy && mine < stop) {
-                        busy = w.begin(ds, n, ps, mine, prm);
-                        if (!busy) { mfull[off + mine] = 0; if (prm.need_quarter) mquarter[off + mine] = 0; }
-                    }
-                    next += __popc(idle);
-                } else if (idle == full) {
-                    break;
-                }
-            }
-            if (busy && w.step(ds, ps, prm)) {
-                const MatchPair r = w.result();
-                mfull[off + w.p] = r.full;
-                if (prm.need_quarter) mquarter[off + w.p] = r.quarter;
-                busy = false;
-            }
-        }
+    if (prm.mode == MODE_RLE) { mfull[off + p] = rle_at(data, n, p); return; }
+    const MatchPair r = match_at(data, n, prev_all + off, p, prm);
+    mfull[off + p] = r.full;
+    if (prm.need_quarter) mquarter[off + p] = r.quarter;
 }
 
 // ---- phase 3: parse, one chunk per warp (lane 0 walks the tables) ---------------------
@@ -278,6 +204,11 @@ struct ParseTileAcc {
     __device__ __forceinline__ uint32_t byte(uint32_t p) const { return tby[p + bbias]; }
     __device__ __forceinline__ void put(uint32_t sym) { stage[count++] = sym; }
 };
+
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
 
 __global__ void __launch_bounds__(32)
 dfl_parse_kernel(Batch b, DeflateParams prm, const uint32_t *__restrict__ mfull,
@@ -590,7 +521,6 @@ int deflate_init(zb200_ctx *ctx) {
     ZB_CUDA(cudaMemcpy(d, &h, sizeof h, cudaMemcpyHostToDevice));
     ctx->d_deflate_tables = d;
     ZB_CUDA(cudaFuncSetAttribute(dfl_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kChainSmem));
-    ZB_CUDA(cudaFuncSetAttribute(dfl_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMatchSmem));
     return ZB200_OK;
 }
 
@@ -659,8 +589,8 @@ int deflate_launch(zb200_ctx *ctx, const uint8_t *d_in, size_t n, size_t S, int 
             ZB_LAUNCHED(); ZB_CHECK_LAUNCH();
         }
         if (prm.mode != MODE_HUFF) {
-            dim3 g((unsigned)((S + kMatchTile - 1) / kMatchTile), b.nb);
-            dfl_match_kernel<<<g, kMatchWarps * 32, kMatchSmem, s>>>(b, prm, w.prev, w.mfull, w.mquarter);
+            dim3 g((unsigned)((S + 255) / 256), b.nb);
+            dfl_match_kernel<<<g, 256, 0, s>>>(b, prm, w.prev, w.mfull, w.mquarter);
             ZB_LAUNCHED(); ZB_CHECK_LAUNCH();
         }
         dfl_parse_kernel<<<b.nb, 32, 0, s>>>(b, prm, w.mfull, w.mquarter, w.syms, w.blocks, w.nblocks);

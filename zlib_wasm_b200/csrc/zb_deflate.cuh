@@ -77,97 +77,42 @@ ZB_HD uint32_t hash3(const uint8_t *s) {
 // Result encoding: 0 = no match of length >= 3, else (len << 16) | dist.
 struct MatchPair { uint32_t full, quarter; };
 
-// Four bytes at an arbitrary address, little-endian, without unaligned accesses:
-// the two aligned words around it, funnel-shifted.
-ZB_HD uint32_t load4(const uint8_t *p) {
-#if defined(__CUDA_ARCH__)
-    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
-    const uint32_t *w = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3);
-    return __funnelshift_r(w[0], w[1], (uint32_t)(a & 3) * 8);
-#else
-    return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
-#endif
-}
-ZB_HD uint32_t ctz32(uint32_t x) {
-#if defined(__CUDA_ARCH__)
-    return (uint32_t)__ffs((int)x) - 1u;
-#else
-    return (uint32_t)__builtin_ctz(x);
-#endif
-}
-
-// The walk over one position's hash chain as a resumable object: begin() loads
-// the head, step() examines ONE candidate.  The kernel keeps one walk per lane and
-// hands a lane a new position as soon as its walk ends, so lanes with short chains
-// do not idle behind the longest chain of the warp.
-struct MatchWalk {
-    uint32_t p, q;                    // position, current candidate
-    uint32_t best, best_dist, examined;
-    uint32_t maxlen, nice;
-    uint32_t quarter; bool have_q;
-    uint32_t off;                     // 0xffffffff: candidate not yet screened; else bytes [0, off) are known equal
-
-    // Returns false if the position has no candidate at all (result() is then 0/0).
-    ZB_HD bool begin(const uint8_t *data, uint32_t n, const uint16_t *prev_dist, uint32_t pos, const DeflateParams &prm) {
-        (void)data;
-        p = pos; best = kMinMatch - 1; best_dist = 0; examined = 0; quarter = 0; have_q = false; off = 0xffffffffu;
-        if (p + kMinMatch > n) return false;              // lookahead < MIN_MATCH: no insertion, no search
-        const uint32_t d = prev_dist[p];
-        if (d == 0 || d > (uint32_t)kMaxDist) return false;   // deflate.c:1857/1958: head must be within MAX_DIST
-        const uint32_t look = n - p;
-        maxlen = look < (uint32_t)kMaxMatch ? look : (uint32_t)kMaxMatch;
-        nice = (uint32_t)prm.nice > look ? look : (uint32_t)prm.nice;                  // deflate.c:1396
-        q = p - d;
-        return true;
-    }
-    // One unit of work = one 4-byte comparison, so that the lanes of a warp stay in
-    // step whatever their candidates look like.  Returns true when the walk is over.
-    //   screening (the quick rejects of deflate.c:1449-1452): a candidate can only beat
-    //   `best` if bytes [best-3, best] agree (best < maxlen holds, see the nice clamp);
-    //   measuring: common prefix from byte 0, four bytes per unit.
-    ZB_HD bool step(const uint8_t *data, const uint16_t *prev_dist, const DeflateParams &prm) {
-        const uint8_t *scan = data + p, *m = data + q;
-        uint32_t len;
-        if (off == 0xffffffffu) {
-            const uint32_t o = best >= 3 ? best - 3 : 0;
-            uint32_t x = load4(m + o) ^ load4(scan + o);
-            if (best < 3) x &= 0x00ffffffu;               // best == 2: only bytes 0..2 have to agree
-            if (x == 0) { off = 0; return false; }        // promising: measure it
-            len = 0;                                       // cannot beat best
-        } else {
-            uint32_t x = load4(m + off) ^ load4(scan + off);
-            const uint32_t room = maxlen - off;            // > 0
-            if (room < 4) x &= (1u << (8 * room)) - 1u;
-            if (x == 0 && room > 4) { off += 4; return false; }
-            len = x ? off + (ctz32(x) >> 3) : maxlen;
-        }
-        off = 0xffffffffu;
-        if (len > best) {
-            best = len; best_dist = p - q;
-            if (len >= nice) return true;
-        }
-        ++examined;
-        if (examined == ((uint32_t)prm.chain >> 2) && !have_q) { quarter = best >= (uint32_t)kMinMatch ? (best << 16) | best_dist : 0; have_q = true; }
-        if (examined == (uint32_t)prm.chain) return true; // deflate.c:1482 --chain_length
-        const uint32_t d2 = prev_dist[q];
-        if (d2 == 0) return true;
-        q -= d2;
-        return p - q >= (uint32_t)kMaxDist;               // deflate.c:1481: cur_match > limit
-    }
-    ZB_HD MatchPair result() const {
-        MatchPair r;
-        r.full = best >= (uint32_t)kMinMatch ? (best << 16) | best_dist : 0;
-        r.quarter = have_q ? quarter : r.full;
-        return r;
-    }
-};
-
 ZB_HD MatchPair match_at(const uint8_t *data, uint32_t n, const uint16_t *prev_dist, uint32_t p,
                          const DeflateParams &prm) {
-    MatchWalk w;
-    if (w.begin(data, n, prev_dist, p, prm))
-        while (!w.step(data, prev_dist, prm)) {}
-    return w.result();
+    MatchPair r{0, 0};
+    if (p + kMinMatch > n) return r;                  // lookahead < MIN_MATCH: no insertion, no search
+    uint32_t d = prev_dist[p];
+    if (d == 0 || d > (uint32_t)kMaxDist) return r;   // deflate.c:1857/1958: head must be within MAX_DIST
+    const uint32_t look = n - p;
+    const uint32_t maxlen = look < (uint32_t)kMaxMatch ? look : (uint32_t)kMaxMatch;
+    const uint32_t nice = (uint32_t)prm.nice > look ? look : (uint32_t)prm.nice;      // deflate.c:1396
+    const uint32_t chain_q = (uint32_t)prm.chain >> 2;
+    const uint8_t *scan = data + p;
+    uint32_t best = kMinMatch - 1, best_dist = 0, examined = 0;
+    uint32_t q = p - d;
+    bool have_q = false;
+    for (;;) {
+        const uint8_t *m = data + q;
+        // quick rejects (deflate.c:1449-1452); best < maxlen holds here (see nice clamp)
+        if (m[best] == scan[best] && m[0] == scan[0] && m[1] == scan[1]) {
+            uint32_t len = 2;                         // m[2]==scan[2] follows from the equal hash when bytes 0,1 agree
+            while (len < maxlen && m[len] == scan[len]) ++len;
+            if (len > best) {
+                best = len; best_dist = p - q;
+                if (len >= nice) break;
+            }
+        }
+        ++examined;
+        if (examined == chain_q && !have_q) { r.quarter = best >= (uint32_t)kMinMatch ? (best << 16) | best_dist : 0; have_q = true; }
+        if (examined == (uint32_t)prm.chain) break;  // deflate.c:1482 --chain_length
+        const uint32_t d2 = prev_dist[q];
+        if (d2 == 0) break;
+        q -= d2;
+        if (p - q >= (uint32_t)kMaxDist) break;       // deflate.c:1481: cur_match > limit
+    }
+    r.full = best >= (uint32_t)kMinMatch ? (best << 16) | best_dist : 0;
+    if (!have_q) r.quarter = r.full;
+    return r;
 }
 
 // Z_RLE (deflate.c:2051-2115): run of the previous byte, distance 1 only.
