@@ -521,12 +521,6 @@ int deflate_init(zb200_ctx *ctx) {
     ZB_CUDA(cudaMemcpy(d, &h, sizeof h, cudaMemcpyHostToDevice));
     ctx->d_deflate_tables = d;
     ZB_CUDA(cudaFuncSetAttribute(dfl_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kChainSmem));
-    for (int k = 0; k < zb200_ctx::kLanes; ++k) {
-        ZB_CUDA(cudaStreamCreateWithFlags(&ctx->lane_stream[k], cudaStreamNonBlocking));
-        ZB_CUDA(cudaEventCreateWithFlags(&ctx->lane_done[k], cudaEventDisableTiming));
-        ZB_CUDA(cudaEventCreateWithFlags(&ctx->lane_scan[k], cudaEventDisableTiming));
-    }
-    ZB_CUDA(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
     return ZB200_OK;
 }
 
@@ -537,7 +531,7 @@ static size_t chunk_bound(size_t len) {
 
 static size_t frame_overhead(int frame) { return frame == ZB200_FRAME_ZLIB ? 6 : frame == ZB200_FRAME_GZIP ? 18 : 0; }
 
-constexpr size_t kBatchBytes = 128u << 20;    // input bytes per sub-batch; kLanes of them are in flight (scratch ~14x each)
+constexpr size_t kBatchBytes = 512u << 20;    // input bytes per sub-batch (bounds scratch at ~14x this)
 
 static size_t batch_chunks(size_t n, size_t S) {
     size_t nch = (n + S - 1) / S;
@@ -563,14 +557,10 @@ int deflate_launch(zb200_ctx *ctx, const uint8_t *d_in, size_t n, size_t S, int 
     const DeflateParams prm = deflate_params(level, strategy);
     const uint32_t MB = max_blocks_for((uint32_t)S);
     const size_t nb_max = batch_chunks(n, S);
-    const size_t nbatches = (nch + nb_max - 1) / nb_max;
-    const int lanes = (int)(nbatches < (size_t)zb200_ctx::kLanes ? (nbatches ? nbatches : 1) : zb200_ctx::kLanes);
-    const size_t lane_bytes = (work_bytes(nb_max, S, MB) + 255) & ~(size_t)255;
-    int r = ensure_scratch(ctx, lane_bytes * lanes);
+    int r = ensure_scratch(ctx, work_bytes(nb_max, S, MB));
     if (r) return r;
-    DeflateWork works[zb200_ctx::kLanes];
-    for (int k = 0; k < lanes; ++k) carve(works[k], (uint8_t *)ctx->d_scratch + lane_bytes * k, nb_max, S, MB);
-    cudaStream_t user = s;
+    DeflateWork w;
+    carve(w, ctx->d_scratch, nb_max, S, MB);
     const DeflateDeviceTables *tabs = (const DeflateDeviceTables *)ctx->d_deflate_tables;
     uint64_t *running = ctx->d_small + 16;                         // stream length so far (device)
     uint32_t *sums = (uint32_t *)(ctx->d_small + 20);              // crc, adler of the whole input
@@ -584,14 +574,7 @@ int deflate_launch(zb200_ctx *ctx, const uint8_t *d_in, size_t n, size_t S, int 
         if (r) return r;
         if (d_sums_out) ZB_CUDA(cudaMemcpyAsync(d_sums_out, sums, 8, cudaMemcpyDeviceToDevice, s));
     }
-    // fork: the sub-batch lanes start after the setup work queued on the caller's stream
-    ZB_CUDA(cudaEventRecord(ctx->ev_fork, user));
-    for (int k = 0; k < lanes; ++k) ZB_CUDA(cudaStreamWaitEvent(ctx->lane_stream[k], ctx->ev_fork, 0));
-    size_t bi = 0;
-    for (size_t c0 = 0; c0 < nch; c0 += nb_max, ++bi) {
-        const int lane = (int)(bi % lanes);
-        s = ctx->lane_stream[lane];
-        DeflateWork &w = works[lane];
+    for (size_t c0 = 0; c0 < nch; c0 += nb_max) {
         Batch b;
         b.nb = (uint32_t)(nch - c0 < nb_max ? nch - c0 : nb_max);
         b.in = d_in + c0 * S;
@@ -616,11 +599,8 @@ int deflate_launch(zb200_ctx *ctx, const uint8_t *d_in, size_t n, size_t S, int 
         ZB_LAUNCHED(); ZB_CHECK_LAUNCH();
         dfl_layout_kernel<<<(b.nb + 127) / 128, 128, 0, s>>>(b, w.blocks, w.codes, w.nblocks, w.chunk_bytes, members ? 18 : 0);
         ZB_LAUNCHED(); ZB_CHECK_LAUNCH();
-        // stream offsets are a running sum over sub-batches: scans run in sub-batch order
-        if (bi > 0) ZB_CUDA(cudaStreamWaitEvent(s, ctx->lane_scan[(bi - 1) % lanes], 0));
         dfl_scan_kernel<<<1, 1024, 0, s>>>(b.nb, w.chunk_bytes, w.chunk_off, running, d_chunk_end ? d_chunk_end + c0 : nullptr);
         ZB_LAUNCHED(); ZB_CHECK_LAUNCH();
-        ZB_CUDA(cudaEventRecord(ctx->lane_scan[lane], s));
         dfl_pack_kernel<<<dim3(MB + 1, b.nb), 256, 0, s>>>(b, w.syms, w.blocks, w.codes, w.nblocks, w.chunk_off, w.chunk_bytes,
                                                           tabs, (uint32_t *)d_out, members ? 10 : 0);
         ZB_LAUNCHED(); ZB_CHECK_LAUNCH();
@@ -633,12 +613,6 @@ int deflate_launch(zb200_ctx *ctx, const uint8_t *d_in, size_t n, size_t S, int 
             ZB_LAUNCHED(); ZB_CHECK_LAUNCH();
         }
     }
-    // join: the caller's stream continues once every lane has drained
-    for (int k = 0; k < lanes; ++k) {
-        ZB_CUDA(cudaEventRecord(ctx->lane_done[k], ctx->lane_stream[k]));
-        ZB_CUDA(cudaStreamWaitEvent(user, ctx->lane_done[k], 0));
-    }
-    s = user;
     dfl_frame_kernel<<<1, 32, 0, s>>>(d_out, frame, level, strategy, finish, 1, running, sums, n, d_total);
     ZB_LAUNCHED(); ZB_CHECK_LAUNCH();
     return ZB200_OK;
@@ -663,7 +637,7 @@ size_t zb200_deflate_bound(size_t n, size_t chunk_size, int frame) {
 
 size_t zb200_deflate_scratch_bytes(size_t n, size_t chunk_size) {
     if (chunk_size == 0 || chunk_size > 0x40000000ull) return 0;
-    return zb200_ctx::kLanes * work_bytes(batch_chunks(n, chunk_size), chunk_size, max_blocks_for((uint32_t)chunk_size));
+    return work_bytes(batch_chunks(n, chunk_size), chunk_size, max_blocks_for((uint32_t)chunk_size));
 }
 
 int zb200_deflate_dev(zb200_ctx *ctx, const void *d_in, size_t n, size_t chunk_size, int level, int strategy,

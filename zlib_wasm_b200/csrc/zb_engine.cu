@@ -195,12 +195,6 @@ void zb200_destroy(zb200_ctx *ctx) {
     if (ctx->d_scratch) cudaFree(ctx->d_scratch);
     if (ctx->d_io_in) cudaFree(ctx->d_io_in);
     if (ctx->d_io_out) cudaFree(ctx->d_io_out);
-    for (int k = 0; k < zb200_ctx::kLanes; ++k) {
-        if (ctx->lane_stream[k]) cudaStreamDestroy(ctx->lane_stream[k]);
-        if (ctx->lane_done[k]) cudaEventDestroy(ctx->lane_done[k]);
-        if (ctx->lane_scan[k]) cudaEventDestroy(ctx->lane_scan[k]);
-    }
-    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     cudaGetLastError();

@@ -60,13 +60,6 @@ struct zb200_ctx {
     zb::CrcTables *d_crc_tables = nullptr;
     void *d_deflate_tables = nullptr;       // zb::DeflateDeviceTables (zb_deflate.cu)
     void *d_inflate_tables = nullptr;       // zb::InflateDeviceTables (zb_inflate.cu)
-    // deflate sub-batch pipeline: sub-batches go round-robin over these streams so that the
-    // latency-bound phases of one overlap the throughput-bound phases of the others
-    static constexpr int kLanes = 4;
-    cudaStream_t lane_stream[kLanes] = {nullptr, nullptr, nullptr, nullptr};
-    cudaEvent_t lane_done[kLanes] = {nullptr, nullptr, nullptr, nullptr};
-    cudaEvent_t lane_scan[kLanes] = {nullptr, nullptr, nullptr, nullptr};
-    cudaEvent_t ev_fork = nullptr;
 
     // grow-only device scratch (checksum accumulators, deflate/inflate workspaces)
     void *d_scratch = nullptr;
