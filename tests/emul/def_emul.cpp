@@ -48,9 +48,23 @@ extern "C" long emul_deflate_chunk(const uint8_t *data, uint32_t n, int level, i
     {
         ParseState ps; parse_init(ps, blocks.data(), n, prm);
         ParseArrays acc{data, mf.data(), mq.data(), syms.data(), 0};
-        while (ps.p < n) { uint32_t lim = ps.p + 1000 < n ? ps.p + 1000 : n; parse_steps(ps, lim, n, prm, acc); }
-        parse_finish(ps, n, prm, final_chunk != 0, acc);
-        sink.nsyms = ps.nsyms; sink.nblocks = ps.nblocks;
+        if (prm.mode != MODE_SLOW) {
+            // the kernel's split greedy parse: serial chase per tile, then per-symbol work in any order
+            std::vector<uint32_t> visited(1100);
+            uint32_t flushed = 0;
+            const bool use_m = prm.mode != MODE_HUFF;
+            while (ps.p < n) {
+                uint32_t lim = ps.p + 1000 < n ? ps.p + 1000 : n;
+                const uint32_t made = greedy_chase(ps.p, lim, use_m, acc, visited.data());
+                for (uint32_t i = made; i-- > 0;) syms[flushed + i] = greedy_symbol(visited[i], use_m, acc, flushed + i, blocks.data());
+                flushed += made;
+            }
+            sink.nsyms = flushed; sink.nblocks = greedy_finish(blocks.data(), flushed, n, prm, final_chunk != 0);
+        } else {
+            while (ps.p < n) { uint32_t lim = ps.p + 1000 < n ? ps.p + 1000 : n; parse_steps(ps, lim, n, prm, acc); }
+            parse_finish(ps, n, prm, final_chunk != 0, acc);
+            sink.nsyms = ps.nsyms; sink.nblocks = ps.nblocks;
+        }
     }
     if (sink.nblocks > blocks.size()) return -2;
     if (stats) { stats[0] = sink.nsyms; stats[1] = sink.nblocks; }

@@ -246,8 +246,10 @@ dfl_parse_kernel(Batch b, DeflateParams prm, const uint32_t *__restrict__ mfull,
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
 
+    BlockInfo *blk = blocks + (uint64_t)c * b.MB;
+    const bool greedy = prm.mode != MODE_SLOW;
     ParseState st;
-    parse_init(st, blocks + (uint64_t)c * b.MB, n, prm);
+    parse_init(st, blk, n, prm);
     ParseTileAcc acc;
     acc.stage = stage; acc.count = 0;
     uint32_t flushed = 0;                              // symbols already written to global memory
@@ -263,25 +265,43 @@ dfl_parse_kernel(Batch b, DeflateParams prm, const uint32_t *__restrict__ mfull,
         }
         __syncwarp();
         const uint32_t t1 = (t + 1) * kParseTile < n ? (t + 1) * kParseTile : n;
-        if (lane == 0 && st.p < t1) {
+        // operands of this tile, as seen by every lane
+        {
             const uint64_t m_first = (m_abs0 + (uint64_t)t * kParseTile) & ~3ull;
             const uintptr_t a_first = ((b_abs0 + (uintptr_t)t * kParseTile) & ~(uintptr_t)15) - 16;
             acc.tmf = reinterpret_cast<const uint32_t *>(pb.mf);
             acc.tmq = use_q ? reinterpret_cast<const uint32_t *>(pb.mq) : acc.tmf;
             acc.tby = reinterpret_cast<const uint8_t *>(pb.by);
-            acc.mbias = (uint32_t)(m_abs0 - m_first);              // entry of position p sits at p + m_abs0 - m_first ...
-            acc.mbias -= t * kParseTile;                           // ... minus nothing: m_first already includes the tile start
-            acc.mbias = (uint32_t)(m_abs0 - m_first);
+            acc.mbias = (uint32_t)(m_abs0 - m_first);              // entry of position p sits at tmf[p + mbias]
             acc.bbias = (uint32_t)(b_abs0 - a_first);
             acc.count = 0;
-            parse_steps(st, t1, n, prm, acc);
         }
+        if (greedy) {
+            // serial part: only the chase; the visited positions go to stage[]
+            uint32_t cnt = 0;
+            if (lane == 0 && st.p < t1) cnt = greedy_chase(st.p, t1, use_m, acc, stage);
+            const uint32_t made = __shfl_sync(0xffffffffu, cnt, 0);
+            __syncwarp();
+            // parallel part: one lane per visited position forms its symbol
+            for (uint32_t i = lane; i < made; i += 32)
+                out[flushed + i] = greedy_symbol(stage[i], use_m, acc, flushed + i, blk);
+            flushed += made;
+            __syncwarp();
+            continue;
+        }
+        if (lane == 0 && st.p < t1) parse_steps(st, t1, n, prm, acc);
         const uint32_t made = __shfl_sync(0xffffffffu, acc.count, 0);
         __syncwarp();
         for (uint32_t i = lane; i < made; i += 32) out[flushed + i] = stage[i];
         flushed += made;
         acc.count = 0;
         __syncwarp();
+    }
+    if (greedy) {
+        __syncwarp();
+        __threadfence_block();
+        if (lane == 0) nblocks[c] = greedy_finish(blk, flushed, n, prm, chunk_final(b, c));
+        return;
     }
     if (lane == 0) {
         // the trailing literal (if any) needs byte n-1: serve it straight from global memory
@@ -296,7 +316,6 @@ dfl_parse_kernel(Batch b, DeflateParams prm, const uint32_t *__restrict__ mfull,
         nblocks[c] = st.nblocks;
     }
 }
-
 
 // ---- phase 4: per-block histogram + Huffman construction -------------------------------
 __global__ void __launch_bounds__(128)

@@ -274,6 +274,71 @@ ZB_HD void parse_chunk(const uint8_t *data, uint32_t n, const uint32_t *mfull, c
     nsyms = s.nsyms; nblocks = s.nblocks;
 }
 
+// ---- greedy parse, split for the GPU ----------------------------------------------
+// With a greedy rule (deflate_fast / deflate_rle / deflate_huff) the only serial part
+// is the chase p -> p + len(p); everything else is a pure function of the visited
+// position and of the symbol's index, so it is done by all lanes afterwards:
+//   greedy_chase   serial: records the visited positions of one tile
+//   greedy_symbol  parallel: symbol word of one visited position; the symbol that
+//                  closes a block (every 16383rd) leaves the block's end offset and
+//                  loop-top position in its BlockInfo slot
+//   greedy_finish  once per chunk: turns those into byte ranges / flags, adds the
+//                  last block.  The window base at a loop top P is a closed form of
+//                  P (every slide trigger <= P has fired), so "stored form allowed"
+//                  needs no serial state either.
+ZB_HD uint32_t parse_base_at(uint32_t P, uint32_t n, const DeflateParams &prm) {
+    uint32_t base = 0;
+    while (P >= parse_next_slide(base, n, prm)) base += kWSize;
+    return base;
+}
+
+template <class Acc>
+ZB_HD uint32_t greedy_chase(uint32_t &p, uint32_t limit, bool use_m, Acc &acc, uint32_t *visited) {
+    uint32_t cnt = 0, q = p;
+    while (q < limit) {
+        const uint32_t m = use_m ? acc.mf(q) : 0u;
+        visited[cnt++] = q;
+        q += m ? (m >> 16) : 1u;
+    }
+    p = q;
+    return cnt;
+}
+
+template <class Acc>
+ZB_HD uint32_t greedy_symbol(uint32_t pos, bool use_m, Acc &acc, uint32_t g, BlockInfo *blocks) {
+    const uint32_t m = use_m ? acc.mf(pos) : 0u;
+    const uint32_t len = m ? (m >> 16) : 1u;
+    if ((g + 1) % kSymLimit == 0) {                    // this symbol fills a block (deflate.h:354-372 flush flag)
+        BlockInfo &b = blocks[g / kSymLimit];
+        b.byte_len = pos + len;                        // provisional: end offset of the block
+        b.pad = pos;                                   // provisional: loop-top position of the flush
+    }
+    return m ? (((m & 0xffff) << 16) | (len - kMinMatch)) : acc.byte(pos);
+}
+
+ZB_HD uint32_t greedy_finish(BlockInfo *blocks, uint32_t nsyms, uint32_t n, const DeflateParams &prm, bool final_chunk) {
+    const uint32_t nfull = nsyms / kSymLimit, rem = nsyms % kSymLimit;
+    uint32_t start = 0;
+    for (uint32_t k = 0; k < nfull; ++k) {
+        BlockInfo &b = blocks[k];
+        const uint32_t end = b.byte_len, top = b.pad;
+        b.sym_start = k * kSymLimit; b.sym_count = kSymLimit;
+        b.byte_start = start; b.byte_len = end - start;
+        b.flags = start >= parse_base_at(top, n, prm) ? BLK_STORED_OK : 0;
+        b.bit_start_lo = b.bit_start_hi = 0; b.pad = 0;
+        start = end;
+    }
+    uint32_t nblocks = nfull;
+    if (final_chunk || rem) {
+        BlockInfo &b = blocks[nblocks++];
+        b.sym_start = nfull * kSymLimit; b.sym_count = rem;
+        b.byte_start = start; b.byte_len = n - start;
+        b.flags = (final_chunk ? BLK_LAST : 0) | (start >= parse_base_at(n, n, prm) ? BLK_STORED_OK : 0);
+        b.bit_start_lo = b.bit_start_hi = 0; b.pad = 0;
+    }
+    return nblocks;
+}
+
 // ---- phase 4: per-block Huffman construction ---------------------------------------
 struct BlockCode {
     uint16_t lcode[288]; uint8_t llen[288];   // bit-reversed codes / lengths, literal-length alphabet
