@@ -40,8 +40,8 @@ extern "C" int emul_inflate(const uint8_t *src, uint64_t n, uint8_t *dst, uint64
     if (hs == ZB200_INF_OK) {
         static QueuedMatch q[kQueue];
         auto copy = [&](const QueuedMatch &m) {
-            const uint32_t dist = m.dist_dep & 0x7fffffffu;
-            for (uint32_t i = 0; i < m.len; ++i) dst[m.dst + i] = dst[m.dst - dist + (dist >= m.len ? i : i % dist)];
+            const uint32_t dist = qm_dist(m.packed), len = qm_len(m.packed);
+            for (uint32_t i = 0; i < len; ++i) dst[m.dst + i] = dst[m.dst - dist + (dist >= len ? i : i % dist)];
         };
         for (;;) {
             InflateEvent ev = st.run_batch(q);
@@ -49,8 +49,8 @@ extern "C" int emul_inflate(const uint8_t *src, uint64_t n, uint8_t *dst, uint64
             if (ev.kind == EV_BATCH) {
                 // the device runs independent matches concurrently: replay them in REVERSE
                 // order (any order must give the same bytes), then the dependent ones in order
-                for (int i = (int)ev.len - 1; i >= 0; --i) if (!(q[i].dist_dep >> 31)) copy(q[i]);
-                for (uint32_t i = 0; i < ev.len; ++i) if (q[i].dist_dep >> 31) copy(q[i]);
+                for (int i = (int)ev.len - 1; i >= 0; --i) if (!qm_dep(q[i].packed)) copy(q[i]);
+                for (uint32_t i = 0; i < ev.len; ++i) if (qm_dep(q[i].packed)) copy(q[i]);
             } else {
                 memcpy(dst + ev.dst, src + ev.src, ev.len);
             }

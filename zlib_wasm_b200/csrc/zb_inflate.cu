@@ -45,35 +45,36 @@ __device__ __forceinline__ void exec_queue(uint8_t *dst, const QueuedMatch *q, u
     for (uint32_t base = 0; base < count; base += 32) {
         const bool mine = base + lane < count;
         QueuedMatch e;
-        e.dst = 0; e.len = 0; e.dist_dep = 0;
+        e.dst = 0; e.packed = 0;
         if (mine) e = q[base + lane];
-        if (mine && !(e.dist_dep >> 31)) {
+        if (mine && !qm_dep(e.packed)) {
+            const uint32_t len = qm_len(e.packed);
             uint8_t *d = dst + e.dst;
-            const uint8_t *s = d - e.dist_dep;                 // dist >= len: source and destination do not overlap
+            const uint8_t *s = d - qm_dist(e.packed);          // dist >= len: source and destination do not overlap
             uint32_t i = 0;
-            for (; i + 8 <= e.len; i += 8) {
+            for (; i + 8 <= len; i += 8) {
                 uint8_t t[8];
 #pragma unroll
                 for (int k = 0; k < 8; ++k) t[k] = s[i + k];
 #pragma unroll
                 for (int k = 0; k < 8; ++k) d[i + k] = t[k];
             }
-            for (; i < e.len; ++i) d[i] = s[i];
+            for (; i < len; ++i) d[i] = s[i];
         }
     }
     __syncwarp(full);
     for (uint32_t base = 0; base < count; base += 32) {
         const bool mine = base + lane < count;
-        uint32_t depmask = __ballot_sync(full, mine && (q[base + lane].dist_dep >> 31));
+        uint32_t depmask = __ballot_sync(full, mine && qm_dep(q[base + lane].packed));
         while (depmask) {
             const int j = __ffs(depmask) - 1;
             depmask &= depmask - 1;
             const QueuedMatch m = q[base + j];
-            const uint32_t dist = m.dist_dep & 0x7fffffffu;
+            const uint32_t dist = qm_dist(m.packed), len = qm_len(m.packed);
             uint8_t *d = dst + m.dst;
             const uint8_t *s = d - dist;
-            if (dist >= m.len) { for (uint32_t i = lane; i < m.len; i += 32) d[i] = s[i]; }
-            else { for (uint32_t i = lane; i < m.len; i += 32) d[i] = s[i % dist]; }   // byte-serial semantics (inffast.c:249-260)
+            if (dist >= len) { for (uint32_t i = lane; i < len; i += 32) d[i] = s[i]; }
+            else { for (uint32_t i = lane; i < len; i += 32) d[i] = s[i % dist]; }   // byte-serial semantics (inffast.c:249-260)
             __syncwarp(full);
         }
     }
@@ -197,7 +198,7 @@ huff_decode_warp(const uint8_t *src, uint64_t in_len, uint8_t *dst, uint64_t out
             if (is_m) {
                 const bool dep = dist < len || mydst - dist + len > qfirst;
                 QueuedMatch m;
-                m.dst = mydst; m.len = len; m.dist_dep = dist | (dep ? 0x80000000u : 0u);
+                m.dst = (uint32_t)mydst; m.packed = qm_pack(len, dist, dep);
                 q[qcount + __popc(mmask & ((1u << lane) - 1u))] = m;
             }
             qcount += __popc(mmask);
@@ -251,7 +252,8 @@ inflate_kernel(const uint8_t *__restrict__ in, uint8_t *out, const zb200_member 
         InflateState st;
         int hs = ZB200_INF_OK;
         if (lane == 0) {
-            st.init(src, mb.in_len, dst, mb.out_cap, &sh.scr[warp], sh.fixed_lit, sh.fixed_dist, &sh.fmt);
+            st.init(src, mb.in_len, dst, mb.out_cap < 0xfffffff0ull ? mb.out_cap : 0xfffffff0ull, &sh.scr[warp],
+                    sh.fixed_lit, sh.fixed_dist, &sh.fmt);   // queue entries hold 32-bit output offsets
             st.huff_external = kWarpParallelHuffman ? 1 : 0;
             if (mb.resume_bit) st.resume(mb.resume_bit, mb.resume_out, wrap);
             else hs = st.parse_header(wrap);

@@ -52,10 +52,13 @@ struct InflateScratch {
 // overlap; the others run afterwards, in order, striped over the warp.
 constexpr uint32_t kQueue = 64;
 struct QueuedMatch {
-    uint64_t dst;                      // output position
-    uint32_t len;
-    uint32_t dist_dep;                 // distance | (dependent ? 0x80000000 : 0)
+    uint32_t dst;                      // output position (members are limited to < 4 GiB of output)
+    uint32_t packed;                   // len (bits 0..8) | dist << 9 (bits 9..24) | dependent << 31
 };
+ZB_HD uint32_t qm_pack(uint32_t len, uint32_t dist, bool dep) { return len | (dist << 9) | (dep ? 0x80000000u : 0u); }
+ZB_HD uint32_t qm_len(uint32_t pk) { return pk & 0x1ffu; }
+ZB_HD uint32_t qm_dist(uint32_t pk) { return (pk >> 9) & 0xffffu; }
+ZB_HD bool qm_dep(uint32_t pk) { return (pk >> 31) != 0; }
 
 // Build a two-level decode table from code lengths (the job of inftrees.c:32-299).
 // Returns 0 = complete code, 1 = incomplete, 2 = no codes at all, -1 = over-subscribed
@@ -443,26 +446,33 @@ struct InflateState {
             if (b > 56 || nx >= in_len) return 0;
             h |= (uint64_t)in[nx++] << b; b += 8;
         }
-        const uint64_t in_end = in_len - 16;
         const uint64_t room = out_cap - 264;
-        if (pos > room) { hold = h; bits = b; next = nx; return 0; }
+        if (pos > room || nx > in_len - 16) { hold = h; bits = b; next = nx; return 0; }
         uint64_t span = room - pos;
         if (span > 0x40000000ull) span = 0x40000000ull;
-        uint8_t *o = out + pos;                         // 32-bit offsets from here on
-        uint32_t rel = 0;
-        const uint32_t lim = (uint32_t)span;
+        const uint32_t lim = (uint32_t)span;            // offsets below are 32-bit, relative to `o`
+        uint8_t *o = out + pos;
+        const uint32_t base = (uint32_t)pos;            // low word of the absolute position (members < 4 GiB)
+        const uint32_t near0 = pos < 65536 ? (uint32_t)pos : 65536u;   // for the "too far back" test
+        // first parked destination relative to `o` (may be negative when parked by the careful path)
+        int32_t first_rel = count ? (int32_t)((int64_t)first_dst - (int64_t)pos) : 0;
+        const uint8_t *ip = in + nx, *ip_end = in + (in_len - 16);
         const uint32_t *L = lt, *D = dt;
+        uint32_t rel = 0;
         int reason = 0;
-        while (nx <= in_end && rel <= lim) {
-            if (b < 32) { h |= (uint64_t)(*reinterpret_cast<const uint32_t *>(in + nx)) << b; nx += 4; b += 32; }
+        for (;;) {
+            if (b < 32) {
+                if (ip > ip_end) break;                  // leaving the safe zone: careful path takes over
+                h |= (uint64_t)(*reinterpret_cast<const uint32_t *>(ip)) << b; ip += 4; b += 32;
+            }
+            if (rel > lim) break;
             uint32_t e = L[(uint32_t)h & ((1u << kLitRoot) - 1)];
-            if (ZB_E_OP(e) == OP_LIT) {                 // the common case: a literal straight from the root table
-                const int k = (int)ZB_E_BITS(e);
+            if ((e & 0xf00u) == 0) {                     // OP_LIT == 0: a literal straight from the root table
+                const int k = (int)(e & 0xffu);
                 h >>= k; b -= k;
-                o[rel++] = (uint8_t)ZB_E_VAL(e);
+                o[rel++] = (uint8_t)(e >> 16);
                 continue;
             }
-            const uint64_t h0 = h, nx0 = nx; const int b0 = b;       // rewind point
             if (ZB_E_OP(e) == OP_SUB) {
                 const uint32_t sub = ZB_E_VAL(e) + (((uint32_t)(h >> kLitRoot)) & ((1u << ZB_E_EXTRA(e)) - 1u));
                 h >>= kLitRoot; b -= kLitRoot;
@@ -470,13 +480,14 @@ struct InflateState {
             }
             { const int k = (int)ZB_E_BITS(e); h >>= k; b -= k; }
             const uint32_t op = ZB_E_OP(e);
-            if (op == OP_LIT) { o[rel++] = (uint8_t)ZB_E_VAL(e); continue; }
+            if (op == OP_LIT) { o[rel++] = (uint8_t)(e >> 16); continue; }
             if (op == OP_EOB) { in_block = 0; reason = 2; break; }
-            if (op != OP_BASE) { h = h0; b = b0; nx = nx0; break; }
+            // In the safe zone the whole symbol is present, so a bad code is final (no rewind needed).
+            if (op != OP_BASE) { status = ZB200_INF_LITLEN_CODE; reason = 3; break; }
             const uint32_t x = ZB_E_EXTRA(e);
             const uint32_t len = ZB_E_VAL(e) + ((uint32_t)h & ((1u << x) - 1u));
             h >>= x; b -= (int)x;
-            if (b < 32) { h |= (uint64_t)(*reinterpret_cast<const uint32_t *>(in + nx)) << b; nx += 4; b += 32; }
+            if (b < 32) { h |= (uint64_t)(*reinterpret_cast<const uint32_t *>(ip)) << b; ip += 4; b += 32; }   // ip <= ip_end + 4: still 12 bytes of slack
             uint32_t d = D[(uint32_t)h & ((1u << kDistRoot) - 1)];
             if (ZB_E_OP(d) == OP_SUB) {
                 const uint32_t sub = ZB_E_VAL(d) + (((uint32_t)(h >> kDistRoot)) & ((1u << ZB_E_EXTRA(d)) - 1u));
@@ -484,19 +495,18 @@ struct InflateState {
                 d = D[sub];
             }
             { const int k = (int)ZB_E_BITS(d); h >>= k; b -= k; }
-            if (ZB_E_OP(d) != OP_BASE) { h = h0; b = b0; nx = nx0; break; }
+            if (ZB_E_OP(d) != OP_BASE) { status = ZB200_INF_DIST_CODE; reason = 3; break; }
             const uint32_t dx = ZB_E_EXTRA(d);
             const uint32_t dist = ZB_E_VAL(d) + ((uint32_t)h & ((1u << dx) - 1u));
             h >>= dx; b -= (int)dx;
-            const uint64_t at = pos + rel;
-            if (dist > at) { h = h0; b = b0; nx = nx0; break; }
-            const bool dep = dist < len || (count && at - dist + len > first_dst);
-            if (!count) first_dst = at;
-            q[count].dst = at; q[count].len = len; q[count].dist_dep = dist | (dep ? 0x80000000u : 0u);
+            if (dist > rel + near0) { status = ZB200_INF_DIST_FAR; reason = 3; break; }   // inffast.c:152-161
+            const bool dep = dist < len || (count && (int32_t)(rel + len - dist) > first_rel);
+            if (!count) { first_rel = (int32_t)rel; first_dst = pos + rel; }
+            q[count].dst = base + rel; q[count].packed = qm_pack(len, dist, dep);
             rel += len;
             if (++count == kQueue) { reason = 1; break; }
         }
-        hold = h; bits = b; next = nx; pos += rel;
+        hold = h; bits = b; next = (uint64_t)(ip - in); pos += rel;
         return reason;
     }
 
@@ -513,13 +523,19 @@ struct InflateState {
                 const int r = fast_symbols(q, count, first_dst);
                 if (r == 1) break;
                 if (r == 2) continue;                  // block done: step() reads the next header
+                if (r == 3) {                          // a final decoding error met in the fast loop
+                    ev = done(status);
+                    if (!count) return ev;
+                    parked = ev; has_parked = 1;
+                    break;
+                }
             }
             ev = step();
             if (ev.kind == EV_MATCH) {
                 // dependent: overlaps itself, or may read what an earlier parked match will write
                 const bool dep = ev.dist < ev.len || (count && ev.dst - ev.dist + ev.len > first_dst);
                 if (!count) first_dst = ev.dst;
-                q[count].dst = ev.dst; q[count].len = ev.len; q[count].dist_dep = ev.dist | (dep ? 0x80000000u : 0u);
+                q[count].dst = (uint32_t)ev.dst; q[count].packed = qm_pack(ev.len, ev.dist, dep);
                 if (++count == kQueue) break;
                 continue;
             }
