@@ -227,7 +227,7 @@ __global__ void __launch_bounds__(kInfWarps * 32)
 inflate_kernel(const uint8_t *__restrict__ in, uint8_t *out, const zb200_member *__restrict__ members,
                uint32_t n_members, int wrap, zb200_member_result *__restrict__ results,
                const InflateDeviceTables *__restrict__ tabs, unsigned int *__restrict__ counter,
-               uint64_t *__restrict__ seg_off, uint64_t *__restrict__ seg_len) {
+               const uint32_t *__restrict__ order, uint64_t *__restrict__ seg_off, uint64_t *__restrict__ seg_len) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     InflateShared &sh = *reinterpret_cast<InflateShared *>(smem_raw);
     {
@@ -242,7 +242,7 @@ inflate_kernel(const uint8_t *__restrict__ in, uint8_t *out, const zb200_member 
 
     for (;;) {
         unsigned int m = 0;
-        if (lane == 0) m = atomicAdd(counter, 1u);
+        if (lane == 0) { m = atomicAdd(counter, 1u); if (m < n_members) m = order[m]; }   // largest members first
         m = __shfl_sync(full, m, 0);
         if (m >= n_members) break;
         const zb200_member mb = members[m];
@@ -307,6 +307,25 @@ inflate_kernel(const uint8_t *__restrict__ in, uint8_t *out, const zb200_member 
     }
 }
 
+// Members are handed out by an atomic counter.  A member is decoded serially by its
+// warp, so the launch ends when the slowest member ends: hand out the largest first
+// (bucketed by log2 of the compressed size; one CTA builds the order).
+__global__ void __launch_bounds__(1024)
+inflate_order_kernel(const zb200_member *__restrict__ members, uint32_t n, uint32_t *__restrict__ order) {
+    __shared__ unsigned int hist[64];
+    if (threadIdx.x < 64) hist[threadIdx.x] = 0;
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) atomicAdd(&hist[63 - __clzll((long long)(members[i].in_len | 1))], 1u);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int run = 0;
+        for (int bkt = 63; bkt >= 0; --bkt) { const unsigned int c = hist[bkt]; hist[bkt] = run; run += c; }
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x)
+        order[atomicAdd(&hist[63 - __clzll((long long)(members[i].in_len | 1))], 1u)] = i;
+}
+
 // Trailer check: inflate.c:1183-1219 ("incorrect data check" / "incorrect length check").
 __global__ void inflate_verify_kernel(zb200_member_result *__restrict__ results, uint32_t n, int verify,
                                       const uint32_t *__restrict__ crc, const uint32_t *__restrict__ adler) {
@@ -356,9 +375,9 @@ static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 // scratch layout for one call
 struct InflateWork {
-    unsigned int *counter; uint64_t *seg_off, *seg_len; uint32_t *crc, *adler; CkAccum *acc;
+    unsigned int *counter; uint64_t *seg_off, *seg_len; uint32_t *crc, *adler, *order; CkAccum *acc;
     static size_t bytes(size_t n) {
-        return 256 + align_up(n * 8, 256) * 2 + align_up(n * 4, 256) * 2 + align_up(n * sizeof(CkAccum), 256);
+        return 256 + align_up(n * 8, 256) * 2 + align_up(n * 4, 256) * 3 + align_up(n * sizeof(CkAccum), 256);
     }
     void carve(void *base, size_t n) {
         uint8_t *p = (uint8_t *)base;
@@ -367,6 +386,7 @@ struct InflateWork {
         seg_len = (uint64_t *)p; p += align_up(n * 8, 256);
         crc = (uint32_t *)p; p += align_up(n * 4, 256);
         adler = (uint32_t *)p; p += align_up(n * 4, 256);
+        order = (uint32_t *)p; p += align_up(n * 4, 256);
         acc = (CkAccum *)p;
     }
 };
@@ -378,13 +398,16 @@ int inflate_launch(zb200_ctx *ctx, const uint8_t *d_in, uint8_t *d_out, const zb
     InflateWork w;
     w.carve(d_work, n);
     ZB_CUDA(cudaMemsetAsync(w.counter, 0, 256, s));
-    const int per_sm = 6;                                      // 6 CTAs x 4 warps x 6.9 KiB tables fit one SM
+    inflate_order_kernel<<<1, 1024, 0, s>>>(d_members, (uint32_t)n, w.order);
+    ZB_LAUNCHED();
+    ZB_CHECK_LAUNCH();
+    const int per_sm = 7;                                      // 7 CTAs x 4 warps x 7.3 KiB of tables + queue fit one SM
     size_t ctas = (n + kInfWarps - 1) / kInfWarps;
     const size_t cap = (size_t)ctx->sm_count * per_sm;
     if (ctas > cap) ctas = cap;
     inflate_kernel<<<(unsigned)ctas, kInfWarps * 32, sizeof(InflateShared), s>>>(
         d_in, d_out, d_members, (uint32_t)n, wrap, d_results,
-        (const InflateDeviceTables *)ctx->d_inflate_tables, w.counter, w.seg_off, w.seg_len);
+        (const InflateDeviceTables *)ctx->d_inflate_tables, w.counter, w.order, w.seg_off, w.seg_len);
     ZB_LAUNCHED();
     ZB_CHECK_LAUNCH();
     const int which = wrap == ZB200_WRAP_ZLIB ? ZB200_ADLER32 : wrap == ZB200_WRAP_AUTO ? (ZB200_CRC32 | ZB200_ADLER32) : ZB200_CRC32;
