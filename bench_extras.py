@@ -4,8 +4,9 @@ roofline fraction and the reference CPU timed beside it on rank 0.
 
   deflate_l1  config C4: level 1, Markov text, 256 KiB Z_FULL_FLUSH chunks
   deflate_l6  config C5: level 6, mixed-entropy data, same chunking (ratio vs reference)
-  inflate     config C3: multi-member gzip, members log-uniform 64 KiB..1 MiB,
-              compressed by the REFERENCE at level 6, one warp per member
+  inflate     config C3: multi-member gzip, members of 64 KiB..1 MiB at level 6 (made on
+              the GPU; byte-identical to the reference's gzip members, re-checked on a
+              sample), one warp per member, 4x the deflate workload size
 """
 import concurrent.futures as cf
 import ctypes as C

@@ -62,12 +62,8 @@ def test_zlib_surface_exported():
     (the reference's zlib.h names and the src/wasm_module.c exports)."""
     src = open(os.path.join(ROOT, "include", "zb200_zlib.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    body = src[src.index("/* ---- basic") if "/* ---- basic" in src else 0:]
-    body = src.split("#endif /* ZLIB_H */")[-1] if "#endif /* ZLIB_H */" in open(os.path.join(ROOT, "include", "zb200_zlib.h")).read() else src
-    # after comment stripping the marker is gone: take everything after the last #define block instead
-    body = src[src.rindex("#define inflateInit2"):]
-    names = sorted(set(re.findall(r"\b([A-Za-z_][A-Za-z0-9_]*)\s*\(", body)) - {"inflateInit2", "inflateInit2_"} | {"inflateInit2_"})
-    names = [n for n in names if n not in ("defined", "sizeof", "push", "pop", "visibility")]
+    body = src[src.rindex("#define inflateInit2"):]          # the prototypes follow the last init macro
+    names = sorted(set(re.findall(r"\b([A-Za-z_][A-Za-z0-9_]*)\s*\(", body)) - {"inflateInit2", "defined", "sizeof"})
     L = C.CDLL(zb.LIB_PATH, mode=C.RTLD_LOCAL)
     missing = [n for n in names if not hasattr(L, n)]
     assert len(names) >= 45 and not missing, missing
