@@ -91,7 +91,7 @@ ZB_HD CkPart ck_make_part(const uint8_t *seg, uint64_t seg_len, uint32_t part, u
 
 // Contribution of thread t (of T) to the checksums of the segment, over the
 // body blocks of part `p`.  TabFn(j, v) returns the Horner table entry for byte j of v.
-template <bool DO_CRC, bool DO_ADLER, class TabFn>
+template <bool DO_CRC, bool DO_ADLER, int UNROLL = 4, class TabFn>
 ZB_HD CkPartial ck_thread_body(const CkPart &p, uint32_t t, uint32_t T, TabFn tab,
                                const uint32_t *x2n, uint32_t x32) {
     CkPartial out{0, 0, 0};
@@ -127,12 +127,12 @@ ZB_HD CkPartial ck_thread_body(const CkPart &p, uint32_t t, uint32_t T, TabFn ta
     };
 
     uint64_t m = 0;
-    for (; m + 4 <= M; m += 4) {                          // 4 x 16 B in flight per thread
-        U4 w0 = load_block(blk + (m + 0) * T);
-        U4 w1 = load_block(blk + (m + 1) * T);
-        U4 w2 = load_block(blk + (m + 2) * T);
-        U4 w3 = load_block(blk + (m + 3) * T);
-        step(w0); step(w1); step(w2); step(w3);
+    for (; m + UNROLL <= M; m += UNROLL) {                // UNROLL x 16 B in flight per thread
+        U4 w[UNROLL];
+#pragma unroll
+        for (int j = 0; j < UNROLL; ++j) w[j] = load_block(blk + (m + j) * T);
+#pragma unroll
+        for (int j = 0; j < UNROLL; ++j) step(w[j]);
     }
     for (; m < M; ++m) step(load_block(blk + m * T));
 
