@@ -77,42 +77,97 @@ ZB_HD uint32_t hash3(const uint8_t *s) {
 // Result encoding: 0 = no match of length >= 3, else (len << 16) | dist.
 struct MatchPair { uint32_t full, quarter; };
 
+// Four bytes at an arbitrary address, little-endian, from two aligned words.
+ZB_HD uint32_t load4(const uint8_t *p) {
+#if defined(__CUDA_ARCH__)
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3);
+    return __funnelshift_r(w[0], w[1], (uint32_t)(a & 3) * 8);
+#else
+    return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
+#endif
+}
+ZB_HD uint32_t ctz32(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+    return (uint32_t)__ffs((int)x) - 1u;
+#else
+    return (uint32_t)__builtin_ctz(x);
+#endif
+}
+
+// The walk over one position's hash chain, cut into the three pieces the kernel
+// schedules separately (so that the lanes of a warp run the same piece together):
+//   screen()   the quick rejects of deflate.c:1449-1452 for the current candidate
+//   measure()  common prefix length of a candidate that passed, update of the best
+//   advance()  chain budget / quarter snapshot / next link (deflate.c:1481-1482)
+struct MatchWalk {
+    uint32_t p, q;                    // position, current candidate
+    uint32_t best, best_dist, examined;
+    uint32_t maxlen, nice;
+    uint32_t quarter; bool have_q;
+
+    // Returns false if the position has no candidate at all (result() is then 0/0).
+    ZB_HD bool begin(uint32_t n, const uint16_t *prev_dist, uint32_t pos, const DeflateParams &prm) {
+        p = pos; best = kMinMatch - 1; best_dist = 0; examined = 0; quarter = 0; have_q = false;
+        if (p + kMinMatch > n) return false;              // lookahead < MIN_MATCH: no insertion, no search
+        const uint32_t d = prev_dist[p];
+        if (d == 0 || d > (uint32_t)kMaxDist) return false;   // deflate.c:1857/1958: head must be within MAX_DIST
+        const uint32_t look = n - p;
+        maxlen = look < (uint32_t)kMaxMatch ? look : (uint32_t)kMaxMatch;
+        nice = (uint32_t)prm.nice > look ? look : (uint32_t)prm.nice;                  // deflate.c:1396
+        q = p - d;
+        return true;
+    }
+    // best < maxlen holds whenever a candidate is screened (see the nice clamp).
+    ZB_HD bool screen(const uint8_t *data) const {
+        const uint8_t *scan = data + p, *m = data + q;
+        const uint32_t a = m[best], b0 = m[0], b1 = m[1];  // the three loads are independent: issue them together
+        return a == scan[best] && b0 == scan[0] && b1 == scan[1];
+    }
+    // Returns true if the walk ends here (a match of at least nice_match).
+    ZB_HD bool measure(const uint8_t *data) {
+        const uint8_t *scan = data + p, *m = data + q;
+        uint32_t len = 2;                                 // m[2]==scan[2] follows from the equal hash when bytes 0,1 agree
+        while (len + 8 <= maxlen) {                       // four bytes per step while the aligned reads stay inside the chunk
+            const uint32_t x = load4(m + len) ^ load4(scan + len);
+            if (x) { len += ctz32(x) >> 3; goto measured; }
+            len += 4;
+        }
+        while (len < maxlen && m[len] == scan[len]) ++len;
+    measured:
+        if (len > best) {
+            best = len; best_dist = p - q;
+            if (len >= nice) return true;
+        }
+        return false;
+    }
+    // Returns true when the walk is over.
+    ZB_HD bool advance(const uint16_t *prev_dist, const DeflateParams &prm) {
+        ++examined;
+        if (examined == ((uint32_t)prm.chain >> 2) && !have_q) { quarter = best >= (uint32_t)kMinMatch ? (best << 16) | best_dist : 0; have_q = true; }
+        if (examined == (uint32_t)prm.chain) return true; // deflate.c:1482 --chain_length
+        const uint32_t d2 = prev_dist[q];
+        if (d2 == 0) return true;
+        q -= d2;
+        return p - q >= (uint32_t)kMaxDist;               // deflate.c:1481: cur_match > limit
+    }
+    ZB_HD MatchPair result() const {
+        MatchPair r;
+        r.full = best >= (uint32_t)kMinMatch ? (best << 16) | best_dist : 0;
+        r.quarter = have_q ? quarter : r.full;
+        return r;
+    }
+};
+
 ZB_HD MatchPair match_at(const uint8_t *data, uint32_t n, const uint16_t *prev_dist, uint32_t p,
                          const DeflateParams &prm) {
-    MatchPair r{0, 0};
-    if (p + kMinMatch > n) return r;                  // lookahead < MIN_MATCH: no insertion, no search
-    uint32_t d = prev_dist[p];
-    if (d == 0 || d > (uint32_t)kMaxDist) return r;   // deflate.c:1857/1958: head must be within MAX_DIST
-    const uint32_t look = n - p;
-    const uint32_t maxlen = look < (uint32_t)kMaxMatch ? look : (uint32_t)kMaxMatch;
-    const uint32_t nice = (uint32_t)prm.nice > look ? look : (uint32_t)prm.nice;      // deflate.c:1396
-    const uint32_t chain_q = (uint32_t)prm.chain >> 2;
-    const uint8_t *scan = data + p;
-    uint32_t best = kMinMatch - 1, best_dist = 0, examined = 0;
-    uint32_t q = p - d;
-    bool have_q = false;
-    for (;;) {
-        const uint8_t *m = data + q;
-        // quick rejects (deflate.c:1449-1452); best < maxlen holds here (see nice clamp)
-        if (m[best] == scan[best] && m[0] == scan[0] && m[1] == scan[1]) {
-            uint32_t len = 2;                         // m[2]==scan[2] follows from the equal hash when bytes 0,1 agree
-            while (len < maxlen && m[len] == scan[len]) ++len;
-            if (len > best) {
-                best = len; best_dist = p - q;
-                if (len >= nice) break;
-            }
+    MatchWalk w;
+    if (w.begin(n, prev_dist, p, prm))
+        for (;;) {
+            if (w.screen(data) && w.measure(data)) break;
+            if (w.advance(prev_dist, prm)) break;
         }
-        ++examined;
-        if (examined == chain_q && !have_q) { r.quarter = best >= (uint32_t)kMinMatch ? (best << 16) | best_dist : 0; have_q = true; }
-        if (examined == (uint32_t)prm.chain) break;  // deflate.c:1482 --chain_length
-        const uint32_t d2 = prev_dist[q];
-        if (d2 == 0) break;
-        q -= d2;
-        if (p - q >= (uint32_t)kMaxDist) break;       // deflate.c:1481: cur_match > limit
-    }
-    r.full = best >= (uint32_t)kMinMatch ? (best << 16) | best_dist : 0;
-    if (!have_q) r.quarter = r.full;
-    return r;
+    return w.result();
 }
 
 // Z_RLE (deflate.c:2051-2115): run of the previous byte, distance 1 only.
