@@ -166,70 +166,23 @@ __global__ void __launch_bounds__(32) dfl_chain_kernel(Batch b, uint16_t *__rest
 }
 
 // ---- phase 2: longest match per position --------------------------------------------
-// Scheduling inside a warp.  Chain lengths and match lengths differ wildly between
-// neighbouring positions; with one position per thread and the whole walk inline only
-// 8 of 32 lanes were active on average (ncu).  Here:
-//   * positions are not bound to lanes: a warp owns kMatchPerWarp consecutive positions
-//     and a lane takes the next unprocessed one as soon as its walk ends;
-//   * a walk is cut into screen / measure / advance (MatchWalk).  Lanes whose candidate
-//     passed the screen WAIT; the (long, variable) measure loop only runs once half the
-//     warp is waiting or nobody else can make progress, so it runs with many lanes.
-constexpr uint32_t kMatchPerWarp = 512, kMatchWarps = 8;
-
-__global__ void __launch_bounds__(kMatchWarps * 32)
+// One position per thread.  The walk itself (MatchWalk: screen / measure / advance) is
+// irregular -- ncu: 8 of 32 lanes active on average, issue slots 74 % busy -- and four
+// re-schedulings of it inside the warp were measured and dropped:
+// they raise the active-lane count but add as many scheduling instructions as they save.
+__global__ void __launch_bounds__(256)
 dfl_match_kernel(Batch b, DeflateParams prm, const uint16_t *__restrict__ prev_all,
                  uint32_t *__restrict__ mfull, uint32_t *__restrict__ mquarter) {
     const uint32_t c = blockIdx.y;
     const uint32_t n = chunk_len(b, c);
-    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t p = blockIdx.x * 256 + threadIdx.x;
+    if (p >= n) return;
     const uint64_t off = (uint64_t)c * b.S;
     const uint8_t *data = b.in + off;
-    const uint16_t *prev = prev_all + off;
-    uint32_t next = (blockIdx.x * kMatchWarps + warp) * kMatchPerWarp;
-    if (next >= n) return;
-    const uint32_t wend = next + kMatchPerWarp < n ? next + kMatchPerWarp : n;
-    if (prm.mode == MODE_RLE) {
-        for (uint32_t p = next + lane; p < wend; p += 32) mfull[off + p] = rle_at(data, n, p);
-        return;
-    }
-    const unsigned full = 0xffffffffu;
-    MatchWalk w;
-    bool busy = false, waiting = false;
-    auto finish = [&]() {
-        const MatchPair r = w.result();
-        mfull[off + w.p] = r.full;
-        if (prm.need_quarter) mquarter[off + w.p] = r.quarter;
-        busy = false;
-    };
-    for (;;) {
-        const uint32_t idle = __ballot_sync(full, !busy);
-        if (idle) {
-            if (next < wend) {
-                const uint32_t mine = next + __popc(idle & ((1u << lane) - 1u));
-                if (!busy && mine < wend) {
-                    busy = w.begin(n, prev, mine, prm);
-                    if (!busy) { mfull[off + mine] = 0; if (prm.need_quarter) mquarter[off + mine] = 0; }
-                }
-                next += __popc(idle);
-            } else if (idle == full) {
-                break;
-            }
-        }
-        // screen round: every running lane checks its current candidate
-        if (busy && !waiting) {
-            if (w.screen(data)) waiting = true;
-            else if (w.advance(prev, prm)) finish();
-        }
-        const uint32_t wmask = __ballot_sync(full, waiting);
-        const uint32_t rmask = __ballot_sync(full, busy && !waiting);
-        // measure round: when enough lanes wait for it, or nothing else can run
-        if (wmask && (__popc(wmask) >= 16 || (rmask == 0 && next >= wend) || rmask == 0)) {
-            if (waiting) {
-                waiting = false;
-                if (w.measure(data) || w.advance(prev, prm)) finish();
-            }
-        }
-    }
+    if (prm.mode == MODE_RLE) { mfull[off + p] = rle_at(data, n, p); return; }
+    const MatchPair r = match_at(data, n, prev_all + off, p, prm);
+    mfull[off + p] = r.full;
+    if (prm.need_quarter) mquarter[off + p] = r.quarter;
 }
 
 // ---- phase 3: parse, one chunk per warp (lane 0 walks the tables) ---------------------
@@ -659,9 +612,8 @@ int deflate_launch(zb200_ctx *ctx, const uint8_t *d_in, size_t n, size_t S, int 
             ZB_LAUNCHED(); ZB_CHECK_LAUNCH();
         }
         if (prm.mode != MODE_HUFF) {
-            const uint32_t per_cta = kMatchPerWarp * kMatchWarps;
-            dim3 g((unsigned)((S + per_cta - 1) / per_cta), b.nb);
-            dfl_match_kernel<<<g, kMatchWarps * 32, 0, s>>>(b, prm, w.prev, w.mfull, w.mquarter);
+            dim3 g((unsigned)((S + 255) / 256), b.nb);
+            dfl_match_kernel<<<g, 256, 0, s>>>(b, prm, w.prev, w.mfull, w.mquarter);
             ZB_LAUNCHED(); ZB_CHECK_LAUNCH();
         }
         dfl_parse_kernel<<<b.nb, 32, 0, s>>>(b, prm, w.mfull, w.mquarter, w.syms, w.blocks, w.nblocks);
