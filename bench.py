@@ -359,7 +359,33 @@ def main():
     if not args.no_extras:
         try:
             import bench_extras
-            extra = bench_extras.run(ctx, rank, world, args.extras_mib << 20, barrier)
+            extra = {}
+            # the two checksums on their own ("report both separate and fused"), same 4 GiB shard
+            for name, w in (("crc32_only", zb.CRC32), ("adler32_only", zb.ADLER32)):
+                def one(w=w):
+                    r = L.zb200_checksum_dev(ctx.handle, d_in.data_ptr(), n, w, 0, 1, d_out2.data_ptr(), sp)
+                    if r != 0:
+                        raise zb.ZB200Error(r, "zb200_checksum_dev")
+                for _ in range(3):
+                    one()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                barrier()
+                a.record(stream)
+                for _ in range(args.steps):
+                    one()
+                b.record(stream)
+                barrier()
+                ms1 = a.elapsed_time(b) / args.steps
+                if world > 1:
+                    t = torch.tensor([ms1], dtype=torch.float64, device="cuda")
+                    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                    ms1 = float(t.item())
+                pk, _src = peaks()
+                extra[name] = {"value": round(world * n / (ms1 * 1e-3) / 1e9, 1), "unit": UNIT, "ms_per_step": round(ms1, 4),
+                               "roofline_frac": round(n / (ms1 * 1e-3) / 1e9 / pk, 4)}
+            del d_in                                   # free the 4 GiB shard before the deflate / inflate workloads
+            torch.cuda.empty_cache()
+            extra.update(bench_extras.run(ctx, rank, world, args.extras_mib << 20, barrier))
             if line is not None:
                 line["extra"] = extra
         except Exception as e:  # a side measurement must never take the headline down
