@@ -5,6 +5,8 @@
 #include <stddef.h>
 #include <string.h>
 #include "../../zlib_wasm_b200/csrc/zb_inflate.cuh"
+#include "../../zlib_wasm_b200/csrc/zb_inflate_round.cuh"
+#include <vector>
 
 using namespace zb;
 
@@ -49,6 +51,135 @@ extern "C" int emul_inflate(const uint8_t *src, uint64_t n, uint8_t *dst, uint64
             if (ev.kind == EV_BATCH) {
                 // the device runs independent matches concurrently: replay them in REVERSE
                 // order (any order must give the same bytes), then the dependent ones in order
+                for (int i = (int)ev.len - 1; i >= 0; --i) if (!qm_dep(q[i].packed)) copy(q[i]);
+                for (uint32_t i = 0; i < ev.len; ++i) if (qm_dep(q[i].packed)) copy(q[i]);
+            } else {
+                memcpy(dst + ev.dst, src + ev.src, ev.len);
+            }
+        }
+    } else st.status = hs;
+    *in_used = st.in_used; *out_len = st.pos; *check = st.stored_check; *isize = st.stored_isize;
+    *ck_bit = st.ck_bit; *ck_out = st.ck_out; *kind = st.wrap_kind;
+    return st.status;
+}
+
+
+// ---- the warp-parallel rounds (zb_inflate_round.cuh) replayed with loops over the 32 lanes.
+// The per-lane phases are the product's; only the cross-lane glue (shuffles, ballots,
+// scans) of zb_inflate.cu huff_rounds_warp is restated here.
+struct RoundStats { uint64_t rounds, fix_passes, fix_lane_runs, serial_returns, matches, dep_matches; };
+static RoundStats g_stats;
+extern "C" void emul_round_stats(uint64_t *o) { memcpy(o, &g_stats, sizeof g_stats); }
+
+static int host_rounds(const uint8_t *src, uint64_t in_len, uint8_t *dst, uint64_t out_cap, uint64_t &bitpos, uint64_t &pos,
+                       const uint32_t *lt, const uint32_t *dt, int force_lg) {
+    static RoundShared rs;
+    static std::vector<QueuedMatch> gq(kRoundQueueCap);
+    const uint32_t bias = (uint32_t)(reinterpret_cast<uintptr_t>(src) & 3) * 8;
+    const uint64_t total_bits = bias + in_len * 8, nwords = (total_bits + 31) >> 5;
+    for (;;) {
+        const uint64_t B = bias + bitpos;
+        if (B >= total_bits) { g_stats.serial_returns++; return 1; }
+        int lg = round_pick_lg(total_bits - B);
+        if (lg < 0) { g_stats.serial_returns++; return 1; }
+        if (force_lg >= kRoundLgMin && force_lg < lg) lg = force_lg;
+        const uint32_t S = 32u << lg;
+        const uint64_t W0 = B >> 5;
+        const uint32_t nw = (32u << lg) + kStageTail;
+        for (uint32_t k = 0; k < nw; ++k) {
+            const uint64_t w = W0 + k;
+            uint32_t v = 0;
+            if (w < nwords) {                           // byte-wise: the host buffer has no alignment slack to read whole words from
+                for (int b = 0; b < 4; ++b) {
+                    const uint64_t byte = w * 4 + b;    // relative to a0
+                    const uint64_t lo = bias / 8, hi = lo + in_len;
+                    if (byte >= lo && byte < hi) v |= (uint32_t)src[byte - lo] << (8 * b);
+                }
+            }
+            rs.stage[k + (k >> lg)] = v;
+        }
+        RoundLane r[32];
+        for (uint32_t l = 0; l < 32; ++l) round_speculate(r[l], l, lg, l ? l * S : (uint32_t)(B & 31u), rs, lt, dt);
+        g_stats.rounds++;
+        for (;;) {
+            uint32_t nvalid = 32;
+            for (uint32_t l = 0; l < 32; ++l) if (r[l].stop != STOP_NONE) { nvalid = l + 1; break; }
+            uint32_t t[32]; bool need[32]; bool any = false;
+            for (uint32_t l = 0; l < 32; ++l) {
+                t[l] = l ? r[l - 1].end : 0;
+                need[l] = l > 0 && l < nvalid && t[l] != r[l].start;
+                any |= need[l];
+            }
+            if (!any) break;
+            g_stats.fix_passes++;
+            for (uint32_t l = 0; l < 32; ++l) if (need[l]) { round_fix(r[l], l, lg, t[l], rs, lt, dt); g_stats.fix_lane_runs++; }
+        }
+        uint32_t last = 31;
+        for (uint32_t l = 0; l < 32; ++l) if (r[l].stop != STOP_NONE) { last = l; break; }
+        if (r[last].stop == STOP_BAD) { g_stats.serial_returns++; return 1; }
+        if (W0 * 32 + r[last].end > total_bits) { g_stats.serial_returns++; return 1; }
+        uint32_t off_o[33], off_m[33];
+        off_o[0] = off_m[0] = 0;
+        for (uint32_t l = 0; l < 32; ++l) {
+            off_o[l + 1] = off_o[l] + (l <= last ? r[l].out : 0);
+            off_m[l + 1] = off_m[l] + (l <= last ? r[l].m : 0);
+        }
+        if (off_o[32] > out_cap - pos) { g_stats.serial_returns++; return 1; }
+        if (off_m[32] > kRoundQueueCap) return -1;
+        bool err = false;
+        for (int l = (int)last; l >= 0; --l)             // any lane order must do: run them backwards
+            err |= round_emit(r[l], (uint32_t)l, lg, rs, lt, dt, dst, (uint32_t)pos + off_o[l], gq.data(), off_m[l]) != 0;
+        if (err) { g_stats.serial_returns++; return 1; }
+        // P4 as on the device: waves of 32, independent matches first (replayed in reverse), dependents in order
+        const uint32_t count = off_m[32];
+        auto copy = [&](const QueuedMatch &m) {
+            const uint32_t dist = qm_dist(m.packed), len = qm_len(m.packed);
+            for (uint32_t i = 0; i < len; ++i) dst[m.dst + i] = dst[m.dst - dist + (dist >= len ? i : i % dist)];
+        };
+        for (uint32_t base = 0; base < count; base += 32) {
+            const uint32_t n = count - base < 32 ? count - base : 32;
+            const uint32_t first = gq[base].dst;
+            bool dep[32];
+            for (uint32_t k = 0; k < n; ++k) {
+                const QueuedMatch &m = gq[base + k];
+                const uint32_t dist = qm_dist(m.packed), len = qm_len(m.packed);
+                dep[k] = dist < len || m.dst - dist + len > first;
+                g_stats.matches++; g_stats.dep_matches += dep[k];
+            }
+            for (int k = (int)n - 1; k >= 0; --k) if (!dep[k]) copy(gq[base + k]);
+            for (uint32_t k = 0; k < n; ++k) if (dep[k]) copy(gq[base + k]);
+        }
+        pos += off_o[32];
+        bitpos = W0 * 32 + r[last].end - bias;
+        if (r[last].stop == STOP_EOB) return 0;
+    }
+}
+
+extern "C" int emul_inflate_rounds(const uint8_t *src, uint64_t n, uint8_t *dst, uint64_t cap, int wrap, int force_lg,
+                                   uint64_t *in_used, uint64_t *out_len, uint32_t *check, uint32_t *isize,
+                                   uint64_t *ck_bit, uint64_t *ck_out, int *kind) {
+    if (!g_ready) setup();
+    static InflateScratch scr;
+    InflateState st;
+    st.init(src, n, dst, cap < 0xfffffff0ull ? cap : 0xfffffff0ull, &scr, g_flit, g_fdist, &g_fmt);
+    st.huff_external = 1;
+    int hs = st.parse_header(wrap);
+    if (hs == ZB200_INF_OK) {
+        static QueuedMatch q[kQueue];
+        auto copy = [&](const QueuedMatch &m) {
+            const uint32_t dist = qm_dist(m.packed), len = qm_len(m.packed);
+            for (uint32_t i = 0; i < len; ++i) dst[m.dst + i] = dst[m.dst - dist + (dist >= len ? i : i % dist)];
+        };
+        for (;;) {
+            InflateEvent ev = st.run_batch(q);
+            if (ev.kind == EV_DONE) break;
+            if (ev.kind == EV_HUFF) {
+                uint64_t bp = ev.src, op = ev.dst;
+                const uint32_t *lt = ev.len ? g_flit : scr.lit, *dt = ev.len ? g_fdist : scr.dist;
+                const int r = host_rounds(src, n, dst, cap < 0xfffffff0ull ? cap : 0xfffffff0ull, bp, op, lt, dt, force_lg);
+                if (r < 0) return -100;
+                st.seek(bp, op, r);
+            } else if (ev.kind == EV_BATCH) {
                 for (int i = (int)ev.len - 1; i >= 0; --i) if (!qm_dep(q[i].packed)) copy(q[i]);
                 for (uint32_t i = 0; i < ev.len; ++i) if (qm_dep(q[i].packed)) copy(q[i]);
             } else {

@@ -91,6 +91,88 @@ def test_inflate_state_machine(golden):
     assert st == 0 and out == d and iu == len(s)
 
 
+def _rounds_emul():
+    L = _build("inf_emul")
+    u64 = C.c_uint64
+    L.emul_inflate_rounds.argtypes = [C.c_void_p, u64, C.c_void_p, u64, C.c_int, C.c_int] + [C.POINTER(u64)] * 2 + \
+        [C.POINTER(C.c_uint32)] * 2 + [C.POINTER(u64)] * 2 + [C.POINTER(C.c_int)]
+    L.emul_round_stats.argtypes = [C.POINTER(u64 * 6)]
+
+    def run(data, wrap, cap, off=0, force_lg=-1):
+        buf = C.create_string_buffer(len(data) + 8 + off)
+        C.memmove(C.addressof(buf) + off, data, len(data))
+        dst = C.create_string_buffer(max(cap, 1))
+        iu, ol, cb, co = u64(), u64(), u64(), u64()
+        ck, isz, kind = C.c_uint32(), C.c_uint32(), C.c_int()
+        st = L.emul_inflate_rounds(C.addressof(buf) + off, len(data), dst, cap, wrap, force_lg, C.byref(iu), C.byref(ol),
+                                   C.byref(ck), C.byref(isz), C.byref(cb), C.byref(co), C.byref(kind))
+        return st, dst.raw[:ol.value], iu.value, ck.value, isz.value
+
+    def stats():
+        a = (u64 * 6)()
+        L.emul_round_stats(C.byref(a))
+        return dict(zip(("rounds", "fix_passes", "fix_lane_runs", "serial_returns", "matches", "dep_matches"), a))
+    return run, stats
+
+
+def test_inflate_rounds(golden):
+    """The self-synchronising rounds (zb_inflate_round.cuh) give the bytes, the consumed
+    length and — through the serial fallback — the status of the serial state machine."""
+    run, stats = _rounds_emul()
+    serial = _inflate_emul()
+    o = refz.oracle()
+    msgs = [o.c_inflate_msg(i).decode() for i in range(22)]
+    rng = random.Random(5)
+    for kind in (refz.GEN_TEXT, refz.GEN_MARKOV, refz.GEN_MIXED, refz.GEN_RANDOM):
+        d = refz.gen(400000, kind, seed=77 + kind)
+        for lvl, strat, wrap, chunk in ((1, 0, 0, 0), (6, 0, 1, 100000), (9, 0, 2, 0), (6, 4, 0, 65536), (6, 2, 1, 0), (1, 3, 2, 0), (6, 1, 2, 0)):
+            s = o.deflate_stream(d, lvl, strat, wrap, chunk)
+            for lg in (-1, 2, 3):
+                st, out, iu, ck, isz = run(s, wrap, len(d) + rng.randrange(0, 4), off=rng.randrange(0, 8), force_lg=lg)
+                assert st == 0 and out == d and iu == len(s), (kind, lvl, strat, wrap, lg, msgs[st])
+                if wrap == 2:
+                    assert ck == zlib.crc32(d) and isz == len(d)
+    st = stats()
+    assert st["rounds"] > 100 and st["fix_passes"] < 6 * st["rounds"], st      # incl. the forced S = 128 / 256 runs
+    d = refz.gen(1 << 20, refz.GEN_MARKOV, seed=3)
+    s = o.deflate_stream(d, 6, 0, 2, 0)
+    assert run(s, 2, len(d))[1] == d
+    st2 = stats()
+    rounds, fixes = st2["rounds"] - st["rounds"], st2["fix_passes"] - st["fix_passes"]
+    assert rounds > 50 and fixes < 2 * rounds, (rounds, fixes)                 # S = 1024: ~1.4 fix-up passes per round
+    # small and degenerate members: below the round threshold everything runs on the serial path
+    for n in (0, 1, 10, 600, 5000, 20000):
+        d = refz.gen(n, refz.GEN_TEXT, seed=n)
+        s = o.deflate_stream(d, 6, 0, 2, 0)
+        st_, out, iu = run(s, 2, n)[:3]
+        assert st_ == 0 and out == d and iu == len(s)
+    # errors: same status and the same bytes before the error as the serial machine
+    d = refz.gen(300000, refz.GEN_MARKOV, seed=5)
+    s = bytearray(o.deflate_stream(d, 6, 0, 1, 0))
+    for trial in range(40):
+        bad = bytearray(s)
+        where = rng.randrange(2, len(bad) - 4)
+        bad[where] ^= 1 << rng.randrange(8)
+        cap = len(d) + 64
+        a = run(bytes(bad), 1, cap)
+        b = serial(bytes(bad), 1, cap)
+        assert a[0] == b[0] and a[2] == b[2], (trial, where, msgs[a[0]], msgs[b[0]])
+        if a[0] == 0:
+            assert a[1] == b[1]
+        else:
+            n = min(len(a[1]), len(b[1]))
+            assert len(a[1]) == len(b[1]) and a[1][:n] == b[1][:n]
+    # truncated input and short output
+    for cut in (len(s) // 3, len(s) - 5, len(s) - 1):
+        a, b = run(bytes(s[:cut]), 1, len(d)), serial(bytes(s[:cut]), 1, len(d))
+        assert a[0] == b[0] and msgs[a[0]] == "truncated input" and a[1] == b[1]
+    a, b = run(bytes(s), 1, len(d) - 1000), serial(bytes(s), 1, len(d) - 1000)
+    assert a[0] == b[0] and msgs[a[0]] == "output buffer full"
+    for v in golden["puff_vectors"]:
+        a, b = run(bytes.fromhex(v["hex"]), 0, 4096), serial(bytes.fromhex(v["hex"]), 0, 4096)
+        assert a[0] == b[0] and a[1] == b[1]
+
+
 def test_deflate_phases_byte_exact():
     L = _build("def_emul")
     L.emul_deflate_chunk.restype = C.c_long

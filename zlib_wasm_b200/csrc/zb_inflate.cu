@@ -11,15 +11,19 @@
 // back-references re-read recently written output from L1/L2.
 #include "zb_internal.h"
 #include "zb_inflate.cuh"
+#include "zb_inflate_round.cuh"
 #include <string.h>
 
 namespace zb {
 
-constexpr int kInfWarps = 4;
-// Two symbol decoders exist: the lean serial loop on lane 0 (InflateState::fast_symbols)
-// and the speculative warp-parallel one (huff_decode_warp).  Measured on B200 the
-// serial loop issues ~4x fewer warp instructions per symbol, so it is the default.
-constexpr bool kWarpParallelHuffman = false;
+constexpr int kInfWarps = 2;
+constexpr int kInfCtasPerSm = 5;          // 5 CTAs x (2 warps x 19.6 KiB + 3.4 KiB) of shared memory fit one SM
+constexpr size_t kMaxGridWarps = 2048;    // upper bound on resident warps (sizes the per-warp match queues)
+// Two symbol decoders exist: the serial loop on lane 0 (InflateState::fast_symbols,
+// ~79 warp instructions per symbol with one lane active) and the warp-parallel rounds
+// (huff_rounds_warp, all lanes active).  The rounds are the default; the serial loop
+// finishes member tails and reports errors.
+constexpr bool kWarpParallelHuffman = true;
 
 struct InflateDeviceTables {
     uint32_t fixed_lit[512];
@@ -30,6 +34,7 @@ struct InflateDeviceTables {
 struct InflateShared {
     InflateScratch scr[kInfWarps];
     QueuedMatch q[kInfWarps][kQueue];
+    RoundShared rnd[kInfWarps];
     uint32_t fixed_lit[512];
     uint32_t fixed_dist[64];
     FormatTables fmt;
@@ -80,22 +85,59 @@ __device__ __forceinline__ void exec_queue(uint8_t *dst, const QueuedMatch *q, u
     }
 }
 
-// ---- warp-parallel Huffman block decode -----------------------------------------
-// Huffman decoding is serial per stream (the start of symbol k+1 is known only
-// once symbol k is decoded).  Inside a warp the serial chain is shortened by
-// speculation: lane i decodes the symbol that WOULD start at bit offset i of the
-// current 32-bit window (one table lookup per lane, in parallel), giving its
-// bit length u_i; the true symbol starts are then the chain 0 -> u_0 -> u_0 +
-// u_{u_0} -> ..., which pointer doubling over the 32 lanes resolves in five
-// shuffle steps.  Every round consumes >= 32 bits (3-5 symbols on text).  Output
-// offsets come from a warp scan; literals are stored by their own lanes;
-// matches whose source lies before this round's output are copied by their own
-// lanes concurrently, the few that depend on this round's output follow in order.
-struct HuffResult { int status; uint64_t bitpos; uint64_t pos; };   // status 0: end-of-block reached
+// ---- warp-parallel Huffman block decode (rounds: zb_inflate_round.cuh) ---------------
+// Execute the `count` matches of a round, parked in stream order, in waves of 32:
+// a match whose source ends before the wave's first destination cannot depend on a
+// wave-mate and is copied by its own lane (all such copies overlap); the others
+// follow in order, striped over the warp (byte-serial semantics, inffast.c:249-260).
+__device__ __forceinline__ void exec_round_queue(uint8_t *dst, const QueuedMatch *__restrict__ q, uint32_t count) {
+    const unsigned full = 0xffffffffu;
+    const uint32_t lane = threadIdx.x & 31;
+    for (uint32_t base = 0; base < count; base += 32) {
+        const bool mine = base + lane < count;
+        QueuedMatch e;
+        e.dst = 0; e.packed = 0;
+        if (mine) e = q[base + lane];
+        const uint32_t first = __shfl_sync(full, e.dst, 0);
+        const uint32_t len = qm_len(e.packed), dist = qm_dist(e.packed);
+        const bool dep = mine && (dist < len || e.dst - dist + len > first);
+        if (mine && !dep) {
+            uint8_t *d = dst + e.dst;
+            const uint8_t *s = d - dist;
+            uint32_t i = 0;
+            for (; i + 8 <= len; i += 8) {
+                uint8_t t[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) t[k] = s[i + k];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) d[i + k] = t[k];
+            }
+            for (; i < len; ++i) d[i] = s[i];
+        }
+        uint32_t depmask = __ballot_sync(full, dep);
+        __syncwarp(full);
+        while (depmask) {
+            const int j = __ffs(depmask) - 1;
+            depmask &= depmask - 1;
+            const uint32_t md = __shfl_sync(full, e.dst, j), mp = __shfl_sync(full, e.packed, j);
+            const uint32_t mdist = qm_dist(mp), mlen = qm_len(mp);
+            uint8_t *d = dst + md;
+            const uint8_t *s = d - mdist;
+            if (mdist >= mlen) { for (uint32_t i = lane; i < mlen; i += 32) d[i] = s[i]; }
+            else { for (uint32_t i = lane; i < mlen; i += 32) d[i] = s[i % mdist]; }
+            __syncwarp(full);
+        }
+    }
+}
+
+// status 0: the block's end-of-block code was consumed; 1: lane 0 continues inside
+// the block on the serial path from (bitpos, pos) — end of the member's input, or a
+// condition the careful path has to report.
+struct HuffResult { int status; uint64_t bitpos; uint64_t pos; };
 
 __device__ __forceinline__ HuffResult
-huff_decode_warp(const uint8_t *src, uint64_t in_len, uint8_t *dst, uint64_t out_cap, uint64_t bitpos, uint64_t pos,
-                 const uint32_t *__restrict__ lt, const uint32_t *__restrict__ dt, QueuedMatch *q) {
+huff_rounds_warp(const uint8_t *src, uint64_t in_len, uint8_t *dst, uint64_t out_cap, uint64_t bitpos, uint64_t pos,
+                 const uint32_t *__restrict__ lt, const uint32_t *__restrict__ dt, RoundShared &rs, QueuedMatch *gq) {
     const unsigned full = 0xffffffffu;
     const uint32_t lane = threadIdx.x & 31;
     const uintptr_t a0 = reinterpret_cast<uintptr_t>(src) & ~(uintptr_t)3;
@@ -103,123 +145,56 @@ huff_decode_warp(const uint8_t *src, uint64_t in_len, uint8_t *dst, uint64_t out
     const uint32_t *words = reinterpret_cast<const uint32_t *>(a0);
     const uint64_t total_bits = bias + in_len * 8;                  // valid bits are [bias, total_bits)
     const uint64_t nwords = (total_bits + 31) >> 5;
-    uint64_t B = bias + bitpos;
-    uint64_t wbase = ~0ull;
-    uint32_t win = 0;
-    enum { K_LIT = 0, K_MATCH = 1, K_EOB = 2, K_BADLIT = 3, K_BADDIST = 4, K_TRUNC = 5 };
     HuffResult res;
-    uint32_t qcount = 0;                                            // matches parked in q[]
-    uint64_t qfirst = 0;                                            // destination of the first parked match
     for (;;) {
-        const uint64_t wi = B >> 5;
-        if (wbase == ~0ull || wi < wbase || wi + 3 >= wbase + 32) {  // (re)load the 32-word register window
-            wbase = wi;
-            const uint64_t w = wbase + lane;
-            win = w < nwords ? words[w] : 0u;
-        }
-        const int k = (int)(wi - wbase);
-        const uint32_t sh = (uint32_t)B & 31u;
-        const uint32_t W0 = __shfl_sync(full, win, k), W1 = __shfl_sync(full, win, k + 1);
-        const uint32_t W2 = __shfl_sync(full, win, k + 2), W3 = __shfl_sync(full, win, k + 3);
-        const uint32_t o = sh + lane;
-        const uint32_t x0 = o < 32 ? W0 : W1, x1 = o < 32 ? W1 : W2, x2 = o < 32 ? W2 : W3;
-        const uint32_t lo = __funnelshift_r(x0, x1, o & 31), hi = __funnelshift_r(x1, x2, o & 31);
-        const uint64_t v = ((uint64_t)hi << 32) | lo;               // the stream as seen from bit B + lane
-
-        // speculative decode of the symbol starting here
-        uint32_t e = lt[lo & ((1u << kLitRoot) - 1)];
-        uint32_t u = 0;
-        if (ZB_E_OP(e) == OP_SUB) { e = lt[ZB_E_VAL(e) + ((lo >> kLitRoot) & ((1u << ZB_E_EXTRA(e)) - 1u))]; u = kLitRoot; }
-        u += ZB_E_BITS(e);
-        const uint32_t op = ZB_E_OP(e);
-        uint32_t kind = op == OP_LIT ? K_LIT : op == OP_EOB ? K_EOB : op == OP_BASE ? K_MATCH : K_BADLIT;
-        uint32_t val = ZB_E_VAL(e), len = 0, dist = 0;
-        if (op == OP_BASE) {
-            const uint32_t x = ZB_E_EXTRA(e);
-            len = val + ((uint32_t)(v >> u) & ((1u << x) - 1u));
-            u += x;
-            const uint32_t db = (uint32_t)(v >> u);
-            uint32_t d = dt[db & ((1u << kDistRoot) - 1)], du = 0;
-            if (ZB_E_OP(d) == OP_SUB) { d = dt[ZB_E_VAL(d) + ((db >> kDistRoot) & ((1u << ZB_E_EXTRA(d)) - 1u))]; du = kDistRoot; }
-            du += ZB_E_BITS(d);
-            if (ZB_E_OP(d) != OP_BASE) kind = K_BADDIST;
-            else { const uint32_t dx = ZB_E_EXTRA(d); dist = ZB_E_VAL(d) + ((db >> du) & ((1u << dx) - 1u)); du += dx; }
-            u += du;
-        }
-        const uint64_t left = total_bits - B;                         // real bits from the window start
-        if ((uint64_t)lane + u > left) kind = K_TRUNC;
-        const bool stop = kind >= K_EOB;
-
-        // chain of true symbol starts from lane 0: pointer doubling with visit masks
-        uint32_t j = stop ? 32u : (lane + u < 32u ? lane + u : 32u);
-        uint32_t reach = 1u << lane;
-#pragma unroll
-        for (int r = 0; r < 5; ++r) {
-            const uint32_t jj = j < 32u ? j : 0u;
-            const uint32_t rj = __shfl_sync(full, reach, jj), j2 = __shfl_sync(full, j, jj);
-            if (j < 32u) { reach |= rj; j = j2; }
-        }
-        uint32_t vmask = __shfl_sync(full, reach, 0);
-        bool valid = (vmask >> lane) & 1u;
-
-        // output offsets: exclusive scan of produced lengths over the valid lanes
-        uint32_t olen = valid ? (kind == K_LIT ? 1u : kind == K_MATCH ? len : 0u) : 0u;
-        uint32_t inc = olen;
-#pragma unroll
-        for (int dlt = 1; dlt < 32; dlt <<= 1) { const uint32_t y = __shfl_up_sync(full, inc, dlt); if (lane >= (uint32_t)dlt) inc += y; }
-        uint64_t mydst = pos + (inc - olen);
-
-        // the first valid lane that cannot be committed ends the round
-        int err = 0;
-        if (valid) {
-            if (kind == K_BADLIT) err = ZB200_INF_LITLEN_CODE;
-            else if (kind == K_BADDIST) err = ZB200_INF_DIST_CODE;
-            else if (kind == K_TRUNC) err = ZB200_INF_TRUNCATED;
-            else if (kind == K_MATCH && dist > mydst) err = ZB200_INF_DIST_FAR;
-            else if (olen && olen > out_cap - mydst) err = ZB200_INF_OUTPUT_FULL;
-        }
-        const uint32_t emask = __ballot_sync(full, err != 0);
-        if (emask) {
-            const int first = __ffs(emask) - 1;
-            valid = valid && (int)lane < first;
-            if ((int)lane >= first) olen = 0;
-            vmask &= (1u << first) - 1u;
-            res.status = __shfl_sync(full, err, first);
-            res.pos = __shfl_sync(full, mydst, first);
-            res.bitpos = B + (uint32_t)first - bias;
-        }
-        if (valid && kind == K_LIT) dst[mydst] = (uint8_t)val;
-        // park the matches of this round; they are executed in batches so that their
-        // memory round trips overlap instead of stalling every round
-        const bool is_m = valid && kind == K_MATCH;
-        const uint32_t mmask = __ballot_sync(full, is_m);
-        if (mmask) {
-            if (qcount == 0) qfirst = __shfl_sync(full, mydst, __ffs(mmask) - 1);
-            if (is_m) {
-                const bool dep = dist < len || mydst - dist + len > qfirst;
-                QueuedMatch m;
-                m.dst = (uint32_t)mydst; m.packed = qm_pack(len, dist, dep);
-                q[qcount + __popc(mmask & ((1u << lane) - 1u))] = m;
+        res.status = 1; res.bitpos = bitpos; res.pos = pos;
+        const uint64_t B = bias + bitpos;
+        if (B >= total_bits) return res;
+        const int lg = round_pick_lg(total_bits - B);
+        if (lg < 0) return res;
+        const uint32_t S = 32u << lg;
+        const uint64_t W0 = B >> 5;
+        {   // stage the round's words (coalesced), one pad word per subsequence
+            const uint32_t nw = (32u << lg) + kStageTail;
+            for (uint32_t k = lane; k < nw; k += 32) {
+                const uint64_t w = W0 + k;
+                rs.stage[k + (k >> lg)] = w < nwords ? words[w] : 0u;
             }
-            qcount += __popc(mmask);
         }
-        if (qcount > kQueue - 32 || emask) {
-            __syncwarp(full);
-            exec_queue(dst, q, qcount);
-            qcount = 0;
+        __syncwarp(full);
+        RoundLane r;
+        round_speculate(r, lane, lg, lane ? lane * S : (uint32_t)(B & 31u), rs, lt, dt);
+        for (;;) {                                                   // P2: until no start moves
+            const uint32_t stopmask = __ballot_sync(full, r.stop != STOP_NONE);
+            const uint32_t nvalid = stopmask ? (uint32_t)__ffs(stopmask) : 32u;
+            const uint32_t t = __shfl_up_sync(full, r.end, 1);
+            const bool need = lane > 0 && lane < nvalid && t != r.start;
+            if (!__ballot_sync(full, need)) break;
+            if (need) round_fix(r, lane, lg, t, rs, lt, dt);
         }
-        if (emask) return res;
-        const int last = 31 - __clz(vmask);
-        const uint32_t consumed = __shfl_sync(full, lane + u, last);
-        const bool ended = __shfl_sync(full, (uint32_t)stop, last) != 0;   // only an EOB can be a committed stop
-        pos += __shfl_sync(full, inc, 31);
-        B += consumed;
-        if (ended) {
-            __syncwarp(full);
-            exec_queue(dst, q, qcount);
-            res.status = 0; res.bitpos = B - bias; res.pos = pos;
-            return res;
+        const uint32_t stopmask = __ballot_sync(full, r.stop != STOP_NONE);
+        const uint32_t last = stopmask ? (uint32_t)__ffs(stopmask) - 1u : 31u;
+        const uint32_t stop_l = __shfl_sync(full, r.stop, last), end_l = __shfl_sync(full, r.end, last);
+        if (stop_l == STOP_BAD) return res;
+        if (W0 * 32 + end_l > total_bits) return res;               // ran past the input: the serial path reports it
+        const bool valid = lane <= last;
+        const uint32_t myout = valid ? r.out : 0u, mym = valid ? r.m : 0u;
+        uint32_t inc_o = myout, inc_m = mym;
+#pragma unroll
+        for (int dlt = 1; dlt < 32; dlt <<= 1) {
+            const uint32_t yo = __shfl_up_sync(full, inc_o, dlt), ym = __shfl_up_sync(full, inc_m, dlt);
+            if (lane >= (uint32_t)dlt) { inc_o += yo; inc_m += ym; }
         }
+        const uint32_t tot_o = __shfl_sync(full, inc_o, 31), tot_m = __shfl_sync(full, inc_m, 31);
+        if (tot_o > out_cap - pos) return res;
+        int err = 0;
+        if (valid) err = round_emit(r, lane, lg, rs, lt, dt, dst, (uint32_t)pos + inc_o - myout, gq, inc_m - mym);
+        if (__ballot_sync(full, err != 0)) return res;
+        __syncwarp(full);                                            // literals and queue entries -> visible to every lane
+        exec_round_queue(dst, gq, tot_m);
+        pos += tot_o;
+        bitpos = W0 * 32 + end_l - bias;
+        if (stop_l == STOP_EOB) { res.status = 0; res.bitpos = bitpos; res.pos = pos; return res; }
     }
 }
 
@@ -227,7 +202,8 @@ __global__ void __launch_bounds__(kInfWarps * 32)
 inflate_kernel(const uint8_t *__restrict__ in, uint8_t *out, const zb200_member *__restrict__ members,
                uint32_t n_members, int wrap, zb200_member_result *__restrict__ results,
                const InflateDeviceTables *__restrict__ tabs, unsigned int *__restrict__ counter,
-               const uint32_t *__restrict__ order, uint64_t *__restrict__ seg_off, uint64_t *__restrict__ seg_len) {
+               const uint32_t *__restrict__ order, uint64_t *__restrict__ seg_off, uint64_t *__restrict__ seg_len,
+               QueuedMatch *__restrict__ round_queues) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     InflateShared &sh = *reinterpret_cast<InflateShared *>(smem_raw);
     {
@@ -273,12 +249,10 @@ inflate_kernel(const uint8_t *__restrict__ in, uint8_t *out, const zb200_member 
                 const uint64_t bp = __shfl_sync(full, ev.src, 0), op = __shfl_sync(full, ev.dst, 0);
                 const uint32_t *lt = len ? sh.fixed_lit : sh.scr[warp].lit;
                 const uint32_t *dt = len ? sh.fixed_dist : sh.scr[warp].dist;
-                const HuffResult hr = huff_decode_warp(src, mb.in_len, dst, mb.out_cap, bp, op, lt, dt, q);
-                if (lane == 0) {
-                    st.seek(hr.bitpos, hr.pos);
-                    if (hr.status) { st.status = hr.status; }
-                }
-                if (hr.status) break;
+                const uint64_t cap = mb.out_cap < 0xfffffff0ull ? mb.out_cap : 0xfffffff0ull;
+                const HuffResult hr = huff_rounds_warp(src, mb.in_len, dst, cap, bp, op, lt, dt, sh.rnd[warp],
+                                                       round_queues + (size_t)(blockIdx.x * kInfWarps + warp) * kRoundQueueCap);
+                if (lane == 0) st.seek(hr.bitpos, hr.pos, hr.status);   // status 1: the serial path finishes the block
             } else if (kind == EV_BATCH) {
                 exec_queue(dst, q, len);
             } else {                                           // stored block: input -> output
@@ -375,9 +349,11 @@ static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 // scratch layout for one call
 struct InflateWork {
-    unsigned int *counter; uint64_t *seg_off, *seg_len; uint32_t *crc, *adler, *order; CkAccum *acc;
+    unsigned int *counter; uint64_t *seg_off, *seg_len; uint32_t *crc, *adler, *order; CkAccum *acc; QueuedMatch *queues;
+    static size_t grid_warps(size_t n) { return n < kMaxGridWarps ? (n + kInfWarps - 1) / kInfWarps * kInfWarps : kMaxGridWarps; }
     static size_t bytes(size_t n) {
-        return 256 + align_up(n * 8, 256) * 2 + align_up(n * 4, 256) * 3 + align_up(n * sizeof(CkAccum), 256);
+        return 256 + align_up(n * 8, 256) * 2 + align_up(n * 4, 256) * 3 + align_up(n * sizeof(CkAccum), 256) +
+               grid_warps(n) * kRoundQueueCap * sizeof(QueuedMatch);
     }
     void carve(void *base, size_t n) {
         uint8_t *p = (uint8_t *)base;
@@ -387,7 +363,8 @@ struct InflateWork {
         crc = (uint32_t *)p; p += align_up(n * 4, 256);
         adler = (uint32_t *)p; p += align_up(n * 4, 256);
         order = (uint32_t *)p; p += align_up(n * 4, 256);
-        acc = (CkAccum *)p;
+        acc = (CkAccum *)p; p += align_up(n * sizeof(CkAccum), 256);
+        queues = (QueuedMatch *)p;
     }
 };
 
@@ -401,13 +378,13 @@ int inflate_launch(zb200_ctx *ctx, const uint8_t *d_in, uint8_t *d_out, const zb
     inflate_order_kernel<<<1, 1024, 0, s>>>(d_members, (uint32_t)n, w.order);
     ZB_LAUNCHED();
     ZB_CHECK_LAUNCH();
-    const int per_sm = 7;                                      // 7 CTAs x 4 warps x 7.3 KiB of tables + queue fit one SM
     size_t ctas = (n + kInfWarps - 1) / kInfWarps;
-    const size_t cap = (size_t)ctx->sm_count * per_sm;
+    size_t cap = (size_t)ctx->sm_count * kInfCtasPerSm;
+    if (cap * kInfWarps > kMaxGridWarps) cap = kMaxGridWarps / kInfWarps;
     if (ctas > cap) ctas = cap;
     inflate_kernel<<<(unsigned)ctas, kInfWarps * 32, sizeof(InflateShared), s>>>(
         d_in, d_out, d_members, (uint32_t)n, wrap, d_results,
-        (const InflateDeviceTables *)ctx->d_inflate_tables, w.counter, w.order, w.seg_off, w.seg_len);
+        (const InflateDeviceTables *)ctx->d_inflate_tables, w.counter, w.order, w.seg_off, w.seg_len, w.queues);
     ZB_LAUNCHED();
     ZB_CHECK_LAUNCH();
     const int which = wrap == ZB200_WRAP_ZLIB ? ZB200_ADLER32 : wrap == ZB200_WRAP_AUTO ? (ZB200_CRC32 | ZB200_ADLER32) : ZB200_CRC32;

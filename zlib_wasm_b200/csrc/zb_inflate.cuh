@@ -212,12 +212,13 @@ struct InflateState {
         pos = out_pos; wrap_kind = kind; ck_bit = bit_off; ck_out = out_pos;
     }
 
-    // Re-seed the bit reader at an absolute bit offset (after an externally decoded block).
-    ZB_HD void seek(uint64_t bit_off, uint64_t out_pos) {
+    // Re-seed the bit reader at an absolute bit offset: after an externally decoded
+    // block (still_open = 0), or inside one whose remainder is decoded here.
+    ZB_HD void seek(uint64_t bit_off, uint64_t out_pos, int still_open = 0) {
         next = bit_off >> 3; hold = 0; bits = 0;
         refill();
         drop((int)(bit_off & 7));
-        pos = out_pos; in_block = 0;
+        pos = out_pos; in_block = still_open;
     }
 
     // Wrapper header: inflate.c:622-669 (zlib), :671-808 (gzip).  Returns status.

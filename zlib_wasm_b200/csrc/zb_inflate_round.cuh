@@ -1,0 +1,215 @@
+// zb_inflate_round.cuh — warp-parallel decoding of an open Huffman block.
+//
+// The symbol chain of a DEFLATE block is serial: the start of unit k+1 (a unit is a
+// literal, an end-of-block, or a length/distance pair with its extra bits) is known
+// only once unit k is decoded (inffast.c:100-287).  One lane decoding alone is what
+// bounds a member at ~12 MB/s.  A ROUND breaks the chain with the self-synchronising
+// property of prefix codes: the next 32*S bits of the block are cut into 32
+// subsequences of S bits; lane i starts decoding at bit i*S — usually in the middle
+// of a unit — and after a few (wrong) units its unit starts coincide with the true
+// ones and stay so (measured on zlib streams: 96.5 % of the subsequences synchronise
+// within S = 512 bits, 99 % within 1024; median ~100 bits).
+//
+//   P1  speculate  every lane decodes its subsequence from the guessed start and
+//                  records (a) a bitmask of the unit starts it visited and (b) per
+//                  32-bit word the output / match counts accumulated before the
+//                  first unit starting in that word.
+//   P2  fix up     lane 0 started at a true unit start.  Lane i re-decodes from the
+//                  true start handed over by lane i-1 (its end position) only until
+//                  it lands on a unit start of its own speculative path — from
+//                  there on the two paths are identical, so the speculative counts
+//                  are spliced in at the next word boundary.  A lane that never
+//                  meets its speculative path simply keeps its own decode.  This
+//                  repeats until no lane's start moves (usually 1-2 short passes).
+//   scan           exclusive sums of the per-lane output bytes and match counts.
+//   P3  emit       every lane decodes its (now true) subsequence once more, storing
+//                  literals at their final positions and parking matches in the
+//                  round's queue, in stream order.
+//   P4  copy       the queue is executed in waves of 32 matches (zb_inflate.cu).
+//
+// Anything unusual in a round — an invalid code on the true path, a distance
+// reaching before the start of the output, output overflow, truncated input — makes
+// the warp abandon the round; lane 0 then decodes from the round's start on the
+// careful serial path (zb_inflate.cuh), which reports the reference's exact status.
+//
+// The per-lane phases are __host__ __device__: tests/emul/inf_emul.cpp replays them
+// with plain loops over the 32 lanes.
+#pragma once
+#include "zb_inflate.cuh"
+
+namespace zb {
+
+constexpr int kRoundLgMin = 2, kRoundLgMax = 5;              // words per lane = 1 << lg  (S = 128 .. 1024 bits)
+constexpr int kRoundWordsMax = 1 << kRoundLgMax;
+constexpr int kStageTail = 4;                                // words a lane may read past the last subsequence
+constexpr int kStageWords = 32 * kRoundWordsMax + 32 + kStageTail + 4;
+constexpr uint32_t kRoundQueueCap = 32u * (32u << kRoundLgMax) / 2u;   // a match costs at least 2 bits
+
+// Per-warp working memory of a round (shared memory on the device).
+struct RoundShared {
+    uint32_t stage[kStageWords];                 // the round's input words; one pad word per subsequence (bank spread)
+    uint32_t mask[kRoundWordsMax * 32];          // [word][lane] unit starts visited by the speculative pass
+    uint32_t cm[kRoundWordsMax * 32];            // [word][lane] (output bytes << 12 | matches) before the word's first unit
+};
+
+// LSB-first bit reader of one lane over the staged words.
+struct LaneBits {
+    const uint32_t *stage; int lg;
+    uint64_t hold; int nb; uint32_t wp;
+    ZB_HD uint32_t word(uint32_t w) const { return stage[w + (w >> lg)]; }
+    ZB_HD void seek(uint32_t p) {
+        wp = p >> 5;
+        hold = (uint64_t)word(wp) | ((uint64_t)word(wp + 1) << 32);
+        wp += 2;
+        hold >>= (p & 31u);
+        nb = 64 - (int)(p & 31u);
+    }
+    ZB_HD void fill() { if (nb <= 32) { hold |= (uint64_t)word(wp) << nb; ++wp; nb += 32; } }
+    ZB_HD void drop(uint32_t k) { hold >>= k; nb -= (int)k; }
+};
+
+enum : uint32_t { U_LIT = 0, U_MATCH = 1, U_EOB = 2, U_BAD = 3 };
+struct Unit { uint32_t kind, used, val, dist; };             // val: literal byte or match length
+
+// Decode the unit at the reader's position (the work of one trip of inffast.c:100-287).
+template <bool kWantDist>
+ZB_HD Unit decode_unit(LaneBits &lb, const uint32_t *__restrict__ L, const uint32_t *__restrict__ D) {
+    Unit u;
+    u.dist = 0; u.val = 0;
+    lb.fill();                                               // >= 33 bits: a literal/length code and its extra bits
+    uint32_t used = 0;
+    uint32_t e = L[(uint32_t)lb.hold & ((1u << kLitRoot) - 1u)];
+    if (ZB_E_OP(e) == OP_SUB) {
+        const uint32_t sub = ZB_E_VAL(e) + (((uint32_t)(lb.hold >> kLitRoot)) & ((1u << ZB_E_EXTRA(e)) - 1u));
+        lb.drop(kLitRoot); used = kLitRoot;
+        e = L[sub];
+    }
+    { const uint32_t k = ZB_E_BITS(e); lb.drop(k); used += k; }
+    const uint32_t op = ZB_E_OP(e);
+    if (op == OP_LIT) { u.kind = U_LIT; u.val = e >> 16; u.used = used; return u; }
+    if (op == OP_EOB) { u.kind = U_EOB; u.used = used; return u; }
+    if (op != OP_BASE) { u.kind = U_BAD; u.used = used; return u; }
+    {
+        const uint32_t x = ZB_E_EXTRA(e);
+        u.val = ZB_E_VAL(e) + ((uint32_t)lb.hold & ((1u << x) - 1u));
+        lb.drop(x); used += x;
+    }
+    lb.fill();                                               // >= 33 bits again: a distance code and its extra bits
+    uint32_t d = D[(uint32_t)lb.hold & ((1u << kDistRoot) - 1u)];
+    if (ZB_E_OP(d) == OP_SUB) {
+        const uint32_t sub = ZB_E_VAL(d) + (((uint32_t)(lb.hold >> kDistRoot)) & ((1u << ZB_E_EXTRA(d)) - 1u));
+        lb.drop(kDistRoot); used += kDistRoot;
+        d = D[sub];
+    }
+    { const uint32_t k = ZB_E_BITS(d); lb.drop(k); used += k; }
+    if (ZB_E_OP(d) != OP_BASE) { u.kind = U_BAD; u.used = used; return u; }
+    {
+        const uint32_t dx = ZB_E_EXTRA(d);
+        if (kWantDist) u.dist = ZB_E_VAL(d) + ((uint32_t)lb.hold & ((1u << dx) - 1u));
+        lb.drop(dx); used += dx;
+    }
+    u.kind = U_MATCH; u.used = used;
+    return u;
+}
+
+// What a lane knows about its subsequence.  Positions are bits relative to the
+// round's word-aligned base.
+struct RoundLane {
+    uint32_t spec_end, spec_stop, spec_out, spec_m;          // the speculative path (never changes after P1)
+    uint32_t start, end, stop, out, m;                       // the current path (true once P2 has settled)
+};
+enum : uint32_t { STOP_NONE = 0, STOP_EOB = 1, STOP_BAD = 2 };
+
+// P1.  `start` is lane*S, except for lane 0 which starts at the block's true position.
+ZB_HD void round_speculate(RoundLane &r, uint32_t lane, int lg, uint32_t start, RoundShared &rs,
+                           const uint32_t *__restrict__ L, const uint32_t *__restrict__ D) {
+    const uint32_t W = 1u << lg, S = 32u << lg, base = lane * S, bend = base + S;
+    for (uint32_t w = 0; w < W; ++w) rs.mask[w * 32 + lane] = 0;
+    LaneBits lb; lb.stage = rs.stage; lb.lg = lg;
+    uint32_t p = start;
+    lb.seek(p);
+    uint32_t curw = (p - base) >> 5, mw = 0, out = 0, m = 0, stop = STOP_NONE;
+    rs.cm[curw * 32 + lane] = 0;
+    while (p < bend) {
+        const uint32_t w = (p - base) >> 5;
+        if (w != curw) {
+            rs.mask[curw * 32 + lane] = mw;
+            mw = 0; curw = w;
+            rs.cm[w * 32 + lane] = (out << 12) | m;
+        }
+        mw |= 1u << (p & 31u);
+        const Unit u = decode_unit<false>(lb, L, D);
+        p += u.used;
+        if (u.kind >= U_EOB) { stop = u.kind == U_EOB ? STOP_EOB : STOP_BAD; break; }
+        out += u.kind == U_LIT ? 1u : u.val;
+        m += u.kind;
+    }
+    rs.mask[curw * 32 + lane] = mw;
+    r.spec_end = r.end = p; r.spec_stop = r.stop = stop; r.spec_out = r.out = out; r.spec_m = r.m = m;
+    r.start = start;
+}
+
+// P2.  Re-decode from the true start `t` until the path joins the speculative one.
+ZB_HD void round_fix(RoundLane &r, uint32_t lane, int lg, uint32_t t, const RoundShared &rs,
+                     const uint32_t *__restrict__ L, const uint32_t *__restrict__ D) {
+    const uint32_t S = 32u << lg, base = lane * S, bend = base + S;
+    LaneBits lb; lb.stage = rs.stage; lb.lg = lg;
+    uint32_t p = t;
+    lb.seek(p);
+    uint32_t out = 0, m = 0, stop = STOP_NONE, syncw = 0;
+    bool synced = false;
+    r.start = t;
+    while (p < bend) {
+        const uint32_t w = (p - base) >> 5;
+        if (synced) {
+            if (w != syncw) {                                // first unit of a later word: splice the speculative tail in
+                const uint32_t c = rs.cm[w * 32 + lane];
+                r.out = out + (r.spec_out - (c >> 12));
+                r.m = m + (r.spec_m - (c & 0xfffu));
+                r.end = r.spec_end; r.stop = r.spec_stop;
+                return;
+            }
+        } else if ((rs.mask[w * 32 + lane] >> (p & 31u)) & 1u) {
+            synced = true; syncw = w;
+        }
+        const Unit u = decode_unit<false>(lb, L, D);
+        p += u.used;
+        if (u.kind >= U_EOB) { stop = u.kind == U_EOB ? STOP_EOB : STOP_BAD; break; }
+        out += u.kind == U_LIT ? 1u : u.val;
+        m += u.kind;
+    }
+    r.end = p; r.stop = stop; r.out = out; r.m = m;
+}
+
+// P3.  Decode the settled subsequence, store literals, park matches (stream order).
+// `o` is the lane's first output position inside the member, `qi` its first queue slot.
+// Returns 0, or a nonzero reason to abandon the round.
+ZB_HD int round_emit(const RoundLane &r, uint32_t lane, int lg, const RoundShared &rs,
+                     const uint32_t *__restrict__ L, const uint32_t *__restrict__ D,
+                     uint8_t *__restrict__ out, uint32_t o, QueuedMatch *__restrict__ q, uint32_t qi) {
+    const uint32_t S = 32u << lg, bend = lane * S + S;
+    LaneBits lb; lb.stage = rs.stage; lb.lg = lg;
+    uint32_t p = r.start;
+    lb.seek(p);
+    while (p < bend) {
+        const Unit u = decode_unit<true>(lb, L, D);
+        p += u.used;
+        if (u.kind == U_LIT) { out[o++] = (uint8_t)u.val; continue; }
+        if (u.kind != U_MATCH) return u.kind == U_EOB ? 0 : 1;
+        if (u.dist > o) return 2;                            // inffast.c:152-161 "invalid distance too far back"
+        q[qi].dst = o; q[qi].packed = qm_pack(u.val, u.dist, false);
+        ++qi;
+        o += u.val;
+    }
+    return 0;
+}
+
+// Subsequence size for a round: the largest S with 32*S bits still inside the member, or -1
+// when too little input is left for a round to pay off (the serial path finishes the member).
+ZB_HD int round_pick_lg(uint64_t remaining_bits) {
+    for (int lg = kRoundLgMax; lg >= kRoundLgMin; --lg)
+        if (remaining_bits >= (uint64_t)(32u << lg) * 32u) return lg;
+    return -1;
+}
+
+}  // namespace zb
