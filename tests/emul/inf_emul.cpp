@@ -83,41 +83,43 @@ static int host_rounds(const uint8_t *src, uint64_t in_len, uint8_t *dst, uint64
         int lg = round_pick_lg(total_bits - B);
         if (lg < 0) { g_stats.serial_returns++; return 1; }
         if (force_lg >= kRoundLgMin && force_lg < lg) lg = force_lg;
-        const uint32_t S = 32u << lg;
+        const uint32_t S = 32u << lg, W = 1u << lg, stride = stage_row_stride(lg);
         const uint64_t W0 = B >> 5;
-        const uint32_t nw = (32u << lg) + kStageTail;
-        for (uint32_t k = 0; k < nw; ++k) {
-            const uint64_t w = W0 + k;
+        uint32_t *stage = rs.stage[g_stats.rounds & 1];
+        for (uint32_t k = 0; k < 32 * stride; ++k) {
+            const uint32_t row = k / stride, col = k - row * stride;
+            const uint64_t w = W0 + row * W + col;
             uint32_t v = 0;
             if (w < nwords) {                           // byte-wise: the host buffer has no alignment slack to read whole words from
                 for (int b = 0; b < 4; ++b) {
-                    const uint64_t byte = w * 4 + b;    // relative to a0
+                    const uint64_t byte = w * 4 + b;    // relative to the aligned base
                     const uint64_t lo = bias / 8, hi = lo + in_len;
                     if (byte >= lo && byte < hi) v |= (uint32_t)src[byte - lo] << (8 * b);
                 }
             }
-            rs.stage[k + (k >> lg)] = v;
+            stage[k] = v;
         }
         RoundLane r[32];
-        for (uint32_t l = 0; l < 32; ++l) round_speculate(r[l], l, lg, l ? l * S : (uint32_t)(B & 31u), rs, lt, dt);
+        for (uint32_t l = 0; l < 32; ++l) round_speculate(r[l], l, lg, l ? 0u : (uint32_t)(B & 31u), stage, rs, lt, dt);
         g_stats.rounds++;
         for (;;) {
             uint32_t nvalid = 32;
             for (uint32_t l = 0; l < 32; ++l) if (r[l].stop != STOP_NONE) { nvalid = l + 1; break; }
             uint32_t t[32]; bool need[32]; bool any = false;
             for (uint32_t l = 0; l < 32; ++l) {
-                t[l] = l ? r[l - 1].end : 0;
+                t[l] = l ? r[l - 1].end - S : 0;
                 need[l] = l > 0 && l < nvalid && t[l] != r[l].start;
                 any |= need[l];
             }
             if (!any) break;
             g_stats.fix_passes++;
-            for (uint32_t l = 0; l < 32; ++l) if (need[l]) { round_fix(r[l], l, lg, t[l], rs, lt, dt); g_stats.fix_lane_runs++; }
+            for (uint32_t l = 0; l < 32; ++l) if (need[l]) { round_fix(r[l], l, lg, t[l], stage, rs, lt, dt); g_stats.fix_lane_runs++; }
         }
         uint32_t last = 31;
         for (uint32_t l = 0; l < 32; ++l) if (r[l].stop != STOP_NONE) { last = l; break; }
+        const uint64_t end_abs = W0 * 32 + (uint64_t)last * S + r[last].end;
         if (r[last].stop == STOP_BAD) { g_stats.serial_returns++; return 1; }
-        if (W0 * 32 + r[last].end > total_bits) { g_stats.serial_returns++; return 1; }
+        if (end_abs > total_bits) { g_stats.serial_returns++; return 1; }
         uint32_t off_o[33], off_m[33];
         off_o[0] = off_m[0] = 0;
         for (uint32_t l = 0; l < 32; ++l) {
@@ -128,7 +130,7 @@ static int host_rounds(const uint8_t *src, uint64_t in_len, uint8_t *dst, uint64
         if (off_m[32] > kRoundQueueCap) return -1;
         bool err = false;
         for (int l = (int)last; l >= 0; --l)             // any lane order must do: run them backwards
-            err |= round_emit(r[l], (uint32_t)l, lg, rs, lt, dt, dst, (uint32_t)pos + off_o[l], gq.data(), off_m[l]) != 0;
+            err |= round_emit(r[l], (uint32_t)l, lg, stage, lt, dt, dst, (uint32_t)pos + off_o[l], gq.data(), off_m[l]) != 0;
         if (err) { g_stats.serial_returns++; return 1; }
         // P4 as on the device: waves of 32, independent matches first (replayed in reverse), dependents in order
         const uint32_t count = off_m[32];
@@ -150,7 +152,7 @@ static int host_rounds(const uint8_t *src, uint64_t in_len, uint8_t *dst, uint64
             for (uint32_t k = 0; k < n; ++k) if (dep[k]) copy(gq[base + k]);
         }
         pos += off_o[32];
-        bitpos = W0 * 32 + r[last].end - bias;
+        bitpos = end_abs - bias;
         if (r[last].stop == STOP_EOB) return 0;
     }
 }

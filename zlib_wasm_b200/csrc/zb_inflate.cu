@@ -17,7 +17,7 @@
 namespace zb {
 
 constexpr int kInfWarps = 2;
-constexpr int kInfCtasPerSm = 5;          // 5 CTAs x (2 warps x 19.6 KiB + 3.4 KiB) of shared memory fit one SM
+constexpr int kInfCtasPerSm = 4;          // 4 CTAs x (2 warps x 24 KiB + 3.4 KiB) of shared memory fit one SM
 constexpr size_t kMaxGridWarps = 2048;    // upper bound on resident warps (sizes the per-warp match queues)
 // Two symbol decoders exist: the serial loop on lane 0 (InflateState::fast_symbols,
 // ~79 warp instructions per symbol with one lane active) and the warp-parallel rounds
@@ -86,6 +86,19 @@ __device__ __forceinline__ void exec_queue(uint8_t *dst, const QueuedMatch *q, u
 }
 
 // ---- warp-parallel Huffman block decode (rounds: zb_inflate_round.cuh) ---------------
+// Copy one match owned by this lane (source and destination do not overlap): all loads
+// of a 16-byte step are issued before its stores, so a step costs one memory round
+// trip instead of one per byte.
+__device__ __forceinline__ void copy_own(uint8_t *__restrict__ d, const uint8_t *__restrict__ s, uint32_t len) {
+    for (uint32_t i = 0; i < len; i += 16) {
+        uint8_t t[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) if (i + k < len) t[k] = s[i + k];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) if (i + k < len) d[i + k] = t[k];
+    }
+}
+
 // Execute the `count` matches of a round, parked in stream order, in waves of 32:
 // a match whose source ends before the wave's first destination cannot depend on a
 // wave-mate and is copied by its own lane (all such copies overlap); the others
@@ -93,27 +106,17 @@ __device__ __forceinline__ void exec_queue(uint8_t *dst, const QueuedMatch *q, u
 __device__ __forceinline__ void exec_round_queue(uint8_t *dst, const QueuedMatch *__restrict__ q, uint32_t count) {
     const unsigned full = 0xffffffffu;
     const uint32_t lane = threadIdx.x & 31;
+    QueuedMatch nxt;
+    nxt.dst = 0; nxt.packed = 0;
+    if (lane < count) nxt = q[lane];
     for (uint32_t base = 0; base < count; base += 32) {
         const bool mine = base + lane < count;
-        QueuedMatch e;
-        e.dst = 0; e.packed = 0;
-        if (mine) e = q[base + lane];
+        const QueuedMatch e = nxt;
+        if (base + 32 + lane < count) nxt = q[base + 32 + lane];   // the next wave's entries travel while this one is copied
         const uint32_t first = __shfl_sync(full, e.dst, 0);
         const uint32_t len = qm_len(e.packed), dist = qm_dist(e.packed);
         const bool dep = mine && (dist < len || e.dst - dist + len > first);
-        if (mine && !dep) {
-            uint8_t *d = dst + e.dst;
-            const uint8_t *s = d - dist;
-            uint32_t i = 0;
-            for (; i + 8 <= len; i += 8) {
-                uint8_t t[8];
-#pragma unroll
-                for (int k = 0; k < 8; ++k) t[k] = s[i + k];
-#pragma unroll
-                for (int k = 0; k < 8; ++k) d[i + k] = t[k];
-            }
-            for (; i < len; ++i) d[i] = s[i];
-        }
+        if (mine && !dep) copy_own(dst + e.dst, dst + e.dst - dist, len);
         uint32_t depmask = __ballot_sync(full, dep);
         __syncwarp(full);
         while (depmask) {
@@ -129,6 +132,31 @@ __device__ __forceinline__ void exec_round_queue(uint8_t *dst, const QueuedMatch
         }
     }
 }
+
+// Fetch a round's rows into shared memory with cp.async (4-byte copies, zero-filled
+// past the end of the member's input): row i = words [W0 + i*W, W0 + i*W + W + 3).
+template <int LG>
+__device__ __forceinline__ void stage_fetch_lg(uint32_t *stage, const uint32_t *__restrict__ words, uint64_t W0, uint64_t nwords, uint32_t lane) {
+    constexpr uint32_t W = 1u << LG, stride = W + kRowExtra, total = 32 * stride;
+    for (uint32_t k = lane; k < total; k += 32) {
+        const uint32_t row = k / stride, col = k - row * stride;
+        const uint64_t w = W0 + row * W + col;
+        const uint32_t sa = (uint32_t)__cvta_generic_to_shared(stage + k);
+        const uint32_t *g = words + (w < nwords ? w : nwords - 1);
+        const int bytes = w < nwords ? 4 : 0;
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(sa), "l"(g), "r"(bytes) : "memory");
+    }
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+}
+__device__ __forceinline__ void stage_fetch(uint32_t *stage, const uint32_t *words, uint64_t W0, uint64_t nwords, int lg, uint32_t lane) {
+    switch (lg) {
+        case 2: stage_fetch_lg<2>(stage, words, W0, nwords, lane); break;
+        case 3: stage_fetch_lg<3>(stage, words, W0, nwords, lane); break;
+        case 4: stage_fetch_lg<4>(stage, words, W0, nwords, lane); break;
+        default: stage_fetch_lg<5>(stage, words, W0, nwords, lane); break;
+    }
+}
+__device__ __forceinline__ void stage_wait() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
 
 // status 0: the block's end-of-block code was consumed; 1: lane 0 continues inside
 // the block on the serial path from (bitpos, pos) — end of the member's input, or a
@@ -146,37 +174,42 @@ huff_rounds_warp(const uint8_t *src, uint64_t in_len, uint8_t *dst, uint64_t out
     const uint64_t total_bits = bias + in_len * 8;                  // valid bits are [bias, total_bits)
     const uint64_t nwords = (total_bits + 31) >> 5;
     HuffResult res;
+    res.status = 1; res.bitpos = bitpos; res.pos = pos;
+    uint64_t B = bias + bitpos;
+    if (B >= total_bits) return res;
+    int lg = round_pick_lg(total_bits - B);
+    if (lg < 0) return res;
+    int buf = 0;
+    stage_fetch(rs.stage[0], words, B >> 5, nwords, lg, lane);
     for (;;) {
-        res.status = 1; res.bitpos = bitpos; res.pos = pos;
-        const uint64_t B = bias + bitpos;
-        if (B >= total_bits) return res;
-        const int lg = round_pick_lg(total_bits - B);
-        if (lg < 0) return res;
+        res.status = 1; res.bitpos = bitpos; res.pos = pos;         // where the serial path would take over
         const uint32_t S = 32u << lg;
         const uint64_t W0 = B >> 5;
-        {   // stage the round's words (coalesced), one pad word per subsequence
-            const uint32_t nw = (32u << lg) + kStageTail;
-            for (uint32_t k = lane; k < nw; k += 32) {
-                const uint64_t w = W0 + k;
-                rs.stage[k + (k >> lg)] = w < nwords ? words[w] : 0u;
-            }
-        }
+        const uint32_t *stage = rs.stage[buf];
+        stage_wait();
         __syncwarp(full);
         RoundLane r;
-        round_speculate(r, lane, lg, lane ? lane * S : (uint32_t)(B & 31u), rs, lt, dt);
+        round_speculate(r, lane, lg, lane ? 0u : (uint32_t)(B & 31u), stage, rs, lt, dt);
         for (;;) {                                                   // P2: until no start moves
             const uint32_t stopmask = __ballot_sync(full, r.stop != STOP_NONE);
             const uint32_t nvalid = stopmask ? (uint32_t)__ffs(stopmask) : 32u;
-            const uint32_t t = __shfl_up_sync(full, r.end, 1);
+            const uint32_t t = __shfl_up_sync(full, r.end, 1) - S;   // lane i-1's end, in lane i's coordinates
             const bool need = lane > 0 && lane < nvalid && t != r.start;
             if (!__ballot_sync(full, need)) break;
-            if (need) round_fix(r, lane, lg, t, rs, lt, dt);
+            if (need) round_fix(r, lane, lg, t, stage, rs, lt, dt);
         }
         const uint32_t stopmask = __ballot_sync(full, r.stop != STOP_NONE);
         const uint32_t last = stopmask ? (uint32_t)__ffs(stopmask) - 1u : 31u;
-        const uint32_t stop_l = __shfl_sync(full, r.stop, last), end_l = __shfl_sync(full, r.end, last);
+        const uint32_t stop_l = __shfl_sync(full, r.stop, last);
+        const uint64_t end_abs = W0 * 32 + (uint64_t)last * S + __shfl_sync(full, r.end, last);
         if (stop_l == STOP_BAD) return res;
-        if (W0 * 32 + end_l > total_bits) return res;               // ran past the input: the serial path reports it
+        if (end_abs > total_bits) return res;                        // ran past the input: the serial path reports it
+        // the next round's rows travel while this one is emitted and copied
+        int next_lg = -1;
+        if (stop_l == STOP_NONE) {
+            next_lg = end_abs < total_bits ? round_pick_lg(total_bits - end_abs) : -1;
+            if (next_lg >= 0) stage_fetch(rs.stage[buf ^ 1], words, end_abs >> 5, nwords, next_lg, lane);
+        }
         const bool valid = lane <= last;
         const uint32_t myout = valid ? r.out : 0u, mym = valid ? r.m : 0u;
         uint32_t inc_o = myout, inc_m = mym;
@@ -186,15 +219,19 @@ huff_rounds_warp(const uint8_t *src, uint64_t in_len, uint8_t *dst, uint64_t out
             if (lane >= (uint32_t)dlt) { inc_o += yo; inc_m += ym; }
         }
         const uint32_t tot_o = __shfl_sync(full, inc_o, 31), tot_m = __shfl_sync(full, inc_m, 31);
-        if (tot_o > out_cap - pos) return res;
-        int err = 0;
-        if (valid) err = round_emit(r, lane, lg, rs, lt, dt, dst, (uint32_t)pos + inc_o - myout, gq, inc_m - mym);
-        if (__ballot_sync(full, err != 0)) return res;
+        int err = tot_o > out_cap - pos;
+        if (!err && valid) err = round_emit(r, lane, lg, stage, lt, dt, dst, (uint32_t)pos + inc_o - myout, gq, inc_m - mym);
+        if (__ballot_sync(full, err != 0)) { stage_wait(); return res; }
         __syncwarp(full);                                            // literals and queue entries -> visible to every lane
         exec_round_queue(dst, gq, tot_m);
         pos += tot_o;
-        bitpos = W0 * 32 + end_l - bias;
-        if (stop_l == STOP_EOB) { res.status = 0; res.bitpos = bitpos; res.pos = pos; return res; }
+        B = end_abs;
+        bitpos = B - bias;
+        res.bitpos = bitpos; res.pos = pos;
+        if (stop_l == STOP_EOB) { res.status = 0; return res; }
+        if (next_lg < 0) { res.status = 1; return res; }
+        lg = next_lg;
+        buf ^= 1;
     }
 }
 

@@ -41,104 +41,108 @@ namespace zb {
 
 constexpr int kRoundLgMin = 2, kRoundLgMax = 5;              // words per lane = 1 << lg  (S = 128 .. 1024 bits)
 constexpr int kRoundWordsMax = 1 << kRoundLgMax;
-constexpr int kStageTail = 4;                                // words a lane may read past the last subsequence
-constexpr int kStageWords = 32 * kRoundWordsMax + 32 + kStageTail + 4;
+constexpr int kRowExtra = 3;                                 // words of the following subsequence repeated at the end of a row
+constexpr int kStageWords = 32 * (kRoundWordsMax + kRowExtra);
 constexpr uint32_t kRoundQueueCap = 32u * (32u << kRoundLgMax) / 2u;   // a match costs at least 2 bits
 
 // Per-warp working memory of a round (shared memory on the device).
+// stage: lane i owns row i = the W words of its subsequence followed by the next 3
+// words of the stream (a unit may start on the row's last bit and is up to 48 bits
+// long).  The row stride W + 3 is odd, so the 32 lanes reading the same column of
+// their rows hit 32 different banks.
 struct RoundShared {
-    uint32_t stage[kStageWords];                 // the round's input words; one pad word per subsequence (bank spread)
+    uint32_t stage[2][kStageWords];              // double-buffered: the next round is fetched while this one is emitted
     uint32_t mask[kRoundWordsMax * 32];          // [word][lane] unit starts visited by the speculative pass
     uint32_t cm[kRoundWordsMax * 32];            // [word][lane] (output bytes << 12 | matches) before the word's first unit
 };
+ZB_HD uint32_t stage_row_stride(int lg) { return (1u << lg) + kRowExtra; }
 
-// LSB-first bit reader of one lane over the staged words.
-struct LaneBits {
-    const uint32_t *stage; int lg;
-    uint64_t hold; int nb; uint32_t wp;
-    ZB_HD uint32_t word(uint32_t w) const { return stage[w + (w >> lg)]; }
-    ZB_HD void seek(uint32_t p) {
-        wp = p >> 5;
-        hold = (uint64_t)word(wp) | ((uint64_t)word(wp + 1) << 32);
-        wp += 2;
-        hold >>= (p & 31u);
-        nb = 64 - (int)(p & 31u);
-    }
-    ZB_HD void fill() { if (nb <= 32) { hold |= (uint64_t)word(wp) << nb; ++wp; nb += 32; } }
-    ZB_HD void drop(uint32_t k) { hold >>= k; nb -= (int)k; }
+ZB_HD uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t s) {
+#ifdef __CUDA_ARCH__
+    return __funnelshift_r(lo, hi, s);
+#else
+    s &= 31u;
+    return s ? (lo >> s) | (hi << (32u - s)) : lo;
+#endif
+}
+
+// LSB-first view of one lane's row: at(p) = the 32 stream bits that start at bit p of
+// the lane's subsequence.  No running state: a unit re-derives its window from the bit
+// position, which costs two shared-memory loads and one funnel shift.
+struct LaneWin {
+    const uint32_t *row;
+    ZB_HD uint32_t at(uint32_t p) const { const uint32_t r = p >> 5; return funnel_r(row[r], row[r + 1], p); }
 };
 
 enum : uint32_t { U_LIT = 0, U_MATCH = 1, U_EOB = 2, U_BAD = 3 };
 struct Unit { uint32_t kind, used, val, dist; };             // val: literal byte or match length
 
-// Decode the unit at the reader's position (the work of one trip of inffast.c:100-287).
+// Decode the unit at bit p (the work of one trip of inffast.c:100-287).  A literal /
+// length code with its extra bits is at most 20 bits, a distance code with its extra
+// bits at most 28: each half fits one 32-bit window.
 template <bool kWantDist>
-ZB_HD Unit decode_unit(LaneBits &lb, const uint32_t *__restrict__ L, const uint32_t *__restrict__ D) {
+ZB_HD Unit decode_unit(const LaneWin &lw, uint32_t p, const uint32_t *__restrict__ L, const uint32_t *__restrict__ D) {
     Unit u;
     u.dist = 0; u.val = 0;
-    lb.fill();                                               // >= 33 bits: a literal/length code and its extra bits
-    uint32_t used = 0;
-    uint32_t e = L[(uint32_t)lb.hold & ((1u << kLitRoot) - 1u)];
+    uint32_t w = lw.at(p), used = 0;
+    uint32_t e = L[w & ((1u << kLitRoot) - 1u)];
     if (ZB_E_OP(e) == OP_SUB) {
-        const uint32_t sub = ZB_E_VAL(e) + (((uint32_t)(lb.hold >> kLitRoot)) & ((1u << ZB_E_EXTRA(e)) - 1u));
-        lb.drop(kLitRoot); used = kLitRoot;
-        e = L[sub];
+        e = L[ZB_E_VAL(e) + ((w >> kLitRoot) & ((1u << ZB_E_EXTRA(e)) - 1u))];
+        w >>= kLitRoot; used = kLitRoot;
     }
-    { const uint32_t k = ZB_E_BITS(e); lb.drop(k); used += k; }
+    { const uint32_t k = ZB_E_BITS(e); w >>= k; used += k; }
     const uint32_t op = ZB_E_OP(e);
     if (op == OP_LIT) { u.kind = U_LIT; u.val = e >> 16; u.used = used; return u; }
-    if (op == OP_EOB) { u.kind = U_EOB; u.used = used; return u; }
-    if (op != OP_BASE) { u.kind = U_BAD; u.used = used; return u; }
+    if (op != OP_BASE) { u.kind = op == OP_EOB ? U_EOB : U_BAD; u.used = used; return u; }
     {
         const uint32_t x = ZB_E_EXTRA(e);
-        u.val = ZB_E_VAL(e) + ((uint32_t)lb.hold & ((1u << x) - 1u));
-        lb.drop(x); used += x;
+        u.val = ZB_E_VAL(e) + (w & ((1u << x) - 1u));
+        used += x;
     }
-    lb.fill();                                               // >= 33 bits again: a distance code and its extra bits
-    uint32_t d = D[(uint32_t)lb.hold & ((1u << kDistRoot) - 1u)];
+    w = lw.at(p + used);
+    uint32_t d = D[w & ((1u << kDistRoot) - 1u)];
     if (ZB_E_OP(d) == OP_SUB) {
-        const uint32_t sub = ZB_E_VAL(d) + (((uint32_t)(lb.hold >> kDistRoot)) & ((1u << ZB_E_EXTRA(d)) - 1u));
-        lb.drop(kDistRoot); used += kDistRoot;
-        d = D[sub];
+        d = D[ZB_E_VAL(d) + ((w >> kDistRoot) & ((1u << ZB_E_EXTRA(d)) - 1u))];
+        w >>= kDistRoot; used += kDistRoot;
     }
-    { const uint32_t k = ZB_E_BITS(d); lb.drop(k); used += k; }
+    { const uint32_t k = ZB_E_BITS(d); w >>= k; used += k; }
     if (ZB_E_OP(d) != OP_BASE) { u.kind = U_BAD; u.used = used; return u; }
     {
         const uint32_t dx = ZB_E_EXTRA(d);
-        if (kWantDist) u.dist = ZB_E_VAL(d) + ((uint32_t)lb.hold & ((1u << dx) - 1u));
-        lb.drop(dx); used += dx;
+        if (kWantDist) u.dist = ZB_E_VAL(d) + (w & ((1u << dx) - 1u));
+        used += dx;
     }
     u.kind = U_MATCH; u.used = used;
     return u;
 }
 
-// What a lane knows about its subsequence.  Positions are bits relative to the
-// round's word-aligned base.
+// What a lane knows about its subsequence.  Positions are bits relative to the START
+// OF THE LANE'S OWN subsequence (lane i's bit 0 = bit i*S of the round); a path ends at
+// the first unit start >= S, i.e. at bit (end - S) of the next lane.
 struct RoundLane {
     uint32_t spec_end, spec_stop, spec_out, spec_m;          // the speculative path (never changes after P1)
     uint32_t start, end, stop, out, m;                       // the current path (true once P2 has settled)
 };
 enum : uint32_t { STOP_NONE = 0, STOP_EOB = 1, STOP_BAD = 2 };
 
-// P1.  `start` is lane*S, except for lane 0 which starts at the block's true position.
-ZB_HD void round_speculate(RoundLane &r, uint32_t lane, int lg, uint32_t start, RoundShared &rs,
+// P1.  `start` is 0, except for lane 0 which starts at the block's true position.
+ZB_HD void round_speculate(RoundLane &r, uint32_t lane, int lg, uint32_t start, const uint32_t *stage, RoundShared &rs,
                            const uint32_t *__restrict__ L, const uint32_t *__restrict__ D) {
-    const uint32_t W = 1u << lg, S = 32u << lg, base = lane * S, bend = base + S;
+    const uint32_t W = 1u << lg, S = 32u << lg;
     for (uint32_t w = 0; w < W; ++w) rs.mask[w * 32 + lane] = 0;
-    LaneBits lb; lb.stage = rs.stage; lb.lg = lg;
+    LaneWin lw; lw.row = stage + lane * stage_row_stride(lg);
     uint32_t p = start;
-    lb.seek(p);
-    uint32_t curw = (p - base) >> 5, mw = 0, out = 0, m = 0, stop = STOP_NONE;
+    uint32_t curw = p >> 5, mw = 0, out = 0, m = 0, stop = STOP_NONE;
     rs.cm[curw * 32 + lane] = 0;
-    while (p < bend) {
-        const uint32_t w = (p - base) >> 5;
+    while (p < S) {
+        const uint32_t w = p >> 5;
         if (w != curw) {
             rs.mask[curw * 32 + lane] = mw;
             mw = 0; curw = w;
             rs.cm[w * 32 + lane] = (out << 12) | m;
         }
         mw |= 1u << (p & 31u);
-        const Unit u = decode_unit<false>(lb, L, D);
+        const Unit u = decode_unit<false>(lw, p, L, D);
         p += u.used;
         if (u.kind >= U_EOB) { stop = u.kind == U_EOB ? STOP_EOB : STOP_BAD; break; }
         out += u.kind == U_LIT ? 1u : u.val;
@@ -150,17 +154,16 @@ ZB_HD void round_speculate(RoundLane &r, uint32_t lane, int lg, uint32_t start, 
 }
 
 // P2.  Re-decode from the true start `t` until the path joins the speculative one.
-ZB_HD void round_fix(RoundLane &r, uint32_t lane, int lg, uint32_t t, const RoundShared &rs,
+ZB_HD void round_fix(RoundLane &r, uint32_t lane, int lg, uint32_t t, const uint32_t *stage, const RoundShared &rs,
                      const uint32_t *__restrict__ L, const uint32_t *__restrict__ D) {
-    const uint32_t S = 32u << lg, base = lane * S, bend = base + S;
-    LaneBits lb; lb.stage = rs.stage; lb.lg = lg;
+    const uint32_t S = 32u << lg;
+    LaneWin lw; lw.row = stage + lane * stage_row_stride(lg);
     uint32_t p = t;
-    lb.seek(p);
     uint32_t out = 0, m = 0, stop = STOP_NONE, syncw = 0;
     bool synced = false;
     r.start = t;
-    while (p < bend) {
-        const uint32_t w = (p - base) >> 5;
+    while (p < S) {
+        const uint32_t w = p >> 5;
         if (synced) {
             if (w != syncw) {                                // first unit of a later word: splice the speculative tail in
                 const uint32_t c = rs.cm[w * 32 + lane];
@@ -172,7 +175,7 @@ ZB_HD void round_fix(RoundLane &r, uint32_t lane, int lg, uint32_t t, const Roun
         } else if ((rs.mask[w * 32 + lane] >> (p & 31u)) & 1u) {
             synced = true; syncw = w;
         }
-        const Unit u = decode_unit<false>(lb, L, D);
+        const Unit u = decode_unit<false>(lw, p, L, D);
         p += u.used;
         if (u.kind >= U_EOB) { stop = u.kind == U_EOB ? STOP_EOB : STOP_BAD; break; }
         out += u.kind == U_LIT ? 1u : u.val;
@@ -184,15 +187,14 @@ ZB_HD void round_fix(RoundLane &r, uint32_t lane, int lg, uint32_t t, const Roun
 // P3.  Decode the settled subsequence, store literals, park matches (stream order).
 // `o` is the lane's first output position inside the member, `qi` its first queue slot.
 // Returns 0, or a nonzero reason to abandon the round.
-ZB_HD int round_emit(const RoundLane &r, uint32_t lane, int lg, const RoundShared &rs,
+ZB_HD int round_emit(const RoundLane &r, uint32_t lane, int lg, const uint32_t *stage,
                      const uint32_t *__restrict__ L, const uint32_t *__restrict__ D,
                      uint8_t *__restrict__ out, uint32_t o, QueuedMatch *__restrict__ q, uint32_t qi) {
-    const uint32_t S = 32u << lg, bend = lane * S + S;
-    LaneBits lb; lb.stage = rs.stage; lb.lg = lg;
+    const uint32_t S = 32u << lg;
+    LaneWin lw; lw.row = stage + lane * stage_row_stride(lg);
     uint32_t p = r.start;
-    lb.seek(p);
-    while (p < bend) {
-        const Unit u = decode_unit<true>(lb, L, D);
+    while (p < S) {
+        const Unit u = decode_unit<true>(lw, p, L, D);
         p += u.used;
         if (u.kind == U_LIT) { out[o++] = (uint8_t)u.val; continue; }
         if (u.kind != U_MATCH) return u.kind == U_EOB ? 0 : 1;
