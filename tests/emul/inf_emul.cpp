@@ -85,7 +85,7 @@ static int host_rounds(const uint8_t *src, uint64_t in_len, uint8_t *dst, uint64
         if (force_lg >= kRoundLgMin && force_lg < lg) lg = force_lg;
         const uint32_t S = 32u << lg, W = 1u << lg, stride = stage_row_stride(lg);
         const uint64_t W0 = B >> 5;
-        uint32_t *stage = rs.stage[g_stats.rounds & 1];
+        uint32_t *stage = rs.stage;
         for (uint32_t k = 0; k < 32 * stride; ++k) {
             const uint32_t row = k / stride, col = k - row * stride;
             const uint64_t w = W0 + row * W + col;

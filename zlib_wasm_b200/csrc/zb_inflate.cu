@@ -13,11 +13,12 @@
 #include "zb_inflate.cuh"
 #include "zb_inflate_round.cuh"
 #include <string.h>
+#include <stdlib.h>
 
 namespace zb {
 
-constexpr int kInfWarps = 2;
-constexpr int kInfCtasPerSm = 4;          // 4 CTAs x (2 warps x 24 KiB + 3.4 KiB) of shared memory fit one SM
+constexpr int kInfWarps = 4;
+constexpr int kInfCtasPerSm = 4;          // 4 CTAs x (4 warps x 12.6 KiB + 3.4 KiB) of shared memory, 128 registers: 16 warps per SM
 constexpr size_t kMaxGridWarps = 2048;    // upper bound on resident warps (sizes the per-warp match queues)
 // Two symbol decoders exist: the serial loop on lane 0 (InflateState::fast_symbols,
 // ~79 warp instructions per symbol with one lane active) and the warp-parallel rounds
@@ -31,10 +32,19 @@ struct InflateDeviceTables {
     FormatTables fmt;
 };
 
+// Per-warp shared memory: the two decode tables of the open dynamic block, and an area
+// that serves the table construction + the serial path's queue while lane 0 reads a
+// header, and the rounds while the block's symbols are decoded (never both at once).
+struct InflateWarpShared {
+    uint32_t lit[kLitEntries];
+    uint32_t dist[kDistEntries];
+    union {
+        struct { uint16_t work[320]; uint8_t lens[320]; QueuedMatch q[kQueue]; } serial;
+        RoundShared rnd;
+    };
+};
 struct InflateShared {
-    InflateScratch scr[kInfWarps];
-    QueuedMatch q[kInfWarps][kQueue];
-    RoundShared rnd[kInfWarps];
+    InflateWarpShared w[kInfWarps];
     uint32_t fixed_lit[512];
     uint32_t fixed_dist[64];
     FormatTables fmt;
@@ -88,14 +98,24 @@ __device__ __forceinline__ void exec_queue(uint8_t *dst, const QueuedMatch *q, u
 // ---- warp-parallel Huffman block decode (rounds: zb_inflate_round.cuh) ---------------
 // Copy one match owned by this lane (source and destination do not overlap): all loads
 // of a 16-byte step are issued before its stores, so a step costs one memory round
-// trip instead of one per byte.
-__device__ __forceinline__ void copy_own(uint8_t *__restrict__ d, const uint8_t *__restrict__ s, uint32_t len) {
-    for (uint32_t i = 0; i < len; i += 16) {
-        uint8_t t[16];
-#pragma unroll
-        for (int k = 0; k < 16; ++k) if (i + k < len) t[k] = s[i + k];
-#pragma unroll
-        for (int k = 0; k < 16; ++k) if (i + k < len) d[i + k] = t[k];
+// trip instead of one per byte.  Written as predicated PTX (one setp + one ld/st per
+// byte slot, immediate offsets): the compiler's version rebuilt a 64-bit address and
+// spilled predicates for every slot (14 instructions per byte).
+#define ZB_LDB(t, p, n, k) asm volatile("{ .reg .pred q; setp.gt.u32 q, %2, " #k "; @q ld.global.u8 %0, [%1+" #k "]; }" : "+r"(t) : "l"(p), "r"(n))
+#define ZB_STB(t, p, n, k) asm volatile("{ .reg .pred q; setp.gt.u32 q, %2, " #k "; @q st.global.u8 [%1+" #k "], %0; }" :: "r"(t), "l"(p), "r"(n) : "memory")
+__device__ __forceinline__ void copy_own(uint8_t *d, const uint8_t *s, uint32_t len) {
+    for (;;) {
+        uint32_t t0 = 0, t1 = 0, t2 = 0, t3 = 0, t4 = 0, t5 = 0, t6 = 0, t7 = 0, t8 = 0, t9 = 0, ta = 0, tb = 0, tc = 0, td = 0, te = 0, tf = 0;
+        ZB_LDB(t0, s, len, 0); ZB_LDB(t1, s, len, 1); ZB_LDB(t2, s, len, 2); ZB_LDB(t3, s, len, 3);
+        ZB_LDB(t4, s, len, 4); ZB_LDB(t5, s, len, 5); ZB_LDB(t6, s, len, 6); ZB_LDB(t7, s, len, 7);
+        ZB_LDB(t8, s, len, 8); ZB_LDB(t9, s, len, 9); ZB_LDB(ta, s, len, 10); ZB_LDB(tb, s, len, 11);
+        ZB_LDB(tc, s, len, 12); ZB_LDB(td, s, len, 13); ZB_LDB(te, s, len, 14); ZB_LDB(tf, s, len, 15);
+        ZB_STB(t0, d, len, 0); ZB_STB(t1, d, len, 1); ZB_STB(t2, d, len, 2); ZB_STB(t3, d, len, 3);
+        ZB_STB(t4, d, len, 4); ZB_STB(t5, d, len, 5); ZB_STB(t6, d, len, 6); ZB_STB(t7, d, len, 7);
+        ZB_STB(t8, d, len, 8); ZB_STB(t9, d, len, 9); ZB_STB(ta, d, len, 10); ZB_STB(tb, d, len, 11);
+        ZB_STB(tc, d, len, 12); ZB_STB(td, d, len, 13); ZB_STB(te, d, len, 14); ZB_STB(tf, d, len, 15);
+        if (len <= 16) break;
+        len -= 16; s += 16; d += 16;
     }
 }
 
@@ -179,13 +199,13 @@ huff_rounds_warp(const uint8_t *src, uint64_t in_len, uint8_t *dst, uint64_t out
     if (B >= total_bits) return res;
     int lg = round_pick_lg(total_bits - B);
     if (lg < 0) return res;
-    int buf = 0;
-    stage_fetch(rs.stage[0], words, B >> 5, nwords, lg, lane);
     for (;;) {
         res.status = 1; res.bitpos = bitpos; res.pos = pos;         // where the serial path would take over
         const uint32_t S = 32u << lg;
         const uint64_t W0 = B >> 5;
-        const uint32_t *stage = rs.stage[buf];
+        const uint32_t *stage = rs.stage;
+        __syncwarp(full);                                            // every lane is done with the previous round's rows
+        stage_fetch(rs.stage, words, W0, nwords, lg, lane);
         stage_wait();
         __syncwarp(full);
         RoundLane r;
@@ -204,12 +224,7 @@ huff_rounds_warp(const uint8_t *src, uint64_t in_len, uint8_t *dst, uint64_t out
         const uint64_t end_abs = W0 * 32 + (uint64_t)last * S + __shfl_sync(full, r.end, last);
         if (stop_l == STOP_BAD) return res;
         if (end_abs > total_bits) return res;                        // ran past the input: the serial path reports it
-        // the next round's rows travel while this one is emitted and copied
-        int next_lg = -1;
-        if (stop_l == STOP_NONE) {
-            next_lg = end_abs < total_bits ? round_pick_lg(total_bits - end_abs) : -1;
-            if (next_lg >= 0) stage_fetch(rs.stage[buf ^ 1], words, end_abs >> 5, nwords, next_lg, lane);
-        }
+        const int next_lg = stop_l == STOP_NONE && end_abs < total_bits ? round_pick_lg(total_bits - end_abs) : -1;
         const bool valid = lane <= last;
         const uint32_t myout = valid ? r.out : 0u, mym = valid ? r.m : 0u;
         uint32_t inc_o = myout, inc_m = mym;
@@ -221,7 +236,7 @@ huff_rounds_warp(const uint8_t *src, uint64_t in_len, uint8_t *dst, uint64_t out
         const uint32_t tot_o = __shfl_sync(full, inc_o, 31), tot_m = __shfl_sync(full, inc_m, 31);
         int err = tot_o > out_cap - pos;
         if (!err && valid) err = round_emit(r, lane, lg, stage, lt, dt, dst, (uint32_t)pos + inc_o - myout, gq, inc_m - mym);
-        if (__ballot_sync(full, err != 0)) { stage_wait(); return res; }
+        if (__ballot_sync(full, err != 0)) return res;
         __syncwarp(full);                                            // literals and queue entries -> visible to every lane
         exec_round_queue(dst, gq, tot_m);
         pos += tot_o;
@@ -231,11 +246,10 @@ huff_rounds_warp(const uint8_t *src, uint64_t in_len, uint8_t *dst, uint64_t out
         if (stop_l == STOP_EOB) { res.status = 0; return res; }
         if (next_lg < 0) { res.status = 1; return res; }
         lg = next_lg;
-        buf ^= 1;
     }
 }
 
-__global__ void __launch_bounds__(kInfWarps * 32)
+__global__ void __launch_bounds__(kInfWarps * 32, kInfCtasPerSm)
 inflate_kernel(const uint8_t *__restrict__ in, uint8_t *out, const zb200_member *__restrict__ members,
                uint32_t n_members, int wrap, zb200_member_result *__restrict__ results,
                const InflateDeviceTables *__restrict__ tabs, unsigned int *__restrict__ counter,
@@ -265,15 +279,16 @@ inflate_kernel(const uint8_t *__restrict__ in, uint8_t *out, const zb200_member 
         InflateState st;
         int hs = ZB200_INF_OK;
         if (lane == 0) {
-            st.init(src, mb.in_len, dst, mb.out_cap < 0xfffffff0ull ? mb.out_cap : 0xfffffff0ull, &sh.scr[warp],
+            st.init(src, mb.in_len, dst, mb.out_cap < 0xfffffff0ull ? mb.out_cap : 0xfffffff0ull, nullptr,
                     sh.fixed_lit, sh.fixed_dist, &sh.fmt);   // queue entries hold 32-bit output offsets
+            st.bind(sh.w[warp].lit, sh.w[warp].dist, sh.w[warp].serial.work, sh.w[warp].serial.lens);
             st.huff_external = kWarpParallelHuffman ? 1 : 0;
             if (mb.resume_bit) st.resume(mb.resume_bit, mb.resume_out, wrap);
             else hs = st.parse_header(wrap);
             if (hs) st.status = hs;
         }
         hs = __shfl_sync(full, hs, 0);
-        QueuedMatch *q = sh.q[warp];
+        QueuedMatch *q = sh.w[warp].serial.q;
         while (hs == ZB200_INF_OK) {
             InflateEvent ev;
             ev.kind = EV_DONE; ev.len = 0; ev.dist = 0; ev.src = 0; ev.dst = 0;
@@ -284,10 +299,10 @@ inflate_kernel(const uint8_t *__restrict__ in, uint8_t *out, const zb200_member 
             __syncwarp(full);                                  // lane 0's literal stores and queue writes -> visible
             if (kWarpParallelHuffman && kind == EV_HUFF) {     // a Huffman block: all 32 lanes decode it
                 const uint64_t bp = __shfl_sync(full, ev.src, 0), op = __shfl_sync(full, ev.dst, 0);
-                const uint32_t *lt = len ? sh.fixed_lit : sh.scr[warp].lit;
-                const uint32_t *dt = len ? sh.fixed_dist : sh.scr[warp].dist;
+                const uint32_t *lt = len ? sh.fixed_lit : sh.w[warp].lit;
+                const uint32_t *dt = len ? sh.fixed_dist : sh.w[warp].dist;
                 const uint64_t cap = mb.out_cap < 0xfffffff0ull ? mb.out_cap : 0xfffffff0ull;
-                const HuffResult hr = huff_rounds_warp(src, mb.in_len, dst, cap, bp, op, lt, dt, sh.rnd[warp],
+                const HuffResult hr = huff_rounds_warp(src, mb.in_len, dst, cap, bp, op, lt, dt, sh.w[warp].rnd,
                                                        round_queues + (size_t)(blockIdx.x * kInfWarps + warp) * kRoundQueueCap);
                 if (lane == 0) st.seek(hr.bitpos, hr.pos, hr.status);   // status 1: the serial path finishes the block
             } else if (kind == EV_BATCH) {
@@ -416,7 +431,8 @@ int inflate_launch(zb200_ctx *ctx, const uint8_t *d_in, uint8_t *d_out, const zb
     ZB_LAUNCHED();
     ZB_CHECK_LAUNCH();
     size_t ctas = (n + kInfWarps - 1) / kInfWarps;
-    size_t cap = (size_t)ctx->sm_count * kInfCtasPerSm;
+    static const int per_sm_knob = [] { const char *e = getenv("ZB200_INF_CTAS_PER_SM"); return e ? atoi(e) : 0; }();   // profiling knob
+    size_t cap = (size_t)ctx->sm_count * (per_sm_knob > 0 && per_sm_knob < kInfCtasPerSm ? per_sm_knob : kInfCtasPerSm);
     if (cap * kInfWarps > kMaxGridWarps) cap = kMaxGridWarps / kInfWarps;
     if (ctas > cap) ctas = cap;
     inflate_kernel<<<(unsigned)ctas, kInfWarps * 32, sizeof(InflateShared), s>>>(

@@ -168,7 +168,8 @@ struct InflateState {
     uint64_t ck_bit, ck_out;                               // last block boundary (resume point)
     uint32_t stored_check, stored_isize;                   // trailer values
     uint64_t in_used;
-    InflateScratch *scr;
+    uint32_t *tlit, *tdist;                                // decode tables of a dynamic block (kLitEntries / kDistEntries)
+    uint16_t *work; uint8_t *lens;                         // table-construction scratch (320 entries each)
     const uint32_t *fixed_lit, *fixed_dist;
     const FormatTables *fmt;
     InflateEvent parked; int has_parked;                   // event held back until the queue has been executed
@@ -195,12 +196,18 @@ struct InflateState {
     // bytes really available as bits (negative bits means we consumed zero padding)
     ZB_HD bool overrun() const { return bits < 0; }
 
+    // Rebind the working memory (the device keeps the construction scratch in memory it
+    // shares with the rounds, which never run while a header is being read).
+    ZB_HD void bind(uint32_t *lit, uint32_t *dist, uint16_t *w, uint8_t *l) { tlit = lit; tdist = dist; work = w; lens = l; }
+
     ZB_HD void init(const uint8_t *src, uint64_t n, uint8_t *dst, uint64_t cap, InflateScratch *s,
                     const uint32_t *flit, const uint32_t *fdist, const FormatTables *f) {
         in = src; in_len = n; next = 0; hold = 0; bits = 0;
         out = dst; out_cap = cap; pos = 0; last = 0; in_block = 0; lt = dt = nullptr;
         wrap_kind = 0; status = ZB200_INF_OK; ck_bit = 0; ck_out = 0; stored_check = 0; stored_isize = 0;
-        in_used = 0; scr = s; fixed_lit = flit; fixed_dist = fdist; fmt = f; has_parked = 0; huff_external = 0;
+        in_used = 0; fixed_lit = flit; fixed_dist = fdist; fmt = f; has_parked = 0; huff_external = 0;
+        if (s) { tlit = s->lit; tdist = s->dist; work = s->work; lens = s->lens; }
+        else { tlit = tdist = nullptr; work = nullptr; lens = nullptr; }
     }
 
     // Continue a member at a block boundary reported by an earlier, truncated run
@@ -267,15 +274,14 @@ struct InflateState {
         const int nlen = (int)take(5) + 257, ndist = (int)take(5) + 1, ncode = (int)take(4) + 4;
         if (overrun()) return ZB200_INF_TRUNCATED;
         if (nlen > 286 || ndist > 30) return ZB200_INF_TOO_MANY_SYMS;
-        uint8_t *lens = scr->lens;
         for (int i = 0; i < 19; ++i) lens[i] = 0;
         for (int i = 0; i < ncode; ++i) {
             refill();
             lens[fmt->cl_order[i]] = (uint8_t)take(3);
         }
         if (overrun()) return ZB200_INF_TRUNCATED;
-        uint32_t *cl = scr->dist;                      // reuse: the distance table is built afterwards
-        int r = build_decode_table(TBL_CODELEN, lens, 19, cl, kClEntries, kClRoot, scr->work, *fmt);
+        uint32_t *cl = tdist;                          // reuse: the distance table is built afterwards
+        int r = build_decode_table(TBL_CODELEN, lens, 19, cl, kClEntries, kClRoot, work, *fmt);
         if (r < 0 || r == 1) return ZB200_INF_CODE_LENGTHS;       // inftrees.c:131: incomplete CODES set is an error
         const int total = nlen + ndist;
         int have = 0;
@@ -305,21 +311,21 @@ struct InflateState {
             while (rep--) lens[have++] = val;
         }
         if (lens[256] == 0) return ZB200_INF_NO_EOB;
-        r = build_decode_table(TBL_LITLEN, lens, nlen, scr->lit, kLitEntries, kLitRoot, scr->work, *fmt);
+        r = build_decode_table(TBL_LITLEN, lens, nlen, tlit, kLitEntries, kLitRoot, work, *fmt);
         if (r < 0) return ZB200_INF_LITLEN_SET;
         if (r == 1) {                                  // inftrees.c:131-132: incomplete only if a single 1-bit code
             int nz = 0, ones = 0;
             for (int i = 0; i < nlen; ++i) { nz += lens[i] != 0; ones += lens[i] == 1; }
             if (!(nz == 1 && ones == 1)) return ZB200_INF_LITLEN_SET;
         }
-        r = build_decode_table(TBL_DIST, lens + nlen, ndist, scr->dist, kDistEntries, kDistRoot, scr->work, *fmt);
+        r = build_decode_table(TBL_DIST, lens + nlen, ndist, tdist, kDistEntries, kDistRoot, work, *fmt);
         if (r < 0) return ZB200_INF_DIST_SET;
         if (r == 1) {
             int nz = 0, ones = 0;
             for (int i = 0; i < ndist; ++i) { nz += lens[nlen + i] != 0; ones += lens[nlen + i] == 1; }
             if (!(nz == 1 && ones == 1)) return ZB200_INF_DIST_SET;
         }
-        lt = scr->lit; dt = scr->dist;
+        lt = tlit; dt = tdist;
         return ZB200_INF_OK;
     }
 

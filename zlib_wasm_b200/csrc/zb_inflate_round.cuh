@@ -11,16 +11,15 @@
 // within S = 512 bits, 99 % within 1024; median ~100 bits).
 //
 //   P1  speculate  every lane decodes its subsequence from the guessed start and
-//                  records (a) a bitmask of the unit starts it visited and (b) per
-//                  32-bit word the output / match counts accumulated before the
-//                  first unit starting in that word.
+//                  records, per 64-bit double word, the first unit start it visited
+//                  there and the output / match counts accumulated before it.
 //   P2  fix up     lane 0 started at a true unit start.  Lane i re-decodes from the
 //                  true start handed over by lane i-1 (its end position) only until
-//                  it lands on a unit start of its own speculative path — from
-//                  there on the two paths are identical, so the speculative counts
-//                  are spliced in at the next word boundary.  A lane that never
-//                  meets its speculative path simply keeps its own decode.  This
-//                  repeats until no lane's start moves (usually 1-2 short passes).
+//                  its first unit start in a double word equals the recorded one —
+//                  from there on the two paths are identical, so the speculative
+//                  counts are spliced in.  A lane that never meets its speculative
+//                  path simply keeps its own decode.  This repeats until no lane's
+//                  start moves (usually 1-2 short passes).
 //   scan           exclusive sums of the per-lane output bytes and match counts.
 //   P3  emit       every lane decodes its (now true) subsequence once more, storing
 //                  literals at their final positions and parking matches in the
@@ -50,10 +49,15 @@ constexpr uint32_t kRoundQueueCap = 32u * (32u << kRoundLgMax) / 2u;   // a matc
 // words of the stream (a unit may start on the row's last bit and is up to 48 bits
 // long).  The row stride W + 3 is odd, so the 32 lanes reading the same column of
 // their rows hit 32 different banks.
+// fs / cm: what the speculative pass leaves behind per 64-bit double word of a
+// subsequence: the bit offset of the first unit starting there (kNoUnit: none) and the
+// output / match counts accumulated before that unit.
+constexpr int kRoundDwordsMax = kRoundWordsMax / 2;
+constexpr uint8_t kNoUnit = 0xff;
 struct RoundShared {
-    uint32_t stage[2][kStageWords];              // double-buffered: the next round is fetched while this one is emitted
-    uint32_t mask[kRoundWordsMax * 32];          // [word][lane] unit starts visited by the speculative pass
-    uint32_t cm[kRoundWordsMax * 32];            // [word][lane] (output bytes << 12 | matches) before the word's first unit
+    uint32_t stage[kStageWords];
+    uint32_t cm[kRoundDwordsMax * 32];           // [dword][lane] output bytes << 12 | matches
+    uint8_t  fs[kRoundDwordsMax * 32];           // [dword][lane]
 };
 ZB_HD uint32_t stage_row_stride(int lg) { return (1u << lg) + kRowExtra; }
 
@@ -128,52 +132,50 @@ enum : uint32_t { STOP_NONE = 0, STOP_EOB = 1, STOP_BAD = 2 };
 // P1.  `start` is 0, except for lane 0 which starts at the block's true position.
 ZB_HD void round_speculate(RoundLane &r, uint32_t lane, int lg, uint32_t start, const uint32_t *stage, RoundShared &rs,
                            const uint32_t *__restrict__ L, const uint32_t *__restrict__ D) {
-    const uint32_t W = 1u << lg, S = 32u << lg;
-    for (uint32_t w = 0; w < W; ++w) rs.mask[w * 32 + lane] = 0;
+    const uint32_t DW = 1u << (lg - 1), S = 32u << lg;
+    for (uint32_t w = 0; w < DW; ++w) rs.fs[w * 32 + lane] = kNoUnit;
     LaneWin lw; lw.row = stage + lane * stage_row_stride(lg);
     uint32_t p = start;
-    uint32_t curw = p >> 5, mw = 0, out = 0, m = 0, stop = STOP_NONE;
-    rs.cm[curw * 32 + lane] = 0;
+    uint32_t curdw = 0xffffffffu, out = 0, m = 0, stop = STOP_NONE;
     while (p < S) {
-        const uint32_t w = p >> 5;
-        if (w != curw) {
-            rs.mask[curw * 32 + lane] = mw;
-            mw = 0; curw = w;
-            rs.cm[w * 32 + lane] = (out << 12) | m;
+        const uint32_t dw = p >> 6;
+        if (dw != curdw) {                                   // the first unit starting in this double word
+            curdw = dw;
+            rs.fs[dw * 32 + lane] = (uint8_t)(p & 63u);
+            rs.cm[dw * 32 + lane] = (out << 12) | m;
         }
-        mw |= 1u << (p & 31u);
         const Unit u = decode_unit<false>(lw, p, L, D);
         p += u.used;
         if (u.kind >= U_EOB) { stop = u.kind == U_EOB ? STOP_EOB : STOP_BAD; break; }
         out += u.kind == U_LIT ? 1u : u.val;
         m += u.kind;
     }
-    rs.mask[curw * 32 + lane] = mw;
     r.spec_end = r.end = p; r.spec_stop = r.stop = stop; r.spec_out = r.out = out; r.spec_m = r.m = m;
     r.start = start;
 }
 
-// P2.  Re-decode from the true start `t` until the path joins the speculative one.
+// P2.  Re-decode from the true start `t` until the path joins the speculative one: two
+// paths that have a unit start on the same bit are identical from there on, and once
+// joined they share the first unit start of every later double word — which is where
+// the join is looked for and the speculative counts are spliced in.
 ZB_HD void round_fix(RoundLane &r, uint32_t lane, int lg, uint32_t t, const uint32_t *stage, const RoundShared &rs,
                      const uint32_t *__restrict__ L, const uint32_t *__restrict__ D) {
     const uint32_t S = 32u << lg;
     LaneWin lw; lw.row = stage + lane * stage_row_stride(lg);
     uint32_t p = t;
-    uint32_t out = 0, m = 0, stop = STOP_NONE, syncw = 0;
-    bool synced = false;
+    uint32_t out = 0, m = 0, stop = STOP_NONE, curdw = 0xffffffffu;
     r.start = t;
     while (p < S) {
-        const uint32_t w = p >> 5;
-        if (synced) {
-            if (w != syncw) {                                // first unit of a later word: splice the speculative tail in
-                const uint32_t c = rs.cm[w * 32 + lane];
+        const uint32_t dw = p >> 6;
+        if (dw != curdw) {
+            curdw = dw;
+            if (rs.fs[dw * 32 + lane] == (uint8_t)(p & 63u)) {
+                const uint32_t c = rs.cm[dw * 32 + lane];
                 r.out = out + (r.spec_out - (c >> 12));
                 r.m = m + (r.spec_m - (c & 0xfffu));
                 r.end = r.spec_end; r.stop = r.spec_stop;
                 return;
             }
-        } else if ((rs.mask[w * 32 + lane] >> (p & 31u)) & 1u) {
-            synced = true; syncw = w;
         }
         const Unit u = decode_unit<false>(lw, p, L, D);
         p += u.used;
