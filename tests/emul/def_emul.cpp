@@ -37,7 +37,14 @@ extern "C" long emul_deflate_chunk(const uint8_t *data, uint32_t n, int level, i
             prev[p] = (q > 0 && p - (uint32_t)q <= 65535u) ? (uint16_t)(p - (uint32_t)q) : 0;
             head[h] = (int32_t)p;
         }
-        for (uint32_t p = 0; p < n; ++p) { MatchPair r = match_at(data, n, prev.data(), p, prm); mf[p] = r.full; mq[p] = r.quarter; }
+        for (uint32_t p = 0; p < n; ++p) {
+            MatchPair r = match_at(data, n, prev.data(), p, prm); mf[p] = r.full; mq[p] = r.quarter;
+            if (prm.mode == MODE_FAST && prm.level <= 2 && p + kUniformTail <= n) {   // the kernel's branch-free walk must agree
+                const PlainWin pw{data, prev.data()};
+                const uint32_t u = prm.level == 1 ? match_uniform<4, 8>(pw, p) : match_uniform<8, 16>(pw, p);
+                if (u != r.full) return -10;
+            }
+        }
     } else if (prm.mode == MODE_RLE) {
         for (uint32_t p = 0; p < n; ++p) mf[p] = rle_at(data, n, p);
     }

@@ -181,7 +181,7 @@ def test_deflate_phases_byte_exact():
     for kind in range(5):
         for n in (0, 1, 3, 300, 70000, 262144):
             d = refz.gen(n, kind, seed=7 + kind)
-            for level, strat in ((1, 0), (3, 0), (4, 0), (6, 0), (6, 1), (6, 2), (6, 3), (6, 4), (9, 0)):
+            for level, strat in ((1, 0), (2, 0), (3, 0), (4, 0), (6, 0), (6, 1), (6, 2), (6, 3), (6, 4), (9, 0)):
                 for final in (0, 1):
                     cap = n + n // 8 + 1024
                     out, st = C.create_string_buffer(cap), (C.c_uint32 * 2)()

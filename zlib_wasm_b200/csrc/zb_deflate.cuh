@@ -170,6 +170,83 @@ ZB_HD MatchPair match_at(const uint8_t *data, uint32_t n, const uint16_t *prev_d
     return w.result();
 }
 
+// ---- levels 1-2: the same walk without data-dependent control flow -----------------
+// With a small chain budget and a small nice_match the walk of longest_match has a
+// closed form: let len_k be the common prefix length of candidate k capped at NICE;
+// the walk stops at the first k with len_k == NICE, and the winner is the first
+// candidate that reaches the maximum of the len_k seen up to there (a candidate is
+// taken only when strictly longer than the best so far, deflate.c:1466-1476; the
+// quick rejects of :1449-1452 only skip candidates that could not be longer).  So
+// every lane runs the same CH steps of "load NICE bytes, compare, select" — no lane
+// waits for another's longer walk — and only the winner that reached NICE is then
+// extended to its true length.  Needs p + kUniformTail <= n (all reads stay inside the
+// chunk, lookahead >= MAX_MATCH so neither nice nor the match is clamped).
+constexpr uint32_t kUniformTail = kMaxMatch + 16;
+
+template <int NW>
+ZB_HD void load_words(const uint8_t *p, uint32_t (&w)[NW]) {       // NW little-endian words from an arbitrary address
+#if defined(__CUDA_ARCH__)
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    const uint32_t *src = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3);
+    const uint32_t sh = (uint32_t)(a & 3) * 8;
+    uint32_t raw[NW + 1];
+#pragma unroll
+    for (int i = 0; i <= NW; ++i) raw[i] = src[i];
+#pragma unroll
+    for (int i = 0; i < NW; ++i) w[i] = __funnelshift_r(raw[i], raw[i + 1], sh);
+#else
+    for (int i = 0; i < NW; ++i) w[i] = load4(p + 4 * i);
+#endif
+}
+
+// Operand access for match_uniform.
+struct PlainWin {
+    const uint8_t *data; const uint16_t *prev;
+    template <int NW> ZB_HD void words(uint32_t pos, uint32_t (&w)[NW]) const { load_words<NW>(data + pos, w); }
+    ZB_HD uint32_t dist(uint32_t pos) const { return prev[pos]; }
+};
+template <int CH, int NICE, class Win>
+ZB_HD uint32_t match_uniform(const Win &win, uint32_t p) {
+    constexpr int NW = NICE / 4;
+    const uint32_t d = win.dist(p);
+    if (d == 0 || d > (uint32_t)kMaxDist) return 0;            // deflate.c:1857: head must be within MAX_DIST
+    uint32_t sw[NW];
+    win.template words<NW>(p, sw);
+    uint32_t q = p - d, best = kMinMatch - 1, best_q = 0;
+    bool open = true;
+#pragma unroll
+    for (int k = 0; k < CH; ++k) {
+        if (open) {
+            uint32_t mw[NW];
+            win.template words<NW>(q, mw);
+            uint32_t len = NICE;
+#pragma unroll
+            for (int j = NW - 1; j >= 0; --j) { const uint32_t x = mw[j] ^ sw[j]; if (x) len = 4u * (uint32_t)j + (ctz32(x) >> 3); }
+            if (len > best) { best = len; best_q = q; }
+            if (len >= (uint32_t)NICE) open = false;
+            else if (k + 1 < CH) {
+                const uint32_t d2 = win.dist(q);
+                if (d2 == 0) open = false;
+                else { q -= d2; if (p - q >= (uint32_t)kMaxDist) open = false; }
+            }
+        }
+    }
+    if (best < (uint32_t)kMinMatch) return 0;
+    if (best >= (uint32_t)NICE) {                                 // the winner reached nice_match: its true length
+        uint32_t len = NICE;
+        while (len < (uint32_t)kMaxMatch) {                       // reads up to byte p + 259 (< p + kUniformTail)
+            uint32_t a[1], c[1];
+            win.template words<1>(best_q + len, a);
+            win.template words<1>(p + len, c);
+            const uint32_t x = a[0] ^ c[0];
+            if (x) { len += ctz32(x) >> 3; break; }
+            len += 4;
+        }
+        best = len < (uint32_t)kMaxMatch ? len : (uint32_t)kMaxMatch;
+    }
+    return (best << 16) | (p - best_q);
+}
+
 // Z_RLE (deflate.c:2051-2115): run of the previous byte, distance 1 only.
 ZB_HD uint32_t rle_at(const uint8_t *data, uint32_t n, uint32_t p) {
     if (p == 0 || p + kMinMatch > n) return 0;
