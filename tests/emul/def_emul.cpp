@@ -51,26 +51,65 @@ extern "C" long emul_deflate_chunk(const uint8_t *data, uint32_t n, int level, i
     std::vector<uint32_t> syms(n + 2);
     std::vector<BlockInfo> blocks(max_blocks_for(n));
     struct { uint32_t nsyms, nblocks; } sink;
-    // walk the chunk in tiles of odd size, as the kernel does, to exercise the resumable parse
-    {
-        ParseState ps; parse_init(ps, blocks.data(), n, prm);
+    // the kernel's segmented parse (zb_deflate.cuh seg_*), the lanes replayed by loops;
+    // the serial whole-chunk parse must give the same symbols and blocks
+    if (prm.mode != MODE_SLOW) {
+        // greedy rules: serial chase per tile, then per-symbol work in any order (zb_deflate.cu dfl_parse_greedy_kernel)
         ParseArrays acc{data, mf.data(), mq.data(), syms.data(), 0};
-        if (prm.mode != MODE_SLOW) {
-            // the kernel's split greedy parse: serial chase per tile, then per-symbol work in any order
-            std::vector<uint32_t> visited(1100);
-            uint32_t flushed = 0;
-            const bool use_m = prm.mode != MODE_HUFF;
-            while (ps.p < n) {
-                uint32_t lim = ps.p + 1000 < n ? ps.p + 1000 : n;
-                const uint32_t made = greedy_chase(ps.p, lim, use_m, acc, visited.data());
-                for (uint32_t i = made; i-- > 0;) syms[flushed + i] = greedy_symbol(visited[i], use_m, acc, flushed + i, blocks.data());
-                flushed += made;
+        std::vector<uint32_t> visited(1100);
+        uint32_t flushed = 0, p = 0;
+        const bool use_m = prm.mode != MODE_HUFF;
+        while (p < n) {
+            uint32_t lim = p + 1000 < n ? p + 1000 : n;
+            const uint32_t made = greedy_chase(p, lim, use_m, acc, visited.data());
+            for (uint32_t i = made; i-- > 0;) syms[flushed + i] = greedy_symbol(visited[i], use_m, acc, flushed + i, blocks.data(), n, prm);
+            flushed += made;
+        }
+        sink.nsyms = flushed; sink.nblocks = seg_finish(blocks.data(), flushed, false, n, prm, final_chunk != 0);
+    } else {
+        const SegGeom g = seg_geometry(n);
+        std::vector<SegRec> rec((kSegRecs - 1) * kSegLanes);
+        SegLane r[kSegLanes];
+        NoPut cacc{data, mf.data(), mq.data()};
+        for (uint32_t l = 0; l < g.nact; ++l) seg_speculate(r[l], l, g, n, prm, cacc, rec.data());
+        for (int pass = 0;; ++pass) {
+            if (pass > (int)kSegLanes + 8) return -20;
+            SegState t[kSegLanes]; bool need[kSegLanes], any = false;
+            for (uint32_t l = 0; l < g.nact; ++l) {
+                if (l) t[l] = r[l - 1].end;
+                need[l] = l > 0 && (t[l].p != r[l].start.p || t[l].w0 != r[l].start.w0);
+                any |= need[l];
             }
-            sink.nsyms = flushed; sink.nblocks = greedy_finish(blocks.data(), flushed, n, prm, final_chunk != 0);
-        } else {
-            while (ps.p < n) { uint32_t lim = ps.p + 1000 < n ? ps.p + 1000 : n; parse_steps(ps, lim, n, prm, acc); }
-            parse_finish(ps, n, prm, final_chunk != 0, acc);
-            sink.nsyms = ps.nsyms; sink.nblocks = ps.nblocks;
+            if (!any) break;
+            for (uint32_t l = 0; l < g.nact; ++l) if (need[l]) seg_fix(r[l], l, g, n, prm, cacc, rec.data(), t[l]);
+        }
+        uint32_t first[kSegLanes + 1]; first[0] = 0;
+        for (uint32_t l = 0; l < g.nact; ++l) first[l + 1] = first[l] + r[l].count;
+        const uint32_t total = first[g.nact];
+        for (int l = (int)g.nact - 1; l >= 0; --l) {               // any lane order must do
+            struct { const uint8_t *data; const uint32_t *mfull, *mquarter; uint32_t *out; uint32_t at;
+                     uint32_t mf(uint32_t p) const { return mfull[p]; } uint32_t mq(uint32_t p) const { return mquarter[p]; }
+                     uint32_t byte(uint32_t p) const { return data[p]; } void put(uint32_t sym) { out[at++] = sym; } }
+                eacc{data, mf.data(), mq.data(), syms.data(), first[l]};
+            seg_emit(r[l], (uint32_t)l, g, n, prm, eacc, blocks.data(), first[l]);
+            if (eacc.at != first[l + 1]) return -21;
+        }
+        const bool pending = prm.mode == MODE_SLOW && ((r[g.nact - 1].end.w0 >> 25) & 1u);
+        if (pending) syms[total] = data[n - 1];
+        sink.nsyms = total + (pending ? 1 : 0);
+        sink.nblocks = seg_finish(blocks.data(), total, pending, n, prm, final_chunk != 0);
+    }
+    {   // cross-check against the serial whole-chunk parse
+        std::vector<uint32_t> syms2(n + 2);
+        std::vector<BlockInfo> blocks2(max_blocks_for(n));
+        uint32_t ns2 = 0, nb2 = 0;
+        parse_chunk(data, n, mf.data(), mq.data(), prm, final_chunk != 0, syms2.data(), blocks2.data(), ns2, nb2);
+        if (ns2 != sink.nsyms || nb2 != sink.nblocks) return -22;
+        if (memcmp(syms2.data(), syms.data(), 4ull * ns2)) return -23;
+        for (uint32_t k = 0; k < nb2; ++k) {
+            const BlockInfo &x = blocks[k], &y = blocks2[k];
+            if (x.sym_start != y.sym_start || x.sym_count != y.sym_count || x.byte_start != y.byte_start ||
+                x.byte_len != y.byte_len || x.flags != y.flags) return -24;
         }
     }
     if (sink.nblocks > blocks.size()) return -2;

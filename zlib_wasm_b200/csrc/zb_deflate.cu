@@ -193,7 +193,7 @@ dfl_match_kernel(Batch b, DeflateParams prm, const uint16_t *__restrict__ prev_a
     if (prm.need_quarter) mquarter[off + p] = r.quarter;
 }
 
-// ---- phase 3: parse, one chunk per warp (lane 0 walks the tables) ---------------------
+// ---- phase 3, greedy rules (deflate_fast / deflate_rle / deflate_huff): one chunk per warp ----
 // The walk is a dependent chain (the next position depends on the entry just
 // read), so its operands are staged in shared memory: positions are cut into
 // fixed tiles of kParseTile; while lane 0 walks tile k, tile k+1 (match entries
@@ -223,7 +223,7 @@ __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src)
 }
 
 __global__ void __launch_bounds__(32)
-dfl_parse_kernel(Batch b, DeflateParams prm, const uint32_t *__restrict__ mfull,
+dfl_parse_greedy_kernel(Batch b, DeflateParams prm, const uint32_t *__restrict__ mfull,
                  const uint32_t *__restrict__ mquarter, uint32_t *__restrict__ syms,
                  BlockInfo *__restrict__ blocks, uint32_t *__restrict__ nblocks) {
     __shared__ __align__(16) ParseBuf buf[2];
@@ -259,7 +259,6 @@ dfl_parse_kernel(Batch b, DeflateParams prm, const uint32_t *__restrict__ mfull,
     };
 
     BlockInfo *blk = blocks + (uint64_t)c * b.MB;
-    const bool greedy = prm.mode != MODE_SLOW;
     ParseState st;
     parse_init(st, blk, n, prm);
     ParseTileAcc acc;
@@ -288,7 +287,7 @@ dfl_parse_kernel(Batch b, DeflateParams prm, const uint32_t *__restrict__ mfull,
             acc.bbias = (uint32_t)(b_abs0 - a_first);
             acc.count = 0;
         }
-        if (greedy) {
+        {
             // serial part: only the chase; the visited positions go to stage[]
             uint32_t cnt = 0;
             if (lane == 0 && st.p < t1) cnt = greedy_chase(st.p, t1, use_m, acc, stage);
@@ -296,36 +295,115 @@ dfl_parse_kernel(Batch b, DeflateParams prm, const uint32_t *__restrict__ mfull,
             __syncwarp();
             // parallel part: one lane per visited position forms its symbol
             for (uint32_t i = lane; i < made; i += 32)
-                out[flushed + i] = greedy_symbol(stage[i], use_m, acc, flushed + i, blk);
+                out[flushed + i] = greedy_symbol(stage[i], use_m, acc, flushed + i, blk, n, prm);
             flushed += made;
             __syncwarp();
-            continue;
         }
-        if (lane == 0 && st.p < t1) parse_steps(st, t1, n, prm, acc);
-        const uint32_t made = __shfl_sync(0xffffffffu, acc.count, 0);
-        __syncwarp();
-        for (uint32_t i = lane; i < made; i += 32) out[flushed + i] = stage[i];
-        flushed += made;
-        acc.count = 0;
-        __syncwarp();
     }
-    if (greedy) {
-        __syncwarp();
-        __threadfence_block();
-        if (lane == 0) nblocks[c] = greedy_finish(blk, flushed, n, prm, chunk_final(b, c));
-        return;
+    __syncwarp();
+    __threadfence_block();
+    if (lane == 0) nblocks[c] = seg_finish(blk, flushed, false, n, prm, chunk_final(b, c));
+}
+
+
+// ---- phase 3, lazy rule (deflate_slow): one chunk per CTA, one segment per thread -------------------------
+// zb_deflate.cuh seg_*: speculate / fix up / scan / emit.  Every thread walks its own
+// 1/128 of the chunk.
+// Operand streams of one thread.  A thread reads its match-table entries in increasing
+// order, a few per 32-byte sector; read straight from global memory every entry costs a
+// whole sector through the L1 (128 threads x 3 streams thrash it: 8x traffic
+// amplification, measured 12.5 ms per 512 MiB at level 6).  So each stream keeps its
+// current sector in shared memory — slot [entry][thread], bank = thread, conflict-free
+// for any entry — and refills it with two 16-byte loads when the walk leaves it.
+struct WalkAcc {
+    const uint8_t *data; const uint32_t *mfull, *mquarter; uint32_t *out; uint32_t at;
+    uint32_t *sm_f, *sm_q, *sm_b;                      // this thread's column of the three sector buffers
+    uint64_t abs0;                                     // absolute entry index of chunk position 0 (sector alignment is absolute)
+    uintptr_t in_lo, in_hi;                            // bounds of the input buffer (byte sectors are clipped to it)
+    uint64_t cur_f, cur_q; uintptr_t cur_b;            // sector currently held per stream (~0: none)
+    __device__ __forceinline__ void reset() { cur_f = cur_q = ~0ull; cur_b = ~(uintptr_t)0; }
+    __device__ __forceinline__ static void fill(uint32_t *col, const uint32_t *src) {
+        const uint4 a = __ldcg(reinterpret_cast<const uint4 *>(src)), c = __ldcg(reinterpret_cast<const uint4 *>(src) + 1);
+        col[0 * kSegLanes] = a.x; col[1 * kSegLanes] = a.y; col[2 * kSegLanes] = a.z; col[3 * kSegLanes] = a.w;
+        col[4 * kSegLanes] = c.x; col[5 * kSegLanes] = c.y; col[6 * kSegLanes] = c.z; col[7 * kSegLanes] = c.w;
     }
-    if (lane == 0) {
-        // the trailing literal (if any) needs byte n-1: serve it straight from global memory
-        struct TailAcc {
-            const uint8_t *data; uint32_t *out; uint32_t at;
-            __device__ uint32_t mf(uint32_t) const { return 0; }
-            __device__ uint32_t mq(uint32_t) const { return 0; }
-            __device__ uint32_t byte(uint32_t p) const { return data[p]; }
-            __device__ void put(uint32_t sym) { out[at++] = sym; }
-        } tail{data, out, flushed};
-        parse_finish(st, n, prm, chunk_final(b, c), tail);
-        nblocks[c] = st.nblocks;
+    __device__ __forceinline__ uint32_t mf(uint32_t p) {
+        const uint64_t e = abs0 + p, sec = e >> 3;
+        if (sec != cur_f) { cur_f = sec; fill(sm_f, mfull + (sec << 3)); }
+        return sm_f[((uint32_t)e & 7u) * kSegLanes];
+    }
+    __device__ __forceinline__ uint32_t mq(uint32_t p) {
+        const uint64_t e = abs0 + p, sec = e >> 3;
+        if (sec != cur_q) { cur_q = sec; fill(sm_q, mquarter + (sec << 3)); }
+        return sm_q[((uint32_t)e & 7u) * kSegLanes];
+    }
+    __device__ __forceinline__ uint32_t byte(uint32_t p) {
+        const uintptr_t a = reinterpret_cast<uintptr_t>(data) + p, sec = a >> 5;
+        if (sec != cur_b) {
+            const uintptr_t s0 = sec << 5;
+            if (s0 < in_lo || s0 + 32 > in_hi) return data[p];   // sector straddles an end of the input buffer: plain read, nothing held
+            cur_b = sec;
+            fill(sm_b, reinterpret_cast<const uint32_t *>(s0));
+        }
+        return (sm_b[(((uint32_t)a >> 2) & 7u) * kSegLanes] >> (((uint32_t)a & 3u) * 8u)) & 0xffu;
+    }
+    __device__ __forceinline__ void put(uint32_t sym) { if (out) out[at++] = sym; }
+};
+
+__global__ void __launch_bounds__(kSegLanes)
+dfl_parse_kernel(Batch b, DeflateParams prm, const uint32_t *__restrict__ mfull,
+                 const uint32_t *__restrict__ mquarter, uint32_t *__restrict__ syms,
+                 BlockInfo *__restrict__ blocks, uint32_t *__restrict__ nblocks) {
+    __shared__ SegRec rec[(kSegRecs - 1) * kSegLanes];
+    __shared__ uint32_t s_sec[3][8 * kSegLanes];
+    __shared__ uint32_t s_p[kSegLanes], s_w0[kSegLanes], s_wsum[kSegLanes / 32];
+    const unsigned full = 0xffffffffu;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t c = blockIdx.x;
+    const uint64_t off = (uint64_t)c * b.S;
+    const uint8_t *data = b.in + off;
+    const uint32_t n = chunk_len(b, c);
+    uint32_t *out = syms + off;
+    BlockInfo *blk = blocks + (uint64_t)c * b.MB;
+    const SegGeom g = seg_geometry(n);
+    const bool active = tid < g.nact;
+
+    SegLane r;
+    r.start = r.end = r.spec_end = seg_cold(0); r.count = r.spec_count = 0;
+    WalkAcc acc;
+    acc.data = data; acc.mfull = mfull; acc.mquarter = prm.need_quarter ? mquarter : mfull; acc.out = nullptr; acc.at = 0;
+    acc.sm_f = s_sec[0] + tid; acc.sm_q = s_sec[1] + tid; acc.sm_b = s_sec[2] + tid;
+    acc.abs0 = off;
+    acc.in_lo = reinterpret_cast<uintptr_t>(b.in); acc.in_hi = acc.in_lo + b.bytes;
+    acc.reset();
+    if (active) seg_speculate(r, tid, g, n, prm, acc, rec);
+    for (;;) {                                                     // until no start moves
+        s_p[tid] = r.end.p; s_w0[tid] = r.end.w0;
+        __syncthreads();
+        SegState t = r.start;
+        if (tid) { t.p = s_p[tid - 1]; t.w0 = s_w0[tid - 1]; }
+        const bool need = tid > 0 && active && (t.p != r.start.p || t.w0 != r.start.w0);
+        if (!__syncthreads_or(need)) break;
+        if (need) seg_fix(r, tid, g, n, prm, acc, rec, t);
+    }
+    // exclusive scan of the symbol counts over the CTA
+    const uint32_t cnt = active ? r.count : 0u;
+    uint32_t inc = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t y = __shfl_up_sync(full, inc, d); if (lane >= (uint32_t)d) inc += y; }
+    if (lane == 31) s_wsum[warp] = inc;
+    __syncthreads();
+    uint32_t before = 0, total = 0;
+#pragma unroll
+    for (uint32_t k = 0; k < kSegLanes / 32; ++k) { const uint32_t x = s_wsum[k]; if (k < warp) before += x; total += x; }
+    const uint32_t first = before + inc - cnt;
+    acc.out = out; acc.at = first;
+    if (active) seg_emit(r, tid, g, n, prm, acc, blk, first);
+    __syncthreads();                                               // provisional BlockInfo of every thread -> visible to thread 0
+    if (tid == 0) {
+        const bool pending = prm.mode == MODE_SLOW && ((s_w0[g.nact - 1] >> 25) & 1u);
+        if (pending) out[total] = data[n - 1];
+        nblocks[c] = seg_finish(blk, total, pending, n, prm, chunk_final(b, c));
     }
 }
 
@@ -624,7 +702,8 @@ int deflate_launch(zb200_ctx *ctx, const uint8_t *d_in, size_t n, size_t S, int 
             dfl_match_kernel<<<g, 256, 0, s>>>(b, prm, w.prev, w.mfull, w.mquarter);
             ZB_LAUNCHED(); ZB_CHECK_LAUNCH();
         }
-        dfl_parse_kernel<<<b.nb, 32, 0, s>>>(b, prm, w.mfull, w.mquarter, w.syms, w.blocks, w.nblocks);
+        if (prm.mode == MODE_SLOW) dfl_parse_kernel<<<b.nb, kSegLanes, 0, s>>>(b, prm, w.mfull, w.mquarter, w.syms, w.blocks, w.nblocks);
+        else dfl_parse_greedy_kernel<<<b.nb, 32, 0, s>>>(b, prm, w.mfull, w.mquarter, w.syms, w.blocks, w.nblocks);
         ZB_LAUNCHED(); ZB_CHECK_LAUNCH();
         dfl_tree_kernel<<<dim3(MB, b.nb), 128, 0, s>>>(b, strategy | (level == 0 ? 0x100 : 0), w.syms, w.blocks, w.nblocks, tabs, w.codes);
         ZB_LAUNCHED(); ZB_CHECK_LAUNCH();

@@ -16,10 +16,11 @@
 //              nice_match, first-longest wins, MAX_DIST limit) and records the
 //              result for the full chain budget and for the quartered budget
 //              (deflate.c:1390-1392 good_match).
-//   3 parse    one sequential pass per chunk picks matches with the reference's
-//              lazy (deflate.c:1923-2043) or greedy (deflate.c:1824-1915) rule
-//              from the precomputed tables, emits symbols and cuts blocks every
-//              16383 symbols (deflate.c:455,512).
+//   3 parse    picks matches with the reference's lazy (deflate.c:1923-2043) or
+//              greedy (deflate.c:1824-1915) rule from the precomputed tables, emits
+//              symbols and cuts blocks every 16383 symbols (deflate.c:455,512); the
+//              32 lanes of a warp parse 32 segments of the chunk concurrently and
+//              are stitched where their states coincide (seg_* below).
 //   4 trees    per block: histogram, the reference's exact heap Huffman
 //              construction + length limiting + header RLE, block type choice
 //              (trees.c:997-1089).
@@ -284,17 +285,29 @@ struct ParseState {
     uint32_t nsyms, nblocks;          // totals so far for the chunk
     uint32_t blk_sym0, blk_byte0;     // start of the open block
     BlockInfo *blocks;
+    uint32_t block_mode;              // PB_SERIAL: complete BlockInfo as the parse goes; PB_DEFERRED: a parse that covers
+                                      // only a segment leaves (end offset, window base) for seg_finish; PB_NONE: counting pass
 };
+enum : uint32_t { PB_SERIAL = 0, PB_DEFERRED = 1, PB_NONE = 2 };
 
 ZB_HD uint32_t parse_next_slide(uint32_t base, uint32_t n, const DeflateParams &prm);
 
 ZB_HD void parse_init(ParseState &s, BlockInfo *blocks, uint32_t n, const DeflateParams &prm) {
     s.slide_at = parse_next_slide(0, n, prm);
     s.p = 0; s.match_length = kMinMatch - 1; s.cur_dist = 0; s.match_available = 0; s.base = 0;
-    s.nsyms = 0; s.nblocks = 0; s.blk_sym0 = 0; s.blk_byte0 = 0; s.blocks = blocks;
+    s.nsyms = 0; s.nblocks = 0; s.blk_sym0 = 0; s.blk_byte0 = 0; s.blocks = blocks; s.block_mode = PB_SERIAL;
 }
 
 ZB_HD void parse_close_block(ParseState &s, uint32_t cover_end, bool last) {
+    if (s.block_mode != PB_SERIAL) {
+        if (s.block_mode == PB_DEFERRED) {             // block index = symbols so far / kSymLimit - 1
+            BlockInfo &d = s.blocks[s.nsyms / kSymLimit - 1];
+            d.byte_len = cover_end;                    // provisional: end offset of the block
+            d.pad = s.base;                            // provisional: window base when the block was closed
+        }
+        s.blk_sym0 = s.nsyms;
+        return;
+    }
     BlockInfo b;
     b.sym_start = s.blk_sym0; b.sym_count = s.nsyms - s.blk_sym0;
     b.byte_start = s.blk_byte0; b.byte_len = cover_end - s.blk_byte0;
@@ -406,6 +419,155 @@ ZB_HD void parse_chunk(const uint8_t *data, uint32_t n, const uint32_t *mfull, c
     nsyms = s.nsyms; nblocks = s.nblocks;
 }
 
+// ---- the parse, cut into segments that are parsed concurrently ---------------------
+// The parse is a serial state machine, but like a prefix-code decoder it forgets its
+// past quickly: two parses that are at the same position in the same state (held match
+// length / distance, pending literal) are identical from there on, and a parse started
+// cold in the middle of the chunk falls into step with the true one within a few
+// symbols.  So the chunk is cut into kSegLanes segments, one per thread of a CTA:
+//   seg_speculate  every lane parses its segment from a cold state, counting symbols,
+//                  and records its state at the first loop top at or after each of up
+//                  to kSegRecs evenly spaced boundaries;
+//   seg_fix        lane i+1 re-parses from the state lane i really ended in, until its
+//                  state at a boundary equals the recorded one; the speculative symbol
+//                  count of the rest is then spliced in (repeated until no start moves);
+//   seg_emit       after an exclusive scan of the counts every lane parses once more
+//                  from its true start state and writes its symbols at their final
+//                  indices; a symbol that fills a block (deflate.h:354-372) leaves the
+//                  block's end offset and the window base in its BlockInfo slot;
+//   seg_finish     once per chunk: pending literal, byte ranges / flags, last block.
+// The window base at a loop top P is a closed form of P (every slide trigger <= P has
+// fired), so a segment needs no history for "stored form allowed" either.
+constexpr uint32_t kSegLanes = 128;                   // segments per chunk (threads of the parse CTA)
+constexpr uint32_t kSegRecs = 16;                     // boundaries per segment (the segment end is the last one)
+
+ZB_HD uint32_t parse_base_at(uint32_t P, uint32_t n, const DeflateParams &prm) {
+    uint32_t base = 0;
+    while (P >= parse_next_slide(base, n, prm)) base += kWSize;
+    return base;
+}
+
+struct SegGeom { uint32_t blk, seg, nact; };          // boundary spacing, segment length, lanes with work
+ZB_HD SegGeom seg_geometry(uint32_t n) {
+    SegGeom g;
+    g.blk = (n + kSegLanes * kSegRecs - 1) / (kSegLanes * kSegRecs);
+    if (g.blk < 32) g.blk = 32;
+    g.seg = g.blk * kSegRecs;
+    g.nact = n ? (n + g.seg - 1) / g.seg : 1;
+    return g;
+}
+
+// A parse state at a loop top, comparable: w0 = held match (distance | length << 16) |
+// pending-literal flag << 25 — the distance only counts while a match is held.
+struct SegState { uint32_t p, w0; };
+ZB_HD SegState seg_state_of(const ParseState &s) {
+    SegState t;
+    t.p = s.p;
+    t.w0 = (s.match_length >= (uint32_t)kMinMatch ? s.cur_dist : 0u) | (s.match_length << 16) | (s.match_available ? 1u << 25 : 0u);
+    return t;
+}
+ZB_HD void seg_state_load(ParseState &s, const SegState &t, uint32_t n, const DeflateParams &prm) {
+    s.p = t.p; s.cur_dist = t.w0 & 0xffffu; s.match_length = (t.w0 >> 16) & 0x1ffu; s.match_available = (t.w0 >> 25) & 1u;
+    s.base = parse_base_at(t.p, n, prm);
+    s.slide_at = parse_next_slide(s.base, n, prm);
+    s.nsyms = 0; s.nblocks = 0; s.blk_sym0 = 0; s.blk_byte0 = 0; s.blocks = nullptr; s.block_mode = PB_NONE;
+}
+ZB_HD SegState seg_cold(uint32_t p) { SegState t; t.p = p; t.w0 = (uint32_t)(kMinMatch - 1) << 16; return t; }
+
+struct SegRec { uint32_t w0, w1; };                   // state at a boundary: w0 as above, w1 = (p - boundary) | symbols before << 9
+struct SegLane {
+    SegState start, end; uint32_t count;              // the current path (true once seg_fix has settled)
+    SegState spec_end; uint32_t spec_count;           // the speculative path
+};
+struct NoPut {                                        // counting passes: operands from plain arrays, symbols dropped
+    const uint8_t *data; const uint32_t *mfull, *mquarter;
+    ZB_HD uint32_t mf(uint32_t p) const { return mfull[p]; }
+    ZB_HD uint32_t mq(uint32_t p) const { return mquarter[p]; }
+    ZB_HD uint32_t byte(uint32_t p) const { return data[p]; }
+    ZB_HD void put(uint32_t) {}
+};
+
+// rec[(k - 1) * kSegLanes + lane] belongs to boundary k (k = 1 .. kSegRecs - 1) of lane's segment.
+template <class Acc>
+ZB_HD void seg_speculate(SegLane &r, uint32_t lane, const SegGeom &g, uint32_t n, const DeflateParams &prm, Acc &acc, SegRec *rec) {
+    const uint32_t s0 = lane * g.seg, bound = s0 + g.seg < n ? s0 + g.seg : n;
+    ParseState st;
+    r.start = seg_cold(s0);
+    seg_state_load(st, r.start, n, prm);
+    for (uint32_t k = 1; k < kSegRecs; ++k) {
+        const uint32_t limit = s0 + k * g.blk;
+        if (limit >= bound) break;
+        parse_steps(st, limit, n, prm, acc);
+        SegRec e;
+        e.w0 = seg_state_of(st).w0; e.w1 = (st.p - limit) | (st.nsyms << 9);
+        rec[(k - 1) * kSegLanes + lane] = e;
+    }
+    parse_steps(st, bound, n, prm, acc);
+    r.end = r.spec_end = seg_state_of(st);
+    r.count = r.spec_count = st.nsyms;
+}
+
+template <class Acc>
+ZB_HD void seg_fix(SegLane &r, uint32_t lane, const SegGeom &g, uint32_t n, const DeflateParams &prm, Acc &acc,
+                   const SegRec *rec, const SegState &t) {
+    const uint32_t s0 = lane * g.seg, bound = s0 + g.seg < n ? s0 + g.seg : n;
+    ParseState st;
+    r.start = t;
+    seg_state_load(st, t, n, prm);
+    for (uint32_t k = 1; k < kSegRecs; ++k) {
+        const uint32_t limit = s0 + k * g.blk;
+        if (limit >= bound) break;
+        if (limit < t.p) continue;                     // the true start lies beyond this boundary
+        parse_steps(st, limit, n, prm, acc);
+        const SegRec e = rec[(k - 1) * kSegLanes + lane];
+        if (e.w0 == seg_state_of(st).w0 && (e.w1 & 0x1ffu) == st.p - limit) {   // joined the speculative path
+            r.count = st.nsyms + (r.spec_count - (e.w1 >> 9));
+            r.end = r.spec_end;
+            return;
+        }
+    }
+    parse_steps(st, bound, n, prm, acc);
+    r.end = seg_state_of(st);
+    r.count = st.nsyms;
+}
+
+// `acc.put` must store symbol number (first + k) of the lane at index first + k.
+template <class Acc>
+ZB_HD void seg_emit(const SegLane &r, uint32_t lane, const SegGeom &g, uint32_t n, const DeflateParams &prm, Acc &acc,
+                    BlockInfo *blocks, uint32_t first) {
+    const uint32_t s0 = lane * g.seg, bound = s0 + g.seg < n ? s0 + g.seg : n;
+    ParseState st;
+    seg_state_load(st, r.start, n, prm);
+    st.nsyms = first; st.blk_sym0 = first - first % kSymLimit; st.blocks = blocks; st.block_mode = PB_DEFERRED;
+    parse_steps(st, bound, n, prm, acc);
+}
+
+// nsyms: symbols emitted by the segments; pending: the last segment ended holding a
+// literal (deflate.c:2026-2030: tallied at the end, its flush flag ignored — the caller
+// has stored it at index nsyms).  Returns the number of blocks.
+ZB_HD uint32_t seg_finish(BlockInfo *blocks, uint32_t nsyms, bool pending, uint32_t n, const DeflateParams &prm, bool final_chunk) {
+    const uint32_t nfull = nsyms / kSymLimit, rem = nsyms % kSymLimit + (pending ? 1u : 0u);
+    uint32_t start = 0;
+    for (uint32_t k = 0; k < nfull; ++k) {
+        BlockInfo &b = blocks[k];
+        const uint32_t end = b.byte_len, base = b.pad;
+        b.sym_start = k * kSymLimit; b.sym_count = kSymLimit;
+        b.byte_start = start; b.byte_len = end - start;
+        b.flags = start >= base ? BLK_STORED_OK : 0;  // deflate.c:1597-1600
+        b.bit_start_lo = b.bit_start_hi = 0; b.pad = 0;
+        start = end;
+    }
+    uint32_t nblocks = nfull;
+    if (final_chunk || rem) {
+        BlockInfo &b = blocks[nblocks++];
+        b.sym_start = nfull * kSymLimit; b.sym_count = rem;
+        b.byte_start = start; b.byte_len = n - start;
+        b.flags = (final_chunk ? BLK_LAST : 0) | (start >= parse_base_at(n, n, prm) ? BLK_STORED_OK : 0);
+        b.bit_start_lo = b.bit_start_hi = 0; b.pad = 0;
+    }
+    return nblocks;
+}
+
 // ---- greedy parse, split for the GPU ----------------------------------------------
 // With a greedy rule (deflate_fast / deflate_rle / deflate_huff) the only serial part
 // is the chase p -> p + len(p); everything else is a pure function of the visited
@@ -414,16 +576,8 @@ ZB_HD void parse_chunk(const uint8_t *data, uint32_t n, const uint32_t *mfull, c
 //   greedy_symbol  parallel: symbol word of one visited position; the symbol that
 //                  closes a block (every 16383rd) leaves the block's end offset and
 //                  loop-top position in its BlockInfo slot
-//   greedy_finish  once per chunk: turns those into byte ranges / flags, adds the
-//                  last block.  The window base at a loop top P is a closed form of
-//                  P (every slide trigger <= P has fired), so "stored form allowed"
-//                  needs no serial state either.
-ZB_HD uint32_t parse_base_at(uint32_t P, uint32_t n, const DeflateParams &prm) {
-    uint32_t base = 0;
-    while (P >= parse_next_slide(base, n, prm)) base += kWSize;
-    return base;
-}
-
+//   seg_finish     once per chunk (shared with the segmented parse below): turns those
+//                  into byte ranges / flags, adds the last block.
 template <class Acc>
 ZB_HD uint32_t greedy_chase(uint32_t &p, uint32_t limit, bool use_m, Acc &acc, uint32_t *visited) {
     uint32_t cnt = 0, q = p;
@@ -437,38 +591,15 @@ ZB_HD uint32_t greedy_chase(uint32_t &p, uint32_t limit, bool use_m, Acc &acc, u
 }
 
 template <class Acc>
-ZB_HD uint32_t greedy_symbol(uint32_t pos, bool use_m, Acc &acc, uint32_t g, BlockInfo *blocks) {
+ZB_HD uint32_t greedy_symbol(uint32_t pos, bool use_m, Acc &acc, uint32_t g, BlockInfo *blocks, uint32_t n, const DeflateParams &prm) {
     const uint32_t m = use_m ? acc.mf(pos) : 0u;
     const uint32_t len = m ? (m >> 16) : 1u;
     if ((g + 1) % kSymLimit == 0) {                    // this symbol fills a block (deflate.h:354-372 flush flag)
         BlockInfo &b = blocks[g / kSymLimit];
         b.byte_len = pos + len;                        // provisional: end offset of the block
-        b.pad = pos;                                   // provisional: loop-top position of the flush
+        b.pad = parse_base_at(pos, n, prm);            // provisional: window base at the flush (seg_finish completes the slot)
     }
     return m ? (((m & 0xffff) << 16) | (len - kMinMatch)) : acc.byte(pos);
-}
-
-ZB_HD uint32_t greedy_finish(BlockInfo *blocks, uint32_t nsyms, uint32_t n, const DeflateParams &prm, bool final_chunk) {
-    const uint32_t nfull = nsyms / kSymLimit, rem = nsyms % kSymLimit;
-    uint32_t start = 0;
-    for (uint32_t k = 0; k < nfull; ++k) {
-        BlockInfo &b = blocks[k];
-        const uint32_t end = b.byte_len, top = b.pad;
-        b.sym_start = k * kSymLimit; b.sym_count = kSymLimit;
-        b.byte_start = start; b.byte_len = end - start;
-        b.flags = start >= parse_base_at(top, n, prm) ? BLK_STORED_OK : 0;
-        b.bit_start_lo = b.bit_start_hi = 0; b.pad = 0;
-        start = end;
-    }
-    uint32_t nblocks = nfull;
-    if (final_chunk || rem) {
-        BlockInfo &b = blocks[nblocks++];
-        b.sym_start = nfull * kSymLimit; b.sym_count = rem;
-        b.byte_start = start; b.byte_len = n - start;
-        b.flags = (final_chunk ? BLK_LAST : 0) | (start >= parse_base_at(n, n, prm) ? BLK_STORED_OK : 0);
-        b.bit_start_lo = b.bit_start_hi = 0; b.pad = 0;
-    }
-    return nblocks;
 }
 
 // ---- phase 4: per-block Huffman construction ---------------------------------------
