@@ -96,79 +96,63 @@ ZB_HD uint32_t ctz32(uint32_t x) {
 #endif
 }
 
-// The walk over one position's hash chain, cut into the three pieces the kernel
-// schedules separately (so that the lanes of a warp run the same piece together):
-//   screen()   the quick rejects of deflate.c:1449-1452 for the current candidate
-//   measure()  common prefix length of a candidate that passed, update of the best
-//   advance()  chain budget / quarter snapshot / next link (deflate.c:1481-1482)
-struct MatchWalk {
-    uint32_t p, q;                    // position, current candidate
-    uint32_t best, best_dist, examined;
-    uint32_t maxlen, nice;
-    uint32_t quarter; bool have_q;
-
-    // Returns false if the position has no candidate at all (result() is then 0/0).
-    ZB_HD bool begin(uint32_t n, const uint16_t *prev_dist, uint32_t pos, const DeflateParams &prm) {
-        p = pos; best = kMinMatch - 1; best_dist = 0; examined = 0; quarter = 0; have_q = false;
-        if (p + kMinMatch > n) return false;              // lookahead < MIN_MATCH: no insertion, no search
-        const uint32_t d = prev_dist[p];
-        if (d == 0 || d > (uint32_t)kMaxDist) return false;   // deflate.c:1857/1958: head must be within MAX_DIST
-        const uint32_t look = n - p;
-        maxlen = look < (uint32_t)kMaxMatch ? look : (uint32_t)kMaxMatch;
-        nice = (uint32_t)prm.nice > look ? look : (uint32_t)prm.nice;                  // deflate.c:1396
-        q = p - d;
-        return true;
-    }
-    // best < maxlen holds whenever a candidate is screened (see the nice clamp).
-    ZB_HD bool screen(const uint8_t *data) const {
-        const uint8_t *scan = data + p, *m = data + q;
-        const uint32_t a = m[best], b0 = m[0], b1 = m[1];  // the three loads are independent: issue them together
-        return a == scan[best] && b0 == scan[0] && b1 == scan[1];
-    }
-    // Returns true if the walk ends here (a match of at least nice_match).
-    ZB_HD bool measure(const uint8_t *data) {
-        const uint8_t *scan = data + p, *m = data + q;
-        uint32_t len = 2;                                 // m[2]==scan[2] follows from the equal hash when bytes 0,1 agree
-        while (len + 8 <= maxlen) {                       // four bytes per step while the aligned reads stay inside the chunk
-            const uint32_t x = load4(m + len) ^ load4(scan + len);
-            if (x) { len += ctz32(x) >> 3; goto measured; }
-            len += 4;
-        }
-        while (len < maxlen && m[len] == scan[len]) ++len;
-    measured:
-        if (len > best) {
-            best = len; best_dist = p - q;
-            if (len >= nice) return true;
-        }
-        return false;
-    }
-    // Returns true when the walk is over.
-    ZB_HD bool advance(const uint16_t *prev_dist, const DeflateParams &prm) {
-        ++examined;
-        if (examined == ((uint32_t)prm.chain >> 2) && !have_q) { quarter = best >= (uint32_t)kMinMatch ? (best << 16) | best_dist : 0; have_q = true; }
-        if (examined == (uint32_t)prm.chain) return true; // deflate.c:1482 --chain_length
-        const uint32_t d2 = prev_dist[q];
-        if (d2 == 0) return true;
-        q -= d2;
-        return p - q >= (uint32_t)kMaxDist;               // deflate.c:1481: cur_match > limit
-    }
-    ZB_HD MatchPair result() const {
-        MatchPair r;
-        r.full = best >= (uint32_t)kMinMatch ? (best << 16) | best_dist : 0;
-        r.quarter = have_q ? quarter : r.full;
-        return r;
-    }
-};
-
+// The walk over one position's hash chain: longest_match (deflate.c:1356-1497) for the
+// full chain budget, with a snapshot of the best match when a quarter of the budget has
+// been spent (what the search would return when entered with prev_length >= good_match,
+// deflate.c:1390-1392).  Per candidate: the quick rejects of deflate.c:1449-1452, the
+// common prefix length of a candidate that passed, the next link (deflate.c:1481-1482).
+// The loop is written for the GPU's issue slots: the byte scan[best] lives in a register
+// (it changes only when the best match does), the next link is requested before the
+// candidate is looked at (the two reads are independent, so their latencies overlap), and
+// the quarter snapshot is a second loop bound instead of per-step bookkeeping.
 ZB_HD MatchPair match_at(const uint8_t *data, uint32_t n, const uint16_t *prev_dist, uint32_t p,
                          const DeflateParams &prm) {
-    MatchWalk w;
-    if (w.begin(n, prev_dist, p, prm))
-        for (;;) {
-            if (w.screen(data) && w.measure(data)) break;
-            if (w.advance(prev_dist, prm)) break;
+    MatchPair r;
+    r.full = r.quarter = 0;
+    if (p + kMinMatch > n) return r;                      // lookahead < MIN_MATCH: no insertion, no search
+    const uint32_t d = prev_dist[p];
+    if (d == 0 || d > (uint32_t)kMaxDist) return r;       // deflate.c:1857/1958: head must be within MAX_DIST
+    const uint32_t look = n - p;
+    const uint32_t maxlen = look < (uint32_t)kMaxMatch ? look : (uint32_t)kMaxMatch;
+    const uint32_t nice = (uint32_t)prm.nice > look ? look : (uint32_t)prm.nice;      // deflate.c:1396
+    const uint8_t *scan = data + p;
+    const uint32_t s0 = scan[0], s1 = scan[1];
+    uint32_t best = kMinMatch - 1, best_dist = 0, sb = scan[kMinMatch - 1];           // best < maxlen whenever a candidate is screened
+    uint32_t q = p - d, examined = 0;
+    const uint32_t budget = (uint32_t)prm.chain, qbudget = budget >> 2;
+    uint32_t stop_at = qbudget ? qbudget : budget;        // the next loop bound: quarter snapshot first, then the full budget
+    bool have_q = false;
+    for (;;) {
+        const uint8_t *m = data + q;
+        const uint32_t d2 = prev_dist[q];
+        if (m[best] == sb && m[0] == s0 && m[1] == s1) {
+            uint32_t len = 2;                             // m[2]==scan[2] follows from the equal hash when bytes 0,1 agree
+            while (len + 8 <= maxlen) {                   // four bytes per step while the aligned reads stay inside the chunk
+                const uint32_t x = load4(m + len) ^ load4(scan + len);
+                if (x) { len += ctz32(x) >> 3; goto measured; }
+                len += 4;
+            }
+            while (len < maxlen && m[len] == scan[len]) ++len;
+        measured:
+            if (len > best) {
+                best = len; best_dist = p - q;
+                if (len >= nice) break;
+                sb = scan[best];
+            }
         }
-    return w.result();
+        if (++examined == stop_at) {
+            if (examined == budget) break;                // deflate.c:1482 --chain_length
+            r.quarter = best >= (uint32_t)kMinMatch ? (best << 16) | best_dist : 0;
+            have_q = true;
+            stop_at = budget;
+        }
+        if (d2 == 0) break;
+        q -= d2;
+        if (p - q >= (uint32_t)kMaxDist) break;           // deflate.c:1481: cur_match > limit
+    }
+    r.full = best >= (uint32_t)kMinMatch ? (best << 16) | best_dist : 0;
+    if (!have_q) r.quarter = r.full;
+    return r;
 }
 
 // ---- levels 1-2: the same walk without data-dependent control flow -----------------
