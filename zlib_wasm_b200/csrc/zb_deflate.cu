@@ -66,73 +66,70 @@ __device__ __forceinline__ bool chunk_final(const Batch &b, uint32_t c) {
     return b.all_final || (b.last_is_final && c + 1 == b.nb);
 }
 
-// ---- phase 1: hash chains, one warp per chunk --------------------------------------
-// 32 consecutive positions per step: same-hash positions inside the step are
-// linked with match.any, the rest through a 32K-entry u16 head table in shared
-// memory holding window-relative positions; every 32 KiB the table slides like
-// deflate.c:187-209 so that entries stay 16-bit.
-constexpr int kChainSmem = 65536 + 67 * 16;   // head table + one staged input tile
-__global__ void __launch_bounds__(32) dfl_chain_kernel(Batch b, uint16_t *__restrict__ prev_all) {
+// ---- phase 1: hash chains, one CTA of four warps per chunk ------------------------------
+// 32 consecutive positions per step: same-hash positions inside the step are linked
+// with match.any, the rest through a 32K-entry u16 head table in shared memory holding
+// window-relative positions; every 32 KiB the table slides like deflate.c:187-209 so
+// that entries stay 16-bit.  Only the head-table part of a step is inherently ordered;
+// reading the input, hashing and storing the links are not.  The 64 KiB table allows
+// three CTAs per SM, and a lone warp runs at its own dependent-issue latency (ncu: 46
+// instructions per step at ~5.5 cycles each), so four warps share one table: warp w
+// takes every fourth TRIP of 128 positions, hashes it while the others are busy, waits
+// for its turn (a named barrier shared with the previous trip's warp: a blocked warp
+// takes no issue slots; spinning on a shared-memory counter measured 6.7x slower), does
+// the four ordered head-table steps, passes the turn on and stores its links.
+constexpr int kChainWarps = 4, kChainTrip = 128;
+constexpr int kChainSmem = 65536;             // the head table
+__global__ void __launch_bounds__(kChainWarps * 32) dfl_chain_kernel(Batch b, uint16_t *__restrict__ prev_all) {
     extern __shared__ __align__(16) uint16_t head[];
-    const uint32_t c = blockIdx.x, lane = threadIdx.x;
+    const uint32_t c = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint8_t *data = b.in + (uint64_t)c * b.S;
     const uint32_t n = chunk_len(b, c);
     uint16_t *prev = prev_all + (uint64_t)c * b.S;
     uint4 *h4 = reinterpret_cast<uint4 *>(head);
-    for (int i = lane; i < 4096; i += 32) h4[i] = make_uint4(0, 0, 0, 0);
-    // Input is staged through shared memory in tiles of kChainTile positions so the
-    // per-step byte reads never wait on DRAM: 16-byte aligned loads (by address)
-    // covering [tile, tile + kChainTile + 2), the next tile prefetched into
-    // registers while the current one is processed.
-    constexpr uint32_t kChainTile = 1024, kTileVecs = (kChainTile + 2 + 15) / 16 + 1;   // 66 uint4
-    uint8_t *tile = reinterpret_cast<uint8_t *>(head) + 65536;     // kTileVecs * 16 bytes after the head table
-    uint4 *tile4 = reinterpret_cast<uint4 *>(tile);
-    const uintptr_t addr0 = reinterpret_cast<uintptr_t>(data);
-    const uintptr_t end_addr = addr0 + n;
-    uint4 pre[3];
-    auto prefetch = [&](uint32_t t0) {                             // t0: chunk position of the tile start
-        const uintptr_t a = (addr0 + t0) & ~(uintptr_t)15;
+    for (int i = threadIdx.x; i < 4096; i += kChainWarps * 32) h4[i] = make_uint4(0, 0, 0, 0);
+    __syncthreads();
+    constexpr int G = kChainTrip / 32;
+    const uintptr_t in_hi = reinterpret_cast<uintptr_t>(b.in) + b.bytes;
+    // the three bytes at a position as one little-endian word (bytes past the input read as 0)
+    auto bytes3 = [&](uint32_t p) -> uint32_t {
+        const uintptr_t a = reinterpret_cast<uintptr_t>(data) + p;
+        const uint32_t *w = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3);
+        const uint32_t lo = w[0];
+        const uint32_t hi = (reinterpret_cast<uintptr_t>(w) + 4 < in_hi) ? w[1] : 0u;    // read only words that hold at least one input byte
+        return __funnelshift_r(lo, hi, (uint32_t)(a & 3) * 8);
+    };
+    const uint32_t ntrips = (n + kChainTrip - 1) / kChainTrip;
+    uint32_t hs[G], nxt[G];
+    auto hash_trip = [&](uint32_t t, uint32_t (&h)[G]) {
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            const uint32_t v = lane + 32 * k;
-            const uintptr_t src = a + 16ull * v;
-            pre[k] = make_uint4(0, 0, 0, 0);
-            if (v < kTileVecs && src < end_addr) pre[k] = *reinterpret_cast<const uint4 *>(src);
+        for (int j = 0; j < G; ++j) {
+            const uint32_t p = t * kChainTrip + 32 * j + lane;
+            if (p + kMinMatch <= n) {
+                const uint32_t x = bytes3(p);
+                h[j] = (((x & 0xffu) << (2 * kHashShift)) ^ (((x >> 8) & 0xffu) << kHashShift) ^ ((x >> 16) & 0xffu)) & kHashMask;
+            } else h[j] = 0x10000u | lane;
         }
     };
-    prefetch(0);
-    __syncwarp();
-    uint32_t base = 0;
-    // 4 groups of 32 positions per trip: the hashes and match.any masks of the four
-    // groups do not depend on the head table, so they are issued together (their
-    // latencies overlap); only the short head read / write part runs in order.
-    constexpr int G = 4;
-    for (uint32_t p0 = 0; p0 < n; p0 += 32 * G) {
-        if ((p0 & (kChainTile - 1)) == 0) {                        // publish the prefetched tile, fetch the next
-            __syncwarp();
+    if (warp < ntrips) hash_trip(warp, nxt);
+    for (uint32_t t = warp; t < ntrips; t += kChainWarps) {
 #pragma unroll
-            for (int k = 0; k < 3; ++k) if (lane + 32 * k < kTileVecs) tile4[lane + 32 * k] = pre[k];
-            if (p0 + kChainTile < n) prefetch(p0 + kChainTile);
-            __syncwarp();
-        }
-        if (p0 - base == 65536u) {                                 // slide: subtract 32768, saturating at 0 (= NIL)
+        for (int j = 0; j < G; ++j) hs[j] = nxt[j];
+        if (t + kChainWarps < ntrips) hash_trip(t + kChainWarps, nxt);     // the next trip's hashes: off the ordered path
+        const uint32_t p0 = t * kChainTrip;
+        // window origin after every slide due up to this trip (the first one happens at position 64 Ki)
+        const uint32_t base = p0 < 65536u ? 0u : ((p0 >> 15) - 1u) << 15;
+        if (t) asm volatile("bar.sync %0, 64;" ::"r"(warp + 1) : "memory");   // trip t-1 has left the head table (its warp arrived here)
+        if (p0 >= 65536u && (p0 & 32767u) == 0) {                  // slide: subtract 32768, saturating at 0 (= NIL)
             for (int i = lane; i < 4096; i += 32) {
                 uint4 v = h4[i];
                 v.x = __vsubus2(v.x, 0x80008000u); v.y = __vsubus2(v.y, 0x80008000u);
                 v.z = __vsubus2(v.z, 0x80008000u); v.w = __vsubus2(v.w, 0x80008000u);
                 h4[i] = v;
             }
-            base += 32768u;
             __syncwarp();
         }
-        const uint32_t tile_pos = p0 & ~(kChainTile - 1);
-        const uint8_t *tbase = tile + ((addr0 + tile_pos) & 15) - tile_pos;
-        uint32_t hs[G];
-#pragma unroll
-        for (int j = 0; j < G; ++j) {
-            const uint32_t p = p0 + 32 * j + lane;
-            hs[j] = (p + kMinMatch <= n) ? hash3(tbase + p) : (0x10000u | lane);
-        }
+        uint32_t dists[G];
 #pragma unroll
         for (int j = 0; j < G; ++j) {
             const uint32_t g0 = p0 + 32 * j, p = g0 + lane;
@@ -160,7 +157,13 @@ __global__ void __launch_bounds__(32) dfl_chain_kernel(Batch b, uint16_t *__rest
                 if (valid && (mask >> lane) == 1u) head[hs[j]] = (uint16_t)rel;   // the group's highest lane wins
                 __syncwarp();
             }
-            if (p < n) prev[p] = (uint16_t)dist;
+            dists[j] = dist;
+        }
+        if (t + 1 < ntrips) asm volatile("bar.arrive %0, 64;" ::"r"(((warp + 1) & (kChainWarps - 1)) + 1) : "memory");   // pass the turn on
+#pragma unroll
+        for (int j = 0; j < G; ++j) {
+            const uint32_t p = p0 + 32 * j + lane;
+            if (p < n) prev[p] = (uint16_t)dists[j];
         }
     }
 }
@@ -694,7 +697,7 @@ int deflate_launch(zb200_ctx *ctx, const uint8_t *d_in, size_t n, size_t S, int 
         b.last_is_final = (finish && c0 + b.nb == nch) ? 1 : 0;
         b.all_final = members ? 1 : 0;
         if (prm.mode == MODE_FAST || prm.mode == MODE_SLOW) {
-            dfl_chain_kernel<<<b.nb, 32, kChainSmem, s>>>(b, w.prev);
+            dfl_chain_kernel<<<b.nb, kChainWarps * 32, kChainSmem, s>>>(b, w.prev);
             ZB_LAUNCHED(); ZB_CHECK_LAUNCH();
         }
         if (prm.mode != MODE_HUFF) {
