@@ -79,16 +79,26 @@ __device__ __forceinline__ bool chunk_final(const Batch &b, uint32_t c) {
 // takes no issue slots; spinning on a shared-memory counter measured 6.7x slower), does
 // the four ordered head-table steps, passes the turn on and stores its links.
 constexpr int kChainWarps = 4, kChainTrip = 128;
-constexpr int kChainSmem = 65536;             // the head table
-__global__ void __launch_bounds__(kChainWarps * 32) dfl_chain_kernel(Batch b, uint16_t *__restrict__ prev_all) {
+//
+// kDepth: also count, per hash, the positions seen so far (u8, saturating, halved at
+// every slide so that it tracks the window) and store the count a position found as its
+// DEPTH — an estimate of how long its chain walk will be, which the match kernel uses
+// to put positions with similar walks into the same warp.  The count table costs 32 KiB
+// more shared memory (two CTAs per SM instead of three), so it is built only for the
+// levels that use it.
+constexpr int kChainSmem = 65536, kChainSmemDepth = 65536 + 32768;
+template <bool kDepth>
+__global__ void __launch_bounds__(kChainWarps * 32) dfl_chain_kernel(Batch b, uint16_t *__restrict__ prev_all, uint8_t *__restrict__ depth_all) {
     extern __shared__ __align__(16) uint16_t head[];
+    uint8_t *hcnt = reinterpret_cast<uint8_t *>(head) + 65536;
     const uint32_t c = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint8_t *data = b.in + (uint64_t)c * b.S;
     const uint32_t n = chunk_len(b, c);
     uint16_t *prev = prev_all + (uint64_t)c * b.S;
     uint4 *h4 = reinterpret_cast<uint4 *>(head);
-    for (int i = threadIdx.x; i < 4096; i += kChainWarps * 32) h4[i] = make_uint4(0, 0, 0, 0);
+    for (int i = threadIdx.x; i < (kDepth ? 6144 : 4096); i += kChainWarps * 32) h4[i] = make_uint4(0, 0, 0, 0);
     __syncthreads();
+    uint8_t *depth = depth_all + (uint64_t)c * b.S;
     constexpr int G = kChainTrip / 32;
     const uintptr_t in_hi = reinterpret_cast<uintptr_t>(b.in) + b.bytes;
     // the three bytes at a position as one little-endian word (bytes past the input read as 0)
@@ -127,9 +137,15 @@ __global__ void __launch_bounds__(kChainWarps * 32) dfl_chain_kernel(Batch b, ui
                 v.z = __vsubus2(v.z, 0x80008000u); v.w = __vsubus2(v.w, 0x80008000u);
                 h4[i] = v;
             }
+            if (kDepth)
+                for (int i = lane; i < 2048; i += 32) {
+                    uint4 v = h4[4096 + i];
+                    v.x = (v.x >> 1) & 0x7f7f7f7fu; v.y = (v.y >> 1) & 0x7f7f7f7fu; v.z = (v.z >> 1) & 0x7f7f7f7fu; v.w = (v.w >> 1) & 0x7f7f7f7fu;
+                    h4[4096 + i] = v;
+                }
             __syncwarp();
         }
-        uint32_t dists[G];
+        uint32_t dists[G], deps[G];
 #pragma unroll
         for (int j = 0; j < G; ++j) {
             const uint32_t g0 = p0 + 32 * j, p = g0 + lane;
@@ -139,10 +155,10 @@ __global__ void __launch_bounds__(kChainWarps * 32) dfl_chain_kernel(Batch b, ui
             // read back.  If every lane reads back its own value the 32 hashes were distinct
             // and the old heads are the links.  match.any (whose cost grows with the number
             // of distinct values) is only needed when two lanes of the group collide.
-            uint32_t old = 0;
-            if (valid) old = head[hs[j]];
+            uint32_t old = 0, oc = 0;
+            if (valid) { old = head[hs[j]]; if (kDepth) oc = hcnt[hs[j]]; }
             __syncwarp();
-            if (valid) head[hs[j]] = (uint16_t)rel;
+            if (valid) { head[hs[j]] = (uint16_t)rel; if (kDepth) hcnt[hs[j]] = (uint8_t)(oc < 255u ? oc + 1u : 255u); }
             __syncwarp();
             const bool clash = valid && head[hs[j]] != (uint16_t)rel;
             uint32_t dist = (valid && old) ? rel - old : 0;
@@ -152,18 +168,22 @@ __global__ void __launch_bounds__(kChainWarps * 32) dfl_chain_kernel(Batch b, ui
                 if (valid && lower) {
                     const uint32_t q = g0 + (31u - (uint32_t)__clz(lower));
                     dist = q ? p - q : 0;                          // position 0 is never a match target (deflate.c:1366)
+                    if (kDepth) oc += (uint32_t)__popc(lower);
                 }
                 __syncwarp();
-                if (valid && (mask >> lane) == 1u) head[hs[j]] = (uint16_t)rel;   // the group's highest lane wins
+                if (valid && (mask >> lane) == 1u) {               // the group's highest lane wins
+                    head[hs[j]] = (uint16_t)rel;
+                    if (kDepth) hcnt[hs[j]] = (uint8_t)(oc < 255u ? oc + 1u : 255u);
+                }
                 __syncwarp();
             }
-            dists[j] = dist;
+            dists[j] = dist; deps[j] = oc < 255u ? oc : 255u;
         }
         if (t + 1 < ntrips) asm volatile("bar.arrive %0, 64;" ::"r"(((warp + 1) & (kChainWarps - 1)) + 1) : "memory");   // pass the turn on
 #pragma unroll
         for (int j = 0; j < G; ++j) {
             const uint32_t p = p0 + 32 * j + lane;
-            if (p < n) prev[p] = (uint16_t)dists[j];
+            if (p < n) { prev[p] = (uint16_t)dists[j]; if (kDepth) depth[p] = (uint8_t)deps[j]; }
         }
     }
 }
@@ -194,6 +214,119 @@ dfl_match_kernel(Batch b, DeflateParams prm, const uint16_t *__restrict__ prev_a
     const MatchPair r = match_at(data, n, prev_all + off, p, prm);
     mfull[off + p] = r.full;
     if (prm.need_quarter) mquarter[off + p] = r.quarter;
+}
+
+// The same walk with the positions of a tile handed to the warps in order of their
+// chain depth.  A warp costs as many steps as its longest walk; consecutive positions
+// have unrelated walk lengths (ncu: 8 of 32 lanes active; host replay: 30 % of the
+// lane-steps useful on text at level 6), while positions with the same depth bucket
+// have similar ones (75 % useful with quarter-octave buckets, 90 % on mixed data).
+// Per tile: bucket of every position (0 = no candidate at all), counting sort in shared
+// memory, then thread i of the CTA takes the sorted entries i, i + 256, ...
+//
+// The walks themselves run on shared memory.  From global memory every lane's candidate
+// byte and chain link is a different cache line, and the kernel is bound by the L1's tag
+// stage (one line per cycle: 10 G scattered reads per 512 MiB at level 6 ~ 28 ms, the
+// time measured with and without the sort).  So the CTA first stages everything the
+// walks of its tile can touch — the 32 KiB of history before the tile, the tile and its
+// lookahead (input bytes) and the chain links of the same positions — with coalesced
+// 16-byte loads; a 16 Ki-position tile makes that 9 bytes of staging per position.
+constexpr uint32_t kMsTile = 16384, kMsThreads = 1024, kMsBuckets = 32;
+constexpr uint32_t kMsLook = kMaxMatch + 16;                                  // bytes a walk may read past its position
+constexpr uint32_t kMsDataBytes = (kWSize + kMsTile + kMsLook + 32 + 15) & ~15u;   // + alignment skew / slack
+constexpr uint32_t kMsLinkBytes = ((kWSize + kMsTile) * 2 + 32 + 15) & ~15u;
+constexpr uint32_t kMsSmem = kMsDataBytes + kMsLinkBytes + kMsTile * 2;
+__device__ __forceinline__ uint32_t depth_bucket(uint32_t e) {   // 0,1,2,3, then four buckets per octave
+    if (e < 4u) return e;
+    const uint32_t l = 31u - (uint32_t)__clz(e);
+    return 4u + (l - 2u) * 4u + ((e >> (l - 2u)) & 3u);          // e <= 255 -> at most 27
+}
+extern __shared__ __align__(16) uint8_t ms_smem[];
+struct StagedMem {                                       // operands from the staged window: 32-bit shared-memory addressing
+    uint32_t doff, loff;                                 // byte offset of chunk position 0 in ms_smem (wraps), same for link 0
+    __device__ __forceinline__ uint32_t byte(uint32_t pos) const { return ms_smem[doff + pos]; }
+    __device__ __forceinline__ uint32_t word(uint32_t pos) const {
+        const uint32_t a = doff + pos;
+        const uint32_t *w = reinterpret_cast<const uint32_t *>(ms_smem + (a & ~3u));
+        return __funnelshift_r(w[0], w[1], (a & 3u) * 8u);
+    }
+    __device__ __forceinline__ uint32_t link(uint32_t pos) const { return *reinterpret_cast<const uint16_t *>(ms_smem + loff + 2u * pos); }
+};
+
+__global__ void __launch_bounds__(kMsThreads)
+dfl_match_sorted_kernel(Batch b, DeflateParams prm, const uint16_t *__restrict__ prev_all, const uint8_t *__restrict__ depth_all,
+                        uint32_t *__restrict__ mfull, uint32_t *__restrict__ mquarter) {
+    __shared__ uint32_t s_hist[kMsBuckets], s_cur[kMsBuckets];
+    uint4 *sdata = reinterpret_cast<uint4 *>(ms_smem);
+    uint4 *slink = reinterpret_cast<uint4 *>(ms_smem + kMsDataBytes);
+    uint16_t *s_order = reinterpret_cast<uint16_t *>(ms_smem + kMsDataBytes + kMsLinkBytes);
+    const uint32_t c = blockIdx.y, n = chunk_len(b, c), t0 = blockIdx.x * kMsTile;
+    if (t0 >= n) return;
+    const uint64_t off = (uint64_t)c * b.S;
+    const uint8_t *data = b.in + off;
+    const uint16_t *prev = prev_all + off;
+    const uint8_t *depth = depth_all + off;
+    const uint32_t cnt = n - t0 < kMsTile ? n - t0 : kMsTile, t1 = t0 + cnt;
+    const uint32_t lo = t0 > (uint32_t)kWSize ? t0 - kWSize : 0;             // candidates lie less than 32 KiB back
+    const uint32_t hi = t1 + kMsLook < n ? t1 + kMsLook : n;                  // bytes [lo, hi) can be read
+    if (threadIdx.x < kMsBuckets) s_hist[threadIdx.x] = 0;
+    // input bytes: 16-byte vectors by ADDRESS; vectors that straddle the ends of the input buffer are read bytewise
+    const uintptr_t in_lo = reinterpret_cast<uintptr_t>(b.in), in_hi = in_lo + b.bytes;
+    const uintptr_t d_first = ((reinterpret_cast<uintptr_t>(data) + lo) & ~(uintptr_t)15) - 16;   // one vector of slack before
+    const uint32_t dskew = (uint32_t)(reinterpret_cast<uintptr_t>(data) + lo - d_first);
+    const uint32_t dvecs = (uint32_t)((reinterpret_cast<uintptr_t>(data) + hi - d_first + 15) >> 4) + 1;   // and one after
+    for (uint32_t v = threadIdx.x; v < dvecs; v += kMsThreads) {
+        const uintptr_t a = d_first + 16ull * v;
+        uint4 x = make_uint4(0, 0, 0, 0);
+        if (a >= in_lo && a + 16 <= in_hi) x = *reinterpret_cast<const uint4 *>(a);
+        else if (a + 16 > in_lo && a < in_hi) {
+            uint8_t *xb = reinterpret_cast<uint8_t *>(&x);
+            for (int k = 0; k < 16; ++k) if (a + k >= in_lo && a + k < in_hi) xb[k] = *reinterpret_cast<const uint8_t *>(a + k);
+        }
+        sdata[v] = x;
+    }
+    // chain links of [lo, t1): the array sits inside the engine's scratch (16-byte aligned, followed by other arrays)
+    const uintptr_t p_first = reinterpret_cast<uintptr_t>(prev + lo) & ~(uintptr_t)15;
+    const uint32_t pskew = (uint32_t)((reinterpret_cast<uintptr_t>(prev + lo) - p_first) >> 1);
+    const uint32_t pvecs = (uint32_t)((reinterpret_cast<uintptr_t>(prev + t1) - p_first + 15) >> 4);
+    for (uint32_t v = threadIdx.x; v < pvecs; v += kMsThreads) slink[v] = *reinterpret_cast<const uint4 *>(p_first + 16ull * v);
+    __syncthreads();
+    StagedMem mem;
+    mem.doff = dskew - lo;                                         // chunk position p lives at ms_smem[doff + p]
+    mem.loff = kMsDataBytes + 2u * pskew - 2u * lo;                // link p at ms_smem[loff + 2 p]
+    uint32_t bk[kMsTile / kMsThreads];
+#pragma unroll
+    for (uint32_t k = 0; k < kMsTile / kMsThreads; ++k) {
+        const uint32_t i = k * kMsThreads + threadIdx.x;
+        bk[k] = 0xffffffffu;
+        if (i < cnt) {
+            const uint32_t p = t0 + i, d = mem.link(p);
+            uint32_t e = 0;
+            if (p + kMinMatch <= n && d != 0 && d <= (uint32_t)kMaxDist) {
+                e = (uint32_t)depth[p] + 1u;                       // at least one candidate
+                if (e > (uint32_t)prm.chain) e = (uint32_t)prm.chain;
+                if (e > 255u) e = 255u;
+            }
+            bk[k] = depth_bucket(e);
+            atomicAdd(&s_hist[bk[k]], 1u);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {                                        // longest walks first
+        uint32_t run = 0;
+        for (int q = kMsBuckets - 1; q >= 0; --q) { s_cur[q] = run; run += s_hist[q]; }
+    }
+    __syncthreads();
+#pragma unroll
+    for (uint32_t k = 0; k < kMsTile / kMsThreads; ++k)
+        if (bk[k] != 0xffffffffu) s_order[atomicAdd(&s_cur[bk[k]], 1u)] = (uint16_t)(k * kMsThreads + threadIdx.x);
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < cnt; i += kMsThreads) {
+        const uint32_t p = t0 + s_order[i];
+        const MatchPair r = match_walk(mem, n, p, prm);
+        mfull[off + p] = r.full;
+        if (prm.need_quarter) mquarter[off + p] = r.quarter;
+    }
 }
 
 // ---- phase 3, greedy rules (deflate_fast / deflate_rle / deflate_huff): one chunk per warp ----
@@ -632,7 +765,9 @@ int deflate_init(zb200_ctx *ctx) {
     ZB_CUDA(cudaMalloc(&d, sizeof h));
     ZB_CUDA(cudaMemcpy(d, &h, sizeof h, cudaMemcpyHostToDevice));
     ctx->d_deflate_tables = d;
-    ZB_CUDA(cudaFuncSetAttribute(dfl_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kChainSmem));
+    ZB_CUDA(cudaFuncSetAttribute(dfl_chain_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kChainSmem));
+    ZB_CUDA(cudaFuncSetAttribute(dfl_chain_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kChainSmemDepth));
+    ZB_CUDA(cudaFuncSetAttribute(dfl_match_sorted_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMsSmem));
     return ZB200_OK;
 }
 
@@ -667,6 +802,8 @@ int deflate_launch(zb200_ctx *ctx, const uint8_t *d_in, size_t n, size_t S, int 
     if (nch == 0 && (finish || members)) nch = 1;
     if (out_cap < zb200_deflate_bound(n, S, frame)) { set_error("deflate: output capacity below zb200_deflate_bound()"); return ZB200_ERR_OUTPUT; }
     const DeflateParams prm = deflate_params(level, strategy);
+    // levels 3..9: chain walks of very different lengths -> depth-sorted scheduling (levels 1-2 use the branch-free walk)
+    const bool sorted_walks = (prm.mode == MODE_SLOW || prm.mode == MODE_FAST) && prm.level >= 3;
     const uint32_t MB = max_blocks_for((uint32_t)S);
     const size_t nb_max = batch_chunks(n, S);
     int r = ensure_scratch(ctx, work_bytes(nb_max, S, MB));
@@ -697,10 +834,16 @@ int deflate_launch(zb200_ctx *ctx, const uint8_t *d_in, size_t n, size_t S, int 
         b.last_is_final = (finish && c0 + b.nb == nch) ? 1 : 0;
         b.all_final = members ? 1 : 0;
         if (prm.mode == MODE_FAST || prm.mode == MODE_SLOW) {
-            dfl_chain_kernel<<<b.nb, kChainWarps * 32, kChainSmem, s>>>(b, w.prev);
+            // depth counts ride in the symbol array, which the parse kernel overwrites only after the matches are done
+            if (sorted_walks) dfl_chain_kernel<true><<<b.nb, kChainWarps * 32, kChainSmemDepth, s>>>(b, w.prev, (uint8_t *)w.syms);
+            else dfl_chain_kernel<false><<<b.nb, kChainWarps * 32, kChainSmem, s>>>(b, w.prev, nullptr);
             ZB_LAUNCHED(); ZB_CHECK_LAUNCH();
         }
-        if (prm.mode != MODE_HUFF) {
+        if (sorted_walks) {
+            dim3 g((unsigned)((S + kMsTile - 1) / kMsTile), b.nb);
+            dfl_match_sorted_kernel<<<g, kMsThreads, kMsSmem, s>>>(b, prm, w.prev, (const uint8_t *)w.syms, w.mfull, w.mquarter);
+            ZB_LAUNCHED(); ZB_CHECK_LAUNCH();
+        } else if (prm.mode != MODE_HUFF) {
             dim3 g((unsigned)((S + 255) / 256), b.nb);
             dfl_match_kernel<<<g, 256, 0, s>>>(b, prm, w.prev, w.mfull, w.mquarter);
             ZB_LAUNCHED(); ZB_CHECK_LAUNCH();

@@ -105,39 +105,73 @@ ZB_HD uint32_t ctz32(uint32_t x) {
 // (it changes only when the best match does), the next link is requested before the
 // candidate is looked at (the two reads are independent, so their latencies overlap), and
 // the quarter snapshot is a second loop bound instead of per-step bookkeeping.
-ZB_HD MatchPair match_at(const uint8_t *data, uint32_t n, const uint16_t *prev_dist, uint32_t p,
-                         const DeflateParams &prm) {
+// `Mem` supplies the operands by chunk position: byte(pos), word(pos) (four bytes,
+// little-endian, any alignment) and link(pos) — plain arrays here, a window staged in
+// shared memory in the depth-sorted kernel (32-bit shared addresses instead of generic
+// 64-bit pointer arithmetic: a fifth of that kernel's instructions).
+struct PlainMem {
+    const uint8_t *data; const uint16_t *prev;
+    ZB_HD uint32_t byte(uint32_t pos) const { return data[pos]; }
+    ZB_HD uint32_t word(uint32_t pos) const { return load4(data + pos); }
+    ZB_HD uint32_t link(uint32_t pos) const { return prev[pos]; }
+};
+
+template <class Mem>
+ZB_HD MatchPair match_walk(const Mem &mem, uint32_t n, uint32_t p, const DeflateParams &prm) {
     MatchPair r;
     r.full = r.quarter = 0;
     if (p + kMinMatch > n) return r;                      // lookahead < MIN_MATCH: no insertion, no search
-    const uint32_t d = prev_dist[p];
+    const uint32_t d = mem.link(p);
     if (d == 0 || d > (uint32_t)kMaxDist) return r;       // deflate.c:1857/1958: head must be within MAX_DIST
     const uint32_t look = n - p;
     const uint32_t maxlen = look < (uint32_t)kMaxMatch ? look : (uint32_t)kMaxMatch;
     const uint32_t nice = (uint32_t)prm.nice > look ? look : (uint32_t)prm.nice;      // deflate.c:1396
-    const uint8_t *scan = data + p;
-    const uint32_t s0 = scan[0], s1 = scan[1];
-    uint32_t best = kMinMatch - 1, best_dist = 0, sb = scan[kMinMatch - 1];           // best < maxlen whenever a candidate is screened
+    // The first 12 bytes of the string live in registers: most candidates that pass the quick
+    // rejects differ within them, so measuring costs candidate loads only.  (In a warp, the few
+    // lanes that measure hold up all the others: the cheaper this path, the better.)
+    const bool regs = look >= 16;                         // else: chunk tail, everything bytewise below
+    const uint32_t sw0 = regs ? mem.word(p) : 0, sw4 = regs ? mem.word(p + 4) : 0, sw8 = regs ? mem.word(p + 8) : 0;
+    uint32_t best = kMinMatch - 1, best_dist = 0, sb = mem.byte(p + kMinMatch - 1);           // best < maxlen whenever a candidate is screened
     uint32_t q = p - d, examined = 0;
     const uint32_t budget = (uint32_t)prm.chain, qbudget = budget >> 2;
     uint32_t stop_at = qbudget ? qbudget : budget;        // the next loop bound: quarter snapshot first, then the full budget
     bool have_q = false;
     for (;;) {
-        const uint8_t *m = data + q;
-        const uint32_t d2 = prev_dist[q];
-        if (m[best] == sb && m[0] == s0 && m[1] == s1) {
-            uint32_t len = 2;                             // m[2]==scan[2] follows from the equal hash when bytes 0,1 agree
-            while (len + 8 <= maxlen) {                   // four bytes per step while the aligned reads stay inside the chunk
-                const uint32_t x = load4(m + len) ^ load4(scan + len);
-                if (x) { len += ctz32(x) >> 3; goto measured; }
-                len += 4;
+        const uint32_t d2 = mem.link(q);
+        if (mem.byte(q + best) == sb) {                              // deflate.c:1449-1452: the cheapest reject first
+            uint32_t len;
+            bool pass;
+            if (regs) {
+                uint32_t x = mem.word(q) ^ sw0;
+                pass = (x & 0xffffu) == 0;
+                if (x) len = ctz32(x) >> 3;
+                else {
+                    x = mem.word(q + 4) ^ sw4;
+                    if (x) len = 4 + (ctz32(x) >> 3);
+                    else {
+                        x = mem.word(q + 8) ^ sw8;
+                        if (x) len = 8 + (ctz32(x) >> 3);
+                        else {
+                            len = 12;
+                            while (len + 8 <= maxlen) {   // four bytes per step while the aligned reads stay inside the chunk
+                                const uint32_t y = mem.word(q + len) ^ mem.word(p + len);
+                                if (y) { len += ctz32(y) >> 3; goto measured; }
+                                len += 4;
+                            }
+                            while (len < maxlen && mem.byte(q + len) == mem.byte(p + len)) ++len;
+                        measured:;
+                        }
+                    }
+                }
+            } else {
+                pass = mem.byte(q) == mem.byte(p) && mem.byte(q + 1) == mem.byte(p + 1);
+                len = 2;                                  // m[2]==scan[2] follows from the equal hash when bytes 0,1 agree
+                if (pass) while (len < maxlen && mem.byte(q + len) == mem.byte(p + len)) ++len;
             }
-            while (len < maxlen && m[len] == scan[len]) ++len;
-        measured:
-            if (len > best) {
+            if (pass && len > best) {
                 best = len; best_dist = p - q;
                 if (len >= nice) break;
-                sb = scan[best];
+                sb = mem.byte(p + best);
             }
         }
         if (++examined == stop_at) {
@@ -153,6 +187,12 @@ ZB_HD MatchPair match_at(const uint8_t *data, uint32_t n, const uint16_t *prev_d
     r.full = best >= (uint32_t)kMinMatch ? (best << 16) | best_dist : 0;
     if (!have_q) r.quarter = r.full;
     return r;
+}
+
+ZB_HD MatchPair match_at(const uint8_t *data, uint32_t n, const uint16_t *prev_dist, uint32_t p,
+                         const DeflateParams &prm) {
+    const PlainMem mem{data, prev_dist};
+    return match_walk(mem, n, p, prm);
 }
 
 // ---- levels 1-2: the same walk without data-dependent control flow -----------------
