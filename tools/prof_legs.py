@@ -34,7 +34,7 @@ def timed(fn, reps=2):
     return (time.perf_counter() - t0) / reps
 
 
-host = refz.gen(n, refz.GEN_MARKOV)
+host = refz.gen(n, int(os.environ.get("ZB_GEN", refz.GEN_MARKOV)))
 d_in = torch.frombuffer(bytearray(host), dtype=torch.uint8).cuda()
 cap = L.zb200_deflate_bound(n, CH, zb.FRAME_GZIP_MEMBERS)
 d_out = torch.empty(cap, dtype=torch.uint8, device="cuda")
