@@ -193,9 +193,9 @@ __global__ void __launch_bounds__(kChainWarps * 32) dfl_chain_kernel(Batch b, ui
 // irregular -- ncu: 8 of 32 lanes active on average, issue slots 74 % busy -- and four
 // re-schedulings of it inside the warp were measured and dropped:
 // they raise the active-lane count but add as many scheduling instructions as they save.
-// Levels 1-2 have a closed form without data-dependent control flow (match_uniform):
-// 10.9 -> 7.6 ms per 512 MiB, then bound by dependent L1/L2 loads (the same walk over a
-// window staged in shared memory measured 8.5 ms: bank conflicts + the staging traffic).
+// This plain form (operands from global memory) now serves Z_RLE only; levels 1-2 run
+// dfl_match_uniform_kernel and levels 3-9 dfl_match_sorted_kernel, both on a window
+// staged in shared memory.
 __global__ void __launch_bounds__(256)
 dfl_match_kernel(Batch b, DeflateParams prm, const uint16_t *__restrict__ prev_all,
                  uint32_t *__restrict__ mfull, uint32_t *__restrict__ mquarter) {
@@ -206,11 +206,6 @@ dfl_match_kernel(Batch b, DeflateParams prm, const uint16_t *__restrict__ prev_a
     const uint64_t off = (uint64_t)c * b.S;
     const uint8_t *data = b.in + off;
     if (prm.mode == MODE_RLE) { mfull[off + p] = rle_at(data, n, p); return; }
-    if (prm.mode == MODE_FAST && prm.level <= 2 && p + kUniformTail <= n) {   // levels 1-2: the branch-free walk
-        const PlainWin win{data, prev_all + off};
-        mfull[off + p] = prm.level == 1 ? match_uniform<4, 8>(win, p) : match_uniform<8, 16>(win, p);
-        return;
-    }
     const MatchPair r = match_at(data, n, prev_all + off, p, prm);
     mfull[off + p] = r.full;
     if (prm.need_quarter) mquarter[off + p] = r.quarter;
@@ -251,31 +246,31 @@ struct StagedMem {                                       // operands from the st
         return __funnelshift_r(w[0], w[1], (a & 3u) * 8u);
     }
     __device__ __forceinline__ uint32_t link(uint32_t pos) const { return *reinterpret_cast<const uint16_t *>(ms_smem + loff + 2u * pos); }
+    // the accessors match_uniform uses
+    template <int NW> __device__ __forceinline__ void words(uint32_t pos, uint32_t (&w)[NW]) const {
+        const uint32_t a = doff + pos, sh = (a & 3u) * 8u;
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(ms_smem + (a & ~3u));
+        uint32_t raw[NW + 1];
+#pragma unroll
+        for (int i = 0; i <= NW; ++i) raw[i] = src[i];
+#pragma unroll
+        for (int i = 0; i < NW; ++i) w[i] = __funnelshift_r(raw[i], raw[i + 1], sh);
+    }
+    __device__ __forceinline__ uint32_t dist(uint32_t pos) const { return link(pos); }
 };
 
-__global__ void __launch_bounds__(kMsThreads)
-dfl_match_sorted_kernel(Batch b, DeflateParams prm, const uint16_t *__restrict__ prev_all, const uint8_t *__restrict__ depth_all,
-                        uint32_t *__restrict__ mfull, uint32_t *__restrict__ mquarter) {
-    __shared__ uint32_t s_hist[kMsBuckets], s_cur[kMsBuckets];
+// Stage bytes [lo, hi) and links [lo, t1) of a chunk into ms_smem (all threads of the CTA;
+// ends with a barrier) and return the accessor.
+__device__ __forceinline__ StagedMem stage_window(const Batch &b, const uint8_t *data, const uint16_t *prev,
+                                                  uint32_t lo, uint32_t hi, uint32_t t1) {
     uint4 *sdata = reinterpret_cast<uint4 *>(ms_smem);
     uint4 *slink = reinterpret_cast<uint4 *>(ms_smem + kMsDataBytes);
-    uint16_t *s_order = reinterpret_cast<uint16_t *>(ms_smem + kMsDataBytes + kMsLinkBytes);
-    const uint32_t c = blockIdx.y, n = chunk_len(b, c), t0 = blockIdx.x * kMsTile;
-    if (t0 >= n) return;
-    const uint64_t off = (uint64_t)c * b.S;
-    const uint8_t *data = b.in + off;
-    const uint16_t *prev = prev_all + off;
-    const uint8_t *depth = depth_all + off;
-    const uint32_t cnt = n - t0 < kMsTile ? n - t0 : kMsTile, t1 = t0 + cnt;
-    const uint32_t lo = t0 > (uint32_t)kWSize ? t0 - kWSize : 0;             // candidates lie less than 32 KiB back
-    const uint32_t hi = t1 + kMsLook < n ? t1 + kMsLook : n;                  // bytes [lo, hi) can be read
-    if (threadIdx.x < kMsBuckets) s_hist[threadIdx.x] = 0;
     // input bytes: 16-byte vectors by ADDRESS; vectors that straddle the ends of the input buffer are read bytewise
     const uintptr_t in_lo = reinterpret_cast<uintptr_t>(b.in), in_hi = in_lo + b.bytes;
     const uintptr_t d_first = ((reinterpret_cast<uintptr_t>(data) + lo) & ~(uintptr_t)15) - 16;   // one vector of slack before
     const uint32_t dskew = (uint32_t)(reinterpret_cast<uintptr_t>(data) + lo - d_first);
     const uint32_t dvecs = (uint32_t)((reinterpret_cast<uintptr_t>(data) + hi - d_first + 15) >> 4) + 1;   // and one after
-    for (uint32_t v = threadIdx.x; v < dvecs; v += kMsThreads) {
+    for (uint32_t v = threadIdx.x; v < dvecs; v += blockDim.x) {
         const uintptr_t a = d_first + 16ull * v;
         uint4 x = make_uint4(0, 0, 0, 0);
         if (a >= in_lo && a + 16 <= in_hi) x = *reinterpret_cast<const uint4 *>(a);
@@ -289,11 +284,53 @@ dfl_match_sorted_kernel(Batch b, DeflateParams prm, const uint16_t *__restrict__
     const uintptr_t p_first = reinterpret_cast<uintptr_t>(prev + lo) & ~(uintptr_t)15;
     const uint32_t pskew = (uint32_t)((reinterpret_cast<uintptr_t>(prev + lo) - p_first) >> 1);
     const uint32_t pvecs = (uint32_t)((reinterpret_cast<uintptr_t>(prev + t1) - p_first + 15) >> 4);
-    for (uint32_t v = threadIdx.x; v < pvecs; v += kMsThreads) slink[v] = *reinterpret_cast<const uint4 *>(p_first + 16ull * v);
+    for (uint32_t v = threadIdx.x; v < pvecs; v += blockDim.x) slink[v] = *reinterpret_cast<const uint4 *>(p_first + 16ull * v);
     __syncthreads();
     StagedMem mem;
     mem.doff = dskew - lo;                                         // chunk position p lives at ms_smem[doff + p]
     mem.loff = kMsDataBytes + 2u * pskew - 2u * lo;                // link p at ms_smem[loff + 2 p]
+    return mem;
+}
+
+// Levels 1-2 on the staged window: the branch-free walk reads 16 scattered words and 4
+// links per position; from global memory that is bound by the L1's tag stage (7.6 ms per
+// 512 MiB at level 1), from shared memory by bank conflicts (~3.5 wavefronts per request).
+template <int CH, int NICE>
+__global__ void __launch_bounds__(kMsThreads)
+dfl_match_uniform_kernel(Batch b, DeflateParams prm, const uint16_t *__restrict__ prev_all, uint32_t *__restrict__ mfull) {
+    const uint32_t c = blockIdx.y, n = chunk_len(b, c), t0 = blockIdx.x * kMsTile;
+    if (t0 >= n) return;
+    const uint64_t off = (uint64_t)c * b.S;
+    const uint8_t *data = b.in + off;
+    const uint16_t *prev = prev_all + off;
+    const uint32_t cnt = n - t0 < kMsTile ? n - t0 : kMsTile, t1 = t0 + cnt;
+    const uint32_t lo = t0 > (uint32_t)kWSize ? t0 - kWSize : 0;
+    const uint32_t hi = t1 + kMsLook < n ? t1 + kMsLook : n;
+    const StagedMem mem = stage_window(b, data, prev, lo, hi, t1);
+    for (uint32_t p = t0 + threadIdx.x; p < t1; p += kMsThreads) {
+        uint32_t r;
+        if (p + kUniformTail <= n) r = match_uniform<CH, NICE>(mem, p);
+        else r = match_walk(mem, n, p, prm).full;                  // chunk tail: lookahead clamps apply
+        mfull[off + p] = r;
+    }
+}
+
+__global__ void __launch_bounds__(kMsThreads)
+dfl_match_sorted_kernel(Batch b, DeflateParams prm, const uint16_t *__restrict__ prev_all, const uint8_t *__restrict__ depth_all,
+                        uint32_t *__restrict__ mfull, uint32_t *__restrict__ mquarter) {
+    __shared__ uint32_t s_hist[kMsBuckets], s_cur[kMsBuckets];
+    uint16_t *s_order = reinterpret_cast<uint16_t *>(ms_smem + kMsDataBytes + kMsLinkBytes);
+    const uint32_t c = blockIdx.y, n = chunk_len(b, c), t0 = blockIdx.x * kMsTile;
+    if (t0 >= n) return;
+    const uint64_t off = (uint64_t)c * b.S;
+    const uint8_t *data = b.in + off;
+    const uint16_t *prev = prev_all + off;
+    const uint8_t *depth = depth_all + off;
+    const uint32_t cnt = n - t0 < kMsTile ? n - t0 : kMsTile, t1 = t0 + cnt;
+    const uint32_t lo = t0 > (uint32_t)kWSize ? t0 - kWSize : 0;             // candidates lie less than 32 KiB back
+    const uint32_t hi = t1 + kMsLook < n ? t1 + kMsLook : n;                  // bytes [lo, hi) can be read
+    if (threadIdx.x < kMsBuckets) s_hist[threadIdx.x] = 0;
+    const StagedMem mem = stage_window(b, data, prev, lo, hi, t1);
     uint32_t bk[kMsTile / kMsThreads];
 #pragma unroll
     for (uint32_t k = 0; k < kMsTile / kMsThreads; ++k) {
@@ -768,6 +805,8 @@ int deflate_init(zb200_ctx *ctx) {
     ZB_CUDA(cudaFuncSetAttribute(dfl_chain_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kChainSmem));
     ZB_CUDA(cudaFuncSetAttribute(dfl_chain_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kChainSmemDepth));
     ZB_CUDA(cudaFuncSetAttribute(dfl_match_sorted_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMsSmem));
+    ZB_CUDA(cudaFuncSetAttribute(dfl_match_uniform_kernel<4, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMsSmem));
+    ZB_CUDA(cudaFuncSetAttribute(dfl_match_uniform_kernel<8, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMsSmem));
     return ZB200_OK;
 }
 
@@ -842,6 +881,11 @@ int deflate_launch(zb200_ctx *ctx, const uint8_t *d_in, size_t n, size_t S, int 
         if (sorted_walks) {
             dim3 g((unsigned)((S + kMsTile - 1) / kMsTile), b.nb);
             dfl_match_sorted_kernel<<<g, kMsThreads, kMsSmem, s>>>(b, prm, w.prev, (const uint8_t *)w.syms, w.mfull, w.mquarter);
+            ZB_LAUNCHED(); ZB_CHECK_LAUNCH();
+        } else if (prm.mode == MODE_FAST) {                        // levels 1-2
+            dim3 g((unsigned)((S + kMsTile - 1) / kMsTile), b.nb);
+            if (prm.level == 1) dfl_match_uniform_kernel<4, 8><<<g, kMsThreads, kMsSmem, s>>>(b, prm, w.prev, w.mfull);
+            else dfl_match_uniform_kernel<8, 16><<<g, kMsThreads, kMsSmem, s>>>(b, prm, w.prev, w.mfull);
             ZB_LAUNCHED(); ZB_CHECK_LAUNCH();
         } else if (prm.mode != MODE_HUFF) {
             dim3 g((unsigned)((S + 255) / 256), b.nb);
