@@ -54,18 +54,32 @@ extern "C" long emul_deflate_chunk(const uint8_t *data, uint32_t n, int level, i
     // the kernel's segmented parse (zb_deflate.cuh seg_*), the lanes replayed by loops;
     // the serial whole-chunk parse must give the same symbols and blocks
     if (prm.mode != MODE_SLOW) {
-        // greedy rules: serial chase per tile, then per-symbol work in any order (zb_deflate.cu dfl_parse_greedy_kernel)
-        ParseArrays acc{data, mf.data(), mq.data(), syms.data(), 0};
-        std::vector<uint32_t> visited(1100);
-        uint32_t flushed = 0, p = 0;
+        // greedy rules: exit tables per tile (zb_deflate.cu dfl_parse_greedy_kernel), the lanes replayed by loops
         const bool use_m = prm.mode != MODE_HUFF;
-        while (p < n) {
-            uint32_t lim = p + 1000 < n ? p + 1000 : n;
-            const uint32_t made = greedy_chase(p, lim, use_m, acc, visited.data());
-            for (uint32_t i = made; i-- > 0;) syms[flushed + i] = greedy_symbol(visited[i], use_m, acc, flushed + i, blocks.data(), n, prm);
-            flushed += made;
+        std::vector<uint32_t> mfv(kGtSlots); std::vector<uint16_t> lc(kGtSlots);
+        uint32_t entry = 0, nsyms = 0;
+        struct GA { const uint32_t *mfv; const uint8_t *data; uint32_t t0;
+                    uint32_t mf(uint32_t p) const { return mfv[gt_slot(p - t0)]; } uint32_t byte(uint32_t p) const { return data[p]; } };
+        for (uint32_t t0 = 0; t0 < n; t0 += kGtTile) {
+            for (uint32_t r = 0; r < kGtTile; ++r) mfv[gt_slot(r)] = (use_m && t0 + r < n) ? mf[t0 + r] : 0u;
+            for (int l = 31; l >= 0; --l) gt_fill((uint32_t)l, n - t0, mfv.data(), lc.data());
+            uint32_t exit_rel = 0, total = 0;
+            for (int l = 31; l >= 0; --l) {
+                uint32_t my_entry, my_first;
+                exit_rel = gt_hop((uint32_t)l, entry - t0, n - t0, lc.data(), my_entry, my_first, total);
+                if (my_entry == 0xffffffffu) continue;
+                GA acc{mfv.data(), data, t0};
+                const uint32_t seg_end = ((uint32_t)l + 1) * kGtSeg, lim = n - t0;
+                uint32_t r = my_entry, g = nsyms + my_first;
+                while (r < seg_end && r < lim) {
+                    const uint32_t m = mfv[gt_slot(r)];
+                    syms[g] = greedy_symbol(t0 + r, use_m, acc, g, blocks.data(), n, prm);
+                    ++g; r += m ? (m >> 16) : 1u;
+                }
+            }
+            entry = t0 + exit_rel; nsyms += total;
         }
-        sink.nsyms = flushed; sink.nblocks = seg_finish(blocks.data(), flushed, false, n, prm, final_chunk != 0);
+        sink.nsyms = nsyms; sink.nblocks = seg_finish(blocks.data(), nsyms, false, n, prm, final_chunk != 0);
     } else {
         const SegGeom g = seg_geometry(n);
         std::vector<SegRec> rec((kSegRecs - 1) * kSegLanes);

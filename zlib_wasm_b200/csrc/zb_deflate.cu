@@ -366,118 +366,71 @@ dfl_match_sorted_kernel(Batch b, DeflateParams prm, const uint16_t *__restrict__
     }
 }
 
-// ---- phase 3, greedy rules (deflate_fast / deflate_rle / deflate_huff): one chunk per warp ----
-// The walk is a dependent chain (the next position depends on the entry just
-// read), so its operands are staged in shared memory: positions are cut into
-// fixed tiles of kParseTile; while lane 0 walks tile k, tile k+1 (match entries
-// and input bytes) is already in flight as 16-byte cp.async copies into the other
-// buffer.  Emitted symbols are staged too and flushed with coalesced stores.
-constexpr uint32_t kParseTile = 512;
-constexpr uint32_t kPtVecsM = kParseTile / 4 + 1;      // uint4 of match entries per tile (+1: alignment slack)
-constexpr uint32_t kPtVecsB = kParseTile / 16 + 2;     // uint4 of input bytes per tile (+1 before, +1 slack)
-
-struct ParseBuf {
-    uint4 mf[kPtVecsM], mq[kPtVecsM], by[kPtVecsB];
+// ---- phase 3, greedy rules (deflate_fast / deflate_rle / deflate_huff): one chunk per CTA ----
+// Exit tables per tile (zb_deflate.cuh gt_*): warp w takes tiles w, w + 4, ...; it loads
+// the tile's match entries, fills the tables, waits for the previous tile's exit (named
+// barrier, as in the chain kernel), crosses its tile in 32 dependent table reads, passes
+// (exit position, symbol count) on and then forms its symbols.
+constexpr int kGtWarps = 4;
+struct GtWarpShared {
+    uint32_t mfv[kGtSlots];
+    uint16_t lc[kGtSlots];
+};
+struct GtAcc {                                         // greedy_symbol's operands: entries from the tile, bytes from global memory
+    const uint32_t *mfv; const uint8_t *data; uint32_t t0;
+    __device__ __forceinline__ uint32_t mf(uint32_t p) const { return mfv[gt_slot(p - t0)]; }
+    __device__ __forceinline__ uint32_t byte(uint32_t p) const { return data[p]; }
 };
 
-struct ParseTileAcc {
-    const uint32_t *tmf, *tmq; const uint8_t *tby; uint32_t *stage;
-    uint32_t mbias, bbias;     // index of chunk position 0 inside tmf/tmq, resp. tby (may be "negative": wraps)
-    uint32_t count;            // symbols staged for this tile
-    __device__ __forceinline__ uint32_t mf(uint32_t p) const { return tmf[p + mbias]; }
-    __device__ __forceinline__ uint32_t mq(uint32_t p) const { return tmq[p + mbias]; }
-    __device__ __forceinline__ uint32_t byte(uint32_t p) const { return tby[p + bbias]; }
-    __device__ __forceinline__ void put(uint32_t sym) { stage[count++] = sym; }
-};
-
-__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
-    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
-}
-
-__global__ void __launch_bounds__(32)
+__global__ void __launch_bounds__(kGtWarps * 32)
 dfl_parse_greedy_kernel(Batch b, DeflateParams prm, const uint32_t *__restrict__ mfull,
-                 const uint32_t *__restrict__ mquarter, uint32_t *__restrict__ syms,
-                 BlockInfo *__restrict__ blocks, uint32_t *__restrict__ nblocks) {
-    __shared__ __align__(16) ParseBuf buf[2];
-    __shared__ uint32_t stage[kParseTile + kMaxMatch + 8];
-    const uint32_t c = blockIdx.x, lane = threadIdx.x;
+                        uint32_t *__restrict__ syms, BlockInfo *__restrict__ blocks, uint32_t *__restrict__ nblocks) {
+    __shared__ GtWarpShared sh[kGtWarps];
+    __shared__ volatile uint32_t s_entry, s_nsyms;     // handed from tile to tile: absolute entry position, symbols so far
+    const uint32_t c = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint64_t off = (uint64_t)c * b.S;
     const uint8_t *data = b.in + off;
     const uint32_t n = chunk_len(b, c);
-    const bool use_m = prm.mode != MODE_HUFF, use_q = prm.need_quarter != 0;
+    const bool use_m = prm.mode != MODE_HUFF;
+    const uint32_t *mf = mfull + off;
     uint32_t *out = syms + off;
-    // absolute (array) indices / addresses, so that every cp.async is 16-byte aligned
-    const uint64_t m_abs0 = off;                                   // entry index of chunk position 0 in mfull/mquarter
-    const uintptr_t b_abs0 = reinterpret_cast<uintptr_t>(data);    // address of chunk position 0
-    const uintptr_t in_lo = reinterpret_cast<uintptr_t>(b.in), in_hi = in_lo + b.bytes;
-    const uint64_t m_hi = (uint64_t)b.nb * b.S + 4;                // entries allocated (see work_bytes: +16 bytes slack)
-
-    auto issue = [&](uint32_t tile, ParseBuf &pb) {                // start the copies for positions [tile*T, tile*T + T)
-        const uint64_t m_first = (m_abs0 + (uint64_t)tile * kParseTile) & ~3ull;
-        if (use_m)
-            for (uint32_t v = lane; v < kPtVecsM; v += 32) {
-                const uint64_t e = m_first + 4ull * v;
-                if (e + 4 <= m_hi) {
-                    cp_async16(&pb.mf[v], mfull + e);
-                    if (use_q) cp_async16(&pb.mq[v], mquarter + e);
-                }
-            }
-        const uintptr_t a_first = ((b_abs0 + (uintptr_t)tile * kParseTile) & ~(uintptr_t)15) - 16;
-        for (uint32_t v = lane; v < kPtVecsB; v += 32) {
-            const uintptr_t a = a_first + 16ull * v;
-            if (a + 16 > in_lo && a < in_hi) cp_async16(&pb.by[v], reinterpret_cast<const void *>(a));
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-    };
-
     BlockInfo *blk = blocks + (uint64_t)c * b.MB;
-    ParseState st;
-    parse_init(st, blk, n, prm);
-    ParseTileAcc acc;
-    acc.stage = stage; acc.count = 0;
-    uint32_t flushed = 0;                              // symbols already written to global memory
-    const uint32_t ntiles = (n + kParseTile - 1) / kParseTile;
-    if (ntiles) issue(0, buf[0]);
-    for (uint32_t t = 0; t < ntiles; ++t) {
-        ParseBuf &pb = buf[t & 1];
-        if (t + 1 < ntiles) {
-            issue(t + 1, buf[(t + 1) & 1]);
-            asm volatile("cp.async.wait_group 1;" ::: "memory");   // tile t has landed, tile t+1 may still be in flight
-        } else {
-            asm volatile("cp.async.wait_group 0;" ::: "memory");
+    if (threadIdx.x == 0) { s_entry = 0; s_nsyms = 0; }
+    __syncthreads();
+    GtWarpShared &w = sh[warp];
+    const uint32_t ntiles = (n + kGtTile - 1) / kGtTile;
+    for (uint32_t t = warp; t < ntiles; t += kGtWarps) {
+        const uint32_t t0 = t * kGtTile;
+        __syncwarp();                                  // the previous tile's tables are no longer read
+#pragma unroll
+        for (uint32_t k = 0; k < kGtSeg; ++k) {        // coalesced loads, transposed (padded) stores
+            const uint32_t r = k * 32 + lane, p = t0 + r;
+            w.mfv[gt_slot(r)] = (use_m && p < n) ? mf[p] : 0u;
         }
         __syncwarp();
-        const uint32_t t1 = (t + 1) * kParseTile < n ? (t + 1) * kParseTile : n;
-        // operands of this tile, as seen by every lane
-        {
-            const uint64_t m_first = (m_abs0 + (uint64_t)t * kParseTile) & ~3ull;
-            const uintptr_t a_first = ((b_abs0 + (uintptr_t)t * kParseTile) & ~(uintptr_t)15) - 16;
-            acc.tmf = reinterpret_cast<const uint32_t *>(pb.mf);
-            acc.tmq = use_q ? reinterpret_cast<const uint32_t *>(pb.mq) : acc.tmf;
-            acc.tby = reinterpret_cast<const uint8_t *>(pb.by);
-            acc.mbias = (uint32_t)(m_abs0 - m_first);              // entry of position p sits at tmf[p + mbias]
-            acc.bbias = (uint32_t)(b_abs0 - a_first);
-            acc.count = 0;
-        }
-        {
-            // serial part: only the chase; the visited positions go to stage[]
-            uint32_t cnt = 0;
-            if (lane == 0 && st.p < t1) cnt = greedy_chase(st.p, t1, use_m, acc, stage);
-            const uint32_t made = __shfl_sync(0xffffffffu, cnt, 0);
-            __syncwarp();
-            // parallel part: one lane per visited position forms its symbol
-            for (uint32_t i = lane; i < made; i += 32)
-                out[flushed + i] = greedy_symbol(stage[i], use_m, acc, flushed + i, blk, n, prm);
-            flushed += made;
-            __syncwarp();
+        gt_fill(lane, n - t0, w.mfv, w.lc);
+        __syncwarp();
+        if (t) asm volatile("bar.sync %0, 64;" ::"r"(warp + 1) : "memory");   // the previous tile has been crossed
+        const uint32_t entry = s_entry, first_sym = s_nsyms;
+        uint32_t my_entry, my_first, total;
+        const uint32_t exit_rel = gt_hop(lane, entry - t0, n - t0, w.lc, my_entry, my_first, total);
+        if (lane == 0) { s_entry = t0 + exit_rel; s_nsyms = first_sym + total; }
+        if (t + 1 < ntiles) asm volatile("bar.arrive %0, 64;" ::"r"(((warp + 1) & (kGtWarps - 1)) + 1) : "memory");
+        if (my_entry != 0xffffffffu) {                 // the symbols of this lane's segment
+            GtAcc acc{w.mfv, data, t0};
+            const uint32_t seg_end = (lane + 1) * kGtSeg, lim = n - t0;
+            uint32_t r = my_entry, g = first_sym + my_first;
+            while (r < seg_end && r < lim) {
+                const uint32_t m = w.mfv[gt_slot(r)];
+                out[g] = greedy_symbol(t0 + r, use_m, acc, g, blk, n, prm);
+                ++g;
+                r += m ? (m >> 16) : 1u;
+            }
         }
     }
-    __syncwarp();
-    __threadfence_block();
-    if (lane == 0) nblocks[c] = seg_finish(blk, flushed, false, n, prm, chunk_final(b, c));
+    __syncthreads();
+    if (threadIdx.x == 0) nblocks[c] = seg_finish(blk, s_nsyms, false, n, prm, chunk_final(b, c));
 }
-
 
 // ---- phase 3, lazy rule (deflate_slow): one chunk per CTA, one segment per thread -------------------------
 // zb_deflate.cuh seg_*: speculate / fix up / scan / emit.  Every thread walks its own
@@ -893,7 +846,7 @@ int deflate_launch(zb200_ctx *ctx, const uint8_t *d_in, size_t n, size_t S, int 
             ZB_LAUNCHED(); ZB_CHECK_LAUNCH();
         }
         if (prm.mode == MODE_SLOW) dfl_parse_kernel<<<b.nb, kSegLanes, 0, s>>>(b, prm, w.mfull, w.mquarter, w.syms, w.blocks, w.nblocks);
-        else dfl_parse_greedy_kernel<<<b.nb, 32, 0, s>>>(b, prm, w.mfull, w.mquarter, w.syms, w.blocks, w.nblocks);
+        else dfl_parse_greedy_kernel<<<b.nb, kGtWarps * 32, 0, s>>>(b, prm, w.mfull, w.syms, w.blocks, w.nblocks);
         ZB_LAUNCHED(); ZB_CHECK_LAUNCH();
         dfl_tree_kernel<<<dim3(MB, b.nb), 128, 0, s>>>(b, strategy | (level == 0 ? 0x100 : 0), w.syms, w.blocks, w.nblocks, tabs, w.codes);
         ZB_LAUNCHED(); ZB_CHECK_LAUNCH();

@@ -626,6 +626,55 @@ ZB_HD uint32_t greedy_symbol(uint32_t pos, bool use_m, Acc &acc, uint32_t g, Blo
     return m ? (((m & 0xffff) << 16) | (len - kMinMatch)) : acc.byte(pos);
 }
 
+// ---- greedy parse with exit tables ---------------------------------------------------
+// The chase p -> p + len(p) is a functional graph: whatever position the parse enters a
+// short segment at, where it leaves the segment and how many symbols it emits on the way
+// depend on the segment alone.  A tile of kGtTile positions is cut into 32 segments of
+// kGtSeg; lane i fills, for every position of segment i (backwards), the position at which
+// a parse entering there leaves the segment and the symbols it emits until then
+// (gt_fill).  With the tables in place the true parse crosses the tile in one dependent
+// table read per segment (gt_hop) instead of one per symbol, and each lane then forms the
+// symbols of its own segment from its entry point (gt_emit).  Only gt_hop is ordered
+// between tiles, so the four warps of a CTA work on four tiles at once and pass (entry
+// position, symbol count) from tile to tile.
+constexpr uint32_t kGtSeg = 16, kGtTile = 32 * kGtSeg;
+ZB_HD uint32_t gt_slot(uint32_t r) { return (r % kGtSeg) * 33u + r / kGtSeg; }   // tile-relative position -> table slot (bank = lane + offset)
+constexpr uint32_t kGtSlots = kGtSeg * 33u;
+
+// mfv[gt_slot(r)] = match entry of tile position r (0 beyond the chunk).  Fills lc[] for the lane's
+// segment: tile-relative position at which the parse leaves the segment (may exceed the tile by up
+// to MAX_MATCH: 10 bits) | symbols emitted until then << 10.  `limit`: tile-relative end of the
+// chunk (a parse leaves the tile there at the latest).
+ZB_HD void gt_fill(uint32_t lane, uint32_t limit, const uint32_t *mfv, uint16_t *lc) {
+    const uint32_t s0 = lane * kGtSeg, s1 = s0 + kGtSeg < limit ? s0 + kGtSeg : limit;
+    for (int j = (int)kGtSeg - 1; j >= 0; --j) {
+        const uint32_t r = s0 + (uint32_t)j, m = mfv[j * 33 + lane];
+        if (r >= limit) continue;
+        const uint32_t nx = r + (m ? (m >> 16) : 1u);
+        lc[j * 33 + lane] = (uint16_t)(nx >= s1 ? (nx | (1u << 10)) : (lc[(nx - s0) * 33 + lane] + (1u << 10)));
+    }
+}
+
+// Cross the tile from tile-relative position `e` (may lie beyond the tile: a match carried over it).
+// Every lane runs this redundantly; it learns where the parse enters ITS segment (my_entry, or
+// 0xffffffff) and how many symbols the segments before it emit (my_first).  Returns the tile-relative
+// exit position; `total` = symbols of the tile.  `limit`: tile-relative end of the chunk.
+ZB_HD uint32_t gt_hop(uint32_t lane, uint32_t e, uint32_t limit, const uint16_t *lc,
+                      uint32_t &my_entry, uint32_t &my_first, uint32_t &total) {
+    uint32_t cur = e, sum = 0;
+    my_entry = 0xffffffffu; my_first = 0;
+    const uint32_t end = limit < kGtTile ? limit : kGtTile;
+    while (cur < end) {
+        const uint32_t seg = cur / kGtSeg;
+        if (seg == lane) { my_entry = cur; my_first = sum; }
+        const uint32_t v = lc[(cur % kGtSeg) * 33u + seg];
+        sum += v >> 10;
+        cur = v & 1023u;
+    }
+    total = sum;
+    return cur;
+}
+
 // ---- phase 4: per-block Huffman construction ---------------------------------------
 struct BlockCode {
     uint16_t lcode[288]; uint8_t llen[288];   // bit-reversed codes / lengths, literal-length alphabet
