@@ -40,6 +40,7 @@ typedef unsigned long uLong;
 typedef uLong uLongf;
 typedef void *voidpf;
 typedef size_t z_size_t;
+typedef unsigned int z_crc_t;            /* zconf.h:396-436 */
 typedef long z_off_t;
 
 typedef voidpf (*alloc_func)(voidpf opaque, uInt items, uInt size);
@@ -131,6 +132,7 @@ uLong adler32(uLong adler, const Bytef *buf, uInt len);
 uLong adler32_z(uLong adler, const Bytef *buf, z_size_t len);
 uLong adler32_combine(uLong adler1, uLong adler2, z_off_t len2);
 const char *zError(int err);
+const z_crc_t *get_crc_table(void);                                      /* zlib.h:1935, crc32.c:549 */
 
 /* ---- the reference's WASM C exports (src/wasm_module.c:34-311) ---- */
 typedef struct zlib_stream_s zlib_stream_t;                                  /* wasm_module.c:146-150 */

@@ -69,6 +69,21 @@ def test_zlib_surface_exported():
     assert len(names) >= 45 and not missing, missing
 
 
+def test_crc_table_is_the_reference_table():
+    """get_crc_table() (crc32.c:549): the 256-entry table equals the one the byte-wise CRC definition gives."""
+    L = C.CDLL(zb.LIB_PATH, mode=C.RTLD_LOCAL)
+    L.get_crc_table.restype = C.POINTER(C.c_uint32)
+    t = L.get_crc_table()
+    # table[n] = crc of the single byte n with zero pre/post conditioning
+    def raw(n):
+        c = n
+        for _ in range(8):
+            c = (0xedb88320 ^ (c >> 1)) if c & 1 else c >> 1
+        return c
+    assert [t[n] for n in range(256)] == [raw(n) for n in range(256)]
+    assert t[1] == 0x77073096 and t[255] == 0x2d02ef8d          # crc32.h:5-58 first row / last entry
+
+
 def test_z_stream_layout_matches_reference():
     assert C.sizeof(refz.ZStream) == 112          # zlib.h:90-110 on LP64
     z = refz.ZlibBinding(zb.LIB_PATH, "")

@@ -1,0 +1,28 @@
+"""A small end-to-end pass of every kernel on the hot path (checksums, deflate at a greedy
+and a lazy level, gzip members, inflate) for compute-sanitizer:
+    compute-sanitizer --tool memcheck  python tools/sanitize_small.py
+    compute-sanitizer --tool racecheck python tools/sanitize_small.py
+Inputs are a few hundred KiB so the instrumented run stays in the minutes."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import refz  # noqa: E402
+import zlib_wasm_b200 as zb  # noqa: E402
+
+ctx = zb.Context(0)
+ok = True
+for kind in (refz.GEN_MARKOV, refz.GEN_MIXED):
+    d = refz.gen(300000 + 12345, kind, seed=11)
+    for level in (1, 3, 6):
+        s = ctx.deflate_host(d, level, 0, zb.FRAME_GZIP, 131072)
+        out, res = ctx.inflate_host(s, [(0, len(s), 0, len(d))], zb.WRAP_GZIP, 1, out_size=len(d) + 8)
+        good = res[0].status == 0 and out[:res[0].out_len] == d
+        print("kind %d level %d: %d -> %d bytes, round trip %s" % (kind, level, len(d), len(s), good), flush=True)
+        ok &= good
+    crc, adler = ctx.checksum_host(d)
+    ok &= crc == refz.oracle().crc32(d) and adler == refz.oracle().adler32(d)
+print("ALL OK" if ok else "FAILED", flush=True)
+sys.exit(0 if ok else 1)

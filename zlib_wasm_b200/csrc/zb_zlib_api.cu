@@ -493,4 +493,19 @@ uLong crc32_combine_gen(z_off_t len2) { return zb200_crc32_combine_gen((uint64_t
 uLong crc32_combine_op(uLong c1, uLong c2, uLong op) { return zb200_crc32_combine_op((uint32_t)c1, (uint32_t)c2, (uint32_t)op); }
 uLong adler32_combine(uLong a1, uLong a2, z_off_t len2) { return zb200_adler32_combine((uint32_t)a1, (uint32_t)a2, (int64_t)len2); }
 
+// crc32.c:549 get_crc_table: the 256-entry byte-wise table of the reflected polynomial
+// 0xedb88320 (crc32.c:149), generated rather than transcribed (crc32.h:5-58 holds the same values).
+const z_crc_t *get_crc_table(void) {
+    static z_crc_t table[256];
+    static std::once_flag once;
+    std::call_once(once, [] {
+        for (unsigned n = 0; n < 256; ++n) {
+            unsigned c = n;
+            for (int k = 0; k < 8; ++k) c = (c & 1) ? 0xedb88320u ^ (c >> 1) : c >> 1;
+            table[n] = c;
+        }
+    });
+    return table;
+}
+
 }  // extern "C"
