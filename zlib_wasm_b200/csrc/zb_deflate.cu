@@ -237,22 +237,27 @@ __device__ __forceinline__ uint32_t depth_bucket(uint32_t e) {   // 0,1,2,3, the
     return 4u + (l - 2u) * 4u + ((e >> (l - 2u)) & 3u);          // e <= 255 -> at most 27
 }
 extern __shared__ __align__(16) uint8_t ms_smem[];
-struct StagedMem {                                       // operands from the staged window: 32-bit shared-memory addressing
-    uint32_t doff, loff;                                 // byte offset of chunk position 0 in ms_smem (wraps), same for link 0
-    __device__ __forceinline__ uint32_t byte(uint32_t pos) const { return ms_smem[doff + pos]; }
+// Operands from the staged window.  Addresses are 32-bit shared-space addresses held in
+// registers and the loads are ld.shared in PTX: written as C++ indexing of ms_smem the
+// compiler rebuilt the CTA's shared-window base (S2UR CgaCtaId, ULEA, ...) in every
+// iteration of the walk, a quarter of its instructions.
+__device__ __forceinline__ uint32_t lds_u8(uint32_t a) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ uint32_t lds_u16(uint32_t a) { uint32_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
+struct StagedMem {
+    uint32_t dbase, lbase;                               // shared address of chunk position 0 (wraps), same for link 0
+    __device__ __forceinline__ uint32_t byte(uint32_t pos) const { return lds_u8(dbase + pos); }
     __device__ __forceinline__ uint32_t word(uint32_t pos) const {
-        const uint32_t a = doff + pos;
-        const uint32_t *w = reinterpret_cast<const uint32_t *>(ms_smem + (a & ~3u));
-        return __funnelshift_r(w[0], w[1], (a & 3u) * 8u);
+        const uint32_t a = dbase + pos, w = a & ~3u;
+        return __funnelshift_r(lds_u32(w), lds_u32(w + 4), (a & 3u) * 8u);
     }
-    __device__ __forceinline__ uint32_t link(uint32_t pos) const { return *reinterpret_cast<const uint16_t *>(ms_smem + loff + 2u * pos); }
+    __device__ __forceinline__ uint32_t link(uint32_t pos) const { return lds_u16(lbase + 2u * pos); }
     // the accessors match_uniform uses
     template <int NW> __device__ __forceinline__ void words(uint32_t pos, uint32_t (&w)[NW]) const {
-        const uint32_t a = doff + pos, sh = (a & 3u) * 8u;
-        const uint32_t *src = reinterpret_cast<const uint32_t *>(ms_smem + (a & ~3u));
+        const uint32_t a = dbase + pos, sh = (a & 3u) * 8u, w0 = a & ~3u;
         uint32_t raw[NW + 1];
 #pragma unroll
-        for (int i = 0; i <= NW; ++i) raw[i] = src[i];
+        for (int i = 0; i <= NW; ++i) raw[i] = lds_u32(w0 + 4u * i);
 #pragma unroll
         for (int i = 0; i < NW; ++i) w[i] = __funnelshift_r(raw[i], raw[i + 1], sh);
     }
@@ -287,8 +292,9 @@ __device__ __forceinline__ StagedMem stage_window(const Batch &b, const uint8_t 
     for (uint32_t v = threadIdx.x; v < pvecs; v += blockDim.x) slink[v] = *reinterpret_cast<const uint4 *>(p_first + 16ull * v);
     __syncthreads();
     StagedMem mem;
-    mem.doff = dskew - lo;                                         // chunk position p lives at ms_smem[doff + p]
-    mem.loff = kMsDataBytes + 2u * pskew - 2u * lo;                // link p at ms_smem[loff + 2 p]
+    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(ms_smem);
+    mem.dbase = sbase + dskew - lo;                                // chunk position p lives at shared address dbase + p
+    mem.lbase = sbase + kMsDataBytes + 2u * pskew - 2u * lo;       // link p at lbase + 2 p
     return mem;
 }
 
