@@ -84,7 +84,16 @@ extern "C" long emul_deflate_chunk(const uint8_t *data, uint32_t n, int level, i
         const SegGeom g = seg_geometry(n);
         std::vector<SegRec> rec((kSegRecs - 1) * kSegLanes);
         SegLane r[kSegLanes];
-        NoPut cacc{data, mf.data(), mq.data()};
+        // operands paced in windows of 16 positions at an arbitrary alignment, as the kernel stages them
+        struct WinAcc { const uint8_t *data; const uint32_t *mfull, *mquarter; uint32_t *out; uint32_t at, skew, lo, hi;
+                        uint32_t mf(uint32_t p) const { if (p < lo || p >= hi) abort(); return mfull[p]; }
+                        uint32_t mq(uint32_t p) const { if (p < lo || p >= hi) abort(); return mquarter[p]; }
+                        uint32_t byte(uint32_t p) const { if (p + 1 < lo || p >= hi) abort(); return data[p]; }
+                        void put(uint32_t sym) { if (out) out[at++] = sym; }
+                        uint32_t windows(uint32_t seg) const { return seg / 16 + 2; }
+                        uint32_t open(uint32_t w, uint32_t s0) { const uint32_t a = (s0 + skew) / 16 * 16 + w * 16; lo = a > skew ? a - skew : 0; hi = a + 16 - skew; return hi; }
+                        bool any(bool b) const { return b; } };
+        WinAcc cacc{data, mf.data(), mq.data(), nullptr, 0, (uint32_t)(n % 13), 0, 0};
         for (uint32_t l = 0; l < g.nact; ++l) seg_speculate(r[l], l, g, n, prm, cacc, rec.data());
         for (int pass = 0;; ++pass) {
             if (pass > (int)kSegLanes + 8) return -20;
@@ -101,10 +110,7 @@ extern "C" long emul_deflate_chunk(const uint8_t *data, uint32_t n, int level, i
         for (uint32_t l = 0; l < g.nact; ++l) first[l + 1] = first[l] + r[l].count;
         const uint32_t total = first[g.nact];
         for (int l = (int)g.nact - 1; l >= 0; --l) {               // any lane order must do
-            struct { const uint8_t *data; const uint32_t *mfull, *mquarter; uint32_t *out; uint32_t at;
-                     uint32_t mf(uint32_t p) const { return mfull[p]; } uint32_t mq(uint32_t p) const { return mquarter[p]; }
-                     uint32_t byte(uint32_t p) const { return data[p]; } void put(uint32_t sym) { out[at++] = sym; } }
-                eacc{data, mf.data(), mq.data(), syms.data(), first[l]};
+            WinAcc eacc{data, mf.data(), mq.data(), syms.data(), first[l], (uint32_t)(n % 13), 0, 0};
             seg_emit(r[l], (uint32_t)l, g, n, prm, eacc, blocks.data(), first[l]);
             if (eacc.at != first[l + 1]) return -21;
         }

@@ -9,6 +9,10 @@
 
 namespace zb {
 
+// ld.shared through 32-bit shared-space addresses held in registers
+__device__ __forceinline__ uint32_t lds_u8(uint32_t a) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ uint32_t lds_u16(uint32_t a) { uint32_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
 struct DeflateDeviceTables {
     FormatTables fmt;
     StaticTrees st;
@@ -241,9 +245,6 @@ extern __shared__ __align__(16) uint8_t ms_smem[];
 // registers and the loads are ld.shared in PTX: written as C++ indexing of ms_smem the
 // compiler rebuilt the CTA's shared-window base (S2UR CgaCtaId, ULEA, ...) in every
 // iteration of the walk, a quarter of its instructions.
-__device__ __forceinline__ uint32_t lds_u8(uint32_t a) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
-__device__ __forceinline__ uint32_t lds_u16(uint32_t a) { uint32_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
-__device__ __forceinline__ uint32_t lds_u32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
 struct StagedMem {
     uint32_t dbase, lbase;                               // shared address of chunk position 0 (wraps), same for link 0
     __device__ __forceinline__ uint32_t byte(uint32_t pos) const { return lds_u8(dbase + pos); }
@@ -441,54 +442,89 @@ dfl_parse_greedy_kernel(Batch b, DeflateParams prm, const uint32_t *__restrict__
 // ---- phase 3, lazy rule (deflate_slow): one chunk per CTA, one segment per thread -------------------------
 // zb_deflate.cuh seg_*: speculate / fix up / scan / emit.  Every thread walks its own
 // 1/128 of the chunk.
-// Operand streams of one thread.  A thread reads its match-table entries in increasing
-// order, a few per 32-byte sector; read straight from global memory every entry costs a
-// whole sector through the L1 (128 threads x 3 streams thrash it: 8x traffic
-// amplification, measured 12.5 ms per 512 MiB at level 6).  So each stream keeps its
-// current sector in shared memory — slot [entry][thread], bank = thread, conflict-free
-// for any entry — and refills it with two 16-byte loads when the walk leaves it.
-struct WalkAcc {
+// Operands of one thread's walk, a window of kPw positions at a time.  Read straight from
+// global memory every 4-byte entry costs a sector through a thrashed L1 (8x traffic, 12.5 ms
+// per 512 MiB at level 6); with a per-thread sector buffer refilled on demand the refill is a
+// divergent branch whose load stalls the whole warp (58 % of the stall samples, 9.3 ms).  So
+// the windows are WARP-SYNCHRONOUS: every thread of a warp steps through the windows of its
+// own segment together; opening window w waits for its cp.async copies (issued one window
+// earlier) and starts those of window w + 1, all lanes at the same instruction, and inside a
+// window every operand is one ld.shared from the thread's own row.
+constexpr uint32_t kPw = 16, kPwRow = kPw + 4;            // entries per window / words per row (stride keeps 16-byte alignment)
+constexpr uint32_t kPwBytesRow = 8;                       // words per byte row: [start - 1, start + 16) at any alignment
+struct WinAcc {
     const uint8_t *data; const uint32_t *mfull, *mquarter; uint32_t *out; uint32_t at;
-    uint32_t *sm_f, *sm_q, *sm_b;                      // this thread's column of the three sector buffers
-    uint64_t abs0;                                     // absolute entry index of chunk position 0 (sector alignment is absolute)
-    uintptr_t in_lo, in_hi;                            // bounds of the input buffer (byte sectors are clipped to it)
-    uint64_t cur_f, cur_q; uintptr_t cur_b;            // sector currently held per stream (~0: none)
-    __device__ __forceinline__ void reset() { cur_f = cur_q = ~0ull; cur_b = ~(uintptr_t)0; }
-    __device__ __forceinline__ static void fill(uint32_t *col, const uint32_t *src) {
-        const uint4 a = __ldcg(reinterpret_cast<const uint4 *>(src)), c = __ldcg(reinterpret_cast<const uint4 *>(src) + 1);
-        col[0 * kSegLanes] = a.x; col[1 * kSegLanes] = a.y; col[2 * kSegLanes] = a.z; col[3 * kSegLanes] = a.w;
-        col[4 * kSegLanes] = c.x; col[5 * kSegLanes] = c.y; col[6 * kSegLanes] = c.z; col[7 * kSegLanes] = c.w;
-    }
-    __device__ __forceinline__ uint32_t mf(uint32_t p) {
-        const uint64_t e = abs0 + p, sec = e >> 3;
-        if (sec != cur_f) { cur_f = sec; fill(sm_f, mfull + (sec << 3)); }
-        return sm_f[((uint32_t)e & 7u) * kSegLanes];
-    }
-    __device__ __forceinline__ uint32_t mq(uint32_t p) {
-        const uint64_t e = abs0 + p, sec = e >> 3;
-        if (sec != cur_q) { cur_q = sec; fill(sm_q, mquarter + (sec << 3)); }
-        return sm_q[((uint32_t)e & 7u) * kSegLanes];
-    }
-    __device__ __forceinline__ uint32_t byte(uint32_t p) {
-        const uintptr_t a = reinterpret_cast<uintptr_t>(data) + p, sec = a >> 5;
-        if (sec != cur_b) {
-            const uintptr_t s0 = sec << 5;
-            if (s0 < in_lo || s0 + 32 > in_hi) return data[p];   // sector straddles an end of the input buffer: plain read, nothing held
-            cur_b = sec;
-            fill(sm_b, reinterpret_cast<const uint32_t *>(s0));
-        }
-        return (sm_b[(((uint32_t)a >> 2) & 7u) * kSegLanes] >> (((uint32_t)a & 3u) * 8u)) & 0xffu;
-    }
+    uint32_t row_f, row_q, row_b;                        // shared addresses of this thread's rows (buffer 0)
+    uint64_t abs0;                                       // absolute entry index of chunk position 0
+    uintptr_t in_lo, in_hi;
+    bool use_q;
+    uint32_t nw;
+    uint32_t fadj, qadj, badj;                           // current window: entry p at fadj + 4 p, byte p at badj + p
+    uint32_t nb[kPwBytesRow - 2];                        // bytes of the next window, on their way in registers
+    __device__ __forceinline__ uint32_t mf(uint32_t p) const { return lds_u32(fadj + 4u * p); }
+    __device__ __forceinline__ uint32_t mq(uint32_t p) const { return lds_u32(qadj + 4u * p); }
+    __device__ __forceinline__ uint32_t byte(uint32_t p) const { return lds_u8(badj + p); }
     __device__ __forceinline__ void put(uint32_t sym) { if (out) out[at++] = sym; }
+    __device__ __forceinline__ uint32_t windows(uint32_t seg) { nw = seg / kPw + 2; return nw; }
+    __device__ __forceinline__ bool any(bool b) const { return __any_sync(__activemask(), b); }
+    __device__ __forceinline__ void issue(uint32_t w, uint64_t wabs) {            // cp.async the entries of window w (absolute start wabs)
+        const uint32_t bo = (w & 1u) * kPwRow * 4u * kSegLanes;
+#pragma unroll
+        for (uint32_t v = 0; v < kPw / 4; ++v) {
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(row_f + bo + 16u * v), "l"(mfull + wabs + 4u * v) : "memory");
+            if (use_q) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(row_q + bo + 16u * v), "l"(mquarter + wabs + 4u * v) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    __device__ __forceinline__ void fetch_bytes(uint64_t wabs) {                  // words covering bytes [start - 1, start + kPw) -> nb[]
+        const uintptr_t a = (reinterpret_cast<uintptr_t>(data) + (uintptr_t)(wabs - abs0) - 1) & ~(uintptr_t)3;
+#pragma unroll
+        for (uint32_t k = 0; k < kPwBytesRow - 2; ++k) {
+            const uintptr_t wa = a + 4u * k;
+            nb[k] = (wa >= (in_lo & ~(uintptr_t)3) && wa < in_hi) ? *reinterpret_cast<const uint32_t *>(wa) : 0u;
+        }
+    }
+    // Called by all threads of the warp that run the pass, at the same point.
+    __device__ __forceinline__ uint32_t open(uint32_t w, uint32_t s0) {
+        const uint64_t first = (abs0 + s0) / kPw * kPw;                           // absolute start of window 0
+        const uint64_t wabs = first + (uint64_t)w * kPw;
+        if (w == 0) {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");                  // nothing of an earlier pass still in flight
+            issue(0, wabs);
+            fetch_bytes(wabs);
+        }
+        // bytes of this window: registers -> row
+#pragma unroll
+        for (uint32_t k = 0; k < kPwBytesRow - 2; ++k) asm volatile("st.shared.u32 [%0], %1;" ::"r"(row_b + 4u * k), "r"(nb[k]) : "memory");
+        if (w + 1 < nw) {
+            issue(w + 1, wabs + kPw);
+            fetch_bytes(wabs + kPw);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");                  // window w has landed
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        const uint32_t bo = (w & 1u) * kPwRow * 4u * kSegLanes;
+        const uint32_t wrel = (uint32_t)(wabs - abs0);                            // chunk-relative window start (wraps below 0 for the first window)
+        fadj = row_f + bo - 4u * wrel;
+        qadj = row_q + bo - 4u * wrel;
+        const uintptr_t a = (reinterpret_cast<uintptr_t>(data) + (uintptr_t)(wabs - abs0) - 1) & ~(uintptr_t)3;
+        badj = row_b - (uint32_t)(a - reinterpret_cast<uintptr_t>(data));         // byte p sits at row_b + (addr(p) - a)
+        return wrel + kPw;
+    }
 };
 
+constexpr uint32_t kParseSmem = (2 * 2 * kPwRow + kPwBytesRow) * kSegLanes * 4 + (kSegRecs - 1) * kSegLanes * 8 + 2 * kSegLanes * 4 + 64;
 __global__ void __launch_bounds__(kSegLanes)
 dfl_parse_kernel(Batch b, DeflateParams prm, const uint32_t *__restrict__ mfull,
                  const uint32_t *__restrict__ mquarter, uint32_t *__restrict__ syms,
                  BlockInfo *__restrict__ blocks, uint32_t *__restrict__ nblocks) {
-    __shared__ SegRec rec[(kSegRecs - 1) * kSegLanes];
-    __shared__ uint32_t s_sec[3][8 * kSegLanes];
-    __shared__ uint32_t s_p[kSegLanes], s_w0[kSegLanes], s_wsum[kSegLanes / 32];
+    extern __shared__ __align__(16) uint8_t ps_smem[];             // 60 KiB: over the static limit, carved by hand
+    uint32_t *s_f = reinterpret_cast<uint32_t *>(ps_smem);         // [2][kSegLanes][kPwRow]
+    uint32_t *s_q = s_f + 2 * kPwRow * kSegLanes;
+    uint32_t *s_b = s_q + 2 * kPwRow * kSegLanes;                  // [kSegLanes][kPwBytesRow]
+    SegRec *rec = reinterpret_cast<SegRec *>(s_b + kPwBytesRow * kSegLanes);   // [(kSegRecs - 1)][kSegLanes]
+    uint32_t *s_p = reinterpret_cast<uint32_t *>(rec + (kSegRecs - 1) * kSegLanes);
+    uint32_t *s_w0 = s_p + kSegLanes, *s_wsum = s_w0 + kSegLanes;
     const unsigned full = 0xffffffffu;
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t c = blockIdx.x;
@@ -502,12 +538,13 @@ dfl_parse_kernel(Batch b, DeflateParams prm, const uint32_t *__restrict__ mfull,
 
     SegLane r;
     r.start = r.end = r.spec_end = seg_cold(0); r.count = r.spec_count = 0;
-    WalkAcc acc;
+    WinAcc acc;
     acc.data = data; acc.mfull = mfull; acc.mquarter = prm.need_quarter ? mquarter : mfull; acc.out = nullptr; acc.at = 0;
-    acc.sm_f = s_sec[0] + tid; acc.sm_q = s_sec[1] + tid; acc.sm_b = s_sec[2] + tid;
-    acc.abs0 = off;
+    acc.row_f = (uint32_t)__cvta_generic_to_shared(s_f + tid * kPwRow);
+    acc.row_q = (uint32_t)__cvta_generic_to_shared(s_q + tid * kPwRow);
+    acc.row_b = (uint32_t)__cvta_generic_to_shared(s_b + tid * kPwBytesRow);
+    acc.abs0 = off; acc.use_q = prm.need_quarter != 0; acc.nw = 0;
     acc.in_lo = reinterpret_cast<uintptr_t>(b.in); acc.in_hi = acc.in_lo + b.bytes;
-    acc.reset();
     if (active) seg_speculate(r, tid, g, n, prm, acc, rec);
     for (;;) {                                                     // until no start moves
         s_p[tid] = r.end.p; s_w0[tid] = r.end.w0;
@@ -763,6 +800,7 @@ int deflate_init(zb200_ctx *ctx) {
     ctx->d_deflate_tables = d;
     ZB_CUDA(cudaFuncSetAttribute(dfl_chain_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kChainSmem));
     ZB_CUDA(cudaFuncSetAttribute(dfl_chain_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kChainSmemDepth));
+    ZB_CUDA(cudaFuncSetAttribute(dfl_parse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kParseSmem));
     ZB_CUDA(cudaFuncSetAttribute(dfl_match_sorted_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMsSmem));
     ZB_CUDA(cudaFuncSetAttribute(dfl_match_uniform_kernel<4, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMsSmem));
     ZB_CUDA(cudaFuncSetAttribute(dfl_match_uniform_kernel<8, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMsSmem));
@@ -851,7 +889,7 @@ int deflate_launch(zb200_ctx *ctx, const uint8_t *d_in, size_t n, size_t S, int 
             dfl_match_kernel<<<g, 256, 0, s>>>(b, prm, w.prev, w.mfull, w.mquarter);
             ZB_LAUNCHED(); ZB_CHECK_LAUNCH();
         }
-        if (prm.mode == MODE_SLOW) dfl_parse_kernel<<<b.nb, kSegLanes, 0, s>>>(b, prm, w.mfull, w.mquarter, w.syms, w.blocks, w.nblocks);
+        if (prm.mode == MODE_SLOW) dfl_parse_kernel<<<b.nb, kSegLanes, kParseSmem, s>>>(b, prm, w.mfull, w.mquarter, w.syms, w.blocks, w.nblocks);
         else dfl_parse_greedy_kernel<<<b.nb, kGtWarps * 32, 0, s>>>(b, prm, w.mfull, w.syms, w.blocks, w.nblocks);
         ZB_LAUNCHED(); ZB_CHECK_LAUNCH();
         dfl_tree_kernel<<<dim3(MB, b.nb), 128, 0, s>>>(b, strategy | (level == 0 ? 0x100 : 0), w.syms, w.blocks, w.nblocks, tabs, w.codes);

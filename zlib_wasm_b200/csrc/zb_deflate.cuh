@@ -503,12 +503,21 @@ struct SegLane {
     SegState start, end; uint32_t count;              // the current path (true once seg_fix has settled)
     SegState spec_end; uint32_t spec_count;           // the speculative path
 };
+// The operand accessor also paces the walk: a thread's operands may be staged a WINDOW of
+// positions at a time (the device stages them in shared memory, all threads of a warp
+// together, so that no thread's fetch stalls the others mid-step).  windows(): how many
+// windows to go through (the same for every thread); open(w, s0): make window w of the
+// segment starting at s0 readable and return its end position; any(b): does any thread
+// that is running this pass with me still have b set.
 struct NoPut {                                        // counting passes: operands from plain arrays, symbols dropped
     const uint8_t *data; const uint32_t *mfull, *mquarter;
     ZB_HD uint32_t mf(uint32_t p) const { return mfull[p]; }
     ZB_HD uint32_t mq(uint32_t p) const { return mquarter[p]; }
     ZB_HD uint32_t byte(uint32_t p) const { return data[p]; }
     ZB_HD void put(uint32_t) {}
+    ZB_HD uint32_t windows(uint32_t) const { return 1; }
+    ZB_HD uint32_t open(uint32_t, uint32_t) { return 0xffffffffu; }
+    ZB_HD bool any(bool b) const { return b; }
 };
 
 // rec[(k - 1) * kSegLanes + lane] belongs to boundary k (k = 1 .. kSegRecs - 1) of lane's segment.
@@ -518,15 +527,22 @@ ZB_HD void seg_speculate(SegLane &r, uint32_t lane, const SegGeom &g, uint32_t n
     ParseState st;
     r.start = seg_cold(s0);
     seg_state_load(st, r.start, n, prm);
-    for (uint32_t k = 1; k < kSegRecs; ++k) {
-        const uint32_t limit = s0 + k * g.blk;
-        if (limit >= bound) break;
-        parse_steps(st, limit, n, prm, acc);
-        SegRec e;
-        e.w0 = seg_state_of(st).w0; e.w1 = (st.p - limit) | (st.nsyms << 9);
-        rec[(k - 1) * kSegLanes + lane] = e;
+    uint32_t k = 1;
+    const uint32_t nw = acc.windows(g.seg);
+    for (uint32_t w = 0; w < nw; ++w) {
+        const uint32_t we = acc.open(w, s0), wend = we < bound ? we : bound;
+        while (st.p < wend) {
+            const uint32_t nextb = s0 + k * g.blk;
+            const bool more = k < kSegRecs && nextb < bound;
+            parse_steps(st, more && nextb < wend ? nextb : wend, n, prm, acc);
+            while (k < kSegRecs && s0 + k * g.blk < bound && st.p >= s0 + k * g.blk) {   // boundaries reached (a match may pass several)
+                SegRec e;
+                e.w0 = seg_state_of(st).w0; e.w1 = (st.p - (s0 + k * g.blk)) | (st.nsyms << 9);
+                rec[(k - 1) * kSegLanes + lane] = e;
+                ++k;
+            }
+        }
     }
-    parse_steps(st, bound, n, prm, acc);
     r.end = r.spec_end = seg_state_of(st);
     r.count = r.spec_count = st.nsyms;
 }
@@ -538,21 +554,29 @@ ZB_HD void seg_fix(SegLane &r, uint32_t lane, const SegGeom &g, uint32_t n, cons
     ParseState st;
     r.start = t;
     seg_state_load(st, t, n, prm);
-    for (uint32_t k = 1; k < kSegRecs; ++k) {
-        const uint32_t limit = s0 + k * g.blk;
-        if (limit >= bound) break;
-        if (limit < t.p) continue;                     // the true start lies beyond this boundary
-        parse_steps(st, limit, n, prm, acc);
-        const SegRec e = rec[(k - 1) * kSegLanes + lane];
-        if (e.w0 == seg_state_of(st).w0 && (e.w1 & 0x1ffu) == st.p - limit) {   // joined the speculative path
-            r.count = st.nsyms + (r.spec_count - (e.w1 >> 9));
-            r.end = r.spec_end;
-            return;
+    uint32_t k = 1;
+    while (k < kSegRecs && s0 + k * g.blk < bound && s0 + k * g.blk < t.p) ++k;      // boundaries before the true start are not compared
+    bool joined = false;
+    const uint32_t nw = acc.windows(g.seg);
+    for (uint32_t w = 0; w < nw; ++w) {
+        if (!acc.any(!joined && st.p < bound)) break;
+        const uint32_t we = acc.open(w, s0), wend = we < bound ? we : bound;
+        while (!joined && st.p < wend) {
+            const uint32_t nextb = s0 + k * g.blk;
+            const bool more = k < kSegRecs && nextb < bound;
+            parse_steps(st, more && nextb < wend ? nextb : wend, n, prm, acc);
+            while (!joined && k < kSegRecs && s0 + k * g.blk < bound && st.p >= s0 + k * g.blk) {
+                const SegRec e = rec[(k - 1) * kSegLanes + lane];
+                if (e.w0 == seg_state_of(st).w0 && (e.w1 & 0x1ffu) == st.p - (s0 + k * g.blk)) {   // joined the speculative path
+                    r.count = st.nsyms + (r.spec_count - (e.w1 >> 9));
+                    r.end = r.spec_end;
+                    joined = true;
+                }
+                ++k;
+            }
         }
     }
-    parse_steps(st, bound, n, prm, acc);
-    r.end = seg_state_of(st);
-    r.count = st.nsyms;
+    if (!joined) { r.end = seg_state_of(st); r.count = st.nsyms; }
 }
 
 // `acc.put` must store symbol number (first + k) of the lane at index first + k.
@@ -563,7 +587,11 @@ ZB_HD void seg_emit(const SegLane &r, uint32_t lane, const SegGeom &g, uint32_t 
     ParseState st;
     seg_state_load(st, r.start, n, prm);
     st.nsyms = first; st.blk_sym0 = first - first % kSymLimit; st.blocks = blocks; st.block_mode = PB_DEFERRED;
-    parse_steps(st, bound, n, prm, acc);
+    const uint32_t nw = acc.windows(g.seg);
+    for (uint32_t w = 0; w < nw; ++w) {
+        const uint32_t we = acc.open(w, s0), wend = we < bound ? we : bound;
+        if (st.p < wend) parse_steps(st, wend, n, prm, acc);
+    }
 }
 
 // nsyms: symbols emitted by the segments; pending: the last segment ended holding a
