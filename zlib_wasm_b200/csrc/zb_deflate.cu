@@ -83,26 +83,16 @@ __device__ __forceinline__ bool chunk_final(const Batch &b, uint32_t c) {
 // takes no issue slots; spinning on a shared-memory counter measured 6.7x slower), does
 // the four ordered head-table steps, passes the turn on and stores its links.
 constexpr int kChainWarps = 4, kChainTrip = 128;
-//
-// kDepth: also count, per hash, the positions seen so far (u8, saturating, halved at
-// every slide so that it tracks the window) and store the count a position found as its
-// DEPTH — an estimate of how long its chain walk will be, which the match kernel uses
-// to put positions with similar walks into the same warp.  The count table costs 32 KiB
-// more shared memory (two CTAs per SM instead of three), so it is built only for the
-// levels that use it.
-constexpr int kChainSmem = 65536, kChainSmemDepth = 65536 + 32768;
-template <bool kDepth>
-__global__ void __launch_bounds__(kChainWarps * 32) dfl_chain_kernel(Batch b, uint16_t *__restrict__ prev_all, uint8_t *__restrict__ depth_all) {
+constexpr int kChainSmem = 65536;             // the head table
+__global__ void __launch_bounds__(kChainWarps * 32) dfl_chain_kernel(Batch b, uint16_t *__restrict__ prev_all) {
     extern __shared__ __align__(16) uint16_t head[];
-    uint8_t *hcnt = reinterpret_cast<uint8_t *>(head) + 65536;
     const uint32_t c = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint8_t *data = b.in + (uint64_t)c * b.S;
     const uint32_t n = chunk_len(b, c);
     uint16_t *prev = prev_all + (uint64_t)c * b.S;
     uint4 *h4 = reinterpret_cast<uint4 *>(head);
-    for (int i = threadIdx.x; i < (kDepth ? 6144 : 4096); i += kChainWarps * 32) h4[i] = make_uint4(0, 0, 0, 0);
+    for (int i = threadIdx.x; i < 4096; i += kChainWarps * 32) h4[i] = make_uint4(0, 0, 0, 0);
     __syncthreads();
-    uint8_t *depth = depth_all + (uint64_t)c * b.S;
     constexpr int G = kChainTrip / 32;
     const uintptr_t in_hi = reinterpret_cast<uintptr_t>(b.in) + b.bytes;
     // the three bytes at a position as one little-endian word (bytes past the input read as 0)
@@ -141,15 +131,9 @@ __global__ void __launch_bounds__(kChainWarps * 32) dfl_chain_kernel(Batch b, ui
                 v.z = __vsubus2(v.z, 0x80008000u); v.w = __vsubus2(v.w, 0x80008000u);
                 h4[i] = v;
             }
-            if (kDepth)
-                for (int i = lane; i < 2048; i += 32) {
-                    uint4 v = h4[4096 + i];
-                    v.x = (v.x >> 1) & 0x7f7f7f7fu; v.y = (v.y >> 1) & 0x7f7f7f7fu; v.z = (v.z >> 1) & 0x7f7f7f7fu; v.w = (v.w >> 1) & 0x7f7f7f7fu;
-                    h4[4096 + i] = v;
-                }
             __syncwarp();
         }
-        uint32_t dists[G], deps[G];
+        uint32_t dists[G];
 #pragma unroll
         for (int j = 0; j < G; ++j) {
             const uint32_t g0 = p0 + 32 * j, p = g0 + lane;
@@ -159,10 +143,10 @@ __global__ void __launch_bounds__(kChainWarps * 32) dfl_chain_kernel(Batch b, ui
             // read back.  If every lane reads back its own value the 32 hashes were distinct
             // and the old heads are the links.  match.any (whose cost grows with the number
             // of distinct values) is only needed when two lanes of the group collide.
-            uint32_t old = 0, oc = 0;
-            if (valid) { old = head[hs[j]]; if (kDepth) oc = hcnt[hs[j]]; }
+            uint32_t old = 0;
+            if (valid) old = head[hs[j]];
             __syncwarp();
-            if (valid) { head[hs[j]] = (uint16_t)rel; if (kDepth) hcnt[hs[j]] = (uint8_t)(oc < 255u ? oc + 1u : 255u); }
+            if (valid) head[hs[j]] = (uint16_t)rel;
             __syncwarp();
             const bool clash = valid && head[hs[j]] != (uint16_t)rel;
             uint32_t dist = (valid && old) ? rel - old : 0;
@@ -172,22 +156,18 @@ __global__ void __launch_bounds__(kChainWarps * 32) dfl_chain_kernel(Batch b, ui
                 if (valid && lower) {
                     const uint32_t q = g0 + (31u - (uint32_t)__clz(lower));
                     dist = q ? p - q : 0;                          // position 0 is never a match target (deflate.c:1366)
-                    if (kDepth) oc += (uint32_t)__popc(lower);
                 }
                 __syncwarp();
-                if (valid && (mask >> lane) == 1u) {               // the group's highest lane wins
-                    head[hs[j]] = (uint16_t)rel;
-                    if (kDepth) hcnt[hs[j]] = (uint8_t)(oc < 255u ? oc + 1u : 255u);
-                }
+                if (valid && (mask >> lane) == 1u) head[hs[j]] = (uint16_t)rel;   // the group's highest lane wins
                 __syncwarp();
             }
-            dists[j] = dist; deps[j] = oc < 255u ? oc : 255u;
+            dists[j] = dist;
         }
         if (t + 1 < ntrips) asm volatile("bar.arrive %0, 64;" ::"r"(((warp + 1) & (kChainWarps - 1)) + 1) : "memory");   // pass the turn on
 #pragma unroll
         for (int j = 0; j < G; ++j) {
             const uint32_t p = p0 + 32 * j + lane;
-            if (p < n) { prev[p] = (uint16_t)dists[j]; if (kDepth) depth[p] = (uint8_t)deps[j]; }
+            if (p < n) prev[p] = (uint16_t)dists[j];
         }
     }
 }
@@ -216,7 +196,7 @@ dfl_match_kernel(Batch b, DeflateParams prm, const uint16_t *__restrict__ prev_a
 }
 
 // The same walk with the positions of a tile handed to the warps in order of their
-// chain depth.  A warp costs as many steps as its longest walk; consecutive positions
+// chain length (links inside the window, up to the budget: counted on the staged links).  A warp costs as many steps as its longest walk; consecutive positions
 // have unrelated walk lengths (ncu: 8 of 32 lanes active; host replay: 30 % of the
 // lane-steps useful on text at level 6), while positions with the same depth bucket
 // have similar ones (75 % useful with quarter-octave buckets, 90 % on mixed data).
@@ -323,7 +303,7 @@ dfl_match_uniform_kernel(Batch b, DeflateParams prm, const uint16_t *__restrict_
 }
 
 __global__ void __launch_bounds__(kMsThreads)
-dfl_match_sorted_kernel(Batch b, DeflateParams prm, const uint16_t *__restrict__ prev_all, const uint8_t *__restrict__ depth_all,
+dfl_match_sorted_kernel(Batch b, DeflateParams prm, const uint16_t *__restrict__ prev_all,
                         uint32_t *__restrict__ mfull, uint32_t *__restrict__ mquarter) {
     __shared__ uint32_t s_hist[kMsBuckets], s_cur[kMsBuckets];
     uint16_t *s_order = reinterpret_cast<uint16_t *>(ms_smem + kMsDataBytes + kMsLinkBytes);
@@ -332,7 +312,6 @@ dfl_match_sorted_kernel(Batch b, DeflateParams prm, const uint16_t *__restrict__
     const uint64_t off = (uint64_t)c * b.S;
     const uint8_t *data = b.in + off;
     const uint16_t *prev = prev_all + off;
-    const uint8_t *depth = depth_all + off;
     const uint32_t cnt = n - t0 < kMsTile ? n - t0 : kMsTile, t1 = t0 + cnt;
     const uint32_t lo = t0 > (uint32_t)kWSize ? t0 - kWSize : 0;             // candidates lie less than 32 KiB back
     const uint32_t hi = t1 + kMsLook < n ? t1 + kMsLook : n;                  // bytes [lo, hi) can be read
@@ -347,9 +326,17 @@ dfl_match_sorted_kernel(Batch b, DeflateParams prm, const uint16_t *__restrict__
             const uint32_t p = t0 + i, d = mem.link(p);
             uint32_t e = 0;
             if (p + kMinMatch <= n && d != 0 && d <= (uint32_t)kMaxDist) {
-                e = (uint32_t)depth[p] + 1u;                       // at least one candidate
-                if (e > (uint32_t)prm.chain) e = (uint32_t)prm.chain;
-                if (e > 255u) e = 255u;
+                // length of the walk if no candidate ends it early: links inside the window, up to the budget
+                const uint32_t cap = (uint32_t)prm.chain < 255u ? (uint32_t)prm.chain : 255u;
+                uint32_t q = p - d;
+                e = 1;
+                while (e < cap) {
+                    const uint32_t d2 = mem.link(q);
+                    if (d2 == 0) break;
+                    q -= d2;
+                    if (p - q >= (uint32_t)kMaxDist) break;
+                    ++e;
+                }
             }
             bk[k] = depth_bucket(e);
             atomicAdd(&s_hist[bk[k]], 1u);
@@ -798,8 +785,7 @@ int deflate_init(zb200_ctx *ctx) {
     ZB_CUDA(cudaMalloc(&d, sizeof h));
     ZB_CUDA(cudaMemcpy(d, &h, sizeof h, cudaMemcpyHostToDevice));
     ctx->d_deflate_tables = d;
-    ZB_CUDA(cudaFuncSetAttribute(dfl_chain_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kChainSmem));
-    ZB_CUDA(cudaFuncSetAttribute(dfl_chain_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kChainSmemDepth));
+    ZB_CUDA(cudaFuncSetAttribute(dfl_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kChainSmem));
     ZB_CUDA(cudaFuncSetAttribute(dfl_parse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kParseSmem));
     ZB_CUDA(cudaFuncSetAttribute(dfl_match_sorted_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMsSmem));
     ZB_CUDA(cudaFuncSetAttribute(dfl_match_uniform_kernel<4, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMsSmem));
@@ -870,14 +856,12 @@ int deflate_launch(zb200_ctx *ctx, const uint8_t *d_in, size_t n, size_t S, int 
         b.last_is_final = (finish && c0 + b.nb == nch) ? 1 : 0;
         b.all_final = members ? 1 : 0;
         if (prm.mode == MODE_FAST || prm.mode == MODE_SLOW) {
-            // depth counts ride in the symbol array, which the parse kernel overwrites only after the matches are done
-            if (sorted_walks) dfl_chain_kernel<true><<<b.nb, kChainWarps * 32, kChainSmemDepth, s>>>(b, w.prev, (uint8_t *)w.syms);
-            else dfl_chain_kernel<false><<<b.nb, kChainWarps * 32, kChainSmem, s>>>(b, w.prev, nullptr);
+            dfl_chain_kernel<<<b.nb, kChainWarps * 32, kChainSmem, s>>>(b, w.prev);
             ZB_LAUNCHED(); ZB_CHECK_LAUNCH();
         }
         if (sorted_walks) {
             dim3 g((unsigned)((S + kMsTile - 1) / kMsTile), b.nb);
-            dfl_match_sorted_kernel<<<g, kMsThreads, kMsSmem, s>>>(b, prm, w.prev, (const uint8_t *)w.syms, w.mfull, w.mquarter);
+            dfl_match_sorted_kernel<<<g, kMsThreads, kMsSmem, s>>>(b, prm, w.prev, w.mfull, w.mquarter);
             ZB_LAUNCHED(); ZB_CHECK_LAUNCH();
         } else if (prm.mode == MODE_FAST) {                        // levels 1-2
             dim3 g((unsigned)((S + kMsTile - 1) / kMsTile), b.nb);
