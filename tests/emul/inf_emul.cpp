@@ -77,12 +77,14 @@ static int host_rounds(const uint8_t *src, uint64_t in_len, uint8_t *dst, uint64
     static std::vector<QueuedMatch> gq(kRoundQueueCap);
     const uint32_t bias = (uint32_t)(reinterpret_cast<uintptr_t>(src) & 3) * 8;
     const uint64_t total_bits = bias + in_len * 8, nwords = (total_bits + 31) >> 5;
+    int lg_cap = kRoundLgMax;
     for (;;) {
         const uint64_t B = bias + bitpos;
         if (B >= total_bits) { g_stats.serial_returns++; return 1; }
         int lg = round_pick_lg(total_bits - B);
         if (lg < 0) { g_stats.serial_returns++; return 1; }
         if (force_lg >= kRoundLgMin && force_lg < lg) lg = force_lg;
+        if (lg > lg_cap) lg = lg_cap;                   // an overfull round shortens the subsequences for the rest of the block
         const uint32_t S = 32u << lg, W = 1u << lg, stride = stage_row_stride(lg);
         const uint64_t W0 = B >> 5;
         uint32_t *stage = rs.stage;
@@ -127,7 +129,7 @@ static int host_rounds(const uint8_t *src, uint64_t in_len, uint8_t *dst, uint64
             off_m[l + 1] = off_m[l] + (l <= last ? r[l].m : 0);
         }
         if (off_o[32] > out_cap - pos) { g_stats.serial_returns++; return 1; }
-        if (off_m[32] > kRoundQueueCap) return -1;
+        if (off_m[32] > kRoundQueueCap) { lg_cap = lg >= kRoundLgMin + 2 ? lg - 2 : kRoundLgMin; continue; }   // as on the device
         bool err = false;
         for (int l = (int)last; l >= 0; --l)             // any lane order must do: run them backwards
             err |= round_emit(r[l], (uint32_t)l, lg, stage, lt, dt, dst, (uint32_t)pos + off_o[l], gq.data(), off_m[l]) != 0;

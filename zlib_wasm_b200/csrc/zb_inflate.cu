@@ -19,7 +19,7 @@ namespace zb {
 
 constexpr int kInfWarps = 4;
 constexpr int kInfCtasPerSm = 4;          // 4 CTAs x (4 warps x 12.6 KiB + 3.4 KiB) of shared memory, 128 registers: 16 warps per SM
-constexpr size_t kMaxGridWarps = 2048;    // upper bound on resident warps (sizes the per-warp match queues)
+constexpr size_t kMaxGridWarps = 4096;    // upper bound on resident warps (sizes the per-warp match queues: 48 KiB each)
 // Two symbol decoders exist: the serial loop on lane 0 (InflateState::fast_symbols,
 // ~79 warp instructions per symbol with one lane active) and the warp-parallel rounds
 // (huff_rounds_warp, all lanes active).  The rounds are the default; the serial loop
@@ -197,7 +197,7 @@ huff_rounds_warp(const uint8_t *src, uint64_t in_len, uint8_t *dst, uint64_t out
     res.status = 1; res.bitpos = bitpos; res.pos = pos;
     uint64_t B = bias + bitpos;
     if (B >= total_bits) return res;
-    int lg = round_pick_lg(total_bits - B);
+    int lg = round_pick_lg(total_bits - B), lg_cap = kRoundLgMax;
     if (lg < 0) return res;
     for (;;) {
         res.status = 1; res.bitpos = bitpos; res.pos = pos;         // where the serial path would take over
@@ -234,6 +234,11 @@ huff_rounds_warp(const uint8_t *src, uint64_t in_len, uint8_t *dst, uint64_t out
             if (lane >= (uint32_t)dlt) { inc_o += yo; inc_m += ym; }
         }
         const uint32_t tot_o = __shfl_sync(full, inc_o, 31), tot_m = __shfl_sync(full, inc_m, 31);
+        if (tot_m > kRoundQueueCap) {                                // runs: matches of 2-3 bits.  Redo the round with shorter subsequences
+            lg_cap = lg >= kRoundLgMin + 2 ? lg - 2 : kRoundLgMin;   // (at S = 128 a round holds at most 2048 matches), and keep
+            lg = lg_cap;                                             // them short for the rest of the block
+            continue;
+        }
         int err = tot_o > out_cap - pos;
         if (!err && valid) err = round_emit(r, lane, lg, stage, lt, dt, dst, (uint32_t)pos + inc_o - myout, gq, inc_m - mym);
         if (__ballot_sync(full, err != 0)) return res;
@@ -245,7 +250,7 @@ huff_rounds_warp(const uint8_t *src, uint64_t in_len, uint8_t *dst, uint64_t out
         res.bitpos = bitpos; res.pos = pos;
         if (stop_l == STOP_EOB) { res.status = 0; return res; }
         if (next_lg < 0) { res.status = 1; return res; }
-        lg = next_lg;
+        lg = next_lg < lg_cap ? next_lg : lg_cap;
     }
 }
 

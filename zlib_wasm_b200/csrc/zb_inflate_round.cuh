@@ -42,7 +42,9 @@ constexpr int kRoundLgMin = 2, kRoundLgMax = 5;              // words per lane =
 constexpr int kRoundWordsMax = 1 << kRoundLgMax;
 constexpr int kRowExtra = 3;                                 // words of the following subsequence repeated at the end of a row
 constexpr int kStageWords = 32 * (kRoundWordsMax + kRowExtra);
-constexpr uint32_t kRoundQueueCap = 32u * (32u << kRoundLgMax) / 2u;   // a match costs at least 2 bits
+// Matches a round may park.  The worst case is 32 * S / 2 (a match costs at least 2 bits); text
+// parks ~1500.  A round that would park more is left to the serial path like any other oddity.
+constexpr uint32_t kRoundQueueCap = 6144;
 
 // Per-warp working memory of a round (shared memory on the device).
 // stage: lane i owns row i = the W words of its subsequence followed by the next 3
