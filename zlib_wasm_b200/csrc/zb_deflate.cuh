@@ -131,14 +131,15 @@ ZB_HD MatchPair match_walk(const Mem &mem, uint32_t n, uint32_t p, const Deflate
     // lanes that measure hold up all the others: the cheaper this path, the better.)
     const bool regs = look >= 16;                         // else: chunk tail, everything bytewise below
     const uint32_t sw0 = regs ? mem.word(p) : 0, sw4 = regs ? mem.word(p + 4) : 0, sw8 = regs ? mem.word(p + 8) : 0;
-    uint32_t best = kMinMatch - 1, best_dist = 0, sb = mem.byte(p + kMinMatch - 1);           // best < maxlen whenever a candidate is screened
+    uint32_t best = kMinMatch - 1, best_dist = 0;                                     // best < maxlen whenever a candidate is screened
+    uint32_t sb = mem.byte(p + kMinMatch - 1), sb1 = mem.byte(p + kMinMatch - 2);     // scan[best], scan[best - 1] (deflate.c:1449-1450 scan_end, scan_end1)
     uint32_t q = p - d, examined = 0;
     const uint32_t budget = (uint32_t)prm.chain, qbudget = budget >> 2;
     uint32_t stop_at = qbudget ? qbudget : budget;        // the next loop bound: quarter snapshot first, then the full budget
     bool have_q = false;
     for (;;) {
         const uint32_t d2 = mem.link(q);
-        if (mem.byte(q + best) == sb) {                              // deflate.c:1449-1452: the cheapest reject first
+        if (mem.byte(q + best) == sb && mem.byte(q + best - 1) == sb1) {   // deflate.c:1449-1452: the cheapest rejects first
             uint32_t len;
             bool pass;
             if (regs) {
@@ -171,7 +172,7 @@ ZB_HD MatchPair match_walk(const Mem &mem, uint32_t n, uint32_t p, const Deflate
             if (pass && len > best) {
                 best = len; best_dist = p - q;
                 if (len >= nice) break;
-                sb = mem.byte(p + best);
+                sb = mem.byte(p + best); sb1 = mem.byte(p + best - 1);
             }
         }
         if (++examined == stop_at) {
