@@ -73,6 +73,45 @@ def test_edge_sizes_and_chunkings(ctx):
                     assert s == ref_stream(d, level, 0, refz.WRAP_ZLIB, chunk), (chunk, n, level)
 
 
+def test_odd_chunk_sizes_and_alignments(ctx):
+    """Chunk sizes that are no multiple of anything (the kernels stage windows by ABSOLUTE
+    alignment of the tables and of the input address) on text and mixed data, levels that
+    exercise every match / parse kernel."""
+    for kind, n in ((refz.GEN_MARKOV, 700001), (refz.GEN_MIXED, 1234567)):
+        d = refz.gen(n, kind, seed=31 + kind)
+        for chunk in (7777, 100003, 65537, 300000):
+            for level in (1, 2, 3, 5, 6, 9):
+                s = ctx.deflate_host(d, level, 0, zb.FRAME_GZIP, chunk)
+                assert decode_ok(s, refz.WRAP_GZIP, d), (kind, chunk, level)
+                if level >= 4:
+                    assert s == ref_stream(d, level, 0, refz.WRAP_GZIP, chunk), (kind, chunk, level)
+
+
+def test_device_entry_point_unaligned_input(ctx):
+    """zb200_deflate_dev on device input that starts at odd addresses: same bytes as the
+    host entry point (which stages into an aligned buffer)."""
+    import ctypes as C
+    import torch
+    L = zb.lib()
+    d = refz.gen(600011, refz.GEN_MARKOV, seed=77)
+    chunk = 131072
+    for level in (1, 6):
+        want = ctx.deflate_host(d, level, 0, zb.FRAME_RAW, chunk)
+        for skew in (1, 5, 13):
+            buf = torch.zeros(len(d) + 64, dtype=torch.uint8, device="cuda")
+            buf[skew:skew + len(d)] = torch.frombuffer(bytearray(d), dtype=torch.uint8).cuda()
+            cap = L.zb200_deflate_bound(len(d), chunk, zb.FRAME_RAW)
+            out = torch.zeros(cap, dtype=torch.uint8, device="cuda")
+            tot = torch.zeros(1, dtype=torch.int64, device="cuda")
+            torch.cuda.synchronize()
+            r = L.zb200_deflate_dev(ctx.handle, C.c_void_p(buf.data_ptr() + skew), len(d), chunk, level, 0, zb.FRAME_RAW, 1,
+                                    C.c_void_p(out.data_ptr()), cap, None, C.c_void_p(tot.data_ptr()), None)
+            assert r == 0, zb.last_error()
+            torch.cuda.synchronize()
+            got = bytes(out[:int(tot.item())].cpu().numpy())
+            assert got == want, (level, skew, len(got), len(want))
+
+
 def test_runs_and_slides(ctx):
     """Long runs (258-byte matches, distance-1 overlaps) and chunks far larger
     than the 64 KiB window (many slides, block_start going negative)."""
