@@ -108,8 +108,12 @@ ZB_HD int build_decode_table(int type, const uint8_t *lens, int n, uint32_t *tab
         for (int k = count[len]; k > 0; --k, ++idx, ++code) {
             const int sym = work[idx];
             // bit-reverse the len-bit code: DEFLATE packs Huffman codes MSB first into an LSB-first stream
+#if defined(__CUDA_ARCH__)
+            const uint32_t rc = __brev(code) >> (32 - len);
+#else
             uint32_t rc = 0;
             for (int b = 0; b < len; ++b) rc |= ((code >> b) & 1u) << (len - 1 - b);
+#endif
             if (len <= root) {
                 const uint32_t e = entry_for(sym, len);
                 for (uint32_t i = rc; i < (uint32_t)root_size; i += 1u << len) table[i] = e;
