@@ -112,6 +112,43 @@ def test_device_entry_point_unaligned_input(ctx):
             assert got == want, (level, skew, len(got), len(want))
 
 
+def test_pipelined_host_entry_point(ctx):
+    """Large inputs in pinned memory take the pipelined path of zb200_deflate_host (pieces
+    travel while others are compressed): the bytes, the length and the input checksums are
+    those of the plain path on pageable memory, for every frame kind."""
+    import ctypes as C
+    import zlib
+    L = zb.lib()
+    n = (300 << 20) + 12345
+    d = refz.gen(n, refz.GEN_MARKOV, seed=5)
+    chunk = 262144
+    h_in = L.zb200_host_alloc(n)
+    assert h_in
+    C.memmove(h_in, d, n)
+    try:
+        for level, frame in ((1, zb.FRAME_GZIP), (1, zb.FRAME_RAW), (6, zb.FRAME_ZLIB), (1, zb.FRAME_GZIP_MEMBERS)):
+            want = ctx.deflate_host(d, level, 0, frame, chunk)
+            cap = L.zb200_deflate_bound(n, chunk, frame)
+            h_out = L.zb200_host_alloc(cap)
+            assert h_out
+            olen, ad, cr = C.c_size_t(cap), C.c_uint32(0), C.c_uint32(0)
+            r = L.zb200_deflate_host(ctx.handle, C.c_void_p(h_in), n, chunk, level, 0, frame, 1, C.c_void_p(h_out), C.byref(olen),
+                                     C.byref(ad), C.byref(cr))
+            assert r == 0, zb.last_error()
+            got = C.string_at(h_out, olen.value)
+            L.zb200_host_free(C.c_void_p(h_out))
+            assert got == want, (level, frame, len(got), len(want))
+            assert (cr.value, ad.value) == (zlib.crc32(d), zlib.adler32(d))
+            # too small an output buffer is reported, not overrun
+            small = L.zb200_host_alloc(1 << 20)
+            olen = C.c_size_t(1 << 20)
+            r = L.zb200_deflate_host(ctx.handle, C.c_void_p(h_in), n, chunk, level, 0, frame, 1, C.c_void_p(small), C.byref(olen), None, None)
+            L.zb200_host_free(C.c_void_p(small))
+            assert r != 0
+    finally:
+        L.zb200_host_free(C.c_void_p(h_in))
+
+
 def test_runs_and_slides(ctx):
     """Long runs (258-byte matches, distance-1 overlaps) and chunks far larger
     than the 64 KiB window (many slides, block_start going negative)."""

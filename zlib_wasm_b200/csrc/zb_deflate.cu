@@ -933,11 +933,104 @@ int zb200_deflate_dev(zb200_ctx *ctx, const void *d_in, size_t n, size_t chunk_s
                           (uint8_t *)d_out, out_cap, d_chunk_end, d_total, nullptr, pick_stream(ctx, stream));
 }
 
+// Large inputs in pinned memory: the input is cut into up to 9 pieces (whole chunks); piece
+// k+1 travels to the device and piece k-1 travels back while piece k is compressed (three
+// streams, PCIe is full duplex).  Pieces are raw deflate runs — exactly the chunks a single
+// call would emit — so their concatenation is the same byte stream; the stream header and
+// trailer (deflate.c:1004-1054,1239-1256) are written here on the host, the input checksums
+// of the pieces merged with crc32_combine / adler32_combine.
+static int deflate_host_pipelined(zb200_ctx *ctx, const uint8_t *in, size_t n, size_t S, int level, int strategy,
+                                  int frame, int finish, uint8_t *out, size_t *out_len, uint32_t *in_adler, uint32_t *in_crc) {
+    const int pframe = frame == ZB200_FRAME_GZIP_MEMBERS ? ZB200_FRAME_GZIP_MEMBERS : ZB200_FRAME_RAW;
+    // pieces of at least 128 MiB: smaller ones leave the GPU underfilled (the chain kernel needs ~450 chunks in flight)
+    size_t piece = n / 8 > ((size_t)128 << 20) ? n / 8 : ((size_t)128 << 20);
+    piece = (piece + S - 1) / S * S;
+    const size_t np = (n + piece - 1) / piece;                     // <= 9
+    size_t ooff[17], bound[16], total_bound = 0;
+    for (size_t k = 0; k < np; ++k) {
+        const size_t len = k + 1 < np ? piece : n - k * piece;
+        bound[k] = zb200_deflate_bound(len, S, pframe);
+        ooff[k] = total_bound; total_bound += bound[k];
+    }
+    int r = ensure_io(ctx, n + 16, total_bound + 16);
+    if (r) return r;
+    if ((r = ensure_scratch(ctx, zb200_deflate_scratch_bytes(piece, S)))) return r;   // no reallocation (= implicit sync) mid-pipeline
+    cudaEvent_t ev_in[16], ev_out[16];
+    for (size_t k = 0; k < np; ++k) {
+        ZB_CUDA(cudaEventCreateWithFlags(&ev_in[k], cudaEventDisableTiming));
+        ZB_CUDA(cudaEventCreateWithFlags(&ev_out[k], cudaEventDisableTiming));
+    }
+    auto cleanup = [&]() { for (size_t k = 0; k < np; ++k) { cudaEventDestroy(ev_in[k]); cudaEventDestroy(ev_out[k]); } };
+    cudaStream_t s = ctx->stream;
+    for (size_t k = 0; k < np; ++k) {
+        const size_t len = k + 1 < np ? piece : n - k * piece;
+        if (cudaMemcpyAsync(ctx->d_io_in + k * piece, in + k * piece, len, cudaMemcpyHostToDevice, ctx->copy_stream) != cudaSuccess ||
+            cudaEventRecord(ev_in[k], ctx->copy_stream) != cudaSuccess) { cleanup(); set_error("deflate: H2D of piece %zu failed", k); return ZB200_ERR_CUDA; }
+    }
+    for (size_t k = 0; k < np; ++k) {
+        const size_t len = k + 1 < np ? piece : n - k * piece;
+        cudaStreamWaitEvent(s, ev_in[k], 0);
+        r = deflate_launch(ctx, ctx->d_io_in + k * piece, len, S, level, strategy, pframe, (finish && k + 1 == np) ? 1 : 0,
+                           ctx->d_io_out + ooff[k], bound[k], nullptr, ctx->d_pipe + 2 * k, (uint32_t *)(ctx->d_pipe + 2 * k + 1), s);
+        if (r) { cudaStreamSynchronize(s); cudaStreamSynchronize(ctx->copy_stream); cleanup(); return r; }
+        cudaMemcpyAsync(ctx->h_pipe + 2 * k, ctx->d_pipe + 2 * k, 16, cudaMemcpyDeviceToHost, s);
+        cudaEventRecord(ev_out[k], s);
+    }
+    // header
+    size_t pos = 0;
+    uint8_t hdr[10];
+    size_t hlen = 0;
+    if (frame == ZB200_FRAME_ZLIB) {
+        const unsigned lf = (strategy >= STRAT_HUFFMAN || level < 2) ? 0 : level < 6 ? 1 : level == 6 ? 2 : 3;
+        unsigned h = (0x78u << 8) | (lf << 6);
+        h += 31 - h % 31;
+        hdr[0] = (uint8_t)(h >> 8); hdr[1] = (uint8_t)h; hlen = 2;
+    } else if (frame == ZB200_FRAME_GZIP) {
+        const uint8_t g[10] = {0x1f, 0x8b, 8, 0, 0, 0, 0, 0, (uint8_t)(level == 9 ? 2 : (strategy >= STRAT_HUFFMAN || level < 2) ? 4 : 0), 3};
+        memcpy(hdr, g, 10); hlen = 10;
+    }
+    int rc = ZB200_OK;
+    if (hlen > *out_len) rc = ZB200_ERR_OUTPUT; else { memcpy(out, hdr, hlen); pos = hlen; }
+    uint32_t crc = 0, adler = 1;
+    for (size_t k = 0; k < np; ++k) {
+        const size_t len = k + 1 < np ? piece : n - k * piece;
+        if (cudaEventSynchronize(ev_out[k]) != cudaSuccess) { rc = ZB200_ERR_CUDA; break; }
+        const uint64_t total = ctx->h_pipe[2 * k];
+        const uint32_t *sums = (const uint32_t *)(ctx->h_pipe + 2 * k + 1);
+        crc = zb200_crc32_combine(crc, sums[0], len);
+        adler = zb200_adler32_combine(adler, sums[1], (int64_t)len);
+        if (rc == ZB200_OK && pos + total > *out_len) rc = ZB200_ERR_OUTPUT;
+        if (rc == ZB200_OK && cudaMemcpyAsync(out + pos, ctx->d_io_out + ooff[k], (size_t)total, cudaMemcpyDeviceToHost, ctx->back_stream) != cudaSuccess) rc = ZB200_ERR_CUDA;
+        pos += (size_t)total;
+    }
+    cudaStreamSynchronize(ctx->back_stream);
+    cudaStreamSynchronize(s);
+    cleanup();
+    if (rc == ZB200_OK && finish) {
+        uint8_t tr[8];
+        size_t tlen = 0;
+        if (frame == ZB200_FRAME_ZLIB) { for (int i = 0; i < 4; ++i) tr[i] = (uint8_t)(adler >> (24 - 8 * i)); tlen = 4; }
+        else if (frame == ZB200_FRAME_GZIP) { for (int i = 0; i < 4; ++i) { tr[i] = (uint8_t)(crc >> (8 * i)); tr[4 + i] = (uint8_t)((uint32_t)n >> (8 * i)); } tlen = 8; }
+        if (pos + tlen > *out_len) rc = ZB200_ERR_OUTPUT; else memcpy(out + pos, tr, tlen);
+        pos += tlen;
+    }
+    if (in_crc) *in_crc = crc;
+    if (in_adler) *in_adler = adler;
+    if (rc == ZB200_ERR_OUTPUT) { *out_len = pos; set_error("deflate: %zu bytes do not fit the output buffer", pos); return rc; }
+    if (rc != ZB200_OK) { set_error("deflate: pipelined transfer failed"); return rc; }
+    *out_len = pos;
+    return ZB200_OK;
+}
+
 int zb200_deflate_host(zb200_ctx *ctx, const void *in, size_t n, size_t chunk_size, int level, int strategy,
                        int frame, int finish, void *out, size_t *out_len, uint32_t *in_adler, uint32_t *in_crc) {
     if (!ctx || (!in && n) || !out || !out_len) return ZB200_ERR_PARAM;
     ZB_CUDA(cudaSetDevice(ctx->device));
     std::lock_guard<std::mutex> g(ctx->mu);
+    if (n >= ((size_t)256 << 20) && chunk_size >= 1 && chunk_size <= ((size_t)16 << 20) && level >= 0 && level <= 9 &&
+        strategy >= 0 && strategy <= 4 && frame >= 0 && frame <= 3 && is_pinned(in) && is_pinned(out))
+        return deflate_host_pipelined(ctx, (const uint8_t *)in, n, chunk_size, level, strategy, frame, finish,
+                                      (uint8_t *)out, out_len, in_adler, in_crc);
     const size_t bound = zb200_deflate_bound(n, chunk_size ? chunk_size : 1, frame);
     int r = ensure_io(ctx, n + 16, bound + 16);
     if (r) return r;

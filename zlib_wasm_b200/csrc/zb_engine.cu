@@ -107,7 +107,7 @@ int d2h_staged(zb200_ctx *ctx, void *h_dst, const void *d_src, size_t n, cudaStr
     return ZB200_OK;
 }
 
-static bool is_pinned(const void *p) {
+bool is_pinned(const void *p) {
     cudaPointerAttributes attr;
     bool pinned = cudaPointerGetAttributes(&attr, p) == cudaSuccess && attr.type == cudaMemoryTypeHost;
     cudaGetLastError();
@@ -163,6 +163,9 @@ int zb200_create(int device, zb200_ctx **out) {
     }
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) return fail(ZB200_ERR_CUDA);
     if (cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess) return fail(ZB200_ERR_CUDA);
+    if (cudaStreamCreateWithFlags(&ctx->back_stream, cudaStreamNonBlocking) != cudaSuccess) return fail(ZB200_ERR_CUDA);
+    if (cudaMalloc((void **)&ctx->d_pipe, 32 * sizeof(uint64_t)) != cudaSuccess) return fail(ZB200_ERR_NOMEM);
+    if (cudaMallocHost((void **)&ctx->h_pipe, 32 * sizeof(uint64_t)) != cudaSuccess) return fail(ZB200_ERR_NOMEM);
     ctx->stage_bytes = 32u << 20;
     for (int k = 0; k < zb200_ctx::kStages; ++k) {
         if (cudaMallocHost((void **)&ctx->h_stage[k], ctx->stage_bytes) != cudaSuccess) return fail(ZB200_ERR_NOMEM);
@@ -197,6 +200,9 @@ void zb200_destroy(zb200_ctx *ctx) {
     if (ctx->d_io_out) cudaFree(ctx->d_io_out);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->back_stream) cudaStreamDestroy(ctx->back_stream);
+    if (ctx->d_pipe) cudaFree(ctx->d_pipe);
+    if (ctx->h_pipe) cudaFreeHost(ctx->h_pipe);
     cudaGetLastError();
     delete ctx;
 }

@@ -55,6 +55,8 @@ struct zb200_ctx {
     int sm_count = 0;
     cudaStream_t stream = nullptr;          // the context's own stream
     cudaStream_t copy_stream = nullptr;     // H2D/D2H staging stream
+    cudaStream_t back_stream = nullptr;     // D2H of finished pieces while later ones are still computed
+    uint64_t *d_pipe = nullptr, *h_pipe = nullptr;   // per-piece (total, crc|adler<<32) of the pipelined host entry points: 2 x 16 u64
     std::mutex mu;                          // serialises use of the scratch/staging below
 
     zb::CrcTables *d_crc_tables = nullptr;
@@ -84,6 +86,7 @@ int ensure_io(zb200_ctx *ctx, size_t in_bytes, size_t out_bytes);
 int h2d_staged(zb200_ctx *ctx, void *d_dst, const void *h_src, size_t n, cudaStream_t s);
 int d2h_staged(zb200_ctx *ctx, void *h_dst, const void *d_src, size_t n, cudaStream_t s);
 // pinned host memory is DMA-ed directly (async); pageable memory goes through the stages
+bool is_pinned(const void *p);
 int h2d_auto(zb200_ctx *ctx, void *d_dst, const void *h_src, size_t n, cudaStream_t s);
 int d2h_auto(zb200_ctx *ctx, void *h_dst, const void *d_src, size_t n, cudaStream_t s);
 inline cudaStream_t pick_stream(zb200_ctx *ctx, void *stream) {
