@@ -137,3 +137,40 @@ def test_output_full_and_resume(ctx):
     # output too small
     st, _, r = one(ctx, s, zb.WRAP_GZIP, len(d) - 1)
     assert msg(st) == "output buffer full"
+
+
+def test_pipelined_host_entry_point(ctx):
+    """Many members in pinned memory take the pipelined path of zb200_inflate_host: same
+    bytes and per-member results as the plain path."""
+    import ctypes as C
+    import torch
+    L = zb.lib()
+    n, chunk = 2112 << 20, 1 << 20                      # > 1.5 GiB of output: two pieces
+    d = refz.gen(n, refz.GEN_MARKOV, seed=8)
+    d_in = torch.frombuffer(bytearray(d), dtype=torch.uint8).cuda()
+    cap = L.zb200_deflate_bound(n, chunk, zb.FRAME_GZIP_MEMBERS)
+    d_blob = torch.empty(cap, dtype=torch.uint8, device="cuda")
+    d_end = torch.zeros(n // chunk, dtype=torch.int64, device="cuda")
+    d_tot = torch.zeros(1, dtype=torch.int64, device="cuda")
+    assert L.zb200_deflate_dev(ctx.handle, C.c_void_p(d_in.data_ptr()), n, chunk, 6, 0, zb.FRAME_GZIP_MEMBERS, 1,
+                               C.c_void_p(d_blob.data_ptr()), cap, C.c_void_p(d_end.data_ptr()), C.c_void_p(d_tot.data_ptr()), None) == 0
+    torch.cuda.synchronize()
+    ends, total = d_end.cpu().tolist(), int(d_tot.item())
+    members, prev = [], 0
+    for i, e in enumerate(ends):
+        members.append(zb.Member(prev, e - prev, i * chunk, chunk, 0, 0))
+        prev = e
+    arr = (zb.Member * len(members))(*members)
+    h_in, h_out = L.zb200_host_alloc(total), L.zb200_host_alloc(n)
+    assert h_in and h_out
+    try:
+        C.memmove(h_in, d_blob[:total].cpu().numpy().tobytes(), total)
+        res = (zb.MemberResult * len(members))()
+        assert L.zb200_inflate_host(ctx.handle, C.c_void_p(h_in), C.c_void_p(h_out), arr, len(members), zb.WRAP_GZIP, 1, res) == 0, zb.last_error()
+        assert all(r.status == 0 and r.out_len == chunk for r in res)
+        assert C.string_at(h_out + (n - (64 << 20)), 64 << 20) == d[n - (64 << 20):] and C.string_at(h_out, 64 << 20) == d[:64 << 20]
+        o = refz.oracle()
+        assert res[7].check == o.crc32(d[7 * chunk:8 * chunk]) and res[7].in_used == members[7].in_len
+    finally:
+        L.zb200_host_free(C.c_void_p(h_in))
+        L.zb200_host_free(C.c_void_p(h_out))

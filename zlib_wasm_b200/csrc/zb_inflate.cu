@@ -485,6 +485,66 @@ int zb200_inflate_dev(zb200_ctx *ctx, const void *d_in, void *d_out, const zb200
                           d_results, ctx->d_scratch, pick_stream(ctx, stream));
 }
 
+// Many members, pinned buffers, members laid out in order: the member list is cut into up to
+// 8 pieces of similar output size (1 GiB or more); piece k+1's input travels to the device and piece k-1's
+// output travels back while piece k is decoded (three streams).
+static int inflate_host_pipelined(zb200_ctx *ctx, const uint8_t *in, uint8_t *out, const zb200_member *members, size_t n,
+                                  int wrap, int verify, zb200_member_result *results, size_t in_bytes, size_t out_bytes) {
+    const size_t tbl = align_up(n * sizeof(zb200_member), 256), rsl = align_up(n * sizeof(zb200_member_result), 256);
+    int r = ensure_io(ctx, in_bytes + 16, out_bytes + 16);
+    if (r) return r;
+    if ((r = ensure_scratch(ctx, tbl + rsl + InflateWork::bytes(n)))) return r;
+    cudaStream_t s = ctx->stream;
+    uint8_t *base = (uint8_t *)ctx->d_scratch;
+    zb200_member *d_members = (zb200_member *)base;
+    zb200_member_result *d_results = (zb200_member_result *)(base + tbl);
+    void *d_work = base + tbl + rsl;
+    // pieces of >= 1 GiB of output: a piece's kernel cannot be shorter than its largest member's own
+    // decode (14 ms for 1 MiB), so small pieces would only queue those latencies one after the other
+    size_t target = out_bytes / 8 > ((size_t)1 << 30) ? out_bytes / 8 : ((size_t)1 << 30);
+    size_t first[10], np = 0;
+    first[0] = 0;
+    {
+        size_t acc = 0;
+        for (size_t i = 0; i < n; ++i) {
+            acc += members[i].out_cap;
+            if (acc >= target && i + 1 < n && np + 1 < 8) { first[++np] = i + 1; acc = 0; }
+        }
+        first[++np] = n;
+    }
+    cudaEvent_t ev_in[8], ev_out[8];
+    for (size_t k = 0; k < np; ++k) {
+        ZB_CUDA(cudaEventCreateWithFlags(&ev_in[k], cudaEventDisableTiming));
+        ZB_CUDA(cudaEventCreateWithFlags(&ev_out[k], cudaEventDisableTiming));
+    }
+    auto cleanup = [&]() { for (size_t k = 0; k < np; ++k) { cudaEventDestroy(ev_in[k]); cudaEventDestroy(ev_out[k]); } };
+    int rc = ZB200_OK;
+    if (cudaMemcpyAsync(d_members, members, n * sizeof(zb200_member), cudaMemcpyHostToDevice, s) != cudaSuccess) rc = ZB200_ERR_CUDA;
+    for (size_t k = 0; k < np && rc == ZB200_OK; ++k) {
+        const size_t lo = members[first[k]].in_off, hi = members[first[k + 1] - 1].in_off + members[first[k + 1] - 1].in_len;
+        if (cudaMemcpyAsync(ctx->d_io_in + lo, in + lo, hi - lo, cudaMemcpyHostToDevice, ctx->copy_stream) != cudaSuccess ||
+            cudaEventRecord(ev_in[k], ctx->copy_stream) != cudaSuccess) rc = ZB200_ERR_CUDA;
+    }
+    for (size_t k = 0; k < np && rc == ZB200_OK; ++k) {
+        cudaStreamWaitEvent(s, ev_in[k], 0);
+        rc = inflate_launch(ctx, ctx->d_io_in, ctx->d_io_out, d_members + first[k], first[k + 1] - first[k], wrap, verify,
+                            d_results + first[k], d_work, s);
+        if (rc == ZB200_OK && cudaEventRecord(ev_out[k], s) != cudaSuccess) rc = ZB200_ERR_CUDA;
+    }
+    for (size_t k = 0; k < np && rc == ZB200_OK; ++k) {
+        if (cudaEventSynchronize(ev_out[k]) != cudaSuccess) { rc = ZB200_ERR_CUDA; break; }
+        const size_t lo = members[first[k]].out_off, hi = members[first[k + 1] - 1].out_off + members[first[k + 1] - 1].out_cap;
+        if (cudaMemcpyAsync(out + lo, ctx->d_io_out + lo, hi - lo, cudaMemcpyDeviceToHost, ctx->back_stream) != cudaSuccess) rc = ZB200_ERR_CUDA;
+    }
+    if (rc == ZB200_OK && cudaMemcpyAsync(results, d_results, n * sizeof(zb200_member_result), cudaMemcpyDeviceToHost, s) != cudaSuccess) rc = ZB200_ERR_CUDA;
+    cudaStreamSynchronize(ctx->copy_stream);
+    cudaStreamSynchronize(s);
+    cudaStreamSynchronize(ctx->back_stream);
+    cleanup();
+    if (rc == ZB200_ERR_CUDA) set_error("inflate: pipelined transfer failed");
+    return rc;
+}
+
 int zb200_inflate_host(zb200_ctx *ctx, const void *in, void *out, const zb200_member *members,
                        size_t n_members, int wrap, int verify, zb200_member_result *results) {
     if (!ctx || !members || !results || wrap < 0 || wrap > 3) return ZB200_ERR_PARAM;
@@ -495,6 +555,16 @@ int zb200_inflate_host(zb200_ctx *ctx, const void *in, void *out, const zb200_me
     for (size_t i = 0; i < n_members; ++i) {
         if (members[i].in_off + members[i].in_len > in_bytes) in_bytes = members[i].in_off + members[i].in_len;
         if (members[i].out_off + members[i].out_cap > out_bytes) out_bytes = members[i].out_off + members[i].out_cap;
+    }
+    // the pipelined path: enough work, pinned data buffers, members in order, nothing to resume
+    if (n_members >= 64 && out_bytes >= ((size_t)1536 << 20) && is_pinned(in) && is_pinned(out)) {
+        bool ordered = true;
+        for (size_t i = 0; i < n_members && ordered; ++i) {
+            if (members[i].resume_bit) ordered = false;
+            if (i && (members[i].in_off < members[i - 1].in_off + members[i - 1].in_len ||
+                      members[i].out_off < members[i - 1].out_off + members[i - 1].out_cap)) ordered = false;
+        }
+        if (ordered) return inflate_host_pipelined(ctx, (const uint8_t *)in, (uint8_t *)out, members, n_members, wrap, verify, results, in_bytes, out_bytes);
     }
     const size_t tbl = align_up(n_members * sizeof(zb200_member), 256);
     const size_t rsl = align_up(n_members * sizeof(zb200_member_result), 256);
