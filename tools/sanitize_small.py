@@ -2,7 +2,9 @@
 and a lazy level, gzip members, inflate) for compute-sanitizer:
     compute-sanitizer --tool memcheck  python tools/sanitize_small.py
     compute-sanitizer --tool racecheck python tools/sanitize_small.py
-Inputs are a few hundred KiB so the instrumented run stays in the minutes."""
+Inputs are a few hundred KiB so the instrumented run stays in the minutes.
+(On the pool this was developed on compute-sanitizer is closed; the script then serves as a
+quick round-trip check of all legs.)"""
 import os
 import sys
 
