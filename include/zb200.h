@@ -158,6 +158,14 @@ int zb200_inflate_host(zb200_ctx *ctx, const void *in, void *out,
                        const zb200_member *members, size_t n_members, int wrap, int verify,
                        zb200_member_result *results);
 
+/* Self-test of the warp-parallel decode-table construction (csrc/zb_inflate_tables.cuh) against the
+ * serial one that follows inftrees.c:32-299: for each of n_cases sets of code lengths (lens: 320 bytes
+ * per case = nlen literal/length lengths followed by ndist distance lengths; counts: nlen, ndist per
+ * case) verdict[i] = 0 when both give the same status and, where accepted, identical tables.
+ * Host pointers; synchronous.  Used by tests/test_gpu_inflate.py. */
+int zb200_selftest_tables(zb200_ctx *ctx, const uint8_t *lens, const uint32_t *counts, size_t n_cases,
+                          uint32_t *verdict);
+
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif

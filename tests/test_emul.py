@@ -96,7 +96,7 @@ def _rounds_emul():
     u64 = C.c_uint64
     L.emul_inflate_rounds.argtypes = [C.c_void_p, u64, C.c_void_p, u64, C.c_int, C.c_int] + [C.POINTER(u64)] * 2 + \
         [C.POINTER(C.c_uint32)] * 2 + [C.POINTER(u64)] * 2 + [C.POINTER(C.c_int)]
-    L.emul_round_stats.argtypes = [C.POINTER(u64 * 6)]
+    L.emul_round_stats.argtypes = [C.POINTER(u64 * 7)]
 
     def run(data, wrap, cap, off=0, force_lg=-1):
         buf = C.create_string_buffer(len(data) + 8 + off)
@@ -109,9 +109,9 @@ def _rounds_emul():
         return st, dst.raw[:ol.value], iu.value, ck.value, isz.value
 
     def stats():
-        a = (u64 * 6)()
+        a = (u64 * 7)()
         L.emul_round_stats(C.byref(a))
-        return dict(zip(("rounds", "fix_passes", "fix_lane_runs", "serial_returns", "matches", "dep_matches"), a))
+        return dict(zip(("rounds", "fix_passes", "fix_lane_runs", "serial_returns", "matches", "dep_matches", "copy_passes"), a))
     return run, stats
 
 
@@ -127,7 +127,7 @@ def test_inflate_rounds(golden):
         d = refz.gen(400000, kind, seed=77 + kind)
         for lvl, strat, wrap, chunk in ((1, 0, 0, 0), (6, 0, 1, 100000), (9, 0, 2, 0), (6, 4, 0, 65536), (6, 2, 1, 0), (1, 3, 2, 0), (6, 1, 2, 0)):
             s = o.deflate_stream(d, lvl, strat, wrap, chunk)
-            for lg in (-1, 2, 3):
+            for lg in (-1, 2, 3, 1000, 1003):                      # 1000 + k: a team of 128 lanes, S forced to 32 << (k - 1)
                 st, out, iu, ck, isz = run(s, wrap, len(d) + rng.randrange(0, 4), off=rng.randrange(0, 8), force_lg=lg)
                 assert st == 0 and out == d and iu == len(s), (kind, lvl, strat, wrap, lg, msgs[st])
                 if wrap == 2:
@@ -154,7 +154,7 @@ def test_inflate_rounds(golden):
         where = rng.randrange(2, len(bad) - 4)
         bad[where] ^= 1 << rng.randrange(8)
         cap = len(d) + 64
-        a = run(bytes(bad), 1, cap)
+        a = run(bytes(bad), 1, cap, force_lg=1000 if trial % 2 else -1)
         b = serial(bytes(bad), 1, cap)
         assert a[0] == b[0] and a[2] == b[2], (trial, where, msgs[a[0]], msgs[b[0]])
         if a[0] == 0:

@@ -174,3 +174,101 @@ def test_pipelined_host_entry_point(ctx):
     finally:
         L.zb200_host_free(C.c_void_p(h_in))
         L.zb200_host_free(C.c_void_p(h_out))
+
+
+def _complete_lengths(rng, n_used, max_len):
+    """Code lengths of a random complete prefix code over n_used symbols (Kraft sum 1):
+    leaves are split at random until there are enough of them."""
+    leaves = [0]
+    while len(leaves) < n_used:
+        cand = [i for i, d in enumerate(leaves) if d < max_len]
+        i = rng.choice(cand) if rng.random() < 0.5 else max(cand, key=lambda k: -leaves[k] + rng.random())
+        d = leaves.pop(i)
+        leaves += [d + 1, d + 1]
+    rng.shuffle(leaves)
+    return leaves
+
+
+def _skewed_lengths(rng, n_used):
+    """Huffman lengths of Zipf-like frequencies; None when a code comes out longer than 15 bits."""
+    import heapq
+    a = rng.uniform(0.4, 1.6)
+    ranks = list(range(1, n_used + 1))
+    rng.shuffle(ranks)
+    f = sorted((1.0 / r ** a, i) for i, r in enumerate(ranks))
+    heap = [(w, i, None) for w, i in f]
+    heapq.heapify(heap)
+    k = n_used
+    while len(heap) > 1:
+        a, b = heapq.heappop(heap), heapq.heappop(heap)
+        heapq.heappush(heap, (a[0] + b[0], k, (a, b)))
+        k += 1
+    lens = [0] * n_used
+
+    def walk(node, d):
+        if node[2] is None:
+            lens[node[1]] = max(d, 1)
+        else:
+            walk(node[2][0], d + 1); walk(node[2][1], d + 1)
+    walk(heap[0], 0)
+    return lens if max(lens) <= 15 else None
+
+
+def test_warp_table_builder(ctx):
+    """csrc/zb_inflate_tables.cuh (every table entry finds its symbol) against the serial
+    construction that follows inftrees.c:32-299: same status, identical tables."""
+    import ctypes as C
+    rng = random.Random(11)
+    cases = []
+
+    def add(lit, dist):
+        assert 257 <= len(lit) <= 286 and 1 <= len(dist) <= 30
+        cases.append((list(lit), list(dist)))
+
+    def spread(lens, n, must=None):
+        out = [0] * n
+        where = rng.sample(range(n), len(lens))
+        if must is not None and must not in where:
+            where[0] = must
+        for w, l in zip(where, lens):
+            out[w] = l
+        return out
+
+    for _ in range(1500):
+        nlen, ndist = rng.randint(257, 286), rng.randint(1, 30)
+        nu = rng.randint(2, nlen)
+        lit = spread(_complete_lengths(rng, nu, 15), nlen, must=256)
+        du = rng.randint(1, ndist)
+        dist = spread(_complete_lengths(rng, du, 15), ndist) if du > 1 else spread([1], ndist)
+        add(lit, dist)
+    for _ in range(300):                                     # Huffman-shaped codes (the common case)
+        nlen, ndist = rng.randint(257, 286), rng.randint(2, 30)
+        lit = _skewed_lengths(rng, nlen) or spread(_complete_lengths(rng, nlen, 15), nlen)
+        dist = _skewed_lengths(rng, ndist) or spread(_complete_lengths(rng, ndist, 15), ndist)
+        add(lit, dist)
+    for _ in range(300):                                     # damaged: one length changed -> over-subscribed or incomplete
+        lit, dist = cases[rng.randrange(1500)]
+        lit, dist = list(lit), list(dist)
+        tgt = lit if rng.random() < 0.6 else dist
+        tgt[rng.randrange(len(tgt))] = rng.randint(0, 15)
+        add(lit, dist)
+    add([15] * 257 + [0] * 29, [0] * 30)                    # incomplete, no distance codes
+    add([0] * 256 + [1] + [0] * 29, [1])                    # the single one-bit codes inftrees.c:131-132 lets pass
+    add([0] * 256 + [1, 1], [0, 1])
+    add([0] * 256 + [2] + [0] * 29, [2])                    # single codes of two bits: rejected
+    add([8] * 144 + [9] * 112 + [7] * 24 + [8] * 6, [5] * 30)   # the fixed code's shape (286 / 30 symbols)
+    add([9] * 254 + [8] * 3 + [9] * 29, [1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 15])
+    add([1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 15] + [0] * 240 + [0] + [0] * 10, [1])   # 256 unused: still a table
+    n = len(cases)
+    lens = bytearray(n * 320)
+    counts = (C.c_uint32 * (2 * n))()
+    for i, (lit, dist) in enumerate(cases):
+        lens[i * 320:i * 320 + len(lit)] = bytes(lit)
+        lens[i * 320 + len(lit):i * 320 + len(lit) + len(dist)] = bytes(dist)
+        counts[2 * i], counts[2 * i + 1] = len(lit), len(dist)
+    verdict = (C.c_uint32 * n)()
+    buf = (C.c_uint8 * len(lens)).from_buffer(lens)
+    r = zb.lib().zb200_selftest_tables(ctx.handle, C.addressof(buf), C.addressof(counts), n, C.addressof(verdict))
+    assert r == 0, zb.last_error()
+    bad = [(i, hex(v)) for i, v in enumerate(verdict) if v]
+    assert not bad, (len(bad), bad[:10], [cases[i] for i, _ in bad[:2]])

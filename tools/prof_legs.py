@@ -21,7 +21,7 @@ ctx = zb.Context(0)
 stream = torch.cuda.Stream()
 torch.cuda.set_stream(stream)
 sp = C.c_void_p(stream.cuda_stream)
-CH = 262144
+CH = int(os.environ.get("ZB_CH", 262144))
 
 
 def timed(fn, reps=2):

@@ -74,6 +74,7 @@ ABI = {
     "zb200_inflate_msg": (C.c_char_p, _i),
     "zb200_inflate_dev": (_i, _vp, _vp, _vp, _vp, _sz, _i, _i, _vp, _vp),
     "zb200_inflate_host": (_i, _vp, _vp, _vp, _vp, _sz, _i, _i, _vp),
+    "zb200_selftest_tables": (_i, _vp, _vp, _vp, _sz, _vp),
 }
 
 

@@ -12,6 +12,7 @@
 #include "zb_internal.h"
 #include "zb_inflate.cuh"
 #include "zb_inflate_round.cuh"
+#include "zb_inflate_tables.cuh"
 #include <string.h>
 #include <stdlib.h>
 
@@ -39,7 +40,7 @@ struct InflateWarpShared {
     uint32_t lit[kLitEntries];
     uint32_t dist[kDistEntries];
     union {
-        struct { uint16_t work[320]; uint8_t lens[320]; QueuedMatch q[kQueue]; } serial;
+        struct { uint16_t work[320]; uint8_t lens[320]; QueuedMatch q[kQueue]; TableScratch tb; } serial;
         RoundShared rnd;
     };
 };
@@ -119,10 +120,32 @@ __device__ __forceinline__ void copy_own(uint8_t *d, const uint8_t *s, uint32_t 
     }
 }
 
-// Execute the `count` matches of a round, parked in stream order, in waves of 32:
-// a match whose source ends before the wave's first destination cannot depend on a
-// wave-mate and is copied by its own lane (all such copies overlap); the others
-// follow in order, striped over the warp (byte-serial semantics, inffast.c:249-260).
+// Execute the `count` matches of a round, parked in stream order, in waves of 32.  Only
+// match destinations are holes (the literals are stored already), and they ascend: a match
+// whose source — [dst - dist, dst - dist + min(len, dist)) — ends before the wave's first
+// destination cannot depend on a wave-mate and is copied by its own lane at once (all such
+// copies overlap).  The rest (2-8 %) know which earlier wave-mates' destinations their source
+// touches (a bit set, built against the dependent ones only: the others are done by then)
+// and go in passes: whoever has no unfinished wave-mate in its set copies, so a pass costs
+// one L2 round trip however many matches it carries; chains (runs) take a pass per link.
+// A lane copies its match alone when 16-byte load-then-store steps reproduce the byte-serial
+// semantics of inffast.c:249-260 (dist >= len, or dist >= 16); short periods are striped
+// over the warp, one match at a time.
+__device__ __forceinline__ void copy_striped(uint8_t *d, uint32_t mdist, uint32_t mlen, uint32_t lane) {
+    const uint8_t *s = d - mdist;
+    for (uint32_t i = lane; i < mlen; i += 32) d[i] = s[i % mdist];
+}
+__device__ __forceinline__ void copy_ready(uint8_t *dst, bool ready, uint32_t edst, uint32_t len, uint32_t dist, uint32_t lane) {
+    const unsigned full = 0xffffffffu;
+    const bool simple = dist >= len || dist >= 16;
+    if (ready && simple) copy_own(dst + edst, dst + edst - dist, len);
+    uint32_t pm = __ballot_sync(full, ready && !simple);
+    while (pm) {
+        const int j = __ffs(pm) - 1;
+        pm &= pm - 1;
+        copy_striped(dst + __shfl_sync(full, edst, j), __shfl_sync(full, dist, j), __shfl_sync(full, len, j), lane);
+    }
+}
 __device__ __forceinline__ void exec_round_queue(uint8_t *dst, const QueuedMatch *__restrict__ q, uint32_t count) {
     const unsigned full = 0xffffffffu;
     const uint32_t lane = threadIdx.x & 31;
@@ -135,19 +158,21 @@ __device__ __forceinline__ void exec_round_queue(uint8_t *dst, const QueuedMatch
         if (base + 32 + lane < count) nxt = q[base + 32 + lane];   // the next wave's entries travel while this one is copied
         const uint32_t first = __shfl_sync(full, e.dst, 0);
         const uint32_t len = qm_len(e.packed), dist = qm_dist(e.packed);
-        const bool dep = mine && (dist < len || e.dst - dist + len > first);
-        if (mine && !dep) copy_own(dst + e.dst, dst + e.dst - dist, len);
-        uint32_t depmask = __ballot_sync(full, dep);
+        const uint32_t srcb = e.dst - dist, srce = srcb + (len < dist ? len : dist);
+        const bool dep = mine && srce > first;
+        copy_ready(dst, mine && !dep, e.dst, len, dist, lane);
+        uint32_t undone = __ballot_sync(full, dep);
+        uint32_t waits = 0;                                          // dependent wave-mates whose destination my source touches
+        for (uint32_t m = undone; m; m &= m - 1) {
+            const uint32_t j = (uint32_t)__ffs(m) - 1u;
+            const uint32_t dj = __shfl_sync(full, e.dst, j), lj = __shfl_sync(full, len, j);
+            if (dep && j < lane && dj < srce && dj + lj > srcb) waits |= 1u << j;
+        }
         __syncwarp(full);
-        while (depmask) {
-            const int j = __ffs(depmask) - 1;
-            depmask &= depmask - 1;
-            const uint32_t md = __shfl_sync(full, e.dst, j), mp = __shfl_sync(full, e.packed, j);
-            const uint32_t mdist = qm_dist(mp), mlen = qm_len(mp);
-            uint8_t *d = dst + md;
-            const uint8_t *s = d - mdist;
-            if (mdist >= mlen) { for (uint32_t i = lane; i < mlen; i += 32) d[i] = s[i]; }
-            else { for (uint32_t i = lane; i < mlen; i += 32) d[i] = s[i % mdist]; }
+        while (undone) {
+            const bool ready = ((undone >> lane) & 1u) && !(waits & undone);
+            copy_ready(dst, ready, e.dst, len, dist, lane);
+            undone &= ~__ballot_sync(full, ready);
             __syncwarp(full);
         }
     }
@@ -155,10 +180,10 @@ __device__ __forceinline__ void exec_round_queue(uint8_t *dst, const QueuedMatch
 
 // Fetch a round's rows into shared memory with cp.async (4-byte copies, zero-filled
 // past the end of the member's input): row i = words [W0 + i*W, W0 + i*W + W + 3).
-template <int LG>
+template <int LG, int NL>
 __device__ __forceinline__ void stage_fetch_lg(uint32_t *stage, const uint32_t *__restrict__ words, uint64_t W0, uint64_t nwords, uint32_t lane) {
-    constexpr uint32_t W = 1u << LG, stride = W + kRowExtra, total = 32 * stride;
-    for (uint32_t k = lane; k < total; k += 32) {
+    constexpr uint32_t W = 1u << LG, stride = W + kRowExtra, total = NL * stride;
+    for (uint32_t k = lane; k < total; k += NL) {
         const uint32_t row = k / stride, col = k - row * stride;
         const uint64_t w = W0 + row * W + col;
         const uint32_t sa = (uint32_t)__cvta_generic_to_shared(stage + k);
@@ -168,12 +193,13 @@ __device__ __forceinline__ void stage_fetch_lg(uint32_t *stage, const uint32_t *
     }
     asm volatile("cp.async.commit_group;\n" ::: "memory");
 }
+template <int NL>                                       // NL threads fetch the rows of NL lanes
 __device__ __forceinline__ void stage_fetch(uint32_t *stage, const uint32_t *words, uint64_t W0, uint64_t nwords, int lg, uint32_t lane) {
     switch (lg) {
-        case 2: stage_fetch_lg<2>(stage, words, W0, nwords, lane); break;
-        case 3: stage_fetch_lg<3>(stage, words, W0, nwords, lane); break;
-        case 4: stage_fetch_lg<4>(stage, words, W0, nwords, lane); break;
-        default: stage_fetch_lg<5>(stage, words, W0, nwords, lane); break;
+        case 2: stage_fetch_lg<2, NL>(stage, words, W0, nwords, lane); break;
+        case 3: stage_fetch_lg<3, NL>(stage, words, W0, nwords, lane); break;
+        case 4: stage_fetch_lg<4, NL>(stage, words, W0, nwords, lane); break;
+        default: stage_fetch_lg<5, NL>(stage, words, W0, nwords, lane); break;
     }
 }
 __device__ __forceinline__ void stage_wait() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
@@ -205,7 +231,7 @@ huff_rounds_warp(const uint8_t *src, uint64_t in_len, uint8_t *dst, uint64_t out
         const uint64_t W0 = B >> 5;
         const uint32_t *stage = rs.stage;
         __syncwarp(full);                                            // every lane is done with the previous round's rows
-        stage_fetch(rs.stage, words, W0, nwords, lg, lane);
+        stage_fetch<32>(rs.stage, words, W0, nwords, lg, lane);
         stage_wait();
         __syncwarp(full);
         RoundLane r;
@@ -288,6 +314,7 @@ inflate_kernel(const uint8_t *__restrict__ in, uint8_t *out, const zb200_member 
                     sh.fixed_lit, sh.fixed_dist, &sh.fmt);   // queue entries hold 32-bit output offsets
             st.bind(sh.w[warp].lit, sh.w[warp].dist, sh.w[warp].serial.work, sh.w[warp].serial.lens);
             st.huff_external = kWarpParallelHuffman ? 1 : 0;
+            st.tables_external = 1;
             if (mb.resume_bit) st.resume(mb.resume_bit, mb.resume_out, wrap);
             else hs = st.parse_header(wrap);
             if (hs) st.status = hs;
@@ -298,10 +325,19 @@ inflate_kernel(const uint8_t *__restrict__ in, uint8_t *out, const zb200_member 
             InflateEvent ev;
             ev.kind = EV_DONE; ev.len = 0; ev.dist = 0; ev.src = 0; ev.dst = 0;
             if (lane == 0) ev = st.run_batch(q);
-            const uint32_t kind = __shfl_sync(full, ev.kind, 0);
+            uint32_t kind = __shfl_sync(full, ev.kind, 0);
             if (kind == EV_DONE) break;
-            const uint32_t len = __shfl_sync(full, ev.len, 0);
+            uint32_t len = __shfl_sync(full, ev.len, 0);
             __syncwarp(full);                                  // lane 0's literal stores and queue writes -> visible
+            if (kind == EV_TABLES) {                           // a dynamic header's lengths are in: the warp builds both tables
+                const int ts = build_dynamic_tables_warp(sh.w[warp].serial.lens, (int)len, (int)__shfl_sync(full, ev.dist, 0),
+                                                         sh.w[warp].lit, sh.w[warp].dist, sh.w[warp].serial.work,
+                                                         sh.w[warp].serial.tb, sh.fmt, (uint32_t)lane);
+                if (lane == 0) ev = st.tables_done(ts);
+                kind = __shfl_sync(full, ev.kind, 0);
+                if (kind == EV_DONE) break;
+                len = 0;
+            }
             if (kWarpParallelHuffman && kind == EV_HUFF) {     // a Huffman block: all 32 lanes decode it
                 const uint64_t bp = __shfl_sync(full, ev.src, 0), op = __shfl_sync(full, ev.dst, 0);
                 const uint32_t *lt = len ? sh.fixed_lit : sh.w[warp].lit;
@@ -335,6 +371,314 @@ inflate_kernel(const uint8_t *__restrict__ in, uint8_t *out, const zb200_member 
             seg_off[m] = mb.out_off;
             seg_len[m] = st.status == ZB200_INF_OK ? st.pos : 0;
         }
+    }
+}
+
+// ---- one member across a TEAM of four warps ---------------------------------------------
+// With few members in the batch a member's own latency is what counts (72 MB/s per warp: 14 ms
+// per MiB).  The rounds do not care how many lanes share them: a team runs them with 128
+// subsequences — the fix-up chain and the scans cross the warps through shared memory, the
+// copy waves are 128 matches wide — while thread 0 remains the serial skeleton.  Tails too
+// short for a team round go to warp 0's 32-lane rounds, oddities to the serial path as ever.
+constexpr int kTeamWarps = 4, kTeamLanes = kTeamWarps * 32, kTeamCtasPerSm = 4, kTeamLgDefault = 4;
+struct TeamShared {
+    uint32_t lit[kLitEntries];
+    uint32_t dist[kDistEntries];
+    union {
+        struct { uint16_t work[320]; uint8_t lens[320]; QueuedMatch q[kQueue]; TableScratch tb; } serial;
+        RoundSharedT<kTeamLanes> rnd;
+        RoundShared rnd1;                                    // warp 0's rounds over a tail
+    };
+    uint32_t fixed_lit[512];
+    uint32_t fixed_dist[64];
+    FormatTables fmt;
+    uint32_t x_end[kTeamLanes], x_stop[kTeamLanes];          // the fix-up chain across warps
+    uint32_t x_wfirst[kTeamWarps], x_wsum_o[kTeamWarps], x_wsum_m[kTeamWarps], x_dep[2][kTeamWarps];
+    QueuedMatch x_q[kTeamLanes];                             // the copy wave in flight
+    InflateEvent ev;
+    int hs;
+    unsigned int member;
+};
+
+// The copy waves of exec_round_queue, 128 matches wide: the wave and the sets of unfinished
+// matches live in shared memory, a pass ends at a block barrier.
+__device__ __forceinline__ void exec_team_queue(uint8_t *dst, const QueuedMatch *__restrict__ q, uint32_t count, TeamShared &ts) {
+    const unsigned full = 0xffffffffu;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (uint32_t base = 0; base < count; base += kTeamLanes) {
+        const bool mine = base + tid < count;
+        QueuedMatch e;
+        e.dst = 0; e.packed = 0;
+        if (mine) e = q[base + tid];
+        const uint32_t first = q[base].dst;                  // same address in every thread: one transaction
+        const uint32_t len = qm_len(e.packed), dist = qm_dist(e.packed);
+        const uint32_t srcb = e.dst - dist, srce = srcb + (len < dist ? len : dist);
+        const bool dep = mine && srce > first;
+        ts.x_q[tid] = e;
+        const uint32_t dm = __ballot_sync(full, dep);
+        if (lane == 0) ts.x_dep[0][warp] = dm;
+        copy_ready(dst, mine && !dep, e.dst, len, dist, lane);
+        __syncthreads();                                     // independent copies done and visible, wave published
+        uint32_t waits[kTeamWarps];
+#pragma unroll
+        for (int w = 0; w < kTeamWarps; ++w) waits[w] = 0;
+        if (dep) {
+#pragma unroll
+            for (int w = 0; w < kTeamWarps; ++w) {
+                uint32_t m = ts.x_dep[0][w];
+                if ((uint32_t)w > warp) m = 0;
+                else if ((uint32_t)w == warp) m &= (1u << lane) - 1u;
+                for (; m; m &= m - 1) {
+                    const uint32_t j = (uint32_t)__ffs(m) - 1u;
+                    const QueuedMatch o = ts.x_q[w * 32 + j];
+                    if (o.dst < srce && o.dst + qm_len(o.packed) > srcb) waits[w] |= 1u << j;
+                }
+            }
+        }
+        uint32_t mine_undone = dm;                           // my warp's share of the unfinished set
+        for (int p = 0; __syncthreads_or(mine_undone != 0); p ^= 1) {
+            uint32_t blocked = 0;
+#pragma unroll
+            for (int w = 0; w < kTeamWarps; ++w) blocked |= waits[w] & ts.x_dep[p][w];
+            const bool ready = ((mine_undone >> lane) & 1u) && !blocked;
+            copy_ready(dst, ready, e.dst, len, dist, lane);
+            mine_undone &= ~__ballot_sync(full, ready);
+            if (lane == 0) ts.x_dep[p ^ 1][warp] = mine_undone;
+        }
+    }
+}
+
+__device__ __forceinline__ HuffResult
+huff_rounds_team(const uint8_t *src, uint64_t in_len, uint8_t *dst, uint64_t out_cap, uint64_t bitpos, uint64_t pos,
+                 const uint32_t *__restrict__ lt, const uint32_t *__restrict__ dt, TeamShared &ts, QueuedMatch *gq, int team_lg_cap) {
+    const unsigned full = 0xffffffffu;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    RoundSharedT<kTeamLanes> &rs = ts.rnd;
+    const uintptr_t a0 = reinterpret_cast<uintptr_t>(src) & ~(uintptr_t)3;
+    const uint32_t bias = (uint32_t)(reinterpret_cast<uintptr_t>(src) & 3) * 8;
+    const uint32_t *words = reinterpret_cast<const uint32_t *>(a0);
+    const uint64_t total_bits = bias + in_len * 8;
+    const uint64_t nwords = (total_bits + 31) >> 5;
+    HuffResult res;
+    res.status = 1; res.bitpos = bitpos; res.pos = pos;
+    uint64_t B = bias + bitpos;
+    if (B >= total_bits) return res;
+    int lg = round_pick_lg(total_bits - B, kTeamLanes), lg_cap = team_lg_cap;
+    if (lg < 0) return res;
+    if (lg > lg_cap) lg = lg_cap;
+    for (;;) {
+        res.status = 1; res.bitpos = bitpos; res.pos = pos;
+        const uint32_t S = 32u << lg;
+        const uint64_t W0 = B >> 5;
+        __syncthreads();                                             // every thread is done with the previous round's rows
+        stage_fetch<kTeamLanes>(rs.stage, words, W0, nwords, lg, tid);
+        stage_wait();
+        __syncthreads();
+        RoundLane r;
+        round_speculate(r, tid, lg, tid ? 0u : (uint32_t)(B & 31u), rs.stage, rs, lt, dt);
+        uint32_t firststop;
+        for (;;) {                                                   // P2 across the team: until no start moves
+            ts.x_end[tid] = r.end; ts.x_stop[tid] = r.stop;
+            const uint32_t sm = __ballot_sync(full, r.stop != STOP_NONE);
+            if (lane == 0) ts.x_wfirst[warp] = sm ? warp * 32 + (uint32_t)__ffs(sm) - 1u : (uint32_t)kTeamLanes;
+            __syncthreads();
+            firststop = ts.x_wfirst[0];
+#pragma unroll
+            for (int w = 1; w < kTeamWarps; ++w) firststop = ts.x_wfirst[w] < firststop ? ts.x_wfirst[w] : firststop;
+            const uint32_t nvalid = firststop < (uint32_t)kTeamLanes ? firststop + 1u : (uint32_t)kTeamLanes;
+            const uint32_t t = tid ? ts.x_end[tid - 1] - S : 0u;
+            const bool need = tid > 0 && tid < nvalid && t != r.start;
+            if (!__syncthreads_or(need)) break;                      // (the barrier also orders these reads before the next writes)
+            if (need) round_fix(r, tid, lg, t, rs.stage, rs, lt, dt);
+        }
+        const uint32_t last = firststop < (uint32_t)kTeamLanes ? firststop : (uint32_t)kTeamLanes - 1u;
+        const uint32_t stop_l = ts.x_stop[last];
+        const uint64_t end_abs = W0 * 32 + (uint64_t)last * S + ts.x_end[last];
+        if (stop_l == STOP_BAD) return res;
+        if (end_abs > total_bits) return res;
+        const int next_lg = stop_l == STOP_NONE && end_abs < total_bits ? round_pick_lg(total_bits - end_abs, kTeamLanes) : -1;
+        const bool valid = tid <= last;
+        const uint32_t myout = valid ? r.out : 0u, mym = valid ? r.m : 0u;
+        uint32_t inc_o = myout, inc_m = mym;
+#pragma unroll
+        for (int dlt = 1; dlt < 32; dlt <<= 1) {
+            const uint32_t yo = __shfl_up_sync(full, inc_o, dlt), ym = __shfl_up_sync(full, inc_m, dlt);
+            if (lane >= (uint32_t)dlt) { inc_o += yo; inc_m += ym; }
+        }
+        if (lane == 31) { ts.x_wsum_o[warp] = inc_o; ts.x_wsum_m[warp] = inc_m; }
+        __syncthreads();
+        uint32_t before_o = 0, before_m = 0, tot_o = 0, tot_m = 0;
+#pragma unroll
+        for (uint32_t w = 0; w < (uint32_t)kTeamWarps; ++w) {
+            const uint32_t xo = ts.x_wsum_o[w], xm = ts.x_wsum_m[w];
+            if (w < warp) { before_o += xo; before_m += xm; }
+            tot_o += xo; tot_m += xm;
+        }
+        if (tot_m > kRoundQueueCap * kTeamWarps) {                   // runs: redo the round with shorter subsequences
+            lg_cap = lg >= kRoundLgMin + 2 ? lg - 2 : kRoundLgMin;
+            lg = lg_cap;
+            continue;
+        }
+        int err = tot_o > out_cap - pos;
+        if (!err && valid) err = round_emit(r, tid, lg, rs.stage, lt, dt, dst, (uint32_t)pos + before_o + inc_o - myout, gq, before_m + inc_m - mym);
+        if (__syncthreads_or(err != 0)) return res;                  // (the barrier also publishes literals and queue entries)
+        exec_team_queue(dst, gq, tot_m, ts);
+        pos += tot_o;
+        B = end_abs;
+        bitpos = B - bias;
+        res.bitpos = bitpos; res.pos = pos;
+        if (stop_l == STOP_EOB) { res.status = 0; return res; }
+        if (next_lg < 0) { res.status = 1; return res; }
+        lg = next_lg < lg_cap ? next_lg : lg_cap;
+    }
+}
+
+__global__ void __launch_bounds__(kTeamLanes, kTeamCtasPerSm)
+inflate_team_kernel(const uint8_t *__restrict__ in, uint8_t *out, const zb200_member *__restrict__ members,
+                    uint32_t n_members, int wrap, zb200_member_result *__restrict__ results,
+                    const InflateDeviceTables *__restrict__ tabs, unsigned int *__restrict__ counter,
+                    const uint32_t *__restrict__ order, uint64_t *__restrict__ seg_off, uint64_t *__restrict__ seg_len,
+                    QueuedMatch *__restrict__ round_queues, int team_lg_cap) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    TeamShared &ts = *reinterpret_cast<TeamShared *>(smem_raw);
+    {
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(tabs);
+        uint32_t *dst = ts.fixed_lit;
+        constexpr int words = (int)(sizeof(InflateDeviceTables) / 4);
+        for (int i = threadIdx.x; i < words; i += blockDim.x) dst[i] = src[i];
+    }
+    const uint32_t tid = threadIdx.x, warp = tid >> 5;
+    QueuedMatch *gq = round_queues + (size_t)blockIdx.x * kTeamWarps * kRoundQueueCap;
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) { unsigned int m = atomicAdd(counter, 1u); ts.member = m < n_members ? order[m] : 0xffffffffu; }
+        __syncthreads();
+        const unsigned int m = ts.member;
+        if (m == 0xffffffffu) break;
+        const zb200_member mb = members[m];
+        const uint8_t *src = in + mb.in_off;
+        uint8_t *dst = out + mb.out_off;
+        const uint64_t cap = mb.out_cap < 0xfffffff0ull ? mb.out_cap : 0xfffffff0ull;
+        InflateState st;
+        if (tid == 0) {
+            int hs = ZB200_INF_OK;
+            st.init(src, mb.in_len, dst, cap, nullptr, ts.fixed_lit, ts.fixed_dist, &ts.fmt);
+            st.bind(ts.lit, ts.dist, ts.serial.work, ts.serial.lens);
+            st.huff_external = 1;
+            st.tables_external = 1;
+            if (mb.resume_bit) st.resume(mb.resume_bit, mb.resume_out, wrap);
+            else hs = st.parse_header(wrap);
+            if (hs) st.status = hs;
+            ts.hs = hs;
+        }
+        __syncthreads();
+        const int hs = ts.hs;
+        while (hs == ZB200_INF_OK) {
+            if (tid == 0) ts.ev = st.run_batch(ts.serial.q);
+            __syncthreads();
+            if (ts.ev.kind == EV_TABLES) {                         // a dynamic header's lengths are in: warp 0 builds both tables
+                __syncthreads();                                   // (everybody has seen the event's kind)
+                if (warp == 0) {
+                    const int bs = build_dynamic_tables_warp(ts.serial.lens, (int)ts.ev.len, (int)ts.ev.dist, ts.lit, ts.dist,
+                                                             ts.serial.work, ts.serial.tb, ts.fmt, tid);
+                    __syncwarp(0xffffffffu);                       // every lane has read the event
+                    if (tid == 0) ts.ev = st.tables_done(bs);
+                }
+                __syncthreads();
+            }
+            const InflateEvent ev = ts.ev;
+            __syncthreads();                                       // everybody has the event before thread 0 writes the next
+            if (ev.kind == EV_DONE) break;
+            if (ev.kind == EV_HUFF) {
+                const uint32_t *lt = ev.len ? ts.fixed_lit : ts.lit;
+                const uint32_t *dt = ev.len ? ts.fixed_dist : ts.dist;
+                HuffResult hr = huff_rounds_team(src, mb.in_len, dst, cap, ev.src, ev.dst, lt, dt, ts, gq, team_lg_cap);
+                __syncthreads();
+                if (hr.status == 1 && warp == 0) hr = huff_rounds_warp(src, mb.in_len, dst, cap, hr.bitpos, hr.pos, lt, dt, ts.rnd1, gq);
+                if (tid == 0) st.seek(hr.bitpos, hr.pos, hr.status);   // status 1: the serial path finishes the block
+                __syncthreads();
+            } else if (ev.kind == EV_BATCH) {
+                if (warp == 0) exec_queue(dst, ts.serial.q, ev.len);
+                __syncthreads();
+            } else {                                               // stored block: input -> output
+                const uint8_t *s = src + ev.src;
+                uint8_t *d = dst + ev.dst;
+                for (uint32_t i = tid; i < ev.len; i += kTeamLanes) d[i] = s[i];
+                __syncthreads();
+            }
+        }
+        if (tid == 0) {
+            zb200_member_result r;
+            r.status = st.status;
+            r.wrap_kind = (uint32_t)st.wrap_kind;
+            r.check = st.stored_check;
+            r.isize = st.stored_isize;
+            r.out_len = st.pos;
+            r.in_used = st.in_used;
+            r.resume_bit = st.ck_bit;
+            r.resume_out = st.ck_out;
+            results[m] = r;
+            seg_off[m] = mb.out_off;
+            seg_len[m] = st.status == ZB200_INF_OK ? st.pos : 0;
+        }
+    }
+}
+
+// ---- self-test of the warp table builder (zb_inflate_tables.cuh) --------------------------
+// One warp per case: lane 0 builds both tables of a set of code lengths the serial way
+// (build_decode_table + read_dynamic's acceptance rules), the warp builds them again, and
+// the two are compared entry by entry over tables pre-filled with one sentinel.
+// verdict: 0 equal, 1 status differs, 2 literal/length table differs, 3 distance table differs
+// (| first differing index << 8).
+__global__ void __launch_bounds__(32)
+tables_selftest_kernel(const uint8_t *__restrict__ lens_all, const uint32_t *__restrict__ counts, uint32_t ncases,
+                       const InflateDeviceTables *__restrict__ tabs, uint32_t *__restrict__ verdict) {
+    __shared__ uint32_t a_lit[kLitEntries], a_dist[kDistEntries], b_lit[kLitEntries], b_dist[kDistEntries];
+    __shared__ uint16_t work[320];
+    __shared__ uint8_t lens[320];
+    __shared__ TableScratch tb;
+    __shared__ FormatTables fmt;
+    __shared__ int st_a;
+    const uint32_t lane = threadIdx.x;
+    const unsigned full = 0xffffffffu;
+    for (uint32_t i = lane; i < sizeof(FormatTables) / 4; i += 32)
+        reinterpret_cast<uint32_t *>(&fmt)[i] = reinterpret_cast<const uint32_t *>(&tabs->fmt)[i];
+    for (uint32_t c = blockIdx.x; c < ncases; c += gridDim.x) {
+        __syncwarp(full);
+        const int nlen = (int)counts[2 * c], ndist = (int)counts[2 * c + 1];
+        for (uint32_t i = lane; i < 320; i += 32) lens[i] = lens_all[(size_t)c * 320 + i];
+        for (uint32_t i = lane; i < (uint32_t)kLitEntries; i += 32) a_lit[i] = b_lit[i] = 0xdeadbeefu;
+        for (uint32_t i = lane; i < (uint32_t)kDistEntries; i += 32) a_dist[i] = b_dist[i] = 0xdeadbeefu;
+        __syncwarp(full);
+        if (lane == 0) {
+            int st = ZB200_INF_OK;
+            int r = build_decode_table(TBL_LITLEN, lens, nlen, a_lit, kLitEntries, kLitRoot, work, fmt);
+            if (r == 1) { int nz = 0, ones = 0; for (int i = 0; i < nlen; ++i) { nz += lens[i] != 0; ones += lens[i] == 1; } if (!(nz == 1 && ones == 1)) r = -1; }
+            if (r < 0) st = ZB200_INF_LITLEN_SET;
+            else {
+                r = build_decode_table(TBL_DIST, lens + nlen, ndist, a_dist, kDistEntries, kDistRoot, work, fmt);
+                if (r == 1) { int nz = 0, ones = 0; for (int i = 0; i < ndist; ++i) { nz += lens[nlen + i] != 0; ones += lens[nlen + i] == 1; } if (!(nz == 1 && ones == 1)) r = -1; }
+                if (r < 0) st = ZB200_INF_DIST_SET;
+            }
+            st_a = st;
+        }
+        __syncwarp(full);
+        const int st_b = build_dynamic_tables_warp(lens, nlen, ndist, b_lit, b_dist, work, tb, fmt, lane);
+        __syncwarp(full);
+        uint32_t v = 0;
+        if (st_a != st_b) v = 1;
+        else if (st_a == ZB200_INF_OK) {
+            uint32_t bad = 0xffffffffu;
+            for (uint32_t i = lane; i < (uint32_t)kLitEntries; i += 32) if (a_lit[i] != b_lit[i] && i < bad) bad = i;
+            for (int d = 16; d; d >>= 1) { const uint32_t o = __shfl_xor_sync(full, bad, d); bad = o < bad ? o : bad; }
+            if (bad != 0xffffffffu) v = 2 | (bad << 8);
+            else {
+                for (uint32_t i = lane; i < (uint32_t)kDistEntries; i += 32) if (a_dist[i] != b_dist[i] && i < bad) bad = i;
+                for (int d = 16; d; d >>= 1) { const uint32_t o = __shfl_xor_sync(full, bad, d); bad = o < bad ? o : bad; }
+                if (bad != 0xffffffffu) v = 3 | (bad << 8);
+            }
+        }
+        if (lane == 0) verdict[c] = v;
     }
 }
 
@@ -399,6 +743,7 @@ int inflate_init(zb200_ctx *ctx) {
     ZB_CUDA(cudaMemcpy(d, &h, sizeof h, cudaMemcpyHostToDevice));
     ctx->d_inflate_tables = d;
     ZB_CUDA(cudaFuncSetAttribute(inflate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(InflateShared)));
+    ZB_CUDA(cudaFuncSetAttribute(inflate_team_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TeamShared)));
     return ZB200_OK;
 }
 
@@ -407,7 +752,8 @@ static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 // scratch layout for one call
 struct InflateWork {
     unsigned int *counter; uint64_t *seg_off, *seg_len; uint32_t *crc, *adler, *order; CkAccum *acc; QueuedMatch *queues;
-    static size_t grid_warps(size_t n) { return n < kMaxGridWarps ? (n + kInfWarps - 1) / kInfWarps * kInfWarps : kMaxGridWarps; }
+    // warps that may own a queue: one per member, or four when few members run as teams
+    static size_t grid_warps(size_t n) { return 4 * n < kMaxGridWarps ? 4 * n : kMaxGridWarps; }
     static size_t bytes(size_t n) {
         return 256 + align_up(n * 8, 256) * 2 + align_up(n * 4, 256) * 3 + align_up(n * sizeof(CkAccum), 256) +
                grid_warps(n) * kRoundQueueCap * sizeof(QueuedMatch);
@@ -435,14 +781,30 @@ int inflate_launch(zb200_ctx *ctx, const uint8_t *d_in, uint8_t *d_out, const zb
     inflate_order_kernel<<<1, 1024, 0, s>>>(d_members, (uint32_t)n, w.order);
     ZB_LAUNCHED();
     ZB_CHECK_LAUNCH();
-    size_t ctas = (n + kInfWarps - 1) / kInfWarps;
-    static const int per_sm_knob = [] { const char *e = getenv("ZB200_INF_CTAS_PER_SM"); return e ? atoi(e) : 0; }();   // profiling knob
-    size_t cap = (size_t)ctx->sm_count * (per_sm_knob > 0 && per_sm_knob < kInfCtasPerSm ? per_sm_knob : kInfCtasPerSm);
-    if (cap * kInfWarps > kMaxGridWarps) cap = kMaxGridWarps / kInfWarps;
-    if (ctas > cap) ctas = cap;
-    inflate_kernel<<<(unsigned)ctas, kInfWarps * 32, sizeof(InflateShared), s>>>(
-        d_in, d_out, d_members, (uint32_t)n, wrap, d_results,
-        (const InflateDeviceTables *)ctx->d_inflate_tables, w.counter, w.order, w.seg_off, w.seg_len, w.queues);
+    // Few members: a team of four warps per member (a member's own latency is what counts);
+    // many: one warp per member (throughput).  $ZB200_INF_TEAM = 0 / 1 forces either.
+    static const int team_knob = [] { const char *e = getenv("ZB200_INF_TEAM"); return e ? atoi(e) : -1; }();
+    const bool team = team_knob >= 0 ? team_knob != 0 : n <= (size_t)ctx->sm_count * kTeamCtasPerSm;   // every member a resident team
+    if (team) {
+        size_t ctas = n;
+        const size_t cap = (size_t)ctx->sm_count * kTeamCtasPerSm;
+        if (ctas > cap) ctas = cap;
+        if (ctas * kTeamWarps > kMaxGridWarps) ctas = kMaxGridWarps / kTeamWarps;
+        static const int lg_knob = [] { const char *e = getenv("ZB200_INF_TEAM_LG"); return e ? atoi(e) : kTeamLgDefault; }();
+        const int team_lg = lg_knob < kRoundLgMin ? kRoundLgMin : lg_knob > kRoundLgMax ? kRoundLgMax : lg_knob;
+        inflate_team_kernel<<<(unsigned)ctas, kTeamLanes, sizeof(TeamShared), s>>>(
+            d_in, d_out, d_members, (uint32_t)n, wrap, d_results,
+            (const InflateDeviceTables *)ctx->d_inflate_tables, w.counter, w.order, w.seg_off, w.seg_len, w.queues, team_lg);
+    } else {
+        size_t ctas = (n + kInfWarps - 1) / kInfWarps;
+        static const int per_sm_knob = [] { const char *e = getenv("ZB200_INF_CTAS_PER_SM"); return e ? atoi(e) : 0; }();   // profiling knob
+        size_t cap = (size_t)ctx->sm_count * (per_sm_knob > 0 && per_sm_knob < kInfCtasPerSm ? per_sm_knob : kInfCtasPerSm);
+        if (cap * kInfWarps > kMaxGridWarps) cap = kMaxGridWarps / kInfWarps;
+        if (ctas > cap) ctas = cap;
+        inflate_kernel<<<(unsigned)ctas, kInfWarps * 32, sizeof(InflateShared), s>>>(
+            d_in, d_out, d_members, (uint32_t)n, wrap, d_results,
+            (const InflateDeviceTables *)ctx->d_inflate_tables, w.counter, w.order, w.seg_off, w.seg_len, w.queues);
+    }
     ZB_LAUNCHED();
     ZB_CHECK_LAUNCH();
     const int which = wrap == ZB200_WRAP_ZLIB ? ZB200_ADLER32 : wrap == ZB200_WRAP_AUTO ? (ZB200_CRC32 | ZB200_ADLER32) : ZB200_CRC32;
@@ -543,6 +905,30 @@ static int inflate_host_pipelined(zb200_ctx *ctx, const uint8_t *in, uint8_t *ou
     cleanup();
     if (rc == ZB200_ERR_CUDA) set_error("inflate: pipelined transfer failed");
     return rc;
+}
+
+int zb200_selftest_tables(zb200_ctx *ctx, const uint8_t *lens, const uint32_t *counts, size_t n_cases, uint32_t *verdict) {
+    if (!ctx || !lens || !counts || !verdict) return ZB200_ERR_PARAM;
+    if (n_cases == 0) return ZB200_OK;
+    for (size_t i = 0; i < n_cases; ++i)
+        if (counts[2 * i] < 257 || counts[2 * i] > 288 || counts[2 * i + 1] < 1 || counts[2 * i + 1] > 32) return ZB200_ERR_PARAM;
+    ZB_CUDA(cudaSetDevice(ctx->device));
+    std::lock_guard<std::mutex> g(ctx->mu);
+    const size_t lb = align_up(n_cases * 320, 256), cb = align_up(n_cases * 8, 256), vb = align_up(n_cases * 4, 256);
+    int r = ensure_scratch(ctx, lb + cb + vb);
+    if (r) return r;
+    cudaStream_t s = ctx->stream;
+    uint8_t *base = (uint8_t *)ctx->d_scratch;
+    ZB_CUDA(cudaMemcpyAsync(base, lens, n_cases * 320, cudaMemcpyHostToDevice, s));
+    ZB_CUDA(cudaMemcpyAsync(base + lb, counts, n_cases * 8, cudaMemcpyHostToDevice, s));
+    const unsigned grid = (unsigned)(n_cases < (size_t)ctx->sm_count * 16 ? n_cases : (size_t)ctx->sm_count * 16);
+    tables_selftest_kernel<<<grid, 32, 0, s>>>(base, (const uint32_t *)(base + lb), (uint32_t)n_cases,
+                                               (const InflateDeviceTables *)ctx->d_inflate_tables, (uint32_t *)(base + lb + cb));
+    ZB_LAUNCHED();
+    ZB_CHECK_LAUNCH();
+    ZB_CUDA(cudaMemcpyAsync(verdict, base + lb + cb, n_cases * 4, cudaMemcpyDeviceToHost, s));
+    ZB_CUDA(cudaStreamSynchronize(s));
+    return ZB200_OK;
 }
 
 int zb200_inflate_host(zb200_ctx *ctx, const void *in, void *out, const zb200_member *members,

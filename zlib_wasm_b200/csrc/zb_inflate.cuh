@@ -148,7 +148,7 @@ ZB_HD int build_decode_table(int type, const uint8_t *lens, int n, uint32_t *tab
 }
 
 // ---- events handed from lane 0 to the whole warp ---------------------------------
-enum : uint32_t { EV_MATCH = 1, EV_STORED = 2, EV_DONE = 3, EV_BATCH = 4, EV_HUFF = 5 };
+enum : uint32_t { EV_MATCH = 1, EV_STORED = 2, EV_DONE = 3, EV_BATCH = 4, EV_HUFF = 5, EV_TABLES = 6 };
 struct InflateEvent {
     uint32_t kind;
     uint32_t len;        // match length / stored byte count
@@ -168,6 +168,7 @@ struct InflateState {
     int last; int in_block;                                // in_block: 1 = Huffman block open
     const uint32_t *lt, *dt;                               // tables of the open block
     int wrap_kind;                                         // 0 raw, 1 zlib, 2 gzip (resolved)
+    int dyn_nlen, dyn_ndist;                               // symbol counts of the dynamic header just read
     int status;
     uint64_t ck_bit, ck_out;                               // last block boundary (resume point)
     uint32_t stored_check, stored_isize;                   // trailer values
@@ -178,6 +179,9 @@ struct InflateState {
     const FormatTables *fmt;
     InflateEvent parked; int has_parked;                   // event held back until the queue has been executed
     int huff_external;                                     // 1: hand Huffman blocks to the caller (EV_HUFF) instead of decoding them here
+    int tables_external;                                   // 1: a dynamic header's code lengths are read here, its two decode tables
+                                                           //    are built by the caller (EV_TABLES: len = nlen, dist = ndist), who
+                                                           //    reports back through tables_done()
 
     ZB_HD void refill() {
         while (bits <= 32) {
@@ -209,7 +213,7 @@ struct InflateState {
         in = src; in_len = n; next = 0; hold = 0; bits = 0;
         out = dst; out_cap = cap; pos = 0; last = 0; in_block = 0; lt = dt = nullptr;
         wrap_kind = 0; status = ZB200_INF_OK; ck_bit = 0; ck_out = 0; stored_check = 0; stored_isize = 0;
-        in_used = 0; fixed_lit = flit; fixed_dist = fdist; fmt = f; has_parked = 0; huff_external = 0;
+        in_used = 0; fixed_lit = flit; fixed_dist = fdist; fmt = f; has_parked = 0; huff_external = 0; tables_external = 0;
         if (s) { tlit = s->lit; tdist = s->dist; work = s->work; lens = s->lens; }
         else { tlit = tdist = nullptr; work = nullptr; lens = nullptr; }
     }
@@ -315,6 +319,7 @@ struct InflateState {
             while (rep--) lens[have++] = val;
         }
         if (lens[256] == 0) return ZB200_INF_NO_EOB;
+        if (tables_external) { dyn_nlen = nlen; dyn_ndist = ndist; return ZB200_INF_OK; }
         r = build_decode_table(TBL_LITLEN, lens, nlen, tlit, kLitEntries, kLitRoot, work, *fmt);
         if (r < 0) return ZB200_INF_LITLEN_SET;
         if (r == 1) {                                  // inftrees.c:131-132: incomplete only if a single 1-bit code
@@ -331,6 +336,16 @@ struct InflateState {
         }
         lt = tlit; dt = tdist;
         return ZB200_INF_OK;
+    }
+
+    // The caller has built the tables of the dynamic block announced by EV_TABLES (st = the
+    // status the serial construction would have returned): the block opens, or the member ends.
+    ZB_HD InflateEvent tables_done(int st) {
+        if (st) return done(st);
+        lt = tlit; dt = tdist;
+        in_block = 1;
+        InflateEvent ev; ev.kind = EV_HUFF; ev.len = 0; ev.dist = 0; ev.src = bitpos(); ev.dst = pos;
+        return ev;
     }
 
     ZB_HD InflateEvent done(int st) {
@@ -388,6 +403,10 @@ struct InflateState {
                 } else if (type == 2) {
                     const int st = read_dynamic();
                     if (st) return done(st);
+                    if (tables_external) {
+                        InflateEvent ev; ev.kind = EV_TABLES; ev.len = (uint32_t)dyn_nlen; ev.dist = (uint32_t)dyn_ndist; ev.src = 0; ev.dst = pos;
+                        return ev;
+                    }
                 } else {
                     return done(ZB200_INF_BLOCK_TYPE);
                 }

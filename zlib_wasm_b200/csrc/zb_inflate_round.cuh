@@ -41,7 +41,6 @@ namespace zb {
 constexpr int kRoundLgMin = 2, kRoundLgMax = 5;              // words per lane = 1 << lg  (S = 128 .. 1024 bits)
 constexpr int kRoundWordsMax = 1 << kRoundLgMax;
 constexpr int kRowExtra = 3;                                 // words of the following subsequence repeated at the end of a row
-constexpr int kStageWords = 32 * (kRoundWordsMax + kRowExtra);
 // Matches a round may park.  The worst case is 32 * S / 2 (a match costs at least 2 bits); text
 // parks ~1500.  A round that would park more is left to the serial path like any other oddity.
 constexpr uint32_t kRoundQueueCap = 6144;
@@ -56,11 +55,15 @@ constexpr uint32_t kRoundQueueCap = 6144;
 // output / match counts accumulated before that unit.
 constexpr int kRoundDwordsMax = kRoundWordsMax / 2;
 constexpr uint8_t kNoUnit = 0xff;
-struct RoundShared {
-    uint32_t stage[kStageWords];
-    uint32_t cm[kRoundDwordsMax * 32];           // [dword][lane] output bytes << 12 | matches
-    uint8_t  fs[kRoundDwordsMax * 32];           // [dword][lane]
+// NL = lanes that share a round: 32 (one warp per member) or 128 (a team of four warps per member).
+template <int NL>
+struct RoundSharedT {
+    static constexpr int kLanes = NL;
+    uint32_t stage[NL * (kRoundWordsMax + kRowExtra)];
+    uint32_t cm[kRoundDwordsMax * NL];           // [dword][lane] output bytes << 12 | matches
+    uint8_t  fs[kRoundDwordsMax * NL];           // [dword][lane]
 };
+using RoundShared = RoundSharedT<32>;
 ZB_HD uint32_t stage_row_stride(int lg) { return (1u << lg) + kRowExtra; }
 
 ZB_HD uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t s) {
@@ -132,10 +135,11 @@ struct RoundLane {
 enum : uint32_t { STOP_NONE = 0, STOP_EOB = 1, STOP_BAD = 2 };
 
 // P1.  `start` is 0, except for lane 0 which starts at the block's true position.
-ZB_HD void round_speculate(RoundLane &r, uint32_t lane, int lg, uint32_t start, const uint32_t *stage, RoundShared &rs,
+template <class RS>
+ZB_HD void round_speculate(RoundLane &r, uint32_t lane, int lg, uint32_t start, const uint32_t *stage, RS &rs,
                            const uint32_t *__restrict__ L, const uint32_t *__restrict__ D) {
     const uint32_t DW = 1u << (lg - 1), S = 32u << lg;
-    for (uint32_t w = 0; w < DW; ++w) rs.fs[w * 32 + lane] = kNoUnit;
+    for (uint32_t w = 0; w < DW; ++w) rs.fs[w * RS::kLanes + lane] = kNoUnit;
     LaneWin lw; lw.row = stage + lane * stage_row_stride(lg);
     uint32_t p = start;
     uint32_t curdw = 0xffffffffu, out = 0, m = 0, stop = STOP_NONE;
@@ -143,8 +147,8 @@ ZB_HD void round_speculate(RoundLane &r, uint32_t lane, int lg, uint32_t start, 
         const uint32_t dw = p >> 6;
         if (dw != curdw) {                                   // the first unit starting in this double word
             curdw = dw;
-            rs.fs[dw * 32 + lane] = (uint8_t)(p & 63u);
-            rs.cm[dw * 32 + lane] = (out << 12) | m;
+            rs.fs[dw * RS::kLanes + lane] = (uint8_t)(p & 63u);
+            rs.cm[dw * RS::kLanes + lane] = (out << 12) | m;
         }
         const Unit u = decode_unit<false>(lw, p, L, D);
         p += u.used;
@@ -160,7 +164,8 @@ ZB_HD void round_speculate(RoundLane &r, uint32_t lane, int lg, uint32_t start, 
 // paths that have a unit start on the same bit are identical from there on, and once
 // joined they share the first unit start of every later double word — which is where
 // the join is looked for and the speculative counts are spliced in.
-ZB_HD void round_fix(RoundLane &r, uint32_t lane, int lg, uint32_t t, const uint32_t *stage, const RoundShared &rs,
+template <class RS>
+ZB_HD void round_fix(RoundLane &r, uint32_t lane, int lg, uint32_t t, const uint32_t *stage, const RS &rs,
                      const uint32_t *__restrict__ L, const uint32_t *__restrict__ D) {
     const uint32_t S = 32u << lg;
     LaneWin lw; lw.row = stage + lane * stage_row_stride(lg);
@@ -171,8 +176,8 @@ ZB_HD void round_fix(RoundLane &r, uint32_t lane, int lg, uint32_t t, const uint
         const uint32_t dw = p >> 6;
         if (dw != curdw) {
             curdw = dw;
-            if (rs.fs[dw * 32 + lane] == (uint8_t)(p & 63u)) {
-                const uint32_t c = rs.cm[dw * 32 + lane];
+            if (rs.fs[dw * RS::kLanes + lane] == (uint8_t)(p & 63u)) {
+                const uint32_t c = rs.cm[dw * RS::kLanes + lane];
                 r.out = out + (r.spec_out - (c >> 12));
                 r.m = m + (r.spec_m - (c & 0xfffu));
                 r.end = r.spec_end; r.stop = r.spec_stop;
@@ -212,9 +217,9 @@ ZB_HD int round_emit(const RoundLane &r, uint32_t lane, int lg, const uint32_t *
 
 // Subsequence size for a round: the largest S with 32*S bits still inside the member, or -1
 // when too little input is left for a round to pay off (the serial path finishes the member).
-ZB_HD int round_pick_lg(uint64_t remaining_bits) {
+ZB_HD int round_pick_lg(uint64_t remaining_bits, uint32_t lanes = 32) {
     for (int lg = kRoundLgMax; lg >= kRoundLgMin; --lg)
-        if (remaining_bits >= (uint64_t)(32u << lg) * 32u) return lg;
+        if (remaining_bits >= (uint64_t)(32u << lg) * lanes) return lg;
     return -1;
 }
 
