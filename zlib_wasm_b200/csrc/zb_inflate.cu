@@ -19,7 +19,10 @@
 namespace zb {
 
 constexpr int kInfWarps = 4;
-constexpr int kInfCtasPerSm = 4;          // 4 CTAs x (4 warps x 12.6 KiB + 3.4 KiB) of shared memory, 128 registers: 16 warps per SM
+#ifndef ZB_INF_CTAS_PER_SM
+#define ZB_INF_CTAS_PER_SM 4
+#endif
+constexpr int kInfCtasPerSm = ZB_INF_CTAS_PER_SM;          // 4 CTAs x (4 warps x 12.6 KiB + 3.4 KiB) of shared memory, 128 registers: 16 warps per SM
 constexpr size_t kMaxGridWarps = 4096;    // upper bound on resident warps (sizes the per-warp match queues: 48 KiB each)
 // Two symbol decoders exist: the serial loop on lane 0 (InflateState::fast_symbols,
 // ~79 warp instructions per symbol with one lane active) and the warp-parallel rounds

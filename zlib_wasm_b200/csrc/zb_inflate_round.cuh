@@ -38,7 +38,10 @@
 
 namespace zb {
 
-constexpr int kRoundLgMin = 2, kRoundLgMax = 5;              // words per lane = 1 << lg  (S = 128 .. 1024 bits)
+#ifndef ZB_ROUND_LG_MAX
+#define ZB_ROUND_LG_MAX 5
+#endif
+constexpr int kRoundLgMin = 2, kRoundLgMax = ZB_ROUND_LG_MAX;              // words per lane = 1 << lg  (S = 128 .. 1024 bits)
 constexpr int kRoundWordsMax = 1 << kRoundLgMax;
 constexpr int kRowExtra = 3;                                 // words of the following subsequence repeated at the end of a row
 // Matches a round may park.  The worst case is 32 * S / 2 (a match costs at least 2 bits); text
