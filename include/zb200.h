@@ -133,6 +133,11 @@ typedef struct {
     uint64_t out_off, out_cap;   /* where its output goes inside d_out           */
     uint64_t resume_bit;         /* 0 = fresh member (parse the wrapper header); else continue at this */
     uint64_t resume_out;         /*     block boundary with resume_out bytes of output already in place */
+    uint64_t dict_len;           /* preset dictionary (inflateSetDictionary, inflate.c:1278-1312): the dict_len */
+                                 /*     (<= 32768) bytes just BEFORE out_off in d_out; distances may reach into */
+                                 /*     them; they are not part of the output, its length or its check value.   */
+                                 /*     A zlib header with FDICT and dict_len == 0 gives ZB200_INF_NEED_DICT    */
+                                 /*     with the DICTID in `check` (inflate.c:660-669)                          */
 } zb200_member;
 
 typedef struct {
@@ -157,6 +162,14 @@ int zb200_inflate_dev(zb200_ctx *ctx, const void *d_in, void *d_out,
 int zb200_inflate_host(zb200_ctx *ctx, const void *in, void *out,
                        const zb200_member *members, size_t n_members, int wrap, int verify,
                        zb200_member_result *results);
+
+/* One raw-deflate chunk compressed with a preset dictionary (deflateSetDictionary, deflate.c:550-632): the
+ * first dict_len (<= 32768) bytes of `in` are history only — hashed and searched like any window content,
+ * never emitted — and in[dict_len .. n) is compressed as one Z_FULL_FLUSH- (finish = 0) or Z_FINISH-terminated
+ * run of blocks whose matches may reach into the dictionary.  Levels 4-9 and Z_RLE / Z_HUFFMAN_ONLY emit the
+ * reference's bytes.  in_adler / in_crc cover in[dict_len .. n).  Host pointers; synchronous. */
+int zb200_deflate_host_dict(zb200_ctx *ctx, const void *in, size_t n, size_t dict_len, int level, int strategy,
+                            int finish, void *out, size_t *out_len, uint32_t *in_adler, uint32_t *in_crc);
 
 /* Self-test of the warp-parallel decode-table construction (csrc/zb_inflate_tables.cuh) against the
  * serial one that follows inftrees.c:32-299: for each of n_cases sets of code lengths (lens: 320 bytes

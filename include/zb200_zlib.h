@@ -107,6 +107,7 @@ int deflate(z_streamp strm, int flush);
 int deflateEnd(z_streamp strm);
 int deflateReset(z_streamp strm);
 int deflateParams(z_streamp strm, int level, int strategy);
+int deflateSetDictionary(z_streamp strm, const Bytef *dictionary, uInt dictLength);   /* zlib.h:612, deflate.c:550 */
 uLong deflateBound(z_streamp strm, uLong sourceLen);
 int inflateInit_(z_streamp strm, const char *version, int stream_size);
 int inflateInit2_(z_streamp strm, int windowBits, const char *version, int stream_size);
@@ -114,6 +115,7 @@ int inflate(z_streamp strm, int flush);
 int inflateEnd(z_streamp strm);
 int inflateReset(z_streamp strm);
 int inflateReset2(z_streamp strm, int windowBits);
+int inflateSetDictionary(z_streamp strm, const Bytef *dictionary, uInt dictLength);   /* zlib.h:887, inflate.c:1278 */
 
 /* ---- utility (compress.c:22-75, uncompr.c:27-85) ---- */
 int compress(Bytef *dest, uLongf *destLen, const Bytef *source, uLong sourceLen);

@@ -23,8 +23,9 @@ struct BitSink {
 };
 
 // One chunk -> raw deflate bytes (blocks + marker when !final).  Returns size or -1.
-extern "C" long emul_deflate_chunk(const uint8_t *data, uint32_t n, int level, int strategy, int final_chunk,
-                                   uint8_t *out, size_t cap, uint32_t *stats /* nsyms, nblocks */) {
+// `skip`: the first skip bytes are a preset dictionary (history only).
+extern "C" long emul_deflate_chunk_dict(const uint8_t *data, uint32_t n, uint32_t skip, int level, int strategy, int final_chunk,
+                                        uint8_t *out, size_t cap, uint32_t *stats /* nsyms, nblocks */) {
     if (!g_ready) { format_fill(g_fmt); static_trees_fill(g_st); g_ready = 1; }
     const DeflateParams prm = deflate_params(level, strategy);
     std::vector<uint16_t> prev(n + 1, 0);
@@ -57,10 +58,10 @@ extern "C" long emul_deflate_chunk(const uint8_t *data, uint32_t n, int level, i
         // greedy rules: exit tables per tile (zb_deflate.cu dfl_parse_greedy_kernel), the lanes replayed by loops
         const bool use_m = prm.mode != MODE_HUFF;
         std::vector<uint32_t> mfv(kGtSlots); std::vector<uint16_t> lc(kGtSlots);
-        uint32_t entry = 0, nsyms = 0;
+        uint32_t entry = skip, nsyms = 0;
         struct GA { const uint32_t *mfv; const uint8_t *data; uint32_t t0;
                     uint32_t mf(uint32_t p) const { return mfv[gt_slot(p - t0)]; } uint32_t byte(uint32_t p) const { return data[p]; } };
-        for (uint32_t t0 = 0; t0 < n; t0 += kGtTile) {
+        for (uint32_t t0 = skip / kGtTile * kGtTile; t0 < n; t0 += kGtTile) {
             for (uint32_t r = 0; r < kGtTile; ++r) mfv[gt_slot(r)] = (use_m && t0 + r < n) ? mf[t0 + r] : 0u;
             for (int l = 31; l >= 0; --l) gt_fill((uint32_t)l, n - t0, mfv.data(), lc.data());
             uint32_t exit_rel = 0, total = 0;
@@ -79,9 +80,9 @@ extern "C" long emul_deflate_chunk(const uint8_t *data, uint32_t n, int level, i
             }
             entry = t0 + exit_rel; nsyms += total;
         }
-        sink.nsyms = nsyms; sink.nblocks = seg_finish(blocks.data(), nsyms, false, n, prm, final_chunk != 0);
+        sink.nsyms = nsyms; sink.nblocks = seg_finish(blocks.data(), nsyms, false, n, prm, final_chunk != 0, skip);
     } else {
-        const SegGeom g = seg_geometry(n);
+        const SegGeom g = seg_geometry(n, skip);
         std::vector<SegRec> rec((kSegRecs - 1) * kSegLanes);
         SegLane r[kSegLanes];
         // operands paced in windows of 16 positions at an arbitrary alignment, as the kernel stages them
@@ -117,13 +118,13 @@ extern "C" long emul_deflate_chunk(const uint8_t *data, uint32_t n, int level, i
         const bool pending = prm.mode == MODE_SLOW && ((r[g.nact - 1].end.w0 >> 25) & 1u);
         if (pending) syms[total] = data[n - 1];
         sink.nsyms = total + (pending ? 1 : 0);
-        sink.nblocks = seg_finish(blocks.data(), total, pending, n, prm, final_chunk != 0);
+        sink.nblocks = seg_finish(blocks.data(), total, pending, n, prm, final_chunk != 0, skip);
     }
     {   // cross-check against the serial whole-chunk parse
         std::vector<uint32_t> syms2(n + 2);
         std::vector<BlockInfo> blocks2(max_blocks_for(n));
         uint32_t ns2 = 0, nb2 = 0;
-        parse_chunk(data, n, mf.data(), mq.data(), prm, final_chunk != 0, syms2.data(), blocks2.data(), ns2, nb2);
+        parse_chunk(data, n, mf.data(), mq.data(), prm, final_chunk != 0, syms2.data(), blocks2.data(), ns2, nb2, skip);
         if (ns2 != sink.nsyms || nb2 != sink.nblocks) return -22;
         if (memcmp(syms2.data(), syms.data(), 4ull * ns2)) return -23;
         for (uint32_t k = 0; k < nb2; ++k) {
@@ -171,4 +172,9 @@ extern "C" long emul_deflate_chunk(const uint8_t *data, uint32_t n, int level, i
     if (!final_chunk) { bs.put(0, 3); bs.bit = (bs.bit + 7) & ~7ull; bs.put(0xffff0000u, 32); }
     const size_t bytes = (size_t)((bs.bit + 7) >> 3);
     return bytes > cap ? -1 : (long)bytes;
+}
+
+extern "C" long emul_deflate_chunk(const uint8_t *data, uint32_t n, int level, int strategy, int final_chunk,
+                                   uint8_t *out, size_t cap, uint32_t *stats /* nsyms, nblocks */) {
+    return emul_deflate_chunk_dict(data, n, 0, level, strategy, final_chunk, out, cap, stats);
 }

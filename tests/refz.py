@@ -65,6 +65,8 @@ class ZlibBinding:
         f("adler32_z", C.c_ulong, C.c_ulong, C.c_void_p, C.c_size_t)
         f("adler32_combine", C.c_ulong, C.c_ulong, C.c_ulong, C.c_long)
         f("zError", C.c_char_p, C.c_int)
+        f("deflateSetDictionary", C.c_int, C.POINTER(ZStream), C.c_void_p, C.c_uint)
+        f("inflateSetDictionary", C.c_int, C.POINTER(ZStream), C.c_void_p, C.c_uint)
         self.version = self.zlibVersion()
 
     def _f(self, name, res, *args):
@@ -75,7 +77,7 @@ class ZlibBinding:
 
     # ---- helpers -------------------------------------------------------
     def deflate_stream(self, data, level=6, strategy=0, wrap=WRAP_ZLIB, chunk=0, mem_level=8,
-                       out_slice=None, in_slice=None):
+                       out_slice=None, in_slice=None, dictionary=None):
         """deflate(Z_FULL_FLUSH) per `chunk` bytes, Z_FINISH on the last one
         (SURVEY.md appendix C.1).  chunk=0: one Z_FINISH call.  in_slice /
         out_slice feed avail_in / avail_out in small pieces (zpipe style)."""
@@ -86,6 +88,11 @@ class ZlibBinding:
                                self.version, C.sizeof(ZStream))
         if r != Z_OK:
             raise RuntimeError("deflateInit2 %d" % r)
+        if dictionary is not None:                         # deflate.c:550-632
+            r = self.deflateSetDictionary(C.byref(strm), bytes(dictionary), len(dictionary))
+            if r != Z_OK:
+                self.deflateEnd(C.byref(strm))
+                raise RuntimeError("deflateSetDictionary %d" % r)
         src = C.create_string_buffer(data, max(n, 1))
         cap = n + (n >> 8) + 1024 + 16 * (n // chunk + 1 if chunk else 1)
         dst = C.create_string_buffer(cap)
@@ -125,8 +132,9 @@ class ZlibBinding:
         self.deflateEnd(C.byref(strm))
         return dst.raw[:produced]
 
-    def inflate_all(self, data, wrap=WRAP_ZLIB, cap=None, in_slice=None, out_slice=None):
-        """Returns (ret, msg, output bytes, total_in)."""
+    def inflate_all(self, data, wrap=WRAP_ZLIB, cap=None, in_slice=None, out_slice=None, dictionary=None):
+        """Returns (ret, msg, output bytes, total_in).  `dictionary` is handed over when inflate asks
+        for it (Z_NEED_DICT), or before the first call for a raw stream (inflate.c:1278-1312)."""
         data = bytes(data)
         n = len(data)
         cap = cap if cap is not None else max(64, n * 1100 + 1024)
@@ -139,6 +147,12 @@ class ZlibBinding:
         base_in, base_out = C.addressof(src), C.addressof(dst)
         fed = produced = 0
         ret = Z_OK
+        if dictionary is not None and wrap == WRAP_RAW:
+            r = self.inflateSetDictionary(C.byref(strm), bytes(dictionary), len(dictionary))
+            if r != Z_OK:
+                self.inflateEnd(C.byref(strm))
+                raise RuntimeError("inflateSetDictionary %d" % r)
+            dictionary = None
         while True:
             step = n - fed if not in_slice else min(in_slice, n - fed)
             strm.next_in = base_in + fed
@@ -150,6 +164,11 @@ class ZlibBinding:
                 strm.avail_out = room
                 ret = self.inflate(C.byref(strm), Z_NO_FLUSH)
                 produced += room - strm.avail_out
+                if ret == 2 and dictionary is not None:    # Z_NEED_DICT
+                    ret = self.inflateSetDictionary(C.byref(strm), bytes(dictionary), len(dictionary))
+                    dictionary = None
+                    if ret == Z_OK:
+                        continue
                 if ret != Z_OK:
                     break
                 if strm.avail_out != 0:

@@ -196,3 +196,38 @@ def test_deflate_phases_byte_exact():
                         s = e if final else e + b"\x03\x00"
                         err, msg, back, used = o.inflate_all(s, 0, cap=n + 16)
                         assert err == 0 and back == d and len(e) <= 1.03 * rn + 8
+
+
+def test_deflate_preset_dictionary_byte_exact():
+    """A preset dictionary (deflate.c:550-632) = history ahead of the first chunk: the phases, entered at the
+    dictionary's end, emit the bytes the reference emits after deflateSetDictionary (levels 4-9, Z_RLE,
+    Z_HUFFMAN_ONLY); levels 1-3 decode with the reference's inflate + inflateSetDictionary."""
+    if not refz.have_ref():
+        pytest.skip("oracle/_ref/libzref.so not built")
+    L = _build("def_emul")
+    L.emul_deflate_chunk_dict.restype = C.c_long
+    L.emul_deflate_chunk_dict.argtypes = [C.c_char_p, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t,
+                                          C.POINTER(C.c_uint32)]
+    ref = refz.ref()
+    rng = random.Random(3)
+    for kind in (refz.GEN_TEXT, refz.GEN_MARKOV, refz.GEN_MIXED):
+        base = refz.gen(400000, kind, seed=21 + kind)
+        for dl, n in ((1, 5000), (2, 1), (3, 0), (100, 300), (262, 70000), (5000, 262144), (32768, 100000), (32767, 40000), (32768, 262144),
+                      (40000, 90000)):
+            # the dictionary shares material with the data so that matches reach into it
+            dictionary = base[100000:100000 + dl]
+            data = (base[100000 + dl // 2:100000 + dl // 2 + n // 2] + base[:n - n // 2])[:n]
+            tail = dictionary[-32768:]
+            for level, strat in ((1, 0), (3, 0), (4, 0), (6, 0), (6, 1), (6, 2), (6, 3), (9, 0), (0, 0)):
+                want = ref.deflate_stream(data, level, strat, refz.WRAP_RAW, 0, dictionary=dictionary)
+                joined = tail + data
+                cap = len(joined) + len(joined) // 8 + 1024
+                out, st = C.create_string_buffer(cap), (C.c_uint32 * 2)()
+                r = L.emul_deflate_chunk_dict(joined, len(joined), len(tail), level, strat, 1, out, cap, st)
+                assert r >= 0, (r, kind, dl, n, level, strat)
+                got = out.raw[:r]
+                if level >= 4 or strat in (2, 3):
+                    assert got == want, (kind, dl, n, level, strat, len(got), len(want))
+                else:
+                    err, msg, back, used = ref.inflate_all(got, refz.WRAP_RAW, cap=n + 16, dictionary=dictionary)
+                    assert err == 1 and back == data and len(got) <= 1.03 * len(want) + 8, (kind, dl, n, level, strat, err, msg)

@@ -272,3 +272,34 @@ def test_warp_table_builder(ctx):
     assert r == 0, zb.last_error()
     bad = [(i, hex(v)) for i, v in enumerate(verdict) if v]
     assert not bad, (len(bad), bad[:10], [cases[i] for i, _ in bad[:2]])
+
+
+def test_members_with_preset_dictionaries(ctx):
+    """zb200_member.dict_len: the dictionary lies just before the member's output (inflate.c:1278-1312);
+    raw and zlib members made by the reference with deflateSetDictionary, several per call, each with its own."""
+    if not refz.have_ref():
+        pytest.skip("oracle/_ref/libzref.so not built")
+    ref = refz.ref()
+    base = refz.gen(900000, refz.GEN_TEXT, seed=31)
+    for wrap in (refz.WRAP_RAW, refz.WRAP_ZLIB):
+        blob, members, want, out_buf, opos = b"", [], [], bytearray(), 0
+        for k, (dl, n, lvl) in enumerate(((1, 1000, 6), (777, 300000, 6), (32768, 200000, 9), (20000, 70000, 1), (32768, 0, 6))):
+            dic = base[k * 50000:k * 50000 + dl]
+            data = base[k * 50000 + dl // 2:k * 50000 + dl // 2 + n]
+            s = ref.deflate_stream(data, lvl, 0, wrap, 0, dictionary=dic)
+            out_buf += dic
+            opos += dl
+            members.append((len(blob), len(s), opos, n + 16, 0, 0, dl))
+            want.append((opos, data))
+            out_buf += bytes(n + 16)
+            opos += n + 16
+            blob += s
+        out, res = ctx.inflate_host(blob, members, wrap, 1, out_size=opos, prefill=bytes(out_buf))
+        for (off, data), r, m in zip(want, res, members):
+            assert r.status == 0 and r.out_len == len(data) and r.in_used == m[1], (wrap, msg(r.status), r.out_len, len(data))
+            assert out[off:off + len(data)] == data
+        if wrap == refz.WRAP_ZLIB:                           # without the dictionary: the reference's Z_NEED_DICT, DICTID reported
+            m = members[1]
+            out, res = ctx.inflate_host(blob, [(m[0], m[1], 0, m[3])], wrap, 1)
+            dictid = int.from_bytes(blob[m[0] + 2:m[0] + 6], "big")
+            assert msg(res[0].status) == "need dictionary" and res[0].check == dictid and res[0].out_len == 0

@@ -174,3 +174,35 @@ def test_reference_zpipe_linked_against_product(tmp_path):
     if refz.have_ref():
         zp = os.path.join(refz.ROOT, "oracle", "_ref", "zpipe")
         assert subprocess.run([zp, "-d"], input=comp.stdout, capture_output=True, timeout=120).stdout == d
+
+
+@pytest.mark.parametrize("wrap", [refz.WRAP_RAW, refz.WRAP_ZLIB])
+def test_preset_dictionary(z, wrap):
+    """deflateSetDictionary / inflateSetDictionary (deflate.c:550-632, inflate.c:1278-1312): the reference's bytes
+    at levels >= 4 on the same chunking, and either side decodes the other's stream."""
+    if not refz.have_ref():
+        pytest.skip("oracle/_ref/libzref.so not built")
+    ref = refz.ref()
+    base = refz.gen(1200000, refz.GEN_TEXT, seed=41)
+    for dl, n in ((100, 5000), (32768, 600000), (50000, 262144 + 1000), (1000, 0)):
+        dic = base[:dl]
+        d = base[dl // 2:dl // 2 + n]
+        for level in (1, 6, 9):
+            s = z.deflate_stream(d, level, 0, wrap, chunk=0, dictionary=dic)
+            want = ref.deflate_stream(d, level, 0, wrap, 262144, dictionary=dic)
+            if level >= 4:
+                assert s == want, (dl, n, level, len(s), len(want))
+            else:
+                assert len(s) <= 1.03 * len(want) + 8
+            ret, m, out, tin = ref.inflate_all(s, wrap, cap=n + 64, dictionary=dic)
+            assert ret == refz.Z_STREAM_END and out == d, (dl, n, level, ret, m)
+            ret, m, out, tin = z.inflate_all(want, wrap, cap=n + 64, dictionary=dic, in_slice=50000)
+            assert ret == refz.Z_STREAM_END and out == d and tin == len(want), (dl, n, level, ret, m)
+    if wrap == refz.WRAP_ZLIB:
+        s = ref.deflate_stream(base[:100000], 6, 0, wrap, 0, dictionary=base[200000:230000])
+        ret, m, out, tin = z.inflate_all(s, wrap, cap=100064)                       # nobody supplies it
+        assert ret == refz.Z_NEED_DICT and out == b""
+        ret, m, out, tin = z.inflate_all(s, wrap, cap=100064, dictionary=base[1:30001])   # the wrong one: inflate.c:1293-1296
+        assert ret == refz.Z_DATA_ERROR
+    with pytest.raises(RuntimeError):                                               # gzip takes no dictionary: deflate.c:562
+        z.deflate_stream(base[:1000], 6, 0, refz.WRAP_GZIP, 0, dictionary=base[:100])

@@ -29,7 +29,7 @@ WRAP_RAW, WRAP_ZLIB, WRAP_GZIP, WRAP_AUTO = 0, 1, 2, 3
 
 class Member(C.Structure):
     _fields_ = [("in_off", C.c_uint64), ("in_len", C.c_uint64), ("out_off", C.c_uint64), ("out_cap", C.c_uint64),
-                ("resume_bit", C.c_uint64), ("resume_out", C.c_uint64)]
+                ("resume_bit", C.c_uint64), ("resume_out", C.c_uint64), ("dict_len", C.c_uint64)]
 
 
 class MemberResult(C.Structure):
@@ -75,6 +75,7 @@ ABI = {
     "zb200_inflate_dev": (_i, _vp, _vp, _vp, _vp, _sz, _i, _i, _vp, _vp),
     "zb200_inflate_host": (_i, _vp, _vp, _vp, _vp, _sz, _i, _i, _vp),
     "zb200_selftest_tables": (_i, _vp, _vp, _vp, _sz, _vp),
+    "zb200_deflate_host_dict": (_i, _vp, _vp, _sz, _sz, _i, _i, _i, _vp, _vp, _vp, _vp),
 }
 
 
@@ -146,14 +147,18 @@ class Context:
             raise ZB200Error(r, "zb200_deflate_host")
         return out.raw[:olen.value]
 
-    def inflate_host(self, blob, members, wrap=WRAP_GZIP, verify=1, out_size=None):
-        """members: list of (in_off, in_len, out_off, out_cap).  Returns (output bytes, [MemberResult])."""
+    def inflate_host(self, blob, members, wrap=WRAP_GZIP, verify=1, out_size=None, prefill=None):
+        """members: list of (in_off, in_len, out_off, out_cap[, resume_bit, resume_out[, dict_len]]).  `prefill`:
+        bytes placed at the start of the output buffer before the call (preset dictionaries, resumed output).
+        Returns (output bytes, [MemberResult])."""
         n = len(members)
-        arr = (Member * max(n, 1))(*[Member(*(tuple(m) + (0, 0))[:6]) for m in members])
+        arr = (Member * max(n, 1))(*[Member(*(tuple(m) + (0, 0, 0))[:7]) for m in members])
         res = (MemberResult * max(n, 1))()
         if out_size is None:
             out_size = max([m[2] + m[3] for m in members] + [1])
         out = C.create_string_buffer(out_size)
+        if prefill:
+            C.memmove(out, bytes(prefill), len(prefill))
         r = lib().zb200_inflate_host(self._h, bytes(blob), out, arr, n, wrap, verify, res)
         if r != OK:
             raise ZB200Error(r, "zb200_inflate_host")

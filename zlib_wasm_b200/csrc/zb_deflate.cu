@@ -59,6 +59,7 @@ struct Batch {                 // one sub-batch of chunks, passed by value to th
     uint32_t MB;               // block slots per chunk
     int last_is_final;         // the last chunk of this sub-batch ends the stream (Z_FINISH)
     int all_final;             // every chunk is its own stream (gzip members)
+    uint32_t skip;             // a preset dictionary: the first `skip` bytes of chunk 0 are history only (single-chunk calls)
 };
 
 __device__ __forceinline__ uint32_t chunk_len(const Batch &b, uint32_t c) {
@@ -391,11 +392,12 @@ dfl_parse_greedy_kernel(Batch b, DeflateParams prm, const uint32_t *__restrict__
     const uint32_t *mf = mfull + off;
     uint32_t *out = syms + off;
     BlockInfo *blk = blocks + (uint64_t)c * b.MB;
-    if (threadIdx.x == 0) { s_entry = 0; s_nsyms = 0; }
+    const uint32_t lo = c == 0 ? b.skip : 0u, tile0 = lo / kGtTile;   // the parse enters at `lo` (history before it)
+    if (threadIdx.x == 0) { s_entry = lo; s_nsyms = 0; }
     __syncthreads();
     GtWarpShared &w = sh[warp];
     const uint32_t ntiles = (n + kGtTile - 1) / kGtTile;
-    for (uint32_t t = warp; t < ntiles; t += kGtWarps) {
+    for (uint32_t t = tile0 + warp; t < ntiles; t += kGtWarps) {
         const uint32_t t0 = t * kGtTile;
         __syncwarp();                                  // the previous tile's tables are no longer read
 #pragma unroll
@@ -406,7 +408,7 @@ dfl_parse_greedy_kernel(Batch b, DeflateParams prm, const uint32_t *__restrict__
         __syncwarp();
         gt_fill(lane, n - t0, w.mfv, w.lc);
         __syncwarp();
-        if (t) asm volatile("bar.sync %0, 64;" ::"r"(warp + 1) : "memory");   // the previous tile has been crossed
+        if (t != tile0) asm volatile("bar.sync %0, 64;" ::"r"(warp + 1) : "memory");   // the previous tile has been crossed
         const uint32_t entry = s_entry, first_sym = s_nsyms;
         uint32_t my_entry, my_first, total;
         const uint32_t exit_rel = gt_hop(lane, entry - t0, n - t0, w.lc, my_entry, my_first, total);
@@ -425,7 +427,7 @@ dfl_parse_greedy_kernel(Batch b, DeflateParams prm, const uint32_t *__restrict__
         }
     }
     __syncthreads();
-    if (threadIdx.x == 0) nblocks[c] = seg_finish(blk, s_nsyms, false, n, prm, chunk_final(b, c));
+    if (threadIdx.x == 0) nblocks[c] = seg_finish(blk, s_nsyms, false, n, prm, chunk_final(b, c), lo);
 }
 
 // ---- phase 3, lazy rule (deflate_slow): one chunk per CTA, one segment per thread -------------------------
@@ -522,11 +524,11 @@ dfl_parse_kernel(Batch b, DeflateParams prm, const uint32_t *__restrict__ mfull,
     const uint32_t n = chunk_len(b, c);
     uint32_t *out = syms + off;
     BlockInfo *blk = blocks + (uint64_t)c * b.MB;
-    const SegGeom g = seg_geometry(n);
+    const SegGeom g = seg_geometry(n, c == 0 ? b.skip : 0u);
     const bool active = tid < g.nact;
 
     SegLane r;
-    r.start = r.end = r.spec_end = seg_cold(0); r.count = r.spec_count = 0;
+    r.start = r.end = r.spec_end = seg_cold(g.lo); r.count = r.spec_count = 0;
     WinAcc acc;
     acc.data = data; acc.mfull = mfull; acc.mquarter = prm.need_quarter ? mquarter : mfull; acc.out = nullptr; acc.at = 0;
     acc.row_f = (uint32_t)__cvta_generic_to_shared(s_f + tid * kPwRow);
@@ -561,7 +563,7 @@ dfl_parse_kernel(Batch b, DeflateParams prm, const uint32_t *__restrict__ mfull,
     if (tid == 0) {
         const bool pending = prm.mode == MODE_SLOW && ((s_w0[g.nact - 1] >> 25) & 1u);
         if (pending) out[total] = data[n - 1];
-        nblocks[c] = seg_finish(blk, total, pending, n, prm, chunk_final(b, c));
+        nblocks[c] = seg_finish(blk, total, pending, n, prm, chunk_final(b, c), g.lo);
     }
 }
 
@@ -815,7 +817,11 @@ static size_t batch_chunks(size_t n, size_t S) {
 
 int deflate_launch(zb200_ctx *ctx, const uint8_t *d_in, size_t n, size_t S, int level, int strategy, int frame,
                    int finish, uint8_t *d_out, size_t out_cap, uint64_t *d_chunk_end, uint64_t *d_total,
-                   uint32_t *d_sums_out, cudaStream_t s) {
+                   uint32_t *d_sums_out, cudaStream_t s, size_t skip) {
+    if (skip && (skip > kWSize || skip > n || n > S || frame != ZB200_FRAME_RAW)) {
+        set_error("deflate: a preset dictionary is at most 32768 bytes at the head of a single raw chunk");
+        return ZB200_ERR_PARAM;
+    }
     if (level < 0 || level > 9 || strategy < 0 || strategy > 4 || frame < 0 || frame > 3 || S < 1 ||
         S > 0x40000000ull || ((uintptr_t)d_out & 3)) {
         set_error("deflate: bad parameter (level 0..9, strategy 0..4, frame 0..3, chunk 1..2^30, 4-byte aligned output)");
@@ -843,7 +849,7 @@ int deflate_launch(zb200_ctx *ctx, const uint8_t *d_in, size_t n, size_t S, int 
     const uint64_t hdr = frame == ZB200_FRAME_ZLIB ? 2 : frame == ZB200_FRAME_GZIP ? 10 : 0;
     ZB_CUDA(cudaMemcpyAsync(running, &ctx->h_small[32 + (hdr == 2 ? 1 : hdr == 10 ? 2 : 0)], 8, cudaMemcpyHostToDevice, s));
     if (frame == ZB200_FRAME_ZLIB || frame == ZB200_FRAME_GZIP || d_sums_out) {
-        r = checksum_launch(ctx, d_in, nullptr, nullptr, n, 1, ZB200_CRC32 | ZB200_ADLER32, 0, 1, sums, sums + 1, acc1, s);
+        r = checksum_launch(ctx, d_in + skip, nullptr, nullptr, n - skip, 1, ZB200_CRC32 | ZB200_ADLER32, 0, 1, sums, sums + 1, acc1, s);
         if (r) return r;
         if (d_sums_out) ZB_CUDA(cudaMemcpyAsync(d_sums_out, sums, 8, cudaMemcpyDeviceToDevice, s));
     }
@@ -857,6 +863,7 @@ int deflate_launch(zb200_ctx *ctx, const uint8_t *d_in, size_t n, size_t S, int 
         b.S = (uint32_t)S; b.MB = MB;
         b.last_is_final = (finish && c0 + b.nb == nch) ? 1 : 0;
         b.all_final = members ? 1 : 0;
+        b.skip = (uint32_t)skip;
         if (prm.mode == MODE_FAST || prm.mode == MODE_SLOW) {
             dfl_chain_kernel<<<b.nb, kChainWarps * 32, kChainSmem, s>>>(b, w.prev);
             ZB_LAUNCHED(); ZB_CHECK_LAUNCH();
@@ -896,7 +903,7 @@ int deflate_launch(zb200_ctx *ctx, const uint8_t *d_in, size_t n, size_t S, int 
             ZB_LAUNCHED(); ZB_CHECK_LAUNCH();
         }
     }
-    dfl_frame_kernel<<<1, 32, 0, s>>>(d_out, frame, level, strategy, finish, 1, running, sums, n, d_total);
+    dfl_frame_kernel<<<1, 32, 0, s>>>(d_out, frame, level, strategy, finish, 1, running, sums, n - skip, d_total);
     ZB_LAUNCHED(); ZB_CHECK_LAUNCH();
     return ZB200_OK;
 }
@@ -930,7 +937,7 @@ int zb200_deflate_dev(zb200_ctx *ctx, const void *d_in, size_t n, size_t chunk_s
     ZB_CUDA(cudaSetDevice(ctx->device));
     std::lock_guard<std::mutex> g(ctx->mu);
     return deflate_launch(ctx, (const uint8_t *)d_in, n, chunk_size, level, strategy, frame, finish,
-                          (uint8_t *)d_out, out_cap, d_chunk_end, d_total, nullptr, pick_stream(ctx, stream));
+                          (uint8_t *)d_out, out_cap, d_chunk_end, d_total, nullptr, pick_stream(ctx, stream), 0);
 }
 
 // Large inputs in pinned memory: the input is cut into up to 9 pieces (whole chunks); piece
@@ -1040,6 +1047,35 @@ int zb200_deflate_host(zb200_ctx *ctx, const void *in, size_t n, size_t chunk_si
     uint32_t *d_sums = (uint32_t *)(ctx->d_small + 18);
     r = deflate_launch(ctx, ctx->d_io_in, n, chunk_size, level, strategy, frame, finish, ctx->d_io_out, bound,
                        nullptr, d_total, d_sums, s);
+    if (r) return r;
+    ZB_CUDA(cudaMemcpyAsync(ctx->h_small, ctx->d_small + 17, 16, cudaMemcpyDeviceToHost, s));
+    ZB_CUDA(cudaStreamSynchronize(s));
+    const uint64_t total = ctx->h_small[0];
+    const uint32_t *hs = (const uint32_t *)(ctx->h_small + 1);
+    if (in_crc) *in_crc = hs[0];
+    if (in_adler) *in_adler = hs[1];
+    if (total > *out_len) { *out_len = (size_t)total; set_error("deflate: %llu bytes do not fit the output buffer", (unsigned long long)total); return ZB200_ERR_OUTPUT; }
+    if ((r = d2h_auto(ctx, out, ctx->d_io_out, (size_t)total, s))) return r;
+    ZB_CUDA(cudaStreamSynchronize(s));
+    *out_len = (size_t)total;
+    return ZB200_OK;
+}
+
+int zb200_deflate_host_dict(zb200_ctx *ctx, const void *in, size_t n, size_t dict_len, int level, int strategy,
+                            int finish, void *out, size_t *out_len, uint32_t *in_adler, uint32_t *in_crc) {
+    if (!ctx || !in || !out || !out_len || dict_len > n || dict_len > kWSize || n > 0x40000000ull) return ZB200_ERR_PARAM;
+    ZB_CUDA(cudaSetDevice(ctx->device));
+    std::lock_guard<std::mutex> g(ctx->mu);
+    const size_t S = n ? n : 1;
+    const size_t bound = zb200_deflate_bound(n, S, ZB200_FRAME_RAW);
+    int r = ensure_io(ctx, n + 16, bound + 16);
+    if (r) return r;
+    cudaStream_t s = ctx->stream;
+    if ((r = h2d_auto(ctx, ctx->d_io_in, in, n, s))) return r;
+    uint64_t *d_total = ctx->d_small + 17;
+    uint32_t *d_sums = (uint32_t *)(ctx->d_small + 18);
+    r = deflate_launch(ctx, ctx->d_io_in, n, S, level, strategy, ZB200_FRAME_RAW, finish, ctx->d_io_out, bound,
+                       nullptr, d_total, d_sums, s, dict_len);
     if (r) return r;
     ZB_CUDA(cudaMemcpyAsync(ctx->h_small, ctx->d_small + 17, 16, cudaMemcpyDeviceToHost, s));
     ZB_CUDA(cudaStreamSynchronize(s));

@@ -317,10 +317,12 @@ enum : uint32_t { PB_SERIAL = 0, PB_DEFERRED = 1, PB_NONE = 2 };
 
 ZB_HD uint32_t parse_next_slide(uint32_t base, uint32_t n, const DeflateParams &prm);
 
-ZB_HD void parse_init(ParseState &s, BlockInfo *blocks, uint32_t n, const DeflateParams &prm) {
-    s.slide_at = parse_next_slide(0, n, prm);
-    s.p = 0; s.match_length = kMinMatch - 1; s.cur_dist = 0; s.match_available = 0; s.base = 0;
-    s.nsyms = 0; s.nblocks = 0; s.blk_sym0 = 0; s.blk_byte0 = 0; s.blocks = blocks; s.block_mode = PB_SERIAL;
+ZB_HD uint32_t parse_base_at(uint32_t P, uint32_t n, const DeflateParams &prm);
+ZB_HD void parse_init(ParseState &s, BlockInfo *blocks, uint32_t n, const DeflateParams &prm, uint32_t lo = 0) {
+    s.base = parse_base_at(lo, n, prm);
+    s.slide_at = parse_next_slide(s.base, n, prm);
+    s.p = lo; s.match_length = kMinMatch - 1; s.cur_dist = 0; s.match_available = 0;
+    s.nsyms = 0; s.nblocks = 0; s.blk_sym0 = 0; s.blk_byte0 = lo; s.blocks = blocks; s.block_mode = PB_SERIAL;
 }
 
 ZB_HD void parse_close_block(ParseState &s, uint32_t cover_end, bool last) {
@@ -435,9 +437,9 @@ struct ParseArrays {
 
 ZB_HD void parse_chunk(const uint8_t *data, uint32_t n, const uint32_t *mfull, const uint32_t *mquarter,
                        const DeflateParams &prm, bool final_chunk, uint32_t *syms, BlockInfo *blocks,
-                       uint32_t &nsyms, uint32_t &nblocks) {
+                       uint32_t &nsyms, uint32_t &nblocks, uint32_t lo = 0) {
     ParseState s;
-    parse_init(s, blocks, n, prm);
+    parse_init(s, blocks, n, prm, lo);
     ParseArrays acc{data, mfull, mquarter, syms, 0};
     parse_steps(s, n, n, prm, acc);
     parse_finish(s, n, prm, final_chunk, acc);
@@ -472,13 +474,18 @@ ZB_HD uint32_t parse_base_at(uint32_t P, uint32_t n, const DeflateParams &prm) {
     return base;
 }
 
-struct SegGeom { uint32_t blk, seg, nact; };          // boundary spacing, segment length, lanes with work
-ZB_HD SegGeom seg_geometry(uint32_t n) {
+// `lo`: the chunk's first lo bytes are history only — a preset dictionary (deflate.c:550-632:
+// hashed and searched like any window content, strstart = block_start = lo when the first
+// byte is compressed) — so the segments tile [lo, n).
+struct SegGeom { uint32_t blk, seg, nact, lo; };      // boundary spacing, segment length, lanes with work, first parsed position
+ZB_HD SegGeom seg_geometry(uint32_t n, uint32_t lo = 0) {
     SegGeom g;
-    g.blk = (n + kSegLanes * kSegRecs - 1) / (kSegLanes * kSegRecs);
+    const uint32_t m = n - lo;
+    g.blk = (m + kSegLanes * kSegRecs - 1) / (kSegLanes * kSegRecs);
     if (g.blk < 32) g.blk = 32;
     g.seg = g.blk * kSegRecs;
-    g.nact = n ? (n + g.seg - 1) / g.seg : 1;
+    g.nact = m ? (m + g.seg - 1) / g.seg : 1;
+    g.lo = lo;
     return g;
 }
 
@@ -524,7 +531,7 @@ struct NoPut {                                        // counting passes: operan
 // rec[(k - 1) * kSegLanes + lane] belongs to boundary k (k = 1 .. kSegRecs - 1) of lane's segment.
 template <class Acc>
 ZB_HD void seg_speculate(SegLane &r, uint32_t lane, const SegGeom &g, uint32_t n, const DeflateParams &prm, Acc &acc, SegRec *rec) {
-    const uint32_t s0 = lane * g.seg, bound = s0 + g.seg < n ? s0 + g.seg : n;
+    const uint32_t s0 = g.lo + lane * g.seg, bound = s0 + g.seg < n ? s0 + g.seg : n;
     ParseState st;
     r.start = seg_cold(s0);
     seg_state_load(st, r.start, n, prm);
@@ -551,7 +558,7 @@ ZB_HD void seg_speculate(SegLane &r, uint32_t lane, const SegGeom &g, uint32_t n
 template <class Acc>
 ZB_HD void seg_fix(SegLane &r, uint32_t lane, const SegGeom &g, uint32_t n, const DeflateParams &prm, Acc &acc,
                    const SegRec *rec, const SegState &t) {
-    const uint32_t s0 = lane * g.seg, bound = s0 + g.seg < n ? s0 + g.seg : n;
+    const uint32_t s0 = g.lo + lane * g.seg, bound = s0 + g.seg < n ? s0 + g.seg : n;
     ParseState st;
     r.start = t;
     seg_state_load(st, t, n, prm);
@@ -584,7 +591,7 @@ ZB_HD void seg_fix(SegLane &r, uint32_t lane, const SegGeom &g, uint32_t n, cons
 template <class Acc>
 ZB_HD void seg_emit(const SegLane &r, uint32_t lane, const SegGeom &g, uint32_t n, const DeflateParams &prm, Acc &acc,
                     BlockInfo *blocks, uint32_t first) {
-    const uint32_t s0 = lane * g.seg, bound = s0 + g.seg < n ? s0 + g.seg : n;
+    const uint32_t s0 = g.lo + lane * g.seg, bound = s0 + g.seg < n ? s0 + g.seg : n;
     ParseState st;
     seg_state_load(st, r.start, n, prm);
     st.nsyms = first; st.blk_sym0 = first - first % kSymLimit; st.blocks = blocks; st.block_mode = PB_DEFERRED;
@@ -598,9 +605,10 @@ ZB_HD void seg_emit(const SegLane &r, uint32_t lane, const SegGeom &g, uint32_t 
 // nsyms: symbols emitted by the segments; pending: the last segment ended holding a
 // literal (deflate.c:2026-2030: tallied at the end, its flush flag ignored — the caller
 // has stored it at index nsyms).  Returns the number of blocks.
-ZB_HD uint32_t seg_finish(BlockInfo *blocks, uint32_t nsyms, bool pending, uint32_t n, const DeflateParams &prm, bool final_chunk) {
+ZB_HD uint32_t seg_finish(BlockInfo *blocks, uint32_t nsyms, bool pending, uint32_t n, const DeflateParams &prm, bool final_chunk,
+                          uint32_t lo = 0) {
     const uint32_t nfull = nsyms / kSymLimit, rem = nsyms % kSymLimit + (pending ? 1u : 0u);
-    uint32_t start = 0;
+    uint32_t start = lo;
     for (uint32_t k = 0; k < nfull; ++k) {
         BlockInfo &b = blocks[k];
         const uint32_t end = b.byte_len, base = b.pad;

@@ -308,17 +308,19 @@ inflate_kernel(const uint8_t *__restrict__ in, uint8_t *out, const zb200_member 
         if (m >= n_members) break;
         const zb200_member mb = members[m];
         const uint8_t *src = in + mb.in_off;
-        uint8_t *dst = out + mb.out_off;
+        const uint64_t dict = mb.dict_len <= 32768 && mb.dict_len <= mb.out_off ? mb.dict_len : 0;
+        uint8_t *dst = out + mb.out_off - dict;              // positions count from the dictionary's first byte
+        const uint64_t cap = (mb.out_cap < 0xfffffff0ull - dict ? mb.out_cap : 0xfffffff0ull - dict) + dict;   // queue entries hold 32-bit output offsets
 
         InflateState st;
         int hs = ZB200_INF_OK;
         if (lane == 0) {
-            st.init(src, mb.in_len, dst, mb.out_cap < 0xfffffff0ull ? mb.out_cap : 0xfffffff0ull, nullptr,
-                    sh.fixed_lit, sh.fixed_dist, &sh.fmt);   // queue entries hold 32-bit output offsets
+            st.init(src, mb.in_len, dst, cap, nullptr, sh.fixed_lit, sh.fixed_dist, &sh.fmt);
             st.bind(sh.w[warp].lit, sh.w[warp].dist, sh.w[warp].serial.work, sh.w[warp].serial.lens);
             st.huff_external = kWarpParallelHuffman ? 1 : 0;
             st.tables_external = 1;
-            if (mb.resume_bit) st.resume(mb.resume_bit, mb.resume_out, wrap);
+            st.preset(dict);
+            if (mb.resume_bit) st.resume(mb.resume_bit, mb.resume_out + dict, wrap);
             else hs = st.parse_header(wrap);
             if (hs) st.status = hs;
         }
@@ -345,7 +347,6 @@ inflate_kernel(const uint8_t *__restrict__ in, uint8_t *out, const zb200_member 
                 const uint64_t bp = __shfl_sync(full, ev.src, 0), op = __shfl_sync(full, ev.dst, 0);
                 const uint32_t *lt = len ? sh.fixed_lit : sh.w[warp].lit;
                 const uint32_t *dt = len ? sh.fixed_dist : sh.w[warp].dist;
-                const uint64_t cap = mb.out_cap < 0xfffffff0ull ? mb.out_cap : 0xfffffff0ull;
                 const HuffResult hr = huff_rounds_warp(src, mb.in_len, dst, cap, bp, op, lt, dt, sh.w[warp].rnd,
                                                        round_queues + (size_t)(blockIdx.x * kInfWarps + warp) * kRoundQueueCap);
                 if (lane == 0) st.seek(hr.bitpos, hr.pos, hr.status);   // status 1: the serial path finishes the block
@@ -366,13 +367,13 @@ inflate_kernel(const uint8_t *__restrict__ in, uint8_t *out, const zb200_member 
             r.wrap_kind = (uint32_t)st.wrap_kind;
             r.check = st.stored_check;                         // replaced by the computed value in inflate_verify_kernel
             r.isize = st.stored_isize;
-            r.out_len = st.pos;
+            r.out_len = st.pos - dict;
             r.in_used = st.in_used;
             r.resume_bit = st.ck_bit;
-            r.resume_out = st.ck_out;
+            r.resume_out = st.ck_out - dict;
             results[m] = r;
             seg_off[m] = mb.out_off;
-            seg_len[m] = st.status == ZB200_INF_OK ? st.pos : 0;
+            seg_len[m] = st.status == ZB200_INF_OK ? st.pos - dict : 0;
         }
     }
 }
@@ -560,8 +561,9 @@ inflate_team_kernel(const uint8_t *__restrict__ in, uint8_t *out, const zb200_me
         if (m == 0xffffffffu) break;
         const zb200_member mb = members[m];
         const uint8_t *src = in + mb.in_off;
-        uint8_t *dst = out + mb.out_off;
-        const uint64_t cap = mb.out_cap < 0xfffffff0ull ? mb.out_cap : 0xfffffff0ull;
+        const uint64_t dict = mb.dict_len <= 32768 && mb.dict_len <= mb.out_off ? mb.dict_len : 0;
+        uint8_t *dst = out + mb.out_off - dict;
+        const uint64_t cap = (mb.out_cap < 0xfffffff0ull - dict ? mb.out_cap : 0xfffffff0ull - dict) + dict;
         InflateState st;
         if (tid == 0) {
             int hs = ZB200_INF_OK;
@@ -569,7 +571,8 @@ inflate_team_kernel(const uint8_t *__restrict__ in, uint8_t *out, const zb200_me
             st.bind(ts.lit, ts.dist, ts.serial.work, ts.serial.lens);
             st.huff_external = 1;
             st.tables_external = 1;
-            if (mb.resume_bit) st.resume(mb.resume_bit, mb.resume_out, wrap);
+            st.preset(dict);
+            if (mb.resume_bit) st.resume(mb.resume_bit, mb.resume_out + dict, wrap);
             else hs = st.parse_header(wrap);
             if (hs) st.status = hs;
             ts.hs = hs;
@@ -616,13 +619,13 @@ inflate_team_kernel(const uint8_t *__restrict__ in, uint8_t *out, const zb200_me
             r.wrap_kind = (uint32_t)st.wrap_kind;
             r.check = st.stored_check;
             r.isize = st.stored_isize;
-            r.out_len = st.pos;
+            r.out_len = st.pos - dict;
             r.in_used = st.in_used;
             r.resume_bit = st.ck_bit;
-            r.resume_out = st.ck_out;
+            r.resume_out = st.ck_out - dict;
             results[m] = r;
             seg_off[m] = mb.out_off;
-            seg_len[m] = st.status == ZB200_INF_OK ? st.pos : 0;
+            seg_len[m] = st.status == ZB200_INF_OK ? st.pos - dict : 0;
         }
     }
 }
@@ -944,12 +947,16 @@ int zb200_inflate_host(zb200_ctx *ctx, const void *in, void *out, const zb200_me
     for (size_t i = 0; i < n_members; ++i) {
         if (members[i].in_off + members[i].in_len > in_bytes) in_bytes = members[i].in_off + members[i].in_len;
         if (members[i].out_off + members[i].out_cap > out_bytes) out_bytes = members[i].out_off + members[i].out_cap;
+        if (members[i].dict_len > 32768 || members[i].dict_len > members[i].out_off) {
+            set_error("inflate: a preset dictionary is at most 32768 bytes and lies before out_off");
+            return ZB200_ERR_PARAM;
+        }
     }
     // the pipelined path: enough work, pinned data buffers, members in order, nothing to resume
     if (n_members >= 64 && out_bytes >= ((size_t)1536 << 20) && is_pinned(in) && is_pinned(out)) {
         bool ordered = true;
         for (size_t i = 0; i < n_members && ordered; ++i) {
-            if (members[i].resume_bit) ordered = false;
+            if (members[i].resume_bit || members[i].dict_len) ordered = false;
             if (i && (members[i].in_off < members[i - 1].in_off + members[i - 1].in_len ||
                       members[i].out_off < members[i - 1].out_off + members[i - 1].out_cap)) ordered = false;
         }
@@ -972,6 +979,10 @@ int zb200_inflate_host(zb200_ctx *ctx, const void *in, void *out, const zb200_me
         if (members[i].resume_bit && members[i].resume_out)
             if ((r = h2d_auto(ctx, ctx->d_io_out + members[i].out_off, (const uint8_t *)out + members[i].out_off,
                               members[i].resume_out, s))) return r;
+    for (size_t i = 0; i < n_members; ++i)                      // preset dictionaries travel with their members
+        if (members[i].dict_len)
+            if ((r = h2d_auto(ctx, ctx->d_io_out + members[i].out_off - members[i].dict_len,
+                              (const uint8_t *)out + members[i].out_off - members[i].dict_len, members[i].dict_len, s))) return r;
     if ((r = h2d_auto(ctx, d_members, members, n_members * sizeof(zb200_member), s))) return r;
     r = inflate_launch(ctx, ctx->d_io_in, ctx->d_io_out, d_members, n_members, wrap, verify, d_results, d_work, s);
     if (r) return r;

@@ -169,6 +169,7 @@ struct InflateState {
     const uint32_t *lt, *dt;                               // tables of the open block
     int wrap_kind;                                         // 0 raw, 1 zlib, 2 gzip (resolved)
     int dyn_nlen, dyn_ndist;                               // symbol counts of the dynamic header just read
+    int have_dict;                                         // a preset dictionary lies before the output (pos starts behind it)
     int status;
     uint64_t ck_bit, ck_out;                               // last block boundary (resume point)
     uint32_t stored_check, stored_isize;                   // trailer values
@@ -213,10 +214,14 @@ struct InflateState {
         in = src; in_len = n; next = 0; hold = 0; bits = 0;
         out = dst; out_cap = cap; pos = 0; last = 0; in_block = 0; lt = dt = nullptr;
         wrap_kind = 0; status = ZB200_INF_OK; ck_bit = 0; ck_out = 0; stored_check = 0; stored_isize = 0;
-        in_used = 0; fixed_lit = flit; fixed_dist = fdist; fmt = f; has_parked = 0; huff_external = 0; tables_external = 0;
+        in_used = 0; fixed_lit = flit; fixed_dist = fdist; fmt = f; has_parked = 0; huff_external = 0; tables_external = 0; have_dict = 0;
         if (s) { tlit = s->lit; tdist = s->dist; work = s->work; lens = s->lens; }
         else { tlit = tdist = nullptr; work = nullptr; lens = nullptr; }
     }
+
+    // A preset dictionary of n bytes occupies out[0..n): the member's output follows it
+    // (inflate.c:1278-1312 copies it into the window instead).  Call after init().
+    ZB_HD void preset(uint64_t n) { if (n) { pos = n; ck_out = n; have_dict = 1; } }
 
     // Continue a member at a block boundary reported by an earlier, truncated run
     // (the streaming inflate() of the host API feeds input piecewise).
@@ -271,8 +276,13 @@ struct InflateState {
         if (((h0 << 8) + h1) % 31) return ZB200_INF_HEADER_CHECK;
         if ((h0 & 0xf) != 8) return ZB200_INF_METHOD;
         if ((h0 >> 4) + 8 > 15) return ZB200_INF_WINDOW;
-        if (h1 & 0x20) return ZB200_INF_NEED_DICT;
         wrap_kind = 1; next = 2;
+        if (h1 & 0x20) {                               // FDICT: inflate.c:660-669 reads the DICTID, then wants the dictionary
+            if (in_len < 6) return ZB200_INF_TRUNCATED;
+            stored_check = ((uint32_t)in[2] << 24) | ((uint32_t)in[3] << 16) | ((uint32_t)in[4] << 8) | (uint32_t)in[5];
+            if (!have_dict) return ZB200_INF_NEED_DICT;
+            next = 6;
+        }
         return ZB200_INF_OK;
     }
 

@@ -104,7 +104,7 @@ int checksum_launch(zb200_ctx *ctx, const uint8_t *d_base, const uint64_t *d_off
 int deflate_init(zb200_ctx *ctx);
 int deflate_launch(zb200_ctx *ctx, const uint8_t *d_in, size_t n, size_t S, int level, int strategy, int frame,
                    int finish, uint8_t *d_out, size_t out_cap, uint64_t *d_chunk_end, uint64_t *d_total,
-                   uint32_t *d_sums_out, cudaStream_t s);
+                   uint32_t *d_sums_out, cudaStream_t s, size_t skip = 0);   // skip: preset dictionary at the head of a single raw chunk
 // zb_inflate.cu
 int inflate_init(zb200_ctx *ctx);
 size_t inflate_work_bytes(size_t n_members);

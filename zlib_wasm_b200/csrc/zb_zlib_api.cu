@@ -60,6 +60,9 @@ struct DeflateStream {
     uint32_t crc, adler;                 // running checksums of all compressed input
     uint64_t total_in_hashed;
     int last_flush;
+    std::vector<uint8_t> dict;           // preset dictionary not yet consumed (the last <= 32768 bytes of it)
+    uint32_t dictid;                     // Adler-32 of the whole dictionary (zlib header DICTID)
+    bool have_dictid;
 };
 
 struct InflateStream {
@@ -78,6 +81,9 @@ struct InflateStream {
     int error;                           // sticky ZB200_INF_* data error
     uint64_t in_used;
     uint32_t check;
+    size_t dict_len;                     // preset dictionary: d_out[0 .. dict_len), the output follows it
+    uint32_t dictid;                     // DICTID of the zlib header that asked for one
+    bool retry;                          // inflateSetDictionary was called: decode again with no new input
 };
 
 int dev_grow(uint8_t **p, size_t *cap, size_t need, size_t keep, cudaStream_t s) {
@@ -103,12 +109,37 @@ int compress_buffered(DeflateStream &st, bool finish) {
     if (n == 0 && !finish) return Z_OK;
     const size_t chunk = api_chunk();
     size_t cap = zb200_deflate_bound(n, chunk, ZB200_FRAME_RAW);
+    if (!st.dict.empty()) cap += zb200_deflate_bound(st.dict.size() + chunk, st.dict.size() + chunk, ZB200_FRAME_RAW);
     const size_t at = st.pending.size();
     st.pending.resize(at + cap);
     uint32_t adler = 1, crc = 0;
-    int r = zb200_deflate_host(ctx, n ? st.in.data() : (const uint8_t *)"", n, chunk, st.level,
+    int r;
+    if (!st.dict.empty() && n) {
+        // deflate.c:550-632: the dictionary is window content ahead of the first byte.  The first chunk goes to the
+        // engine behind it (history only); the rest follows as usual, its checksums merged.
+        const size_t first = n < chunk ? n : chunk, dl = st.dict.size();
+        std::vector<uint8_t> joined(dl + first);
+        memcpy(joined.data(), st.dict.data(), dl);
+        memcpy(joined.data() + dl, st.in.data(), first);
+        size_t cap1 = cap;
+        r = zb200_deflate_host_dict(ctx, joined.data(), dl + first, dl, st.level, st.strategy, (finish && first == n) ? 1 : 0,
+                                    st.pending.data() + at, &cap1, &adler, &crc);
+        if (r == ZB200_OK && first < n) {
+            size_t cap2 = cap - cap1;
+            uint32_t a2 = 1, c2 = 0;
+            r = zb200_deflate_host(ctx, st.in.data() + first, n - first, chunk, st.level, st.strategy, ZB200_FRAME_RAW,
+                                   finish ? 1 : 0, st.pending.data() + at + cap1, &cap2, &a2, &c2);
+            crc = zb200_crc32_combine(crc, c2, n - first);
+            adler = zb200_adler32_combine(adler, a2, (int64_t)(n - first));
+            cap1 += cap2;
+        }
+        cap = cap1;
+        if (r == ZB200_OK) st.dict.clear();
+    } else {
+        r = zb200_deflate_host(ctx, n ? st.in.data() : (const uint8_t *)"", n, chunk, st.level,
                                st.strategy, ZB200_FRAME_RAW, finish ? 1 : 0,
                                st.pending.data() + at, &cap, &adler, &crc);
+    }
     if (r != ZB200_OK) { st.pending.resize(at); return map_engine_error(r); }
     st.pending.resize(at + cap);
     st.crc = zb200_crc32_combine(st.crc, crc, n);
@@ -122,8 +153,11 @@ void put_header(DeflateStream &st) {
     if (st.wrap == 1) {                                        // deflate.c:1004-1037
         const unsigned lf = (st.strategy >= Z_HUFFMAN_ONLY || st.level < 2) ? 0 : st.level < 6 ? 1 : st.level == 6 ? 2 : 3;
         unsigned hdr = (0x78u << 8) | (lf << 6);
+        if (st.have_dictid) hdr |= 0x20;                       // PRESET_DICT, deflate.c:1026
         hdr += 31 - hdr % 31;
         st.pending.push_back((uint8_t)(hdr >> 8)); st.pending.push_back((uint8_t)hdr);
+        if (st.have_dictid)                                    // deflate.c:1031-1034: DICTID, most significant byte first
+            for (int i = 3; i >= 0; --i) st.pending.push_back((uint8_t)(st.dictid >> (8 * i)));
     } else if (st.wrap == 2) {                                 // deflate.c:1042-1054
         const uint8_t g[10] = {0x1f, 0x8b, 8, 0, 0, 0, 0, 0,
                                (uint8_t)(st.level == 9 ? 2 : (st.strategy >= Z_HUFFMAN_ONLY || st.level < 2) ? 4 : 0), 3};
@@ -156,6 +190,7 @@ InflateStream *istate(z_streamp strm) {
 void inflate_reset_state(InflateStream &s) {
     s.kind = 0; s.in.clear(); s.d_in_have = 0; s.out.clear(); s.out_pos = 0; s.out_base = 0; s.decoded = 0;
     s.resume_bit = s.resume_out = 0; s.started = s.done = false; s.error = 0; s.in_used = 0; s.check = 0;
+    s.dict_len = 0; s.dictid = 0; s.retry = false;
 }
 
 // One decode attempt over everything received so far, resuming at the last
@@ -172,12 +207,12 @@ int inflate_attempt(InflateStream &s) {
         if (cudaMemcpyAsync(s.d_in + s.d_in_have, s.in.data() + s.d_in_have, n - s.d_in_have, cudaMemcpyHostToDevice, st) != cudaSuccess) return -1;
         s.d_in_have = n;
     }
-    if (s.d_out_cap == 0 && dev_grow(&s.d_out, &s.d_out_cap, n * 4 + (1u << 20), 0, st)) return -1;
+    if (s.d_out_cap == 0 && dev_grow(&s.d_out, &s.d_out_cap, n * 4 + (1u << 20) + s.dict_len, 0, st)) return -1;
     if (ensure_scratch(ctx, 1024 + inflate_work_bytes(1)) != ZB200_OK) return -1;
     for (;;) {
         zb200_member m;
-        m.in_off = 0; m.in_len = n; m.out_off = 0; m.out_cap = s.d_out_cap;
-        m.resume_bit = s.resume_bit; m.resume_out = s.resume_out;
+        m.in_off = 0; m.in_len = n; m.out_off = s.dict_len; m.out_cap = s.d_out_cap - s.dict_len;
+        m.resume_bit = s.resume_bit; m.resume_out = s.resume_out; m.dict_len = s.dict_len;
         uint8_t *base = (uint8_t *)ctx->d_scratch;
         zb200_member *d_m = (zb200_member *)base;
         zb200_member_result *d_r = (zb200_member_result *)(base + 256);
@@ -192,7 +227,7 @@ int inflate_attempt(InflateStream &s) {
         if (r.status == ZB200_INF_OUTPUT_FULL) {                 // grow the device output and go again from the checkpoint
             s.kind = (int)r.wrap_kind; s.resume_bit = r.resume_bit; s.resume_out = r.resume_out;
             if (r.resume_bit == 0) { s.resume_bit = 0; s.resume_out = 0; }
-            if (dev_grow(&s.d_out, &s.d_out_cap, s.d_out_cap * 2 + (1u << 20), (size_t)r.out_len, st)) return -1;
+            if (dev_grow(&s.d_out, &s.d_out_cap, s.d_out_cap * 2 + (1u << 20), (size_t)r.out_len + s.dict_len, st)) return -1;
             continue;
         }
         // fetch the newly valid bytes
@@ -200,11 +235,12 @@ int inflate_attempt(InflateStream &s) {
             const size_t add = (size_t)(r.out_len - s.decoded);
             const size_t at = s.out.size();
             s.out.resize(at + add);
-            if (cudaMemcpyAsync(s.out.data() + at, s.d_out + s.decoded, add, cudaMemcpyDeviceToHost, st) != cudaSuccess) return -1;
+            if (cudaMemcpyAsync(s.out.data() + at, s.d_out + s.dict_len + s.decoded, add, cudaMemcpyDeviceToHost, st) != cudaSuccess) return -1;
             if (cudaStreamSynchronize(st) != cudaSuccess) return -1;
             s.decoded = r.out_len;
         }
         s.kind = (int)r.wrap_kind;
+        if (r.status == ZB200_INF_NEED_DICT) s.dictid = r.check;
         if (r.status == ZB200_INF_TRUNCATED) {
             if (r.resume_bit) { s.resume_bit = r.resume_bit; s.resume_out = r.resume_out; }
         } else if (r.status == ZB200_INF_OK) {
@@ -253,6 +289,7 @@ int deflateReset(z_streamp strm) {
     s->in.clear(); s->pending.clear(); s->pending_pos = 0;
     s->header_done = s->finished = s->trailer_done = false;
     s->crc = 0; s->adler = 1; s->total_in_hashed = 0; s->last_flush = -2;
+    s->dict.clear(); s->dictid = 0; s->have_dictid = false;
     strm->total_in = strm->total_out = 0; strm->msg = Z_NULL; strm->data_type = Z_UNKNOWN;
     strm->adler = s->wrap == 2 ? 0 : 1;                         // deflate.c:656-660
     return Z_OK;
@@ -269,6 +306,27 @@ int deflateParams(z_streamp strm, int level, int strategy) {
         if (r != Z_OK) return r;
     }
     s->level = level; s->strategy = strategy;
+    return Z_OK;
+}
+
+// deflate.c:550-632.  Accepted where the reference accepts it at the start of a stream: before the first
+// deflate() call (zlib / raw wrappers; gzip streams take no dictionary).  Mid-stream use on a raw stream
+// (deflate.c:566, lookahead == 0 after a full flush) is not offered: Z_STREAM_ERROR.
+int deflateSetDictionary(z_streamp strm, const Bytef *dictionary, uInt dictLength) {
+    DeflateStream *s = dstate(strm);
+    if (!s || dictionary == Z_NULL) return Z_STREAM_ERROR;
+    if (s->wrap == 2 || s->header_done || !s->in.empty() || s->total_in_hashed || strm->total_in || s->finished) return Z_STREAM_ERROR;
+    if (s->wrap == 1) {                                         // deflate.c:570-571
+        zb200_ctx *ctx = api_ctx();
+        if (!ctx) return Z_STREAM_ERROR;
+        uint32_t a = (uint32_t)strm->adler;
+        if (dictLength && zb200_checksum_host(ctx, dictionary, dictLength, ZB200_ADLER32, 0, (uint32_t)strm->adler, nullptr, &a) != ZB200_OK)
+            return Z_STREAM_ERROR;
+        strm->adler = a;
+        s->dictid = a; s->have_dictid = true;
+    }
+    const uInt keep = dictLength > 32768u ? 32768u : dictLength;   // deflate.c:575-583: the tail of a long dictionary
+    s->dict.assign(dictionary + (dictLength - keep), dictionary + dictLength);
     return Z_OK;
 }
 
@@ -382,7 +440,8 @@ int inflate(z_streamp strm, int flush) {
     const uInt in0 = strm->avail_in, out0 = strm->avail_out;
     const uLong total_in0 = strm->total_in;
     int status = s->error ? s->error : (s->done ? ZB200_INF_OK : ZB200_INF_TRUNCATED);
-    if (!s->done && !s->error && strm->avail_in) {
+    if (!s->done && !s->error && (strm->avail_in || s->retry)) {
+        s->retry = false;
         s->in.insert(s->in.end(), strm->next_in, strm->next_in + strm->avail_in);
         status = inflate_attempt(*s);
         if (status < 0) { strm->msg = "zlib-b200: device error"; return Z_STREAM_ERROR; }
@@ -402,13 +461,41 @@ int inflate(z_streamp strm, int flush) {
     }
     const bool drained = s->out.empty();
     if (s->error && drained) {
-        if (s->error == ZB200_INF_NEED_DICT) return Z_NEED_DICT;
+        if (s->error == ZB200_INF_NEED_DICT) { strm->adler = s->dictid; return Z_NEED_DICT; }   // inflate.c:667-669
         strm->msg = zb200_inflate_msg(s->error);
         return Z_DATA_ERROR;
     }
     if (s->done && drained) return Z_STREAM_END;
     if ((in0 == strm->avail_in && out0 == strm->avail_out) || (flush == Z_FINISH && !(s->done && drained)))
         return Z_BUF_ERROR;                                     // inflate.c:1259-1261
+    return Z_OK;
+}
+
+// inflate.c:1278-1312.  zlib streams: only when inflate() has just returned Z_NEED_DICT, and the dictionary's
+// Adler-32 must be the header's DICTID (else Z_DATA_ERROR); raw streams: before any output has been produced.
+int inflateSetDictionary(z_streamp strm, const Bytef *dictionary, uInt dictLength) {
+    InflateStream *s = istate(strm);
+    if (!s || dictionary == Z_NULL) return Z_STREAM_ERROR;
+    zb200_ctx *ctx = api_ctx();
+    if (!ctx) return Z_STREAM_ERROR;
+    if (s->wrap != ZB200_WRAP_RAW) {
+        if (s->error != ZB200_INF_NEED_DICT) return Z_STREAM_ERROR;
+        uint32_t a = 1;
+        if (dictLength && zb200_checksum_host(ctx, dictionary, dictLength, ZB200_ADLER32, 0, 1, nullptr, &a) != ZB200_OK) return Z_STREAM_ERROR;
+        if (a != s->dictid) return Z_DATA_ERROR;
+    } else if (s->decoded || s->done || s->error || s->dict_len) return Z_STREAM_ERROR;
+    const size_t keep = dictLength > 32768u ? 32768u : dictLength;
+    {
+        std::lock_guard<std::mutex> g(ctx->mu);
+        if (cudaSetDevice(ctx->device) != cudaSuccess) return Z_STREAM_ERROR;
+        cudaStream_t st = ctx->stream;
+        if (dev_grow(&s->d_out, &s->d_out_cap, keep + (1u << 20), 0, st)) return Z_MEM_ERROR;
+        if (keep && cudaMemcpyAsync(s->d_out, dictionary + (dictLength - keep), keep, cudaMemcpyHostToDevice, st) != cudaSuccess) return Z_STREAM_ERROR;
+        if (cudaStreamSynchronize(st) != cudaSuccess) return Z_STREAM_ERROR;
+    }
+    s->dict_len = keep;
+    if (s->error == ZB200_INF_NEED_DICT) { s->error = 0; s->retry = true; }
+    if (s->wrap != ZB200_WRAP_RAW) strm->adler = 1;               // inflate.c:671: adler32(0L, Z_NULL, 0)
     return Z_OK;
 }
 
@@ -451,7 +538,7 @@ int uncompress2(Bytef *dest, uLongf *destLen, const Bytef *source, uLong *source
     Bytef one[1];
     const bool probe = (*destLen == 0);                         // uncompr.c:37-42: detect "would need output"
     zb200_member m;
-    m.in_off = 0; m.in_len = *sourceLen; m.out_off = 0; m.out_cap = probe ? 1 : *destLen; m.resume_bit = m.resume_out = 0;
+    m.in_off = 0; m.in_len = *sourceLen; m.out_off = 0; m.out_cap = probe ? 1 : *destLen; m.resume_bit = m.resume_out = 0; m.dict_len = 0;
     zb200_member_result res;
     const int r = zb200_inflate_host(ctx, source, probe ? one : dest, &m, 1, ZB200_WRAP_ZLIB, 1, &res);
     if (r != ZB200_OK) return map_engine_error(r);
