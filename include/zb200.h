@@ -171,6 +171,19 @@ int zb200_inflate_host(zb200_ctx *ctx, const void *in, void *out,
 int zb200_deflate_host_dict(zb200_ctx *ctx, const void *in, size_t n, size_t dict_len, int level, int strategy,
                             int finish, void *out, size_t *out_len, uint32_t *in_adler, uint32_t *in_crc);
 
+/* A whole gzip FILE — any number of members back to back (RFC 1952 2.2; what gzread.c:76-234 walks one
+ * member at a time) — decoded without an index: member starts are discovered on the device (header
+ * candidates, each sized by the ISIZE in front of the next one), all members are inflated in one batch and the
+ * chain is verified from the front; candidates that turn out to lie inside a member are dropped and the batch
+ * redone.  Bytes after the last valid member that are no gzip member are ignored, as gzread does.
+ *   out / out_cap   the concatenated output; ZB200_ERR_OUTPUT with *out_len = the size needed if it does not fit
+ *   inf_status      ZB200_INF_OK, or the status of the first member that failed (*out_len = valid bytes before it)
+ *   members         optional: the discovered table (in_off, in_len, out_off, out_cap = output length), up to
+ *                   max_members entries; *n_members = members found
+ * Host pointers; synchronous. */
+int zb200_gunzip_host(zb200_ctx *ctx, const void *in, size_t n, void *out, size_t out_cap, size_t *out_len,
+                      int *inf_status, zb200_member *members, size_t max_members, size_t *n_members);
+
 /* Self-test of the warp-parallel decode-table construction (csrc/zb_inflate_tables.cuh) against the
  * serial one that follows inftrees.c:32-299: for each of n_cases sets of code lengths (lens: 320 bytes
  * per case = nlen literal/length lengths followed by ndist distance lengths; counts: nlen, ndist per

@@ -58,6 +58,10 @@ typedef struct z_stream_s {                               /* zlib.h:90-110 */
     uLong reserved;
 } z_stream;
 typedef z_stream *z_streamp;
+typedef void *voidp;
+typedef const void *voidpc;
+struct gzFile_s { unsigned have; unsigned char *next; long pos; };   /* zlib.h:1819-1823 */
+typedef struct gzFile_s *gzFile;
 
 #define Z_NO_FLUSH 0                                      /* zlib.h:172-189 */
 #define Z_PARTIAL_FLUSH 1
@@ -116,6 +120,35 @@ int inflateEnd(z_streamp strm);
 int inflateReset(z_streamp strm);
 int inflateReset2(z_streamp strm, int windowBits);
 int inflateSetDictionary(z_streamp strm, const Bytef *dictionary, uInt dictLength);   /* zlib.h:887, inflate.c:1278 */
+
+/* ---- gz* file layer (zlib.h:1300-1823; gzlib.c, gzread.c, gzwrite.c, gzclose.c) ---- */
+gzFile gzopen(const char *path, const char *mode);
+gzFile gzdopen(int fd, const char *mode);
+int gzbuffer(gzFile file, unsigned size);
+int gzsetparams(gzFile file, int level, int strategy);
+int gzread(gzFile file, voidp buf, unsigned len);
+z_size_t gzfread(voidp buf, z_size_t size, z_size_t nitems, gzFile file);
+int gzwrite(gzFile file, voidpc buf, unsigned len);
+z_size_t gzfwrite(voidpc buf, z_size_t size, z_size_t nitems, gzFile file);
+int gzprintf(gzFile file, const char *format, ...);
+int gzputs(gzFile file, const char *s);
+char *gzgets(gzFile file, char *buf, int len);
+int gzputc(gzFile file, int c);
+int gzgetc(gzFile file);
+int gzgetc_(gzFile file);                                /* zlib.h:1825: what the gzgetc() macro falls back to */
+int gzungetc(int c, gzFile file);
+int gzflush(gzFile file, int flush);
+z_off_t gzseek(gzFile file, z_off_t offset, int whence);
+int gzrewind(gzFile file);
+z_off_t gztell(gzFile file);
+z_off_t gzoffset(gzFile file);
+int gzeof(gzFile file);
+int gzdirect(gzFile file);
+int gzclose(gzFile file);
+int gzclose_r(gzFile file);
+int gzclose_w(gzFile file);
+const char *gzerror(gzFile file, int *errnum);
+void gzclearerr(gzFile file);
 
 /* ---- utility (compress.c:22-75, uncompr.c:27-85) ---- */
 int compress(Bytef *dest, uLongf *destLen, const Bytef *source, uLong sourceLen);

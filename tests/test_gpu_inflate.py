@@ -303,3 +303,63 @@ def test_members_with_preset_dictionaries(ctx):
             out, res = ctx.inflate_host(blob, [(m[0], m[1], 0, m[3])], wrap, 1)
             dictid = int.from_bytes(blob[m[0] + 2:m[0] + 6], "big")
             assert msg(res[0].status) == "need dictionary" and res[0].check == dictid and res[0].out_len == 0
+
+
+def _gunzip(ctx, blob, cap, max_members=0):
+    import ctypes as C
+    L = zb.lib()
+    out = C.create_string_buffer(max(cap, 1))
+    olen, nm, st = C.c_size_t(0), C.c_size_t(0), C.c_int(0)
+    tab = (zb.Member * max(max_members, 1))()
+    r = L.zb200_gunzip_host(ctx.handle, bytes(blob), len(blob), out, cap, C.byref(olen), C.byref(st),
+                            tab if max_members else None, max_members, C.byref(nm))
+    return r, st.value, out.raw[:min(olen.value, cap)], olen.value, nm.value, list(tab)[:min(nm.value, max_members)]
+
+
+def test_gunzip_discovers_members(ctx):
+    """zb200_gunzip_host: a gzip file's members found without an index (gzread.c:76-234 walks them serially),
+    incl. look-alike headers inside stored data, optional header fields, and bytes after the last member."""
+    ref = refz.ref() if refz.have_ref() else refz.oracle()
+    rng = random.Random(17)
+    base = refz.gen(3000000, refz.GEN_MARKOV, seed=5)
+    noise = bytearray(refz.gen(400000, refz.GEN_RANDOM, seed=6))
+    for at in range(1000, len(noise) - 100, 37000):            # look-alike member headers inside incompressible data
+        noise[at:at + 10] = b"\x1f\x8b\x08\x00\x00\x00\x00\x00\x00\x03"
+    pieces, blob = [], b""
+    for k in range(300):
+        n = rng.choice((0, 1, 77, 5000, 70000, 200000))
+        d = base[rng.randrange(0, len(base) - n):][:n]
+        s = ref.deflate_stream(d, rng.choice((1, 6, 9)), 0, refz.WRAP_GZIP, 0)
+        if k % 50 == 7:                                         # FNAME + FCOMMENT + FEXTRA + FHCRC (RFC 1952 2.3)
+            import zlib as pz
+            hdr = bytearray(s[:10]); hdr[3] = 0x1e
+            extra = b"\x04\x00ab\x01\x02" + b"name.txt\x00" + b"a comment\x00"
+            h = bytes(hdr) + extra
+            s = h + (pz.crc32(h) & 0xffff).to_bytes(2, "little") + s[10:]
+        pieces.append((d, len(s)))
+        blob += s
+    for lvl in (0, 6):                                          # stored blocks carry the look-alikes verbatim
+        s = ref.deflate_stream(bytes(noise), lvl, 0, refz.WRAP_GZIP, 0)
+        pieces.append((bytes(noise), len(s)))
+        blob += s
+    want = b"".join(d for d, _ in pieces)
+    r, st, out, need, nm, tab = _gunzip(ctx, blob, len(want) + 100, max_members=len(pieces) + 8)
+    assert r == 0 and st == 0 and nm == len(pieces) and out == want, (r, msg(st), nm, len(pieces), need, len(want))
+    off = opos = 0
+    for (d, cl), m in zip(pieces, tab):
+        assert (m.in_off, m.in_len, m.out_off, m.out_cap) == (off, cl, opos, len(d))
+        off += cl; opos += len(d)
+    # too small an output buffer: the size needed comes back
+    r, st, out, need, nm, tab = _gunzip(ctx, blob, 1000)
+    assert r == zb.ERR_OUTPUT and need == len(want)
+    # bytes after the last member that are no member are ignored; a member cut short is reported
+    r, st, out, need, nm, tab = _gunzip(ctx, blob + b"\x00" * 5000 + b"junk", len(want) + 100)
+    assert r == 0 and st == 0 and out == want and nm == len(pieces)
+    cut = len(blob) - pieces[-1][1] // 2
+    r, st, out, need, nm, tab = _gunzip(ctx, blob[:cut], len(want) + 100)
+    assert r == 0 and msg(st) == "truncated input" and nm == len(pieces) - 1 and out == want[:len(want) - len(noise)]
+    bad = bytearray(blob); bad[pieces[0][1] + pieces[1][1] + 30] ^= 0x10
+    r, st, out, need, nm, tab = _gunzip(ctx, bytes(bad), len(want) + 100)
+    assert r == 0 and st != 0 and nm <= 2 and out == want[:len(out)]
+    r, st, out, need, nm, tab = _gunzip(ctx, b"not a gzip file at all....", 100)
+    assert r == 0 and msg(st) == "incorrect header check" and out == b""

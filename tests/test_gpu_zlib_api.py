@@ -206,3 +206,91 @@ def test_preset_dictionary(z, wrap):
         assert ret == refz.Z_DATA_ERROR
     with pytest.raises(RuntimeError):                                               # gzip takes no dictionary: deflate.c:562
         z.deflate_stream(base[:1000], 6, 0, refz.WRAP_GZIP, 0, dictionary=base[:100])
+
+
+def _gz(z):
+    L = z.lib
+    if not hasattr(z, "_gz_bound"):
+        L.gzopen.restype = C.c_void_p; L.gzopen.argtypes = [C.c_char_p, C.c_char_p]
+        L.gzread.restype = C.c_int; L.gzread.argtypes = [C.c_void_p, C.c_void_p, C.c_uint]
+        L.gzwrite.restype = C.c_int; L.gzwrite.argtypes = [C.c_void_p, C.c_void_p, C.c_uint]
+        L.gzclose.restype = C.c_int; L.gzclose.argtypes = [C.c_void_p]
+        L.gzeof.restype = C.c_int; L.gzeof.argtypes = [C.c_void_p]
+        L.gzdirect.restype = C.c_int; L.gzdirect.argtypes = [C.c_void_p]
+        L.gzgets.restype = C.c_void_p; L.gzgets.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        L.gzputs.restype = C.c_int; L.gzputs.argtypes = [C.c_void_p, C.c_char_p]
+        L.gzgetc.restype = C.c_int; L.gzgetc.argtypes = [C.c_void_p]
+        L.gzungetc.restype = C.c_int; L.gzungetc.argtypes = [C.c_int, C.c_void_p]
+        L.gzseek.restype = C.c_long; L.gzseek.argtypes = [C.c_void_p, C.c_long, C.c_int]
+        L.gztell.restype = C.c_long; L.gztell.argtypes = [C.c_void_p]
+        L.gzflush.restype = C.c_int; L.gzflush.argtypes = [C.c_void_p, C.c_int]
+        L.gzerror.restype = C.c_char_p; L.gzerror.argtypes = [C.c_void_p, C.POINTER(C.c_int)]
+        L.gzrewind.restype = C.c_int; L.gzrewind.argtypes = [C.c_void_p]
+        z._gz_bound = True
+    return L
+
+
+def _gz_read_all(L, path, step=1 << 20):
+    f = L.gzopen(path.encode(), b"rb")
+    assert f
+    buf, out = C.create_string_buffer(step), b""
+    while True:
+        k = L.gzread(f, buf, step)
+        assert k >= 0, k
+        out += buf.raw[:k]
+        if k < step:
+            break
+    return f, out
+
+
+def test_gz_file_layer(z, tmp_path):
+    """gzopen / gzwrite / gzread / gzgets / gzseek / gzclose (gzlib.c, gzread.c, gzwrite.c): files written here are
+    read by Python's gzip module (an independent reader) and equal the reference's gzip stream; multi-member files
+    written by others — concatenation, append mode — are read back whole; plain files pass through."""
+    import gzip
+    L = _gz(z)
+    d = refz.gen(3000000, refz.GEN_TEXT, seed=77)
+    p1 = str(tmp_path / "a.gz")
+    f = L.gzopen(p1.encode(), b"wb6")
+    assert f
+    for off in range(0, len(d), 700001):
+        piece = d[off:off + 700001]
+        assert L.gzwrite(f, piece, len(piece)) == len(piece)
+    assert L.gztell(f) == len(d) and L.gzclose(f) == 0
+    raw = open(p1, "rb").read()
+    assert gzip.decompress(raw) == d
+    assert raw == ref_or_oracle_stream(d, 6, 0, refz.WRAP_GZIP, 262144)
+    # append mode adds a member; another writer's members follow; everything is read back as one stream
+    f = L.gzopen(p1.encode(), b"ab9")
+    assert L.gzputs(f, b"appended line\n") == 14 and L.gzclose(f) == 0
+    more = [refz.gen(n, refz.GEN_MARKOV, seed=n) for n in (0, 10, 99999, 400000)]
+    with open(p1, "ab") as fh:
+        for m in more:
+            fh.write(gzip.compress(m, 6))
+    want = d + b"appended line\n" + b"".join(more)
+    f, out = _gz_read_all(L, p1)
+    assert out == want and L.gzeof(f) == 1 and L.gzdirect(f) == 0
+    # seeking, single characters, lines
+    assert L.gzseek(f, len(d), 0) == len(d) and L.gzeof(f) == 0
+    line = C.create_string_buffer(64)
+    assert L.gzgets(f, line, 64) and line.value == b"appended line\n"
+    assert L.gzseek(f, -5, 1) == len(d) + 9 and L.gzgetc(f) == ord("l") and L.gzungetc(ord("L"), f) == ord("L")
+    assert L.gzgetc(f) == ord("L") and L.gztell(f) == len(d) + 10
+    assert L.gzrewind(f) == 0 and L.gzgetc(f) == d[0]
+    assert L.gzclose(f) == 0
+    # a plain file passes through (gzread.c:gz_look direct mode); "T" writes one
+    p2 = str(tmp_path / "plain.txt")
+    f = L.gzopen(p2.encode(), b"wT")
+    assert L.gzwrite(f, d[:5000], 5000) == 5000 and L.gzclose(f) == 0
+    assert open(p2, "rb").read() == d[:5000]
+    f, out = _gz_read_all(L, p2)
+    assert out == d[:5000] and L.gzdirect(f) == 1 and L.gzclose(f) == 0
+    # a file cut short: what is there is delivered, the error says so (gzread.c:gz_decomp)
+    p3 = str(tmp_path / "cut.gz")
+    open(p3, "wb").write(raw[:len(raw) // 2])
+    f, out = _gz_read_all(L, p3)
+    err = C.c_int(0)
+    m = L.gzerror(f, C.byref(err))
+    assert out == b"" or d.startswith(out)
+    assert err.value == refz.Z_BUF_ERROR and m == b"unexpected end of file" and L.gzclose(f) == refz.Z_BUF_ERROR
+    assert not L.gzopen(p1.encode(), b"r+") and not L.gzopen(str(tmp_path / "nope.gz").encode(), b"rb")

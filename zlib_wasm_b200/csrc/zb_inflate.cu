@@ -14,6 +14,8 @@
 #include "zb_inflate_round.cuh"
 #include "zb_inflate_tables.cuh"
 #include <string.h>
+#include <algorithm>
+#include <vector>
 #include <stdlib.h>
 
 namespace zb {
@@ -688,6 +690,26 @@ tables_selftest_kernel(const uint8_t *__restrict__ lens_all, const uint32_t *__r
     }
 }
 
+// ---- members of a gzip file, discovered (gzread.c:76-234 walks them one after another) -----
+// A gzip file has no index: a member's length is known once it has been decoded.  Every byte
+// position that looks like a member header (1f 8b 08, no reserved flag, a known XFL) is a
+// candidate; the host takes each candidate's extent to be "up to the next candidate" and its
+// output size from the ISIZE field in front of the next candidate, all of them are decoded in one
+// batch, and the chain is then checked from the front.  A candidate inside another member's
+// data makes that member come out truncated or over-full: it is dropped and the batch redone.
+__global__ void __launch_bounds__(256)
+gz_candidates_kernel(const uint8_t *__restrict__ in, uint64_t n, uint64_t *__restrict__ list, uint32_t cap, uint32_t *__restrict__ count) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i + 10 <= n; i += stride) {
+        if (in[i] != 0x1f) continue;
+        if (in[i + 1] != 0x8b || in[i + 2] != 8 || (in[i + 3] & 0xe0)) continue;
+        const uint32_t xfl = in[i + 8];
+        if (xfl != 0 && xfl != 2 && xfl != 4) continue;         // deflate.c:1049-1052 writes nothing else
+        const uint32_t k = atomicAdd(count, 1u);
+        if (k < cap) list[k] = i;
+    }
+}
+
 // Members are handed out by an atomic counter.  A member is decoded serially by its
 // warp, so the launch ends when the slowest member ends: hand out the largest first
 // (bucketed by log2 of the compressed size; one CTA builds the order).
@@ -933,6 +955,112 @@ int zb200_selftest_tables(zb200_ctx *ctx, const uint8_t *lens, const uint32_t *c
     ZB_LAUNCHED();
     ZB_CHECK_LAUNCH();
     ZB_CUDA(cudaMemcpyAsync(verdict, base + lb + cb, n_cases * 4, cudaMemcpyDeviceToHost, s));
+    ZB_CUDA(cudaStreamSynchronize(s));
+    return ZB200_OK;
+}
+
+int zb200_gunzip_host(zb200_ctx *ctx, const void *in, size_t n, void *out, size_t out_cap, size_t *out_len,
+                      int *inf_status, zb200_member *members, size_t max_members, size_t *n_members) {
+    if (!ctx || (!in && n) || (!out && out_cap) || !out_len || !inf_status) return ZB200_ERR_PARAM;
+    *out_len = 0; *inf_status = ZB200_INF_OK;
+    if (n_members) *n_members = 0;
+    const uint8_t *src = (const uint8_t *)in;
+    if (n < 18 || src[0] != 0x1f || src[1] != 0x8b) { *inf_status = n < 2 ? ZB200_INF_TRUNCATED : ZB200_INF_HEADER_CHECK; return ZB200_OK; }
+    ZB_CUDA(cudaSetDevice(ctx->device));
+    std::lock_guard<std::mutex> g(ctx->mu);
+    cudaStream_t s = ctx->stream;
+    int r = ensure_io(ctx, n + 16, 16);
+    if (r) return r;
+    if ((r = h2d_auto(ctx, ctx->d_io_in, in, n, s))) return r;
+    // 1. candidates
+    const uint32_t cand_cap = (uint32_t)(n / 18 + 16 < (1u << 24) ? n / 18 + 16 : (1u << 24));
+    if ((r = ensure_scratch(ctx, 256 + (size_t)cand_cap * 8))) return r;
+    uint32_t *d_count = (uint32_t *)ctx->d_scratch;
+    uint64_t *d_list = (uint64_t *)((uint8_t *)ctx->d_scratch + 256);
+    ZB_CUDA(cudaMemsetAsync(d_count, 0, 256, s));
+    gz_candidates_kernel<<<ctx->sm_count * 8, 256, 0, s>>>(ctx->d_io_in, n, d_list, cand_cap, d_count);
+    ZB_LAUNCHED();
+    ZB_CHECK_LAUNCH();
+    ZB_CUDA(cudaMemcpyAsync(ctx->h_small, d_count, 8, cudaMemcpyDeviceToHost, s));
+    ZB_CUDA(cudaStreamSynchronize(s));
+    const uint32_t nc = *(const uint32_t *)ctx->h_small;
+    if (nc > cand_cap) { set_error("gunzip: more than %u member candidates", cand_cap); return ZB200_ERR_PARAM; }
+    std::vector<uint64_t> cand(nc);
+    if (nc) ZB_CUDA(cudaMemcpy(cand.data(), d_list, (size_t)nc * 8, cudaMemcpyDeviceToHost));
+    std::sort(cand.begin(), cand.end());
+    if (cand.empty() || cand[0] != 0) { *inf_status = ZB200_INF_HEADER_CHECK; return ZB200_OK; }
+    auto le32 = [&](uint64_t at) { return (uint32_t)src[at] | ((uint32_t)src[at + 1] << 8) | ((uint32_t)src[at + 2] << 16) | ((uint32_t)src[at + 3] << 24); };
+    // 2. hypotheses -> batch -> chain check; a false candidate is dropped and the batch redone
+    std::vector<zb200_member> tab;
+    std::vector<zb200_member_result> res;
+    size_t good = 0, total = 0;
+    bool last_at_max = false;                            // bytes after the last member hid its ISIZE: size it by the format's maximum
+    for (int pass = 0;; ++pass) {
+        if (pass > 64) { set_error("gunzip: too many false member candidates"); return ZB200_ERR_PARAM; }
+        // a candidate whose predecessor's implied output size is impossible lies inside that predecessor
+        for (size_t i = 0; i + 1 < cand.size();) {
+            const uint64_t len = cand[i + 1] - cand[i];
+            if (len < 18 || (uint64_t)le32(cand[i + 1] - 4) > len * 1032 + 65536) cand.erase(cand.begin() + (long)i + 1);
+            else ++i;
+        }
+        const size_t m = cand.size();
+        tab.assign(m, zb200_member());
+        total = 0;
+        for (size_t i = 0; i < m; ++i) {
+            const uint64_t end = i + 1 < m ? cand[i + 1] : n, most = (end - cand[i]) * 1032 + 65536;
+            uint64_t isz = le32(end - 4);
+            if (i + 1 == m && (last_at_max || isz > most)) isz = most;
+            tab[i].in_off = cand[i]; tab[i].in_len = end - cand[i];
+            tab[i].out_off = total; tab[i].out_cap = isz;
+            tab[i].resume_bit = tab[i].resume_out = tab[i].dict_len = 0;
+            total += isz;
+        }
+        const size_t tbl = align_up(m * sizeof(zb200_member), 256), rsl = align_up(m * sizeof(zb200_member_result), 256);
+        if ((r = ensure_io(ctx, n + 16, total + 16))) return r;
+        if ((r = ensure_scratch(ctx, tbl + rsl + InflateWork::bytes(m)))) return r;
+        uint8_t *base = (uint8_t *)ctx->d_scratch;
+        zb200_member *d_members = (zb200_member *)base;
+        zb200_member_result *d_results = (zb200_member_result *)(base + tbl);
+        ZB_CUDA(cudaMemcpyAsync(d_members, tab.data(), m * sizeof(zb200_member), cudaMemcpyHostToDevice, s));
+        if ((r = inflate_launch(ctx, ctx->d_io_in, ctx->d_io_out, d_members, m, ZB200_WRAP_GZIP, 1, d_results, base + tbl + rsl, s))) return r;
+        res.resize(m);
+        ZB_CUDA(cudaMemcpyAsync(res.data(), d_results, m * sizeof(zb200_member_result), cudaMemcpyDeviceToHost, s));
+        ZB_CUDA(cudaStreamSynchronize(s));
+        bool redo = false;
+        good = 0;
+        *inf_status = ZB200_INF_OK;
+        for (size_t i = 0; i < m; ++i) {
+            const zb200_member_result &q = res[i];
+            const bool last = i + 1 == m;
+            if (q.status == ZB200_INF_OK) {
+                ++good;
+                if (last || q.in_used == tab[i].in_len) continue;
+                break;                                   // bytes that are no member follow: gzread.c:gz_look ignores them
+            }
+            if (!last && (q.status == ZB200_INF_TRUNCATED || q.status == ZB200_INF_OUTPUT_FULL)) {
+                cand.erase(cand.begin() + (long)i + 1);  // the next candidate was none
+                redo = true;
+            } else if (last && q.status == ZB200_INF_OUTPUT_FULL && !last_at_max) {
+                last_at_max = true;
+                redo = true;
+            } else *inf_status = q.status;
+            break;
+        }
+        if (!redo) break;
+    }
+    // 3. the valid prefix: members' outputs lie back to back (ISIZE was right for each of them)
+    size_t produced = 0;
+    for (size_t i = 0; i < good; ++i) produced += (size_t)res[i].out_len;
+    if (n_members) *n_members = good;
+    if (members)
+        for (size_t k = 0, at = 0; k < good && k < max_members; ++k) {
+            members[k] = tab[k];
+            members[k].in_len = res[k].in_used; members[k].out_off = at; members[k].out_cap = res[k].out_len;
+            at += (size_t)res[k].out_len;
+        }
+    *out_len = produced;
+    if (produced > out_cap) { set_error("gunzip: %zu bytes do not fit the output buffer", produced); return ZB200_ERR_OUTPUT; }
+    if (produced && (r = d2h_auto(ctx, out, ctx->d_io_out, produced, s))) return r;
     ZB_CUDA(cudaStreamSynchronize(s));
     return ZB200_OK;
 }

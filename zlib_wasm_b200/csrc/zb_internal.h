@@ -105,6 +105,8 @@ int deflate_init(zb200_ctx *ctx);
 int deflate_launch(zb200_ctx *ctx, const uint8_t *d_in, size_t n, size_t S, int level, int strategy, int frame,
                    int finish, uint8_t *d_out, size_t out_cap, uint64_t *d_chunk_end, uint64_t *d_total,
                    uint32_t *d_sums_out, cudaStream_t s, size_t skip = 0);   // skip: preset dictionary at the head of a single raw chunk
+// zb_zlib_api.cu: the process-wide context behind the zlib.h surface (nullptr without a usable device)
+zb200_ctx *zlib_api_ctx();
 // zb_inflate.cu
 int inflate_init(zb200_ctx *ctx);
 size_t inflate_work_bytes(size_t n_members);

@@ -31,6 +31,10 @@ zb200_ctx *api_ctx() {
     return g_ctx;
 }
 
+}  // namespace
+namespace zb { zb200_ctx *zlib_api_ctx() { return api_ctx(); } }
+namespace {
+
 size_t api_chunk() {
     static size_t c = [] {
         const char *e = getenv("ZB200_CHUNK");
