@@ -217,6 +217,25 @@ def run(ctx, rank, world, nbytes, barrier, steps=3, warmup=1):
         e["e2e"] = {"value": round(world * inf_bytes / dt / 1e9, 3), "unit": "GB/s", "h2d_bytes_per_step": int(comp_total),
                     "d2h_bytes_per_step": inf_bytes, "bit_exact": bool(ok2),
                     "api": "zb200_inflate_host on pinned host memory (pieces pipelined over three streams)"}
+        # the same file with NO member table: members discovered on the device (zb200_gunzip_host)
+        olen, nm, st = C.c_size_t(0), C.c_size_t(0), C.c_int(0)
+
+        def step_scan():
+            r = L.zb200_gunzip_host(ctx.handle, C.c_void_p(h_in), comp_total, C.c_void_p(h_out), inf_bytes, C.byref(olen), C.byref(st),
+                                    None, 0, C.byref(nm))
+            if r != 0:
+                raise zb.ZB200Error(r, "zb200_gunzip_host")
+
+        step_scan()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            step_scan()
+        dt = maxr((time.perf_counter() - t0) / steps)
+        ok3 = st.value == 0 and nm.value == n_m and olen.value == inf_bytes and all(
+            C.string_at(h_out + fm.out_off, fm.out_cap) == host[m.out_off:m.out_off + m.out_cap]
+            for fm, m in list(zip(file_members, members))[:: max(1, n_m // 16)])
+        e["e2e_no_index"] = {"value": round(world * inf_bytes / dt / 1e9, 3), "unit": "GB/s", "members_found": int(nm.value), "bit_exact": bool(ok3),
+                             "api": "zb200_gunzip_host on pinned host memory: member starts discovered on the device, one batch"}
     if h_in:
         L.zb200_host_free(C.c_void_p(h_in))
     if h_out:
