@@ -77,7 +77,7 @@ class ZlibBinding:
 
     # ---- helpers -------------------------------------------------------
     def deflate_stream(self, data, level=6, strategy=0, wrap=WRAP_ZLIB, chunk=0, mem_level=8,
-                       out_slice=None, in_slice=None, dictionary=None):
+                       out_slice=None, in_slice=None, dictionary=None, chunk_flush=Z_FULL_FLUSH):
         """deflate(Z_FULL_FLUSH) per `chunk` bytes, Z_FINISH on the last one
         (SURVEY.md appendix C.1).  chunk=0: one Z_FINISH call.  in_slice /
         out_slice feed avail_in / avail_out in small pieces (zpipe style)."""
@@ -102,7 +102,7 @@ class ZlibBinding:
         produced = 0
         while True:
             k = min(chunk, n - off)
-            flush = Z_FINISH if off + k >= n else Z_FULL_FLUSH
+            flush = Z_FINISH if off + k >= n else chunk_flush
             fed = 0
             while True:
                 step = k - fed if not in_slice else min(in_slice, k - fed)

@@ -294,3 +294,29 @@ def test_gz_file_layer(z, tmp_path):
     assert out == b"" or d.startswith(out)
     assert err.value == refz.Z_BUF_ERROR and m == b"unexpected end of file" and L.gzclose(f) == refz.Z_BUF_ERROR
     assert not L.gzopen(p1.encode(), b"r+") and not L.gzopen(str(tmp_path / "nope.gz").encode(), b"rb")
+
+
+@pytest.mark.parametrize("wrap", [refz.WRAP_RAW, refz.WRAP_GZIP])
+def test_sync_flush_keeps_history(z, wrap):
+    """Z_SYNC_FLUSH / Z_PARTIAL_FLUSH do not reset the window (deflate.c:1211-1218): small messages flushed one by
+    one compress against what went before.  While the stream fits the window the bytes are the reference's."""
+    if not refz.have_ref():
+        pytest.skip("oracle/_ref/libzref.so not built")
+    ref = refz.ref()
+    d = refz.gen(30000, refz.GEN_TEXT, seed=51)
+    for level in (6, 9):
+        s = z.deflate_stream(d, level, 0, wrap, chunk=3000, chunk_flush=refz.Z_SYNC_FLUSH)
+        assert s == ref.deflate_stream(d, level, 0, wrap, chunk=3000, chunk_flush=refz.Z_SYNC_FLUSH), level
+    d = refz.gen(2000000, refz.GEN_MARKOV, seed=52)
+    for level, fl in ((1, refz.Z_SYNC_FLUSH), (6, refz.Z_SYNC_FLUSH), (6, refz.Z_PARTIAL_FLUSH)):
+        s = z.deflate_stream(d, level, 0, wrap, chunk=4096, chunk_flush=fl)
+        want = ref.deflate_stream(d, level, 0, wrap, chunk=4096, chunk_flush=refz.Z_SYNC_FLUSH)
+        full = ref.deflate_stream(d, level, 0, wrap, chunk=4096, chunk_flush=refz.Z_FULL_FLUSH)
+        assert len(s) <= 1.03 * len(want) and len(s) < 0.9 * len(full), (level, len(s), len(want), len(full))
+        ret, m, out, tin = ref.inflate_all(s, wrap, cap=len(d) + 64)
+        assert ret == refz.Z_STREAM_END and out == d
+        ret, m, out, tin = z.inflate_all(s, wrap, cap=len(d) + 64, in_slice=300000)
+        assert ret == refz.Z_STREAM_END and out == d
+    # a full flush does reset it: the chunks decode on their own (zlib.h:286-291)
+    s = z.deflate_stream(d[:100000], 6, 0, refz.WRAP_RAW, chunk=20000, chunk_flush=refz.Z_FULL_FLUSH)
+    assert s == ref.deflate_stream(d[:100000], 6, 0, refz.WRAP_RAW, chunk=20000, chunk_flush=refz.Z_FULL_FLUSH)

@@ -64,7 +64,9 @@ struct DeflateStream {
     uint32_t crc, adler;                 // running checksums of all compressed input
     uint64_t total_in_hashed;
     int last_flush;
-    std::vector<uint8_t> dict;           // preset dictionary not yet consumed (the last <= 32768 bytes of it)
+    std::vector<uint8_t> dict;           // history ahead of the next byte: a preset dictionary not yet consumed, or the
+                                         // last <= 32768 bytes before a Z_SYNC_FLUSH / Z_PARTIAL_FLUSH / Z_BLOCK point
+    bool keep_history;                   // the flush in progress does not reset the history (deflate.c:1211-1218)
     uint32_t dictid;                     // Adler-32 of the whole dictionary (zlib header DICTID)
     bool have_dictid;
 };
@@ -138,7 +140,6 @@ int compress_buffered(DeflateStream &st, bool finish) {
             cap1 += cap2;
         }
         cap = cap1;
-        if (r == ZB200_OK) st.dict.clear();
     } else {
         r = zb200_deflate_host(ctx, n ? st.in.data() : (const uint8_t *)"", n, chunk, st.level,
                                st.strategy, ZB200_FRAME_RAW, finish ? 1 : 0,
@@ -149,6 +150,16 @@ int compress_buffered(DeflateStream &st, bool finish) {
     st.crc = zb200_crc32_combine(st.crc, crc, n);
     st.adler = zb200_adler32_combine(st.adler, adler, (int64_t)n);
     st.total_in_hashed += n;
+    if (st.keep_history) {                                     // what a sync flush leaves in the window: the last 32 KiB
+        std::vector<uint8_t> h;
+        if (n >= 32768) h.assign(st.in.end() - 32768, st.in.end());
+        else {
+            const size_t from_old = st.dict.size() + n > 32768 ? 32768 - n : st.dict.size();
+            h.assign(st.dict.end() - (long)from_old, st.dict.end());
+            h.insert(h.end(), st.in.begin(), st.in.end());
+        }
+        st.dict.swap(h);
+    } else if (n) st.dict.clear();
     st.in.clear();
     return Z_OK;
 }
@@ -293,7 +304,7 @@ int deflateReset(z_streamp strm) {
     s->in.clear(); s->pending.clear(); s->pending_pos = 0;
     s->header_done = s->finished = s->trailer_done = false;
     s->crc = 0; s->adler = 1; s->total_in_hashed = 0; s->last_flush = -2;
-    s->dict.clear(); s->dictid = 0; s->have_dictid = false;
+    s->dict.clear(); s->dictid = 0; s->have_dictid = false; s->keep_history = false;
     strm->total_in = strm->total_out = 0; strm->msg = Z_NULL; strm->data_type = Z_UNKNOWN;
     strm->adler = s->wrap == 2 ? 0 : 1;                         // deflate.c:656-660
     return Z_OK;
@@ -306,6 +317,7 @@ int deflateParams(z_streamp strm, int level, int strategy) {
     if (level < 0 || level > 9 || strategy < 0 || strategy > Z_FIXED) return Z_STREAM_ERROR;
     if ((level != s->level || strategy != s->strategy) && !s->in.empty()) {
         if (!s->header_done) put_header(*s);                    // deflate.c:779-790: flush what was taken with the old setting
+        s->keep_history = true;                                 // (a Z_BLOCK flush there: the window stays)
         const int r = compress_buffered(*s, false);
         if (r != Z_OK) return r;
     }
@@ -359,6 +371,9 @@ int deflate(z_streamp strm, int flush) {
         const bool spill = !want_flush && s->in.size() >= (size_t)64 * api_chunk();
         if (want_flush || spill) {
             if (!s->header_done) put_header(*s);
+            // Z_SYNC_FLUSH / Z_PARTIAL_FLUSH / Z_BLOCK keep the window (deflate.c:1211-1218 clears the hash only for
+            // Z_FULL_FLUSH): the first chunk after such a point is compressed behind the last 32 KiB before it
+            s->keep_history = !spill && (flush == Z_SYNC_FLUSH || flush == Z_PARTIAL_FLUSH || flush == Z_BLOCK);
             int r;
             if (spill) {
                 const size_t keep = s->in.size() % api_chunk();
