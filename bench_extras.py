@@ -127,6 +127,27 @@ def run(ctx, rank, world, nbytes, barrier, steps=3, warmup=1):
             dt = maxr((time.perf_counter() - t0) / steps)
             e["e2e"] = {"value": round(world * nbytes / dt / 1e9, 3), "unit": "GB/s", "h2d_bytes_per_step": nbytes,
                         "d2h_bytes_per_step": int(olen.value), "api": "zb200_deflate_host on pinned host memory (pieces pipelined over three streams)"}
+            # ... and back: that ONE raw stream (no member table, no index) decoded at its flush points in parallel
+            h_back = L.zb200_host_alloc(nbytes + 64)
+            if h_back:
+                q = zb.MemberResult()
+                clen = int(olen.value)
+
+                def step_back():
+                    r = L.zb200_inflate_stream_host(ctx.handle, C.c_void_p(h_out), clen, zb.WRAP_RAW, C.c_void_p(h_back), nbytes + 64, C.byref(q))
+                    if r != 0:
+                        raise zb.ZB200Error(r, "zb200_inflate_stream_host")
+
+                step_back()
+                t0 = time.perf_counter()
+                for _ in range(steps):
+                    step_back()
+                dt = maxr((time.perf_counter() - t0) / steps)
+                okb = q.status == 0 and q.out_len == nbytes and C.string_at(h_back, 1 << 20) == host[:1 << 20] and \
+                    C.string_at(h_back + nbytes - (1 << 20), 1 << 20) == host[-(1 << 20):]
+                e["inflate_back_e2e"] = {"value": round(world * nbytes / dt / 1e9, 3), "unit": "GB/s", "bit_exact_ends": bool(okb),
+                                         "api": "zb200_inflate_stream_host: one stream, runs between flush points found and decoded in one batch"}
+                L.zb200_host_free(C.c_void_p(h_back))
         if h_in:
             L.zb200_host_free(C.c_void_p(h_in))
         if h_out:

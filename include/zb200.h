@@ -184,6 +184,17 @@ int zb200_deflate_host_dict(zb200_ctx *ctx, const void *in, size_t n, size_t dic
 int zb200_gunzip_host(zb200_ctx *ctx, const void *in, size_t n, void *out, size_t out_cap, size_t *out_len,
                       int *inf_status, zb200_member *members, size_t max_members, size_t *n_members);
 
+/* ONE raw / zlib / gzip stream decoded in parallel at its flush points: every byte-aligned 00 00 FF FF (the empty
+ * stored block deflate.c:1211-1226 emits for Z_SYNC_FLUSH / Z_FULL_FLUSH — all of this library's deflate output,
+ * pigz -i files, zlib's own full flushes) is a candidate boundary; the runs between candidates are inflated as
+ * one batch and the chain is verified from the front (a run that stops mid-block had a false successor, a run that
+ * reaches behind its start follows a sync flush: both are merged and redone).  A stream with nothing to split on,
+ * or damaged, takes the one-member path of zb200_inflate_host — same statuses either way.
+ * result: status, wrap_kind, check (computed), out_len (when it exceeds out_cap: ZB200_INF_OUTPUT_FULL), in_used.
+ * Host pointers; synchronous. */
+int zb200_inflate_stream_host(zb200_ctx *ctx, const void *in, size_t n, int wrap, void *out, size_t out_cap,
+                              zb200_member_result *result);
+
 /* Self-test of the warp-parallel decode-table construction (csrc/zb_inflate_tables.cuh) against the
  * serial one that follows inftrees.c:32-299: for each of n_cases sets of code lengths (lens: 320 bytes
  * per case = nlen literal/length lengths followed by ndist distance lengths; counts: nlen, ndist per

@@ -363,3 +363,46 @@ def test_gunzip_discovers_members(ctx):
     assert r == 0 and st != 0 and nm <= 2 and out == want[:len(out)]
     r, st, out, need, nm, tab = _gunzip(ctx, b"not a gzip file at all....", 100)
     assert r == 0 and msg(st) == "incorrect header check" and out == b""
+
+
+def _stream(ctx, blob, wrap, cap):
+    import ctypes as C
+    out = C.create_string_buffer(max(cap, 1))
+    res = zb.MemberResult()
+    r = zb.lib().zb200_inflate_stream_host(ctx.handle, bytes(blob), len(blob), wrap, out, cap, C.byref(res))
+    assert r == 0, zb.last_error()
+    return res, out.raw[:min(res.out_len, cap)]
+
+
+def test_stream_decoded_in_parallel_at_flush_points(ctx):
+    """zb200_inflate_stream_host: full-flush runs in parallel, sync-flush runs merged (they reach behind their
+    start), look-alike markers inside stored data merged, the reference's statuses for damaged input."""
+    ref = refz.ref() if refz.have_ref() else refz.oracle()
+    d = refz.gen(6000000, refz.GEN_MARKOV, seed=61)
+    noise = bytearray(refz.gen(300000, refz.GEN_RANDOM, seed=62))
+    for at in range(500, len(noise) - 8, 9973):
+        noise[at:at + 4] = b"\x00\x00\xff\xff"
+    mixed = d[:1000000] + bytes(noise) + d[1000000:2000000]
+    for wrap in (refz.WRAP_RAW, refz.WRAP_ZLIB, refz.WRAP_GZIP):
+        for data, level, chunk in ((d, 6, 262144), (d, 1, 100000), (mixed, 6, 65536), (mixed, 0, 50000), (d[:70000], 6, 0)):
+            s = ref.deflate_stream(data, level, 0, wrap, chunk)
+            res, out = _stream(ctx, s, wrap, len(data) + 16)
+            assert res.status == 0 and out == data and res.in_used == len(s), (wrap, level, chunk, msg(res.status), res.out_len, len(data))
+            res, out = _stream(ctx, s + b"tail", wrap, len(data) + 16)
+            assert res.status == 0 and res.in_used == len(s) and out == data
+    if refz.have_ref():                                       # sync flushes: the runs need their predecessors
+        s = refz.ref().deflate_stream(d[:3000000], 6, 0, refz.WRAP_ZLIB, 200000, chunk_flush=refz.Z_SYNC_FLUSH)
+        res, out = _stream(ctx, s, refz.WRAP_ZLIB, 3000016)
+        assert res.status == 0 and out == d[:3000000]
+    s = ref.deflate_stream(d, 6, 0, refz.WRAP_GZIP, 262144)
+    res, out = _stream(ctx, s, refz.WRAP_GZIP, 1000)          # too small: the size needed
+    assert msg(res.status) == "output buffer full" and res.out_len == len(d)
+    res, out = _stream(ctx, s[:len(s) // 2], refz.WRAP_GZIP, len(d) + 16)
+    assert msg(res.status) == "truncated input" and d.startswith(out) and len(out) > len(d) // 3
+    bad = bytearray(s); bad[len(s) // 3] ^= 0x40
+    res, out = _stream(ctx, bytes(bad), refz.WRAP_GZIP, len(d) + 16)
+    one, res1 = ctx.inflate_host(bytes(bad), [(0, len(bad), 0, len(d) + 16)], refz.WRAP_GZIP, 1)
+    assert res.status == res1[0].status and res.status != 0
+    bad = bytearray(s); bad[-6] ^= 1
+    res, out = _stream(ctx, bytes(bad), refz.WRAP_GZIP, len(d) + 16)
+    assert msg(res.status) == "incorrect data check"

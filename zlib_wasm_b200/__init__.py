@@ -75,6 +75,7 @@ ABI = {
     "zb200_inflate_dev": (_i, _vp, _vp, _vp, _vp, _sz, _i, _i, _vp, _vp),
     "zb200_inflate_host": (_i, _vp, _vp, _vp, _vp, _sz, _i, _i, _vp),
     "zb200_selftest_tables": (_i, _vp, _vp, _vp, _sz, _vp),
+    "zb200_inflate_stream_host": (_i, _vp, _vp, _sz, _i, _vp, _sz, _vp),
     "zb200_gunzip_host": (_i, _vp, _vp, _sz, _vp, _sz, _psz, C.POINTER(_i), _vp, _sz, _psz),
     "zb200_deflate_host_dict": (_i, _vp, _vp, _sz, _sz, _i, _i, _i, _vp, _vp, _vp, _vp),
 }

@@ -124,6 +124,17 @@ int gz_load(GzState *s) {
     if (!ctx) { gz_set_error(s, Z_STREAM_ERROR, "zlib-b200: no usable CUDA device (no CPU path)"); return -1; }
     size_t cap = raw.size() * 4 + 65536, len = 0;
     int st = 0;
+    // a file that is ONE member with flush points inside (what gzwrite above produces, pigz -i): its runs in parallel
+    if (raw.size() >= ((size_t)1 << 20)) {
+        zb200_member_result q;
+        for (int attempt = 0; attempt < 2; ++attempt) {
+            s->data.resize(cap);
+            if (zb200_inflate_stream_host(ctx, raw.data(), raw.size(), ZB200_WRAP_GZIP, s->data.data(), cap, &q) != ZB200_OK) break;
+            if (q.status == ZB200_INF_OUTPUT_FULL && q.out_len > cap && attempt == 0) { cap = (size_t)q.out_len; continue; }
+            if (q.status == ZB200_INF_OK && q.in_used == raw.size()) { s->data.resize((size_t)q.out_len); return 0; }
+            break;
+        }
+    }
     for (int attempt = 0; attempt < 2; ++attempt) {
         s->data.resize(cap);
         const int r = zb200_gunzip_host(ctx, raw.data(), raw.size(), s->data.data(), cap, &len, &st, nullptr, 0, nullptr);

@@ -710,6 +710,57 @@ gz_candidates_kernel(const uint8_t *__restrict__ in, uint64_t n, uint64_t *__res
     }
 }
 
+// ---- one stream, decoded in parallel at its flush points -------------------------------------
+// A deflate stream written with Z_FULL_FLUSH points (deflate.c:1211-1226: byte-aligned empty
+// stored block 00 00 FF FF, history reset) — everything this library's deflate() emits, pigz -i
+// output, zlib's own full flushes — falls into runs of blocks that decode on their own.  Nothing
+// in the stream marks those points, and a member decoded by one warp runs at 80-155 MB/s, so:
+// every 00 00 FF FF is a candidate boundary, the runs between candidates are inflated as one batch
+// of raw members into slots of a scratch buffer (a run's output size is not known beforehand),
+// and the chain is checked from the front — a run is good when it ends exactly on the next
+// candidate, at a block boundary.  A run that stops mid-block had a false successor (the pattern
+// inside compressed or stored data): merged with it.  A run that reaches behind its own start
+// ("invalid distance too far back") follows a sync flush, not a full one: merged into its
+// predecessor.  The good runs are then packed, the check value is computed over the whole.
+__global__ void __launch_bounds__(256)
+flush_candidates_kernel(const uint8_t *__restrict__ in, uint64_t lo, uint64_t n, uint64_t *__restrict__ list, uint32_t cap, uint32_t *__restrict__ count) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = lo + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i + 4 <= n; i += stride) {
+        if (in[i + 2] != 0xff) continue;
+        if (in[i + 3] != 0xff || in[i] != 0 || in[i + 1] != 0) continue;
+        const uint32_t k = atomicAdd(count, 1u);
+        if (k < cap) list[k] = i + 4;                        // the next run starts behind the marker
+    }
+}
+
+struct GatherSeg { uint64_t src, dst, len; };
+__global__ void __launch_bounds__(256)
+gather_segments_kernel(const uint8_t *__restrict__ from, uint8_t *__restrict__ to, const GatherSeg *__restrict__ segs) {
+    const GatherSeg g = segs[blockIdx.y];
+    const uint8_t *s = from + g.src;
+    uint8_t *d = to + g.dst;
+    const uint64_t per = (g.len + gridDim.x - 1) / gridDim.x;
+    uint64_t a = (uint64_t)blockIdx.x * per, e = a + per < g.len ? a + per : g.len;
+    if (a >= e) return;
+    // destination words; the source is read as aligned words and funnel-shifted into place
+    const uint64_t head = (4 - ((reinterpret_cast<uintptr_t>(d) + a) & 3)) & 3;
+    for (uint64_t i = a + threadIdx.x; i < a + head && i < e; i += 256) d[i] = s[i];
+    const uint64_t w0 = a + head;
+    if (w0 < e) {
+        const uint64_t nw = (e - w0) >> 2;
+        uint32_t *dw = reinterpret_cast<uint32_t *>(d + w0);
+        const uintptr_t sa = reinterpret_cast<uintptr_t>(s + w0);
+        const uint32_t *sw = reinterpret_cast<const uint32_t *>(sa & ~(uintptr_t)3);
+        const uint32_t sh = (uint32_t)(sa & 3) * 8;
+        for (uint64_t w = threadIdx.x; w < nw; w += 256) {
+            const uint32_t lo32 = sw[w];
+            const uint32_t hi32 = sh ? sw[w + 1] : 0u;       // (never reads past the source run: sh != 0 => bytes of word w+1 belong to it)
+            dw[w] = __funnelshift_r(lo32, hi32, sh);
+        }
+        for (uint64_t i = w0 + nw * 4 + threadIdx.x; i < e; i += 256) d[i] = s[i];
+    }
+}
+
 // Members are handed out by an atomic counter.  A member is decoded serially by its
 // warp, so the launch ends when the slowest member ends: hand out the largest first
 // (bucketed by log2 of the compressed size; one CTA builds the order).
@@ -841,6 +892,166 @@ int inflate_launch(zb200_ctx *ctx, const uint8_t *d_in, uint8_t *d_out, const zb
     inflate_verify_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(d_results, (uint32_t)n, verify, w.crc, w.adler);
     ZB_LAUNCHED();
     ZB_CHECK_LAUNCH();
+    return ZB200_OK;
+}
+
+// One raw / zlib / gzip stream (host pointers), decoded run by run in parallel (see flush_candidates_kernel).
+// *applicable = 0: the stream offers nothing to split on (no candidate, a preset dictionary, a header that does
+// not parse) and nothing has been written — the caller takes the one-member path.  Otherwise *status is the
+// ZB200_INF_* outcome, *out_len the valid output bytes (also when they exceed out_cap: ZB200_INF_OUTPUT_FULL and
+// nothing copied), *in_used the stream's length, *check its computed check value.
+int inflate_stream_parallel(zb200_ctx *ctx, const uint8_t *src, size_t n, int wrap, uint8_t *out, size_t out_cap,
+                            size_t *out_len, int *status, size_t *in_used, uint32_t *check, int *applicable) {
+    *applicable = 0; *out_len = 0; *status = ZB200_INF_OK; *in_used = 0; *check = 0;
+    if (n < 64) return ZB200_OK;
+    InflateState hs;
+    hs.init(src, n, nullptr, 0, nullptr, nullptr, nullptr, nullptr);
+    if (hs.parse_header(wrap) != ZB200_INF_OK) return ZB200_OK;
+    const uint64_t hdr = hs.next;
+    const int kind = hs.wrap_kind;
+    cudaStream_t s = ctx->stream;
+    int r = ensure_io(ctx, n + 16, 16);
+    if (r) return r;
+    if ((r = h2d_auto(ctx, ctx->d_io_in, src, n, s))) return r;
+    const uint32_t cand_cap = (uint32_t)(n / 5 + 16 < (1u << 22) ? n / 5 + 16 : (1u << 22));
+    if ((r = ensure_scratch(ctx, 256 + (size_t)cand_cap * 8))) return r;
+    uint32_t *d_count = (uint32_t *)ctx->d_scratch;
+    uint64_t *d_list = (uint64_t *)((uint8_t *)ctx->d_scratch + 256);
+    ZB_CUDA(cudaMemsetAsync(d_count, 0, 256, s));
+    flush_candidates_kernel<<<ctx->sm_count * 8, 256, 0, s>>>(ctx->d_io_in, hdr, n, d_list, cand_cap, d_count);
+    ZB_LAUNCHED();
+    ZB_CHECK_LAUNCH();
+    ZB_CUDA(cudaMemcpyAsync(ctx->h_small, d_count, 8, cudaMemcpyDeviceToHost, s));
+    ZB_CUDA(cudaStreamSynchronize(s));
+    const uint32_t nc = *(const uint32_t *)ctx->h_small;
+    if (nc == 0 || nc > cand_cap) return ZB200_OK;
+    std::vector<uint64_t> start(nc + 1);
+    ZB_CUDA(cudaMemcpy(start.data() + 1, d_list, (size_t)nc * 8, cudaMemcpyDeviceToHost));
+    start[0] = hdr;
+    std::sort(start.begin() + 1, start.end());
+    while (!start.empty() && start.back() >= n) start.pop_back();          // a marker at the very end starts nothing
+    if (start.size() < 2) return ZB200_OK;
+    *applicable = 1;
+    struct Run { uint64_t in_off, in_len, cap, slot; zb200_member_result res; bool done; };
+    std::vector<Run> runs(start.size());
+    for (size_t k = 0; k < runs.size(); ++k) {
+        runs[k].in_off = start[k];
+        runs[k].in_len = (k + 1 < runs.size() ? start[k + 1] : n) - start[k];
+        runs[k].cap = 0; runs[k].done = false;
+    }
+    auto first_cap = [](uint64_t len) { const uint64_t a = len * 8 + 65536, b = len * 1032 + 65536; return a < b ? a : b; };
+    std::vector<zb200_member> tab;
+    std::vector<uint32_t> which;
+    size_t good = 0;                                         // runs [0, good) are verified
+    int final_status = -1;                                   // set when the chain ends (stream end or an error)
+    for (int pass = 0; final_status < 0; ++pass) {
+        if (pass > 8) { *applicable = 0; return ZB200_OK; }  // a damaged or pattern-ridden stream: the one-member path reports it
+        // slots for all runs; decode those that are not done
+        uint64_t total = 0;
+        for (size_t k = 0; k < runs.size(); ++k) {
+            Run &u = runs[k];
+            if (!u.cap) u.cap = first_cap(u.in_len);
+            u.slot = total;
+            total += (u.cap + 15) & ~(uint64_t)15;
+        }
+        const uint8_t *before = ctx->d_io_out;
+        if ((r = ensure_io(ctx, n + 16, total + 16))) return r;
+        if (ctx->d_io_out != before) for (size_t k = 0; k < runs.size(); ++k) runs[k].done = false;   // the buffer moved: bytes are gone
+        tab.clear(); which.clear();
+        for (size_t k = 0; k < runs.size(); ++k) {
+            const Run &u = runs[k];
+            if (u.done) continue;
+            zb200_member m;
+            m.in_off = u.in_off; m.in_len = u.in_len; m.out_off = u.slot; m.out_cap = u.cap; m.resume_bit = m.resume_out = m.dict_len = 0;
+            tab.push_back(m); which.push_back((uint32_t)k);
+        }
+        const size_t m = tab.size();
+        if (m) {
+            const size_t tbl = align_up(m * sizeof(zb200_member), 256), rsl = align_up(m * sizeof(zb200_member_result), 256);
+            if ((r = ensure_scratch(ctx, tbl + rsl + InflateWork::bytes(m)))) return r;
+            uint8_t *base = (uint8_t *)ctx->d_scratch;
+            zb200_member *d_members = (zb200_member *)base;
+            zb200_member_result *d_results = (zb200_member_result *)(base + tbl);
+            ZB_CUDA(cudaMemcpyAsync(d_members, tab.data(), m * sizeof(zb200_member), cudaMemcpyHostToDevice, s));
+            if ((r = inflate_launch(ctx, ctx->d_io_in, ctx->d_io_out, d_members, m, ZB200_WRAP_RAW, 0, d_results, base + tbl + rsl, s))) return r;
+            std::vector<zb200_member_result> res(m);
+            ZB_CUDA(cudaMemcpyAsync(res.data(), d_results, m * sizeof(zb200_member_result), cudaMemcpyDeviceToHost, s));
+            ZB_CUDA(cudaStreamSynchronize(s));
+            for (size_t j = 0; j < m; ++j) { runs[which[j]].res = res[j]; runs[which[j]].done = true; }
+        }
+        // the verified prefix grows over runs that end exactly on the next candidate
+        auto clean = [](const Run &u) { return u.res.status == ZB200_INF_TRUNCATED && u.res.resume_bit == u.in_len * 8 && u.res.resume_out == u.res.out_len; };
+        while (good < runs.size() && clean(runs[good])) ++good;
+        if (good == runs.size()) { final_status = ZB200_INF_TRUNCATED; break; }                    // the input ends on a boundary
+        if (runs[good].res.status == ZB200_INF_OK) { ++good; final_status = ZB200_INF_OK; break; } // BFINAL: the stream ends here
+        // repairs, for every run from there on (a merge never harms: it only removes a split)
+        bool changed = false;
+        for (size_t k = good; k < runs.size(); ++k) {
+            Run &u = runs[k];
+            const int st = u.res.status;
+            const uint64_t most = u.in_len * 1032 + 65536;
+            if (st < 0 || st == ZB200_INF_OK || clean(u)) continue;                                // (st < 0: merged in this pass, decoded in the next)
+            if (st == ZB200_INF_TRUNCATED && k + 1 == runs.size()) continue;                       // the input ends inside the last run
+            if (st == ZB200_INF_OUTPUT_FULL && u.cap < most) { u.cap = u.cap * 8 < most ? u.cap * 8 : most; changed = true; }
+            else if (st == ZB200_INF_TRUNCATED && k + 1 < runs.size()) {                           // stopped mid-block: the successor was none
+                u.in_len += runs[k + 1].in_len; u.cap = 0; u.res.status = -1;
+                runs.erase(runs.begin() + (long)k + 1);
+                changed = true;
+            } else if (k > good || (st == ZB200_INF_DIST_FAR && k > 0)) {                          // needs what came before (a sync flush point), or started on a false boundary
+                Run &pv = runs[k - 1];
+                pv.in_len += u.in_len; pv.cap = 0; pv.res.status = -1;
+                runs.erase(runs.begin() + (long)k);
+                if (k == good) --good;
+                --k;
+                changed = true;
+            }
+        }
+        if (!changed) { final_status = runs[good].res.status; break; }                             // the stream's own error (or its end of input)
+        for (size_t k = good; k < runs.size(); ++k) runs[k].done = false;                          // slots behind move: redo them
+    }
+    // pack the verified runs
+    std::vector<GatherSeg> gs(good);
+    uint64_t produced = 0;
+    for (size_t k = 0; k < good; ++k) { gs[k].src = runs[k].slot; gs[k].dst = produced; gs[k].len = runs[k].res.out_len; produced += runs[k].res.out_len; }
+    *out_len = (size_t)produced;
+    *status = final_status;
+    uint64_t end = good ? runs[good - 1].in_off + (final_status == ZB200_INF_OK ? runs[good - 1].res.in_used : runs[good - 1].in_len) : hdr;
+    uint32_t stored = 0, isize = 0;
+    if (final_status == ZB200_INF_OK) {                      // trailer: inflate.c:1183-1219
+        if (kind == 2) {
+            if (end + 8 > n) *status = ZB200_INF_TRUNCATED;
+            else { stored = (uint32_t)src[end] | ((uint32_t)src[end + 1] << 8) | ((uint32_t)src[end + 2] << 16) | ((uint32_t)src[end + 3] << 24);
+                   isize = (uint32_t)src[end + 4] | ((uint32_t)src[end + 5] << 8) | ((uint32_t)src[end + 6] << 16) | ((uint32_t)src[end + 7] << 24); end += 8; }
+        } else if (kind == 1) {
+            if (end + 4 > n) *status = ZB200_INF_TRUNCATED;
+            else { stored = ((uint32_t)src[end] << 24) | ((uint32_t)src[end + 1] << 16) | ((uint32_t)src[end + 2] << 8) | (uint32_t)src[end + 3]; end += 4; }
+        }
+    }
+    *in_used = (size_t)end;
+    if (produced > out_cap) { *status = ZB200_INF_OUTPUT_FULL; return ZB200_OK; }
+    const size_t gtab = align_up(good * sizeof(GatherSeg) + 16, 256);
+    if ((r = ensure_scratch(ctx, gtab + 1024 + produced + 16))) return r;
+    uint8_t *base = (uint8_t *)ctx->d_scratch;
+    GatherSeg *d_gs = (GatherSeg *)base;
+    uint32_t *d_sum = (uint32_t *)(base + gtab);
+    CkAccum *d_acc = (CkAccum *)(base + gtab + 256);
+    uint8_t *d_final = base + gtab + 1024;
+    if (good) {
+        ZB_CUDA(cudaMemcpyAsync(d_gs, gs.data(), good * sizeof(GatherSeg), cudaMemcpyHostToDevice, s));
+        gather_segments_kernel<<<dim3(16, (unsigned)good), 256, 0, s>>>(ctx->d_io_out, d_final, d_gs);
+        ZB_LAUNCHED();
+        ZB_CHECK_LAUNCH();
+    }
+    if ((r = checksum_launch(ctx, d_final, nullptr, nullptr, produced, 1, kind == 1 ? ZB200_ADLER32 : ZB200_CRC32, 0, 1, d_sum, d_sum + 1, d_acc, s))) return r;
+    ZB_CUDA(cudaMemcpyAsync(ctx->h_small, d_sum, 8, cudaMemcpyDeviceToHost, s));
+    if (produced && (r = d2h_auto(ctx, out, d_final, (size_t)produced, s))) return r;
+    ZB_CUDA(cudaStreamSynchronize(s));
+    const uint32_t *hsum = (const uint32_t *)ctx->h_small;
+    *check = kind == 1 ? hsum[1] : hsum[0];
+    if (*status == ZB200_INF_OK) {
+        if (kind != 0 && stored != *check) *status = ZB200_INF_DATA_CHECK;
+        else if (kind == 2 && isize != (uint32_t)produced) *status = ZB200_INF_LENGTH_CHECK;
+    }
     return ZB200_OK;
 }
 
@@ -1136,6 +1347,31 @@ int zb200_inflate_host(zb200_ctx *ctx, const void *in, void *out, const zb200_me
     }
     ZB_CUDA(cudaStreamSynchronize(s));
     return ZB200_OK;
+}
+
+int zb200_inflate_stream_host(zb200_ctx *ctx, const void *in, size_t n, int wrap, void *out, size_t out_cap,
+                              zb200_member_result *result) {
+    if (!ctx || (!in && n) || (!out && out_cap) || !result || wrap < 0 || wrap > 3) return ZB200_ERR_PARAM;
+    {
+        ZB_CUDA(cudaSetDevice(ctx->device));
+        std::lock_guard<std::mutex> g(ctx->mu);
+        size_t out_len = 0, in_used = 0;
+        int status = 0, applicable = 0;
+        uint32_t check = 0;
+        const int r = inflate_stream_parallel(ctx, (const uint8_t *)in, n, wrap, (uint8_t *)out, out_cap, &out_len, &status, &in_used, &check, &applicable);
+        if (r != ZB200_OK) return r;
+        if (applicable) {
+            memset(result, 0, sizeof *result);
+            result->status = status; result->check = check; result->out_len = out_len; result->in_used = in_used;
+            result->isize = (uint32_t)out_len;
+            const uint8_t *p = (const uint8_t *)in;
+            result->wrap_kind = wrap == ZB200_WRAP_RAW ? 0u : (n >= 2 && p[0] == 0x1f && p[1] == 0x8b && (wrap & ZB200_WRAP_GZIP)) ? 2u : 1u;
+            return ZB200_OK;
+        }
+    }
+    zb200_member m;
+    m.in_off = 0; m.in_len = n; m.out_off = 0; m.out_cap = out_cap; m.resume_bit = m.resume_out = m.dict_len = 0;
+    return zb200_inflate_host(ctx, in, out, &m, 1, wrap, 1, result);
 }
 
 }  // extern "C"

@@ -100,6 +100,10 @@ int checksum_launch(zb200_ctx *ctx, const uint8_t *d_base, const uint64_t *d_off
                     uint32_t *d_crc, uint32_t *d_adler, CkAccum *d_acc, cudaStream_t s,
                     const uint32_t *d_init2 = nullptr);
 
+// zb_inflate.cu: one stream decoded in parallel at its flush points (host pointers); *applicable = 0 -> take the one-member path
+int inflate_stream_parallel(zb200_ctx *ctx, const uint8_t *src, size_t n, int wrap, uint8_t *out, size_t out_cap,
+                            size_t *out_len, int *status, size_t *in_used, uint32_t *check, int *applicable);
+
 // zb_deflate.cu
 int deflate_init(zb200_ctx *ctx);
 int deflate_launch(zb200_ctx *ctx, const uint8_t *d_in, size_t n, size_t S, int level, int strategy, int frame,

@@ -462,7 +462,25 @@ int inflate(z_streamp strm, int flush) {
     if (!s->done && !s->error && (strm->avail_in || s->retry)) {
         s->retry = false;
         s->in.insert(s->in.end(), strm->next_in, strm->next_in + strm->avail_in);
-        status = inflate_attempt(*s);
+        status = -2;
+        if (s->decoded == 0 && s->resume_bit == 0 && s->dict_len == 0 && s->out.empty() && s->in.size() >= 262144) {
+            // a whole stream handed over at once: its flush-point runs in parallel (zb200_inflate_stream_host)
+            zb200_member_result q;
+            size_t cap = s->in.size() * 4 + (1u << 20);
+            for (int attempt = 0; attempt < 2; ++attempt) {
+                s->out.resize(cap);
+                if (zb200_inflate_stream_host(api_ctx(), s->in.data(), s->in.size(), s->wrap, s->out.data(), cap, &q) != ZB200_OK) break;
+                if (q.status == ZB200_INF_OUTPUT_FULL && q.out_len > cap && attempt == 0) { cap = (size_t)q.out_len; continue; }
+                if (q.status == ZB200_INF_OK) {
+                    s->out.resize((size_t)q.out_len); s->out_pos = 0;
+                    s->decoded = q.out_len; s->kind = (int)q.wrap_kind; s->done = true; s->in_used = q.in_used; s->check = q.check;
+                    status = ZB200_INF_OK;
+                }
+                break;
+            }
+            if (status != ZB200_INF_OK) { s->out.clear(); s->out_pos = 0; }
+        }
+        if (status == -2) status = inflate_attempt(*s);
         if (status < 0) { strm->msg = "zlib-b200: device error"; return Z_STREAM_ERROR; }
         uLong used = in0;
         if (status == ZB200_INF_OK) used = (uLong)(s->in_used - total_in0);   // give back bytes after the stream end
@@ -559,8 +577,15 @@ int uncompress2(Bytef *dest, uLongf *destLen, const Bytef *source, uLong *source
     zb200_member m;
     m.in_off = 0; m.in_len = *sourceLen; m.out_off = 0; m.out_cap = probe ? 1 : *destLen; m.resume_bit = m.resume_out = 0; m.dict_len = 0;
     zb200_member_result res;
-    const int r = zb200_inflate_host(ctx, source, probe ? one : dest, &m, 1, ZB200_WRAP_ZLIB, 1, &res);
+    // streams with flush points (all of this library's deflate output) are decoded run by run in parallel
+    const int r = (!probe && *sourceLen >= 65536)
+                      ? zb200_inflate_stream_host(ctx, source, *sourceLen, ZB200_WRAP_ZLIB, dest, *destLen, &res)
+                      : zb200_inflate_host(ctx, source, probe ? one : dest, &m, 1, ZB200_WRAP_ZLIB, 1, &res);
     if (r != ZB200_OK) return map_engine_error(r);
+    if (res.status == ZB200_INF_OUTPUT_FULL && res.out_len > *destLen) {   // the parallel path copies nothing then; uncompr.c fills dest as far as it goes
+        const int r2 = zb200_inflate_host(ctx, source, dest, &m, 1, ZB200_WRAP_ZLIB, 1, &res);
+        if (r2 != ZB200_OK) return map_engine_error(r2);
+    }
     *sourceLen = res.status == ZB200_INF_OK ? (uLong)res.in_used : *sourceLen;
     *destLen = probe ? 0 : (uLong)res.out_len;
     switch (res.status) {
