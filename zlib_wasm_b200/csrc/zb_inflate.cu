@@ -932,7 +932,7 @@ int inflate_stream_parallel(zb200_ctx *ctx, const uint8_t *src, size_t n, int wr
     while (!start.empty() && start.back() >= n) start.pop_back();          // a marker at the very end starts nothing
     if (start.size() < 2) return ZB200_OK;
     *applicable = 1;
-    struct Run { uint64_t in_off, in_len, cap, slot; zb200_member_result res; bool done; };
+    struct Run { uint64_t in_off, in_len, cap, slot; zb200_member_result res; bool done; };   // done: decoded into its slot, res valid
     std::vector<Run> runs(start.size());
     for (size_t k = 0; k < runs.size(); ++k) {
         runs[k].in_off = start[k];
@@ -944,19 +944,24 @@ int inflate_stream_parallel(zb200_ctx *ctx, const uint8_t *src, size_t n, int wr
     std::vector<uint32_t> which;
     size_t good = 0;                                         // runs [0, good) are verified
     int final_status = -1;                                   // set when the chain ends (stream end or an error)
+    uint64_t total = 0;                                      // scratch bytes handed out so far
     for (int pass = 0; final_status < 0; ++pass) {
-        if (pass > 8) { *applicable = 0; return ZB200_OK; }  // a damaged or pattern-ridden stream: the one-member path reports it
-        // slots for all runs; decode those that are not done
-        uint64_t total = 0;
+        if (pass > 24) { *applicable = 0; return ZB200_OK; } // a damaged or pattern-ridden stream: the one-member path reports it
+        // a run that has to be (re)decoded gets a fresh slot behind all others: the bytes of the rest stay where they are
         for (size_t k = 0; k < runs.size(); ++k) {
             Run &u = runs[k];
+            if (u.done) continue;
             if (!u.cap) u.cap = first_cap(u.in_len);
             u.slot = total;
             total += (u.cap + 15) & ~(uint64_t)15;
         }
-        const uint8_t *before = ctx->d_io_out;
+        const size_t before = ctx->io_out_bytes;
         if ((r = ensure_io(ctx, n + 16, total + 16))) return r;
-        if (ctx->d_io_out != before) for (size_t k = 0; k < runs.size(); ++k) runs[k].done = false;   // the buffer moved: bytes are gone
+        if (ctx->io_out_bytes != before && pass) {           // the buffer was replaced: every run's bytes are gone, lay them out afresh
+            total = 0;
+            for (size_t k = 0; k < runs.size(); ++k) { Run &u = runs[k]; u.done = false; u.slot = total; total += (u.cap + 15) & ~(uint64_t)15; }
+            if ((r = ensure_io(ctx, n + 16, total + 16))) return r;
+        }
         tab.clear(); which.clear();
         for (size_t k = 0; k < runs.size(); ++k) {
             const Run &u = runs[k];
@@ -992,14 +997,14 @@ int inflate_stream_parallel(zb200_ctx *ctx, const uint8_t *src, size_t n, int wr
             const uint64_t most = u.in_len * 1032 + 65536;
             if (st < 0 || st == ZB200_INF_OK || clean(u)) continue;                                // (st < 0: merged in this pass, decoded in the next)
             if (st == ZB200_INF_TRUNCATED && k + 1 == runs.size()) continue;                       // the input ends inside the last run
-            if (st == ZB200_INF_OUTPUT_FULL && u.cap < most) { u.cap = u.cap * 8 < most ? u.cap * 8 : most; changed = true; }
+            if (st == ZB200_INF_OUTPUT_FULL && u.cap < most) { u.cap = u.cap * 8 < most ? u.cap * 8 : most; u.done = false; changed = true; }
             else if (st == ZB200_INF_TRUNCATED && k + 1 < runs.size()) {                           // stopped mid-block: the successor was none
-                u.in_len += runs[k + 1].in_len; u.cap = 0; u.res.status = -1;
+                u.in_len += runs[k + 1].in_len; u.cap = 0; u.res.status = -1; u.done = false;
                 runs.erase(runs.begin() + (long)k + 1);
                 changed = true;
             } else if (k > good || (st == ZB200_INF_DIST_FAR && k > 0)) {                          // needs what came before (a sync flush point), or started on a false boundary
                 Run &pv = runs[k - 1];
-                pv.in_len += u.in_len; pv.cap = 0; pv.res.status = -1;
+                pv.in_len += u.in_len; pv.cap = 0; pv.res.status = -1; pv.done = false;
                 runs.erase(runs.begin() + (long)k);
                 if (k == good) --good;
                 --k;
@@ -1007,7 +1012,6 @@ int inflate_stream_parallel(zb200_ctx *ctx, const uint8_t *src, size_t n, int wr
             }
         }
         if (!changed) { final_status = runs[good].res.status; break; }                             // the stream's own error (or its end of input)
-        for (size_t k = good; k < runs.size(); ++k) runs[k].done = false;                          // slots behind move: redo them
     }
     // pack the verified runs
     std::vector<GatherSeg> gs(good);
