@@ -102,7 +102,7 @@ class ZlibBinding:
         produced = 0
         while True:
             k = min(chunk, n - off)
-            flush = Z_FINISH if off + k >= n else chunk_flush
+            flush = Z_FINISH if off + k >= n else (chunk_flush[(off // chunk) % len(chunk_flush)] if isinstance(chunk_flush, (list, tuple)) else chunk_flush)
             fed = 0
             while True:
                 step = k - fed if not in_slice else min(in_slice, k - fed)

@@ -406,3 +406,25 @@ def test_stream_decoded_in_parallel_at_flush_points(ctx):
     bad = bytearray(s); bad[-6] ^= 1
     res, out = _stream(ctx, bytes(bad), refz.WRAP_GZIP, len(d) + 16)
     assert msg(res.status) == "incorrect data check"
+
+
+def test_stream_runs_random_flush_mixtures(ctx):
+    """Random chunk sizes and flush kinds (sync / partial / full mixed): whatever the chain of runs looks like,
+    the stream decodes to the reference's bytes."""
+    if not refz.have_ref():
+        pytest.skip("oracle/_ref/libzref.so not built")
+    ref = refz.ref()
+    rng = random.Random(23)
+    for trial in range(24):
+        kind = rng.choice((refz.GEN_TEXT, refz.GEN_MARKOV, refz.GEN_MIXED))
+        n = rng.choice((70000, 300000, 1200000))
+        d = refz.gen(n, kind, seed=100 + trial)
+        chunk = rng.choice((60, 700, 5000, 40000, 200000))
+        if n // chunk > 4000:
+            chunk = n // 4000
+        flushes = [rng.choice((refz.Z_SYNC_FLUSH, refz.Z_FULL_FLUSH, refz.Z_FULL_FLUSH, refz.Z_PARTIAL_FLUSH)) for _ in range(rng.randint(1, 7))]
+        wrap = rng.choice((refz.WRAP_RAW, refz.WRAP_ZLIB, refz.WRAP_GZIP))
+        level = rng.choice((0, 1, 6, 9))
+        s = ref.deflate_stream(d, level, rng.choice((0, 0, 1, 2, 3, 4)), wrap, chunk, chunk_flush=flushes)
+        res, out = _stream(ctx, s, wrap, n + 16)
+        assert res.status == 0 and out == d and res.in_used == len(s), (trial, kind, n, chunk, flushes, wrap, level, msg(res.status), res.out_len)
