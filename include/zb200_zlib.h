@@ -61,6 +61,14 @@ typedef z_stream *z_streamp;
 typedef void *voidp;
 typedef const void *voidpc;
 struct gzFile_s { unsigned have; unsigned char *next; long pos; };   /* zlib.h:1819-1823 */
+typedef struct gz_header_s {                              /* zlib.h:116-131 */
+    int text; uLong time; int xflags; int os;
+    Bytef *extra; uInt extra_len; uInt extra_max;
+    Bytef *name; uInt name_max;
+    Bytef *comment; uInt comm_max;
+    int hcrc; int done;
+} gz_header;
+typedef gz_header *gz_headerp;
 typedef struct gzFile_s *gzFile;
 
 #define Z_NO_FLUSH 0                                      /* zlib.h:172-189 */
@@ -120,6 +128,19 @@ int inflateEnd(z_streamp strm);
 int inflateReset(z_streamp strm);
 int inflateReset2(z_streamp strm, int windowBits);
 int inflateSetDictionary(z_streamp strm, const Bytef *dictionary, uInt dictLength);   /* zlib.h:887, inflate.c:1278 */
+int deflateGetDictionary(z_streamp strm, Bytef *dictionary, uInt *dictLength);        /* zlib.h:655, deflate.c:638 */
+int inflateGetDictionary(z_streamp strm, Bytef *dictionary, uInt *dictLength);        /* zlib.h:910, inflate.c:1258 */
+int deflateSetHeader(z_streamp strm, gz_headerp head);                                 /* zlib.h:802, deflate.c:692 */
+int inflateGetHeader(z_streamp strm, gz_headerp head);                                 /* zlib.h:1040, inflate.c:1331 */
+int deflatePending(z_streamp strm, unsigned *pending, int *bits);                      /* zlib.h:779, deflate.c:703 */
+int deflateCopy(z_streamp dest, z_streamp source);                                     /* zlib.h:677, deflate.c:1297 */
+int inflateCopy(z_streamp dest, z_streamp source);                                     /* zlib.h:929, inflate.c:1433 */
+int deflateResetKeep(z_streamp strm);                                                  /* deflate.c:644 */
+int inflateResetKeep(z_streamp strm);                                                  /* inflate.c:102 */
+int inflateValidate(z_streamp strm, int check);                                        /* zlib.h:1807, inflate.c:1495 */
+int inflateUndermine(z_streamp strm, int subvert);                                     /* inflate.c:1478 */
+long inflateMark(z_streamp strm);                                                      /* zlib.h:1012, inflate.c:1510 */
+uLong zlibCompileFlags(void);                                                          /* zlib.h:1227, zutil.c:32 */
 
 /* ---- gz* file layer (zlib.h:1300-1823; gzlib.c, gzread.c, gzwrite.c, gzclose.c) ---- */
 gzFile gzopen(const char *path, const char *mode);

@@ -320,3 +320,112 @@ def test_sync_flush_keeps_history(z, wrap):
     # a full flush does reset it: the chunks decode on their own (zlib.h:286-291)
     s = z.deflate_stream(d[:100000], 6, 0, refz.WRAP_RAW, chunk=20000, chunk_flush=refz.Z_FULL_FLUSH)
     assert s == ref.deflate_stream(d[:100000], 6, 0, refz.WRAP_RAW, chunk=20000, chunk_flush=refz.Z_FULL_FLUSH)
+
+
+class GzHeader(C.Structure):
+    _fields_ = [("text", C.c_int), ("time", C.c_ulong), ("xflags", C.c_int), ("os", C.c_int),
+                ("extra", C.c_void_p), ("extra_len", C.c_uint), ("extra_max", C.c_uint),
+                ("name", C.c_void_p), ("name_max", C.c_uint), ("comment", C.c_void_p), ("comm_max", C.c_uint),
+                ("hcrc", C.c_int), ("done", C.c_int)]
+
+
+def _advanced(zb_):
+    for name, res, args in (("deflateSetHeader", C.c_int, [C.POINTER(refz.ZStream), C.POINTER(GzHeader)]),
+                            ("inflateGetHeader", C.c_int, [C.POINTER(refz.ZStream), C.POINTER(GzHeader)]),
+                            ("deflatePending", C.c_int, [C.POINTER(refz.ZStream), C.POINTER(C.c_uint), C.POINTER(C.c_int)]),
+                            ("deflateCopy", C.c_int, [C.POINTER(refz.ZStream), C.POINTER(refz.ZStream)]),
+                            ("inflateCopy", C.c_int, [C.POINTER(refz.ZStream), C.POINTER(refz.ZStream)]),
+                            ("inflateGetDictionary", C.c_int, [C.POINTER(refz.ZStream), C.c_void_p, C.POINTER(C.c_uint)]),
+                            ("deflateGetDictionary", C.c_int, [C.POINTER(refz.ZStream), C.c_void_p, C.POINTER(C.c_uint)]),
+                            ("inflateValidate", C.c_int, [C.POINTER(refz.ZStream), C.c_int]),
+                            ("inflateMark", C.c_long, [C.POINTER(refz.ZStream)]),
+                            ("zlibCompileFlags", C.c_ulong, [])):
+        if not hasattr(zb_, name):
+            zb_._f(name, res, *args)
+    return zb_
+
+
+def _deflate_with_header(zz, d, level, hdr):
+    s = refz.ZStream()
+    assert zz.deflateInit2_(C.byref(s), level, 8, 31, 8, 0, zz.version, C.sizeof(refz.ZStream)) == 0
+    assert zz.deflateSetHeader(C.byref(s), C.byref(hdr)) == 0
+    src = C.create_string_buffer(d, len(d))
+    dst = C.create_string_buffer(len(d) + 4096)
+    s.next_in, s.avail_in, s.next_out, s.avail_out = C.addressof(src), len(d), C.addressof(dst), len(dst)
+    assert zz.deflate(C.byref(s), refz.Z_FINISH) == refz.Z_STREAM_END
+    out = dst.raw[:len(dst) - s.avail_out]
+    zz.deflateEnd(C.byref(s))
+    return out
+
+
+def test_advanced_stream_functions(z):
+    """deflateSetHeader / inflateGetHeader / deflatePending / deflateCopy / inflateCopy / inflateGetDictionary /
+    inflateValidate / zlibCompileFlags next to the reference (zlib.h "advanced functions")."""
+    if not refz.have_ref():
+        pytest.skip("oracle/_ref/libzref.so not built")
+    z = _advanced(z)
+    ref = _advanced(refz.ref())
+    assert z.zlibCompileFlags() & 0xff == ref.zlibCompileFlags() & 0xff           # the type-size fields
+    d = refz.gen(200000, refz.GEN_TEXT, seed=91)
+    extra, name, comment = C.create_string_buffer(b"\x41\x42\x03\x00xyz", 7), C.create_string_buffer(b"file.txt"), C.create_string_buffer(b"made on a GPU")
+    for hcrc in (0, 1):
+        hdr = GzHeader(1, 1234567890, 0, 7, C.addressof(extra), 7, 0, C.addressof(name), 0, C.addressof(comment), 0, hcrc, 0)
+        a, b = _deflate_with_header(z, d, 6, hdr), _deflate_with_header(ref, d, 6, hdr)
+        assert a == b, (hcrc, a[:40].hex(), b[:40].hex())
+        for zz in (z, ref):                                                        # ... and read back
+            s = refz.ZStream()
+            assert zz.inflateInit2_(C.byref(s), 31, zz.version, C.sizeof(refz.ZStream)) == 0
+            eb, nb, cb = C.create_string_buffer(16), C.create_string_buffer(32), C.create_string_buffer(6)
+            got = GzHeader(0, 0, 0, 0, C.addressof(eb), 0, 16, C.addressof(nb), 32, C.addressof(cb), 6, 0, 0)
+            assert zz.inflateGetHeader(C.byref(s), C.byref(got)) == 0
+            src, dst = C.create_string_buffer(a, len(a)), C.create_string_buffer(len(d) + 64)
+            s.next_in, s.avail_in, s.next_out, s.avail_out = C.addressof(src), len(a), C.addressof(dst), len(dst)
+            assert zz.inflate(C.byref(s), refz.Z_NO_FLUSH) == refz.Z_STREAM_END and dst.raw[:len(d)] == d   # (Z_FINISH: the reference keeps no window)
+            assert (got.done, got.text, got.time, got.os, got.extra_len, got.hcrc) == (1, 1, 1234567890, 7, 7, hcrc)
+            assert eb.raw[:7] == extra.raw[:7] and nb.value == b"file.txt" and cb.raw == b"made o"   # comm_max reached: not terminated
+            # the window after the stream: its last 32 KiB
+            win, wl = C.create_string_buffer(32768), C.c_uint(0)
+            assert zz.inflateGetDictionary(C.byref(s), win, C.byref(wl)) == 0
+            if zz is z:                                       # (the reference keeps no window when one call decodes the whole stream)
+                assert wl.value == 32768 and win.raw == d[-32768:]
+            zz.inflateEnd(C.byref(s))
+    # deflatePending, deflateCopy: a copy taken mid-stream finishes to the same bytes
+    s = refz.ZStream()
+    assert z.deflateInit2_(C.byref(s), 6, 8, 15, 8, 0, z.version, C.sizeof(refz.ZStream)) == 0
+    src, dst, dst2 = C.create_string_buffer(d, len(d)), C.create_string_buffer(len(d) + 4096), C.create_string_buffer(len(d) + 4096)
+    s.next_in, s.avail_in, s.next_out, s.avail_out = C.addressof(src), 100000, C.addressof(dst), 10
+    assert z.deflate(C.byref(s), refz.Z_SYNC_FLUSH) == 0 and s.avail_out == 0
+    pend, bits = C.c_uint(0), C.c_int(9)
+    assert z.deflatePending(C.byref(s), C.byref(pend), C.byref(bits)) == 0 and pend.value > 0 and bits.value == 0
+    s2 = refz.ZStream()
+    assert z.deflateCopy(C.byref(s2), C.byref(s)) == 0
+    outs = []
+    for st, buf in ((s, dst), (s2, dst2)):
+        st.next_in, st.avail_in, st.next_out, st.avail_out = C.addressof(src) + 100000, len(d) - 100000, C.addressof(buf) + 10, len(buf) - 10
+        assert z.deflate(C.byref(st), refz.Z_FINISH) == refz.Z_STREAM_END
+        outs.append(dst.raw[:10] + buf.raw[10:len(buf) - st.avail_out])
+        z.deflateEnd(C.byref(st))
+    assert outs[0] == outs[1] and ref.inflate_all(outs[0], refz.WRAP_ZLIB, cap=len(d) + 64)[2] == d
+    # inflateCopy mid-stream; inflateValidate(0) lets a damaged trailer pass (inflate.c:1495)
+    stream = ref.deflate_stream(d, 6, 0, refz.WRAP_ZLIB, 50000)
+    s = refz.ZStream()
+    assert z.inflateInit2_(C.byref(s), 15, z.version, C.sizeof(refz.ZStream)) == 0
+    src, o1, o2 = C.create_string_buffer(stream, len(stream)), C.create_string_buffer(len(d) + 64), C.create_string_buffer(len(d) + 64)
+    s.next_in, s.avail_in, s.next_out, s.avail_out = C.addressof(src), len(stream) // 2, C.addressof(o1), len(o1)
+    assert z.inflate(C.byref(s), 0) == 0
+    got1 = len(o1) - s.avail_out
+    s2 = refz.ZStream()
+    assert z.inflateCopy(C.byref(s2), C.byref(s)) == 0
+    C.memmove(o2, o1, got1)
+    for st, buf in ((s, o1), (s2, o2)):
+        st.next_in, st.avail_in, st.next_out, st.avail_out = C.addressof(src) + len(stream) // 2, len(stream) - len(stream) // 2, C.addressof(buf) + got1, len(buf) - got1
+        assert z.inflate(C.byref(st), refz.Z_FINISH) == refz.Z_STREAM_END and buf.raw[:len(d)] == d
+        z.inflateEnd(C.byref(st))
+    bad = bytearray(stream); bad[-1] ^= 0xff
+    for check, want in ((1, refz.Z_DATA_ERROR), (0, refz.Z_STREAM_END)):
+        s = refz.ZStream()
+        assert z.inflateInit2_(C.byref(s), 15, z.version, C.sizeof(refz.ZStream)) == 0 and z.inflateValidate(C.byref(s), check) == 0
+        src, o1 = C.create_string_buffer(bytes(bad), len(bad)), C.create_string_buffer(len(d) + 64)
+        s.next_in, s.avail_in, s.next_out, s.avail_out = C.addressof(src), len(bad), C.addressof(o1), len(o1)
+        assert z.inflate(C.byref(s), refz.Z_FINISH) == want and z.inflateMark(C.byref(s)) == -65536
+        z.inflateEnd(C.byref(s))

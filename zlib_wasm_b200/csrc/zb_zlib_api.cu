@@ -69,6 +69,7 @@ struct DeflateStream {
     bool keep_history;                   // the flush in progress does not reset the history (deflate.c:1211-1218)
     uint32_t dictid;                     // Adler-32 of the whole dictionary (zlib header DICTID)
     bool have_dictid;
+    gz_headerp gzhead;                   // deflateSetHeader: the caller's header fields (read when the header is written)
 };
 
 struct InflateStream {
@@ -87,6 +88,8 @@ struct InflateStream {
     int error;                           // sticky ZB200_INF_* data error
     uint64_t in_used;
     uint32_t check;
+    gz_headerp gzhead;                   // inflateGetHeader: where the gzip header fields go
+    bool verify;                         // inflateValidate: compare the trailer's check value
     size_t dict_len;                     // preset dictionary: d_out[0 .. dict_len), the output follows it
     uint32_t dictid;                     // DICTID of the zlib header that asked for one
     bool retry;                          // inflateSetDictionary was called: decode again with no new input
@@ -173,10 +176,31 @@ void put_header(DeflateStream &st) {
         st.pending.push_back((uint8_t)(hdr >> 8)); st.pending.push_back((uint8_t)hdr);
         if (st.have_dictid)                                    // deflate.c:1031-1034: DICTID, most significant byte first
             for (int i = 3; i >= 0; --i) st.pending.push_back((uint8_t)(st.dictid >> (8 * i)));
-    } else if (st.wrap == 2) {                                 // deflate.c:1042-1054
+    } else if (st.wrap == 2 && st.gzhead == Z_NULL) {          // deflate.c:1042-1054
         const uint8_t g[10] = {0x1f, 0x8b, 8, 0, 0, 0, 0, 0,
                                (uint8_t)(st.level == 9 ? 2 : (st.strategy >= Z_HUFFMAN_ONLY || st.level < 2) ? 4 : 0), 3};
         st.pending.insert(st.pending.end(), g, g + 10);
+    } else if (st.wrap == 2) {                                 // deflate.c:1056-1170: the caller's fields
+        const gz_header &h = *st.gzhead;
+        const size_t at = st.pending.size();
+        const uint8_t g[10] = {0x1f, 0x8b, 8,
+                               (uint8_t)((h.text ? 1 : 0) + (h.hcrc ? 2 : 0) + (h.extra == Z_NULL ? 0 : 4) + (h.name == Z_NULL ? 0 : 8) + (h.comment == Z_NULL ? 0 : 16)),
+                               (uint8_t)h.time, (uint8_t)(h.time >> 8), (uint8_t)(h.time >> 16), (uint8_t)(h.time >> 24),
+                               (uint8_t)(st.level == 9 ? 2 : (st.strategy >= Z_HUFFMAN_ONLY || st.level < 2) ? 4 : 0), (uint8_t)(h.os & 0xff)};
+        st.pending.insert(st.pending.end(), g, g + 10);
+        if (h.extra != Z_NULL) {
+            st.pending.push_back((uint8_t)h.extra_len); st.pending.push_back((uint8_t)(h.extra_len >> 8));
+            st.pending.insert(st.pending.end(), h.extra, h.extra + (h.extra_len & 0xffff));
+        }
+        if (h.name != Z_NULL) st.pending.insert(st.pending.end(), h.name, h.name + strlen((const char *)h.name) + 1);
+        if (h.comment != Z_NULL) st.pending.insert(st.pending.end(), h.comment, h.comment + strlen((const char *)h.comment) + 1);
+        if (h.hcrc) {
+            const z_crc_t *t = get_crc_table();
+            uint32_t c = 0xffffffffu;
+            for (size_t i = at; i < st.pending.size(); ++i) c = t[(c ^ st.pending[i]) & 0xff] ^ (c >> 8);
+            c = ~c;
+            st.pending.push_back((uint8_t)c); st.pending.push_back((uint8_t)(c >> 8));
+        }
     }
     st.header_done = true;
 }
@@ -205,7 +229,39 @@ InflateStream *istate(z_streamp strm) {
 void inflate_reset_state(InflateStream &s) {
     s.kind = 0; s.in.clear(); s.d_in_have = 0; s.out.clear(); s.out_pos = 0; s.out_base = 0; s.decoded = 0;
     s.resume_bit = s.resume_out = 0; s.started = s.done = false; s.error = 0; s.in_used = 0; s.check = 0;
-    s.dict_len = 0; s.dictid = 0; s.retry = false;
+    s.dict_len = 0; s.dictid = 0; s.retry = false; s.gzhead = Z_NULL; s.verify = true;
+}
+
+// inflate.c:671-808 as far as inflateGetHeader needs it: the gzip header fields out of the input seen so far.
+// Returns false while the header is incomplete.
+bool fill_gz_header(const std::vector<uint8_t> &in, gz_header &h) {
+    const size_t n = in.size();
+    if (n < 10) return false;
+    const unsigned flg = in[3];
+    size_t p = 10;
+    const uint8_t *ex = nullptr, *nm = nullptr, *cm = nullptr;
+    size_t exl = 0, nml = 0, cml = 0;
+    if (flg & 4) {
+        if (p + 2 > n) return false;
+        exl = in[p] | (in[p + 1] << 8); p += 2;
+        if (p + exl > n) return false;
+        ex = in.data() + p; p += exl;
+    }
+    if (flg & 8) { nm = in.data() + p; while (p < n && in[p]) ++p; if (p >= n) return false; ++p; nml = (size_t)(in.data() + p - nm); }
+    if (flg & 16) { cm = in.data() + p; while (p < n && in[p]) ++p; if (p >= n) return false; ++p; cml = (size_t)(in.data() + p - cm); }
+    if ((flg & 2) && p + 2 > n) return false;
+    h.text = (int)(flg & 1);
+    h.time = (uLong)in[4] | ((uLong)in[5] << 8) | ((uLong)in[6] << 16) | ((uLong)in[7] << 24);
+    h.xflags = in[8]; h.os = in[9];
+    if (ex) { h.extra_len = (uInt)exl; if (h.extra != Z_NULL) memcpy(h.extra, ex, exl < h.extra_max ? exl : h.extra_max); }
+    else h.extra = Z_NULL;
+    if (nm) { if (h.name != Z_NULL) memcpy(h.name, nm, nml < h.name_max ? nml : h.name_max); }
+    else h.name = Z_NULL;
+    if (cm) { if (h.comment != Z_NULL) memcpy(h.comment, cm, cml < h.comm_max ? cml : h.comm_max); }
+    else h.comment = Z_NULL;
+    h.hcrc = (int)((flg >> 1) & 1);
+    h.done = 1;
+    return true;
 }
 
 // One decode attempt over everything received so far, resuming at the last
@@ -235,7 +291,7 @@ int inflate_attempt(InflateStream &s) {
         memcpy(ctx->h_small + 40, &m, sizeof m);                 // pinned bounce for the descriptor
         if (cudaMemcpyAsync(d_m, ctx->h_small + 40, sizeof m, cudaMemcpyHostToDevice, st) != cudaSuccess) return -1;
         const int wrap = s.resume_bit ? s.kind : s.wrap;
-        if (inflate_launch(ctx, s.d_in, s.d_out, d_m, 1, wrap, 1, d_r, base + 1024, st) != ZB200_OK) return -1;
+        if (inflate_launch(ctx, s.d_in, s.d_out, d_m, 1, wrap, s.verify ? 1 : 0, d_r, base + 1024, st) != ZB200_OK) return -1;
         if (cudaMemcpyAsync(h_r, d_r, sizeof *h_r, cudaMemcpyDeviceToHost, st) != cudaSuccess) return -1;
         if (cudaStreamSynchronize(st) != cudaSuccess) return -1;
         const zb200_member_result r = *h_r;
@@ -304,7 +360,7 @@ int deflateReset(z_streamp strm) {
     s->in.clear(); s->pending.clear(); s->pending_pos = 0;
     s->header_done = s->finished = s->trailer_done = false;
     s->crc = 0; s->adler = 1; s->total_in_hashed = 0; s->last_flush = -2;
-    s->dict.clear(); s->dictid = 0; s->have_dictid = false; s->keep_history = false;
+    s->dict.clear(); s->dictid = 0; s->have_dictid = false; s->keep_history = false; s->gzhead = Z_NULL;
     strm->total_in = strm->total_out = 0; strm->msg = Z_NULL; strm->data_type = Z_UNKNOWN;
     strm->adler = s->wrap == 2 ? 0 : 1;                         // deflate.c:656-660
     return Z_OK;
@@ -344,6 +400,46 @@ int deflateSetDictionary(z_streamp strm, const Bytef *dictionary, uInt dictLengt
     const uInt keep = dictLength > 32768u ? 32768u : dictLength;   // deflate.c:575-583: the tail of a long dictionary
     s->dict.assign(dictionary + (dictLength - keep), dictionary + dictLength);
     return Z_OK;
+}
+
+int deflateGetDictionary(z_streamp strm, Bytef *dictionary, uInt *dictLength) {   // deflate.c:638: what the next byte would be compressed against
+    DeflateStream *s = dstate(strm);
+    if (!s) return Z_STREAM_ERROR;
+    if (dictionary != Z_NULL && !s->dict.empty()) memcpy(dictionary, s->dict.data(), s->dict.size());
+    if (dictLength != Z_NULL) *dictLength = (uInt)s->dict.size();
+    return Z_OK;
+}
+
+int deflateSetHeader(z_streamp strm, gz_headerp head) {      // deflate.c:692-697
+    DeflateStream *s = dstate(strm);
+    if (!s || s->wrap != 2) return Z_STREAM_ERROR;
+    s->gzhead = head;
+    return Z_OK;
+}
+
+int deflatePending(z_streamp strm, unsigned *pending, int *bits) {   // deflate.c:703-713; output here is always whole bytes
+    DeflateStream *s = dstate(strm);
+    if (!s) return Z_STREAM_ERROR;
+    if (pending != Z_NULL) *pending = (unsigned)(s->pending.size() - s->pending_pos);
+    if (bits != Z_NULL) *bits = 0;
+    return Z_OK;
+}
+
+int deflateResetKeep(z_streamp strm) { return deflateReset(strm); }   // deflate.c:644: no match-finder state to keep here
+
+int deflateCopy(z_streamp dest, z_streamp source) {          // deflate.c:1297-1345
+    DeflateStream *s = dstate(source);
+    if (!s || dest == Z_NULL) return Z_STREAM_ERROR;
+    DeflateStream *d = new (std::nothrow) DeflateStream(*s);
+    if (!d) return Z_MEM_ERROR;
+    *dest = *source;
+    dest->state = reinterpret_cast<struct internal_state *>(d);
+    return Z_OK;
+}
+
+uLong zlibCompileFlags(void) {                               // zutil.c:32-113: type sizes; no debug, no asm, gz* present
+    auto code = [](size_t n) -> uLong { return n == 2 ? 0 : n == 4 ? 1 : n == 8 ? 2 : 3; };
+    return code(sizeof(uInt)) | (code(sizeof(uLong)) << 2) | (code(sizeof(voidpf)) << 4) | (code(sizeof(z_off_t)) << 6);
 }
 
 uLong deflateBound(z_streamp strm, uLong n) {
@@ -463,7 +559,7 @@ int inflate(z_streamp strm, int flush) {
         s->retry = false;
         s->in.insert(s->in.end(), strm->next_in, strm->next_in + strm->avail_in);
         status = -2;
-        if (s->decoded == 0 && s->resume_bit == 0 && s->dict_len == 0 && s->out.empty() && s->in.size() >= 262144) {
+        if (s->decoded == 0 && s->resume_bit == 0 && s->dict_len == 0 && s->out.empty() && s->in.size() >= 262144 && s->verify) {
             // a whole stream handed over at once: its flush-point runs in parallel (zb200_inflate_stream_host)
             zb200_member_result q;
             size_t cap = s->in.size() * 4 + (1u << 20);
@@ -487,6 +583,10 @@ int inflate(z_streamp strm, int flush) {
         else if (status != ZB200_INF_TRUNCATED) s->error = status;
         strm->next_in += used; strm->avail_in -= (uInt)used; strm->total_in += used;
         if (status == ZB200_INF_OK) strm->adler = s->check;
+        if (s->gzhead != Z_NULL && s->gzhead->done == 0) {          // inflateGetHeader: inflate.c:1331-1345
+            if (s->in.size() >= 2 && !(s->in[0] == 0x1f && s->in[1] == 0x8b)) s->gzhead->done = -1;
+            else if (s->kind == 2 || (s->in.size() >= 2 && (s->wrap & ZB200_WRAP_GZIP))) fill_gz_header(s->in, *s->gzhead);
+        }
     }
     // deliver decoded bytes
     const size_t avail = s->out.size() - s->out_pos;
@@ -533,6 +633,80 @@ int inflateSetDictionary(z_streamp strm, const Bytef *dictionary, uInt dictLengt
     s->dict_len = keep;
     if (s->error == ZB200_INF_NEED_DICT) { s->error = 0; s->retry = true; }
     if (s->wrap != ZB200_WRAP_RAW) strm->adler = 1;               // inflate.c:671: adler32(0L, Z_NULL, 0)
+    return Z_OK;
+}
+
+int inflateGetDictionary(z_streamp strm, Bytef *dictionary, uInt *dictLength) {   // inflate.c:1258-1276: the sliding window = the last 32 KiB produced
+    InflateStream *s = istate(strm);
+    if (!s) return Z_STREAM_ERROR;
+    const size_t have = (size_t)s->decoded + s->dict_len;    // bytes in d_out: dictionary + output
+    const size_t k = have < 32768 ? have : 32768;
+    if (k && dictionary != Z_NULL) {
+        zb200_ctx *ctx = api_ctx();
+        if (!ctx) return Z_STREAM_ERROR;
+        std::lock_guard<std::mutex> g(ctx->mu);
+        if (cudaSetDevice(ctx->device) != cudaSuccess) return Z_STREAM_ERROR;
+        if (s->d_out == nullptr) return Z_STREAM_ERROR;
+        if (cudaMemcpyAsync(dictionary, s->d_out + (have - k), k, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) return Z_STREAM_ERROR;
+        if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return Z_STREAM_ERROR;
+    }
+    if (dictLength != Z_NULL) *dictLength = (uInt)k;
+    return Z_OK;
+}
+
+int inflateGetHeader(z_streamp strm, gz_headerp head) {      // inflate.c:1331-1345
+    InflateStream *s = istate(strm);
+    if (!s || !(s->wrap & ZB200_WRAP_GZIP)) return Z_STREAM_ERROR;
+    s->gzhead = head;
+    if (head != Z_NULL) head->done = 0;
+    return Z_OK;
+}
+
+int inflateResetKeep(z_streamp strm) { return inflateReset(strm); }   // inflate.c:102
+
+int inflateValidate(z_streamp strm, int check) {             // inflate.c:1495-1508
+    InflateStream *s = istate(strm);
+    if (!s) return Z_STREAM_ERROR;
+    s->verify = check != 0;
+    return Z_OK;
+}
+
+int inflateUndermine(z_streamp strm, int subvert) {          // inflate.c:1478-1493 without INFLATE_ALLOW_INVALID_DISTANCE_TOOFAR_ARRR
+    (void)subvert;
+    return istate(strm) ? Z_DATA_ERROR : Z_STREAM_ERROR;
+}
+
+long inflateMark(z_streamp strm) {                           // inflate.c:1510-1521: this inflate() stops between blocks only (back = -1, nothing pending)
+    (void)strm;
+    return -(1L << 16);
+}
+
+int inflateCopy(z_streamp dest, z_streamp source) {          // inflate.c:1433-1476
+    InflateStream *s = istate(source);
+    if (!s || dest == Z_NULL) return Z_STREAM_ERROR;
+    zb200_ctx *ctx = api_ctx();
+    if (!ctx) return Z_STREAM_ERROR;
+    InflateStream *d = new (std::nothrow) InflateStream(*s);
+    if (!d) return Z_MEM_ERROR;
+    d->d_in = d->d_out = nullptr;
+    {
+        std::lock_guard<std::mutex> g(ctx->mu);
+        bool ok = cudaSetDevice(ctx->device) == cudaSuccess;
+        if (ok && s->d_in) ok = cudaMalloc((void **)&d->d_in, s->d_in_cap) == cudaSuccess &&
+                                cudaMemcpyAsync(d->d_in, s->d_in, s->d_in_have, cudaMemcpyDeviceToDevice, ctx->stream) == cudaSuccess;
+        if (ok && s->d_out) ok = cudaMalloc((void **)&d->d_out, s->d_out_cap) == cudaSuccess &&
+                                 cudaMemcpyAsync(d->d_out, s->d_out, (size_t)s->decoded + s->dict_len, cudaMemcpyDeviceToDevice, ctx->stream) == cudaSuccess;
+        if (ok) ok = cudaStreamSynchronize(ctx->stream) == cudaSuccess;
+        if (!ok) {
+            cudaGetLastError();
+            if (d->d_in) cudaFree(d->d_in);
+            if (d->d_out) cudaFree(d->d_out);
+            delete d;
+            return Z_MEM_ERROR;
+        }
+    }
+    *dest = *source;
+    dest->state = reinterpret_cast<struct internal_state *>(d);
     return Z_OK;
 }
 
