@@ -386,7 +386,10 @@ inflate_kernel(const uint8_t *__restrict__ in, uint8_t *out, const zb200_member 
 // subsequences — the fix-up chain and the scans cross the warps through shared memory, the
 // copy waves are 128 matches wide — while thread 0 remains the serial skeleton.  Tails too
 // short for a team round go to warp 0's 32-lane rounds, oddities to the serial path as ever.
-constexpr int kTeamWarps = 4, kTeamLanes = kTeamWarps * 32, kTeamCtasPerSm = 4, kTeamLgDefault = 4;
+#ifndef ZB_TEAM_WARPS
+#define ZB_TEAM_WARPS 4
+#endif
+constexpr int kTeamWarps = ZB_TEAM_WARPS, kTeamLanes = kTeamWarps * 32, kTeamCtasPerSm = 16 / kTeamWarps, kTeamLgDefault = 4;
 struct TeamShared {
     uint32_t lit[kLitEntries];
     uint32_t dist[kDistEntries];
