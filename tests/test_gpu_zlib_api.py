@@ -429,3 +429,21 @@ def test_advanced_stream_functions(z):
         s.next_in, s.avail_in, s.next_out, s.avail_out = C.addressof(src), len(bad), C.addressof(o1), len(o1)
         assert z.inflate(C.byref(s), refz.Z_FINISH) == want and z.inflateMark(C.byref(s)) == -65536
         z.inflateEnd(C.byref(s))
+
+
+def test_reference_gun_linked_against_product(tmp_path):
+    """The reference's examples/gun.c — gunzip through inflateBack() (infback.c:242) and crc32(), several members
+    per file — compiled against the reference's zlib.h and linked to libzb200.so."""
+    import gzip
+    exe = os.path.join(refz.ROOT, "tests", "_bin", "gun_b200")
+    if not os.path.exists(exe):
+        pytest.skip("gun_b200 was not prebuilt (needs /root/reference at build time)")
+    parts = [refz.gen(n, refz.GEN_TEXT, seed=n) for n in (300000, 0, 70000)]
+    blob = b"".join(gzip.compress(p, 6) for p in parts)
+    back = subprocess.run([exe], input=blob, capture_output=True, timeout=300)
+    assert back.returncode == 0 and back.stdout == b"".join(parts), (back.returncode, back.stderr[:300])
+    bad = bytearray(blob); bad[len(blob) // 3] ^= 0x20
+    r = subprocess.run([exe], input=bytes(bad), capture_output=True, timeout=300)
+    assert b"gun data error" in r.stderr                             # gun.c:595-630 reports, the exit code stays 0 for stdin
+    r = subprocess.run([exe, "-t"], input=blob[:len(blob) // 2], capture_output=True, timeout=300)
+    assert b"gun" in r.stderr and r.stdout == b""

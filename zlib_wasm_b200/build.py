@@ -120,6 +120,11 @@ def build_dropin_demo():
         os.makedirs(os.path.dirname(out), exist_ok=True)
         _run(["gcc", "-O2", "-w", "-I/root/reference", "-o", out, src, "-L" + PKG, "-lzb200",
               "-Wl,-rpath,$ORIGIN/../../zlib_wasm_b200"])
+    # examples/gun.c: gunzip through inflateBack() (infback.c) + crc32()
+    src2, out2 = "/root/reference/examples/gun.c", os.path.join(ROOT, "tests", "_bin", "gun_b200")
+    if os.path.exists(src2) and _newer(out2, [src2, LIB]):
+        _run(["gcc", "-O2", "-w", "-I/root/reference", "-o", out2, src2, "-L" + PKG, "-lzb200",
+              "-Wl,-rpath,$ORIGIN/../../zlib_wasm_b200"])
     return out
 
 

@@ -710,6 +710,68 @@ int inflateCopy(z_streamp dest, z_streamp source) {          // inflate.c:1433-1
     return Z_OK;
 }
 
+// ---- inflateBack (infback.c): a raw stream pulled through in() and pushed through out(), window by window.
+// The reference decodes straight into the caller's window; here the caller's window is the staging buffer
+// between this library's inflate() and out().
+struct BackState { uint32_t magic; unsigned char *window; unsigned wsize; };
+constexpr uint32_t kBackMagic = 0x5a42424bu;
+
+int inflateBackInit_(z_streamp strm, int windowBits, unsigned char *window, const char *version, int stream_size) {
+    if (version == Z_NULL || version[0] != ZLIB_VERSION[0] || stream_size != (int)sizeof(z_stream)) return Z_VERSION_ERROR;
+    if (strm == Z_NULL || window == Z_NULL || windowBits < 8 || windowBits > 15) return Z_STREAM_ERROR;   // infback.c:33-35
+    strm->msg = Z_NULL;
+    if (!api_ctx()) { strm->msg = "zlib-b200: no usable CUDA device (no CPU path)"; return Z_STREAM_ERROR; }
+    BackState *b = new (std::nothrow) BackState();
+    if (!b) return Z_MEM_ERROR;
+    b->magic = kBackMagic; b->window = window; b->wsize = 1u << windowBits;
+    strm->state = reinterpret_cast<struct internal_state *>(b);
+    return Z_OK;
+}
+
+int inflateBack(z_streamp strm, in_func in, void *in_desc, out_func out, void *out_desc) {
+    BackState *b = strm ? reinterpret_cast<BackState *>(strm->state) : nullptr;
+    if (!b || b->magic != kBackMagic || !in || !out) return Z_STREAM_ERROR;
+    strm->msg = Z_NULL;
+    z_stream inner;
+    memset(&inner, 0, sizeof inner);
+    if (inflateInit2_(&inner, -15, ZLIB_VERSION, (int)sizeof(z_stream)) != Z_OK) return Z_MEM_ERROR;
+    const unsigned char *next = strm->next_in;
+    unsigned have = next != Z_NULL ? strm->avail_in : 0;
+    int ret;
+    for (;;) {
+        if (have == 0) {
+            have = in(in_desc, &next);
+            if (have == 0) { next = Z_NULL; ret = Z_BUF_ERROR; break; }          // infback.c:PULL: input exhausted
+        }
+        inner.next_in = const_cast<Bytef *>(next); inner.avail_in = have;
+        int r;
+        bool out_failed = false;
+        do {
+            inner.next_out = b->window; inner.avail_out = b->wsize;
+            r = inflate(&inner, Z_NO_FLUSH);
+            const unsigned got = b->wsize - inner.avail_out;
+            if (got && out(out_desc, b->window, got)) { out_failed = true; break; }   // infback.c:ROOM: output error
+        } while (inner.avail_out == 0 && r != Z_STREAM_END && r != Z_DATA_ERROR);
+        next += have - inner.avail_in; have = inner.avail_in;
+        if (out_failed) { ret = Z_BUF_ERROR; break; }
+        if (r == Z_STREAM_END) { ret = Z_STREAM_END; break; }
+        if (r == Z_DATA_ERROR || r == Z_NEED_DICT) { strm->msg = inner.msg; ret = Z_DATA_ERROR; break; }
+        if (r == Z_STREAM_ERROR || r == Z_MEM_ERROR) { strm->msg = inner.msg; ret = r; break; }
+    }
+    strm->next_in = const_cast<Bytef *>(next); strm->avail_in = have;
+    inflateEnd(&inner);
+    return ret;
+}
+
+int inflateBackEnd(z_streamp strm) {
+    BackState *b = strm ? reinterpret_cast<BackState *>(strm->state) : nullptr;
+    if (!b || b->magic != kBackMagic) return Z_STREAM_ERROR;
+    b->magic = 0;
+    delete b;
+    strm->state = Z_NULL;
+    return Z_OK;
+}
+
 int inflateEnd(z_streamp strm) {
     InflateStream *s = istate(strm);
     if (!s) return Z_STREAM_ERROR;
