@@ -149,7 +149,7 @@ extern "C" long emul_deflate_chunk_dict(const uint8_t *data, uint32_t n, uint32_
             if (!dist) w.lt[lc].fc++;
             else { w.lt[257 + g_fmt.len_code[lc]].fc++; w.dt[dist_to_code(g_fmt, dist)].fc++; }
         }
-        block_build(w, bi, strategy, g_st, g_fmt, code);
+        block_build(w, bi, strategy | (level == 0 ? 0x100 : 0), g_st, g_fmt, code);   // as deflate_launch passes it
         const uint64_t start = bs.bit;
         const uint32_t last = bi.flags & BLK_LAST;
         bs.put(last | (code.type << 1), 3);

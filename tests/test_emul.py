@@ -181,7 +181,7 @@ def test_deflate_phases_byte_exact():
     for kind in range(5):
         for n in (0, 1, 3, 300, 70000, 262144):
             d = refz.gen(n, kind, seed=7 + kind)
-            for level, strat in ((1, 0), (2, 0), (3, 0), (4, 0), (6, 0), (6, 1), (6, 2), (6, 3), (6, 4), (9, 0)):
+            for level, strat in ((0, 0), (1, 0), (2, 0), (3, 0), (4, 0), (6, 0), (6, 1), (6, 2), (6, 3), (6, 4), (9, 0)):
                 for final in (0, 1):
                     cap = n + n // 8 + 1024
                     out, st = C.create_string_buffer(cap), (C.c_uint32 * 2)()
@@ -190,7 +190,13 @@ def test_deflate_phases_byte_exact():
                     e = out.raw[:r]
                     rb = C.create_string_buffer(cap)
                     rn = o.c_deflate_chunk(d, n, level, strat, final, rb, cap)
-                    if level >= 4 or strat in (2, 3):
+                    if level == 0:                         # stored blocks of MAX_STORED bytes: the reference's bytes when it has room (deflate.c:1635-1815)
+                        if refz.have_ref() and final:
+                            assert e == refz.ref().deflate_stream(d, 0, 0, refz.WRAP_RAW, 0), (kind, n)
+                        s = e if final else e + b"\x03\x00"
+                        err, msg, back, used = o.inflate_all(s, 0, cap=n + 16)
+                        assert err == 0 and back == d and len(e) <= n + 5 * (n // 65535 + 2) + 5
+                    elif level >= 4 or strat in (2, 3):
                         assert e == rb.raw[:rn], (kind, n, level, strat, final)
                     else:
                         s = e if final else e + b"\x03\x00"
@@ -226,7 +232,7 @@ def test_deflate_preset_dictionary_byte_exact():
                 r = L.emul_deflate_chunk_dict(joined, len(joined), len(tail), level, strat, 1, out, cap, st)
                 assert r >= 0, (r, kind, dl, n, level, strat)
                 got = out.raw[:r]
-                if level >= 4 or strat in (2, 3):
+                if level >= 4 or strat in (2, 3) or level == 0:
                     assert got == want, (kind, dl, n, level, strat, len(got), len(want))
                 else:
                     err, msg, back, used = ref.inflate_all(got, refz.WRAP_RAW, cap=n + 16, dictionary=dictionary)

@@ -54,6 +54,8 @@ struct DeflateParams {
     int level, strategy, mode;
     int good, lazy, nice, chain;      // deflate.c:112-124 configuration_table
     int need_quarter;                 // the quartered-chain result can be asked for by the parse
+    uint32_t sym_limit;               // symbols that fill a block: lit_bufsize - 1 (deflate.c:455,512); level 0 cuts its
+                                      // stored blocks at MAX_STORED bytes instead (deflate.c:1615,1664)
 };
 
 ZB_HD DeflateParams deflate_params(int level, int strategy) {
@@ -67,6 +69,7 @@ ZB_HD DeflateParams deflate_params(int level, int strategy) {
     p.mode = (strategy == STRAT_HUFFMAN || level == 0) ? MODE_HUFF : strategy == STRAT_RLE ? MODE_RLE : level >= 4 ? MODE_SLOW : MODE_FAST;
     // a search happens only while prev_length < lazy; it is quartered when prev_length >= good
     p.need_quarter = (p.mode == MODE_SLOW && p.good < p.lazy) ? 1 : 0;
+    p.sym_limit = level == 0 ? 65535u : kSymLimit;
     return p;
 }
 
@@ -369,7 +372,7 @@ ZB_HD void parse_steps(ParseState &s, uint32_t limit, uint32_t n, const DeflateP
     auto emit = [&](uint32_t sym, uint32_t cover_end) {
         acc.put(sym);
         ++s.nsyms;
-        if (s.nsyms - s.blk_sym0 == kSymLimit) parse_close_block(s, cover_end, false);
+        if (s.nsyms - s.blk_sym0 == prm.sym_limit) parse_close_block(s, cover_end, false);
     };
     uint32_t p = s.p;
     if (prm.mode != MODE_SLOW) {                       // greedy: deflate_fast / deflate_rle / deflate_huff
@@ -607,12 +610,13 @@ ZB_HD void seg_emit(const SegLane &r, uint32_t lane, const SegGeom &g, uint32_t 
 // has stored it at index nsyms).  Returns the number of blocks.
 ZB_HD uint32_t seg_finish(BlockInfo *blocks, uint32_t nsyms, bool pending, uint32_t n, const DeflateParams &prm, bool final_chunk,
                           uint32_t lo = 0) {
-    const uint32_t nfull = nsyms / kSymLimit, rem = nsyms % kSymLimit + (pending ? 1u : 0u);
+    const uint32_t lim = prm.sym_limit;
+    const uint32_t nfull = nsyms / lim, rem = nsyms % lim + (pending ? 1u : 0u);
     uint32_t start = lo;
     for (uint32_t k = 0; k < nfull; ++k) {
         BlockInfo &b = blocks[k];
         const uint32_t end = b.byte_len, base = b.pad;
-        b.sym_start = k * kSymLimit; b.sym_count = kSymLimit;
+        b.sym_start = k * lim; b.sym_count = lim;
         b.byte_start = start; b.byte_len = end - start;
         b.flags = start >= base ? BLK_STORED_OK : 0;  // deflate.c:1597-1600
         b.bit_start_lo = b.bit_start_hi = 0; b.pad = 0;
@@ -621,7 +625,7 @@ ZB_HD uint32_t seg_finish(BlockInfo *blocks, uint32_t nsyms, bool pending, uint3
     uint32_t nblocks = nfull;
     if (final_chunk || rem) {
         BlockInfo &b = blocks[nblocks++];
-        b.sym_start = nfull * kSymLimit; b.sym_count = rem;
+        b.sym_start = nfull * lim; b.sym_count = rem;
         b.byte_start = start; b.byte_len = n - start;
         b.flags = (final_chunk ? BLK_LAST : 0) | (start >= parse_base_at(n, n, prm) ? BLK_STORED_OK : 0);
         b.bit_start_lo = b.bit_start_hi = 0; b.pad = 0;
@@ -655,8 +659,8 @@ template <class Acc>
 ZB_HD uint32_t greedy_symbol(uint32_t pos, bool use_m, Acc &acc, uint32_t g, BlockInfo *blocks, uint32_t n, const DeflateParams &prm) {
     const uint32_t m = use_m ? acc.mf(pos) : 0u;
     const uint32_t len = m ? (m >> 16) : 1u;
-    if ((g + 1) % kSymLimit == 0) {                    // this symbol fills a block (deflate.h:354-372 flush flag)
-        BlockInfo &b = blocks[g / kSymLimit];
+    if ((g + 1) % prm.sym_limit == 0) {                // this symbol fills a block (deflate.h:354-372 flush flag)
+        BlockInfo &b = blocks[g / prm.sym_limit];
         b.byte_len = pos + len;                        // provisional: end offset of the block
         b.pad = parse_base_at(pos, n, prm);            // provisional: window base at the flush (seg_finish completes the slot)
     }
