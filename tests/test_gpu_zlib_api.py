@@ -447,3 +447,35 @@ def test_reference_gun_linked_against_product(tmp_path):
     assert b"gun data error" in r.stderr                             # gun.c:595-630 reports, the exit code stays 0 for stdin
     r = subprocess.run([exe, "-t"], input=blob[:len(blob) // 2], capture_output=True, timeout=300)
     assert b"gun" in r.stderr and r.stdout == b""
+
+
+@pytest.mark.parametrize("wrap", [refz.WRAP_RAW, refz.WRAP_ZLIB, refz.WRAP_GZIP])
+def test_inflate_big_slices_run_parallel(z, wrap):
+    """inflate() fed in large slices: the runs between flush points that are complete in the input so far are decoded
+    in one batch, the stream is re-based behind them, the wrapper's trailer is checked over the pieces (combine)."""
+    ref = refz.ref() if refz.have_ref() else refz.oracle()
+    d = refz.gen(12000000, refz.GEN_MARKOV, seed=71)
+    s = ref.deflate_stream(d, 6, 0, wrap, 200000)                 # 60 full-flush runs
+    for in_slice, out_slice in ((1000000, None), (700001, 3000000), (300000, 65536), (len(s) - 3, None), (len(s) - 9, 1 << 20)):
+        ret, m, out, tin = z.inflate_all(s + b"after", wrap, cap=len(d) + 64, in_slice=in_slice, out_slice=out_slice)
+        assert ret == refz.Z_STREAM_END and out == d and tin == len(s), (wrap, in_slice, out_slice, ret, m, len(out), tin, len(s))
+    # damage: the reference's verdict, whatever the slicing
+    for where, flip in ((len(s) // 2, 0x08), (len(s) - 2, 0x01), (40, 0x80)):
+        bad = bytearray(s); bad[where] ^= flip
+        want = ref.inflate_all(bytes(bad), wrap, cap=len(d) + 64)
+        for in_slice in (1000000, 5000):
+            got = z.inflate_all(bytes(bad), wrap, cap=len(d) + 64, in_slice=in_slice)
+            assert got[0] == want[0] and (got[1] == want[1] or wrap == refz.WRAP_RAW), (wrap, where, in_slice, got[:2], want[:2])
+            k = min(len(got[2]), len(want[2]))                  # whatever both delivered before stopping is the same bytes
+            assert got[2][:k] == want[2][:k]
+    # cut short: everything complete is delivered, Z_BUF_ERROR at the end (inflate.c:1259-1261)
+    ret, m, out, tin = z.inflate_all(s[:len(s) * 2 // 3], wrap, cap=len(d) + 64, in_slice=900000)
+    assert ret == refz.Z_BUF_ERROR and d.startswith(out) and len(out) > len(d) // 2
+    # sync flushes (runs need their predecessors) and a stream with no flush point at all stay correct
+    if refz.have_ref():
+        s2 = refz.ref().deflate_stream(d[:4000000], 6, 0, wrap, 300000, chunk_flush=[refz.Z_SYNC_FLUSH, refz.Z_FULL_FLUSH, refz.Z_SYNC_FLUSH])
+        ret, m, out, tin = z.inflate_all(s2, wrap, cap=4000064, in_slice=500000)
+        assert ret == refz.Z_STREAM_END and out == d[:4000000] and tin == len(s2)
+    s3 = ref.deflate_stream(d[:3000000], 6, 0, wrap, 0)
+    ret, m, out, tin = z.inflate_all(s3, wrap, cap=3000064, in_slice=400000)
+    assert ret == refz.Z_STREAM_END and out == d[:3000000] and tin == len(s3)

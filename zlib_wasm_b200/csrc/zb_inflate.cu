@@ -904,9 +904,12 @@ int inflate_launch(zb200_ctx *ctx, const uint8_t *d_in, uint8_t *d_out, const zb
 // ZB200_INF_* outcome, *out_len the valid output bytes (also when they exceed out_cap: ZB200_INF_OUTPUT_FULL and
 // nothing copied), *in_used the stream's length, *check its computed check value.
 int inflate_stream_parallel(zb200_ctx *ctx, const uint8_t *src, size_t n, int wrap, uint8_t *out, size_t out_cap,
-                            size_t *out_len, int *status, size_t *in_used, uint32_t *check, int *applicable) {
+                            size_t *out_len, int *status, size_t *in_used, uint32_t *check, int *applicable,
+                            const StreamContinuation *cont) {
     *applicable = 0; *out_len = 0; *status = ZB200_INF_OK; *in_used = 0; *check = 0;
     if (n < 64) return ZB200_OK;
+    const size_t hist_len = cont ? cont->hist_len : 0;
+    if (cont && (wrap != ZB200_WRAP_RAW || hist_len > 32768 || cont->bit0 > 7)) return ZB200_ERR_PARAM;
     InflateState hs;
     hs.init(src, n, nullptr, 0, nullptr, nullptr, nullptr, nullptr);
     if (hs.parse_header(wrap) != ZB200_INF_OK) return ZB200_OK;
@@ -934,7 +937,7 @@ int inflate_stream_parallel(zb200_ctx *ctx, const uint8_t *src, size_t n, int wr
     std::sort(start.begin() + 1, start.end());
     while (!start.empty() && start.back() >= n) start.pop_back();          // a marker at the very end starts nothing
     if (start.size() < 2) return ZB200_OK;
-    *applicable = 1;
+    *applicable = 1;                                         // (2 once the deflate data is seen to end: BFINAL reached)
     struct Run { uint64_t in_off, in_len, cap, slot; zb200_member_result res; bool done; };   // done: decoded into its slot, res valid
     std::vector<Run> runs(start.size());
     for (size_t k = 0; k < runs.size(); ++k) {
@@ -956,13 +959,13 @@ int inflate_stream_parallel(zb200_ctx *ctx, const uint8_t *src, size_t n, int wr
             if (u.done) continue;
             if (!u.cap) u.cap = first_cap(u.in_len);
             u.slot = total;
-            total += (u.cap + 15) & ~(uint64_t)15;
+            total += (u.cap + (k == 0 ? hist_len : 0) + 15) & ~(uint64_t)15;
         }
         const size_t before = ctx->io_out_bytes;
         if ((r = ensure_io(ctx, n + 16, total + 16))) return r;
         if (ctx->io_out_bytes != before && pass) {           // the buffer was replaced: every run's bytes are gone, lay them out afresh
             total = 0;
-            for (size_t k = 0; k < runs.size(); ++k) { Run &u = runs[k]; u.done = false; u.slot = total; total += (u.cap + 15) & ~(uint64_t)15; }
+            for (size_t k = 0; k < runs.size(); ++k) { Run &u = runs[k]; u.done = false; u.slot = total; total += (u.cap + (k == 0 ? hist_len : 0) + 15) & ~(uint64_t)15; }
             if ((r = ensure_io(ctx, n + 16, total + 16))) return r;
         }
         tab.clear(); which.clear();
@@ -971,6 +974,10 @@ int inflate_stream_parallel(zb200_ctx *ctx, const uint8_t *src, size_t n, int wr
             if (u.done) continue;
             zb200_member m;
             m.in_off = u.in_off; m.in_len = u.in_len; m.out_off = u.slot; m.out_cap = u.cap; m.resume_bit = m.resume_out = m.dict_len = 0;
+            if (k == 0 && cont) {                            // a continued stream: what came before lies ahead of run 0's output
+                m.out_off = u.slot + hist_len; m.dict_len = hist_len; m.resume_bit = cont->bit0;
+                if (hist_len) ZB_CUDA(cudaMemcpyAsync(ctx->d_io_out + u.slot, cont->hist, hist_len, cudaMemcpyHostToDevice, s));
+            }
             tab.push_back(m); which.push_back((uint32_t)k);
         }
         const size_t m = tab.size();
@@ -1019,9 +1026,10 @@ int inflate_stream_parallel(zb200_ctx *ctx, const uint8_t *src, size_t n, int wr
     // pack the verified runs
     std::vector<GatherSeg> gs(good);
     uint64_t produced = 0;
-    for (size_t k = 0; k < good; ++k) { gs[k].src = runs[k].slot; gs[k].dst = produced; gs[k].len = runs[k].res.out_len; produced += runs[k].res.out_len; }
+    for (size_t k = 0; k < good; ++k) { gs[k].src = runs[k].slot + (k == 0 ? hist_len : 0); gs[k].dst = produced; gs[k].len = runs[k].res.out_len; produced += runs[k].res.out_len; }
     *out_len = (size_t)produced;
     *status = final_status;
+    if (final_status == ZB200_INF_OK) *applicable = 2;
     uint64_t end = good ? runs[good - 1].in_off + (final_status == ZB200_INF_OK ? runs[good - 1].res.in_used : runs[good - 1].in_len) : hdr;
     uint32_t stored = 0, isize = 0;
     if (final_status == ZB200_INF_OK) {                      // trailer: inflate.c:1183-1219
@@ -1049,12 +1057,13 @@ int inflate_stream_parallel(zb200_ctx *ctx, const uint8_t *src, size_t n, int wr
         ZB_LAUNCHED();
         ZB_CHECK_LAUNCH();
     }
-    if ((r = checksum_launch(ctx, d_final, nullptr, nullptr, produced, 1, kind == 1 ? ZB200_ADLER32 : ZB200_CRC32, 0, 1, d_sum, d_sum + 1, d_acc, s))) return r;
+    const int ck = cont ? cont->check_kind : kind;           // a continued stream: the caller says which check its wrapper wants
+    if ((r = checksum_launch(ctx, d_final, nullptr, nullptr, produced, 1, ck == 1 ? ZB200_ADLER32 : ZB200_CRC32, 0, 1, d_sum, d_sum + 1, d_acc, s))) return r;
     ZB_CUDA(cudaMemcpyAsync(ctx->h_small, d_sum, 8, cudaMemcpyDeviceToHost, s));
     if (produced && (r = d2h_auto(ctx, out, d_final, (size_t)produced, s))) return r;
     ZB_CUDA(cudaStreamSynchronize(s));
     const uint32_t *hsum = (const uint32_t *)ctx->h_small;
-    *check = kind == 1 ? hsum[1] : hsum[0];
+    *check = ck == 1 ? hsum[1] : hsum[0];
     if (*status == ZB200_INF_OK) {
         if (kind != 0 && stored != *check) *status = ZB200_INF_DATA_CHECK;
         else if (kind == 2 && isize != (uint32_t)produced) *status = ZB200_INF_LENGTH_CHECK;
@@ -1365,7 +1374,7 @@ int zb200_inflate_stream_host(zb200_ctx *ctx, const void *in, size_t n, int wrap
         size_t out_len = 0, in_used = 0;
         int status = 0, applicable = 0;
         uint32_t check = 0;
-        const int r = inflate_stream_parallel(ctx, (const uint8_t *)in, n, wrap, (uint8_t *)out, out_cap, &out_len, &status, &in_used, &check, &applicable);
+        const int r = inflate_stream_parallel(ctx, (const uint8_t *)in, n, wrap, (uint8_t *)out, out_cap, &out_len, &status, &in_used, &check, &applicable, nullptr);
         if (r != ZB200_OK) return r;
         if (applicable) {
             memset(result, 0, sizeof *result);

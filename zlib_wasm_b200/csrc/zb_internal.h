@@ -100,9 +100,14 @@ int checksum_launch(zb200_ctx *ctx, const uint8_t *d_base, const uint64_t *d_off
                     uint32_t *d_crc, uint32_t *d_adler, CkAccum *d_acc, cudaStream_t s,
                     const uint32_t *d_init2 = nullptr);
 
-// zb_inflate.cu: one stream decoded in parallel at its flush points (host pointers); *applicable = 0 -> take the one-member path
+// zb_inflate.cu: one stream decoded in parallel at its flush points (host pointers); *applicable = 0 -> take the one-member path,
+// 1 -> *status etc. are set, 2 -> ... and the deflate data was seen to end (a TRUNCATED status then means: the trailer is missing)
+// cont != nullptr: src continues a raw stream at a block boundary (bit `bit0` of src[0]) whose last hist_len (<= 32768)
+// output bytes are `hist`; *check then covers the bytes produced by this call only (check_kind 1: Adler-32, else CRC-32).
+struct StreamContinuation { const uint8_t *hist; size_t hist_len; uint32_t bit0; int check_kind; };
 int inflate_stream_parallel(zb200_ctx *ctx, const uint8_t *src, size_t n, int wrap, uint8_t *out, size_t out_cap,
-                            size_t *out_len, int *status, size_t *in_used, uint32_t *check, int *applicable);
+                            size_t *out_len, int *status, size_t *in_used, uint32_t *check, int *applicable,
+                            const StreamContinuation *cont = nullptr);
 
 // zb_deflate.cu
 int deflate_init(zb200_ctx *ctx);

@@ -90,6 +90,14 @@ struct InflateStream {
     uint32_t check;
     gz_headerp gzhead;                   // inflateGetHeader: where the gzip header fields go
     bool verify;                         // inflateValidate: compare the trailer's check value
+    // A stream continued after a run-parallel step (parallel_step): the input before in_erased and the output before
+    // out_before have left the buffers; from there on the engine sees a RAW stream behind a 32 KiB history, and the
+    // wrapper's trailer is checked here (check_before = check value of the output before the base, in stream_kind).
+    bool rebased, seq_ready, trailer_pending;
+    int stream_kind;                     // 0 raw, 1 zlib, 2 gzip
+    uint64_t in_erased, out_before;
+    uint32_t check_before;
+    std::vector<uint8_t> hist;           // the last <= 32768 bytes of output produced so far
     size_t dict_len;                     // preset dictionary: d_out[0 .. dict_len), the output follows it
     uint32_t dictid;                     // DICTID of the zlib header that asked for one
     bool retry;                          // inflateSetDictionary was called: decode again with no new input
@@ -230,6 +238,37 @@ void inflate_reset_state(InflateStream &s) {
     s.kind = 0; s.in.clear(); s.d_in_have = 0; s.out.clear(); s.out_pos = 0; s.out_base = 0; s.decoded = 0;
     s.resume_bit = s.resume_out = 0; s.started = s.done = false; s.error = 0; s.in_used = 0; s.check = 0;
     s.dict_len = 0; s.dictid = 0; s.retry = false; s.gzhead = Z_NULL; s.verify = true;
+    s.rebased = s.seq_ready = s.trailer_pending = false; s.stream_kind = 0; s.in_erased = s.out_before = 0; s.check_before = 0; s.hist.clear();
+}
+
+void hist_push(InflateStream &s, const uint8_t *p, size_t n) {   // keep the last 32 KiB of output
+    if (n >= 32768) { s.hist.assign(p + (n - 32768), p + n); return; }
+    if (s.hist.size() + n > 32768) s.hist.erase(s.hist.begin(), s.hist.begin() + (long)(s.hist.size() + n - 32768));
+    s.hist.insert(s.hist.end(), p, p + n);
+}
+
+// The deflate data of a rebased stream ended at s.in[end] with `tail_len` bytes of output since the base whose check
+// value (in stream_kind) is tail_check: verify the wrapper's trailer (inflate.c:1183-1219).  Returns the status;
+// ZB200_INF_TRUNCATED while the trailer has not arrived in full.
+int finish_rebased(InflateStream &s, uint32_t tail_check, uint64_t tail_len, size_t end) {
+    const uint32_t total = s.stream_kind == 1 ? zb200_adler32_combine(s.check_before, tail_check, (int64_t)tail_len)
+                                              : zb200_crc32_combine(s.check_before, tail_check, tail_len);
+    const uint64_t out_total = s.out_before + tail_len;
+    const size_t need = s.stream_kind == 2 ? 8 : s.stream_kind == 1 ? 4 : 0;
+    if (s.in.size() < end + need) return ZB200_INF_TRUNCATED;
+    const uint8_t *t = s.in.data() + end;
+    int st = ZB200_INF_OK;
+    if (s.stream_kind == 2) {
+        const uint32_t c = (uint32_t)t[0] | ((uint32_t)t[1] << 8) | ((uint32_t)t[2] << 16) | ((uint32_t)t[3] << 24);
+        const uint32_t z = (uint32_t)t[4] | ((uint32_t)t[5] << 8) | ((uint32_t)t[6] << 16) | ((uint32_t)t[7] << 24);
+        if (c != total) st = ZB200_INF_DATA_CHECK;
+        else if (z != (uint32_t)out_total) st = ZB200_INF_LENGTH_CHECK;
+    } else if (s.stream_kind == 1) {
+        const uint32_t c = ((uint32_t)t[0] << 24) | ((uint32_t)t[1] << 16) | ((uint32_t)t[2] << 8) | (uint32_t)t[3];
+        if (c != total) st = ZB200_INF_DATA_CHECK;
+    }
+    if (st == ZB200_INF_OK) { s.done = true; s.in_used = s.in_erased + end + need; s.check = total; }
+    return st;
 }
 
 // inflate.c:671-808 as far as inflateGetHeader needs it: the gzip header fields out of the input seen so far.
@@ -278,6 +317,13 @@ int inflate_attempt(InflateStream &s) {
         if (cudaMemcpyAsync(s.d_in + s.d_in_have, s.in.data() + s.d_in_have, n - s.d_in_have, cudaMemcpyHostToDevice, st) != cudaSuccess) return -1;
         s.d_in_have = n;
     }
+    if (s.rebased && !s.seq_ready) {                            // the one-member path takes over behind the history
+        s.dict_len = s.hist.size();
+        if (dev_grow(&s.d_out, &s.d_out_cap, n * 4 + (1u << 20) + s.dict_len, 0, st)) return -1;
+        if (s.dict_len && cudaMemcpyAsync(s.d_out, s.hist.data(), s.dict_len, cudaMemcpyHostToDevice, st) != cudaSuccess) return -1;
+        if (cudaStreamSynchronize(st) != cudaSuccess) return -1;
+        s.seq_ready = true;
+    }
     if (s.d_out_cap == 0 && dev_grow(&s.d_out, &s.d_out_cap, n * 4 + (1u << 20) + s.dict_len, 0, st)) return -1;
     if (ensure_scratch(ctx, 1024 + inflate_work_bytes(1)) != ZB200_OK) return -1;
     for (;;) {
@@ -290,8 +336,8 @@ int inflate_attempt(InflateStream &s) {
         zb200_member_result *h_r = (zb200_member_result *)ctx->h_small;
         memcpy(ctx->h_small + 40, &m, sizeof m);                 // pinned bounce for the descriptor
         if (cudaMemcpyAsync(d_m, ctx->h_small + 40, sizeof m, cudaMemcpyHostToDevice, st) != cudaSuccess) return -1;
-        const int wrap = s.resume_bit ? s.kind : s.wrap;
-        if (inflate_launch(ctx, s.d_in, s.d_out, d_m, 1, wrap, s.verify ? 1 : 0, d_r, base + 1024, st) != ZB200_OK) return -1;
+        const int wrap = s.rebased ? ZB200_WRAP_RAW : s.resume_bit ? s.kind : s.wrap;
+        if (inflate_launch(ctx, s.d_in, s.d_out, d_m, 1, wrap, (s.verify && !s.rebased) ? 1 : 0, d_r, base + 1024, st) != ZB200_OK) return -1;
         if (cudaMemcpyAsync(h_r, d_r, sizeof *h_r, cudaMemcpyDeviceToHost, st) != cudaSuccess) return -1;
         if (cudaStreamSynchronize(st) != cudaSuccess) return -1;
         const zb200_member_result r = *h_r;
@@ -308,17 +354,92 @@ int inflate_attempt(InflateStream &s) {
             s.out.resize(at + add);
             if (cudaMemcpyAsync(s.out.data() + at, s.d_out + s.dict_len + s.decoded, add, cudaMemcpyDeviceToHost, st) != cudaSuccess) return -1;
             if (cudaStreamSynchronize(st) != cudaSuccess) return -1;
+            hist_push(s, s.out.data() + at, add);
             s.decoded = r.out_len;
+        }
+        if (s.rebased) {
+            if (r.status == ZB200_INF_TRUNCATED && r.resume_bit) { s.resume_bit = r.resume_bit; s.resume_out = r.resume_out; }
+            if (r.status != ZB200_INF_OK) return r.status;
+            uint32_t tail = r.check;                             // CRC-32 of the bytes since the base (raw members get a CRC)
+            if (s.stream_kind == 1) {                            // a zlib wrapper wants their Adler-32
+                uint32_t *d_sum = (uint32_t *)(base + 512);
+                if (checksum_launch(ctx, s.d_out + s.dict_len, nullptr, nullptr, r.out_len, 1, ZB200_ADLER32, 0, 1, d_sum, d_sum + 1,
+                                    (CkAccum *)(base + 768), st) != ZB200_OK) return -1;
+                if (cudaMemcpyAsync(ctx->h_small, d_sum, 8, cudaMemcpyDeviceToHost, st) != cudaSuccess) return -1;
+                if (cudaStreamSynchronize(st) != cudaSuccess) return -1;
+                tail = ((const uint32_t *)ctx->h_small)[1];
+            }
+            return finish_rebased(s, tail, r.out_len, (size_t)r.in_used);
         }
         s.kind = (int)r.wrap_kind;
         if (r.status == ZB200_INF_NEED_DICT) s.dictid = r.check;
         if (r.status == ZB200_INF_TRUNCATED) {
             if (r.resume_bit) { s.resume_bit = r.resume_bit; s.resume_out = r.resume_out; }
         } else if (r.status == ZB200_INF_OK) {
-            s.done = true; s.in_used = r.in_used; s.check = r.check;
+            s.done = true; s.in_used = s.in_erased + r.in_used; s.check = r.check;
         }
         return r.status;
     }
+}
+
+// A call that brings (or has piled up) at least 256 KiB of undecoded input at a point where a run may start:
+// the runs between flush points are decoded in one batch (inflate_stream_parallel).  Whatever prefix of runs is
+// verified is delivered, the stream is re-based behind it — the input and output before the base leave the
+// buffers — and the rest waits for the next call; the last run of a complete stream ends it.  Returns 1 when the
+// step made this call's progress (status in *st_out), 0 when the one-member path should take the call.
+int parallel_step(InflateStream &s, int *st_out) {
+    if (!s.verify || s.decoded || s.resume_bit || s.seq_ready || (s.dict_len && !s.rebased) || s.in.size() < 262144) return 0;
+    zb200_ctx *ctx = api_ctx();
+    if (!ctx) return 0;
+    const size_t at = s.out.size();
+    size_t cap = s.in.size() * 4 + (1u << 20), out_len = 0, in_used = 0;
+    int status = 0, applicable = 0;
+    uint32_t check = 0;
+    const StreamContinuation cont = {s.hist.data(), s.hist.size(), 0u, s.stream_kind};
+    {
+        std::lock_guard<std::mutex> g(ctx->mu);
+        if (cudaSetDevice(ctx->device) != cudaSuccess) return 0;
+        for (int attempt = 0; attempt < 2; ++attempt) {
+            s.out.resize(at + cap);
+            const int r = inflate_stream_parallel(ctx, s.in.data(), s.in.size(), s.rebased ? ZB200_WRAP_RAW : s.wrap, s.out.data() + at, cap,
+                                                  &out_len, &status, &in_used, &check, &applicable, s.rebased ? &cont : nullptr);
+            if (r != ZB200_OK) applicable = 0;
+            if (applicable && status == ZB200_INF_OUTPUT_FULL && out_len > cap && attempt == 0) { cap = out_len; continue; }
+            break;
+        }
+    }
+    if (!applicable || status == ZB200_INF_OUTPUT_FULL || (status != ZB200_INF_OK && out_len == 0)) { s.out.resize(at); return 0; }
+    s.out.resize(at + out_len);
+    hist_push(s, s.out.data() + at, out_len);
+    if (!s.rebased) {
+        const int kind = s.wrap == ZB200_WRAP_RAW ? 0 : ((s.wrap & ZB200_WRAP_GZIP) && s.in[0] == 0x1f && s.in[1] == 0x8b) ? 2 : 1;
+        if (status == ZB200_INF_OK) {                           // the whole stream, trailer verified
+            s.kind = kind; s.done = true; s.in_used = in_used; s.check = check;
+            *st_out = ZB200_INF_OK;
+            return 1;
+        }
+        if (status == ZB200_INF_DATA_CHECK || status == ZB200_INF_LENGTH_CHECK) { s.kind = kind; *st_out = status; return 1; }   // whole stream, bad trailer
+        s.stream_kind = kind; s.kind = kind; s.rebased = true;
+        s.check_before = check; s.out_before = out_len;
+        if (applicable == 2) s.trailer_pending = true;          // all of the deflate data is out; the trailer has not arrived in full
+    } else if (status == ZB200_INF_OK) {                        // the deflate data ends in this step: the trailer is checked here
+        const int fs = finish_rebased(s, check, out_len, in_used);
+        if (fs == ZB200_INF_TRUNCATED) {                        // ... once it has arrived
+            s.check_before = s.stream_kind == 1 ? zb200_adler32_combine(s.check_before, check, (int64_t)out_len) : zb200_crc32_combine(s.check_before, check, out_len);
+            s.out_before += out_len; s.trailer_pending = true;
+            s.in_erased += in_used; s.in.erase(s.in.begin(), s.in.begin() + (long)in_used); s.d_in_have = 0;
+        }
+        *st_out = fs;
+        return 1;
+    } else {
+        s.check_before = s.stream_kind == 1 ? zb200_adler32_combine(s.check_before, check, (int64_t)out_len) : zb200_crc32_combine(s.check_before, check, out_len);
+        s.out_before += out_len;
+    }
+    s.in_erased += in_used;
+    s.in.erase(s.in.begin(), s.in.begin() + (long)in_used);
+    s.d_in_have = 0;
+    *st_out = ZB200_INF_TRUNCATED;                              // more to come; an error met behind the prefix shows up when its run is reached
+    return 1;
 }
 
 }  // namespace
@@ -558,24 +679,13 @@ int inflate(z_streamp strm, int flush) {
     if (!s->done && !s->error && (strm->avail_in || s->retry)) {
         s->retry = false;
         s->in.insert(s->in.end(), strm->next_in, strm->next_in + strm->avail_in);
-        status = -2;
-        if (s->decoded == 0 && s->resume_bit == 0 && s->dict_len == 0 && s->out.empty() && s->in.size() >= 262144 && s->verify) {
-            // a whole stream handed over at once: its flush-point runs in parallel (zb200_inflate_stream_host)
-            zb200_member_result q;
-            size_t cap = s->in.size() * 4 + (1u << 20);
-            for (int attempt = 0; attempt < 2; ++attempt) {
-                s->out.resize(cap);
-                if (zb200_inflate_stream_host(api_ctx(), s->in.data(), s->in.size(), s->wrap, s->out.data(), cap, &q) != ZB200_OK) break;
-                if (q.status == ZB200_INF_OUTPUT_FULL && q.out_len > cap && attempt == 0) { cap = (size_t)q.out_len; continue; }
-                if (q.status == ZB200_INF_OK) {
-                    s->out.resize((size_t)q.out_len); s->out_pos = 0;
-                    s->decoded = q.out_len; s->kind = (int)q.wrap_kind; s->done = true; s->in_used = q.in_used; s->check = q.check;
-                    status = ZB200_INF_OK;
-                }
-                break;
-            }
-            if (status != ZB200_INF_OK) { s->out.clear(); s->out_pos = 0; }
+        if (s->gzhead != Z_NULL && s->gzhead->done == 0 && !s->rebased) {   // inflateGetHeader (inflate.c:1331-1345), while the header bytes are here
+            if (s->in.size() >= 2 && !(s->in[0] == 0x1f && s->in[1] == 0x8b)) s->gzhead->done = -1;
+            else if (s->in.size() >= 2 && (s->wrap & ZB200_WRAP_GZIP)) fill_gz_header(s->in, *s->gzhead);
         }
+        status = -2;
+        if (s->trailer_pending) status = finish_rebased(*s, s->stream_kind == 1 ? 1u : 0u, 0, 0);   // (combining with an empty tail leaves check_before)
+        else if (parallel_step(*s, &status) == 0) status = -2;
         if (status == -2) status = inflate_attempt(*s);
         if (status < 0) { strm->msg = "zlib-b200: device error"; return Z_STREAM_ERROR; }
         uLong used = in0;
@@ -583,10 +693,6 @@ int inflate(z_streamp strm, int flush) {
         else if (status != ZB200_INF_TRUNCATED) s->error = status;
         strm->next_in += used; strm->avail_in -= (uInt)used; strm->total_in += used;
         if (status == ZB200_INF_OK) strm->adler = s->check;
-        if (s->gzhead != Z_NULL && s->gzhead->done == 0) {          // inflateGetHeader: inflate.c:1331-1345
-            if (s->in.size() >= 2 && !(s->in[0] == 0x1f && s->in[1] == 0x8b)) s->gzhead->done = -1;
-            else if (s->kind == 2 || (s->in.size() >= 2 && (s->wrap & ZB200_WRAP_GZIP))) fill_gz_header(s->in, *s->gzhead);
-        }
     }
     // deliver decoded bytes
     const size_t avail = s->out.size() - s->out_pos;
@@ -631,6 +737,7 @@ int inflateSetDictionary(z_streamp strm, const Bytef *dictionary, uInt dictLengt
         if (cudaStreamSynchronize(st) != cudaSuccess) return Z_STREAM_ERROR;
     }
     s->dict_len = keep;
+    hist_push(*s, dictionary + (dictLength - keep), keep);      // (it is window content: inflateGetDictionary returns it)
     if (s->error == ZB200_INF_NEED_DICT) { s->error = 0; s->retry = true; }
     if (s->wrap != ZB200_WRAP_RAW) strm->adler = 1;               // inflate.c:671: adler32(0L, Z_NULL, 0)
     return Z_OK;
@@ -639,18 +746,8 @@ int inflateSetDictionary(z_streamp strm, const Bytef *dictionary, uInt dictLengt
 int inflateGetDictionary(z_streamp strm, Bytef *dictionary, uInt *dictLength) {   // inflate.c:1258-1276: the sliding window = the last 32 KiB produced
     InflateStream *s = istate(strm);
     if (!s) return Z_STREAM_ERROR;
-    const size_t have = (size_t)s->decoded + s->dict_len;    // bytes in d_out: dictionary + output
-    const size_t k = have < 32768 ? have : 32768;
-    if (k && dictionary != Z_NULL) {
-        zb200_ctx *ctx = api_ctx();
-        if (!ctx) return Z_STREAM_ERROR;
-        std::lock_guard<std::mutex> g(ctx->mu);
-        if (cudaSetDevice(ctx->device) != cudaSuccess) return Z_STREAM_ERROR;
-        if (s->d_out == nullptr) return Z_STREAM_ERROR;
-        if (cudaMemcpyAsync(dictionary, s->d_out + (have - k), k, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) return Z_STREAM_ERROR;
-        if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return Z_STREAM_ERROR;
-    }
-    if (dictLength != Z_NULL) *dictLength = (uInt)k;
+    if (!s->hist.empty() && dictionary != Z_NULL) memcpy(dictionary, s->hist.data(), s->hist.size());
+    if (dictLength != Z_NULL) *dictLength = (uInt)s->hist.size();
     return Z_OK;
 }
 
