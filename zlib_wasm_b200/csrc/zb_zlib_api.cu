@@ -11,6 +11,8 @@
 #include <stdlib.h>
 #include <string.h>
 #include <vector>
+#include <memory>
+#include <utility>
 #include <new>
 
 using namespace zb;
@@ -72,6 +74,14 @@ struct DeflateStream {
     gz_headerp gzhead;                   // deflateSetHeader: the caller's header fields (read when the header is written)
 };
 
+// resize() without the zero fill: output buffers are sized for the worst case and then written by DMA
+template <class T> struct NoInitAlloc : std::allocator<T> {
+    template <class U> struct rebind { using other = NoInitAlloc<U>; };
+    template <class U, class... A> void construct(U *p, A &&...a) {
+        if (sizeof...(A) == 0) ::new ((void *)p) U; else ::new ((void *)p) U(std::forward<A>(a)...);
+    }
+};
+
 struct InflateStream {
     uint32_t magic;
     int wrap;                            // ZB200_WRAP_*
@@ -79,7 +89,7 @@ struct InflateStream {
     std::vector<uint8_t> in;             // all compressed input seen so far
     uint8_t *d_in, *d_out;               // device mirrors (grow-only)
     size_t d_in_cap, d_out_cap, d_in_have;
-    std::vector<uint8_t> out;            // decoded bytes not yet delivered
+    std::vector<uint8_t, NoInitAlloc<uint8_t>> out;   // decoded bytes not yet delivered
     size_t out_pos;                      // next byte of `out` to deliver
     uint64_t out_base;                   // stream offset of out[0]
     uint64_t decoded;                    // valid decoded bytes on the device
