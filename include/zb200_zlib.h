@@ -106,8 +106,10 @@ typedef struct gzFile_s *gzFile;
 #define inflateInit(strm) inflateInit_((strm), ZLIB_VERSION, (int)sizeof(z_stream))
 #define deflateInit2(strm, level, method, windowBits, memLevel, strategy) \
     deflateInit2_((strm), (level), (method), (windowBits), (memLevel), (strategy), ZLIB_VERSION, (int)sizeof(z_stream))
-#define inflateInit2(strm, windowBits) inflateInit2_((strm), (windowBits), ZLIB_VERSION, (int)sizeof(z_stream))
+typedef unsigned (*in_func)(void *, const unsigned char **);                            /* zlib.h:1116-1118 */
+typedef int (*out_func)(void *, unsigned char *, unsigned);
 #define inflateBackInit(strm, windowBits, window) inflateBackInit_((strm), (windowBits), (window), ZLIB_VERSION, (int)sizeof(z_stream))
+#define inflateInit2(strm, windowBits) inflateInit2_((strm), (windowBits), ZLIB_VERSION, (int)sizeof(z_stream))
 
 #endif /* ZLIB_H */
 
@@ -141,8 +143,6 @@ int inflateResetKeep(z_streamp strm);                                           
 int inflateValidate(z_streamp strm, int check);                                        /* zlib.h:1807, inflate.c:1495 */
 int inflateUndermine(z_streamp strm, int subvert);                                     /* inflate.c:1478 */
 long inflateMark(z_streamp strm);                                                      /* zlib.h:1012, inflate.c:1510 */
-typedef unsigned (*in_func)(void *, const unsigned char **);                            /* zlib.h:1116-1118 */
-typedef int (*out_func)(void *, unsigned char *, unsigned);
 int inflateBackInit_(z_streamp strm, int windowBits, unsigned char *window, const char *version, int stream_size);   /* infback.c:25 */
 int inflateBack(z_streamp strm, in_func in, void *in_desc, out_func out, void *out_desc);                           /* infback.c:242 */
 int inflateBackEnd(z_streamp strm);                                                                                  /* infback.c:622 */
