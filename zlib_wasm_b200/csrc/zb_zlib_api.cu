@@ -686,7 +686,9 @@ int inflate(z_streamp strm, int flush) {
     const uInt in0 = strm->avail_in, out0 = strm->avail_out;
     const uLong total_in0 = strm->total_in;
     int status = s->error ? s->error : (s->done ? ZB200_INF_OK : ZB200_INF_TRUNCATED);
-    if (!s->done && !s->error && (strm->avail_in || s->retry)) {
+    // a call without input while the cut run of a re-based stream waits: its complete blocks are owed to the caller
+    const bool flush_tail = strm->avail_in == 0 && s->rebased && !s->seq_ready && !s->trailer_pending && !s->in.empty() && s->out.empty();
+    if (!s->done && !s->error && (strm->avail_in || s->retry || flush_tail)) {
         s->retry = false;
         s->in.insert(s->in.end(), strm->next_in, strm->next_in + strm->avail_in);
         if (s->gzhead != Z_NULL && s->gzhead->done == 0 && !s->rebased) {   // inflateGetHeader (inflate.c:1331-1345), while the header bytes are here
@@ -695,7 +697,7 @@ int inflate(z_streamp strm, int flush) {
         }
         status = -2;
         if (s->trailer_pending) status = finish_rebased(*s, s->stream_kind == 1 ? 1u : 0u, 0, 0);   // (combining with an empty tail leaves check_before)
-        else if (parallel_step(*s, &status) == 0) status = -2;
+        else if (flush_tail || parallel_step(*s, &status) == 0) status = -2;
         if (status == -2) status = inflate_attempt(*s);
         if (status < 0) { strm->msg = "zlib-b200: device error"; return Z_STREAM_ERROR; }
         uLong used = in0;
