@@ -135,6 +135,7 @@ int deflateGetDictionary(z_streamp strm, Bytef *dictionary, uInt *dictLength);  
 int inflateGetDictionary(z_streamp strm, Bytef *dictionary, uInt *dictLength);        /* zlib.h:910, inflate.c:1258 */
 int deflateSetHeader(z_streamp strm, gz_headerp head);                                 /* zlib.h:802, deflate.c:692 */
 int inflateGetHeader(z_streamp strm, gz_headerp head);                                 /* zlib.h:1040, inflate.c:1331 */
+int deflateTune(z_streamp strm, int good_length, int max_lazy, int nice_length, int max_chain);   /* zlib.h:744, deflate.c:805 */
 int deflatePending(z_streamp strm, unsigned *pending, int *bits);                      /* zlib.h:779, deflate.c:703 */
 int deflateCopy(z_streamp dest, z_streamp source);                                     /* zlib.h:677, deflate.c:1297 */
 int inflateCopy(z_streamp dest, z_streamp source);                                     /* zlib.h:929, inflate.c:1433 */

@@ -481,3 +481,35 @@ def test_inflate_big_slices_run_parallel(z, wrap):
     s3 = ref.deflate_stream(d[:3000000], 6, 0, wrap, 0)
     ret, m, out, tin = z.inflate_all(s3, wrap, cap=3000064, in_slice=400000)
     assert ret == refz.Z_STREAM_END and out == d[:3000000] and tin == len(s3)
+
+
+def test_deflate_tune(z):
+    """deflateTune (deflate.c:805-816): the four search parameters replace the level's table values — the
+    reference's bytes for the same tuning at the lazy levels."""
+    if not refz.have_ref():
+        pytest.skip("oracle/_ref/libzref.so not built")
+    ref = refz.ref()
+    for lib in (z, ref):
+        if not hasattr(lib, "deflateTune"):
+            lib._f("deflateTune", C.c_int, C.POINTER(refz.ZStream), C.c_int, C.c_int, C.c_int, C.c_int)
+    d = refz.gen(600000, refz.GEN_MIXED, seed=13)
+    outs = {}
+    for level, tune in ((6, (4, 8, 32, 64)), (9, (8, 16, 64, 32)), (6, (32, 258, 258, 1024)), (6, None)):
+        for name, lib in (("z", z), ("ref", ref)):
+            s = refz.ZStream()
+            assert lib.deflateInit2_(C.byref(s), level, 8, 15, 8, 0, lib.version, C.sizeof(refz.ZStream)) == 0
+            if tune:
+                assert lib.deflateTune(C.byref(s), *tune) == 0
+            src, dst = C.create_string_buffer(d, len(d)), C.create_string_buffer(len(d) + 4096)
+            produced = 0
+            for off in range(0, len(d), 262144):
+                k = min(262144, len(d) - off)
+                s.next_in, s.avail_in = C.addressof(src) + off, k
+                s.next_out, s.avail_out = C.addressof(dst) + produced, len(dst) - produced
+                r = lib.deflate(C.byref(s), refz.Z_FINISH if off + k >= len(d) else refz.Z_FULL_FLUSH)
+                produced = len(dst) - s.avail_out
+            assert r == refz.Z_STREAM_END
+            lib.deflateEnd(C.byref(s))
+            outs[(name, level, tune)] = dst.raw[:produced]
+        assert outs[("z", level, tune)] == outs[("ref", level, tune)], (level, tune)
+    assert outs[("z", 6, (4, 8, 32, 64))] != outs[("z", 6, None)]

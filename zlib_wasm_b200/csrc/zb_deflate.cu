@@ -815,6 +815,10 @@ static size_t batch_chunks(size_t n, size_t S) {
     return nb < nch ? nb : nch;
 }
 
+static thread_local const int *tl_deflate_tune = nullptr;
+const int *deflate_tune_override() { return tl_deflate_tune; }
+void deflate_tune_set(const int *four) { tl_deflate_tune = four; }
+
 int deflate_launch(zb200_ctx *ctx, const uint8_t *d_in, size_t n, size_t S, int level, int strategy, int frame,
                    int finish, uint8_t *d_out, size_t out_cap, uint64_t *d_chunk_end, uint64_t *d_total,
                    uint32_t *d_sums_out, cudaStream_t s, size_t skip) {
@@ -831,9 +835,15 @@ int deflate_launch(zb200_ctx *ctx, const uint8_t *d_in, size_t n, size_t S, int 
     size_t nch = (n + S - 1) / S;
     if (nch == 0 && (finish || members)) nch = 1;
     if (out_cap < zb200_deflate_bound(n, S, frame)) { set_error("deflate: output capacity below zb200_deflate_bound()"); return ZB200_ERR_OUTPUT; }
-    const DeflateParams prm = deflate_params(level, strategy);
-    // levels 3..9: chain walks of very different lengths -> depth-sorted scheduling (levels 1-2 use the branch-free walk)
-    const bool sorted_walks = (prm.mode == MODE_SLOW || prm.mode == MODE_FAST) && prm.level >= 3;
+    DeflateParams prm = deflate_params(level, strategy);
+    const int *tune = deflate_tune_override();                     // deflateTune (deflate.c:805-816): this thread's next calls
+    if (tune && (prm.mode == MODE_SLOW || prm.mode == MODE_FAST)) {
+        prm.good = tune[0]; prm.lazy = tune[1]; prm.nice = tune[2]; prm.chain = tune[3];
+        prm.need_quarter = (prm.mode == MODE_SLOW && prm.good < prm.lazy) ? 1 : 0;
+    }
+    // levels 3..9: chain walks of very different lengths -> depth-sorted scheduling (levels 1-2 use the branch-free walk,
+    // which is compiled for their table values)
+    const bool sorted_walks = (prm.mode == MODE_SLOW || prm.mode == MODE_FAST) && (prm.level >= 3 || tune);
     const uint32_t MB = max_blocks_for((uint32_t)S);
     const size_t nb_max = batch_chunks(n, S);
     int r = ensure_scratch(ctx, work_bytes(nb_max, S, MB));

@@ -111,6 +111,9 @@ int inflate_stream_parallel(zb200_ctx *ctx, const uint8_t *src, size_t n, int wr
 
 // zb_deflate.cu
 int deflate_init(zb200_ctx *ctx);
+// deflateTune: {good_length, max_lazy, nice_length, max_chain} for the deflate calls this thread makes next (nullptr: the level's own)
+const int *deflate_tune_override();
+void deflate_tune_set(const int *four);
 int deflate_launch(zb200_ctx *ctx, const uint8_t *d_in, size_t n, size_t S, int level, int strategy, int frame,
                    int finish, uint8_t *d_out, size_t out_cap, uint64_t *d_chunk_end, uint64_t *d_total,
                    uint32_t *d_sums_out, cudaStream_t s, size_t skip = 0);   // skip: preset dictionary at the head of a single raw chunk

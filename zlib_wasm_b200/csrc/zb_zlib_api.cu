@@ -72,6 +72,7 @@ struct DeflateStream {
     uint32_t dictid;                     // Adler-32 of the whole dictionary (zlib header DICTID)
     bool have_dictid;
     gz_headerp gzhead;                   // deflateSetHeader: the caller's header fields (read when the header is written)
+    int tune[4]; bool tuned;             // deflateTune: good_length, max_lazy, nice_length, max_chain
 };
 
 // resize() without the zero fill: output buffers are sized for the worst case and then written by DMA
@@ -135,6 +136,10 @@ int compress_buffered(DeflateStream &st, bool finish) {
     const size_t n = st.in.size();
     if (n == 0 && !finish) return Z_OK;
     const size_t chunk = api_chunk();
+    struct TuneScope {                                         // the engine reads the override on this thread
+        explicit TuneScope(const int *t) { deflate_tune_set(t); }
+        ~TuneScope() { deflate_tune_set(nullptr); }
+    } tune_scope(st.tuned ? st.tune : nullptr);
     size_t cap = zb200_deflate_bound(n, chunk, ZB200_FRAME_RAW);
     if (!st.dict.empty()) cap += zb200_deflate_bound(st.dict.size() + chunk, st.dict.size() + chunk, ZB200_FRAME_RAW);
     const size_t at = st.pending.size();
@@ -492,6 +497,7 @@ int deflateReset(z_streamp strm) {
     s->header_done = s->finished = s->trailer_done = false;
     s->crc = 0; s->adler = 1; s->total_in_hashed = 0; s->last_flush = -2;
     s->dict.clear(); s->dictid = 0; s->have_dictid = false; s->keep_history = false; s->gzhead = Z_NULL;
+    s->tuned = false;                                           // lm_init reloads the level's table values (deflate.c:1307-1326)
     strm->total_in = strm->total_out = 0; strm->msg = Z_NULL; strm->data_type = Z_UNKNOWN;
     strm->adler = s->wrap == 2 ? 0 : 1;                         // deflate.c:656-660
     return Z_OK;
@@ -508,6 +514,7 @@ int deflateParams(z_streamp strm, int level, int strategy) {
         const int r = compress_buffered(*s, false);
         if (r != Z_OK) return r;
     }
+    if (level != s->level) s->tuned = false;                    // deflate.c:792-800: a new level reloads its table values
     s->level = level; s->strategy = strategy;
     return Z_OK;
 }
@@ -530,6 +537,14 @@ int deflateSetDictionary(z_streamp strm, const Bytef *dictionary, uInt dictLengt
     }
     const uInt keep = dictLength > 32768u ? 32768u : dictLength;   // deflate.c:575-583: the tail of a long dictionary
     s->dict.assign(dictionary + (dictLength - keep), dictionary + dictLength);
+    return Z_OK;
+}
+
+int deflateTune(z_streamp strm, int good_length, int max_lazy, int nice_length, int max_chain) {   // deflate.c:805-816
+    DeflateStream *s = dstate(strm);
+    if (!s) return Z_STREAM_ERROR;
+    s->tune[0] = good_length; s->tune[1] = max_lazy; s->tune[2] = nice_length; s->tune[3] = max_chain;
+    s->tuned = true;
     return Z_OK;
 }
 
