@@ -195,6 +195,23 @@ int zb200_gunzip_host(zb200_ctx *ctx, const void *in, size_t n, void *out, size_
 int zb200_inflate_stream_host(zb200_ctx *ctx, const void *in, size_t n, int wrap, void *out, size_t out_cap,
                               zb200_member_result *result);
 
+/* ---- one process, every GPU of the box ----
+ * A zb200_multi holds one context per device (devices == NULL: all visible ones).  Each call below gives every
+ * GPU a contiguous range of the units — checksum bytes, deflate chunks, inflate members — on its own host thread
+ * and does the exchange step on the host: partial checksums folded with the combine functions, compressed pieces
+ * laid end to end (whole chunks per piece: the bytes are those of the single-GPU call), header / trailer written
+ * last.  Host pointers (pinned memory is DMA-ed directly); synchronous; same arguments as the single-GPU calls. */
+typedef struct zb200_multi zb200_multi;
+int zb200_multi_create(const int *devices, int n_devices, zb200_multi **out);
+void zb200_multi_destroy(zb200_multi *m);
+int zb200_multi_count(const zb200_multi *m);
+int zb200_multi_checksum_host(zb200_multi *m, const void *data, size_t n, int which, uint32_t init_crc, uint32_t init_adler,
+                              uint32_t *crc, uint32_t *adler);
+int zb200_multi_deflate_host(zb200_multi *m, const void *in, size_t n, size_t chunk_size, int level, int strategy, int frame,
+                             int finish, void *out, size_t *out_len, uint32_t *in_adler, uint32_t *in_crc);
+int zb200_multi_inflate_host(zb200_multi *m, const void *in, void *out, const zb200_member *members, size_t n_members,
+                             int wrap, int verify, zb200_member_result *results);
+
 /* Self-test of the warp-parallel decode-table construction (csrc/zb_inflate_tables.cuh) against the
  * serial one that follows inftrees.c:32-299: for each of n_cases sets of code lengths (lens: 320 bytes
  * per case = nlen literal/length lengths followed by ndist distance lengths; counts: nlen, ndist per

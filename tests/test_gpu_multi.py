@@ -1,0 +1,61 @@
+"""GPU: the one-process multi-GPU entry points (zb200_multi_*) give the results of the single-GPU calls —
+the same checksum, the same compressed bytes, the same member results — on however many GPUs the box shows."""
+import ctypes as C
+
+import pytest
+
+import refz
+import zlib_wasm_b200 as zb
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def both():
+    L = zb.lib()
+    m = C.c_void_p()
+    assert L.zb200_multi_create(None, 0, C.byref(m)) == 0, zb.last_error()
+    ctx = zb.Context(0)
+    yield L, m, ctx
+    L.zb200_multi_destroy(m)
+    ctx.close()
+
+
+def test_multi_matches_single(both):
+    L, m, ctx = both
+    g = L.zb200_multi_count(m)
+    assert g >= 1
+    d = refz.gen(24 * 262144 + 12345, refz.GEN_MIXED, seed=77)
+    o = refz.oracle()
+    crc, adler = C.c_uint32(0), C.c_uint32(0)
+    assert L.zb200_multi_checksum_host(m, d, len(d), 3, 0, 1, C.byref(crc), C.byref(adler)) == 0
+    assert (crc.value, adler.value) == (o.crc32(d), o.adler32(d))
+    assert L.zb200_multi_checksum_host(m, d, len(d), 3, 0x1234, 0x00050006, C.byref(crc), C.byref(adler)) == 0
+    assert (crc.value, adler.value) == (o.crc32(d, 0x1234), o.adler32(d, 0x00050006))
+    for level, frame, finish in ((6, zb.FRAME_ZLIB, 1), (1, zb.FRAME_GZIP, 1), (6, zb.FRAME_RAW, 0), (6, zb.FRAME_GZIP_MEMBERS, 1), (9, zb.FRAME_GZIP, 1)):
+        for data in (d, d[:100], b"", d[:262144 * 3]):
+            cap = L.zb200_deflate_bound(len(data), 262144, frame) + 4096
+            out = C.create_string_buffer(cap)
+            olen, a, c = C.c_size_t(cap), C.c_uint32(0), C.c_uint32(0)
+            r = L.zb200_multi_deflate_host(m, data, len(data), 262144, level, 0, frame, finish, out, C.byref(olen), C.byref(a), C.byref(c))
+            assert r == 0, zb.last_error()
+            want = ctx.deflate_host(data, level, 0, frame, 262144, finish)
+            assert out.raw[:olen.value] == want, (g, level, frame, finish, len(data), olen.value, len(want))
+            assert (c.value, a.value) == (o.crc32(data), o.adler32(data))
+    # members: the file the GZIP_MEMBERS frame wrote, split by the discovery call, inflated on all GPUs
+    cap = L.zb200_deflate_bound(len(d), 65536, zb.FRAME_GZIP_MEMBERS)
+    out = C.create_string_buffer(cap)
+    olen = C.c_size_t(cap)
+    assert L.zb200_multi_deflate_host(m, d, len(d), 65536, 6, 0, zb.FRAME_GZIP_MEMBERS, 1, out, C.byref(olen), None, None) == 0
+    blob = out.raw[:olen.value]
+    nmax = len(d) // 65536 + 2
+    tab = (zb.Member * nmax)()
+    back = C.create_string_buffer(len(d) + 16)
+    blen, nm, st = C.c_size_t(0), C.c_size_t(0), C.c_int(0)
+    assert L.zb200_gunzip_host(ctx.handle, blob, len(blob), back, len(d) + 16, C.byref(blen), C.byref(st), tab, nmax, C.byref(nm)) == 0
+    assert st.value == 0 and back.raw[:blen.value] == d and nm.value == len(d) // 65536 + 1
+    res = (zb.MemberResult * nm.value)()
+    back2 = C.create_string_buffer(len(d) + 16)
+    assert L.zb200_multi_inflate_host(m, blob, back2, tab, nm.value, zb.WRAP_GZIP, 1, res) == 0, zb.last_error()
+    assert all(r.status == 0 for r in res) and back2.raw[:len(d)] == d
+    assert sum(r.out_len for r in res) == len(d)

@@ -75,6 +75,12 @@ ABI = {
     "zb200_inflate_dev": (_i, _vp, _vp, _vp, _vp, _sz, _i, _i, _vp, _vp),
     "zb200_inflate_host": (_i, _vp, _vp, _vp, _vp, _sz, _i, _i, _vp),
     "zb200_selftest_tables": (_i, _vp, _vp, _vp, _sz, _vp),
+    "zb200_multi_create": (_i, _vp, _i, C.POINTER(_vp)),
+    "zb200_multi_destroy": (None, _vp),
+    "zb200_multi_count": (_i, _vp),
+    "zb200_multi_checksum_host": (_i, _vp, _vp, _sz, _i, _u32, _u32, _p32, _p32),
+    "zb200_multi_deflate_host": (_i, _vp, _vp, _sz, _sz, _i, _i, _i, _i, _vp, _psz, _p32, _p32),
+    "zb200_multi_inflate_host": (_i, _vp, _vp, _vp, _vp, _sz, _i, _i, _vp),
     "zb200_inflate_stream_host": (_i, _vp, _vp, _sz, _i, _vp, _sz, _vp),
     "zb200_gunzip_host": (_i, _vp, _vp, _sz, _vp, _sz, _psz, C.POINTER(_i), _vp, _sz, _psz),
     "zb200_deflate_host_dict": (_i, _vp, _vp, _sz, _sz, _i, _i, _i, _vp, _vp, _vp, _vp),

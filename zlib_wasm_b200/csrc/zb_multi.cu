@@ -1,0 +1,217 @@
+// zb_multi.cu — one process, every GPU of the box (the path shards with no data-path collective).
+//
+// bench.py drives one process per GPU under torchrun; a caller that links the library wants the same
+// sharding behind one call.  A zb200_multi holds one engine context per device; each entry point gives
+// every context a contiguous range of the units (checksum bytes, deflate chunks, inflate members), runs
+// the ranges on one host thread per GPU, and does the exchange step on the host: partial checksums are
+// folded left to right with crc32_combine / adler32_combine (crc32.c:1021, adler32.c:133), compressed
+// pieces are laid end to end (every piece but the last ends on a full-flush marker, so the concatenation
+// is the very stream one GPU would emit), the stream header and trailer (deflate.c:1004-1054,1239-1256)
+// are written here.  Host code only.
+#include "zb_internal.h"
+#include <condition_variable>
+#include <string.h>
+#include <thread>
+#include <vector>
+
+using namespace zb;
+
+struct zb200_multi {
+    std::vector<zb200_ctx *> ctx;
+};
+
+namespace {
+
+struct Rendezvous {                         // every thread arrives once; all leave together
+    std::mutex m; std::condition_variable cv; size_t expected, arrived = 0;
+    explicit Rendezvous(size_t n) : expected(n) {}
+    void arrive_and_wait() {
+        std::unique_lock<std::mutex> l(m);
+        if (++arrived == expected) cv.notify_all();
+        else cv.wait(l, [&] { return arrived >= expected; });
+    }
+};
+
+template <class F> void on_all(size_t n, F f) {
+    std::vector<std::thread> th;
+    for (size_t k = 1; k < n; ++k) th.emplace_back(f, k);
+    f(0);
+    for (auto &t : th) t.join();
+}
+
+}  // namespace
+
+extern "C" {
+
+int zb200_multi_create(const int *devices, int n_devices, zb200_multi **out) {
+    if (!out || n_devices < 0) return ZB200_ERR_PARAM;
+    *out = nullptr;
+    const int have = zb200_device_count();
+    if (have <= 0) { set_error("no CUDA device available; this library has no CPU path"); return ZB200_ERR_NO_DEVICE; }
+    std::vector<int> dev;
+    if (devices && n_devices) dev.assign(devices, devices + n_devices);
+    else for (int d = 0; d < have; ++d) dev.push_back(d);
+    zb200_multi *m = new (std::nothrow) zb200_multi();
+    if (!m) return ZB200_ERR_NOMEM;
+    for (int d : dev) {
+        zb200_ctx *c = nullptr;
+        const int r = zb200_create(d, &c);
+        if (r != ZB200_OK) { zb200_multi_destroy(m); return r; }
+        m->ctx.push_back(c);
+    }
+    *out = m;
+    return ZB200_OK;
+}
+
+void zb200_multi_destroy(zb200_multi *m) {
+    if (!m) return;
+    for (zb200_ctx *c : m->ctx) zb200_destroy(c);
+    delete m;
+}
+
+int zb200_multi_count(const zb200_multi *m) { return m ? (int)m->ctx.size() : 0; }
+
+int zb200_multi_checksum_host(zb200_multi *m, const void *data, size_t n, int which, uint32_t init_crc, uint32_t init_adler,
+                              uint32_t *crc, uint32_t *adler) {
+    if (!m || m->ctx.empty() || (!data && n)) return ZB200_ERR_PARAM;
+    const size_t g = m->ctx.size();
+    const size_t per = ((n + g - 1) / g + 4095) & ~(size_t)4095;
+    std::vector<uint32_t> pc(g, 0), pa(g, 1);
+    std::vector<size_t> len(g, 0);
+    std::vector<int> rc(g, ZB200_OK);
+    on_all(g, [&](size_t k) {
+        const size_t off = k * per < n ? k * per : n;
+        len[k] = n - off < per ? n - off : per;
+        if (!len[k] && k) return;
+        rc[k] = zb200_checksum_host(m->ctx[k], (const uint8_t *)data + off, len[k], which, k ? 0u : init_crc, k ? 1u : init_adler, &pc[k], &pa[k]);
+    });
+    uint32_t c = pc[0], a = pa[0];
+    for (size_t k = 0; k < g; ++k) if (rc[k] != ZB200_OK) return rc[k];
+    for (size_t k = 1; k < g; ++k) {
+        if (!len[k]) continue;
+        c = zb200_crc32_combine(c, pc[k], len[k]);
+        a = zb200_adler32_combine(a, pa[k], (int64_t)len[k]);
+    }
+    if (crc) *crc = c;
+    if (adler) *adler = a;
+    return ZB200_OK;
+}
+
+int zb200_multi_deflate_host(zb200_multi *m, const void *in, size_t n, size_t chunk_size, int level, int strategy, int frame,
+                             int finish, void *out, size_t *out_len, uint32_t *in_adler, uint32_t *in_crc) {
+    if (!m || m->ctx.empty() || (!in && n) || !out || !out_len || chunk_size == 0 || frame < 0 || frame > 3) return ZB200_ERR_PARAM;
+    const size_t S = chunk_size, g0 = m->ctx.size();
+    const size_t nch = (n + S - 1) / S;
+    const size_t g = nch < g0 ? (nch ? nch : 1) : g0;                  // no more pieces than chunks
+    const size_t per = (nch + g - 1) / g * S;                         // bytes per piece: whole chunks
+    const int pframe = frame == ZB200_FRAME_GZIP_MEMBERS ? ZB200_FRAME_GZIP_MEMBERS : ZB200_FRAME_RAW;
+    uint8_t hdr[10];
+    size_t hlen = 0;
+    if (frame == ZB200_FRAME_ZLIB) {                                  // deflate.c:1004-1037
+        const unsigned lf = (strategy >= 2 || level < 2) ? 0 : level < 6 ? 1 : level == 6 ? 2 : 3;
+        unsigned h = (0x78u << 8) | (lf << 6);
+        h += 31 - h % 31;
+        hdr[0] = (uint8_t)(h >> 8); hdr[1] = (uint8_t)h; hlen = 2;
+    } else if (frame == ZB200_FRAME_GZIP) {                           // deflate.c:1042-1054
+        const uint8_t gz[10] = {0x1f, 0x8b, 8, 0, 0, 0, 0, 0, (uint8_t)(level == 9 ? 2 : (strategy >= 2 || level < 2) ? 4 : 0), 3};
+        memcpy(hdr, gz, 10); hlen = 10;
+    }
+    std::vector<size_t> off(g), len(g), total(g, 0), final_off(g, 0);
+    std::vector<uint32_t> pc(g, 0), pa(g, 1);
+    std::vector<int> rc(g, ZB200_OK);
+    Rendezvous sized(g);
+    size_t need = 0;
+    const size_t cap = *out_len;
+    on_all(g, [&](size_t k) {
+        zb200_ctx *ctx = m->ctx[k];
+        off[k] = k * per < n ? k * per : n;
+        len[k] = n - off[k] < per ? n - off[k] : per;
+        const bool last = k + 1 == g;
+        cudaStream_t s = nullptr;
+        {
+            std::lock_guard<std::mutex> lk(ctx->mu);
+            int r = cudaSetDevice(ctx->device) == cudaSuccess ? ZB200_OK : ZB200_ERR_CUDA;
+            const size_t bound = zb200_deflate_bound(len[k], S, pframe);
+            if (!r) r = ensure_io(ctx, len[k] + 16, bound + 16);
+            s = ctx->stream;
+            if (!r) r = h2d_auto(ctx, ctx->d_io_in, (const uint8_t *)in + off[k], len[k], s);
+            uint64_t *d_total = ctx->d_small + 17;
+            uint32_t *d_sums = (uint32_t *)(ctx->d_small + 18);
+            if (!r) r = deflate_launch(ctx, ctx->d_io_in, len[k], S, level, strategy, pframe, (finish && last) ? 1 : 0, ctx->d_io_out, bound,
+                                       nullptr, d_total, d_sums, s);
+            if (!r && cudaMemcpyAsync(ctx->h_small, ctx->d_small + 17, 16, cudaMemcpyDeviceToHost, s) != cudaSuccess) r = ZB200_ERR_CUDA;
+            if (!r && cudaStreamSynchronize(s) != cudaSuccess) r = ZB200_ERR_CUDA;
+            if (!r) { total[k] = (size_t)ctx->h_small[0]; const uint32_t *hs = (const uint32_t *)(ctx->h_small + 1); pc[k] = hs[0]; pa[k] = hs[1]; }
+            rc[k] = r;
+        }
+        sized.arrive_and_wait();                                      // every piece knows its size: the exchange step
+        bool ok = true;
+        size_t at = hlen;
+        for (size_t j = 0; j < g; ++j) { if (rc[j] != ZB200_OK) ok = false; if (j < k) at += total[j]; }
+        final_off[k] = at;
+        if (k + 1 == g) need = at + total[k] + ((finish && frame == ZB200_FRAME_ZLIB) ? 4 : (finish && frame == ZB200_FRAME_GZIP) ? 8 : 0);
+        if (!ok || at + total[k] > cap) return;
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        if (cudaSetDevice(ctx->device) != cudaSuccess) { rc[k] = ZB200_ERR_CUDA; return; }
+        int r = total[k] ? d2h_auto(ctx, (uint8_t *)out + at, ctx->d_io_out, total[k], s) : ZB200_OK;
+        if (!r && cudaStreamSynchronize(s) != cudaSuccess) r = ZB200_ERR_CUDA;
+        rc[k] = r;
+    });
+    for (size_t k = 0; k < g; ++k) if (rc[k] != ZB200_OK) return rc[k];
+    uint32_t c = pc[0], a = pa[0];
+    for (size_t k = 1; k < g; ++k) {
+        c = zb200_crc32_combine(c, pc[k], len[k]);
+        a = zb200_adler32_combine(a, pa[k], (int64_t)len[k]);
+    }
+    if (in_crc) *in_crc = c;
+    if (in_adler) *in_adler = a;
+    if (need > cap) { *out_len = need; set_error("deflate: %zu bytes do not fit the output buffer", need); return ZB200_ERR_OUTPUT; }
+    memcpy(out, hdr, hlen);
+    size_t pos = final_off[g - 1] + total[g - 1];
+    if (finish && frame == ZB200_FRAME_ZLIB) for (int i = 0; i < 4; ++i) ((uint8_t *)out)[pos++] = (uint8_t)(a >> (24 - 8 * i));   // deflate.c:1254-1255
+    if (finish && frame == ZB200_FRAME_GZIP) {                                                                                    // deflate.c:1241-1250
+        for (int i = 0; i < 4; ++i) ((uint8_t *)out)[pos++] = (uint8_t)(c >> (8 * i));
+        for (int i = 0; i < 4; ++i) ((uint8_t *)out)[pos++] = (uint8_t)((uint32_t)n >> (8 * i));
+    }
+    *out_len = pos;
+    return ZB200_OK;
+}
+
+int zb200_multi_inflate_host(zb200_multi *m, const void *in, void *out, const zb200_member *members, size_t n_members,
+                             int wrap, int verify, zb200_member_result *results) {
+    if (!m || m->ctx.empty() || !members || !results) return ZB200_ERR_PARAM;
+    if (n_members == 0) return ZB200_OK;
+    const size_t g0 = m->ctx.size(), g = n_members < g0 ? n_members : g0;
+    // contiguous member ranges of about equal output capacity
+    uint64_t total = 0;
+    for (size_t i = 0; i < n_members; ++i) total += members[i].out_cap + 1;
+    std::vector<size_t> lo(g + 1, n_members);
+    lo[0] = 0;
+    {
+        uint64_t run = 0;
+        size_t k = 1;
+        for (size_t i = 0; i < n_members && k < g; ++i) {
+            run += members[i].out_cap + 1;
+            if (run >= total * k / g) lo[k++] = i + 1;
+        }
+    }
+    std::vector<int> rc(g, ZB200_OK);
+    on_all(g, [&](size_t k) {
+        const size_t a = lo[k], b = lo[k + 1];
+        if (a >= b) return;
+        // the range's own window of the two buffers (the single-GPU entry moves [0, max offset) otherwise)
+        uint64_t in_lo = ~0ull, out_lo = ~0ull;
+        for (size_t i = a; i < b; ++i) {
+            if (members[i].in_off < in_lo) in_lo = members[i].in_off;
+            const uint64_t o = members[i].out_off - members[i].dict_len;
+            if (o < out_lo) out_lo = o;
+        }
+        std::vector<zb200_member> tab(members + a, members + b);
+        for (auto &t : tab) { t.in_off -= in_lo; t.out_off -= out_lo; }
+        rc[k] = zb200_inflate_host(m->ctx[k], (const uint8_t *)in + in_lo, (uint8_t *)out + out_lo, tab.data(), tab.size(), wrap, verify, results + a);
+    });
+    for (size_t k = 0; k < g; ++k) if (rc[k] != ZB200_OK) return rc[k];
+    return ZB200_OK;
+}
+
+}  // extern "C"
