@@ -59,3 +59,32 @@ def test_multi_matches_single(both):
     assert L.zb200_multi_inflate_host(m, blob, back2, tab, nm.value, zb.WRAP_GZIP, 1, res) == 0, zb.last_error()
     assert all(r.status == 0 for r in res) and back2.raw[:len(d)] == d
     assert sum(r.out_len for r in res) == len(d)
+
+
+def test_zlib_api_over_all_devices(tmp_path):
+    """$ZB200_DEVICES=all: compress2 / crc32_z / adler32_z of large buffers behind the zlib.h names run on every GPU and
+    give what one GPU gives (read once per process: checked in a child process)."""
+    import os
+    import subprocess
+    import sys
+    code = r'''
+import ctypes as C, sys, hashlib
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+import refz, zlib_wasm_b200 as zb
+z = refz.ZlibBinding(zb.LIB_PATH, "")
+d = refz.gen(40 << 20, refz.GEN_MARKOV, seed=8)
+cap = C.c_ulong(z.compressBound(len(d)))
+dst = C.create_string_buffer(cap.value)
+assert z.compress2(dst, C.byref(cap), d, len(d), 6) == 0
+print(hashlib.sha256(dst.raw[:cap.value]).hexdigest(), z.crc32_z(0, d, len(d)), z.adler32_z(1, d, len(d)))
+''' % (refz.ROOT, os.path.join(refz.ROOT, "tests"))
+    outs = []
+    for env_val in (None, "all"):
+        env = dict(os.environ)
+        env.pop("ZB200_DEVICES", None)
+        if env_val:
+            env["ZB200_DEVICES"] = env_val
+        r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, timeout=300)
+        assert r.returncode == 0, r.stderr[-400:]
+        outs.append(r.stdout.strip())
+    assert outs[0] == outs[1] and len(outs[0]) > 64

@@ -33,6 +33,32 @@ zb200_ctx *api_ctx() {
     return g_ctx;
 }
 
+// $ZB200_DEVICES = "all" or a list "0,1,3": large one-shot jobs behind the zlib API (compress2, deflate() flushes,
+// crc32_z / adler32_z of >= 32 MiB) are sharded over those GPUs (zb200_multi_*, zb_multi.cu).  Unset: one GPU.
+zb200_multi *api_multi() {
+    static zb200_multi *m = [] () -> zb200_multi * {
+        const char *e = getenv("ZB200_DEVICES");
+        if (!e || !*e) return nullptr;
+        std::vector<int> dev;
+        if (strcmp(e, "all") != 0) {
+            for (const char *p = e; *p;) {
+                char *end = nullptr;
+                const long v = strtol(p, &end, 10);
+                if (end == p) break;
+                dev.push_back((int)v);
+                p = *end == ',' ? end + 1 : end;
+            }
+            if (dev.empty()) return nullptr;
+        }
+        zb200_multi *mm = nullptr;
+        if (zb200_multi_create(dev.empty() ? nullptr : dev.data(), (int)dev.size(), &mm) != ZB200_OK) return nullptr;
+        if (zb200_multi_count(mm) < 2) { zb200_multi_destroy(mm); return nullptr; }
+        return mm;
+    }();
+    return m;
+}
+constexpr size_t kMultiMin = (size_t)32 << 20;
+
 }  // namespace
 namespace zb { zb200_ctx *zlib_api_ctx() { return api_ctx(); } }
 namespace {
@@ -166,6 +192,9 @@ int compress_buffered(DeflateStream &st, bool finish) {
             cap1 += cap2;
         }
         cap = cap1;
+    } else if (n >= kMultiMin && !st.tuned && api_multi()) {
+        r = zb200_multi_deflate_host(api_multi(), st.in.data(), n, chunk, st.level, st.strategy, ZB200_FRAME_RAW, finish ? 1 : 0,
+                                     st.pending.data() + at, &cap, &adler, &crc);
     } else {
         r = zb200_deflate_host(ctx, n ? st.in.data() : (const uint8_t *)"", n, chunk, st.level,
                                st.strategy, ZB200_FRAME_RAW, finish ? 1 : 0,
@@ -916,8 +945,10 @@ int compress2(Bytef *dest, uLongf *destLen, const Bytef *source, uLong sourceLen
     if (level == Z_DEFAULT_COMPRESSION) level = 6;
     if (level < 0 || level > 9 || !dest || !destLen || (!source && sourceLen)) return Z_STREAM_ERROR;
     size_t cap = *destLen;
-    const int r = zb200_deflate_host(ctx, source ? source : (const Bytef *)"", sourceLen, api_chunk(), level,
-                                     0, ZB200_FRAME_ZLIB, 1, dest, &cap, nullptr, nullptr);
+    const int r = (sourceLen >= kMultiMin && api_multi())
+                      ? zb200_multi_deflate_host(api_multi(), source, sourceLen, api_chunk(), level, 0, ZB200_FRAME_ZLIB, 1, dest, &cap, nullptr, nullptr)
+                      : zb200_deflate_host(ctx, source ? source : (const Bytef *)"", sourceLen, api_chunk(), level,
+                                           0, ZB200_FRAME_ZLIB, 1, dest, &cap, nullptr, nullptr);
     if (r == ZB200_ERR_OUTPUT) return Z_BUF_ERROR;
     if (r != ZB200_OK) return map_engine_error(r);
     *destLen = cap;
@@ -966,6 +997,10 @@ uLong crc32_z(uLong crc, const Bytef *buf, z_size_t len) {
     zb200_ctx *ctx = api_ctx();
     if (!ctx) die_no_device("crc32");
     uint32_t c = (uint32_t)crc;
+    if (len >= kMultiMin && api_multi()) {
+        if (zb200_multi_checksum_host(api_multi(), buf, len, ZB200_CRC32, (uint32_t)crc, 1, &c, nullptr) != ZB200_OK) die_no_device("crc32");
+        return c;
+    }
     if (zb200_checksum_host(ctx, buf, len, ZB200_CRC32, (uint32_t)crc, 1, &c, nullptr) != ZB200_OK) die_no_device("crc32");
     return c;
 }
@@ -975,6 +1010,10 @@ uLong adler32_z(uLong adler, const Bytef *buf, z_size_t len) {
     zb200_ctx *ctx = api_ctx();
     if (!ctx) die_no_device("adler32");
     uint32_t a = (uint32_t)adler;
+    if (len >= kMultiMin && api_multi()) {
+        if (zb200_multi_checksum_host(api_multi(), buf, len, ZB200_ADLER32, 0, (uint32_t)adler, nullptr, &a) != ZB200_OK) die_no_device("adler32");
+        return a;
+    }
     if (zb200_checksum_host(ctx, buf, len, ZB200_ADLER32, 0, (uint32_t)adler, nullptr, &a) != ZB200_OK) die_no_device("adler32");
     return a;
 }
