@@ -513,3 +513,28 @@ def test_deflate_tune(z):
             outs[(name, level, tune)] = dst.raw[:produced]
         assert outs[("z", level, tune)] == outs[("ref", level, tune)], (level, tune)
     assert outs[("z", 6, (4, 8, 32, 64))] != outs[("z", 6, None)]
+
+
+def test_many_host_threads_distinct_streams(z):
+    """zlib.h is re-entrant: one thread per z_stream, no shared mutable state (FAQ:151-160).  Eight host threads drive
+    their own deflate / inflate streams (sliced calls, different levels and wrappers, dictionaries, big slices) and
+    checksums through the one process-wide engine context at once; every result is the single-threaded one."""
+    import concurrent.futures as cf
+    ref = refz.ref() if refz.have_ref() else refz.oracle()
+    base = refz.gen(6000000, refz.GEN_MARKOV, seed=81)
+
+    def job(k):
+        d = base[k * 300000:k * 300000 + 1500000 + 77 * k]
+        wrap = (refz.WRAP_RAW, refz.WRAP_ZLIB, refz.WRAP_GZIP)[k % 3]
+        level = (1, 6, 9, 4)[k % 4]
+        s = z.deflate_stream(d, level, 0, wrap, chunk=(0, 100000)[k % 2], in_slice=(None, 70000)[k % 2], out_slice=(None, 50000)[(k // 2) % 2])
+        want = ref.deflate_stream(d, level, 0, wrap, 262144 if k % 2 == 0 else 100000)
+        ok = s == want if level >= 4 else len(s) <= 1.03 * len(want) + 16
+        ret, m, out, tin = z.inflate_all(s, wrap, cap=len(d) + 64, in_slice=(None, 400000, 16384)[k % 3])
+        ok = ok and ret == refz.Z_STREAM_END and out == d and tin == len(s)
+        ok = ok and z.crc32_z(0, d, len(d)) == refz.oracle().crc32(d) and z.adler32_z(1, d, len(d)) == refz.oracle().adler32(d)
+        return ok
+
+    with cf.ThreadPoolExecutor(max_workers=8) as ex:
+        results = list(ex.map(job, range(16)))
+    assert all(results), results
