@@ -122,26 +122,68 @@ int zb200_multi_deflate_host(zb200_multi *m, const void *in, size_t n, size_t ch
     Rendezvous sized(g);
     size_t need = 0;
     const size_t cap = *out_len;
+    constexpr size_t kSub = 16;                                       // sub-pieces per GPU at most (ctx->d_pipe holds 16 records)
     on_all(g, [&](size_t k) {
         zb200_ctx *ctx = m->ctx[k];
         off[k] = k * per < n ? k * per : n;
         len[k] = n - off[k] < per ? n - off[k] : per;
         const bool last = k + 1 == g;
+        // A GPU's piece goes through in sub-pieces of >= 128 MiB (whole chunks): sub-piece j+1 travels to the device
+        // while sub-piece j is compressed.  The copies back wait for the rendezvous: a piece's place in the caller's
+        // buffer depends on the sizes of all pieces before it.
+        size_t sub = len[k] / 8 > ((size_t)128 << 20) ? len[k] / 8 : ((size_t)128 << 20);
+        sub = (sub + S - 1) / S * S;
+        const size_t ns = len[k] ? (len[k] + sub - 1) / sub : 1;
+        size_t sub_off[kSub + 1] = {0}, sub_total[kSub] = {0};
         cudaStream_t s = nullptr;
         {
             std::lock_guard<std::mutex> lk(ctx->mu);
             int r = cudaSetDevice(ctx->device) == cudaSuccess ? ZB200_OK : ZB200_ERR_CUDA;
-            const size_t bound = zb200_deflate_bound(len[k], S, pframe);
-            if (!r) r = ensure_io(ctx, len[k] + 16, bound + 16);
+            size_t bound_total = 0;
+            for (size_t j = 0; j < ns; ++j) {
+                const size_t l = j + 1 < ns ? sub : len[k] - j * sub;
+                sub_off[j] = bound_total;
+                bound_total += zb200_deflate_bound(l, S, pframe);
+            }
+            if (!r) r = ensure_io(ctx, len[k] + 16, bound_total + 16);
+            if (!r) r = ensure_scratch(ctx, zb200_deflate_scratch_bytes(ns > 1 ? sub : len[k], S));   // no reallocation (= implicit sync) mid-pipeline
             s = ctx->stream;
-            if (!r) r = h2d_auto(ctx, ctx->d_io_in, (const uint8_t *)in + off[k], len[k], s);
-            uint64_t *d_total = ctx->d_small + 17;
-            uint32_t *d_sums = (uint32_t *)(ctx->d_small + 18);
-            if (!r) r = deflate_launch(ctx, ctx->d_io_in, len[k], S, level, strategy, pframe, (finish && last) ? 1 : 0, ctx->d_io_out, bound,
-                                       nullptr, d_total, d_sums, s);
-            if (!r && cudaMemcpyAsync(ctx->h_small, ctx->d_small + 17, 16, cudaMemcpyDeviceToHost, s) != cudaSuccess) r = ZB200_ERR_CUDA;
-            if (!r && cudaStreamSynchronize(s) != cudaSuccess) r = ZB200_ERR_CUDA;
-            if (!r) { total[k] = (size_t)ctx->h_small[0]; const uint32_t *hs = (const uint32_t *)(ctx->h_small + 1); pc[k] = hs[0]; pa[k] = hs[1]; }
+            const bool pinned = is_pinned(in);
+            cudaEvent_t ev[kSub];
+            size_t nev = 0;
+            for (size_t j = 0; j < ns && !r; ++j) {
+                const size_t l = j + 1 < ns ? sub : len[k] - j * sub;
+                const uint8_t *src = (const uint8_t *)in + off[k] + j * sub;
+                if (pinned && ns > 1) {
+                    if (cudaEventCreateWithFlags(&ev[nev], cudaEventDisableTiming) != cudaSuccess) { r = ZB200_ERR_CUDA; break; }
+                    ++nev;
+                    if (cudaMemcpyAsync(ctx->d_io_in + j * sub, src, l, cudaMemcpyHostToDevice, ctx->copy_stream) != cudaSuccess ||
+                        cudaEventRecord(ev[j], ctx->copy_stream) != cudaSuccess) r = ZB200_ERR_CUDA;
+                } else r = h2d_auto(ctx, ctx->d_io_in + j * sub, src, l, s);
+            }
+            for (size_t j = 0; j < ns && !r; ++j) {
+                const size_t l = j + 1 < ns ? sub : len[k] - j * sub;
+                if (pinned && ns > 1) cudaStreamWaitEvent(s, ev[j], 0);
+                r = deflate_launch(ctx, ctx->d_io_in + j * sub, l, S, level, strategy, pframe, (finish && last && j + 1 == ns) ? 1 : 0,
+                                   ctx->d_io_out + sub_off[j], zb200_deflate_bound(l, S, pframe), nullptr, ctx->d_pipe + 2 * j,
+                                   (uint32_t *)(ctx->d_pipe + 2 * j + 1), s);
+                if (!r && cudaMemcpyAsync(ctx->h_pipe + 2 * j, ctx->d_pipe + 2 * j, 16, cudaMemcpyDeviceToHost, s) != cudaSuccess) r = ZB200_ERR_CUDA;
+            }
+            if (cudaStreamSynchronize(s) != cudaSuccess && !r) r = ZB200_ERR_CUDA;
+            if (cudaStreamSynchronize(ctx->copy_stream) != cudaSuccess && !r) r = ZB200_ERR_CUDA;
+            for (size_t j = 0; j < nev; ++j) cudaEventDestroy(ev[j]);
+            if (!r) {
+                uint32_t c = 0, a = 1;
+                for (size_t j = 0; j < ns; ++j) {
+                    const size_t l = j + 1 < ns ? sub : len[k] - j * sub;
+                    sub_total[j] = (size_t)ctx->h_pipe[2 * j];
+                    const uint32_t *hs = (const uint32_t *)(ctx->h_pipe + 2 * j + 1);
+                    c = j ? zb200_crc32_combine(c, hs[0], l) : hs[0];
+                    a = j ? zb200_adler32_combine(a, hs[1], (int64_t)l) : hs[1];
+                    total[k] += sub_total[j];
+                }
+                pc[k] = c; pa[k] = a;
+            }
             rc[k] = r;
         }
         sized.arrive_and_wait();                                      // every piece knows its size: the exchange step
@@ -153,7 +195,11 @@ int zb200_multi_deflate_host(zb200_multi *m, const void *in, size_t n, size_t ch
         if (!ok || at + total[k] > cap) return;
         std::lock_guard<std::mutex> lk(ctx->mu);
         if (cudaSetDevice(ctx->device) != cudaSuccess) { rc[k] = ZB200_ERR_CUDA; return; }
-        int r = total[k] ? d2h_auto(ctx, (uint8_t *)out + at, ctx->d_io_out, total[k], s) : ZB200_OK;
+        int r = ZB200_OK;
+        for (size_t j = 0; j < ns && !r; ++j) {
+            if (sub_total[j]) r = d2h_auto(ctx, (uint8_t *)out + at, ctx->d_io_out + sub_off[j], sub_total[j], s);
+            at += sub_total[j];
+        }
         if (!r && cudaStreamSynchronize(s) != cudaSuccess) r = ZB200_ERR_CUDA;
         rc[k] = r;
     });
