@@ -164,6 +164,9 @@ class ZlibBinding:
                 strm.avail_out = room
                 ret = self.inflate(C.byref(strm), Z_NO_FLUSH)
                 produced += room - strm.avail_out
+                if ret == Z_BUF_ERROR and strm.avail_in == 0 and fed + step < n:
+                    ret = Z_OK                              # nothing pending and no input left in this slice: not an error
+                    break                                   # (zlib.h:522-527; examples/zpipe.c ignores it the same way)
                 if ret == 2 and dictionary is not None:    # Z_NEED_DICT
                     ret = self.inflateSetDictionary(C.byref(strm), bytes(dictionary), len(dictionary))
                     dictionary = None

@@ -392,15 +392,18 @@ int inflate_attempt(InflateStream &s) {
             if (dev_grow(&s.d_out, &s.d_out_cap, s.d_out_cap * 2 + (1u << 20), (size_t)r.out_len + s.dict_len, st)) return -1;
             continue;
         }
-        // fetch the newly valid bytes
-        if (r.out_len > s.decoded) {
-            const size_t add = (size_t)(r.out_len - s.decoded);
+        // fetch the newly valid bytes.  An attempt that ran out of input delivers up to the last block boundary only:
+        // the open block is decoded again from its start by the next attempt, and what this one produced of it is
+        // not handed out (tools/repro_slices.py: with 7-byte slices ten such bytes differed from the final decode).
+        const uint64_t valid = r.status == ZB200_INF_TRUNCATED ? (r.resume_bit ? r.resume_out : 0) : r.out_len;
+        if (valid > s.decoded) {
+            const size_t add = (size_t)(valid - s.decoded);
             const size_t at = s.out.size();
             s.out.resize(at + add);
             if (cudaMemcpyAsync(s.out.data() + at, s.d_out + s.dict_len + s.decoded, add, cudaMemcpyDeviceToHost, st) != cudaSuccess) return -1;
             if (cudaStreamSynchronize(st) != cudaSuccess) return -1;
             hist_push(s, s.out.data() + at, add);
-            s.decoded = r.out_len;
+            s.decoded = valid;
         }
         if (s.rebased) {
             if (r.status == ZB200_INF_TRUNCATED && r.resume_bit) { s.resume_bit = r.resume_bit; s.resume_out = r.resume_out; }
