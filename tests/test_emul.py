@@ -237,3 +237,69 @@ def test_deflate_preset_dictionary_byte_exact():
                 else:
                     err, msg, back, used = ref.inflate_all(got, refz.WRAP_RAW, cap=n + 16, dictionary=dictionary)
                     assert err == 1 and back == data and len(got) <= 1.03 * len(want) + 8, (kind, dl, n, level, strat, err, msg)
+
+
+def _bits_stream_of_31_bit_matches(n_matches):
+    """stored block of 20000 bytes, then a fixed-Huffman block of matches that take 31 bits each (length code 284 +
+    5 extra bits, distance code 28 + 13 extra bits): the pattern on which the lean symbol loop refills in the
+    middle of every match, 13 matches in a row, without passing its safe-zone check."""
+    rng = random.Random(3)
+    raw = bytes(rng.randrange(256) for _ in range(20000))
+    out = bytearray([0x00]) + (20000).to_bytes(2, "little") + (20000 ^ 0xffff).to_bytes(2, "little") + raw
+    acc, nb = 0, 0
+
+    def put(v, k):                                    # LSB-first field
+        nonlocal acc, nb
+        acc |= v << nb; nb += k
+
+    def put_code(code, k):                            # Huffman code: most significant bit first
+        for i in range(k - 1, -1, -1):
+            put((code >> i) & 1, 1)
+    put(0, 1); put(1, 2)                              # BFINAL = 0, fixed block
+    expect = bytearray(raw)
+    for j in range(n_matches):
+        put_code(0xC0 + 4, 8); put(j % 31, 5)         # length symbol 284: 227 + extra
+        put_code(28, 5); put((j * 37) % 3000, 13)     # distance symbol 28: 16385 + extra
+        ln, dist = 227 + j % 31, 16385 + (j * 37) % 3000
+        for _ in range(ln):
+            expect.append(expect[-dist])
+    while nb >= 8 or (nb and True):
+        out.append(acc & 0xff); acc >>= 8; nb = max(0, nb - 8)
+        if nb == 0:
+            break
+    return bytes(out), bytes(expect)
+
+
+def test_truncated_input_never_reads_past_its_end():
+    """A stream cut at any byte decodes to a prefix of the full output, whatever bytes happen to follow the cut in
+    memory (the lean symbol loop once chained its unconditional mid-match refills past the end of the input)."""
+    L = _build("inf_emul")
+    u64 = C.c_uint64
+    L.emul_inflate.argtypes = [C.c_void_p, u64, C.c_void_p, u64, C.c_int, u64, u64] + [C.POINTER(u64)] * 2 + \
+        [C.POINTER(C.c_uint32)] * 2 + [C.POINTER(u64)] * 2 + [C.POINTER(C.c_int)]
+    o = refz.oracle()
+    rng = random.Random(7)
+    synth, synth_out = _bits_stream_of_31_bit_matches(60)
+    cases = [(synth, synth_out, list(range(20006, len(synth))))]
+    for kind, level in ((refz.GEN_MARKOV, 6), (refz.GEN_MARKOV, 1)):
+        d = refz.gen(150000, kind, seed=40 + kind)
+        s = o.deflate_stream(d, level, 0, refz.WRAP_RAW, 0)
+        cases.append((s, d, sorted(set([rng.randrange(1, len(s)) for _ in range(200)] + list(range(len(s) - 600, len(s)))))))
+    for s, d, cuts in cases:
+        cap = len(d) + 64
+        last = 0
+        kind = level = 0
+        for k in cuts:
+            outs = []
+            for pad in (b"\x00", b"\xff", b"\x5a"):
+                buf = C.create_string_buffer(s[:k] + pad * 32, k + 32)
+                dst = C.create_string_buffer(cap)
+                iu, ol, cb, co = u64(), u64(), u64(), u64()
+                ck, isz, kd = C.c_uint32(), C.c_uint32(), C.c_int()
+                st = L.emul_inflate(C.addressof(buf), k, dst, cap, 0, 0, 0, C.byref(iu), C.byref(ol), C.byref(ck), C.byref(isz),
+                                    C.byref(cb), C.byref(co), C.byref(kd))
+                outs.append((st, dst.raw[:ol.value]))
+            assert outs[0] == outs[1] == outs[2], (kind, level, k)
+            st, out = outs[0]
+            assert st == 19 and d.startswith(out) and len(out) >= last, (kind, level, k, st, len(out), last)   # 19: truncated input
+            last = len(out)

@@ -501,10 +501,12 @@ struct InflateState {
         uint32_t rel = 0;
         int reason = 0;
         for (;;) {
-            if (b < 32) {
-                if (ip > ip_end) break;                  // leaving the safe zone: careful path takes over
-                h |= (uint64_t)(*reinterpret_cast<const uint32_t *>(ip)) << b; ip += 4; b += 32;
-            }
+            // Leaving the safe zone: the careful path takes over.  Checked before EVERY symbol, not only when a refill
+            // is due: the refill in the middle of a match below is unconditional, and a run of symbols that each
+            // reach it with 32 or more bits left at their start would otherwise walk past the end of the input
+            // (found by tools/fuzz_inflate_slices.py: a truncated stream decoded bytes that were not there).
+            if (ip > ip_end) break;
+            if (b < 32) { h |= (uint64_t)(*reinterpret_cast<const uint32_t *>(ip)) << b; ip += 4; b += 32; }
             if (rel > lim) break;
             uint32_t e = L[(uint32_t)h & ((1u << kLitRoot) - 1)];
             if ((e & 0xf00u) == 0) {                     // OP_LIT == 0: a literal straight from the root table
