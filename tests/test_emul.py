@@ -303,3 +303,30 @@ def test_truncated_input_never_reads_past_its_end():
             st, out = outs[0]
             assert st == 19 and d.startswith(out) and len(out) >= last, (kind, level, k, st, len(out), last)   # 19: truncated input
             last = len(out)
+
+
+def test_truncated_input_rounds_replay():
+    """The same property through the rounds (32 and 128 lanes) with the serial tail behind them: a cut stream gives a
+    prefix of the output that does not depend on what follows the cut in memory."""
+    L = _build("inf_emul")
+    u64 = C.c_uint64
+    L.emul_inflate_rounds.argtypes = [C.c_void_p, u64, C.c_void_p, u64, C.c_int, C.c_int] + [C.POINTER(u64)] * 2 + \
+        [C.POINTER(C.c_uint32)] * 2 + [C.POINTER(u64)] * 2 + [C.POINTER(C.c_int)]
+    o = refz.oracle()
+    rng = random.Random(12)
+    synth, synth_out = _bits_stream_of_31_bit_matches(300)
+    d = refz.gen(300000, refz.GEN_MARKOV, seed=66)
+    for s, want in ((synth, synth_out), (o.deflate_stream(d, 6, 0, refz.WRAP_RAW, 120000), d)):
+        cap = len(want) + 64
+        for k in sorted(set(rng.randrange(1, len(s)) for _ in range(120)) | set(range(len(s) - 80, len(s)))):
+            for lanes in (-1, 1000):
+                outs = []
+                for pad in (b"\x00", b"\xff"):
+                    buf = C.create_string_buffer(s[:k] + pad * 64, k + 64)
+                    dst = C.create_string_buffer(cap)
+                    iu, ol, cb, co = u64(), u64(), u64(), u64()
+                    ck, isz, kd = C.c_uint32(), C.c_uint32(), C.c_int()
+                    st = L.emul_inflate_rounds(C.addressof(buf), k, dst, cap, 0, lanes, C.byref(iu), C.byref(ol), C.byref(ck), C.byref(isz),
+                                               C.byref(cb), C.byref(co), C.byref(kd))
+                    outs.append((st, dst.raw[:ol.value]))
+                assert outs[0] == outs[1] and outs[0][0] == 19 and want.startswith(outs[0][1]), (len(s), k, lanes)
