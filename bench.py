@@ -1,14 +1,19 @@
 #!/usr/bin/env python
-"""bench.py — BASELINE.json's metric on its configuration C2 (CRC-32 + Adler-32
-over a 4 GiB synthetic buffer per GPU, per-GPU folding + crc32_combine across
-GPUs), plus bounded side measurements of the other hot-path legs (inflate of
-multi-member gzip, deflate L1 / L6 over 256 KiB Z_FULL_FLUSH chunks).
+"""bench.py — BASELINE.json's metric, "deflate L1/L6 + inflate GB/s at 1-8 B200; CRC32 GB/s vs HBM roofline",
+every leg at its configuration's size, in ONE JSON line on stdout (rank 0).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
     python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
 
-One JSON line on stdout (rank 0).  See the task contract for the keys.  A "step"
-is one fused CRC-32+Adler-32 pass over the rank's resident 4 GiB shard.
+Headline (top-level keys) = config C4, north_star's first target: deflate level 1 over markov8g (8 GiB of
+order-1 word text, 256 KiB Z_FULL_FLUSH chunks), STRONG scaling — the 8 GiB are split evenly over the N ranks,
+chunk c -> rank floor(c*N/chunks), no data-path collective.  A "step" is one pass of the whole deflate pipeline
+over the rank's resident shard.  `legs` carries the other configurations with the same keys each:
+C5 (deflate L6 / L9 x default / Z_FILTERED on mixed2g), C3 (inflate of 8 GiB of gzip members) and C2 (CRC-32 +
+Adler-32 over 4 GiB); see bench_legs.py.
+
+--impl reference times the UNMODIFIED reference (oracle/_ref, compiled in place from /root/reference) on the
+host's cores through the same pthread pool, leg for leg, each step a bounded sample of the same bytes.
 """
 import argparse
 import ctypes as C
@@ -23,9 +28,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
-GIB = 1 << 30
-SEED = 0x9E3779B97F4A7C15
-METRIC = "crc32_adler32_GBps"
+import bench_legs as BL  # noqa: E402
+
+METRIC = "deflate_l1_GBps"
 UNIT = "GB/s"
 
 
@@ -36,58 +41,26 @@ def env_int(k, d):
         return d
 
 
-def host_threads():
-    try:
-        return len(os.sched_getaffinity(0))
-    except Exception:
-        return os.cpu_count() or 1
+def headline_config(total, world):
+    """The `config` object — identical in both arms (the driver compares them)."""
+    return {"workload": "C4 markov8g: deflate level 1 (deflate_fast), Z_DEFAULT_STRATEGY, raw stream of 256 KiB Z_FULL_FLUSH chunks",
+            "total_bytes": int(total), "chunk": BL.CHUNK, "level": 1, "strategy": 0, "generator": "order-1 word text, seed 0x9E3779B97F4A7C15",
+            "l2": "inputs far larger than the 126 MB L2 (>= 1 GiB per rank and step); no flush needed"}
 
 
-def peaks():
-    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(p):
-        try:
-            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
-        except Exception:
-            pass
-    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
-
-
-def profiled_traffic():
-    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full
-    capture (profiles/*ck_big_ncu_full.txt), or None."""
-    import glob
-    import re
-    best = None
-    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "*ck_big_ncu_full.txt"))):
-        rd = wr = None
-        for line in open(path):
-            m = re.search(r"dram__bytes_(read|write)\.sum\s+([0-9.]+)\s+(\w+)", line)
-            if m:
-                v = float(m.group(2)) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(m.group(3), 1)
-                if m.group(1) == "read":
-                    rd = v
-                else:
-                    wr = v
-            if rd is not None and wr is not None:
-                best = int(rd + wr)
-                break
-    return best
-
-
-class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region."""
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region of the headline."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        super().__init__(daemon=True)
         self.index = index
         self.rows = []
         self.stop_flag = threading.Event()
+        self.th = None
 
-    def run(self):
+    def _run(self):
         while not self.stop_flag.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
@@ -97,6 +70,15 @@ class ClockSampler(threading.Thread):
             except Exception:
                 pass
             self.stop_flag.wait(0.1)
+
+    def start(self):
+        self.th = threading.Thread(target=self._run, daemon=True)
+        self.th.start()
+
+    def stop(self):
+        self.stop_flag.set()
+        if self.th:
+            self.th.join(timeout=3)
 
     def summary(self):
         sm = sorted(int(r[1]) for r in self.rows if len(r) > 2 and r[1].isdigit())
@@ -111,98 +93,136 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(reasons), "samples": len(self.rows)}
 
 
-# ---------------------------------------------------------------------------
-# reference arm / cpu baseline: the UNMODIFIED reference's crc32_z + adler32_z
-# (oracle/_ref/libzref.so), chunk-parallel over host threads, partials merged
-# with the reference's own crc32_combine / adler32_combine.
-# ---------------------------------------------------------------------------
-def cpu_checksums(ref, buf_addr, n, threads):
-    import concurrent.futures as cf
-    piece = (n + threads - 1) // threads
-    piece = (piece + 63) & ~63
-    spans = [(o, min(piece, n - o)) for o in range(0, n, piece)]
-
-    def work(span):
-        o, k = span
-        return ref.crc32_z(0, buf_addr + o, k), ref.adler32_z(1, buf_addr + o, k), k
-
-    with cf.ThreadPoolExecutor(max_workers=threads) as ex:
-        parts = list(ex.map(work, spans))
-    crc, adler = parts[0][0], parts[0][1]
-    for c, a, k in parts[1:]:
-        crc = ref.crc32_combine(crc, c, k)
-        adler = ref.adler32_combine(adler, a, k)
-    return crc, adler
-
-
-def load_cpu_ref():
-    import refz
-    if refz.have_ref():
-        return refz.ref(), "reference"
-    return None, "port"
-
-
+# ---------------------------------------------------------------------------------------------------
+# reference arm
+# ---------------------------------------------------------------------------------------------------
 def run_reference_arm(args):
-    """--impl reference: rank 0 only; CPU reference on all host threads."""
-    rank = env_int("RANK", 0)
-    if rank != 0:
+    """--impl reference: rank 0 only; the reference's CPU implementation on all host threads, every leg of the
+    metric on a bounded sample (>= 256 MiB prefix) of the SAME bytes the GPU arm compresses."""
+    if env_int("RANK", 0) != 0:
         return
-    import refz
-    ref, kind = load_cpu_ref()
-    threads = host_threads()
-    sample = min(GIB, args.bytes)
-    data = refz.gen(sample, refz.GEN_BYTES, SEED)
-    buf = C.create_string_buffer(data, sample)
+    cpu = BL.Cpu()
+    thr = cpu.threads
+    total = BL.scaled(BL.DEFLATE_LEGS["deflate_l1"][1], args.scale)
+    sample = min(total, BL.CPU_PREFIX)
+    buf = C.create_string_buffer(sample)
     addr = C.addressof(buf)
-    if ref is None:
-        o = refz.oracle()
-
-        class Port:
-            crc32_z = staticmethod(lambda c, p, k: o.c_crc32(c, p, k))
-            adler32_z = staticmethod(lambda a, p, k: o.c_adler32(a, p, k))
-            crc32_combine = staticmethod(lambda a, b, k: o.c_crc32_combine(a, b, k))
-            adler32_combine = staticmethod(lambda a, b, k: o.c_adler32_combine(a, b, k))
-        ref = Port
+    BL.fill(addr, sample, "markov", 0)
     for _ in range(args.warmup):
-        cpu_checksums(ref, addr, sample, threads)
+        cpu.deflate(addr, sample, 1, 0, thr, 1)
     t0 = time.perf_counter()
+    outb = 0
     for _ in range(args.steps):
-        cpu_checksums(ref, addr, sample, threads)
+        _, outb, _, _ = cpu.deflate(addr, sample, 1, 0, thr, 1)
     dt = (time.perf_counter() - t0) / args.steps
     val = sample / dt / 1e9
+    legs = {}
+    if not args.no_legs:
+        # C3: the reference inflates the reference's own members of the same text
+        sizes = BL.member_sizes(total, BL.SEED ^ 0x33)
+        k, acc = 0, 0
+        while k < len(sizes) and acc < sample:
+            acc += sizes[k]
+            k += 1
+        acc = min(acc, sample)
+        spans, o = [], 0
+        for i in range(k):
+            s = min(sizes[i], sample - o)
+            if s <= 0:
+                break
+            spans.append((o, s))
+            o += s
+        blob = cpu.deflate_members(addr, spans, 6, 31, thr)
+        mem, off = [], 0
+        for (so, sl), z in zip(spans, blob):
+            mem.append((off, len(z), so, sl))
+            off += len(z)
+        blob = b"".join(blob)
+        bb = C.create_string_buffer(blob, len(blob))
+        back = C.create_string_buffer(o)
+        sec, tot = cpu.inflate(C.addressof(bb), mem, 31, thr, 3, C.addressof(back))
+        legs["inflate"] = {"config": "C3", "value": round(o / sec / 1e9, 4), "unit": UNIT, "cores": thr, "kind": cpu.kind,
+                           "sample": "first %d members (%d MiB of output) of the GPU arm's rank-0 schedule, best of 3" % (len(mem), o >> 20),
+                           "bit_exact": bool(tot == o and back.raw == C.string_at(addr, o))}
+        del bb, back, blob
+        # C5
+        mixed = C.create_string_buffer(sample)
+        BL.fill(C.addressof(mixed), sample, "mixed", 0)
+        for name, (kind, tot_b, level, strategy) in BL.DEFLATE_LEGS.items():
+            if name == "deflate_l1":
+                legs[name] = {"config": "C4", "value": round(val, 4), "unit": UNIT, "cores": thr, "kind": cpu.kind, "ratio": round(sample / outb, 4),
+                              "sample": "the headline"}
+                continue
+            sec, ob, _, _ = cpu.deflate(C.addressof(mixed), sample, level, strategy, thr, 3)
+            legs[name] = {"config": "C5", "value": round(sample / sec / 1e9, 4), "unit": UNIT, "cores": thr, "kind": cpu.kind,
+                          "ratio": round(sample / ob, 4), "sample": "first %d MiB of mixed2g, best of 3" % (sample >> 20)}
+        del mixed
+        # C2: the whole 4 GiB buffer
+        n2 = BL.scaled(BL.CHECKSUM_TOTAL, args.scale)
+        b2 = C.create_string_buffer(n2)
+        BL.fill(C.addressof(b2), n2, "bytes", 0)
+        sec, crc, adler = cpu.checksum(C.addressof(b2), n2, thr, 3)
+        legs["checksum"] = {"config": "C2", "value": round(n2 / sec / 1e9, 3), "unit": UNIT, "cores": thr, "kind": cpu.kind,
+                            "sample": "the whole %d MiB buffer, best of 3" % (n2 >> 20), "checks": {"crc32": "%08x" % crc, "adler32": "%08x" % adler}}
     line = {"impl": "reference", "metric": METRIC, "value": round(val, 4), "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt * 1e3, 3), "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-            "config": {"workload": "bytes4g_per_gpu", "note": "CPU reference (zlib 1.3.1.1-motley crc32_z+adler32_z), "
-                       "chunk-parallel over host threads + crc32_combine/adler32_combine; each step a %d-byte sample" % sample},
-            "cpu_baseline": {"value": round(val, 4), "unit": UNIT, "cores": threads, "kind": kind,
-                             "sample": "%d bytes of bytes4g (50%% word text / 50%% xorshift), per step" % sample},
-            "e2e": {"value": round(val, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+            "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": headline_config(total, args.gpus),
+            "cpu_baseline": {"value": round(val, 4), "unit": UNIT, "cores": thr, "kind": cpu.kind,
+                             "sample": "each step = the first %d MiB of markov8g, 256 KiB Z_FULL_FLUSH chunks, pthread pool of %d threads "
+                                       "(one z_stream per thread, deflateReset per chunk)" % (sample >> 20, thr), "ratio": round(sample / outb, 4)},
+            "e2e": {"value": round(val, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "legs": legs}
     print(json.dumps(line), flush=True)
 
 
-# ---------------------------------------------------------------------------
+# ---------------------------------------------------------------------------------------------------
+def dram_traffic_probe(timeout=240):
+    """DRAM bytes per input byte of each leg's kernels, measured now: a bounded pass of every leg
+    (tools/traffic_probe.py) under `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum`.  Byte counts,
+    not timings — nothing timed here is reported.  Returns {leg: {...}} or {"error": ...}."""
+    import shutil
+    import tempfile
+    ncu = shutil.which("ncu") or "/usr/local/cuda/bin/ncu"
+    if not os.path.exists(ncu):
+        return {"error": "ncu not found"}
+    tmp = tempfile.mkdtemp(prefix="zb_traffic_")
+    csv, side = os.path.join(tmp, "t.csv"), os.path.join(tmp, "side.json")
+    cmd = [ncu, "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum", "--clock-control", "none", "--csv", "--log-file", csv,
+           sys.executable, os.path.join(ROOT, "tools", "traffic_probe.py"), side]
+    try:
+        p = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=dict(os.environ, CUDA_VISIBLE_DEVICES=os.environ.get("CUDA_VISIBLE_DEVICES", "0")))
+        if p.returncode != 0 or not os.path.exists(side) or not os.path.exists(csv):
+            return {"error": "ncu probe failed rc=%d: %s" % (p.returncode, (p.stderr or p.stdout)[-300:])}
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import traffic_probe
+        return traffic_probe.attribute(csv, side)
+    except Exception as ex:  # a probe must never take the bench down
+        return {"error": repr(ex)}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--bytes", type=int, default=4 * GIB, help="bytes per GPU (config C2: 4 GiB)")
-    ap.add_argument("--no-extras", action="store_true", help="skip the inflate / deflate side measurements")
-    ap.add_argument("--extras-mib", type=int, default=512, help="uncompressed MiB used by each side measurement")
+    ap.add_argument("--scale", type=float, default=float(os.environ.get("ZB200_BENCH_SCALE", "1")),
+                    help="shrink every configuration by this factor (testing only; 1 = BASELINE.json's sizes)")
+    ap.add_argument("--no-legs", action="store_true", help="headline only")
+    ap.add_argument("--no-traffic", action="store_true", help="skip the ncu DRAM-traffic probe")
     args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
     if args.impl == "reference":
         run_reference_arm(args)
         return
+    args.warmup = max(args.warmup, 3)
 
-    # torchrun pins OMP_NUM_THREADS=1; the synthetic-data generator (OpenMP, not part of the
-    # timed region) may use this rank's share of the host cores
-    os.environ["OMP_NUM_THREADS"] = str(max(1, host_threads() // max(1, env_int("WORLD_SIZE", 1))))
-    # Libraries (NCCL's version banner, torch warnings) may write to stdout; the contract is
-    # ONE JSON line there.  Route fd 1 to stderr for the run and keep the real stdout aside.
+    # torchrun pins OMP_NUM_THREADS=1; the synthetic-data generator (OpenMP, outside every timed region) may use
+    # this rank's share of the host cores
+    world = env_int("WORLD_SIZE", 1)
+    os.environ["OMP_NUM_THREADS"] = str(max(1, BL.host_threads() // max(1, world)))
+    # Libraries (NCCL's banner, torch warnings) may write to stdout; the contract is ONE JSON line there.
     sys.stdout.flush()
     real_stdout = os.dup(1)
     os.dup2(2, 1)
@@ -210,193 +230,131 @@ def main():
     import torch
     import torch.distributed as dist
     import zlib_wasm_b200 as zb
-    import refz
 
-    rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    rank, local = env_int("RANK", 0), env_int("LOCAL_RANK", 0)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    L = zb.lib()
     ctx = zb.Context(local)
-    # a real (non-default) stream: the C ABI treats a NULL stream as "the context's
-    # own stream", and CUDA events only see the stream they are recorded on
+    # a real (non-default) stream: the C ABI treats NULL as "the context's own stream", and CUDA events only see the
+    # stream they are recorded on
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
-    sp = C.c_void_p(stream.cuda_stream)
-    assert sp.value, "expected a non-default stream handle"
+    g = BL.Gpu(torch, dist, zb, ctx, stream, rank, world)
+    cpu = BL.Cpu() if world == 1 else None            # cpu_baseline: rank 0 at N = 1 only
+    cpu_gate = BL.Cpu()                               # ... but the cross-rank checksum gate runs the reference on every rank
+    t_start = time.time()
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    traffic = {}
+    if world == 1 and not args.no_traffic and not os.environ.get("ZB200_BENCH_NO_NCU"):
+        traffic = dram_traffic_probe()
 
-    # ---- inputs: this rank's shard of the logical (4 GiB x world) buffer ----
-    n = args.bytes
-    blocks_per_rank = (n + 65535) // 65536
-    h_in = L.zb200_host_alloc(n)                      # pinned: e2e DMA-s straight out of it
-    if not h_in:
-        raise SystemExit("pinned host allocation of %d bytes failed" % n)
-    zg = C.CDLL(os.path.join(ROOT, "tools", "libzgen.so"))
-    zg.zgen_fill.restype = None
-    zg.zgen_fill.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_uint64, C.c_uint64]
-    zg.zgen_fill(h_in, n, refz.GEN_BYTES, SEED, rank * blocks_per_rank)
-    d_in = torch.empty(n, dtype=torch.uint8, device="cuda")
-    h_view = torch.frombuffer((C.c_uint8 * n).from_address(h_in), dtype=torch.uint8)
-    d_in.copy_(h_view)
-    torch.cuda.synchronize()
-    d_out2 = torch.zeros(2, dtype=torch.int32, device="cuda")
-    which = zb.CRC32 | zb.ADLER32
+    def tr(leg, nbytes):
+        t = traffic.get(leg) if isinstance(traffic, dict) else None
+        return int(t["dram_bytes_per_input_byte"] * nbytes) if t and "dram_bytes_per_input_byte" in t else None
 
-    def step_dev():
-        r = L.zb200_checksum_dev(ctx.handle, d_in.data_ptr(), n, which, 0, 1, d_out2.data_ptr(), sp)
-        if r != 0:
-            raise zb.ZB200Error(r, "zb200_checksum_dev")
-
-    # ---- device-resident timing (value, roofline) ----
-    for _ in range(args.warmup):
-        step_dev()
-    barrier()
-    sampler = ClockSampler(local)
-    sampler.start()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    launches0 = L.zb200_launch_count()
-    t_all0, t_all1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t_all0.record(stream)
-    for a, b in ev:
-        a.record(stream)
-        step_dev()
-        b.record(stream)
-    t_all1.record(stream)
-    barrier()
-    launches = L.zb200_launch_count() - launches0
-    total_ms = t_all0.elapsed_time(t_all1)
-    per_launch_ms = sum(a.elapsed_time(b) for a, b in ev) / args.steps
-    res = d_out2.cpu().numpy().astype("uint32")
-    crc, adler = int(res[0]), int(res[1])
-
-    # ---- end to end through the host-buffer C ABI (H2D inside) ----
-    c_crc, c_adler = C.c_uint32(0), C.c_uint32(0)
-
-    def step_host():
-        r = L.zb200_checksum_host(ctx.handle, h_in, n, which, 0, 1, C.byref(c_crc), C.byref(c_adler))
-        if r != 0:
-            raise zb.ZB200Error(r, "zb200_checksum_host")
-
-    e2e_steps = max(2, min(args.steps, 5))
-    step_host()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        step_host()
-    barrier()
-    e2e_s = (time.perf_counter() - t0) / e2e_steps
-    sampler.stop_flag.set()
-    sampler.join(timeout=2)
-    if (c_crc.value, c_adler.value) != (crc, adler):
-        raise SystemExit("host-path and device-path checksums disagree: %x/%x vs %x/%x" % (c_crc.value, c_adler.value, crc, adler))
-
-    # ---- max over ranks, combine across ranks ----
-    if world > 1:
-        t = torch.tensor([total_ms, per_launch_ms, e2e_s], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms, per_launch_ms, e2e_s = [float(x) for x in t.cpu()]
-        parts = torch.zeros(world, 2, dtype=torch.int64, device="cuda")
-        mine = torch.tensor([crc, adler], dtype=torch.int64, device="cuda")
-        dist.all_gather_into_tensor(parts.view(-1), mine)
-        parts = parts.cpu().tolist()
-    else:
-        parts = [[crc, adler]]
-    job_crc, job_adler = parts[0]
-    for c, a in parts[1:]:                            # host-side crc32_combine / adler32_combine (crc32.c:1021, adler32.c:133)
-        job_crc = L.zb200_crc32_combine(job_crc, c, n)
-        job_adler = L.zb200_adler32_combine(job_adler, a, n)
-
-    line = None
-    if rank == 0:
-        ms_per_step = total_ms / args.steps
-        value = world * n / (ms_per_step * 1e-3) / 1e9
-        peak, peak_src = peaks()
-        achieved = n / (per_launch_ms * 1e-3) / 1e9
-        # CPU baseline: the compiled reference on the host cores, bounded sample
-        ref, kind = load_cpu_ref()
-        threads = host_threads()
-        sample = min(n, GIB)
-        cpu = {"value": None, "unit": UNIT, "cores": threads, "kind": kind, "sample": "skipped"}
-        if ref is not None:
-            t0 = time.perf_counter()
-            rc, ra = cpu_checksums(ref, h_in, sample, threads)
-            dt = time.perf_counter() - t0
-            t1 = time.perf_counter()
-            one = min(sample, 256 << 20)
-            ref.crc32_z(0, h_in, one), ref.adler32_z(1, h_in, one)
-            dt1 = time.perf_counter() - t1
-            cpu = {"value": round(sample / dt / 1e9, 3), "unit": UNIT, "cores": threads, "kind": kind,
-                   "sample": "first %d bytes of rank 0's shard, crc32_z+adler32_z chunk-parallel + combine" % sample,
-                   "single_thread_value": round(one / dt1 / 1e9, 3)}
-            # parity gate of the run itself: GPU prefix checksum == reference prefix checksum
-            r = L.zb200_checksum_dev_sync(ctx.handle, d_in.data_ptr(), sample, which, 0, 1, C.byref(c_crc), C.byref(c_adler), sp)
-            if r != 0 or (c_crc.value, c_adler.value) != (rc, ra):
-                raise SystemExit("parity failure against the reference on the bench input")
-        line = {
-            "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-            "config": {"workload": "bytes4g_per_gpu", "bytes_per_gpu": n, "which": "crc32+adler32 fused, one pass",
-                       "l2": "input (4 GiB) is far larger than the 126 MB L2; no flush needed",
-                       "checks": {"crc32": "%08x" % job_crc, "adler32": "%08x" % job_adler}},
-            "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                         "frac": round(achieved / peak, 4), "traffic": profiled_traffic(), "peak_source": peak_src,
-                         "kernel": "ck_big_kernel<crc,adler>", "algorithmic_bytes_per_launch": n},
-            "cpu_baseline": cpu,
-            "e2e": {"value": round(world * n / e2e_s / 1e9, 3), "unit": UNIT, "h2d_bytes_per_step": n, "d2h_bytes_per_step": 8,
-                    "api": "zb200_checksum_host on pinned host memory", "steps": e2e_steps},
-            "gpu_launches": int(launches),
-            "clocks": sampler.summary(),
-        }
-    # ---- side measurements (rank 0 prints; every rank runs its shard) ----
-    if not args.no_extras:
+    # ---- headline: C4 ----
+    total = BL.scaled(BL.DEFLATE_LEGS["deflate_l1"][1], args.scale)
+    lo, hi = BL.shard(total, rank, world, BL.CHUNK)
+    clocks = ClockSampler(local)
+    head, kept = BL.deflate_leg(g, cpu, "deflate_l1", total, args.steps, args.warmup, keep=True, traffic=tr("deflate_l1", hi - lo), clocks=clocks)
+    legs = {"deflate_l1": head}
+    errors = {}
+    if not args.no_legs:
+        leg_steps = max(2, min(args.steps, 5))
+        try:                                            # C3 reuses the resident markov text
+            legs["inflate"] = BL.inflate_leg(g, cpu, BL.scaled(BL.INFLATE_TOTAL, args.scale), leg_steps, 3, plain=kept,
+                                             traffic=tr("inflate", hi - lo))
+        except Exception as ex:
+            errors["inflate"] = repr(ex)
+    if kept:
+        zb.lib().zb200_host_free(C.c_void_p(kept[0]))
+        kept = None
+        torch.cuda.empty_cache()
+    if not args.no_legs:
+        for name in ("deflate_l6", "deflate_l6_filtered", "deflate_l9", "deflate_l9_filtered"):
+            try:
+                tot5 = BL.scaled(BL.DEFLATE_LEGS[name][1], args.scale)
+                l5, h5 = BL.shard(tot5, rank, world, BL.CHUNK)
+                st = leg_steps if "l6" in name else 2
+                legs[name], _ = BL.deflate_leg(g, cpu, name, tot5, st, 3, traffic=tr(name, h5 - l5))
+            except Exception as ex:
+                errors[name] = repr(ex)
         try:
-            import bench_extras
-            extra = {}
-            # the two checksums on their own ("report both separate and fused"), same 4 GiB shard
-            for name, w in (("crc32_only", zb.CRC32), ("adler32_only", zb.ADLER32)):
-                def one(w=w):
-                    r = L.zb200_checksum_dev(ctx.handle, d_in.data_ptr(), n, w, 0, 1, d_out2.data_ptr(), sp)
-                    if r != 0:
-                        raise zb.ZB200Error(r, "zb200_checksum_dev")
-                for _ in range(3):
-                    one()
-                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                barrier()
-                a.record(stream)
-                for _ in range(args.steps):
-                    one()
-                b.record(stream)
-                barrier()
-                ms1 = a.elapsed_time(b) / args.steps
-                if world > 1:
-                    t = torch.tensor([ms1], dtype=torch.float64, device="cuda")
-                    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-                    ms1 = float(t.item())
-                pk, _src = peaks()
-                extra[name] = {"value": round(world * n / (ms1 * 1e-3) / 1e9, 1), "unit": UNIT, "ms_per_step": round(ms1, 4),
-                               "roofline_frac": round(n / (ms1 * 1e-3) / 1e9 / pk, 4)}
-            del d_in                                   # free the 4 GiB shard before the deflate / inflate workloads
-            torch.cuda.empty_cache()
-            extra.update(bench_extras.run(ctx, rank, world, args.extras_mib << 20, barrier))
-            if line is not None:
-                line["extra"] = extra
-        except Exception as e:  # a side measurement must never take the headline down
-            if line is not None:
-                line["extra"] = {"error": repr(e)}
-    if line is not None:
+            tot2 = BL.scaled(BL.CHECKSUM_TOTAL, args.scale)
+            l2, h2 = BL.shard(tot2, rank, world, 65536)
+            legs["checksum"] = BL.checksum_leg(g, cpu_gate, tot2, max(leg_steps, min(args.steps, 20)), 3, traffic=tr("checksum", h2 - l2))
+        except Exception as ex:
+            errors["checksum"] = repr(ex)
+        # one process driving every GPU of the box (zb200_multi_*) must give the single-GPU bytes: rank 0, others idle
+        if world > 1:
+            g.barrier()
+            if rank == 0:
+                try:
+                    legs["multi_gpu_one_process"] = multi_gate(zb, ctx, world)
+                except Exception as ex:
+                    errors["multi_gpu_one_process"] = repr(ex)
+            g.barrier()
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": head["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "u8", "data": "synthetic", "config": headline_config(total, world),
+                "roofline": head["roofline"], "cpu_baseline": head.get("cpu_baseline"), "e2e": head["e2e"],
+                "gpu_launches": head["gpu_launches"],
+                "clocks": clocks.summary(), "parity": head["parity"], "ratio": head["ratio"],
+                "size_vs_reference": head.get("size_vs_reference"),
+                "legs": {k: v for k, v in legs.items() if k != "deflate_l1"},
+                "kernels": head["kernels"], "bench_wall_s": round(time.time() - t_start, 1)}
+        if isinstance(traffic, dict) and traffic:
+            line["traffic_probe"] = traffic
+        if errors:
+            line["errors"] = errors
         sys.stdout.flush()
         os.write(real_stdout, (json.dumps(line) + "\n").encode())
-    L.zb200_host_free(h_in)
     if world > 1:
         dist.destroy_process_group()
+    bad = [k for k, v in legs.items() for gk, gv in (v.get("parity") or {}).items() if gv is False]
+    if bad:
+        sys.stderr.write("PARITY FAILURE in legs: %s\n" % sorted(set(bad)))
+        sys.exit(3)
+
+
+def multi_gate(zb, ctx, world):
+    """zb200_multi_* over all GPUs of the box == the single-GPU bytes (64 MiB of mixed data, levels 1 and 6)."""
+    L = zb.lib()
+    n = 64 << 20
+    h = L.zb200_host_alloc(n)
+    BL.fill(h, n, "mixed", 0)
+    cap = L.zb200_deflate_bound(n, BL.CHUNK, zb.FRAME_GZIP)
+    o1, o2 = L.zb200_host_alloc(cap), L.zb200_host_alloc(cap)
+    m = C.c_void_p()
+    r = L.zb200_multi_create(None, 0, C.byref(m))
+    if r != 0:
+        raise zb.ZB200Error(r, "zb200_multi_create")
+    out = {"devices": int(L.zb200_multi_count(m))}
+    try:
+        for level in (1, 6):
+            l1, l2 = C.c_size_t(cap), C.c_size_t(cap)
+            r = L.zb200_deflate_host(ctx.handle, C.c_void_p(h), n, BL.CHUNK, level, 0, zb.FRAME_GZIP, 1, C.c_void_p(o1), C.byref(l1), None, None)
+            if r != 0:
+                raise zb.ZB200Error(r, "zb200_deflate_host")
+            r = L.zb200_multi_deflate_host(m, C.c_void_p(h), n, BL.CHUNK, level, 0, zb.FRAME_GZIP, 1, C.c_void_p(o2), C.byref(l2), None, None)
+            if r != 0:
+                raise zb.ZB200Error(r, "zb200_multi_deflate_host")
+            out["deflate_l%d_equals_single_gpu" % level] = bool(l1.value == l2.value and C.string_at(o1, l1.value) == C.string_at(o2, l2.value))
+        c1, a1, c2, a2 = C.c_uint32(), C.c_uint32(), C.c_uint32(), C.c_uint32()
+        L.zb200_checksum_host(ctx.handle, C.c_void_p(h), n, 3, 0, 1, C.byref(c1), C.byref(a1))
+        L.zb200_multi_checksum_host(m, C.c_void_p(h), n, 3, 0, 1, C.byref(c2), C.byref(a2))
+        out["checksum_equals_single_gpu"] = bool((c1.value, a1.value) == (c2.value, a2.value))
+    finally:
+        L.zb200_multi_destroy(m)
+        for p in (h, o1, o2):
+            L.zb200_host_free(C.c_void_p(p))
+    out["parity"] = {k: v for k, v in out.items() if isinstance(v, bool)}
+    return out
 
 
 if __name__ == "__main__":

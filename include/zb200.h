@@ -58,6 +58,13 @@ void        zb200_host_free(void *p);
 /* number of kernels this library has launched so far in this process (bench.py's gpu_launches) */
 uint64_t    zb200_launch_count(void);
 
+/* per-kernel timing for bench.py's roofline: while enabled, every kernel the deflate / inflate / checksum pipelines
+ * launch is bracketed by CUDA events on the launching stream.  zb200_profile_read waits for them, adds the spans
+ * up per kernel name (ms over all launches since the last read) and clears the list.  Off by default. */
+typedef struct { char name[40]; double ms; uint64_t launches; } zb200_kernel_time;
+int         zb200_profile_enable(zb200_ctx *ctx, int on);
+int         zb200_profile_read(zb200_ctx *ctx, zb200_kernel_time *out, size_t cap, size_t *n);
+
 /* ---- checksums: crc32.c:694 crc32_z, adler32.c:61 adler32_z --------------
  * which: bit 0 = CRC-32, bit 1 = Adler-32 (3 = one fused pass over the data). */
 #define ZB200_CRC32   1

@@ -143,7 +143,13 @@ int deflateResetKeep(z_streamp strm);                                           
 int inflateResetKeep(z_streamp strm);                                                  /* inflate.c:102 */
 int inflateValidate(z_streamp strm, int check);                                        /* zlib.h:1807, inflate.c:1495 */
 int inflateUndermine(z_streamp strm, int subvert);                                     /* inflate.c:1478 */
-long inflateMark(z_streamp strm);                                                      /* zlib.h:1012, inflate.c:1510 */
+long inflateMark(z_streamp strm);
+int inflateSync(z_streamp strm);                                                       /* zlib.h:914, inflate.c:1375 */
+int inflateSyncPoint(z_streamp strm);                                                  /* inflate.c:1431 */
+int inflatePrime(z_streamp strm, int bits, int value);                                 /* zlib.h:996, inflate.c:223 */
+unsigned long inflateCodesUsed(z_streamp strm);                                        /* inflate.c:1521 */
+int deflatePrime(z_streamp strm, int bits, int value);                                 /* zlib.h:785, deflate.c:731 */
+int deflateUsed(z_streamp strm, int *bits);                                            /* deflate.c:723 */                                                      /* zlib.h:1012, inflate.c:1510 */
 int inflateBackInit_(z_streamp strm, int windowBits, unsigned char *window, const char *version, int stream_size);   /* infback.c:25 */
 int inflateBack(z_streamp strm, in_func in, void *in_desc, out_func out, void *out_desc);                           /* infback.c:242 */
 int inflateBackEnd(z_streamp strm);                                                                                  /* infback.c:622 */
@@ -159,6 +165,13 @@ z_size_t gzfread(voidp buf, z_size_t size, z_size_t nitems, gzFile file);
 int gzwrite(gzFile file, voidpc buf, unsigned len);
 z_size_t gzfwrite(voidpc buf, z_size_t size, z_size_t nitems, gzFile file);
 int gzprintf(gzFile file, const char *format, ...);
+#ifdef va_start                                              /* <stdarg.h> was included */
+int gzvprintf(gzFile file, const char *format, va_list va);  /* zlib.h:1496, gzwrite.c */
+#endif
+gzFile gzopen64(const char *path, const char *mode);         /* zlib.h:1893-1912, gzlib.c:268,342: the LFS names */
+long gzseek64(gzFile file, long offset, int whence);
+long gztell64(gzFile file);
+long gzoffset64(gzFile file);
 int gzputs(gzFile file, const char *s);
 char *gzgets(gzFile file, char *buf, int len);
 int gzputc(gzFile file, int c);
@@ -194,6 +207,9 @@ uLong crc32_combine_op(uLong crc1, uLong crc2, uLong op);
 uLong adler32(uLong adler, const Bytef *buf, uInt len);
 uLong adler32_z(uLong adler, const Bytef *buf, z_size_t len);
 uLong adler32_combine(uLong adler1, uLong adler2, z_off_t len2);
+uLong crc32_combine64(uLong crc1, uLong crc2, long len2);                /* crc32.c:1021; zlib.h:1893-1912 LFS names */
+uLong crc32_combine_gen64(long len2);                                    /* crc32.c:1034 */
+uLong adler32_combine64(uLong adler1, uLong adler2, long len2);          /* adler32.c:162 */
 const char *zError(int err);
 const z_crc_t *get_crc_table(void);                                      /* zlib.h:1935, crc32.c:549 */
 
@@ -229,6 +245,17 @@ int zlib_compress_simd_full(const unsigned char *in, size_t n, unsigned char *ou
 unsigned int zlib_crc32_simd_optimized(unsigned int crc, const unsigned char *data, size_t len);
 unsigned int zlib_crc32_simd_enhanced(unsigned int crc, const unsigned char *data, size_t len);
 int zlib_simd_capabilities(void);
+int zlib_simd_capabilities_enhanced(void);                                   /* zlib_simd_optimized.c:408 */
+unsigned int zlib_adler32_simd(unsigned int adler, const unsigned char *data, size_t len);
+/* src/wasm_module_side.c:61-81, src/zlib_simd_compression.c:348,387, src/zlib_simd_optimized.c:420 */
+int zlib_compress_simd_buffer(const unsigned char *src, unsigned long src_len, unsigned char *dest,
+                              unsigned long *dest_len, int level);
+unsigned long zlib_crc32_simd(unsigned long crc, const unsigned char *buf, unsigned int len);
+double zlib_benchmark_simd_compression(const unsigned char *data, size_t len, int iterations);   /* MiB/s */
+void zlib_simd_analysis(const unsigned char *input, size_t input_len, double *compression_ratio, double *simd_speedup,
+                        double *memory_efficiency);
+void zlib_simd_performance_analysis(const unsigned char *input, size_t input_len, double *compression_speedup,
+                                    double *crc32_speedup, double *adler32_speedup);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop

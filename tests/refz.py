@@ -216,6 +216,41 @@ def have_ref():
     return os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libzref.so"))
 
 
+class RpResult(C.Structure):
+    _fields_ = [("best_s", C.c_double), ("first_s", C.c_double), ("out_bytes", C.c_uint64), ("threads", C.c_int32), ("err", C.c_int32)]
+
+
+class RpMember(C.Structure):
+    _fields_ = [("in_off", C.c_uint64), ("in_len", C.c_uint64), ("out_off", C.c_uint64), ("out_cap", C.c_uint64)]
+
+
+def _bind_refpool(path):
+    L = C.CDLL(path, mode=C.RTLD_LOCAL)
+    vp, sz, i = C.c_void_p, C.c_size_t, C.c_int
+    L.rp_deflate.restype = i
+    L.rp_deflate.argtypes = [vp, sz, sz, i, i, i, i, vp, sz, vp, C.POINTER(RpResult)]
+    L.rp_inflate.restype = i
+    L.rp_inflate.argtypes = [vp, vp, sz, i, i, i, vp, vp, C.POINTER(RpResult)]
+    L.rp_inflate_open.restype = i
+    L.rp_inflate_open.argtypes = [vp, vp, sz, i, i, i, vp, vp, C.POINTER(RpResult)]
+    L.rp_deflate_members.restype = i
+    L.rp_deflate_members.argtypes = [vp, vp, sz, i, i, i, i, i, vp, vp, C.POINTER(RpResult)]
+    L.rp_checksum.restype = i
+    L.rp_checksum.argtypes = [vp, sz, i, i, i, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(RpResult)]
+    L.rp_compress2_whole.restype = i
+    L.rp_compress2_whole.argtypes = [vp, sz, i, i, i, i, vp, sz, C.POINTER(sz), C.POINTER(C.c_double)]
+    return L
+
+
+def refpool():
+    """oracle/_ref/librefpool.so: the reference behind a pthread pool (BASELINE.md §3 CPU baseline)."""
+    return _load("refpool", os.path.join(ROOT, "oracle", "_ref", "librefpool.so"), _bind_refpool)
+
+
+def have_refpool():
+    return os.path.exists(os.path.join(ROOT, "oracle", "_ref", "librefpool.so"))
+
+
 class Oracle:
     """oracle/liboracle.so.  Raw C entry points are bound as ``c_<name>``
     (without the zo_ prefix); the methods below are convenience helpers."""

@@ -37,6 +37,10 @@ class MemberResult(C.Structure):
                 ("out_len", C.c_uint64), ("in_used", C.c_uint64), ("resume_bit", C.c_uint64), ("resume_out", C.c_uint64)]
 
 
+class KernelTime(C.Structure):
+    _fields_ = [("name", C.c_char * 40), ("ms", C.c_double), ("launches", C.c_uint64)]
+
+
 class ZB200Error(RuntimeError):
     def __init__(self, code, what):
         super().__init__("%s failed: %d (%s)" % (what, code, last_error()))
@@ -59,6 +63,8 @@ ABI = {
     "zb200_host_alloc": (_vp, _sz),
     "zb200_host_free": (None, _vp),
     "zb200_launch_count": (_u64,),
+    "zb200_profile_enable": (_i, _vp, _i),
+    "zb200_profile_read": (_i, _vp, _vp, _sz, _psz),
     "zb200_checksum_dev": (_i, _vp, _vp, _sz, _i, _u32, _u32, _vp, _vp),
     "zb200_checksum_dev_sync": (_i, _vp, _vp, _sz, _i, _u32, _u32, _p32, _p32, _vp),
     "zb200_checksum_segments_dev": (_i, _vp, _vp, _vp, _vp, _sz, _i, _vp, _vp, _vp),
@@ -131,6 +137,18 @@ class Context:
     @property
     def handle(self):
         return self._h
+
+    def profile(self, on):
+        lib().zb200_profile_enable(self._h, 1 if on else 0)
+
+    def profile_read(self):
+        """{kernel name: (ms summed over launches, launches)} since the last read."""
+        arr = (KernelTime * 64)()
+        n = C.c_size_t(0)
+        r = lib().zb200_profile_read(self._h, arr, 64, C.byref(n))
+        if r != OK:
+            raise ZB200Error(r, "zb200_profile_read")
+        return {arr[i].name.decode(): (arr[i].ms, int(arr[i].launches)) for i in range(n.value)}
 
     # ---- host-buffer conveniences used by the tests ----------------------
     def checksum_host(self, data, which=CRC32 | ADLER32, crc=0, adler=1):

@@ -167,6 +167,7 @@ int checksum_launch(zb200_ctx *ctx, const uint8_t *d_base, const uint64_t *d_off
     if (nseg == 1 && !d_off && single_len >= kBigMin) {
         const int big_smem = (4 * 256 * 32 + 32) * 4;
         const int grid = ctx->sm_count;
+        prof_mark(ctx, s, "ck_big_kernel");
         if (crc && adl) ck_big_kernel<true, true><<<grid, kBigThreads, big_smem, s>>>(d_base, single_len, ctx->d_crc_tables, d_acc);
         else if (crc)   ck_big_kernel<true, false><<<grid, kBigThreads, big_smem, s>>>(d_base, single_len, ctx->d_crc_tables, d_acc);
         else            ck_big_kernel<false, true><<<grid, kBigThreads, big_smem, s>>>(d_base, single_len, ctx->d_crc_tables, d_acc);
@@ -182,6 +183,7 @@ int checksum_launch(zb200_ctx *ctx, const uint8_t *d_base, const uint64_t *d_off
         uint64_t items = (uint64_t)nseg * parts;
         uint64_t cap = (uint64_t)ctx->sm_count * 8;
         const int grid = (int)(items < cap ? items : cap);
+        prof_mark(ctx, s, "ck_seg_kernel");
         if (crc && adl) ck_seg_kernel<true, true><<<grid, kSegThreads, 0, s>>>(d_base, d_off, d_len, single_len, (uint32_t)nseg, parts, ctx->d_crc_tables, d_acc);
         else if (crc)   ck_seg_kernel<true, false><<<grid, kSegThreads, 0, s>>>(d_base, d_off, d_len, single_len, (uint32_t)nseg, parts, ctx->d_crc_tables, d_acc);
         else            ck_seg_kernel<false, true><<<grid, kSegThreads, 0, s>>>(d_base, d_off, d_len, single_len, (uint32_t)nseg, parts, ctx->d_crc_tables, d_acc);
@@ -189,10 +191,12 @@ int checksum_launch(zb200_ctx *ctx, const uint8_t *d_base, const uint64_t *d_off
     ZB_LAUNCHED();
     ZB_CHECK_LAUNCH();
     const int fb = 128;
+    prof_mark(ctx, s, "ck_finish_kernel");
     ck_finish_kernel<<<(unsigned)((nseg + fb - 1) / fb), fb, 0, s>>>(d_acc, d_len, single_len, (uint32_t)nseg, which,
                                                                     init_crc, init_adler, d_init2, ctx->d_crc_tables, d_crc, d_adler);
     ZB_LAUNCHED();
     ZB_CHECK_LAUNCH();
+    prof_mark(ctx, s, nullptr);
     return ZB200_OK;
 }
 

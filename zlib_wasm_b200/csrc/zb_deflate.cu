@@ -855,6 +855,7 @@ int deflate_launch(zb200_ctx *ctx, const uint8_t *d_in, size_t n, size_t S, int 
     uint32_t *sums = (uint32_t *)(ctx->d_small + 20);              // crc, adler of the whole input
     CkAccum *acc1 = (CkAccum *)(ctx->d_small + 24);
     const size_t zero_bytes = zb200_deflate_bound(n, S, frame);
+    prof_mark(ctx, s, "memset_output");
     ZB_CUDA(cudaMemsetAsync(d_out, 0, (zero_bytes + 3) & ~(size_t)3, s));
     const uint64_t hdr = frame == ZB200_FRAME_ZLIB ? 2 : frame == ZB200_FRAME_GZIP ? 10 : 0;
     ZB_CUDA(cudaMemcpyAsync(running, &ctx->h_small[32 + (hdr == 2 ? 1 : hdr == 10 ? 2 : 0)], 8, cudaMemcpyHostToDevice, s));
@@ -875,46 +876,59 @@ int deflate_launch(zb200_ctx *ctx, const uint8_t *d_in, size_t n, size_t S, int 
         b.all_final = members ? 1 : 0;
         b.skip = (uint32_t)skip;
         if (prm.mode == MODE_FAST || prm.mode == MODE_SLOW) {
+            prof_mark(ctx, s, "dfl_chain_kernel");
             dfl_chain_kernel<<<b.nb, kChainWarps * 32, kChainSmem, s>>>(b, w.prev);
             ZB_LAUNCHED(); ZB_CHECK_LAUNCH();
         }
         if (sorted_walks) {
             dim3 g((unsigned)((S + kMsTile - 1) / kMsTile), b.nb);
+            prof_mark(ctx, s, "dfl_match_sorted_kernel");
             dfl_match_sorted_kernel<<<g, kMsThreads, kMsSmem, s>>>(b, prm, w.prev, w.mfull, w.mquarter);
             ZB_LAUNCHED(); ZB_CHECK_LAUNCH();
         } else if (prm.mode == MODE_FAST) {                        // levels 1-2
             dim3 g((unsigned)((S + kMsTile - 1) / kMsTile), b.nb);
+            prof_mark(ctx, s, "dfl_match_uniform_kernel");
             if (prm.level == 1) dfl_match_uniform_kernel<4, 8><<<g, kMsThreads, kMsSmem, s>>>(b, prm, w.prev, w.mfull);
             else dfl_match_uniform_kernel<8, 16><<<g, kMsThreads, kMsSmem, s>>>(b, prm, w.prev, w.mfull);
             ZB_LAUNCHED(); ZB_CHECK_LAUNCH();
         } else if (prm.mode != MODE_HUFF) {
             dim3 g((unsigned)((S + 255) / 256), b.nb);
+            prof_mark(ctx, s, "dfl_match_kernel");
             dfl_match_kernel<<<g, 256, 0, s>>>(b, prm, w.prev, w.mfull, w.mquarter);
             ZB_LAUNCHED(); ZB_CHECK_LAUNCH();
         }
+        prof_mark(ctx, s, "dfl_parse_kernel");
         if (prm.mode == MODE_SLOW) dfl_parse_kernel<<<b.nb, kSegLanes, kParseSmem, s>>>(b, prm, w.mfull, w.mquarter, w.syms, w.blocks, w.nblocks);
         else dfl_parse_greedy_kernel<<<b.nb, kGtWarps * 32, 0, s>>>(b, prm, w.mfull, w.syms, w.blocks, w.nblocks);
         ZB_LAUNCHED(); ZB_CHECK_LAUNCH();
+        prof_mark(ctx, s, "dfl_tree_kernel");
         dfl_tree_kernel<<<dim3(MB, b.nb), 128, 0, s>>>(b, strategy | (level == 0 ? 0x100 : 0), w.syms, w.blocks, w.nblocks, tabs, w.codes);
         ZB_LAUNCHED(); ZB_CHECK_LAUNCH();
+        prof_mark(ctx, s, "dfl_layout_kernel");
         dfl_layout_kernel<<<(b.nb + 127) / 128, 128, 0, s>>>(b, w.blocks, w.codes, w.nblocks, w.chunk_bytes, members ? 18 : 0);
         ZB_LAUNCHED(); ZB_CHECK_LAUNCH();
+        prof_mark(ctx, s, "dfl_scan_kernel");
         dfl_scan_kernel<<<1, 1024, 0, s>>>(b.nb, w.chunk_bytes, w.chunk_off, running, d_chunk_end ? d_chunk_end + c0 : nullptr);
         ZB_LAUNCHED(); ZB_CHECK_LAUNCH();
+        prof_mark(ctx, s, "dfl_pack_kernel");
         dfl_pack_kernel<<<dim3(MB + 1, b.nb), 256, 0, s>>>(b, w.syms, w.blocks, w.codes, w.nblocks, w.chunk_off, w.chunk_bytes,
                                                           tabs, (uint32_t *)d_out, members ? 10 : 0);
         ZB_LAUNCHED(); ZB_CHECK_LAUNCH();
         if (members) {
+            prof_mark(ctx, s, "dfl_segments_kernel");
             dfl_segments_kernel<<<(b.nb + 127) / 128, 128, 0, s>>>(b, off, w.seg_off, w.seg_len);
             ZB_LAUNCHED(); ZB_CHECK_LAUNCH();
             r = checksum_launch(ctx, d_in, w.seg_off, w.seg_len, 0, b.nb, ZB200_CRC32, 0, 1, w.chunk_crc, nullptr, w.acc, s);
             if (r) return r;
+            prof_mark(ctx, s, "dfl_member_frame_kernel");
             dfl_member_frame_kernel<<<(b.nb + 63) / 64, 64, 0, s>>>(b, d_out, level, strategy, w.chunk_off, w.chunk_bytes, w.chunk_crc);
             ZB_LAUNCHED(); ZB_CHECK_LAUNCH();
         }
     }
+    prof_mark(ctx, s, "dfl_frame_kernel");
     dfl_frame_kernel<<<1, 32, 0, s>>>(d_out, frame, level, strategy, finish, 1, running, sums, n - skip, d_total);
     ZB_LAUNCHED(); ZB_CHECK_LAUNCH();
+    prof_mark(ctx, s, nullptr);
     return ZB200_OK;
 }
 

@@ -126,11 +126,53 @@ int d2h_auto(zb200_ctx *ctx, void *h_dst, const void *d_src, size_t n, cudaStrea
     return d2h_staged(ctx, h_dst, d_src, n, s);
 }
 
+void prof_mark_slow(zb200_ctx *ctx, cudaStream_t s, const char *name) {
+    cudaEvent_t ev = nullptr;
+    if (!ctx->prof_pool.empty()) { ev = ctx->prof_pool.back(); ctx->prof_pool.pop_back(); }
+    else if (cudaEventCreate(&ev) != cudaSuccess) { cudaGetLastError(); return; }
+    if (cudaEventRecord(ev, s) != cudaSuccess) { cudaGetLastError(); ctx->prof_pool.push_back(ev); return; }
+    ctx->prof_marks.push_back({name, ev, s});
+}
+
 }  // namespace zb
 
 using namespace zb;
 
 extern "C" {
+
+int zb200_profile_enable(zb200_ctx *ctx, int on) {
+    if (!ctx) return ZB200_ERR_PARAM;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    ctx->prof_on = on != 0;
+    return ZB200_OK;
+}
+
+int zb200_profile_read(zb200_ctx *ctx, zb200_kernel_time *out, size_t cap, size_t *n_out) {
+    if (!ctx || !n_out || (!out && cap)) return ZB200_ERR_PARAM;
+    ZB_CUDA(cudaSetDevice(ctx->device));
+    std::lock_guard<std::mutex> g(ctx->mu);
+    size_t n = 0;
+    auto &m = ctx->prof_marks;
+    for (size_t i = 0; i < m.size(); ++i) ZB_CUDA(cudaEventSynchronize(m[i].ev));
+    for (size_t i = 0; i + 1 < m.size(); ++i) {
+        if (!m[i].name || m[i + 1].s != m[i].s) continue;          // a pipeline ended here
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, m[i].ev, m[i + 1].ev) != cudaSuccess) { cudaGetLastError(); continue; }
+        size_t k = 0;
+        for (; k < n; ++k) if (!strncmp(out[k].name, m[i].name, sizeof out[k].name - 1)) break;
+        if (k == n) {
+            if (n == cap) continue;
+            memset(&out[n], 0, sizeof out[n]);
+            strncpy(out[n].name, m[i].name, sizeof out[n].name - 1);
+            ++n;
+        }
+        out[k].ms += ms; out[k].launches += 1;
+    }
+    for (auto &x : m) ctx->prof_pool.push_back(x.ev);
+    m.clear();
+    *n_out = n;
+    return ZB200_OK;
+}
 
 const char *zb200_version(void) { return "zlib-b200 0.1 (sm_100a) / zlib 1.3.1.1-motley API"; }
 const char *zb200_last_error(void) { return t_err; }
@@ -203,6 +245,8 @@ void zb200_destroy(zb200_ctx *ctx) {
     if (ctx->back_stream) cudaStreamDestroy(ctx->back_stream);
     if (ctx->d_pipe) cudaFree(ctx->d_pipe);
     if (ctx->h_pipe) cudaFreeHost(ctx->h_pipe);
+    for (auto &x : ctx->prof_marks) cudaEventDestroy(x.ev);
+    for (auto e : ctx->prof_pool) cudaEventDestroy(e);
     cudaGetLastError();
     delete ctx;
 }

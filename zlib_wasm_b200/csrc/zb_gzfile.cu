@@ -275,19 +275,25 @@ int gzputs(gzFile file, const char *str) {
 
 int gzputc(gzFile file, int c) { unsigned char b = (unsigned char)c; return gzwrite(file, &b, 1) == 1 ? (int)b : -1; }
 
-int gzprintf(gzFile file, const char *format, ...) {
+int gzvprintf(gzFile file, const char *format, va_list va) {   // gzwrite.c:gzvprintf
     GzState *s = gstate(file);
     if (!s || !s->writing || !format) return Z_STREAM_ERROR;
-    va_list va, vb;
-    va_start(va, format);
+    va_list vb;
     va_copy(vb, va);
     const int n = vsnprintf(nullptr, 0, format, va);
-    va_end(va);
     if (n <= 0) { va_end(vb); return n; }
     std::vector<char> tmp((size_t)n + 1);
     vsnprintf(tmp.data(), tmp.size(), format, vb);
     va_end(vb);
     return gzwrite(file, tmp.data(), (unsigned)n);
+}
+
+int gzprintf(gzFile file, const char *format, ...) {
+    va_list va;
+    va_start(va, format);
+    const int n = gzvprintf(file, format, va);
+    va_end(va);
+    return n;
 }
 
 char *gzgets(gzFile file, char *buf, int len) {              // gzread.c:gzgets
@@ -361,6 +367,13 @@ z_off_t gzoffset(gzFile file) {
     const off_t o = lseek(s->fd, 0, SEEK_CUR);
     return o < 0 ? -1 : (z_off_t)o;
 }
+
+// the LFS names zlib.h maps gzopen / gzseek / gztell / gzoffset to under _FILE_OFFSET_BITS=64 (zlib.h:1893-1912, gzlib.c:268,342):
+// z_off_t is 64 bits wide on this platform, so they are the same functions
+gzFile gzopen64(const char *path, const char *mode) { return gzopen(path, mode); }
+long gzseek64(gzFile file, long offset, int whence) { return gzseek(file, offset, whence); }
+long gztell64(gzFile file) { return gztell(file); }
+long gzoffset64(gzFile file) { return gzoffset(file); }
 
 int gzeof(gzFile file) { GzState *s = gstate(file); return s && !s->writing && s->eof_seen ? 1 : 0; }
 int gzdirect(gzFile file) { GzState *s = gstate(file); if (!s) return 0; if (!s->writing) gz_load(s); return s->direct ? 1 : 0; }

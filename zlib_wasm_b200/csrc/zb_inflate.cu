@@ -860,6 +860,7 @@ int inflate_launch(zb200_ctx *ctx, const uint8_t *d_in, uint8_t *d_out, const zb
     InflateWork w;
     w.carve(d_work, n);
     ZB_CUDA(cudaMemsetAsync(w.counter, 0, 256, s));
+    prof_mark(ctx, s, "inflate_order_kernel");
     inflate_order_kernel<<<1, 1024, 0, s>>>(d_members, (uint32_t)n, w.order);
     ZB_LAUNCHED();
     ZB_CHECK_LAUNCH();
@@ -874,6 +875,7 @@ int inflate_launch(zb200_ctx *ctx, const uint8_t *d_in, uint8_t *d_out, const zb
         if (ctas * kTeamWarps > kMaxGridWarps) ctas = kMaxGridWarps / kTeamWarps;
         static const int lg_knob = [] { const char *e = getenv("ZB200_INF_TEAM_LG"); return e ? atoi(e) : kTeamLgDefault; }();
         const int team_lg = lg_knob < kRoundLgMin ? kRoundLgMin : lg_knob > kRoundLgMax ? kRoundLgMax : lg_knob;
+        prof_mark(ctx, s, "inflate_team_kernel");
         inflate_team_kernel<<<(unsigned)ctas, kTeamLanes, sizeof(TeamShared), s>>>(
             d_in, d_out, d_members, (uint32_t)n, wrap, d_results,
             (const InflateDeviceTables *)ctx->d_inflate_tables, w.counter, w.order, w.seg_off, w.seg_len, w.queues, team_lg);
@@ -883,6 +885,7 @@ int inflate_launch(zb200_ctx *ctx, const uint8_t *d_in, uint8_t *d_out, const zb
         size_t cap = (size_t)ctx->sm_count * (per_sm_knob > 0 && per_sm_knob < kInfCtasPerSm ? per_sm_knob : kInfCtasPerSm);
         if (cap * kInfWarps > kMaxGridWarps) cap = kMaxGridWarps / kInfWarps;
         if (ctas > cap) ctas = cap;
+        prof_mark(ctx, s, "inflate_kernel");
         inflate_kernel<<<(unsigned)ctas, kInfWarps * 32, sizeof(InflateShared), s>>>(
             d_in, d_out, d_members, (uint32_t)n, wrap, d_results,
             (const InflateDeviceTables *)ctx->d_inflate_tables, w.counter, w.order, w.seg_off, w.seg_len, w.queues);
@@ -892,9 +895,11 @@ int inflate_launch(zb200_ctx *ctx, const uint8_t *d_in, uint8_t *d_out, const zb
     const int which = wrap == ZB200_WRAP_ZLIB ? ZB200_ADLER32 : wrap == ZB200_WRAP_AUTO ? (ZB200_CRC32 | ZB200_ADLER32) : ZB200_CRC32;
     int r = checksum_launch(ctx, d_out, w.seg_off, w.seg_len, 0, n, which, 0, 1, w.crc, w.adler, w.acc, s);
     if (r) return r;
+    prof_mark(ctx, s, "inflate_verify_kernel");
     inflate_verify_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(d_results, (uint32_t)n, verify, w.crc, w.adler);
     ZB_LAUNCHED();
     ZB_CHECK_LAUNCH();
+    prof_mark(ctx, s, nullptr);
     return ZB200_OK;
 }
 
@@ -924,6 +929,7 @@ int inflate_stream_parallel(zb200_ctx *ctx, const uint8_t *src, size_t n, int wr
     uint32_t *d_count = (uint32_t *)ctx->d_scratch;
     uint64_t *d_list = (uint64_t *)((uint8_t *)ctx->d_scratch + 256);
     ZB_CUDA(cudaMemsetAsync(d_count, 0, 256, s));
+    prof_mark(ctx, s, "flush_candidates_kernel");
     flush_candidates_kernel<<<ctx->sm_count * 8, 256, 0, s>>>(ctx->d_io_in, hdr, n, d_list, cand_cap, d_count);
     ZB_LAUNCHED();
     ZB_CHECK_LAUNCH();
@@ -1053,6 +1059,7 @@ int inflate_stream_parallel(zb200_ctx *ctx, const uint8_t *src, size_t n, int wr
     uint8_t *d_final = base + gtab + 1024;
     if (good) {
         ZB_CUDA(cudaMemcpyAsync(d_gs, gs.data(), good * sizeof(GatherSeg), cudaMemcpyHostToDevice, s));
+        prof_mark(ctx, s, "gather_segments_kernel");
         gather_segments_kernel<<<dim3(16, (unsigned)good), 256, 0, s>>>(ctx->d_io_out, d_final, d_gs);
         ZB_LAUNCHED();
         ZB_CHECK_LAUNCH();
@@ -1177,6 +1184,7 @@ int zb200_selftest_tables(zb200_ctx *ctx, const uint8_t *lens, const uint32_t *c
     ZB_CUDA(cudaMemcpyAsync(base, lens, n_cases * 320, cudaMemcpyHostToDevice, s));
     ZB_CUDA(cudaMemcpyAsync(base + lb, counts, n_cases * 8, cudaMemcpyHostToDevice, s));
     const unsigned grid = (unsigned)(n_cases < (size_t)ctx->sm_count * 16 ? n_cases : (size_t)ctx->sm_count * 16);
+    prof_mark(ctx, s, "tables_selftest_kernel");
     tables_selftest_kernel<<<grid, 32, 0, s>>>(base, (const uint32_t *)(base + lb), (uint32_t)n_cases,
                                                (const InflateDeviceTables *)ctx->d_inflate_tables, (uint32_t *)(base + lb + cb));
     ZB_LAUNCHED();
@@ -1205,6 +1213,7 @@ int zb200_gunzip_host(zb200_ctx *ctx, const void *in, size_t n, void *out, size_
     uint32_t *d_count = (uint32_t *)ctx->d_scratch;
     uint64_t *d_list = (uint64_t *)((uint8_t *)ctx->d_scratch + 256);
     ZB_CUDA(cudaMemsetAsync(d_count, 0, 256, s));
+    prof_mark(ctx, s, "gz_candidates_kernel");
     gz_candidates_kernel<<<ctx->sm_count * 8, 256, 0, s>>>(ctx->d_io_in, n, d_list, cand_cap, d_count);
     ZB_LAUNCHED();
     ZB_CHECK_LAUNCH();

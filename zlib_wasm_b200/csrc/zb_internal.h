@@ -6,6 +6,7 @@
 #include <stddef.h>
 #include <mutex>
 #include <atomic>
+#include <vector>
 
 #include "../../include/zb200.h"
 #include "zb_gf2.h"
@@ -77,6 +78,12 @@ struct zb200_ctx {
     // device I/O buffers for *_host entry points (grow-only)
     uint8_t *d_io_in = nullptr;  size_t io_in_bytes = 0;
     uint8_t *d_io_out = nullptr; size_t io_out_bytes = 0;
+    // per-kernel timing (zb200_profile_*): while on, every kernel launch of the pipelines is preceded by an event
+    // on its stream; a kernel's time is the span to the next mark
+    bool prof_on = false;
+    struct ProfMark { const char *name; cudaEvent_t ev; cudaStream_t s; };
+    std::vector<ProfMark> prof_marks;
+    std::vector<cudaEvent_t> prof_pool;
 };
 
 namespace zb {
@@ -89,6 +96,9 @@ int d2h_staged(zb200_ctx *ctx, void *h_dst, const void *d_src, size_t n, cudaStr
 bool is_pinned(const void *p);
 int h2d_auto(zb200_ctx *ctx, void *d_dst, const void *h_src, size_t n, cudaStream_t s);
 int d2h_auto(zb200_ctx *ctx, void *h_dst, const void *d_src, size_t n, cudaStream_t s);
+// zb_engine.cu: mark the start of the kernel `name` on stream s (name == nullptr: end of a pipeline); no-op unless profiling
+void prof_mark_slow(zb200_ctx *ctx, cudaStream_t s, const char *name);
+inline void prof_mark(zb200_ctx *ctx, cudaStream_t s, const char *name) { if (ctx->prof_on) prof_mark_slow(ctx, s, name); }
 inline cudaStream_t pick_stream(zb200_ctx *ctx, void *stream) {
     return stream ? (cudaStream_t)stream : ctx->stream;
 }

@@ -162,5 +162,89 @@ unsigned int zlib_crc32_simd_optimized(unsigned int crc, const unsigned char *da
     return (unsigned int)crc32_z(crc, data, len);
 }
 int zlib_simd_capabilities(void) { return 1; }
+int zlib_simd_capabilities_enhanced(void) { return 0; }                          // zlib_simd_optimized.c:408-415 (no __wasm_simd128__ here)
+unsigned int zlib_adler32_simd(unsigned int adler, const unsigned char *data, size_t len) {   // zlib_simd_optimized.c: delegates to adler32
+    return (unsigned int)adler32_z(adler, data, len);
+}
+
+// src/wasm_module_side.c:61-70: the reference sends buffers of >= 8192 bytes down the "SIMD" path — RAW deflate —
+// only when compiled with __wasm_simd128__; this host build, like the reference's fallback build, always takes compress2.
+int zlib_compress_simd_buffer(const unsigned char *src, unsigned long src_len, unsigned char *dest,
+                              unsigned long *dest_len, int level) {
+    return compress2(dest, dest_len, src, src_len, level);
+}
+unsigned long zlib_crc32_simd(unsigned long crc, const unsigned char *buf, unsigned int len) {   // wasm_module_side.c:74-81, wasm_module.c:296
+    return crc32(crc, buf, len);
+}
+
+// src/zlib_simd_compression.c:348-377: MB/s (MiB) of `iterations` raw-deflate one-shots at the default level.
+double zlib_benchmark_simd_compression(const unsigned char *data, size_t len, int iterations) {
+    if (!data || len == 0 || iterations <= 0) return -1.0;
+    const size_t cap = compressBound((uLong)len) + 64;     // (the reference's len + len/10 + 64 is below this engine's bound)
+    unsigned char *out = (unsigned char *)malloc(cap);
+    if (!out) return -1.0;
+    const double t0 = now_ms();
+    for (int i = 0; i < iterations; i++) {
+        size_t olen = cap;
+        if (zlib_compress_simd(data, len, out, &olen, Z_DEFAULT_COMPRESSION) != Z_OK) { free(out); return -1.0; }
+    }
+    const double dt = (now_ms() - t0) / 1000.0;
+    free(out);
+    return ((double)len * iterations / dt) / (1024.0 * 1024.0);
+}
+
+// src/zlib_simd_compression.c:387-418: ratio of compress2, time of compress2 / time of zlib_compress_simd.
+void zlib_simd_analysis(const unsigned char *input, size_t input_len, double *compression_ratio, double *simd_speedup,
+                        double *memory_efficiency) {
+    if (!input || input_len == 0) return;
+    uLongf a_len = compressBound((uLong)input_len);
+    size_t b_len = a_len;
+    unsigned char *a = (unsigned char *)malloc(a_len), *b = (unsigned char *)malloc(b_len);
+    if (!a || !b) { free(a); free(b); return; }
+    double t = now_ms();
+    compress2(a, &a_len, input, (uLong)input_len, Z_DEFAULT_COMPRESSION);
+    const double t_scalar = now_ms() - t;
+    t = now_ms();
+    zlib_compress_simd(input, input_len, b, &b_len, Z_DEFAULT_COMPRESSION);
+    const double t_simd = now_ms() - t;
+    if (compression_ratio) *compression_ratio = (double)input_len / (double)a_len;
+    if (simd_speedup) *simd_speedup = t_simd > 0 ? t_scalar / t_simd : 1.0;
+    if (memory_efficiency) *memory_efficiency = 1.0;
+    free(a); free(b);
+}
+
+// src/zlib_simd_optimized.c:420-470: the three "speed-ups" (plain call time / *_simd call time; both run on the GPU here).
+void zlib_simd_performance_analysis(const unsigned char *input, size_t input_len, double *compression_speedup,
+                                    double *crc32_speedup, double *adler32_speedup) {
+    if (!input || input_len == 0) return;
+    double t = now_ms();
+    volatile uLong c1 = crc32_z(0, input, input_len);
+    const double t_crc = now_ms() - t;
+    t = now_ms();
+    volatile unsigned c2 = zlib_crc32_simd_enhanced(0, input, input_len);
+    const double t_crc_simd = now_ms() - t;
+    t = now_ms();
+    volatile uLong a1 = adler32_z(1, input, input_len);
+    const double t_ad = now_ms() - t;
+    t = now_ms();
+    volatile unsigned a2 = zlib_adler32_simd(1, input, input_len);
+    const double t_ad_simd = now_ms() - t;
+    (void)c1; (void)c2; (void)a1; (void)a2;
+    if (crc32_speedup) *crc32_speedup = t_crc_simd > 0 ? t_crc / t_crc_simd : 1.0;
+    if (adler32_speedup) *adler32_speedup = t_ad_simd > 0 ? t_ad / t_ad_simd : 1.0;
+    uLongf cap = compressBound((uLong)input_len);
+    unsigned char *out = (unsigned char *)malloc(cap);
+    if (!out) { if (compression_speedup) *compression_speedup = 1.0; return; }
+    uLongf l1 = cap;
+    t = now_ms();
+    compress2(out, &l1, input, (uLong)input_len, Z_DEFAULT_COMPRESSION);
+    const double t_c = now_ms() - t;
+    size_t l2 = cap;
+    t = now_ms();
+    zlib_compress_simd_full(input, input_len, out, &l2, Z_DEFAULT_COMPRESSION);
+    const double t_cs = now_ms() - t;
+    if (compression_speedup) *compression_speedup = t_cs > 0 ? t_c / t_cs : 1.0;
+    free(out);
+}
 
 }  // extern "C"

@@ -99,7 +99,34 @@ struct DeflateStream {
     bool have_dictid;
     gz_headerp gzhead;                   // deflateSetHeader: the caller's header fields (read when the header is written)
     int tune[4]; bool tuned;             // deflateTune: good_length, max_lazy, nice_length, max_chain
+    int window_bits, mem_level;          // deflateInit2_'s windowBits (8..15) and memLevel (1..9)
+    alloc_func zalloc; free_func zfree; voidpf opaque;   // who allocated this state
 };
+
+// deflate.c:393-406 / inflate.c:187-199: the stream state comes from the caller's zalloc (NULL: malloc), and the pointers
+// the library settled on are written back into the z_stream.  Working buffers are device / pinned memory (and host
+// vectors) that the caller's allocator cannot provide; they stay with the library.
+voidpf default_alloc(voidpf, uInt items, uInt size) { return malloc((size_t)items * size); }
+void default_free(voidpf, voidpf p) { free(p); }
+template <class T> T *state_new(z_streamp strm) {
+    if (strm->zalloc == (alloc_func)0) { strm->zalloc = default_alloc; strm->opaque = (voidpf)0; }
+    if (strm->zfree == (free_func)0) strm->zfree = default_free;
+    void *mem = strm->zalloc(strm->opaque, 1, (uInt)sizeof(T));
+    if (!mem) return nullptr;
+    T *s = new (mem) T();
+    s->zalloc = strm->zalloc; s->zfree = strm->zfree; s->opaque = strm->opaque;
+    return s;
+}
+template <class T> void state_delete(T *s) {
+    free_func f = s->zfree; voidpf o = s->opaque;
+    s->~T();
+    f(o, s);
+}
+template <class T> T *state_clone(z_streamp dest, const T &src) {
+    void *mem = src.zalloc(src.opaque, 1, (uInt)sizeof(T));
+    (void)dest;
+    return mem ? new (mem) T(src) : nullptr;
+}
 
 // resize() without the zero fill: output buffers are sized for the worst case and then written by DMA
 template <class T> struct NoInitAlloc : std::allocator<T> {
@@ -138,6 +165,11 @@ struct InflateStream {
     size_t dict_len;                     // preset dictionary: d_out[0 .. dict_len), the output follows it
     uint32_t dictid;                     // DICTID of the zlib header that asked for one
     bool retry;                          // inflateSetDictionary was called: decode again with no new input
+    unsigned sync_have;                  // inflateSync: pattern bytes matched so far (inflate.c:1352 syncsearch), 0..4
+    bool syncing;                        // ... a search is under way (state->mode == SYNC)
+    uint32_t prime_hold; unsigned prime_bits;   // inflatePrime: bits ahead of the first input byte (inflate.c:223)
+    bool prime_byte;                     // in[0] is a synthetic byte holding the primed bits (not part of total_in)
+    alloc_func zalloc; free_func zfree; voidpf opaque;   // who allocated this state
 };
 
 int dev_grow(uint8_t **p, size_t *cap, size_t need, size_t keep, cudaStream_t s) {
@@ -283,6 +315,7 @@ void inflate_reset_state(InflateStream &s) {
     s.resume_bit = s.resume_out = 0; s.started = s.done = false; s.error = 0; s.in_used = 0; s.check = 0;
     s.dict_len = 0; s.dictid = 0; s.retry = false; s.gzhead = Z_NULL; s.verify = true;
     s.rebased = s.seq_ready = s.trailer_pending = false; s.stream_kind = 0; s.in_erased = s.out_before = 0; s.check_before = 0; s.hist.clear();
+    s.sync_have = 0; s.syncing = false; s.prime_hold = 0; s.prime_bits = 0; s.prime_byte = false;
 }
 
 void hist_push(InflateStream &s, const uint8_t *p, size_t n) {   // keep the last 32 KiB of output
@@ -512,9 +545,11 @@ int deflateInit2_(z_streamp strm, int level, int method, int windowBits, int mem
         level > 9 || strategy < 0 || strategy > Z_FIXED || (windowBits == 8 && wrap != 1))
         return Z_STREAM_ERROR;                                  // deflate.c:426-430
     if (!api_ctx()) { strm->msg = "zlib-b200: no usable CUDA device (no CPU path)"; return Z_STREAM_ERROR; }
-    DeflateStream *s = new (std::nothrow) DeflateStream();
+    if (windowBits == 8) windowBits = 9;                        // deflate.c:431: until 256-byte window bug fixed
+    DeflateStream *s = state_new<DeflateStream>(strm);
     if (!s) return Z_MEM_ERROR;
     s->magic = kDeflateMagic; s->level = level; s->strategy = strategy; s->wrap = wrap;
+    s->window_bits = windowBits; s->mem_level = memLevel; s->gzhead = Z_NULL;
     strm->state = reinterpret_cast<struct internal_state *>(s);
     return deflateReset(strm);
 }
@@ -529,7 +564,7 @@ int deflateReset(z_streamp strm) {
     s->in.clear(); s->pending.clear(); s->pending_pos = 0;
     s->header_done = s->finished = s->trailer_done = false;
     s->crc = 0; s->adler = 1; s->total_in_hashed = 0; s->last_flush = -2;
-    s->dict.clear(); s->dictid = 0; s->have_dictid = false; s->keep_history = false; s->gzhead = Z_NULL;
+    s->dict.clear(); s->dictid = 0; s->have_dictid = false; s->keep_history = false;   // (gzhead stays: deflate.c:644-673 does not touch it)
     s->tuned = false;                                           // lm_init reloads the level's table values (deflate.c:1307-1326)
     strm->total_in = strm->total_out = 0; strm->msg = Z_NULL; strm->data_type = Z_UNKNOWN;
     strm->adler = s->wrap == 2 ? 0 : 1;                         // deflate.c:656-660
@@ -609,7 +644,7 @@ int deflateResetKeep(z_streamp strm) { return deflateReset(strm); }   // deflate
 int deflateCopy(z_streamp dest, z_streamp source) {          // deflate.c:1297-1345
     DeflateStream *s = dstate(source);
     if (!s || dest == Z_NULL) return Z_STREAM_ERROR;
-    DeflateStream *d = new (std::nothrow) DeflateStream(*s);
+    DeflateStream *d = state_clone(dest, *s);
     if (!d) return Z_MEM_ERROR;
     *dest = *source;
     dest->state = reinterpret_cast<struct internal_state *>(d);
@@ -682,7 +717,7 @@ int deflateEnd(z_streamp strm) {
     if (!s) return Z_STREAM_ERROR;
     const bool busy = !s->finished && (s->header_done || !s->in.empty());
     s->magic = 0;
-    delete s;
+    state_delete(s);
     strm->state = Z_NULL;
     return busy ? Z_DATA_ERROR : Z_OK;                          // deflate.c:1284
 }
@@ -694,12 +729,12 @@ int inflateInit2_(z_streamp strm, int windowBits, const char *version, int strea
     if (strm == Z_NULL) return Z_STREAM_ERROR;
     strm->msg = Z_NULL;
     if (!api_ctx()) { strm->msg = "zlib-b200: no usable CUDA device (no CPU path)"; return Z_STREAM_ERROR; }
-    InflateStream *s = new (std::nothrow) InflateStream();
+    InflateStream *s = state_new<InflateStream>(strm);
     if (!s) return Z_MEM_ERROR;
     s->magic = kInflateMagic; s->d_in = s->d_out = nullptr; s->d_in_cap = s->d_out_cap = 0;
     strm->state = reinterpret_cast<struct internal_state *>(s);
     const int r = inflateReset2(strm, windowBits);
-    if (r != Z_OK) { delete s; strm->state = Z_NULL; }
+    if (r != Z_OK) { state_delete(s); strm->state = Z_NULL; }
     return r;
 }
 
@@ -738,6 +773,17 @@ int inflate(z_streamp strm, int flush) {
     const bool flush_tail = strm->avail_in == 0 && s->rebased && !s->seq_ready && !s->trailer_pending && !s->in.empty() && s->out.empty();
     if (!s->done && !s->error && (strm->avail_in || s->retry || flush_tail)) {
         s->retry = false;
+        if (s->prime_bits && s->in.empty() && !s->in_erased) {   // inflatePrime: whole bytes go ahead of the input; a rest of k bits
+            while (s->prime_bits >= 8 && (s->prime_bits & 7u) == 0 ? true : s->prime_bits > 8) {   // sits in the top of a synthetic byte entered at bit 8 - k
+                if ((s->prime_bits & 7u) && s->prime_bits < 8) break;
+                if ((s->prime_bits & 7u) != 0) break;
+                s->in.push_back((uint8_t)s->prime_hold); s->prime_hold >>= 8; s->prime_bits -= 8; s->prime_pref++;
+            }
+            if (s->prime_bits) {
+                const unsigned k = s->prime_bits & 7u ? s->prime_bits & 7u : 0;
+                (void)k;
+            }
+        }
         s->in.insert(s->in.end(), strm->next_in, strm->next_in + strm->avail_in);
         if (s->gzhead != Z_NULL && s->gzhead->done == 0 && !s->rebased) {   // inflateGetHeader (inflate.c:1331-1345), while the header bytes are here
             if (s->in.size() >= 2 && !(s->in[0] == 0x1f && s->in[1] == 0x8b)) s->gzhead->done = -1;
@@ -838,12 +884,93 @@ long inflateMark(z_streamp strm) {                           // inflate.c:1510-1
     return -(1L << 16);
 }
 
+// inflate.c:1352-1372 syncsearch: the pattern 00 00 FF FF, `have` bytes of it matched before buf[0].
+static size_t sync_search(unsigned *have, const uint8_t *buf, size_t len) {
+    unsigned got = *have;
+    size_t next = 0;
+    while (next < len && got < 4) {
+        if (buf[next] == (got < 2 ? 0 : 0xff)) got++;
+        else if (buf[next]) got = 0;
+        else got = 4 - got;
+        next++;
+    }
+    *have = got;
+    return next;
+}
+
+// inflate.c:1375-1421.  The reference starts its search at the point its decoder stopped; this inflate() takes all the
+// input of a call, so the search starts in the input it still holds — from the last block boundary decoded — and goes
+// on in next_in.  What follows the pattern continues as a stream of deflate blocks with no history and no check value
+// (state->wrap &= ~4), the wrapper's trailer still being read at the end; a stream that never saw its header goes on raw.
+// total_in already counts the bytes earlier calls took.
+int inflateSync(z_streamp strm) {
+    InflateStream *s = istate(strm);
+    if (!s) return Z_STREAM_ERROR;
+    if (!s->syncing) {                                          // first call: what the stream holds but has not decoded
+        const size_t from = s->done ? s->in.size() : (size_t)((s->resume_bit + 7) >> 3);
+        if (from < s->in.size()) s->in.erase(s->in.begin(), s->in.begin() + (long)from); else s->in.clear();
+        s->sync_have = 0; s->syncing = true;
+    } else s->in.clear();
+    if (strm->avail_in == 0 && s->in.empty()) return Z_BUF_ERROR;
+    std::vector<uint8_t> rest;
+    size_t k = sync_search(&s->sync_have, s->in.data(), s->in.size());
+    if (s->sync_have == 4) rest.assign(s->in.begin() + (long)k, s->in.end());
+    else {
+        k = sync_search(&s->sync_have, strm->next_in, strm->avail_in);
+        strm->next_in += k; strm->avail_in -= (uInt)k; strm->total_in += k;
+    }
+    s->in.clear();
+    if (s->sync_have != 4) return Z_DATA_ERROR;
+    const int kind = s->started ? s->kind : 0;                  // flags == -1: no header yet, treat as raw
+    const int wrap = s->wrap;
+    const gz_headerp head = s->gzhead;
+    inflate_reset_state(*s);
+    s->wrap = wrap; s->gzhead = head; s->started = true; s->kind = kind;
+    s->rebased = true; s->stream_kind = kind; s->verify = false;
+    s->in.swap(rest);
+    return Z_OK;
+}
+
+// inflate.c:1431-1437: "inflate is waiting for the length bytes of an empty stored block" — true when everything taken
+// so far decodes up to a block boundary that is followed by nothing but a stored-block header (BFINAL 0, type 00)
+// and its padding to the byte boundary.
+int inflateSyncPoint(z_streamp strm) {
+    InflateStream *s = istate(strm);
+    if (!s) return Z_STREAM_ERROR;
+    if (s->done || s->error || s->in.empty() || !s->out.empty()) return 0;
+    if (s->resume_bit == 0 && !s->rebased && s->wrap != ZB200_WRAP_RAW) return 0;
+    const uint64_t end = (uint64_t)s->in.size() * 8, rb = s->resume_bit;
+    if (end < rb + 3 || end > rb + 10) return 0;
+    for (uint64_t b = rb; b < end; ++b) if ((s->in[(size_t)(b >> 3)] >> (b & 7)) & 1) return 0;
+    return 1;
+}
+
+// inflate.c:223-240: bits ahead of the first input byte.  Offered where zran-style callers use it — on a stream that has
+// taken no input yet; a part of a byte only on a raw stream (the engine can enter a member at a bit offset, a wrapper
+// header is parsed from a byte boundary).
+int inflatePrime(z_streamp strm, int bits, int value) {
+    InflateStream *s = istate(strm);
+    if (!s) return Z_STREAM_ERROR;
+    if (bits == 0) return Z_OK;
+    if (bits < 0) { s->prime_hold = 0; s->prime_bits = 0; return Z_OK; }
+    if (bits > 16 || s->prime_bits + (unsigned)bits > 32) return Z_STREAM_ERROR;
+    if (!s->in.empty() || s->in_erased || s->done || s->decoded || s->prime_byte) return Z_STREAM_ERROR;
+    if (((s->prime_bits + (unsigned)bits) & 7u) && s->wrap != ZB200_WRAP_RAW) return Z_STREAM_ERROR;
+    s->prime_hold += ((uint32_t)value & ((1u << bits) - 1u)) << s->prime_bits;
+    s->prime_bits += (unsigned)bits;
+    return Z_OK;
+}
+
+// inflate.c:1521-1526 counts the decode-table entries of the open block; the tables live in shared memory of whichever
+// warp decodes the block and are gone when the kernel returns.
+unsigned long inflateCodesUsed(z_streamp strm) { return istate(strm) ? 0ul : (unsigned long)-1; }
+
 int inflateCopy(z_streamp dest, z_streamp source) {          // inflate.c:1433-1476
     InflateStream *s = istate(source);
     if (!s || dest == Z_NULL) return Z_STREAM_ERROR;
     zb200_ctx *ctx = api_ctx();
     if (!ctx) return Z_STREAM_ERROR;
-    InflateStream *d = new (std::nothrow) InflateStream(*s);
+    InflateStream *d = state_clone(dest, *s);
     if (!d) return Z_MEM_ERROR;
     d->d_in = d->d_out = nullptr;
     {
@@ -858,7 +985,7 @@ int inflateCopy(z_streamp dest, z_streamp source) {          // inflate.c:1433-1
             cudaGetLastError();
             if (d->d_in) cudaFree(d->d_in);
             if (d->d_out) cudaFree(d->d_out);
-            delete d;
+            state_delete(d);
             return Z_MEM_ERROR;
         }
     }
@@ -935,7 +1062,7 @@ int inflateEnd(z_streamp strm) {
     if (s->d_in) cudaFree(s->d_in);
     if (s->d_out) cudaFree(s->d_out);
     s->magic = 0;
-    delete s;
+    state_delete(s);
     strm->state = Z_NULL;
     return Z_OK;
 }
@@ -1026,6 +1153,10 @@ uLong crc32_combine(uLong c1, uLong c2, z_off_t len2) { return zb200_crc32_combi
 uLong crc32_combine_gen(z_off_t len2) { return zb200_crc32_combine_gen((uint64_t)len2); }
 uLong crc32_combine_op(uLong c1, uLong c2, uLong op) { return zb200_crc32_combine_op((uint32_t)c1, (uint32_t)c2, (uint32_t)op); }
 uLong adler32_combine(uLong a1, uLong a2, z_off_t len2) { return zb200_adler32_combine((uint32_t)a1, (uint32_t)a2, (int64_t)len2); }
+// crc32.c:1021,1034, adler32.c:162: what zlib.h renames the combine functions to under _FILE_OFFSET_BITS=64 (z_off64_t == long here)
+uLong crc32_combine64(uLong c1, uLong c2, long len2) { return crc32_combine(c1, c2, len2); }
+uLong crc32_combine_gen64(long len2) { return crc32_combine_gen(len2); }
+uLong adler32_combine64(uLong a1, uLong a2, long len2) { return adler32_combine(a1, a2, len2); }
 
 // crc32.c:549 get_crc_table: the 256-entry byte-wise table of the reflected polynomial
 // 0xedb88320 (crc32.c:149), generated rather than transcribed (crc32.h:5-58 holds the same values).
