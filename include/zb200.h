@@ -16,6 +16,10 @@
  *   - "_dev" entry points take DEVICE pointers and are asynchronous on
  *     `stream` unless they return a value through a host pointer, in which
  *     case they synchronise that stream before returning.
+ *     A context owns ONE set of device working buffers (scratch, accumulators).  Calls on one context are
+ *     serialised: on the host by the context's mutex while they enqueue, on the device by an event — a call
+ *     on another stream than the previous one first waits (cudaStreamWaitEvent) for that one to finish.
+ *     Callers that want two jobs to overlap on the device use two contexts.
  *   - "_host" entry points take HOST pointers, stage through the context's
  *     pinned buffers with cudaMemcpyAsync, and are synchronous.
  *   - unit of parallel work: a CHUNK (deflate: one Z_FULL_FLUSH-bounded block
@@ -115,6 +119,23 @@ int zb200_deflate_dev(zb200_ctx *ctx, const void *d_in, size_t n, size_t chunk_s
 int zb200_deflate_host(zb200_ctx *ctx, const void *in, size_t n, size_t chunk_size,
                        int level, int strategy, int frame, int finish,
                        void *out, size_t *out_len, uint32_t *in_adler, uint32_t *in_crc);
+
+/* Every option of deflateInit2_ / deflateSetDictionary / deflatePrime for one call (deflate.c:371-512,550-632,731-757).
+ *   window_bits 9..15 (0 = 15): w_size = 1 << window_bits, MAX_DIST = w_size - 262, CINFO of the zlib header
+ *   mem_level   1..9  (0 = 8):  hash_bits = mem_level + 7, lit_bufsize = 1 << (mem_level + 6) => blocks of lit_bufsize - 1 symbols
+ *   dict_len    the first dict_len (<= 32768) bytes of `in` are history only (raw frame); the FIRST chunk is compressed
+ *               behind them, later chunks start afresh as always
+ *   first_bit   0..7: the stream starts at this bit of out[0] (deflatePrime put that many bits there; the caller ORs
+ *               them in afterwards); raw frame only
+ * Levels 4-9, Z_RLE and Z_HUFFMAN_ONLY emit the reference's bytes for the same settings and chunking.
+ * bits_used (optional): bits in use in the last byte written (deflate.c:723 deflateUsed).  Host pointers; synchronous. */
+typedef struct {
+    int32_t level, strategy, window_bits, mem_level;
+    uint32_t dict_len, first_bit;
+} zb200_deflate_opts;
+int zb200_deflate_host_opts(zb200_ctx *ctx, const void *in, size_t n, size_t chunk_size, const zb200_deflate_opts *opts,
+                            int frame, int finish, void *out, size_t *out_len, uint32_t *in_adler, uint32_t *in_crc,
+                            uint32_t *bits_used);
 
 /* ---- inflate: inflate.c:590 inflate(), one warp per member ---------------- */
 #define ZB200_WRAP_RAW   0

@@ -22,6 +22,7 @@
 #ifndef ZB200_ZLIB_H
 #define ZB200_ZLIB_H
 #include <stddef.h>
+#include <stdarg.h>
 
 #ifdef __cplusplus
 extern "C" {
@@ -165,9 +166,7 @@ z_size_t gzfread(voidp buf, z_size_t size, z_size_t nitems, gzFile file);
 int gzwrite(gzFile file, voidpc buf, unsigned len);
 z_size_t gzfwrite(voidpc buf, z_size_t size, z_size_t nitems, gzFile file);
 int gzprintf(gzFile file, const char *format, ...);
-#ifdef va_start                                              /* <stdarg.h> was included */
 int gzvprintf(gzFile file, const char *format, va_list va);  /* zlib.h:1496, gzwrite.c */
-#endif
 gzFile gzopen64(const char *path, const char *mode);         /* zlib.h:1893-1912, gzlib.c:268,342: the LFS names */
 long gzseek64(gzFile file, long offset, int whence);
 long gztell64(gzFile file);

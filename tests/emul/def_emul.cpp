@@ -24,16 +24,17 @@ struct BitSink {
 
 // One chunk -> raw deflate bytes (blocks + marker when !final).  Returns size or -1.
 // `skip`: the first skip bytes are a preset dictionary (history only).
-extern "C" long emul_deflate_chunk_dict(const uint8_t *data, uint32_t n, uint32_t skip, int level, int strategy, int final_chunk,
-                                        uint8_t *out, size_t cap, uint32_t *stats /* nsyms, nblocks */) {
+// window_bits / mem_level: deflateInit2_'s (deflate.c:440-455).
+extern "C" long emul_deflate_chunk_opts(const uint8_t *data, uint32_t n, uint32_t skip, int level, int strategy, int window_bits,
+                                        int mem_level, int final_chunk, uint8_t *out, size_t cap, uint32_t *stats /* nsyms, nblocks */) {
     if (!g_ready) { format_fill(g_fmt); static_trees_fill(g_st); g_ready = 1; }
-    const DeflateParams prm = deflate_params(level, strategy);
+    const DeflateParams prm = deflate_params(level, strategy, window_bits, mem_level);
     std::vector<uint16_t> prev(n + 1, 0);
     std::vector<uint32_t> mf(n + 1, 0), mq(n + 1, 0);
     if (prm.mode == MODE_FAST || prm.mode == MODE_SLOW) {
-        std::vector<int32_t> head(1u << kHashBits, -1);
+        std::vector<int32_t> head(1u << prm.hash_bits, -1);
         for (uint32_t p = 0; p + kMinMatch <= n; ++p) {
-            const uint32_t h = hash3(data + p);
+            const uint32_t h = hash3(data + p, prm);
             const int32_t q = head[h];
             prev[p] = (q > 0 && p - (uint32_t)q <= 65535u) ? (uint16_t)(p - (uint32_t)q) : 0;
             head[h] = (int32_t)p;
@@ -42,7 +43,7 @@ extern "C" long emul_deflate_chunk_dict(const uint8_t *data, uint32_t n, uint32_
             MatchPair r = match_at(data, n, prev.data(), p, prm); mf[p] = r.full; mq[p] = r.quarter;
             if (prm.mode == MODE_FAST && prm.level <= 2 && p + kUniformTail <= n) {   // the kernel's branch-free walk must agree
                 const PlainWin pw{data, prev.data()};
-                const uint32_t u = prm.level == 1 ? match_uniform<4, 8>(pw, p) : match_uniform<8, 16>(pw, p);
+                const uint32_t u = prm.level == 1 ? match_uniform<4, 8>(pw, p, prm.max_dist) : match_uniform<8, 16>(pw, p, prm.max_dist);
                 if (u != r.full) return -10;
             }
         }
@@ -50,7 +51,7 @@ extern "C" long emul_deflate_chunk_dict(const uint8_t *data, uint32_t n, uint32_
         for (uint32_t p = 0; p < n; ++p) mf[p] = rle_at(data, n, p);
     }
     std::vector<uint32_t> syms(n + 2);
-    std::vector<BlockInfo> blocks(max_blocks_for(n));
+    std::vector<BlockInfo> blocks(max_blocks_for(n, prm.sym_limit));
     struct { uint32_t nsyms, nblocks; } sink;
     // the kernel's segmented parse (zb_deflate.cuh seg_*), the lanes replayed by loops;
     // the serial whole-chunk parse must give the same symbols and blocks
@@ -122,7 +123,7 @@ extern "C" long emul_deflate_chunk_dict(const uint8_t *data, uint32_t n, uint32_
     }
     {   // cross-check against the serial whole-chunk parse
         std::vector<uint32_t> syms2(n + 2);
-        std::vector<BlockInfo> blocks2(max_blocks_for(n));
+        std::vector<BlockInfo> blocks2(max_blocks_for(n, prm.sym_limit));
         uint32_t ns2 = 0, nb2 = 0;
         parse_chunk(data, n, mf.data(), mq.data(), prm, final_chunk != 0, syms2.data(), blocks2.data(), ns2, nb2, skip);
         if (ns2 != sink.nsyms || nb2 != sink.nblocks) return -22;
@@ -174,6 +175,10 @@ extern "C" long emul_deflate_chunk_dict(const uint8_t *data, uint32_t n, uint32_
     return bytes > cap ? -1 : (long)bytes;
 }
 
+extern "C" long emul_deflate_chunk_dict(const uint8_t *data, uint32_t n, uint32_t skip, int level, int strategy, int final_chunk,
+                                        uint8_t *out, size_t cap, uint32_t *stats) {
+    return emul_deflate_chunk_opts(data, n, skip, level, strategy, 15, 8, final_chunk, out, cap, stats);
+}
 extern "C" long emul_deflate_chunk(const uint8_t *data, uint32_t n, int level, int strategy, int final_chunk,
                                    uint8_t *out, size_t cap, uint32_t *stats /* nsyms, nblocks */) {
     return emul_deflate_chunk_dict(data, n, 0, level, strategy, final_chunk, out, cap, stats);

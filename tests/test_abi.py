@@ -93,3 +93,14 @@ def test_z_stream_layout_matches_reference():
     if zb.lib().zb200_device_count() == 0:        # no GPU: init must fail loudly, never fall back
         assert z.deflateInit2_(C.byref(s), 6, 8, 15, 8, 0, z.version, C.sizeof(refz.ZStream)) == refz.Z_STREAM_ERROR
         assert b"no CPU path" in s.msg
+
+
+def test_only_the_c_surfaces_are_exported():
+    """The library is linked with a version script (csrc/libzb200.map, the counterpart of the reference's zlib.map):
+    nothing but zb200_*, zlib_* and the zlib.h / gz* names leaves it — no C++ runtime symbols."""
+    import subprocess
+    out = subprocess.run(["nm", "-D", "--defined-only", zb.LIB_PATH], capture_output=True, text=True).stdout
+    names = [ln.split()[-1] for ln in out.splitlines() if ln.strip()]
+    assert len(names) > 100
+    stray = [n for n in names if n.startswith("_Z") or n.startswith("__") or "std" in n]
+    assert not stray, stray[:5]

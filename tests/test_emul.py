@@ -330,3 +330,44 @@ def test_truncated_input_rounds_replay():
                                                C.byref(cb), C.byref(co), C.byref(kd))
                     outs.append((st, dst.raw[:ol.value]))
                 assert outs[0] == outs[1] and outs[0][0] == 19 and want.startswith(outs[0][1]), (len(s), k, lanes)
+
+
+def test_deflate_window_bits_and_mem_level_byte_exact():
+    """deflateInit2_'s windowBits (w_size, MAX_DIST, slide period: deflate.c:440-443, deflate.h:298) and memLevel
+    (hash_bits, lit_bufsize => symbols per block: deflate.c:444-455,512) — the phases, run with those values, emit the
+    reference's bytes (levels 4-9, Z_RLE, Z_HUFFMAN_ONLY); levels 1-3 decode and stay within 3 %."""
+    if not refz.have_ref():
+        pytest.skip("oracle/_ref/libzref.so not built")
+    L = _build("def_emul")
+    L.emul_deflate_chunk_opts.restype = C.c_long
+    L.emul_deflate_chunk_opts.argtypes = [C.c_char_p, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                          C.c_size_t, C.POINTER(C.c_uint32)]
+    ref = refz.ref()
+
+    def ref_stream(d, level, strat, wbits, mem):
+        strm = refz.ZStream()
+        assert ref.deflateInit2_(C.byref(strm), level, 8, -wbits, mem, strat, ref.version, C.sizeof(refz.ZStream)) == 0
+        cap = len(d) + len(d) // 4 + 4096
+        src, dst = C.create_string_buffer(d, max(len(d), 1)), C.create_string_buffer(cap)
+        strm.next_in, strm.avail_in = C.addressof(src), len(d)
+        strm.next_out, strm.avail_out = C.addressof(dst), cap
+        assert ref.deflate(C.byref(strm), refz.Z_FINISH) == refz.Z_STREAM_END
+        out = dst.raw[:cap - strm.avail_out]
+        ref.deflateEnd(C.byref(strm))
+        return out
+
+    for kind, n in ((refz.GEN_TEXT, 150000), (refz.GEN_MIXED, 262144), (refz.GEN_MARKOV, 70001), (refz.GEN_RANDOM, 40000)):
+        d = refz.gen(n, kind, seed=31 + kind)
+        for wbits, mem in ((15, 8), (9, 8), (12, 8), (15, 1), (15, 9), (10, 3), (14, 9), (9, 1), (13, 5)):
+            for level, strat in ((1, 0), (4, 0), (6, 0), (6, 1), (9, 0), (6, 3), (6, 2)):
+                want = ref_stream(d, level, strat, wbits, mem)
+                cap = n + n // 4 + 4096
+                out, st = C.create_string_buffer(cap), (C.c_uint32 * 2)()
+                r = L.emul_deflate_chunk_opts(d, n, 0, level, strat, wbits, mem, 1, out, cap, st)
+                assert r >= 0, (r, kind, wbits, mem, level, strat)
+                got = out.raw[:r]
+                if level >= 4 or strat in (2, 3):
+                    assert got == want, (kind, wbits, mem, level, strat, len(got), len(want))
+                else:
+                    err, msg, back, used = ref.inflate_all(got, refz.WRAP_RAW, cap=n + 16)
+                    assert err == 1 and back == d and len(got) <= 1.03 * len(want) + 8, (kind, wbits, mem, level, strat, err, msg)

@@ -1,0 +1,344 @@
+"""GPU parity of the boundary items added in round 2: deflateInit2_'s windowBits / memLevel honoured byte for byte,
+deflatePrime / deflateUsed, inflatePrime / inflateSync / inflateSyncPoint, zalloc / zfree, the LFS *64 names, the five
+remaining Boundary-B exports, and deflateBound / compressBound on incompressible input."""
+import ctypes as C
+import os
+import random
+import subprocess
+import sys
+
+import pytest
+
+import refz
+import zlib_wasm_b200 as zb
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ZS = C.sizeof(refz.ZStream)
+
+
+@pytest.fixture(scope="module")
+def z():
+    return refz.ZlibBinding(zb.LIB_PATH, "")
+
+
+def _deflate_all(lib, d, level, wbits, mem, strat, flush_every=0, prime=None):
+    """One z_stream through `lib` (product or reference): Z_FULL_FLUSH every `flush_every` bytes, Z_FINISH at the end."""
+    strm = refz.ZStream()
+    assert lib.deflateInit2_(C.byref(strm), level, 8, wbits, mem, strat, lib.version, ZS) == 0
+    if prime:
+        fn = getattr(lib.lib, lib.prefix + "deflatePrime")
+        fn.restype, fn.argtypes = C.c_int, [C.POINTER(refz.ZStream), C.c_int, C.c_int]
+        assert fn(C.byref(strm), prime[0], prime[1]) == 0
+    cap = len(d) + len(d) // 4 + 65536
+    src, dst = C.create_string_buffer(d, max(len(d), 1)), C.create_string_buffer(cap)
+    step = flush_every or max(len(d), 1)
+    off = produced = 0
+    while True:
+        k = min(step, len(d) - off)
+        last = off + k >= len(d)
+        strm.next_in, strm.avail_in = C.addressof(src) + off, k
+        strm.next_out, strm.avail_out = C.addressof(dst) + produced, cap - produced
+        r = lib.deflate(C.byref(strm), refz.Z_FINISH if last else refz.Z_FULL_FLUSH)
+        assert r in (0, 1), r
+        produced = cap - strm.avail_out
+        off += k
+        if last:
+            assert r == 1
+            break
+    used = C.c_int(-1)
+    if hasattr(lib.lib, lib.prefix + "deflateUsed"):
+        fn = getattr(lib.lib, lib.prefix + "deflateUsed")
+        fn.restype, fn.argtypes = C.c_int, [C.POINTER(refz.ZStream), C.POINTER(C.c_int)]
+        fn(C.byref(strm), C.byref(used))
+    lib.deflateEnd(C.byref(strm))
+    return dst.raw[:produced], used.value
+
+
+def test_window_bits_and_mem_level_are_the_references(z):
+    """deflate.c:440-455,1006: w_size / MAX_DIST / slide period, hash_bits, lit_bufsize and the CINFO of the zlib header.
+    Levels 4-9 byte-identical with the reference's stream for the same settings and Z_FULL_FLUSH chunking; the
+    reference's inflateInit2 with the SAME windowBits decodes every level."""
+    if not refz.have_ref():
+        pytest.skip("oracle/_ref/libzref.so not built")
+    ref = refz.ref()
+    chunk = 262144
+    for kind, n in ((refz.GEN_MIXED, 3 * chunk + 777), (refz.GEN_TEXT, 200000)):
+        d = refz.gen(n, kind, seed=91 + kind)
+        for wbits, mem in ((9, 8), (12, 8), (15, 1), (15, 9), (10, 3), (14, 9), (9, 1)):
+            for level, strat in ((6, 0), (9, 0), (4, 1), (1, 0), (6, 3)):
+                for wrapped in (wbits, -wbits, wbits + 16):
+                    if wrapped != wbits and (level, strat) != (6, 0):
+                        continue
+                    got, _ = _deflate_all(z, d, level, wrapped, mem, strat, chunk)
+                    want, _ = _deflate_all(ref, d, level, wrapped, mem, strat, chunk)
+                    if level >= 4 or strat == 3:
+                        assert got == want, (kind, wbits, mem, level, strat, wrapped, len(got), len(want))
+                    else:
+                        assert len(got) <= 1.03 * len(want) + 16
+                    # the reference's decoder with the same (small) window takes it
+                    strm = refz.ZStream()
+                    assert ref.inflateInit2_(C.byref(strm), wrapped, ref.version, ZS) == 0
+                    src, dst = C.create_string_buffer(got, len(got)), C.create_string_buffer(n + 16)
+                    strm.next_in, strm.avail_in, strm.next_out, strm.avail_out = C.addressof(src), len(got), C.addressof(dst), n + 16
+                    assert ref.inflate(C.byref(strm), refz.Z_FINISH) == refz.Z_STREAM_END, (wbits, mem, level, strm.msg)
+                    assert dst.raw[:n] == d
+                    ref.inflateEnd(C.byref(strm))
+            if wbits < 15:                                  # CINFO advertises the window that was asked for
+                hdr, _ = _deflate_all(z, d[:1000], 6, wbits, mem, 0)
+                assert hdr[0] >> 4 == wbits - 8 and (hdr[0] * 256 + hdr[1]) % 31 == 0
+
+
+def test_deflate_prime_and_used(z):
+    """deflate.c:731-757 / :723: bits ahead of the first block, the blocks follow at that bit offset (the reference's
+    bytes), and deflateUsed reports the bits in use in the last byte."""
+    if not refz.have_ref():
+        pytest.skip("oracle/_ref/libzref.so not built")
+    ref = refz.ref()
+    d = refz.gen(300000, refz.GEN_MARKOV, seed=5)
+    for bits, value in ((3, 5), (8, 0xa5), (11, 0x5a5), (16, 0xbeef), (1, 1)):
+        for level in (6, 9, 4):
+            got, used_g = _deflate_all(z, d, level, -15, 8, 0, 0, prime=(bits, value))
+            want, used_r = _deflate_all(ref, d, level, -15, 8, 0, 0, prime=(bits, value))
+            assert got == want, (bits, level, len(got), len(want))
+            if used_r >= 0:
+                assert used_g == used_r, (bits, level, used_g, used_r)
+        got, _ = _deflate_all(z, d, 6, -15, 8, 0, 100000, prime=(bits, value))     # ... with flush points behind it
+        want, _ = _deflate_all(ref, d, 6, -15, 8, 0, 100000, prime=(bits, value))
+        assert got == want
+    # the primed bits decode as part of the stream: prime an empty stored block header's first 3 bits? no — check by decode:
+    # a stream primed with the 3 header bits of a non-final stored block of length 0 would need alignment; instead
+    # verify with inflatePrime below.
+
+
+def _bind(z, name, res, *args):
+    fn = getattr(z.lib, z.prefix + name)
+    fn.restype, fn.argtypes = res, list(args)
+    return fn
+
+
+def test_inflate_prime(z):
+    """inflate.c:223-240: bits ahead of the first input byte — a raw stream entered at a bit offset (examples/zran.c)."""
+    if not refz.have_ref():
+        pytest.skip("oracle/_ref/libzref.so not built")
+    ref = refz.ref()
+    d = refz.gen(200000, refz.GEN_TEXT, seed=12)
+    s = ref.deflate_stream(d, 6, 0, refz.WRAP_RAW, 0)
+    big = int.from_bytes(s, "little")
+    for k in (3, 7, 8, 13, 16):
+        value = big & ((1 << k) - 1)
+        rest = (big >> k).to_bytes((len(s) * 8 - k + 7) // 8, "little")
+        for lib in (z, ref):
+            strm = refz.ZStream()
+            assert lib.inflateInit2_(C.byref(strm), -15, lib.version, ZS) == 0
+            prime = _bind(lib, "inflatePrime", C.c_int, C.POINTER(refz.ZStream), C.c_int, C.c_int)
+            assert prime(C.byref(strm), k, value) == 0
+            src, dst = C.create_string_buffer(rest, len(rest)), C.create_string_buffer(len(d) + 16)
+            strm.next_in, strm.avail_in, strm.next_out, strm.avail_out = C.addressof(src), len(rest), C.addressof(dst), len(d) + 16
+            r = lib.inflate(C.byref(strm), refz.Z_FINISH)
+            assert r == refz.Z_STREAM_END, (k, r, strm.msg)
+            assert dst.raw[:len(d)] == d and strm.total_out == len(d)
+            assert strm.total_in <= len(rest)
+            lib.inflateEnd(C.byref(strm))
+    strm = refz.ZStream()
+    assert z.inflateInit2_(C.byref(strm), -15, z.version, ZS) == 0
+    prime = _bind(z, "inflatePrime", C.c_int, C.POINTER(refz.ZStream), C.c_int, C.c_int)
+    assert prime(C.byref(strm), 17, 0) == refz.Z_STREAM_ERROR and prime(C.byref(strm), -1, 0) == 0 and prime(C.byref(strm), 0, 0) == 0
+    z.inflateEnd(C.byref(strm))
+
+
+def test_inflate_sync_and_sync_point(z):
+    """inflate.c:1375-1421: after a data error, skip to the next full flush point (00 00 FF FF) and go on decoding from
+    there; the bytes after the point are the reference's.  inflate.c:1431: inflateSyncPoint."""
+    if not refz.have_ref():
+        pytest.skip("oracle/_ref/libzref.so not built")
+    ref = refz.ref()
+    chunk = 100000
+    d = refz.gen(4 * chunk, refz.GEN_MARKOV, seed=44)
+    for wrap, wbits in ((refz.WRAP_ZLIB, 15), (refz.WRAP_RAW, -15), (refz.WRAP_GZIP, 31)):
+        s = bytearray(ref.deflate_stream(d, 6, 0, wrap, chunk))
+        marks = [i for i in range(len(s) - 3) if s[i:i + 4] == b"\x00\x00\xff\xff"]
+        assert len(marks) >= 3
+        bad = marks[0] + 4 + 2000                            # inside the second run
+        s[bad] ^= 0xff
+        s[bad + 1] ^= 0x55
+        results = []
+        for lib in (z, ref):
+            strm = refz.ZStream()
+            assert lib.inflateInit2_(C.byref(strm), wbits, lib.version, ZS) == 0
+            sync = _bind(lib, "inflateSync", C.c_int, C.POINTER(refz.ZStream))
+            src, dst = C.create_string_buffer(bytes(s), len(s)), C.create_string_buffer(len(d) + 64)
+            cut = marks[1] + 4 + 10                          # first call: up to a little past the second marker
+            strm.next_in, strm.avail_in, strm.next_out, strm.avail_out = C.addressof(src), cut, C.addressof(dst), len(d) + 64
+            r = lib.inflate(C.byref(strm), refz.Z_NO_FLUSH)
+            while r == refz.Z_OK and strm.avail_in:
+                r = lib.inflate(C.byref(strm), refz.Z_NO_FLUSH)
+            assert r == refz.Z_DATA_ERROR, (wrap, r)
+            first = strm.total_out
+            # the caller goes on from wherever the library left next_in (the reference stops at the error, this library
+            # has taken the whole slice): sync over what is left of the slice, then feed the rest of the file
+            r = sync(C.byref(strm))
+            assert r == refz.Z_OK, (wrap, lib.prefix, r)
+            out2 = C.create_string_buffer(len(d) + 64)
+            strm.next_out, strm.avail_out = C.addressof(out2), len(d) + 64
+            t0 = strm.total_out
+            r = lib.inflate(C.byref(strm), refz.Z_NO_FLUSH)
+            assert r in (refz.Z_OK, refz.Z_BUF_ERROR), (wrap, lib.prefix, r, strm.msg)
+            assert strm.avail_in == 0
+            strm.next_in, strm.avail_in = C.addressof(src) + cut, len(s) - cut
+            r = lib.inflate(C.byref(strm), refz.Z_FINISH)
+            assert r == refz.Z_STREAM_END, (wrap, lib.prefix, r, strm.msg)
+            results.append((first <= chunk * 2, out2.raw[:strm.total_out - t0]))
+            lib.inflateEnd(C.byref(strm))
+        assert results[0][1] == results[1][1] == d[2 * chunk:], wrap
+    # no pattern at all: everything is consumed, Z_DATA_ERROR; no input: Z_BUF_ERROR
+    strm = refz.ZStream()
+    assert z.inflateInit2_(C.byref(strm), -15, z.version, ZS) == 0
+    sync = _bind(z, "inflateSync", C.c_int, C.POINTER(refz.ZStream))
+    assert sync(C.byref(strm)) == refz.Z_BUF_ERROR
+    junk = C.create_string_buffer(b"\x01\x02\x03" * 100, 300)
+    strm.next_in, strm.avail_in = C.addressof(junk), 300
+    assert sync(C.byref(strm)) == refz.Z_DATA_ERROR and strm.avail_in == 0 and strm.total_in == 300
+    z.inflateEnd(C.byref(strm))
+    # inflateSyncPoint: input that stops between a sync flush's stored-block header and its LEN bytes (how PPP uses it)
+    s = ref.deflate_stream(d[:50000], 6, 0, refz.WRAP_RAW, 0, chunk_flush=refz.Z_SYNC_FLUSH)
+    s2 = ref.deflate_stream(d[:100000], 6, 0, refz.WRAP_RAW, 50000, chunk_flush=refz.Z_SYNC_FLUSH)
+    m = s2.index(b"\x00\x00\xff\xff")
+    for lib in (z, ref):
+        sp = _bind(lib, "inflateSyncPoint", C.c_int, C.POINTER(refz.ZStream))
+        strm = refz.ZStream()
+        assert lib.inflateInit2_(C.byref(strm), -15, lib.version, ZS) == 0
+        src, dst = C.create_string_buffer(s2, len(s2)), C.create_string_buffer(200000)
+        strm.next_in, strm.avail_in, strm.next_out, strm.avail_out = C.addressof(src), m, C.addressof(dst), 200000
+        lib.inflate(C.byref(strm), refz.Z_NO_FLUSH)
+        assert sp(C.byref(strm)) == 1, lib.prefix
+        strm.next_in, strm.avail_in = C.addressof(src) + m, 7
+        lib.inflate(C.byref(strm), refz.Z_NO_FLUSH)
+        assert sp(C.byref(strm)) == 0, lib.prefix
+        lib.inflateEnd(C.byref(strm))
+
+
+def test_zalloc_zfree_are_honoured(z):
+    """deflate.c:393-406 / inflate.c:187-199: the stream state comes from the caller's allocator, and every block it
+    handed out comes back through zfree by the End call."""
+    ALLOC = C.CFUNCTYPE(C.c_void_p, C.c_void_p, C.c_uint, C.c_uint)
+    FREE = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p)
+    libc = C.CDLL(None)
+    libc.malloc.restype, libc.malloc.argtypes = C.c_void_p, [C.c_size_t]
+    libc.free.argtypes = [C.c_void_p]
+    live, stats = set(), {"alloc": 0, "free": 0, "opaque": 0}
+
+    def alloc(opaque, items, size):
+        p = libc.malloc(items * size)
+        live.add(p)
+        stats["alloc"] += 1
+        stats["opaque"] = opaque
+        return p
+
+    def free(opaque, p):
+        assert p in live
+        live.discard(p)
+        stats["free"] += 1
+        libc.free(p)
+
+    a, f = ALLOC(alloc), FREE(free)
+    d = refz.gen(100000, refz.GEN_TEXT, seed=8)
+    strm = refz.ZStream()
+    strm.zalloc, strm.zfree, strm.opaque = C.cast(a, C.c_void_p), C.cast(f, C.c_void_p), 0x1234
+    assert z.deflateInit2_(C.byref(strm), 6, 8, 15, 8, 0, z.version, ZS) == 0
+    assert stats["alloc"] >= 1 and stats["opaque"] == 0x1234
+    src, dst = C.create_string_buffer(d, len(d)), C.create_string_buffer(len(d) + 1024)
+    strm.next_in, strm.avail_in, strm.next_out, strm.avail_out = C.addressof(src), len(d), C.addressof(dst), len(d) + 1024
+    assert z.deflate(C.byref(strm), refz.Z_FINISH) == refz.Z_STREAM_END
+    comp = dst.raw[:strm.total_out]
+    assert z.deflateEnd(C.byref(strm)) == 0 and not live and stats["free"] == stats["alloc"]
+    strm = refz.ZStream()
+    strm.zalloc, strm.zfree, strm.opaque = C.cast(a, C.c_void_p), C.cast(f, C.c_void_p), 0x77
+    assert z.inflateInit2_(C.byref(strm), 15, z.version, ZS) == 0 and live
+    src, dst = C.create_string_buffer(comp, len(comp)), C.create_string_buffer(len(d))
+    strm.next_in, strm.avail_in, strm.next_out, strm.avail_out = C.addressof(src), len(comp), C.addressof(dst), len(d)
+    assert z.inflate(C.byref(strm), refz.Z_FINISH) == refz.Z_STREAM_END and dst.raw == d
+    assert z.inflateEnd(C.byref(strm)) == 0 and not live
+    # zalloc == NULL: the library settles on its own pair and writes it back (deflate.c:393-406)
+    strm = refz.ZStream()
+    assert z.deflateInit2_(C.byref(strm), 6, 8, 15, 8, 0, z.version, ZS) == 0 and strm.zalloc and strm.zfree
+    z.deflateEnd(C.byref(strm))
+
+
+def test_lfs_names_and_remaining_exports(z):
+    """zlib.map's *64 names and the Boundary-B exports of src/wasm_module_side.c, zlib_simd_compression.c,
+    zlib_simd_optimized.c."""
+    L = C.CDLL(zb.LIB_PATH, mode=C.RTLD_LOCAL)
+    o = refz.oracle()
+    d = refz.gen(300000, refz.GEN_TEXT, seed=3)
+    for nm in ("crc32_combine64", "adler32_combine64"):
+        getattr(L, nm).restype, getattr(L, nm).argtypes = C.c_ulong, [C.c_ulong, C.c_ulong, C.c_long]
+    L.crc32_combine_gen64.restype, L.crc32_combine_gen64.argtypes = C.c_ulong, [C.c_long]
+    assert L.crc32_combine64(o.crc32(d[:7]), o.crc32(d[7:]), len(d) - 7) == o.crc32(d)
+    assert L.adler32_combine64(o.adler32(d[:7]), o.adler32(d[7:]), len(d) - 7) == o.adler32(d)
+    assert L.crc32_combine_gen64(12345) == z.crc32_combine_gen(12345)
+    for nm in ("gzopen64", "gzseek64", "gztell64", "gzoffset64", "gzvprintf", "inflateCodesUsed", "deflateUsed"):
+        assert hasattr(L, nm), nm
+    # Boundary B
+    L.zlib_compress_simd_buffer.restype = C.c_int
+    L.zlib_compress_simd_buffer.argtypes = [C.c_char_p, C.c_ulong, C.c_void_p, C.POINTER(C.c_ulong), C.c_int]
+    cap = z.compressBound(len(d))
+    out, ol = C.create_string_buffer(cap), C.c_ulong(cap)
+    assert L.zlib_compress_simd_buffer(d, len(d), out, C.byref(ol), 6) == 0
+    back, bl = C.create_string_buffer(len(d)), C.c_ulong(len(d))
+    assert z.uncompress(back, C.byref(bl), out.raw[:ol.value], ol.value) == 0 and back.raw == d
+    L.zlib_crc32_simd.restype, L.zlib_crc32_simd.argtypes = C.c_ulong, [C.c_ulong, C.c_char_p, C.c_uint]
+    assert L.zlib_crc32_simd(0, d, len(d)) == o.crc32(d)
+    L.zlib_adler32_simd.restype, L.zlib_adler32_simd.argtypes = C.c_uint, [C.c_uint, C.c_char_p, C.c_size_t]
+    assert L.zlib_adler32_simd(1, d, len(d)) == o.adler32(d)
+    L.zlib_benchmark_simd_compression.restype = C.c_double
+    L.zlib_benchmark_simd_compression.argtypes = [C.c_char_p, C.c_size_t, C.c_int]
+    assert L.zlib_benchmark_simd_compression(d, len(d), 2) > 0 and L.zlib_benchmark_simd_compression(None, 0, 1) == -1.0
+    a, b, c = C.c_double(0), C.c_double(0), C.c_double(0)
+    L.zlib_simd_analysis.restype = None
+    L.zlib_simd_analysis.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    L.zlib_simd_analysis(d, len(d), C.byref(a), C.byref(b), C.byref(c))
+    assert 2.0 < a.value < 5.0 and b.value > 0 and c.value == 1.0
+    L.zlib_simd_performance_analysis.restype = None
+    L.zlib_simd_performance_analysis.argtypes = L.zlib_simd_analysis.argtypes
+    L.zlib_simd_performance_analysis(d, len(d), C.byref(a), C.byref(b), C.byref(c))
+    assert a.value > 0 and b.value > 0 and c.value > 0
+
+
+BOUND_SCRIPT = r"""
+import ctypes as C, os, sys
+sys.path.insert(0, os.path.join(%(root)r, "tests")); sys.path.insert(0, %(root)r)
+import refz, zlib_wasm_b200 as zb
+z = refz.ZlibBinding(zb.LIB_PATH, "")
+ZS = C.sizeof(refz.ZStream)
+for n in (0, 1, 1000, 100000, 5 * 262144 + 17, 16 << 20):
+    d = refz.gen(n, refz.GEN_RANDOM, seed=n + 1)
+    # compress() into exactly compressBound() bytes
+    cap = z.compressBound(n)
+    dst, dl = C.create_string_buffer(cap), C.c_ulong(cap)
+    assert z.compress2(dst, C.byref(dl), d, n, 6) == 0, ("compress2", n, cap)
+    for level, strat, mem in ((6, 2, 8), (6, 3, 8), (1, 0, 8), (9, 0, 8), (6, 2, 1), (6, 0, 9)):
+        strm = refz.ZStream()
+        assert z.deflateInit2_(C.byref(strm), level, 8, 15, mem, strat, z.version, ZS) == 0
+        bound = z.deflateBound(C.byref(strm), n)
+        src, out = C.create_string_buffer(d, max(n, 1)), C.create_string_buffer(bound)
+        strm.next_in, strm.avail_in, strm.next_out, strm.avail_out = C.addressof(src), n, C.addressof(out), bound
+        r = z.deflate(C.byref(strm), refz.Z_FINISH)
+        assert r == refz.Z_STREAM_END, ("deflateBound", n, level, strat, mem, bound, r)
+        z.deflateEnd(C.byref(strm))
+print("ok")
+"""
+
+
+@pytest.mark.parametrize("chunk", ["", "100000", "1024"])
+def test_bounds_hold_for_incompressible_input(chunk):
+    """compress.c:72 / deflate.c:842: compress() into a compressBound() buffer and deflate(Z_FINISH) into a deflateBound()
+    buffer always succeed — random bytes, Z_HUFFMAN_ONLY / Z_RLE (literal-only blocks), memLevel 1 (127-symbol blocks),
+    and chunk sizes that are no multiple of the block size ($ZB200_CHUNK is read once per process: subprocess)."""
+    env = dict(os.environ)
+    if chunk:
+        env["ZB200_CHUNK"] = chunk
+    else:
+        env.pop("ZB200_CHUNK", None)
+    p = subprocess.run([sys.executable, "-c", BOUND_SCRIPT % {"root": ROOT}], env=env, capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0 and "ok" in p.stdout, p.stderr[-2000:]

@@ -24,7 +24,9 @@ def both():
 def test_multi_matches_single(both):
     L, m, ctx = both
     g = L.zb200_multi_count(m)
-    assert g >= 1
+    if L.zb200_device_count() < 2:
+        pytest.skip("one GPU visible: the multi-GPU entry points need two (bench.py --gpus N runs the same gate at N > 1)")
+    assert g >= 2
     d = refz.gen(24 * 262144 + 12345, refz.GEN_MIXED, seed=77)
     o = refz.oracle()
     crc, adler = C.c_uint32(0), C.c_uint32(0)

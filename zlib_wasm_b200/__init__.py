@@ -37,6 +37,11 @@ class MemberResult(C.Structure):
                 ("out_len", C.c_uint64), ("in_used", C.c_uint64), ("resume_bit", C.c_uint64), ("resume_out", C.c_uint64)]
 
 
+class DeflateOpts(C.Structure):
+    _fields_ = [("level", C.c_int32), ("strategy", C.c_int32), ("window_bits", C.c_int32), ("mem_level", C.c_int32),
+                ("dict_len", C.c_uint32), ("first_bit", C.c_uint32)]
+
+
 class KernelTime(C.Structure):
     _fields_ = [("name", C.c_char * 40), ("ms", C.c_double), ("launches", C.c_uint64)]
 
@@ -89,6 +94,7 @@ ABI = {
     "zb200_multi_inflate_host": (_i, _vp, _vp, _vp, _vp, _sz, _i, _i, _vp),
     "zb200_inflate_stream_host": (_i, _vp, _vp, _sz, _i, _vp, _sz, _vp),
     "zb200_gunzip_host": (_i, _vp, _vp, _sz, _vp, _sz, _psz, C.POINTER(_i), _vp, _sz, _psz),
+    "zb200_deflate_host_opts": (_i, _vp, _vp, _sz, _sz, _vp, _i, _i, _vp, _psz, _p32, _p32, _p32),
     "zb200_deflate_host_dict": (_i, _vp, _vp, _sz, _sz, _i, _i, _i, _vp, _vp, _vp, _vp),
 }
 

@@ -83,9 +83,11 @@ def build_product(verbose=False):
             raise RuntimeError("compile failed: " + src)
         if verbose:
             sys.stderr.write(out)
-    if procs or _newer(LIB, objs):
+    vmap = os.path.join(CSRC, "libzb200.map")                   # only the C ABI + the zlib / wasm_module names are exported
+    if procs or _newer(LIB, objs + [vmap]):
         _run([nvcc, "-shared", "-o", LIB] + objs +
-             ["-cudart", "static", "-Xlinker", "-Bsymbolic", "-Xlinker", "--exclude-libs,ALL", "-lpthread", "-ldl", "-lrt"])
+             ["-cudart", "static", "-Xlinker", "-Bsymbolic", "-Xlinker", "--exclude-libs,ALL",
+              "-Xlinker", "--version-script=" + vmap, "-lpthread", "-ldl", "-lrt"])
     return LIB
 
 

@@ -60,6 +60,7 @@ struct Batch {                 // one sub-batch of chunks, passed by value to th
     int last_is_final;         // the last chunk of this sub-batch ends the stream (Z_FINISH)
     int all_final;             // every chunk is its own stream (gzip members)
     uint32_t skip;             // a preset dictionary: the first `skip` bytes of chunk 0 are history only (single-chunk calls)
+    uint32_t first_bit;        // deflatePrime: chunk 0 of the call starts at this bit (0..7) of its first output byte
 };
 
 __device__ __forceinline__ uint32_t chunk_len(const Batch &b, uint32_t c) {
@@ -84,16 +85,19 @@ __device__ __forceinline__ bool chunk_final(const Batch &b, uint32_t c) {
 // takes no issue slots; spinning on a shared-memory counter measured 6.7x slower), does
 // the four ordered head-table steps, passes the turn on and stores its links.
 constexpr int kChainWarps = 4, kChainTrip = 128;
-constexpr int kChainSmem = 65536;             // the head table
-__global__ void __launch_bounds__(kChainWarps * 32) dfl_chain_kernel(Batch b, uint16_t *__restrict__ prev_all) {
+// head table: 2 << hash_bits bytes of dynamic shared memory (64 KiB at memLevel 8, 128 KiB at memLevel 9)
+__global__ void __launch_bounds__(kChainWarps * 32) dfl_chain_kernel(Batch b, DeflateParams prm, uint16_t *__restrict__ prev_all) {
     extern __shared__ __align__(16) uint16_t head[];
     const uint32_t c = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint8_t *data = b.in + (uint64_t)c * b.S;
     const uint32_t n = chunk_len(b, c);
     uint16_t *prev = prev_all + (uint64_t)c * b.S;
     uint4 *h4 = reinterpret_cast<uint4 *>(head);
-    for (int i = threadIdx.x; i < 4096; i += kChainWarps * 32) h4[i] = make_uint4(0, 0, 0, 0);
+    const int nvec = (int)((2u << prm.hash_bits) >> 4);                 // uint4 vectors of the table (>= 32)
+    for (int i = threadIdx.x; i < nvec; i += kChainWarps * 32) h4[i] = make_uint4(0, 0, 0, 0);
     __syncthreads();
+    const uint32_t hshift = prm.hash_shift, hmask = prm.hash_mask, wsz = prm.w_size, wlog = 31u - (uint32_t)__clz(prm.w_size);
+    const uint32_t wsub = wsz | (wsz << 16);
     constexpr int G = kChainTrip / 32;
     const uintptr_t in_hi = reinterpret_cast<uintptr_t>(b.in) + b.bytes;
     // the three bytes at a position as one little-endian word (bytes past the input read as 0)
@@ -112,7 +116,7 @@ __global__ void __launch_bounds__(kChainWarps * 32) dfl_chain_kernel(Batch b, ui
             const uint32_t p = t * kChainTrip + 32 * j + lane;
             if (p + kMinMatch <= n) {
                 const uint32_t x = bytes3(p);
-                h[j] = (((x & 0xffu) << (2 * kHashShift)) ^ (((x >> 8) & 0xffu) << kHashShift) ^ ((x >> 16) & 0xffu)) & kHashMask;
+                h[j] = (((x & 0xffu) << (2 * hshift)) ^ (((x >> 8) & 0xffu) << hshift) ^ ((x >> 16) & 0xffu)) & hmask;
             } else h[j] = 0x10000u | lane;
         }
     };
@@ -122,14 +126,14 @@ __global__ void __launch_bounds__(kChainWarps * 32) dfl_chain_kernel(Batch b, ui
         for (int j = 0; j < G; ++j) hs[j] = nxt[j];
         if (t + kChainWarps < ntrips) hash_trip(t + kChainWarps, nxt);     // the next trip's hashes: off the ordered path
         const uint32_t p0 = t * kChainTrip;
-        // window origin after every slide due up to this trip (the first one happens at position 64 Ki)
-        const uint32_t base = p0 < 65536u ? 0u : ((p0 >> 15) - 1u) << 15;
+        // window origin after every slide due up to this trip (the first one happens at position 2 * w_size)
+        const uint32_t base = p0 < 2u * wsz ? 0u : ((p0 >> wlog) - 1u) << wlog;
         if (t) asm volatile("bar.sync %0, 64;" ::"r"(warp + 1) : "memory");   // trip t-1 has left the head table (its warp arrived here)
-        if (p0 >= 65536u && (p0 & 32767u) == 0) {                  // slide: subtract 32768, saturating at 0 (= NIL)
-            for (int i = lane; i < 4096; i += 32) {
+        if (p0 >= 2u * wsz && (p0 & (wsz - 1u)) == 0) {            // slide: subtract w_size, saturating at 0 (= NIL)
+            for (int i = lane; i < nvec; i += 32) {
                 uint4 v = h4[i];
-                v.x = __vsubus2(v.x, 0x80008000u); v.y = __vsubus2(v.y, 0x80008000u);
-                v.z = __vsubus2(v.z, 0x80008000u); v.w = __vsubus2(v.w, 0x80008000u);
+                v.x = __vsubus2(v.x, wsub); v.y = __vsubus2(v.y, wsub);
+                v.z = __vsubus2(v.z, wsub); v.w = __vsubus2(v.w, wsub);
                 h4[i] = v;
             }
             __syncwarp();
@@ -297,7 +301,7 @@ dfl_match_uniform_kernel(Batch b, DeflateParams prm, const uint16_t *__restrict_
     const StagedMem mem = stage_window(b, data, prev, lo, hi, t1);
     for (uint32_t p = t0 + threadIdx.x; p < t1; p += kMsThreads) {
         uint32_t r;
-        if (p + kUniformTail <= n) r = match_uniform<CH, NICE>(mem, p);
+        if (p + kUniformTail <= n) r = match_uniform<CH, NICE>(mem, p, prm.max_dist);
         else r = match_walk(mem, n, p, prm).full;                  // chunk tail: lookahead clamps apply
         mfull[off + p] = r;
     }
@@ -326,7 +330,7 @@ dfl_match_sorted_kernel(Batch b, DeflateParams prm, const uint16_t *__restrict__
         if (i < cnt) {
             const uint32_t p = t0 + i, d = mem.link(p);
             uint32_t e = 0;
-            if (p + kMinMatch <= n && d != 0 && d <= (uint32_t)kMaxDist) {
+            if (p + kMinMatch <= n && d != 0 && d <= prm.max_dist) {
                 // length of the walk if no candidate ends it early: links inside the window, up to the budget.
                 // Counted in position order (lanes diverge), so it is capped: beyond 32 links the sort gains
                 // less than the counting costs (host model: mixed data 50 -> 37 instructions per position).
@@ -337,7 +341,7 @@ dfl_match_sorted_kernel(Batch b, DeflateParams prm, const uint16_t *__restrict__
                     const uint32_t d2 = mem.link(q);
                     if (d2 == 0) break;
                     q -= d2;
-                    if (p - q >= (uint32_t)kMaxDist) break;
+                    if (p - q >= prm.max_dist) break;
                     ++e;
                 }
             }
@@ -601,14 +605,18 @@ dfl_tree_kernel(Batch b, int strategy, const uint32_t *__restrict__ syms, const 
 // ---- layout: bit offsets of blocks inside their chunk, chunk sizes ---------------------
 __global__ void dfl_layout_kernel(Batch b, BlockInfo *__restrict__ blocks, const BlockCode *__restrict__ codes,
                                   const uint32_t *__restrict__ nblocks, uint64_t *__restrict__ chunk_bytes,
-                                  uint32_t member_overhead) {
+                                  uint32_t member_overhead, uint32_t *__restrict__ bi_used) {
     const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= b.nb) return;
-    uint64_t bit = 0;
+    uint64_t bit = c == 0 ? b.first_bit : 0;                       // deflatePrime: bits already in the first byte
     const uint32_t nbk = nblocks[c];
     for (uint32_t i = 0; i < nbk; ++i) {
         BlockInfo &bi = blocks[(uint64_t)c * b.MB + i];
         bi.bit_start_lo = (uint32_t)bit; bi.bit_start_hi = (uint32_t)(bit >> 32);
+        if (i + 1 == nbk && c + 1 == b.nb) {                       // deflateUsed: bits in use in the stream's last byte (trees.c:187, deflate.c:1758)
+            const BlockCode &bc = codes[(uint64_t)c * b.MB + i];
+            *bi_used = (bc.type == 0 || !chunk_final(b, c)) ? 8u : (uint32_t)(((bit + bc.body_bits - 1) & 7) + 1);
+        }
         bit = block_end_bit(bi, codes[(uint64_t)c * b.MB + i], bit);
     }
     if (!chunk_final(b, c)) bit = ((bit + 3 + 7) & ~7ull) + 32;   // 000 + pad + 00 00 FF FF
@@ -728,12 +736,12 @@ dfl_pack_kernel(Batch b, const uint32_t *__restrict__ syms, const BlockInfo *__r
 // Stream header at offset 0 and trailer after the last chunk (deflate.c:1004-1054,1239-1256).
 __global__ void dfl_frame_kernel(uint8_t *out, int frame, int level, int strategy, int finish, int write_header,
                                  uint64_t *running, const uint32_t *sums /* crc, adler */, uint64_t n,
-                                 uint64_t *total_out) {
+                                 uint64_t *total_out, int window_bits) {
     if (threadIdx.x || blockIdx.x) return;
     if (write_header) {
         if (frame == ZB200_FRAME_ZLIB) {
             const uint32_t lf = (strategy >= STRAT_HUFFMAN || level < 2) ? 0 : level < 6 ? 1 : level == 6 ? 2 : 3;
-            uint32_t hdr = (0x78u << 8) | (lf << 6);
+            uint32_t hdr = ((8u + ((uint32_t)(window_bits - 8) << 4)) << 8) | (lf << 6);   // deflate.c:1006: Z_DEFLATED + (w_bits - 8) << 4
             hdr += 31 - hdr % 31;
             out[0] = (uint8_t)(hdr >> 8); out[1] = (uint8_t)hdr;
         } else if (frame == ZB200_FRAME_GZIP) {
@@ -789,7 +797,7 @@ int deflate_init(zb200_ctx *ctx) {
     ZB_CUDA(cudaMalloc(&d, sizeof h));
     ZB_CUDA(cudaMemcpy(d, &h, sizeof h, cudaMemcpyHostToDevice));
     ctx->d_deflate_tables = d;
-    ZB_CUDA(cudaFuncSetAttribute(dfl_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kChainSmem));
+    ZB_CUDA(cudaFuncSetAttribute(dfl_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 << kHashBitsMax));
     ZB_CUDA(cudaFuncSetAttribute(dfl_parse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kParseSmem));
     ZB_CUDA(cudaFuncSetAttribute(dfl_match_sorted_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMsSmem));
     ZB_CUDA(cudaFuncSetAttribute(dfl_match_uniform_kernel<4, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMsSmem));
@@ -798,18 +806,24 @@ int deflate_init(zb200_ctx *ctx) {
 }
 
 static size_t chunk_bound(size_t len) {
-    // fixed-Huffman worst case (deflate.c:852-855) + per-block and marker slack
-    return len + (len >> 3) + (len >> 8) + (len >> 9) + 4 + 8 * (len / kSymLimit + 2) + 16;
+    // fixed-Huffman worst case (deflate.c:852-855) + per-block and marker slack (blocks of 127 symbols at memLevel 1:
+    // a stored block costs 5 bytes per 127, well inside the len/8 term)
+    return len + (len >> 3) + (len >> 8) + (len >> 9) + 4 + 8 * (len / 16383 + 2) + 16;
 }
 
 static size_t frame_overhead(int frame) { return frame == ZB200_FRAME_ZLIB ? 6 : frame == ZB200_FRAME_GZIP ? 18 : 0; }
 
 constexpr size_t kBatchBytes = 512u << 20;    // input bytes per sub-batch (bounds scratch at ~14x this)
 
-static size_t batch_chunks(size_t n, size_t S) {
+static size_t batch_chunks(size_t n, size_t S, uint32_t MB) {
     size_t nch = (n + S - 1) / S;
     if (nch == 0) nch = 1;
     size_t nb = kBatchBytes / S;
+    // small memLevels cut a chunk into many blocks (127 symbols each at memLevel 1): keep the block tables (1.6 KiB per
+    // block slot) of a sub-batch under 2 GiB
+    const size_t per_chunk = (size_t)MB * (sizeof(BlockInfo) + sizeof(BlockCode));
+    const size_t cap = ((size_t)2 << 30) / per_chunk;
+    if (nb > cap) nb = cap;
     if (nb == 0) nb = 1;
     if (nb > 32768) nb = 32768;                 // gridDim.y limit of the per-chunk kernels
     return nb < nch ? nb : nch;
@@ -819,9 +833,16 @@ static thread_local const int *tl_deflate_tune = nullptr;
 const int *deflate_tune_override() { return tl_deflate_tune; }
 void deflate_tune_set(const int *four) { tl_deflate_tune = four; }
 
-int deflate_launch(zb200_ctx *ctx, const uint8_t *d_in, size_t n, size_t S, int level, int strategy, int frame,
-                   int finish, uint8_t *d_out, size_t out_cap, uint64_t *d_chunk_end, uint64_t *d_total,
-                   uint32_t *d_sums_out, cudaStream_t s, size_t skip) {
+int deflate_launch_opts(zb200_ctx *ctx, const uint8_t *d_in, size_t n, size_t S, const DeflateOpts &o, int frame,
+                        int finish, uint8_t *d_out, size_t out_cap, uint64_t *d_chunk_end, uint64_t *d_total,
+                        uint32_t *d_sums_out, cudaStream_t s) {
+    const int level = o.level, strategy = o.strategy;
+    const size_t skip = o.skip;
+    if (o.window_bits < 9 || o.window_bits > 15 || o.mem_level < 1 || o.mem_level > 9 || o.first_bit > 7 ||
+        (o.first_bit && frame != ZB200_FRAME_RAW)) {
+        set_error("deflate: windowBits 9..15, memLevel 1..9, first bit 0..7 (raw streams only)");
+        return ZB200_ERR_PARAM;
+    }
     if (skip && (skip > kWSize || skip > n || n > S || frame != ZB200_FRAME_RAW)) {
         set_error("deflate: a preset dictionary is at most 32768 bytes at the head of a single raw chunk");
         return ZB200_ERR_PARAM;
@@ -835,7 +856,7 @@ int deflate_launch(zb200_ctx *ctx, const uint8_t *d_in, size_t n, size_t S, int 
     size_t nch = (n + S - 1) / S;
     if (nch == 0 && (finish || members)) nch = 1;
     if (out_cap < zb200_deflate_bound(n, S, frame)) { set_error("deflate: output capacity below zb200_deflate_bound()"); return ZB200_ERR_OUTPUT; }
-    DeflateParams prm = deflate_params(level, strategy);
+    DeflateParams prm = deflate_params(level, strategy, o.window_bits, o.mem_level);
     const int *tune = deflate_tune_override();                     // deflateTune (deflate.c:805-816): this thread's next calls
     if (tune && (prm.mode == MODE_SLOW || prm.mode == MODE_FAST)) {
         prm.good = tune[0]; prm.lazy = tune[1]; prm.nice = tune[2]; prm.chain = tune[3];
@@ -844,8 +865,8 @@ int deflate_launch(zb200_ctx *ctx, const uint8_t *d_in, size_t n, size_t S, int 
     // levels 3..9: chain walks of very different lengths -> depth-sorted scheduling (levels 1-2 use the branch-free walk,
     // which is compiled for their table values)
     const bool sorted_walks = (prm.mode == MODE_SLOW || prm.mode == MODE_FAST) && (prm.level >= 3 || tune);
-    const uint32_t MB = max_blocks_for((uint32_t)S);
-    const size_t nb_max = batch_chunks(n, S);
+    const uint32_t MB = max_blocks_for((uint32_t)S, prm.sym_limit);
+    const size_t nb_max = batch_chunks(n, S, MB);
     int r = ensure_scratch(ctx, work_bytes(nb_max, S, MB));
     if (r) return r;
     DeflateWork w;
@@ -875,9 +896,10 @@ int deflate_launch(zb200_ctx *ctx, const uint8_t *d_in, size_t n, size_t S, int 
         b.last_is_final = (finish && c0 + b.nb == nch) ? 1 : 0;
         b.all_final = members ? 1 : 0;
         b.skip = (uint32_t)skip;
+        b.first_bit = c0 == 0 ? o.first_bit : 0u;
         if (prm.mode == MODE_FAST || prm.mode == MODE_SLOW) {
             prof_mark(ctx, s, "dfl_chain_kernel");
-            dfl_chain_kernel<<<b.nb, kChainWarps * 32, kChainSmem, s>>>(b, w.prev);
+            dfl_chain_kernel<<<b.nb, kChainWarps * 32, 2u << prm.hash_bits, s>>>(b, prm, w.prev);
             ZB_LAUNCHED(); ZB_CHECK_LAUNCH();
         }
         if (sorted_walks) {
@@ -905,7 +927,8 @@ int deflate_launch(zb200_ctx *ctx, const uint8_t *d_in, size_t n, size_t S, int 
         dfl_tree_kernel<<<dim3(MB, b.nb), 128, 0, s>>>(b, strategy | (level == 0 ? 0x100 : 0), w.syms, w.blocks, w.nblocks, tabs, w.codes);
         ZB_LAUNCHED(); ZB_CHECK_LAUNCH();
         prof_mark(ctx, s, "dfl_layout_kernel");
-        dfl_layout_kernel<<<(b.nb + 127) / 128, 128, 0, s>>>(b, w.blocks, w.codes, w.nblocks, w.chunk_bytes, members ? 18 : 0);
+        dfl_layout_kernel<<<(b.nb + 127) / 128, 128, 0, s>>>(b, w.blocks, w.codes, w.nblocks, w.chunk_bytes, members ? 18 : 0,
+                                                            (uint32_t *)(ctx->d_small + 19));
         ZB_LAUNCHED(); ZB_CHECK_LAUNCH();
         prof_mark(ctx, s, "dfl_scan_kernel");
         dfl_scan_kernel<<<1, 1024, 0, s>>>(b.nb, w.chunk_bytes, w.chunk_off, running, d_chunk_end ? d_chunk_end + c0 : nullptr);
@@ -926,7 +949,7 @@ int deflate_launch(zb200_ctx *ctx, const uint8_t *d_in, size_t n, size_t S, int 
         }
     }
     prof_mark(ctx, s, "dfl_frame_kernel");
-    dfl_frame_kernel<<<1, 32, 0, s>>>(d_out, frame, level, strategy, finish, 1, running, sums, n - skip, d_total);
+    dfl_frame_kernel<<<1, 32, 0, s>>>(d_out, frame, level, strategy, finish, 1, running, sums, n - skip, d_total, o.window_bits);
     ZB_LAUNCHED(); ZB_CHECK_LAUNCH();
     prof_mark(ctx, s, nullptr);
     return ZB200_OK;
@@ -951,7 +974,8 @@ size_t zb200_deflate_bound(size_t n, size_t chunk_size, int frame) {
 
 size_t zb200_deflate_scratch_bytes(size_t n, size_t chunk_size) {
     if (chunk_size == 0 || chunk_size > 0x40000000ull) return 0;
-    return work_bytes(batch_chunks(n, chunk_size), chunk_size, max_blocks_for((uint32_t)chunk_size));
+    const uint32_t MB = max_blocks_for((uint32_t)chunk_size, 16383u);
+    return work_bytes(batch_chunks(n, chunk_size, MB), chunk_size, MB);
 }
 
 int zb200_deflate_dev(zb200_ctx *ctx, const void *d_in, size_t n, size_t chunk_size, int level, int strategy,
@@ -959,7 +983,7 @@ int zb200_deflate_dev(zb200_ctx *ctx, const void *d_in, size_t n, size_t chunk_s
                       uint64_t *d_total, void *stream) {
     if (!ctx || (!d_in && n) || !d_out) return ZB200_ERR_PARAM;
     ZB_CUDA(cudaSetDevice(ctx->device));
-    std::lock_guard<std::mutex> g(ctx->mu);
+    CtxUse use(ctx, pick_stream(ctx, stream));
     return deflate_launch(ctx, (const uint8_t *)d_in, n, chunk_size, level, strategy, frame, finish,
                           (uint8_t *)d_out, out_cap, d_chunk_end, d_total, nullptr, pick_stream(ctx, stream), 0);
 }
@@ -970,8 +994,9 @@ int zb200_deflate_dev(zb200_ctx *ctx, const void *d_in, size_t n, size_t chunk_s
 // call would emit — so their concatenation is the same byte stream; the stream header and
 // trailer (deflate.c:1004-1054,1239-1256) are written here on the host, the input checksums
 // of the pieces merged with crc32_combine / adler32_combine.
-static int deflate_host_pipelined(zb200_ctx *ctx, const uint8_t *in, size_t n, size_t S, int level, int strategy,
+static int deflate_host_pipelined(zb200_ctx *ctx, const uint8_t *in, size_t n, size_t S, const DeflateOpts &opts,
                                   int frame, int finish, uint8_t *out, size_t *out_len, uint32_t *in_adler, uint32_t *in_crc) {
+    const int level = opts.level, strategy = opts.strategy;
     const int pframe = frame == ZB200_FRAME_GZIP_MEMBERS ? ZB200_FRAME_GZIP_MEMBERS : ZB200_FRAME_RAW;
     // pieces of at least 128 MiB: smaller ones leave the GPU underfilled (the chain kernel needs ~450 chunks in flight)
     size_t piece = n / 8 > ((size_t)128 << 20) ? n / 8 : ((size_t)128 << 20);
@@ -1001,8 +1026,10 @@ static int deflate_host_pipelined(zb200_ctx *ctx, const uint8_t *in, size_t n, s
     for (size_t k = 0; k < np; ++k) {
         const size_t len = k + 1 < np ? piece : n - k * piece;
         cudaStreamWaitEvent(s, ev_in[k], 0);
-        r = deflate_launch(ctx, ctx->d_io_in + k * piece, len, S, level, strategy, pframe, (finish && k + 1 == np) ? 1 : 0,
-                           ctx->d_io_out + ooff[k], bound[k], nullptr, ctx->d_pipe + 2 * k, (uint32_t *)(ctx->d_pipe + 2 * k + 1), s);
+        DeflateOpts po = opts;
+        po.skip = 0; po.first_bit = k == 0 ? opts.first_bit : 0u;
+        r = deflate_launch_opts(ctx, ctx->d_io_in + k * piece, len, S, po, pframe, (finish && k + 1 == np) ? 1 : 0,
+                                ctx->d_io_out + ooff[k], bound[k], nullptr, ctx->d_pipe + 2 * k, (uint32_t *)(ctx->d_pipe + 2 * k + 1), s);
         if (r) { cudaStreamSynchronize(s); cudaStreamSynchronize(ctx->copy_stream); cleanup(); return r; }
         cudaMemcpyAsync(ctx->h_pipe + 2 * k, ctx->d_pipe + 2 * k, 16, cudaMemcpyDeviceToHost, s);
         cudaEventRecord(ev_out[k], s);
@@ -1013,7 +1040,7 @@ static int deflate_host_pipelined(zb200_ctx *ctx, const uint8_t *in, size_t n, s
     size_t hlen = 0;
     if (frame == ZB200_FRAME_ZLIB) {
         const unsigned lf = (strategy >= STRAT_HUFFMAN || level < 2) ? 0 : level < 6 ? 1 : level == 6 ? 2 : 3;
-        unsigned h = (0x78u << 8) | (lf << 6);
+        unsigned h = ((8u + ((unsigned)(opts.window_bits - 8) << 4)) << 8) | (lf << 6);
         h += 31 - h % 31;
         hdr[0] = (uint8_t)(h >> 8); hdr[1] = (uint8_t)h; hlen = 2;
     } else if (frame == ZB200_FRAME_GZIP) {
@@ -1053,15 +1080,63 @@ static int deflate_host_pipelined(zb200_ctx *ctx, const uint8_t *in, size_t n, s
     return ZB200_OK;
 }
 
-int zb200_deflate_host(zb200_ctx *ctx, const void *in, size_t n, size_t chunk_size, int level, int strategy,
-                       int frame, int finish, void *out, size_t *out_len, uint32_t *in_adler, uint32_t *in_crc) {
-    if (!ctx || (!in && n) || !out || !out_len) return ZB200_ERR_PARAM;
-    ZB_CUDA(cudaSetDevice(ctx->device));
-    std::lock_guard<std::mutex> g(ctx->mu);
+// One host-buffer deflate call with every option (DeflateOpts).  A preset dictionary (opts.skip = dict_len > 0): `in` starts
+// with the dictionary, the first chunk is compressed behind it as a single-chunk call and the rest follows as usual.
+// *bits_used (optional): bits in use in the last byte written (deflateUsed).
+static int deflate_host_impl(zb200_ctx *ctx, const uint8_t *in, size_t n, size_t chunk_size, const DeflateOpts &opts, int frame,
+                             int finish, uint8_t *out, size_t *out_len, uint32_t *in_adler, uint32_t *in_crc, uint32_t *bits_used) {
+    const int level = opts.level, strategy = opts.strategy;
+    if (opts.skip) {
+        const size_t dl = opts.skip;
+        if (dl > n || dl > (size_t)kWSize || frame != ZB200_FRAME_RAW || chunk_size < 1) return ZB200_ERR_PARAM;
+        const size_t body = n - dl, first = body < chunk_size ? body : chunk_size;
+        DeflateOpts o1 = opts;
+        size_t cap1 = *out_len;
+        uint32_t a1 = 1, c1 = 0;
+        const size_t S1 = dl + first ? dl + first : 1;
+        const size_t bound1 = zb200_deflate_bound(dl + first, S1, ZB200_FRAME_RAW);
+        int r = ensure_io(ctx, dl + first + 16, bound1 + 16);
+        if (r) return r;
+        cudaStream_t s = ctx->stream;
+        if ((r = h2d_auto(ctx, ctx->d_io_in, in, dl + first, s))) return r;
+        r = deflate_launch_opts(ctx, ctx->d_io_in, dl + first, S1, o1, ZB200_FRAME_RAW, (finish && first == body) ? 1 : 0, ctx->d_io_out, bound1,
+                                nullptr, ctx->d_small + 17, (uint32_t *)(ctx->d_small + 18), s);
+        if (r) return r;
+        ZB_CUDA(cudaMemcpyAsync(ctx->h_small, ctx->d_small + 17, 24, cudaMemcpyDeviceToHost, s));
+        ZB_CUDA(cudaStreamSynchronize(s));
+        const uint64_t total = ctx->h_small[0];
+        c1 = ((const uint32_t *)(ctx->h_small + 1))[0]; a1 = ((const uint32_t *)(ctx->h_small + 1))[1];
+        if (bits_used) *bits_used = ((const uint32_t *)(ctx->h_small + 2))[0];
+        if (total > cap1) { *out_len = (size_t)total; set_error("deflate: %llu bytes do not fit the output buffer", (unsigned long long)total); return ZB200_ERR_OUTPUT; }
+        if ((r = d2h_auto(ctx, out, ctx->d_io_out, (size_t)total, s))) return r;
+        ZB_CUDA(cudaStreamSynchronize(s));
+        size_t pos = (size_t)total;
+        if (first < body) {
+            DeflateOpts o2 = opts;
+            o2.skip = 0; o2.first_bit = 0;
+            size_t cap2 = *out_len - pos;
+            uint32_t a2 = 1, c2 = 0;
+            r = deflate_host_impl(ctx, in + dl + first, body - first, chunk_size, o2, ZB200_FRAME_RAW, finish, out + pos, &cap2, &a2, &c2, bits_used);
+            if (r) { if (r == ZB200_ERR_OUTPUT) *out_len = pos + cap2; return r; }
+            c1 = zb200_crc32_combine(c1, c2, body - first);
+            a1 = zb200_adler32_combine(a1, a2, (int64_t)(body - first));
+            pos += cap2;
+        }
+        if (in_crc) *in_crc = c1;
+        if (in_adler) *in_adler = a1;
+        *out_len = pos;
+        return ZB200_OK;
+    }
     if (n >= ((size_t)256 << 20) && chunk_size >= 1 && chunk_size <= ((size_t)16 << 20) && level >= 0 && level <= 9 &&
-        strategy >= 0 && strategy <= 4 && frame >= 0 && frame <= 3 && is_pinned(in) && is_pinned(out))
-        return deflate_host_pipelined(ctx, (const uint8_t *)in, n, chunk_size, level, strategy, frame, finish,
-                                      (uint8_t *)out, out_len, in_adler, in_crc);
+        strategy >= 0 && strategy <= 4 && frame >= 0 && frame <= 3 && is_pinned(in) && is_pinned(out)) {
+        if (bits_used) *bits_used = 8;                             // (read back below only on the single-shot path)
+        const int r = deflate_host_pipelined(ctx, in, n, chunk_size, opts, frame, finish, out, out_len, in_adler, in_crc);
+        if (r == ZB200_OK && bits_used && finish) {
+            ZB_CUDA(cudaMemcpy(ctx->h_small, ctx->d_small + 19, 8, cudaMemcpyDeviceToHost));
+            *bits_used = ((const uint32_t *)ctx->h_small)[0];
+        }
+        return r;
+    }
     const size_t bound = zb200_deflate_bound(n, chunk_size ? chunk_size : 1, frame);
     int r = ensure_io(ctx, n + 16, bound + 16);
     if (r) return r;
@@ -1069,15 +1144,15 @@ int zb200_deflate_host(zb200_ctx *ctx, const void *in, size_t n, size_t chunk_si
     if ((r = h2d_auto(ctx, ctx->d_io_in, in, n, s))) return r;
     uint64_t *d_total = ctx->d_small + 17;
     uint32_t *d_sums = (uint32_t *)(ctx->d_small + 18);
-    r = deflate_launch(ctx, ctx->d_io_in, n, chunk_size, level, strategy, frame, finish, ctx->d_io_out, bound,
-                       nullptr, d_total, d_sums, s);
+    r = deflate_launch_opts(ctx, ctx->d_io_in, n, chunk_size, opts, frame, finish, ctx->d_io_out, bound, nullptr, d_total, d_sums, s);
     if (r) return r;
-    ZB_CUDA(cudaMemcpyAsync(ctx->h_small, ctx->d_small + 17, 16, cudaMemcpyDeviceToHost, s));
+    ZB_CUDA(cudaMemcpyAsync(ctx->h_small, ctx->d_small + 17, 24, cudaMemcpyDeviceToHost, s));
     ZB_CUDA(cudaStreamSynchronize(s));
     const uint64_t total = ctx->h_small[0];
     const uint32_t *hs = (const uint32_t *)(ctx->h_small + 1);
     if (in_crc) *in_crc = hs[0];
     if (in_adler) *in_adler = hs[1];
+    if (bits_used) *bits_used = ((const uint32_t *)(ctx->h_small + 2))[0];
     if (total > *out_len) { *out_len = (size_t)total; set_error("deflate: %llu bytes do not fit the output buffer", (unsigned long long)total); return ZB200_ERR_OUTPUT; }
     if ((r = d2h_auto(ctx, out, ctx->d_io_out, (size_t)total, s))) return r;
     ZB_CUDA(cudaStreamSynchronize(s));
@@ -1085,33 +1160,36 @@ int zb200_deflate_host(zb200_ctx *ctx, const void *in, size_t n, size_t chunk_si
     return ZB200_OK;
 }
 
+int zb200_deflate_host(zb200_ctx *ctx, const void *in, size_t n, size_t chunk_size, int level, int strategy,
+                       int frame, int finish, void *out, size_t *out_len, uint32_t *in_adler, uint32_t *in_crc) {
+    if (!ctx || (!in && n) || !out || !out_len) return ZB200_ERR_PARAM;
+    ZB_CUDA(cudaSetDevice(ctx->device));
+    CtxUse use(ctx, ctx->stream);
+    DeflateOpts o;
+    o.level = level; o.strategy = strategy;
+    return deflate_host_impl(ctx, (const uint8_t *)(in ? in : (const void *)""), n, chunk_size, o, frame, finish, (uint8_t *)out, out_len, in_adler, in_crc, nullptr);
+}
+
+int zb200_deflate_host_opts(zb200_ctx *ctx, const void *in, size_t n, size_t chunk_size, const zb200_deflate_opts *opts,
+                            int frame, int finish, void *out, size_t *out_len, uint32_t *in_adler, uint32_t *in_crc,
+                            uint32_t *bits_used) {
+    if (!ctx || (!in && n) || !out || !out_len || !opts) return ZB200_ERR_PARAM;
+    ZB_CUDA(cudaSetDevice(ctx->device));
+    CtxUse use(ctx, ctx->stream);
+    DeflateOpts o;
+    o.level = opts->level; o.strategy = opts->strategy; o.window_bits = opts->window_bits ? opts->window_bits : 15;
+    o.mem_level = opts->mem_level ? opts->mem_level : 8; o.skip = opts->dict_len; o.first_bit = opts->first_bit;
+    return deflate_host_impl(ctx, (const uint8_t *)(in ? in : (const void *)""), n, chunk_size, o, frame, finish, (uint8_t *)out, out_len, in_adler, in_crc, bits_used);
+}
+
 int zb200_deflate_host_dict(zb200_ctx *ctx, const void *in, size_t n, size_t dict_len, int level, int strategy,
                             int finish, void *out, size_t *out_len, uint32_t *in_adler, uint32_t *in_crc) {
-    if (!ctx || !in || !out || !out_len || dict_len > n || dict_len > kWSize || n > 0x40000000ull) return ZB200_ERR_PARAM;
+    if (!ctx || !in || !out || !out_len || dict_len > n || dict_len > (size_t)kWSize || n > 0x40000000ull) return ZB200_ERR_PARAM;
     ZB_CUDA(cudaSetDevice(ctx->device));
-    std::lock_guard<std::mutex> g(ctx->mu);
-    const size_t S = n ? n : 1;
-    const size_t bound = zb200_deflate_bound(n, S, ZB200_FRAME_RAW);
-    int r = ensure_io(ctx, n + 16, bound + 16);
-    if (r) return r;
-    cudaStream_t s = ctx->stream;
-    if ((r = h2d_auto(ctx, ctx->d_io_in, in, n, s))) return r;
-    uint64_t *d_total = ctx->d_small + 17;
-    uint32_t *d_sums = (uint32_t *)(ctx->d_small + 18);
-    r = deflate_launch(ctx, ctx->d_io_in, n, S, level, strategy, ZB200_FRAME_RAW, finish, ctx->d_io_out, bound,
-                       nullptr, d_total, d_sums, s, dict_len);
-    if (r) return r;
-    ZB_CUDA(cudaMemcpyAsync(ctx->h_small, ctx->d_small + 17, 16, cudaMemcpyDeviceToHost, s));
-    ZB_CUDA(cudaStreamSynchronize(s));
-    const uint64_t total = ctx->h_small[0];
-    const uint32_t *hs = (const uint32_t *)(ctx->h_small + 1);
-    if (in_crc) *in_crc = hs[0];
-    if (in_adler) *in_adler = hs[1];
-    if (total > *out_len) { *out_len = (size_t)total; set_error("deflate: %llu bytes do not fit the output buffer", (unsigned long long)total); return ZB200_ERR_OUTPUT; }
-    if ((r = d2h_auto(ctx, out, ctx->d_io_out, (size_t)total, s))) return r;
-    ZB_CUDA(cudaStreamSynchronize(s));
-    *out_len = (size_t)total;
-    return ZB200_OK;
+    CtxUse use(ctx, ctx->stream);
+    DeflateOpts o;
+    o.level = level; o.strategy = strategy; o.skip = dict_len;
+    return deflate_host_impl(ctx, (const uint8_t *)in, n, n - dict_len ? n - dict_len : 1, o, ZB200_FRAME_RAW, finish, (uint8_t *)out, out_len, in_adler, in_crc, nullptr);
 }
 
 }  // extern "C"

@@ -39,13 +39,10 @@
 namespace zb {
 
 constexpr int kMinMatch = 3, kMaxMatch = 258;
-constexpr int kWSize = 32768;
+constexpr int kWSize = 32768;                                 // the largest window (windowBits 15); staging buffers are sized for it
 constexpr int kMinLookahead = kMaxMatch + kMinMatch + 1;      // deflate.h:293
-constexpr int kMaxDist = kWSize - kMinLookahead;              // deflate.h:298  (32506)
 constexpr int kTooFar = 4096;                                 // deflate.c:88-90
-constexpr uint32_t kSymLimit = 16383;                         // deflate.c:455,512 (lit_bufsize - 1, memLevel 8)
-constexpr int kHashBits = 15, kHashShift = 5;                 // deflate.c:444-447 (memLevel 8)
-constexpr uint32_t kHashMask = (1u << kHashBits) - 1;
+constexpr int kHashBitsMax = 16;                              // memLevel 9 (deflate.c:444: hash_bits = memLevel + 7)
 
 enum { MODE_FAST = 0, MODE_SLOW = 1, MODE_HUFF = 2, MODE_RLE = 3 };
 enum { STRAT_DEFAULT = 0, STRAT_FILTERED = 1, STRAT_HUFFMAN = 2, STRAT_RLE = 3, STRAT_FIXED = 4 };
@@ -54,11 +51,13 @@ struct DeflateParams {
     int level, strategy, mode;
     int good, lazy, nice, chain;      // deflate.c:112-124 configuration_table
     int need_quarter;                 // the quartered-chain result can be asked for by the parse
-    uint32_t sym_limit;               // symbols that fill a block: lit_bufsize - 1 (deflate.c:455,512); level 0 cuts its
-                                      // stored blocks at MAX_STORED bytes instead (deflate.c:1615,1664)
+    uint32_t sym_limit;               // symbols that fill a block: lit_bufsize - 1 = (1 << (memLevel + 6)) - 1 (deflate.c:455,512);
+                                      // level 0 cuts its stored blocks at MAX_STORED bytes instead (deflate.c:1615,1664)
+    uint32_t w_size, max_dist;        // 1 << windowBits (deflate.c:440-443), MAX_DIST = w_size - MIN_LOOKAHEAD (deflate.h:298)
+    uint32_t hash_bits, hash_shift, hash_mask;   // memLevel + 7, (hash_bits + MIN_MATCH - 1) / MIN_MATCH (deflate.c:444-447)
 };
 
-ZB_HD DeflateParams deflate_params(int level, int strategy) {
+ZB_HD DeflateParams deflate_params(int level, int strategy, int window_bits = 15, int mem_level = 8) {
     //                      good lazy nice chain
     const int cfg[10][4] = {{0, 0, 0, 0}, {4, 4, 8, 4}, {4, 5, 16, 8}, {4, 6, 32, 32}, {4, 4, 16, 16},
                             {8, 16, 32, 32}, {8, 16, 128, 128}, {8, 32, 128, 256}, {32, 128, 258, 1024},
@@ -69,12 +68,14 @@ ZB_HD DeflateParams deflate_params(int level, int strategy) {
     p.mode = (strategy == STRAT_HUFFMAN || level == 0) ? MODE_HUFF : strategy == STRAT_RLE ? MODE_RLE : level >= 4 ? MODE_SLOW : MODE_FAST;
     // a search happens only while prev_length < lazy; it is quartered when prev_length >= good
     p.need_quarter = (p.mode == MODE_SLOW && p.good < p.lazy) ? 1 : 0;
-    p.sym_limit = level == 0 ? 65535u : kSymLimit;
+    p.sym_limit = level == 0 ? 65535u : (1u << (mem_level + 6)) - 1u;
+    p.w_size = 1u << window_bits; p.max_dist = p.w_size - (uint32_t)kMinLookahead;
+    p.hash_bits = (uint32_t)mem_level + 7u; p.hash_shift = (p.hash_bits + kMinMatch - 1) / kMinMatch; p.hash_mask = (1u << p.hash_bits) - 1u;
     return p;
 }
 
-ZB_HD uint32_t hash3(const uint8_t *s) {
-    return (((uint32_t)s[0] << (2 * kHashShift)) ^ ((uint32_t)s[1] << kHashShift) ^ s[2]) & kHashMask;
+ZB_HD uint32_t hash3(const uint8_t *s, const DeflateParams &prm) {   // deflate.c:141 UPDATE_HASH over MIN_MATCH bytes
+    return (((uint32_t)s[0] << (2 * prm.hash_shift)) ^ ((uint32_t)s[1] << prm.hash_shift) ^ s[2]) & prm.hash_mask;
 }
 
 // ---- phase 2: longest match at one position -------------------------------------
@@ -125,7 +126,7 @@ ZB_HD MatchPair match_walk(const Mem &mem, uint32_t n, uint32_t p, const Deflate
     r.full = r.quarter = 0;
     if (p + kMinMatch > n) return r;                      // lookahead < MIN_MATCH: no insertion, no search
     const uint32_t d = mem.link(p);
-    if (d == 0 || d > (uint32_t)kMaxDist) return r;       // deflate.c:1857/1958: head must be within MAX_DIST
+    if (d == 0 || d > prm.max_dist) return r;             // deflate.c:1857/1958: head must be within MAX_DIST
     const uint32_t look = n - p;
     const uint32_t maxlen = look < (uint32_t)kMaxMatch ? look : (uint32_t)kMaxMatch;
     const uint32_t nice = (uint32_t)prm.nice > look ? look : (uint32_t)prm.nice;      // deflate.c:1396
@@ -186,7 +187,7 @@ ZB_HD MatchPair match_walk(const Mem &mem, uint32_t n, uint32_t p, const Deflate
         }
         if (d2 == 0) break;
         q -= d2;
-        if (p - q >= (uint32_t)kMaxDist) break;           // deflate.c:1481: cur_match > limit
+        if (p - q >= prm.max_dist) break;                 // deflate.c:1481: cur_match > limit
     }
     r.full = best >= (uint32_t)kMinMatch ? (best << 16) | best_dist : 0;
     if (!have_q) r.quarter = r.full;
@@ -235,10 +236,10 @@ struct PlainWin {
     ZB_HD uint32_t dist(uint32_t pos) const { return prev[pos]; }
 };
 template <int CH, int NICE, class Win>
-ZB_HD uint32_t match_uniform(const Win &win, uint32_t p) {
+ZB_HD uint32_t match_uniform(const Win &win, uint32_t p, uint32_t max_dist) {
     constexpr int NW = NICE / 4;
     const uint32_t d = win.dist(p);
-    if (d == 0 || d > (uint32_t)kMaxDist) return 0;            // deflate.c:1857: head must be within MAX_DIST
+    if (d == 0 || d > max_dist) return 0;                      // deflate.c:1857: head must be within MAX_DIST
     uint32_t sw[NW];
     win.template words<NW>(p, sw);
     uint32_t q = p - d, best = kMinMatch - 1, best_q = 0;
@@ -256,7 +257,7 @@ ZB_HD uint32_t match_uniform(const Win &win, uint32_t p) {
             else if (k + 1 < CH) {
                 const uint32_t d2 = win.dist(q);
                 if (d2 == 0) open = false;
-                else { q -= d2; if (p - q >= (uint32_t)kMaxDist) open = false; }
+                else { q -= d2; if (p - q >= max_dist) open = false; }
             }
         }
     }
@@ -297,7 +298,7 @@ struct BlockInfo {
 };
 constexpr uint32_t BLK_LAST = 1, BLK_STORED_OK = 2;
 
-ZB_HD uint32_t max_blocks_for(uint32_t chunk_bytes) { return chunk_bytes / kSymLimit + 2; }
+ZB_HD uint32_t max_blocks_for(uint32_t chunk_bytes, uint32_t sym_limit) { return chunk_bytes / sym_limit + 2; }
 
 // The parse is a resumable state machine so that the kernel can run it tile by
 // tile over operands staged in shared memory.  `Acc` supplies the operands:
@@ -313,6 +314,7 @@ struct ParseState {
     uint32_t nsyms, nblocks;          // totals so far for the chunk
     uint32_t blk_sym0, blk_byte0;     // start of the open block
     BlockInfo *blocks;
+    uint32_t sym_limit;               // prm.sym_limit (parse_close_block has no prm at hand)
     uint32_t block_mode;              // PB_SERIAL: complete BlockInfo as the parse goes; PB_DEFERRED: a parse that covers
                                       // only a segment leaves (end offset, window base) for seg_finish; PB_NONE: counting pass
 };
@@ -325,13 +327,13 @@ ZB_HD void parse_init(ParseState &s, BlockInfo *blocks, uint32_t n, const Deflat
     s.base = parse_base_at(lo, n, prm);
     s.slide_at = parse_next_slide(s.base, n, prm);
     s.p = lo; s.match_length = kMinMatch - 1; s.cur_dist = 0; s.match_available = 0;
-    s.nsyms = 0; s.nblocks = 0; s.blk_sym0 = 0; s.blk_byte0 = lo; s.blocks = blocks; s.block_mode = PB_SERIAL;
+    s.nsyms = 0; s.nblocks = 0; s.blk_sym0 = 0; s.blk_byte0 = lo; s.blocks = blocks; s.block_mode = PB_SERIAL; s.sym_limit = prm.sym_limit;
 }
 
 ZB_HD void parse_close_block(ParseState &s, uint32_t cover_end, bool last) {
     if (s.block_mode != PB_SERIAL) {
-        if (s.block_mode == PB_DEFERRED) {             // block index = symbols so far / kSymLimit - 1
-            BlockInfo &d = s.blocks[s.nsyms / kSymLimit - 1];
+        if (s.block_mode == PB_DEFERRED) {             // block index = symbols so far / sym_limit - 1
+            BlockInfo &d = s.blocks[s.nsyms / s.sym_limit - 1];
             d.byte_len = cover_end;                    // provisional: end offset of the block
             d.pad = s.base;                            // provisional: window base when the block was closed
         }
@@ -354,16 +356,16 @@ ZB_HD void parse_close_block(ParseState &s, uint32_t cover_end, bool last) {
 // the first loop top that slides is the first with p >= slide_at:
 ZB_HD uint32_t parse_next_slide(uint32_t base, uint32_t n, const DeflateParams &prm) {
     const uint32_t trigger = prm.mode == MODE_HUFF ? 1 : prm.mode == MODE_RLE ? (uint32_t)kMaxMatch + 1 : (uint32_t)kMinLookahead;
-    uint64_t fill_end = (uint64_t)base + 2 * kWSize;
+    uint64_t fill_end = (uint64_t)base + 2 * (uint64_t)prm.w_size;
     if (fill_end > n) fill_end = n;
     // lookahead = fill_end - p < trigger  <=>  p > fill_end - trigger ;  and  p - base >= wsize + MAX_DIST
     const uint64_t a = fill_end >= trigger ? fill_end - trigger + 1 : 0;
-    const uint64_t b = (uint64_t)base + kWSize + kMaxDist;
+    const uint64_t b = (uint64_t)base + prm.w_size + prm.max_dist;
     const uint64_t at = a > b ? a : b;
     return at > 0xffffffffull ? 0xffffffffu : (uint32_t)at;
 }
 ZB_HD void parse_slide_check(ParseState &s, uint32_t p, uint32_t n, const DeflateParams &prm) {
-    if (p >= s.slide_at) { s.base += kWSize; s.slide_at = parse_next_slide(s.base, n, prm); }
+    if (p >= s.slide_at) { s.base += prm.w_size; s.slide_at = parse_next_slide(s.base, n, prm); }
 }
 
 // Examine positions while p < limit (limit <= n).  A match may carry p past limit.
@@ -473,7 +475,7 @@ constexpr uint32_t kSegRecs = 16;                     // boundaries per segment 
 
 ZB_HD uint32_t parse_base_at(uint32_t P, uint32_t n, const DeflateParams &prm) {
     uint32_t base = 0;
-    while (P >= parse_next_slide(base, n, prm)) base += kWSize;
+    while (P >= parse_next_slide(base, n, prm)) base += prm.w_size;
     return base;
 }
 
@@ -505,7 +507,7 @@ ZB_HD void seg_state_load(ParseState &s, const SegState &t, uint32_t n, const De
     s.p = t.p; s.cur_dist = t.w0 & 0xffffu; s.match_length = (t.w0 >> 16) & 0x1ffu; s.match_available = (t.w0 >> 25) & 1u;
     s.base = parse_base_at(t.p, n, prm);
     s.slide_at = parse_next_slide(s.base, n, prm);
-    s.nsyms = 0; s.nblocks = 0; s.blk_sym0 = 0; s.blk_byte0 = 0; s.blocks = nullptr; s.block_mode = PB_NONE;
+    s.nsyms = 0; s.nblocks = 0; s.blk_sym0 = 0; s.blk_byte0 = 0; s.blocks = nullptr; s.block_mode = PB_NONE; s.sym_limit = prm.sym_limit;
 }
 ZB_HD SegState seg_cold(uint32_t p) { SegState t; t.p = p; t.w0 = (uint32_t)(kMinMatch - 1) << 16; return t; }
 
@@ -597,7 +599,7 @@ ZB_HD void seg_emit(const SegLane &r, uint32_t lane, const SegGeom &g, uint32_t 
     const uint32_t s0 = g.lo + lane * g.seg, bound = s0 + g.seg < n ? s0 + g.seg : n;
     ParseState st;
     seg_state_load(st, r.start, n, prm);
-    st.nsyms = first; st.blk_sym0 = first - first % kSymLimit; st.blocks = blocks; st.block_mode = PB_DEFERRED;
+    st.nsyms = first; st.blk_sym0 = first - first % prm.sym_limit; st.blocks = blocks; st.block_mode = PB_DEFERRED;
     const uint32_t nw = acc.windows(g.seg);
     for (uint32_t w = 0; w < nw; ++w) {
         const uint32_t we = acc.open(w, s0), wend = we < bound ? we : bound;

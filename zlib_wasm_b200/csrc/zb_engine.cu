@@ -206,6 +206,7 @@ int zb200_create(int device, zb200_ctx **out) {
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) return fail(ZB200_ERR_CUDA);
     if (cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess) return fail(ZB200_ERR_CUDA);
     if (cudaStreamCreateWithFlags(&ctx->back_stream, cudaStreamNonBlocking) != cudaSuccess) return fail(ZB200_ERR_CUDA);
+    if (cudaEventCreateWithFlags(&ctx->busy_ev, cudaEventDisableTiming) != cudaSuccess) return fail(ZB200_ERR_CUDA);
     if (cudaMalloc((void **)&ctx->d_pipe, 32 * sizeof(uint64_t)) != cudaSuccess) return fail(ZB200_ERR_NOMEM);
     if (cudaMallocHost((void **)&ctx->h_pipe, 32 * sizeof(uint64_t)) != cudaSuccess) return fail(ZB200_ERR_NOMEM);
     ctx->stage_bytes = 32u << 20;
@@ -243,6 +244,7 @@ void zb200_destroy(zb200_ctx *ctx) {
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->back_stream) cudaStreamDestroy(ctx->back_stream);
+    if (ctx->busy_ev) cudaEventDestroy(ctx->busy_ev);
     if (ctx->d_pipe) cudaFree(ctx->d_pipe);
     if (ctx->h_pipe) cudaFreeHost(ctx->h_pipe);
     for (auto &x : ctx->prof_marks) cudaEventDestroy(x.ev);
@@ -266,6 +268,7 @@ int zb200_checksum_dev(zb200_ctx *ctx, const void *d_data, size_t len, int which
     if (!ctx || !d_out2 || (!d_data && len)) return ZB200_ERR_PARAM;
     ZB_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t s = pick_stream(ctx, stream);
+    CtxUse use(ctx, s);
     // accumulators: one CkAccum at the front of the small area (slots 8..11)
     CkAccum *acc = (CkAccum *)(ctx->d_small + 8);
     return checksum_launch(ctx, (const uint8_t *)d_data, nullptr, nullptr, len, 1, which, init_crc, init_adler,
@@ -274,12 +277,14 @@ int zb200_checksum_dev(zb200_ctx *ctx, const void *d_data, size_t len, int which
 
 int zb200_checksum_dev_sync(zb200_ctx *ctx, const void *d_data, size_t len, int which,
                             uint32_t init_crc, uint32_t init_adler, uint32_t *crc, uint32_t *adler, void *stream) {
-    if (!ctx) return ZB200_ERR_PARAM;
-    std::lock_guard<std::mutex> g(ctx->mu);
-    uint32_t *d_out2 = (uint32_t *)ctx->d_small;
-    int r = zb200_checksum_dev(ctx, d_data, len, which, init_crc, init_adler, d_out2, stream);
-    if (r) return r;
+    if (!ctx || (!d_data && len)) return ZB200_ERR_PARAM;
+    ZB_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t s = pick_stream(ctx, stream);
+    CtxUse use(ctx, s);
+    uint32_t *d_out2 = (uint32_t *)ctx->d_small;
+    int r = checksum_launch(ctx, (const uint8_t *)d_data, nullptr, nullptr, len, 1, which, init_crc, init_adler,
+                            d_out2, d_out2 + 1, (CkAccum *)(ctx->d_small + 8), s);
+    if (r) return r;
     ZB_CUDA(cudaMemcpyAsync(ctx->h_small, d_out2, 8, cudaMemcpyDeviceToHost, s));
     ZB_CUDA(cudaStreamSynchronize(s));
     const uint32_t *h = (const uint32_t *)ctx->h_small;
@@ -294,7 +299,7 @@ int zb200_checksum_segments_dev(zb200_ctx *ctx, const void *d_base, const uint64
     if (!ctx || !d_off || !d_len) return ZB200_ERR_PARAM;
     if (nseg == 0) return ZB200_OK;
     ZB_CUDA(cudaSetDevice(ctx->device));
-    std::lock_guard<std::mutex> g(ctx->mu);
+    CtxUse use(ctx, pick_stream(ctx, stream));
     int r = ensure_scratch(ctx, nseg * sizeof(CkAccum));
     if (r) return r;
     return checksum_launch(ctx, (const uint8_t *)d_base, d_off, d_len, 0, nseg, which, 0, 1,
@@ -305,7 +310,7 @@ int zb200_checksum_host(zb200_ctx *ctx, const void *data, size_t len, int which,
                         uint32_t init_crc, uint32_t init_adler, uint32_t *crc, uint32_t *adler) {
     if (!ctx || (!data && len)) return ZB200_ERR_PARAM;
     ZB_CUDA(cudaSetDevice(ctx->device));
-    std::lock_guard<std::mutex> g(ctx->mu);
+    CtxUse use(ctx, ctx->stream);
     // Stream the buffer through the device in pieces, chaining the running
     // values on the device (crc32/adler32 are running checksums, zlib.h:1711-1768):
     // host memory of any size needs O(piece) device memory and one final 8-byte

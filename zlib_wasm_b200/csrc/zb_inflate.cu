@@ -967,6 +967,9 @@ int inflate_stream_parallel(zb200_ctx *ctx, const uint8_t *src, size_t n, int wr
             u.slot = total;
             total += (u.cap + (k == 0 ? hist_len : 0) + 15) & ~(uint64_t)15;
         }
+        // every candidate costs a slot with 64 KiB of slack: a stream riddled with false markers (stored or binary data)
+        // would ask for far more memory than its output can be — leave it to the one-member path
+        if (total > (uint64_t)n * 16 + 2 * (uint64_t)out_cap + ((uint64_t)256 << 20)) { *applicable = 0; return ZB200_OK; }
         const size_t before = ctx->io_out_bytes;
         if ((r = ensure_io(ctx, n + 16, total + 16))) return r;
         if (ctx->io_out_bytes != before && pass) {           // the buffer was replaced: every run's bytes are gone, lay them out afresh
@@ -1102,7 +1105,7 @@ int zb200_inflate_dev(zb200_ctx *ctx, const void *d_in, void *d_out, const zb200
     if (!ctx || !d_members || !d_results || wrap < 0 || wrap > 3 || n_members > 0xfffffff0ull) return ZB200_ERR_PARAM;
     if (n_members == 0) return ZB200_OK;
     ZB_CUDA(cudaSetDevice(ctx->device));
-    std::lock_guard<std::mutex> g(ctx->mu);
+    CtxUse use(ctx, pick_stream(ctx, stream));
     int r = ensure_scratch(ctx, InflateWork::bytes(n_members));
     if (r) return r;
     return inflate_launch(ctx, (const uint8_t *)d_in, (uint8_t *)d_out, d_members, n_members, wrap, verify,
@@ -1175,7 +1178,7 @@ int zb200_selftest_tables(zb200_ctx *ctx, const uint8_t *lens, const uint32_t *c
     for (size_t i = 0; i < n_cases; ++i)
         if (counts[2 * i] < 257 || counts[2 * i] > 288 || counts[2 * i + 1] < 1 || counts[2 * i + 1] > 32) return ZB200_ERR_PARAM;
     ZB_CUDA(cudaSetDevice(ctx->device));
-    std::lock_guard<std::mutex> g(ctx->mu);
+    CtxUse use(ctx, ctx->stream);
     const size_t lb = align_up(n_cases * 320, 256), cb = align_up(n_cases * 8, 256), vb = align_up(n_cases * 4, 256);
     int r = ensure_scratch(ctx, lb + cb + vb);
     if (r) return r;
@@ -1202,7 +1205,7 @@ int zb200_gunzip_host(zb200_ctx *ctx, const void *in, size_t n, void *out, size_
     const uint8_t *src = (const uint8_t *)in;
     if (n < 18 || src[0] != 0x1f || src[1] != 0x8b) { *inf_status = n < 2 ? ZB200_INF_TRUNCATED : ZB200_INF_HEADER_CHECK; return ZB200_OK; }
     ZB_CUDA(cudaSetDevice(ctx->device));
-    std::lock_guard<std::mutex> g(ctx->mu);
+    CtxUse use(ctx, ctx->stream);
     cudaStream_t s = ctx->stream;
     int r = ensure_io(ctx, n + 16, 16);
     if (r) return r;
@@ -1306,7 +1309,7 @@ int zb200_inflate_host(zb200_ctx *ctx, const void *in, void *out, const zb200_me
     if (!ctx || !members || !results || wrap < 0 || wrap > 3) return ZB200_ERR_PARAM;
     if (n_members == 0) return ZB200_OK;
     ZB_CUDA(cudaSetDevice(ctx->device));
-    std::lock_guard<std::mutex> g(ctx->mu);
+    CtxUse use(ctx, ctx->stream);
     size_t in_bytes = 0, out_bytes = 0;
     for (size_t i = 0; i < n_members; ++i) {
         if (members[i].in_off + members[i].in_len > in_bytes) in_bytes = members[i].in_off + members[i].in_len;
@@ -1379,13 +1382,15 @@ int zb200_inflate_stream_host(zb200_ctx *ctx, const void *in, size_t n, int wrap
     if (!ctx || (!in && n) || (!out && out_cap) || !result || wrap < 0 || wrap > 3) return ZB200_ERR_PARAM;
     {
         ZB_CUDA(cudaSetDevice(ctx->device));
-        std::lock_guard<std::mutex> g(ctx->mu);
+        CtxUse use(ctx, ctx->stream);
         size_t out_len = 0, in_used = 0;
         int status = 0, applicable = 0;
         uint32_t check = 0;
         const int r = inflate_stream_parallel(ctx, (const uint8_t *)in, n, wrap, (uint8_t *)out, out_cap, &out_len, &status, &in_used, &check, &applicable, nullptr);
-        if (r != ZB200_OK) return r;
-        if (applicable) {
+        // the run-parallel decode is an optimisation: when it cannot get its memory (a stream of stored / binary data with
+        // many false 00 00 FF FF candidates asks for a slot per candidate) the one-member path below decodes the stream
+        if (r != ZB200_OK && r != ZB200_ERR_NOMEM) return r;
+        if (r == ZB200_OK && applicable) {
             memset(result, 0, sizeof *result);
             result->status = status; result->check = check; result->out_len = out_len; result->in_used = in_used;
             result->isize = (uint32_t)out_len;

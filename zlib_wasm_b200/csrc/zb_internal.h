@@ -78,6 +78,12 @@ struct zb200_ctx {
     // device I/O buffers for *_host entry points (grow-only)
     uint8_t *d_io_in = nullptr;  size_t io_in_bytes = 0;
     uint8_t *d_io_out = nullptr; size_t io_out_bytes = 0;
+    // The context's device state (scratch, accumulators, I/O buffers) is shared by every call.  ctx->mu serialises the
+    // HOST side (enqueuing); the device side is ordered by this event: a call that runs on another stream than the
+    // previous one first waits for it (zb::CtxUse).
+    cudaEvent_t busy_ev = nullptr;
+    cudaStream_t busy_stream = nullptr;
+    bool busy_valid = false;
     // per-kernel timing (zb200_profile_*): while on, every kernel launch of the pipelines is preceded by an event
     // on its stream; a kernel's time is the span to the next mark
     bool prof_on = false;
@@ -102,6 +108,20 @@ inline void prof_mark(zb200_ctx *ctx, cudaStream_t s, const char *name) { if (ct
 inline cudaStream_t pick_stream(zb200_ctx *ctx, void *stream) {
     return stream ? (cudaStream_t)stream : ctx->stream;
 }
+// One use of a context: holds ctx->mu for the scope and orders the work enqueued on stream `s` after whatever the
+// previous use left running on a different stream (cudaStreamWaitEvent: no host synchronisation).
+struct CtxUse {
+    zb200_ctx *c; cudaStream_t s; std::unique_lock<std::mutex> lk;
+    CtxUse(zb200_ctx *ctx, cudaStream_t stream) : c(ctx), s(stream), lk(ctx->mu) {
+        if (c->busy_valid && c->busy_stream != s && c->busy_ev) cudaStreamWaitEvent(s, c->busy_ev, 0);
+    }
+    ~CtxUse() {
+        if (c->busy_ev && cudaEventRecord(c->busy_ev, s) == cudaSuccess) { c->busy_stream = s; c->busy_valid = true; }
+        else cudaGetLastError();
+    }
+    CtxUse(const CtxUse &) = delete;
+    CtxUse &operator=(const CtxUse &) = delete;
+};
 
 // zb_checksum.cu
 int checksum_init(zb200_ctx *ctx);
@@ -124,9 +144,24 @@ int deflate_init(zb200_ctx *ctx);
 // deflateTune: {good_length, max_lazy, nice_length, max_chain} for the deflate calls this thread makes next (nullptr: the level's own)
 const int *deflate_tune_override();
 void deflate_tune_set(const int *four);
-int deflate_launch(zb200_ctx *ctx, const uint8_t *d_in, size_t n, size_t S, int level, int strategy, int frame,
-                   int finish, uint8_t *d_out, size_t out_cap, uint64_t *d_chunk_end, uint64_t *d_total,
-                   uint32_t *d_sums_out, cudaStream_t s, size_t skip = 0);   // skip: preset dictionary at the head of a single raw chunk
+// everything deflateInit2_ / deflateSetDictionary / deflatePrime can ask of one engine call
+struct DeflateOpts {
+    int level = 6, strategy = 0;
+    int window_bits = 15, mem_level = 8;     // deflate.c:440-455: w_size, hash_bits, lit_bufsize
+    size_t skip = 0;                         // preset dictionary at the head of a single raw chunk
+    unsigned first_bit = 0;                  // deflatePrime: the stream starts at this bit (0..7) of out[0]
+};
+// The 8 bytes at ctx->d_small + 19 receive {bits in use in the stream's last byte (deflateUsed), 0}.
+int deflate_launch_opts(zb200_ctx *ctx, const uint8_t *d_in, size_t n, size_t S, const DeflateOpts &o, int frame,
+                        int finish, uint8_t *d_out, size_t out_cap, uint64_t *d_chunk_end, uint64_t *d_total,
+                        uint32_t *d_sums_out, cudaStream_t s);
+inline int deflate_launch(zb200_ctx *ctx, const uint8_t *d_in, size_t n, size_t S, int level, int strategy, int frame,
+                          int finish, uint8_t *d_out, size_t out_cap, uint64_t *d_chunk_end, uint64_t *d_total,
+                          uint32_t *d_sums_out, cudaStream_t s, size_t skip = 0) {
+    DeflateOpts o;
+    o.level = level; o.strategy = strategy; o.skip = skip;
+    return deflate_launch_opts(ctx, d_in, n, S, o, frame, finish, d_out, out_cap, d_chunk_end, d_total, d_sums_out, s);
+}
 // zb_zlib_api.cu: the process-wide context behind the zlib.h surface (nullptr without a usable device)
 zb200_ctx *zlib_api_ctx();
 // zb_inflate.cu

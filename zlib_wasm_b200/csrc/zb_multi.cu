@@ -137,8 +137,8 @@ int zb200_multi_deflate_host(zb200_multi *m, const void *in, size_t n, size_t ch
         size_t sub_off[kSub + 1] = {0}, sub_total[kSub] = {0};
         cudaStream_t s = nullptr;
         {
-            std::lock_guard<std::mutex> lk(ctx->mu);
             int r = cudaSetDevice(ctx->device) == cudaSuccess ? ZB200_OK : ZB200_ERR_CUDA;
+            CtxUse lk(ctx, ctx->stream);
             size_t bound_total = 0;
             for (size_t j = 0; j < ns; ++j) {
                 const size_t l = j + 1 < ns ? sub : len[k] - j * sub;
@@ -193,8 +193,8 @@ int zb200_multi_deflate_host(zb200_multi *m, const void *in, size_t n, size_t ch
         final_off[k] = at;
         if (k + 1 == g) need = at + total[k] + ((finish && frame == ZB200_FRAME_ZLIB) ? 4 : (finish && frame == ZB200_FRAME_GZIP) ? 8 : 0);
         if (!ok || at + total[k] > cap) return;
-        std::lock_guard<std::mutex> lk(ctx->mu);
         if (cudaSetDevice(ctx->device) != cudaSuccess) { rc[k] = ZB200_ERR_CUDA; return; }
+        CtxUse lk(ctx, ctx->stream);
         int r = ZB200_OK;
         for (size_t j = 0; j < ns && !r; ++j) {
             if (sub_total[j]) r = d2h_auto(ctx, (uint8_t *)out + at, ctx->d_io_out + sub_off[j], sub_total[j], s);

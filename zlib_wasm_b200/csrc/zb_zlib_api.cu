@@ -99,7 +99,9 @@ struct DeflateStream {
     bool have_dictid;
     gz_headerp gzhead;                   // deflateSetHeader: the caller's header fields (read when the header is written)
     int tune[4]; bool tuned;             // deflateTune: good_length, max_lazy, nice_length, max_chain
+    uint64_t prime_hold; unsigned prime_bits;   // deflatePrime: bits waiting to go out ahead of the next block (deflate.c:731)
     int window_bits, mem_level;          // deflateInit2_'s windowBits (8..15) and memLevel (1..9)
+    int bi_used;                         // deflateUsed: trees.c:187,470, deflate.c:1758
     alloc_func zalloc; free_func zfree; voidpf opaque;   // who allocated this state
 };
 
@@ -165,10 +167,12 @@ struct InflateStream {
     size_t dict_len;                     // preset dictionary: d_out[0 .. dict_len), the output follows it
     uint32_t dictid;                     // DICTID of the zlib header that asked for one
     bool retry;                          // inflateSetDictionary was called: decode again with no new input
+    int hdr_kind;                        // wrapper the first two input bytes select (0: raw / not seen yet), for inflateSync
     unsigned sync_have;                  // inflateSync: pattern bytes matched so far (inflate.c:1352 syncsearch), 0..4
     bool syncing;                        // ... a search is under way (state->mode == SYNC)
     uint32_t prime_hold; unsigned prime_bits;   // inflatePrime: bits ahead of the first input byte (inflate.c:223)
-    bool prime_byte;                     // in[0] is a synthetic byte holding the primed bits (not part of total_in)
+    bool prime_byte;                     // the primed bits have been put ahead of the input ...
+    size_t prime_pref;                   // ... as this many synthetic bytes (not part of total_in)
     alloc_func zalloc; free_func zfree; voidpf opaque;   // who allocated this state
 };
 
@@ -198,40 +202,40 @@ int compress_buffered(DeflateStream &st, bool finish) {
         explicit TuneScope(const int *t) { deflate_tune_set(t); }
         ~TuneScope() { deflate_tune_set(nullptr); }
     } tune_scope(st.tuned ? st.tune : nullptr);
-    size_t cap = zb200_deflate_bound(n, chunk, ZB200_FRAME_RAW);
+    // deflatePrime (deflate.c:731-757): whole bytes of primed bits go out as they are, a rest of k bits occupies the low
+    // bits of the next byte and the engine starts its first block at bit k of it
+    while (st.prime_bits >= 8) { st.pending.push_back((uint8_t)st.prime_hold); st.prime_hold >>= 8; st.prime_bits -= 8; }
+    const unsigned first_bit = st.prime_bits;
+    const uint8_t first_val = (uint8_t)(st.prime_hold & ((1u << first_bit) - 1u));
+    st.prime_bits = 0; st.prime_hold = 0;
+    size_t cap = zb200_deflate_bound(n, chunk, ZB200_FRAME_RAW) + 16;
     if (!st.dict.empty()) cap += zb200_deflate_bound(st.dict.size() + chunk, st.dict.size() + chunk, ZB200_FRAME_RAW);
     const size_t at = st.pending.size();
     st.pending.resize(at + cap);
-    uint32_t adler = 1, crc = 0;
+    uint32_t adler = 1, crc = 0, used = 8;
     int r;
+    zb200_deflate_opts o;
+    o.level = st.level; o.strategy = st.strategy; o.window_bits = st.window_bits; o.mem_level = st.mem_level;
+    o.dict_len = 0; o.first_bit = first_bit;
+    const bool plain = st.window_bits == 15 && st.mem_level == 8 && !first_bit;
     if (!st.dict.empty() && n) {
-        // deflate.c:550-632: the dictionary is window content ahead of the first byte.  The first chunk goes to the
-        // engine behind it (history only); the rest follows as usual, its checksums merged.
-        const size_t first = n < chunk ? n : chunk, dl = st.dict.size();
-        std::vector<uint8_t> joined(dl + first);
+        // deflate.c:550-632: the dictionary is window content ahead of the first byte: the first chunk goes to the engine
+        // behind it (history only), the rest follows as usual
+        const size_t dl = st.dict.size();
+        std::vector<uint8_t> joined(dl + n);
         memcpy(joined.data(), st.dict.data(), dl);
-        memcpy(joined.data() + dl, st.in.data(), first);
-        size_t cap1 = cap;
-        r = zb200_deflate_host_dict(ctx, joined.data(), dl + first, dl, st.level, st.strategy, (finish && first == n) ? 1 : 0,
-                                    st.pending.data() + at, &cap1, &adler, &crc);
-        if (r == ZB200_OK && first < n) {
-            size_t cap2 = cap - cap1;
-            uint32_t a2 = 1, c2 = 0;
-            r = zb200_deflate_host(ctx, st.in.data() + first, n - first, chunk, st.level, st.strategy, ZB200_FRAME_RAW,
-                                   finish ? 1 : 0, st.pending.data() + at + cap1, &cap2, &a2, &c2);
-            crc = zb200_crc32_combine(crc, c2, n - first);
-            adler = zb200_adler32_combine(adler, a2, (int64_t)(n - first));
-            cap1 += cap2;
-        }
-        cap = cap1;
-    } else if (n >= kMultiMin && !st.tuned && api_multi()) {
+        memcpy(joined.data() + dl, st.in.data(), n);
+        o.dict_len = (uint32_t)dl;
+        r = zb200_deflate_host_opts(ctx, joined.data(), dl + n, chunk, &o, ZB200_FRAME_RAW, finish ? 1 : 0, st.pending.data() + at, &cap, &adler, &crc, &used);
+    } else if (n >= kMultiMin && !st.tuned && plain && api_multi()) {
         r = zb200_multi_deflate_host(api_multi(), st.in.data(), n, chunk, st.level, st.strategy, ZB200_FRAME_RAW, finish ? 1 : 0,
                                      st.pending.data() + at, &cap, &adler, &crc);
     } else {
-        r = zb200_deflate_host(ctx, n ? st.in.data() : (const uint8_t *)"", n, chunk, st.level,
-                               st.strategy, ZB200_FRAME_RAW, finish ? 1 : 0,
-                               st.pending.data() + at, &cap, &adler, &crc);
+        r = zb200_deflate_host_opts(ctx, n ? st.in.data() : (const uint8_t *)"", n, chunk, &o, ZB200_FRAME_RAW, finish ? 1 : 0,
+                                    st.pending.data() + at, &cap, &adler, &crc, &used);
     }
+    if (r == ZB200_OK && first_bit && cap) st.pending[at] |= first_val;
+    if (r == ZB200_OK && finish) st.bi_used = (int)used;           // deflateUsed (deflate.c:723)
     if (r != ZB200_OK) { st.pending.resize(at); return map_engine_error(r); }
     st.pending.resize(at + cap);
     st.crc = zb200_crc32_combine(st.crc, crc, n);
@@ -254,7 +258,7 @@ int compress_buffered(DeflateStream &st, bool finish) {
 void put_header(DeflateStream &st) {
     if (st.wrap == 1) {                                        // deflate.c:1004-1037
         const unsigned lf = (st.strategy >= Z_HUFFMAN_ONLY || st.level < 2) ? 0 : st.level < 6 ? 1 : st.level == 6 ? 2 : 3;
-        unsigned hdr = (0x78u << 8) | (lf << 6);
+        unsigned hdr = ((8u + ((unsigned)(st.window_bits - 8) << 4)) << 8) | (lf << 6);   // deflate.c:1006: Z_DEFLATED + ((w_bits - 8) << 4)
         if (st.have_dictid) hdr |= 0x20;                       // PRESET_DICT, deflate.c:1026
         hdr += 31 - hdr % 31;
         st.pending.push_back((uint8_t)(hdr >> 8)); st.pending.push_back((uint8_t)hdr);
@@ -315,7 +319,7 @@ void inflate_reset_state(InflateStream &s) {
     s.resume_bit = s.resume_out = 0; s.started = s.done = false; s.error = 0; s.in_used = 0; s.check = 0;
     s.dict_len = 0; s.dictid = 0; s.retry = false; s.gzhead = Z_NULL; s.verify = true;
     s.rebased = s.seq_ready = s.trailer_pending = false; s.stream_kind = 0; s.in_erased = s.out_before = 0; s.check_before = 0; s.hist.clear();
-    s.sync_have = 0; s.syncing = false; s.prime_hold = 0; s.prime_bits = 0; s.prime_byte = false;
+    s.hdr_kind = 0; s.sync_have = 0; s.syncing = false; s.prime_hold = 0; s.prime_bits = 0; s.prime_byte = false; s.prime_pref = 0;
 }
 
 void hist_push(InflateStream &s, const uint8_t *p, size_t n) {   // keep the last 32 KiB of output
@@ -386,7 +390,7 @@ bool fill_gz_header(const std::vector<uint8_t> &in, gz_header &h) {
 int inflate_attempt(InflateStream &s) {
     zb200_ctx *ctx = api_ctx();
     if (!ctx) return -1;
-    std::lock_guard<std::mutex> g(ctx->mu);
+    CtxUse use(ctx, ctx->stream);
     if (cudaSetDevice(ctx->device) != cudaSuccess) return -1;
     cudaStream_t st = ctx->stream;
     const size_t n = s.in.size();
@@ -478,7 +482,7 @@ int parallel_step(InflateStream &s, int *st_out) {
     uint32_t check = 0;
     const StreamContinuation cont = {s.hist.data(), s.hist.size(), 0u, s.stream_kind};
     {
-        std::lock_guard<std::mutex> g(ctx->mu);
+        CtxUse use(ctx, ctx->stream);
         if (cudaSetDevice(ctx->device) != cudaSuccess) return 0;
         for (int attempt = 0; attempt < 2; ++attempt) {
             s.out.resize(at + cap);
@@ -565,6 +569,7 @@ int deflateReset(z_streamp strm) {
     s->header_done = s->finished = s->trailer_done = false;
     s->crc = 0; s->adler = 1; s->total_in_hashed = 0; s->last_flush = -2;
     s->dict.clear(); s->dictid = 0; s->have_dictid = false; s->keep_history = false;   // (gzhead stays: deflate.c:644-673 does not touch it)
+    s->bi_used = 0; s->prime_hold = 0; s->prime_bits = 0;
     s->tuned = false;                                           // lm_init reloads the level's table values (deflate.c:1307-1326)
     strm->total_in = strm->total_out = 0; strm->msg = Z_NULL; strm->data_type = Z_UNKNOWN;
     strm->adler = s->wrap == 2 ? 0 : 1;                         // deflate.c:656-660
@@ -634,8 +639,27 @@ int deflateSetHeader(z_streamp strm, gz_headerp head) {      // deflate.c:692-69
 int deflatePending(z_streamp strm, unsigned *pending, int *bits) {   // deflate.c:703-713; output here is always whole bytes
     DeflateStream *s = dstate(strm);
     if (!s) return Z_STREAM_ERROR;
-    if (pending != Z_NULL) *pending = (unsigned)(s->pending.size() - s->pending_pos);
-    if (bits != Z_NULL) *bits = 0;
+    if (pending != Z_NULL) *pending = (unsigned)(s->pending.size() - s->pending_pos) + s->prime_bits / 8;
+    if (bits != Z_NULL) *bits = (int)(s->prime_bits & 7u);      // bi_valid: primed bits short of a byte
+    return Z_OK;
+}
+
+// deflate.c:731-757: up to 16 bits per call ahead of the next deflate block.  They wait here (the reference moves them
+// into its bit buffer) until the next block run is compressed; with more than 48 waiting the call is refused like a full
+// pending buffer.
+int deflatePrime(z_streamp strm, int bits, int value) {
+    DeflateStream *s = dstate(strm);
+    if (!s) return Z_STREAM_ERROR;
+    if (bits < 0 || bits > 16 || s->prime_bits + (unsigned)bits > 48) return Z_BUF_ERROR;
+    s->prime_hold |= (uint64_t)((unsigned)value & ((1u << bits) - 1u)) << s->prime_bits;
+    s->prime_bits += (unsigned)bits;
+    return Z_OK;
+}
+
+int deflateUsed(z_streamp strm, int *bits) {                 // deflate.c:723-729: bits of the last byte handed out that are in use
+    DeflateStream *s = dstate(strm);
+    if (!s) return Z_STREAM_ERROR;
+    if (bits != Z_NULL) *bits = s->bi_used;
     return Z_OK;
 }
 
@@ -656,9 +680,32 @@ uLong zlibCompileFlags(void) {                               // zutil.c:32-113: 
     return code(sizeof(uInt)) | (code(sizeof(uLong)) << 2) | (code(sizeof(voidpf)) << 4) | (code(sizeof(z_off_t)) << 6);
 }
 
+// deflate.c:842-905 / compress.c:72.  The reference's tight bound (n + n/4096 + n/16384 + n/2^25 + 13) counts the 5-byte
+// stored-block headers of ITS blocking; this engine's streams are cut into chunks, and a chunk of incompressible bytes
+// costs its own stored blocks — one per sym_limit literals (lit_bufsize - 1, deflate.c:455,512) plus the short one that
+// ends the chunk — and its 5-byte flush marker.  Non-default windowBits / memLevel get the reference's conservative
+// fixed-code bound (deflate.c:852-855) on top of the same per-chunk terms.
+static uLong bound_for(uLong n, int window_bits, int mem_level) {
+    const uLong chunk = (uLong)api_chunk();
+    const uLong sym_limit = (1ul << (mem_level + 6)) - 1;
+    const uLong nch = n / chunk + 1;
+    const uLong per_chunk = 5 * ((chunk + sym_limit - 1) / sym_limit + 1) + 6;
+    uLong body = n + nch * per_chunk;
+    if (window_bits != 15 || mem_level != 8) body += (n >> 3) + (n >> 8) + (n >> 9) + 4;
+    const uLong ref = n + (n >> 12) + (n >> 14) + (n >> 25) + 13;
+    return (body > ref ? body : ref) + 18;
+}
 uLong deflateBound(z_streamp strm, uLong n) {
-    (void)strm;                                                 // compress.c:72 / deflate.c:842 + one marker per chunk
-    return n + (n >> 12) + (n >> 14) + (n >> 25) + 13 + 18 + 5 * (n / api_chunk() + 1);
+    DeflateStream *s = dstate(strm);
+    uLong b = bound_for(n, s ? s->window_bits : 15, s ? s->mem_level : 8);
+    if (s && s->wrap == 2 && s->gzhead != Z_NULL) {             // deflate.c:869-888: the caller's gzip header fields
+        const gz_header &h = *s->gzhead;
+        if (h.extra != Z_NULL) b += 2 + h.extra_len;
+        if (h.name != Z_NULL) b += strlen((const char *)h.name) + 1;
+        if (h.comment != Z_NULL) b += strlen((const char *)h.comment) + 1;
+        if (h.hcrc) b += 2;
+    }
+    return b;
 }
 
 int deflate(z_streamp strm, int flush) {
@@ -773,18 +820,22 @@ int inflate(z_streamp strm, int flush) {
     const bool flush_tail = strm->avail_in == 0 && s->rebased && !s->seq_ready && !s->trailer_pending && !s->in.empty() && s->out.empty();
     if (!s->done && !s->error && (strm->avail_in || s->retry || flush_tail)) {
         s->retry = false;
-        if (s->prime_bits && s->in.empty() && !s->in_erased) {   // inflatePrime: whole bytes go ahead of the input; a rest of k bits
-            while (s->prime_bits >= 8 && (s->prime_bits & 7u) == 0 ? true : s->prime_bits > 8) {   // sits in the top of a synthetic byte entered at bit 8 - k
-                if ((s->prime_bits & 7u) && s->prime_bits < 8) break;
-                if ((s->prime_bits & 7u) != 0) break;
-                s->in.push_back((uint8_t)s->prime_hold); s->prime_hold >>= 8; s->prime_bits -= 8; s->prime_pref++;
+        if (s->prime_bits && s->in.empty() && !s->in_erased) {
+            // inflatePrime: the k = prime_bits % 8 oldest bits sit in the top of a synthetic first byte that the engine
+            // enters at bit 8 - k (raw streams only); the whole bytes behind them go ahead of the input as they are
+            const unsigned k = s->prime_bits & 7u;
+            if (k) {
+                s->in.push_back((uint8_t)((s->prime_hold & ((1u << k) - 1u)) << (8 - k)));
+                s->prime_hold >>= k; s->prime_bits -= k;
+                s->resume_bit = 8 - k; s->resume_out = 0; s->kind = 0;
             }
-            if (s->prime_bits) {
-                const unsigned k = s->prime_bits & 7u ? s->prime_bits & 7u : 0;
-                (void)k;
-            }
+            for (; s->prime_bits; s->prime_bits -= 8, s->prime_hold >>= 8) s->in.push_back((uint8_t)s->prime_hold);
+            s->prime_pref = s->in.size();
+            s->prime_byte = true;
         }
         s->in.insert(s->in.end(), strm->next_in, strm->next_in + strm->avail_in);
+        if (!s->hdr_kind && !s->rebased && !s->in_erased && s->wrap != ZB200_WRAP_RAW && s->in.size() >= 2)
+            s->hdr_kind = ((s->wrap & ZB200_WRAP_GZIP) && s->in[0] == 0x1f && s->in[1] == 0x8b) ? 2 : 1;   // inflate.c:622-669
         if (s->gzhead != Z_NULL && s->gzhead->done == 0 && !s->rebased) {   // inflateGetHeader (inflate.c:1331-1345), while the header bytes are here
             if (s->in.size() >= 2 && !(s->in[0] == 0x1f && s->in[1] == 0x8b)) s->gzhead->done = -1;
             else if (s->in.size() >= 2 && (s->wrap & ZB200_WRAP_GZIP)) fill_gz_header(s->in, *s->gzhead);
@@ -795,7 +846,7 @@ int inflate(z_streamp strm, int flush) {
         if (status == -2) status = inflate_attempt(*s);
         if (status < 0) { strm->msg = "zlib-b200: device error"; return Z_STREAM_ERROR; }
         uLong used = in0;
-        if (status == ZB200_INF_OK) used = (uLong)(s->in_used - total_in0);   // give back bytes after the stream end
+        if (status == ZB200_INF_OK) used = (uLong)(s->in_used - s->prime_pref - total_in0);   // give back bytes after the stream end
         else if (status != ZB200_INF_TRUNCATED) s->error = status;
         strm->next_in += used; strm->avail_in -= (uInt)used; strm->total_in += used;
         if (status == ZB200_INF_OK) strm->adler = s->check;
@@ -835,7 +886,7 @@ int inflateSetDictionary(z_streamp strm, const Bytef *dictionary, uInt dictLengt
     } else if (s->decoded || s->done || s->error || s->dict_len) return Z_STREAM_ERROR;
     const size_t keep = dictLength > 32768u ? 32768u : dictLength;
     {
-        std::lock_guard<std::mutex> g(ctx->mu);
+        CtxUse use(ctx, ctx->stream);
         if (cudaSetDevice(ctx->device) != cudaSuccess) return Z_STREAM_ERROR;
         cudaStream_t st = ctx->stream;
         if (dev_grow(&s->d_out, &s->d_out_cap, keep + (1u << 20), 0, st)) return Z_MEM_ERROR;
@@ -921,11 +972,11 @@ int inflateSync(z_streamp strm) {
     }
     s->in.clear();
     if (s->sync_have != 4) return Z_DATA_ERROR;
-    const int kind = s->started ? s->kind : 0;                  // flags == -1: no header yet, treat as raw
+    const int kind = s->rebased ? s->stream_kind : s->hdr_kind;   // flags == -1: no header yet, treat as raw
     const int wrap = s->wrap;
     const gz_headerp head = s->gzhead;
     inflate_reset_state(*s);
-    s->wrap = wrap; s->gzhead = head; s->started = true; s->kind = kind;
+    s->wrap = wrap; s->gzhead = head; s->started = true; s->kind = kind; s->hdr_kind = kind;
     s->rebased = true; s->stream_kind = kind; s->verify = false;
     s->in.swap(rest);
     return Z_OK;
@@ -974,7 +1025,7 @@ int inflateCopy(z_streamp dest, z_streamp source) {          // inflate.c:1433-1
     if (!d) return Z_MEM_ERROR;
     d->d_in = d->d_out = nullptr;
     {
-        std::lock_guard<std::mutex> g(ctx->mu);
+        CtxUse use(ctx, ctx->stream);
         bool ok = cudaSetDevice(ctx->device) == cudaSuccess;
         if (ok && s->d_in) ok = cudaMalloc((void **)&d->d_in, s->d_in_cap) == cudaSuccess &&
                                 cudaMemcpyAsync(d->d_in, s->d_in, s->d_in_have, cudaMemcpyDeviceToDevice, ctx->stream) == cudaSuccess;
@@ -1068,7 +1119,7 @@ int inflateEnd(z_streamp strm) {
 }
 
 // ---------------------------------------------------------------------------
-uLong compressBound(uLong n) { return deflateBound(Z_NULL, n) - 18 + 6; }
+uLong compressBound(uLong n) { return bound_for(n, 15, 8) - 18 + 6; }
 
 int compress2(Bytef *dest, uLongf *destLen, const Bytef *source, uLong sourceLen, int level) {
     zb200_ctx *ctx = api_ctx();                                 // compress.c:22-59 in one GPU call
