@@ -183,3 +183,27 @@ extern "C" long emul_deflate_chunk(const uint8_t *data, uint32_t n, int level, i
                                    uint8_t *out, size_t cap, uint32_t *stats /* nsyms, nblocks */) {
     return emul_deflate_chunk_dict(data, n, 0, level, strategy, final_chunk, out, cap, stats);
 }
+
+// The kernel's construction (keyed heap, tree_build_fast) against the transliterated one (tree_build), on one set of
+// frequencies: 0 when type, sizes, every code and length, and the dynamic header agree.
+extern "C" int emul_tree_compare(const uint16_t *lfreq /* 286 */, const uint16_t *dfreq /* 30 */, uint32_t byte_len, int strategy) {
+    if (!g_ready) { format_fill(g_fmt); static_trees_fill(g_st); g_ready = 1; }
+    static TreeWork wa, wb;
+    static BlockCode a, b;
+    memset(&wa, 0, sizeof wa); memset(&wb, 0, sizeof wb); memset(&a, 0, sizeof a); memset(&b, 0, sizeof b);
+    for (int i = 0; i < 286; ++i) wa.lt[i].fc = wb.lt[i].fc = lfreq[i];
+    for (int i = 0; i < 30; ++i) wa.dt[i].fc = wb.dt[i].fc = dfreq[i];
+    wa.lt[256].fc = wb.lt[256].fc = 1;
+    BlockInfo blk;
+    memset(&blk, 0, sizeof blk);
+    blk.byte_len = byte_len; blk.flags = BLK_STORED_OK;
+    block_build(wa, blk, strategy, g_st, g_fmt, a);
+    block_build_fast(wb, blk, strategy, g_st, g_fmt, b);
+    if (a.type != b.type) return 1;
+    if (a.hdr_bits != b.hdr_bits || a.body_bits != b.body_bits) return 2;
+    if (a.type == 0) return 0;
+    if (memcmp(a.lcode, b.lcode, sizeof a.lcode) || memcmp(a.llen, b.llen, sizeof a.llen)) return 3;
+    if (memcmp(a.dcode, b.dcode, sizeof a.dcode) || memcmp(a.dlen, b.dlen, sizeof a.dlen)) return 4;
+    if (memcmp(a.hdr, b.hdr, sizeof a.hdr)) return 5;
+    return 0;
+}

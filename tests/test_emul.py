@@ -371,3 +371,60 @@ def test_deflate_window_bits_and_mem_level_byte_exact():
                 else:
                     err, msg, back, used = ref.inflate_all(got, refz.WRAP_RAW, cap=n + 16)
                     assert err == 1 and back == d and len(got) <= 1.03 * len(want) + 8, (kind, wbits, mem, level, strat, err, msg)
+
+
+def test_keyed_heap_tree_builder_equals_the_transliterated_one():
+    """tree_build_fast (what dfl_tree_kernel runs: the active heap carries (Freq << 8 | depth) beside the node number)
+    must reproduce trees.c:627-706 exactly — the tie-breaks of trees.c:499-501 decide the code lengths.  Random, flat,
+    geometric (length-limit overflow, trees.c:573-612), all-equal and depth-wrapping histograms."""
+    L = _build("def_emul")
+    L.emul_tree_compare.restype = C.c_int
+    L.emul_tree_compare.argtypes = [C.POINTER(C.c_uint16), C.POINTER(C.c_uint16), C.c_uint32, C.c_int]
+    rng = random.Random(11)
+
+    def run(lf, df, byte_len=1 << 20, strategy=0):
+        a = (C.c_uint16 * 286)(*[min(65535, x) for x in lf])
+        b = (C.c_uint16 * 30)(*[min(65535, x) for x in df])
+        return L.emul_tree_compare(a, b, byte_len, strategy)
+
+    cases = 0
+    for trial in range(400):
+        kind = trial % 8
+        if kind == 0:
+            lf = [rng.randrange(0, 200) for _ in range(286)]; df = [rng.randrange(0, 100) for _ in range(30)]
+        elif kind == 1:                                   # many equal frequencies: ties everywhere
+            v = rng.randrange(1, 5)
+            lf = [v if rng.random() < 0.8 else 0 for _ in range(286)]; df = [v] * 30
+        elif kind == 2:                                   # geometric: overflows the 15-bit limit
+            lf = [0] * 286
+            for i in range(rng.randrange(17, 40)):
+                lf[rng.randrange(286)] = min(65535, int(1.6 ** i) + 1)
+            df = [min(65535, 2 ** i) for i in range(30)]
+        elif kind == 3:                                   # Fibonacci: the deepest trees
+            f = [1, 1]
+            while len(f) < 24:
+                f.append(f[-1] + f[-2])
+            lf = [0] * 286
+            for i, x in enumerate(f):
+                lf[i * 11] = min(65535, x)
+            df = [min(65535, x) for x in f] + [0] * 6
+        elif kind == 4:                                   # one or two symbols only (trees.c:655-661 forces two codes)
+            lf = [0] * 286; df = [0] * 30
+            lf[rng.randrange(256)] = rng.randrange(1, 1000)
+            if rng.random() < 0.5:
+                df[rng.randrange(30)] = 3
+        elif kind == 5:                                   # text-like: skewed literals, some lengths / distances
+            lf = [int(1000 / (1 + abs(i - 101))) if 32 <= i < 127 else 0 for i in range(286)]
+            for i in range(257, 286):
+                lf[i] = rng.randrange(0, 300)
+            df = [rng.randrange(0, 400) for _ in range(30)]
+        elif kind == 6:                                   # all 286 symbols in use with equal counts
+            lf = [57] * 286; df = [57] * 30
+        else:                                             # large counts (ush sums wrap like the reference's)
+            lf = [rng.randrange(0, 65535) if rng.random() < 0.1 else rng.randrange(0, 3) for _ in range(286)]
+            df = [rng.randrange(0, 65535) for _ in range(30)]
+        for strategy in (0, 4):
+            for byte_len in (1 << 20, 10):
+                assert run(lf, df, byte_len, strategy) == 0, (trial, kind, strategy, byte_len)
+                cases += 1
+    assert cases == 1600

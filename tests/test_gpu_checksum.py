@@ -93,8 +93,8 @@ def test_full_size_4gib_vs_reference(ctx):
         crc, adler = C.c_uint32(), C.c_uint32()
         assert L.zb200_checksum_host(ctx.handle, h, n, 3, 0, 1, C.byref(crc), C.byref(adler)) == 0, zb.last_error()
         # reference over the same bytes, 8 threads + its own combine
-        import bench
-        rc, ra = bench.cpu_checksums(r, h, n, bench.host_threads())
+        import bench_legs
+        _, rc, ra = bench_legs.Cpu().checksum(h, n, bench_legs.host_threads(), 1)
         assert (crc.value, adler.value) == (rc, ra)
         # device-resident single launch over the whole 4 GiB and the split property
         d = torch.empty(n, dtype=torch.uint8, device="cuda")

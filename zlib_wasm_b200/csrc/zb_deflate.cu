@@ -572,34 +572,77 @@ dfl_parse_kernel(Batch b, DeflateParams prm, const uint32_t *__restrict__ mfull,
 }
 
 // ---- phase 4: per-block histogram + Huffman construction -------------------------------
-__global__ void __launch_bounds__(128)
+// One WARP per block.  The construction itself is the reference's heap algorithm — its tie-breaks (trees.c:499-501) decide
+// the code lengths, so it is replayed exactly, and it is serial — which makes this kernel latency-bound on ONE thread per
+// block: what counts is how many blocks an SM works on at once (a warp per block: ~40 per SM, against 16 with a
+// 128-thread CTA per block) and how short the thread's dependent chain is (keyed heap, zb_deflate.cuh tree_build_fast).
+// The warp's other lanes count the frequencies beforehand and copy the tables out afterwards.
+constexpr int kTreeWarps = 4;
+__global__ void __launch_bounds__(kTreeWarps * 32)
 dfl_tree_kernel(Batch b, int strategy, const uint32_t *__restrict__ syms, const BlockInfo *__restrict__ blocks,
                 const uint32_t *__restrict__ nblocks, const DeflateDeviceTables *__restrict__ tabs,
                 BlockCode *__restrict__ codes) {
-    const uint32_t c = blockIdx.y, bi = blockIdx.x;
-    if (bi >= nblocks[c]) return;
-    __shared__ TreeWork w;
-    __shared__ uint32_t hist[288 + 32];
-    for (int i = threadIdx.x; i < 320; i += 128) hist[i] = 0;
+    __shared__ TreeWork ws[kTreeWarps];
+    __shared__ StaticTrees s_st;                                   // the serial thread's operands: never a global-memory round trip
+    __shared__ FormatTables s_fmt;
+    const uint32_t c = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (uint32_t i = threadIdx.x; i < sizeof(StaticTrees) / 4; i += blockDim.x)
+        reinterpret_cast<uint32_t *>(&s_st)[i] = reinterpret_cast<const uint32_t *>(&tabs->st)[i];
+    for (uint32_t i = threadIdx.x; i < sizeof(FormatTables) / 4; i += blockDim.x)
+        reinterpret_cast<uint32_t *>(&s_fmt)[i] = reinterpret_cast<const uint32_t *>(&tabs->fmt)[i];
     __syncthreads();
+    const uint32_t bi = blockIdx.x * kTreeWarps + warp;
+    if (bi >= nblocks[c]) return;                                  // (warp-uniform; no CTA-wide barrier from here on)
+    TreeWork &w = ws[warp];
+    const unsigned full = 0xffffffffu;
+    for (uint32_t i = lane; i < 288; i += 32) w.hkey[i] = 0;
+    w.dhist[lane] = 0;
+    __syncwarp(full);
     const BlockInfo blk = blocks[(uint64_t)c * b.MB + bi];
     const uint32_t *s = syms + (uint64_t)c * b.S + blk.sym_start;
-    for (uint32_t i = threadIdx.x; i < blk.sym_count; i += 128) {
-        const uint32_t v = s[i], dist = v >> 16, lc = v & 0xffff;
-        if (!dist) atomicAdd(&hist[lc], 1u);
-        else {
-            atomicAdd(&hist[257 + tabs->fmt.len_code[lc]], 1u);
-            atomicAdd(&hist[288 + dist_to_code(tabs->fmt, dist)], 1u);
+    constexpr uint32_t U = 16;                                     // symbols in flight per lane: the loop is bound by load latency
+    for (uint32_t base = 0; base < blk.sym_count; base += 32 * U) {
+        uint32_t v[U];
+#pragma unroll
+        for (uint32_t k = 0; k < U; ++k) { const uint32_t i = base + k * 32 + lane; v[k] = i < blk.sym_count ? s[i] : 0xffffffffu; }
+#pragma unroll
+        for (uint32_t k = 0; k < U; ++k) {
+            if (v[k] == 0xffffffffu) continue;                     // (no symbol has distance 65535)
+            const uint32_t dist = v[k] >> 16, lc = v[k] & 0xffff;
+            if (!dist) atomicAdd(&w.hkey[lc], 1u);
+            else {
+                atomicAdd(&w.hkey[257 + s_fmt.len_code[lc]], 1u);
+                atomicAdd(&w.dhist[dist_to_code(s_fmt, dist)], 1u);
+            }
         }
     }
-    __syncthreads();
-    for (int i = threadIdx.x; i < 286; i += 128) w.lt[i].fc = (uint16_t)hist[i];
-    for (int i = threadIdx.x; i < 30; i += 128) w.dt[i].fc = (uint16_t)hist[288 + i];
-    __syncthreads();
-    if (threadIdx.x == 0) {
+    __syncwarp(full);
+    for (uint32_t i = lane; i < 286; i += 32) w.lt[i].fc = (uint16_t)w.hkey[i];
+    if (lane < 30) w.dt[lane].fc = (uint16_t)w.dhist[lane];
+    __syncwarp(full);
+    BlockCode &out = codes[(uint64_t)c * b.MB + bi];
+    if (lane == 0) {
         w.lt[256].fc = 1;                                          // END_BLOCK (trees.c:480 init_block)
-        block_build(w, blk, strategy, tabs->st, tabs->fmt, codes[(uint64_t)c * b.MB + bi]);
+        block_build_t<true, false>(w, blk, strategy, s_st, s_fmt, out, w.hkey);
     }
+    __syncwarp(full);
+    const uint32_t type = out.type;
+    if (type == 1) {
+        for (uint32_t n = lane; n < 288; n += 32) { out.lcode[n] = s_st.lcode[n]; out.llen[n] = s_st.llen[n]; }
+        out.dcode[lane] = s_st.dcode[lane]; out.dlen[lane] = s_st.dlen[lane];
+    } else if (type == 2) {
+        const uint32_t l_max = out.pad & 0xffffu, d_max = out.pad >> 16;
+        for (uint32_t n = lane; n < 288; n += 32) {
+            out.lcode[n] = n < 286 ? w.lt[n].fc : (uint16_t)0;
+            out.llen[n] = n <= l_max ? (uint8_t)w.lt[n].dl : (uint8_t)0;
+        }
+        out.dcode[lane] = lane < 30 ? w.dt[lane].fc : (uint16_t)0;
+        out.dlen[lane] = lane <= d_max ? (uint8_t)w.dt[lane].dl : (uint8_t)0;
+        const uint32_t nw = (out.hdr_bits + 31) >> 5;
+        for (uint32_t i = lane; i < nw; i += 32) out.hdr[i] = w.hkey[i];
+    }
+    __syncwarp(full);
+    if (lane == 0) out.pad = 0;
 }
 
 // ---- layout: bit offsets of blocks inside their chunk, chunk sizes ---------------------
@@ -924,7 +967,7 @@ int deflate_launch_opts(zb200_ctx *ctx, const uint8_t *d_in, size_t n, size_t S,
         else dfl_parse_greedy_kernel<<<b.nb, kGtWarps * 32, 0, s>>>(b, prm, w.mfull, w.syms, w.blocks, w.nblocks);
         ZB_LAUNCHED(); ZB_CHECK_LAUNCH();
         prof_mark(ctx, s, "dfl_tree_kernel");
-        dfl_tree_kernel<<<dim3(MB, b.nb), 128, 0, s>>>(b, strategy | (level == 0 ? 0x100 : 0), w.syms, w.blocks, w.nblocks, tabs, w.codes);
+        dfl_tree_kernel<<<dim3((MB + kTreeWarps - 1) / kTreeWarps, b.nb), kTreeWarps * 32, 0, s>>>(b, strategy | (level == 0 ? 0x100 : 0), w.syms, w.blocks, w.nblocks, tabs, w.codes);
         ZB_LAUNCHED(); ZB_CHECK_LAUNCH();
         prof_mark(ctx, s, "dfl_layout_kernel");
         dfl_layout_kernel<<<(b.nb + 127) / 128, 128, 0, s>>>(b, w.blocks, w.codes, w.nblocks, w.chunk_bytes, members ? 18 : 0,

@@ -743,6 +743,9 @@ struct TreeWork {                             // one per CTA (shared memory)
     uint16_t bl_count[16];
     int heap_len, heap_max;
     uint32_t opt_len, static_len;
+    uint32_t hkey[286 + 2];                   // tree_build_fast: (Freq << 8) | depth of heap[1 .. heap_len]; the kernel also
+                                              // counts literal/length frequencies here and stages the dynamic header here
+    uint32_t dhist[32];                       // ... and distance-code frequencies here
 };
 
 ZB_HD uint32_t bit_reverse(uint32_t code, int len) {   // trees.c:154
@@ -862,6 +865,82 @@ ZB_HD int tree_build(TreeWork &w, TreeNode *t, int elems, const uint8_t *st_len,
     return max_code;
 }
 
+// ---- the same construction, arranged for one GPU thread ------------------------------------
+// pqdownheap's comparison (trees.c:499-501: smaller by frequency, ties by subtree depth, `<=`) reads heap[j], then the
+// node's Freq, then its depth: three dependent shared-memory round trips per heap level.  Here the active heap carries
+// its sort key beside the node number — (Freq << 8) | depth, compared with one `<=` — so a level costs one round trip
+// (both children are requested together).  Merge order, heap contents and therefore every code length are those of
+// tree_build (the host replay compares the two over random and adversarial histograms).
+ZB_HD void tree_sift_fast(TreeWork &w, int k) {
+    const uint32_t vk = w.hkey[k];
+    const int16_t vn = w.heap[k];
+    const int len = w.heap_len;
+    int j = k << 1;
+    while (j <= len) {
+        uint32_t kj = w.hkey[j];
+        if (j < len) { const uint32_t kr = w.hkey[j + 1]; if (kr <= kj) { kj = kr; ++j; } }
+        if (vk <= kj) break;
+        w.hkey[k] = kj; w.heap[k] = w.heap[j];
+        k = j; j <<= 1;
+    }
+    w.hkey[k] = vk; w.heap[k] = vn;
+}
+
+ZB_HD uint32_t bit_reverse_fast(uint32_t code, int len) {
+#if defined(__CUDA_ARCH__)
+    return __brev(code) >> (32 - len);
+#else
+    return bit_reverse(code, len);
+#endif
+}
+
+ZB_HD int tree_build_fast(TreeWork &w, TreeNode *t, int elems, const uint8_t *st_len,
+                          const uint8_t *extra, int base, int max_length) {
+    constexpr int HEAP_SIZE = 2 * 286 + 1;
+    int max_code = -1, node;
+    w.heap_len = 0; w.heap_max = HEAP_SIZE;
+    for (int n = 0; n < elems; ++n) {
+        const uint32_t f = t[n].fc;
+        if (f) { w.heap[++w.heap_len] = (int16_t)(max_code = n); w.hkey[w.heap_len] = f << 8; w.depth[n] = 0; }
+        else t[n].dl = 0;
+    }
+    while (w.heap_len < 2) {                           // trees.c:655-661: force two codes
+        node = w.heap[++w.heap_len] = (int16_t)(max_code < 2 ? ++max_code : 0);
+        t[node].fc = 1; w.depth[node] = 0; w.hkey[w.heap_len] = 1u << 8;
+        w.opt_len--; if (st_len) w.static_len -= st_len[node];
+    }
+    for (int n = w.heap_len / 2; n >= 1; --n) tree_sift_fast(w, n);
+    node = elems;
+    do {
+        const int n = w.heap[1];
+        const uint32_t kn = w.hkey[1];
+        w.heap[1] = w.heap[w.heap_len]; w.hkey[1] = w.hkey[w.heap_len]; --w.heap_len;
+        tree_sift_fast(w, 1);
+        const int m = w.heap[1];
+        const uint32_t km = w.hkey[1];
+        w.heap[--w.heap_max] = (int16_t)n;
+        w.heap[--w.heap_max] = (int16_t)m;
+        const uint32_t f = ((kn >> 8) + (km >> 8)) & 0xffffu;                       // ush arithmetic, as deflate.h:75-90
+        const uint32_t dn = kn & 0xffu, dm = km & 0xffu, d = ((dn >= dm ? dn : dm) + 1u) & 0xffu;   // uch depth
+        t[node].fc = (uint16_t)f; w.depth[node] = (uint8_t)d;
+        t[n].dl = t[m].dl = (uint16_t)node;
+        w.heap[1] = (int16_t)node++; w.hkey[1] = (f << 8) | d;
+        tree_sift_fast(w, 1);
+    } while (w.heap_len >= 2);
+    w.heap[--w.heap_max] = w.heap[1];
+    tree_gen_bitlen(w, t, max_code, st_len, extra, base, max_length);
+    {                                                  // trees.c:203-232 gen_codes
+        uint16_t next[16];
+        uint32_t code = 0;
+        for (int b = 1; b <= 15; ++b) { code = (code + w.bl_count[b - 1]) << 1; next[b] = (uint16_t)code; }
+        for (int n = 0; n <= max_code; ++n) {
+            const int len = t[n].dl;
+            if (len) t[n].fc = (uint16_t)bit_reverse_fast(next[len]++, len);
+        }
+    }
+    return max_code;
+}
+
 struct HdrWriter {                                    // LSB-first appender for the dynamic header
     uint32_t *words; uint32_t nbits;
     ZB_HD void put(uint32_t v, int len) {
@@ -909,16 +988,20 @@ ZB_HD void tree_walk(TreeWork &w, TreeNode *t, int max_code, HdrWriter *out) {
 // trees.c:997-1089 _tr_flush_block for one block whose symbol frequencies are
 // already in w.lt[0..285].fc / w.dt[0..29].fc (END_BLOCK counted).  Decides
 // stored / fixed / dynamic and fills `out`.
-ZB_HD void block_build(TreeWork &w, const BlockInfo &blk, int strategy, const StaticTrees &st,
-                       const FormatTables &fmt, BlockCode &out) {
+// kFast: the keyed heap (tree_build_fast).  kCopy: also copy the chosen code tables into `out` (the GPU kernel lets
+// the whole warp do that afterwards: out.pad = l_max | d_max << 16 tells it how far the dynamic lengths reach).
+// hdr: where the dynamic header's bit string goes (160 words; out.hdr, or a staging area the caller copies out).
+template <bool kFast, bool kCopy>
+ZB_HD void block_build_t(TreeWork &w, const BlockInfo &blk, int strategy, const StaticTrees &st,
+                         const FormatTables &fmt, BlockCode &out, uint32_t *hdr) {
     const uint8_t bl_extra[19] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 2, 3, 7};
     w.opt_len = 0; w.static_len = 0;
     for (int n = 0; n < 19; ++n) w.bt[n].fc = 0;
-    const int l_max = tree_build(w, w.lt, 286, st.llen, fmt.len_extra, 257, 15);
-    const int d_max = tree_build(w, w.dt, 30, st.dlen, fmt.dist_extra, 0, 15);
+    const int l_max = kFast ? tree_build_fast(w, w.lt, 286, st.llen, fmt.len_extra, 257, 15) : tree_build(w, w.lt, 286, st.llen, fmt.len_extra, 257, 15);
+    const int d_max = kFast ? tree_build_fast(w, w.dt, 30, st.dlen, fmt.dist_extra, 0, 15) : tree_build(w, w.dt, 30, st.dlen, fmt.dist_extra, 0, 15);
     tree_walk(w, w.lt, l_max, nullptr);                // trees.c:800-829 build_bl_tree
     tree_walk(w, w.dt, d_max, nullptr);
-    tree_build(w, w.bt, 19, nullptr, bl_extra, 0, 7);
+    if (kFast) tree_build_fast(w, w.bt, 19, nullptr, bl_extra, 0, 7); else tree_build(w, w.bt, 19, nullptr, bl_extra, 0, 7);
     int mb;
     for (mb = 18; mb >= 3; --mb) if (w.bt[fmt.cl_order[mb]].dl) break;
     w.opt_len += 3 * ((uint32_t)mb + 1) + 5 + 5 + 4;
@@ -927,19 +1010,23 @@ ZB_HD void block_build(TreeWork &w, const BlockInfo &blk, int strategy, const St
     const bool force_stored = (strategy & 0x100) != 0;   // level 0: trees.c:1041-1043 forces stored blocks
     strategy &= 0xff;
     if (static_lenb <= opt_lenb || strategy == STRAT_FIXED) opt_lenb = static_lenb;
-    out.hdr_bits = 0; out.pad = 0;
+    out.hdr_bits = 0; out.pad = (uint32_t)l_max | ((uint32_t)d_max << 16);
     if (force_stored || (blk.byte_len + 4 <= opt_lenb && (blk.flags & BLK_STORED_OK))) {
         out.type = 0; out.body_bits = 0;
     } else if (static_lenb == opt_lenb) {
         out.type = 1; out.body_bits = 3 + w.static_len;
-        for (int n = 0; n < 288; ++n) { out.lcode[n] = st.lcode[n]; out.llen[n] = st.llen[n]; }
-        for (int n = 0; n < 32; ++n) { out.dcode[n] = st.dcode[n]; out.dlen[n] = st.dlen[n]; }
+        if (kCopy) {
+            for (int n = 0; n < 288; ++n) { out.lcode[n] = st.lcode[n]; out.llen[n] = st.llen[n]; }
+            for (int n = 0; n < 32; ++n) { out.dcode[n] = st.dcode[n]; out.dlen[n] = st.dlen[n]; }
+        }
     } else {
         out.type = 2; out.body_bits = 3 + w.opt_len;
-        for (int n = 0; n < 288; ++n) { out.lcode[n] = n < 286 ? w.lt[n].fc : 0; out.llen[n] = n <= l_max ? (uint8_t)w.lt[n].dl : 0; }
-        for (int n = 0; n < 32; ++n) { out.dcode[n] = n < 30 ? w.dt[n].fc : 0; out.dlen[n] = n <= d_max ? (uint8_t)w.dt[n].dl : 0; }
-        for (int i = 0; i < 160; ++i) out.hdr[i] = 0;
-        HdrWriter hw{out.hdr, 0};
+        if (kCopy) {
+            for (int n = 0; n < 288; ++n) { out.lcode[n] = n < 286 ? w.lt[n].fc : 0; out.llen[n] = n <= l_max ? (uint8_t)w.lt[n].dl : 0; }
+            for (int n = 0; n < 32; ++n) { out.dcode[n] = n < 30 ? w.dt[n].fc : 0; out.dlen[n] = n <= d_max ? (uint8_t)w.dt[n].dl : 0; }
+        }
+        for (int i = 0; i < 160; ++i) hdr[i] = 0;
+        HdrWriter hw{hdr, 0};
         hw.put((uint32_t)l_max + 1 - 257, 5);         // trees.c:833-855 send_all_trees
         hw.put((uint32_t)d_max + 1 - 1, 5);
         hw.put((uint32_t)mb + 1 - 4, 4);
@@ -948,6 +1035,16 @@ ZB_HD void block_build(TreeWork &w, const BlockInfo &blk, int strategy, const St
         tree_walk(w, w.dt, d_max, &hw);
         out.hdr_bits = hw.nbits;
     }
+}
+ZB_HD void block_build_fast(TreeWork &w, const BlockInfo &blk, int strategy, const StaticTrees &st,
+                            const FormatTables &fmt, BlockCode &out) {   // host replay of the kernel's construction
+    block_build_t<true, true>(w, blk, strategy, st, fmt, out, out.hdr);
+    out.pad = 0;
+}
+ZB_HD void block_build(TreeWork &w, const BlockInfo &blk, int strategy, const StaticTrees &st,
+                       const FormatTables &fmt, BlockCode &out) {
+    block_build_t<false, true>(w, blk, strategy, st, fmt, out, out.hdr);
+    out.pad = 0;
 }
 
 // ---- phase 5: symbol -> bits (trees.c:900-951 compress_block) ----------------------

@@ -443,7 +443,8 @@ int inflate_attempt(InflateStream &s) {
             s.decoded = valid;
         }
         if (s.rebased) {
-            if (r.status == ZB200_INF_TRUNCATED && r.resume_bit) { s.resume_bit = r.resume_bit; s.resume_out = r.resume_out; }
+            // (a data error keeps the last block boundary too: inflateSync starts its search there)
+            if (r.status != ZB200_INF_OK && r.status != ZB200_INF_OUTPUT_FULL && r.resume_bit) { s.resume_bit = r.resume_bit; s.resume_out = r.resume_out; }
             if (r.status != ZB200_INF_OK) return r.status;
             uint32_t tail = r.check;                             // CRC-32 of the bytes since the base (raw members get a CRC)
             if (s.stream_kind == 1) {                            // a zlib wrapper wants their Adler-32
@@ -460,7 +461,10 @@ int inflate_attempt(InflateStream &s) {
         if (r.status == ZB200_INF_NEED_DICT) s.dictid = r.check;
         if (r.status == ZB200_INF_TRUNCATED) {
             if (r.resume_bit) { s.resume_bit = r.resume_bit; s.resume_out = r.resume_out; }
-        } else if (r.status == ZB200_INF_OK) {
+        } else if (r.status != ZB200_INF_OK) {                    // a data error: the last block boundary is where inflateSync starts its search
+            if (r.resume_bit) { s.resume_bit = r.resume_bit; s.resume_out = r.resume_out; }
+        }
+        if (r.status == ZB200_INF_OK) {
             s.done = true; s.in_used = s.in_erased + r.in_used; s.check = r.check;
         }
         return r.status;
