@@ -321,7 +321,13 @@ dfl_match_sorted_kernel(Batch b, DeflateParams prm, const uint16_t *__restrict__
     const uint32_t lo = t0 > (uint32_t)kWSize ? t0 - kWSize : 0;             // candidates lie less than 32 KiB back
     const uint32_t hi = t1 + kMsLook < n ? t1 + kMsLook : n;                  // bytes [lo, hi) can be read
     if (threadIdx.x < kMsBuckets) s_hist[threadIdx.x] = 0;
-    const StagedMem mem = stage_window(b, data, prev, lo, hi, t1);
+    StagedMem mem = stage_window(b, data, prev, lo, hi, t1);
+    // Pin the two bases in registers.  At 64 registers per thread the compiler otherwise REMATERIALISES them inside the
+    // walk loop — 21 instructions (S2UR ctaid, LDC, S2UR CgaCtaId, ULEA, ...) per candidate step, half of the step
+    // (ncu source page, round 2).  The result of an asm statement cannot be recomputed, so it has to stay live.
+    uint32_t n_pin = n;                                            // (the chunk length too: it is read in the measuring path)
+    asm volatile("" : "+r"(mem.dbase), "+r"(mem.lbase), "+r"(n_pin));
+
     uint32_t bk[kMsTile / kMsThreads];
 #pragma unroll
     for (uint32_t k = 0; k < kMsTile / kMsThreads; ++k) {
@@ -361,7 +367,7 @@ dfl_match_sorted_kernel(Batch b, DeflateParams prm, const uint16_t *__restrict__
     __syncthreads();
     for (uint32_t i = threadIdx.x; i < cnt; i += kMsThreads) {
         const uint32_t p = t0 + s_order[i];
-        const MatchPair r = match_walk(mem, n, p, prm);
+        const MatchPair r = match_walk(mem, n_pin, p, prm);
         mfull[off + p] = r.full;
         if (prm.need_quarter) mquarter[off + p] = r.quarter;
     }
