@@ -340,3 +340,48 @@ def test_bounds_hold_for_incompressible_input(chunk):
         env.pop("ZB200_CHUNK", None)
     p = subprocess.run([sys.executable, "-c", BOUND_SCRIPT % {"root": ROOT}], env=env, capture_output=True, text=True, timeout=600)
     assert p.returncode == 0 and "ok" in p.stdout, p.stderr[-2000:]
+
+
+@pytest.mark.parametrize("wbits", [15, 31, -15])
+def test_streaming_inflate_memory_is_bounded(z, wbits):
+    """A long stream WITHOUT flush points (the reference's one-shot compress2 / deflate(Z_FINISH): one run of blocks) fed in
+    slices: the one-member path re-bases at block boundaries (32 KiB of history, as inflate.c:368-412 keeps), so what the
+    stream holds stays small, and output, trailer verdict and total counts are the reference's."""
+    if not refz.have_refpool():
+        pytest.skip("oracle/_ref/librefpool.so not built")
+    rp = refz.refpool()
+    n = 48 << 20
+    d = refz.gen(n, refz.GEN_MARKOV, seed=99)
+    cap = n // 2 + (1 << 20)
+    comp = C.create_string_buffer(cap)
+    clen, sec = C.c_size_t(0), C.c_double(0)
+    assert rp.rp_compress2_whole(d, n, 6, 0, wbits, 8, comp, cap, C.byref(clen), C.byref(sec)) == 0
+    s = comp.raw[:clen.value]
+    assert s.count(b"\x00\x00\xff\xff") < 50                 # no flush points (only chance occurrences)
+    for slice_in, slice_out in ((1 << 16, 1 << 20), (3 << 20, 1 << 17)):
+        strm = refz.ZStream()
+        assert z.inflateInit2_(C.byref(strm), wbits, z.version, ZS) == 0
+        src, dst = C.create_string_buffer(s, len(s)), C.create_string_buffer(n + 64)
+        fed = produced = 0
+        r = 0
+        while r == 0 or r == refz.Z_BUF_ERROR:
+            if strm.avail_in == 0 and fed < len(s):
+                k = min(slice_in, len(s) - fed)
+                strm.next_in, strm.avail_in = C.addressof(src) + fed, k
+                fed += k
+            room = min(slice_out, n + 64 - produced)
+            strm.next_out, strm.avail_out = C.addressof(dst) + produced, room
+            r = z.inflate(C.byref(strm), refz.Z_NO_FLUSH)
+            produced += room - strm.avail_out
+            if r == refz.Z_BUF_ERROR and strm.avail_in == 0 and fed >= len(s) and room == strm.avail_out:
+                break
+        assert r == refz.Z_STREAM_END, (wbits, slice_in, r, strm.msg, produced)
+        assert produced == n == strm.total_out and strm.total_in == len(s)
+        assert dst.raw[:n] == d
+        z.inflateEnd(C.byref(strm))
+    # a damaged trailer is still caught after any number of re-bases
+    if wbits != -15:
+        bad = bytearray(s)
+        bad[-5 if wbits == 31 else -1] ^= 1
+        ret, msg, out, tin = z.inflate_all(bytes(bad), {15: refz.WRAP_ZLIB, 31: refz.WRAP_GZIP}[wbits], cap=n + 64, in_slice=1 << 18)
+        assert ret == refz.Z_DATA_ERROR and msg == "incorrect data check", (ret, msg)

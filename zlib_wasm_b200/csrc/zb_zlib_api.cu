@@ -385,6 +385,40 @@ bool fill_gz_header(const std::vector<uint8_t> &in, gz_header &h) {
     return true;
 }
 
+// Bounded memory for a stream without flush points (the reference needs a 32 KiB window, inflate.c:368-412): the
+// one-member path RE-BASES at a deflate-block boundary once enough has piled up behind it — the input before the
+// boundary and the output delivered so far leave the buffers, the check value of that output is folded into
+// check_before, and the engine continues at the boundary as a raw stream behind the last 32 KiB of output (the
+// dictionary mechanism), exactly as parallel_step does at flush points.  rbit: bit offset of the boundary in s.in;
+// rout: output bytes since the current base that lie before it (all delivered, the tail of them in s.hist).
+constexpr uint64_t kRebaseIn = (uint64_t)1 << 20, kRebaseOut = (uint64_t)4 << 20;    // re-base after 1 MiB in / 4 MiB out
+constexpr size_t kDevOutCap = (size_t)1 << 30;                                        // ... and rather than growing the device output past 1 GiB
+constexpr size_t kTakeMax = (size_t)256 << 20, kOwedMax = (size_t)256 << 20;           // input taken per inflate() call / output owed before more is taken
+int rebase_here(InflateStream &s, zb200_ctx *ctx, cudaStream_t st, uint64_t rbit, uint64_t rout) {
+    const int kind = s.rebased ? s.stream_kind : s.kind;
+    uint32_t part = kind == 1 ? 1u : 0u;
+    if (rout) {
+        uint8_t *base = (uint8_t *)ctx->d_scratch;
+        uint32_t *d_sum = (uint32_t *)(base + 512);
+        if (checksum_launch(ctx, s.d_out + s.dict_len, nullptr, nullptr, rout, 1, kind == 1 ? ZB200_ADLER32 : ZB200_CRC32, 0, 1, d_sum, d_sum + 1,
+                            (CkAccum *)(base + 768), st) != ZB200_OK) return -1;
+        if (cudaMemcpyAsync(ctx->h_small, d_sum, 8, cudaMemcpyDeviceToHost, st) != cudaSuccess) return -1;
+        if (cudaStreamSynchronize(st) != cudaSuccess) return -1;
+        part = ((const uint32_t *)ctx->h_small)[kind == 1 ? 1 : 0];
+    }
+    if (!s.rebased) { s.stream_kind = kind; s.check_before = part; s.out_before = rout; s.rebased = true; }
+    else {
+        s.check_before = kind == 1 ? zb200_adler32_combine(s.check_before, part, (int64_t)rout) : zb200_crc32_combine(s.check_before, part, rout);
+        s.out_before += rout;
+    }
+    const size_t drop = (size_t)(rbit >> 3);
+    s.in_erased += drop;
+    s.in.erase(s.in.begin(), s.in.begin() + (long)drop);
+    s.d_in_have = 0;
+    s.resume_bit = rbit & 7u; s.resume_out = 0; s.decoded = 0; s.seq_ready = false;
+    return 0;
+}
+
 // One decode attempt over everything received so far, resuming at the last
 // block boundary.  Updates the stream state; returns a ZB200_INF_* status.
 int inflate_attempt(InflateStream &s) {
@@ -393,6 +427,8 @@ int inflate_attempt(InflateStream &s) {
     CtxUse use(ctx, ctx->stream);
     if (cudaSetDevice(ctx->device) != cudaSuccess) return -1;
     cudaStream_t st = ctx->stream;
+    if (ensure_scratch(ctx, 1024 + inflate_work_bytes(1)) != ZB200_OK) return -1;
+    for (;;) {
     const size_t n = s.in.size();
     if (dev_grow(&s.d_in, &s.d_in_cap, n + 16, s.d_in_have, st)) return -1;
     if (n > s.d_in_have) {
@@ -407,7 +443,7 @@ int inflate_attempt(InflateStream &s) {
         s.seq_ready = true;
     }
     if (s.d_out_cap == 0 && dev_grow(&s.d_out, &s.d_out_cap, n * 4 + (1u << 20) + s.dict_len, 0, st)) return -1;
-    if (ensure_scratch(ctx, 1024 + inflate_work_bytes(1)) != ZB200_OK) return -1;
+    bool again = false;                                          // re-based mid-call: go round once more from the new base
     for (;;) {
         zb200_member m;
         m.in_off = 0; m.in_len = n; m.out_off = s.dict_len; m.out_cap = s.d_out_cap - s.dict_len;
@@ -423,9 +459,21 @@ int inflate_attempt(InflateStream &s) {
         if (cudaMemcpyAsync(h_r, d_r, sizeof *h_r, cudaMemcpyDeviceToHost, st) != cudaSuccess) return -1;
         if (cudaStreamSynchronize(st) != cudaSuccess) return -1;
         const zb200_member_result r = *h_r;
-        if (r.status == ZB200_INF_OUTPUT_FULL) {                 // grow the device output and go again from the checkpoint
-            s.kind = (int)r.wrap_kind; s.resume_bit = r.resume_bit; s.resume_out = r.resume_out;
+        if (r.status == ZB200_INF_OUTPUT_FULL) {                 // grow the device output and go again from the checkpoint ...
+            if (!s.rebased) s.kind = (int)r.wrap_kind;
+            s.resume_bit = r.resume_bit; s.resume_out = r.resume_out;
             if (r.resume_bit == 0) { s.resume_bit = 0; s.resume_out = 0; }
+            if (s.d_out_cap >= kDevOutCap && r.resume_bit && r.resume_out > s.decoded) {
+                // ... or, once the buffer is large, hand out what is complete and re-base at the checkpoint instead
+                const size_t add = (size_t)(r.resume_out - s.decoded), at = s.out.size();
+                s.out.resize(at + add);
+                if (cudaMemcpyAsync(s.out.data() + at, s.d_out + s.dict_len + s.decoded, add, cudaMemcpyDeviceToHost, st) != cudaSuccess) return -1;
+                if (cudaStreamSynchronize(st) != cudaSuccess) return -1;
+                hist_push(s, s.out.data() + at, add);
+                if (rebase_here(s, ctx, st, r.resume_bit, r.resume_out)) return -1;
+                again = true;
+                break;
+            }
             if (dev_grow(&s.d_out, &s.d_out_cap, s.d_out_cap * 2 + (1u << 20), (size_t)r.out_len + s.dict_len, st)) return -1;
             continue;
         }
@@ -441,6 +489,13 @@ int inflate_attempt(InflateStream &s) {
             if (cudaStreamSynchronize(st) != cudaSuccess) return -1;
             hist_push(s, s.out.data() + at, add);
             s.decoded = valid;
+        }
+        // bounded memory: enough has piled up behind the last block boundary -> continue from there as a re-based stream
+        if (r.status == ZB200_INF_TRUNCATED && r.resume_bit && ((r.resume_bit >> 3) >= kRebaseIn || r.resume_out >= kRebaseOut) &&
+            (s.rebased || r.wrap_kind == 0 || r.resume_bit > 16)) {
+            if (!s.rebased) s.kind = (int)r.wrap_kind;
+            if (rebase_here(s, ctx, st, r.resume_bit, r.resume_out)) return -1;
+            return ZB200_INF_TRUNCATED;
         }
         if (s.rebased) {
             // (a data error keeps the last block boundary too: inflateSync starts its search there)
@@ -468,6 +523,8 @@ int inflate_attempt(InflateStream &s) {
             s.done = true; s.in_used = s.in_erased + r.in_used; s.check = r.check;
         }
         return r.status;
+    }
+    if (!again) return -1;                                       // (not reached: the inner loop leaves by return or with `again`)
     }
 }
 
@@ -822,7 +879,9 @@ int inflate(z_streamp strm, int flush) {
     int status = s->error ? s->error : (s->done ? ZB200_INF_OK : ZB200_INF_TRUNCATED);
     // a call without input while the cut run of a re-based stream waits: its complete blocks are owed to the caller
     const bool flush_tail = strm->avail_in == 0 && s->rebased && !s->seq_ready && !s->trailer_pending && !s->in.empty() && s->out.empty();
-    if (!s->done && !s->error && (strm->avail_in || s->retry || flush_tail)) {
+    const bool owed_full = s->out.size() - s->out_pos > kOwedMax;   // the caller drains first (bounds the host-side queue)
+    const uInt take = strm->avail_in > kTakeMax ? (uInt)kTakeMax : strm->avail_in;
+    if (!s->done && !s->error && !owed_full && (strm->avail_in || s->retry || flush_tail)) {
         s->retry = false;
         if (s->prime_bits && s->in.empty() && !s->in_erased) {
             // inflatePrime: the k = prime_bits % 8 oldest bits sit in the top of a synthetic first byte that the engine
@@ -837,7 +896,7 @@ int inflate(z_streamp strm, int flush) {
             s->prime_pref = s->in.size();
             s->prime_byte = true;
         }
-        s->in.insert(s->in.end(), strm->next_in, strm->next_in + strm->avail_in);
+        s->in.insert(s->in.end(), strm->next_in, strm->next_in + take);
         if (!s->hdr_kind && !s->rebased && !s->in_erased && s->wrap != ZB200_WRAP_RAW && s->in.size() >= 2)
             s->hdr_kind = ((s->wrap & ZB200_WRAP_GZIP) && s->in[0] == 0x1f && s->in[1] == 0x8b) ? 2 : 1;   // inflate.c:622-669
         if (s->gzhead != Z_NULL && s->gzhead->done == 0 && !s->rebased) {   // inflateGetHeader (inflate.c:1331-1345), while the header bytes are here
@@ -849,7 +908,7 @@ int inflate(z_streamp strm, int flush) {
         else if (flush_tail || parallel_step(*s, &status) == 0) status = -2;
         if (status == -2) status = inflate_attempt(*s);
         if (status < 0) { strm->msg = "zlib-b200: device error"; return Z_STREAM_ERROR; }
-        uLong used = in0;
+        uLong used = take;
         if (status == ZB200_INF_OK) used = (uLong)(s->in_used - s->prime_pref - total_in0);   // give back bytes after the stream end
         else if (status != ZB200_INF_TRUNCATED) s->error = status;
         strm->next_in += used; strm->avail_in -= (uInt)used; strm->total_in += used;
