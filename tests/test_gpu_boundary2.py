@@ -385,3 +385,32 @@ def test_streaming_inflate_memory_is_bounded(z, wbits):
         bad[-5 if wbits == 31 else -1] ^= 1
         ret, msg, out, tin = z.inflate_all(bytes(bad), {15: refz.WRAP_ZLIB, 31: refz.WRAP_GZIP}[wbits], cap=n + 64, in_slice=1 << 18)
         assert ret == refz.Z_DATA_ERROR and msg == "incorrect data check", (ret, msg)
+
+
+def test_one_shot_calls_emit_the_references_own_stream(z):
+    """compress.c:22-59: the reference's compress2() emits ONE run of blocks.  Up to 1 MiB ($ZB200_SINGLE_RUN_MAX, config
+    C1's size) so does this library — levels 4-9 byte for byte the reference's compress2 output, on all five generators;
+    levels 1-3 decode and stay within 3 %; longer inputs are cut into Z_FULL_FLUSH chunks (the reference's bytes for THAT
+    chunking, tests/test_gpu_zlib_api.py)."""
+    if not refz.have_ref():
+        pytest.skip("oracle/_ref/libzref.so not built")
+    ref = refz.ref()
+    for kind in (refz.GEN_TEXT, refz.GEN_MARKOV, refz.GEN_RANDOM, refz.GEN_MIXED, refz.GEN_BYTES):
+        for n in (1 << 20, 700001, 262145):
+            d = refz.gen(n, kind, seed=7 * kind + 1)
+            for level in (1, 4, 6, 9):
+                cap = z.compressBound(n)
+                a, al = C.create_string_buffer(cap), C.c_ulong(cap)
+                b, bl = C.create_string_buffer(cap + 1024), C.c_ulong(cap + 1024)
+                assert z.compress2(a, C.byref(al), d, n, level) == 0
+                assert ref.compress2(b, C.byref(bl), d, n, level) == 0
+                if level >= 4:
+                    assert a.raw[:al.value] == b.raw[:bl.value], (kind, n, level, al.value, bl.value)
+                else:
+                    assert al.value <= 1.03 * bl.value + 16
+                    back, kl = C.create_string_buffer(n), C.c_ulong(n)
+                    assert ref.uncompress(back, C.byref(kl), a.raw[:al.value], al.value) == 0 and back.raw == d
+    # the streaming API, fed in slices with no flush until Z_FINISH, is the same stream (zlib.h:253-262)
+    d = refz.gen(900000, refz.GEN_MARKOV, seed=77)
+    for wrap in (refz.WRAP_RAW, refz.WRAP_ZLIB, refz.WRAP_GZIP):
+        assert z.deflate_stream(d, 6, 0, wrap, chunk=0, in_slice=10000, out_slice=4096) == ref.deflate_stream(d, 6, 0, wrap, 0)

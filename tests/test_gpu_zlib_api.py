@@ -23,6 +23,12 @@ def ref_or_oracle_stream(d, level, strategy, wrap, chunk):
     return (refz.ref() if refz.have_ref() else refz.oracle()).deflate_stream(d, level, strategy, wrap, chunk)
 
 
+def lib_chunking(n):
+    """How the zlib layer cuts one call's input: up to 1 MiB ($ZB200_SINGLE_RUN_MAX) not at all — the reference's own
+    one-shot stream — beyond that into 256 KiB Z_FULL_FLUSH runs ($ZB200_CHUNK)."""
+    return 0 if n <= (1 << 20) else 262144
+
+
 def test_version_and_init_errors(z):
     assert z.zlibVersion() == b"1.3.1.1-motley"
     s = refz.ZStream()
@@ -57,8 +63,10 @@ def test_compress2_uncompress_config_c1(z):
     dl = C.c_ulong(bound)
     assert z.compress2(dst, C.byref(dl), d, len(d), 6) == refz.Z_OK
     s = dst.raw[:dl.value]
-    assert s == ref_or_oracle_stream(d, 6, 0, refz.WRAP_ZLIB, 262144)      # byte-identical on the same chunking
+    assert s == ref_or_oracle_stream(d, 6, 0, refz.WRAP_ZLIB, 0)           # byte-identical with the reference's own compress2()
     if refz.have_ref():                                                     # the reference's own uncompress takes it
+        rdst, rdl = C.create_string_buffer(bound), C.c_ulong(bound)
+        assert refz.ref().compress2(rdst, C.byref(rdl), d, len(d), 6) == refz.Z_OK and rdst.raw[:rdl.value] == s
         r = refz.ref()
         back = C.create_string_buffer(len(d))
         bl = C.c_ulong(len(d))
@@ -128,7 +136,7 @@ def test_wasm_module_exports():
     dst = C.create_string_buffer(cap)
     dl = C.c_ulong(cap)
     assert L.zlib_compress_buffer(d, len(d), dst, C.byref(dl), 99) == 0     # bad level -> default (wasm_module.c:41-43)
-    assert dst.raw[:dl.value] == ref_or_oracle_stream(d, 6, 0, refz.WRAP_ZLIB, 262144)
+    assert dst.raw[:dl.value] == ref_or_oracle_stream(d, 6, 0, refz.WRAP_ZLIB, lib_chunking(len(d)))
     assert L.zlib_compress_buffer(None, len(d), dst, C.byref(dl), 6) == refz.Z_STREAM_ERROR
     assert L.zlib_compress_buffer(d, 0, dst, C.byref(dl), 6) == refz.Z_STREAM_ERROR
     back = C.create_string_buffer(len(d))
@@ -156,7 +164,7 @@ def test_wasm_module_exports():
     L.zlib_compress_simd.argtypes = [C.c_char_p, C.c_size_t, C.c_void_p, C.POINTER(C.c_size_t), C.c_int]
     ol = C.c_size_t(cap)
     assert L.zlib_compress_simd(d, len(d), out, C.byref(ol), 6) == 0
-    assert out.raw[:ol.value] == ref_or_oracle_stream(d, 6, 0, refz.WRAP_RAW, 262144)
+    assert out.raw[:ol.value] == ref_or_oracle_stream(d, 6, 0, refz.WRAP_RAW, lib_chunking(len(d)))
 
 
 def test_reference_zpipe_linked_against_product(tmp_path):
@@ -168,7 +176,7 @@ def test_reference_zpipe_linked_against_product(tmp_path):
     d = refz.gen(1 << 20, refz.GEN_TEXT)
     comp = subprocess.run([exe], input=d, capture_output=True, timeout=120)
     assert comp.returncode == 0, comp.stderr
-    assert comp.stdout == ref_or_oracle_stream(d, 6, 0, refz.WRAP_ZLIB, 262144)   # zpipe uses Z_DEFAULT_COMPRESSION
+    assert comp.stdout == ref_or_oracle_stream(d, 6, 0, refz.WRAP_ZLIB, 0)        # zpipe uses Z_DEFAULT_COMPRESSION; 1 MiB = one run
     back = subprocess.run([exe, "-d"], input=comp.stdout, capture_output=True, timeout=120)
     assert back.returncode == 0 and back.stdout == d
     if refz.have_ref():
@@ -189,7 +197,7 @@ def test_preset_dictionary(z, wrap):
         d = base[dl // 2:dl // 2 + n]
         for level in (1, 6, 9):
             s = z.deflate_stream(d, level, 0, wrap, chunk=0, dictionary=dic)
-            want = ref.deflate_stream(d, level, 0, wrap, 262144, dictionary=dic)
+            want = ref.deflate_stream(d, level, 0, wrap, lib_chunking(len(d)), dictionary=dic)
             if level >= 4:
                 assert s == want, (dl, n, level, len(s), len(want))
             else:

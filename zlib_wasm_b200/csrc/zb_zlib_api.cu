@@ -72,6 +72,20 @@ size_t api_chunk() {
     return c;
 }
 
+// How one call's input is cut.  Up to $ZB200_SINGLE_RUN_MAX bytes (default 1 MiB: config C1's size) it is NOT cut:
+// one run of blocks, no flush marker inside — for levels 4-9 that is byte for byte what the reference's one-shot
+// compress2() / deflate(Z_FINISH) emits (compress.c:22-59), at the price of one CTA walking the whole run in the
+// ordered phases.  Longer inputs are cut into $ZB200_CHUNK-byte Z_FULL_FLUSH runs that are compressed concurrently
+// (the reference's bytes for that chunking).
+size_t run_chunk(size_t n) {
+    static size_t single = [] {
+        const char *e = getenv("ZB200_SINGLE_RUN_MAX");
+        const long long v = e ? atoll(e) : (1ll << 20);
+        return (size_t)(v < 0 ? 0 : v > (1ll << 30) ? (1ll << 30) : v);
+    }();
+    return (n && n <= single && n > api_chunk()) ? n : api_chunk();
+}
+
 [[noreturn]] void die_no_device(const char *fn) {
     fprintf(stderr, "zlib-b200: %s: no usable CUDA device (%s); this library has no CPU path\n", fn, zb200_last_error());
     abort();
@@ -197,7 +211,7 @@ int compress_buffered(DeflateStream &st, bool finish) {
     if (!ctx) return Z_STREAM_ERROR;
     const size_t n = st.in.size();
     if (n == 0 && !finish) return Z_OK;
-    const size_t chunk = api_chunk();
+    const size_t chunk = run_chunk(n);
     struct TuneScope {                                         // the engine reads the override on this thread
         explicit TuneScope(const int *t) { deflate_tune_set(t); }
         ~TuneScope() { deflate_tune_set(nullptr); }
@@ -1192,7 +1206,7 @@ int compress2(Bytef *dest, uLongf *destLen, const Bytef *source, uLong sourceLen
     size_t cap = *destLen;
     const int r = (sourceLen >= kMultiMin && api_multi())
                       ? zb200_multi_deflate_host(api_multi(), source, sourceLen, api_chunk(), level, 0, ZB200_FRAME_ZLIB, 1, dest, &cap, nullptr, nullptr)
-                      : zb200_deflate_host(ctx, source ? source : (const Bytef *)"", sourceLen, api_chunk(), level,
+                      : zb200_deflate_host(ctx, source ? source : (const Bytef *)"", sourceLen, run_chunk(sourceLen), level,
                                            0, ZB200_FRAME_ZLIB, 1, dest, &cap, nullptr, nullptr);
     if (r == ZB200_ERR_OUTPUT) return Z_BUF_ERROR;
     if (r != ZB200_OK) return map_engine_error(r);
