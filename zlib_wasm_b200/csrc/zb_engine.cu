@@ -207,8 +207,8 @@ int zb200_create(int device, zb200_ctx **out) {
     if (cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess) return fail(ZB200_ERR_CUDA);
     if (cudaStreamCreateWithFlags(&ctx->back_stream, cudaStreamNonBlocking) != cudaSuccess) return fail(ZB200_ERR_CUDA);
     if (cudaEventCreateWithFlags(&ctx->busy_ev, cudaEventDisableTiming) != cudaSuccess) return fail(ZB200_ERR_CUDA);
-    if (cudaMalloc((void **)&ctx->d_pipe, 32 * sizeof(uint64_t)) != cudaSuccess) return fail(ZB200_ERR_NOMEM);
-    if (cudaMallocHost((void **)&ctx->h_pipe, 32 * sizeof(uint64_t)) != cudaSuccess) return fail(ZB200_ERR_NOMEM);
+    if (cudaMalloc((void **)&ctx->d_pipe, 160 * sizeof(uint64_t)) != cudaSuccess) return fail(ZB200_ERR_NOMEM);
+    if (cudaMallocHost((void **)&ctx->h_pipe, 160 * sizeof(uint64_t)) != cudaSuccess) return fail(ZB200_ERR_NOMEM);
     ctx->stage_bytes = 32u << 20;
     for (int k = 0; k < zb200_ctx::kStages; ++k) {
         if (cudaMallocHost((void **)&ctx->h_stage[k], ctx->stage_bytes) != cudaSuccess) return fail(ZB200_ERR_NOMEM);

@@ -57,7 +57,7 @@ struct zb200_ctx {
     cudaStream_t stream = nullptr;          // the context's own stream
     cudaStream_t copy_stream = nullptr;     // H2D/D2H staging stream
     cudaStream_t back_stream = nullptr;     // D2H of finished pieces while later ones are still computed
-    uint64_t *d_pipe = nullptr, *h_pipe = nullptr;   // per-piece (total, crc|adler<<32) of the pipelined host entry points: 2 x 16 u64
+    uint64_t *d_pipe = nullptr, *h_pipe = nullptr;   // per-piece (total, crc|adler<<32) of the pipelined host entry points: 2 x 80 u64
     std::mutex mu;                          // serialises use of the scratch/staging below
 
     zb::CrcTables *d_crc_tables = nullptr;
