@@ -414,3 +414,60 @@ def test_one_shot_calls_emit_the_references_own_stream(z):
     d = refz.gen(900000, refz.GEN_MARKOV, seed=77)
     for wrap in (refz.WRAP_RAW, refz.WRAP_ZLIB, refz.WRAP_GZIP):
         assert z.deflate_stream(d, 6, 0, wrap, chunk=0, in_slice=10000, out_slice=4096) == ref.deflate_stream(d, 6, 0, wrap, 0)
+
+
+def _run(exe, args, stdin=None, timeout=300):
+    return subprocess.run([exe] + args, input=stdin, capture_output=True, timeout=timeout)
+
+
+def test_reference_block_level_examples_linked_against_product(tmp_path):
+    """inflate(Z_BLOCK) + strm->data_type (zlib.h:540-560, inflate.c:824-826,1248-1251), inflatePrime, inflateSetDictionary,
+    deflatePrime: the reference's own block-level tools — examples/zran.c (random access through an index of block
+    boundaries), gzjoin.c (members spliced at the bit level) and gzappend.c — compiled against the reference's zlib.h and
+    linked to libzb200.so, untouched, give the results of the same tools linked to the reference."""
+    import gzip
+    bins = os.path.join(ROOT, "tests", "_bin")
+    refs = os.path.join(ROOT, "oracle", "_ref")
+    need = [os.path.join(bins, n + "_b200") for n in ("zran", "gzjoin", "gzappend")] + [os.path.join(refs, n) for n in ("zran", "gzjoin", "gzappend")]
+    if not all(os.path.exists(p) for p in need) or not refz.have_ref():
+        pytest.skip("the example binaries were not prebuilt (needs /root/reference at build time)")
+    ref = refz.ref()
+    d = refz.gen(6 << 20, refz.GEN_MARKOV, seed=61)
+    # ---- zran: index of access points ~1 MiB apart, then 16 KiB extracted at several offsets
+    files = {"a.gz": ref.deflate_stream(d, 6, 0, refz.WRAP_GZIP, 0), "a.zz": ref.deflate_stream(d, 9, 0, refz.WRAP_ZLIB, 0),
+             "a.raw": ref.deflate_stream(d[:3 << 20], 6, 0, refz.WRAP_RAW, 0),
+             "two.gz": ref.deflate_stream(d[:2 << 20], 6, 0, refz.WRAP_GZIP, 0) + ref.deflate_stream(d[2 << 20:], 1, 0, refz.WRAP_GZIP, 0)}
+    for name, blob in files.items():
+        p = str(tmp_path / name)
+        open(p, "wb").write(blob)
+        n = (3 << 20) if name == "a.raw" else len(d)
+        for off in (0, 1, 1234567, n - 20000, n - 5, (n * 2 + 2) // 3):
+            a = _run(need[0], [p, str(off)])
+            b = _run(need[3], [p, str(off)])
+            assert a.returncode == b.returncode == 0, (name, off, a.stderr, b.stderr)
+            assert a.stdout == b.stdout == d[off:off + 16384][:max(0, n - off)], (name, off, len(a.stdout), len(b.stdout))
+            assert a.stderr == b.stderr, (name, off, a.stderr, b.stderr)       # same number of access points, same byte counts
+    # ---- gzjoin: the members' deflate streams spliced into ONE member at the bit level (no recompression)
+    parts = [d[:700000], d[700000:700001], d[700001:2500000], d[2500000:2600000]]
+    names = []
+    for i, part in enumerate(parts):
+        p = str(tmp_path / ("p%d.gz" % i))
+        open(p, "wb").write(ref.deflate_stream(part, (6, 9, 1, 4)[i], 0, refz.WRAP_GZIP, 0))
+        names.append(p)
+    a = _run(need[1], names)
+    b = _run(need[4], names)
+    assert a.returncode == b.returncode == 0, (a.stderr, b.stderr)
+    assert a.stdout == b.stdout, (len(a.stdout), len(b.stdout))
+    assert gzip.decompress(b.stdout) == b"".join(parts)
+    # ---- gzappend: scan to the last block (Z_BLOCK), then deflate behind it (deflatePrime + deflateSetDictionary)
+    more = d[3 << 20:(3 << 20) + 600000]
+    for tool, tag in ((need[2], "x"), (need[5], "y")):
+        p = str(tmp_path / ("app_%s.gz" % tag))
+        open(p, "wb").write(ref.deflate_stream(d[:900000], 6, 0, refz.WRAP_GZIP, 0))
+        q = str(tmp_path / ("more_%s.bin" % tag))
+        open(q, "wb").write(more)
+        r = _run(tool, ["-6", p, q])
+        assert r.returncode == 0, r.stderr
+    xa, ya = open(str(tmp_path / "app_x.gz"), "rb").read(), open(str(tmp_path / "app_y.gz"), "rb").read()
+    assert gzip.decompress(xa) == d[:900000] + more
+    assert xa == ya

@@ -127,6 +127,14 @@ def build_dropin_demo():
     if os.path.exists(src2) and _newer(out2, [src2, LIB]):
         _run(["gcc", "-O2", "-w", "-I/root/reference", "-o", out2, src2, "-L" + PKG, "-lzb200",
               "-Wl,-rpath,$ORIGIN/../../zlib_wasm_b200"])
+    # examples/zran.c (random access: inflate(Z_BLOCK) + data_type, inflatePrime, inflateSetDictionary), gzjoin.c and
+    # gzappend.c (Z_BLOCK, deflatePrime): the reference's own users of the block-level API, untouched
+    for name, extra in (("zran", ["-DTEST"]), ("gzjoin", []), ("gzappend", [])):
+        srcn = "/root/reference/examples/%s.c" % name
+        outn = os.path.join(ROOT, "tests", "_bin", name + "_b200")
+        if os.path.exists(srcn) and _newer(outn, [srcn, LIB]):
+            _run(["gcc", "-O2", "-w", "-I/root/reference", "-I/root/reference/examples"] + extra + ["-o", outn, srcn, "-L" + PKG, "-lzb200",
+                  "-Wl,-rpath,$ORIGIN/../../zlib_wasm_b200"])
     return out
 
 

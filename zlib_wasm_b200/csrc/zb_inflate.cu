@@ -290,7 +290,7 @@ inflate_kernel(const uint8_t *__restrict__ in, uint8_t *out, const zb200_member 
                uint32_t n_members, int wrap, zb200_member_result *__restrict__ results,
                const InflateDeviceTables *__restrict__ tabs, unsigned int *__restrict__ counter,
                const uint32_t *__restrict__ order, uint64_t *__restrict__ seg_off, uint64_t *__restrict__ seg_len,
-               QueuedMatch *__restrict__ round_queues) {
+               QueuedMatch *__restrict__ round_queues, uint64_t *blog, uint32_t blog_cap) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     InflateShared &sh = *reinterpret_cast<InflateShared *>(smem_raw);
     {
@@ -321,6 +321,7 @@ inflate_kernel(const uint8_t *__restrict__ in, uint8_t *out, const zb200_member 
             st.bind(sh.w[warp].lit, sh.w[warp].dist, sh.w[warp].serial.work, sh.w[warp].serial.lens);
             st.huff_external = kWarpParallelHuffman ? 1 : 0;
             st.tables_external = 1;
+            if (blog && n_members == 1) { st.blog = blog; st.blog_cap = blog_cap; }
             st.preset(dict);
             if (mb.resume_bit) st.resume(mb.resume_bit, mb.resume_out + dict, wrap);
             else hs = st.parse_header(wrap);
@@ -547,7 +548,7 @@ inflate_team_kernel(const uint8_t *__restrict__ in, uint8_t *out, const zb200_me
                     uint32_t n_members, int wrap, zb200_member_result *__restrict__ results,
                     const InflateDeviceTables *__restrict__ tabs, unsigned int *__restrict__ counter,
                     const uint32_t *__restrict__ order, uint64_t *__restrict__ seg_off, uint64_t *__restrict__ seg_len,
-                    QueuedMatch *__restrict__ round_queues, int team_lg_cap) {
+                    QueuedMatch *__restrict__ round_queues, int team_lg_cap, uint64_t *blog, uint32_t blog_cap) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     TeamShared &ts = *reinterpret_cast<TeamShared *>(smem_raw);
     {
@@ -576,6 +577,7 @@ inflate_team_kernel(const uint8_t *__restrict__ in, uint8_t *out, const zb200_me
             st.bind(ts.lit, ts.dist, ts.serial.work, ts.serial.lens);
             st.huff_external = 1;
             st.tables_external = 1;
+            if (blog && n_members == 1) { st.blog = blog; st.blog_cap = blog_cap; }
             st.preset(dict);
             if (mb.resume_bit) st.resume(mb.resume_bit, mb.resume_out + dict, wrap);
             else hs = st.parse_header(wrap);
@@ -856,10 +858,12 @@ struct InflateWork {
 size_t inflate_work_bytes(size_t n_members) { return InflateWork::bytes(n_members); }
 
 int inflate_launch(zb200_ctx *ctx, const uint8_t *d_in, uint8_t *d_out, const zb200_member *d_members,
-                   size_t n, int wrap, int verify, zb200_member_result *d_results, void *d_work, cudaStream_t s) {
+                   size_t n, int wrap, int verify, zb200_member_result *d_results, void *d_work, cudaStream_t s,
+                   uint64_t *d_blog, uint32_t blog_cap) {
     InflateWork w;
     w.carve(d_work, n);
     ZB_CUDA(cudaMemsetAsync(w.counter, 0, 256, s));
+    if (d_blog) ZB_CUDA(cudaMemsetAsync(d_blog, 0, 16, s));
     prof_mark(ctx, s, "inflate_order_kernel");
     inflate_order_kernel<<<1, 1024, 0, s>>>(d_members, (uint32_t)n, w.order);
     ZB_LAUNCHED();
@@ -878,7 +882,7 @@ int inflate_launch(zb200_ctx *ctx, const uint8_t *d_in, uint8_t *d_out, const zb
         prof_mark(ctx, s, "inflate_team_kernel");
         inflate_team_kernel<<<(unsigned)ctas, kTeamLanes, sizeof(TeamShared), s>>>(
             d_in, d_out, d_members, (uint32_t)n, wrap, d_results,
-            (const InflateDeviceTables *)ctx->d_inflate_tables, w.counter, w.order, w.seg_off, w.seg_len, w.queues, team_lg);
+            (const InflateDeviceTables *)ctx->d_inflate_tables, w.counter, w.order, w.seg_off, w.seg_len, w.queues, team_lg, d_blog, blog_cap);
     } else {
         size_t ctas = (n + kInfWarps - 1) / kInfWarps;
         static const int per_sm_knob = [] { const char *e = getenv("ZB200_INF_CTAS_PER_SM"); return e ? atoi(e) : 0; }();   // profiling knob
@@ -888,7 +892,7 @@ int inflate_launch(zb200_ctx *ctx, const uint8_t *d_in, uint8_t *d_out, const zb
         prof_mark(ctx, s, "inflate_kernel");
         inflate_kernel<<<(unsigned)ctas, kInfWarps * 32, sizeof(InflateShared), s>>>(
             d_in, d_out, d_members, (uint32_t)n, wrap, d_results,
-            (const InflateDeviceTables *)ctx->d_inflate_tables, w.counter, w.order, w.seg_off, w.seg_len, w.queues);
+            (const InflateDeviceTables *)ctx->d_inflate_tables, w.counter, w.order, w.seg_off, w.seg_len, w.queues, d_blog, blog_cap);
     }
     ZB_LAUNCHED();
     ZB_CHECK_LAUNCH();

@@ -180,6 +180,10 @@ struct InflateState {
     const FormatTables *fmt;
     InflateEvent parked; int has_parked;                   // event held back until the queue has been executed
     int huff_external;                                     // 1: hand Huffman blocks to the caller (EV_HUFF) instead of decoding them here
+    // Optional log of every deflate-block boundary passed (inflate(Z_BLOCK), zlib.h:540-560): blog[0] = entries, entry k at
+    // blog[2 + 2k]: bit offset inside the member, output position | (BFINAL of the block that ended there) << 63.  When the log
+    // is full the member stops at that boundary as if its input ended there (the caller resumes from it).
+    uint64_t *blog; uint32_t blog_cap, blog_n;
     int tables_external;                                   // 1: a dynamic header's code lengths are read here, its two decode tables
                                                            //    are built by the caller (EV_TABLES: len = nlen, dist = ndist), who
                                                            //    reports back through tables_done()
@@ -215,6 +219,7 @@ struct InflateState {
         out = dst; out_cap = cap; pos = 0; last = 0; in_block = 0; lt = dt = nullptr;
         wrap_kind = 0; status = ZB200_INF_OK; ck_bit = 0; ck_out = 0; stored_check = 0; stored_isize = 0;
         in_used = 0; fixed_lit = flit; fixed_dist = fdist; fmt = f; has_parked = 0; huff_external = 0; tables_external = 0; have_dict = 0;
+        blog = nullptr; blog_cap = 0; blog_n = 0;
         if (s) { tlit = s->lit; tdist = s->dist; work = s->work; lens = s->lens; }
         else { tlit = tdist = nullptr; work = nullptr; lens = nullptr; }
     }
@@ -388,6 +393,12 @@ struct InflateState {
     ZB_HD InflateEvent step() {
         for (;;) {
             if (!in_block) {
+                if (blog) {                            // a block boundary (the one after the last block included)
+                    if (blog_n >= blog_cap) { ck_bit = bitpos(); ck_out = pos; return done(ZB200_INF_TRUNCATED); }
+                    blog[2 + 2 * blog_n] = bitpos();
+                    blog[3 + 2 * blog_n] = pos | ((uint64_t)(last ? 1 : 0) << 63);
+                    blog[0] = ++blog_n;
+                }
                 if (last) return finish();
                 ck_bit = bitpos(); ck_out = pos;       // a block boundary: safe resume point
                 refill();

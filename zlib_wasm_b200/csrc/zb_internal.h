@@ -167,7 +167,10 @@ zb200_ctx *zlib_api_ctx();
 // zb_inflate.cu
 int inflate_init(zb200_ctx *ctx);
 size_t inflate_work_bytes(size_t n_members);
+// d_blog (optional, single-member calls): blog_cap entries of (bit offset, output position | BFINAL << 63) for every block
+// boundary passed, count in d_blog[0], entries from d_blog[2] (zb_inflate.cuh InflateState::blog)
 int inflate_launch(zb200_ctx *ctx, const uint8_t *d_in, uint8_t *d_out, const zb200_member *d_members,
-                   size_t n, int wrap, int verify, zb200_member_result *d_results, void *d_work, cudaStream_t s);
+                   size_t n, int wrap, int verify, zb200_member_result *d_results, void *d_work, cudaStream_t s,
+                   uint64_t *d_blog = nullptr, uint32_t blog_cap = 0);
 
 }  // namespace zb

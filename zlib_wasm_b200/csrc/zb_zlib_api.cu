@@ -11,6 +11,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <vector>
+#include <deque>
 #include <memory>
 #include <utility>
 #include <new>
@@ -182,6 +183,12 @@ struct InflateStream {
     uint32_t dictid;                     // DICTID of the zlib header that asked for one
     bool retry;                          // inflateSetDictionary was called: decode again with no new input
     int hdr_kind;                        // wrapper the first two input bytes select (0: raw / not seen yet), for inflateSync
+    // inflate(Z_BLOCK): deflate-block boundaries decoded but not yet reported — the caller's stream position in bits, the
+    // output position, BFINAL of the block that ends there
+    struct Bound { uint64_t bit_abs, out_abs; bool last; };
+    std::deque<Bound> bounds;
+    bool want_bounds;
+    int64_t last_bound_bit;
     unsigned sync_have;                  // inflateSync: pattern bytes matched so far (inflate.c:1352 syncsearch), 0..4
     bool syncing;                        // ... a search is under way (state->mode == SYNC)
     uint32_t prime_hold; unsigned prime_bits;   // inflatePrime: bits ahead of the first input byte (inflate.c:223)
@@ -333,7 +340,7 @@ void inflate_reset_state(InflateStream &s) {
     s.resume_bit = s.resume_out = 0; s.started = s.done = false; s.error = 0; s.in_used = 0; s.check = 0;
     s.dict_len = 0; s.dictid = 0; s.retry = false; s.gzhead = Z_NULL; s.verify = true;
     s.rebased = s.seq_ready = s.trailer_pending = false; s.stream_kind = 0; s.in_erased = s.out_before = 0; s.check_before = 0; s.hist.clear();
-    s.hdr_kind = 0; s.sync_have = 0; s.syncing = false; s.prime_hold = 0; s.prime_bits = 0; s.prime_byte = false; s.prime_pref = 0;
+    s.bounds.clear(); s.want_bounds = false; s.last_bound_bit = -1; s.hdr_kind = 0; s.sync_have = 0; s.syncing = false; s.prime_hold = 0; s.prime_bits = 0; s.prime_byte = false; s.prime_pref = 0;
 }
 
 void hist_push(InflateStream &s, const uint8_t *p, size_t n) {   // keep the last 32 KiB of output
@@ -441,7 +448,9 @@ int inflate_attempt(InflateStream &s) {
     CtxUse use(ctx, ctx->stream);
     if (cudaSetDevice(ctx->device) != cudaSuccess) return -1;
     cudaStream_t st = ctx->stream;
-    if (ensure_scratch(ctx, 1024 + inflate_work_bytes(1)) != ZB200_OK) return -1;
+    constexpr uint32_t kBlogCap = 2048;                          // block boundaries logged per attempt (a fuller log ends the attempt there)
+    const size_t blog_at = (1024 + inflate_work_bytes(1) + 255) & ~(size_t)255;
+    if (ensure_scratch(ctx, blog_at + 16 + 16 * (size_t)kBlogCap) != ZB200_OK) return -1;
     for (;;) {
     const size_t n = s.in.size();
     if (dev_grow(&s.d_in, &s.d_in_cap, n + 16, s.d_in_have, st)) return -1;
@@ -469,10 +478,30 @@ int inflate_attempt(InflateStream &s) {
         memcpy(ctx->h_small + 40, &m, sizeof m);                 // pinned bounce for the descriptor
         if (cudaMemcpyAsync(d_m, ctx->h_small + 40, sizeof m, cudaMemcpyHostToDevice, st) != cudaSuccess) return -1;
         const int wrap = s.rebased ? ZB200_WRAP_RAW : s.resume_bit ? s.kind : s.wrap;
-        if (inflate_launch(ctx, s.d_in, s.d_out, d_m, 1, wrap, (s.verify && !s.rebased) ? 1 : 0, d_r, base + 1024, st) != ZB200_OK) return -1;
+        uint64_t *d_blog = s.want_bounds ? (uint64_t *)(base + blog_at) : nullptr;
+        if (inflate_launch(ctx, s.d_in, s.d_out, d_m, 1, wrap, (s.verify && !s.rebased) ? 1 : 0, d_r, base + 1024, st, d_blog, kBlogCap) != ZB200_OK) return -1;
         if (cudaMemcpyAsync(h_r, d_r, sizeof *h_r, cudaMemcpyDeviceToHost, st) != cudaSuccess) return -1;
         if (cudaStreamSynchronize(st) != cudaSuccess) return -1;
         const zb200_member_result r = *h_r;
+        if (d_blog) {                                            // the block boundaries this attempt passed, in the caller's coordinates
+            uint64_t cnt = 0;
+            if (cudaMemcpy(&cnt, d_blog, 8, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+            if (cnt > kBlogCap) cnt = kBlogCap;
+            std::vector<uint64_t> e(2 * (size_t)cnt);
+            if (cnt && cudaMemcpy(e.data(), d_blog + 2, 16 * (size_t)cnt, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+            const uint64_t valid_out = r.status == ZB200_INF_OK ? r.out_len : (r.resume_bit ? r.resume_out : 0);
+            for (uint64_t i = 0; i < cnt; ++i) {
+                const uint64_t bit = e[2 * i], pos = e[2 * i + 1] & ~(1ull << 63);
+                const bool last = (e[2 * i + 1] >> 63) != 0;
+                const int64_t bit_abs = (int64_t)bit + 8 * ((int64_t)s.in_erased - (int64_t)s.prime_pref);
+                const uint64_t out_rel = pos - s.dict_len;
+                if (out_rel > valid_out) break;                  // (behind what this attempt hands out)
+                if (bit_abs <= 0 || bit_abs <= s.last_bound_bit) continue;  // (inside primed bits / logged by an earlier attempt; a raw
+                                                                            //  stream's very start is no stop: inflate.c:627-630 enters at TYPEDO)
+                s.last_bound_bit = bit_abs;
+                s.bounds.push_back({(uint64_t)bit_abs, s.out_before + out_rel, last});
+            }
+        }
         if (r.status == ZB200_INF_OUTPUT_FULL) {                 // grow the device output and go again from the checkpoint ...
             if (!s.rebased) s.kind = (int)r.wrap_kind;
             s.resume_bit = r.resume_bit; s.resume_out = r.resume_out;
@@ -818,7 +847,8 @@ int deflate(z_streamp strm, int flush) {
             }
             if (r != Z_OK) { strm->msg = kErrMsg[2 - r]; return r; }
             if (flush == Z_FINISH) { s->finished = true; put_trailer(*s); }
-            strm->adler = s->wrap == 2 ? s->crc : s->adler;
+            if (s->wrap) strm->adler = s->wrap == 2 ? s->crc : s->adler;   // (a raw stream leaves strm->adler to the caller: deflate.c:218-239;
+                                                                           //  examples/gzappend.c keeps its own CRC there)
         }
     }
     s->last_flush = flush;
@@ -888,14 +918,26 @@ int inflateReset(z_streamp strm) {
 int inflate(z_streamp strm, int flush) {
     InflateStream *s = istate(strm);
     if (!s || strm->next_out == Z_NULL || (strm->next_in == Z_NULL && strm->avail_in != 0)) return Z_STREAM_ERROR;   // inflate.c:611-613
+    const Bytef *const in_ptr0 = strm->next_in;
     const uInt in0 = strm->avail_in, out0 = strm->avail_out;
     const uLong total_in0 = strm->total_in;
+    // Z_BLOCK / Z_TREES (zlib.h:540-560, inflate.c:824-826): stop at every deflate-block boundary.  The engine then logs the
+    // boundaries it passes; a call hands out output up to the next one only, and reports as consumed only the input up
+    // to it — what lies behind stays in this stream's buffer AND with the caller, who passes it again (the bytes are
+    // recognised by their position and not taken twice).
+    const bool block_mode = flush == Z_BLOCK || flush == Z_TREES;
+    if (block_mode) s->want_bounds = true;
     int status = s->error ? s->error : (s->done ? ZB200_INF_OK : ZB200_INF_TRUNCATED);
-    // a call without input while the cut run of a re-based stream waits: its complete blocks are owed to the caller
-    const bool flush_tail = strm->avail_in == 0 && s->rebased && !s->seq_ready && !s->trailer_pending && !s->in.empty() && s->out.empty();
+    const uint64_t have_abs = s->in_erased + s->in.size() - s->prime_pref;       // caller's stream position up to which input is held
+    const uint64_t again = have_abs > total_in0 ? have_abs - total_in0 : 0;      // bytes of this call that were given back earlier
+    const uInt skip = again < in0 ? (uInt)again : in0;
+    const uInt fresh = in0 - skip;
+    // a call without new input while the cut run of a re-based stream waits: its complete blocks are owed to the caller
+    const bool flush_tail = fresh == 0 && s->rebased && !s->seq_ready && !s->trailer_pending && !s->in.empty() && s->out.empty() && s->bounds.empty();
     const bool owed_full = s->out.size() - s->out_pos > kOwedMax;   // the caller drains first (bounds the host-side queue)
-    const uInt take = strm->avail_in > kTakeMax ? (uInt)kTakeMax : strm->avail_in;
-    if (!s->done && !s->error && !owed_full && (strm->avail_in || s->retry || flush_tail)) {
+    const uInt take = fresh > kTakeMax ? (uInt)kTakeMax : fresh;
+    uint64_t fed_abs = total_in0 + skip;                            // ... after this call's new bytes
+    if (!s->done && !s->error && !owed_full && (take || s->retry || flush_tail)) {
         s->retry = false;
         if (s->prime_bits && s->in.empty() && !s->in_erased) {
             // inflatePrime: the k = prime_bits % 8 oldest bits sit in the top of a synthetic first byte that the engine
@@ -910,7 +952,8 @@ int inflate(z_streamp strm, int flush) {
             s->prime_pref = s->in.size();
             s->prime_byte = true;
         }
-        s->in.insert(s->in.end(), strm->next_in, strm->next_in + take);
+        s->in.insert(s->in.end(), in_ptr0 + skip, in_ptr0 + skip + take);
+        fed_abs += take;
         if (!s->hdr_kind && !s->rebased && !s->in_erased && s->wrap != ZB200_WRAP_RAW && s->in.size() >= 2)
             s->hdr_kind = ((s->wrap & ZB200_WRAP_GZIP) && s->in[0] == 0x1f && s->in[1] == 0x8b) ? 2 : 1;   // inflate.c:622-669
         if (s->gzhead != Z_NULL && s->gzhead->done == 0 && !s->rebased) {   // inflateGetHeader (inflate.c:1331-1345), while the header bytes are here
@@ -919,30 +962,56 @@ int inflate(z_streamp strm, int flush) {
         }
         status = -2;
         if (s->trailer_pending) status = finish_rebased(*s, s->stream_kind == 1 ? 1u : 0u, 0, 0);   // (combining with an empty tail leaves check_before)
-        else if (flush_tail || parallel_step(*s, &status) == 0) status = -2;
+        else if (flush_tail || s->want_bounds || parallel_step(*s, &status) == 0) status = -2;   // (the run-parallel step logs no block boundaries)
         if (status == -2) status = inflate_attempt(*s);
         if (status < 0) { strm->msg = "zlib-b200: device error"; return Z_STREAM_ERROR; }
-        uLong used = take;
-        if (status == ZB200_INF_OK) used = (uLong)(s->in_used - s->prime_pref - total_in0);   // give back bytes after the stream end
-        else if (status != ZB200_INF_TRUNCATED) s->error = status;
-        strm->next_in += used; strm->avail_in -= (uInt)used; strm->total_in += used;
+        if (status != ZB200_INF_OK && status != ZB200_INF_TRUNCATED) s->error = status;
         if (status == ZB200_INF_OK) strm->adler = s->check;
     }
+    // ---- how far this call goes: output up to `stop_out`, input up to `cons_abs` ----
+    uint64_t cons_abs = s->done ? s->in_used - s->prime_pref : fed_abs;          // (bytes behind the stream's end are given back)
+    uint64_t stop_out = ~0ull;
+    const bool have_bound = block_mode && !s->bounds.empty();
+    if (have_bound) {
+        const InflateStream::Bound &nb = s->bounds.front();
+        stop_out = nb.out_abs;
+        const uint64_t upto = (nb.bit_abs + 7) >> 3;
+        if (upto < cons_abs) cons_abs = upto;
+    }
+    if (cons_abs < total_in0) cons_abs = total_in0;                               // (never backwards: a boundary behind what an earlier call reported)
+    if (cons_abs > total_in0 + in0) cons_abs = total_in0 + in0;
     // deliver decoded bytes
     const size_t avail = s->out.size() - s->out_pos;
-    const size_t k = avail < strm->avail_out ? avail : strm->avail_out;
+    size_t k = avail < strm->avail_out ? avail : strm->avail_out;
+    if (stop_out != ~0ull && (uint64_t)strm->total_out + k > stop_out) k = (size_t)(stop_out - strm->total_out);
     if (k) {
         memcpy(strm->next_out, s->out.data() + s->out_pos, k);
         strm->next_out += k; strm->avail_out -= (uInt)k; strm->total_out += k; s->out_pos += k;
         if (s->out_pos == s->out.size()) { s->out.clear(); s->out_pos = 0; }
     }
+    bool at_bound = false;
+    if (have_bound && (uint64_t)strm->total_out == stop_out) {                   // the block's output is out in full: report its end
+        const InflateStream::Bound nb = s->bounds.front();
+        s->bounds.pop_front();
+        at_bound = true;
+        strm->data_type = (int)((8 - (nb.bit_abs & 7)) & 7) + 128 + (nb.last ? 64 : 0);
+    } else {
+        strm->data_type = s->done ? 64 : 0;
+        while (!block_mode && !s->bounds.empty() && s->bounds.front().out_abs < (uint64_t)strm->total_out) s->bounds.pop_front();
+    }
+    {
+        const uint64_t used = cons_abs - total_in0;
+        strm->next_in = in_ptr0 + used; strm->avail_in = in0 - (uInt)used; strm->total_in = (uLong)cons_abs;
+    }
     const bool drained = s->out.empty();
+    if (at_bound) return (in0 == strm->avail_in && out0 == strm->avail_out) ? Z_BUF_ERROR : Z_OK;
     if (s->error && drained) {
         if (s->error == ZB200_INF_NEED_DICT) { strm->adler = s->dictid; return Z_NEED_DICT; }   // inflate.c:667-669
         strm->msg = zb200_inflate_msg(s->error);
         return Z_DATA_ERROR;
     }
-    if (s->done && drained) return Z_STREAM_END;
+    if (s->done && drained && s->bounds.empty()) return Z_STREAM_END;
+    if (s->done && drained && !block_mode) { s->bounds.clear(); return Z_STREAM_END; }
     if ((in0 == strm->avail_in && out0 == strm->avail_out) || (flush == Z_FINISH && !(s->done && drained)))
         return Z_BUF_ERROR;                                     // inflate.c:1259-1261
     return Z_OK;
