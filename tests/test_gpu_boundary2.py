@@ -471,3 +471,33 @@ def test_reference_block_level_examples_linked_against_product(tmp_path):
     xa, ya = open(str(tmp_path / "app_x.gz"), "rb").read(), open(str(tmp_path / "app_y.gz"), "rb").read()
     assert gzip.decompress(xa) == d[:900000] + more
     assert xa == ya
+
+
+SINGLE_RUN_SCRIPT = r"""
+import ctypes as C, os, sys
+sys.path.insert(0, os.path.join(%(root)r, "tests")); sys.path.insert(0, %(root)r)
+import refz, zlib_wasm_b200 as zb
+z = refz.ZlibBinding(zb.LIB_PATH, "")
+ref = refz.ref()
+n = 64 << 20
+for kind in (refz.GEN_TEXT, refz.GEN_MARKOV, refz.GEN_RANDOM, refz.GEN_MIXED, refz.GEN_BYTES):
+    d = refz.gen(n, kind, seed=40 + kind)
+    cap = z.compressBound(n)
+    a, al = C.create_string_buffer(cap), C.c_ulong(cap)
+    b, bl = C.create_string_buffer(cap), C.c_ulong(cap)
+    assert z.compress2(a, C.byref(al), d, n, 6) == 0
+    assert ref.compress2(b, C.byref(bl), d, n, 6) == 0
+    assert al.value == bl.value and a.raw[:al.value] == b.raw[:bl.value], (kind, al.value, bl.value)
+print("ok")
+"""
+
+
+def test_one_shot_64mib_is_the_references_stream_when_asked():
+    """$ZB200_SINGLE_RUN_MAX raises the size up to which a call is compressed as ONE run of blocks: at 64 MiB compress2()
+    still equals the reference's compress2() byte for byte on all five generators (one CTA walks the run in the ordered
+    phases: slower than the chunked default, still several times the reference's single core)."""
+    if not refz.have_ref():
+        pytest.skip("oracle/_ref/libzref.so not built")
+    env = dict(os.environ, ZB200_SINGLE_RUN_MAX=str(64 << 20))
+    p = subprocess.run([sys.executable, "-c", SINGLE_RUN_SCRIPT % {"root": ROOT}], env=env, capture_output=True, text=True, timeout=900)
+    assert p.returncode == 0 and "ok" in p.stdout, p.stderr[-2000:]
