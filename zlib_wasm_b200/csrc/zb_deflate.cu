@@ -6,6 +6,7 @@
 #include "zb_internal.h"
 #include "zb_deflate.cuh"
 #include <string.h>
+#include <stdlib.h>
 
 namespace zb {
 
@@ -231,6 +232,7 @@ extern __shared__ __align__(16) uint8_t ms_smem[];
 // compiler rebuilt the CTA's shared-window base (S2UR CgaCtaId, ULEA, ...) in every
 // iteration of the walk, a quarter of its instructions.
 struct StagedMem {
+    static constexpr bool kNilIsFar = true;              // stage_window stores the end of a chain (link 0) as 65535: farther than any window
     uint32_t dbase, lbase;                               // shared address of chunk position 0 (wraps), same for link 0
     __device__ __forceinline__ uint32_t byte(uint32_t pos) const { return lds_u8(dbase + pos); }
     __device__ __forceinline__ uint32_t word(uint32_t pos) const {
@@ -275,7 +277,12 @@ __device__ __forceinline__ StagedMem stage_window(const Batch &b, const uint8_t 
     const uintptr_t p_first = reinterpret_cast<uintptr_t>(prev + lo) & ~(uintptr_t)15;
     const uint32_t pskew = (uint32_t)((reinterpret_cast<uintptr_t>(prev + lo) - p_first) >> 1);
     const uint32_t pvecs = (uint32_t)((reinterpret_cast<uintptr_t>(prev + t1) - p_first + 15) >> 4);
-    for (uint32_t v = threadIdx.x; v < pvecs; v += blockDim.x) slink[v] = *reinterpret_cast<const uint4 *>(p_first + 16ull * v);
+    for (uint32_t v = threadIdx.x; v < pvecs; v += blockDim.x) {
+        uint4 x = *reinterpret_cast<const uint4 *>(p_first + 16ull * v);
+        x.x |= __vcmpeq2(x.x, 0u); x.y |= __vcmpeq2(x.y, 0u);      // NIL (0) -> 65535: one test (the window limit) ends a walk
+        x.z |= __vcmpeq2(x.z, 0u); x.w |= __vcmpeq2(x.w, 0u);
+        slink[v] = x;
+    }
     __syncthreads();
     StagedMem mem;
     const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(ms_smem);
@@ -309,7 +316,7 @@ dfl_match_uniform_kernel(Batch b, DeflateParams prm, const uint16_t *__restrict_
 
 __global__ void __launch_bounds__(kMsThreads)
 dfl_match_sorted_kernel(Batch b, DeflateParams prm, const uint16_t *__restrict__ prev_all,
-                        uint32_t *__restrict__ mfull, uint32_t *__restrict__ mquarter) {
+                        uint32_t *__restrict__ mfull, uint32_t *__restrict__ mquarter, uint32_t key_cap) {
     __shared__ uint32_t s_hist[kMsBuckets], s_cur[kMsBuckets];
     uint16_t *s_order = reinterpret_cast<uint16_t *>(ms_smem + kMsDataBytes + kMsLinkBytes);
     const uint32_t c = blockIdx.y, n = chunk_len(b, c), t0 = blockIdx.x * kMsTile;
@@ -338,9 +345,10 @@ dfl_match_sorted_kernel(Batch b, DeflateParams prm, const uint16_t *__restrict__
             uint32_t e = 0;
             if (p + kMinMatch <= n && d != 0 && d <= prm.max_dist) {
                 // length of the walk if no candidate ends it early: links inside the window, up to the budget.
-                // Counted in position order (lanes diverge), so it is capped: beyond 32 links the sort gains
-                // less than the counting costs (host model: mixed data 50 -> 37 instructions per position).
-                const uint32_t cap = (uint32_t)prm.chain < 32u ? (uint32_t)prm.chain : 32u;
+                // Counted in position order (lanes diverge: 12 of 32 active), so it is capped at $ZB200_KEY_CAP links, 8 by
+                // default: with the walk's step at its present cost a finer key costs more than it saves (512 MiB at level 6,
+                // text / mixed: cap 4 22.0 / 37.4 ms, 8 19.2 / 36.1, 16 19.6 / 36.7, 32 21.3 / 38.4, 64 22.4 / 41.3).
+                const uint32_t cap = (uint32_t)prm.chain < key_cap ? (uint32_t)prm.chain : key_cap;
                 uint32_t q = p - d;
                 e = 1;
                 while (e < cap) {
@@ -958,7 +966,8 @@ int deflate_launch_opts(zb200_ctx *ctx, const uint8_t *d_in, size_t n, size_t S,
         if (sorted_walks) {
             dim3 g((unsigned)((S + kMsTile - 1) / kMsTile), b.nb);
             prof_mark(ctx, s, "dfl_match_sorted_kernel");
-            dfl_match_sorted_kernel<<<g, kMsThreads, kMsSmem, s>>>(b, prm, w.prev, w.mfull, w.mquarter);
+            static const uint32_t key_cap = [] { const char *e = getenv("ZB200_KEY_CAP"); const int v = e ? atoi(e) : 8; return (uint32_t)(v < 1 ? 1 : v > 255 ? 255 : v); }();
+            dfl_match_sorted_kernel<<<g, kMsThreads, kMsSmem, s>>>(b, prm, w.prev, w.mfull, w.mquarter, key_cap);
             ZB_LAUNCHED(); ZB_CHECK_LAUNCH();
         } else if (prm.mode == MODE_FAST) {                        // levels 1-2
             dim3 g((unsigned)((S + kMsTile - 1) / kMsTile), b.nb);

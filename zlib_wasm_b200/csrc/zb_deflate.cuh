@@ -114,6 +114,7 @@ ZB_HD uint32_t ctz32(uint32_t x) {
 // shared memory in the depth-sorted kernel (32-bit shared addresses instead of generic
 // 64-bit pointer arithmetic: a fifth of that kernel's instructions).
 struct PlainMem {
+    static constexpr bool kNilIsFar = false;              // a chain's end is link 0
     const uint8_t *data; const uint16_t *prev;
     ZB_HD uint32_t byte(uint32_t pos) const { return data[pos]; }
     ZB_HD uint32_t word(uint32_t pos) const { return load4(data + pos); }
@@ -185,7 +186,7 @@ ZB_HD MatchPair match_walk(const Mem &mem, uint32_t n, uint32_t p, const Deflate
             have_q = true;
             stop_at = budget;
         }
-        if (d2 == 0) break;
+        if (!Mem::kNilIsFar && d2 == 0) break;            // (a staged window stores NIL as 65535: the window test below ends the walk)
         q -= d2;
         if (p - q >= prm.max_dist) break;                 // deflate.c:1481: cur_match > limit
     }
