@@ -288,6 +288,11 @@ def main():
             legs["checksum"] = BL.checksum_leg(g, cpu_gate, tot2, max(leg_steps, min(args.steps, 20)), 3, traffic=tr("checksum", h2 - l2))
         except Exception as ex:
             errors["checksum"] = repr(ex)
+        if world == 1:
+            try:
+                legs["small_calls"] = BL.small_call_leg(cpu)
+            except Exception as ex:
+                errors["small_calls"] = repr(ex)
         # one process driving every GPU of the box (zb200_multi_*) must give the single-GPU bytes: rank 0, others idle
         if world > 1:
             g.barrier()

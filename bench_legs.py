@@ -672,3 +672,52 @@ def checksum_leg(g, cpu, total, steps, warmup, traffic=None):
     del d_in
     torch.cuda.empty_cache()
     return e
+
+
+def small_call_leg(cpu):
+    """Latency of small calls through the zlib.h surface itself (pageable host buffers, one host thread), this library next
+    to the reference: crc32, compress2 (level 6), uncompress, and deflate() fed in 16 KiB slices (zlib_deflate_process /
+    zpipe style).  Median of 15 calls after 3 warm-up calls, microseconds."""
+    import refz
+    import zlib_wasm_b200 as zb
+    libs = {"b200": refz.ZlibBinding(zb.LIB_PATH, "")}
+    if cpu is not None and cpu.ref is not None:
+        libs["reference"] = cpu.ref
+    out = {"unit": "us per call (median of 15)", "sizes": {}}
+
+    def med(fn):
+        for _ in range(3):
+            fn()
+        ts = []
+        for _ in range(15):
+            t0 = time.perf_counter()
+            fn()
+            ts.append(time.perf_counter() - t0)
+        ts.sort()
+        return round(ts[len(ts) // 2] * 1e6, 1)
+
+    for n in (64, 1024, 16384, 262144, 1048576):
+        d = refz.gen(n, refz.GEN_TEXT, seed=n)
+        row = {}
+        for name, z in libs.items():
+            cap = z.compressBound(n) + 64
+            dst, back = C.create_string_buffer(cap), C.create_string_buffer(n)
+            dl = C.c_ulong(cap)
+            z.compress2(dst, C.byref(dl), d, n, 6)
+            comp = dst.raw[:dl.value]
+
+            def f_comp():
+                l = C.c_ulong(cap)
+                z.compress2(dst, C.byref(l), d, n, 6)
+
+            def f_unc():
+                l = C.c_ulong(n)
+                z.uncompress(back, C.byref(l), comp, len(comp))
+
+            def f_stream():
+                z.deflate_stream(d, 6, 0, refz.WRAP_ZLIB, 0, in_slice=16384, out_slice=16384)
+
+            row[name] = {"crc32": med(lambda: z.crc32(0, d, n)), "compress2_l6": med(f_comp), "uncompress": med(f_unc),
+                         "deflate_16k_slices": med(f_stream)}
+        out["sizes"][str(n)] = row
+    return out
