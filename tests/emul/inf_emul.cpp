@@ -228,3 +228,132 @@ extern "C" int emul_inflate_rounds(const uint8_t *src, uint64_t n, uint8_t *dst,
 }
 
 extern "C" const char *emul_msg(int s);
+
+// ---- one member decoded chunk by chunk (zb_inflate_blocks.cuh) replayed on the host ------------------------------
+// The product's header test over every bit position, the product's state machine in its two chunk modes (count /
+// list; the serial path stands in for the rounds, which are replayed above), then the chain, the source pointers, the
+// pointer jumping and the gather restated with plain loops as zb_inflate.cu inflate_stream_blocks drives them.
+#include "../../zlib_wasm_b200/csrc/zb_inflate_blocks.cuh"
+#include <algorithm>
+
+static std::vector<uint32_t> words_of(const uint8_t *src, uint64_t n) {
+    std::vector<uint32_t> w((n + 3) / 4 + 4, 0u);
+    memcpy(w.data(), src, n);
+    return w;
+}
+
+extern "C" uint64_t emul_blk_candidates(const uint8_t *src, uint64_t n, uint64_t bit_lo, uint64_t *list, uint64_t cap, uint64_t *quick_pass) {
+    if (!g_ready) setup();
+    const std::vector<uint32_t> w = words_of(src, n);
+    const uint64_t nwords = (n + 3) / 4, bit_hi = n * 8;
+    uint64_t cnt = 0, qp = 0;
+    uint8_t tab[128];
+    for (uint64_t b = bit_lo; b + 20 <= bit_hi; ++b) {
+        const uint64_t x = blk_bits64(w.data(), nwords, b);
+        if (!blk_quick((uint32_t)x)) continue;
+        if (!blk_cl_complete(blk_bits64(w.data(), nwords, b + 17), (((uint32_t)x >> 13) & 15u) + 4u)) continue;
+        ++qp;
+        uint64_t end;
+        if (!blk_header_valid(w.data(), nwords, bit_hi, b, tab, g_fmt.cl_order, &end)) continue;
+        if (cnt < cap) list[cnt] = b;
+        ++cnt;
+    }
+    if (quick_pass) *quick_pass = qp;
+    return cnt;
+}
+
+struct ChunkOut { int status; uint64_t out_len, resume_bit, resume_out, nm, in_used; uint32_t check, isize; };
+// mode 1: count, mode 2: list (literals stored into dst, matches appended to ml)
+static ChunkOut host_chunk(const uint8_t *src, uint64_t n, int kind, uint64_t start_bit, uint64_t out_pos, const uint64_t *cand, uint32_t nc,
+                           int mode, uint8_t *dst, uint64_t cap, std::vector<QueuedMatch> *ml) {
+    static InflateScratch scr;
+    InflateState st;
+    st.init(src, n, dst, cap, &scr, g_flit, g_fdist, &g_fmt);
+    st.cand = cand; st.cand_n = nc; st.count_only = mode == 1;
+    int hs = ZB200_INF_OK;
+    if (start_bit) st.resume(start_bit, out_pos, kind);
+    else { hs = st.parse_header(kind); st.start_bit = st.bitpos(); }
+    ChunkOut o;
+    memset(&o, 0, sizeof o);
+    if (hs == ZB200_INF_OK) {
+        static QueuedMatch q[kQueue];
+        for (;;) {
+            InflateEvent ev = st.run_batch(q);
+            if (ev.kind == EV_DONE) break;
+            if (ev.kind == EV_BATCH) {
+                if (mode == 2) for (uint32_t i = 0; i < ev.len; ++i) ml->push_back(q[i]);
+                o.nm += ev.len;
+            } else if (mode == 2) memcpy(dst + ev.dst, src + ev.src, ev.len);
+        }
+    } else st.status = hs;
+    o.status = st.status; o.out_len = st.pos; o.resume_bit = st.ck_bit; o.resume_out = st.ck_out; o.in_used = st.in_used;
+    o.check = st.stored_check; o.isize = st.stored_isize;
+    return o;
+}
+
+// Returns the number of chunks on the chain (0: not applicable), -1 on an inconsistency between the two decodes.
+// stats: [0] candidates, [1] chunks on the chain, [2] jump passes, [3] matches
+extern "C" int emul_inflate_blocks(const uint8_t *src, uint64_t n, int wrap, uint8_t *dst, uint64_t cap,
+                                   uint64_t *out_len, int *status, uint64_t *in_used, uint32_t *check, uint32_t *isize, uint64_t *stats) {
+    if (!g_ready) setup();
+    InflateState hs;
+    hs.init(src, n, nullptr, 0, nullptr, nullptr, nullptr, nullptr);
+    if (hs.parse_header(wrap) != ZB200_INF_OK) return 0;
+    const int kind = hs.wrap_kind;
+    const uint64_t bit0 = hs.next * 8;
+    std::vector<uint64_t> cand(n / 8 + 64);
+    const uint64_t nc64 = emul_blk_candidates(src, n, bit0, cand.data(), cand.size(), nullptr);
+    if (nc64 > cand.size()) return 0;
+    cand.resize(nc64);
+    const uint32_t nc = (uint32_t)nc64;
+    stats[0] = nc;
+    if (nc < 2) return 0;
+    std::vector<ChunkOut> res(nc + 1);
+    for (uint32_t k = 0; k <= nc; ++k)
+        res[k] = host_chunk(src, n, kind, k ? cand[k - 1] : 0, 0, cand.data(), nc, 1, nullptr, 0xfffffff0ull, nullptr);
+    struct Link { uint32_t idx; uint64_t out_off; };
+    std::vector<Link> chain;
+    uint64_t total = 0;
+    int fin = ZB200_INF_TRUNCATED;
+    for (uint32_t cur = 0;;) {
+        const ChunkOut &q = res[cur];
+        const uint64_t begin = cur ? cand[cur - 1] : bit0;
+        if (q.status == ZB200_INF_OK) { chain.push_back({cur, total}); total += q.out_len; fin = ZB200_INF_OK; break; }
+        if (q.status != ZB200_INF_TRUNCATED || q.resume_out != q.out_len || q.resume_bit <= begin) break;
+        const auto it = std::lower_bound(cand.begin(), cand.end(), q.resume_bit);
+        if (it == cand.end() || *it != q.resume_bit) break;
+        chain.push_back({cur, total}); total += q.out_len;
+        cur = (uint32_t)(it - cand.begin()) + 1;
+    }
+    stats[1] = chain.size();
+    if (chain.size() < 2 || fin != ZB200_INF_OK) return 0;
+    *out_len = total; *status = fin;
+    if (total > cap) { *status = ZB200_INF_OUTPUT_FULL; return (int)chain.size(); }
+    std::vector<QueuedMatch> ml;
+    for (size_t k = 0; k < chain.size(); ++k) {
+        const uint32_t i = chain[k].idx;
+        const ChunkOut b = host_chunk(src, n, kind, i ? cand[i - 1] : 0, chain[k].out_off, cand.data(), nc, 2, dst, total, &ml);
+        const ChunkOut &a = res[i];
+        if (a.status != b.status || b.out_len != chain[k].out_off + a.out_len || a.resume_bit != b.resume_bit) return -1;
+        if (k + 1 == chain.size()) { *in_used = b.in_used; *check = b.check; *isize = b.isize; }
+    }
+    stats[3] = ml.size();
+    std::vector<uint32_t> sp(total, kSrcLiteral);
+    for (const QueuedMatch &m : ml) {
+        const uint32_t len = qm_len(m.packed), dist = qm_dist(m.packed);
+        for (uint32_t i = 0; i < len; ++i) sp[m.dst + i] = m.dst - dist + (i < dist ? i : i % dist);
+    }
+    uint64_t passes = 0;
+    for (bool any = true; any; ++passes) {
+        any = false;
+        for (uint64_t p = total; p-- > 0;) {                 // (backwards: the least favourable order for in-place updates)
+            const uint32_t s = sp[p];
+            if (s == kSrcLiteral) continue;
+            const uint32_t t = sp[s];
+            if (t != kSrcLiteral) { sp[p] = t; any = true; }
+        }
+    }
+    stats[2] = passes;
+    for (uint64_t p = 0; p < total; ++p) if (sp[p] != kSrcLiteral) dst[p] = dst[sp[p]];
+    return (int)chain.size();
+}

@@ -428,3 +428,32 @@ def test_keyed_heap_tree_builder_equals_the_transliterated_one():
                 assert run(lf, df, byte_len, strategy) == 0, (trial, kind, strategy, byte_len)
                 cases += 1
     assert cases == 1600
+
+
+def test_block_parallel_decode_replay():
+    """zb_inflate_blocks.cuh on the host: the header test over every bit position of reference-made streams, the
+    state machine's count / list chunk modes, chain, source pointers, pointer jumping, gather — the original bytes."""
+    L = _build("inf_emul")
+    u64 = C.c_uint64
+    L.emul_inflate_blocks.argtypes = [C.c_void_p, u64, C.c_int, C.c_void_p, u64, C.POINTER(u64), C.POINTER(C.c_int), C.POINTER(u64),
+                                      C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(u64)]
+    L.emul_inflate_blocks.restype = C.c_int
+    cases = [(refz.GEN_TEXT, 700000, 6, 15), (refz.GEN_TEXT, 400000, 1, 31), (refz.GEN_MIXED, 900000, 9, -15),
+             (refz.GEN_TEXT, 300000, 4, 15), (refz.GEN_MIXED, 500000, 6, 31)]
+    for gen, n, level, wbits in cases:
+        d = refz.gen(n, gen, seed=n + level)
+        co = zlib.compressobj(level, zlib.DEFLATED, wbits)
+        comp = co.compress(d) + co.flush()
+        wrap = 0 if wbits < 0 else 2 if wbits > 15 else 1
+        dst = C.create_string_buffer(n + 64)
+        ol, st, iu, ck, isz = u64(), C.c_int(), u64(), C.c_uint32(), C.c_uint32()
+        stats = (u64 * 4)()
+        r = L.emul_inflate_blocks(comp, len(comp), wrap, dst, n + 64, C.byref(ol), C.byref(st), C.byref(iu), C.byref(ck), C.byref(isz), stats)
+        assert r >= 2, (gen, n, level, wbits, r, list(stats))
+        assert st.value == 0 and ol.value == n and dst.raw[:n] == d, (gen, n, level, wbits, list(stats))
+        assert iu.value == len(comp)
+        if wrap == 2:
+            assert ck.value == zlib.crc32(d) and isz.value == n
+        if wrap == 1:
+            assert ck.value == zlib.adler32(d)
+        assert stats[0] <= stats[1] + 2, list(stats)          # next to no false candidates

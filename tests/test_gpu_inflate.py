@@ -432,3 +432,47 @@ def test_stream_runs_random_flush_mixtures(ctx):
         s = ref.deflate_stream(d, level, rng.choice((0, 0, 1, 2, 3, 4)), wrap, chunk, chunk_flush=flushes)
         res, out = _stream(ctx, s, wrap, n + 16)
         assert res.status == 0 and out == d and res.in_used == len(s), (trial, kind, n, chunk, flushes, wrap, level, msg(res.status), res.out_len)
+
+
+def test_one_member_decoded_in_parallel_at_block_headers(ctx):
+    """A member without flush points (what compress2 / gzip write): its dynamic block headers are found on the device,
+    the chunks between them are counted, placed, decoded at once and the matches resolved by pointer jumping
+    (csrc/zb_inflate_blocks.cuh).  The original bytes, the stream's length, the reference's verdict on damage."""
+    import zlib
+    cases = [(refz.GEN_TEXT, 1 << 20, 6, 15), (refz.GEN_MARKOV, 5000000, 6, 31), (refz.GEN_MIXED, 6000000, 9, -15),
+             (refz.GEN_TEXT, 300000, 1, 15), (refz.GEN_MIXED, 3000000, 1, 31), (refz.GEN_MARKOV, 40 << 20, 6, 15),
+             (refz.GEN_TEXT, 2500000, 4, -15)]
+    for gen, n, level, wbits in cases:
+        d = refz.gen(n, gen, seed=n ^ level)
+        co = zlib.compressobj(level, zlib.DEFLATED, wbits)
+        s = co.compress(d) + co.flush()
+        wrap = refz.WRAP_RAW if wbits < 0 else refz.WRAP_GZIP if wbits > 15 else refz.WRAP_ZLIB
+        ctx.profile(True)
+        res, out = _stream(ctx, s, wrap, n + 16)
+        prof = ctx.profile_read()
+        ctx.profile(False)
+        assert res.status == 0 and res.out_len == n and out == d and res.in_used == len(s), (gen, n, level, wbits, msg(res.status), res.out_len)
+        assert any(k.startswith("inflate_") and "count" in k for k in prof), (sorted(prof), gen, n, level)   # the chunk path decoded it
+        res, out = _stream(ctx, s + b"tail", wrap, n + 16)
+        assert res.status == 0 and res.in_used == len(s) and out == d
+    # the reference's statuses: output too small, truncated, damaged data, damaged trailer
+    d = refz.gen(3000000, refz.GEN_MARKOV, seed=77)
+    co = zlib.compressobj(6, zlib.DEFLATED, 31)
+    s = co.compress(d) + co.flush()
+    res, out = _stream(ctx, s, refz.WRAP_GZIP, 1000)
+    assert msg(res.status) == "output buffer full" and res.out_len == len(d)
+    for cut in (len(s) // 2, len(s) - 3, len(s) - 9):
+        res, out = _stream(ctx, s[:cut], refz.WRAP_GZIP, len(d) + 16)
+        one, res1 = ctx.inflate_host(s[:cut], [(0, cut, 0, len(d) + 16)], refz.WRAP_GZIP, 1)
+        assert msg(res.status) == "truncated input" and res.status == res1[0].status and d.startswith(out), (cut, msg(res.status))
+    for at, bit in ((len(s) // 3, 0x40), (len(s) // 2 + 7, 1), (40, 0x10)):
+        bad = bytearray(s); bad[at] ^= bit
+        res, out = _stream(ctx, bytes(bad), refz.WRAP_GZIP, len(d) + 16)
+        one, res1 = ctx.inflate_host(bytes(bad), [(0, len(bad), 0, len(d) + 16)], refz.WRAP_GZIP, 1)
+        assert res.status == res1[0].status and res.status != 0, (at, bit, msg(res.status), msg(res1[0].status))
+    bad = bytearray(s); bad[-6] ^= 1
+    res, out = _stream(ctx, bytes(bad), refz.WRAP_GZIP, len(d) + 16)
+    assert msg(res.status) == "incorrect data check"
+    bad = bytearray(s); bad[-2] ^= 1
+    res, out = _stream(ctx, bytes(bad), refz.WRAP_GZIP, len(d) + 16)
+    assert msg(res.status) == "incorrect length check"

@@ -13,6 +13,7 @@
 #include "zb_inflate.cuh"
 #include "zb_inflate_round.cuh"
 #include "zb_inflate_tables.cuh"
+#include "zb_inflate_blocks.cuh"
 #include <string.h>
 #include <algorithm>
 #include <vector>
@@ -31,6 +32,20 @@ constexpr size_t kMaxGridWarps = 4096;    // upper bound on resident warps (size
 // (huff_rounds_warp, all lanes active).  The rounds are the default; the serial loop
 // finishes member tails and reports errors.
 constexpr bool kWarpParallelHuffman = true;
+
+// What a launch of the decode kernels does with the members it is given.
+//   INF_MEMBER  members decoded into their output (the batch path: one warp / team per member)
+//   INF_COUNT   CHUNKS of one member (zb_inflate_blocks.cuh): every chunk's output bytes and matches are counted,
+//               nothing is written — the chunk's place in the output is not known yet
+//   INF_LIST    chunks again, each at its place: literals are stored, matches are appended to the member's match
+//               list instead of being copied (what lies before a chunk may not be there yet)
+enum : int { INF_MEMBER = 0, INF_COUNT = 1, INF_LIST = 2 };
+struct ChunkArgs {
+    const uint64_t *cand; uint32_t n_cand;     // sorted candidate block starts (bit offsets inside the member)
+    const uint64_t *mbase;                     // INF_LIST: per chunk, index of its first entry in mlist
+    QueuedMatch *mlist;                        // INF_LIST: the matches, chunk after chunk, in stream order inside a chunk
+    uint64_t *nmatch;                          // INF_COUNT: per chunk, matches counted
+};
 
 struct InflateDeviceTables {
     uint32_t fixed_lit[512];
@@ -212,8 +227,9 @@ __device__ __forceinline__ void stage_wait() { asm volatile("cp.async.wait_all;\
 // status 0: the block's end-of-block code was consumed; 1: lane 0 continues inside
 // the block on the serial path from (bitpos, pos) — end of the member's input, or a
 // condition the careful path has to report.
-struct HuffResult { int status; uint64_t bitpos; uint64_t pos; };
+struct HuffResult { int status; uint64_t bitpos; uint64_t pos; uint64_t nm; };   // nm: matches passed (chunk modes)
 
+template <int MODE>
 __device__ __forceinline__ HuffResult
 huff_rounds_warp(const uint8_t *src, uint64_t in_len, uint8_t *dst, uint64_t out_cap, uint64_t bitpos, uint64_t pos,
                  const uint32_t *__restrict__ lt, const uint32_t *__restrict__ dt, RoundShared &rs, QueuedMatch *gq) {
@@ -225,7 +241,7 @@ huff_rounds_warp(const uint8_t *src, uint64_t in_len, uint8_t *dst, uint64_t out
     const uint64_t total_bits = bias + in_len * 8;                  // valid bits are [bias, total_bits)
     const uint64_t nwords = (total_bits + 31) >> 5;
     HuffResult res;
-    res.status = 1; res.bitpos = bitpos; res.pos = pos;
+    res.status = 1; res.bitpos = bitpos; res.pos = pos; res.nm = 0;
     uint64_t B = bias + bitpos;
     if (B >= total_bits) return res;
     int lg = round_pick_lg(total_bits - B), lg_cap = kRoundLgMax;
@@ -265,32 +281,36 @@ huff_rounds_warp(const uint8_t *src, uint64_t in_len, uint8_t *dst, uint64_t out
             if (lane >= (uint32_t)dlt) { inc_o += yo; inc_m += ym; }
         }
         const uint32_t tot_o = __shfl_sync(full, inc_o, 31), tot_m = __shfl_sync(full, inc_m, 31);
-        if (tot_m > kRoundQueueCap) {                                // runs: matches of 2-3 bits.  Redo the round with shorter subsequences
+        if (MODE == INF_MEMBER && tot_m > kRoundQueueCap) {          // runs: matches of 2-3 bits.  Redo the round with shorter subsequences
             lg_cap = lg >= kRoundLgMin + 2 ? lg - 2 : kRoundLgMin;   // (at S = 128 a round holds at most 2048 matches), and keep
             lg = lg_cap;                                             // them short for the rest of the block
             continue;
         }
         int err = tot_o > out_cap - pos;
-        if (!err && valid) err = round_emit(r, lane, lg, stage, lt, dt, dst, (uint32_t)pos + inc_o - myout, gq, inc_m - mym);
+        if (MODE != INF_COUNT) {                                     // (INF_LIST: gq is the chunk's part of the match list, filled round after round)
+            QueuedMatch *rq = MODE == INF_LIST ? gq + res.nm : gq;
+            if (!err && valid) err = round_emit(r, lane, lg, stage, lt, dt, dst, (uint32_t)pos + inc_o - myout, rq, inc_m - mym);
+        }
         if (__ballot_sync(full, err != 0)) return res;
         __syncwarp(full);                                            // literals and queue entries -> visible to every lane
-        exec_round_queue(dst, gq, tot_m);
+        if (MODE == INF_MEMBER) exec_round_queue(dst, gq, tot_m);
         pos += tot_o;
         B = end_abs;
         bitpos = B - bias;
-        res.bitpos = bitpos; res.pos = pos;
+        res.bitpos = bitpos; res.pos = pos; res.nm += tot_m;
         if (stop_l == STOP_EOB) { res.status = 0; return res; }
         if (next_lg < 0) { res.status = 1; return res; }
         lg = next_lg < lg_cap ? next_lg : lg_cap;
     }
 }
 
+template <int MODE>
 __global__ void __launch_bounds__(kInfWarps * 32, kInfCtasPerSm)
 inflate_kernel(const uint8_t *__restrict__ in, uint8_t *out, const zb200_member *__restrict__ members,
                uint32_t n_members, int wrap, zb200_member_result *__restrict__ results,
                const InflateDeviceTables *__restrict__ tabs, unsigned int *__restrict__ counter,
                const uint32_t *__restrict__ order, uint64_t *__restrict__ seg_off, uint64_t *__restrict__ seg_len,
-               QueuedMatch *__restrict__ round_queues, uint64_t *blog, uint32_t blog_cap) {
+               QueuedMatch *__restrict__ round_queues, uint64_t *blog, uint32_t blog_cap, const ChunkArgs ca) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     InflateShared &sh = *reinterpret_cast<InflateShared *>(smem_raw);
     {
@@ -305,7 +325,7 @@ inflate_kernel(const uint8_t *__restrict__ in, uint8_t *out, const zb200_member 
 
     for (;;) {
         unsigned int m = 0;
-        if (lane == 0) { m = atomicAdd(counter, 1u); if (m < n_members) m = order[m]; }   // largest members first
+        if (lane == 0) { m = atomicAdd(counter, 1u); if (MODE == INF_MEMBER && m < n_members) m = order[m]; }   // largest members first
         m = __shfl_sync(full, m, 0);
         if (m >= n_members) break;
         const zb200_member mb = members[m];
@@ -313,6 +333,8 @@ inflate_kernel(const uint8_t *__restrict__ in, uint8_t *out, const zb200_member 
         const uint64_t dict = mb.dict_len <= 32768 && mb.dict_len <= mb.out_off ? mb.dict_len : 0;
         uint8_t *dst = out + mb.out_off - dict;              // positions count from the dictionary's first byte
         const uint64_t cap = (mb.out_cap < 0xfffffff0ull - dict ? mb.out_cap : 0xfffffff0ull - dict) + dict;   // queue entries hold 32-bit output offsets
+        uint64_t nm = 0;                                     // chunk modes: matches of this chunk so far
+        QueuedMatch *const ml = MODE == INF_LIST ? ca.mlist + ca.mbase[m] : nullptr;
 
         InflateState st;
         int hs = ZB200_INF_OK;
@@ -321,10 +343,11 @@ inflate_kernel(const uint8_t *__restrict__ in, uint8_t *out, const zb200_member 
             st.bind(sh.w[warp].lit, sh.w[warp].dist, sh.w[warp].serial.work, sh.w[warp].serial.lens);
             st.huff_external = kWarpParallelHuffman ? 1 : 0;
             st.tables_external = 1;
-            if (blog && n_members == 1) { st.blog = blog; st.blog_cap = blog_cap; }
+            if (MODE == INF_MEMBER && blog && n_members == 1) { st.blog = blog; st.blog_cap = blog_cap; }
+            if (MODE != INF_MEMBER) { st.cand = ca.cand; st.cand_n = ca.n_cand; st.count_only = MODE == INF_COUNT; }
             st.preset(dict);
             if (mb.resume_bit) st.resume(mb.resume_bit, mb.resume_out + dict, wrap);
-            else hs = st.parse_header(wrap);
+            else { hs = st.parse_header(wrap); st.start_bit = st.bitpos(); }
             if (hs) st.status = hs;
         }
         hs = __shfl_sync(full, hs, 0);
@@ -350,12 +373,15 @@ inflate_kernel(const uint8_t *__restrict__ in, uint8_t *out, const zb200_member 
                 const uint64_t bp = __shfl_sync(full, ev.src, 0), op = __shfl_sync(full, ev.dst, 0);
                 const uint32_t *lt = len ? sh.fixed_lit : sh.w[warp].lit;
                 const uint32_t *dt = len ? sh.fixed_dist : sh.w[warp].dist;
-                const HuffResult hr = huff_rounds_warp(src, mb.in_len, dst, cap, bp, op, lt, dt, sh.w[warp].rnd,
-                                                       round_queues + (size_t)(blockIdx.x * kInfWarps + warp) * kRoundQueueCap);
+                const HuffResult hr = huff_rounds_warp<MODE>(src, mb.in_len, dst, cap, bp, op, lt, dt, sh.w[warp].rnd,
+                    MODE == INF_MEMBER ? round_queues + (size_t)(blockIdx.x * kInfWarps + warp) * kRoundQueueCap : ml + nm);
+                nm += hr.nm;
                 if (lane == 0) st.seek(hr.bitpos, hr.pos, hr.status);   // status 1: the serial path finishes the block
             } else if (kind == EV_BATCH) {
-                exec_queue(dst, q, len);
-            } else {                                           // stored block: input -> output
+                if (MODE == INF_MEMBER) exec_queue(dst, q, len);
+                if (MODE == INF_LIST) { for (uint32_t i = lane; i < len; i += 32) ml[nm + i] = q[i]; __syncwarp(full); }
+                nm += len;
+            } else if (MODE != INF_COUNT) {                    // stored block: input -> output
                 const uint64_t to = __shfl_sync(full, ev.dst, 0);
                 const uint64_t from = __shfl_sync(full, ev.src, 0);
                 const uint8_t *s = src + from;
@@ -375,8 +401,11 @@ inflate_kernel(const uint8_t *__restrict__ in, uint8_t *out, const zb200_member 
             r.resume_bit = st.ck_bit;
             r.resume_out = st.ck_out - dict;
             results[m] = r;
-            seg_off[m] = mb.out_off;
-            seg_len[m] = st.status == ZB200_INF_OK ? st.pos - dict : 0;
+            if (MODE == INF_MEMBER) {
+                seg_off[m] = mb.out_off;
+                seg_len[m] = st.status == ZB200_INF_OK ? st.pos - dict : 0;
+            }
+            if (MODE == INF_COUNT) ca.nmatch[m] = nm;
         }
     }
 }
@@ -458,6 +487,7 @@ __device__ __forceinline__ void exec_team_queue(uint8_t *dst, const QueuedMatch 
     }
 }
 
+template <int MODE>
 __device__ __forceinline__ HuffResult
 huff_rounds_team(const uint8_t *src, uint64_t in_len, uint8_t *dst, uint64_t out_cap, uint64_t bitpos, uint64_t pos,
                  const uint32_t *__restrict__ lt, const uint32_t *__restrict__ dt, TeamShared &ts, QueuedMatch *gq, int team_lg_cap) {
@@ -470,7 +500,7 @@ huff_rounds_team(const uint8_t *src, uint64_t in_len, uint8_t *dst, uint64_t out
     const uint64_t total_bits = bias + in_len * 8;
     const uint64_t nwords = (total_bits + 31) >> 5;
     HuffResult res;
-    res.status = 1; res.bitpos = bitpos; res.pos = pos;
+    res.status = 1; res.bitpos = bitpos; res.pos = pos; res.nm = 0;
     uint64_t B = bias + bitpos;
     if (B >= total_bits) return res;
     int lg = round_pick_lg(total_bits - B, kTeamLanes), lg_cap = team_lg_cap;
@@ -524,31 +554,35 @@ huff_rounds_team(const uint8_t *src, uint64_t in_len, uint8_t *dst, uint64_t out
             if (w < warp) { before_o += xo; before_m += xm; }
             tot_o += xo; tot_m += xm;
         }
-        if (tot_m > kRoundQueueCap * kTeamWarps) {                   // runs: redo the round with shorter subsequences
+        if (MODE == INF_MEMBER && tot_m > kRoundQueueCap * kTeamWarps) {   // runs: redo the round with shorter subsequences
             lg_cap = lg >= kRoundLgMin + 2 ? lg - 2 : kRoundLgMin;
             lg = lg_cap;
             continue;
         }
         int err = tot_o > out_cap - pos;
-        if (!err && valid) err = round_emit(r, tid, lg, rs.stage, lt, dt, dst, (uint32_t)pos + before_o + inc_o - myout, gq, before_m + inc_m - mym);
+        if (MODE != INF_COUNT) {
+            QueuedMatch *rq = MODE == INF_LIST ? gq + res.nm : gq;
+            if (!err && valid) err = round_emit(r, tid, lg, rs.stage, lt, dt, dst, (uint32_t)pos + before_o + inc_o - myout, rq, before_m + inc_m - mym);
+        }
         if (__syncthreads_or(err != 0)) return res;                  // (the barrier also publishes literals and queue entries)
-        exec_team_queue(dst, gq, tot_m, ts);
+        if (MODE == INF_MEMBER) exec_team_queue(dst, gq, tot_m, ts);
         pos += tot_o;
         B = end_abs;
         bitpos = B - bias;
-        res.bitpos = bitpos; res.pos = pos;
+        res.bitpos = bitpos; res.pos = pos; res.nm += tot_m;
         if (stop_l == STOP_EOB) { res.status = 0; return res; }
         if (next_lg < 0) { res.status = 1; return res; }
         lg = next_lg < lg_cap ? next_lg : lg_cap;
     }
 }
 
+template <int MODE>
 __global__ void __launch_bounds__(kTeamLanes, kTeamCtasPerSm)
 inflate_team_kernel(const uint8_t *__restrict__ in, uint8_t *out, const zb200_member *__restrict__ members,
                     uint32_t n_members, int wrap, zb200_member_result *__restrict__ results,
                     const InflateDeviceTables *__restrict__ tabs, unsigned int *__restrict__ counter,
                     const uint32_t *__restrict__ order, uint64_t *__restrict__ seg_off, uint64_t *__restrict__ seg_len,
-                    QueuedMatch *__restrict__ round_queues, int team_lg_cap, uint64_t *blog, uint32_t blog_cap) {
+                    QueuedMatch *__restrict__ round_queues, int team_lg_cap, uint64_t *blog, uint32_t blog_cap, const ChunkArgs ca) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     TeamShared &ts = *reinterpret_cast<TeamShared *>(smem_raw);
     {
@@ -561,7 +595,7 @@ inflate_team_kernel(const uint8_t *__restrict__ in, uint8_t *out, const zb200_me
     QueuedMatch *gq = round_queues + (size_t)blockIdx.x * kTeamWarps * kRoundQueueCap;
     for (;;) {
         __syncthreads();
-        if (tid == 0) { unsigned int m = atomicAdd(counter, 1u); ts.member = m < n_members ? order[m] : 0xffffffffu; }
+        if (tid == 0) { unsigned int m = atomicAdd(counter, 1u); ts.member = m < n_members ? (MODE == INF_MEMBER ? order[m] : m) : 0xffffffffu; }
         __syncthreads();
         const unsigned int m = ts.member;
         if (m == 0xffffffffu) break;
@@ -570,6 +604,8 @@ inflate_team_kernel(const uint8_t *__restrict__ in, uint8_t *out, const zb200_me
         const uint64_t dict = mb.dict_len <= 32768 && mb.dict_len <= mb.out_off ? mb.dict_len : 0;
         uint8_t *dst = out + mb.out_off - dict;
         const uint64_t cap = (mb.out_cap < 0xfffffff0ull - dict ? mb.out_cap : 0xfffffff0ull - dict) + dict;
+        uint64_t nm = 0;                                         // chunk modes: matches of this chunk so far
+        QueuedMatch *const ml = MODE == INF_LIST ? ca.mlist + ca.mbase[m] : nullptr;
         InflateState st;
         if (tid == 0) {
             int hs = ZB200_INF_OK;
@@ -577,10 +613,11 @@ inflate_team_kernel(const uint8_t *__restrict__ in, uint8_t *out, const zb200_me
             st.bind(ts.lit, ts.dist, ts.serial.work, ts.serial.lens);
             st.huff_external = 1;
             st.tables_external = 1;
-            if (blog && n_members == 1) { st.blog = blog; st.blog_cap = blog_cap; }
+            if (MODE == INF_MEMBER && blog && n_members == 1) { st.blog = blog; st.blog_cap = blog_cap; }
+            if (MODE != INF_MEMBER) { st.cand = ca.cand; st.cand_n = ca.n_cand; st.count_only = MODE == INF_COUNT; }
             st.preset(dict);
             if (mb.resume_bit) st.resume(mb.resume_bit, mb.resume_out + dict, wrap);
-            else hs = st.parse_header(wrap);
+            else { hs = st.parse_header(wrap); st.start_bit = st.bitpos(); }
             if (hs) st.status = hs;
             ts.hs = hs;
         }
@@ -605,14 +642,24 @@ inflate_team_kernel(const uint8_t *__restrict__ in, uint8_t *out, const zb200_me
             if (ev.kind == EV_HUFF) {
                 const uint32_t *lt = ev.len ? ts.fixed_lit : ts.lit;
                 const uint32_t *dt = ev.len ? ts.fixed_dist : ts.dist;
-                HuffResult hr = huff_rounds_team(src, mb.in_len, dst, cap, ev.src, ev.dst, lt, dt, ts, gq, team_lg_cap);
+                HuffResult hr = huff_rounds_team<MODE>(src, mb.in_len, dst, cap, ev.src, ev.dst, lt, dt, ts, MODE == INF_MEMBER ? gq : ml + nm, team_lg_cap);
+                nm += hr.nm;
                 __syncthreads();
-                if (hr.status == 1 && warp == 0) hr = huff_rounds_warp(src, mb.in_len, dst, cap, hr.bitpos, hr.pos, lt, dt, ts.rnd1, gq);
+                if (hr.status == 1) {                              // a tail too short for a team round: warp 0's rounds
+                    if (warp == 0) {
+                        hr = huff_rounds_warp<MODE>(src, mb.in_len, dst, cap, hr.bitpos, hr.pos, lt, dt, ts.rnd1, MODE == INF_MEMBER ? gq : ml + nm);
+                        if (tid == 0) ts.x_wsum_m[0] = (uint32_t)hr.nm;
+                    }
+                    if (MODE != INF_MEMBER) { __syncthreads(); nm += ts.x_wsum_m[0]; }
+                }
                 if (tid == 0) st.seek(hr.bitpos, hr.pos, hr.status);   // status 1: the serial path finishes the block
                 __syncthreads();
             } else if (ev.kind == EV_BATCH) {
-                if (warp == 0) exec_queue(dst, ts.serial.q, ev.len);
+                if (MODE == INF_MEMBER && warp == 0) exec_queue(dst, ts.serial.q, ev.len);
+                if (MODE == INF_LIST) for (uint32_t i = tid; i < ev.len; i += kTeamLanes) ml[nm + i] = ts.serial.q[i];
+                nm += ev.len;
                 __syncthreads();
+            } else if (MODE == INF_COUNT) {                        // (a stored block: nothing is written)
             } else {                                               // stored block: input -> output
                 const uint8_t *s = src + ev.src;
                 uint8_t *d = dst + ev.dst;
@@ -631,8 +678,11 @@ inflate_team_kernel(const uint8_t *__restrict__ in, uint8_t *out, const zb200_me
             r.resume_bit = st.ck_bit;
             r.resume_out = st.ck_out - dict;
             results[m] = r;
-            seg_off[m] = mb.out_off;
-            seg_len[m] = st.status == ZB200_INF_OK ? st.pos - dict : 0;
+            if (MODE == INF_MEMBER) {
+                seg_off[m] = mb.out_off;
+                seg_len[m] = st.status == ZB200_INF_OK ? st.pos - dict : 0;
+            }
+            if (MODE == INF_COUNT) ca.nmatch[m] = nm;
         }
     }
 }
@@ -738,6 +788,10 @@ flush_candidates_kernel(const uint8_t *__restrict__ in, uint64_t lo, uint64_t n,
     }
 }
 
+int inflate_stream_blocks(zb200_ctx *ctx, const uint8_t *src, size_t n, int wrap, uint8_t *out, size_t out_cap,
+                          size_t *out_len, int *status, size_t *in_used, uint32_t *check, int *applicable,
+                          const StreamContinuation *cont, bool uploaded, bool prefix_ok, uint32_t *end_bit);
+
 struct GatherSeg { uint64_t src, dst, len; };
 __global__ void __launch_bounds__(256)
 gather_segments_kernel(const uint8_t *__restrict__ from, uint8_t *__restrict__ to, const GatherSeg *__restrict__ segs) {
@@ -826,8 +880,12 @@ int inflate_init(zb200_ctx *ctx) {
     ZB_CUDA(cudaMalloc(&d, sizeof h));
     ZB_CUDA(cudaMemcpy(d, &h, sizeof h, cudaMemcpyHostToDevice));
     ctx->d_inflate_tables = d;
-    ZB_CUDA(cudaFuncSetAttribute(inflate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(InflateShared)));
-    ZB_CUDA(cudaFuncSetAttribute(inflate_team_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TeamShared)));
+    ZB_CUDA(cudaFuncSetAttribute(inflate_kernel<INF_MEMBER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(InflateShared)));
+    ZB_CUDA(cudaFuncSetAttribute(inflate_kernel<INF_COUNT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(InflateShared)));
+    ZB_CUDA(cudaFuncSetAttribute(inflate_kernel<INF_LIST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(InflateShared)));
+    ZB_CUDA(cudaFuncSetAttribute(inflate_team_kernel<INF_MEMBER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TeamShared)));
+    ZB_CUDA(cudaFuncSetAttribute(inflate_team_kernel<INF_COUNT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TeamShared)));
+    ZB_CUDA(cudaFuncSetAttribute(inflate_team_kernel<INF_LIST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TeamShared)));
     return ZB200_OK;
 }
 
@@ -880,9 +938,9 @@ int inflate_launch(zb200_ctx *ctx, const uint8_t *d_in, uint8_t *d_out, const zb
         static const int lg_knob = [] { const char *e = getenv("ZB200_INF_TEAM_LG"); return e ? atoi(e) : kTeamLgDefault; }();
         const int team_lg = lg_knob < kRoundLgMin ? kRoundLgMin : lg_knob > kRoundLgMax ? kRoundLgMax : lg_knob;
         prof_mark(ctx, s, "inflate_team_kernel");
-        inflate_team_kernel<<<(unsigned)ctas, kTeamLanes, sizeof(TeamShared), s>>>(
+        inflate_team_kernel<INF_MEMBER><<<(unsigned)ctas, kTeamLanes, sizeof(TeamShared), s>>>(
             d_in, d_out, d_members, (uint32_t)n, wrap, d_results,
-            (const InflateDeviceTables *)ctx->d_inflate_tables, w.counter, w.order, w.seg_off, w.seg_len, w.queues, team_lg, d_blog, blog_cap);
+            (const InflateDeviceTables *)ctx->d_inflate_tables, w.counter, w.order, w.seg_off, w.seg_len, w.queues, team_lg, d_blog, blog_cap, ChunkArgs{});
     } else {
         size_t ctas = (n + kInfWarps - 1) / kInfWarps;
         static const int per_sm_knob = [] { const char *e = getenv("ZB200_INF_CTAS_PER_SM"); return e ? atoi(e) : 0; }();   // profiling knob
@@ -890,9 +948,9 @@ int inflate_launch(zb200_ctx *ctx, const uint8_t *d_in, uint8_t *d_out, const zb
         if (cap * kInfWarps > kMaxGridWarps) cap = kMaxGridWarps / kInfWarps;
         if (ctas > cap) ctas = cap;
         prof_mark(ctx, s, "inflate_kernel");
-        inflate_kernel<<<(unsigned)ctas, kInfWarps * 32, sizeof(InflateShared), s>>>(
+        inflate_kernel<INF_MEMBER><<<(unsigned)ctas, kInfWarps * 32, sizeof(InflateShared), s>>>(
             d_in, d_out, d_members, (uint32_t)n, wrap, d_results,
-            (const InflateDeviceTables *)ctx->d_inflate_tables, w.counter, w.order, w.seg_off, w.seg_len, w.queues, d_blog, blog_cap);
+            (const InflateDeviceTables *)ctx->d_inflate_tables, w.counter, w.order, w.seg_off, w.seg_len, w.queues, d_blog, blog_cap, ChunkArgs{});
     }
     ZB_LAUNCHED();
     ZB_CHECK_LAUNCH();
@@ -914,9 +972,16 @@ int inflate_launch(zb200_ctx *ctx, const uint8_t *d_in, uint8_t *d_out, const zb
 // nothing copied), *in_used the stream's length, *check its computed check value.
 int inflate_stream_parallel(zb200_ctx *ctx, const uint8_t *src, size_t n, int wrap, uint8_t *out, size_t out_cap,
                             size_t *out_len, int *status, size_t *in_used, uint32_t *check, int *applicable,
-                            const StreamContinuation *cont) {
+                            const StreamContinuation *cont, int blocks_mode, uint32_t *end_bit) {
     *applicable = 0; *out_len = 0; *status = ZB200_INF_OK; *in_used = 0; *check = 0;
+    if (end_bit) *end_bit = 0;
     if (n < 64) return ZB200_OK;
+    // nothing (or too little) to split on at flush points: the stream's dynamic block headers are the next thing to try
+    auto blocks = [&](bool uploaded) {
+        if (!blocks_mode) return (int)ZB200_OK;
+        return inflate_stream_blocks(ctx, src, n, wrap, out, out_cap, out_len, status, in_used, check, applicable, cont, uploaded,
+                                     blocks_mode == 2, end_bit);
+    };
     const size_t hist_len = cont ? cont->hist_len : 0;
     if (cont && (wrap != ZB200_WRAP_RAW || hist_len > 32768 || cont->bit0 > 7)) return ZB200_ERR_PARAM;
     InflateState hs;
@@ -940,13 +1005,14 @@ int inflate_stream_parallel(zb200_ctx *ctx, const uint8_t *src, size_t n, int wr
     ZB_CUDA(cudaMemcpyAsync(ctx->h_small, d_count, 8, cudaMemcpyDeviceToHost, s));
     ZB_CUDA(cudaStreamSynchronize(s));
     const uint32_t nc = *(const uint32_t *)ctx->h_small;
-    if (nc == 0 || nc > cand_cap) return ZB200_OK;
+    if (nc > cand_cap) return ZB200_OK;
+    if ((uint64_t)(nc + 1) * ((uint64_t)1 << 20) < n) return blocks(true);   // runs of more than 1 MiB on average: too few to fill the GPU
     std::vector<uint64_t> start(nc + 1);
     ZB_CUDA(cudaMemcpy(start.data() + 1, d_list, (size_t)nc * 8, cudaMemcpyDeviceToHost));
     start[0] = hdr;
     std::sort(start.begin() + 1, start.end());
     while (!start.empty() && start.back() >= n) start.pop_back();          // a marker at the very end starts nothing
-    if (start.size() < 2) return ZB200_OK;
+    if (start.size() < 2) return blocks(true);
     *applicable = 1;                                         // (2 once the deflate data is seen to end: BFINAL reached)
     struct Run { uint64_t in_off, in_len, cap, slot; zb200_member_result res; bool done; };   // done: decoded into its slot, res valid
     std::vector<Run> runs(start.size());
@@ -1081,6 +1147,259 @@ int inflate_stream_parallel(zb200_ctx *ctx, const uint8_t *src, size_t n, int wr
     if (*status == ZB200_INF_OK) {
         if (kind != 0 && stored != *check) *status = ZB200_INF_DATA_CHECK;
         else if (kind == 2 && isize != (uint32_t)produced) *status = ZB200_INF_LENGTH_CHECK;
+    }
+    return ZB200_OK;
+}
+
+// ---- one member, decoded chunk by chunk in parallel (zb_inflate_blocks.cuh) -------------------------------------
+// Launch the decode kernels over chunks of ONE member (mode INF_COUNT / INF_LIST): a team of four warps per chunk while
+// every chunk can have one, a warp per chunk beyond.  `kind`: the member's resolved wrapper (0 raw, 1 zlib, 2 gzip).
+static int inflate_chunks_launch(zb200_ctx *ctx, int mode, const uint8_t *d_in, uint8_t *d_out, const zb200_member *d_members, size_t n,
+                                 int kind, zb200_member_result *d_results, unsigned int *d_counter, const ChunkArgs &ca, cudaStream_t s) {
+    ZB_CUDA(cudaMemsetAsync(d_counter, 0, 256, s));
+    const InflateDeviceTables *tabs = (const InflateDeviceTables *)ctx->d_inflate_tables;
+    static const int team_knob = [] { const char *e = getenv("ZB200_INF_TEAM"); return e ? atoi(e) : -1; }();
+    const bool team = team_knob >= 0 ? team_knob != 0 : n <= (size_t)ctx->sm_count * kTeamCtasPerSm;
+    if (team) {
+        size_t ctas = n;
+        const size_t cap = (size_t)ctx->sm_count * kTeamCtasPerSm;
+        if (ctas > cap) ctas = cap;
+        prof_mark(ctx, s, mode == INF_COUNT ? "inflate_team_count_kernel" : "inflate_team_list_kernel");
+        if (mode == INF_COUNT)
+            inflate_team_kernel<INF_COUNT><<<(unsigned)ctas, kTeamLanes, sizeof(TeamShared), s>>>(
+                d_in, d_out, d_members, (uint32_t)n, kind, d_results, tabs, d_counter, nullptr, nullptr, nullptr, nullptr, kTeamLgDefault, nullptr, 0, ca);
+        else
+            inflate_team_kernel<INF_LIST><<<(unsigned)ctas, kTeamLanes, sizeof(TeamShared), s>>>(
+                d_in, d_out, d_members, (uint32_t)n, kind, d_results, tabs, d_counter, nullptr, nullptr, nullptr, nullptr, kTeamLgDefault, nullptr, 0, ca);
+    } else {
+        size_t ctas = (n + kInfWarps - 1) / kInfWarps;
+        const size_t cap = (size_t)ctx->sm_count * kInfCtasPerSm;
+        if (ctas > cap) ctas = cap;
+        prof_mark(ctx, s, mode == INF_COUNT ? "inflate_count_kernel" : "inflate_list_kernel");
+        if (mode == INF_COUNT)
+            inflate_kernel<INF_COUNT><<<(unsigned)ctas, kInfWarps * 32, sizeof(InflateShared), s>>>(
+                d_in, d_out, d_members, (uint32_t)n, kind, d_results, tabs, d_counter, nullptr, nullptr, nullptr, nullptr, nullptr, 0, ca);
+        else
+            inflate_kernel<INF_LIST><<<(unsigned)ctas, kInfWarps * 32, sizeof(InflateShared), s>>>(
+                d_in, d_out, d_members, (uint32_t)n, kind, d_results, tabs, d_counter, nullptr, nullptr, nullptr, nullptr, nullptr, 0, ca);
+    }
+    ZB_LAUNCHED();
+    ZB_CHECK_LAUNCH();
+    return ZB200_OK;
+}
+
+// One raw / zlib / gzip stream (host pointers, or already on the device in ctx->d_io_in when `uploaded`), decoded in
+// parallel at its dynamic block headers.  Same contract as inflate_stream_parallel; in addition *end_bit receives the
+// bit (0..7) inside src[*in_used] at which a prefix delivered with ZB200_INF_TRUNCATED ends (a block boundary).
+// Streams this has nothing to offer to (fewer than two chunks, a damaged chain, output of 4 GiB or more) come back
+// with *applicable = 0 and nothing written: the one-member path decodes them and reports their exact status.
+constexpr uint64_t kBlkGroupOut = (uint64_t)256 << 20;       // output bytes resolved together (4 bytes of scratch per byte)
+int inflate_stream_blocks(zb200_ctx *ctx, const uint8_t *src, size_t n, int wrap, uint8_t *out, size_t out_cap,
+                          size_t *out_len, int *status, size_t *in_used, uint32_t *check, int *applicable,
+                          const StreamContinuation *cont, bool uploaded, bool prefix_ok, uint32_t *end_bit) {
+    *applicable = 0; *out_len = 0; *status = ZB200_INF_OK; *in_used = 0; *check = 0;
+    if (end_bit) *end_bit = 0;
+    static const int knob = [] { const char *e = getenv("ZB200_INF_BLOCKS"); return e ? atoi(e) : 1; }();
+    if (!knob || n < 4096) return ZB200_OK;
+    const size_t hist_len = cont ? cont->hist_len : 0;
+    if (cont && (wrap != ZB200_WRAP_RAW || hist_len > 32768 || cont->bit0 > 7)) return ZB200_ERR_PARAM;
+    InflateState hs;
+    hs.init(src, n, nullptr, 0, nullptr, nullptr, nullptr, nullptr);
+    if (hs.parse_header(wrap) != ZB200_INF_OK) return ZB200_OK;
+    const uint64_t hdr = hs.next;
+    const int kind = hs.wrap_kind;
+    const uint64_t bit0 = hdr * 8 + (cont ? cont->bit0 : 0);  // the member's first block
+    cudaStream_t s = ctx->stream;
+    int r = ensure_io(ctx, n + 16, 16);
+    if (r) return r;
+    if (!uploaded && (r = h2d_auto(ctx, ctx->d_io_in, src, n, s))) return r;
+    // 1. candidates
+    const uint32_t cand_cap = (uint32_t)(n / 64 + 1024 < (1u << 24) ? n / 64 + 1024 : (1u << 24));
+    if ((r = ensure_scratch(ctx, 512 + (size_t)cand_cap * 8))) return r;
+    uint32_t *d_count = (uint32_t *)ctx->d_scratch;
+    uint64_t *d_list = (uint64_t *)((uint8_t *)ctx->d_scratch + 512);
+    ZB_CUDA(cudaMemsetAsync(d_count, 0, 512, s));
+    {
+        const uint64_t nwords = ((uint64_t)n + 3) / 4;       // (the buffer holds n + 16 bytes; what follows the stream is never taken for part of it)
+        const uint64_t want = (nwords + 127) / 128;
+        const unsigned grid = (unsigned)(want < (uint64_t)ctx->sm_count * 16 ? (want ? want : 1) : (uint64_t)ctx->sm_count * 16);
+        prof_mark(ctx, s, "blk_candidates_kernel");
+        blk_candidates_kernel<<<grid, 128, 0, s>>>((const uint32_t *)ctx->d_io_in, nwords, bit0, (uint64_t)n * 8, d_list, cand_cap, d_count,
+                                                   &((const InflateDeviceTables *)ctx->d_inflate_tables)->fmt);
+        ZB_LAUNCHED();
+        ZB_CHECK_LAUNCH();
+    }
+    ZB_CUDA(cudaMemcpyAsync(ctx->h_small, d_count, 8, cudaMemcpyDeviceToHost, s));
+    ZB_CUDA(cudaStreamSynchronize(s));
+    const uint32_t nc = *(const uint32_t *)ctx->h_small;
+    if (nc < 2 || nc > cand_cap) return ZB200_OK;
+    std::vector<uint64_t> cand(nc);
+    ZB_CUDA(cudaMemcpy(cand.data(), d_list, (size_t)nc * 8, cudaMemcpyDeviceToHost));
+    std::sort(cand.begin(), cand.end());
+    // 2. count: chunk 0 = the member's first block, chunk k = candidate k - 1
+    const size_t nA = (size_t)nc + 1;
+    std::vector<zb200_member> tab(nA);
+    for (size_t k = 0; k < nA; ++k) {
+        zb200_member &m = tab[k];
+        m.in_off = 0; m.in_len = n; m.out_off = 0; m.out_cap = 0xfffffff0ull; m.resume_out = 0; m.dict_len = 0;
+        m.resume_bit = k == 0 ? (cont && cont->bit0 ? bit0 : 0) : cand[k - 1];
+    }
+    const size_t cand_b = align_up((size_t)nc * 8, 256), tab_b = align_up(nA * sizeof(zb200_member), 256),
+                 res_b = align_up(nA * sizeof(zb200_member_result), 256), u64_b = align_up(nA * 8, 256);
+    if ((r = ensure_scratch(ctx, 512 + cand_b + tab_b + res_b + u64_b))) return r;
+    uint8_t *base = (uint8_t *)ctx->d_scratch;
+    unsigned int *d_counter = (unsigned int *)base;
+    uint64_t *d_cand = (uint64_t *)(base + 512);
+    zb200_member *d_members = (zb200_member *)(base + 512 + cand_b);
+    zb200_member_result *d_results = (zb200_member_result *)(base + 512 + cand_b + tab_b);
+    uint64_t *d_nmatch = (uint64_t *)(base + 512 + cand_b + tab_b + res_b);
+    ZB_CUDA(cudaMemcpyAsync(d_cand, cand.data(), (size_t)nc * 8, cudaMemcpyHostToDevice, s));
+    ZB_CUDA(cudaMemcpyAsync(d_members, tab.data(), nA * sizeof(zb200_member), cudaMemcpyHostToDevice, s));
+    ChunkArgs ca;
+    ca.cand = d_cand; ca.n_cand = nc; ca.mbase = nullptr; ca.mlist = nullptr; ca.nmatch = d_nmatch;
+    if ((r = inflate_chunks_launch(ctx, INF_COUNT, ctx->d_io_in, nullptr, d_members, nA, kind, d_results, d_counter, ca, s))) return r;
+    std::vector<zb200_member_result> res(nA);
+    std::vector<uint64_t> nmatch(nA);
+    ZB_CUDA(cudaMemcpyAsync(res.data(), d_results, nA * sizeof(zb200_member_result), cudaMemcpyDeviceToHost, s));
+    ZB_CUDA(cudaMemcpyAsync(nmatch.data(), d_nmatch, nA * 8, cudaMemcpyDeviceToHost, s));
+    ZB_CUDA(cudaStreamSynchronize(s));
+    // 3. chain
+    struct Link { size_t idx; uint64_t out_off, m_off; };
+    std::vector<Link> chain;
+    uint64_t total = 0, total_m = 0;
+    int final_status = ZB200_INF_TRUNCATED;                  // a prefix, unless the chain reaches the end of the deflate data
+    uint64_t stop_bit = bit0;                                // where the delivered prefix ends
+    for (size_t cur = 0;;) {
+        const zb200_member_result &q = res[cur];
+        const uint64_t begin = cur == 0 ? bit0 : cand[cur - 1];
+        if (q.status == ZB200_INF_OK) {                      // BFINAL and the trailer: the member ends inside this chunk
+            chain.push_back({cur, total, total_m});
+            total += q.out_len; total_m += nmatch[cur];
+            final_status = ZB200_INF_OK;
+            break;
+        }
+        if (q.status != ZB200_INF_TRUNCATED || q.resume_out != q.out_len || q.resume_bit <= begin) break;
+        const auto it = std::lower_bound(cand.begin(), cand.end(), q.resume_bit);
+        if (it == cand.end() || *it != q.resume_bit) break;  // stopped for another reason (the input ends inside the chunk)
+        chain.push_back({cur, total, total_m});
+        total += q.out_len; total_m += nmatch[cur];
+        stop_bit = q.resume_bit;
+        cur = (size_t)(it - cand.begin()) + 1;
+    }
+    if (chain.size() < 2 || hist_len + total >= 0xfffffff0ull) return ZB200_OK;
+    if (final_status != ZB200_INF_OK && !prefix_ok) return ZB200_OK;
+    *applicable = final_status == ZB200_INF_OK ? 2 : 1;
+    *out_len = (size_t)total;
+    *status = final_status;
+    const zb200_member_result &fin = res[chain.back().idx];
+    uint64_t end = final_status == ZB200_INF_OK ? fin.in_used : stop_bit >> 3;
+    *in_used = (size_t)end;
+    if (end_bit) *end_bit = final_status == ZB200_INF_OK ? 0u : (uint32_t)(stop_bit & 7);
+    if (total > out_cap) { *status = ZB200_INF_OUTPUT_FULL; return ZB200_OK; }
+    // 4. list + 5. resolve, group after group of chunks
+    if ((r = ensure_io(ctx, n + 16, hist_len + total + 16))) return r;
+    uint8_t *d_out = ctx->d_io_out;
+    if (hist_len) ZB_CUDA(cudaMemcpyAsync(d_out, cont->hist, hist_len, cudaMemcpyHostToDevice, s));
+    const size_t nB = chain.size();
+    uint64_t grp_m_max = 0, grp_o_max = 0;
+    std::vector<size_t> grp_first;                           // groups of consecutive chunks with <= kBlkGroupOut bytes of output
+    for (size_t k = 0; k < nB;) {
+        grp_first.push_back(k);
+        const uint64_t o0 = chain[k].out_off, m0 = chain[k].m_off;
+        size_t e = k + 1;
+        auto o_end = [&](size_t j) { return j < nB ? chain[j].out_off : total; };
+        while (e < nB && o_end(e + 1) - o0 <= kBlkGroupOut) ++e;
+        const uint64_t go = o_end(e) - o0, gm = (e < nB ? chain[e].m_off : total_m) - m0;
+        if (go > grp_o_max) grp_o_max = go;
+        if (gm > grp_m_max) grp_m_max = gm;
+        k = e;
+    }
+    grp_first.push_back(nB);
+    const size_t tabB_b = align_up(nB * sizeof(zb200_member), 256), resB_b = align_up(nB * sizeof(zb200_member_result), 256), mb_b = align_up(nB * 8, 256),
+                 ml_b = align_up((size_t)grp_m_max * sizeof(QueuedMatch) + 16, 256), src_b = align_up((size_t)grp_o_max * 4 + 16, 256);
+    if ((r = ensure_scratch(ctx, 1024 + cand_b + tabB_b + resB_b + mb_b + ml_b + src_b))) return r;
+    base = (uint8_t *)ctx->d_scratch;                        // (the block may have been replaced: everything is laid out afresh)
+    d_counter = (unsigned int *)base;
+    uint32_t *d_flag = (uint32_t *)(base + 512);
+    uint32_t *d_sum = (uint32_t *)(base + 640);
+    CkAccum *d_acc = (CkAccum *)(base + 768);
+    d_cand = (uint64_t *)(base + 1024);
+    d_members = (zb200_member *)(base + 1024 + cand_b);
+    d_results = (zb200_member_result *)(base + 1024 + cand_b + tabB_b);
+    uint64_t *d_mbase = (uint64_t *)(base + 1024 + cand_b + tabB_b + resB_b);
+    QueuedMatch *d_ml = (QueuedMatch *)(base + 1024 + cand_b + tabB_b + resB_b + mb_b);
+    uint32_t *d_src = (uint32_t *)(base + 1024 + cand_b + tabB_b + resB_b + mb_b + ml_b);
+    ZB_CUDA(cudaMemcpyAsync(d_cand, cand.data(), (size_t)nc * 8, cudaMemcpyHostToDevice, s));
+    std::vector<zb200_member> tabB(nB);
+    std::vector<uint64_t> mbase(nB);
+    std::vector<zb200_member_result> resB(nB);
+    for (size_t g = 0; g + 1 < grp_first.size(); ++g) {
+        const size_t k0 = grp_first[g], k1 = grp_first[g + 1], ng = k1 - k0;
+        const uint64_t o0 = chain[k0].out_off, o1 = k1 < nB ? chain[k1].out_off : total;
+        const uint64_t m0 = chain[k0].m_off, m1 = k1 < nB ? chain[k1].m_off : total_m;
+        for (size_t k = k0; k < k1; ++k) {
+            zb200_member &m = tabB[k];
+            m = tab[chain[k].idx];
+            m.out_off = hist_len; m.dict_len = hist_len; m.out_cap = total; m.resume_out = chain[k].out_off;
+            mbase[k] = chain[k].m_off - m0;
+        }
+        ZB_CUDA(cudaMemcpyAsync(d_members + k0, tabB.data() + k0, ng * sizeof(zb200_member), cudaMemcpyHostToDevice, s));
+        ZB_CUDA(cudaMemcpyAsync(d_mbase + k0, mbase.data() + k0, ng * 8, cudaMemcpyHostToDevice, s));
+        ZB_CUDA(cudaMemsetAsync(d_src, 0xff, (size_t)(o1 - o0) * 4, s));
+        ca.cand = d_cand; ca.n_cand = nc; ca.mbase = d_mbase + k0; ca.mlist = d_ml; ca.nmatch = nullptr;
+        if ((r = inflate_chunks_launch(ctx, INF_LIST, ctx->d_io_in, d_out, d_members + k0, ng, kind, d_results + k0, d_counter, ca, s))) return r;
+        ZB_CUDA(cudaMemcpyAsync(resB.data() + k0, d_results + k0, ng * sizeof(zb200_member_result), cudaMemcpyDeviceToHost, s));
+        const uint32_t lo = (uint32_t)(hist_len + o0);
+        const uint64_t gn = o1 - o0, gm = m1 - m0;
+        if (gm) {
+            const uint64_t want = (gm + 255) / 256;          // 8 warps x 32 matches per CTA
+            const unsigned grid = (unsigned)(want < (uint64_t)ctx->sm_count * 32 ? want : (uint64_t)ctx->sm_count * 32);
+            prof_mark(ctx, s, "blk_src_build_kernel");
+            blk_src_build_kernel<<<grid, 256, 0, s>>>(d_ml, gm, d_src, lo);
+            ZB_LAUNCHED();
+            ZB_CHECK_LAUNCH();
+            const uint64_t wantj = (gn / 4 + 255) / 256 + 1;
+            const unsigned gridj = (unsigned)(wantj < (uint64_t)ctx->sm_count * 32 ? wantj : (uint64_t)ctx->sm_count * 32);
+            for (int pass = 0; pass < 64; pass += 4) {       // the flag is looked at every fourth pass
+                ZB_CUDA(cudaMemsetAsync(d_flag, 0, 4, s));
+                for (int k = 0; k < 4; ++k) {
+                    prof_mark(ctx, s, "blk_jump_kernel");
+                    blk_jump_kernel<<<gridj, 256, 0, s>>>(d_src, gn, lo, d_flag + (k == 3 ? 0 : 1));
+                    ZB_LAUNCHED();
+                }
+                ZB_CHECK_LAUNCH();
+                ZB_CUDA(cudaMemcpyAsync(ctx->h_small, d_flag, 4, cudaMemcpyDeviceToHost, s));
+                ZB_CUDA(cudaStreamSynchronize(s));
+                if (*(const uint32_t *)ctx->h_small == 0) break;
+            }
+            prof_mark(ctx, s, "blk_gather_kernel");
+            blk_gather_kernel<<<gridj, 256, 0, s>>>(d_out, d_src, gn, lo);
+            ZB_LAUNCHED();
+            ZB_CHECK_LAUNCH();
+        }
+        ZB_CUDA(cudaStreamSynchronize(s));
+        for (size_t k = k0; k < k1; ++k) {                   // the second decode must tell the first one's story (it adds the "too far back" test)
+            const zb200_member_result &a = res[chain[k].idx], &b = resB[k];
+            if (a.status != b.status || b.out_len != chain[k].out_off + a.out_len || a.resume_bit != b.resume_bit) {
+                *applicable = 0; *out_len = 0; *status = ZB200_INF_OK; *in_used = 0;
+                return ZB200_OK;
+            }
+        }
+    }
+    prof_mark(ctx, s, nullptr);
+    // the check value over the whole, the bytes back, the trailer (inflate.c:1183-1219)
+    const int ck = cont ? cont->check_kind : kind;
+    uint8_t *d_final = d_out + hist_len;
+    if ((r = checksum_launch(ctx, d_final, nullptr, nullptr, total, 1, ck == 1 ? ZB200_ADLER32 : ZB200_CRC32, 0, 1, d_sum, d_sum + 1, d_acc, s))) return r;
+    ZB_CUDA(cudaMemcpyAsync(ctx->h_small, d_sum, 8, cudaMemcpyDeviceToHost, s));
+    if (total && (r = d2h_auto(ctx, out, d_final, (size_t)total, s))) return r;
+    ZB_CUDA(cudaStreamSynchronize(s));
+    const uint32_t *hsum = (const uint32_t *)ctx->h_small;
+    *check = ck == 1 ? hsum[1] : hsum[0];
+    if (final_status == ZB200_INF_OK) {
+        if (kind == 1 && fin.check != *check) *status = ZB200_INF_DATA_CHECK;
+        else if (kind == 2 && fin.check != *check) *status = ZB200_INF_DATA_CHECK;
+        else if (kind == 2 && fin.isize != (uint32_t)total) *status = ZB200_INF_LENGTH_CHECK;
     }
     return ZB200_OK;
 }
@@ -1390,7 +1709,7 @@ int zb200_inflate_stream_host(zb200_ctx *ctx, const void *in, size_t n, int wrap
         size_t out_len = 0, in_used = 0;
         int status = 0, applicable = 0;
         uint32_t check = 0;
-        const int r = inflate_stream_parallel(ctx, (const uint8_t *)in, n, wrap, (uint8_t *)out, out_cap, &out_len, &status, &in_used, &check, &applicable, nullptr);
+        const int r = inflate_stream_parallel(ctx, (const uint8_t *)in, n, wrap, (uint8_t *)out, out_cap, &out_len, &status, &in_used, &check, &applicable, nullptr, 1);
         // the run-parallel decode is an optimisation: when it cannot get its memory (a stream of stored / binary data with
         // many false 00 00 FF FF candidates asks for a slot per candidate) the one-member path below decodes the stream
         if (r != ZB200_OK && r != ZB200_ERR_NOMEM) return r;

@@ -187,6 +187,13 @@ struct InflateState {
     int tables_external;                                   // 1: a dynamic header's code lengths are read here, its two decode tables
                                                            //    are built by the caller (EV_TABLES: len = nlen, dist = ndist), who
                                                            //    reports back through tables_done()
+    // A CHUNK of a member decoded on its own (zb_inflate_blocks.cuh): the member's blocks from a known block start up to
+    // the first later boundary that is one of the `cand_n` sorted candidate block starts in cand[] (bit offsets inside
+    // the member) — the chunk stops there like a member whose input ends (ZB200_INF_TRUNCATED, ck_bit = the boundary).
+    const uint64_t *cand; uint32_t cand_n; uint64_t start_bit;
+    int count_only;                                        // 1: nothing is written — pos counts the output, the caller counts
+                                                           //    the matches; what lies before the chunk is unknown, so no
+                                                           //    distance is "too far back" yet
 
     ZB_HD void refill() {
         while (bits <= 32) {
@@ -220,6 +227,7 @@ struct InflateState {
         wrap_kind = 0; status = ZB200_INF_OK; ck_bit = 0; ck_out = 0; stored_check = 0; stored_isize = 0;
         in_used = 0; fixed_lit = flit; fixed_dist = fdist; fmt = f; has_parked = 0; huff_external = 0; tables_external = 0; have_dict = 0;
         blog = nullptr; blog_cap = 0; blog_n = 0;
+        cand = nullptr; cand_n = 0; start_bit = 0; count_only = 0;
         if (s) { tlit = s->lit; tdist = s->dist; work = s->work; lens = s->lens; }
         else { tlit = tdist = nullptr; work = nullptr; lens = nullptr; }
     }
@@ -234,7 +242,19 @@ struct InflateState {
         next = bit_off >> 3; hold = 0; bits = 0;
         refill();
         drop((int)(bit_off & 7));
-        pos = out_pos; wrap_kind = kind; ck_bit = bit_off; ck_out = out_pos;
+        pos = out_pos; wrap_kind = kind; ck_bit = bit_off; ck_out = out_pos; start_bit = bit_off;
+    }
+
+    // Is bit offset b one of the candidate block starts?  (binary search; a few probes per deflate block)
+    ZB_HD bool is_candidate(uint64_t b) const {
+        uint32_t lo = 0, hi = cand_n;
+        while (lo < hi) {
+            const uint32_t mid = (lo + hi) >> 1;
+            const uint64_t v = cand[mid];
+            if (v == b) return true;
+            if (v < b) lo = mid + 1; else hi = mid;
+        }
+        return false;
     }
 
     // Re-seed the bit reader at an absolute bit offset: after an externally decoded
@@ -401,6 +421,7 @@ struct InflateState {
                 }
                 if (last) return finish();
                 ck_bit = bitpos(); ck_out = pos;       // a block boundary: safe resume point
+                if (cand_n && ck_bit != start_bit && is_candidate(ck_bit)) return done(ZB200_INF_TRUNCATED);   // the next chunk starts here
                 refill();
                 last = (int)take(1);
                 const uint32_t type = take(2);         // inflate.c:827-862
@@ -452,7 +473,8 @@ struct InflateState {
                 if (op == OP_LIT) {
                     if (overrun()) return done(ZB200_INF_TRUNCATED);
                     if (pos >= out_cap) return done(ZB200_INF_OUTPUT_FULL);
-                    out[pos++] = (uint8_t)ZB_E_VAL(e);
+                    if (!count_only) out[pos] = (uint8_t)ZB_E_VAL(e);
+                    ++pos;
                     continue;
                 }
                 if (op == OP_EOB) {
@@ -473,7 +495,7 @@ struct InflateState {
                 if (ZB_E_OP(d) != OP_BASE) return done(overrun() ? ZB200_INF_TRUNCATED : ZB200_INF_DIST_CODE);
                 const uint32_t dist = ZB_E_VAL(d) + take((int)ZB_E_EXTRA(d));
                 if (overrun()) return done(ZB200_INF_TRUNCATED);
-                if (dist > pos) return done(ZB200_INF_DIST_FAR);          // inffast.c:152-161
+                if (dist > pos && !count_only) return done(ZB200_INF_DIST_FAR);   // inffast.c:152-161
                 if (len > out_cap - pos) return done(ZB200_INF_OUTPUT_FULL);
                 InflateEvent ev; ev.kind = EV_MATCH; ev.len = len; ev.dist = dist; ev.src = 0; ev.dst = pos;
                 pos += len;
@@ -490,7 +512,7 @@ struct InflateState {
     // the offending symbol and returns to the careful path (step()), which reports it.
     // Returns 0: continue on the careful path, 1: queue full, 2: end of block consumed.
     ZB_HD int fast_symbols(QueuedMatch *q, uint32_t &count, uint64_t &first_dst) {
-        if (in_len < 16 || out_cap < 264) return 0;
+        if (in_len < 16 || out_cap < 264 || count_only) return 0;
         uint64_t h = hold; int b = bits; uint64_t nx = next;
         // byte-align the loader to 4 so every refill is one aligned word
         while (((reinterpret_cast<uintptr_t>(in) + nx) & 3) != 0) {
