@@ -258,6 +258,14 @@ extern "C" uint64_t emul_blk_candidates(const uint8_t *src, uint64_t n, uint64_t
         if (cnt < cap) list[cnt] = b;
         ++cnt;
     }
+    for (uint64_t P = 4; P + 4 <= n; ++P) {              // stored blocks, as blk_scan_kernel looks for them
+        const uint32_t len = src[P] | (src[P + 1] << 8), nlen = src[P + 2] | (src[P + 3] << 8);
+        if ((len ^ nlen) != 0xffffu || P * 8 < bit_lo + 3) continue;
+        const uint32_t before = (uint32_t)src[P - 2] | ((uint32_t)src[P - 1] << 8);
+        const uint32_t ns = blk_stored_starts(before, P * 8, bit_lo);
+        for (uint32_t k = 0; k < ns; ++k, ++cnt) if (cnt < cap) list[cnt] = P * 8 - 3 - k;
+    }
+    if (cnt <= cap) std::sort(list, list + cnt);
     if (quick_pass) *quick_pass = qp;
     return cnt;
 }

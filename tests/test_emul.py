@@ -456,4 +456,4 @@ def test_block_parallel_decode_replay():
             assert ck.value == zlib.crc32(d) and isz.value == n
         if wrap == 1:
             assert ck.value == zlib.adler32(d)
-        assert stats[0] <= stats[1] + 2, list(stats)          # next to no false candidates
+        assert stats[0] <= 8 * stats[1] + 2, list(stats)      # next to no false candidates (a stored block has up to 8 possible starts)

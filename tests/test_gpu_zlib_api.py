@@ -491,6 +491,31 @@ def test_inflate_big_slices_run_parallel(z, wrap):
     assert ret == refz.Z_STREAM_END and out == d[:3000000] and tin == len(s3)
 
 
+@pytest.mark.parametrize("wrap", [refz.WRAP_RAW, refz.WRAP_ZLIB, refz.WRAP_GZIP])
+def test_inflate_big_slices_block_parallel(z, wrap):
+    """inflate() fed a stream WITHOUT flush points in large slices: the chunks between dynamic block headers that are
+    complete in the input so far are decoded in one batch (csrc/zb_inflate_blocks.cuh), the stream is re-based behind
+    them at a block boundary INSIDE a byte, and so on; output, totals and verdicts are the reference's."""
+    import zlib
+    d = refz.gen(20000000, refz.GEN_MARKOV, seed=73) + refz.gen(4000000, refz.GEN_MIXED, seed=74)
+    co = zlib.compressobj(6, zlib.DEFLATED, {refz.WRAP_RAW: -15, refz.WRAP_ZLIB: 15, refz.WRAP_GZIP: 31}[wrap])
+    s = co.compress(d) + co.flush()
+    ref = refz.ref() if refz.have_ref() else refz.oracle()
+    for in_slice, out_slice in ((None, None), (2500000, None), (700001, 3000000), (300000, 1 << 20), (len(s) - 5, None)):
+        ret, m, out, tin = z.inflate_all(s + b"after", wrap, cap=len(d) + 64, in_slice=in_slice, out_slice=out_slice)
+        assert ret == refz.Z_STREAM_END and out == d and tin == len(s), (wrap, in_slice, out_slice, ret, m, len(out), tin, len(s))
+    for where, flip in ((len(s) // 2, 0x08), (len(s) - 2, 0x01), (len(s) // 7, 0x80)):
+        bad = bytearray(s); bad[where] ^= flip
+        want = ref.inflate_all(bytes(bad), wrap, cap=len(d) + 64)
+        for in_slice in (None, 1500000):
+            got = z.inflate_all(bytes(bad), wrap, cap=len(d) + 64, in_slice=in_slice)
+            assert got[0] == want[0] and (got[1] == want[1] or wrap == refz.WRAP_RAW), (wrap, where, in_slice, got[:2], want[:2])
+            k = min(len(got[2]), len(want[2]))
+            assert got[2][:k] == want[2][:k]
+    ret, m, out, tin = z.inflate_all(s[:len(s) * 2 // 3], wrap, cap=len(d) + 64, in_slice=2000000)
+    assert ret in (refz.Z_OK, refz.Z_BUF_ERROR) and d.startswith(out) and len(out) > len(d) // 2
+
+
 def test_deflate_tune(z):
     """deflateTune (deflate.c:805-816): the four search parameters replace the level's table values — the
     reference's bytes for the same tuning at the lazy levels."""

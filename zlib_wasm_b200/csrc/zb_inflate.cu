@@ -15,6 +15,7 @@
 #include "zb_inflate_tables.cuh"
 #include "zb_inflate_blocks.cuh"
 #include <string.h>
+#include <stdio.h>
 #include <algorithm>
 #include <vector>
 #include <stdlib.h>
@@ -114,6 +115,29 @@ __device__ __forceinline__ void exec_queue(uint8_t *dst, const QueuedMatch *q, u
             __syncwarp(full);
         }
     }
+}
+
+// A stored block (inflate.c:863-897): len bytes from the member's input to its output, by the nt threads that share the
+// member.  Destination words are aligned, the source is read as aligned words and funnel-shifted into place, four words
+// in flight per thread (a byte-by-byte loop whose stores may alias its loads ran at one memory round trip per 32 bytes:
+// 20 ms per MiB of incompressible data).
+__device__ __forceinline__ void copy_stored(uint8_t *__restrict__ d, const uint8_t *__restrict__ s, uint32_t len, uint32_t tid, uint32_t nt) {
+    const uint32_t head = (uint32_t)((4 - (reinterpret_cast<uintptr_t>(d) & 3)) & 3);
+    if (len < 64 + head) { for (uint32_t i = tid; i < len; i += nt) d[i] = s[i]; return; }
+    if (tid < head) d[tid] = s[tid];
+    const uint32_t nw = (len - head) >> 2;
+    uint32_t *__restrict__ dw = reinterpret_cast<uint32_t *>(d + head);
+    const uintptr_t sa = reinterpret_cast<uintptr_t>(s + head);
+    const uint32_t *__restrict__ sw = reinterpret_cast<const uint32_t *>(sa & ~(uintptr_t)3);
+    const uint32_t sh = (uint32_t)(sa & 3) * 8;
+    if (sh) {
+#pragma unroll 4
+        for (uint32_t w = tid; w < nw; w += nt) dw[w] = __funnelshift_r(sw[w], sw[w + 1], sh);   // (word w + 1 holds a byte of the block)
+    } else {
+#pragma unroll 4
+        for (uint32_t w = tid; w < nw; w += nt) dw[w] = sw[w];
+    }
+    for (uint32_t i = head + nw * 4 + tid; i < len; i += nt) d[i] = s[i];
 }
 
 // ---- warp-parallel Huffman block decode (rounds: zb_inflate_round.cuh) ---------------
@@ -384,9 +408,7 @@ inflate_kernel(const uint8_t *__restrict__ in, uint8_t *out, const zb200_member 
             } else if (MODE != INF_COUNT) {                    // stored block: input -> output
                 const uint64_t to = __shfl_sync(full, ev.dst, 0);
                 const uint64_t from = __shfl_sync(full, ev.src, 0);
-                const uint8_t *s = src + from;
-                uint8_t *d = dst + to;
-                for (uint32_t i = lane; i < len; i += 32) d[i] = s[i];
+                copy_stored(dst + to, src + from, len, lane, 32);
                 __syncwarp(full);
             }
         }
@@ -661,9 +683,7 @@ inflate_team_kernel(const uint8_t *__restrict__ in, uint8_t *out, const zb200_me
                 __syncthreads();
             } else if (MODE == INF_COUNT) {                        // (a stored block: nothing is written)
             } else {                                               // stored block: input -> output
-                const uint8_t *s = src + ev.src;
-                uint8_t *d = dst + ev.dst;
-                for (uint32_t i = tid; i < ev.len; i += kTeamLanes) d[i] = s[i];
+                copy_stored(dst + ev.dst, src + ev.src, ev.len, tid, kTeamLanes);
                 __syncthreads();
             }
         }
@@ -1213,26 +1233,34 @@ int inflate_stream_blocks(zb200_ctx *ctx, const uint8_t *src, size_t n, int wrap
     int r = ensure_io(ctx, n + 16, 16);
     if (r) return r;
     if (!uploaded && (r = h2d_auto(ctx, ctx->d_io_in, src, n, s))) return r;
-    // 1. candidates
+    // 1. candidates: positions that pass the cheap part of the test (one in ~1100), then those of them that pass all of it
     const uint32_t cand_cap = (uint32_t)(n / 64 + 1024 < (1u << 24) ? n / 64 + 1024 : (1u << 24));
-    if ((r = ensure_scratch(ctx, 512 + (size_t)cand_cap * 8))) return r;
-    uint32_t *d_count = (uint32_t *)ctx->d_scratch;
+    const uint32_t surv_cap = (uint32_t)(n / 16 + 4096 < (1u << 26) ? n / 16 + 4096 : (1u << 26));
+    if ((r = ensure_scratch(ctx, 512 + (size_t)cand_cap * 8 + (size_t)surv_cap * 8))) return r;
+    uint32_t *d_count = (uint32_t *)ctx->d_scratch;           // [0] candidates, [1] survivors of stage 1
     uint64_t *d_list = (uint64_t *)((uint8_t *)ctx->d_scratch + 512);
+    uint64_t *d_surv = d_list + cand_cap;
     ZB_CUDA(cudaMemsetAsync(d_count, 0, 512, s));
     {
         const uint64_t nwords = ((uint64_t)n + 3) / 4;       // (the buffer holds n + 16 bytes; what follows the stream is never taken for part of it)
-        const uint64_t want = (nwords + 127) / 128;
+        const uint64_t want = (nwords + 255) / 256;
         const unsigned grid = (unsigned)(want < (uint64_t)ctx->sm_count * 16 ? (want ? want : 1) : (uint64_t)ctx->sm_count * 16);
-        prof_mark(ctx, s, "blk_candidates_kernel");
-        blk_candidates_kernel<<<grid, 128, 0, s>>>((const uint32_t *)ctx->d_io_in, nwords, bit0, (uint64_t)n * 8, d_list, cand_cap, d_count,
-                                                   &((const InflateDeviceTables *)ctx->d_inflate_tables)->fmt);
+        prof_mark(ctx, s, "blk_scan_kernel");
+        blk_scan_kernel<<<grid, 256, 0, s>>>((const uint32_t *)ctx->d_io_in, nwords, bit0, (uint64_t)n * 8, d_surv, surv_cap, d_count + 1, d_list, cand_cap, d_count);
+        ZB_LAUNCHED();
+        ZB_CHECK_LAUNCH();
+        const uint64_t wantv = n / (128 * 137) + 1;          // (about one survivor per 137 bytes)
+        const unsigned gridv = (unsigned)(wantv < (uint64_t)ctx->sm_count * 8 ? wantv : (uint64_t)ctx->sm_count * 8);
+        prof_mark(ctx, s, "blk_validate_kernel");
+        blk_validate_kernel<<<gridv, 128, 0, s>>>((const uint32_t *)ctx->d_io_in, nwords, (uint64_t)n * 8, d_surv, d_count + 1, surv_cap, d_list, cand_cap,
+                                                  d_count, &((const InflateDeviceTables *)ctx->d_inflate_tables)->fmt);
         ZB_LAUNCHED();
         ZB_CHECK_LAUNCH();
     }
     ZB_CUDA(cudaMemcpyAsync(ctx->h_small, d_count, 8, cudaMemcpyDeviceToHost, s));
     ZB_CUDA(cudaStreamSynchronize(s));
     const uint32_t nc = *(const uint32_t *)ctx->h_small;
-    if (nc < 2 || nc > cand_cap) return ZB200_OK;
+    if (nc < 2 || nc > cand_cap || ((const uint32_t *)ctx->h_small)[1] > surv_cap) return ZB200_OK;
     std::vector<uint64_t> cand(nc);
     ZB_CUDA(cudaMemcpy(cand.data(), d_list, (size_t)nc * 8, cudaMemcpyDeviceToHost));
     std::sort(cand.begin(), cand.end());
@@ -1286,6 +1314,19 @@ int inflate_stream_blocks(zb200_ctx *ctx, const uint8_t *src, size_t n, int wrap
         stop_bit = q.resume_bit;
         cur = (size_t)(it - cand.begin()) + 1;
     }
+    static const int debug = [] { const char *e = getenv("ZB200_BLOCKS_DEBUG"); return e ? atoi(e) : 0; }();
+    if (debug) {
+        uint64_t max_out = 0, max_in = 0;
+        for (size_t k = 0; k < chain.size(); ++k) {
+            const zb200_member_result &q = res[chain[k].idx];
+            const uint64_t b0 = chain[k].idx ? cand[chain[k].idx - 1] : bit0;
+            const uint64_t in_bits = (q.status == ZB200_INF_OK ? q.in_used * 8 : q.resume_bit) - b0;
+            if (q.out_len > max_out) max_out = q.out_len;
+            if (in_bits > max_in) max_in = in_bits;
+        }
+        fprintf(stderr, "[blocks] n=%zu candidates=%u chain=%zu out=%llu matches=%llu largest chunk: %llu bytes out, %llu bytes in\n", n, nc, chain.size(),
+                (unsigned long long)total, (unsigned long long)total_m, (unsigned long long)max_out, (unsigned long long)(max_in / 8));
+    }
     if (chain.size() < 2 || hist_len + total >= 0xfffffff0ull) return ZB200_OK;
     if (final_status != ZB200_INF_OK && !prefix_ok) return ZB200_OK;
     *applicable = final_status == ZB200_INF_OK ? 2 : 1;
@@ -1310,6 +1351,7 @@ int inflate_stream_blocks(zb200_ctx *ctx, const uint8_t *src, size_t n, int wrap
         auto o_end = [&](size_t j) { return j < nB ? chain[j].out_off : total; };
         while (e < nB && o_end(e + 1) - o0 <= kBlkGroupOut) ++e;
         const uint64_t go = o_end(e) - o0, gm = (e < nB ? chain[e].m_off : total_m) - m0;
+        if (go >= 0x7fff0000ull) { *applicable = 0; *out_len = 0; *status = ZB200_INF_OK; *in_used = 0; return ZB200_OK; }   // (one chunk of 2 GiB: source offsets hold 31 bits)
         if (go > grp_o_max) grp_o_max = go;
         if (gm > grp_m_max) grp_m_max = gm;
         k = e;
@@ -1349,22 +1391,22 @@ int inflate_stream_blocks(zb200_ctx *ctx, const uint8_t *src, size_t n, int wrap
         ca.cand = d_cand; ca.n_cand = nc; ca.mbase = d_mbase + k0; ca.mlist = d_ml; ca.nmatch = nullptr;
         if ((r = inflate_chunks_launch(ctx, INF_LIST, ctx->d_io_in, d_out, d_members + k0, ng, kind, d_results + k0, d_counter, ca, s))) return r;
         ZB_CUDA(cudaMemcpyAsync(resB.data() + k0, d_results + k0, ng * sizeof(zb200_member_result), cudaMemcpyDeviceToHost, s));
-        const uint32_t lo = (uint32_t)(hist_len + o0);
+        const uint32_t lo = (uint32_t)(hist_len + o0), sbase = lo > 32768u ? lo - 32768u : 0u;
         const uint64_t gn = o1 - o0, gm = m1 - m0;
         if (gm) {
             const uint64_t want = (gm + 255) / 256;          // 8 warps x 32 matches per CTA
             const unsigned grid = (unsigned)(want < (uint64_t)ctx->sm_count * 32 ? want : (uint64_t)ctx->sm_count * 32);
             prof_mark(ctx, s, "blk_src_build_kernel");
-            blk_src_build_kernel<<<grid, 256, 0, s>>>(d_ml, gm, d_src, lo);
+            blk_src_build_kernel<<<grid, 256, 0, s>>>(d_ml, gm, d_src, lo, sbase);
             ZB_LAUNCHED();
             ZB_CHECK_LAUNCH();
             const uint64_t wantj = (gn / 4 + 255) / 256 + 1;
             const unsigned gridj = (unsigned)(wantj < (uint64_t)ctx->sm_count * 32 ? wantj : (uint64_t)ctx->sm_count * 32);
-            for (int pass = 0; pass < 64; pass += 4) {       // the flag is looked at every fourth pass
+            for (int pass = 0; pass < 64; pass += 2) {       // the flag is looked at every other pass
                 ZB_CUDA(cudaMemsetAsync(d_flag, 0, 4, s));
-                for (int k = 0; k < 4; ++k) {
+                for (int k = 0; k < 2; ++k) {
                     prof_mark(ctx, s, "blk_jump_kernel");
-                    blk_jump_kernel<<<gridj, 256, 0, s>>>(d_src, gn, lo, d_flag + (k == 3 ? 0 : 1));
+                    blk_jump_kernel<<<gridj, 256, 0, s>>>(d_src, gn, lo, sbase, d_flag + (k == 1 ? 0 : 1));
                     ZB_LAUNCHED();
                 }
                 ZB_CHECK_LAUNCH();
@@ -1373,7 +1415,7 @@ int inflate_stream_blocks(zb200_ctx *ctx, const uint8_t *src, size_t n, int wrap
                 if (*(const uint32_t *)ctx->h_small == 0) break;
             }
             prof_mark(ctx, s, "blk_gather_kernel");
-            blk_gather_kernel<<<gridj, 256, 0, s>>>(d_out, d_src, gn, lo);
+            blk_gather_kernel<<<gridj, 256, 0, s>>>(d_out, d_src, gn, lo, sbase);
             ZB_LAUNCHED();
             ZB_CHECK_LAUNCH();
         }

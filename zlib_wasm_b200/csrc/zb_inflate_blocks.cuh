@@ -9,8 +9,8 @@
 //      a COMPLETE code-length code (inftrees.c:126-133 rejects anything else for CODES), then 258..316 code lengths that
 //      must decode without a bad repeat, contain an end-of-block code and form a complete (or single-code) literal/length
 //      set and a complete / single-code / empty distance set.  Every BIT position of the member is tested
-//      (blk_candidates_kernel): the first 17 + 3*HCLEN bits reject all but 1 in ~1100 positions with two 64-bit windows,
-//      the survivors read their code lengths.  What passes is, but for a rare accident, a real block start — and the chain
+//      (blk_scan_kernel): the first 17 + 3*HCLEN bits reject all but 1 in ~1100 positions with two 64-bit windows,
+//      the survivors read their code lengths (blk_validate_kernel).  What passes is, but for a rare accident, a real block start — and the chain
 //      check below does not depend on it being one.
 //   2. COUNT       Every candidate (and the member's first block) starts a CHUNK: the blocks from there to the first later
 //      block boundary that is itself a candidate.  All chunks are decoded at once with nothing written (INF_COUNT in
@@ -53,6 +53,20 @@ ZB_HD bool blk_cl_complete(uint64_t y, uint32_t ncode) {
 #pragma unroll
     for (int i = 0; i < 19; ++i) { const uint32_t l = (uint32_t)(y >> (3 * i)) & 7u; k += (128u >> l) & 127u; }
     return k == 128u;
+}
+
+// A stored block (inflate.c:863-897) whose LEN field sits at bit P8 (a byte boundary; LEN and NLEN complement each other):
+// its 3 header bits — BFINAL, BTYPE = 0 — lie at bit e = P8 - 3 - k for some k in 0..7, with zero padding between them and
+// P8 (deflate pads with zeros, trees.c:166-193 bi_windup).  before16: the 16 stream bits in front of P8, bit P8 - 1 on top.
+// Returns how many k = 0, 1, ... qualify (they form a run: one more zero bit is needed for each).
+ZB_HD uint32_t blk_stored_starts(uint32_t before16, uint64_t P8, uint64_t bit_lo) {
+    uint32_t ns = 0;
+    for (uint32_t k = 0; k < 8; ++k) {
+        if ((before16 >> (14 - k)) != 0u) break;             // bits e + 1 .. P8 - 1 (k + 2 of them) must be zero
+        if (P8 - 3 - k < bit_lo) break;
+        ++ns;
+    }
+    return ns;
 }
 
 // The rest of the test: read the HLIT + HDIST + 258 code lengths with the code-length code (inflate.c:930-995) and
@@ -113,117 +127,184 @@ ZB_HD bool blk_header_valid(const uint32_t *__restrict__ w, uint64_t nwords, uin
 }
 
 // Positions are output positions of the member counted like the decoder counts them (from the first byte of the
-// history / dictionary in front of it); src[] covers [lo, lo + n).  kSrcLiteral: the byte is there already.
+// history / dictionary in front of it).  kSrcLiteral: the byte is there already.
 constexpr uint32_t kSrcLiteral = 0xffffffffu;
 
 #ifdef __CUDACC__
-// Every bit position in [bit_lo, bit_hi) of the member (words: the aligned words that hold it, bit 0 = bit 0 of
-// words[0]) that passes the test, appended to list[] in no particular order.
+// Stage 1: every bit position in [bit_lo, bit_hi) of the member (words: the aligned words that hold it, bit 0 = bit 0 of
+// words[0]) whose fixed header fields and code-length code pass, appended to list[] in no particular order.  The fixed
+// fields of all 32 positions of a word are tested at once on the 64-bit window (BTYPE = 2: bit o+1 clear, bit o+2 set;
+// HLIT / HDIST >= 30: their four high bits all set); the Kraft sum of the code-length code comes out of a table of four
+// 3-bit lengths at a time.  One position in ~1100 survives.
+// STORED blocks (inflate.c:863-897) are recognised here too, straight into the candidate list cand[]: a byte position
+// whose LEN / NLEN words complement each other, behind 3 header bits (BTYPE = 0) and zero padding — the block may start
+// at any of up to eight bit positions before it, each is a candidate (the chain picks the one the previous block ends
+// on).  Without them a run of stored blocks (incompressible data) is one chunk, copied by one warp at 1 GB/s.
+__global__ void __launch_bounds__(256)
+blk_scan_kernel(const uint32_t *__restrict__ words, uint64_t nwords, uint64_t bit_lo, uint64_t bit_hi,
+                uint64_t *__restrict__ list, uint32_t cap, uint32_t *__restrict__ count,
+                uint64_t *__restrict__ cand, uint32_t cand_cap, uint32_t *__restrict__ cand_count) {
+    __shared__ uint16_t kraft4[4096];                         // Kraft sum (units of 2^-7) of four 3-bit code lengths
+    for (uint32_t i = threadIdx.x; i < 4096; i += blockDim.x) {
+        uint32_t k = 0;
+        for (int f = 0; f < 4; ++f) { const uint32_t l = (i >> (3 * f)) & 7u; k += (128u >> l) & 127u; }
+        kraft4[i] = (uint16_t)k;
+    }
+    __syncthreads();
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t wi = (bit_lo >> 5) + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; wi * 32 < bit_hi; wi += stride) {
+        const uint32_t w0 = words[wi], w1 = wi + 1 < nwords ? words[wi + 1] : 0u;
+        const uint64_t W = (uint64_t)w0 | ((uint64_t)w1 << 32);
+#pragma unroll
+        for (uint32_t j = 0; j < 4; ++j) {                    // LEN / NLEN at byte 4 wi + j ?
+            const uint32_t v = (uint32_t)(W >> (8 * j));
+            if (((v ^ (v >> 16)) & 0xffffu) != 0xffffu) continue;
+            const uint64_t P8 = wi * 32 + 8 * j;             // bit position of the LEN field
+            if (P8 < bit_lo + 3 || P8 + 32 > bit_hi || wi == 0) continue;
+            const uint32_t before = __funnelshift_r(words[wi - 1], w0, 8 * j) >> 16;   // the 16 bits in front of it, bit P8 - 1 on top
+            const uint32_t ns = blk_stored_starts(before, P8, bit_lo);
+            for (uint32_t k = 0; k < ns; ++k) {
+                const uint32_t at = atomicAdd(cand_count, 1u);
+                if (at < cand_cap) cand[at] = P8 - 3 - k;
+            }
+        }
+        uint32_t mask = (uint32_t)(~(W >> 1) & (W >> 2) & ~((W >> 4) & (W >> 5) & (W >> 6) & (W >> 7)) & ~((W >> 9) & (W >> 10) & (W >> 11) & (W >> 12)));
+        if (!mask) continue;
+        const uint32_t w2 = wi + 2 < nwords ? words[wi + 2] : 0u, w3 = wi + 3 < nwords ? words[wi + 3] : 0u;
+        while (mask) {
+            const uint32_t o = (uint32_t)__ffs(mask) - 1u;
+            mask &= mask - 1;
+            const uint64_t b = wi * 32 + o;
+            if (b < bit_lo || b + 20 > bit_hi) continue;
+            const uint32_t ncode = ((__funnelshift_r(w0, w1, o) >> 13) & 15u) + 4u;
+            const uint32_t sft = o + 17;                      // the code-length-code lengths: up to 57 bits from bit o + 17
+            const uint32_t a0 = sft < 32 ? w0 : w1, a1 = sft < 32 ? w1 : w2, a2 = sft < 32 ? w2 : w3;
+            uint64_t y = (uint64_t)__funnelshift_r(a0, a1, sft) | ((uint64_t)__funnelshift_r(a1, a2, sft) << 32);
+            if (ncode < 19) y &= ((uint64_t)1 << (3 * ncode)) - 1;
+            const uint32_t ylo = (uint32_t)y, yhi = (uint32_t)(y >> 32);
+            const uint32_t k = kraft4[ylo & 4095u] + kraft4[(ylo >> 12) & 4095u] + kraft4[(uint32_t)(y >> 24) & 4095u] +
+                               kraft4[(yhi >> 4) & 4095u] + kraft4[(yhi >> 16) & 4095u];
+            if (k != 128u) continue;
+            const uint32_t at = atomicAdd(count, 1u);
+            if (at < cap) list[at] = b;
+        }
+    }
+}
+
+// Stage 2: the survivors read their code lengths (blk_header_valid), one thread each; what passes is a candidate.
 __global__ void __launch_bounds__(128)
-blk_candidates_kernel(const uint32_t *__restrict__ words, uint64_t nwords, uint64_t bit_lo, uint64_t bit_hi,
-                      uint64_t *__restrict__ list, uint32_t cap, uint32_t *__restrict__ count, const FormatTables *__restrict__ fmt) {
+blk_validate_kernel(const uint32_t *__restrict__ words, uint64_t nwords, uint64_t bit_hi, const uint64_t *__restrict__ in_list,
+                    const uint32_t *__restrict__ in_count, uint32_t in_cap, uint64_t *__restrict__ list, uint32_t cap,
+                    uint32_t *__restrict__ count, const FormatTables *__restrict__ fmt) {
     __shared__ uint8_t tabs[128 * 128];
     __shared__ uint8_t order[20];
     if (threadIdx.x < 20) order[threadIdx.x] = fmt->cl_order[threadIdx.x];
     __syncthreads();
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t wi = (bit_lo >> 5) + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; wi * 32 < bit_hi; wi += stride) {
-        const uint32_t w0 = words[wi], w1 = wi + 1 < nwords ? words[wi + 1] : 0u, w2 = wi + 2 < nwords ? words[wi + 2] : 0u,
-                       w3 = wi + 3 < nwords ? words[wi + 3] : 0u;
-#pragma unroll 4
-        for (uint32_t o = 0; o < 32; ++o) {
-            const uint32_t x = __funnelshift_r(w0, w1, o);
-            if (!blk_quick(x)) continue;
-            const uint64_t b = wi * 32 + o;
-            if (b < bit_lo || b + 20 > bit_hi) continue;
-            const uint32_t s = o + 17;                        // the code-length-code lengths: 57 bits from bit o + 17
-            const uint32_t a0 = s < 32 ? w0 : w1, a1 = s < 32 ? w1 : w2, a2 = s < 32 ? w2 : w3;
-            const uint64_t y = (uint64_t)__funnelshift_r(a0, a1, s) | ((uint64_t)__funnelshift_r(a1, a2, s) << 32);
-            if (!blk_cl_complete(y, ((x >> 13) & 15u) + 4u)) continue;
-            uint64_t end;
-            if (!blk_header_valid(words, nwords, bit_hi, b, tabs + threadIdx.x * 128, order, &end)) continue;
-            const uint32_t k = atomicAdd(count, 1u);
-            if (k < cap) list[k] = b;
-        }
+    const uint32_t n = *in_count < in_cap ? *in_count : in_cap;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint64_t b = in_list[i];
+        uint64_t end;
+        if (!blk_header_valid(words, nwords, bit_hi, b, tabs + threadIdx.x * 128, order, &end)) continue;
+        const uint32_t k = atomicAdd(count, 1u);
+        if (k < cap) list[k] = b;
     }
 }
 
 // ---- resolve ------------------------------------------------------------------------------------------------
+// src[] covers the output positions [lo, lo + n) of one group of chunks (n <= 256 MiB).  An entry is kSrcLiteral, or the
+// position its byte is copied from, counted from `base` = lo - 32768 (0 for the member's first 32 KiB: no source lies
+// further back than a window) — 29 bits — with bit 31 set once that position is known to hold a final byte (a literal,
+// or a byte before lo).
+constexpr uint32_t kSrcFinal = 0x80000000u;
+
 // One warp per 32 matches: byte i of a match comes from dst - dist + i (dist >= len), or from the first period of
 // its own output (inffast.c:249-260 byte-serial semantics: dst - dist + i mod dist).
 __global__ void __launch_bounds__(256)
-blk_src_build_kernel(const QueuedMatch *__restrict__ ml, uint64_t n_matches, uint32_t *__restrict__ src, uint32_t lo) {
+blk_src_build_kernel(const QueuedMatch *__restrict__ ml, uint64_t n_matches, uint32_t *__restrict__ src, uint32_t lo, uint32_t base) {
     const unsigned full = 0xffffffffu;
     const uint32_t lane = threadIdx.x & 31;
     const uint64_t warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
-    for (uint64_t base = ((((uint64_t)blockIdx.x * blockDim.x) + threadIdx.x) >> 5) * 32; base < n_matches; base += warps * 32) {
+    for (uint64_t at = ((((uint64_t)blockIdx.x * blockDim.x) + threadIdx.x) >> 5) * 32; at < n_matches; at += warps * 32) {
         QueuedMatch e;
         e.dst = 0; e.packed = 0;
-        if (base + lane < n_matches) e = ml[base + lane];
-        const uint32_t cnt = n_matches - base < 32 ? (uint32_t)(n_matches - base) : 32u;
+        if (at + lane < n_matches) e = ml[at + lane];
+        const uint32_t cnt = n_matches - at < 32 ? (uint32_t)(n_matches - at) : 32u;
         for (uint32_t j = 0; j < cnt; ++j) {
             const uint32_t dst = __shfl_sync(full, e.dst, j), pk = __shfl_sync(full, e.packed, j);
             const uint32_t len = qm_len(pk), dist = qm_dist(pk);
             const uint32_t from = dst - dist;
-            for (uint32_t i = lane; i < len; i += 32) src[dst - lo + i] = from + (i < dist ? i : i % dist);
+            for (uint32_t i = lane; i < len; i += 32) {
+                const uint32_t sp = from + (i < dist ? i : i % dist);
+                src[dst - lo + i] = (sp - base) | (sp < lo ? kSrcFinal : 0u);
+            }
         }
     }
 }
 
-// One pass of pointer jumping over src[0, n): a byte whose source is itself a copied byte of this range takes over
-// that byte's source.  Updates are made in place — any value read is a valid ancestor, so stale reads only cost a pass.
+// One pass of pointer jumping over src[0, n): an entry that is not final yet follows its source's entry — up to
+// kJumpHops times in a row — and is final as soon as it meets a literal, a final entry or a byte before lo.  Sources
+// lie behind their bytes and CTAs run in ascending order, so most entries meet a final one in the first pass; entries
+// that are final cost later passes one streamed read.  Updates are made in place: any value read is a valid ancestor.
+constexpr int kJumpHops = 4;
+__device__ __forceinline__ uint32_t blk_follow(const uint32_t *__restrict__ src, uint32_t v, uint32_t lo, uint32_t base, bool &open) {
+    if (v & kSrcFinal) return v;                             // (kSrcLiteral included)
+    uint32_t cur = v;
+#pragma unroll
+    for (int h = 0; h < kJumpHops; ++h) {
+        if (cur + base < lo) return cur | kSrcFinal;
+        const uint32_t t = src[cur + base - lo];
+        if (t == kSrcLiteral) return cur | kSrcFinal;
+        if (t & kSrcFinal) return t;
+        cur = t;
+    }
+    open = true;
+    return cur;
+}
 __global__ void __launch_bounds__(256)
-blk_jump_kernel(uint32_t *__restrict__ src, uint64_t n, uint32_t lo, uint32_t *__restrict__ changed) {
+blk_jump_kernel(uint32_t *__restrict__ src, uint64_t n, uint32_t lo, uint32_t base, uint32_t *__restrict__ changed) {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x * 4;
     bool any = false;
     for (uint64_t i = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
         if (i + 4 <= n) {
             uint4 v = *reinterpret_cast<const uint4 *>(src + i);
-            uint32_t t0 = kSrcLiteral, t1 = kSrcLiteral, t2 = kSrcLiteral, t3 = kSrcLiteral;
-            if (v.x != kSrcLiteral && v.x >= lo) t0 = src[v.x - lo];
-            if (v.y != kSrcLiteral && v.y >= lo) t1 = src[v.y - lo];
-            if (v.z != kSrcLiteral && v.z >= lo) t2 = src[v.z - lo];
-            if (v.w != kSrcLiteral && v.w >= lo) t3 = src[v.w - lo];
-            const bool c = (t0 & t1 & t2 & t3) != kSrcLiteral;
-            if (c) {
-                if (t0 != kSrcLiteral) v.x = t0;
-                if (t1 != kSrcLiteral) v.y = t1;
-                if (t2 != kSrcLiteral) v.z = t2;
-                if (t3 != kSrcLiteral) v.w = t3;
-                *reinterpret_cast<uint4 *>(src + i) = v;
-                any = true;
-            }
+            if ((v.x & v.y & v.z & v.w) & kSrcFinal) continue;
+            bool open = false;
+            v.x = blk_follow(src, v.x, lo, base, open); v.y = blk_follow(src, v.y, lo, base, open);
+            v.z = blk_follow(src, v.z, lo, base, open); v.w = blk_follow(src, v.w, lo, base, open);
+            *reinterpret_cast<uint4 *>(src + i) = v;
+            any |= open;
         } else {
             for (uint64_t k = i; k < n; ++k) {
-                const uint32_t s = src[k];
-                if (s == kSrcLiteral || s < lo) continue;
-                const uint32_t t = src[s - lo];
-                if (t != kSrcLiteral) { src[k] = t; any = true; }
+                const uint32_t v = src[k];
+                if (v & kSrcFinal) continue;
+                bool open = false;
+                src[k] = blk_follow(src, v, lo, base, open);
+                any |= open;
             }
         }
     }
     if (__syncthreads_or(any) && threadIdx.x == 0) *changed = 1u;
 }
 
-// out[p] = out[src[p]] for every copied byte of [lo, lo + n): all sources are literals (or lie before lo) by now.
+// out[p] = out[source of p] for every copied byte of [lo, lo + n): all entries are final by now.
 __global__ void __launch_bounds__(256)
-blk_gather_kernel(uint8_t *out, const uint32_t *__restrict__ src, uint64_t n, uint32_t lo) {
+blk_gather_kernel(uint8_t *out, const uint32_t *__restrict__ src, uint64_t n, uint32_t lo, uint32_t base) {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x * 4;
     for (uint64_t i = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
         if (i + 4 <= n) {
             const uint4 v = *reinterpret_cast<const uint4 *>(src + i);
             uint8_t *o = out + lo + i;
             uint32_t b0 = 0, b1 = 0, b2 = 0, b3 = 0;
-            if (v.x != kSrcLiteral) b0 = out[v.x];
-            if (v.y != kSrcLiteral) b1 = out[v.y];
-            if (v.z != kSrcLiteral) b2 = out[v.z];
-            if (v.w != kSrcLiteral) b3 = out[v.w];
+            if (v.x != kSrcLiteral) b0 = out[(v.x & ~kSrcFinal) + base];
+            if (v.y != kSrcLiteral) b1 = out[(v.y & ~kSrcFinal) + base];
+            if (v.z != kSrcLiteral) b2 = out[(v.z & ~kSrcFinal) + base];
+            if (v.w != kSrcLiteral) b3 = out[(v.w & ~kSrcFinal) + base];
             if (v.x != kSrcLiteral) o[0] = (uint8_t)b0;
             if (v.y != kSrcLiteral) o[1] = (uint8_t)b1;
             if (v.z != kSrcLiteral) o[2] = (uint8_t)b2;
             if (v.w != kSrcLiteral) o[3] = (uint8_t)b3;
         } else {
-            for (uint64_t k = i; k < n; ++k) { const uint32_t s = src[k]; if (s != kSrcLiteral) out[lo + k] = out[s]; }
+            for (uint64_t k = i; k < n; ++k) { const uint32_t v = src[k]; if (v != kSrcLiteral) out[lo + k] = out[(v & ~kSrcFinal) + base]; }
         }
     }
 }

@@ -577,21 +577,23 @@ int inflate_attempt(InflateStream &s) {
 // buffers — and the rest waits for the next call; the last run of a complete stream ends it.  Returns 1 when the
 // step made this call's progress (status in *st_out), 0 when the one-member path should take the call.
 int parallel_step(InflateStream &s, int *st_out) {
-    if (!s.verify || s.decoded || s.resume_bit || s.seq_ready || (s.dict_len && !s.rebased) || s.in.size() < 262144) return 0;
+    // (a re-based stream waits at bit resume_bit < 8 of its first buffered byte — a block boundary — with nothing decoded yet)
+    const bool at_base = s.rebased ? s.resume_bit < 8 : s.resume_bit == 0;
+    if (!s.verify || s.decoded || !at_base || s.seq_ready || (s.dict_len && !s.rebased) || s.in.size() < 262144) return 0;
     zb200_ctx *ctx = api_ctx();
     if (!ctx) return 0;
     const size_t at = s.out.size();
     size_t cap = s.in.size() * 4 + (1u << 20), out_len = 0, in_used = 0;
     int status = 0, applicable = 0;
-    uint32_t check = 0;
-    const StreamContinuation cont = {s.hist.data(), s.hist.size(), 0u, s.stream_kind};
+    uint32_t check = 0, end_bit = 0;
+    const StreamContinuation cont = {s.hist.data(), s.hist.size(), s.rebased ? (uint32_t)s.resume_bit : 0u, s.stream_kind};
     {
         CtxUse use(ctx, ctx->stream);
         if (cudaSetDevice(ctx->device) != cudaSuccess) return 0;
         for (int attempt = 0; attempt < 2; ++attempt) {
             s.out.resize(at + cap);
             const int r = inflate_stream_parallel(ctx, s.in.data(), s.in.size(), s.rebased ? ZB200_WRAP_RAW : s.wrap, s.out.data() + at, cap,
-                                                  &out_len, &status, &in_used, &check, &applicable, s.rebased ? &cont : nullptr);
+                                                  &out_len, &status, &in_used, &check, &applicable, s.rebased ? &cont : nullptr, 2, &end_bit);
             if (r != ZB200_OK) applicable = 0;
             if (applicable && status == ZB200_INF_OUTPUT_FULL && out_len > cap && attempt == 0) { cap = out_len; continue; }
             break;
@@ -627,6 +629,7 @@ int parallel_step(InflateStream &s, int *st_out) {
     s.in_erased += in_used;
     s.in.erase(s.in.begin(), s.in.begin() + (long)in_used);
     s.d_in_have = 0;
+    s.resume_bit = end_bit; s.resume_out = 0;                   // (a prefix of chunks ends at a block boundary inside a byte)
     *st_out = ZB200_INF_TRUNCATED;                              // more to come; an error met behind the prefix shows up when its run is reached
     return 1;
 }
