@@ -14,6 +14,8 @@ import zlib_wasm_b200 as zb  # noqa: E402
 mib = int(sys.argv[1]) if len(sys.argv) > 1 else 512
 legs = sys.argv[2].split(",") if len(sys.argv) > 2 else ["l1", "l6", "l6t", "inf"]
 n = mib << 20
+if os.environ.get("ZB_LIB"):
+    zb.LIB_PATH = os.path.join(ROOT, os.environ["ZB_LIB"])   # a variant build (tools/build_variant.sh)
 L = zb.lib()
 ctx = zb.Context(0)
 stream = torch.cuda.Stream()

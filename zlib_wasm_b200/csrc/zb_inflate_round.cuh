@@ -31,6 +31,12 @@
 // the warp abandon the round; lane 0 then decodes from the round's start on the
 // careful serial path (zb_inflate.cuh), which reports the reference's exact status.
 //
+// Measured and dropped (round 2): the three loops in a uniform HALF-step form — one table look-up per trip, a match
+// taking two trips, so that lanes on literals never wait for lanes in the distance half (ncu had shown 13 of 32 lanes
+// active in the unit decoder).  Same bytes, 6 % slower (8.79 -> 9.30 ms per GiB in 4096 members): the kernel is bound
+// by each lane's dependent chain (window fetch -> table look-up -> bit arithmetic), not by issue slots, and the half
+// steps lengthen that chain by a loop trip per match.
+//
 // The per-lane phases are __host__ __device__: tests/emul/inf_emul.cpp replays them
 // with plain loops over the 32 lanes.
 #pragma once
