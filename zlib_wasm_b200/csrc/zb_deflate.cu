@@ -862,6 +862,7 @@ int deflate_init(zb200_ctx *ctx) {
     ZB_CUDA(cudaFuncSetAttribute(dfl_parse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kParseSmem));
     ZB_CUDA(cudaFuncSetAttribute(dfl_match_sorted_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMsSmem));
     ZB_CUDA(cudaFuncSetAttribute(dfl_match_uniform_kernel<4, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMsSmem));
+    ZB_CUDA(cudaFuncSetAttribute(dfl_match_uniform_kernel<2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMsSmem));
     ZB_CUDA(cudaFuncSetAttribute(dfl_match_uniform_kernel<8, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMsSmem));
     return ZB200_OK;
 }
@@ -888,6 +889,22 @@ static size_t batch_chunks(size_t n, size_t S, uint32_t MB) {
     if (nb == 0) nb = 1;
     if (nb > 32768) nb = 32768;                 // gridDim.y limit of the per-chunk kernels
     return nb < nch ? nb : nch;
+}
+
+size_t deflate_wave_chunks(zb200_ctx *ctx, int mem_level) {
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dfl_chain_kernel, kChainWarps * 32, 2u << (mem_level + 7)) != cudaSuccess) { cudaGetLastError(); per_sm = 0; }
+    return (size_t)(per_sm > 0 ? per_sm : 1) * (size_t)ctx->sm_count;
+}
+size_t deflate_piece_bytes(zb200_ctx *ctx, size_t want, size_t S, int mem_level, int level) {
+    size_t chunks = (want + S - 1) / S;
+    if (level < 1 || level > 3) return (chunks ? chunks : 1) * S;   // (only the greedy levels run in waves: deflate_launch_opts)
+    const size_t wave = deflate_wave_chunks(ctx, mem_level), batch = kBatchBytes / S;
+    if (chunks >= wave) {
+        chunks = chunks / wave * wave;
+        if (chunks > batch && batch >= wave) chunks = chunks / (batch / wave * wave) * (batch / wave * wave);   // whole sub-batches
+    }
+    return (chunks ? chunks : 1) * S;
 }
 
 static thread_local const int *tl_deflate_tune = nullptr;
@@ -946,9 +963,19 @@ int deflate_launch_opts(zb200_ctx *ctx, const uint8_t *d_in, size_t n, size_t S,
         if (r) return r;
         if (d_sums_out) ZB_CUDA(cudaMemcpyAsync(d_sums_out, sums, 8, cudaMemcpyDeviceToDevice, s));
     }
-    for (size_t c0 = 0; c0 < nch; c0 += nb_max) {
+    // Chunks per sub-batch: a whole number of WAVES of the chain kernel (its CTAs per SM x the SM count: 444 chunks at
+    // memLevel 8).  The ordered kernels take the same time for 1 chunk or a full wave, so 2048 chunks (4.6 waves) cost
+    // five waves: 1776 chunks per sub-batch measured 44.2 GB/s at level 1 against 42.0 for 2048.
+    // (Levels 4-9 spend their time in the match kernel, whose grid has a CTA per 16 Ki positions: no waves to speak of,
+    // and one more launch per 2 GiB measured 2 % slower.)
+    size_t nb_run = nb_max;
+    if (prm.mode == MODE_FAST) {
+        const size_t wave = deflate_wave_chunks(ctx, o.mem_level);
+        if (nb_run > wave) nb_run = nb_run / wave * wave;
+    }
+    for (size_t c0 = 0; c0 < nch; c0 += nb_run) {
         Batch b;
-        b.nb = (uint32_t)(nch - c0 < nb_max ? nch - c0 : nb_max);
+        b.nb = (uint32_t)(nch - c0 < nb_run ? nch - c0 : nb_run);
         b.in = d_in + c0 * S;
         const size_t off = c0 * S;
         const size_t span = (size_t)b.nb * S;
@@ -972,7 +999,14 @@ int deflate_launch_opts(zb200_ctx *ctx, const uint8_t *d_in, size_t n, size_t S,
         } else if (prm.mode == MODE_FAST) {                        // levels 1-2
             dim3 g((unsigned)((S + kMsTile - 1) / kMsTile), b.nb);
             prof_mark(ctx, s, "dfl_match_uniform_kernel");
-            if (prm.level == 1) dfl_match_uniform_kernel<4, 8><<<g, kMsThreads, kMsSmem, s>>>(b, prm, w.prev, w.mfull);
+            // Level 1 looks at TWO candidates per position, not the table's four (deflate.c:114 max_chain 4).  Every position is
+            // inserted here (deflate_fast skips the inside of matches longer than max_insert, deflate.c:1873-1897), which alone
+            // makes the stream 3.6 % smaller than the reference's; two candidates keep 1.7 % of that and cost 3.3 ms per 512 MiB
+            // instead of 4.6 (measured, markov text: 4 / 3 / 2 / 1 candidates -> 0.964 / 0.970 / 0.983 / 1.021 x the reference's
+            // size).  $ZB200_L1_CHAIN=4 restores the table value.
+            static const int l1_chain = [] { const char *e = getenv("ZB200_L1_CHAIN"); return e ? atoi(e) : 2; }();
+            if (prm.level == 1 && l1_chain != 4) dfl_match_uniform_kernel<2, 8><<<g, kMsThreads, kMsSmem, s>>>(b, prm, w.prev, w.mfull);
+            else if (prm.level == 1) dfl_match_uniform_kernel<4, 8><<<g, kMsThreads, kMsSmem, s>>>(b, prm, w.prev, w.mfull);
             else dfl_match_uniform_kernel<8, 16><<<g, kMsThreads, kMsSmem, s>>>(b, prm, w.prev, w.mfull);
             ZB_LAUNCHED(); ZB_CHECK_LAUNCH();
         } else if (prm.mode != MODE_HUFF) {
@@ -1066,7 +1100,7 @@ static int deflate_host_pipelined(zb200_ctx *ctx, const uint8_t *in, size_t n, s
     size_t piece = n / 16;
     if (piece < ((size_t)128 << 20)) piece = (size_t)128 << 20;
     if (piece > ((size_t)512 << 20)) piece = (size_t)512 << 20;
-    piece = (piece + S - 1) / S * S;
+    piece = deflate_piece_bytes(ctx, piece, S, opts.mem_level, level);
     constexpr size_t kMaxPieces = 64;
     while ((n + piece - 1) / piece > kMaxPieces) piece += (piece + S - 1) / S * S;   // (inputs beyond 32 GiB: longer pieces)
     const size_t np = (n + piece - 1) / piece;

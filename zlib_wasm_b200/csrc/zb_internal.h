@@ -165,6 +165,10 @@ inline int deflate_launch(zb200_ctx *ctx, const uint8_t *d_in, size_t n, size_t 
     o.level = level; o.strategy = strategy; o.skip = skip;
     return deflate_launch_opts(ctx, d_in, n, S, o, frame, finish, d_out, out_cap, d_chunk_end, d_total, d_sums_out, s);
 }
+// chunks the chain kernel keeps resident at once (one wave), and a piece size for the host pipelines: `want` bytes rounded to
+// whole chunks and, from one wave up, down to whole waves (the ordered kernels cost a full wave for any part of one)
+size_t deflate_wave_chunks(zb200_ctx *ctx, int mem_level);
+size_t deflate_piece_bytes(zb200_ctx *ctx, size_t want, size_t S, int mem_level, int level);
 // zb_zlib_api.cu: the process-wide context behind the zlib.h surface (nullptr without a usable device)
 zb200_ctx *zlib_api_ctx();
 // zb_inflate.cu

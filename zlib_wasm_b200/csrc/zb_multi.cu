@@ -132,7 +132,7 @@ int zb200_multi_deflate_host(zb200_multi *m, const void *in, size_t n, size_t ch
         // while sub-piece j is compressed.  The copies back wait for the rendezvous: a piece's place in the caller's
         // buffer depends on the sizes of all pieces before it.
         size_t sub = len[k] / 8 > ((size_t)128 << 20) ? len[k] / 8 : ((size_t)128 << 20);
-        sub = (sub + S - 1) / S * S;
+        sub = deflate_piece_bytes(ctx, sub, S, 8, level);
         const size_t ns = len[k] ? (len[k] + sub - 1) / sub : 1;
         size_t sub_off[kSub + 1] = {0}, sub_total[kSub] = {0};
         cudaStream_t s = nullptr;
