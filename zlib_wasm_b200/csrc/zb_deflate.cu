@@ -14,6 +14,25 @@ namespace zb {
 __device__ __forceinline__ uint32_t lds_u8(uint32_t a) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
 __device__ __forceinline__ uint32_t lds_u16(uint32_t a) { uint32_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
 __device__ __forceinline__ uint32_t lds_u32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
+// Named barriers 1..4 with IMMEDIATE ids.  With the id in a register the compiler has to assume that all 16 barriers of a
+// CTA are in use, and the SM's barrier budget then allows four CTAs (ncu: launch__occupancy_limit_barriers = 4) — which
+// is what bounded the greedy parse, a latency-bound kernel, at 16 of 64 warps per SM.
+__device__ __forceinline__ void bar_sync64(uint32_t id) {
+    switch (id) {
+        case 1: asm volatile("bar.sync 1, 64;" ::: "memory"); break;
+        case 2: asm volatile("bar.sync 2, 64;" ::: "memory"); break;
+        case 3: asm volatile("bar.sync 3, 64;" ::: "memory"); break;
+        default: asm volatile("bar.sync 4, 64;" ::: "memory"); break;
+    }
+}
+__device__ __forceinline__ void bar_arrive64(uint32_t id) {
+    switch (id) {
+        case 1: asm volatile("bar.arrive 1, 64;" ::: "memory"); break;
+        case 2: asm volatile("bar.arrive 2, 64;" ::: "memory"); break;
+        case 3: asm volatile("bar.arrive 3, 64;" ::: "memory"); break;
+        default: asm volatile("bar.arrive 4, 64;" ::: "memory"); break;
+    }
+}
 struct DeflateDeviceTables {
     FormatTables fmt;
     StaticTrees st;
@@ -129,6 +148,8 @@ __global__ void __launch_bounds__(kChainWarps * 32) dfl_chain_kernel(Batch b, De
         const uint32_t p0 = t * kChainTrip;
         // window origin after every slide due up to this trip (the first one happens at position 2 * w_size)
         const uint32_t base = p0 < 2u * wsz ? 0u : ((p0 >> wlog) - 1u) << wlog;
+        // (barrier ids in registers here: the 64 KiB head table bounds this kernel at 3 CTAs per SM, the barrier budget would
+        //  allow 4 — and the switch of bar_sync64 in the ordered section measured 11 % slower)
         if (t) asm volatile("bar.sync %0, 64;" ::"r"(warp + 1) : "memory");   // trip t-1 has left the head table (its warp arrived here)
         if (p0 >= 2u * wsz && (p0 & (wsz - 1u)) == 0) {            // slide: subtract w_size, saturating at 0 (= NIL)
             for (int i = lane; i < nvec; i += 32) {
@@ -426,12 +447,12 @@ dfl_parse_greedy_kernel(Batch b, DeflateParams prm, const uint32_t *__restrict__
         __syncwarp();
         gt_fill(lane, n - t0, w.mfv, w.lc);
         __syncwarp();
-        if (t != tile0) asm volatile("bar.sync %0, 64;" ::"r"(warp + 1) : "memory");   // the previous tile has been crossed
+        if (t != tile0) bar_sync64(warp + 1);          // the previous tile has been crossed
         const uint32_t entry = s_entry, first_sym = s_nsyms;
         uint32_t my_entry, my_first, total;
         const uint32_t exit_rel = gt_hop(lane, entry - t0, n - t0, w.lc, my_entry, my_first, total);
         if (lane == 0) { s_entry = t0 + exit_rel; s_nsyms = first_sym + total; }
-        if (t + 1 < ntiles) asm volatile("bar.arrive %0, 64;" ::"r"(((warp + 1) & (kGtWarps - 1)) + 1) : "memory");
+        if (t + 1 < ntiles) bar_arrive64(((warp + 1) & (kGtWarps - 1)) + 1);
         if (my_entry != 0xffffffffu) {                 // the symbols of this lane's segment
             GtAcc acc{w.mfv, data, t0};
             const uint32_t seg_end = (lane + 1) * kGtSeg, lim = n - t0;
@@ -860,6 +881,8 @@ int deflate_init(zb200_ctx *ctx) {
     ctx->d_deflate_tables = d;
     ZB_CUDA(cudaFuncSetAttribute(dfl_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 << kHashBitsMax));
     ZB_CUDA(cudaFuncSetAttribute(dfl_parse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kParseSmem));
+    ZB_CUDA(cudaFuncSetAttribute(dfl_parse_greedy_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+    ZB_CUDA(cudaFuncSetAttribute(dfl_tree_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
     ZB_CUDA(cudaFuncSetAttribute(dfl_match_sorted_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMsSmem));
     ZB_CUDA(cudaFuncSetAttribute(dfl_match_uniform_kernel<4, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMsSmem));
     ZB_CUDA(cudaFuncSetAttribute(dfl_match_uniform_kernel<2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMsSmem));
