@@ -53,7 +53,7 @@ def timed(fn, reps=3):
 
 cur = None
 for leg in legs:
-    gen = "markov" if leg in ("l1", "l6t", "inf") else "mixed"
+    gen = "markov" if leg in ("l1", "l2", "l3", "l6t", "inf") else "mixed"
     if gen != cur:
         BL.fill(host, n, gen, 0)
         d_in.copy_(view)
@@ -78,7 +78,7 @@ for leg in legs:
         ok = bool(torch.equal(d_back, d_in))
         print("inflate %d MiB (%d members): %.2f ms  %.1f GB/s  ok=%s  %s" % (mib, len(members), ms, n / ms / 1e6, ok, k), flush=True)
         continue
-    level = {"l1": 1, "l6": 6, "l6t": 6, "l9": 9, "l3": 3, "l4": 4}[leg]
+    level = {"l1": 1, "l2": 2, "l6": 6, "l6t": 6, "l9": 9, "l3": 3, "l4": 4}[leg]
     ms, k = timed(lambda: L.zb200_deflate_dev(ctx.handle, d_in.data_ptr(), n, BL.CHUNK, level, 0, zb.FRAME_RAW, 1, d_out.data_ptr(), cap,
                                               None, d_tot.data_ptr(), sp), 2 if level == 9 else 3)
     print("deflate %s %s %d MiB: %.2f ms  %.2f GB/s  ratio %.4f  %s" % (leg, gen, mib, ms, n / ms / 1e6, n / int(d_tot.item()), k), flush=True)

@@ -106,16 +106,19 @@ __device__ __forceinline__ bool chunk_final(const Batch &b, uint32_t c) {
 // the four ordered head-table steps, passes the turn on and stores its links.
 constexpr int kChainWarps = 4, kChainTrip = 128;
 // head table: 2 << hash_bits bytes of dynamic shared memory (64 KiB at memLevel 8, 128 KiB at memLevel 9)
-__global__ void __launch_bounds__(kChainWarps * 32) dfl_chain_kernel(Batch b, DeflateParams prm, uint16_t *__restrict__ prev_all) {
-    extern __shared__ __align__(16) uint16_t head[];
-    const uint32_t c = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+// The body is compiled once per warp of the CTA (W = the warp's index): the ids of the two named barriers a warp uses
+// are then immediates, and ptxas counts 5 barriers instead of assuming all 16 — with a register id the SM's barrier budget
+// allows 4 CTAs (ncu: launch__occupancy_limit_barriers), which binds as soon as the head table is smaller than 64 KiB.
+template <uint32_t W, bool IMM>
+__device__ __forceinline__ void chain_body(const Batch &b, const DeflateParams &prm, uint16_t *__restrict__ prev_all, uint16_t *head) {
+    const uint32_t lane_warp = threadIdx.x >> 5;             // (IMM: W is this warp's index, known at compile time)
+    const uint32_t warp = IMM ? W : lane_warp;
+    const uint32_t c = blockIdx.x, lane = threadIdx.x & 31;
     const uint8_t *data = b.in + (uint64_t)c * b.S;
     const uint32_t n = chunk_len(b, c);
     uint16_t *prev = prev_all + (uint64_t)c * b.S;
     uint4 *h4 = reinterpret_cast<uint4 *>(head);
     const int nvec = (int)((2u << prm.hash_bits) >> 4);                 // uint4 vectors of the table (>= 32)
-    for (int i = threadIdx.x; i < nvec; i += kChainWarps * 32) h4[i] = make_uint4(0, 0, 0, 0);
-    __syncthreads();
     const uint32_t hshift = prm.hash_shift, hmask = prm.hash_mask, wsz = prm.w_size, wlog = 31u - (uint32_t)__clz(prm.w_size);
     const uint32_t wsub = wsz | (wsz << 16);
     constexpr int G = kChainTrip / 32;
@@ -148,9 +151,10 @@ __global__ void __launch_bounds__(kChainWarps * 32) dfl_chain_kernel(Batch b, De
         const uint32_t p0 = t * kChainTrip;
         // window origin after every slide due up to this trip (the first one happens at position 2 * w_size)
         const uint32_t base = p0 < 2u * wsz ? 0u : ((p0 >> wlog) - 1u) << wlog;
-        // (barrier ids in registers here: the 64 KiB head table bounds this kernel at 3 CTAs per SM, the barrier budget would
-        //  allow 4 — and the switch of bar_sync64 in the ordered section measured 11 % slower)
-        if (t) asm volatile("bar.sync %0, 64;" ::"r"(warp + 1) : "memory");   // trip t-1 has left the head table (its warp arrived here)
+        if (t) {                                                   // trip t-1 has left the head table (its warp arrived here)
+            if (IMM) asm volatile("bar.sync %0, 64;" ::"n"(W + 1) : "memory");
+            else asm volatile("bar.sync %0, 64;" ::"r"(lane_warp + 1) : "memory");
+        }
         if (p0 >= 2u * wsz && (p0 & (wsz - 1u)) == 0) {            // slide: subtract w_size, saturating at 0 (= NIL)
             for (int i = lane; i < nvec; i += 32) {
                 uint4 v = h4[i];
@@ -190,12 +194,34 @@ __global__ void __launch_bounds__(kChainWarps * 32) dfl_chain_kernel(Batch b, De
             }
             dists[j] = dist;
         }
-        if (t + 1 < ntrips) asm volatile("bar.arrive %0, 64;" ::"r"(((warp + 1) & (kChainWarps - 1)) + 1) : "memory");   // pass the turn on
+        if (t + 1 < ntrips) {                                      // pass the turn on
+            if (IMM) asm volatile("bar.arrive %0, 64;" ::"n"(((W + 1) & (kChainWarps - 1)) + 1) : "memory");
+            else asm volatile("bar.arrive %0, 64;" ::"r"(((lane_warp + 1) & (kChainWarps - 1)) + 1) : "memory");
+        }
 #pragma unroll
         for (int j = 0; j < G; ++j) {
             const uint32_t p = p0 + 32 * j + lane;
             if (p < n) prev[p] = (uint16_t)dists[j];
         }
+    }
+}
+// IMM = false: one copy of the body, barrier ids in registers — the form for 64 KiB tables and more (levels 4-9: the table
+// bounds the kernel at 3 CTAs per SM, the barrier budget would allow 4, and the four copies measured 7 % slower there).
+template <bool IMM>
+__global__ void __launch_bounds__(kChainWarps * 32) dfl_chain_kernel(Batch b, DeflateParams prm, uint16_t *__restrict__ prev_all) {
+    extern __shared__ __align__(16) uint16_t head[];
+    {
+        uint4 *h4 = reinterpret_cast<uint4 *>(head);
+        const int nvec = (int)((2u << prm.hash_bits) >> 4);
+        for (int i = threadIdx.x; i < nvec; i += kChainWarps * 32) h4[i] = make_uint4(0, 0, 0, 0);
+    }
+    __syncthreads();
+    if (!IMM) { chain_body<0, false>(b, prm, prev_all, head); return; }
+    switch (threadIdx.x >> 5) {
+        case 0: chain_body<0, IMM>(b, prm, prev_all, head); break;
+        case 1: chain_body<1, IMM>(b, prm, prev_all, head); break;
+        case 2: chain_body<2, IMM>(b, prm, prev_all, head); break;
+        default: chain_body<3, IMM>(b, prm, prev_all, head); break;
     }
 }
 
@@ -879,7 +905,9 @@ int deflate_init(zb200_ctx *ctx) {
     ZB_CUDA(cudaMalloc(&d, sizeof h));
     ZB_CUDA(cudaMemcpy(d, &h, sizeof h, cudaMemcpyHostToDevice));
     ctx->d_deflate_tables = d;
-    ZB_CUDA(cudaFuncSetAttribute(dfl_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 << kHashBitsMax));
+    ZB_CUDA(cudaFuncSetAttribute(dfl_chain_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 << kHashBitsMax));
+    ZB_CUDA(cudaFuncSetAttribute(dfl_chain_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 << kHashBitsMax));
+    ZB_CUDA(cudaFuncSetAttribute(dfl_chain_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
     ZB_CUDA(cudaFuncSetAttribute(dfl_parse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kParseSmem));
     ZB_CUDA(cudaFuncSetAttribute(dfl_parse_greedy_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
     ZB_CUDA(cudaFuncSetAttribute(dfl_tree_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
@@ -916,13 +944,16 @@ static size_t batch_chunks(size_t n, size_t S, uint32_t MB) {
 
 size_t deflate_wave_chunks(zb200_ctx *ctx, int mem_level) {
     int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dfl_chain_kernel, kChainWarps * 32, 2u << (mem_level + 7)) != cudaSuccess) { cudaGetLastError(); per_sm = 0; }
+    const int hb = mem_level + 7;
+    const cudaError_t e = hb < 15 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dfl_chain_kernel<true>, kChainWarps * 32, 2u << hb)
+                                  : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dfl_chain_kernel<false>, kChainWarps * 32, 2u << hb);
+    if (e != cudaSuccess) { cudaGetLastError(); per_sm = 0; }
     return (size_t)(per_sm > 0 ? per_sm : 1) * (size_t)ctx->sm_count;
 }
 size_t deflate_piece_bytes(zb200_ctx *ctx, size_t want, size_t S, int mem_level, int level) {
     size_t chunks = (want + S - 1) / S;
     if (level < 1 || level > 3) return (chunks ? chunks : 1) * S;   // (only the greedy levels run in waves: deflate_launch_opts)
-    const size_t wave = deflate_wave_chunks(ctx, mem_level), batch = kBatchBytes / S;
+    const size_t wave = deflate_wave_chunks(ctx, level <= 2 && mem_level > 7 ? 7 : mem_level), batch = kBatchBytes / S;   // (levels 1-2 hash into 14 bits at most)
     if (chunks >= wave) {
         chunks = chunks / wave * wave;
         if (chunks > batch && batch >= wave) chunks = chunks / (batch / wave * wave) * (batch / wave * wave);   // whole sub-batches
@@ -963,6 +994,18 @@ int deflate_launch_opts(zb200_ctx *ctx, const uint8_t *d_in, size_t n, size_t S,
         prm.good = tune[0]; prm.lazy = tune[1]; prm.nice = tune[2]; prm.chain = tune[3];
         prm.need_quarter = (prm.mode == MODE_SLOW && prm.good < prm.lazy) ? 1 : 0;
     }
+    // Levels 1 and 2 hash into 14 bits, whatever memLevel says (deflate.c:444 hash_bits = memLevel + 7 = 15 by default):
+    // a 32 KiB head table lets six chunks share an SM where 64 KiB allows three, and the chain kernel — bound by the latency
+    // of its ordered steps, not by issue slots — goes from 3.33 to 1.99 ms per 444 MiB.  Their streams are not the
+    // reference's byte for byte anyway (every position is inserted); the shorter hash costs 1.4 % of size (level 1 on
+    // markov text: 0.983 -> 0.997 x the reference's size; 13 bits: 1.46 ms but 1.020 x).  Level 3 walks 32 links: the
+    // fuller chains of a shorter hash cost its match kernel more (15.1 -> 18.9 ms) than the chain kernel gains, it keeps
+    // memLevel's table.  $ZB200_FAST_HASH_BITS overrides.
+    if (prm.mode == MODE_FAST && level <= 2 && !tune) {
+        static const int fast_hash = [] { const char *e = getenv("ZB200_FAST_HASH_BITS"); return e ? atoi(e) : 14; }();
+        const uint32_t hb = (uint32_t)(fast_hash >= 9 && fast_hash <= 16 ? fast_hash : 14);
+        if (prm.hash_bits > hb) { prm.hash_bits = hb; prm.hash_shift = (hb + kMinMatch - 1) / kMinMatch; prm.hash_mask = (1u << hb) - 1u; }
+    }
     // levels 3..9: chain walks of very different lengths -> depth-sorted scheduling (levels 1-2 use the branch-free walk,
     // which is compiled for their table values)
     const bool sorted_walks = (prm.mode == MODE_SLOW || prm.mode == MODE_FAST) && (prm.level >= 3 || tune);
@@ -993,7 +1036,7 @@ int deflate_launch_opts(zb200_ctx *ctx, const uint8_t *d_in, size_t n, size_t S,
     // and one more launch per 2 GiB measured 2 % slower.)
     size_t nb_run = nb_max;
     if (prm.mode == MODE_FAST) {
-        const size_t wave = deflate_wave_chunks(ctx, o.mem_level);
+        const size_t wave = deflate_wave_chunks(ctx, (int)prm.hash_bits - 7);
         if (nb_run > wave) nb_run = nb_run / wave * wave;
     }
     for (size_t c0 = 0; c0 < nch; c0 += nb_run) {
@@ -1010,7 +1053,8 @@ int deflate_launch_opts(zb200_ctx *ctx, const uint8_t *d_in, size_t n, size_t S,
         b.first_bit = c0 == 0 ? o.first_bit : 0u;
         if (prm.mode == MODE_FAST || prm.mode == MODE_SLOW) {
             prof_mark(ctx, s, "dfl_chain_kernel");
-            dfl_chain_kernel<<<b.nb, kChainWarps * 32, 2u << prm.hash_bits, s>>>(b, prm, w.prev);
+            if (prm.hash_bits < 15) dfl_chain_kernel<true><<<b.nb, kChainWarps * 32, 2u << prm.hash_bits, s>>>(b, prm, w.prev);
+            else dfl_chain_kernel<false><<<b.nb, kChainWarps * 32, 2u << prm.hash_bits, s>>>(b, prm, w.prev);
             ZB_LAUNCHED(); ZB_CHECK_LAUNCH();
         }
         if (sorted_walks) {
