@@ -293,6 +293,14 @@ def main():
                 legs["small_calls"] = BL.small_call_leg(cpu)
             except Exception as ex:
                 errors["small_calls"] = repr(ex)
+            try:
+                legs["inflate_one_member"] = BL.single_member_leg(g, cpu, BL.scaled(256 << 20, args.scale))
+            except Exception as ex:
+                errors["inflate_one_member"] = repr(ex)
+        try:                                            # the host link with every rank copying at once, no kernels
+            legs["link_probe"] = BL.link_probe(g)
+        except Exception as ex:
+            errors["link_probe"] = repr(ex)
         # one process driving every GPU of the box (zb200_multi_*) must give the single-GPU bytes: rank 0, others idle
         if world > 1:
             g.barrier()

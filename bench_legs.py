@@ -44,6 +44,56 @@ def host_threads():
         return os.cpu_count() or 1
 
 
+_numa = {}
+
+
+def gpu_numa(dev):
+    """NUMA node of CUDA device `dev` and that node's CPUs (sysfs), or (None, None) when the platform does not say."""
+    if dev in _numa:
+        return _numa[dev]
+    node, cpus = None, None
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = int(vis.split(",")[dev]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else dev
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(idx)).busId
+        bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
+        if len(bus.split(":")[0]) == 8:                       # nvml prints an 8-digit domain, sysfs a 4-digit one
+            bus = bus[4:]
+        with open("/sys/bus/pci/devices/%s/numa_node" % bus) as f:
+            node = int(f.read().strip())
+        if node >= 0:
+            with open("/sys/devices/system/node/node%d/cpulist" % node) as f:
+                cpus = set()
+                for part in f.read().strip().split(","):
+                    a, _, b = part.partition("-")
+                    cpus.update(range(int(a), int(b or a) + 1))
+            cpus &= os.sched_getaffinity(0)
+        else:
+            node = None
+    except Exception:
+        node, cpus = None, None
+    _numa[dev] = (node, cpus or None)
+    return _numa[dev]
+
+
+def host_alloc(L, n, dev=None):
+    """zb200_host_alloc with the calling thread on the GPU's own NUMA node while the pages are pinned (they are placed
+    where the thread that touches them first runs): a DMA from the other socket's memory crosses the inter-socket link."""
+    if dev is None:
+        dev = int(os.environ.get("LOCAL_RANK", "0"))
+    node, cpus = gpu_numa(dev)
+    if not cpus:
+        return L.zb200_host_alloc(n)
+    old = os.sched_getaffinity(0)
+    try:
+        os.sched_setaffinity(0, cpus)
+        return L.zb200_host_alloc(n)
+    finally:
+        os.sched_setaffinity(0, old)
+
+
 def peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -323,7 +373,7 @@ def deflate_leg(g, cpu, name, total, steps, warmup, host=None, keep=False, traff
     n = hi - lo
     own_host = host is None
     if own_host:
-        host = L.zb200_host_alloc(n)
+        host = host_alloc(L, n)
         if not host:
             raise RuntimeError("pinned allocation of %d bytes failed" % n)
         fill(host, n, kind, lo)
@@ -368,7 +418,7 @@ def deflate_leg(g, cpu, name, total, steps, warmup, host=None, keep=False, traff
                                 "achieved/frac = (U + C) of this rank's shard / the whole step (all kernels); kernel_* = the dominant kernel alone")}
 
     # ---- end to end: pinned host input -> pinned host output through the C ABI ----
-    h_out = L.zb200_host_alloc(cap)
+    h_out = host_alloc(L, cap)
     if not h_out:
         raise RuntimeError("pinned allocation of %d bytes failed" % cap)
     olen = C.c_size_t(cap)
@@ -394,7 +444,7 @@ def deflate_leg(g, cpu, name, total, steps, warmup, host=None, keep=False, traff
     same = olen.value == clen and host_equals_device(torch, h_out, clen, d_out)
     gates["host_path_equals_device_path"] = bool(same)
     # (2) full-size round trip: the rank's whole stream back through the run-parallel decoder
-    h_back = L.zb200_host_alloc(n + 64)
+    h_back = host_alloc(L, n + 64)
     if h_back:
         q = zb.MemberResult()
 
@@ -459,7 +509,7 @@ def inflate_leg(g, cpu, total, steps, warmup, plain=None, traffic=None):
     n = hi - lo
     own = plain is None or plain[2] < n
     if own:
-        host = L.zb200_host_alloc(n)
+        host = host_alloc(L, n)
         fill(host, n, "markov", lo)
         d_plain = torch.empty(n, dtype=torch.uint8, device="cuda")
         d_plain.copy_(torch.frombuffer((C.c_uint8 * n).from_address(host), dtype=torch.uint8))
@@ -536,7 +586,7 @@ def inflate_leg(g, cpu, total, steps, warmup, plain=None, traffic=None):
          "roofline": g.roofline(n + ctot, ms, kernels, traffic, "achieved/frac = (C + U) of this rank's shard / the whole step"),
          "parity": {"bit_exact_full_size": bool(ok)}}
     # ---- end to end: the multi-member file in pinned host memory -> pinned host output ----
-    h_in, h_out = L.zb200_host_alloc(ctot + 64), L.zb200_host_alloc(n)
+    h_in, h_out = host_alloc(L, ctot + 64), host_alloc(L, n)
     if h_in and h_out:
         torch.frombuffer((C.c_uint8 * ctot).from_address(h_in), dtype=torch.uint8).copy_(d_file[:ctot])
         torch.cuda.synchronize()
@@ -603,7 +653,7 @@ def checksum_leg(g, cpu, total, steps, warmup, traffic=None):
     torch, zb, L = g.torch, g.zb, g.L
     lo, hi = shard(total, g.rank, g.world, 65536)
     n = hi - lo
-    host = L.zb200_host_alloc(n)
+    host = host_alloc(L, n)
     fill(host, n, "bytes", lo)
     d_in = torch.empty(n, dtype=torch.uint8, device="cuda")
     d_in.copy_(torch.frombuffer((C.c_uint8 * n).from_address(host), dtype=torch.uint8))
@@ -721,3 +771,96 @@ def small_call_leg(cpu):
                          "deflate_16k_slices": med(f_stream)}
         out["sizes"][str(n)] = row
     return out
+
+
+def link_probe(g, nbytes=1 << 30, reps=4):
+    """What the host link gives THIS box with every rank copying at once and no kernel running: pinned host memory (placed
+    on the GPU's NUMA node) -> device, device -> host, and both directions together.  The end-to-end legs cannot beat
+    these; N ranks sharing PCIe switches / memory controllers show here, not in the kernels."""
+    torch, L = g.torch, g.L
+    dev = torch.cuda.current_device()
+    host = host_alloc(L, 2 * nbytes, dev)
+    h = torch.frombuffer((C.c_uint8 * (2 * nbytes)).from_address(host), dtype=torch.uint8)
+    h[::4096] = 1                                            # (every page touched)
+    d = torch.empty(2 * nbytes, dtype=torch.uint8, device="cuda")
+    s2 = torch.cuda.Stream()
+    out = {"bytes_per_copy": nbytes, "copies": reps, "numa_node": gpu_numa(dev)[0]}
+
+    def run(kind):
+        def once():
+            if kind in ("h2d", "both"):
+                d[:nbytes].copy_(h[:nbytes], non_blocking=True)
+            if kind == "d2h":
+                h[nbytes:].copy_(d[nbytes:], non_blocking=True)
+            if kind == "both":
+                with torch.cuda.stream(s2):
+                    h[nbytes:].copy_(d[nbytes:], non_blocking=True)
+        once()
+        torch.cuda.synchronize()
+        g.barrier()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            once()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        mine = nbytes * reps * (2 if kind == "both" else 1) / dt / 1e9
+        worst = g.maxr(dt)
+        return round(mine, 2), round(g.world * nbytes * reps * (2 if kind == "both" else 1) / worst / 1e9, 2)
+
+    for kind in ("h2d", "d2h", "both"):
+        mine, agg = run(kind)
+        out[kind + "_GBps_this_rank"] = mine
+        out[kind + "_GBps_all_ranks"] = agg
+    del d, h
+    L.zb200_host_free(C.c_void_p(host))
+    torch.cuda.empty_cache()
+    return out
+
+
+def single_member_leg(g, cpu, total=256 * MIB):
+    """ONE zlib stream without flush points (what compress2 / gzip write), the reference's bytes: decoded through
+    zb200_inflate_stream_host (chunks between dynamic block headers in parallel, csrc/zb_inflate_blocks.cuh) from pinned
+    host memory, next to the reference's inflate of the same stream on one core (a stream is serial for it)."""
+    import zlib
+    torch, L = g.torch, g.L
+    n = total
+    host = host_alloc(L, n)
+    fill(host, n, "markov", 0)
+    raw = C.string_at(host, n)
+    t0 = time.perf_counter()
+    comp = zlib.compress(raw, 6)                              # (system zlib 1.3: the reference's bytes, SURVEY 8c)
+    t_comp = time.perf_counter() - t0
+    h_in, h_out = host_alloc(L, len(comp) + 64), host_alloc(L, n + 64)
+    C.memmove(h_in, comp, len(comp))
+    res = g.zb.MemberResult()
+
+    def call():
+        r = L.zb200_inflate_stream_host(g.ctx.handle, C.c_void_p(h_in), len(comp), g.zb.WRAP_ZLIB, C.c_void_p(h_out), n + 64, C.byref(res))
+        if r != 0 or res.status != 0 or res.out_len != n:
+            raise RuntimeError("single member: r=%d status=%d out_len=%d" % (r, res.status, res.out_len))
+
+    call()
+    ok = C.string_at(h_out, n) == raw
+    ts = []
+    for _ in range(3):
+        t0 = time.perf_counter()
+        call()
+        ts.append(time.perf_counter() - t0)
+    kern = g.kernel_shares(call, 1)
+    e = {"config": "one member of %d MiB (zlib level 6, no flush points), pinned host buffers" % (n >> 20), "compressed_bytes": len(comp),
+         "e2e": {"value": round(n / min(ts) / 1e9, 3), "unit": "GB/s", "ms": round(min(ts) * 1e3, 2), "h2d_bytes_per_step": len(comp),
+                 "d2h_bytes_per_step": n, "api": "zb200_inflate_stream_host"},
+         "device_ms": round(sum(v["ms_per_step"] for v in kern.values()), 3), "kernels": kern, "parity": {"bit_exact": bool(ok)},
+         "reference_compress_one_core_s": round(t_comp, 2)}
+    if cpu is not None and cpu.ref is not None:
+        import refz
+        back = C.create_string_buffer(n)
+        bl = C.c_ulong(n)
+        t0 = time.perf_counter()
+        rc = cpu.ref.uncompress(back, C.byref(bl), comp, len(comp))
+        dt = time.perf_counter() - t0
+        e["cpu_baseline"] = {"value": round(n / dt / 1e9, 3), "unit": "GB/s", "cores": 1, "kind": "reference",
+                             "sample": "the same stream through the reference's uncompress(): one stream is one core's work", "rc": int(rc)}
+    for p in (host, h_in, h_out):
+        L.zb200_host_free(C.c_void_p(p))
+    return e

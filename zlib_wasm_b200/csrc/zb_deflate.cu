@@ -299,8 +299,32 @@ struct StagedMem {
     __device__ __forceinline__ uint32_t dist(uint32_t pos) const { return link(pos); }
 };
 
-// Stage bytes [lo, hi) and links [lo, t1) of a chunk into ms_smem (all threads of the CTA;
+// Bytes from the staged window, chain links straight from global memory: what levels 1-2 use.  Their walk reads two links
+// per position — its own (coalesced) and its first candidate's — so staging the 48 Ki links of a tile's window (96 KiB of
+// the 180) cost more than it saved: it held the kernel at one CTA per SM, whose staging and walking phases then took turns.
+struct StagedDataMem {
+    static constexpr bool kNilIsFar = false;             // a chain's end is link 0
+    uint32_t dbase; const uint16_t *prev;
+    __device__ __forceinline__ uint32_t byte(uint32_t pos) const { return lds_u8(dbase + pos); }
+    __device__ __forceinline__ uint32_t word(uint32_t pos) const {
+        const uint32_t a = dbase + pos, w = a & ~3u;
+        return __funnelshift_r(lds_u32(w), lds_u32(w + 4), (a & 3u) * 8u);
+    }
+    __device__ __forceinline__ uint32_t link(uint32_t pos) const { return prev[pos]; }
+    template <int NW> __device__ __forceinline__ void words(uint32_t pos, uint32_t (&w)[NW]) const {
+        const uint32_t a = dbase + pos, sh = (a & 3u) * 8u, w0 = a & ~3u;
+        uint32_t raw[NW + 1];
+#pragma unroll
+        for (int i = 0; i <= NW; ++i) raw[i] = lds_u32(w0 + 4u * i);
+#pragma unroll
+        for (int i = 0; i < NW; ++i) w[i] = __funnelshift_r(raw[i], raw[i + 1], sh);
+    }
+    __device__ __forceinline__ uint32_t dist(uint32_t pos) const { return prev[pos]; }
+};
+
+// Stage bytes [lo, hi) and (LINKS) links [lo, t1) of a chunk into ms_smem (all threads of the CTA;
 // ends with a barrier) and return the accessor.
+template <bool LINKS = true>
 __device__ __forceinline__ StagedMem stage_window(const Batch &b, const uint8_t *data, const uint16_t *prev,
                                                   uint32_t lo, uint32_t hi, uint32_t t1) {
     uint4 *sdata = reinterpret_cast<uint4 *>(ms_smem);
@@ -323,7 +347,7 @@ __device__ __forceinline__ StagedMem stage_window(const Batch &b, const uint8_t 
     // chain links of [lo, t1): the array sits inside the engine's scratch (16-byte aligned, followed by other arrays)
     const uintptr_t p_first = reinterpret_cast<uintptr_t>(prev + lo) & ~(uintptr_t)15;
     const uint32_t pskew = (uint32_t)((reinterpret_cast<uintptr_t>(prev + lo) - p_first) >> 1);
-    const uint32_t pvecs = (uint32_t)((reinterpret_cast<uintptr_t>(prev + t1) - p_first + 15) >> 4);
+    const uint32_t pvecs = LINKS ? (uint32_t)((reinterpret_cast<uintptr_t>(prev + t1) - p_first + 15) >> 4) : 0u;
     for (uint32_t v = threadIdx.x; v < pvecs; v += blockDim.x) {
         uint4 x = *reinterpret_cast<const uint4 *>(p_first + 16ull * v);
         x.x |= __vcmpeq2(x.x, 0u); x.y |= __vcmpeq2(x.y, 0u);      // NIL (0) -> 65535: one test (the window limit) ends a walk
@@ -341,8 +365,10 @@ __device__ __forceinline__ StagedMem stage_window(const Batch &b, const uint8_t 
 // Levels 1-2 on the staged window: the branch-free walk reads 16 scattered words and 4
 // links per position; from global memory that is bound by the L1's tag stage (7.6 ms per
 // 512 MiB at level 1), from shared memory by bank conflicts (~3.5 wavefronts per request).
-template <int CH, int NICE>
-__global__ void __launch_bounds__(kMsThreads)
+// GLINKS: links from global memory (level 1: two per position; measured 2.90 -> 2.54 ms per 444 MiB, two CTAs per SM),
+// else from the staged window (level 2 reads up to eight per position: from global memory 8.5 -> 10.4 ms).
+template <int CH, int NICE, bool GLINKS>
+__global__ void __launch_bounds__(kMsThreads, GLINKS ? 2 : 1)
 dfl_match_uniform_kernel(Batch b, DeflateParams prm, const uint16_t *__restrict__ prev_all, uint32_t *__restrict__ mfull) {
     const uint32_t c = blockIdx.y, n = chunk_len(b, c), t0 = blockIdx.x * kMsTile;
     if (t0 >= n) return;
@@ -352,11 +378,18 @@ dfl_match_uniform_kernel(Batch b, DeflateParams prm, const uint16_t *__restrict_
     const uint32_t cnt = n - t0 < kMsTile ? n - t0 : kMsTile, t1 = t0 + cnt;
     const uint32_t lo = t0 > (uint32_t)kWSize ? t0 - kWSize : 0;
     const uint32_t hi = t1 + kMsLook < n ? t1 + kMsLook : n;
-    const StagedMem mem = stage_window(b, data, prev, lo, hi, t1);
+    const StagedMem smem = stage_window<!GLINKS>(b, data, prev, lo, hi, t1);
+    StagedDataMem gmem;
+    gmem.dbase = smem.dbase; gmem.prev = prev;
     for (uint32_t p = t0 + threadIdx.x; p < t1; p += kMsThreads) {
         uint32_t r;
-        if (p + kUniformTail <= n) r = match_uniform<CH, NICE>(mem, p, prm.max_dist);
-        else r = match_walk(mem, n, p, prm).full;                  // chunk tail: lookahead clamps apply
+        if (GLINKS) {
+            if (p + kUniformTail <= n) r = match_uniform<CH, NICE>(gmem, p, prm.max_dist);
+            else r = match_walk(gmem, n, p, prm).full;             // chunk tail: lookahead clamps apply
+        } else {
+            if (p + kUniformTail <= n) r = match_uniform<CH, NICE>(smem, p, prm.max_dist);
+            else r = match_walk(smem, n, p, prm).full;
+        }
         mfull[off + p] = r;
     }
 }
@@ -912,9 +945,12 @@ int deflate_init(zb200_ctx *ctx) {
     ZB_CUDA(cudaFuncSetAttribute(dfl_parse_greedy_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
     ZB_CUDA(cudaFuncSetAttribute(dfl_tree_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
     ZB_CUDA(cudaFuncSetAttribute(dfl_match_sorted_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMsSmem));
-    ZB_CUDA(cudaFuncSetAttribute(dfl_match_uniform_kernel<4, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMsSmem));
-    ZB_CUDA(cudaFuncSetAttribute(dfl_match_uniform_kernel<2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMsSmem));
-    ZB_CUDA(cudaFuncSetAttribute(dfl_match_uniform_kernel<8, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMsSmem));
+    ZB_CUDA(cudaFuncSetAttribute(dfl_match_uniform_kernel<4, 8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMsDataBytes));
+    ZB_CUDA(cudaFuncSetAttribute(dfl_match_uniform_kernel<4, 8, true>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+    ZB_CUDA(cudaFuncSetAttribute(dfl_match_uniform_kernel<2, 8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMsDataBytes));
+    ZB_CUDA(cudaFuncSetAttribute(dfl_match_uniform_kernel<2, 8, true>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+    ZB_CUDA(cudaFuncSetAttribute(dfl_match_uniform_kernel<8, 16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMsSmem));
+    ZB_CUDA(cudaFuncSetAttribute(dfl_match_uniform_kernel<8, 16, false>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
     return ZB200_OK;
 }
 
@@ -1072,9 +1108,10 @@ int deflate_launch_opts(zb200_ctx *ctx, const uint8_t *d_in, size_t n, size_t S,
             // instead of 4.6 (measured, markov text: 4 / 3 / 2 / 1 candidates -> 0.964 / 0.970 / 0.983 / 1.021 x the reference's
             // size).  $ZB200_L1_CHAIN=4 restores the table value.
             static const int l1_chain = [] { const char *e = getenv("ZB200_L1_CHAIN"); return e ? atoi(e) : 2; }();
-            if (prm.level == 1 && l1_chain != 4) dfl_match_uniform_kernel<2, 8><<<g, kMsThreads, kMsSmem, s>>>(b, prm, w.prev, w.mfull);
-            else if (prm.level == 1) dfl_match_uniform_kernel<4, 8><<<g, kMsThreads, kMsSmem, s>>>(b, prm, w.prev, w.mfull);
-            else dfl_match_uniform_kernel<8, 16><<<g, kMsThreads, kMsSmem, s>>>(b, prm, w.prev, w.mfull);
+            // (a small memLevel's short hash fills the chains with other strings: there all four are looked at)
+            if (prm.level == 1 && l1_chain != 4 && prm.hash_bits >= 14) dfl_match_uniform_kernel<2, 8, true><<<g, kMsThreads, kMsDataBytes, s>>>(b, prm, w.prev, w.mfull);
+            else if (prm.level == 1) dfl_match_uniform_kernel<4, 8, true><<<g, kMsThreads, kMsDataBytes, s>>>(b, prm, w.prev, w.mfull);
+            else dfl_match_uniform_kernel<8, 16, false><<<g, kMsThreads, kMsSmem, s>>>(b, prm, w.prev, w.mfull);
             ZB_LAUNCHED(); ZB_CHECK_LAUNCH();
         } else if (prm.mode != MODE_HUFF) {
             dim3 g((unsigned)((S + 255) / 256), b.nb);
