@@ -988,7 +988,7 @@ size_t deflate_wave_chunks(zb200_ctx *ctx, int mem_level) {
 }
 size_t deflate_piece_bytes(zb200_ctx *ctx, size_t want, size_t S, int mem_level, int level) {
     size_t chunks = (want + S - 1) / S;
-    if (level < 1 || level > 3) return (chunks ? chunks : 1) * S;   // (only the greedy levels run in waves: deflate_launch_opts)
+    if (level < 1) return (chunks ? chunks : 1) * S;
     const size_t wave = deflate_wave_chunks(ctx, level <= 2 && mem_level > 7 ? 7 : mem_level), batch = kBatchBytes / S;   // (levels 1-2 hash into 14 bits at most)
     if (chunks >= wave) {
         chunks = chunks / wave * wave;
@@ -1201,9 +1201,16 @@ static int deflate_host_pipelined(zb200_ctx *ctx, const uint8_t *in, size_t n, s
     // Pieces of 128 .. 512 MiB: smaller ones leave the GPU underfilled (the chain kernel needs ~450 chunks in flight),
     // larger ones lengthen the two ends of the pipeline that nothing overlaps — the first piece's way in and the last
     // piece's way out (8 GiB in 1 GiB pieces: 21 + 9 ms of 269; in 512 MiB pieces half of that).
-    size_t piece = n / 16;
+    // Levels 3-9 take long pieces: on data of mixed kinds a chunk's cost in the ordered kernels varies several-fold, and a
+    // piece of one wave (444 chunks) then lasts as long as its slowest chunk — 2 GiB of the mixed generator at level 6 in
+    // 19 pieces: chain 44.6 + parse 42.8 ms against 27.9 + 27.3 in four sub-batches of 2048 chunks.
+    size_t piece = level >= 3 ? n / 4 : n / 16;
     if (piece < ((size_t)128 << 20)) piece = (size_t)128 << 20;
-    if (piece > ((size_t)512 << 20)) piece = (size_t)512 << 20;
+    // (levels 1-2 run at the speed of the link: there the ends weigh more — 8 GiB at level 1 in pieces of 444 / 222 / 111 MiB:
+    //  47.8 / 49.5 / 38.8 GB/s end to end, the last being half a wave of the chain kernel)
+    static const size_t piece_knob = [] { const char *e = getenv("ZB200_PIPE_PIECE_MIB"); const long v = e ? atol(e) : 0; return (size_t)(v >= 16 ? v : 0) << 20; }();
+    const size_t piece_max = piece_knob ? piece_knob : (size_t)(level >= 1 && level <= 2 ? 256 : 512) << 20;
+    if (piece > piece_max) piece = piece_max;
     piece = deflate_piece_bytes(ctx, piece, S, opts.mem_level, level);
     constexpr size_t kMaxPieces = 64;
     while ((n + piece - 1) / piece > kMaxPieces) piece += (piece + S - 1) / S * S;   // (inputs beyond 32 GiB: longer pieces)
