@@ -388,10 +388,10 @@ def test_streaming_inflate_memory_is_bounded(z, wbits):
 
 
 def test_one_shot_calls_emit_the_references_own_stream(z):
-    """compress.c:22-59: the reference's compress2() emits ONE run of blocks.  Up to 1 MiB ($ZB200_SINGLE_RUN_MAX, config
-    C1's size) so does this library — levels 4-9 byte for byte the reference's compress2 output, on all five generators;
-    levels 1-3 decode and stay within 3 %; longer inputs are cut into Z_FULL_FLUSH chunks (the reference's bytes for THAT
-    chunking, tests/test_gpu_zlib_api.py)."""
+    """compress.c:22-59: the reference's compress2() emits ONE run of blocks, and so does this library — levels 4-9 byte for
+    byte the reference's compress2 output, on all five generators (here at config C1's size; long inputs in
+    test_one_shot_calls_of_any_size_are_the_references_stream); levels 1-3 decode and stay within 3 % (theirs is one run up
+    to 1 MiB, Z_FULL_FLUSH chunks beyond)."""
     if not refz.have_ref():
         pytest.skip("oracle/_ref/libzref.so not built")
     ref = refz.ref()
@@ -473,31 +473,50 @@ def test_reference_block_level_examples_linked_against_product(tmp_path):
     assert xa == ya
 
 
-SINGLE_RUN_SCRIPT = r"""
-import ctypes as C, os, sys
-sys.path.insert(0, os.path.join(%(root)r, "tests")); sys.path.insert(0, %(root)r)
-import refz, zlib_wasm_b200 as zb
-z = refz.ZlibBinding(zb.LIB_PATH, "")
-ref = refz.ref()
-n = 64 << 20
-for kind in (refz.GEN_TEXT, refz.GEN_MARKOV, refz.GEN_RANDOM, refz.GEN_MIXED, refz.GEN_BYTES):
-    d = refz.gen(n, kind, seed=40 + kind)
+def _deflate_whole(lib, d, level, wbits, mem, strat):
+    """deflateInit2 + one deflate(Z_FINISH) over the whole input: (stream bytes, adler)."""
+    strm = refz.ZStream()
+    assert lib.deflateInit2_(C.byref(strm), level, 8, wbits, mem, strat, lib.version, ZS) == 0
+    cap = lib.deflateBound(C.byref(strm), len(d)) + 64
+    src, dst = C.create_string_buffer(d, max(len(d), 1)), C.create_string_buffer(cap)
+    strm.next_in, strm.avail_in, strm.next_out, strm.avail_out = C.addressof(src), len(d), C.addressof(dst), cap
+    assert lib.deflate(C.byref(strm), refz.Z_FINISH) == refz.Z_STREAM_END
+    out = dst.raw[:cap - strm.avail_out]
+    lib.deflateEnd(C.byref(strm))
+    return out
+
+
+def test_one_shot_calls_of_any_size_are_the_references_stream(z):
+    """compress.c:22-59 / deflate(Z_FINISH): ONE run of blocks however long the input.  Levels 4-9 emit it by default up to
+    the engine's largest chunk (1 GiB): the ordered phases of the long chunk are shared by many CTAs — chain ranges behind
+    32 KiB of re-inserted history, the lazy parse handed from CTA to CTA (zb_deflate.cu dfl_parse_multi_kernel), block
+    ends from a scan.  Byte for byte the reference's stream: five generators at 64 MiB, a 300 MiB input, levels 4 / 6 / 9,
+    Z_FILTERED / Z_FIXED, small windows and memLevels, sizes around the CTA ranges."""
+    if not refz.have_ref():
+        pytest.skip("oracle/_ref/libzref.so not built")
+    ref = refz.ref()
+    n = 64 << 20
+    for kind in (refz.GEN_TEXT, refz.GEN_MARKOV, refz.GEN_RANDOM, refz.GEN_MIXED, refz.GEN_BYTES):
+        d = refz.gen(n, kind, seed=40 + kind)
+        cap = z.compressBound(n)
+        a, al = C.create_string_buffer(cap), C.c_ulong(cap)
+        b, bl = C.create_string_buffer(cap), C.c_ulong(cap)
+        assert z.compress2(a, C.byref(al), d, n, 6) == 0
+        assert ref.compress2(b, C.byref(bl), d, n, 6) == 0
+        assert al.value == bl.value and a.raw[:al.value] == b.raw[:bl.value], (kind, al.value, bl.value)
+    d = refz.gen(9000000, refz.GEN_MIXED, seed=51)
+    for n in (524288, 524289, 786432 + 5, 2 * 262144 * 3 + 131, 9000000):
+        for level, wbits, mem, strat in ((4, 15, 8, 0), (9, 15, 8, 0), (6, 15, 8, 1), (6, 15, 8, 4), (6, -12, 8, 0), (6, 31, 9, 0),
+                                         (5, 10, 3, 0), (8, 15, 1, 0), (7, -15, 8, 1)):
+            if n == 9000000 and level == 9:
+                continue
+            got, want = _deflate_whole(z, d[:n], level, wbits, mem, strat), _deflate_whole(ref, d[:n], level, wbits, mem, strat)
+            assert got == want, (n, level, wbits, mem, strat, len(got), len(want))
+    n = 300 << 20
+    d = refz.gen(n, refz.GEN_MARKOV, seed=52)
     cap = z.compressBound(n)
     a, al = C.create_string_buffer(cap), C.c_ulong(cap)
     b, bl = C.create_string_buffer(cap), C.c_ulong(cap)
-    assert z.compress2(a, C.byref(al), d, n, 6) == 0
-    assert ref.compress2(b, C.byref(bl), d, n, 6) == 0
-    assert al.value == bl.value and a.raw[:al.value] == b.raw[:bl.value], (kind, al.value, bl.value)
-print("ok")
-"""
-
-
-def test_one_shot_64mib_is_the_references_stream_when_asked():
-    """$ZB200_SINGLE_RUN_MAX raises the size up to which a call is compressed as ONE run of blocks: at 64 MiB compress2()
-    still equals the reference's compress2() byte for byte on all five generators (one CTA walks the run in the ordered
-    phases: slower than the chunked default, still several times the reference's single core)."""
-    if not refz.have_ref():
-        pytest.skip("oracle/_ref/libzref.so not built")
-    env = dict(os.environ, ZB200_SINGLE_RUN_MAX=str(64 << 20))
-    p = subprocess.run([sys.executable, "-c", SINGLE_RUN_SCRIPT % {"root": ROOT}], env=env, capture_output=True, text=True, timeout=900)
-    assert p.returncode == 0 and "ok" in p.stdout, p.stderr[-2000:]
+    assert z.compress2(a, C.byref(al), d, n, 4) == 0
+    assert ref.compress2(b, C.byref(bl), d, n, 4) == 0
+    assert al.value == bl.value and a.raw[:al.value] == b.raw[:bl.value], (al.value, bl.value)

@@ -1,5 +1,5 @@
 """zb200_deflate_host end to end (pinned host buffers, pieces pipelined over three streams) next to the same bytes compressed
-device-resident: python tools/e2e_time.py MiB level [markov|mixed]   — GB/s of both and the library's per-kernel times of the
+device-resident: python tools/e2e_time.py MiB level [markov|mixed] [chunk bytes: 0 = ONE run of blocks]   — GB/s of both and the library's per-kernel times of the
 host call (ZB200_PIPE_PIECE_MIB changes the piece size)."""
 import ctypes as C
 import os
@@ -16,11 +16,14 @@ import zlib_wasm_b200 as zb  # noqa: E402
 mib, level = int(sys.argv[1]), int(sys.argv[2])
 gen = sys.argv[3] if len(sys.argv) > 3 else ("markov" if level < 4 else "mixed")
 n = mib << 20
+CH = int(sys.argv[4]) if len(sys.argv) > 4 else BL.CHUNK
+if CH == 0:
+    CH = n
 L = zb.lib()
 ctx = zb.Context(0)
 host = BL.host_alloc(L, n)
 BL.fill(host, n, gen, 0)
-cap = L.zb200_deflate_bound(n, BL.CHUNK, zb.FRAME_RAW)
+cap = L.zb200_deflate_bound(n, CH, zb.FRAME_RAW)
 h_out = BL.host_alloc(L, cap)
 olen = C.c_size_t(cap)
 ad, cr = C.c_uint32(0), C.c_uint32(0)
@@ -28,7 +31,7 @@ ad, cr = C.c_uint32(0), C.c_uint32(0)
 
 def call():
     olen.value = cap
-    r = L.zb200_deflate_host(ctx.handle, C.c_void_p(host), n, BL.CHUNK, level, 0, zb.FRAME_RAW, 1, C.c_void_p(h_out), C.byref(olen), C.byref(ad), C.byref(cr))
+    r = L.zb200_deflate_host(ctx.handle, C.c_void_p(host), n, CH, level, 0, zb.FRAME_RAW, 1, C.c_void_p(h_out), C.byref(olen), C.byref(ad), C.byref(cr))
     assert r == 0, zb.last_error()
 
 

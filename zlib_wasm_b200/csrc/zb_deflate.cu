@@ -38,7 +38,9 @@ struct DeflateDeviceTables {
     StaticTrees st;
 };
 
+struct ParseLink;
 struct DeflateWork {
+    ParseLink *links; unsigned int *mstate;        // one long chunk parsed by many CTAs (dfl_parse_multi_kernel)
     uint16_t *prev; uint32_t *mfull, *mquarter, *syms;
     BlockInfo *blocks; BlockCode *codes;
     uint32_t *nblocks; uint64_t *chunk_bytes, *chunk_off;
@@ -46,11 +48,12 @@ struct DeflateWork {
 };
 
 static size_t al(size_t v) { return (v + 255) & ~(size_t)255; }
+constexpr size_t kMultiRange = 262144;        // one long chunk: positions per CTA of the chain and parse kernels
 
 static size_t work_bytes(size_t nb, size_t S, uint32_t MB) {
     const size_t np = nb * S;
     return al(np * 2) + 3 * al(np * 4 + 16) + al(nb * MB * sizeof(BlockInfo)) + al(nb * MB * sizeof(BlockCode)) +
-           al(nb * 4) * 2 + al(nb * 8) * 4 + al(nb * sizeof(CkAccum)) + 4096;
+           al(nb * 4) * 2 + al(nb * 8) * 4 + al(nb * sizeof(CkAccum)) + al((np / kMultiRange + 2) * 32) + 256 + 4096;
 }
 
 static void carve(DeflateWork &w, void *base, size_t nb, size_t S, uint32_t MB) {
@@ -68,7 +71,9 @@ static void carve(DeflateWork &w, void *base, size_t nb, size_t S, uint32_t MB) 
     w.chunk_off = (uint64_t *)p; p += al(nb * 8);
     w.seg_off = (uint64_t *)p; p += al(nb * 8);
     w.seg_len = (uint64_t *)p; p += al(nb * 8);
-    w.acc = (CkAccum *)p;
+    w.acc = (CkAccum *)p; p += al(nb * sizeof(CkAccum));
+    w.links = (ParseLink *)p; p += al((np / kMultiRange + 2) * 32);
+    w.mstate = (unsigned int *)p;
 }
 
 struct Batch {                 // one sub-batch of chunks, passed by value to the kernels
@@ -81,6 +86,7 @@ struct Batch {                 // one sub-batch of chunks, passed by value to th
     int all_final;             // every chunk is its own stream (gzip members)
     uint32_t skip;             // a preset dictionary: the first `skip` bytes of chunk 0 are history only (single-chunk calls)
     uint32_t first_bit;        // deflatePrime: chunk 0 of the call starts at this bit (0..7) of its first output byte
+    uint32_t range;            // ONE long chunk (nb = 1) worked on by many CTAs of the ordered kernels: positions per CTA (0: off)
 };
 
 __device__ __forceinline__ uint32_t chunk_len(const Batch &b, uint32_t c) {
@@ -113,7 +119,7 @@ template <uint32_t W, bool IMM>
 __device__ __forceinline__ void chain_body(const Batch &b, const DeflateParams &prm, uint16_t *__restrict__ prev_all, uint16_t *head) {
     const uint32_t lane_warp = threadIdx.x >> 5;             // (IMM: W is this warp's index, known at compile time)
     const uint32_t warp = IMM ? W : lane_warp;
-    const uint32_t c = blockIdx.x, lane = threadIdx.x & 31;
+    const uint32_t c = b.range ? 0u : blockIdx.x, lane = threadIdx.x & 31;
     const uint8_t *data = b.in + (uint64_t)c * b.S;
     const uint32_t n = chunk_len(b, c);
     uint16_t *prev = prev_all + (uint64_t)c * b.S;
@@ -131,7 +137,17 @@ __device__ __forceinline__ void chain_body(const Batch &b, const DeflateParams &
         const uint32_t hi = (reinterpret_cast<uintptr_t>(w) + 4 < in_hi) ? w[1] : 0u;    // read only words that hold at least one input byte
         return __funnelshift_r(lo, hi, (uint32_t)(a & 3) * 8);
     };
-    const uint32_t ntrips = (n + kChainTrip - 1) / kChainTrip;
+    // One long chunk in RANGES (b.range positions per CTA): a CTA first re-inserts the w_size positions before its range —
+    // no candidate of its own positions lies further back (MAX_DIST < w_size) — and stores the links of its range only.
+    // Links that the one-CTA walk would have drawn to positions further back than that come out as NIL here; both end a
+    // match walk (deflate.c:1481 cur_match > limit), so the matches found are the same.
+    uint32_t t_first = 0, t_last = (n + kChainTrip - 1) / kChainTrip, store_lo = 0;
+    if (b.range) {
+        const uint32_t lo_r = blockIdx.x * b.range, hi_r = n - lo_r < b.range ? n : lo_r + b.range;
+        t_first = (lo_r > wsz ? lo_r - wsz : 0u) / kChainTrip;
+        t_last = (hi_r + kChainTrip - 1) / kChainTrip;
+        store_lo = lo_r;
+    }
     uint32_t hs[G], nxt[G];
     auto hash_trip = [&](uint32_t t, uint32_t (&h)[G]) {
 #pragma unroll
@@ -143,15 +159,15 @@ __device__ __forceinline__ void chain_body(const Batch &b, const DeflateParams &
             } else h[j] = 0x10000u | lane;
         }
     };
-    if (warp < ntrips) hash_trip(warp, nxt);
-    for (uint32_t t = warp; t < ntrips; t += kChainWarps) {
+    if (t_first + warp < t_last) hash_trip(t_first + warp, nxt);
+    for (uint32_t t = t_first + warp; t < t_last; t += kChainWarps) {
 #pragma unroll
         for (int j = 0; j < G; ++j) hs[j] = nxt[j];
-        if (t + kChainWarps < ntrips) hash_trip(t + kChainWarps, nxt);     // the next trip's hashes: off the ordered path
+        if (t + kChainWarps < t_last) hash_trip(t + kChainWarps, nxt);     // the next trip's hashes: off the ordered path
         const uint32_t p0 = t * kChainTrip;
         // window origin after every slide due up to this trip (the first one happens at position 2 * w_size)
         const uint32_t base = p0 < 2u * wsz ? 0u : ((p0 >> wlog) - 1u) << wlog;
-        if (t) {                                                   // trip t-1 has left the head table (its warp arrived here)
+        if (t != t_first) {                                        // trip t-1 has left the head table (its warp arrived here)
             if (IMM) asm volatile("bar.sync %0, 64;" ::"n"(W + 1) : "memory");
             else asm volatile("bar.sync %0, 64;" ::"r"(lane_warp + 1) : "memory");
         }
@@ -194,14 +210,14 @@ __device__ __forceinline__ void chain_body(const Batch &b, const DeflateParams &
             }
             dists[j] = dist;
         }
-        if (t + 1 < ntrips) {                                      // pass the turn on
+        if (t + 1 < t_last) {                                      // pass the turn on
             if (IMM) asm volatile("bar.arrive %0, 64;" ::"n"(((W + 1) & (kChainWarps - 1)) + 1) : "memory");
             else asm volatile("bar.arrive %0, 64;" ::"r"(((lane_warp + 1) & (kChainWarps - 1)) + 1) : "memory");
         }
 #pragma unroll
         for (int j = 0; j < G; ++j) {
             const uint32_t p = p0 + 32 * j + lane;
-            if (p < n) prev[p] = (uint16_t)dists[j];
+            if (p < n && p >= store_lo) prev[p] = (uint16_t)dists[j];
         }
     }
 }
@@ -665,6 +681,154 @@ dfl_parse_kernel(Batch b, DeflateParams prm, const uint32_t *__restrict__ mfull,
     }
 }
 
+
+// ---- phase 3, lazy rule, ONE long chunk parsed by many CTAs -------------------------------------------------------
+// compress2() / deflate(Z_FINISH) emit one run of blocks however long the input is (compress.c:22-59), and the parse of
+// a run is one state machine from its first byte to its last.  The segment scheme above does not care how many segments
+// there are, only that lane i+1 learns where lane i really ended — so a long chunk gets G CTAs of kSegLanes segments each
+// and the hand-over crosses the CTAs as well: CTA k (tickets are drawn in order, so every CTA before it is running or
+// done) settles its own segments from a cold start, waits for the LINK of CTA k-1 — its true end state and the number of
+// symbols before CTA k — lets its first lane fall into step with that (a re-parse of a few dozen bytes, which as a rule
+// changes nothing behind it), publishes its own link, and emits its symbols at their final indices.  The chain of links
+// costs a few microseconds per CTA; everything else runs at once.  The last CTA to finish closes the block table.
+// Two chains: the end state of a CTA's last segment (`ready`) — the one whose latency counts — and, behind it, the number of
+// symbols up to and including the CTA (`counted`).
+// The state chain is walked TWICE: a CTA publishes the end state it reaches from its cold start at once (`pready`), its
+// successor falls into step with that while the true states are still on their way, and when the true one arrives and
+// is the same — the rule: a parse forgets its start within a segment — the successor's own state is true as it stands.
+// A link of the chain then costs a flag's round trip instead of a re-parse (6-18 us per CTA before).
+struct ParseLink { uint32_t p, w0, ready, syms, counted, pp, pw0, pready; };
+__global__ void __launch_bounds__(kSegLanes)
+dfl_parse_multi_kernel(Batch b, DeflateParams prm, const uint32_t *__restrict__ mfull,
+                       const uint32_t *__restrict__ mquarter, uint32_t *__restrict__ syms,
+                       BlockInfo *__restrict__ blocks, uint32_t *__restrict__ nblocks, uint32_t G,
+                       unsigned int *__restrict__ mstate, volatile ParseLink *links) {
+    extern __shared__ __align__(16) uint8_t ps_smem[];
+    uint32_t *s_f = reinterpret_cast<uint32_t *>(ps_smem);         // [2][kSegLanes][kPwRow]
+    uint32_t *s_q = s_f + 2 * kPwRow * kSegLanes;
+    uint32_t *s_b = s_q + 2 * kPwRow * kSegLanes;                  // [kSegLanes][kPwBytesRow]
+    SegRec *rec = reinterpret_cast<SegRec *>(s_b + kPwBytesRow * kSegLanes);   // [(kSegRecs - 1)][kSegLanes]
+    uint32_t *s_p = reinterpret_cast<uint32_t *>(rec + (kSegRecs - 1) * kSegLanes);
+    uint32_t *s_w0 = s_p + kSegLanes, *s_wsum = s_w0 + kSegLanes;
+    __shared__ uint32_t s_k, s_pred[3];
+    const unsigned full = 0xffffffffu;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_k = atomicAdd(&mstate[0], 1u);
+    __syncthreads();
+    const uint32_t k = s_k;
+    const uint8_t *data = b.in;
+    const uint32_t n = chunk_len(b, 0), lo = b.skip;
+    uint32_t *out = syms;
+    SegGeom g;
+    {
+        const uint32_t m = n - lo;
+        const uint64_t lanes = (uint64_t)G * kSegLanes * kSegRecs;
+        g.blk = (uint32_t)((m + lanes - 1) / lanes);
+        if (g.blk < 32) g.blk = 32;
+        g.seg = g.blk * kSegRecs;
+        const uint32_t nact_total = m ? (m + g.seg - 1) / g.seg : 1;
+        const uint64_t first = (uint64_t)k * kSegLanes;
+        g.nact = nact_total > first ? (nact_total - first < kSegLanes ? (uint32_t)(nact_total - first) : kSegLanes) : 0u;
+        g.lo = g.nact ? lo + (uint32_t)first * g.seg : n;
+    }
+    const bool active = tid < g.nact;
+
+    SegLane r;
+    r.start = r.end = r.spec_end = seg_cold(g.lo); r.count = r.spec_count = 0;
+    WinAcc acc;
+    acc.data = data; acc.mfull = mfull; acc.mquarter = prm.need_quarter ? mquarter : mfull; acc.out = nullptr; acc.at = 0;
+    acc.row_f = (uint32_t)__cvta_generic_to_shared(s_f + tid * kPwRow);
+    acc.row_q = (uint32_t)__cvta_generic_to_shared(s_q + tid * kPwRow);
+    acc.row_b = (uint32_t)__cvta_generic_to_shared(s_b + tid * kPwBytesRow);
+    acc.abs0 = 0; acc.use_q = prm.need_quarter != 0; acc.nw = 0;
+    acc.in_lo = reinterpret_cast<uintptr_t>(b.in); acc.in_hi = acc.in_lo + b.bytes;
+    if (active) seg_speculate(r, tid, g, n, prm, acc, rec);
+    SegState pred0 = seg_cold(g.lo);                               // where the segment before this CTA's first one ended (cold: not known yet)
+    auto settle = [&]() {                                          // until no start moves
+        for (;;) {
+            s_p[tid] = r.end.p; s_w0[tid] = r.end.w0;
+            __syncthreads();
+            SegState t = pred0;
+            if (tid) { t.p = s_p[tid - 1]; t.w0 = s_w0[tid - 1]; }
+            const bool need = active && (t.p != r.start.p || t.w0 != r.start.w0);
+            if (!__syncthreads_or(need)) break;
+            if (need) seg_fix(r, tid, g, n, prm, acc, rec, t);
+        }
+    };
+    settle();
+    if (tid == 0) {                                                // what this CTA ends in when started cold
+        links[k].pp = g.nact ? s_p[g.nact - 1] : pred0.p;
+        links[k].pw0 = g.nact ? s_w0[g.nact - 1] : pred0.w0;
+        __threadfence();
+        links[k].pready = 1u;
+    }
+    if (k > 0) {
+        if (tid == 0) {
+            while (links[k - 1].pready == 0u) __nanosleep(32);
+            __threadfence();
+            s_pred[0] = links[k - 1].pp; s_pred[1] = links[k - 1].pw0;
+        }
+        __syncthreads();
+        pred0.p = s_pred[0]; pred0.w0 = s_pred[1];
+        settle();                                                  // in step with the predecessor's provisional end
+        __syncthreads();
+        if (tid == 0) {
+            while (links[k - 1].ready == 0u) __nanosleep(32);
+            __threadfence();
+            s_pred[0] = links[k - 1].p; s_pred[1] = links[k - 1].w0;
+        }
+        __syncthreads();
+        if (s_pred[0] != pred0.p || s_pred[1] != pred0.w0) {       // (uniform) the true end is another one: once more
+            pred0.p = s_pred[0]; pred0.w0 = s_pred[1];
+            settle();
+        }
+    }
+    if (tid == 0) {                                                // the state link: the next CTA may go on
+        links[k].p = g.nact ? s_p[g.nact - 1] : pred0.p;
+        links[k].w0 = g.nact ? s_w0[g.nact - 1] : pred0.w0;
+        __threadfence();
+        links[k].ready = 1u;
+    }
+    // exclusive scan of the symbol counts over the CTA
+    const uint32_t cnt = active ? r.count : 0u;
+    uint32_t inc = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t y = __shfl_up_sync(full, inc, d); if (lane >= (uint32_t)d) inc += y; }
+    if (lane == 31) s_wsum[warp] = inc;
+    __syncthreads();
+    uint32_t before = 0, total = 0;
+#pragma unroll
+    for (uint32_t q = 0; q < kSegLanes / 32; ++q) { const uint32_t x = s_wsum[q]; if (q < warp) before += x; total += x; }
+    if (tid == 0) {                                                // the count link
+        uint32_t sb = 0;
+        if (k > 0) {
+            while (links[k - 1].counted == 0u) __nanosleep(32);
+            __threadfence();
+            sb = links[k - 1].syms;
+        }
+        links[k].syms = sb + total;
+        __threadfence();
+        links[k].counted = 1u;
+        s_pred[2] = sb;
+    }
+    __syncthreads();
+    const uint32_t syms_before = s_pred[2];
+    const uint32_t first = syms_before + before + inc - cnt;
+    acc.out = out; acc.at = first;
+    if (active) seg_emit(r, tid, g, n, prm, acc, blocks, first);
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence();                                           // this CTA's symbols and provisional BlockInfo entries -> visible
+        if (atomicAdd(&mstate[1], 1u) == G - 1) {                  // the last CTA to get here closes the chunk
+            __threadfence();
+            const uint32_t all = links[G - 1].syms;
+            const bool pending = prm.mode == MODE_SLOW && ((links[G - 1].w0 >> 25) & 1u);
+            if (pending) out[all] = data[n - 1];
+            nblocks[0] = seg_finish(blocks, all, pending, n, prm, chunk_final(b, 0), lo);
+        }
+    }
+}
+
 // ---- phase 4: per-block histogram + Huffman construction -------------------------------
 // One WARP per block.  The construction itself is the reference's heap algorithm — its tie-breaks (trees.c:499-501) decide
 // the code lengths, so it is replayed exactly, and it is serial — which makes this kernel latency-bound on ONE thread per
@@ -758,6 +922,59 @@ __global__ void dfl_layout_kernel(Batch b, BlockInfo *__restrict__ blocks, const
     }
     if (!chunk_final(b, c)) bit = ((bit + 3 + 7) & ~7ull) + 32;   // 000 + pad + 00 00 FF FF
     chunk_bytes[c] = ((bit + 7) >> 3) + member_overhead;
+}
+
+// The same for ONE long chunk with thousands of blocks: one CTA scans them.  Where a block ends is a function of where it
+// starts — start + its bits, or, for a stored block, the next byte boundary behind its 3 header bits + 32 + 8 bytes per
+// byte (block_end_bit) — and functions of the form x -> x + d and x -> ((x + c) & ~7) + d are closed under composition, so
+// the ends come out of an ordinary prefix scan over (aligning?, c, d) instead of a walk from block to block.
+struct EndFn { uint32_t al; uint64_t c, d; };
+__device__ __forceinline__ EndFn endfn_of(const BlockInfo &bi, const BlockCode &bc) {
+    EndFn f;
+    if (bc.type == 0) { f.al = 1; f.c = 10; f.d = 32 + 8ull * bi.byte_len; }
+    else { f.al = 0; f.c = 0; f.d = bc.body_bits; }
+    return f;
+}
+__device__ __forceinline__ EndFn endfn_then(const EndFn &f, const EndFn &g) {   // first f, then g
+    EndFn h;
+    if (!g.al) { h.al = f.al; h.c = f.c; h.d = f.d + g.d; }
+    else if (!f.al) { h.al = 1; h.c = f.d + g.c; h.d = g.d; }
+    else { h.al = 1; h.c = f.c; h.d = ((f.d + g.c) & ~7ull) + g.d; }
+    return h;
+}
+__device__ __forceinline__ uint64_t endfn_apply(const EndFn &f, uint64_t x) { return f.al ? ((x + f.c) & ~7ull) + f.d : x + f.d; }
+__global__ void __launch_bounds__(1024)
+dfl_layout_long_kernel(Batch b, BlockInfo *__restrict__ blocks, const BlockCode *__restrict__ codes,
+                       const uint32_t *__restrict__ nblocks, uint64_t *__restrict__ chunk_bytes,
+                       uint32_t member_overhead, uint32_t *__restrict__ bi_used) {
+    __shared__ EndFn s_fn[1024];
+    const uint32_t nbk = nblocks[0], tid = threadIdx.x;
+    const uint32_t per = (nbk + 1023) / 1024, i0 = tid * per, i1 = i0 + per < nbk ? i0 + per : nbk;
+    EndFn mine; mine.al = 0; mine.c = 0; mine.d = 0;                // identity
+    for (uint32_t i = i0; i < i1; ++i) mine = endfn_then(mine, endfn_of(blocks[i], codes[i]));
+    s_fn[tid] = mine;
+    __syncthreads();
+    for (uint32_t d = 1; d < 1024; d <<= 1) {                       // inclusive scan (Hillis-Steele) of the composed functions
+        EndFn prev; prev.al = 0; prev.c = 0; prev.d = 0;
+        if (tid >= d) prev = s_fn[tid - d];
+        __syncthreads();
+        if (tid >= d) s_fn[tid] = endfn_then(prev, s_fn[tid]);
+        __syncthreads();
+    }
+    const uint64_t bit0 = b.first_bit;                              // deflatePrime: bits already in the first byte
+    uint64_t bit = tid ? endfn_apply(s_fn[tid - 1], bit0) : bit0;
+    for (uint32_t i = i0; i < i1; ++i) {
+        BlockInfo &bi = blocks[i];
+        bi.bit_start_lo = (uint32_t)bit; bi.bit_start_hi = (uint32_t)(bit >> 32);
+        if (i + 1 == nbk) {                                         // the chunk's last block: deflateUsed, windup, the chunk's size
+            const BlockCode &bc = codes[i];
+            *bi_used = (bc.type == 0 || !chunk_final(b, 0)) ? 8u : (uint32_t)(((bit + bc.body_bits - 1) & 7) + 1);
+            uint64_t end = block_end_bit(bi, bc, bit);
+            if (!chunk_final(b, 0)) end = ((end + 3 + 7) & ~7ull) + 32;
+            chunk_bytes[0] = ((end + 7) >> 3) + member_overhead;
+        }
+        bit = block_end_bit(bi, codes[i], bit);
+    }
 }
 
 // Exclusive scan of the chunk sizes of a sub-batch onto the running stream length.
@@ -942,6 +1159,7 @@ int deflate_init(zb200_ctx *ctx) {
     ZB_CUDA(cudaFuncSetAttribute(dfl_chain_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 << kHashBitsMax));
     ZB_CUDA(cudaFuncSetAttribute(dfl_chain_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
     ZB_CUDA(cudaFuncSetAttribute(dfl_parse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kParseSmem));
+    ZB_CUDA(cudaFuncSetAttribute(dfl_parse_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kParseSmem));
     ZB_CUDA(cudaFuncSetAttribute(dfl_parse_greedy_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
     ZB_CUDA(cudaFuncSetAttribute(dfl_tree_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
     ZB_CUDA(cudaFuncSetAttribute(dfl_match_sorted_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMsSmem));
@@ -1087,10 +1305,16 @@ int deflate_launch_opts(zb200_ctx *ctx, const uint8_t *d_in, size_t n, size_t S,
         b.all_final = members ? 1 : 0;
         b.skip = (uint32_t)skip;
         b.first_bit = c0 == 0 ? o.first_bit : 0u;
+        // ONE long chunk (a one-shot call's single run of blocks): many CTAs share its ordered phases
+        static const int multi_knob = [] { const char *e = getenv("ZB200_MULTI_CTA_RUN"); return e ? atoi(e) : 1; }();
+        const bool one_long = multi_knob && b.nb == 1 && b.bytes >= 2 * kMultiRange;
+        const uint32_t n_ranges = one_long ? (uint32_t)((b.bytes + kMultiRange - 1) / kMultiRange) : 1u;
+        b.range = one_long ? (uint32_t)kMultiRange : 0u;
         if (prm.mode == MODE_FAST || prm.mode == MODE_SLOW) {
             prof_mark(ctx, s, "dfl_chain_kernel");
-            if (prm.hash_bits < 15) dfl_chain_kernel<true><<<b.nb, kChainWarps * 32, 2u << prm.hash_bits, s>>>(b, prm, w.prev);
-            else dfl_chain_kernel<false><<<b.nb, kChainWarps * 32, 2u << prm.hash_bits, s>>>(b, prm, w.prev);
+            const unsigned chain_grid = one_long ? n_ranges : b.nb;
+            if (prm.hash_bits < 15) dfl_chain_kernel<true><<<chain_grid, kChainWarps * 32, 2u << prm.hash_bits, s>>>(b, prm, w.prev);
+            else dfl_chain_kernel<false><<<chain_grid, kChainWarps * 32, 2u << prm.hash_bits, s>>>(b, prm, w.prev);
             ZB_LAUNCHED(); ZB_CHECK_LAUNCH();
         }
         if (sorted_walks) {
@@ -1120,14 +1344,19 @@ int deflate_launch_opts(zb200_ctx *ctx, const uint8_t *d_in, size_t n, size_t S,
             ZB_LAUNCHED(); ZB_CHECK_LAUNCH();
         }
         prof_mark(ctx, s, "dfl_parse_kernel");
-        if (prm.mode == MODE_SLOW) dfl_parse_kernel<<<b.nb, kSegLanes, kParseSmem, s>>>(b, prm, w.mfull, w.mquarter, w.syms, w.blocks, w.nblocks);
+        if (prm.mode == MODE_SLOW && one_long) {
+            ZB_CUDA(cudaMemsetAsync(w.links, 0, (size_t)n_ranges * sizeof(ParseLink), s));
+            ZB_CUDA(cudaMemsetAsync(w.mstate, 0, 16, s));
+            dfl_parse_multi_kernel<<<n_ranges, kSegLanes, kParseSmem, s>>>(b, prm, w.mfull, w.mquarter, w.syms, w.blocks, w.nblocks, n_ranges, w.mstate, w.links);
+        } else if (prm.mode == MODE_SLOW) dfl_parse_kernel<<<b.nb, kSegLanes, kParseSmem, s>>>(b, prm, w.mfull, w.mquarter, w.syms, w.blocks, w.nblocks);
         else dfl_parse_greedy_kernel<<<b.nb, kGtWarps * 32, 0, s>>>(b, prm, w.mfull, w.syms, w.blocks, w.nblocks);
         ZB_LAUNCHED(); ZB_CHECK_LAUNCH();
         prof_mark(ctx, s, "dfl_tree_kernel");
         dfl_tree_kernel<<<dim3((MB + kTreeWarps - 1) / kTreeWarps, b.nb), kTreeWarps * 32, 0, s>>>(b, strategy | (level == 0 ? 0x100 : 0), w.syms, w.blocks, w.nblocks, tabs, w.codes);
         ZB_LAUNCHED(); ZB_CHECK_LAUNCH();
         prof_mark(ctx, s, "dfl_layout_kernel");
-        dfl_layout_kernel<<<(b.nb + 127) / 128, 128, 0, s>>>(b, w.blocks, w.codes, w.nblocks, w.chunk_bytes, members ? 18 : 0,
+        if (one_long) dfl_layout_long_kernel<<<1, 1024, 0, s>>>(b, w.blocks, w.codes, w.nblocks, w.chunk_bytes, members ? 18 : 0, (uint32_t *)(ctx->d_small + 19));
+        else dfl_layout_kernel<<<(b.nb + 127) / 128, 128, 0, s>>>(b, w.blocks, w.codes, w.nblocks, w.chunk_bytes, members ? 18 : 0,
                                                             (uint32_t *)(ctx->d_small + 19));
         ZB_LAUNCHED(); ZB_CHECK_LAUNCH();
         prof_mark(ctx, s, "dfl_scan_kernel");

@@ -73,18 +73,21 @@ size_t api_chunk() {
     return c;
 }
 
-// How one call's input is cut.  Up to $ZB200_SINGLE_RUN_MAX bytes (default 1 MiB: config C1's size) it is NOT cut:
-// one run of blocks, no flush marker inside — for levels 4-9 that is byte for byte what the reference's one-shot
-// compress2() / deflate(Z_FINISH) emits (compress.c:22-59), at the price of one CTA walking the whole run in the
-// ordered phases.  Longer inputs are cut into $ZB200_CHUNK-byte Z_FULL_FLUSH runs that are compressed concurrently
-// (the reference's bytes for that chunking).
-size_t run_chunk(size_t n) {
-    static size_t single = [] {
-        const char *e = getenv("ZB200_SINGLE_RUN_MAX");
-        const long long v = e ? atoll(e) : (1ll << 20);
-        return (size_t)(v < 0 ? 0 : v > (1ll << 30) ? (1ll << 30) : v);
-    }();
-    return (n && n <= single && n > api_chunk()) ? n : api_chunk();
+// How one call's input is cut.  Up to $ZB200_SINGLE_RUN_MAX bytes it is NOT cut: one run of blocks, no flush marker
+// inside — for levels 4-9 byte for byte what the reference's one-shot compress2() / deflate(Z_FINISH) emits
+// (compress.c:22-59).  The default is the engine's largest chunk, 1 GiB, for the lazy levels (4-9, any strategy but
+// Z_RLE / Z_HUFFMAN_ONLY): their ordered phases are shared by many CTAs (zb_deflate.cu dfl_parse_multi_kernel, chain
+// ranges), a single run costs the device what the same bytes in chunks cost.  The greedy levels (whose streams are not
+// the reference's byte for byte in any case) walk a single run in one CTA: 1 MiB (config C1's size).  Longer inputs
+// are cut into $ZB200_CHUNK-byte Z_FULL_FLUSH runs that are compressed concurrently (the reference's bytes for that
+// chunking).
+size_t run_chunk(size_t n, int level, int strategy) {
+    static long long knob = [] { const char *e = getenv("ZB200_SINGLE_RUN_MAX"); return e ? atoll(e) : -1ll; }();
+    const bool lazy = level >= 4 && strategy != Z_RLE && strategy != Z_HUFFMAN_ONLY;
+    long long v = knob >= 0 ? knob : lazy ? (1ll << 30) : (1ll << 20);
+    if (v > (1ll << 30)) v = 1ll << 30;
+    if (!lazy && knob < 0 && v > (1ll << 20)) v = 1ll << 20;
+    return (n && n <= (size_t)v && n > api_chunk()) ? n : api_chunk();
 }
 
 [[noreturn]] void die_no_device(const char *fn) {
@@ -218,7 +221,7 @@ int compress_buffered(DeflateStream &st, bool finish) {
     if (!ctx) return Z_STREAM_ERROR;
     const size_t n = st.in.size();
     if (n == 0 && !finish) return Z_OK;
-    const size_t chunk = run_chunk(n);
+    const size_t chunk = run_chunk(n, st.level, st.strategy);
     struct TuneScope {                                         // the engine reads the override on this thread
         explicit TuneScope(const int *t) { deflate_tune_set(t); }
         ~TuneScope() { deflate_tune_set(nullptr); }
@@ -831,8 +834,11 @@ int deflate(z_streamp strm, int flush) {
     }
     if (!s->finished) {
         const bool want_flush = flush != Z_NO_FLUSH;
-        // bound host buffering: hand whole chunks to the GPU once enough has piled up
-        const bool spill = !want_flush && s->in.size() >= (size_t)64 * api_chunk();
+        // bound host buffering: hand what has piled up to the GPU — as one run of blocks (levels 4-9) or whole chunks,
+        // ending on a full-flush marker — once it reaches $ZB200_STREAM_HOLD_MIB (default 256: a stream up to that size
+        // comes out as the reference's one run however it is fed)
+        static const size_t hold = [] { const char *e = getenv("ZB200_STREAM_HOLD_MIB"); const long v = e ? atol(e) : 0; return (size_t)(v >= 1 ? v : 256) << 20; }();
+        const bool spill = !want_flush && s->in.size() >= hold;
         if (want_flush || spill) {
             if (!s->header_done) put_header(*s);
             // Z_SYNC_FLUSH / Z_PARTIAL_FLUSH / Z_BLOCK keep the window (deflate.c:1211-1218 clears the hash only for
@@ -1278,7 +1284,7 @@ int compress2(Bytef *dest, uLongf *destLen, const Bytef *source, uLong sourceLen
     size_t cap = *destLen;
     const int r = (sourceLen >= kMultiMin && api_multi())
                       ? zb200_multi_deflate_host(api_multi(), source, sourceLen, api_chunk(), level, 0, ZB200_FRAME_ZLIB, 1, dest, &cap, nullptr, nullptr)
-                      : zb200_deflate_host(ctx, source ? source : (const Bytef *)"", sourceLen, run_chunk(sourceLen), level,
+                      : zb200_deflate_host(ctx, source ? source : (const Bytef *)"", sourceLen, run_chunk(sourceLen, level == Z_DEFAULT_COMPRESSION ? 6 : level, 0), level,
                                            0, ZB200_FRAME_ZLIB, 1, dest, &cap, nullptr, nullptr);
     if (r == ZB200_ERR_OUTPUT) return Z_BUF_ERROR;
     if (r != ZB200_OK) return map_engine_error(r);
