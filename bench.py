@@ -294,6 +294,10 @@ def main():
             except Exception as ex:
                 errors["small_calls"] = repr(ex)
             try:
+                legs["one_shot_calls"] = BL.one_shot_leg(cpu, BL.scaled(64 << 20, args.scale))
+            except Exception as ex:
+                errors["one_shot_calls"] = repr(ex)
+            try:
                 legs["inflate_one_member"] = BL.single_member_leg(g, cpu, BL.scaled(256 << 20, args.scale))
             except Exception as ex:
                 errors["inflate_one_member"] = repr(ex)

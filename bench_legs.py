@@ -864,3 +864,43 @@ def single_member_leg(g, cpu, total=256 * MIB):
     for p in (host, h_in, h_out):
         L.zb200_host_free(C.c_void_p(p))
     return e
+
+
+def one_shot_leg(cpu, n=64 * MIB):
+    """compress2() / uncompress() of one buffer through the zlib.h surface itself (pageable host buffers, one host thread; the
+    reference's API is serial), this library next to the reference: level 6 and 9, wall time of the calls, and whether the
+    two libraries' streams are the same bytes (levels 4-9 emit the reference's one run of blocks whatever the length)."""
+    import refz
+    import zlib_wasm_b200 as zb
+    libs = {"b200": refz.ZlibBinding(zb.LIB_PATH, "")}
+    if cpu is not None and cpu.ref is not None:
+        libs["reference"] = cpu.ref
+    d = refz.gen(n, refz.GEN_TEXT, seed=0x9E37)
+    out = {"bytes": n, "generator": "word text", "unit": "ms per call", "levels": {}}
+    for level in (6, 9):
+        row, streams = {}, {}
+        for name, z in libs.items():
+            cap = z.compressBound(n) + 64
+            dst, back = C.create_string_buffer(cap), C.create_string_buffer(n)
+            best_c = best_u = None
+            for rep in range(2 if name == "b200" else 1):         # (the library's device buffers grow on the first call)
+                dl = C.c_ulong(cap)
+                t0 = time.perf_counter()
+                rc = z.compress2(dst, C.byref(dl), d, n, level)
+                t1 = time.perf_counter()
+                bl = C.c_ulong(n)
+                ru = z.uncompress(back, C.byref(bl), dst, dl.value)
+                t2 = time.perf_counter()
+                if rc != 0 or ru != 0 or bl.value != n:
+                    raise RuntimeError("one_shot %s level %d: compress2 %d uncompress %d" % (name, level, rc, ru))
+                best_c = t1 - t0 if best_c is None else min(best_c, t1 - t0)
+                best_u = t2 - t1 if best_u is None else min(best_u, t2 - t1)
+            streams[name] = dst.raw[:dl.value]
+            row[name] = {"compress2": round(best_c * 1e3, 2), "uncompress": round(best_u * 1e3, 2), "compressed_bytes": dl.value,
+                         "round_trip_ok": bool(back.raw == d)}
+        if len(streams) == 2:
+            row["same_bytes_as_reference"] = bool(streams["b200"] == streams["reference"])
+        out["levels"][str(level)] = row
+    out["parity"] = {"round_trip": all(r[k]["round_trip_ok"] for r in out["levels"].values() for k in r if isinstance(r[k], dict)),
+                     "streams_identical_to_reference": all(r.get("same_bytes_as_reference", True) for r in out["levels"].values())}
+    return out
