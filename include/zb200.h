@@ -216,8 +216,12 @@ int zb200_gunzip_host(zb200_ctx *ctx, const void *in, size_t n, void *out, size_
  * stored block deflate.c:1211-1226 emits for Z_SYNC_FLUSH / Z_FULL_FLUSH — all of this library's deflate output,
  * pigz -i files, zlib's own full flushes) is a candidate boundary; the runs between candidates are inflated as
  * one batch and the chain is verified from the front (a run that stops mid-block had a false successor, a run that
- * reaches behind its start follows a sync flush: both are merged and redone).  A stream with nothing to split on,
- * or damaged, takes the one-member path of zb200_inflate_host — same statuses either way.
+ * reaches behind its start follows a sync flush: both are merged and redone).  A stream with no (or few) flush points
+ * — what the reference's compress2 / gzip write: inflate.c decodes it serially — is decoded chunk by chunk in parallel at
+ * its dynamic and stored block headers instead (csrc/zb_inflate_blocks.cuh: every bit position is tested for a header that
+ * validates itself, chunks are counted, chained from the front, decoded at their places, their matches resolved by pointer
+ * jumping).  A stream with nothing to split on, or damaged, takes the one-member path of zb200_inflate_host — same
+ * statuses either way.
  * result: status, wrap_kind, check (computed), out_len (when it exceeds out_cap: ZB200_INF_OUTPUT_FULL), in_used.
  * Host pointers; synchronous. */
 int zb200_inflate_stream_host(zb200_ctx *ctx, const void *in, size_t n, int wrap, void *out, size_t out_cap,
