@@ -26,5 +26,19 @@ for kind in (refz.GEN_MARKOV, refz.GEN_MIXED):
         ok &= good
     crc, adler = ctx.checksum_host(d)
     ok &= crc == refz.oracle().crc32(d) and adler == refz.oracle().adler32(d)
+# round 2: ONE run of blocks shared by several CTAs (chain ranges, parse links, block-end scan), and ONE member without
+# flush points decoded chunk by chunk (candidate scan / validate, count + list passes, source pointers, jumping, gather)
+import ctypes as C  # noqa: E402
+import zlib  # noqa: E402
+d = refz.gen(1400000 + 321, refz.GEN_MIXED, seed=12)
+for level in (4, 6):
+    s = ctx.deflate_host(d, level, 0, zb.FRAME_ZLIB, len(d))          # chunk = the whole input: one run
+    good = s == zlib.compress(d, level)
+    out = C.create_string_buffer(len(d) + 16)
+    res = zb.MemberResult()
+    r = zb.lib().zb200_inflate_stream_host(ctx.handle, s, len(s), zb.WRAP_ZLIB, out, len(d) + 16, C.byref(res))
+    good = good and r == 0 and res.status == 0 and out.raw[:res.out_len] == d
+    print("one run, level %d: %d -> %d bytes, the reference's bytes and back: %s" % (level, len(d), len(s), good), flush=True)
+    ok &= good
 print("ALL OK" if ok else "FAILED", flush=True)
 sys.exit(0 if ok else 1)

@@ -5,9 +5,67 @@
 #include <stdarg.h>
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
 #include <new>
+#include <condition_variable>
+#include <thread>
 
 namespace zb {
+
+// Pageable caller memory passes through the pinned stages by memcpy, and ONE host thread copies at 10-12 GB/s: that, not
+// the link (55 GB/s) nor the kernels, bounded every zlib.h call on a large malloc'd buffer (crc32 of 512 MiB: 38 ms of which
+// 36 were this memcpy).  Copies of 4 MiB and more are therefore split over the calling thread and three helpers (started
+// on first use, parked on a condition variable in between; one split copy at a time — a second caller copies alone).
+namespace {
+struct CopyPool {
+    static constexpr int kHelpers = 3;
+    std::mutex mu, call_mu;
+    std::condition_variable cv_work, cv_done;
+    struct Job { uint8_t *d; const uint8_t *s; size_t n; } jobs[kHelpers];
+    uint64_t gen = 0;
+    int pending = 0;
+    bool started = false;
+    void helper(int i) {
+        uint64_t seen = 0;
+        for (;;) {
+            std::unique_lock<std::mutex> lk(mu);
+            cv_work.wait(lk, [&] { return gen != seen; });
+            seen = gen;
+            const Job j = jobs[i];
+            lk.unlock();
+            if (j.n) memcpy(j.d, j.s, j.n);
+            lk.lock();
+            if (--pending == 0) cv_done.notify_one();
+        }
+    }
+    void copy(void *dst, const void *src, size_t n) {
+        static const bool off = [] { const char *e = getenv("ZB200_COPY_THREADS"); return e && atoi(e) <= 1; }();
+        if (n < ((size_t)4 << 20) || off || !call_mu.try_lock()) { memcpy(dst, src, n); return; }
+        uint8_t *d = (uint8_t *)dst;
+        const uint8_t *sp = (const uint8_t *)src;
+        const size_t part = ((n / (kHelpers + 1)) + 4095) & ~(size_t)4095;
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            if (!started) { for (int i = 0; i < kHelpers; ++i) std::thread([this, i] { helper(i); }).detach(); started = true; }
+            for (int i = 0; i < kHelpers; ++i) {
+                const size_t a = part * (size_t)(i + 1), b = a + part < n ? a + part : n;
+                jobs[i] = Job{d + a, sp + a, a < n ? (i + 1 == kHelpers ? n - a : b - a) : 0};
+            }
+            pending = kHelpers;
+            ++gen;
+        }
+        cv_work.notify_all();
+        memcpy(d, sp, part < n ? part : n);
+        {
+            std::unique_lock<std::mutex> lk(mu);
+            cv_done.wait(lk, [&] { return pending == 0; });
+        }
+        call_mu.unlock();
+    }
+};
+CopyPool &copy_pool() { static CopyPool *p = new CopyPool; return *p; }   // (never destroyed: its helpers outlive main)
+}  // namespace
+void host_copy(void *dst, const void *src, size_t n) { copy_pool().copy(dst, src, n); }
 
 static thread_local char t_err[512];
 std::atomic<uint64_t> g_launches{0};
@@ -71,7 +129,7 @@ int h2d_staged(zb200_ctx *ctx, void *d_dst, const void *h_src, size_t n, cudaStr
     for (size_t off = 0; off < n;) {
         size_t m = n - off < ctx->stage_bytes ? n - off : ctx->stage_bytes;
         ZB_CUDA(cudaEventSynchronize(ctx->stage_ev[k]));
-        memcpy(ctx->h_stage[k], src + off, m);
+        host_copy(ctx->h_stage[k], src + off, m);
         ZB_CUDA(cudaMemcpyAsync(dst + off, ctx->h_stage[k], m, cudaMemcpyHostToDevice, s));
         ZB_CUDA(cudaEventRecord(ctx->stage_ev[k], s));
         off += m; k ^= 1;
@@ -88,7 +146,7 @@ int d2h_staged(zb200_ctx *ctx, void *h_dst, const void *d_src, size_t n, cudaStr
         size_t m = n - off < ctx->stage_bytes ? n - off : ctx->stage_bytes;
         if (pend_n[k]) {
             ZB_CUDA(cudaEventSynchronize(ctx->stage_ev[k]));
-            memcpy(dst + pend_off[k], ctx->h_stage[k], pend_n[k]);
+            host_copy(dst + pend_off[k], ctx->h_stage[k], pend_n[k]);
             pend_n[k] = 0;
         } else {
             ZB_CUDA(cudaEventSynchronize(ctx->stage_ev[k]));
@@ -101,7 +159,7 @@ int d2h_staged(zb200_ctx *ctx, void *h_dst, const void *d_src, size_t n, cudaStr
     for (int i = 0; i < 2; ++i, k ^= 1)
         if (pend_n[k]) {
             ZB_CUDA(cudaEventSynchronize(ctx->stage_ev[k]));
-            memcpy(dst + pend_off[k], ctx->h_stage[k], pend_n[k]);
+            host_copy(dst + pend_off[k], ctx->h_stage[k], pend_n[k]);
             pend_n[k] = 0;
         }
     return ZB200_OK;
@@ -337,7 +395,7 @@ int zb200_checksum_host(zb200_ctx *ctx, const void *data, size_t len, int which,
             ZB_CUDA(cudaMemcpyAsync(ctx->d_io_in, src + off, m, cudaMemcpyHostToDevice, s));
         } else {
             ZB_CUDA(cudaEventSynchronize(ctx->stage_ev[k]));
-            memcpy(ctx->h_stage[k], src + off, m);
+            host_copy(ctx->h_stage[k], src + off, m);
             ZB_CUDA(cudaMemcpyAsync(ctx->d_io_in, ctx->h_stage[k], m, cudaMemcpyHostToDevice, s));
             ZB_CUDA(cudaEventRecord(ctx->stage_ev[k], s));
         }

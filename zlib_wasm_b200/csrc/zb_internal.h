@@ -100,6 +100,8 @@ int h2d_staged(zb200_ctx *ctx, void *d_dst, const void *h_src, size_t n, cudaStr
 int d2h_staged(zb200_ctx *ctx, void *h_dst, const void *d_src, size_t n, cudaStream_t s);
 // pinned host memory is DMA-ed directly (async); pageable memory goes through the stages
 bool is_pinned(const void *p);
+// memcpy between pageable caller memory and the pinned stages, split over a few host threads from 4 MiB up (zb_engine.cu)
+void host_copy(void *dst, const void *src, size_t n);
 int h2d_auto(zb200_ctx *ctx, void *d_dst, const void *h_src, size_t n, cudaStream_t s);
 int d2h_auto(zb200_ctx *ctx, void *h_dst, const void *d_src, size_t n, cudaStream_t s);
 // zb_engine.cu: mark the start of the kernel `name` on stream s (name == nullptr: end of a pipeline); no-op unless profiling
