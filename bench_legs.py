@@ -74,6 +74,18 @@ def gpu_numa(dev):
             node = None
     except Exception:
         node, cpus = None, None
+    if not cpus:                                              # sysfs does not say (containers often show -1): ask NVML for the GPU's CPUs
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[dev]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else dev
+            words = pynvml.nvmlDeviceGetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(idx), (os.cpu_count() + 63) // 64)
+            got = {64 * w + b for w, v in enumerate(words) for b in range(64) if (int(v) >> b) & 1} & os.sched_getaffinity(0)
+            if got and got != os.sched_getaffinity(0):
+                cpus = got
+        except Exception:
+            pass
     _numa[dev] = (node, cpus or None)
     return _numa[dev]
 
@@ -784,7 +796,8 @@ def link_probe(g, nbytes=1 << 30, reps=4):
     h[::4096] = 1                                            # (every page touched)
     d = torch.empty(2 * nbytes, dtype=torch.uint8, device="cuda")
     s2 = torch.cuda.Stream()
-    out = {"bytes_per_copy": nbytes, "copies": reps, "numa_node": gpu_numa(dev)[0]}
+    out = {"bytes_per_copy": nbytes, "copies": reps, "numa_node": gpu_numa(dev)[0],
+           "local_cpus": len(gpu_numa(dev)[1]) if gpu_numa(dev)[1] else None, "host_cpus": len(os.sched_getaffinity(0))}
 
     def run(kind):
         def once():

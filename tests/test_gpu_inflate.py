@@ -476,3 +476,30 @@ def test_one_member_decoded_in_parallel_at_block_headers(ctx):
     bad = bytearray(s); bad[-2] ^= 1
     res, out = _stream(ctx, bytes(bad), refz.WRAP_GZIP, len(d) + 16)
     assert msg(res.status) == "incorrect length check"
+
+
+def test_gunzip_few_large_members(ctx):
+    """The usual .gz file — one member, or a few, each of many MB without a flush point (gzip / the reference's gzwrite):
+    zb200_gunzip_host takes them one after the other through the single-stream decoders (block-header chunks in parallel)
+    instead of one team per member; same bytes, same member table, trailing bytes ignored, damage reported."""
+    import gzip
+    parts = [refz.gen(n, kind, seed=n) for n, kind in ((7000000, refz.GEN_MARKOV), (5000000, refz.GEN_MIXED), (3000000, refz.GEN_TEXT))]
+    blobs = [gzip.compress(p, 6) for p in parts]
+    whole, plain = b"".join(blobs), b"".join(parts)
+    ctx.profile(True)
+    r, st, out, olen, nm, tab = _gunzip(ctx, whole + b"\0\0trailing", len(plain) + 64, 8)
+    prof = ctx.profile_read()
+    ctx.profile(False)
+    assert r == 0 and st == 0 and out == plain and nm == 3, (r, st, olen, nm)
+    assert any("count" in k for k in prof), sorted(prof)      # the chunk kernels decoded them
+    off_in = off_out = 0
+    for m, b, p in zip(tab, blobs, parts):
+        assert (m.in_off, m.in_len, m.out_off, m.out_cap) == (off_in, len(b), off_out, len(p))
+        off_in += len(b); off_out += len(p)
+    r, st, out, olen, nm, tab = _gunzip(ctx, blobs[0], len(parts[0]) + 64, 8)
+    assert r == 0 and st == 0 and out == parts[0] and nm == 1
+    bad = bytearray(whole); bad[len(blobs[0]) + len(blobs[1]) // 2] ^= 0x20     # damage inside the second member: the first is delivered
+    r, st, out, olen, nm, tab = _gunzip(ctx, bytes(bad), len(plain) + 64, 8)
+    assert r == 0 and st != 0 and nm == 1 and out == parts[0], (r, st, nm, len(out))
+    r, st, out, olen, nm, tab = _gunzip(ctx, whole, 1000, 8)                    # too small an output buffer: the size needed
+    assert r == zb.ERR_OUTPUT and olen == len(plain), (r, olen)
