@@ -478,6 +478,28 @@ def test_one_member_decoded_in_parallel_at_block_headers(ctx):
     assert msg(res.status) == "incorrect length check"
 
 
+def test_block_parallel_decode_sees_distances_too_far_back(ctx):
+    """The counting pass of the chunk decode does not know what lies before a chunk, so it cannot see a distance that
+    reaches before the start of the stream; the second pass does, and its verdict is checked before its match list is
+    used (tools/fuzz_blocks.py found both orders wrong: "output buffer full" reported ahead of the reference's "invalid
+    distance too far back", and a half-written match list resolved).  A raw stream compressed behind a preset
+    dictionary, decoded without it, is such a stream from its first matches on and valid everywhere else."""
+    import zlib
+    dic = refz.gen(32768, refz.GEN_MARKOV, seed=5)
+    d = dic[1000:30000] + refz.gen(3000000, refz.GEN_MARKOV, seed=6)
+    co = zlib.compressobj(6, zlib.DEFLATED, -15, 8, 0, dic)
+    s = co.compress(d) + co.flush()
+    for cap in (len(d) + 64, 100000, 0):
+        res, out = _stream(ctx, s, refz.WRAP_RAW, cap)
+        one, res1 = ctx.inflate_host(s, [(0, len(s), 0, cap)], refz.WRAP_RAW, 1, out_size=max(cap, 1))
+        assert msg(res1[0].status) == "invalid distance too far back"
+        assert res.status == res1[0].status, (cap, msg(res.status))
+    # with the dictionary in place the same stream is fine (and takes the chunk path where it is offered one: members given
+    # a dictionary are decoded by the batch kernels)
+    out, res2 = ctx.inflate_host(s, [(0, len(s), 32768, len(d), 0, 0, 32768)], refz.WRAP_RAW, 1, out_size=32768 + len(d), prefill=dic)
+    assert res2[0].status == 0 and out[32768:32768 + res2[0].out_len] == d
+
+
 def test_gunzip_few_large_members(ctx):
     """The usual .gz file — one member, or a few, each of many MB without a flush point (gzip / the reference's gzwrite):
     zb200_gunzip_host takes them one after the other through the single-stream decoders (block-header chunks in parallel)

@@ -1336,7 +1336,9 @@ int inflate_stream_blocks(zb200_ctx *ctx, const uint8_t *src, size_t n, int wrap
     uint64_t end = final_status == ZB200_INF_OK ? fin.in_used : stop_bit >> 3;
     *in_used = (size_t)end;
     if (end_bit) *end_bit = final_status == ZB200_INF_OK ? 0u : (uint32_t)(stop_bit & 7);
-    if (total > out_cap) { *status = ZB200_INF_OUTPUT_FULL; return ZB200_OK; }
+    // (an output buffer that is too small is reported only once the second decode has confirmed the chain: the counting pass
+    //  does not know what lies before a chunk, so it cannot see a distance that reaches too far back — found by
+    //  tools/fuzz_blocks.py: a spliced stream came back "output buffer full" where the reference says "invalid distance")
     // 4. list + 5. resolve, group after group of chunks
     if ((r = ensure_io(ctx, n + 16, hist_len + total + 16))) return r;
     uint8_t *d_out = ctx->d_io_out;
@@ -1391,6 +1393,16 @@ int inflate_stream_blocks(zb200_ctx *ctx, const uint8_t *src, size_t n, int wrap
         ca.cand = d_cand; ca.n_cand = nc; ca.mbase = d_mbase + k0; ca.mlist = d_ml; ca.nmatch = nullptr;
         if ((r = inflate_chunks_launch(ctx, INF_LIST, ctx->d_io_in, d_out, d_members + k0, ng, kind, d_results + k0, d_counter, ca, s))) return r;
         ZB_CUDA(cudaMemcpyAsync(resB.data() + k0, d_results + k0, ng * sizeof(zb200_member_result), cudaMemcpyDeviceToHost, s));
+        // The second decode must tell the first one's story (it adds the "too far back" test) BEFORE its match list is used:
+        // a chunk that stopped early leaves the rest of its part of the list unwritten (found by tools/fuzz_blocks.py).
+        ZB_CUDA(cudaStreamSynchronize(s));
+        for (size_t k = k0; k < k1; ++k) {
+            const zb200_member_result &a = res[chain[k].idx], &b = resB[k];
+            if (a.status != b.status || b.out_len != chain[k].out_off + a.out_len || a.resume_bit != b.resume_bit) {
+                *applicable = 0; *out_len = 0; *status = ZB200_INF_OK; *in_used = 0;
+                return ZB200_OK;
+            }
+        }
         const uint32_t lo = (uint32_t)(hist_len + o0), sbase = lo > 32768u ? lo - 32768u : 0u;
         const uint64_t gn = o1 - o0, gm = m1 - m0;
         if (gm) {
@@ -1419,16 +1431,9 @@ int inflate_stream_blocks(zb200_ctx *ctx, const uint8_t *src, size_t n, int wrap
             ZB_LAUNCHED();
             ZB_CHECK_LAUNCH();
         }
-        ZB_CUDA(cudaStreamSynchronize(s));
-        for (size_t k = k0; k < k1; ++k) {                   // the second decode must tell the first one's story (it adds the "too far back" test)
-            const zb200_member_result &a = res[chain[k].idx], &b = resB[k];
-            if (a.status != b.status || b.out_len != chain[k].out_off + a.out_len || a.resume_bit != b.resume_bit) {
-                *applicable = 0; *out_len = 0; *status = ZB200_INF_OK; *in_used = 0;
-                return ZB200_OK;
-            }
-        }
     }
     prof_mark(ctx, s, nullptr);
+    if (total > out_cap) { *status = ZB200_INF_OUTPUT_FULL; return ZB200_OK; }   // (*out_len says how much room is needed)
     // the check value over the whole, the bytes back, the trailer (inflate.c:1183-1219)
     const int ck = cont ? cont->check_kind : kind;
     uint8_t *d_final = d_out + hist_len;

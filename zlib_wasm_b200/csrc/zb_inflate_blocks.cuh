@@ -95,19 +95,29 @@ ZB_HD bool blk_header_valid(const uint32_t *__restrict__ w, uint64_t nwords, uin
     uint64_t p = b + 17 + 3 * (uint64_t)ncode;
     const uint32_t total = nlen + ndist;
     uint32_t have = 0, prev = 0, kl = 0, kd = 0, nzl = 0, nzd = 0, eob = 0;   // Kraft sums in units of 2^-15
+    // a 64-bit window over the stream, topped up a word at a time (a code and its extra bits take at most 14)
+    uint64_t hold = blk_bits64(w, nwords, p);
+    uint32_t nb = 64;                                                         // valid bits in hold; the next unread bit is p + nb
     while (have < total) {
         if (p >= total_bits) return false;
-        const uint32_t v = (uint32_t)blk_bits64(w, nwords, p);
+        if (nb < 32) {
+            const uint64_t q = p + nb, i = q >> 5;                            // 32 more bits from bit q on (two words unless q is aligned)
+            const uint32_t sh = (uint32_t)q & 31u;
+            const uint32_t w0 = i < nwords ? w[i] : 0u, w1 = sh && i + 1 < nwords ? w[i + 1] : 0u;
+            hold |= (uint64_t)funnel_r(w0, w1, sh) << nb;
+            nb += 32;
+        }
+        const uint32_t v = (uint32_t)hold;
         const uint32_t e = tab[v & 127u], sym = e & 31u, l = e >> 5;          // (the code is complete: every pattern decodes)
-        uint32_t rep = 1, val = sym;
-        p += l;
+        uint32_t rep = 1, val = sym, used = l;
         if (sym >= 16) {
             const uint32_t xb = v >> l;
-            if (sym == 16) { if (have == 0) return false; val = prev; rep = 3 + (xb & 3u); p += 2; }
-            else if (sym == 17) { val = 0; rep = 3 + (xb & 7u); p += 3; }
-            else { val = 0; rep = 11 + (xb & 127u); p += 7; }
+            if (sym == 16) { if (have == 0) return false; val = prev; rep = 3 + (xb & 3u); used += 2; }
+            else if (sym == 17) { val = 0; rep = 3 + (xb & 7u); used += 3; }
+            else { val = 0; rep = 11 + (xb & 127u); used += 7; }
             if (have + rep > total) return false;                             // inflate.c:979-983 "invalid bit length repeat"
         }
+        p += used; hold >>= used; nb -= used;
         prev = val;
         if (val) {
             const uint32_t unit = 32768u >> val;
