@@ -12,7 +12,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import refz  # noqa: E402
 import zlib_wasm_b200 as zb  # noqa: E402
 
-z = refz.ZlibBinding(zb.LIB_PATH, "")
+z = refz.ZlibBinding(os.path.join(ROOT, os.environ["ZB_LIB"]) if os.environ.get("ZB_LIB") else zb.LIB_PATH, "")
 ref = refz.ref()
 rng = random.Random(int(sys.argv[1]) if len(sys.argv) > 1 else 1)
 base = refz.gen(9000000, refz.GEN_MARKOV, seed=4)

@@ -810,7 +810,7 @@ flush_candidates_kernel(const uint8_t *__restrict__ in, uint64_t lo, uint64_t n,
 
 int inflate_stream_blocks(zb200_ctx *ctx, const uint8_t *src, size_t n, int wrap, uint8_t *out, size_t out_cap,
                           size_t *out_len, int *status, size_t *in_used, uint32_t *check, int *applicable,
-                          const StreamContinuation *cont, bool uploaded, bool prefix_ok, uint32_t *end_bit);
+                          const StreamContinuation *cont, bool uploaded, bool prefix_ok, uint32_t *end_bit, StreamOutAlt *alt);
 
 struct GatherSeg { uint64_t src, dst, len; };
 __global__ void __launch_bounds__(256)
@@ -992,7 +992,7 @@ int inflate_launch(zb200_ctx *ctx, const uint8_t *d_in, uint8_t *d_out, const zb
 // nothing copied), *in_used the stream's length, *check its computed check value.
 int inflate_stream_parallel(zb200_ctx *ctx, const uint8_t *src, size_t n, int wrap, uint8_t *out, size_t out_cap,
                             size_t *out_len, int *status, size_t *in_used, uint32_t *check, int *applicable,
-                            const StreamContinuation *cont, int blocks_mode, uint32_t *end_bit) {
+                            const StreamContinuation *cont, int blocks_mode, uint32_t *end_bit, StreamOutAlt *alt) {
     *applicable = 0; *out_len = 0; *status = ZB200_INF_OK; *in_used = 0; *check = 0;
     if (end_bit) *end_bit = 0;
     if (n < 64) return ZB200_OK;
@@ -1000,7 +1000,7 @@ int inflate_stream_parallel(zb200_ctx *ctx, const uint8_t *src, size_t n, int wr
     auto blocks = [&](bool uploaded) {
         if (!blocks_mode) return (int)ZB200_OK;
         return inflate_stream_blocks(ctx, src, n, wrap, out, out_cap, out_len, status, in_used, check, applicable, cont, uploaded,
-                                     blocks_mode == 2, end_bit);
+                                     blocks_mode == 2, end_bit, alt);
     };
     const size_t hist_len = cont ? cont->hist_len : 0;
     if (cont && (wrap != ZB200_WRAP_RAW || hist_len > 32768 || cont->bit0 > 7)) return ZB200_ERR_PARAM;
@@ -1142,7 +1142,11 @@ int inflate_stream_parallel(zb200_ctx *ctx, const uint8_t *src, size_t n, int wr
         }
     }
     *in_used = (size_t)end;
-    if (produced > out_cap) { *status = ZB200_INF_OUTPUT_FULL; return ZB200_OK; }
+    if (produced > out_cap) {                                // the caller's second chance: a buffer it grows to the size needed
+        uint8_t *p = alt ? alt->grow(alt->self, (size_t)produced) : nullptr;
+        if (!p) { *status = ZB200_INF_OUTPUT_FULL; return ZB200_OK; }
+        out = p; out_cap = (size_t)produced; alt->used = true;
+    }
     const size_t gtab = align_up(good * sizeof(GatherSeg) + 16, 256);
     if ((r = ensure_scratch(ctx, gtab + 1024 + produced + 16))) return r;
     uint8_t *base = (uint8_t *)ctx->d_scratch;
@@ -1216,7 +1220,7 @@ static int inflate_chunks_launch(zb200_ctx *ctx, int mode, const uint8_t *d_in, 
 constexpr uint64_t kBlkGroupOut = (uint64_t)256 << 20;       // output bytes resolved together (4 bytes of scratch per byte)
 int inflate_stream_blocks(zb200_ctx *ctx, const uint8_t *src, size_t n, int wrap, uint8_t *out, size_t out_cap,
                           size_t *out_len, int *status, size_t *in_used, uint32_t *check, int *applicable,
-                          const StreamContinuation *cont, bool uploaded, bool prefix_ok, uint32_t *end_bit) {
+                          const StreamContinuation *cont, bool uploaded, bool prefix_ok, uint32_t *end_bit, StreamOutAlt *alt) {
     *applicable = 0; *out_len = 0; *status = ZB200_INF_OK; *in_used = 0; *check = 0;
     if (end_bit) *end_bit = 0;
     static const int knob = [] { const char *e = getenv("ZB200_INF_BLOCKS"); return e ? atoi(e) : 1; }();
@@ -1433,7 +1437,11 @@ int inflate_stream_blocks(zb200_ctx *ctx, const uint8_t *src, size_t n, int wrap
         }
     }
     prof_mark(ctx, s, nullptr);
-    if (total > out_cap) { *status = ZB200_INF_OUTPUT_FULL; return ZB200_OK; }   // (*out_len says how much room is needed)
+    if (total > out_cap) {                                   // (*out_len says how much room is needed; the caller may offer a buffer it grows)
+        uint8_t *p = alt ? alt->grow(alt->self, (size_t)total) : nullptr;
+        if (!p) { *status = ZB200_INF_OUTPUT_FULL; return ZB200_OK; }
+        out = p; out_cap = (size_t)total; alt->used = true;
+    }
     // the check value over the whole, the bytes back, the trailer (inflate.c:1183-1219)
     const int ck = cont ? cont->check_kind : kind;
     uint8_t *d_final = d_out + hist_len;

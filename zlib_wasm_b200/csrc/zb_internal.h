@@ -137,9 +137,13 @@ int checksum_launch(zb200_ctx *ctx, const uint8_t *d_base, const uint64_t *d_off
 // cont != nullptr: src continues a raw stream at a block boundary (bit `bit0` of src[0]) whose last hist_len (<= 32768)
 // output bytes are `hist`; *check then covers the bytes produced by this call only (check_kind 1: Adler-32, else CRC-32).
 struct StreamContinuation { const uint8_t *hist; size_t hist_len; uint32_t bit0; int check_kind; };
+// alt (optional): where the output goes when it does not fit `out` — grow(self, need) returns a buffer of at least `need` bytes
+// (or nullptr: ZB200_INF_OUTPUT_FULL as without it); `used` tells the caller which of the two holds the bytes.
+struct StreamOutAlt { uint8_t *(*grow)(void *self, size_t need); void *self; bool used; };
 int inflate_stream_parallel(zb200_ctx *ctx, const uint8_t *src, size_t n, int wrap, uint8_t *out, size_t out_cap,
                             size_t *out_len, int *status, size_t *in_used, uint32_t *check, int *applicable,
-                            const StreamContinuation *cont = nullptr, int blocks_mode = 0, uint32_t *end_bit = nullptr);
+                            const StreamContinuation *cont = nullptr, int blocks_mode = 0, uint32_t *end_bit = nullptr,
+                            StreamOutAlt *alt = nullptr);
 // blocks_mode: what to do with a stream that has no (or too few) flush points — 0: leave it to the caller's one-member path,
 // 1: decode it in parallel at its dynamic block headers (zb_inflate_blocks.cuh) when the whole stream is there, 2: also when
 // only a prefix can be delivered (ZB200_INF_TRUNCATED; the prefix ends at bit *end_bit of src[*in_used], a block boundary).
