@@ -13,6 +13,8 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import refz  # noqa: E402
 import zlib_wasm_b200 as zb  # noqa: E402
 
+if os.environ.get("ZB_LIB"):
+    zb.LIB_PATH = os.path.join(ROOT, os.environ["ZB_LIB"])
 ctx = zb.Context(0)
 sizes = [int(a) << 20 for a in sys.argv[1:]] or [1 << 20, 16 << 20, 64 << 20, 256 << 20]
 for n in sizes:

@@ -255,7 +255,10 @@ blk_src_build_kernel(const QueuedMatch *__restrict__ ml, uint64_t n_matches, uin
 // kJumpHops times in a row — and is final as soon as it meets a literal, a final entry or a byte before lo.  Sources
 // lie behind their bytes and CTAs run in ascending order, so most entries meet a final one in the first pass; entries
 // that are final cost later passes one streamed read.  Updates are made in place: any value read is a valid ancestor.
-constexpr int kJumpHops = 4;
+#ifndef ZB_JUMP_HOPS
+#define ZB_JUMP_HOPS 4
+#endif
+constexpr int kJumpHops = ZB_JUMP_HOPS;
 __device__ __forceinline__ uint32_t blk_follow(const uint32_t *__restrict__ src, uint32_t v, uint32_t lo, uint32_t base, bool &open) {
     if (v & kSrcFinal) return v;                             // (kSrcLiteral included)
     uint32_t cur = v;
