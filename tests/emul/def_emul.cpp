@@ -6,6 +6,7 @@
 #include <string.h>
 #include <stdlib.h>
 #include <vector>
+#include <algorithm>
 #include "../../zlib_wasm_b200/csrc/zb_deflate.cuh"
 
 using namespace zb;
@@ -21,6 +22,13 @@ struct BitSink {
             if ((v >> i) & 1) { if ((bit >> 3) < cap) out[bit >> 3] |= (uint8_t)(1u << (bit & 7)); }
     }
 };
+
+// ONE long chunk worked on by many CTAs (zb_deflate.cu: chain kernel in ranges, dfl_parse_multi_kernel): emul_set_multi(G,
+// range) makes the replay below hand the lazy parse from CTA to CTA over G x kSegLanes segments (cold settle, provisional
+// link, settle against the predecessor's provisional end, compare with its true end, count link) and build the chain
+// links range by range behind w_size re-inserted positions; the matches and the parse must still be the serial ones.
+static uint32_t g_multi_G = 0, g_multi_range = 0;
+extern "C" void emul_set_multi(uint32_t G, uint32_t range) { g_multi_G = G; g_multi_range = range; }
 
 // One chunk -> raw deflate bytes (blocks + marker when !final).  Returns size or -1.
 // `skip`: the first skip bytes are a preset dictionary (history only).
@@ -38,6 +46,24 @@ extern "C" long emul_deflate_chunk_opts(const uint8_t *data, uint32_t n, uint32_
             const int32_t q = head[h];
             prev[p] = (q > 0 && p - (uint32_t)q <= 65535u) ? (uint16_t)(p - (uint32_t)q) : 0;
             head[h] = (int32_t)p;
+        }
+        if (g_multi_range) {                                   // links as the ranged chain kernel draws them: the matches must not change
+            std::vector<uint16_t> prev2(n + 1, 0);
+            for (uint32_t lo_r = 0; lo_r < n; lo_r += g_multi_range) {
+                const uint32_t hi_r = n - lo_r < g_multi_range ? n : lo_r + g_multi_range, warm = lo_r > prm.w_size ? lo_r - prm.w_size : 0;
+                std::fill(head.begin(), head.end(), -1);
+                for (uint32_t p = warm; p < hi_r && p + kMinMatch <= n; ++p) {
+                    const uint32_t h = hash3(data + p, prm);
+                    const int32_t q = head[h];
+                    if (p >= lo_r) prev2[p] = (q > 0 && p - (uint32_t)q <= 65535u) ? (uint16_t)(p - (uint32_t)q) : 0;
+                    head[h] = (int32_t)p;
+                }
+            }
+            for (uint32_t p = 0; p < n; ++p) {
+                const MatchPair a = match_at(data, n, prev.data(), p, prm), b = match_at(data, n, prev2.data(), p, prm);
+                if (a.full != b.full || a.quarter != b.quarter) return -11;
+            }
+            prev.swap(prev2);
         }
         for (uint32_t p = 0; p < n; ++p) {
             MatchPair r = match_at(data, n, prev.data(), p, prm); mf[p] = r.full; mq[p] = r.quarter;
@@ -82,6 +108,72 @@ extern "C" long emul_deflate_chunk_opts(const uint8_t *data, uint32_t n, uint32_
             entry = t0 + exit_rel; nsyms += total;
         }
         sink.nsyms = nsyms; sink.nblocks = seg_finish(blocks.data(), nsyms, false, n, prm, final_chunk != 0, skip);
+    } else if (g_multi_G >= 2) {
+        const uint32_t G = g_multi_G, m = n - skip;
+        struct WinAcc { const uint8_t *data; const uint32_t *mfull, *mquarter; uint32_t *out; uint32_t at;
+                        uint32_t mf(uint32_t p) const { return mfull[p]; } uint32_t mq(uint32_t p) const { return mquarter[p]; }
+                        uint32_t byte(uint32_t p) const { return data[p]; } void put(uint32_t sym) { if (out) out[at++] = sym; }
+                        uint32_t windows(uint32_t) const { return 1; } uint32_t open(uint32_t, uint32_t) { return 0xffffffffu; } bool any(bool b) const { return b; } };
+        WinAcc cacc{data, mf.data(), mq.data(), nullptr, 0};
+        std::vector<SegGeom> geo(G);
+        std::vector<std::vector<SegRec>> rec(G, std::vector<SegRec>((kSegRecs - 1) * kSegLanes));
+        std::vector<std::vector<SegLane>> lanes(G, std::vector<SegLane>(kSegLanes));
+        std::vector<SegState> prov(G), fin(G), pred(G);
+        std::vector<uint32_t> total(G, 0), before(G, 0);
+        auto settle = [&](uint32_t k) -> int {
+            SegGeom &g = geo[k];
+            for (int pass = 0;; ++pass) {
+                if (pass > (int)kSegLanes + 8) return -20;
+                SegState t[kSegLanes]; bool need[kSegLanes], any = false;
+                for (uint32_t l = 0; l < g.nact; ++l) {
+                    t[l] = l ? lanes[k][l - 1].end : pred[k];
+                    need[l] = t[l].p != lanes[k][l].start.p || t[l].w0 != lanes[k][l].start.w0;
+                    any |= need[l];
+                }
+                if (!any) return 0;
+                for (uint32_t l = 0; l < g.nact; ++l) if (need[l]) seg_fix(lanes[k][l], l, g, n, prm, cacc, rec[k].data(), t[l]);
+            }
+        };
+        for (uint32_t k = 0; k < G; ++k) {                        // every CTA on its own: speculate, settle from a cold start
+            SegGeom &g = geo[k];
+            const uint64_t all = (uint64_t)G * kSegLanes * kSegRecs;
+            g.blk = (uint32_t)((m + all - 1) / all); if (g.blk < 32) g.blk = 32;
+            g.seg = g.blk * kSegRecs;
+            const uint32_t nact_total = m ? (m + g.seg - 1) / g.seg : 1;
+            const uint64_t first = (uint64_t)k * kSegLanes;
+            g.nact = nact_total > first ? (nact_total - first < kSegLanes ? (uint32_t)(nact_total - first) : kSegLanes) : 0u;
+            g.lo = g.nact ? skip + (uint32_t)first * g.seg : n;
+            for (uint32_t l = 0; l < g.nact; ++l) seg_speculate(lanes[k][l], l, g, n, prm, cacc, rec[k].data());
+            pred[k] = seg_cold(g.lo);
+            if (settle(k)) return -20;
+            prov[k] = g.nact ? lanes[k][g.nact - 1].end : pred[k];
+        }
+        uint32_t refixed = 0;
+        for (uint32_t k = 0; k < G; ++k) {                        // the chain of links, in ticket order
+            if (k) {
+                pred[k] = prov[k - 1];
+                if (settle(k)) return -20;
+                if (fin[k - 1].p != pred[k].p || fin[k - 1].w0 != pred[k].w0) { pred[k] = fin[k - 1]; ++refixed; if (settle(k)) return -20; }
+            }
+            fin[k] = geo[k].nact ? lanes[k][geo[k].nact - 1].end : pred[k];
+            for (uint32_t l = 0; l < geo[k].nact; ++l) total[k] += lanes[k][l].count;
+            before[k] = k ? before[k - 1] + total[k - 1] : 0;
+        }
+        for (int k = (int)G - 1; k >= 0; --k) {                   // any CTA order must do for the emit
+            uint32_t first = before[k];
+            for (uint32_t l = 0; l < geo[k].nact; ++l) {
+                WinAcc eacc{data, mf.data(), mq.data(), syms.data(), first};
+                seg_emit(lanes[k][l], l, geo[k], n, prm, eacc, blocks.data(), first);
+                first += lanes[k][l].count;
+                if (eacc.at != first) return -21;
+            }
+        }
+        const uint32_t all_syms = before[G - 1] + total[G - 1];
+        const bool pending = (fin[G - 1].w0 >> 25) & 1u;
+        if (pending) syms[all_syms] = data[n - 1];
+        sink.nsyms = all_syms + (pending ? 1 : 0);
+        sink.nblocks = seg_finish(blocks.data(), all_syms, pending, n, prm, final_chunk != 0, skip);
+        if (stats) stats[2] = refixed;
     } else {
         const SegGeom g = seg_geometry(n, skip);
         std::vector<SegRec> rec((kSegRecs - 1) * kSegLanes);

@@ -373,6 +373,44 @@ def test_deflate_window_bits_and_mem_level_byte_exact():
                     assert err == 1 and back == d and len(got) <= 1.03 * len(want) + 8, (kind, wbits, mem, level, strat, err, msg)
 
 
+def test_one_run_shared_by_many_ctas_replay():
+    """zb_deflate.cu hands a long chunk's ordered phases to many CTAs: chain links drawn range by range behind w_size
+    re-inserted positions, the lazy parse handed from CTA to CTA (cold settle, provisional link, settle against the
+    predecessor's provisional end, compare with its true end).  The host replay does the same with loops: the matches must
+    be the ones of one head table over the whole chunk, the symbols and blocks the serial parse's, the bytes the
+    reference's one-shot stream."""
+    if not refz.have_ref():
+        pytest.skip("oracle/_ref/libzref.so not built")
+    L = _build("def_emul")
+    L.emul_deflate_chunk_opts.restype = C.c_long
+    L.emul_deflate_chunk_opts.argtypes = [C.c_char_p, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                          C.c_size_t, C.POINTER(C.c_uint32)]
+    L.emul_set_multi.argtypes = [C.c_uint32, C.c_uint32]
+    ref = refz.ref()
+    try:
+        for kind, n in ((refz.GEN_TEXT, 300000), (refz.GEN_MIXED, 524288 + 77), (refz.GEN_MARKOV, 131072)):
+            d = refz.gen(n, kind, seed=61 + kind)
+            for G, rng in ((2, 65536), (3, 40960), (7, 16384), (16, 131072)):
+                for level, strat, wbits, mem in ((6, 0, 15, 8), (9, 0, 15, 8), (4, 1, 15, 8), (6, 4, 12, 8), (5, 0, 15, 3)):
+                    if rng < (1 << wbits) // 4:
+                        continue
+                    L.emul_set_multi(G, rng)
+                    cap = n + n // 4 + 4096
+                    out, st = C.create_string_buffer(cap), (C.c_uint32 * 4)()
+                    r = L.emul_deflate_chunk_opts(d, n, 0, level, strat, wbits, mem, 1, out, cap, st)
+                    assert r >= 0, (r, kind, n, G, rng, level, strat, wbits, mem)
+                    strm = refz.ZStream()
+                    assert ref.deflateInit2_(C.byref(strm), level, 8, -wbits, mem, strat, ref.version, C.sizeof(refz.ZStream)) == 0
+                    src, dst = C.create_string_buffer(d, n), C.create_string_buffer(cap)
+                    strm.next_in, strm.avail_in, strm.next_out, strm.avail_out = C.addressof(src), n, C.addressof(dst), cap
+                    assert ref.deflate(C.byref(strm), refz.Z_FINISH) == refz.Z_STREAM_END
+                    want = dst.raw[:cap - strm.avail_out]
+                    ref.deflateEnd(C.byref(strm))
+                    assert out.raw[:r] == want, (kind, n, G, rng, level, strat, wbits, mem, r, len(want))
+    finally:
+        L.emul_set_multi(0, 0)
+
+
 def test_keyed_heap_tree_builder_equals_the_transliterated_one():
     """tree_build_fast (what dfl_tree_kernel runs: the active heap carries (Freq << 8 | depth) beside the node number)
     must reproduce trees.c:627-706 exactly — the tie-breaks of trees.c:499-501 decide the code lengths.  Random, flat,
