@@ -279,7 +279,7 @@ dfl_match_kernel(Batch b, DeflateParams prm, const uint16_t *__restrict__ prev_a
 // walks of its tile can touch — the 32 KiB of history before the tile, the tile and its
 // lookahead (input bytes) and the chain links of the same positions — with coalesced
 // 16-byte loads; a 16 Ki-position tile makes that 9 bytes of staging per position.
-constexpr uint32_t kMsTile = 16384, kMsThreads = 1024, kMsBuckets = 32;
+constexpr uint32_t kMsTile = 16384, kMsThreads = 1024, kMsBuckets = 48;
 constexpr uint32_t kMsLook = kMaxMatch + 16;                                  // bytes a walk may read past its position
 constexpr uint32_t kMsDataBytes = (kWSize + kMsTile + kMsLook + 32 + 15) & ~15u;   // + alignment skew / slack
 constexpr uint32_t kMsLinkBytes = ((kWSize + kMsTile) * 2 + 32 + 15) & ~15u;
@@ -287,7 +287,7 @@ constexpr uint32_t kMsSmem = kMsDataBytes + kMsLinkBytes + kMsTile * 2;
 __device__ __forceinline__ uint32_t depth_bucket(uint32_t e) {   // 0,1,2,3, then four buckets per octave
     if (e < 4u) return e;
     const uint32_t l = 31u - (uint32_t)__clz(e);
-    return 4u + (l - 2u) * 4u + ((e >> (l - 2u)) & 3u);          // e <= 255 -> at most 27
+    return 4u + (l - 2u) * 4u + ((e >> (l - 2u)) & 3u);          // e <= 4095 -> at most 43
 }
 extern __shared__ __align__(16) uint8_t ms_smem[];
 // Operands from the staged window.  Addresses are 32-bit shared-space addresses held in
@@ -1323,7 +1323,9 @@ int deflate_launch_opts(zb200_ctx *ctx, const uint8_t *d_in, size_t n, size_t S,
         if (sorted_walks) {
             dim3 g((unsigned)((S + kMsTile - 1) / kMsTile), b.nb);
             prof_mark(ctx, s, "dfl_match_sorted_kernel");
-            static const uint32_t key_cap = [] { const char *e = getenv("ZB200_KEY_CAP"); const int v = e ? atoi(e) : 8; return (uint32_t)(v < 1 ? 1 : v > 255 ? 255 : v); }();
+            static const int key_knob = [] { const char *e = getenv("ZB200_KEY_CAP"); return e ? atoi(e) : 0; }();
+            uint32_t key_cap = (uint32_t)(key_knob > 0 ? key_knob : prm.chain / 16);   // (level 6: 8, level 9: 256)
+            key_cap = key_cap < 8 ? 8 : key_cap > 4095 ? 4095 : key_cap;
             dfl_match_sorted_kernel<<<g, kMsThreads, kMsSmem, s>>>(b, prm, w.prev, w.mfull, w.mquarter, key_cap);
             ZB_LAUNCHED(); ZB_CHECK_LAUNCH();
         } else if (prm.mode == MODE_FAST) {                        // levels 1-2
