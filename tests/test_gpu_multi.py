@@ -65,7 +65,7 @@ def test_multi_matches_single(both):
 
 def test_zlib_api_over_all_devices(tmp_path):
     """$ZB200_DEVICES=all: compress2 / crc32_z / adler32_z of large buffers behind the zlib.h names run on every GPU and
-    give what one GPU gives (read once per process: checked in a child process)."""
+    give what one GPU gives for the same chunking (read once per process: checked in child processes)."""
     import os
     import subprocess
     import sys
@@ -81,12 +81,18 @@ assert z.compress2(dst, C.byref(cap), d, len(d), 6) == 0
 print(hashlib.sha256(dst.raw[:cap.value]).hexdigest(), z.crc32_z(0, d, len(d)), z.adler32_z(1, d, len(d)))
 ''' % (refz.ROOT, os.path.join(refz.ROOT, "tests"))
     outs = []
-    for env_val in (None, "all"):
+    # one GPU emits the reference's ONE run of blocks for a one-shot call (round 2); a run cannot be cut across GPUs, so the
+    # sharded call emits the chunked stream — the bytes one GPU gives when it is told to chunk ($ZB200_SINGLE_RUN_MAX=0)
+    for devices, single_run in ((None, "0"), ("all", None), (None, None)):
         env = dict(os.environ)
         env.pop("ZB200_DEVICES", None)
-        if env_val:
-            env["ZB200_DEVICES"] = env_val
+        env.pop("ZB200_SINGLE_RUN_MAX", None)
+        if devices:
+            env["ZB200_DEVICES"] = devices
+        if single_run is not None:
+            env["ZB200_SINGLE_RUN_MAX"] = single_run
         r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, timeout=300)
         assert r.returncode == 0, r.stderr[-400:]
-        outs.append(r.stdout.strip())
-    assert outs[0] == outs[1] and len(outs[0]) > 64
+        outs.append(r.stdout.strip().split())
+    assert outs[0] == outs[1] and len(outs[0]) == 3
+    assert outs[2][1:] == outs[0][1:] and outs[2][0] != outs[0][0]     # same checksums; the default is the one-run stream
