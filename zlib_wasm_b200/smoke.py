@@ -42,5 +42,14 @@ def run():
             assert err == 0 and back == data and used == len(s), ("deflate parity", level, msg)
             if level >= 4:   # levels 4..9 reproduce the reference byte for byte on the same chunking
                 assert s == o.deflate_stream(data, level, 0, refz.WRAP_ZLIB, 262144), "deflate byte parity"
+    # ONE run of blocks (what compress2 emits) by several CTAs: the oracle's own one-shot stream byte for byte; and that
+    # stream — one member without flush points — decoded chunk by chunk at its block headers
+    import ctypes as C
+    one = ctx.deflate_host(data, 6, 0, zb.FRAME_ZLIB, len(data))
+    assert one == o.deflate_stream(data, 6, 0, refz.WRAP_ZLIB, 0), "one-run byte parity"
+    back = C.create_string_buffer(len(data) + 16)
+    res1 = zb.MemberResult()
+    r = zb.lib().zb200_inflate_stream_host(ctx.handle, one, len(one), zb.WRAP_ZLIB, back, len(data) + 16, C.byref(res1))
+    assert r == 0 and res1.status == 0 and back.raw[:res1.out_len] == data, "chunk-parallel inflate parity"
     print("smoke ok: launches =", zb.lib().zb200_launch_count())
     ctx.close()
