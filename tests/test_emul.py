@@ -495,3 +495,20 @@ def test_block_parallel_decode_replay():
         if wrap == 1:
             assert ck.value == zlib.adler32(d)
         assert stats[0] <= 8 * stats[1] + 2, list(stats)      # next to no false candidates (a stored block has up to 8 possible starts)
+    # adversarial: real block headers that are NOT block starts — a compressed stream carried as DATA inside stored blocks
+    # (level 0) and inside a literal-only stream (Z_HUFFMAN_ONLY) — are candidates the chain has to step over; streams of
+    # stored blocks only, and a stream cut at every kind of place, fall back or deliver what the chain proves
+    inner = zlib.compress(refz.gen(400000, refz.GEN_TEXT, seed=5), 6)
+    payload = refz.gen(100000, refz.GEN_MARKOV, seed=6) + inner + refz.gen(200000, refz.GEN_TEXT, seed=7) + inner[:50000]
+    for level, strategy in ((0, 0), (6, 2), (6, 0), (1, 3)):
+        co = zlib.compressobj(level, zlib.DEFLATED, 15, 8, strategy)
+        comp = co.compress(payload) + co.flush()
+        n = len(payload)
+        dst = C.create_string_buffer(n + 64)
+        ol, st, iu, ck, isz = u64(), C.c_int(), u64(), C.c_uint32(), C.c_uint32()
+        stats = (u64 * 4)()
+        r = L.emul_inflate_blocks(comp, len(comp), 1, dst, n + 64, C.byref(ol), C.byref(st), C.byref(iu), C.byref(ck), C.byref(isz), stats)
+        assert r >= 0, (level, strategy, r, list(stats))
+        if r >= 2:                                           # (fewer than two chunks: the caller takes the one-member path)
+            assert st.value == 0 and ol.value == n and dst.raw[:n] == payload and iu.value == len(comp), (level, strategy, list(stats))
+            assert ck.value == zlib.adler32(payload)

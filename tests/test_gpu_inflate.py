@@ -455,6 +455,15 @@ def test_one_member_decoded_in_parallel_at_block_headers(ctx):
         assert any(k.startswith("inflate_") and "count" in k for k in prof), (sorted(prof), gen, n, level)   # the chunk path decoded it
         res, out = _stream(ctx, s + b"tail", wrap, n + 16)
         assert res.status == 0 and res.in_used == len(s) and out == d
+    # adversarial: real block headers that are NOT block starts — a compressed stream carried as DATA inside stored blocks
+    # (level 0), inside a literal-only stream (Z_HUFFMAN_ONLY) and inside a normal one: candidates the chain steps over
+    inner = zlib.compress(refz.gen(2000000, refz.GEN_TEXT, seed=5), 6)
+    payload = refz.gen(300000, refz.GEN_MARKOV, seed=6) + inner + refz.gen(700000, refz.GEN_TEXT, seed=7) + inner[:200000] + bytes(100000) + inner
+    for level, strategy in ((0, 0), (6, 2), (6, 0), (1, 3), (9, 1)):
+        co = zlib.compressobj(level, zlib.DEFLATED, 31, 8, strategy)
+        s = co.compress(payload) + co.flush()
+        res, out = _stream(ctx, s, refz.WRAP_GZIP, len(payload) + 16)
+        assert res.status == 0 and out == payload and res.in_used == len(s), (level, strategy, msg(res.status), res.out_len)
     # the reference's statuses: output too small, truncated, damaged data, damaged trailer
     d = refz.gen(3000000, refz.GEN_MARKOV, seed=77)
     co = zlib.compressobj(6, zlib.DEFLATED, 31)

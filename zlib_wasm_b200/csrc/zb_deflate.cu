@@ -1445,6 +1445,10 @@ static int deflate_host_pipelined(zb200_ctx *ctx, const uint8_t *in, size_t n, s
     static const size_t piece_knob = [] { const char *e = getenv("ZB200_PIPE_PIECE_MIB"); const long v = e ? atol(e) : 0; return (size_t)(v >= 16 ? v : 0) << 20; }();
     const size_t piece_max = piece_knob ? piece_knob : (size_t)(level >= 1 && level <= 2 ? 256 : 512) << 20;
     if (piece > piece_max) piece = piece_max;
+    {   // never less than one wave of the chain kernel while the input holds two (a piece of 0.6 waves costs a whole one)
+        const size_t wave_bytes = deflate_wave_chunks(ctx, level <= 2 && opts.mem_level > 7 ? 7 : opts.mem_level) * S;
+        if (level >= 1 && piece < wave_bytes && n >= 2 * wave_bytes) piece = wave_bytes;
+    }
     piece = deflate_piece_bytes(ctx, piece, S, opts.mem_level, level);
     constexpr size_t kMaxPieces = 64;
     while ((n + piece - 1) / piece > kMaxPieces) piece += (piece + S - 1) / S * S;   // (inputs beyond 32 GiB: longer pieces)
