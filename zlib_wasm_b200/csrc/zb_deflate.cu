@@ -33,6 +33,11 @@ __device__ __forceinline__ void bar_arrive64(uint32_t id) {
         default: asm volatile("bar.arrive 4, 64;" ::: "memory"); break;
     }
 }
+// Match entries are (length << 16 | distance): bits 25..31 are free.  Bit 31 of the FULL-budget entry says that the
+// quartered search (deflate.c:1390-1392) found something else — only then is the second table written and read.  At level 6
+// the two agree at all but a few per cent of the positions: the parse stages one table instead of two (60 -> 40 KiB of
+// shared memory: five CTAs per SM instead of three) and the match kernel writes 4 bytes per position instead of 8.
+constexpr uint32_t kQuarterDiffers = 0x80000000u;
 struct DeflateDeviceTables {
     FormatTables fmt;
     StaticTrees st;
@@ -260,8 +265,9 @@ dfl_match_kernel(Batch b, DeflateParams prm, const uint16_t *__restrict__ prev_a
     const uint8_t *data = b.in + off;
     if (prm.mode == MODE_RLE) { mfull[off + p] = rle_at(data, n, p); return; }
     const MatchPair r = match_at(data, n, prev_all + off, p, prm);
-    mfull[off + p] = r.full;
-    if (prm.need_quarter) mquarter[off + p] = r.quarter;
+    const bool diff = prm.need_quarter && r.quarter != r.full;
+    mfull[off + p] = r.full | (diff ? kQuarterDiffers : 0u);
+    if (diff) mquarter[off + p] = r.quarter;
 }
 
 // The same walk with the positions of a tile handed to the warps in order of their
@@ -472,8 +478,9 @@ dfl_match_sorted_kernel(Batch b, DeflateParams prm, const uint16_t *__restrict__
     for (uint32_t i = threadIdx.x; i < cnt; i += kMsThreads) {
         const uint32_t p = t0 + s_order[i];
         const MatchPair r = match_walk(mem, n_pin, p, prm);
-        mfull[off + p] = r.full;
-        if (prm.need_quarter) mquarter[off + p] = r.quarter;
+        const bool diff = prm.need_quarter && r.quarter != r.full;
+        mfull[off + p] = r.full | (diff ? kQuarterDiffers : 0u);
+        if (diff) mquarter[off + p] = r.quarter;
     }
 }
 
@@ -559,15 +566,17 @@ constexpr uint32_t kPw = 16, kPwRow = kPw + 4;            // entries per window 
 constexpr uint32_t kPwBytesRow = 8;                       // words per byte row: [start - 1, start + 16) at any alignment
 struct WinAcc {
     const uint8_t *data; const uint32_t *mfull, *mquarter; uint32_t *out; uint32_t at;
-    uint32_t row_f, row_q, row_b;                        // shared addresses of this thread's rows (buffer 0)
+    uint32_t row_f, row_b;                               // shared addresses of this thread's rows (buffer 0)
     uint64_t abs0;                                       // absolute entry index of chunk position 0
     uintptr_t in_lo, in_hi;
-    bool use_q;
     uint32_t nw;
-    uint32_t fadj, qadj, badj;                           // current window: entry p at fadj + 4 p, byte p at badj + p
+    uint32_t fadj, badj;                                 // current window: entry p at fadj + 4 p, byte p at badj + p
     uint32_t nb[kPwBytesRow - 2];                        // bytes of the next window, on their way in registers
-    __device__ __forceinline__ uint32_t mf(uint32_t p) const { return lds_u32(fadj + 4u * p); }
-    __device__ __forceinline__ uint32_t mq(uint32_t p) const { return lds_u32(qadj + 4u * p); }
+    __device__ __forceinline__ uint32_t mf(uint32_t p) const { return lds_u32(fadj + 4u * p) & ~kQuarterDiffers; }
+    __device__ __forceinline__ uint32_t mq(uint32_t p) const {                   // (the second table only where it differs: rare)
+        const uint32_t v = lds_u32(fadj + 4u * p);
+        return (v & kQuarterDiffers) ? mquarter[abs0 + p] : v;
+    }
     __device__ __forceinline__ uint32_t byte(uint32_t p) const { return lds_u8(badj + p); }
     __device__ __forceinline__ void put(uint32_t sym) { if (out) out[at++] = sym; }
     __device__ __forceinline__ uint32_t windows(uint32_t seg) { nw = seg / kPw + 2; return nw; }
@@ -577,7 +586,6 @@ struct WinAcc {
 #pragma unroll
         for (uint32_t v = 0; v < kPw / 4; ++v) {
             asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(row_f + bo + 16u * v), "l"(mfull + wabs + 4u * v) : "memory");
-            if (use_q) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(row_q + bo + 16u * v), "l"(mquarter + wabs + 4u * v) : "memory");
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     }
@@ -611,22 +619,20 @@ struct WinAcc {
         const uint32_t bo = (w & 1u) * kPwRow * 4u * kSegLanes;
         const uint32_t wrel = (uint32_t)(wabs - abs0);                            // chunk-relative window start (wraps below 0 for the first window)
         fadj = row_f + bo - 4u * wrel;
-        qadj = row_q + bo - 4u * wrel;
         const uintptr_t a = (reinterpret_cast<uintptr_t>(data) + (uintptr_t)(wabs - abs0) - 1) & ~(uintptr_t)3;
         badj = row_b - (uint32_t)(a - reinterpret_cast<uintptr_t>(data));         // byte p sits at row_b + (addr(p) - a)
         return wrel + kPw;
     }
 };
 
-constexpr uint32_t kParseSmem = (2 * 2 * kPwRow + kPwBytesRow) * kSegLanes * 4 + (kSegRecs - 1) * kSegLanes * 8 + 2 * kSegLanes * 4 + 64;
+constexpr uint32_t kParseSmem = (2 * kPwRow + kPwBytesRow) * kSegLanes * 4 + (kSegRecs - 1) * kSegLanes * 8 + 2 * kSegLanes * 4 + 64;
 __global__ void __launch_bounds__(kSegLanes)
 dfl_parse_kernel(Batch b, DeflateParams prm, const uint32_t *__restrict__ mfull,
                  const uint32_t *__restrict__ mquarter, uint32_t *__restrict__ syms,
                  BlockInfo *__restrict__ blocks, uint32_t *__restrict__ nblocks) {
     extern __shared__ __align__(16) uint8_t ps_smem[];             // 60 KiB: over the static limit, carved by hand
     uint32_t *s_f = reinterpret_cast<uint32_t *>(ps_smem);         // [2][kSegLanes][kPwRow]
-    uint32_t *s_q = s_f + 2 * kPwRow * kSegLanes;
-    uint32_t *s_b = s_q + 2 * kPwRow * kSegLanes;                  // [kSegLanes][kPwBytesRow]
+    uint32_t *s_b = s_f + 2 * kPwRow * kSegLanes;                  // [kSegLanes][kPwBytesRow]
     SegRec *rec = reinterpret_cast<SegRec *>(s_b + kPwBytesRow * kSegLanes);   // [(kSegRecs - 1)][kSegLanes]
     uint32_t *s_p = reinterpret_cast<uint32_t *>(rec + (kSegRecs - 1) * kSegLanes);
     uint32_t *s_w0 = s_p + kSegLanes, *s_wsum = s_w0 + kSegLanes;
@@ -646,9 +652,8 @@ dfl_parse_kernel(Batch b, DeflateParams prm, const uint32_t *__restrict__ mfull,
     WinAcc acc;
     acc.data = data; acc.mfull = mfull; acc.mquarter = prm.need_quarter ? mquarter : mfull; acc.out = nullptr; acc.at = 0;
     acc.row_f = (uint32_t)__cvta_generic_to_shared(s_f + tid * kPwRow);
-    acc.row_q = (uint32_t)__cvta_generic_to_shared(s_q + tid * kPwRow);
     acc.row_b = (uint32_t)__cvta_generic_to_shared(s_b + tid * kPwBytesRow);
-    acc.abs0 = off; acc.use_q = prm.need_quarter != 0; acc.nw = 0;
+    acc.abs0 = off; acc.nw = 0;
     acc.in_lo = reinterpret_cast<uintptr_t>(b.in); acc.in_hi = acc.in_lo + b.bytes;
     if (active) seg_speculate(r, tid, g, n, prm, acc, rec);
     for (;;) {                                                     // until no start moves
@@ -705,8 +710,7 @@ dfl_parse_multi_kernel(Batch b, DeflateParams prm, const uint32_t *__restrict__ 
                        unsigned int *__restrict__ mstate, volatile ParseLink *links) {
     extern __shared__ __align__(16) uint8_t ps_smem[];
     uint32_t *s_f = reinterpret_cast<uint32_t *>(ps_smem);         // [2][kSegLanes][kPwRow]
-    uint32_t *s_q = s_f + 2 * kPwRow * kSegLanes;
-    uint32_t *s_b = s_q + 2 * kPwRow * kSegLanes;                  // [kSegLanes][kPwBytesRow]
+    uint32_t *s_b = s_f + 2 * kPwRow * kSegLanes;                  // [kSegLanes][kPwBytesRow]
     SegRec *rec = reinterpret_cast<SegRec *>(s_b + kPwBytesRow * kSegLanes);   // [(kSegRecs - 1)][kSegLanes]
     uint32_t *s_p = reinterpret_cast<uint32_t *>(rec + (kSegRecs - 1) * kSegLanes);
     uint32_t *s_w0 = s_p + kSegLanes, *s_wsum = s_w0 + kSegLanes;
@@ -738,9 +742,8 @@ dfl_parse_multi_kernel(Batch b, DeflateParams prm, const uint32_t *__restrict__ 
     WinAcc acc;
     acc.data = data; acc.mfull = mfull; acc.mquarter = prm.need_quarter ? mquarter : mfull; acc.out = nullptr; acc.at = 0;
     acc.row_f = (uint32_t)__cvta_generic_to_shared(s_f + tid * kPwRow);
-    acc.row_q = (uint32_t)__cvta_generic_to_shared(s_q + tid * kPwRow);
     acc.row_b = (uint32_t)__cvta_generic_to_shared(s_b + tid * kPwBytesRow);
-    acc.abs0 = 0; acc.use_q = prm.need_quarter != 0; acc.nw = 0;
+    acc.abs0 = 0; acc.nw = 0;
     acc.in_lo = reinterpret_cast<uintptr_t>(b.in); acc.in_hi = acc.in_lo + b.bytes;
     if (active) seg_speculate(r, tid, g, n, prm, acc, rec);
     SegState pred0 = seg_cold(g.lo);                               // where the segment before this CTA's first one ended (cold: not known yet)
