@@ -99,6 +99,14 @@ uint32_t zb200_adler32_combine(uint32_t adler1, uint32_t adler2, int64_t len2);
 #define ZB200_FRAME_ZLIB         1   /* + 2-byte header, Adler-32 trailer (deflate.c:1004-1037,1254) */
 #define ZB200_FRAME_GZIP         2   /* + 10-byte header, CRC-32/ISIZE trailer (deflate.c:1042-1054,1241) */
 #define ZB200_FRAME_GZIP_MEMBERS 3   /* every chunk its own gzip member (config C3 layout) */
+/* OR-ed into `frame` (frames 0-2, levels 1-9): history CARRIED from chunk to chunk.  Every chunk is still its own unit of
+ * parallel work and still ends on the byte-aligned 00 00 FF FF marker, but it is compressed behind the w_size bytes before
+ * it, as if by deflateSetDictionary(previous 32 KiB) + deflate(chunk, Z_SYNC_FLUSH) (deflate.c:550-632,1211-1218: what
+ * pigz does per block): the chunking costs 5 bytes per chunk instead of 0.7-1.3 % of the size.  Levels 4-9, Z_RLE and
+ * Z_HUFFMAN_ONLY emit exactly those bytes.  The result is ONE run of blocks with sync points: a decoder needs the window
+ * across chunks (any inflate has it; zb200_inflate_stream_host decodes it at its block headers).  With a dictionary
+ * (zb200_deflate_opts.dict_len) the first chunk is compressed behind that. */
+#define ZB200_CHUNK_CARRY        0x100
 
 /* Worst-case output bytes for n input bytes cut into chunk_size chunks (compress.c:72, deflate.c:842). */
 size_t zb200_deflate_bound(size_t n, size_t chunk_size, int frame);

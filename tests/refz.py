@@ -77,7 +77,7 @@ class ZlibBinding:
 
     # ---- helpers -------------------------------------------------------
     def deflate_stream(self, data, level=6, strategy=0, wrap=WRAP_ZLIB, chunk=0, mem_level=8,
-                       out_slice=None, in_slice=None, dictionary=None, chunk_flush=Z_FULL_FLUSH):
+                       out_slice=None, in_slice=None, dictionary=None, chunk_flush=Z_FULL_FLUSH, last_flush=Z_FINISH):
         """deflate(Z_FULL_FLUSH) per `chunk` bytes, Z_FINISH on the last one
         (SURVEY.md appendix C.1).  chunk=0: one Z_FINISH call.  in_slice /
         out_slice feed avail_in / avail_out in small pieces (zpipe style)."""
@@ -102,7 +102,7 @@ class ZlibBinding:
         produced = 0
         while True:
             k = min(chunk, n - off)
-            flush = Z_FINISH if off + k >= n else (chunk_flush[(off // chunk) % len(chunk_flush)] if isinstance(chunk_flush, (list, tuple)) else chunk_flush)
+            flush = last_flush if off + k >= n else (chunk_flush[(off // chunk) % len(chunk_flush)] if isinstance(chunk_flush, (list, tuple)) else chunk_flush)
             fed = 0
             while True:
                 step = k - fed if not in_slice else min(in_slice, k - fed)
@@ -127,6 +127,8 @@ class ZlibBinding:
             off += k
             if flush == Z_FINISH:
                 assert r == Z_STREAM_END, r
+                break
+            if off >= n:                                   # last_flush != Z_FINISH: the stream is left open at a flush point
                 break
         adler = strm.adler
         self.deflateEnd(C.byref(strm))

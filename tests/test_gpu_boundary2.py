@@ -520,3 +520,62 @@ def test_one_shot_calls_of_any_size_are_the_references_stream(z):
     assert z.compress2(a, C.byref(al), d, n, 4) == 0
     assert ref.compress2(b, C.byref(bl), d, n, 4) == 0
     assert al.value == bl.value and a.raw[:al.value] == b.raw[:bl.value], (al.value, bl.value)
+
+
+CARRY_SCRIPT = r"""
+import ctypes as C, os, sys, zlib
+sys.path.insert(0, os.path.join(%(root)r, "tests")); sys.path.insert(0, %(root)r)
+import refz, zlib_wasm_b200 as zb
+z = refz.ZlibBinding(zb.LIB_PATH, "")
+ZS = C.sizeof(refz.ZStream)
+d = refz.gen(3000000, refz.GEN_MARKOV, seed=41)
+# compress2 at level 1: beyond 1 MiB the greedy levels are cut into $ZB200_CHUNK chunks — carried, they see each other
+for level in (1, 3, 6):
+    cap = z.compressBound(len(d))
+    dst, dl = C.create_string_buffer(cap), C.c_ulong(cap)
+    assert z.compress2(dst, C.byref(dl), d, len(d), level) == 0
+    s = dst.raw[:dl.value]
+    assert zlib.decompress(s) == d
+    print("size", level, len(s))
+# a stream with flushes, a small window, a dictionary: every combination still the caller's bytes back
+for wbits, mem, dic in ((15, 8, None), (-15, 8, d[:20000]), (9, 8, None), (12, 1, None), (31, 9, None)):
+    strm = refz.ZStream()
+    assert z.deflateInit2_(C.byref(strm), 2, 8, wbits, mem, 0, z.version, ZS) == 0
+    if dic is not None:
+        assert z.deflateSetDictionary(C.byref(strm), dic, len(dic)) == 0
+    cap = len(d) + len(d) // 4 + 65536
+    src, dst = C.create_string_buffer(d, len(d)), C.create_string_buffer(cap)
+    off = produced = 0
+    step = 700001
+    while off < len(d):
+        k = min(step, len(d) - off)
+        strm.next_in, strm.avail_in = C.addressof(src) + off, k
+        strm.next_out, strm.avail_out = C.addressof(dst) + produced, cap - produced
+        fl = refz.Z_FINISH if off + k >= len(d) else (refz.Z_SYNC_FLUSH, refz.Z_FULL_FLUSH, refz.Z_NO_FLUSH)[(off // step) %% 3]
+        r = z.deflate(C.byref(strm), fl)
+        assert r in (0, 1), r
+        produced = cap - strm.avail_out
+        off += k
+    assert r == 1
+    z.deflateEnd(C.byref(strm))
+    s = dst.raw[:produced]
+    o = zlib.decompressobj(wbits if wbits != 9 else 15, zdict=dic) if dic is not None else zlib.decompressobj(wbits if wbits != 9 else 15)
+    assert o.decompress(s) == d and o.eof, (wbits, mem)
+print("ok")
+"""
+
+
+def test_chunk_carry_knob_at_the_zlib_surface():
+    """$ZB200_CHUNK_CARRY=1 (read once per process: subprocess): wherever zlib.h calls are cut into chunks, the chunks are
+    compressed behind the 32 KiB before them (zb200.h ZB200_CHUNK_CARRY).  Streams stay valid for every window size,
+    memLevel, dictionary and flush mixture (Python's zlib = an independent decoder), and the chunked levels get smaller."""
+    sizes = {}
+    for knob in ("0", "1"):
+        env = dict(os.environ)
+        env["ZB200_CHUNK_CARRY"] = knob
+        env["ZB200_CHUNK"] = "65536"
+        p = subprocess.run([sys.executable, "-c", CARRY_SCRIPT % {"root": ROOT}], env=env, capture_output=True, text=True, timeout=600)
+        assert p.returncode == 0 and "ok" in p.stdout, p.stderr[-2000:]
+        sizes[knob] = {int(l.split()[1]): int(l.split()[2]) for l in p.stdout.splitlines() if l.startswith("size")}
+    assert sizes["1"][1] < sizes["0"][1] and sizes["1"][3] < sizes["0"][3]
+    assert sizes["1"][6] == sizes["0"][6]                     # (one run of blocks either way: nothing is cut at level 6)

@@ -267,3 +267,137 @@ def test_full_size_roundtrip_1gib_per_gpu(ctx):
             m = members[i]
             ret, msg, out, tin = refz.ref().inflate_all(z[m.in_off:m.in_off + m.in_len], refz.WRAP_GZIP, cap=chunk + 8)
             assert ret == refz.Z_STREAM_END and out == host[i * chunk:(i + 1) * chunk]
+
+
+# ---- history carried from chunk to chunk (zb200.h ZB200_CHUNK_CARRY; SURVEY 8 f3: pigz-style carry-over) ----
+def _carried_reference(d, level, strategy, chunk, mem_level=8, dictionary=b""):
+    """What the flag promises: chunk c = deflateSetDictionary(the 32 KiB before it) + deflate(chunk, Z_SYNC_FLUSH), the last
+    one Z_FINISH (deflate.c:550-632,1211-1218), laid end to end — made by the unmodified reference."""
+    ref = refz.ref()
+    base = bytes(dictionary) + bytes(d)
+    n, dl = len(d), len(dictionary)
+    nch = max(1, (n + chunk - 1) // chunk)
+    out = []
+    for c in range(nch):
+        pos = dl + c * chunk
+        hist = base[max(0, pos - 32768):pos]
+        out.append(ref.deflate_stream(base[pos:pos + chunk], level, strategy, refz.WRAP_RAW, 0, mem_level=mem_level,
+                                      dictionary=hist if hist else None,
+                                      last_flush=refz.Z_FINISH if c == nch - 1 else refz.Z_SYNC_FLUSH))
+    return b"".join(out)
+
+
+def _deflate_opts(ctx, data, chunk, frame, level, strategy=0, mem_level=0, dict_len=0, finish=1):
+    import ctypes as C
+    L = zb.lib()
+    data = bytes(data)
+    cap = L.zb200_deflate_bound(len(data), chunk, frame)
+    out = C.create_string_buffer(cap)
+    olen = C.c_size_t(cap)
+    o = zb.DeflateOpts(level, strategy, 0, mem_level, dict_len, 0)
+    r = L.zb200_deflate_host_opts(ctx.handle, data, len(data), chunk, C.byref(o), frame, finish, out, C.byref(olen), None, None, None)
+    assert r == 0, zb.last_error()
+    return out.raw[:olen.value]
+
+
+@pytest.mark.skipif(not refz.have_ref(), reason="needs the compiled reference (deflateSetDictionary)")
+@pytest.mark.parametrize("kind", [refz.GEN_TEXT, refz.GEN_MARKOV, refz.GEN_MIXED, refz.GEN_BYTES])
+def test_carried_history_is_the_references_dictionary_chunks(ctx, kind):
+    """Levels 4-9 and the literal-only / run-length strategies: byte for byte the reference's per-chunk streams behind a
+    dictionary of the previous 32 KiB.  Chunk sizes around and below the window, ragged tails, a chunk that is history only
+    in its first tiles.  Every level: the reference's inflate gives the input back; the stream is smaller than the
+    independent chunks'."""
+    d = refz.gen(900000 + 777, kind, seed=900 + kind)
+    for chunk in (262144, 65536, 40000):
+        for level, strategy in ((6, 0), (4, 0), (9, 0), (6, refz.Z_FILTERED), (6, refz.Z_RLE), (6, refz.Z_HUFFMAN_ONLY), (1, 0), (2, 0), (3, 0)):
+            if chunk != 262144 and (level, strategy) not in ((6, 0), (1, 0), (4, 0)):
+                continue
+            s = ctx.deflate_host(d, level, strategy, zb.FRAME_RAW | zb.CHUNK_CARRY, chunk)
+            assert decode_ok(s, refz.WRAP_RAW, d), (kind, chunk, level, strategy)
+            if exact(level, strategy):
+                want = _carried_reference(d, level, strategy, chunk)
+                assert s == want, (kind, chunk, level, strategy, len(s), len(want))
+            if strategy == 0:                                 # history helps where there is something to find in it
+                plain = ctx.deflate_host(d, level, strategy, zb.FRAME_RAW, chunk)
+                assert len(s) <= len(plain) * 1.001 + 16, (kind, chunk, level, len(s), len(plain))   # (levels 1-2 on binary data: +0.007 %)
+                if kind in (refz.GEN_TEXT, refz.GEN_MARKOV):
+                    assert len(s) < len(plain), (kind, chunk, level, len(s), len(plain))
+            if chunk == 65536:                                # this library's own one-stream decoder: sync points, block headers
+                import ctypes as C
+                out = C.create_string_buffer(len(d) + 16)
+                res = zb.MemberResult()
+                r = zb.lib().zb200_inflate_stream_host(ctx.handle, s, len(s), refz.WRAP_RAW, out, len(d) + 16, C.byref(res))
+                assert r == 0 and res.status == 0 and res.in_used == len(s) and out.raw[:res.out_len] == d, (kind, level, res.status)
+    # wrappers: header, trailer and the input's check values are the plain call's
+    for frame in (zb.FRAME_ZLIB, zb.FRAME_GZIP):
+        s = ctx.deflate_host(d, 6, 0, frame | zb.CHUNK_CARRY, 131072)
+        assert decode_ok(s, frame, d)
+        body = _carried_reference(d, 6, 0, 131072)
+        hl, tl = (2, 4) if frame == zb.FRAME_ZLIB else (10, 8)
+        plain = ctx.deflate_host(d, 6, 0, frame, 131072)
+        assert s[hl:-tl] == body and s[:hl] == plain[:hl] and s[-tl:] == plain[-tl:]
+
+
+@pytest.mark.skipif(not refz.have_ref(), reason="needs the compiled reference (deflateSetDictionary)")
+def test_carried_history_edges(ctx):
+    """Chunks far shorter than the window (an early chunk's history is what there is), one chunk, an empty input, a
+    preset dictionary in front of the first chunk, an open end (finish = 0), and sub-batches inside one launch (memLevel 1
+    makes the block tables large enough for a sub-batch to end after ~150 MiB)."""
+    d = refz.gen(150000, refz.GEN_TEXT, seed=77)
+    for chunk in (1000, 4096, 33000, 150000, 1 << 20):
+        s = ctx.deflate_host(d, 6, 0, zb.FRAME_RAW | zb.CHUNK_CARRY, chunk)
+        assert s == _carried_reference(d, 6, 0, chunk), chunk
+        s1 = ctx.deflate_host(d, 1, 0, zb.FRAME_RAW | zb.CHUNK_CARRY, chunk)
+        assert decode_ok(s1, refz.WRAP_RAW, d), chunk
+    assert ctx.deflate_host(b"", 6, 0, zb.FRAME_RAW | zb.CHUNK_CARRY, 65536) == _carried_reference(b"", 6, 0, 65536)
+    # a dictionary ahead of the first chunk: `in` = dictionary + data, dict_len bytes of it history only
+    base = refz.gen(400000, refz.GEN_TEXT, seed=78)
+    for dl in (32768, 5000, 3):
+        dic, body = base[:dl], base[dl:]
+        s = _deflate_opts(ctx, base, 65536, zb.FRAME_RAW | zb.CHUNK_CARRY, 6, dict_len=dl)
+        assert s == _carried_reference(body, 6, 0, 65536, dictionary=dic), dl
+        err, msg, back, used = refz.ref().inflate_all(s, refz.WRAP_RAW, cap=len(body) + 16, dictionary=dic)
+        assert back == body
+    # open end: every chunk on a sync marker, no final block
+    s = ctx.deflate_host(d, 6, 0, zb.FRAME_RAW | zb.CHUNK_CARRY, 50000, finish=0)
+    ref = refz.ref()
+    want = b"".join(ref.deflate_stream(d[p:p + 50000], 6, 0, refz.WRAP_RAW, 0, dictionary=d[max(0, p - 32768):p] or None,
+                                       last_flush=refz.Z_SYNC_FLUSH) for p in range(0, len(d), 50000))
+    assert s == want
+    # level 0 and members: the flag is accepted and changes nothing
+    assert ctx.deflate_host(d, 0, 0, zb.FRAME_ZLIB | zb.CHUNK_CARRY, 65536) == ctx.deflate_host(d, 0, 0, zb.FRAME_ZLIB, 65536)
+    assert ctx.deflate_host(d, 6, 0, zb.FRAME_GZIP_MEMBERS | zb.CHUNK_CARRY, 65536) == ctx.deflate_host(d, 6, 0, zb.FRAME_GZIP_MEMBERS, 65536)
+    # two sub-batches in one launch
+    big = refz.gen(176 << 20, refz.GEN_MARKOV, seed=79)
+    s = _deflate_opts(ctx, big, 262144, zb.FRAME_RAW | zb.CHUNK_CARRY, 4, mem_level=1)
+    assert s == _carried_reference(big, 4, 0, 262144, mem_level=1)
+
+
+def test_carried_history_pipelined_pieces(ctx):
+    """Pinned buffers of 256 MiB and more go through in pieces: piece k is compressed behind the tail of piece k - 1
+    (which lies just before it on the device) — the bytes of the one-launch call on pageable memory."""
+    import ctypes as C
+    L = zb.lib()
+    n = (300 << 20) + 4321
+    d = refz.gen(n, refz.GEN_MARKOV, seed=6)
+    chunk = 262144
+    h_in = L.zb200_host_alloc(n)
+    assert h_in
+    C.memmove(h_in, d, n)
+    try:
+        for level, frame in ((1, zb.FRAME_GZIP), (6, zb.FRAME_RAW)):
+            want = ctx.deflate_host(d, level, 0, frame | zb.CHUNK_CARRY, chunk)
+            assert decode_ok(want, frame, d)
+            cap = L.zb200_deflate_bound(n, chunk, frame)
+            h_out = L.zb200_host_alloc(cap)
+            olen = C.c_size_t(cap)
+            r = L.zb200_deflate_host(ctx.handle, C.c_void_p(h_in), n, chunk, level, 0, frame | zb.CHUNK_CARRY, 1, C.c_void_p(h_out),
+                                     C.byref(olen), None, None)
+            assert r == 0, zb.last_error()
+            got = C.string_at(h_out, olen.value)
+            L.zb200_host_free(C.c_void_p(h_out))
+            assert got == want, (level, frame, len(got), len(want))
+            plain = ctx.deflate_host(d, level, 0, frame, chunk)
+            assert len(got) < len(plain)
+    finally:
+        L.zb200_host_free(C.c_void_p(h_in))

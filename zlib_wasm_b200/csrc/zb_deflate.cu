@@ -82,22 +82,35 @@ static void carve(DeflateWork &w, void *base, size_t nb, size_t S, uint32_t MB) 
 }
 
 struct Batch {                 // one sub-batch of chunks, passed by value to the kernels
-    const uint8_t *in;         // start of the sub-batch's input
-    uint64_t bytes;            // input bytes in the sub-batch
-    uint32_t S;                // chunk size
+    const uint8_t *in;         // start of the sub-batch's input (chunk 0's history first, if it has any)
+    uint64_t bytes;            // input bytes in the sub-batch (history of chunk 0 included)
+    uint32_t S;                // scratch stride: the longest a chunk gets with its history (= step + carry)
     uint32_t nb;               // chunks in the sub-batch
     uint32_t MB;               // block slots per chunk
     int last_is_final;         // the last chunk of this sub-batch ends the stream (Z_FINISH)
     int all_final;             // every chunk is its own stream (gzip members)
-    uint32_t skip;             // a preset dictionary: the first `skip` bytes of chunk 0 are history only (single-chunk calls)
+    uint32_t skip;             // history of chunk 0: its first `skip` bytes are searched, never emitted (a preset dictionary, or
+                               // the tail of the previous sub-batch / piece when history is carried)
     uint32_t first_bit;        // deflatePrime: chunk 0 of the call starts at this bit (0..7) of its first output byte
     uint32_t range;            // ONE long chunk (nb = 1) worked on by many CTAs of the ordered kernels: positions per CTA (0: off)
+    uint32_t step;             // new input bytes per chunk (= S unless history is carried)
+    uint32_t carry;            // history carried from chunk to chunk (pigz-style, deflateSetDictionary of the previous w_size bytes
+                               // per chunk, deflate.c:550-632): every chunk after the first sees the `carry` bytes before it; 0 = off
 };
 
+// A chunk as its kernels see it: `lo` bytes of history (never emitted) followed by its new bytes, scratch at c * S.
+// (chunks shorter than the window: an early chunk's history is what there is — everything from b.in on)
+__device__ __forceinline__ uint32_t chunk_lo(const Batch &b, uint32_t c) {
+    if (c == 0) return b.skip;
+    const uint64_t before = (uint64_t)b.skip + (uint64_t)c * b.step;
+    return before < b.carry ? (uint32_t)before : b.carry;
+}
+__device__ __forceinline__ const uint8_t *chunk_data(const Batch &b, uint32_t c) {
+    return b.in + ((uint64_t)b.skip + (uint64_t)c * b.step - chunk_lo(b, c));
+}
 __device__ __forceinline__ uint32_t chunk_len(const Batch &b, uint32_t c) {
-    const uint64_t off = (uint64_t)c * b.S;
-    const uint64_t rem = b.bytes - off;
-    return (uint32_t)(rem < b.S ? rem : b.S);
+    const uint64_t rem = b.bytes - b.skip - (uint64_t)c * b.step;
+    return chunk_lo(b, c) + (uint32_t)(rem < b.step ? rem : b.step);
 }
 __device__ __forceinline__ bool chunk_final(const Batch &b, uint32_t c) {
     return b.all_final || (b.last_is_final && c + 1 == b.nb);
@@ -125,7 +138,7 @@ __device__ __forceinline__ void chain_body(const Batch &b, const DeflateParams &
     const uint32_t lane_warp = threadIdx.x >> 5;             // (IMM: W is this warp's index, known at compile time)
     const uint32_t warp = IMM ? W : lane_warp;
     const uint32_t c = b.range ? 0u : blockIdx.x, lane = threadIdx.x & 31;
-    const uint8_t *data = b.in + (uint64_t)c * b.S;
+    const uint8_t *data = chunk_data(b, c);
     const uint32_t n = chunk_len(b, c);
     uint16_t *prev = prev_all + (uint64_t)c * b.S;
     uint4 *h4 = reinterpret_cast<uint4 *>(head);
@@ -262,7 +275,7 @@ dfl_match_kernel(Batch b, DeflateParams prm, const uint16_t *__restrict__ prev_a
     const uint32_t p = blockIdx.x * 256 + threadIdx.x;
     if (p >= n) return;
     const uint64_t off = (uint64_t)c * b.S;
-    const uint8_t *data = b.in + off;
+    const uint8_t *data = chunk_data(b, c);
     if (prm.mode == MODE_RLE) { mfull[off + p] = rle_at(data, n, p); return; }
     const MatchPair r = match_at(data, n, prev_all + off, p, prm);
     const bool diff = prm.need_quarter && r.quarter != r.full;
@@ -393,9 +406,9 @@ template <int CH, int NICE, bool GLINKS>
 __global__ void __launch_bounds__(kMsThreads, GLINKS ? 2 : 1)
 dfl_match_uniform_kernel(Batch b, DeflateParams prm, const uint16_t *__restrict__ prev_all, uint32_t *__restrict__ mfull) {
     const uint32_t c = blockIdx.y, n = chunk_len(b, c), t0 = blockIdx.x * kMsTile;
-    if (t0 >= n) return;
+    if (t0 >= n || t0 + kMsTile <= chunk_lo(b, c)) return;         // (a tile of history only: no position of it is ever parsed)
     const uint64_t off = (uint64_t)c * b.S;
-    const uint8_t *data = b.in + off;
+    const uint8_t *data = chunk_data(b, c);
     const uint16_t *prev = prev_all + off;
     const uint32_t cnt = n - t0 < kMsTile ? n - t0 : kMsTile, t1 = t0 + cnt;
     const uint32_t lo = t0 > (uint32_t)kWSize ? t0 - kWSize : 0;
@@ -422,9 +435,9 @@ dfl_match_sorted_kernel(Batch b, DeflateParams prm, const uint16_t *__restrict__
     __shared__ uint32_t s_hist[kMsBuckets], s_cur[kMsBuckets];
     uint16_t *s_order = reinterpret_cast<uint16_t *>(ms_smem + kMsDataBytes + kMsLinkBytes);
     const uint32_t c = blockIdx.y, n = chunk_len(b, c), t0 = blockIdx.x * kMsTile;
-    if (t0 >= n) return;
+    if (t0 >= n || t0 + kMsTile <= chunk_lo(b, c)) return;         // (a tile of history only: no position of it is ever parsed)
     const uint64_t off = (uint64_t)c * b.S;
-    const uint8_t *data = b.in + off;
+    const uint8_t *data = chunk_data(b, c);
     const uint16_t *prev = prev_all + off;
     const uint32_t cnt = n - t0 < kMsTile ? n - t0 : kMsTile, t1 = t0 + cnt;
     const uint32_t lo = t0 > (uint32_t)kWSize ? t0 - kWSize : 0;             // candidates lie less than 32 KiB back
@@ -507,13 +520,13 @@ dfl_parse_greedy_kernel(Batch b, DeflateParams prm, const uint32_t *__restrict__
     __shared__ volatile uint32_t s_entry, s_nsyms;     // handed from tile to tile: absolute entry position, symbols so far
     const uint32_t c = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint64_t off = (uint64_t)c * b.S;
-    const uint8_t *data = b.in + off;
+    const uint8_t *data = chunk_data(b, c);
     const uint32_t n = chunk_len(b, c);
     const bool use_m = prm.mode != MODE_HUFF;
     const uint32_t *mf = mfull + off;
     uint32_t *out = syms + off;
     BlockInfo *blk = blocks + (uint64_t)c * b.MB;
-    const uint32_t lo = c == 0 ? b.skip : 0u, tile0 = lo / kGtTile;   // the parse enters at `lo` (history before it)
+    const uint32_t lo = chunk_lo(b, c), tile0 = lo / kGtTile;   // the parse enters at `lo` (history before it)
     if (threadIdx.x == 0) { s_entry = lo; s_nsyms = 0; }
     __syncthreads();
     GtWarpShared &w = sh[warp];
@@ -640,11 +653,11 @@ dfl_parse_kernel(Batch b, DeflateParams prm, const uint32_t *__restrict__ mfull,
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t c = blockIdx.x;
     const uint64_t off = (uint64_t)c * b.S;
-    const uint8_t *data = b.in + off;
+    const uint8_t *data = chunk_data(b, c);
     const uint32_t n = chunk_len(b, c);
     uint32_t *out = syms + off;
     BlockInfo *blk = blocks + (uint64_t)c * b.MB;
-    const SegGeom g = seg_geometry(n, c == 0 ? b.skip : 0u);
+    const SegGeom g = seg_geometry(n, chunk_lo(b, c));
     const bool active = tid < g.nact;
 
     SegLane r;
@@ -1058,7 +1071,7 @@ dfl_pack_kernel(Batch b, const uint32_t *__restrict__ syms, const BlockInfo *__r
         const uint64_t body = (start + 3 + 7) & ~7ull;
         if (threadIdx.x == 0)
             or_bits(out32, body, (uint64_t)(blk.byte_len & 0xffff) | ((uint64_t)(~blk.byte_len & 0xffff) << 16), 32);
-        const uint8_t *src = b.in + (uint64_t)c * b.S + blk.byte_start;
+        const uint8_t *src = chunk_data(b, c) + blk.byte_start;
         for (uint32_t i = threadIdx.x; i < blk.byte_len; i += 256) or_bits(out32, body + 32 + 8ull * i, src[i], 8);
         return;
     }
@@ -1232,7 +1245,9 @@ int deflate_launch_opts(zb200_ctx *ctx, const uint8_t *d_in, size_t n, size_t S,
         set_error("deflate: windowBits 9..15, memLevel 1..9, first bit 0..7 (raw streams only)");
         return ZB200_ERR_PARAM;
     }
-    if (skip && (skip > kWSize || skip > n || n > S || frame != ZB200_FRAME_RAW)) {
+    // history carried from chunk to chunk: levels 1-9 of one stream (stored blocks have no use for it, members are independent)
+    const bool carry = o.carry && level >= 1 && frame != ZB200_FRAME_GZIP_MEMBERS;
+    if (skip && (skip > kWSize || skip > n || (!carry && n > S) || frame != ZB200_FRAME_RAW)) {
         set_error("deflate: a preset dictionary is at most 32768 bytes at the head of a single raw chunk");
         return ZB200_ERR_PARAM;
     }
@@ -1242,9 +1257,10 @@ int deflate_launch_opts(zb200_ctx *ctx, const uint8_t *d_in, size_t n, size_t S,
         return ZB200_ERR_PARAM;
     }
     const bool members = frame == ZB200_FRAME_GZIP_MEMBERS;
-    size_t nch = (n + S - 1) / S;
+    const size_t n_new = n - skip;                                 // bytes to compress (a dictionary alone may exceed S when not carried: one chunk)
+    size_t nch = carry ? (n_new + S - 1) / S : (n + S - 1) / S;
     if (nch == 0 && (finish || members)) nch = 1;
-    if (out_cap < zb200_deflate_bound(n, S, frame)) { set_error("deflate: output capacity below zb200_deflate_bound()"); return ZB200_ERR_OUTPUT; }
+    if (out_cap < zb200_deflate_bound(n_new, S, frame)) { set_error("deflate: output capacity below zb200_deflate_bound()"); return ZB200_ERR_OUTPUT; }
     DeflateParams prm = deflate_params(level, strategy, o.window_bits, o.mem_level);
     const int *tune = deflate_tune_override();                     // deflateTune (deflate.c:805-816): this thread's next calls
     if (tune && (prm.mode == MODE_SLOW || prm.mode == MODE_FAST)) {
@@ -1270,16 +1286,22 @@ int deflate_launch_opts(zb200_ctx *ctx, const uint8_t *d_in, size_t n, size_t S,
     //  0.66 ms per 444 MiB, the same size on text — cost 1-2 % of size where text and incompressible data alternate: with the
     //  two-candidate search that crossed the 3 % bound on one generator.)
     const uint32_t MB = max_blocks_for((uint32_t)S, prm.sym_limit);
-    const size_t nb_max = batch_chunks(n, S, MB);
-    int r = ensure_scratch(ctx, work_bytes(nb_max, S, MB));
+    // Carried history: chunk c > 0 is worked on as [w_size bytes before it | its own bytes] — deflateSetDictionary of the
+    // previous w_size bytes per chunk (what pigz does; deflate.c:550-632 keeps the last w_size bytes of a dictionary) — so
+    // its working arrays hold E = S + w_size positions.  The kernels see the same picture as for a preset dictionary.
+    // (a dictionary longer than a small window is chunk 0's history all the same: its slot is as long as that takes)
+    const size_t W = carry ? prm.w_size : 0, E = S + (carry && skip > W ? skip : W);
+    if (E > 0x40000000ull) { set_error("deflate: carried history: chunk + window at most 2^30 bytes"); return ZB200_ERR_PARAM; }
+    const size_t nb_max = carry ? batch_chunks((nch ? nch : 1) * E, E, MB) : batch_chunks(n, S, MB);
+    int r = ensure_scratch(ctx, work_bytes(nb_max, E, MB));
     if (r) return r;
     DeflateWork w;
-    carve(w, ctx->d_scratch, nb_max, S, MB);
+    carve(w, ctx->d_scratch, nb_max, E, MB);
     const DeflateDeviceTables *tabs = (const DeflateDeviceTables *)ctx->d_deflate_tables;
     uint64_t *running = ctx->d_small + 16;                         // stream length so far (device)
     uint32_t *sums = (uint32_t *)(ctx->d_small + 20);              // crc, adler of the whole input
     CkAccum *acc1 = (CkAccum *)(ctx->d_small + 24);
-    const size_t zero_bytes = zb200_deflate_bound(n, S, frame);
+    const size_t zero_bytes = zb200_deflate_bound(n_new, S, frame);
     prof_mark(ctx, s, "memset_output");
     ZB_CUDA(cudaMemsetAsync(d_out, 0, (zero_bytes + 3) & ~(size_t)3, s));
     const uint64_t hdr = frame == ZB200_FRAME_ZLIB ? 2 : frame == ZB200_FRAME_GZIP ? 10 : 0;
@@ -1302,14 +1324,14 @@ int deflate_launch_opts(zb200_ctx *ctx, const uint8_t *d_in, size_t n, size_t S,
     for (size_t c0 = 0; c0 < nch; c0 += nb_run) {
         Batch b;
         b.nb = (uint32_t)(nch - c0 < nb_run ? nch - c0 : nb_run);
-        b.in = d_in + c0 * S;
-        const size_t off = c0 * S;
+        const size_t off = c0 * S;                                 // the sub-batch's first new byte, counted from the call's
         const size_t span = (size_t)b.nb * S;
-        b.bytes = n - off < span ? n - off : span;
-        b.S = (uint32_t)S; b.MB = MB;
+        b.skip = (uint32_t)(c0 ? (skip + off < W ? skip + off : W) : skip);   // history in front of it: carried, or the call's own
+        b.in = d_in + skip + off - b.skip;
+        b.bytes = b.skip + (n_new - off < span ? n_new - off : span);
+        b.S = (uint32_t)E; b.step = (uint32_t)S; b.carry = (uint32_t)W; b.MB = MB;
         b.last_is_final = (finish && c0 + b.nb == nch) ? 1 : 0;
         b.all_final = members ? 1 : 0;
-        b.skip = (uint32_t)skip;
         b.first_bit = c0 == 0 ? o.first_bit : 0u;
         // ONE long chunk (a one-shot call's single run of blocks): many CTAs share its ordered phases
         static const int multi_knob = [] { const char *e = getenv("ZB200_MULTI_CTA_RUN"); return e ? atoi(e) : 1; }();
@@ -1324,7 +1346,7 @@ int deflate_launch_opts(zb200_ctx *ctx, const uint8_t *d_in, size_t n, size_t S,
             ZB_LAUNCHED(); ZB_CHECK_LAUNCH();
         }
         if (sorted_walks) {
-            dim3 g((unsigned)((S + kMsTile - 1) / kMsTile), b.nb);
+            dim3 g((unsigned)((E + kMsTile - 1) / kMsTile), b.nb);
             prof_mark(ctx, s, "dfl_match_sorted_kernel");
             static const int key_knob = [] { const char *e = getenv("ZB200_KEY_CAP"); return e ? atoi(e) : 0; }();
             uint32_t key_cap = (uint32_t)(key_knob > 0 ? key_knob : prm.chain / 16);   // (level 6: 8, level 9: 256)
@@ -1332,7 +1354,7 @@ int deflate_launch_opts(zb200_ctx *ctx, const uint8_t *d_in, size_t n, size_t S,
             dfl_match_sorted_kernel<<<g, kMsThreads, kMsSmem, s>>>(b, prm, w.prev, w.mfull, w.mquarter, key_cap);
             ZB_LAUNCHED(); ZB_CHECK_LAUNCH();
         } else if (prm.mode == MODE_FAST) {                        // levels 1-2
-            dim3 g((unsigned)((S + kMsTile - 1) / kMsTile), b.nb);
+            dim3 g((unsigned)((E + kMsTile - 1) / kMsTile), b.nb);
             prof_mark(ctx, s, "dfl_match_uniform_kernel");
             // Level 1 looks at TWO candidates per position, not the table's four (deflate.c:114 max_chain 4).  Every position is
             // inserted here (deflate_fast skips the inside of matches longer than max_insert, deflate.c:1873-1897), which alone
@@ -1346,7 +1368,7 @@ int deflate_launch_opts(zb200_ctx *ctx, const uint8_t *d_in, size_t n, size_t S,
             else dfl_match_uniform_kernel<8, 16, false><<<g, kMsThreads, kMsSmem, s>>>(b, prm, w.prev, w.mfull);
             ZB_LAUNCHED(); ZB_CHECK_LAUNCH();
         } else if (prm.mode != MODE_HUFF) {
-            dim3 g((unsigned)((S + 255) / 256), b.nb);
+            dim3 g((unsigned)((E + 255) / 256), b.nb);
             prof_mark(ctx, s, "dfl_match_kernel");
             dfl_match_kernel<<<g, 256, 0, s>>>(b, prm, w.prev, w.mfull, w.mquarter);
             ZB_LAUNCHED(); ZB_CHECK_LAUNCH();
@@ -1399,6 +1421,7 @@ using namespace zb;
 extern "C" {
 
 size_t zb200_deflate_bound(size_t n, size_t chunk_size, int frame) {
+    frame &= ~ZB200_CHUNK_CARRY;                                   // (carried history changes what a chunk's matches see, not its worst case)
     if (chunk_size == 0) chunk_size = 1;
     size_t nch = (n + chunk_size - 1) / chunk_size;
     if (nch == 0) nch = 1;
@@ -1421,8 +1444,10 @@ int zb200_deflate_dev(zb200_ctx *ctx, const void *d_in, size_t n, size_t chunk_s
     if (!ctx || (!d_in && n) || !d_out) return ZB200_ERR_PARAM;
     ZB_CUDA(cudaSetDevice(ctx->device));
     CtxUse use(ctx, pick_stream(ctx, stream));
-    return deflate_launch(ctx, (const uint8_t *)d_in, n, chunk_size, level, strategy, frame, finish,
-                          (uint8_t *)d_out, out_cap, d_chunk_end, d_total, nullptr, pick_stream(ctx, stream), 0);
+    DeflateOpts o;
+    o.level = level; o.strategy = strategy; o.carry = (frame & ZB200_CHUNK_CARRY) != 0;
+    return deflate_launch_opts(ctx, (const uint8_t *)d_in, n, chunk_size, o, frame & ~ZB200_CHUNK_CARRY, finish,
+                               (uint8_t *)d_out, out_cap, d_chunk_end, d_total, nullptr, pick_stream(ctx, stream));
 }
 
 // Large inputs in pinned memory: the input is cut into up to 9 pieces (whole chunks); piece
@@ -1464,7 +1489,9 @@ static int deflate_host_pipelined(zb200_ctx *ctx, const uint8_t *in, size_t n, s
     }
     int r = ensure_io(ctx, n + 16, total_bound + 16);
     if (r) return r;
-    if ((r = ensure_scratch(ctx, zb200_deflate_scratch_bytes(piece, S)))) return r;   // no reallocation (= implicit sync) mid-pipeline
+    // carried history: piece k > 0 is compressed behind the last W bytes of piece k - 1, which lie just before it on the device
+    const size_t W = (opts.carry && level >= 1 && pframe == ZB200_FRAME_RAW) ? (size_t)1 << opts.window_bits : 0;
+    if ((r = ensure_scratch(ctx, W ? zb200_deflate_scratch_bytes((piece / S + 1) * (S + W), S + W) : zb200_deflate_scratch_bytes(piece, S)))) return r;   // no reallocation (= implicit sync) mid-pipeline
     cudaEvent_t ev_in[kMaxPieces], ev_out[kMaxPieces];
     for (size_t k = 0; k < np; ++k) {
         ZB_CUDA(cudaEventCreateWithFlags(&ev_in[k], cudaEventDisableTiming));
@@ -1481,8 +1508,8 @@ static int deflate_host_pipelined(zb200_ctx *ctx, const uint8_t *in, size_t n, s
         const size_t len = k + 1 < np ? piece : n - k * piece;
         cudaStreamWaitEvent(s, ev_in[k], 0);
         DeflateOpts po = opts;
-        po.skip = 0; po.first_bit = k == 0 ? opts.first_bit : 0u;
-        r = deflate_launch_opts(ctx, ctx->d_io_in + k * piece, len, S, po, pframe, (finish && k + 1 == np) ? 1 : 0,
+        po.skip = k ? W : 0; po.first_bit = k == 0 ? opts.first_bit : 0u;
+        r = deflate_launch_opts(ctx, ctx->d_io_in + k * piece - po.skip, len + po.skip, S, po, pframe, (finish && k + 1 == np) ? 1 : 0,
                                 ctx->d_io_out + ooff[k], bound[k], nullptr, ctx->d_pipe + 2 * k, (uint32_t *)(ctx->d_pipe + 2 * k + 1), s);
         if (r) { cudaStreamSynchronize(s); cudaStreamSynchronize(ctx->copy_stream); cleanup(); return r; }
         cudaMemcpyAsync(ctx->h_pipe + 2 * k, ctx->d_pipe + 2 * k, 16, cudaMemcpyDeviceToHost, s);
@@ -1540,7 +1567,7 @@ static int deflate_host_pipelined(zb200_ctx *ctx, const uint8_t *in, size_t n, s
 static int deflate_host_impl(zb200_ctx *ctx, const uint8_t *in, size_t n, size_t chunk_size, const DeflateOpts &opts, int frame,
                              int finish, uint8_t *out, size_t *out_len, uint32_t *in_adler, uint32_t *in_crc, uint32_t *bits_used) {
     const int level = opts.level, strategy = opts.strategy;
-    if (opts.skip) {
+    if (opts.skip && !opts.carry) {
         const size_t dl = opts.skip;
         if (dl > n || dl > (size_t)kWSize || frame != ZB200_FRAME_RAW || chunk_size < 1) return ZB200_ERR_PARAM;
         const size_t body = n - dl, first = body < chunk_size ? body : chunk_size;
@@ -1582,7 +1609,7 @@ static int deflate_host_impl(zb200_ctx *ctx, const uint8_t *in, size_t n, size_t
         return ZB200_OK;
     }
     if (n >= ((size_t)256 << 20) && chunk_size >= 1 && chunk_size <= ((size_t)16 << 20) && level >= 0 && level <= 9 &&
-        strategy >= 0 && strategy <= 4 && frame >= 0 && frame <= 3 && is_pinned(in) && is_pinned(out)) {
+        strategy >= 0 && strategy <= 4 && frame >= 0 && frame <= 3 && !opts.skip && is_pinned(in) && is_pinned(out)) {
         if (bits_used) *bits_used = 8;                             // (read back below only on the single-shot path)
         const int r = deflate_host_pipelined(ctx, in, n, chunk_size, opts, frame, finish, out, out_len, in_adler, in_crc);
         if (r == ZB200_OK && bits_used && finish) {
@@ -1620,8 +1647,8 @@ int zb200_deflate_host(zb200_ctx *ctx, const void *in, size_t n, size_t chunk_si
     ZB_CUDA(cudaSetDevice(ctx->device));
     CtxUse use(ctx, ctx->stream);
     DeflateOpts o;
-    o.level = level; o.strategy = strategy;
-    return deflate_host_impl(ctx, (const uint8_t *)(in ? in : (const void *)""), n, chunk_size, o, frame, finish, (uint8_t *)out, out_len, in_adler, in_crc, nullptr);
+    o.level = level; o.strategy = strategy; o.carry = (frame & ZB200_CHUNK_CARRY) != 0;
+    return deflate_host_impl(ctx, (const uint8_t *)(in ? in : (const void *)""), n, chunk_size, o, frame & ~ZB200_CHUNK_CARRY, finish, (uint8_t *)out, out_len, in_adler, in_crc, nullptr);
 }
 
 int zb200_deflate_host_opts(zb200_ctx *ctx, const void *in, size_t n, size_t chunk_size, const zb200_deflate_opts *opts,
@@ -1633,7 +1660,8 @@ int zb200_deflate_host_opts(zb200_ctx *ctx, const void *in, size_t n, size_t chu
     DeflateOpts o;
     o.level = opts->level; o.strategy = opts->strategy; o.window_bits = opts->window_bits ? opts->window_bits : 15;
     o.mem_level = opts->mem_level ? opts->mem_level : 8; o.skip = opts->dict_len; o.first_bit = opts->first_bit;
-    return deflate_host_impl(ctx, (const uint8_t *)(in ? in : (const void *)""), n, chunk_size, o, frame, finish, (uint8_t *)out, out_len, in_adler, in_crc, bits_used);
+    o.carry = (frame & ZB200_CHUNK_CARRY) != 0;
+    return deflate_host_impl(ctx, (const uint8_t *)(in ? in : (const void *)""), n, chunk_size, o, frame & ~ZB200_CHUNK_CARRY, finish, (uint8_t *)out, out_len, in_adler, in_crc, bits_used);
 }
 
 int zb200_deflate_host_dict(zb200_ctx *ctx, const void *in, size_t n, size_t dict_len, int level, int strategy,

@@ -1098,6 +1098,21 @@ int inflate_stream_parallel(zb200_ctx *ctx, const uint8_t *src, size_t n, int wr
         while (good < runs.size() && clean(runs[good])) ++good;
         if (good == runs.size()) { final_status = ZB200_INF_TRUNCATED; break; }                    // the input ends on a boundary
         if (runs[good].res.status == ZB200_INF_OK) { ++good; final_status = ZB200_INF_OK; break; } // BFINAL: the stream ends here
+        // Many runs that reach behind their start: the markers are SYNC flushes (pigz, deflate(Z_SYNC_FLUSH), this library's
+        // ZB200_CHUNK_CARRY) — merging would leave one long run for one team of warps (242 MB of level-1 text: 4.2 s).  Such a
+        // stream is one run of blocks: its block headers are what to split on.  If that path declines, the merges go ahead.
+        if (pass == 0 && blocks_mode) {
+            size_t far = 0;
+            for (size_t k = good; k < runs.size(); ++k) far += runs[k].res.status == ZB200_INF_DIST_FAR;
+            if (far >= 2 && far * 8 >= runs.size() - good) {
+                const int rb = blocks(true);
+                if (rb != ZB200_OK || *applicable) return rb;
+                *applicable = 1;                             // (its buffers are gone: every run is decoded again, then repaired as below)
+                for (size_t k = 0; k < runs.size(); ++k) { runs[k].done = false; }
+                total = 0; good = 0;
+                continue;
+            }
+        }
         // repairs, for every run from there on (a merge never harms: it only removes a split)
         bool changed = false;
         for (size_t k = good; k < runs.size(); ++k) {

@@ -159,6 +159,8 @@ struct DeflateOpts {
     int window_bits = 15, mem_level = 8;     // deflate.c:440-455: w_size, hash_bits, lit_bufsize
     size_t skip = 0;                         // preset dictionary at the head of a single raw chunk
     unsigned first_bit = 0;                  // deflatePrime: the stream starts at this bit (0..7) of out[0]
+    bool carry = false;                      // ZB200_CHUNK_CARRY: every chunk is compressed behind the w_size bytes before it; `skip` is
+                                             // then the history in front of the FIRST chunk (a dictionary, or the previous piece's tail)
 };
 // The 8 bytes at ctx->d_small + 19 receive {bits in use in the stream's last byte (deflateUsed), 0}.
 int deflate_launch_opts(zb200_ctx *ctx, const uint8_t *d_in, size_t n, size_t S, const DeflateOpts &o, int frame,

@@ -99,6 +99,9 @@ int zb200_multi_checksum_host(zb200_multi *m, const void *data, size_t n, int wh
 
 int zb200_multi_deflate_host(zb200_multi *m, const void *in, size_t n, size_t chunk_size, int level, int strategy, int frame,
                              int finish, void *out, size_t *out_len, uint32_t *in_adler, uint32_t *in_crc) {
+    // ZB200_CHUNK_CARRY: a GPU's first chunk is compressed behind the 32 KiB before its piece (copied along), like every other chunk
+    const size_t W = ((frame & ZB200_CHUNK_CARRY) && (frame & 0xff) != ZB200_FRAME_GZIP_MEMBERS && level >= 1) ? 32768 : 0;
+    frame &= ~ZB200_CHUNK_CARRY;
     if (!m || m->ctx.empty() || (!in && n) || !out || !out_len || chunk_size == 0 || frame < 0 || frame > 3) return ZB200_ERR_PARAM;
     const size_t S = chunk_size, g0 = m->ctx.size();
     const size_t nch = (n + S - 1) / S;
@@ -145,28 +148,34 @@ int zb200_multi_deflate_host(zb200_multi *m, const void *in, size_t n, size_t ch
                 sub_off[j] = bound_total;
                 bound_total += zb200_deflate_bound(l, S, pframe);
             }
-            if (!r) r = ensure_io(ctx, len[k] + 16, bound_total + 16);
-            if (!r) r = ensure_scratch(ctx, zb200_deflate_scratch_bytes(ns > 1 ? sub : len[k], S));   // no reallocation (= implicit sync) mid-pipeline
+            const size_t H = off[k] < W ? off[k] : W;                          // history in front of this GPU's piece
+            if (!r) r = ensure_io(ctx, H + len[k] + 16, bound_total + 16);
+            if (!r) r = ensure_scratch(ctx, W ? zb200_deflate_scratch_bytes(((ns > 1 ? sub : len[k]) / S + 1) * (S + W), S + W)
+                                              : zb200_deflate_scratch_bytes(ns > 1 ? sub : len[k], S));   // no reallocation (= implicit sync) mid-pipeline
             s = ctx->stream;
             const bool pinned = is_pinned(in);
             cudaEvent_t ev[kSub];
             size_t nev = 0;
             for (size_t j = 0; j < ns && !r; ++j) {
                 const size_t l = j + 1 < ns ? sub : len[k] - j * sub;
-                const uint8_t *src = (const uint8_t *)in + off[k] + j * sub;
+                const size_t h = j ? 0 : H;                           // (the first sub-piece brings the history along)
+                const uint8_t *src = (const uint8_t *)in + off[k] + j * sub - h;
+                uint8_t *dst = ctx->d_io_in + H + j * sub - h;
                 if (pinned && ns > 1) {
                     if (cudaEventCreateWithFlags(&ev[nev], cudaEventDisableTiming) != cudaSuccess) { r = ZB200_ERR_CUDA; break; }
                     ++nev;
-                    if (cudaMemcpyAsync(ctx->d_io_in + j * sub, src, l, cudaMemcpyHostToDevice, ctx->copy_stream) != cudaSuccess ||
+                    if (cudaMemcpyAsync(dst, src, l + h, cudaMemcpyHostToDevice, ctx->copy_stream) != cudaSuccess ||
                         cudaEventRecord(ev[j], ctx->copy_stream) != cudaSuccess) r = ZB200_ERR_CUDA;
-                } else r = h2d_auto(ctx, ctx->d_io_in + j * sub, src, l, s);
+                } else r = h2d_auto(ctx, dst, src, l + h, s);
             }
             for (size_t j = 0; j < ns && !r; ++j) {
                 const size_t l = j + 1 < ns ? sub : len[k] - j * sub;
                 if (pinned && ns > 1) cudaStreamWaitEvent(s, ev[j], 0);
-                r = deflate_launch(ctx, ctx->d_io_in + j * sub, l, S, level, strategy, pframe, (finish && last && j + 1 == ns) ? 1 : 0,
-                                   ctx->d_io_out + sub_off[j], zb200_deflate_bound(l, S, pframe), nullptr, ctx->d_pipe + 2 * j,
-                                   (uint32_t *)(ctx->d_pipe + 2 * j + 1), s);
+                DeflateOpts o;
+                o.level = level; o.strategy = strategy; o.carry = W != 0; o.skip = j ? (H + j * sub < W ? H + j * sub : W) : H;
+                r = deflate_launch_opts(ctx, ctx->d_io_in + H + j * sub - o.skip, l + o.skip, S, o, pframe, (finish && last && j + 1 == ns) ? 1 : 0,
+                                        ctx->d_io_out + sub_off[j], zb200_deflate_bound(l, S, pframe), nullptr, ctx->d_pipe + 2 * j,
+                                        (uint32_t *)(ctx->d_pipe + 2 * j + 1), s);
                 if (!r && cudaMemcpyAsync(ctx->h_pipe + 2 * j, ctx->d_pipe + 2 * j, 16, cudaMemcpyDeviceToHost, s) != cudaSuccess) r = ZB200_ERR_CUDA;
             }
             if (cudaStreamSynchronize(s) != cudaSuccess && !r) r = ZB200_ERR_CUDA;
