@@ -301,6 +301,10 @@ def main():
                 legs["inflate_one_member"] = BL.single_member_leg(g, cpu, BL.scaled(256 << 20, args.scale))
             except Exception as ex:
                 errors["inflate_one_member"] = repr(ex)
+            try:
+                legs["chunk_carry"] = BL.chunk_carry_leg(g, cpu, BL.scaled(512 << 20, args.scale))
+            except Exception as ex:
+                errors["chunk_carry"] = repr(ex)
         try:                                            # the host link with every rank copying at once, no kernels
             legs["link_probe"] = BL.link_probe(g)
         except Exception as ex:

@@ -879,6 +879,63 @@ def single_member_leg(g, cpu, total=256 * MIB):
     return e
 
 
+def chunk_carry_leg(g, cpu, total=512 * MIB):
+    """SURVEY 8 f3, carry-over: the same chunks compressed behind the 32 KiB before them (zb200.h ZB200_CHUNK_CARRY — per chunk
+    what deflateSetDictionary(previous 32 KiB) + deflate(Z_SYNC_FLUSH) gives, the pigz scheme) next to the independent
+    Z_FULL_FLUSH chunks of the headline: size, end-to-end and kernel time of both through zb200_deflate_host on pinned buffers;
+    gates: the reference's uncompress() and this library's one-stream decoder give the input back."""
+    L, zb = g.L, g.zb
+    n = total
+    cap = L.zb200_deflate_bound(n, CHUNK, zb.FRAME_ZLIB)
+    h_out, h_back = host_alloc(L, cap), host_alloc(L, n + 64)
+    out = {"bytes": n, "chunk": CHUNK, "levels": {}}
+    ok_ref = ok_own = True
+    for level, gen in ((1, "markov"), (6, "mixed")):
+        host = host_alloc(L, n)
+        fill(host, n, gen, 0)
+        row = {"generator": gen}
+        for key, flag in (("independent", 0), ("carried", zb.CHUNK_CARRY)):
+            olen = C.c_size_t(cap)
+
+            def call():
+                olen.value = cap
+                r = L.zb200_deflate_host(g.ctx.handle, C.c_void_p(host), n, CHUNK, level, 0, zb.FRAME_ZLIB | flag, 1, C.c_void_p(h_out), C.byref(olen), None, None)
+                if r != 0:
+                    raise RuntimeError("chunk_carry level %d: %s" % (level, zb.last_error()))
+
+            call()
+            ts = []
+            for _ in range(3):
+                t0 = time.perf_counter()
+                call()
+                ts.append(time.perf_counter() - t0)
+            kern = g.kernel_shares(call, 1)
+            row[key] = {"compressed_bytes": olen.value, "e2e_ms": round(min(ts) * 1e3, 2), "e2e_GBps": round(n / min(ts) / 1e9, 2),
+                        "kernel_ms": round(sum(v["ms_per_step"] for v in kern.values()), 2)}
+        # (h_out now holds the carried stream)
+        res = zb.MemberResult()
+        t0 = time.perf_counter()
+        r = L.zb200_inflate_stream_host(g.ctx.handle, C.c_void_p(h_out), row["carried"]["compressed_bytes"], zb.WRAP_ZLIB, C.c_void_p(h_back), n + 64, C.byref(res))
+        row["own_decode_ms"] = round((time.perf_counter() - t0) * 1e3, 2)
+        own = r == 0 and res.status == 0 and res.out_len == n and C.string_at(h_back, n) == C.string_at(host, n)
+        ok_own = ok_own and own
+        if cpu is not None and cpu.ref is not None:
+            C.memset(h_back, 0, n)
+            bl = C.c_ulong(n)
+            rc = cpu.ref.uncompress(C.c_void_p(h_back), C.byref(bl), C.c_void_p(h_out), row["carried"]["compressed_bytes"])
+            ok_ref = ok_ref and rc == 0 and bl.value == n and C.string_at(h_back, n) == C.string_at(host, n)
+        row["size_carried_vs_independent"] = round(row["carried"]["compressed_bytes"] / row["independent"]["compressed_bytes"], 5)
+        row["kernel_time_carried_vs_independent"] = round(row["carried"]["kernel_ms"] / row["independent"]["kernel_ms"], 4)
+        out["levels"][str(level)] = row
+        L.zb200_host_free(C.c_void_p(host))
+    out["parity"] = {"own_stream_decoder_round_trip": bool(ok_own)}
+    if cpu is not None and cpu.ref is not None:
+        out["parity"]["reference_inflates_carried_stream"] = bool(ok_ref)
+    for p in (h_out, h_back):
+        L.zb200_host_free(C.c_void_p(p))
+    return out
+
+
 def one_shot_leg(cpu, n=64 * MIB):
     """compress2() / uncompress() of one buffer through the zlib.h surface itself (pageable host buffers, one host thread; the
     reference's API is serial), this library next to the reference: level 6 and 9, wall time of the calls, and whether the

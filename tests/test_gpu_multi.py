@@ -44,6 +44,15 @@ def test_multi_matches_single(both):
             want = ctx.deflate_host(data, level, 0, frame, 262144, finish)
             assert out.raw[:olen.value] == want, (g, level, frame, finish, len(data), olen.value, len(want))
             assert (c.value, a.value) == (o.crc32(data), o.adler32(data))
+    # carried history (zb200.h ZB200_CHUNK_CARRY): a GPU's first chunk is compressed behind the 32 KiB before its piece
+    for level, frame, chunk, data in ((6, zb.FRAME_ZLIB, 262144, d), (1, zb.FRAME_RAW, 65536, d), (6, zb.FRAME_GZIP, 5000, d[:30011]), (6, zb.FRAME_RAW, 262144, d[:100])):
+        cap = L.zb200_deflate_bound(len(data), chunk, frame) + 4096
+        out = C.create_string_buffer(cap)
+        olen = C.c_size_t(cap)
+        r = L.zb200_multi_deflate_host(m, data, len(data), chunk, level, 0, frame | zb.CHUNK_CARRY, 1, out, C.byref(olen), None, None)
+        assert r == 0, zb.last_error()
+        want = ctx.deflate_host(data, level, 0, frame | zb.CHUNK_CARRY, chunk, 1)
+        assert out.raw[:olen.value] == want, (g, level, frame, chunk, len(data), olen.value, len(want))
     # members: the file the GZIP_MEMBERS frame wrote, split by the discovery call, inflated on all GPUs
     cap = L.zb200_deflate_bound(len(d), 65536, zb.FRAME_GZIP_MEMBERS)
     out = C.create_string_buffer(cap)
