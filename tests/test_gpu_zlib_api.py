@@ -4,6 +4,7 @@ exports served by libzb200.so, driven exactly like the reference's callers
 WASM shim's buffer and streaming functions), compared with the reference."""
 import ctypes as C
 import os
+import random
 import subprocess
 
 import pytest
@@ -571,3 +572,67 @@ def test_many_host_threads_distinct_streams(z):
     with cf.ThreadPoolExecutor(max_workers=8) as ex:
         results = list(ex.map(job, range(16)))
     assert all(results), results
+
+
+def test_zlib_calls_from_many_host_threads(z):
+    """The zlib names are re-entrant (zlib.h; FAQ:151-160: one thread per z_stream): host threads calling at the same time are
+    spread over a pool of engine contexts (zb_zlib_api.cu api_ctx) and every one of them gets its own results — one-shot
+    calls, checksums and streams fed in slices, mixed, checked against an independent zlib (Python's).  One stream is also
+    handed from thread to thread between calls."""
+    import threading
+    import zlib
+    errors = []
+
+    def worker(t):
+        try:
+            rng = random.Random(1000 + t)
+            for it in range(10):
+                n = rng.choice((1000, 70000, 300000, 1 << 20, 3 << 20))
+                d = refz.gen(n, rng.choice((refz.GEN_TEXT, refz.GEN_MARKOV, refz.GEN_MIXED)), seed=t * 100 + it)
+                level = rng.choice((1, 6, 9))
+                cap = z.compressBound(n)
+                dst, dl = C.create_string_buffer(cap), C.c_ulong(cap)
+                assert z.compress2(dst, C.byref(dl), d, n, level) == 0
+                assert zlib.decompress(dst.raw[:dl.value]) == d
+                back, bl = C.create_string_buffer(n + 1), C.c_ulong(n + 1)
+                assert z.uncompress(back, C.byref(bl), zlib.compress(d, 6), len(zlib.compress(d, 6))) == 0 and back.raw[:bl.value] == d
+                assert z.crc32(0, d, n) == zlib.crc32(d) and z.adler32(1, d, n) == zlib.adler32(d)
+                s = z.deflate_stream(d, level, 0, refz.WRAP_GZIP, 0, in_slice=65536, out_slice=50000)
+                assert zlib.decompress(s, 31) == d
+                ret, msg, out, tin = z.inflate_all(zlib.compress(d, 9), refz.WRAP_ZLIB, cap=n + 64, in_slice=30000, out_slice=70000)
+                assert ret == refz.Z_STREAM_END and out == d
+        except BaseException as ex:                          # noqa: BLE001 (reported by the main thread)
+            errors.append((t, repr(ex)))
+
+    ths = [threading.Thread(target=worker, args=(t,)) for t in range(6)]
+    for th in ths:
+        th.start()
+    for th in ths:
+        th.join()
+    assert not errors, errors
+    # one z_stream, every call from another thread (and so, in turn, from another context of the pool)
+    d = refz.gen(2 << 20, refz.GEN_MARKOV, seed=5)
+    comp = zlib.compress(d, 6)
+    strm = refz.ZStream()
+    assert z.inflateInit2_(C.byref(strm), 15, z.version, C.sizeof(refz.ZStream)) == 0
+    src, dst = C.create_string_buffer(comp, len(comp)), C.create_string_buffer(len(d) + 64)
+    state = {"fed": 0, "produced": 0, "ret": 0}
+
+    def one_call():
+        k = min(100000, len(comp) - state["fed"])
+        strm.next_in, strm.avail_in = C.addressof(src) + state["fed"], k
+        state["fed"] += k
+        while True:
+            room = len(d) + 64 - state["produced"]
+            strm.next_out, strm.avail_out = C.addressof(dst) + state["produced"], room
+            state["ret"] = z.inflate(C.byref(strm), refz.Z_NO_FLUSH)
+            state["produced"] += room - strm.avail_out
+            if state["ret"] != 0 or strm.avail_in == 0:
+                break
+
+    while state["ret"] in (0, refz.Z_BUF_ERROR) and state["fed"] < len(comp):
+        th = threading.Thread(target=one_call)
+        th.start()
+        th.join()
+    assert state["ret"] == refz.Z_STREAM_END and dst.raw[:state["produced"]] == d
+    z.inflateEnd(C.byref(strm))

@@ -10,6 +10,8 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <atomic>
+#include <mutex>
 #include <vector>
 #include <deque>
 #include <memory>
@@ -20,18 +22,41 @@ using namespace zb;
 
 namespace {
 
+// The engine contexts behind the zlib API (device: $ZB200_DEVICE, default 0).  A context owns one set of streams, pinned
+// stages and device buffers, and its calls are serialised (zb_internal.h CtxUse) — so host threads that call the zlib names
+// at the same time are spread over a small POOL of contexts: a thread is given a slot the first time it calls (round robin
+// over $ZB200_CONTEXTS slots, default 4, at most 16) and keeps it; a slot's context is created when its first thread
+// arrives (a single-threaded process only ever has slot 0).  Every zlib.h call finishes its device work before it returns,
+// so a z_stream may move between threads — and so between contexts — from call to call, as with the reference (zlib.h:
+// "thread safe" = one thread per stream at a time, FAQ:151-160).
+constexpr int kMaxContexts = 16;
 std::mutex g_mu;
-zb200_ctx *g_ctx = nullptr;
+zb200_ctx *g_pool[kMaxContexts] = {nullptr};
 int g_ctx_err = 0;
+std::atomic<unsigned> g_threads{0};
 
-// The process-wide engine context behind the zlib API (device: $ZB200_DEVICE, default 0).
+int pool_slots() {
+    static const int n = [] { const char *e = getenv("ZB200_CONTEXTS"); const int v = e ? atoi(e) : 4; return v < 1 ? 1 : v > kMaxContexts ? kMaxContexts : v; }();
+    return n;
+}
+
 zb200_ctx *api_ctx() {
+    thread_local int slot = -1;
+    if (slot < 0) slot = (int)(g_threads.fetch_add(1) % (unsigned)pool_slots());
     std::lock_guard<std::mutex> g(g_mu);
-    if (!g_ctx && !g_ctx_err) {
+    if (g_ctx_err) return nullptr;                              // no usable device: said once, true for every thread
+    auto make = [](int *err) -> zb200_ctx * {
         const char *e = getenv("ZB200_DEVICE");
-        g_ctx_err = zb200_create(e ? atoi(e) : 0, &g_ctx);
-    }
-    return g_ctx;
+        zb200_ctx *c = nullptr;
+        *err = zb200_create(e ? atoi(e) : 0, &c);
+        return *err == ZB200_OK ? c : nullptr;
+    };
+    int err = 0;
+    if (!g_pool[slot]) g_pool[slot] = make(&err);
+    if (g_pool[slot]) return g_pool[slot];
+    if (!g_pool[0]) g_pool[0] = make(&err);                     // (a later slot that cannot be had shares the first one)
+    if (!g_pool[0]) g_ctx_err = err;
+    return g_pool[0];
 }
 
 // $ZB200_DEVICES = "all" or a list "0,1,3": large one-shot jobs behind the zlib API (compress2, deflate() flushes,
