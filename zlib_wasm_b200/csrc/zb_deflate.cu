@@ -1293,10 +1293,46 @@ int deflate_launch_opts(zb200_ctx *ctx, const uint8_t *d_in, size_t n, size_t S,
     const size_t W = carry ? prm.w_size : 0, E = S + (carry && skip > W ? skip : W);
     if (E > 0x40000000ull) { set_error("deflate: carried history: chunk + window at most 2^30 bytes"); return ZB200_ERR_PARAM; }
     const size_t nb_max = carry ? batch_chunks((nch ? nch : 1) * E, E, MB) : batch_chunks(n, S, MB);
-    int r = ensure_scratch(ctx, work_bytes(nb_max, E, MB));
+    // Two sub-batches in flight (a call of at least two): sub-batch j runs on stream j & 1 with its own working arrays.  The
+    // ordered kernels (chain, parse) and the tree kernel are bound by latency, not by issue slots (ncu: 43-52 % issue
+    // active), and the match / pack kernels by issue slots: kernels of neighbouring sub-batches fill each other's gaps.
+    // Only the running stream length orders them: layout + scan of sub-batch j wait for the scan of j - 1.
+    // Off while kernels are being timed one by one (zb200_profile_enable) and for gzip members; $ZB200_DUAL_STREAM=0 turns it off.
+    // (Measured: three and four in flight, or sub-batches of one wave, give nothing over two: 60.8 / 60.3 / 60.8 GB/s at level 1.)
+    static const int dual_knob = [] { const char *e = getenv("ZB200_DUAL_STREAM"); const int v = e ? atoi(e) : 2; return v == 1 ? 2 : v; }();
+    constexpr int kMaxFlight = zb200_ctx::kAux + 1;
+    const size_t nch_eff = nch ? nch : 1;
+    const bool may_fly = dual_knob >= 2 && !ctx->prof_on && !members && ctx->aux_stream[0] && level >= 1;
+    // Chunks per sub-batch: a whole number of WAVES of the chain kernel (its CTAs per SM x the SM count: 444 chunks at
+    // memLevel 8).  The ordered kernels take the same time for 1 chunk or a full wave, so 2048 chunks (4.6 waves) cost
+    // five waves: 1776 chunks per sub-batch measured 44.2 GB/s at level 1 against 42.0 for 2048.
+    // (Levels 4-9 spend their time in the match kernel, whose grid has a CTA per 16 Ki positions: no waves to speak of,
+    // and one more launch per 2 GiB measured 2 % slower.)
+    size_t nb_run = nb_max;
+    if (prm.mode == MODE_FAST) {
+        const size_t wave = deflate_wave_chunks(ctx, (int)prm.hash_bits - 7);
+        if (nb_run > wave) nb_run = nb_run / wave * wave;
+        static const int sub_waves = [] { const char *e = getenv("ZB200_SUB_WAVES"); return e ? atoi(e) : 0; }();
+        if (sub_waves > 0 && nb_run > wave * (size_t)sub_waves) nb_run = wave * (size_t)sub_waves;
+    } else if (prm.mode == MODE_SLOW && may_fly && nch_eff <= nb_run) {
+        // the lazy levels know no waves: a call (or a piece of the host pipeline) that would be ONE sub-batch goes as two halves in flight
+        static const size_t split_min = [] { const char *e = getenv("ZB200_SPLIT_MIN"); const long v = e ? atol(e) : 256; return (size_t)(v > 0 ? v : 0); }();
+        if (split_min && nch_eff >= 2 * split_min) nb_run = (nch_eff + 1) / 2;
+    }
+    const bool dual = may_fly && nch_eff > nb_run;
+    const int K = dual ? (dual_knob < kMaxFlight ? dual_knob : kMaxFlight) : 1;   // sub-batches in flight
+    const size_t wb = work_bytes(nb_run, E, MB);
+    int r = ensure_scratch(ctx, (size_t)K * wb);
     if (r) return r;
-    DeflateWork w;
-    carve(w, ctx->d_scratch, nb_max, E, MB);
+    DeflateWork w_set[kMaxFlight];
+    for (int k = 0; k < K; ++k) carve(w_set[k], (uint8_t *)ctx->d_scratch + (size_t)k * wb, nb_run, E, MB);
+    struct Events {                                                // [k]: scan of the latest sub-batch on stream k done; [kMaxFlight]: start / end
+        cudaEvent_t e[kMaxFlight + 1] = {};
+        ~Events() { for (auto x : e) if (x) cudaEventDestroy(x); }
+    } evs;
+    if (dual) for (auto &x : evs.e) ZB_CUDA(cudaEventCreateWithFlags(&x, cudaEventDisableTiming));
+    cudaStream_t const s_main = s;
+    auto flight_stream = [&](size_t j) { const int k = (int)(j % (size_t)K); return k ? ctx->aux_stream[k - 1] : s_main; };
     const DeflateDeviceTables *tabs = (const DeflateDeviceTables *)ctx->d_deflate_tables;
     uint64_t *running = ctx->d_small + 16;                         // stream length so far (device)
     uint32_t *sums = (uint32_t *)(ctx->d_small + 20);              // crc, adler of the whole input
@@ -1311,17 +1347,14 @@ int deflate_launch_opts(zb200_ctx *ctx, const uint8_t *d_in, size_t n, size_t S,
         if (r) return r;
         if (d_sums_out) ZB_CUDA(cudaMemcpyAsync(d_sums_out, sums, 8, cudaMemcpyDeviceToDevice, s));
     }
-    // Chunks per sub-batch: a whole number of WAVES of the chain kernel (its CTAs per SM x the SM count: 444 chunks at
-    // memLevel 8).  The ordered kernels take the same time for 1 chunk or a full wave, so 2048 chunks (4.6 waves) cost
-    // five waves: 1776 chunks per sub-batch measured 44.2 GB/s at level 1 against 42.0 for 2048.
-    // (Levels 4-9 spend their time in the match kernel, whose grid has a CTA per 16 Ki positions: no waves to speak of,
-    // and one more launch per 2 GiB measured 2 % slower.)
-    size_t nb_run = nb_max;
-    if (prm.mode == MODE_FAST) {
-        const size_t wave = deflate_wave_chunks(ctx, (int)prm.hash_bits - 7);
-        if (nb_run > wave) nb_run = nb_run / wave * wave;
+    if (dual) {                                                    // the other streams start behind the memset and the first offset
+        ZB_CUDA(cudaEventRecord(evs.e[kMaxFlight], s_main));
+        for (int k = 1; k < K; ++k) ZB_CUDA(cudaStreamWaitEvent(ctx->aux_stream[k - 1], evs.e[kMaxFlight], 0));
     }
     for (size_t c0 = 0; c0 < nch; c0 += nb_run) {
+        const size_t j = c0 / nb_run;
+        cudaStream_t const s = flight_stream(j);                   // (shadows the call's stream inside the loop)
+        DeflateWork &w = w_set[j % (size_t)K];
         Batch b;
         b.nb = (uint32_t)(nch - c0 < nb_run ? nch - c0 : nb_run);
         const size_t off = c0 * S;                                 // the sub-batch's first new byte, counted from the call's
@@ -1384,6 +1417,7 @@ int deflate_launch_opts(zb200_ctx *ctx, const uint8_t *d_in, size_t n, size_t S,
         prof_mark(ctx, s, "dfl_tree_kernel");
         dfl_tree_kernel<<<dim3((MB + kTreeWarps - 1) / kTreeWarps, b.nb), kTreeWarps * 32, 0, s>>>(b, strategy | (level == 0 ? 0x100 : 0), w.syms, w.blocks, w.nblocks, tabs, w.codes);
         ZB_LAUNCHED(); ZB_CHECK_LAUNCH();
+        if (dual && j > 0) ZB_CUDA(cudaStreamWaitEvent(s, evs.e[(j - 1) % (size_t)K], 0));   // the stream length up to here (and deflateUsed's order)
         prof_mark(ctx, s, "dfl_layout_kernel");
         if (one_long) dfl_layout_long_kernel<<<1, 1024, 0, s>>>(b, w.blocks, w.codes, w.nblocks, w.chunk_bytes, members ? 18 : 0, (uint32_t *)(ctx->d_small + 19));
         else dfl_layout_kernel<<<(b.nb + 127) / 128, 128, 0, s>>>(b, w.blocks, w.codes, w.nblocks, w.chunk_bytes, members ? 18 : 0,
@@ -1392,6 +1426,7 @@ int deflate_launch_opts(zb200_ctx *ctx, const uint8_t *d_in, size_t n, size_t S,
         prof_mark(ctx, s, "dfl_scan_kernel");
         dfl_scan_kernel<<<1, 1024, 0, s>>>(b.nb, w.chunk_bytes, w.chunk_off, running, d_chunk_end ? d_chunk_end + c0 : nullptr);
         ZB_LAUNCHED(); ZB_CHECK_LAUNCH();
+        if (dual) ZB_CUDA(cudaEventRecord(evs.e[j % (size_t)K], s));
         prof_mark(ctx, s, "dfl_pack_kernel");
         dfl_pack_kernel<<<dim3(MB + 1, b.nb), 256, 0, s>>>(b, w.syms, w.blocks, w.codes, w.nblocks, w.chunk_off, w.chunk_bytes,
                                                           tabs, (uint32_t *)d_out, members ? 10 : 0);
@@ -1406,6 +1441,10 @@ int deflate_launch_opts(zb200_ctx *ctx, const uint8_t *d_in, size_t n, size_t S,
             dfl_member_frame_kernel<<<(b.nb + 63) / 64, 64, 0, s>>>(b, d_out, level, strategy, w.chunk_off, w.chunk_bytes, w.chunk_crc);
             ZB_LAUNCHED(); ZB_CHECK_LAUNCH();
         }
+    }
+    for (int k = 1; k < K; ++k) {                                  // the call's stream ends behind everything the others did
+        ZB_CUDA(cudaEventRecord(evs.e[kMaxFlight], ctx->aux_stream[k - 1]));
+        ZB_CUDA(cudaStreamWaitEvent(s_main, evs.e[kMaxFlight], 0));
     }
     prof_mark(ctx, s, "dfl_frame_kernel");
     dfl_frame_kernel<<<1, 32, 0, s>>>(d_out, frame, level, strategy, finish, 1, running, sums, n - skip, d_total, o.window_bits);

@@ -264,6 +264,7 @@ int zb200_create(int device, zb200_ctx **out) {
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) return fail(ZB200_ERR_CUDA);
     if (cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess) return fail(ZB200_ERR_CUDA);
     if (cudaStreamCreateWithFlags(&ctx->back_stream, cudaStreamNonBlocking) != cudaSuccess) return fail(ZB200_ERR_CUDA);
+    for (auto &a : ctx->aux_stream) if (cudaStreamCreateWithFlags(&a, cudaStreamNonBlocking) != cudaSuccess) return fail(ZB200_ERR_CUDA);
     if (cudaEventCreateWithFlags(&ctx->busy_ev, cudaEventDisableTiming) != cudaSuccess) return fail(ZB200_ERR_CUDA);
     if (cudaMalloc((void **)&ctx->d_pipe, 160 * sizeof(uint64_t)) != cudaSuccess) return fail(ZB200_ERR_NOMEM);
     if (cudaMallocHost((void **)&ctx->h_pipe, 160 * sizeof(uint64_t)) != cudaSuccess) return fail(ZB200_ERR_NOMEM);
@@ -302,6 +303,7 @@ void zb200_destroy(zb200_ctx *ctx) {
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->back_stream) cudaStreamDestroy(ctx->back_stream);
+    for (auto a : ctx->aux_stream) if (a) cudaStreamDestroy(a);
     if (ctx->busy_ev) cudaEventDestroy(ctx->busy_ev);
     if (ctx->d_pipe) cudaFree(ctx->d_pipe);
     if (ctx->h_pipe) cudaFreeHost(ctx->h_pipe);

@@ -57,6 +57,8 @@ struct zb200_ctx {
     cudaStream_t stream = nullptr;          // the context's own stream
     cudaStream_t copy_stream = nullptr;     // H2D/D2H staging stream
     cudaStream_t back_stream = nullptr;     // D2H of finished pieces while later ones are still computed
+    static constexpr int kAux = 3;
+    cudaStream_t aux_stream[kAux] = {nullptr, nullptr, nullptr};   // deflate: sub-batch j of a call runs on stream j % K (K in flight)
     uint64_t *d_pipe = nullptr, *h_pipe = nullptr;   // per-piece (total, crc|adler<<32) of the pipelined host entry points: 2 x 80 u64
     std::mutex mu;                          // serialises use of the scratch/staging below
 
