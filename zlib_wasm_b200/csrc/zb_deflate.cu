@@ -1299,6 +1299,9 @@ int deflate_launch_opts(zb200_ctx *ctx, const uint8_t *d_in, size_t n, size_t S,
     // Only the running stream length orders them: layout + scan of sub-batch j wait for the scan of j - 1.
     // Off while kernels are being timed one by one (zb200_profile_enable) and for gzip members; $ZB200_DUAL_STREAM=0 turns it off.
     // (Measured: three and four in flight, or sub-batches of one wave, give nothing over two: 60.8 / 60.3 / 60.8 GB/s at level 1.)
+    // (Also measured: an explicit software pipeline — stage X of sub-batch j gated on stage X of j - 1 by events, so that unlike
+    //  stages are paired by construction — 59.4-59.7 GB/s against 60.8 at level 1, 11.16 against 11.33 at level 6: the block
+    //  scheduler's own drift pairs them as well, the gates only add bubbles.)
     static const int dual_knob = [] { const char *e = getenv("ZB200_DUAL_STREAM"); const int v = e ? atoi(e) : 2; return v == 1 ? 2 : v; }();
     constexpr int kMaxFlight = zb200_ctx::kAux + 1;
     const size_t nch_eff = nch ? nch : 1;
