@@ -110,7 +110,8 @@ uint32_t zb200_adler32_combine(uint32_t adler1, uint32_t adler2, int64_t len2);
 
 /* Worst-case output bytes for n input bytes cut into chunk_size chunks (compress.c:72, deflate.c:842). */
 size_t zb200_deflate_bound(size_t n, size_t chunk_size, int frame);
-/* Bytes of device scratch the engine will hold for a call of this shape. */
+/* Bytes of device scratch one sub-batch of a call of this shape works in; the engine keeps two sub-batches in flight
+ * (and the host pipeline two pieces), so it may hold up to four times this. */
 size_t zb200_deflate_scratch_bytes(size_t n, size_t chunk_size);
 
 /* Compress d_in[0..n).  level 1..9 (deflate.c:112-124), strategy 0..4 (zlib.h:196-200),

@@ -35,6 +35,14 @@ def call():
     assert r == 0, zb.last_error()
 
 
+# the host link on this box (a pinned 1 GiB copy each way): the ceiling of the end-to-end figure
+_probe = torch.empty(min(n, 1 << 30), dtype=torch.uint8, device="cuda")
+_hv = torch.frombuffer((C.c_uint8 * _probe.numel()).from_address(host), dtype=torch.uint8)
+for _ in range(2):
+    torch.cuda.synchronize(); t0 = time.perf_counter(); _probe.copy_(_hv, non_blocking=True); torch.cuda.synchronize(); t_in = time.perf_counter() - t0
+    t0 = time.perf_counter(); _hv.copy_(_probe, non_blocking=True); torch.cuda.synchronize(); t_out = time.perf_counter() - t0
+print("link probe: %.1f GB/s in, %.1f GB/s out" % (_probe.numel() / t_in / 1e9, _probe.numel() / t_out / 1e9), flush=True)
+del _probe
 call()
 ts = []
 for _ in range(3):

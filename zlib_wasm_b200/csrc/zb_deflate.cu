@@ -1302,10 +1302,14 @@ int deflate_launch_opts(zb200_ctx *ctx, const uint8_t *d_in, size_t n, size_t S,
     // (Also measured: an explicit software pipeline — stage X of sub-batch j gated on stage X of j - 1 by events, so that unlike
     //  stages are paired by construction — 59.4-59.7 GB/s against 60.8 at level 1, 11.16 against 11.33 at level 6: the block
     //  scheduler's own drift pairs them as well, the gates only add bubbles.)
-    static const int dual_knob = [] { const char *e = getenv("ZB200_DUAL_STREAM"); const int v = e ? atoi(e) : 2; return v == 1 ? 2 : v; }();
-    constexpr int kMaxFlight = zb200_ctx::kAux + 1;
+    // A caller that keeps two CALLS in flight itself (the host pipeline: piece k on flight slot k & 1) says so in o.slot: slot 1
+    // has its own stream-length / checksum cells, its own part of the scratch and its own second stream.
+    static const int dual_knob = [] { const char *e = getenv("ZB200_DUAL_STREAM"); const int v = e ? atoi(e) : 2; return v >= 1 ? 2 : 0; }();
+    constexpr int kMaxFlight = 2;
+    const size_t so = o.slot ? 32 : 0;                             // u64 cells of ctx->d_small per slot
+    cudaStream_t const s_other = ctx->aux_stream[o.slot ? 2 : 0];
     const size_t nch_eff = nch ? nch : 1;
-    const bool may_fly = dual_knob >= 2 && !ctx->prof_on && !members && ctx->aux_stream[0] && level >= 1;
+    const bool may_fly = dual_knob >= 2 && !ctx->prof_on && !members && s_other && level >= 1;
     // Chunks per sub-batch: a whole number of WAVES of the chain kernel (its CTAs per SM x the SM count: 444 chunks at
     // memLevel 8).  The ordered kernels take the same time for 1 chunk or a full wave, so 2048 chunks (4.6 waves) cost
     // five waves: 1776 chunks per sub-batch measured 44.2 GB/s at level 1 against 42.0 for 2048.
@@ -1323,23 +1327,25 @@ int deflate_launch_opts(zb200_ctx *ctx, const uint8_t *d_in, size_t n, size_t S,
         if (split_min && nch_eff >= 2 * split_min) nb_run = (nch_eff + 1) / 2;
     }
     const bool dual = may_fly && nch_eff > nb_run;
-    const int K = dual ? (dual_knob < kMaxFlight ? dual_knob : kMaxFlight) : 1;   // sub-batches in flight
+    const int K = dual ? 2 : 1;                                    // sub-batches in flight
     const size_t wb = work_bytes(nb_run, E, MB);
-    int r = ensure_scratch(ctx, (size_t)K * wb);
+    const size_t slot_base = o.slot ? o.slot_bytes : 0;           // (the caller sized o.slot_bytes with deflate_call_scratch)
+    int r = ensure_scratch(ctx, slot_base + (size_t)K * wb);
     if (r) return r;
     DeflateWork w_set[kMaxFlight];
-    for (int k = 0; k < K; ++k) carve(w_set[k], (uint8_t *)ctx->d_scratch + (size_t)k * wb, nb_run, E, MB);
+    for (int k = 0; k < K; ++k) carve(w_set[k], (uint8_t *)ctx->d_scratch + slot_base + (size_t)k * wb, nb_run, E, MB);
     struct Events {                                                // [k]: scan of the latest sub-batch on stream k done; [kMaxFlight]: start / end
         cudaEvent_t e[kMaxFlight + 1] = {};
         ~Events() { for (auto x : e) if (x) cudaEventDestroy(x); }
     } evs;
     if (dual) for (auto &x : evs.e) ZB_CUDA(cudaEventCreateWithFlags(&x, cudaEventDisableTiming));
     cudaStream_t const s_main = s;
-    auto flight_stream = [&](size_t j) { const int k = (int)(j % (size_t)K); return k ? ctx->aux_stream[k - 1] : s_main; };
+    auto flight_stream = [&](size_t j) { return (j % (size_t)K) ? s_other : s_main; };
     const DeflateDeviceTables *tabs = (const DeflateDeviceTables *)ctx->d_deflate_tables;
-    uint64_t *running = ctx->d_small + 16;                         // stream length so far (device)
-    uint32_t *sums = (uint32_t *)(ctx->d_small + 20);              // crc, adler of the whole input
-    CkAccum *acc1 = (CkAccum *)(ctx->d_small + 24);
+    uint64_t *running = ctx->d_small + so + 16;                    // stream length so far (device)
+    uint32_t *sums = (uint32_t *)(ctx->d_small + so + 20);         // crc, adler of the whole input
+    CkAccum *acc1 = (CkAccum *)(ctx->d_small + so + 24);
+    uint32_t *bi_used = (uint32_t *)(ctx->d_small + so + 19);      // deflateUsed of the call's last byte
     const size_t zero_bytes = zb200_deflate_bound(n_new, S, frame);
     prof_mark(ctx, s, "memset_output");
     ZB_CUDA(cudaMemsetAsync(d_out, 0, (zero_bytes + 3) & ~(size_t)3, s));
@@ -1352,7 +1358,7 @@ int deflate_launch_opts(zb200_ctx *ctx, const uint8_t *d_in, size_t n, size_t S,
     }
     if (dual) {                                                    // the other streams start behind the memset and the first offset
         ZB_CUDA(cudaEventRecord(evs.e[kMaxFlight], s_main));
-        for (int k = 1; k < K; ++k) ZB_CUDA(cudaStreamWaitEvent(ctx->aux_stream[k - 1], evs.e[kMaxFlight], 0));
+        ZB_CUDA(cudaStreamWaitEvent(s_other, evs.e[kMaxFlight], 0));
     }
     for (size_t c0 = 0; c0 < nch; c0 += nb_run) {
         const size_t j = c0 / nb_run;
@@ -1422,9 +1428,8 @@ int deflate_launch_opts(zb200_ctx *ctx, const uint8_t *d_in, size_t n, size_t S,
         ZB_LAUNCHED(); ZB_CHECK_LAUNCH();
         if (dual && j > 0) ZB_CUDA(cudaStreamWaitEvent(s, evs.e[(j - 1) % (size_t)K], 0));   // the stream length up to here (and deflateUsed's order)
         prof_mark(ctx, s, "dfl_layout_kernel");
-        if (one_long) dfl_layout_long_kernel<<<1, 1024, 0, s>>>(b, w.blocks, w.codes, w.nblocks, w.chunk_bytes, members ? 18 : 0, (uint32_t *)(ctx->d_small + 19));
-        else dfl_layout_kernel<<<(b.nb + 127) / 128, 128, 0, s>>>(b, w.blocks, w.codes, w.nblocks, w.chunk_bytes, members ? 18 : 0,
-                                                            (uint32_t *)(ctx->d_small + 19));
+        if (one_long) dfl_layout_long_kernel<<<1, 1024, 0, s>>>(b, w.blocks, w.codes, w.nblocks, w.chunk_bytes, members ? 18 : 0, bi_used);
+        else dfl_layout_kernel<<<(b.nb + 127) / 128, 128, 0, s>>>(b, w.blocks, w.codes, w.nblocks, w.chunk_bytes, members ? 18 : 0, bi_used);
         ZB_LAUNCHED(); ZB_CHECK_LAUNCH();
         prof_mark(ctx, s, "dfl_scan_kernel");
         dfl_scan_kernel<<<1, 1024, 0, s>>>(b.nb, w.chunk_bytes, w.chunk_off, running, d_chunk_end ? d_chunk_end + c0 : nullptr);
@@ -1445,8 +1450,8 @@ int deflate_launch_opts(zb200_ctx *ctx, const uint8_t *d_in, size_t n, size_t S,
             ZB_LAUNCHED(); ZB_CHECK_LAUNCH();
         }
     }
-    for (int k = 1; k < K; ++k) {                                  // the call's stream ends behind everything the others did
-        ZB_CUDA(cudaEventRecord(evs.e[kMaxFlight], ctx->aux_stream[k - 1]));
+    if (dual) {                                                    // the call's stream ends behind everything the other one did
+        ZB_CUDA(cudaEventRecord(evs.e[kMaxFlight], s_other));
         ZB_CUDA(cudaStreamWaitEvent(s_main, evs.e[kMaxFlight], 0));
     }
     prof_mark(ctx, s, "dfl_frame_kernel");
@@ -1499,7 +1504,8 @@ int zb200_deflate_dev(zb200_ctx *ctx, const void *d_in, size_t n, size_t chunk_s
 // trailer (deflate.c:1004-1054,1239-1256) are written here on the host, the input checksums
 // of the pieces merged with crc32_combine / adler32_combine.
 static int deflate_host_pipelined(zb200_ctx *ctx, const uint8_t *in, size_t n, size_t S, const DeflateOpts &opts,
-                                  int frame, int finish, uint8_t *out, size_t *out_len, uint32_t *in_adler, uint32_t *in_crc) {
+                                  int frame, int finish, uint8_t *out, size_t *out_len, uint32_t *in_adler, uint32_t *in_crc,
+                                  uint32_t *bits_used) {
     const int level = opts.level, strategy = opts.strategy;
     const int pframe = frame == ZB200_FRAME_GZIP_MEMBERS ? ZB200_FRAME_GZIP_MEMBERS : ZB200_FRAME_RAW;
     // Pieces of 128 .. 512 MiB: smaller ones leave the GPU underfilled (the chain kernel needs ~450 chunks in flight),
@@ -1533,14 +1539,21 @@ static int deflate_host_pipelined(zb200_ctx *ctx, const uint8_t *in, size_t n, s
     if (r) return r;
     // carried history: piece k > 0 is compressed behind the last W bytes of piece k - 1, which lie just before it on the device
     const size_t W = (opts.carry && level >= 1 && pframe == ZB200_FRAME_RAW) ? (size_t)1 << opts.window_bits : 0;
-    if ((r = ensure_scratch(ctx, W ? zb200_deflate_scratch_bytes((piece / S + 1) * (S + W), S + W) : zb200_deflate_scratch_bytes(piece, S)))) return r;   // no reallocation (= implicit sync) mid-pipeline
+    // Two PIECES in flight: piece k is compressed on flight slot k & 1 (its own stream, stream-length cells and part of the
+    // scratch, DeflateOpts::slot).  A piece is short — one wave of the chain kernel at levels 1-2 — and its kernels leave the
+    // GPU half idle in turn (the ordered ones wait on latency, the others on issue slots); with 37 pieces of 222 MiB the kernels
+    // of an 8 GiB call summed to 176 ms of its 180: the pipeline was bound by them, not by the link.
+    static const int fly_knob = [] { const char *e = getenv("ZB200_DUAL_STREAM"); return e ? atoi(e) : 2; }();
+    const bool fly = fly_knob >= 1 && !ctx->prof_on && level >= 1 && ctx->aux_stream[1] && np >= 2;
+    const size_t per_slot = 2 * (W ? zb200_deflate_scratch_bytes((piece / S + 1) * (S + W), S + W) : zb200_deflate_scratch_bytes(piece, S)) + 4096;
+    if ((r = ensure_scratch(ctx, fly ? 2 * per_slot : per_slot))) return r;   // no reallocation (= implicit sync) mid-pipeline
     cudaEvent_t ev_in[kMaxPieces], ev_out[kMaxPieces];
     for (size_t k = 0; k < np; ++k) {
         ZB_CUDA(cudaEventCreateWithFlags(&ev_in[k], cudaEventDisableTiming));
         ZB_CUDA(cudaEventCreateWithFlags(&ev_out[k], cudaEventDisableTiming));
     }
     auto cleanup = [&]() { for (size_t k = 0; k < np; ++k) { cudaEventDestroy(ev_in[k]); cudaEventDestroy(ev_out[k]); } };
-    cudaStream_t s = ctx->stream;
+    cudaStream_t const s0 = ctx->stream;
     for (size_t k = 0; k < np; ++k) {
         const size_t len = k + 1 < np ? piece : n - k * piece;
         if (cudaMemcpyAsync(ctx->d_io_in + k * piece, in + k * piece, len, cudaMemcpyHostToDevice, ctx->copy_stream) != cudaSuccess ||
@@ -1548,12 +1561,14 @@ static int deflate_host_pipelined(zb200_ctx *ctx, const uint8_t *in, size_t n, s
     }
     for (size_t k = 0; k < np; ++k) {
         const size_t len = k + 1 < np ? piece : n - k * piece;
+        cudaStream_t const s = fly && (k & 1) ? ctx->aux_stream[1] : s0;
         cudaStreamWaitEvent(s, ev_in[k], 0);
         DeflateOpts po = opts;
         po.skip = k ? W : 0; po.first_bit = k == 0 ? opts.first_bit : 0u;
+        po.slot = fly ? (int)(k & 1) : 0; po.slot_bytes = per_slot;
         r = deflate_launch_opts(ctx, ctx->d_io_in + k * piece - po.skip, len + po.skip, S, po, pframe, (finish && k + 1 == np) ? 1 : 0,
                                 ctx->d_io_out + ooff[k], bound[k], nullptr, ctx->d_pipe + 2 * k, (uint32_t *)(ctx->d_pipe + 2 * k + 1), s);
-        if (r) { cudaStreamSynchronize(s); cudaStreamSynchronize(ctx->copy_stream); cleanup(); return r; }
+        if (r) { cudaStreamSynchronize(s0); for (auto a : ctx->aux_stream) cudaStreamSynchronize(a); cudaStreamSynchronize(ctx->copy_stream); cleanup(); return r; }
         cudaMemcpyAsync(ctx->h_pipe + 2 * k, ctx->d_pipe + 2 * k, 16, cudaMemcpyDeviceToHost, s);
         cudaEventRecord(ev_out[k], s);
     }
@@ -1585,7 +1600,13 @@ static int deflate_host_pipelined(zb200_ctx *ctx, const uint8_t *in, size_t n, s
         pos += (size_t)total;
     }
     cudaStreamSynchronize(ctx->back_stream);
-    cudaStreamSynchronize(s);
+    cudaStreamSynchronize(s0);
+    if (fly) for (auto a : ctx->aux_stream) cudaStreamSynchronize(a);
+    if (rc == ZB200_OK && bits_used && finish) {                   // deflateUsed: left by the last piece in its slot's cell
+        const size_t so = fly && ((np - 1) & 1) ? 32 : 0;
+        if (cudaMemcpy(ctx->h_small, ctx->d_small + so + 19, 8, cudaMemcpyDeviceToHost) == cudaSuccess) *bits_used = ((const uint32_t *)ctx->h_small)[0];
+        else rc = ZB200_ERR_CUDA;
+    }
     cleanup();
     if (rc == ZB200_OK && finish) {
         uint8_t tr[8];
@@ -1653,12 +1674,7 @@ static int deflate_host_impl(zb200_ctx *ctx, const uint8_t *in, size_t n, size_t
     if (n >= ((size_t)256 << 20) && chunk_size >= 1 && chunk_size <= ((size_t)16 << 20) && level >= 0 && level <= 9 &&
         strategy >= 0 && strategy <= 4 && frame >= 0 && frame <= 3 && !opts.skip && is_pinned(in) && is_pinned(out)) {
         if (bits_used) *bits_used = 8;                             // (read back below only on the single-shot path)
-        const int r = deflate_host_pipelined(ctx, in, n, chunk_size, opts, frame, finish, out, out_len, in_adler, in_crc);
-        if (r == ZB200_OK && bits_used && finish) {
-            ZB_CUDA(cudaMemcpy(ctx->h_small, ctx->d_small + 19, 8, cudaMemcpyDeviceToHost));
-            *bits_used = ((const uint32_t *)ctx->h_small)[0];
-        }
-        return r;
+        return deflate_host_pipelined(ctx, in, n, chunk_size, opts, frame, finish, out, out_len, in_adler, in_crc, bits_used);
     }
     const size_t bound = zb200_deflate_bound(n, chunk_size ? chunk_size : 1, frame);
     int r = ensure_io(ctx, n + 16, bound + 16);

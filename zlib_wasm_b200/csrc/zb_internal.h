@@ -161,6 +161,8 @@ struct DeflateOpts {
     int window_bits = 15, mem_level = 8;     // deflate.c:440-455: w_size, hash_bits, lit_bufsize
     size_t skip = 0;                         // preset dictionary at the head of a single raw chunk
     unsigned first_bit = 0;                  // deflatePrime: the stream starts at this bit (0..7) of out[0]
+    int slot = 0;                            // flight slot (0 / 1) of a caller that keeps two calls in flight on two streams of one
+    size_t slot_bytes = 0;                   //   context, and the scratch bytes slot 0 may use (slot 1's part starts there)
     bool carry = false;                      // ZB200_CHUNK_CARRY: every chunk is compressed behind the w_size bytes before it; `skip` is
                                              // then the history in front of the FIRST chunk (a dictionary, or the previous piece's tail)
 };
