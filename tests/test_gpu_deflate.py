@@ -399,5 +399,16 @@ def test_carried_history_pipelined_pieces(ctx):
             assert got == want, (level, frame, len(got), len(want))
             plain = ctx.deflate_host(d, level, 0, frame, chunk)
             assert len(got) < len(plain)
+        # memLevel 4: many more blocks per chunk than the pipeline sized its flight slots for — such a piece runs alone
+        want = _deflate_opts(ctx, d, chunk, zb.FRAME_RAW, 6, mem_level=4)
+        cap = L.zb200_deflate_bound(n, chunk, zb.FRAME_RAW)
+        h_out = L.zb200_host_alloc(cap)
+        olen = C.c_size_t(cap)
+        o = zb.DeflateOpts(6, 0, 0, 4, 0, 0)
+        r = L.zb200_deflate_host_opts(ctx.handle, C.c_void_p(h_in), n, chunk, C.byref(o), zb.FRAME_RAW, 1, C.c_void_p(h_out), C.byref(olen), None, None, None)
+        assert r == 0, zb.last_error()
+        got = C.string_at(h_out, olen.value)
+        L.zb200_host_free(C.c_void_p(h_out))
+        assert got == want
     finally:
         L.zb200_host_free(C.c_void_p(h_in))

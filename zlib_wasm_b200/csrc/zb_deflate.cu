@@ -1329,7 +1329,12 @@ int deflate_launch_opts(zb200_ctx *ctx, const uint8_t *d_in, size_t n, size_t S,
     const bool dual = may_fly && nch_eff > nb_run;
     const int K = dual ? 2 : 1;                                    // sub-batches in flight
     const size_t wb = work_bytes(nb_run, E, MB);
-    const size_t slot_base = o.slot ? o.slot_bytes : 0;           // (the caller sized o.slot_bytes with deflate_call_scratch)
+    const size_t slot_base = o.slot ? o.slot_bytes : 0;
+    // The caller's estimate of a slot's scratch is for memLevel 8; a call that needs more (small memLevels: many more blocks
+    // per chunk) would reach into the other slot's part — it then runs alone: after everything enqueued so far, and to its end
+    // before the caller enqueues the next piece.
+    const bool alone = o.slot_bytes && (size_t)K * wb > o.slot_bytes;
+    if (alone) ZB_CUDA(cudaDeviceSynchronize());
     int r = ensure_scratch(ctx, slot_base + (size_t)K * wb);
     if (r) return r;
     DeflateWork w_set[kMaxFlight];
@@ -1458,6 +1463,7 @@ int deflate_launch_opts(zb200_ctx *ctx, const uint8_t *d_in, size_t n, size_t S,
     dfl_frame_kernel<<<1, 32, 0, s>>>(d_out, frame, level, strategy, finish, 1, running, sums, n - skip, d_total, o.window_bits);
     ZB_LAUNCHED(); ZB_CHECK_LAUNCH();
     prof_mark(ctx, s, nullptr);
+    if (alone) ZB_CUDA(cudaStreamSynchronize(s));
     return ZB200_OK;
 }
 
@@ -1565,7 +1571,7 @@ static int deflate_host_pipelined(zb200_ctx *ctx, const uint8_t *in, size_t n, s
         cudaStreamWaitEvent(s, ev_in[k], 0);
         DeflateOpts po = opts;
         po.skip = k ? W : 0; po.first_bit = k == 0 ? opts.first_bit : 0u;
-        po.slot = fly ? (int)(k & 1) : 0; po.slot_bytes = per_slot;
+        po.slot = fly ? (int)(k & 1) : 0; po.slot_bytes = fly ? per_slot : 0;
         r = deflate_launch_opts(ctx, ctx->d_io_in + k * piece - po.skip, len + po.skip, S, po, pframe, (finish && k + 1 == np) ? 1 : 0,
                                 ctx->d_io_out + ooff[k], bound[k], nullptr, ctx->d_pipe + 2 * k, (uint32_t *)(ctx->d_pipe + 2 * k + 1), s);
         if (r) { cudaStreamSynchronize(s0); for (auto a : ctx->aux_stream) cudaStreamSynchronize(a); cudaStreamSynchronize(ctx->copy_stream); cleanup(); return r; }
