@@ -239,6 +239,41 @@ def test_deflate_preset_dictionary_byte_exact():
                     assert err == 1 and back == data and len(got) <= 1.03 * len(want) + 8, (kind, dl, n, level, strat, err, msg)
 
 
+def test_carried_history_chunks_host_replay():
+    """zb200.h ZB200_CHUNK_CARRY on the host: chunk c of a call is the dictionary picture with the min(32 KiB, bytes before
+    it) in front of it as history and a sync point (finish = 0) or the final block at its end (zb_deflate.cu chunk_lo /
+    chunk_data / chunk_len say exactly that to the kernels).  The phases then emit, chunk by chunk, the bytes of the
+    reference's deflateSetDictionary(previous 32 KiB) + deflate(Z_SYNC_FLUSH) — and the whole is one valid stream."""
+    if not refz.have_ref():
+        pytest.skip("oracle/_ref/libzref.so not built")
+    L = _build("def_emul")
+    L.emul_deflate_chunk_dict.restype = C.c_long
+    L.emul_deflate_chunk_dict.argtypes = [C.c_char_p, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t,
+                                          C.POINTER(C.c_uint32)]
+    ref = refz.ref()
+    for kind, n, chunk in ((refz.GEN_TEXT, 300000, 65536), (refz.GEN_MIXED, 200000, 20000), (refz.GEN_MARKOV, 150000, 100000)):
+        d = refz.gen(n, kind, seed=50 + kind)
+        for level, strat in ((6, 0), (9, 1), (4, 0), (6, 3), (1, 0)):
+            got, want = [], []
+            nch = (n + chunk - 1) // chunk
+            for c in range(nch):
+                pos = c * chunk
+                hist, piece = d[max(0, pos - 32768):pos], d[pos:pos + chunk]
+                last = c == nch - 1
+                joined = hist + piece
+                cap = len(joined) + len(joined) // 8 + 1024
+                out, st = C.create_string_buffer(cap), (C.c_uint32 * 2)()
+                r = L.emul_deflate_chunk_dict(joined, len(joined), len(hist), level, strat, 1 if last else 0, out, cap, st)
+                assert r >= 0, (r, kind, c, level, strat)
+                got.append(out.raw[:r])
+                want.append(ref.deflate_stream(piece, level, strat, refz.WRAP_RAW, 0, dictionary=hist if hist else None,
+                                               last_flush=refz.Z_FINISH if last else refz.Z_SYNC_FLUSH))
+            if level >= 4:
+                assert got == want, (kind, chunk, level, strat, [len(x) for x in got], [len(x) for x in want])
+            err, msg, back, used = ref.inflate_all(b"".join(got), refz.WRAP_RAW, cap=n + 16)
+            assert err == 1 and back == d and used == sum(len(x) for x in got), (kind, chunk, level, strat, msg)
+
+
 def _bits_stream_of_31_bit_matches(n_matches):
     """stored block of 20000 bytes, then a fixed-Huffman block of matches that take 31 bits each (length code 284 +
     5 extra bits, distance code 28 + 13 extra bits): the pattern on which the lean symbol loop refills in the
