@@ -561,6 +561,26 @@ for wbits, mem, dic in ((15, 8, None), (-15, 8, d[:20000]), (9, 8, None), (12, 1
     s = dst.raw[:produced]
     o = zlib.decompressobj(wbits if wbits != 9 else 15, zdict=dic) if dic is not None else zlib.decompressobj(wbits if wbits != 9 else 15)
     assert o.decompress(s) == d and o.eof, (wbits, mem)
+# no flushes at all, $ZB200_STREAM_HOLD_MIB=1: the library cuts the stream itself every MiB — carried, the pieces see each other
+for level in (6, 1):
+    strm = refz.ZStream()
+    assert z.deflateInit2_(C.byref(strm), level, 8, 15, 8, 0, z.version, ZS) == 0
+    cap = len(d) + len(d) // 4 + 65536
+    src, dst = C.create_string_buffer(d, len(d)), C.create_string_buffer(cap)
+    off = produced = 0
+    while True:
+        k = min(300000, len(d) - off)
+        strm.next_in, strm.avail_in = C.addressof(src) + off, k
+        strm.next_out, strm.avail_out = C.addressof(dst) + produced, cap - produced
+        off += k
+        r = z.deflate(C.byref(strm), refz.Z_FINISH if off >= len(d) else refz.Z_NO_FLUSH)
+        produced = cap - strm.avail_out
+        assert r in (0, 1), r
+        if r == 1:
+            break
+    z.deflateEnd(C.byref(strm))
+    assert zlib.decompress(dst.raw[:produced]) == d
+    print("size", 100 + level, produced)
 print("ok")
 """
 
@@ -574,8 +594,10 @@ def test_chunk_carry_knob_at_the_zlib_surface():
         env = dict(os.environ)
         env["ZB200_CHUNK_CARRY"] = knob
         env["ZB200_CHUNK"] = "65536"
+        env["ZB200_STREAM_HOLD_MIB"] = "1"
         p = subprocess.run([sys.executable, "-c", CARRY_SCRIPT % {"root": ROOT}], env=env, capture_output=True, text=True, timeout=600)
         assert p.returncode == 0 and "ok" in p.stdout, p.stderr[-2000:]
         sizes[knob] = {int(l.split()[1]): int(l.split()[2]) for l in p.stdout.splitlines() if l.startswith("size")}
     assert sizes["1"][1] < sizes["0"][1] and sizes["1"][3] < sizes["0"][3]
     assert sizes["1"][6] == sizes["0"][6]                     # (one run of blocks either way: nothing is cut at level 6)
+    assert sizes["1"][106] < sizes["0"][106] and sizes["1"][101] < sizes["0"][101]   # the library's own cuts keep the window, too

@@ -892,7 +892,9 @@ int deflate(z_streamp strm, int flush) {
             if (!s->header_done) put_header(*s);
             // Z_SYNC_FLUSH / Z_PARTIAL_FLUSH / Z_BLOCK keep the window (deflate.c:1211-1218 clears the hash only for
             // Z_FULL_FLUSH): the first chunk after such a point is compressed behind the last 32 KiB before it
-            s->keep_history = !spill && (flush == Z_SYNC_FLUSH || flush == Z_PARTIAL_FLUSH || flush == Z_BLOCK);
+            // (a spill is this library's own cut, not the caller's: with $ZB200_CHUNK_CARRY=1 it keeps the window as well — the reference
+            //  would not have cut there at all)
+            s->keep_history = spill ? api_frame(0) != 0 : (flush == Z_SYNC_FLUSH || flush == Z_PARTIAL_FLUSH || flush == Z_BLOCK);
             int r;
             if (spill) {
                 const size_t keep = s->in.size() % api_chunk();
