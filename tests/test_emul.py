@@ -274,6 +274,40 @@ def test_carried_history_chunks_host_replay():
             assert err == 1 and back == d and used == sum(len(x) for x in got), (kind, chunk, level, strat, msg)
 
 
+def test_carried_history_chunks_golden():
+    """The same claim pinned WITHOUT the compiled reference: tests/golden/carry_golden.json (made from the unmodified
+    reference by tests/golden/make_carry_golden.py) holds length and SHA-256 of the reference's carried-chunk streams;
+    the host replay of the device cores reproduces them."""
+    import hashlib
+    import json
+    g = json.load(open(os.path.join(refz.ROOT, "tests", "golden", "carry_golden.json")))
+    L = _build("def_emul")
+    L.emul_deflate_chunk_dict.restype = C.c_long
+    L.emul_deflate_chunk_dict.argtypes = [C.c_char_p, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t,
+                                          C.POINTER(C.c_uint32)]
+    assert len(g["cases"]) >= 12
+    for e in g["cases"]:
+        d = refz.gen(e["n"], e["kind"], seed=e["seed"])
+        chunk, n = e["chunk"], e["n"]
+        nch = max(1, (n + chunk - 1) // chunk)
+        parts = []
+        for c in range(nch):
+            pos = c * chunk
+            hist, piece = d[max(0, pos - 32768):pos], d[pos:pos + chunk]
+            joined = hist + piece
+            cap = len(joined) + len(joined) // 8 + 1024
+            out, st = C.create_string_buffer(cap), (C.c_uint32 * 2)()
+            r = L.emul_deflate_chunk_dict(joined, len(joined), len(hist), e["level"], e["strategy"], 1 if c == nch - 1 else 0, out, cap, st)
+            assert r >= 0, (r, e)
+            parts.append(out.raw[:r])
+        s = b"".join(parts)
+        assert [len(p) for p in parts] == e["chunk_lens"], (e["kind"], e["n"], e["chunk"], e["level"])
+        assert len(s) == e["len"] and hashlib.sha256(s).hexdigest() == e["sha256"], (e["kind"], e["n"], e["chunk"], e["level"])
+        if "hex" in e:
+            assert s.hex() == e["hex"]
+        assert zlib.decompress(s, -15) == d
+
+
 def _bits_stream_of_31_bit_matches(n_matches):
     """stored block of 20000 bytes, then a fixed-Huffman block of matches that take 31 bits each (length code 284 +
     5 extra bits, distance code 28 + 13 extra bits): the pattern on which the lean symbol loop refills in the
