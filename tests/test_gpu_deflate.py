@@ -412,3 +412,18 @@ def test_carried_history_pipelined_pieces(ctx):
         assert got == want
     finally:
         L.zb200_host_free(C.c_void_p(h_in))
+
+
+def test_carried_history_golden(ctx):
+    """The committed fixture (tests/golden/carry_golden.json, made from the unmodified reference): the engine's carried-chunk
+    streams have the reference's length and SHA-256 — a pin that needs no compiled reference on the box."""
+    import hashlib
+    import json
+    import os
+    g = json.load(open(os.path.join(refz.ROOT, "tests", "golden", "carry_golden.json")))
+    for e in g["cases"]:
+        d = refz.gen(e["n"], e["kind"], seed=e["seed"])
+        s = ctx.deflate_host(d, e["level"], e["strategy"], zb.FRAME_RAW | zb.CHUNK_CARRY, e["chunk"])
+        assert len(s) == e["len"] and hashlib.sha256(s).hexdigest() == e["sha256"], (e["kind"], e["n"], e["chunk"], e["level"], len(s), e["len"])
+        if "hex" in e:
+            assert s.hex() == e["hex"]
