@@ -107,6 +107,12 @@ uint32_t zb200_adler32_combine(uint32_t adler1, uint32_t adler2, int64_t len2);
  * across chunks (any inflate has it; zb200_inflate_stream_host decodes it at its block headers).  With a dictionary
  * (zb200_deflate_opts.dict_len) the first chunk is compressed behind that. */
 #define ZB200_CHUNK_CARRY        0x100
+/* OR-ed into `frame` (levels 1-3, chunks of at least 1 << (memLevel + 7) bytes, no dictionary, no carried history): the greedy
+ * levels with the reference's OWN hash chains — deflate_fast inserts only where its loop stands and inside short matches
+ * (deflate.c:1873-1897), so its chains depend on its parse and a chunk is one serial walk: one thread per chunk, the bytes of
+ * the reference's deflate() for the same chunking, at a small fraction of the default path's speed (which inserts every
+ * position and finds more: 0.95-1.00 x the reference's size, not its bytes).  Ignored where it does not apply. */
+#define ZB200_EXACT_FAST         0x200
 
 /* Worst-case output bytes for n input bytes cut into chunk_size chunks (compress.c:72, deflate.c:842). */
 size_t zb200_deflate_bound(size_t n, size_t chunk_size, int frame);

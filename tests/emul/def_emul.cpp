@@ -30,6 +30,10 @@ struct BitSink {
 static uint32_t g_multi_G = 0, g_multi_range = 0;
 extern "C" void emul_set_multi(uint32_t G, uint32_t range) { g_multi_G = G; g_multi_range = range; }
 
+// deflate_fast with the reference's own chains (zb_deflate.cuh fast_exact_chunk: the opt-in exact form of levels 1-3)
+static int g_exact_fast = 0;
+extern "C" void emul_set_exact_fast(int on) { g_exact_fast = on; }
+
 // One chunk -> raw deflate bytes (blocks + marker when !final).  Returns size or -1.
 // `skip`: the first skip bytes are a preset dictionary (history only).
 // window_bits / mem_level: deflateInit2_'s (deflate.c:440-455).
@@ -39,7 +43,9 @@ extern "C" long emul_deflate_chunk_opts(const uint8_t *data, uint32_t n, uint32_
     const DeflateParams prm = deflate_params(level, strategy, window_bits, mem_level);
     std::vector<uint16_t> prev(n + 1, 0);
     std::vector<uint32_t> mf(n + 1, 0), mq(n + 1, 0);
-    if (prm.mode == MODE_FAST || prm.mode == MODE_SLOW) {
+    const bool exact_fast = g_exact_fast && prm.mode == MODE_FAST && skip == 0;
+    if (exact_fast) {
+    } else if (prm.mode == MODE_FAST || prm.mode == MODE_SLOW) {
         std::vector<int32_t> head(1u << prm.hash_bits, -1);
         for (uint32_t p = 0; p + kMinMatch <= n; ++p) {
             const uint32_t h = hash3(data + p, prm);
@@ -81,7 +87,10 @@ extern "C" long emul_deflate_chunk_opts(const uint8_t *data, uint32_t n, uint32_
     struct { uint32_t nsyms, nblocks; } sink;
     // the kernel's segmented parse (zb_deflate.cuh seg_*), the lanes replayed by loops;
     // the serial whole-chunk parse must give the same symbols and blocks
-    if (prm.mode != MODE_SLOW) {
+    if (exact_fast) {
+        std::vector<uint32_t> head(1u << prm.hash_bits, 0);
+        fast_exact_chunk(data, n, prm, final_chunk != 0, head.data(), prev.data(), syms.data(), blocks.data(), sink.nsyms, sink.nblocks);
+    } else if (prm.mode != MODE_SLOW) {
         // greedy rules: exit tables per tile (zb_deflate.cu dfl_parse_greedy_kernel), the lanes replayed by loops
         const bool use_m = prm.mode != MODE_HUFF;
         std::vector<uint32_t> mfv(kGtSlots); std::vector<uint16_t> lc(kGtSlots);
@@ -213,7 +222,7 @@ extern "C" long emul_deflate_chunk_opts(const uint8_t *data, uint32_t n, uint32_
         sink.nsyms = total + (pending ? 1 : 0);
         sink.nblocks = seg_finish(blocks.data(), total, pending, n, prm, final_chunk != 0, skip);
     }
-    {   // cross-check against the serial whole-chunk parse
+    if (!exact_fast) {   // cross-check against the serial whole-chunk parse
         std::vector<uint32_t> syms2(n + 2);
         std::vector<BlockInfo> blocks2(max_blocks_for(n, prm.sym_limit));
         uint32_t ns2 = 0, nb2 = 0;

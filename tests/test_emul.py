@@ -581,3 +581,51 @@ def test_block_parallel_decode_replay():
         if r >= 2:                                           # (fewer than two chunks: the caller takes the one-member path)
             assert st.value == 0 and ol.value == n and dst.raw[:n] == payload and iu.value == len(comp), (level, strategy, list(stats))
             assert ck.value == zlib.adler32(payload)
+
+
+def test_deflate_fast_exact_chains_byte_exact():
+    """zb_deflate.cuh fast_exact_chunk (ZB200_EXACT_FAST): deflate_fast with the reference's own parse-dependent hash chains
+    (deflate.c:1824-1915: insertions only where the loop stands and inside matches of at most max_insert_length) — levels 1-3
+    byte for byte the reference's streams, on every generator, ragged sizes, Z_FILTERED / Z_FIXED, window sizes and memLevels."""
+    if not refz.have_ref():
+        pytest.skip("oracle/_ref/libzref.so not built")
+    L = _build("def_emul")
+    L.emul_deflate_chunk_opts.restype = C.c_long
+    L.emul_deflate_chunk_opts.argtypes = [C.c_char_p, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                          C.c_size_t, C.POINTER(C.c_uint32)]
+    L.emul_set_exact_fast(1)
+    try:
+        ref = refz.ref()
+        ZS = C.sizeof(refz.ZStream)
+
+        def reference(d, level, strat, wbits, mem, final):
+            strm = refz.ZStream()
+            assert ref.deflateInit2_(C.byref(strm), level, 8, -wbits, mem, strat, ref.version, ZS) == 0
+            cap = len(d) + len(d) // 8 + 1024
+            src, dst = C.create_string_buffer(d, max(len(d), 1)), C.create_string_buffer(cap)
+            strm.next_in, strm.avail_in, strm.next_out, strm.avail_out = C.addressof(src), len(d), C.addressof(dst), cap
+            r = ref.deflate(C.byref(strm), refz.Z_FINISH if final else refz.Z_FULL_FLUSH)
+            assert r == (1 if final else 0) and strm.avail_in == 0
+            out = dst.raw[:cap - strm.avail_out]
+            ref.deflateEnd(C.byref(strm))
+            return out
+
+        rng = random.Random(11)
+        cases = 0
+        for kind in (refz.GEN_TEXT, refz.GEN_MARKOV, refz.GEN_RANDOM, refz.GEN_MIXED, refz.GEN_BYTES):
+            for n in (0, 1, 2, 3, 4, 262, 263, 1000, 32768, 65274, 65275, 65536, 70000, 131072, 262144, 300001):
+                d = refz.gen(n, kind, seed=70 + kind)
+                for level in (1, 2, 3):
+                    strat = rng.choice((0, 0, 1, 4))
+                    wbits, mem = rng.choice(((15, 8), (15, 8), (15, 9), (12, 8), (9, 1), (14, 4), (15, 1)))
+                    final = rng.random() < 0.7
+                    want = reference(d, level, strat, wbits, mem, final)
+                    cap = n + n // 8 + 1024
+                    out, st = C.create_string_buffer(cap), (C.c_uint32 * 2)()
+                    r = L.emul_deflate_chunk_opts(d, n, 0, level, strat, wbits, mem, 1 if final else 0, out, cap, st)
+                    assert r >= 0, (r, kind, n, level, strat, wbits, mem, final)
+                    assert out.raw[:r] == want, (kind, n, level, strat, wbits, mem, final, r, len(want))
+                    cases += 1
+        assert cases >= 200
+    finally:
+        L.emul_set_exact_fast(0)

@@ -427,3 +427,21 @@ def test_carried_history_golden(ctx):
         assert len(s) == e["len"] and hashlib.sha256(s).hexdigest() == e["sha256"], (e["kind"], e["n"], e["chunk"], e["level"], len(s), e["len"])
         if "hex" in e:
             assert s.hex() == e["hex"]
+
+
+def test_exact_fast_levels_1_to_3_are_the_references_bytes(ctx):
+    """zb200.h ZB200_EXACT_FAST: deflate_fast with the reference's own parse-dependent hash chains (one thread per chunk) —
+    levels 1-3 byte for byte the reference's stream on the same chunking, every wrapper; the default path stays the fast,
+    smaller-but-different one.  (The walk itself is proven on the host replay: test_emul.py.)"""
+    for kind in (refz.GEN_TEXT, refz.GEN_MIXED):
+        d = refz.gen(1200000 + 77, kind, seed=500 + kind)
+        for level in (1, 2, 3):
+            for chunk, frame in ((262144, zb.FRAME_RAW), (65536, zb.FRAME_ZLIB), (524288, zb.FRAME_GZIP)):
+                s = ctx.deflate_host(d, level, 0, frame | zb.EXACT_FAST, chunk)
+                r = ref_stream(d, level, 0, frame, chunk)
+                assert s == r, (kind, level, chunk, frame, len(s), len(r))
+                assert ctx.deflate_host(d, level, 0, frame, chunk) != r      # (the default greedy path: not these bytes)
+    # where it does not apply it is ignored: levels 4-9 are the reference's bytes anyway, tiny chunks take the default path
+    d = refz.gen(300000, refz.GEN_TEXT, seed=501)
+    assert ctx.deflate_host(d, 6, 0, zb.FRAME_RAW | zb.EXACT_FAST, 65536) == ref_stream(d, 6, 0, zb.FRAME_RAW, 65536)
+    assert decode_ok(ctx.deflate_host(d, 1, 0, zb.FRAME_RAW | zb.EXACT_FAST, 4096), zb.FRAME_RAW, d)

@@ -24,6 +24,7 @@ OK = 0
 ERR_NO_DEVICE, ERR_CUDA, ERR_PARAM, ERR_NOMEM, ERR_OUTPUT = -101, -102, -103, -104, -105
 CRC32, ADLER32 = 1, 2
 FRAME_RAW, FRAME_ZLIB, FRAME_GZIP, FRAME_GZIP_MEMBERS = 0, 1, 2, 3
+EXACT_FAST = 0x200           # OR-ed into a frame: levels 1-3 with the reference's own chains, its bytes (zb200.h)
 CHUNK_CARRY = 0x100          # OR-ed into a frame: every chunk compressed behind the 32 KiB before it (zb200.h)
 WRAP_RAW, WRAP_ZLIB, WRAP_GZIP, WRAP_AUTO = 0, 1, 2, 3
 

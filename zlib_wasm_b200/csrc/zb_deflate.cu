@@ -497,6 +497,23 @@ dfl_match_sorted_kernel(Batch b, DeflateParams prm, const uint16_t *__restrict__
     }
 }
 
+// ---- levels 1-3 with the reference's own chains (ZB200_EXACT_FAST): one chunk per THREAD ----
+// fast_exact_chunk (zb_deflate.cuh) is one serial walk per chunk — deflate_fast's chains depend on its parse — so the only
+// parallelism is across chunks: a CTA of one working thread per chunk, every chunk resident at once (each thread is its own
+// warp: no lane waits for another chunk's control flow; the walk is bound by the latency of its dependent table reads).
+// head table = the first 1 << hash_bits words of the chunk's (zeroed) match-table slot, links = its link array.
+__global__ void __launch_bounds__(32)
+dfl_fast_exact_kernel(Batch b, DeflateParams prm, uint16_t *__restrict__ prev_all, uint32_t *__restrict__ mfull,
+                      uint32_t *__restrict__ syms, BlockInfo *__restrict__ blocks, uint32_t *__restrict__ nblocks) {
+    if (threadIdx.x != 0) return;
+    const uint32_t c = blockIdx.x;
+    const uint64_t off = (uint64_t)c * b.S;
+    uint32_t ns = 0, nbk = 0;
+    fast_exact_chunk(chunk_data(b, c), chunk_len(b, c), prm, chunk_final(b, c), mfull + off, prev_all + off, syms + off,
+                     blocks + (uint64_t)c * b.MB, ns, nbk);
+    nblocks[c] = nbk;
+}
+
 // ---- phase 3, greedy rules (deflate_fast / deflate_rle / deflate_huff): one chunk per CTA ----
 // Exit tables per tile (zb_deflate.cuh gt_*): warp w takes tiles w, w + 4, ...; it loads
 // the tile's match entries, fills the tables, waits for the previous tile's exit (named
@@ -1274,7 +1291,10 @@ int deflate_launch_opts(zb200_ctx *ctx, const uint8_t *d_in, size_t n, size_t S,
     // markov text: 0.983 -> 0.997 x the reference's size; 13 bits: 1.46 ms but 1.020 x).  Level 3 walks 32 links: the
     // fuller chains of a shorter hash cost its match kernel more (15.1 -> 18.9 ms) than the chain kernel gains, it keeps
     // memLevel's table.  $ZB200_FAST_HASH_BITS overrides.
-    if (prm.mode == MODE_FAST && level <= 2 && !tune) {
+    // ZB200_EXACT_FAST: levels 1-3 as the reference's own deflate_fast (its table's hash width, its chains); needs the head
+    // table to fit the chunk's match-table slot, no history in front of the call
+    const bool exact_fast = o.exact_fast && prm.mode == MODE_FAST && skip == 0 && !o.carry && S >= ((size_t)1 << prm.hash_bits);
+    if (prm.mode == MODE_FAST && level <= 2 && !tune && !exact_fast) {
         static const int fast_hash = [] { const char *e = getenv("ZB200_FAST_HASH_BITS"); return e ? atoi(e) : 14; }();
         const uint32_t hb = (uint32_t)(fast_hash >= 9 && fast_hash <= 16 ? fast_hash : 14);
         if (prm.hash_bits > hb) { prm.hash_bits = hb; prm.hash_shift = (hb + kMinMatch - 1) / kMinMatch; prm.hash_mask = (1u << hb) - 1u; }
@@ -1385,14 +1405,20 @@ int deflate_launch_opts(zb200_ctx *ctx, const uint8_t *d_in, size_t n, size_t S,
         const bool one_long = multi_knob && b.nb == 1 && b.bytes >= 2 * kMultiRange;
         const uint32_t n_ranges = one_long ? (uint32_t)((b.bytes + kMultiRange - 1) / kMultiRange) : 1u;
         b.range = one_long ? (uint32_t)kMultiRange : 0u;
-        if (prm.mode == MODE_FAST || prm.mode == MODE_SLOW) {
+        if (exact_fast) {
+            prof_mark(ctx, s, "dfl_fast_exact_kernel");
+            ZB_CUDA(cudaMemsetAsync(w.mfull, 0, (size_t)b.nb * E * 4, s));   // the head tables
+            dfl_fast_exact_kernel<<<b.nb, 32, 0, s>>>(b, prm, w.prev, w.mfull, w.syms, w.blocks, w.nblocks);
+            ZB_LAUNCHED(); ZB_CHECK_LAUNCH();
+        } else if (prm.mode == MODE_FAST || prm.mode == MODE_SLOW) {
             prof_mark(ctx, s, "dfl_chain_kernel");
             const unsigned chain_grid = one_long ? n_ranges : b.nb;
             if (prm.hash_bits < 15) dfl_chain_kernel<true><<<chain_grid, kChainWarps * 32, 2u << prm.hash_bits, s>>>(b, prm, w.prev);
             else dfl_chain_kernel<false><<<chain_grid, kChainWarps * 32, 2u << prm.hash_bits, s>>>(b, prm, w.prev);
             ZB_LAUNCHED(); ZB_CHECK_LAUNCH();
         }
-        if (sorted_walks) {
+        if (exact_fast) {
+        } else if (sorted_walks) {
             dim3 g((unsigned)((E + kMsTile - 1) / kMsTile), b.nb);
             prof_mark(ctx, s, "dfl_match_sorted_kernel");
             static const int key_knob = [] { const char *e = getenv("ZB200_KEY_CAP"); return e ? atoi(e) : 0; }();
@@ -1420,14 +1446,15 @@ int deflate_launch_opts(zb200_ctx *ctx, const uint8_t *d_in, size_t n, size_t S,
             dfl_match_kernel<<<g, 256, 0, s>>>(b, prm, w.prev, w.mfull, w.mquarter);
             ZB_LAUNCHED(); ZB_CHECK_LAUNCH();
         }
-        prof_mark(ctx, s, "dfl_parse_kernel");
-        if (prm.mode == MODE_SLOW && one_long) {
+        if (!exact_fast) prof_mark(ctx, s, "dfl_parse_kernel");
+        if (exact_fast) {
+        } else if (prm.mode == MODE_SLOW && one_long) {
             ZB_CUDA(cudaMemsetAsync(w.links, 0, (size_t)n_ranges * sizeof(ParseLink), s));
             ZB_CUDA(cudaMemsetAsync(w.mstate, 0, 16, s));
             dfl_parse_multi_kernel<<<n_ranges, kSegLanes, kParseSmem, s>>>(b, prm, w.mfull, w.mquarter, w.syms, w.blocks, w.nblocks, n_ranges, w.mstate, w.links);
         } else if (prm.mode == MODE_SLOW) dfl_parse_kernel<<<b.nb, kSegLanes, kParseSmem, s>>>(b, prm, w.mfull, w.mquarter, w.syms, w.blocks, w.nblocks);
         else dfl_parse_greedy_kernel<<<b.nb, kGtWarps * 32, 0, s>>>(b, prm, w.mfull, w.syms, w.blocks, w.nblocks);
-        ZB_LAUNCHED(); ZB_CHECK_LAUNCH();
+        if (!exact_fast) { ZB_LAUNCHED(); ZB_CHECK_LAUNCH(); }
         prof_mark(ctx, s, "dfl_tree_kernel");
         dfl_tree_kernel<<<dim3((MB + kTreeWarps - 1) / kTreeWarps, b.nb), kTreeWarps * 32, 0, s>>>(b, strategy | (level == 0 ? 0x100 : 0), w.syms, w.blocks, w.nblocks, tabs, w.codes);
         ZB_LAUNCHED(); ZB_CHECK_LAUNCH();
@@ -1474,7 +1501,7 @@ using namespace zb;
 extern "C" {
 
 size_t zb200_deflate_bound(size_t n, size_t chunk_size, int frame) {
-    frame &= ~ZB200_CHUNK_CARRY;                                   // (carried history changes what a chunk's matches see, not its worst case)
+    frame &= 0xff;                                                 // (the flags change what a chunk's matches see, not its worst case)
     if (chunk_size == 0) chunk_size = 1;
     size_t nch = (n + chunk_size - 1) / chunk_size;
     if (nch == 0) nch = 1;
@@ -1498,8 +1525,8 @@ int zb200_deflate_dev(zb200_ctx *ctx, const void *d_in, size_t n, size_t chunk_s
     ZB_CUDA(cudaSetDevice(ctx->device));
     CtxUse use(ctx, pick_stream(ctx, stream));
     DeflateOpts o;
-    o.level = level; o.strategy = strategy; o.carry = (frame & ZB200_CHUNK_CARRY) != 0;
-    return deflate_launch_opts(ctx, (const uint8_t *)d_in, n, chunk_size, o, frame & ~ZB200_CHUNK_CARRY, finish,
+    o.level = level; o.strategy = strategy; o.carry = (frame & ZB200_CHUNK_CARRY) != 0; o.exact_fast = (frame & ZB200_EXACT_FAST) != 0;
+    return deflate_launch_opts(ctx, (const uint8_t *)d_in, n, chunk_size, o, frame & 0xff, finish,
                                (uint8_t *)d_out, out_cap, d_chunk_end, d_total, nullptr, pick_stream(ctx, stream));
 }
 
@@ -1711,8 +1738,8 @@ int zb200_deflate_host(zb200_ctx *ctx, const void *in, size_t n, size_t chunk_si
     ZB_CUDA(cudaSetDevice(ctx->device));
     CtxUse use(ctx, ctx->stream);
     DeflateOpts o;
-    o.level = level; o.strategy = strategy; o.carry = (frame & ZB200_CHUNK_CARRY) != 0;
-    return deflate_host_impl(ctx, (const uint8_t *)(in ? in : (const void *)""), n, chunk_size, o, frame & ~ZB200_CHUNK_CARRY, finish, (uint8_t *)out, out_len, in_adler, in_crc, nullptr);
+    o.level = level; o.strategy = strategy; o.carry = (frame & ZB200_CHUNK_CARRY) != 0; o.exact_fast = (frame & ZB200_EXACT_FAST) != 0;
+    return deflate_host_impl(ctx, (const uint8_t *)(in ? in : (const void *)""), n, chunk_size, o, frame & 0xff, finish, (uint8_t *)out, out_len, in_adler, in_crc, nullptr);
 }
 
 int zb200_deflate_host_opts(zb200_ctx *ctx, const void *in, size_t n, size_t chunk_size, const zb200_deflate_opts *opts,
@@ -1724,8 +1751,8 @@ int zb200_deflate_host_opts(zb200_ctx *ctx, const void *in, size_t n, size_t chu
     DeflateOpts o;
     o.level = opts->level; o.strategy = opts->strategy; o.window_bits = opts->window_bits ? opts->window_bits : 15;
     o.mem_level = opts->mem_level ? opts->mem_level : 8; o.skip = opts->dict_len; o.first_bit = opts->first_bit;
-    o.carry = (frame & ZB200_CHUNK_CARRY) != 0;
-    return deflate_host_impl(ctx, (const uint8_t *)(in ? in : (const void *)""), n, chunk_size, o, frame & ~ZB200_CHUNK_CARRY, finish, (uint8_t *)out, out_len, in_adler, in_crc, bits_used);
+    o.carry = (frame & ZB200_CHUNK_CARRY) != 0; o.exact_fast = (frame & ZB200_EXACT_FAST) != 0;
+    return deflate_host_impl(ctx, (const uint8_t *)(in ? in : (const void *)""), n, chunk_size, o, frame & 0xff, finish, (uint8_t *)out, out_len, in_adler, in_crc, bits_used);
 }
 
 int zb200_deflate_host_dict(zb200_ctx *ctx, const void *in, size_t n, size_t dict_len, int level, int strategy,

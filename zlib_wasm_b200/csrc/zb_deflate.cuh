@@ -452,6 +452,48 @@ ZB_HD void parse_chunk(const uint8_t *data, uint32_t n, const uint32_t *mfull, c
     nsyms = s.nsyms; nblocks = s.nblocks;
 }
 
+// ---- deflate_fast with the reference's OWN chains (levels 1-3 byte for byte; opt-in) ----------
+// deflate_fast (deflate.c:1824-1915) inserts a position into the hash chains only where its loop stands, plus the inside
+// of a match no longer than max_insert_length (= max_lazy: 4 / 5 / 6 at levels 1-3; deflate.c:1873-1897) — so what a search
+// finds depends on every parse decision of the 32 KiB before it, and two parses that differ early need not meet again:
+// unlike the lazy parse there is nothing to speculate on, a chunk is one serial walk.  The walk itself is the greedy rule of
+// parse_steps with an accessor that keeps head / link tables as it goes: mf(p) = INSERT_STRING(p), longest_match from the
+// head it displaced (match_walk: prev_length = 2, no TOO_FAR rule, nice_match clamped to the lookahead), then the
+// insertions deflate_fast does behind a short match.  Position 0 is never a candidate (a head of 0 is NIL, deflate.c:1366);
+// heads that a slide would have cut are further back than MAX_DIST and end the walk either way.
+// head: 1 << hash_bits entries, zeroed; link: one u16 distance per position (what the chain kernel writes for the other levels).
+struct FastExactAcc {
+    const uint8_t *data; uint32_t n; const DeflateParams *prm; uint32_t *head; uint16_t *link; uint32_t *syms; uint32_t count;
+    ZB_HD void insert(uint32_t p) {
+        const uint32_t h = hash3(data + p, *prm), q = head[h];
+        link[p] = (q && p - q <= 65535u) ? (uint16_t)(p - q) : (uint16_t)0;
+        head[h] = p;
+    }
+    ZB_HD uint32_t mf(uint32_t p) {
+        if (p + kMinMatch > n) return 0;                       // lookahead < MIN_MATCH: neither inserted nor searched (deflate.c:1847)
+        insert(p);
+        const PlainMem mem{data, link};
+        const uint32_t m = match_walk(mem, n, p, *prm).full;
+        const uint32_t len = m >> 16;
+        if (len >= (uint32_t)kMinMatch && len <= (uint32_t)prm->lazy && n - (p + len) >= (uint32_t)kMinMatch)
+            for (uint32_t q = p + 1; q < p + len; ++q) insert(q);   // deflate.c:1879-1888
+        return m;
+    }
+    ZB_HD uint32_t mq(uint32_t p) { return mf(p); }
+    ZB_HD uint32_t byte(uint32_t p) const { return data[p]; }
+    ZB_HD void put(uint32_t sym) { syms[count++] = sym; }
+};
+
+ZB_HD void fast_exact_chunk(const uint8_t *data, uint32_t n, const DeflateParams &prm, bool final_chunk, uint32_t *head,
+                            uint16_t *link, uint32_t *syms, BlockInfo *blocks, uint32_t &nsyms, uint32_t &nblocks) {
+    ParseState s;
+    parse_init(s, blocks, n, prm, 0);
+    FastExactAcc acc{data, n, &prm, head, link, syms, 0};
+    parse_steps(s, n, n, prm, acc);
+    parse_finish(s, n, prm, final_chunk, acc);
+    nsyms = s.nsyms; nblocks = s.nblocks;
+}
+
 // ---- the parse, cut into segments that are parsed concurrently ---------------------
 // The parse is a serial state machine, but like a prefix-code decoder it forgets its
 // past quickly: two parses that are at the same position in the same state (held match

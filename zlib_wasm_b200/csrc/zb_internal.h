@@ -163,6 +163,7 @@ struct DeflateOpts {
     unsigned first_bit = 0;                  // deflatePrime: the stream starts at this bit (0..7) of out[0]
     int slot = 0;                            // flight slot (0 / 1) of a caller that keeps two calls in flight on two streams of one
     size_t slot_bytes = 0;                   //   context, and the scratch bytes slot 0 may use (slot 1's part starts there)
+    bool exact_fast = false;                 // ZB200_EXACT_FAST: levels 1-3 with the reference's own parse-dependent chains (one thread per chunk)
     bool carry = false;                      // ZB200_CHUNK_CARRY: every chunk is compressed behind the w_size bytes before it; `skip` is
                                              // then the history in front of the FIRST chunk (a dictionary, or the previous piece's tail)
 };

@@ -101,7 +101,8 @@ int zb200_multi_deflate_host(zb200_multi *m, const void *in, size_t n, size_t ch
                              int finish, void *out, size_t *out_len, uint32_t *in_adler, uint32_t *in_crc) {
     // ZB200_CHUNK_CARRY: a GPU's first chunk is compressed behind the 32 KiB before its piece (copied along), like every other chunk
     const size_t W = ((frame & ZB200_CHUNK_CARRY) && (frame & 0xff) != ZB200_FRAME_GZIP_MEMBERS && level >= 1) ? 32768 : 0;
-    frame &= ~ZB200_CHUNK_CARRY;
+    const bool exact_fast = (frame & ZB200_EXACT_FAST) != 0;
+    frame &= 0xff;
     if (!m || m->ctx.empty() || (!in && n) || !out || !out_len || chunk_size == 0 || frame < 0 || frame > 3) return ZB200_ERR_PARAM;
     const size_t S = chunk_size, g0 = m->ctx.size();
     const size_t nch = (n + S - 1) / S;
@@ -172,7 +173,7 @@ int zb200_multi_deflate_host(zb200_multi *m, const void *in, size_t n, size_t ch
                 const size_t l = j + 1 < ns ? sub : len[k] - j * sub;
                 if (pinned && ns > 1) cudaStreamWaitEvent(s, ev[j], 0);
                 DeflateOpts o;
-                o.level = level; o.strategy = strategy; o.carry = W != 0; o.skip = j ? (H + j * sub < W ? H + j * sub : W) : H;
+                o.level = level; o.strategy = strategy; o.carry = W != 0; o.exact_fast = exact_fast; o.skip = j ? (H + j * sub < W ? H + j * sub : W) : H;
                 r = deflate_launch_opts(ctx, ctx->d_io_in + H + j * sub - o.skip, l + o.skip, S, o, pframe, (finish && last && j + 1 == ns) ? 1 : 0,
                                         ctx->d_io_out + sub_off[j], zb200_deflate_bound(l, S, pframe), nullptr, ctx->d_pipe + 2 * j,
                                         (uint32_t *)(ctx->d_pipe + 2 * j + 1), s);

@@ -121,7 +121,9 @@ size_t run_chunk(size_t n, int level, int strategy) {
 // form decode independently, which this library's own inflate exploits.
 int api_frame(int frame) {
     static const int carry = [] { const char *e = getenv("ZB200_CHUNK_CARRY"); return e && atoi(e) > 0 ? ZB200_CHUNK_CARRY : 0; }();
-    return frame | carry;
+    // $ZB200_EXACT_FAST=1: levels 1-3 emit the reference's own bytes (zb200.h ZB200_EXACT_FAST: one thread per chunk, slow)
+    static const int exact = [] { const char *e = getenv("ZB200_EXACT_FAST"); return e && atoi(e) > 0 ? ZB200_EXACT_FAST : 0; }();
+    return frame | carry | exact;
 }
 
 [[noreturn]] void die_no_device(const char *fn) {
@@ -894,7 +896,7 @@ int deflate(z_streamp strm, int flush) {
             // Z_FULL_FLUSH): the first chunk after such a point is compressed behind the last 32 KiB before it
             // (a spill is this library's own cut, not the caller's: with $ZB200_CHUNK_CARRY=1 it keeps the window as well — the reference
             //  would not have cut there at all)
-            s->keep_history = spill ? api_frame(0) != 0 : (flush == Z_SYNC_FLUSH || flush == Z_PARTIAL_FLUSH || flush == Z_BLOCK);
+            s->keep_history = spill ? (api_frame(0) & ZB200_CHUNK_CARRY) != 0 : (flush == Z_SYNC_FLUSH || flush == Z_PARTIAL_FLUSH || flush == Z_BLOCK);
             int r;
             if (spill) {
                 const size_t keep = s->in.size() % api_chunk();
